@@ -1,0 +1,273 @@
+"""ctypes driver of the CPU oracle (oracle/pnode_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs.  The product package never imports this module.
+
+Right-hand sides reach the oracle as plain C compiled with gcc at run time (``compile_rhs``): ``f`` and
+the analytic Jacobian are printed from the same SymPy trace the product uses, and the initial
+derivatives ``u^(k)(t0)`` are obtained *symbolically* (``y_{k+1} = dy_k/du * f + dy_k/dt``) -- a
+different method from the product's on-device Taylor-series arithmetic, so agreement of the two is a real
+check of TaylorModeInit (reference: src/initialization/autodiffinit.jl:52-67, pinned by
+test/state_init.jl:9-56).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import tempfile
+from typing import Optional
+
+import numpy as np
+import sympy as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+EK0, EK1 = 0, 1
+DIFF_DYNAMIC, DIFF_FIXED = 0, 1
+COV_REF, COV_QR = 0, 1
+RET = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable"}
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "pnode_oracle.c")
+    hdr = os.path.join(_HERE, "pnode_oracle.h")
+    if (not force and os.path.exists(_LIB_PATH)
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        return _LIB_PATH
+    cmd = ["gcc", "-O3", "-march=native", "-fno-fast-math", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared",
+           "-o", _LIB_PATH, src, "-lm"]
+    subprocess.run(cmd, check=True, cwd=_HERE)
+    return _LIB_PATH
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("d", C.c_int32), ("q", C.c_int32), ("n_p", C.c_int32), ("alg", C.c_int32),
+        ("diffusion", C.c_int32), ("calibrate", C.c_int32), ("smooth", C.c_int32), ("adaptive", C.c_int32),
+        ("save_everystep", C.c_int32), ("cov_backend", C.c_int32), ("maxiters", C.c_int64),
+        ("initial_diffusion", C.c_double), ("t0", C.c_double), ("t1", C.c_double), ("dt", C.c_double),
+        ("abstol", C.c_double), ("reltol", C.c_double), ("dtmin", C.c_double), ("dtmax", C.c_double),
+        ("beta1", C.c_double), ("beta2", C.c_double), ("qmin", C.c_double), ("qmax", C.c_double),
+        ("gamma", C.c_double), ("qsteady_min", C.c_double), ("qsteady_max", C.c_double), ("qoldinit", C.c_double),
+        ("tstops", C.POINTER(C.c_double)), ("n_tstops", C.c_int64),
+        ("forced_diffusion", C.POINTER(C.c_double)), ("n_forced", C.c_int64),
+    ]
+
+
+class Traj(C.Structure):
+    _fields_ = [
+        ("n", C.c_int64), ("d", C.c_int32), ("q", C.c_int32), ("D", C.c_int32), ("smooth", C.c_int32),
+        ("alg", C.c_int32), ("retcode", C.c_int32),
+        ("naccept", C.c_int64), ("nreject", C.c_int64), ("nf", C.c_int64), ("njac", C.c_int64),
+        ("loglik", C.c_double), ("global_diffusion", C.c_double),
+        ("t", C.POINTER(C.c_double)), ("diffusions", C.POINTER(C.c_double)),
+        ("x_filt_mu", C.POINTER(C.c_double)), ("x_filt_R", C.POINTER(C.c_double)),
+        ("x_smooth_mu", C.POINTER(C.c_double)), ("x_smooth_R", C.POINTER(C.c_double)),
+        ("pu_mu", C.POINTER(C.c_double)), ("pu_R", C.POINTER(C.c_double)),
+        ("bk_G", C.POINTER(C.c_double)), ("bk_b", C.POINTER(C.c_double)), ("bk_LR", C.POINTER(C.c_double)),
+    ]
+
+
+RHS_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double)
+TAYLOR_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
+                        C.c_int)
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        dp = C.POINTER(C.c_double)
+        _lib.oracle_solve.restype = C.c_int
+        _lib.oracle_solve.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_void_p, dp, dp, C.POINTER(Traj)]
+        _lib.oracle_traj_free.argtypes = [C.POINTER(Traj)]
+        _lib.oracle_solve_ensemble.restype = C.c_int
+        _lib.oracle_solve_ensemble.argtypes = [
+            C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, dp, dp, C.c_int, dp, dp,
+            C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), dp]
+        _lib.oracle_max_threads.restype = C.c_int
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+# ------------------------------------------------------------------------------------------------
+# RHS code generation (plain C for gcc) from a SymPy trace
+# ------------------------------------------------------------------------------------------------
+class CompiledRHS:
+    def __init__(self, so_path, d, n_p, qmax):
+        self.so = C.CDLL(so_path)
+        self.d, self.n_p, self.qmax = d, n_p, qmax
+        self.f = C.cast(self.so.oracle_user_f, C.c_void_p)
+        self.jac = C.cast(self.so.oracle_user_jac, C.c_void_p)
+        self.taylor = C.cast(self.so.oracle_user_taylor, C.c_void_p)
+
+
+def _cblock(exprs, targets, prefix):
+    repl, red = sp.cse(list(exprs), symbols=sp.numbered_symbols(prefix), optimizations="basic")
+    pr = lambda e: sp.ccode(e, standard="c99")  # noqa: E731
+    lines = [f"  const double {s} = {pr(e)};" for s, e in repl]
+    lines += [f"  {t} = {pr(e)};" for t, e in zip(targets, red)]
+    return "\n".join(lines)
+
+
+def symbolic_derivatives(tr, q):
+    """[u, f, y'', ..., y^(q)] as SymPy vectors: y_{k+1} = (dy_k/du) f + dy_k/dt."""
+    f = sp.Matrix(tr.f)
+    u = sp.Matrix(tr.u)
+    ys = [u, f]
+    for _ in range(2, q + 1):
+        yk = ys[-1]
+        ys.append(yk.jacobian(u) * f + yk.diff(tr.t))
+    return ys[: q + 1]
+
+
+def c_source(tr, q):
+    rep = {s: sp.Symbol(f"u[{i}]", real=True) for i, s in enumerate(tr.u)}
+    rep.update({s: sp.Symbol(f"p[{i}]", real=True) for i, s in enumerate(tr.p)})
+    d = tr.d
+    fex = [e.xreplace(rep) for e in tr.f]
+    J = tr.jacobian()
+    jex = [J[a, i].xreplace(rep) for i in range(d) for a in range(d)]
+    jt = [f"J[{a + d * i}]" for i in range(d) for a in range(d)]
+    ys = symbolic_derivatives(tr, q)
+    tex = [ys[k][i].xreplace(rep) for k in range(q + 1) for i in range(d)]
+    tt = [f"out[{k * d + i}]" for k in range(q + 1) for i in range(d)]
+    return f"""/* generated by oracle/oracle.py (test infrastructure) */
+#include <math.h>
+void oracle_user_f(double* du, const double* u, const double* p, double t) {{
+  (void)p; (void)t;
+{_cblock(fex, [f"du[{i}]" for i in range(d)], "x")}
+}}
+void oracle_user_jac(double* J, const double* u, const double* p, double t) {{
+  (void)p; (void)t;
+{_cblock(jex, jt, "y")}
+}}
+void oracle_user_taylor(double* out, const double* u, const double* p, double t, int q) {{
+  (void)p; (void)t; (void)q;
+{_cblock(tex, tt, "z")}
+}}
+"""
+
+
+_rhs_cache = {}
+
+
+def compile_rhs(tr, q) -> CompiledRHS:
+    src = c_source(tr, q)
+    key = hashlib.sha1(src.encode()).hexdigest()[:16]
+    if key in _rhs_cache:
+        return _rhs_cache[key]
+    tmp = os.path.join(tempfile.gettempdir(), f"pnode_oracle_rhs_{os.getuid()}")
+    os.makedirs(tmp, exist_ok=True)
+    cpath = os.path.join(tmp, f"rhs_{key}.c")
+    so = os.path.join(tmp, f"rhs_{key}.so")
+    if not os.path.exists(so):
+        with open(cpath, "w") as fh:
+            fh.write(src)
+        subprocess.run(["gcc", "-O2", "-fno-fast-math", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, cpath,
+                        "-lm"], check=True)
+    r = CompiledRHS(so, tr.d, tr.n_p, q)
+    _rhs_cache[key] = r
+    return r
+
+
+# ------------------------------------------------------------------------------------------------
+def make_config(d, q, n_p, *, alg=EK1, diffusion=DIFF_DYNAMIC, calibrate=True, initial_diffusion=1.0, smooth=True,
+                adaptive=True, save_everystep=True, cov_backend=COV_REF, t0=0.0, t1=1.0, dt=0.0, abstol=1e-6,
+                reltol=1e-3, dtmin=0.0, dtmax=None, maxiters=1_000_000, beta1=None, beta2=None, qmin=0.2, qmax=10.0,
+                gamma=0.9, qsteady_min=1.0, qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None):
+    c = Config()
+    c.d, c.q, c.n_p, c.alg = d, q, n_p, alg
+    c.diffusion, c.calibrate, c.smooth, c.adaptive = diffusion, int(calibrate), int(smooth), int(adaptive)
+    c.save_everystep, c.cov_backend, c.maxiters = int(save_everystep), cov_backend, int(maxiters)
+    c.initial_diffusion = initial_diffusion
+    c.t0, c.t1, c.dt = t0, t1, dt
+    c.abstol, c.reltol, c.dtmin = abstol, reltol, dtmin
+    c.dtmax = (t1 - t0) if dtmax is None else dtmax
+    c.beta2 = 2.0 / (5.0 * q) if beta2 is None else beta2
+    c.beta1 = 7.0 / (10.0 * q) if beta1 is None else beta1
+    c.qmin, c.qmax, c.gamma = qmin, qmax, gamma
+    c.qsteady_min, c.qsteady_max, c.qoldinit = qsteady_min, qsteady_max, qoldinit
+    keep = []
+    if tstops is not None and len(tstops):
+        ts = np.ascontiguousarray(tstops, dtype=np.float64)
+        keep.append(ts)
+        c.tstops, c.n_tstops = _dp(ts), len(ts)
+    if forced_diffusion is not None and len(forced_diffusion):
+        fd = np.ascontiguousarray(forced_diffusion, dtype=np.float64)
+        keep.append(fd)
+        c.forced_diffusion, c.n_forced = _dp(fd), len(fd)
+    c._keep = keep
+    return c
+
+
+def _arr(ptr, shape):
+    if not ptr:
+        return None
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.zeros(shape)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape).copy()
+
+
+def solve(cfg: Config, rhs: CompiledRHS, u0, p) -> dict:
+    u0 = np.ascontiguousarray(u0, dtype=np.float64)
+    p = np.ascontiguousarray(p if len(p) else [0.0], dtype=np.float64)
+    tr = Traj()
+    rc = lib().oracle_solve(C.byref(cfg), rhs.f, rhs.jac, rhs.taylor, _dp(u0), _dp(p), C.byref(tr))
+    if rc != 0:
+        raise RuntimeError(f"oracle_solve failed rc={rc}")
+    n, d, D = tr.n, tr.d, tr.D
+    out = dict(
+        n=n, d=d, q=tr.q, D=D, retcode=RET[tr.retcode], naccept=tr.naccept, nreject=tr.nreject, nf=tr.nf,
+        njac=tr.njac, loglik=tr.loglik, global_diffusion=tr.global_diffusion,
+        t=_arr(tr.t, (n,)), diffusions=_arr(tr.diffusions, (n,)),
+        x_filt_mu=_arr(tr.x_filt_mu, (n, D)),
+        # stored column-major D x D -> numpy [k, col, row]; transpose to [k, row, col]
+        x_filt_R=_arr(tr.x_filt_R, (n, D, D)).transpose(0, 2, 1).copy(),
+        pu_mu=_arr(tr.pu_mu, (n, d)),
+        pu_R=_arr(tr.pu_R, (n, d, D)).transpose(0, 2, 1).copy(),
+    )
+    if tr.x_smooth_mu:
+        out["x_smooth_mu"] = _arr(tr.x_smooth_mu, (n, D))
+        out["x_smooth_R"] = _arr(tr.x_smooth_R, (n, D, D)).transpose(0, 2, 1).copy()
+        out["bk_G"] = _arr(tr.bk_G, (max(n - 1, 1), D, D))[: n - 1].transpose(0, 2, 1).copy()
+        out["bk_b"] = _arr(tr.bk_b, (max(n - 1, 1), D))[: n - 1]
+        out["bk_LR"] = _arr(tr.bk_LR, (max(n - 1, 1), D, 2 * D))[: n - 1].transpose(0, 2, 1).copy()
+    lib().oracle_traj_free(C.byref(tr))
+    out["pu_cov"] = np.einsum("kra,krb->kab", out["pu_R"], out["pu_R"])
+    return out
+
+
+def solve_ensemble(cfg: Config, rhs: CompiledRHS, u0, p, n_threads: int = 0) -> dict:
+    u0 = np.ascontiguousarray(u0, dtype=np.float64)
+    n_traj, d = u0.shape
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    if p.size == 0:
+        p = np.zeros((n_traj, 1))
+    uf = np.zeros((n_traj, d))
+    cf = np.zeros((n_traj, d, d))
+    na = np.zeros(n_traj, dtype=np.int64)
+    nr = np.zeros(n_traj, dtype=np.int64)
+    nf = np.zeros(n_traj, dtype=np.int64)
+    rcodes = np.zeros(n_traj, dtype=np.int32)
+    ll = np.zeros(n_traj)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))  # noqa: E731
+    rc = lib().oracle_solve_ensemble(C.byref(cfg), rhs.f, rhs.jac, rhs.taylor, n_traj, _dp(u0), _dp(p), n_threads,
+                                     _dp(uf), _dp(cf), ip(na), ip(nr), ip(nf),
+                                     rcodes.ctypes.data_as(C.POINTER(C.c_int32)), _dp(ll))
+    if rc != 0:
+        raise RuntimeError(f"oracle_solve_ensemble failed rc={rc}")
+    return dict(u_final=uf, cov_final=cf, naccept=na, nreject=nr, nf=nf, retcode=rcodes, loglik=ll)
+
+
+def max_threads() -> int:
+    return lib().oracle_max_threads()

@@ -1,0 +1,853 @@
+/*
+ * pnode_oracle.c -- CPU ORACLE (test infrastructure; see pnode_oracle.h).
+ *
+ * Plain-C FP64 restatement of ProbNumDiffEq.jl v0.18.0's ODE-filter path.  Citations are
+ * to files under the reference checkout (src/...).  Matrices are column-major.
+ * Nothing here is shared with, or reachable from, the CUDA product.
+ */
+#include "pnode_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define AT(A, i, j, ld) ((A)[(size_t)(i) + (size_t)(j) * (size_t)(ld)])
+
+/* ------------------------------------------------------------------------------------------ */
+/* small dense helpers                                                                        */
+/* ------------------------------------------------------------------------------------------ */
+
+/* C (m x n) = alpha * op(A) * op(B) + beta * C ; op = transpose if t? != 0 ; inner dim k */
+static void gemm(int m, int n, int k, double alpha, const double* A, int lda, int tA, const double* B, int ldb,
+                 int tB, double beta, double* C, int ldc) {
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < m; i++) {
+            double s = 0.0;
+            for (int l = 0; l < k; l++) {
+                double a = tA ? AT(A, l, i, lda) : AT(A, i, l, lda);
+                double b = tB ? AT(B, j, l, ldb) : AT(B, l, j, ldb);
+                s += a * b;
+            }
+            AT(C, i, j, ldc) = (beta == 0.0 ? 0.0 : beta * AT(C, i, j, ldc)) + alpha * s;
+        }
+}
+
+static int all_zero(const double* x, size_t n) {
+    for (size_t i = 0; i < n; i++)
+        if (x[i] != 0.0) return 0;
+    return 1;
+}
+
+static double factorial_d(int k) {
+    double f = 1.0;
+    for (int i = 2; i <= k; i++) f *= (double)i;
+    return f;
+}
+static double binomial_d(int n, int k) {
+    if (k < 0 || k > n) return 0.0;
+    double r = 1.0;
+    for (int i = 1; i <= k; i++) r = r * (double)(n - k + i) / (double)i;
+    return floor(r + 0.5);
+}
+
+/* Upper Cholesky M = U'U in place (LAPACK potrf 'U' semantics); strictly-lower part zeroed.
+   Returns 0 on success, j+1 if the j-th pivot is not positive (issuccess == false). */
+int oracle_cholesky_upper(int n, double* M) {
+    for (int j = 0; j < n; j++) {
+        double s = AT(M, j, j, n);
+        for (int k = 0; k < j; k++) s -= AT(M, k, j, n) * AT(M, k, j, n);
+        if (!(s > 0.0) || isnan(s)) return j + 1;
+        double ujj = sqrt(s);
+        AT(M, j, j, n) = ujj;
+        for (int i = j + 1; i < n; i++) {
+            double v = AT(M, j, i, n);
+            for (int k = 0; k < j; k++) v -= AT(M, k, j, n) * AT(M, k, i, n);
+            AT(M, j, i, n) = v / ujj;
+        }
+    }
+    for (int j = 0; j < n; j++)
+        for (int i = j + 1; i < n; i++) AT(M, i, j, n) = 0.0;
+    return 0;
+}
+
+/* triangularize!(A) = qr!(A).R  (src/fast_linalg.jl:70-79; LAPACK geqrt! == Householder QR with
+   dlarfg conventions; only R is used so blocking (nb=36) does not change the result beyond rounding).
+   A is m x n (m >= n), destroyed.  Rout = triu(A[0:n,0:n]) (getupperright!, fast_linalg.jl:54-57). */
+void oracle_triangularize(int m, int n, double* A, double* Rout) {
+    for (int k = 0; k < n; k++) {
+        double alpha = AT(A, k, k, m);
+        double xn2 = 0.0;
+        for (int i = k + 1; i < m; i++) xn2 += AT(A, i, k, m) * AT(A, i, k, m);
+        if (xn2 == 0.0) continue; /* tau = 0, H = I */
+        double xnorm = sqrt(xn2);
+        double beta = -copysign(hypot(alpha, xnorm), alpha);
+        double tau = (beta - alpha) / beta;
+        double scal = 1.0 / (alpha - beta);
+        for (int i = k + 1; i < m; i++) AT(A, i, k, m) *= scal; /* v (v_k = 1 implicit) */
+        AT(A, k, k, m) = beta;
+        for (int j = k + 1; j < n; j++) {
+            double w = AT(A, k, j, m);
+            for (int i = k + 1; i < m; i++) w += AT(A, i, k, m) * AT(A, i, j, m);
+            w *= tau;
+            AT(A, k, j, m) -= w;
+            for (int i = k + 1; i < m; i++) AT(A, i, j, m) -= w * AT(A, i, k, m);
+        }
+    }
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) AT(Rout, i, j, n) = (i <= j) ? AT(A, i, j, m) : 0.0;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* IWP prior + preconditioning                                                                */
+/* ------------------------------------------------------------------------------------------ */
+
+/* preconditioned_discretize_1d (src/priors/iwp.jl:96-108): A_breve = binomial.(q:-1:0, (q:-1:0)') ;
+   QR_breve = make_preconditioned_iwp_transition_cov_lsqrt_1d (iwp.jl:74-94), lower triangular,
+   Q_breve = L' L  (PSDMatrix(R) == R'R, src/filtering/predict.jl:15-16). */
+void oracle_iwp_preconditioned(int q, double* A_breve, double* L_breve) {
+    int n = q + 1;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            AT(A_breve, i, j, n) = binomial_d(q - i, q - j);
+            AT(L_breve, i, j, n) = 0.0;
+        }
+    for (int m = 0; m <= q; m++)
+        for (int c = 0; c <= m; c++) {
+            double fqn = factorial_d(q - c);
+            AT(L_breve, m, c, n) =
+                sqrt((double)(2 * q - 2 * m + 1)) * (fqn * fqn) / factorial_d(m - c) / factorial_d(2 * q - c - m + 1);
+        }
+}
+
+/* make_preconditioner! / make_preconditioner_inv! (src/preconditioning.jl:30-58), 1-d factors. */
+void oracle_preconditioner(int q, double h, double* P, double* PI) {
+    double val = factorial_d(q) / pow(h, (double)q + 0.5);
+    for (int j = 0; j <= q; j++) {
+        P[j] = val;
+        val /= (double)(q - j) / h;
+    }
+    val = pow(h, (double)q + 0.5) / factorial_d(q);
+    for (int j = 0; j <= q; j++) {
+        PI[j] = val;
+        val *= (double)(q - j) / h;
+    }
+}
+
+/* make_transition_matrices!(cache, ::IWP, dt) (src/priors/iwp.jl:182-190):
+   Ah = PI * (A * P) ; Qh.R = Q.R * PI' = L * diag(PI)  (fast_X_A_Xt!, src/fast_linalg.jl:88-91). */
+void oracle_iwp_transition(int q, double h, double* Ah, double* QhR) {
+    int n = q + 1;
+    double A[32 * 32], L[32 * 32], P[32], PI[32];
+    oracle_iwp_preconditioned(q, A, L);
+    oracle_preconditioner(q, h, P, PI);
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) {
+            AT(Ah, i, j, n) = PI[i] * (AT(A, i, j, n) * P[j]);
+            AT(QhR, i, j, n) = AT(L, i, j, n) * PI[j];
+        }
+}
+
+/* kron(B, I_d) (src/kronecker.jl:7): out[(r*d+i), (c*d+i)] = B[r,c]. */
+void oracle_kron_identity(int d, int n_rows, int n_cols, const double* B, double* out) {
+    int M = n_rows * d, N = n_cols * d;
+    memset(out, 0, sizeof(double) * (size_t)M * (size_t)N);
+    for (int r = 0; r < n_rows; r++)
+        for (int c = 0; c < n_cols; c++)
+            for (int i = 0; i < d; i++) AT(out, r * d + i, c * d + i, M) = AT(B, r, c, n_rows);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* filtering components (generic size N; EK1 dense: N = D, EK0 Kronecker: N = q+1 on factors)  */
+/* ------------------------------------------------------------------------------------------ */
+
+/* predict_cov! (src/filtering/predict.jl:62-94). */
+void oracle_predict_cov(int N, const double* R, const double* Ah, const double* QhR, double diffusion, int backend,
+                        double* Rout, int* used_qr) {
+    if (used_qr) *used_qr = 0;
+    if (diffusion == 0.0) { /* :71-74 */
+        gemm(N, N, N, 1.0, R, N, 0, Ah, N, 1, 0.0, Rout, N);
+        return;
+    }
+    double* S = (double*)malloc(sizeof(double) * 2 * N * N); /* C_2DxD */
+    double* M = (double*)malloc(sizeof(double) * N * N);     /* C_DxD  */
+    double* top = (double*)malloc(sizeof(double) * N * N);
+    gemm(N, N, N, 1.0, R, N, 0, Ah, N, 1, 0.0, top, N); /* :78 */
+    double s = (diffusion == 1.0) ? 1.0 : sqrt(diffusion);
+    for (int j = 0; j < N; j++)
+        for (int i = 0; i < N; i++) {
+            AT(S, i, j, 2 * N) = AT(top, i, j, N);
+            AT(S, N + i, j, 2 * N) = (diffusion == 1.0) ? AT(QhR, i, j, N) : AT(QhR, i, j, N) * s; /* :79-83 */
+        }
+    int ok = 0;
+    if (backend == ORACLE_COV_REF) {
+        gemm(N, N, 2 * N, 1.0, S, 2 * N, 1, S, 2 * N, 0, 0.0, M, N); /* :84 */
+        ok = (oracle_cholesky_upper(N, M) == 0);                     /* :85 */
+        if (ok) memcpy(Rout, M, sizeof(double) * N * N);
+    }
+    if (!ok) { /* :90 */
+        oracle_triangularize(2 * N, N, S, Rout);
+        if (used_qr) *used_qr = 1;
+    }
+    free(S);
+    free(M);
+    free(top);
+}
+
+/* Solve X * (U'U) = B in place for X (rdiv!(B, Cholesky(U,'U'))), B is m x n, U upper n x n
+   (only the upper triangle of U is read, as LAPACK trsm does). */
+static void rdiv_chol_upper(int m, int n, double* B, const double* U) {
+    /* X1 = B U^{-1} */
+    for (int j = 0; j < n; j++) {
+        for (int k = 0; k < j; k++) {
+            double ukj = AT(U, k, j, n);
+            if (ukj != 0.0)
+                for (int i = 0; i < m; i++) AT(B, i, j, m) -= AT(B, i, k, m) * ukj;
+        }
+        double ujj = AT(U, j, j, n);
+        for (int i = 0; i < m; i++) AT(B, i, j, m) /= ujj;
+    }
+    /* X = X1 U^{-T} */
+    for (int j = n - 1; j >= 0; j--) {
+        double ujj = AT(U, j, j, n);
+        for (int i = 0; i < m; i++) AT(B, i, j, m) /= ujj;
+        for (int k = 0; k < j; k++) {
+            double ukj = AT(U, k, j, n);
+            if (ukj != 0.0)
+                for (int i = 0; i < m; i++) AT(B, i, k, m) -= AT(B, i, j, m) * ukj;
+        }
+    }
+}
+
+/* Generic update! (src/filtering/update.jl:65-139) with measurement covariance from
+   compute_measurement_covariance! (src/perform_step.jl:182-188).
+   State mean is an N x nrhs "matrix" addressed mu[r*rs + c*cs]; z is m x nrhs addressed z[a*zs_a + c*zs_c].
+   Dense EK1: N=D, m=d, nrhs=1.  Kronecker EK0: N=q+1, m=1, nrhs=d, rs=d, cs=1 (update.jl:151-195).
+   Returns 0 ok, 1 if S is not positive definite (Julia would throw PosDefException). */
+static int update_generic(int N, int m, int nrhs, const double* mu_p, int rs, int cs, const double* R_p,
+                          const double* z, int zs_a, int zs_c, const double* H /* m x N */, double* mu_out,
+                          double* R_out, double* loglik) {
+    if (all_zero(R_p, (size_t)N * N)) { /* :82-89 */
+        for (int r = 0; r < N; r++)
+            for (int c = 0; c < nrhs; c++) mu_out[r * rs + c * cs] = mu_p[r * rs + c * cs];
+        memcpy(R_out, R_p, sizeof(double) * N * N);
+        int zz = 1;
+        for (int a = 0; a < m; a++)
+            for (int c = 0; c < nrhs; c++)
+                if (z[a * zs_a + c * zs_c] != 0.0) zz = 0;
+        *loglik = zz ? INFINITY : -INFINITY;
+        return 0;
+    }
+    double* K1 = (double*)malloc(sizeof(double) * N * m);
+    double* K = (double*)malloc(sizeof(double) * N * m);
+    double* S = (double*)malloc(sizeof(double) * m * m);
+    double* Mc = (double*)malloc(sizeof(double) * N * N);
+    double* zt = (double*)malloc(sizeof(double) * m * nrhs);
+    gemm(N, m, N, 1.0, R_p, N, 0, H, m, 1, 0.0, K1, N);  /* C_Dxd = R_p H'  (perform_step.jl:183, update.jl:101) */
+    gemm(m, m, N, 1.0, K1, N, 1, K1, N, 0, 0.0, S, m);   /* S = C' C        (perform_step.jl:184) */
+    gemm(N, m, N, 1.0, R_p, N, 1, K1, N, 0, 0.0, K, N);  /* K2 = R_p' K1    (update.jl:102) */
+    double logdet;
+    int fail = 0;
+    if (m == 1) { /* S_chol = S[1] (update.jl:108) */
+        double s = S[0];
+        for (int r = 0; r < N; r++) K[r] /= s;
+        for (int c = 0; c < nrhs; c++) zt[c] = z[c * zs_c] / s;
+        logdet = log(s);
+    } else {
+        if (oracle_cholesky_upper(m, S) != 0) fail = 1;
+        rdiv_chol_upper(N, m, K, S); /* rdiv!(K, S_chol) :109 */
+        /* ldiv!(S_chol, z): solve (U'U) x = z for each rhs */
+        for (int c = 0; c < nrhs; c++) {
+            double* x = zt + (size_t)c * m;
+            for (int a = 0; a < m; a++) x[a] = z[a * zs_a + c * zs_c];
+            for (int a = 0; a < m; a++) { /* U' y = z */
+                for (int k = 0; k < a; k++) x[a] -= AT(S, k, a, m) * x[k];
+                x[a] /= AT(S, a, a, m);
+            }
+            for (int a = m - 1; a >= 0; a--) { /* U x = y */
+                for (int k = a + 1; k < m; k++) x[a] -= AT(S, a, k, m) * x[k];
+                x[a] /= AT(S, a, a, m);
+            }
+        }
+        logdet = 0.0;
+        for (int a = 0; a < m; a++) logdet += log(AT(S, a, a, m));
+        logdet *= 2.0;
+    }
+    /* pn_logpdf! (update.jl:140-148): d = length(reshape(mu,:)) = m*nrhs; logdet NOT multiplied by nrhs */
+    double quad = 0.0;
+    for (int c = 0; c < nrhs; c++)
+        for (int a = 0; a < m; a++) quad += z[a * zs_a + c * zs_c] * zt[(size_t)c * m + a];
+    *loglik = -0.5 * quad - 0.5 * (double)(m * nrhs) * log(2.0 * M_PI) - 0.5 * logdet;
+    /* mu = m_p - K z (:115) */
+    for (int r = 0; r < N; r++)
+        for (int c = 0; c < nrhs; c++) {
+            double s = 0.0;
+            for (int a = 0; a < m; a++) s += AT(K, r, a, N) * z[a * zs_a + c * zs_c];
+            mu_out[r * rs + c * cs] = mu_p[r * rs + c * cs] - s;
+        }
+    /* M = I - K H (:118-121) ; R_out = R_p M' (:123, fast_X_A_Xt!) */
+    gemm(N, N, m, -1.0, K, N, 0, H, m, 0, 0.0, Mc, N);
+    for (int i = 0; i < N; i++) AT(Mc, i, i, N) += 1.0;
+    gemm(N, N, N, 1.0, R_p, N, 0, Mc, N, 1, 0.0, R_out, N);
+    free(K1);
+    free(K);
+    free(S);
+    free(Mc);
+    free(zt);
+    return fail;
+}
+
+int oracle_update(int D, int d, const double* mu_p, const double* R_p, const double* z, const double* H,
+                  double* mu_out, double* R_out, double* loglik) {
+    return update_generic(D, d, 1, mu_p, 1, 0, R_p, z, 1, 0, H, mu_out, R_out, loglik);
+}
+
+/* compute_backward_kernel! (src/filtering/markov_kernel.jl:190-235; Kronecker :237-272). */
+static void backward_kernel_generic(int N, int nrhs, int rs, int cs, const double* mu, const double* R,
+                                    const double* mu_pred, const double* R_pred, const double* Ah,
+                                    const double* QhR, double diffusion, double* G, double* b, double* LR) {
+    double* C = (double*)malloc(sizeof(double) * N * N);
+    gemm(N, N, N, 1.0, R, N, 0, Ah, N, 1, 0.0, C, N); /* C_DxD = x.Sigma.R A' (:210) */
+    gemm(N, N, N, 1.0, R, N, 1, C, N, 0, 0.0, G, N);  /* G = x.Sigma.R' C     (:211) */
+    if (!all_zero(G, (size_t)N * N)) rdiv_chol_upper(N, N, G, R_pred); /* :212-214 */
+    for (int r = 0; r < N; r++) /* b = mu - G mu_pred (:217-218) */
+        for (int c = 0; c < nrhs; c++) {
+            double s = 0.0;
+            for (int k = 0; k < N; k++) s += AT(G, r, k, N) * mu_pred[k * rs + c * cs];
+            b[r * rs + c * cs] = mu[r * rs + c * cs] - s;
+        }
+    gemm(N, N, N, -1.0, Ah, N, 1, G, N, 1, 0.0, C, N); /* C = -A' G' (:221) */
+    for (int i = 0; i < N; i++) AT(C, i, i, N) += 1.0; /* :222-224 */
+    double* top = (double*)malloc(sizeof(double) * N * N);
+    double* bot = (double*)malloc(sizeof(double) * N * N);
+    gemm(N, N, N, 1.0, R, N, 0, C, N, 0, 0.0, top, N); /* Lambda.R[1:D] = R (I - G A)' (:225) */
+    if (diffusion == 1.0) {
+        gemm(N, N, N, 1.0, QhR, N, 0, G, N, 1, 0.0, bot, N); /* :228 */
+    } else {
+        double s = sqrt(diffusion);
+        for (int i = 0; i < N * N; i++) C[i] = QhR[i] * s; /* apply_diffusion! :230 */
+        gemm(N, N, N, 1.0, C, N, 0, G, N, 1, 0.0, bot, N); /* :231 */
+    }
+    for (int j = 0; j < N; j++)
+        for (int i = 0; i < N; i++) {
+            AT(LR, i, j, 2 * N) = AT(top, i, j, N);
+            AT(LR, N + i, j, 2 * N) = AT(bot, i, j, N);
+        }
+    free(C);
+    free(top);
+    free(bot);
+}
+
+void oracle_backward_kernel(int D, const double* mu, const double* R, const double* mu_pred,
+                            const double* R_pred, const double* Ah, const double* QhR, double diffusion,
+                            double* G, double* b, double* LR) {
+    backward_kernel_generic(D, 1, 1, 0, mu, R, mu_pred, R_pred, Ah, QhR, diffusion, G, b, LR);
+}
+
+/* marginalize! (src/filtering/markov_kernel.jl:68-101; Kronecker :103-121). */
+static void marginalize_generic(int N, int nrhs, int rs, int cs, const double* mu_next, const double* R_next,
+                                const double* G, const double* b, const double* LR, double* mu_out,
+                                double* R_out) {
+    for (int r = 0; r < N; r++) /* marginalize_mean! :72-82 */
+        for (int c = 0; c < nrhs; c++) {
+            double s = 0.0;
+            for (int k = 0; k < N; k++) s += AT(G, r, k, N) * mu_next[k * rs + c * cs];
+            mu_out[r * rs + c * cs] = s + b[r * rs + c * cs];
+        }
+    double* S = (double*)malloc(sizeof(double) * 3 * N * N); /* C_3DxD */
+    double* top = (double*)malloc(sizeof(double) * N * N);
+    gemm(N, N, N, 1.0, R_next, N, 0, G, N, 1, 0.0, top, N); /* :95 */
+    for (int j = 0; j < N; j++) {
+        for (int i = 0; i < N; i++) AT(S, i, j, 3 * N) = AT(top, i, j, N);
+        for (int i = 0; i < 2 * N; i++) AT(S, N + i, j, 3 * N) = AT(LR, i, j, 2 * N); /* :96 */
+    }
+    oracle_triangularize(3 * N, N, S, R_out); /* :98 */
+    free(S);
+    free(top);
+}
+
+void oracle_marginalize(int D, const double* mu_next, const double* R_next, const double* G, const double* b,
+                        const double* LR, double* mu_out, double* R_out) {
+    marginalize_generic(D, 1, 1, 0, mu_next, R_next, G, b, LR, mu_out, R_out);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* growable per-trajectory storage                                                             */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    double* p;
+    size_t len, cap;
+} dvec;
+static void dvec_push(dvec* v, const double* src, size_t n) {
+    if (v->len + n > v->cap) {
+        size_t nc = v->cap ? v->cap * 2 : 1024;
+        while (nc < v->len + n) nc *= 2;
+        v->p = (double*)realloc(v->p, nc * sizeof(double));
+        v->cap = nc;
+    }
+    memcpy(v->p + v->len, src, n * sizeof(double));
+    v->len += n;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* the solver loop                                                                             */
+/* ------------------------------------------------------------------------------------------ */
+
+static double rms_norm(const double* x, int n) { /* ODE_DEFAULT_NORM (DiffEqBase, 3rd party) */
+    double s = 0.0;
+    for (int i = 0; i < n; i++) s += x[i] * x[i];
+    return sqrt(s / (double)n);
+}
+
+/* ode_determine_initdt (OrdinaryDiffEqCore, 3rd party; restated from SURVEY.md A.6 -- parity unpinned). */
+static double initial_dt(const oracle_config* c, oracle_rhs_fn f, const double* u0, const double* p, int order) {
+    int d = c->d;
+    double sk[64], tmp[64], f0[64], f1[64], u1[64];
+    double t = c->t0;
+    double dtmax = c->dtmax;
+    double dtmin = nextafter(fmax(c->dtmin, nextafter(fabs(t), INFINITY) - fabs(t)), INFINITY);
+    double smalldt = fmax(dtmin, 1e-6);
+    for (int i = 0; i < d; i++) sk[i] = c->abstol + fabs(u0[i]) * c->reltol;
+    for (int i = 0; i < d; i++) tmp[i] = u0[i] / sk[i];
+    double d0 = rms_norm(tmp, d);
+    f(f0, u0, p, t);
+    for (int i = 0; i < d; i++) tmp[i] = f0[i] / sk[i];
+    double d1 = rms_norm(tmp, d);
+    double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? smalldt : (d0 / d1) / 100.0;
+    dt0 = fmin(dt0, dtmax);
+    if (dt0 < 10.0 * 2.220446049250313e-16) return fmax(smalldt, dtmin);
+    for (int i = 0; i < d; i++) u1[i] = u0[i] + dt0 * f0[i];
+    f(f1, u1, p, t + dt0);
+    for (int i = 0; i < d; i++) tmp[i] = (f1[i] - f0[i]) / sk[i];
+    double d2 = rms_norm(tmp, d) / dt0;
+    double mx = fmax(d1, d2);
+    double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / (double)order);
+    return fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
+}
+
+int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, oracle_taylor_fn taylor,
+                 const double* u0, const double* p, oracle_traj* out) {
+    const int d = c->d, q = c->q, n = q + 1, D = d * n;
+    const int kron = (c->alg == ORACLE_EK0);
+    const int N = kron ? n : D;          /* size of the matrices the filter works on */
+    const int nrhs = kron ? d : 1;       /* mean handled as N x nrhs (update.jl:166-174) */
+    const int rs = kron ? d : 1, cs = kron ? 1 : 0;
+    const int m = kron ? 1 : d;          /* rows of H on this layout */
+    memset(out, 0, sizeof(*out));
+    out->d = d; out->q = q; out->D = D; out->smooth = c->smooth; out->alg = c->alg;
+    out->global_diffusion = NAN;
+    if (d > 64 || n > 32) return -1;
+
+    /* --- work buffers (EKCache, src/caches.jl:198-214) --- */
+    size_t NN = (size_t)N * N;
+    double* Ah1 = (double*)malloc(sizeof(double) * n * n);
+    double* Qh1 = (double*)malloc(sizeof(double) * n * n);
+    double* Ah = (double*)malloc(sizeof(double) * NN);
+    double* QhR = (double*)malloc(sizeof(double) * NN);
+    double* mu = (double*)calloc(D, sizeof(double));
+    double* R = (double*)calloc(NN, sizeof(double));
+    double* mu_pred = (double*)calloc(D, sizeof(double));
+    double* R_pred = (double*)calloc(NN, sizeof(double));
+    double* mu_filt = (double*)calloc(D, sizeof(double));
+    double* R_filt = (double*)calloc(NN, sizeof(double));
+    double* H = (double*)calloc((size_t)m * N, sizeof(double));
+    double* J = (double*)calloc((size_t)d * d, sizeof(double));
+    double* Cq = (double*)malloc(sizeof(double) * (size_t)N * m);
+    double* W = (double*)malloc(sizeof(double) * (size_t)m * m);
+    double* G = (double*)malloc(sizeof(double) * NN);
+    double* bb = (double*)malloc(sizeof(double) * D);
+    double* LR = (double*)malloc(sizeof(double) * 2 * NN);
+    double* Rdense = (double*)malloc(sizeof(double) * (size_t)D * D);
+    double* tmpDD = (double*)malloc(sizeof(double) * (size_t)2 * D * D);
+    double z[64], zt[64], fu[64], uprev[64], upred[64], err[64];
+
+    dvec ts = {0}, diffs = {0}, xmu = {0}, xR = {0}, bG = {0}, bB = {0}, bL = {0};
+
+    /* --- initial state: exact Taylor-mode derivatives, Sigma0.R == 0 exactly
+       (src/initialization/autodiffinit.jl:1-47 + common.jl:122-139; SURVEY H7;
+        test/solution.jl:59-62 asserts iszero(pu[1].Sigma.R)) --- */
+    taylor(mu, u0, p, c->t0, q);
+    out->nf += q; /* autodiffinit.jl:17 */
+    for (int i = 0; i < d; i++) uprev[i] = mu[i];
+
+    double t = c->t0;
+    double dt;
+    const int order = q; /* alg_order (src/alg_utils.jl:45) */
+    if (c->adaptive && !(c->dt > 0.0)) {
+        dt = initial_dt(c, f, u0, p, order);
+        out->nf += 2;
+    } else {
+        dt = c->dt;
+    }
+    const double dtcache = dt;
+    double qold = c->qoldinit;
+    int64_t iter = 0, success_iter = 0;
+    double local_diffusion = NAN;                 /* caches.jl:257 (initdiff * NaN) */
+    double global_diffusion = NAN;
+    const double default_diffusion = c->initial_diffusion;
+    const int dynamic = (c->diffusion == ORACLE_DIFF_DYNAMIC);
+    int retcode = ORACLE_RET_SUCCESS;
+    int64_t tstop_idx = 0;
+    double loglik_total = 0.0;
+
+    /* save initial (perform_step.jl:30-32) */
+    dvec_push(&ts, &t, 1);
+    dvec_push(&xmu, mu, D);
+    dvec_push(&xR, R, NN);
+
+    while (t < c->t1) {
+        double tstop = c->t1;
+        while (tstop_idx < c->n_tstops && c->tstops[tstop_idx] <= t) tstop_idx++;
+        if (tstop_idx < c->n_tstops && c->tstops[tstop_idx] < c->t1) tstop = c->tstops[tstop_idx];
+
+        /* loopheader! (OrdinaryDiffEqCore) */
+        iter++;
+        if (iter > c->maxiters) { retcode = ORACLE_RET_MAXITERS; break; }
+        if (c->adaptive) {
+            dt = fmin(dt, c->dtmax);
+            dt = fmax(dt, c->dtmin);
+            dt = fmin(dt, tstop - t);
+        } else {
+            dt = fmin(dtcache, tstop - t);
+        }
+        if (isnan(dt) || !(t + dt > t) || (c->adaptive && dt <= c->dtmin)) {
+            retcode = ORACLE_RET_DTLESSTHANMIN;
+            break;
+        }
+
+        /* ---- perform_step! (src/perform_step.jl:79-154) ---- */
+        double tnew = t + dt;                                  /* :85 */
+        oracle_iwp_transition(q, dt, Ah1, Qh1);                /* :87-99, make_transition_matrices! */
+        if (kron) {
+            memcpy(Ah, Ah1, sizeof(double) * NN);
+            memcpy(QhR, Qh1, sizeof(double) * NN);
+        } else {
+            oracle_kron_identity(d, n, n, Ah1, Ah);            /* iwp.jl:165-171 (Matrix(A)) */
+            oracle_kron_identity(d, n, n, Qh1, QhR);
+        }
+        /* predict_mean! (:102; predict.jl:53-60) */
+        for (int r = 0; r < N; r++)
+            for (int cc = 0; cc < nrhs; cc++) {
+                double s = 0.0;
+                for (int k = 0; k < N; k++) s += AT(Ah, r, k, N) * mu[k * rs + cc * cs];
+                mu_pred[r * rs + cc * cs] = s;
+            }
+        for (int i = 0; i < d; i++) upred[i] = mu_pred[i];     /* integ.u = E0 mu_pred (:103-104) */
+        /* evaluate_ode! (:107, :167-180): z = E1 mu_pred - f(E0 mu_pred) (measurement_models.jl:11-20) */
+        f(fu, upred, p, tnew);
+        out->nf += 1;
+        for (int i = 0; i < d; i++) z[i] = mu_pred[d + i] - fu[i];
+        /* calc_H! (derivative_utils.jl:1-33) */
+        if (kron) {
+            for (int k = 0; k < N; k++) H[k] = (k == 1) ? 1.0 : 0.0; /* E1.B = e_1' (projection.jl:20-29) */
+        } else {
+            memset(H, 0, sizeof(double) * (size_t)m * N);
+            for (int i = 0; i < d; i++) AT(H, i, d + i, d) = 1.0;    /* H = E1 */
+            jac(J, upred, p, tnew);
+            out->njac += 1;
+            for (int a = 0; a < d; a++)
+                for (int i = 0; i < d; i++) AT(H, a, i, d) -= AT(J, a, i, d); /* H -= J * E0 (:13) */
+        }
+        /* local diffusion (:110-112; calibration.jl:123-133, invquad :9-29) */
+        int have_local = 0;
+        if (c->adaptive || dynamic) {
+            gemm(N, m, N, 1.0, QhR, N, 0, H, m, 1, 0.0, Cq, N); /* C_Dxd = Qh.R H' */
+            gemm(m, m, N, 1.0, Cq, N, 1, Cq, N, 0, 0.0, W, m);  /* HQH = C'C      */
+            double sig;
+            if (kron) {
+                double zz = 0.0;
+                for (int i = 0; i < d; i++) zz += z[i] * z[i];
+                sig = zz / W[0] / (double)d; /* calibration.jl:16-20 */
+            } else {
+                if (oracle_cholesky_upper(m, W) != 0) { retcode = ORACLE_RET_UNSTABLE; break; }
+                for (int a = 0; a < m; a++) zt[a] = z[a];
+                for (int a = 0; a < m; a++) {
+                    for (int k = 0; k < a; k++) zt[a] -= AT(W, k, a, m) * zt[k];
+                    zt[a] /= AT(W, a, a, m);
+                }
+                for (int a = m - 1; a >= 0; a--) {
+                    for (int k = a + 1; k < m; k++) zt[a] -= AT(W, a, k, m) * zt[k];
+                    zt[a] /= AT(W, a, a, m);
+                }
+                double qd = 0.0;
+                for (int a = 0; a < m; a++) qd += z[a] * zt[a];
+                sig = qd / (double)d;
+            }
+            local_diffusion = sig;
+            have_local = 1;
+        }
+        (void)have_local;
+        if (c->forced_diffusion && success_iter < c->n_forced) local_diffusion = c->forced_diffusion[success_iter];
+        /* error estimate (:113-119; :199-247) */
+        double EEst = 0.0;
+        if (c->adaptive) {
+            double s = sqrt(local_diffusion);
+            /* _Q.R = Qh.R * sqrt(sigma^2) ; C = _Q.R H' ; e_i = sqrt(sum_k C[k,i]^2) (:240-247) */
+            double* Qs = tmpDD;
+            for (size_t i = 0; i < NN; i++) Qs[i] = QhR[i] * s;
+            gemm(N, m, N, 1.0, Qs, N, 0, H, m, 1, 0.0, Cq, N);
+            if (kron) {
+                double e = 0.0;
+                for (int k = 0; k < N; k++) e += Cq[k] * Cq[k]; /* diag!(..IsometricKronecker) :251-252 */
+                e = sqrt(e);
+                for (int i = 0; i < d; i++) err[i] = e;
+            } else {
+                for (int i = 0; i < d; i++) {
+                    double e = 0.0;
+                    for (int k = 0; k < N; k++) e += AT(Cq, k, i, N) * AT(Cq, k, i, N);
+                    err[i] = sqrt(e);
+                }
+            }
+            for (int i = 0; i < d; i++) { /* calculate_residuals! (3rd party) */
+                err[i] *= dt;
+                err[i] = err[i] / (c->abstol + fmax(fabs(upred[i]), fabs(uprev[i])) * c->reltol);
+            }
+            EEst = rms_norm(err, d);
+            if (isnan(EEst)) { retcode = ORACLE_RET_UNSTABLE; break; }
+        }
+        int accept = (!c->adaptive) || (EEst < 1.0); /* early return at EEst >= 1 (:116-118) */
+        double q11 = 0.0, qq = 1.0;
+        if (c->adaptive) { /* stepsize_controller!(::PIController) (3rd party; exact pow) */
+            if (EEst == 0.0) {
+                qq = 1.0 / c->qmax;
+            } else {
+                q11 = pow(EEst, c->beta1);
+                qq = q11 / pow(qold, c->beta2);
+                qq = fmax(1.0 / c->qmax, fmin(1.0 / c->qmin, qq / c->gamma));
+            }
+        }
+        if (!accept) { /* step_reject_controller! */
+            out->nreject++;
+            dt = dt / fmin(1.0 / c->qmin, q11 / c->gamma);
+            continue;
+        }
+        /* ---- accepted: covariance predict / backward kernel / update ---- */
+        double ediff = dynamic ? local_diffusion : default_diffusion;               /* :121-122 */
+        if (c->forced_diffusion && success_iter < c->n_forced) ediff = c->forced_diffusion[success_iter];
+        oracle_predict_cov(N, R, Ah, QhR, ediff, c->cov_backend, R_pred, NULL);     /* :122-124 */
+        if (c->smooth)                                                               /* :126-131 */
+            backward_kernel_generic(N, nrhs, rs, cs, mu, R, mu_pred, R_pred, Ah, QhR, ediff, G, bb, LR);
+        double ll;
+        int ufail = update_generic(N, m, nrhs, mu_pred, rs, cs, R_pred, z, 1, 1, H, mu_filt, R_filt, &ll); /* :134-138 */
+        if (ufail) { retcode = ORACLE_RET_UNSTABLE; break; }
+        loglik_total += ll;                                                          /* :142-143 */
+        if (!dynamic) { /* estimate_global_diffusion(::FixedDiffusion) (calibration.jl:49-66) */
+            /* invquad(z, S) / d with S = measurement covariance from the predicted state */
+            gemm(N, m, N, 1.0, R_pred, N, 0, H, m, 1, 0.0, Cq, N);
+            gemm(m, m, N, 1.0, Cq, N, 1, Cq, N, 0, 0.0, W, m);
+            double inc;
+            if (kron) {
+                double zz = 0.0;
+                for (int i = 0; i < d; i++) zz += z[i] * z[i];
+                inc = zz / W[0] / (double)d;
+            } else {
+                if (oracle_cholesky_upper(m, W) != 0) { retcode = ORACLE_RET_UNSTABLE; break; }
+                for (int a = 0; a < m; a++) zt[a] = z[a];
+                for (int a = 0; a < m; a++) {
+                    for (int k = 0; k < a; k++) zt[a] -= AT(W, k, a, m) * zt[k];
+                    zt[a] /= AT(W, a, a, m);
+                }
+                for (int a = m - 1; a >= 0; a--) {
+                    for (int k = a + 1; k < m; k++) zt[a] -= AT(W, a, k, m) * zt[k];
+                    zt[a] /= AT(W, a, a, m);
+                }
+                double qd = 0.0;
+                for (int a = 0; a < m; a++) qd += z[a] * zt[a];
+                inc = qd / (double)d;
+            }
+            /* divisor is success_iter BEFORE this step is counted (:56-62) */
+            global_diffusion = (success_iter == 0) ? inc : global_diffusion + (inc - global_diffusion) / (double)success_iter;
+        }
+        memcpy(mu, mu_filt, sizeof(double) * D); /* x <- x_filt (:151) */
+        memcpy(R, R_filt, sizeof(double) * NN);
+
+        /* loopfooter! accept branch (3rd party) */
+        double dtnew = dt;
+        if (c->adaptive) {
+            if (c->qsteady_min <= qq && qq <= c->qsteady_max) qq = 1.0;
+            qold = fmax(EEst, c->qoldinit);
+            dtnew = dt / qq;
+        }
+        double ttmp = t + dt;
+        double ref = fmax(fabs(t), fabs(tstop));
+        double epsref = nextafter(ref, INFINITY) - ref;
+        t = (fabs(ttmp - tstop) < 100.0 * epsref) ? tstop : ttmp;
+        dt = dtnew;
+        success_iter++;
+        out->naccept++;
+        int nanu = 0;
+        for (int i = 0; i < d; i++) {
+            uprev[i] = mu[i]; /* update_uprev! (integrator_utils.jl:173-183) */
+            if (isnan(mu[i])) nanu = 1;
+        }
+        /* savevalues! (integrator_utils.jl:143-171) */
+        if (c->save_everystep) {
+            dvec_push(&ts, &t, 1);
+            dvec_push(&diffs, &local_diffusion, 1);
+            dvec_push(&xmu, mu, D);
+            dvec_push(&xR, R, NN);
+            if (c->smooth) {
+                dvec_push(&bG, G, NN);
+                dvec_push(&bB, bb, D);
+                dvec_push(&bL, LR, 2 * NN);
+            }
+        }
+        if (nanu) { retcode = ORACLE_RET_UNSTABLE; break; }
+    }
+    if (!c->save_everystep) { /* save_end (integrator_utils.jl:123-141) */
+        dvec_push(&ts, &t, 1);
+        dvec_push(&diffs, &local_diffusion, 1);
+        dvec_push(&xmu, mu, D);
+        dvec_push(&xR, R, NN);
+    }
+
+    /* ---- postamble! (integrator_utils.jl:9-36) ---- */
+    int64_t ns = (int64_t)ts.len;
+    out->n = ns;
+    out->retcode = retcode;
+    out->loglik = loglik_total;
+    out->global_diffusion = global_diffusion;
+    {
+        double pad = NAN;
+        while ((int64_t)diffs.len < ns) dvec_push(&diffs, &pad, 1);
+    }
+    if (!dynamic) {
+        if (c->calibrate && !isnan(global_diffusion)) { /* calibrate_solution! (:46-65) */
+            double sm = sqrt(global_diffusion);
+            for (int64_t k = 0; k < ns; k++) diffs.p[k] = global_diffusion * default_diffusion;
+            for (size_t i = 0; i < xR.len; i++) xR.p[i] *= sm;
+            for (int64_t k = 0; k + 1 < ns && c->smooth; k++) {
+                double* l = bL.p + (size_t)k * 2 * NN;
+                for (size_t i = 0; i < 2 * NN; i++) l[i] *= sm;
+            }
+        } else {
+            for (int64_t k = 0; k < ns; k++) diffs.p[k] = default_diffusion; /* set_diffusions! (:74-88) */
+        }
+    }
+
+    /* ---- outputs in dense form ---- */
+    out->t = ts.p;
+    out->diffusions = diffs.p;
+    out->x_filt_mu = xmu.p;
+    out->x_filt_R = (double*)malloc(sizeof(double) * (size_t)ns * D * D);
+    out->pu_mu = (double*)malloc(sizeof(double) * (size_t)ns * d);
+    out->pu_R = (double*)malloc(sizeof(double) * (size_t)ns * D * d);
+    for (int64_t k = 0; k < ns; k++) {
+        double* dst = out->x_filt_R + (size_t)k * D * D;
+        if (kron) oracle_kron_identity(d, n, n, xR.p + (size_t)k * NN, dst);
+        else memcpy(dst, xR.p + (size_t)k * NN, sizeof(double) * NN);
+    }
+    double* smu = NULL;
+    double* sR = NULL; /* smoothed, on the working layout */
+    if (c->smooth && c->save_everystep) { /* smooth_solution! (:98-121) */
+        smu = (double*)malloc(sizeof(double) * (size_t)ns * D);
+        sR = (double*)malloc(sizeof(double) * (size_t)ns * NN);
+        memcpy(smu, xmu.p, sizeof(double) * (size_t)ns * D);
+        memcpy(sR, xR.p, sizeof(double) * (size_t)ns * NN);
+        for (int64_t i = ns - 2; i >= 0; i--) {
+            double dti = ts.p[i + 1] - ts.p[i];
+            if (dti == 0.0) { /* :109-112 */
+                memcpy(smu + (size_t)i * D, smu + (size_t)(i + 1) * D, sizeof(double) * D);
+                memcpy(sR + (size_t)i * NN, sR + (size_t)(i + 1) * NN, sizeof(double) * NN);
+                continue;
+            }
+            marginalize_generic(N, nrhs, rs, cs, smu + (size_t)(i + 1) * D, sR + (size_t)(i + 1) * NN,
+                                bG.p + (size_t)i * NN, bB.p + (size_t)i * D, bL.p + (size_t)i * 2 * NN,
+                                smu + (size_t)i * D, sR + (size_t)i * NN);
+        }
+        out->x_smooth_mu = smu;
+        out->x_smooth_R = (double*)malloc(sizeof(double) * (size_t)ns * D * D);
+        for (int64_t k = 0; k < ns; k++) {
+            double* dst = out->x_smooth_R + (size_t)k * D * D;
+            if (kron) oracle_kron_identity(d, n, n, sR + (size_t)k * NN, dst);
+            else memcpy(dst, sR + (size_t)k * NN, sizeof(double) * NN);
+        }
+        /* dense-form backward kernels for inspection */
+        int64_t nk = ns - 1;
+        out->bk_G = (double*)malloc(sizeof(double) * (size_t)(nk > 0 ? nk : 1) * D * D);
+        out->bk_b = (double*)malloc(sizeof(double) * (size_t)(nk > 0 ? nk : 1) * D);
+        out->bk_LR = (double*)malloc(sizeof(double) * (size_t)(nk > 0 ? nk : 1) * 2 * D * D);
+        for (int64_t k = 0; k < nk; k++) {
+            if (kron) {
+                oracle_kron_identity(d, n, n, bG.p + (size_t)k * NN, out->bk_G + (size_t)k * D * D);
+                oracle_kron_identity(d, 2 * n, n, bL.p + (size_t)k * 2 * NN, out->bk_LR + (size_t)k * 2 * D * D);
+            } else {
+                memcpy(out->bk_G + (size_t)k * D * D, bG.p + (size_t)k * NN, sizeof(double) * NN);
+                memcpy(out->bk_LR + (size_t)k * 2 * D * D, bL.p + (size_t)k * 2 * NN, sizeof(double) * 2 * NN);
+            }
+            memcpy(out->bk_b + (size_t)k * D, bB.p + (size_t)k * D, sizeof(double) * D);
+        }
+    }
+    /* pu = SolProj * x  (_gaussian_mul!, src/gaussians.jl:135-139): mu_u = E0 mu, R_u = R E0' (D x d) */
+    for (int64_t k = 0; k < ns; k++) {
+        const double* xm = (smu ? smu : xmu.p) + (size_t)k * D;
+        const double* xr = (smu ? out->x_smooth_R : out->x_filt_R) + (size_t)k * D * D;
+        for (int i = 0; i < d; i++) out->pu_mu[(size_t)k * d + i] = xm[i];
+        for (int i = 0; i < d; i++)
+            for (int r = 0; r < D; r++) out->pu_R[(size_t)k * D * d + (size_t)i * D + r] = AT(xr, r, i, D);
+    }
+    free(sR);
+    free(xR.p); free(bG.p); free(bB.p); free(bL.p);
+    free(Ah1); free(Qh1); free(Ah); free(QhR); free(mu); free(R); free(mu_pred); free(R_pred);
+    free(mu_filt); free(R_filt); free(H); free(J); free(Cq); free(W); free(G); free(bb); free(LR);
+    free(Rdense); free(tmpDD);
+    return 0;
+}
+
+void oracle_traj_free(oracle_traj* tr) {
+    free(tr->t); free(tr->diffusions); free(tr->x_filt_mu); free(tr->x_filt_R);
+    free(tr->x_smooth_mu); free(tr->x_smooth_R); free(tr->pu_mu); free(tr->pu_R);
+    free(tr->bk_G); free(tr->bk_b); free(tr->bk_LR);
+    memset(tr, 0, sizeof(*tr));
+}
+
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* "EnsembleThreads" restatement: independent solves, one trajectory per OpenMP task. */
+int oracle_solve_ensemble(const oracle_config* cfg, oracle_rhs_fn f, oracle_jac_fn jac, oracle_taylor_fn taylor,
+                          int64_t n_traj, const double* u0, const double* p, int n_threads, double* u_final,
+                          double* cov_final, int64_t* naccept, int64_t* nreject, int64_t* nf, int32_t* retcode,
+                          double* loglik) {
+    const int d = cfg->d, D = cfg->d * (cfg->q + 1);
+    int err = 0;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t i = 0; i < n_traj; i++) {
+        oracle_traj tr;
+        int rc = oracle_solve(cfg, f, jac, taylor, u0 + (size_t)i * d, p + (size_t)i * cfg->n_p, &tr);
+        if (rc != 0) {
+#pragma omp atomic write
+            err = rc;
+        } else {
+            int64_t last = tr.n - 1;
+            if (u_final)
+                for (int k = 0; k < d; k++) u_final[(size_t)i * d + k] = tr.pu_mu[(size_t)last * d + k];
+            if (cov_final) {
+                const double* ru = tr.pu_R + (size_t)last * D * d; /* D x d */
+                for (int a = 0; a < d; a++)
+                    for (int b = 0; b < d; b++) {
+                        double s = 0.0;
+                        for (int r = 0; r < D; r++) s += ru[(size_t)a * D + r] * ru[(size_t)b * D + r];
+                        cov_final[(size_t)i * d * d + (size_t)a * d + b] = s;
+                    }
+            }
+            if (naccept) naccept[i] = tr.naccept;
+            if (nreject) nreject[i] = tr.nreject;
+            if (nf) nf[i] = tr.nf;
+            if (retcode) retcode[i] = tr.retcode;
+            if (loglik) loglik[i] = tr.loglik;
+        }
+        oracle_traj_free(&tr);
+    }
+    return err;
+}
