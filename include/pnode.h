@@ -1,0 +1,177 @@
+/*
+ * pnode.h -- C ABI of libpnode_cuda.so, the B200 (sm_100a) ODE-filter ensemble solver.
+ *
+ * This is the drop-in boundary for ProbNumDiffEq.jl's filter hot path.  A host package (Julia:
+ * julia/ProbNumDiffEqB200, `EnsembleB200()`; here: the Python ctypes mirror in
+ * probnumdiffeq.jl_b200/lib.py) gathers the per-trajectory u0/p, traces the user RHS to CUDA C++ and makes
+ * ONE call per ensemble solve.  Each entry point names the reference interface it replaces
+ * (paths relative to the reference checkout):
+ *
+ *   pnode_create            OrdinaryDiffEqCore.alg_cache(alg::AbstractEK, ...)     src/caches.jl:78-262
+ *                           + covariance_structure / ekargcheck                     src/algorithms.jl:78-151
+ *                           + make_measurement_model / calc_H! (RHS, Jacobian)      src/measurement_models.jl:11-20,
+ *                                                                                    src/derivative_utils.jl:1-33
+ *   pnode_solve_ensemble    SciMLBase.__solve(::EnsembleProblem, alg, ensemblealg; trajectories), i.e.
+ *                           per trajectory: initialize! src/perform_step.jl:13-35, the solve! loop calling
+ *                           perform_step! src/perform_step.jl:79-154, savevalues! src/integrator_utils.jl:143-171,
+ *                           postamble! (calibrate_solution!, smooth_solution!) src/integrator_utils.jl:9-121
+ *   pnode_result_*          ProbODESolution fields (t, u, pu, x_filt, x_smooth, diffusions, stats, pnstats, retcode)
+ *                           src/solution.jl:33-56, build_solution src/solution.jl:89-151
+ *   pnode_last_error        Julia exceptions thrown at construction (ArgumentError / DimensionMismatch /
+ *                           ErrorException): src/algorithms.jl:87-128, src/caches.jl:96-147, src/checks.jl:1-21
+ *
+ * Conventions
+ *   - All floating-point data is IEEE FP64.  State order is derivative-major: x[j*d + i] = j-th derivative of
+ *     component i (src/preconditioning.jl:34).  D = d*(q+1).
+ *   - Covariances are returned either dense (d x d, row-major, symmetric) or as *right* square-root factors
+ *     R with Sigma = R'R (PSDMatrices.jl convention, src/filtering/predict.jl:15-16), stored row-major D x D.
+ *     Factors are unique only up to an orthogonal transformation from the left: compare R'R, never R.
+ *   - Inputs are caller-owned and only read during the call.  Results are library-owned handles; copy fields out
+ *     with pnode_result_copy and release with pnode_result_free.  No pointer outlives its handle.
+ *   - Every function returns 0 on success and a negative pnode_status otherwise; the message is available from
+ *     pnode_last_error() (thread-local).  Nothing unwinds across the boundary.  Per-trajectory failures of the
+ *     time loop are reported in the RETCODE field, like sol.retcode (src/solution.jl:55).
+ *   - A pnode_solver is bound to one CUDA device and is not thread-safe; use one per thread / per GPU.
+ */
+#ifndef PNODE_H
+#define PNODE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pnode_status {
+    PNODE_OK = 0,
+    PNODE_ERR_ARGUMENT = -1,   /* Julia: ArgumentError     */
+    PNODE_ERR_DIMENSION = -2,  /* Julia: DimensionMismatch */
+    PNODE_ERR_COMPILE = -3,    /* NVRTC / module load      */
+    PNODE_ERR_CUDA = -4,
+    PNODE_ERR_UNSUPPORTED = -5,
+    PNODE_ERR_NO_DEVICE = -6
+} pnode_status;
+
+typedef enum pnode_alg { PNODE_EK0 = 0, PNODE_EK1 = 1 } pnode_alg;                         /* src/algorithms.jl:188-296 */
+typedef enum pnode_cov { PNODE_COV_AUTO = 0, PNODE_COV_DENSE = 1, PNODE_COV_KRONECKER = 2 } pnode_cov; /* src/covariance_structure.jl */
+typedef enum pnode_prior { PNODE_PRIOR_IWP = 0 } pnode_prior;                              /* src/priors/iwp.jl */
+typedef enum pnode_diffusion { PNODE_DIFF_DYNAMIC = 0, PNODE_DIFF_FIXED = 1 } pnode_diffusion; /* src/diffusions/typedefs.jl */
+typedef enum pnode_retcode {
+    PNODE_RET_SUCCESS = 0,
+    PNODE_RET_MAXITERS = 1,
+    PNODE_RET_DTLESSTHANMIN = 2,
+    PNODE_RET_UNSTABLE = 3
+} pnode_retcode;
+
+/* Flattened EK0/EK1 constructor keywords (src/algorithms.jl:195-207, 258-295) + SciML solve keywords. */
+typedef struct pnode_config {
+    int32_t struct_size;       /* sizeof(pnode_config), for ABI checks */
+    int32_t device;            /* CUDA device ordinal */
+    int32_t d, q, n_p;         /* ODE dimension, prior order (num_derivatives), parameters per trajectory */
+    int32_t alg;               /* pnode_alg */
+    int32_t cov;               /* pnode_cov (AUTO: EK0 -> Kronecker, EK1 -> dense; src/algorithms.jl:132-151) */
+    int32_t prior;             /* pnode_prior */
+    int32_t diffusion;         /* pnode_diffusion */
+    int32_t calibrate;         /* FixedDiffusion(calibrate=...) */
+    int32_t smooth;            /* alg.smooth */
+    int32_t adaptive;          /* solve(...; adaptive) */
+    int32_t save_everystep;    /* solve(...; save_everystep) */
+    int32_t save_state;        /* also return the full filter state (x_filt / x_smooth) not only pu */
+    int32_t lanes_per_traj;    /* 0 = auto; else 2,4,8,16,32 lanes cooperating on one trajectory */
+    int32_t reserved0;
+    int64_t maxiters;
+    double initial_diffusion;
+    double t0, t1, dt;         /* dt: fixed step, or initial step if adaptive (0 = automatic) */
+    double abstol, reltol;
+    double dtmin, dtmax;       /* dtmax <= 0: t1 - t0 */
+    /* PI controller (OrdinaryDiffEqCore defaults when beta1/beta2 <= 0: 7/(10q), 2/(5q)) */
+    double beta1, beta2, qmin, qmax, gamma, qsteady_min, qsteady_max, qoldinit;
+    /* right-hand side: either the name of a built-in problem ("builtin:rober", ...) in rhs_name with rhs_src = NULL,
+       or CUDA C++ source defining `struct <rhs_name>` with static d, n_p, f<T>, jac (see tracer.py) */
+    const char* rhs_src;
+    const char* rhs_name;
+    /* optional extra stop times inside (t0, t1), ascending; host pointer, copied at create */
+    const double* tstops;
+    int64_t n_tstops;
+    /* test hook: sigma^2 used for accepted step k instead of the local estimate (host pointer, copied) */
+    const double* forced_diffusion;
+    int64_t n_forced;
+} pnode_config;
+
+typedef struct pnode_solver pnode_solver;
+typedef struct pnode_result pnode_result;
+
+typedef enum pnode_field {
+    PNODE_F_T_END = 0,        /* double [n_traj]              */
+    PNODE_F_U_FINAL = 1,      /* double [n_traj][d]           sol.u[end]                 */
+    PNODE_F_U_FINAL_COV = 2,  /* double [n_traj][d][d]        Matrix(sol.pu[end].Sigma)  */
+    PNODE_F_X_FINAL = 3,      /* double [n_traj][D]           sol.x_filt[end].mu   (save_state) */
+    PNODE_F_X_FINAL_COVFAC = 4, /* double [n_traj][D][D]      sol.x_filt[end].Sigma.R    (save_state) */
+    PNODE_F_LOGLIK = 5,       /* double [n_traj]              sol.pnstats.log_likelihood */
+    PNODE_F_DIFFUSION = 6,    /* double [n_traj]              final / global diffusion   */
+    PNODE_F_DT_LAST = 7,      /* double [n_traj]                                          */
+    PNODE_F_NACCEPT = 8,      /* int64  [n_traj]              sol.stats.naccept          */
+    PNODE_F_NREJECT = 9,      /* int64  [n_traj]              sol.stats.nreject          */
+    PNODE_F_NF = 10,          /* int64  [n_traj]              sol.stats.nf               */
+    PNODE_F_RETCODE = 11,     /* int32  [n_traj]              sol.retcode                */
+    /* save_everystep (CSR over trajectories) */
+    PNODE_F_STEP_OFFSETS = 12, /* int64 [n_traj+1]            saved points of trajectory i are [off[i], off[i+1]) */
+    PNODE_F_T = 13,            /* double [total]              sol.t                      */
+    PNODE_F_U = 14,            /* double [total][d]           sol.u  (smoothed if smooth) */
+    PNODE_F_U_COV = 15,        /* double [total][d][d]        Matrix(sol.pu.Sigma)       */
+    PNODE_F_DIFFUSIONS = 16,   /* double [total]              sol.diffusions (slot k: step k -> k+1) */
+    PNODE_F_X = 17,            /* double [total][D]           sol.x_filt / sol.x_smooth mean (save_state) */
+    PNODE_F_X_COVFAC = 18,     /* double [total][D][D]        ... right factor            (save_state) */
+    PNODE_F_COUNT
+} pnode_field;
+
+typedef struct pnode_result_info {
+    int64_t n_traj;
+    int64_t total_saved;       /* sum of saved points (0 if !save_everystep) */
+    int64_t total_accepted;    /* sum over trajectories of naccept */
+    int64_t total_rejected;
+    int32_t d, q, D;
+    int32_t lanes_per_traj;
+    double kernel_ms;          /* device time of the solve kernels (CUDA events on the solver's stream) */
+    double h2d_ms, d2h_ms;     /* host<->device staging inside pnode_solve_ensemble */
+    int64_t n_launches;        /* kernels launched by this solve */
+    int64_t h2d_bytes, d2h_bytes;
+} pnode_result_info;
+
+/* Number of CUDA devices visible (0 if none / no driver).  Replaces nothing in the reference. */
+int pnode_device_count(void);
+/* Thread-local message of the last failing call ("" if none). */
+const char* pnode_last_error(void);
+/* ABI version of this header. */
+int pnode_abi_version(void);
+
+/* Validate the configuration, compile (NVRTC, sm_100a) or look up the kernels, allocate the work queue. */
+int pnode_create(const pnode_config* cfg, pnode_solver** out);
+void pnode_destroy(pnode_solver* s);
+/* Validate the configuration and run NVRTC only (no device needed); *cubin_bytes = size of the sm_100a CUBIN
+   (0 for built-in problems).  Same argument errors as pnode_create (src/algorithms.jl:78-130). */
+int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes);
+/* Seconds spent in NVRTC + module load for this solver (reported separately from solve time). */
+double pnode_compile_seconds(const pnode_solver* s);
+
+/* Solve n_traj independent trajectories.  u0: [n_traj][d], p: [n_traj][n_p] (host pointers). */
+int pnode_solve_ensemble(pnode_solver* s, int64_t n_traj, const double* u0, const double* p, pnode_result** out);
+/* Same with inputs already resident on the solver's device (device pointers); outputs stay on the device until
+   pnode_result_copy.  Used to time the kernels without staging. */
+int pnode_solve_ensemble_device(pnode_solver* s, int64_t n_traj, const double* d_u0, const double* d_p,
+                                pnode_result** out);
+
+int pnode_result_info_get(const pnode_result* r, pnode_result_info* info);
+/* Bytes needed for a field (0 if the field was not produced). */
+int64_t pnode_result_field_bytes(const pnode_result* r, int field);
+/* Copy a field into caller memory (host). bytes must equal pnode_result_field_bytes. */
+int pnode_result_copy(const pnode_result* r, int field, void* dst, size_t bytes);
+/* Device pointer of a field (NULL if absent); valid until pnode_result_free. */
+const void* pnode_result_device_ptr(const pnode_result* r, int field);
+void pnode_result_free(pnode_result* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNODE_H */

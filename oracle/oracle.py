@@ -31,15 +31,33 @@ COV_REF, COV_QR = 0, 1
 RET = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable"}
 
 
+def _stamp() -> str:
+    """Digest of the sources and of this host's CPU flags (the library is built with -march=native and
+    the repo snapshot, including built .so files, travels to a different machine under gpurun)."""
+    h = hashlib.sha1()
+    for f in ("pnode_oracle.c", "pnode_oracle.h"):
+        h.update(open(os.path.join(_HERE, f), "rb").read())
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                h.update(line.encode())
+                break
+    except OSError:
+        pass
+    return h.hexdigest()
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "pnode_oracle.c")
-    hdr = os.path.join(_HERE, "pnode_oracle.h")
-    if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+    stamp_path = os.path.join(_HERE, "liboracle.stamp")
+    stamp = _stamp()
+    if not force and os.path.exists(_LIB_PATH) and os.path.exists(stamp_path) and open(stamp_path).read() == stamp:
         return _LIB_PATH
     cmd = ["gcc", "-O3", "-march=native", "-fno-fast-math", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared",
            "-o", _LIB_PATH, src, "-lm"]
     subprocess.run(cmd, check=True, cwd=_HERE)
+    with open(os.path.join(_HERE, "liboracle.stamp"), "w") as fh:
+        fh.write(stamp)
     return _LIB_PATH
 
 

@@ -1,0 +1,52 @@
+// pn_params.h -- plain-old-data kernel parameter block shared by host (pnode_api.cu) and device code.
+// NVRTC-compatible: no standard headers.
+#pragma once
+
+#define PN_MAX_N 12 /* q + 1 <= 12 */
+
+enum PnRetcode { PN_RET_SUCCESS = 0, PN_RET_MAXITERS = 1, PN_RET_DTLESSTHANMIN = 2, PN_RET_UNSTABLE = 3 };
+
+struct PnParams {
+    long long n_traj;
+    const double* u0; /* [n_traj][d]   */
+    const double* p;  /* [n_traj][n_p] */
+    double t0, t1, dt0;
+    double abstol, reltol, dtmin, dtmax;
+    double beta1, beta2, qmin, qmax, gamma, qsteady_min, qsteady_max, qoldinit;
+    double initial_diffusion;
+    long long maxiters;
+    int calibrate;
+    int order; /* controller order = q (src/alg_utils.jl:45) */
+    /* optional schedules (device pointers or null) */
+    const double* tstops;
+    long long n_tstops;
+    const double* forced_diffusion;
+    long long n_forced;
+    /* dynamic work queue */
+    unsigned long long* work_counter;
+    /* IWP constants (src/priors/iwp.jl:74-108), row-major n x n, host-computed */
+    double L[PN_MAX_N * PN_MAX_N];
+    /* ---- per-trajectory outputs ---- */
+    double* t_end;      /* [n_traj]       */
+    double* u_mean;     /* [n_traj][d]    */
+    double* u_cov;      /* [n_traj][d][d] */
+    double* x_mean;     /* [n_traj][D]    (may be null) */
+    double* x_covfac;   /* [n_traj][D][D] row-major right factor, Sigma = R'R (may be null) */
+    double* loglik;     /* [n_traj] */
+    double* diffusion;  /* [n_traj] final diffusion (global MLE for FixedDiffusion, last local otherwise) */
+    double* dt_last;    /* [n_traj] */
+    long long* naccept; /* [n_traj] */
+    long long* nreject;
+    long long* nf;
+    int* retcode;
+    /* ---- save_everystep outputs (CSR over trajectories; null in the counting pass) ---- */
+    const long long* step_offsets; /* [n_traj+1] saved points per trajectory incl. the initial one */
+    double* s_t;                   /* [total]         */
+    double* s_u_mean;              /* [total][d]      */
+    double* s_u_cov;               /* [total][d][d]   */
+    double* s_diffusion;           /* [total]         */
+    double* s_x_mean;              /* [total][D]      (smoothing only) */
+    double* s_x_covfac;            /* [total][D][D]   (smoothing only) */
+    /* backward kernels for the smoother, one record per accepted step (index = saved point - 1 - traj) */
+    double* s_bk;                  /* [total - n_traj][PN_BK_RECORD(D)] */
+};

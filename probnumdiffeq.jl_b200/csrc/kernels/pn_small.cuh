@@ -1,0 +1,714 @@
+// pn_small.cuh -- group-per-trajectory ODE-filter kernel for small filter states (D = d(q+1) <= 32).
+//
+// A "group" of G lanes (G in {2,4,8,16,32}, 32/G trajectories per warp) owns one trajectory for the
+// whole time loop.  The square-root covariance factor R (D x D, Sigma = R'R) lives in registers,
+// row-distributed: lane gl owns rows r == gl (mod G).  Row ownership makes every step of the reference
+// algorithm either lane-local or a G-lane butterfly reduction:
+//
+//   reference routine (file:line)                         here
+//   -------------------------------------------------     ---------------------------------------------
+//   make_transition_matrices!   priors/iwp.jl:182-190      h-powers in registers; Ah = T (x) I_d and
+//   make_preconditioner[_inv]!  preconditioning.jl:30-58   Qh.R = (L P^-1) (x) I_d are never materialised
+//   predict_mean!               filtering/predict.jl:53    replicated, n(n+1)/2 * d FMAs
+//   measurement z, H            measurement_models.jl:11   user f / jac inlined (NVRTC or builtin)
+//                               derivative_utils.jl:1-33
+//   local_scalar_diffusion      diffusions/calibration.jl:123-133  W = C'C with C = Qh.R H' (structured)
+//   compute_scaled_error_estimate!  perform_step.jl:199-247  from diag(W)
+//   PI controller, accept/reject    OrdinaryDiffEqCore, per trajectory, in-kernel
+//   predict_cov! + triangularize!   filtering/predict.jl:62-94, fast_linalg.jl:70-79
+//                                   Householder QR of the 2D x D stack [R Ah' ; sqrt(s2) Qh.R], rows in
+//                                   registers, column norms / v'a reduced with warp shuffles
+//   compute_measurement_covariance! perform_step.jl:182-188   row-local C2 = R^- H', S all-reduced
+//   update!                         filtering/update.jl:65-139 K all-reduced, Joseph form R+ = R^- - C2 K'
+//   estimate_global_diffusion       diffusions/calibration.jl:49-66
+//
+// Groups pull trajectories from an atomic work counter (ragged adaptive step counts).
+// All arithmetic is FP64; tensor cores are not used (per-trajectory matrices are <= 32 x 32).
+//
+// NVRTC-compatible: no standard headers.
+#pragma once
+#include "pn_params.h"
+#include "pn_taylor.cuh"
+
+// Butterfly all-reduce over the G lanes of a group.  Called warp-convergently (full mask), so it compiles
+// to bare SHFL.BFLY pairs; every lane of the group ends with the bitwise-identical sum.
+template <int G>
+PN_HD double pn_gsum(double x) {
+#pragma unroll
+    for (int o = G >> 1; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o, 32);
+    return x;
+}
+template <int G>
+PN_HD double pn_gbcast(double x, int src) {
+    return __shfl_sync(0xffffffffu, x, src, G);
+}
+
+// Upper Cholesky of a symmetric M (row-major, only j >= i read) in place: M = U'U.  Returns false if a
+// pivot is not positive.
+template <int M_>
+PN_HD bool pn_chol(double (&A)[M_][M_]) {
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < M_; j++) {
+        double s = A[j][j];
+#pragma unroll
+        for (int k = 0; k < M_; k++)
+            if (k < j) s -= A[k][j] * A[k][j];
+        if (!(s > 0.0)) ok = false;
+        double ujj = sqrt(s);
+        A[j][j] = ujj;
+        double inv = 1.0 / ujj;
+#pragma unroll
+        for (int i = 0; i < M_; i++) {
+            if (i <= j) continue;
+            double v = A[j][i];
+#pragma unroll
+            for (int k = 0; k < M_; k++)
+                if (k < j) v -= A[k][j] * A[k][i];
+            A[j][i] = v * inv;
+        }
+    }
+    return ok;
+}
+// x <- (U'U)^{-1} x
+template <int M_>
+PN_HD void pn_chol_solve(const double (&U)[M_][M_], double (&x)[M_]) {
+#pragma unroll
+    for (int a = 0; a < M_; a++) {
+#pragma unroll
+        for (int k = 0; k < M_; k++)
+            if (k < a) x[a] -= U[k][a] * x[k];
+        x[a] /= U[a][a];
+    }
+#pragma unroll
+    for (int a = M_ - 1; a >= 0; a--) {
+#pragma unroll
+        for (int k = 0; k < M_; k++)
+            if (k > a) x[a] -= U[a][k] * x[k];
+        x[a] /= U[a][a];
+    }
+}
+
+template <class Prob, int Q, int G, bool ADAPTIVE, bool DYNAMIC, int SAVE>
+struct PnSmall {
+    static constexpr int d = Prob::d;
+    static constexpr int n = Q + 1;
+    static constexpr int D = d * n;
+    static constexpr int RPL = (D + G - 1) / G; /* rows per lane, top and bottom block each */
+    static constexpr int NPA = Prob::n_p > 0 ? Prob::n_p : 1;
+
+    // Householder QR of the stack [Rt ; Bt] (2D x D) in place; on return Rt holds the upper-triangular
+    // factor (row r on lane r % G), below-diagonal entries zeroed.  Bt is destroyed.
+    static PN_HD void qr_stack(double (&Rt)[RPL][D], double (&Bt)[RPL][D], int gl) {
+#pragma unroll
+        for (int k = 0; k < D; k++) {
+            const int ks = k / G;  /* slot of the pivot row */
+            const int kl = k % G;  /* lane of the pivot row */
+            double x[RPL];
+            double part = 0.0;
+#pragma unroll
+            for (int lr = 0; lr < RPL; lr++) {
+                const int base = lr * G;
+                if (base + G - 1 < k) {
+                    x[lr] = 0.0; /* finished rows */
+                } else if (base >= k) {
+                    x[lr] = Rt[lr][k];
+                } else {
+                    x[lr] = (base + gl >= k) ? Rt[lr][k] : 0.0;
+                }
+                part += x[lr] * x[lr];
+            }
+#pragma unroll
+            for (int lr = 0; lr < RPL; lr++) part += Bt[lr][k] * Bt[lr][k];
+            const double total = pn_gsum<G>(part);
+            const double alpha = pn_gbcast<G>(x[ks], kl);
+            /* branch-free on purpose: the shuffles below must be executed by the whole warp.
+               A zero column (total == 0) gets gam = 0, i.e. H = I. */
+            const double nrm = sqrt(total);
+            const double beta = -copysign(nrm, alpha);
+            const double vk = alpha - beta;
+            const double den = total + fabs(alpha) * nrm; /* = beta (beta - alpha) = v'v / 2 */
+            const double gam = (den > 0.0) ? 1.0 / den : 0.0;
+            if (gl == kl) x[ks] = vk;
+            /* s_j = v' a_j over the group, j > k */
+            double sj[D];
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                if (j <= k) continue;
+                double s = 0.0;
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++)
+                    if (lr * G + G - 1 >= k) s += x[lr] * Rt[lr][j];
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++) s += Bt[lr][k] * Bt[lr][j];
+                sj[j] = s;
+            }
+#pragma unroll
+            for (int j = 0; j < D; j++)
+                if (j > k) sj[j] = pn_gsum<G>(sj[j]) * gam;
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                if (j <= k) continue;
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++)
+                    if (lr * G + G - 1 >= k) Rt[lr][j] -= sj[j] * x[lr];
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++) Bt[lr][j] -= sj[j] * Bt[lr][k];
+            }
+            /* column k: beta on the pivot, zeros below */
+#pragma unroll
+            for (int lr = 0; lr < RPL; lr++) {
+                const int base = lr * G;
+                if (base + G - 1 < k) continue;
+                const int row = base + gl;
+                if (row == k) Rt[lr][k] = beta;
+                else if (row > k) Rt[lr][k] = 0.0;
+            }
+        }
+    }
+
+    static __device__ void run(const PnParams& P) {
+        constexpr unsigned FULL = 0xffffffffu;
+        const int lane = threadIdx.x & 31;
+        const int gl = lane % G;
+        const int leader = lane - gl;
+
+        /* bottom-block row bookkeeping: slot lr holds stack row D + rb, rb = lr*G + gl = m*d + i */
+        int mB[RPL], iB[RPL];
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++) {
+            const int rb = lr * G + gl;
+            mB[lr] = rb / d;
+            iB[lr] = rb - mB[lr] * d;
+        }
+
+        double mu[D];          /* filter mean, derivative-major, replicated in the group */
+        double R[RPL][D];      /* own rows of the right factor */
+        double pr[NPA];
+        double uprev[d];
+        double t = 0.0, dt = 0.0, dtcache = 0.0, qold = 0.0, loglik = 0.0, gdiff = 0.0, ldiff = 0.0;
+        long long traj = -1, naccept = 0, nreject = 0, nf = 0, iter = 0, tstop_idx = 0, save_pos = 0;
+        int retcode = PN_RET_SUCCESS;
+        bool have = false, queue_empty = false;
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++)
+#pragma unroll
+            for (int c = 0; c < D; c++) R[lr][c] = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; c++) mu[c] = 0.0;
+
+        /* The warp runs this loop convergently (full-mask shuffles); groups differ only in predicates. */
+        for (;;) {
+            /* ============ (A) groups without work fetch the next trajectory ============ */
+            const bool need = !have && !queue_empty;
+            if (__any_sync(FULL, need)) {
+                unsigned long long idx = 0;
+                if (need && gl == 0) idx = atomicAdd(P.work_counter, 1ULL);
+                idx = __shfl_sync(FULL, idx, leader);
+                if (need) {
+                    if ((long long)idx >= P.n_traj) {
+                        queue_empty = true;
+                    } else {
+                        traj = (long long)idx;
+                        {
+                            InitOut io; /* lives in local memory; copied to registers below */
+                            init_trajectory(P, traj, io);
+#pragma unroll
+                            for (int c = 0; c < D; c++) mu[c] = io.mu[c];
+#pragma unroll
+                            for (int i = 0; i < NPA; i++) pr[i] = io.pr[i];
+#pragma unroll
+                            for (int i = 0; i < d; i++) uprev[i] = io.mu[i];
+                            dt = io.dt;
+                            nf = io.nf;
+                            t = P.t0;
+                        }
+#pragma unroll
+                        for (int lr = 0; lr < RPL; lr++)
+#pragma unroll
+                            for (int c = 0; c < D; c++) R[lr][c] = 0.0;
+                        naccept = nreject = iter = tstop_idx = 0;
+                        loglik = 0.0;
+                        gdiff = 0.0;
+                        ldiff = 0.0;
+                        qold = P.qoldinit;
+                        retcode = PN_RET_SUCCESS;
+                        dtcache = dt;
+                        have = true;
+                        if (SAVE >= 1) {
+                            save_pos = P.step_offsets ? P.step_offsets[traj] : 0;
+                            if (P.step_offsets && gl == 0) {
+                                P.s_t[save_pos] = t;
+                                P.s_diffusion[save_pos] = 0.0;
+#pragma unroll
+                                for (int i = 0; i < d; i++) P.s_u_mean[save_pos * d + i] = mu[i];
+#pragma unroll
+                                for (int i = 0; i < d * d; i++) P.s_u_cov[save_pos * d * d + i] = 0.0;
+                            }
+                            save_pos += 1;
+                        }
+                    }
+                }
+            }
+            if (__all_sync(FULL, !have)) break;
+
+            /* ============ (B) phase 1: attempt steps until one is accepted (no cross-lane traffic) ============ */
+            bool finished = !have || !(t < P.t1);
+            bool accept = false;
+            double h = 0.0, tstop = P.t1, EEst = 0.0, qq = 1.0, ediff = 0.0;
+            double hp[n], PIv[n], mup[D], z[d], J[d * d];
+#pragma unroll
+            for (int k = 0; k < n; k++) hp[k] = (k == 0) ? 1.0 : 0.0;
+#pragma unroll
+            for (int c = 0; c < n; c++) PIv[c] = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; c++) mup[c] = mu[c];
+#pragma unroll
+            for (int i = 0; i < d; i++) z[i] = 0.0;
+#pragma unroll
+            for (int i = 0; i < d * d; i++) J[i] = 0.0;
+
+            while (!finished && !accept) {
+                double q11 = 0.0;
+                while (tstop_idx < P.n_tstops && P.tstops[tstop_idx] <= t) tstop_idx++;
+                tstop = P.t1;
+                if (tstop_idx < P.n_tstops && P.tstops[tstop_idx] < P.t1) tstop = P.tstops[tstop_idx];
+                iter++;
+                if (iter > P.maxiters) {
+                    retcode = PN_RET_MAXITERS;
+                    finished = true;
+                    break;
+                }
+                if (ADAPTIVE) {
+                    dt = fmin(dt, P.dtmax);
+                    dt = fmax(dt, P.dtmin);
+                    dt = fmin(dt, tstop - t);
+                } else {
+                    dt = fmin(dtcache, tstop - t);
+                }
+                h = dt;
+                if (h != h || !(t + h > t) || (ADAPTIVE && h <= P.dtmin)) {
+                    retcode = PN_RET_DTLESSTHANMIN;
+                    finished = true;
+                    break;
+                }
+                const double tnew = t + h;
+                /* hp[k] = h^k/k! ; PIv[c] = h^(q-c+1/2)/(q-c)!  (preconditioning.jl:45-54) */
+                hp[0] = 1.0;
+#pragma unroll
+                for (int k = 1; k < n; k++) hp[k] = hp[k - 1] * h / (double)k;
+                const double sqh = sqrt(h);
+#pragma unroll
+                for (int c = 0; c < n; c++) PIv[c] = hp[Q - c] * sqh;
+                /* predict_mean!: mu^- = (T (x) I) mu, T[j][k] = h^(k-j)/(k-j)! */
+#pragma unroll
+                for (int j = 0; j < n; j++)
+#pragma unroll
+                    for (int i = 0; i < d; i++) {
+                        double s = mu[j * d + i];
+#pragma unroll
+                        for (int k = 0; k < n; k++)
+                            if (k > j) s += hp[k > j ? k - j : 0] * mu[k * d + i];
+                        mup[j * d + i] = s;
+                    }
+                /* measurement: z = E1 mu^- - f(E0 mu^-), J = df/du */
+                double fu[d];
+                Prob::template f<double>(fu, mup, pr, tnew);
+                Prob::jac(J, mup, pr, tnew);
+                nf += 1;
+#pragma unroll
+                for (int i = 0; i < d; i++) z[i] = mup[d + i] - fu[i];
+
+                if (ADAPTIVE || DYNAMIC) {
+                    /* C[(m,i),a] = (Qh.R H')[(m,i),a] = -LQ[m][0] J[a][i] + LQ[m][1] (i==a) ; W = C'C */
+                    double W[d][d];
+#pragma unroll
+                    for (int a = 0; a < d; a++)
+#pragma unroll
+                        for (int b = 0; b < d; b++) W[a][b] = 0.0;
+#pragma unroll
+                    for (int m = 0; m < n; m++) {
+                        const double l0 = P.L[m * n + 0] * PIv[0];
+                        const double l1 = (m >= 1) ? P.L[m * n + 1] * PIv[1] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < d; i++) {
+                            double c[d];
+#pragma unroll
+                            for (int a = 0; a < d; a++) c[a] = -l0 * J[a + d * i] + ((i == a) ? l1 : 0.0);
+#pragma unroll
+                            for (int a = 0; a < d; a++)
+#pragma unroll
+                                for (int b = 0; b < d; b++)
+                                    if (b >= a) W[a][b] += c[a] * c[b];
+                        }
+                    }
+                    double wdiag[d];
+#pragma unroll
+                    for (int a = 0; a < d; a++) wdiag[a] = W[a][a];
+                    double zt[d];
+#pragma unroll
+                    for (int a = 0; a < d; a++) zt[a] = z[a];
+                    const bool ok = pn_chol<d>(W);
+                    pn_chol_solve<d>(W, zt);
+                    double qd = 0.0;
+#pragma unroll
+                    for (int a = 0; a < d; a++) qd += z[a] * zt[a];
+                    ldiff = qd / (double)d;
+                    if (P.forced_diffusion && naccept < P.n_forced) ldiff = P.forced_diffusion[naccept];
+                    if (!ok) {
+                        retcode = PN_RET_UNSTABLE;
+                        finished = true;
+                        break;
+                    }
+                    if (ADAPTIVE) {
+                        double e2 = 0.0;
+#pragma unroll
+                        for (int i = 0; i < d; i++) {
+                            const double e = h * sqrt(ldiff * wdiag[i]);
+                            const double r = e / (P.abstol + fmax(fabs(mup[i]), fabs(uprev[i])) * P.reltol);
+                            e2 += r * r;
+                        }
+                        EEst = sqrt(e2 / (double)d);
+                        if (EEst != EEst) {
+                            retcode = PN_RET_UNSTABLE;
+                            finished = true;
+                            break;
+                        }
+                    }
+                }
+                accept = !ADAPTIVE || EEst < 1.0;
+                if (ADAPTIVE) {
+                    /* stepsize_controller!(::PIController) (OrdinaryDiffEqCore) */
+                    if (EEst == 0.0) {
+                        qq = 1.0 / P.qmax;
+                    } else {
+                        q11 = pow(EEst, P.beta1);
+                        qq = q11 / pow(qold, P.beta2);
+                        qq = fmax(1.0 / P.qmax, fmin(1.0 / P.qmin, qq / P.gamma));
+                    }
+                    if (!accept) { /* step_reject_controller! */
+                        nreject++;
+                        dt = dt / fmin(1.0 / P.qmin, q11 / P.gamma);
+                    }
+                }
+                ediff = DYNAMIC ? ldiff : P.initial_diffusion;
+                if (P.forced_diffusion && naccept < P.n_forced) ediff = P.forced_diffusion[naccept];
+            }
+            if (!accept) {
+                /* identity step for groups that have nothing to commit: h = 0, no process noise, K = 0 */
+#pragma unroll
+                for (int k = 1; k < n; k++) hp[k] = 0.0;
+#pragma unroll
+                for (int c = 0; c < D; c++) mup[c] = mu[c];
+                ediff = 0.0;
+            }
+
+            /* ============ (C) phase 2: covariance predict + update (warp-convergent) ============ */
+            if (__any_sync(FULL, accept)) {
+                double B[RPL][D];
+                /* top block: X = R Ah'  (row-local; ascending j is safe in place) */
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++)
+#pragma unroll
+                    for (int i = 0; i < d; i++)
+#pragma unroll
+                        for (int j = 0; j < n; j++) {
+                            double s = R[lr][j * d + i];
+#pragma unroll
+                            for (int k = 0; k < n; k++)
+                                if (k > j) s += hp[k > j ? k - j : 0] * R[lr][k * d + i];
+                            R[lr][j * d + i] = s;
+                        }
+                /* bottom block: sqrt(s2) (L P^-1) (x) I_d, row (m,i) has L[m][c] PI[c] at column (c,i), c <= m */
+                {
+                    const double sd = (ediff == 1.0) ? 1.0 : sqrt(ediff);
+#pragma unroll
+                    for (int lr = 0; lr < RPL; lr++)
+#pragma unroll
+                        for (int c = 0; c < n; c++) {
+                            double lsel = 0.0;
+#pragma unroll
+                            for (int m = 0; m < n; m++)
+                                if (m >= c) lsel = (mB[lr] == m) ? P.L[m * n + c] : lsel;
+                            const double val = lsel * PIv[c] * sd;
+#pragma unroll
+                            for (int i = 0; i < d; i++) B[lr][c * d + i] = (iB[lr] == i) ? val : 0.0;
+                        }
+                }
+                qr_stack(R, B, gl);
+
+                /* C2 = R^- H' (row-local), S = C2'C2 */
+                double C2[RPL][d];
+                double S[d][d];
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++)
+#pragma unroll
+                    for (int a = 0; a < d; a++) {
+                        double s = R[lr][d + a];
+#pragma unroll
+                        for (int i = 0; i < d; i++) s -= R[lr][i] * J[a + d * i];
+                        C2[lr][a] = accept ? s : 0.0;
+                    }
+#pragma unroll
+                for (int a = 0; a < d; a++)
+#pragma unroll
+                    for (int b = 0; b < d; b++) {
+                        if (b < a) continue;
+                        double s = 0.0;
+#pragma unroll
+                        for (int lr = 0; lr < RPL; lr++) s += C2[lr][a] * C2[lr][b];
+                        S[a][b] = pn_gsum<G>(s);
+                    }
+                double tr = 0.0;
+#pragma unroll
+                for (int a = 0; a < d; a++) tr += S[a][a];
+                const bool passthrough = (tr == 0.0); /* Sigma^- H' == 0 (update.jl:82-89) or idle group */
+                if (passthrough) {
+#pragma unroll
+                    for (int a = 0; a < d; a++) S[a][a] = 1.0;
+                }
+                const bool okS = pn_chol<d>(S);
+                double zt[d];
+#pragma unroll
+                for (int a = 0; a < d; a++) zt[a] = z[a];
+                pn_chol_solve<d>(S, zt);
+                double quad = 0.0, logdet = 0.0;
+#pragma unroll
+                for (int a = 0; a < d; a++) {
+                    quad += z[a] * zt[a];
+                    logdet += log(S[a][a]);
+                }
+                if (accept) {
+                    if (!okS) retcode = PN_RET_UNSTABLE;
+                    if (passthrough) {
+                        bool zz = true;
+#pragma unroll
+                        for (int a = 0; a < d; a++) zz = zz && (z[a] == 0.0);
+                        loglik += zz ? 1e308 * 10.0 : -1e308 * 10.0;
+                    } else {
+                        loglik += -0.5 * quad - 0.5 * (double)d * 1.8378770664093453 - logdet;
+                        if (!DYNAMIC) { /* estimate_global_diffusion(::FixedDiffusion), calibration.jl:49-66 */
+                            const double inc = quad / (double)d;
+                            gdiff = (naccept == 0) ? inc : gdiff + (inc - gdiff) / (double)naccept;
+                        }
+                    }
+                }
+                /* V = C2 S^-1 (row-local) ; K = R^-' V all-reduced ; mu = mu^- - K z ; R+ = R^- - C2 K' */
+                double V[RPL][d];
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++) {
+                    double v[d];
+#pragma unroll
+                    for (int a = 0; a < d; a++) v[a] = C2[lr][a];
+                    pn_chol_solve<d>(S, v);
+#pragma unroll
+                    for (int a = 0; a < d; a++) V[lr][a] = v[a];
+                }
+#pragma unroll
+                for (int c = 0; c < D; c++) {
+                    double Kc[d];
+#pragma unroll
+                    for (int a = 0; a < d; a++) {
+                        double s = 0.0;
+#pragma unroll
+                        for (int lr = 0; lr < RPL; lr++) s += R[lr][c] * V[lr][a];
+                        Kc[a] = pn_gsum<G>(s);
+                    }
+                    double s = mup[c];
+#pragma unroll
+                    for (int a = 0; a < d; a++) s -= Kc[a] * z[a];
+                    mu[c] = s;
+#pragma unroll
+                    for (int lr = 0; lr < RPL; lr++) {
+                        double r = R[lr][c];
+#pragma unroll
+                        for (int a = 0; a < d; a++) r -= C2[lr][a] * Kc[a];
+                        R[lr][c] = r;
+                    }
+                }
+                if (accept) {
+                    /* loopfooter! accept branch (OrdinaryDiffEqCore) */
+                    double dtnew = dt;
+                    if (ADAPTIVE) {
+                        if (P.qsteady_min <= qq && qq <= P.qsteady_max) qq = 1.0;
+                        qold = fmax(EEst, P.qoldinit);
+                        dtnew = dt / qq;
+                    }
+                    const double ttmp = t + h;
+                    const double ref = fmax(fabs(t), fabs(tstop));
+                    const double epsref = nextafter(ref, 1e300) - ref;
+                    t = (fabs(ttmp - tstop) < 100.0 * epsref) ? tstop : ttmp;
+                    dt = dtnew;
+                    naccept++;
+                    bool nanu = false;
+#pragma unroll
+                    for (int i = 0; i < d; i++) {
+                        uprev[i] = mu[i];
+                        nanu = nanu || (mu[i] != mu[i]);
+                    }
+                    if (nanu) retcode = PN_RET_UNSTABLE;
+                    if (retcode != PN_RET_SUCCESS) finished = true;
+                    if (!(t < P.t1)) finished = true;
+                }
+                if (SAVE >= 1) {
+                    const bool wr = accept && P.step_offsets;
+                    double cv[d * d];
+#pragma unroll
+                    for (int a = 0; a < d; a++)
+#pragma unroll
+                        for (int b = 0; b < d; b++) {
+                        if (b < a) continue;
+                            double s = 0.0;
+#pragma unroll
+                            for (int lr = 0; lr < RPL; lr++) s += R[lr][a] * R[lr][b];
+                            s = pn_gsum<G>(s);
+                            cv[a * d + b] = s;
+                            cv[b * d + a] = s;
+                        }
+                    if (wr && gl == 0) {
+                        P.s_t[save_pos] = t;
+                        P.s_diffusion[save_pos - 1] = (ADAPTIVE || DYNAMIC) ? ldiff : P.initial_diffusion;
+#pragma unroll
+                        for (int i = 0; i < d; i++) P.s_u_mean[save_pos * d + i] = mu[i];
+#pragma unroll
+                        for (int i = 0; i < d * d; i++) P.s_u_cov[save_pos * d * d + i] = cv[i];
+                    }
+                    if (accept) save_pos += 1;
+                }
+            }
+
+            /* ============ (D) postamble of finished trajectories ============ */
+            const bool fin = have && finished;
+            if (__any_sync(FULL, fin)) {
+                double sc = 1.0, fd = ldiff;
+                if (!DYNAMIC) {
+                    if (P.calibrate && naccept > 0) {
+                        sc = gdiff;
+                        fd = gdiff * P.initial_diffusion;
+                    } else {
+                        fd = P.initial_diffusion;
+                    }
+                }
+                double cv[d * d];
+#pragma unroll
+                for (int a = 0; a < d; a++)
+#pragma unroll
+                    for (int b = 0; b < d; b++) {
+                        if (b < a) continue;
+                        double s = 0.0;
+#pragma unroll
+                        for (int lr = 0; lr < RPL; lr++) s += R[lr][a] * R[lr][b];
+                        s = pn_gsum<G>(s) * sc;
+                        cv[a * d + b] = s;
+                        cv[b * d + a] = s;
+                    }
+                if (fin) {
+                    if (gl == 0) {
+                        P.t_end[traj] = t;
+#pragma unroll
+                        for (int i = 0; i < d; i++) P.u_mean[traj * d + i] = mu[i];
+#pragma unroll
+                        for (int i = 0; i < d * d; i++) P.u_cov[traj * d * d + i] = cv[i];
+                        P.loglik[traj] = loglik;
+                        P.diffusion[traj] = fd;
+                        P.dt_last[traj] = dt;
+                        P.naccept[traj] = naccept;
+                        P.nreject[traj] = nreject;
+                        P.nf[traj] = nf;
+                        P.retcode[traj] = retcode;
+                        if (P.x_mean) {
+#pragma unroll
+                            for (int c = 0; c < D; c++) P.x_mean[traj * D + c] = mu[c];
+                        }
+                    }
+                    if (P.x_covfac) {
+                        const double ss = sqrt(sc);
+#pragma unroll
+                        for (int lr = 0; lr < RPL; lr++) {
+                            const int row = lr * G + gl;
+                            if (row < D) {
+#pragma unroll
+                                for (int c = 0; c < D; c++) P.x_covfac[(traj * D + row) * D + c] = R[lr][c] * ss;
+                            }
+                        }
+                    }
+                    have = false;
+                }
+            }
+        }
+    }
+
+    /* initial state + initial step (cold path, once per trajectory) */
+    struct InitOut {
+        double mu[D];
+        double pr[NPA];
+        double dt;
+        long long nf;
+    };
+    static __device__ __noinline__ void init_trajectory(const PnParams& P, long long traj, InitOut& io) {
+        double u0[d];
+        double mu[D], pr[NPA], dt;
+        long long nf;
+#pragma unroll
+        for (int i = 0; i < NPA; i++) pr[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < d; i++) u0[i] = P.u0[traj * d + i];
+#pragma unroll
+        for (int i = 0; i < Prob::n_p; i++) pr[i] = P.p[traj * Prob::n_p + i];
+        /* exact initial derivatives (TaylorModeInit, autodiffinit.jl:52-67); Sigma0.R = 0 */
+        pn_taylor_init<Prob, Q>(mu, u0, pr, P.t0);
+        nf = Q;
+        if (ADAPTIVE && !(P.dt0 > 0.0)) {
+            /* ode_determine_initdt (OrdinaryDiffEqCore) */
+            double sk[d], f0[d], f1[d], u1[d];
+            const double epst =
+                fabs(P.t0) > 0.0 ? (nextafter(fabs(P.t0), 1e300) - fabs(P.t0)) : 4.9406564584124654e-324;
+            const double dtmin = nextafter(fmax(P.dtmin, epst), 1e300);
+            const double smalldt = fmax(dtmin, 1e-6);
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+            Prob::template f<double>(f0, u0, pr, P.t0);
+#pragma unroll
+            for (int i = 0; i < d; i++) {
+                sk[i] = P.abstol + fabs(u0[i]) * P.reltol;
+                const double a = u0[i] / sk[i], b = f0[i] / sk[i];
+                d0 += a * a;
+                d1 += b * b;
+            }
+            d0 = sqrt(d0 / (double)d);
+            d1 = sqrt(d1 / (double)d);
+            double dta = (d0 < 1e-5 || d1 < 1e-5) ? smalldt : (d0 / d1) / 100.0;
+            dta = fmin(dta, P.dtmax);
+            if (dta < 10.0 * 2.220446049250313e-16) {
+                dt = fmax(smalldt, dtmin);
+            } else {
+#pragma unroll
+                for (int i = 0; i < d; i++) u1[i] = u0[i] + dta * f0[i];
+                Prob::template f<double>(f1, u1, pr, P.t0 + dta);
+#pragma unroll
+                for (int i = 0; i < d; i++) {
+                    const double c = (f1[i] - f0[i]) / sk[i];
+                    d2 += c * c;
+                }
+                d2 = sqrt(d2 / (double)d) / dta;
+                const double mx = fmax(d1, d2);
+                const double dtb =
+                    (mx <= 1e-15) ? fmax(1e-6, dta * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / (double)P.order);
+                dt = fmax(dtmin, fmin(fmin(100.0 * dta, dtb), P.dtmax));
+            }
+            nf += 2;
+        } else {
+            dt = P.dt0;
+        }
+#pragma unroll
+        for (int c = 0; c < D; c++) io.mu[c] = mu[c];
+#pragma unroll
+        for (int i = 0; i < NPA; i++) io.pr[i] = pr[i];
+        io.dt = dt;
+        io.nf = nf;
+    }
+};
+
+template <class Prob, int Q, int G, bool ADAPTIVE, bool DYNAMIC, int SAVE>
+__device__ __forceinline__ void pn_small_entry(const PnParams& P) {
+    PnSmall<Prob, Q, G, ADAPTIVE, DYNAMIC, SAVE>::run(P);
+}

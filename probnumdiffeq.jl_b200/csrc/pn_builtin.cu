@@ -1,0 +1,27 @@
+// pn_builtin.cu -- ahead-of-time (nvcc, sm_100a) instantiations of the step kernels for the built-in
+// problems BASELINE.json names.  Everything else is compiled at run time by NVRTC from the same headers
+// (pnode_api.cu).  Keys must match pnode_api.cu::kernel_key().
+#include "pn_kernel_entry.cuh"
+#include "kernels/pn_builtin_problems.cuh"
+#include "pn_builtin.h"
+
+#define PN_ENTRY(NAME, PROB, Q, G, A, DY, S) \
+    { "builtin:" NAME ":small:q" #Q ":g" #G ":a" #A ":dyn" #DY ":s" #S, \
+      (const void*)&pn_small_kernel<PROB, Q, G, (A != 0), (DY != 0), S>, PROB::d, PROB::n_p }
+
+static const PnBuiltinEntry g_table[] = {
+    /* cfg5: ROBER / OREGO stiff EK1(order=3), adaptive, filter only (bench.py headline) */
+    PN_ENTRY("rober", PnRober, 3, 4, 1, 1, 0),
+    PN_ENTRY("orego", PnOrego, 3, 4, 1, 1, 0),
+    /* cfg1: FitzHugh-Nagumo EK1(order=3) */
+    PN_ENTRY("fitzhugh_nagumo", PnFitzHughNagumo, 3, 4, 1, 1, 0),
+    /* cfg3: Van der Pol EK1(order=5) */
+    PN_ENTRY("vanderpol", PnVanDerPol, 5, 4, 1, 1, 0),
+    /* Lotka-Volterra through the dense EK1 path */
+    PN_ENTRY("lotka_volterra", PnLotkaVolterra, 3, 4, 1, 1, 0),
+};
+
+extern "C" const PnBuiltinEntry* pn_builtin_table(int* count) {
+    *count = (int)(sizeof(g_table) / sizeof(g_table[0]));
+    return g_table;
+}

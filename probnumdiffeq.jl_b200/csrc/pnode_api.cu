@@ -1,0 +1,612 @@
+// pnode_api.cu -- C ABI of libpnode_cuda.so (include/pnode.h): configuration checks, NVRTC compilation of
+// traced right-hand sides together with the step kernels, persistent-kernel launches, result handles.
+//
+// There is deliberately no CPU fallback: without a CUDA device every solve entry point fails with
+// PNODE_ERR_NO_DEVICE.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pnode.h"
+#include "kernels/pn_params.h"
+#include "pn_builtin.h"
+#include "pn_embedded_sources.h" /* generated: kernel headers as strings for NVRTC */
+
+#define PN_THREADS 128
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(PNODE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+    } while (0)
+
+/* ---- driver entry points (libcuda is never linked: the library must load on a CPU-only box) ---- */
+typedef CUresult (*fn_cuModuleLoadData)(CUmodule*, const void*);
+typedef CUresult (*fn_cuModuleUnload)(CUmodule);
+typedef CUresult (*fn_cuModuleGetFunction)(CUfunction*, CUmodule, const char*);
+typedef CUresult (*fn_cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                                      CUstream, void**, void**);
+typedef CUresult (*fn_cuOccupancy)(int*, CUfunction, int, size_t);
+typedef CUresult (*fn_cuGetErrorString)(CUresult, const char**);
+struct DriverApi {
+    fn_cuModuleLoadData ModuleLoadData = nullptr;
+    fn_cuModuleUnload ModuleUnload = nullptr;
+    fn_cuModuleGetFunction ModuleGetFunction = nullptr;
+    fn_cuLaunchKernel LaunchKernel = nullptr;
+    fn_cuOccupancy Occupancy = nullptr;
+    fn_cuGetErrorString GetErrorString = nullptr;
+    bool ok = false;
+};
+static DriverApi g_drv;
+static int load_driver() {
+    if (g_drv.ok) return 0;
+    struct {
+        const char* name;
+        void** slot;
+    } syms[] = {
+        {"cuModuleLoadData", (void**)&g_drv.ModuleLoadData},
+        {"cuModuleUnload", (void**)&g_drv.ModuleUnload},
+        {"cuModuleGetFunction", (void**)&g_drv.ModuleGetFunction},
+        {"cuLaunchKernel", (void**)&g_drv.LaunchKernel},
+        {"cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&g_drv.Occupancy},
+        {"cuGetErrorString", (void**)&g_drv.GetErrorString},
+    };
+    for (auto& s : syms) {
+        cudaDriverEntryPointQueryResult qr;
+        cudaError_t e = cudaGetDriverEntryPoint(s.name, s.slot, cudaEnableDefault, &qr);
+        if (e != cudaSuccess || qr != cudaDriverEntryPointSuccess || !*s.slot)
+            return fail(PNODE_ERR_CUDA, std::string("cudaGetDriverEntryPoint(") + s.name + ") failed");
+    }
+    g_drv.ok = true;
+    return 0;
+}
+static std::string cu_err(CUresult r) {
+    const char* s = nullptr;
+    if (g_drv.GetErrorString) g_drv.GetErrorString(r, &s);
+    return s ? s : "unknown CUDA driver error";
+}
+
+/* ---------------------------------------------------------------------------------------------- */
+struct Kernel {
+    const void* rt_fn = nullptr; /* nvcc-compiled (runtime API) */
+    CUmodule mod = nullptr;      /* NVRTC-compiled */
+    CUfunction drv_fn = nullptr;
+    int blocks_per_sm = 1;
+    bool valid() const { return rt_fn || drv_fn; }
+};
+
+struct pnode_solver {
+    pnode_config cfg;
+    std::string rhs_src, rhs_name;
+    int D = 0, G = 4, n_sm = 0;
+    bool builtin = false;
+    Kernel k_final;  /* SAVE = 0 */
+    Kernel k_save;   /* SAVE = 1 */
+    cudaStream_t stream = nullptr;
+    unsigned long long* d_counter = nullptr;
+    double* d_tstops = nullptr;
+    double* d_forced = nullptr;
+    double compile_s = 0.0;
+    PnParams base; /* constants filled at create */
+};
+
+struct Buf {
+    void* d = nullptr;
+    size_t bytes = 0;
+};
+struct pnode_result {
+    pnode_solver* s = nullptr;
+    int64_t n_traj = 0;
+    Buf f[PNODE_F_COUNT];
+    std::vector<int64_t> offsets;
+    pnode_result_info info;
+    bool owns_inputs = false;
+    double* d_u0 = nullptr;
+    double* d_p = nullptr;
+};
+
+/* ---------------------------------------------------------------------------------------------- */
+extern "C" int pnode_abi_version(void) { return 1; }
+extern "C" const char* pnode_last_error(void) { return g_err.c_str(); }
+extern "C" int pnode_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static double factorial_d(int k) {
+    double f = 1.0;
+    for (int i = 2; i <= k; i++) f *= (double)i;
+    return f;
+}
+
+static int auto_lanes(int D) {
+    /* registers per lane ~ 2 * 2 * D * ceil(D/G) (stack) must stay below ~150 doubles-worth */
+    const int cand[] = {2, 4, 8, 16, 32};
+    for (int g : cand) {
+        int rpl = (D + g - 1) / g;
+        if (2 * rpl * D <= 80) return g;
+    }
+    return 32;
+}
+
+static std::string kernel_key(const pnode_solver* s, int save) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "%s:small:q%d:g%d:a%d:dyn%d:s%d", s->rhs_name.c_str(), s->cfg.q, s->G,
+             s->cfg.adaptive ? 1 : 0, s->cfg.diffusion == PNODE_DIFF_DYNAMIC ? 1 : 0, save);
+    return buf;
+}
+
+/* NVRTC: user RHS + step kernels -> sm_100a CUBIN.  Needs no device. */
+static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_name, int q, int G, bool adaptive,
+                       bool dynamic, int save, std::vector<char>* cubin) {
+    std::string src;
+    src += "#include \"pn_kernel_entry.cuh\"\n";
+    src += rhs_src;
+    src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_entry(const __grid_constant__ "
+           "PnParams P) {\n  pn_small_entry<" +
+           struct_name + ", PN_Q, PN_G, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
+    nvrtcProgram prog;
+    const char* hdr_src[PN_N_EMBEDDED];
+    const char* hdr_name[PN_N_EMBEDDED];
+    for (int i = 0; i < PN_N_EMBEDDED; i++) {
+        hdr_src[i] = pn_embedded_sources[i].text;
+        hdr_name[i] = pn_embedded_sources[i].name;
+    }
+    if (nvrtcCreateProgram(&prog, src.c_str(), "pnode_user.cu", PN_N_EMBEDDED, hdr_src, hdr_name) != NVRTC_SUCCESS)
+        return fail(PNODE_ERR_COMPILE, "nvrtcCreateProgram failed");
+    char dq[32], dg[32], da[32], dd[32], ds[32];
+    snprintf(dq, sizeof dq, "-DPN_Q=%d", q);
+    snprintf(dg, sizeof dg, "-DPN_G=%d", G);
+    snprintf(da, sizeof da, "-DPN_ADAPTIVE=%d", adaptive ? 1 : 0);
+    snprintf(dd, sizeof dd, "-DPN_DYNAMIC=%d", dynamic ? 1 : 0);
+    snprintf(ds, sizeof ds, "-DPN_SAVE=%d", save);
+    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", dq, dg, da, dd, ds};
+    nvrtcResult cr = nvrtcCompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+    if (cr != NVRTC_SUCCESS) {
+        size_t n = 0;
+        nvrtcGetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) nvrtcGetProgramLog(prog, &log[0]);
+        nvrtcDestroyProgram(&prog);
+        return fail(PNODE_ERR_COMPILE, "NVRTC compilation failed:\n" + log);
+    }
+    size_t nb = 0;
+    nvrtcGetCUBINSize(prog, &nb);
+    cubin->resize(nb);
+    nvrtcGetCUBIN(prog, cubin->data());
+    nvrtcDestroyProgram(&prog);
+    return 0;
+}
+
+static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
+    int rc = load_driver();
+    if (rc) return rc;
+    std::vector<char> cubin;
+    rc = nvrtc_cubin(s->rhs_src, s->rhs_name, s->cfg.q, s->G, s->cfg.adaptive != 0,
+                     s->cfg.diffusion == PNODE_DIFF_DYNAMIC, save, &cubin);
+    if (rc) return rc;
+    CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
+    if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
+    r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_entry");
+    if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction: " + cu_err(r));
+    int nblk = 0;
+    r = g_drv.Occupancy(&nblk, out->drv_fn, PN_THREADS, 0);
+    if (r != CUDA_SUCCESS || nblk < 1) return fail(PNODE_ERR_CUDA, "occupancy query failed: " + cu_err(r));
+    out->blocks_per_sm = nblk;
+    return 0;
+}
+
+static int get_kernel(pnode_solver* s, int save, Kernel* out) {
+    if (out->valid()) return 0;
+    auto t0 = std::chrono::steady_clock::now();
+    if (s->builtin) {
+        int n = 0;
+        const PnBuiltinEntry* tab = pn_builtin_table(&n);
+        std::string key = kernel_key(s, save);
+        for (int i = 0; i < n; i++) {
+            if (key == tab[i].key) {
+                out->rt_fn = tab[i].fn;
+                int nblk = 0;
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, out->rt_fn, PN_THREADS, 0));
+                if (nblk < 1) return fail(PNODE_ERR_CUDA, "kernel does not fit on an SM");
+                out->blocks_per_sm = nblk;
+                return 0;
+            }
+        }
+        return fail(PNODE_ERR_UNSUPPORTED,
+                    "no ahead-of-time kernel for '" + key + "'; pass the traced source (rhs_src) to use NVRTC");
+    }
+    int rc = compile_nvrtc(s, save, out);
+    s->compile_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+static int validate_config(const pnode_config* cfg) {
+    if (cfg->struct_size != (int32_t)sizeof(pnode_config))
+        return fail(PNODE_ERR_ARGUMENT, "pnode_config.struct_size mismatch (ABI)");
+    /* ---- argument checks mirroring the reference's constructors ---- */
+    if (cfg->d < 1) return fail(PNODE_ERR_ARGUMENT, "We currently don't support scalar-valued problems (d >= 1 vector required)"); /* caches.jl:96-98 */
+    if (cfg->q < 1 || cfg->q + 1 > PN_MAX_N) return fail(PNODE_ERR_ARGUMENT, "order must satisfy 1 <= order <= 11");
+    if (cfg->prior != PNODE_PRIOR_IWP) return fail(PNODE_ERR_UNSUPPORTED, "only the IWP prior is implemented");
+    if (cfg->alg != PNODE_EK0 && cfg->alg != PNODE_EK1) return fail(PNODE_ERR_ARGUMENT, "Unknown algorithm"); /* derivative_utils.jl:31 */
+    if (cfg->diffusion != PNODE_DIFF_DYNAMIC && cfg->diffusion != PNODE_DIFF_FIXED)
+        return fail(PNODE_ERR_UNSUPPORTED, "only DynamicDiffusion and FixedDiffusion are implemented");
+    if (!cfg->adaptive && !(cfg->dt > 0.0))
+        return fail(PNODE_ERR_ARGUMENT, "Fixed timestep methods require a choice of dt or choosing the tstops"); /* test/errors_thrown.jl:6-8 */
+    if (cfg->smooth && !cfg->save_everystep)
+        return fail(PNODE_ERR_ARGUMENT, "If you set `save_everystep=false` also set `smooth=false` in the alg!"); /* checks.jl:18-20 */
+    if (!(cfg->t1 > cfg->t0)) return fail(PNODE_ERR_ARGUMENT, "tspan must satisfy t1 > t0");
+    if (!cfg->rhs_name) return fail(PNODE_ERR_ARGUMENT, "rhs_name is required");
+    if (cfg->smooth) return fail(PNODE_ERR_UNSUPPORTED, "smooth=true is not implemented yet in this build");
+    const int D = cfg->d * (cfg->q + 1);
+    int cov = cfg->cov;
+    if (cov == PNODE_COV_AUTO) cov = PNODE_COV_DENSE; /* Kronecker fast path: see pn_kron (EK0) */
+    if (cov == PNODE_COV_KRONECKER && cfg->alg != PNODE_EK0)
+        return fail(PNODE_ERR_ARGUMENT, "IsometricKroneckerCovariance requires the EK0"); /* algorithms.jl:101-110 */
+    if (cfg->alg == PNODE_EK0) return fail(PNODE_ERR_UNSUPPORTED, "EK0 is not implemented yet in this build");
+    if (D > 32) return fail(PNODE_ERR_UNSUPPORTED, "D = d(q+1) > 32 needs the CTA-per-trajectory kernel (not in this build)");
+    if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 2 && cfg->lanes_per_traj != 4 && cfg->lanes_per_traj != 8 &&
+        cfg->lanes_per_traj != 16 && cfg->lanes_per_traj != 32)
+        return fail(PNODE_ERR_ARGUMENT, "lanes_per_traj must be one of 0 (auto), 2, 4, 8, 16, 32");
+    const bool builtin = (std::string(cfg->rhs_name).rfind("builtin:", 0) == 0);
+    if (!builtin && !cfg->rhs_src) return fail(PNODE_ERR_ARGUMENT, "rhs_src is required unless rhs_name is a builtin");
+    return 0;
+}
+
+/* Validate + NVRTC-compile only (no device needed).  Used by host-side tests and to pre-warm caches. */
+extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes) {
+    if (!cfg) return fail(PNODE_ERR_ARGUMENT, "null argument");
+    int rc = validate_config(cfg);
+    if (rc) return rc;
+    if (cubin_bytes) *cubin_bytes = 0;
+    if (std::string(cfg->rhs_name).rfind("builtin:", 0) == 0) return 0;
+    const int D = cfg->d * (cfg->q + 1);
+    const int G = cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D);
+    std::vector<char> cubin;
+    rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, cfg->diffusion == PNODE_DIFF_DYNAMIC,
+                     cfg->save_everystep ? 1 : 0, &cubin);
+    if (rc) return rc;
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    return 0;
+}
+
+extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
+    if (!cfg || !out) return fail(PNODE_ERR_ARGUMENT, "null argument");
+    *out = nullptr;
+    {
+        int vrc = validate_config(cfg);
+        if (vrc) return vrc;
+    }
+    const int D = cfg->d * (cfg->q + 1);
+
+    pnode_solver* s = new pnode_solver();
+    s->cfg = *cfg;
+    s->D = D;
+    s->rhs_name = cfg->rhs_name;
+    s->builtin = (s->rhs_name.rfind("builtin:", 0) == 0);
+    if (!s->builtin) s->rhs_src = cfg->rhs_src;
+    s->cfg.rhs_src = nullptr;
+    s->cfg.rhs_name = nullptr;
+    s->G = cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D);
+    /* ---- constants ---- */
+    PnParams& B = s->base;
+    memset(&B, 0, sizeof B);
+    B.t0 = cfg->t0;
+    B.t1 = cfg->t1;
+    B.dt0 = cfg->dt;
+    B.abstol = cfg->abstol;
+    B.reltol = cfg->reltol;
+    B.dtmin = cfg->dtmin;
+    B.dtmax = cfg->dtmax > 0.0 ? cfg->dtmax : (cfg->t1 - cfg->t0);
+    B.beta2 = cfg->beta2 > 0.0 ? cfg->beta2 : 2.0 / (5.0 * cfg->q);
+    B.beta1 = cfg->beta1 > 0.0 ? cfg->beta1 : 7.0 / (10.0 * cfg->q);
+    B.qmin = cfg->qmin > 0.0 ? cfg->qmin : 0.2;
+    B.qmax = cfg->qmax > 0.0 ? cfg->qmax : 10.0;
+    B.gamma = cfg->gamma > 0.0 ? cfg->gamma : 0.9;
+    B.qsteady_min = cfg->qsteady_min > 0.0 ? cfg->qsteady_min : 1.0;
+    B.qsteady_max = cfg->qsteady_max > 0.0 ? cfg->qsteady_max : 1.0;
+    B.qoldinit = cfg->qoldinit > 0.0 ? cfg->qoldinit : 1e-4;
+    B.initial_diffusion = cfg->initial_diffusion > 0.0 ? cfg->initial_diffusion : 1.0;
+    B.maxiters = cfg->maxiters > 0 ? cfg->maxiters : 1000000;
+    B.calibrate = cfg->calibrate;
+    B.order = cfg->q;
+    {
+        /* left square root of the preconditioned IWP covariance (src/priors/iwp.jl:74-94) */
+        const int q = cfg->q, n = q + 1;
+        for (int m = 0; m <= q; m++)
+            for (int c = 0; c <= m; c++) {
+                double fq = factorial_d(q - c);
+                B.L[m * n + c] = std::sqrt((double)(2 * q - 2 * m + 1)) * (fq * fq) / factorial_d(m - c) /
+                                 factorial_d(2 * q - c - m + 1);
+            }
+    }
+    /* ---- device ---- */
+    int ndev = pnode_device_count();
+    if (ndev <= 0) {
+        delete s;
+        return fail(PNODE_ERR_NO_DEVICE, "no CUDA device available: libpnode_cuda has no CPU fallback");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) {
+        delete s;
+        return fail(PNODE_ERR_ARGUMENT, "invalid device ordinal");
+    }
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
+    if (cfg->n_tstops > 0 && cfg->tstops) {
+        CUDA_TRY(cudaMalloc(&s->d_tstops, sizeof(double) * cfg->n_tstops));
+        CUDA_TRY(cudaMemcpy(s->d_tstops, cfg->tstops, sizeof(double) * cfg->n_tstops, cudaMemcpyHostToDevice));
+        B.tstops = s->d_tstops;
+        B.n_tstops = cfg->n_tstops;
+    }
+    if (cfg->n_forced > 0 && cfg->forced_diffusion) {
+        CUDA_TRY(cudaMalloc(&s->d_forced, sizeof(double) * cfg->n_forced));
+        CUDA_TRY(cudaMemcpy(s->d_forced, cfg->forced_diffusion, sizeof(double) * cfg->n_forced, cudaMemcpyHostToDevice));
+        B.forced_diffusion = s->d_forced;
+        B.n_forced = cfg->n_forced;
+    }
+    B.work_counter = s->d_counter;
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, cfg->device) == cudaSuccess) {
+            unsigned long long thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    int rc = get_kernel(s, cfg->save_everystep ? 1 : 0, cfg->save_everystep ? &s->k_save : &s->k_final);
+    if (rc) {
+        pnode_destroy(s);
+        return rc;
+    }
+    *out = s;
+    return 0;
+}
+
+extern "C" double pnode_compile_seconds(const pnode_solver* s) { return s ? s->compile_s : 0.0; }
+
+extern "C" void pnode_destroy(pnode_solver* s) {
+    if (!s) return;
+    cudaSetDevice(s->cfg.device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (Kernel* k : {&s->k_final, &s->k_save})
+        if (k->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(k->mod);
+    if (s->d_counter) cudaFree(s->d_counter);
+    if (s->d_tstops) cudaFree(s->d_tstops);
+    if (s->d_forced) cudaFree(s->d_forced);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+static int launch(pnode_solver* s, Kernel& k, PnParams& P, int64_t n_traj) {
+    const int groups_per_block = PN_THREADS / s->G;
+    long long want = (n_traj + groups_per_block - 1) / groups_per_block;
+    long long cap = (long long)s->n_sm * k.blocks_per_sm; /* persistent: a whole number of CTAs per SM */
+    unsigned grid = (unsigned)std::max(1LL, std::min(want, cap));
+    CUDA_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), s->stream));
+    if (k.rt_fn) {
+        void* args[] = {&P};
+        CUDA_TRY(cudaLaunchKernel(k.rt_fn, dim3(grid), dim3(PN_THREADS), args, 0, s->stream));
+    } else {
+        void* args[] = {&P};
+        CUresult r = g_drv.LaunchKernel(k.drv_fn, grid, 1, 1, PN_THREADS, 1, 1, 0, (CUstream)s->stream, args, nullptr);
+        if (r != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuLaunchKernel: " + cu_err(r));
+    }
+    return 0;
+}
+
+static int alloc_field(pnode_result* r, int field, size_t bytes) {
+    if (bytes == 0) return 0;
+    void* p = nullptr;
+    CUDA_TRY(cudaMallocAsync(&p, bytes, r->s->stream));
+    r->f[field].d = p;
+    r->f[field].bytes = bytes;
+    return 0;
+}
+
+static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const double* d_p, pnode_result* r) {
+    const int d = s->cfg.d, D = s->D;
+    const size_t N = (size_t)n_traj;
+    int rc;
+    if ((rc = alloc_field(r, PNODE_F_T_END, N * 8))) return rc;
+    if ((rc = alloc_field(r, PNODE_F_U_FINAL, N * d * 8))) return rc;
+    if ((rc = alloc_field(r, PNODE_F_U_FINAL_COV, N * d * d * 8))) return rc;
+    if (s->cfg.save_state) {
+        if ((rc = alloc_field(r, PNODE_F_X_FINAL, N * D * 8))) return rc;
+        if ((rc = alloc_field(r, PNODE_F_X_FINAL_COVFAC, N * D * D * 8))) return rc;
+    }
+    if ((rc = alloc_field(r, PNODE_F_LOGLIK, N * 8))) return rc;
+    if ((rc = alloc_field(r, PNODE_F_DIFFUSION, N * 8))) return rc;
+    if ((rc = alloc_field(r, PNODE_F_DT_LAST, N * 8))) return rc;
+    if ((rc = alloc_field(r, PNODE_F_NACCEPT, N * 8))) return rc;
+    if ((rc = alloc_field(r, PNODE_F_NREJECT, N * 8))) return rc;
+    if ((rc = alloc_field(r, PNODE_F_NF, N * 8))) return rc;
+    if ((rc = alloc_field(r, PNODE_F_RETCODE, N * 4))) return rc;
+
+    PnParams P = s->base;
+    P.n_traj = n_traj;
+    P.u0 = d_u0;
+    P.p = d_p;
+    P.t_end = (double*)r->f[PNODE_F_T_END].d;
+    P.u_mean = (double*)r->f[PNODE_F_U_FINAL].d;
+    P.u_cov = (double*)r->f[PNODE_F_U_FINAL_COV].d;
+    P.x_mean = (double*)r->f[PNODE_F_X_FINAL].d;
+    P.x_covfac = (double*)r->f[PNODE_F_X_FINAL_COVFAC].d;
+    P.loglik = (double*)r->f[PNODE_F_LOGLIK].d;
+    P.diffusion = (double*)r->f[PNODE_F_DIFFUSION].d;
+    P.dt_last = (double*)r->f[PNODE_F_DT_LAST].d;
+    P.naccept = (long long*)r->f[PNODE_F_NACCEPT].d;
+    P.nreject = (long long*)r->f[PNODE_F_NREJECT].d;
+    P.nf = (long long*)r->f[PNODE_F_NF].d;
+    P.retcode = (int*)r->f[PNODE_F_RETCODE].d;
+
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0, s->stream));
+    int64_t launches = 0;
+    if (!s->cfg.save_everystep) {
+        if ((rc = launch(s, s->k_final, P, n_traj))) return rc;
+        launches = 1;
+    } else {
+        /* pass 1: count accepted steps with the *same* binary (null step_offsets => no stores), so both
+           passes take bit-identical accept/reject decisions; pass 2 writes at exact CSR positions */
+        if ((rc = launch(s, s->k_save, P, n_traj))) return rc;
+        std::vector<long long> nacc(N);
+        CUDA_TRY(cudaMemcpyAsync(nacc.data(), P.naccept, N * 8, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        r->offsets.resize(N + 1);
+        r->offsets[0] = 0;
+        for (size_t i = 0; i < N; i++) r->offsets[i + 1] = r->offsets[i] + nacc[i] + 1;
+        const size_t T = (size_t)r->offsets[N];
+        if ((rc = alloc_field(r, PNODE_F_STEP_OFFSETS, (N + 1) * 8))) return rc;
+        if ((rc = alloc_field(r, PNODE_F_T, T * 8))) return rc;
+        if ((rc = alloc_field(r, PNODE_F_U, T * d * 8))) return rc;
+        if ((rc = alloc_field(r, PNODE_F_U_COV, T * d * d * 8))) return rc;
+        if ((rc = alloc_field(r, PNODE_F_DIFFUSIONS, T * 8))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(r->f[PNODE_F_STEP_OFFSETS].d, r->offsets.data(), (N + 1) * 8, cudaMemcpyHostToDevice,
+                                 s->stream));
+        P.step_offsets = (const long long*)r->f[PNODE_F_STEP_OFFSETS].d;
+        P.s_t = (double*)r->f[PNODE_F_T].d;
+        P.s_u_mean = (double*)r->f[PNODE_F_U].d;
+        P.s_u_cov = (double*)r->f[PNODE_F_U_COV].d;
+        P.s_diffusion = (double*)r->f[PNODE_F_DIFFUSIONS].d;
+        if ((rc = launch(s, s->k_save, P, n_traj))) return rc;
+        launches = 2;
+        r->info.total_saved = (int64_t)T;
+    }
+    CUDA_TRY(cudaEventRecord(e1, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaGetLastError());
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    r->info.kernel_ms = ms;
+    r->info.n_launches = launches;
+    r->info.n_traj = n_traj;
+    r->info.d = d;
+    r->info.q = s->cfg.q;
+    r->info.D = D;
+    r->info.lanes_per_traj = s->G;
+    /* totals (small D2H of the per-trajectory counters) */
+    {
+        std::vector<long long> a(N), b(N);
+        CUDA_TRY(cudaMemcpy(a.data(), P.naccept, N * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(b.data(), P.nreject, N * 8, cudaMemcpyDeviceToHost));
+        long long sa = 0, sb = 0;
+        for (size_t i = 0; i < N; i++) {
+            sa += a[i];
+            sb += b[i];
+        }
+        r->info.total_accepted = sa;
+        r->info.total_rejected = sb;
+        r->info.d2h_bytes += (int64_t)(2 * N * 8);
+    }
+    return 0;
+}
+
+static int solve_common(pnode_solver* s, int64_t n_traj, const double* u0, const double* p, bool device_inputs,
+                        pnode_result** out) {
+    if (!s || !out) return fail(PNODE_ERR_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (n_traj <= 0) return fail(PNODE_ERR_ARGUMENT, "trajectories must be positive");
+    if (!u0) return fail(PNODE_ERR_ARGUMENT, "u0 is null");
+    if (s->cfg.n_p > 0 && !p) return fail(PNODE_ERR_ARGUMENT, "p is null but n_p > 0");
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+    pnode_result* r = new pnode_result();
+    r->s = s;
+    r->n_traj = n_traj;
+    memset(&r->info, 0, sizeof r->info);
+    const double *d_u0 = u0, *d_p = p;
+    if (!device_inputs) {
+        const size_t bu = (size_t)n_traj * s->cfg.d * 8, bp = (size_t)n_traj * std::max(s->cfg.n_p, 0) * 8;
+        auto t0 = std::chrono::steady_clock::now();
+        cudaError_t e = cudaMallocAsync((void**)&r->d_u0, bu, s->stream);
+        if (e == cudaSuccess && bp) e = cudaMallocAsync((void**)&r->d_p, bp, s->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(r->d_u0, u0, bu, cudaMemcpyHostToDevice, s->stream);
+        if (e == cudaSuccess && bp) e = cudaMemcpyAsync(r->d_p, p, bp, cudaMemcpyHostToDevice, s->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e != cudaSuccess) {
+            pnode_result_free(r);
+            return fail(PNODE_ERR_CUDA, std::string("input staging: ") + cudaGetErrorString(e));
+        }
+        r->info.h2d_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        r->info.h2d_bytes = (int64_t)(bu + bp);
+        r->owns_inputs = true;
+        d_u0 = r->d_u0;
+        d_p = r->d_p;
+    }
+    int rc = solve_impl(s, n_traj, d_u0, d_p, r);
+    if (rc) {
+        std::string keep = g_err;
+        pnode_result_free(r);
+        g_err = keep;
+        return rc;
+    }
+    *out = r;
+    return 0;
+}
+
+extern "C" int pnode_solve_ensemble(pnode_solver* s, int64_t n_traj, const double* u0, const double* p,
+                                    pnode_result** out) {
+    return solve_common(s, n_traj, u0, p, false, out);
+}
+extern "C" int pnode_solve_ensemble_device(pnode_solver* s, int64_t n_traj, const double* d_u0, const double* d_p,
+                                           pnode_result** out) {
+    return solve_common(s, n_traj, d_u0, d_p, true, out);
+}
+
+extern "C" int pnode_result_info_get(const pnode_result* r, pnode_result_info* info) {
+    if (!r || !info) return fail(PNODE_ERR_ARGUMENT, "null argument");
+    *info = r->info;
+    return 0;
+}
+extern "C" int64_t pnode_result_field_bytes(const pnode_result* r, int field) {
+    if (!r || field < 0 || field >= PNODE_F_COUNT) return 0;
+    return (int64_t)r->f[field].bytes;
+}
+extern "C" const void* pnode_result_device_ptr(const pnode_result* r, int field) {
+    if (!r || field < 0 || field >= PNODE_F_COUNT) return nullptr;
+    return r->f[field].d;
+}
+extern "C" int pnode_result_copy(const pnode_result* r, int field, void* dst, size_t bytes) {
+    if (!r || !dst) return fail(PNODE_ERR_ARGUMENT, "null argument");
+    if (field < 0 || field >= PNODE_F_COUNT) return fail(PNODE_ERR_ARGUMENT, "unknown field");
+    const Buf& b = r->f[field];
+    if (!b.d) return fail(PNODE_ERR_ARGUMENT, "field was not produced by this solve");
+    if (bytes != b.bytes) return fail(PNODE_ERR_DIMENSION, "destination size does not match the field size");
+    CUDA_TRY(cudaSetDevice(r->s->cfg.device));
+    CUDA_TRY(cudaMemcpyAsync(dst, b.d, bytes, cudaMemcpyDeviceToHost, r->s->stream));
+    CUDA_TRY(cudaStreamSynchronize(r->s->stream));
+    const_cast<pnode_result*>(r)->info.d2h_bytes += (int64_t)bytes;
+    return 0;
+}
+extern "C" void pnode_result_free(pnode_result* r) {
+    if (!r) return;
+    cudaSetDevice(r->s->cfg.device);
+    for (int i = 0; i < PNODE_F_COUNT; i++)
+        if (r->f[i].d) cudaFreeAsync(r->f[i].d, r->s->stream);
+    if (r->d_u0) cudaFreeAsync(r->d_u0, r->s->stream);
+    if (r->d_p) cudaFreeAsync(r->d_p, r->s->stream);
+    delete r;
+}
