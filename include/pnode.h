@@ -155,6 +155,10 @@ int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes);
 /* Seconds spent in NVRTC + module load for this solver (reported separately from solve time). */
 double pnode_compile_seconds(const pnode_solver* s);
 
+/* Measured FP64 FMA throughput of the device in TFLOP/s (DFMA-saturating probe kernel); the denominator of the
+   FP64 roofline fraction (MEASURED_PEAKS.json carries no FP64 figure). */
+int pnode_measure_fp64_peak(int device, double* tflops);
+
 /* Solve n_traj independent trajectories.  u0: [n_traj][d], p: [n_traj][n_p] (host pointers). */
 int pnode_solve_ensemble(pnode_solver* s, int64_t n_traj, const double* u0, const double* p, pnode_result** out);
 /* Same with inputs already resident on the solver's device (device pointers); outputs stay on the device until

@@ -1,0 +1,248 @@
+"""Host-side mirror of the reference's user-facing surface for the ODE-filter path.
+
+Reference (Julia)                                         here (Python stand-in for the Julia host package)
+--------------------------------------------------------  -------------------------------------------------
+ODEProblem(f, u0, tspan, p)                                ODEProblem(f, u0, tspan, p)
+EK0(; order, smooth, diffusionmodel) src/algorithms.jl:188  EK0(order=3, smooth=True, diffusionmodel=DynamicDiffusion())
+EK1(; order, smooth, diffusionmodel) src/algorithms.jl:250  EK1(...)
+DynamicDiffusion(), FixedDiffusion(; initial_diffusion, calibrate)  src/diffusions/typedefs.jl   same names
+EnsembleProblem(prob; prob_func) (SciMLBase)               EnsembleProblem(prob, prob_func=...)
+solve(ensprob, alg, EnsembleThreads(); trajectories, ...)  solve(ensprob, alg, EnsembleB200(), trajectories=N, ...)
+sol.t, sol.u, sol.pu, sol.stats, sol.retcode  src/solution.jl:33-56   ProbODESolution with the same field names
+
+`EnsembleB200` gathers every trajectory's (u0, p), traces `f` once (tracer.py) and makes ONE call into
+libpnode_cuda.so (include/pnode.h); nothing here computes filter arithmetic on the host.
+Exceptions mirror the reference: ValueError <-> ArgumentError / DimensionMismatch, RuntimeError <-> ErrorException.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import lib as _lib
+from . import problems as _problems
+from . import tracer as _tracer
+
+
+# ---- diffusion models (src/diffusions/typedefs.jl) -------------------------------------------------
+@dataclasses.dataclass(frozen=True)
+class DynamicDiffusion:
+    pass
+
+
+@dataclasses.dataclass(frozen=True)
+class FixedDiffusion:
+    initial_diffusion: float = 1.0
+    calibrate: bool = True
+
+
+@dataclasses.dataclass(frozen=True)
+class IWP:
+    """Integrated Wiener process prior (src/priors/iwp.jl)."""
+    num_derivatives: int = 3
+
+
+@dataclasses.dataclass(frozen=True)
+class _EK:
+    order: int = 3
+    smooth: bool = True
+    diffusionmodel: object = DynamicDiffusion()
+    prior: Optional[IWP] = None
+
+    @property
+    def q(self) -> int:
+        return self.prior.num_derivatives if self.prior is not None else self.order
+
+
+class EK0(_EK):
+    """Gaussian ODE filter with zeroth-order linearisation (src/algorithms.jl:188-208)."""
+    alg = _lib.EK0
+
+
+class EK1(_EK):
+    """Gaussian ODE filter with first-order linearisation (src/algorithms.jl:250-296)."""
+    alg = _lib.EK1
+
+
+@dataclasses.dataclass
+class ODEProblem:
+    f: Callable            # in-place SciML signature f(du, u, p, t)
+    u0: Sequence[float]
+    tspan: Tuple[float, float]
+    p: Sequence[float] = ()
+    builtin: Optional[str] = None   # name in problems.PROBLEMS -> ahead-of-time kernels when available
+
+    @staticmethod
+    def from_library(name: str) -> "ODEProblem":
+        pd = _problems.PROBLEMS[name]
+        return ODEProblem(pd.f, list(pd.u0), tuple(pd.tspan), list(pd.p), builtin=name)
+
+
+def remake(prob: ODEProblem, **kw) -> ODEProblem:
+    return dataclasses.replace(prob, **kw)
+
+
+@dataclasses.dataclass
+class EnsembleProblem:
+    prob: ODEProblem
+    prob_func: Optional[Callable] = None   # (prob, i, repeat) -> prob   (SciMLBase default: identity)
+
+
+@dataclasses.dataclass(frozen=True)
+class EnsembleB200:
+    """Ensemble algorithm: all trajectories in one persistent-kernel launch on a B200."""
+    device: int = 0
+    lanes_per_traj: int = 0
+
+
+@dataclasses.dataclass
+class Stats:
+    nf: int
+    naccept: int
+    nreject: int
+
+
+@dataclasses.dataclass
+class Gaussian:
+    mu: np.ndarray      # mean
+    Sigma: np.ndarray   # dense covariance
+
+
+@dataclasses.dataclass
+class ProbODESolution:
+    """Field names follow src/solution.jl:33-56."""
+    t: np.ndarray
+    u: np.ndarray                 # [n, d]
+    pu_cov: np.ndarray            # [n, d, d]   Matrix(sol.pu[i].Sigma)
+    diffusions: Optional[np.ndarray]
+    stats: Stats
+    log_likelihood: float
+    retcode: str
+
+    @property
+    def pu(self) -> List[Gaussian]:
+        return [Gaussian(m, c) for m, c in zip(self.u, self.pu_cov)]
+
+
+@dataclasses.dataclass
+class EnsembleSolution:
+    u: List[ProbODESolution]
+    elapsedTime: float
+    converged: bool
+    info: object = None
+
+    def __len__(self):
+        return len(self.u)
+
+    def __getitem__(self, i):
+        return self.u[i]
+
+
+def _check_alg(alg, adaptive, dt, save_everystep, dense):
+    if not isinstance(alg, _EK):
+        raise ValueError("alg must be EK0(...) or EK1(...)")
+    if not adaptive and not (dt and dt > 0):
+        # test/errors_thrown.jl:6-8
+        raise ValueError("Fixed timestep methods require a choice of dt or choosing the tstops")
+    if dense and not alg.smooth:
+        raise RuntimeError("To use `dense=true` you need to set `smooth=true`!")  # src/checks.jl:15-17
+    if not save_everystep and alg.smooth:
+        raise RuntimeError("If you set `save_everystep=false` also set `smooth=false` in the alg!")  # checks.jl:18-20
+    if not isinstance(alg.diffusionmodel, (DynamicDiffusion, FixedDiffusion)):
+        raise ValueError("unsupported diffusion model")
+
+
+def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, abstol, reltol, save_everystep, maxiters,
+                dtmin, dtmax, tstops, save_state, forced_diffusion=None):
+    d, n_p = len(prob.u0), len(prob.p)
+    if d < 1:
+        raise RuntimeError("We currently don't support scalar-valued problems")  # src/caches.jl:96-98
+    diff = alg.diffusionmodel
+    kw = dict(d=d, q=alg.q, n_p=n_p, alg=alg.alg, smooth=alg.smooth, adaptive=adaptive, dt=dt or 0.0,
+              abstol=abstol, reltol=reltol, save_everystep=save_everystep, maxiters=maxiters, dtmin=dtmin,
+              dtmax=dtmax or 0.0, t0=prob.tspan[0], t1=prob.tspan[1], tstops=tstops, save_state=save_state,
+              device=ens.device, lanes_per_traj=ens.lanes_per_traj, forced_diffusion=forced_diffusion)
+    if isinstance(diff, FixedDiffusion):
+        kw.update(diffusion=_lib.DIFF_FIXED, initial_diffusion=diff.initial_diffusion, calibrate=diff.calibrate)
+    else:
+        kw.update(diffusion=_lib.DIFF_DYNAMIC)
+    if prob.builtin is not None:
+        kw.update(rhs_name="builtin:" + prob.builtin)
+    else:
+        tr = _tracer.trace(prob.f, d, n_p)
+        kw.update(rhs_name="PnodeUserProblem", rhs_src=_tracer.cuda_source(tr, "PnodeUserProblem"))
+    return _lib.make_config(**kw)
+
+
+_solver_cache = {}
+
+
+def solve(prob, alg, ensemblealg: Optional[EnsembleB200] = None, *, trajectories: Optional[int] = None,
+          adaptive: bool = True, dt: Optional[float] = None, abstol: float = 1e-6, reltol: float = 1e-3,
+          save_everystep: bool = True, dense: Optional[bool] = None, maxiters: int = 1_000_000, dtmin: float = 0.0,
+          dtmax: Optional[float] = None, tstops=None, save_state: bool = False, forced_diffusion=None):
+    """`solve(prob, EK1())` for one trajectory, or `solve(EnsembleProblem(...), EK1(), EnsembleB200(); trajectories=N)`."""
+    import time
+
+    ens = ensemblealg or EnsembleB200()
+    single = isinstance(prob, ODEProblem)
+    eprob = EnsembleProblem(prob) if single else prob
+    n = 1 if single else trajectories
+    if n is None or n < 1:
+        raise ValueError("trajectories must be a positive integer")
+    if dense is None:
+        dense = bool(alg.smooth and save_everystep)
+    _check_alg(alg, adaptive, dt, save_everystep, dense)
+    base = eprob.prob
+    d, n_p = len(base.u0), len(base.p)
+    # prob_func(prob, i, repeat) -> prob  (SciMLBase); only u0 / p may vary across trajectories
+    u0 = np.empty((n, d))
+    p = np.empty((n, max(n_p, 0)))
+    for i in range(n):
+        pi = eprob.prob_func(base, i, 0) if eprob.prob_func else base
+        if len(pi.u0) != d or len(pi.p) != n_p:
+            raise ValueError("prob_func must not change the problem dimensions")  # DimensionMismatch
+        u0[i] = pi.u0
+        if n_p:
+            p[i] = pi.p
+    cfg = _config_for(base, alg, ens, adaptive=adaptive, dt=dt, abstol=abstol, reltol=reltol,
+                      save_everystep=save_everystep, maxiters=maxiters, dtmin=dtmin, dtmax=dtmax, tstops=tstops,
+                      save_state=save_state, forced_diffusion=forced_diffusion)
+    t0 = time.time()
+    solver = _lib.Solver(cfg)
+    try:
+        res = solver.solve(u0, p)
+        sols = _unpack(res, n, d, save_everystep)
+        info = res.info
+        res.free()
+    finally:
+        solver.close()
+    out = EnsembleSolution(sols, time.time() - t0, all(s.retcode == "Success" for s in sols), info)
+    return out.u[0] if single else out
+
+
+def _unpack(res, n, d, save_everystep) -> List[ProbODESolution]:
+    L = _lib
+    na, nr, nf = res.field(L.F_NACCEPT), res.field(L.F_NREJECT), res.field(L.F_NF)
+    rc, ll = res.field(L.F_RETCODE), res.field(L.F_LOGLIK)
+    sols = []
+    if save_everystep and res.has(L.F_STEP_OFFSETS):
+        off = res.field(L.F_STEP_OFFSETS)
+        T = res.field(L.F_T)
+        U = res.field(L.F_U).reshape(-1, d)
+        Cv = res.field(L.F_U_COV).reshape(-1, d, d)
+        Df = res.field(L.F_DIFFUSIONS)
+        for i in range(n):
+            a, b = off[i], off[i + 1]
+            sols.append(ProbODESolution(T[a:b], U[a:b], Cv[a:b], Df[a:b - 1], Stats(int(nf[i]), int(na[i]), int(nr[i])),
+                                        float(ll[i]), L.RETCODES[int(rc[i])]))
+    else:
+        te = res.field(L.F_T_END)
+        uf = res.field(L.F_U_FINAL).reshape(n, d)
+        cf = res.field(L.F_U_FINAL_COV).reshape(n, d, d)
+        for i in range(n):
+            sols.append(ProbODESolution(np.array([te[i]]), uf[i:i + 1], cf[i:i + 1], None,
+                                        Stats(int(nf[i]), int(na[i]), int(nr[i])), float(ll[i]), L.RETCODES[int(rc[i])]))
+    return sols

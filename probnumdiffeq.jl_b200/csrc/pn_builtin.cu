@@ -14,12 +14,28 @@ static const PnBuiltinEntry g_table[] = {
     PN_ENTRY("rober", PnRober, 3, 4, 1, 1, 0),
     PN_ENTRY("orego", PnOrego, 3, 4, 1, 1, 0),
     /* cfg1: FitzHugh-Nagumo EK1(order=3) */
-    PN_ENTRY("fitzhugh_nagumo", PnFitzHughNagumo, 3, 4, 1, 1, 0),
+    PN_ENTRY("fitzhugh_nagumo", PnFitzHughNagumo, 3, 2, 1, 1, 0),
     /* cfg3: Van der Pol EK1(order=5) */
     PN_ENTRY("vanderpol", PnVanDerPol, 5, 4, 1, 1, 0),
     /* Lotka-Volterra through the dense EK1 path */
-    PN_ENTRY("lotka_volterra", PnLotkaVolterra, 3, 4, 1, 1, 0),
+    PN_ENTRY("lotka_volterra", PnLotkaVolterra, 3, 2, 1, 1, 0),
 };
+
+/* rhs_name "builtin:<name>" -> struct in kernels/pn_builtin_problems.cuh (used when a configuration has no
+   ahead-of-time instantiation and is compiled by NVRTC instead) */
+extern "C" const char* pn_builtin_struct_name(const char* name) {
+    static const struct { const char* n; const char* s; } map[] = {
+        {"builtin:fitzhugh_nagumo", "PnFitzHughNagumo"}, {"builtin:lotka_volterra", "PnLotkaVolterra"},
+        {"builtin:vanderpol", "PnVanDerPol"},           {"builtin:rober", "PnRober"},
+        {"builtin:orego", "PnOrego"},                   {"builtin:pleiades", "PnPleiades"},
+    };
+    for (auto& m : map) {
+        const char *a = m.n, *b = name;
+        while (*a && *a == *b) { a++; b++; }
+        if (!*a && !*b) return m.s;
+    }
+    return nullptr;
+}
 
 extern "C" const PnBuiltinEntry* pn_builtin_table(int* count) {
     *count = (int)(sizeof(g_table) / sizeof(g_table[0]));

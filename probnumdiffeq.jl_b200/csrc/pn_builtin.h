@@ -5,3 +5,4 @@ struct PnBuiltinEntry {
     int d, n_p;
 };
 extern "C" const PnBuiltinEntry* pn_builtin_table(int* count);
+extern "C" const char* pn_builtin_struct_name(const char* name);

@@ -23,6 +23,37 @@
 
 #define PN_THREADS 128
 
+/* calibrate_solution! / set_diffusions! (src/integrator_utils.jl:46-88) for the per-step outputs of a
+   FixedDiffusion solve: every saved covariance is scaled by the global MLE and sol.diffusions is overwritten. */
+__global__ void pn_calibrate_saved(long long total, long long n_traj, const long long* __restrict__ off,
+                                   const double* __restrict__ scale /* [n_traj] or null */,
+                                   const double* __restrict__ diffusion /* [n_traj] */, int dd,
+                                   double* __restrict__ u_cov, double* __restrict__ s_diffusion) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    long long lo = 0, hi = n_traj; /* largest tr with off[tr] <= i */
+    while (hi - lo > 1) {
+        long long mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    if (scale) {
+        const double sc = scale[lo];
+        for (int k = 0; k < dd; k++) u_cov[i * dd + k] *= sc;
+    }
+    s_diffusion[i] = diffusion[lo];
+}
+
+/* FP64 roofline probe: 8 independent DFMA chains per thread (the denominator bench.py reports against;
+   MEASURED_PEAKS.json has no FP64 figure). */
+__global__ void pn_dfma_probe(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * (long long)blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -201,7 +232,14 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
     int rc = load_driver();
     if (rc) return rc;
     std::vector<char> cubin;
-    rc = nvrtc_cubin(s->rhs_src, s->rhs_name, s->cfg.q, s->G, s->cfg.adaptive != 0,
+    std::string src = s->rhs_src, name = s->rhs_name;
+    if (s->builtin) { /* built-in problem without an ahead-of-time instantiation for this configuration */
+        const char* sn = pn_builtin_struct_name(s->rhs_name.c_str());
+        if (!sn) return fail(PNODE_ERR_ARGUMENT, "unknown built-in problem '" + s->rhs_name + "'");
+        src = "#include \"kernels/pn_builtin_problems.cuh\"\n";
+        name = sn;
+    }
+    rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0,
                      s->cfg.diffusion == PNODE_DIFF_DYNAMIC, save, &cubin);
     if (rc) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
@@ -232,8 +270,8 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
                 return 0;
             }
         }
-        return fail(PNODE_ERR_UNSUPPORTED,
-                    "no ahead-of-time kernel for '" + key + "'; pass the traced source (rhs_src) to use NVRTC");
+        if (!pn_builtin_struct_name(s->rhs_name.c_str()))
+            return fail(PNODE_ERR_ARGUMENT, "unknown built-in problem '" + s->rhs_name + "'");
     }
     int rc = compile_nvrtc(s, save, out);
     s->compile_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -384,6 +422,36 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
 
 extern "C" double pnode_compile_seconds(const pnode_solver* s) { return s ? s->compile_s : 0.0; }
 
+extern "C" int pnode_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(PNODE_ERR_ARGUMENT, "null argument");
+    if (pnode_device_count() <= 0) return fail(PNODE_ERR_NO_DEVICE, "no CUDA device available");
+    CUDA_TRY(cudaSetDevice(device));
+    int n_sm = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+    const int threads = 256, blocks = n_sm * 8, iters = 1 << 15;
+    double* d_out = nullptr;
+    CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * (size_t)threads * blocks));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        pn_dfma_probe<<<blocks, threads>>>(d_out, iters, 1.0000001, 1e-9);
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
+        if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops = best;
+    return 0;
+}
+
 extern "C" void pnode_destroy(pnode_solver* s) {
     if (!s) return;
     cudaSetDevice(s->cfg.device);
@@ -492,6 +560,22 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         P.s_diffusion = (double*)r->f[PNODE_F_DIFFUSIONS].d;
         if ((rc = launch(s, s->k_save, P, n_traj))) return rc;
         launches = 2;
+        if (s->cfg.diffusion == PNODE_DIFF_FIXED) {
+            /* DIFFUSION holds sigma_hat^2 * initial (calibrate) or the constant initial diffusion */
+            const double* scale = nullptr;
+            if (s->cfg.calibrate) {
+                /* scale = sigma_hat^2 = diffusion / initial_diffusion; the kernel wrote diffusion = mle * initial */
+                scale = P.diffusion;
+            }
+            const int thr = 256;
+            const unsigned blocks = (unsigned)((T + thr - 1) / thr);
+            if (s->cfg.calibrate && s->base.initial_diffusion != 1.0) {
+                return fail(PNODE_ERR_UNSUPPORTED, "save_everystep with calibrate=true needs initial_diffusion == 1");
+            }
+            pn_calibrate_saved<<<blocks, thr, 0, s->stream>>>((long long)T, (long long)N, P.step_offsets, scale,
+                                                             P.diffusion, d * d, P.s_u_cov, P.s_diffusion);
+            launches = 3;
+        }
         r->info.total_saved = (int64_t)T;
     }
     CUDA_TRY(cudaEventRecord(e1, s->stream));

@@ -34,7 +34,7 @@ EXPORTS = [
     "pnode_device_count", "pnode_last_error", "pnode_abi_version", "pnode_create", "pnode_destroy",
     "pnode_compile_check", "pnode_compile_seconds", "pnode_solve_ensemble", "pnode_solve_ensemble_device",
     "pnode_result_info_get", "pnode_result_field_bytes", "pnode_result_copy", "pnode_result_device_ptr",
-    "pnode_result_free",
+    "pnode_result_free", "pnode_measure_fp64_peak",
 ]
 
 
@@ -109,6 +109,8 @@ def load():
     lib.pnode_result_device_ptr.restype = vp
     lib.pnode_result_device_ptr.argtypes = [vp, C.c_int]
     lib.pnode_result_free.argtypes = [vp]
+    lib.pnode_measure_fp64_peak.restype = C.c_int
+    lib.pnode_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = lib
     return lib
 
@@ -151,6 +153,13 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
         c.forced_diffusion, c.n_forced = a.ctypes.data_as(C.POINTER(C.c_double)), len(a)
     c._keep = keep
     return c
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    """TFLOP/s of a DFMA-saturating probe kernel on `device`."""
+    v = C.c_double(0.0)
+    _check(load().pnode_measure_fp64_peak(device, C.byref(v)))
+    return v.value
 
 
 def compile_check(cfg: Config) -> int:

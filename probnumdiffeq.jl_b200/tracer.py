@@ -112,6 +112,24 @@ class _DevicePrinter(C99CodePrinter):
     def _print_Float(self, expr):
         return repr(float(expr))
 
+    def _pn1(self, name, expr):
+        return f"{name}({self._print(expr.args[0])})"
+
+    def _print_exp(self, expr):
+        return self._pn1("pn_exp", expr)
+
+    def _print_log(self, expr):
+        return self._pn1("pn_log", expr)
+
+    def _print_sin(self, expr):
+        return self._pn1("pn_sin", expr)
+
+    def _print_cos(self, expr):
+        return self._pn1("pn_cos", expr)
+
+    def _print_tanh(self, expr):
+        return self._pn1("pn_tanh", expr)
+
 
 def _subs_arrays(tr: TracedRHS):
     rep = {}

@@ -1,0 +1,225 @@
+"""GPU parity: the CUDA path (through the C ABI of libpnode_cuda.so) against the CPU oracle on the same seeded
+inputs, plus size-independent properties at BASELINE.json's full ensemble sizes.
+
+Tolerances (BASELINE.json north_star; SURVEY.md H0 for the measured rounding floor):
+  * fixed steps, static diffusion (FixedDiffusion with/without calibration): means and covariances rtol 1e-10;
+  * fixed steps, DynamicDiffusion: sigma^2 = z'(HQH')^-1 z amplifies one-ulp differences (oracle-vs-oracle floor
+    5e-11 on means, 6e-7 on covariances), so means are held to 1e-9, covariances to 1e-5, and the
+    sigma^2-teacher-forced run (kernel consumes the oracle's sigma^2 sequence) must reach 1e-10 on everything;
+  * adaptive, non-stiff: identical accept/reject counts, |dt| sequences to 1e-7, solutions rtol 1e-8;
+  * adaptive, stiff (Van der Pol, OREGO): step-teacher-forced (kernel replays the oracle's accepted grid) rtol 1e-8,
+    plus free-running step counts within 3 %.
+"""
+import numpy as np
+import pytest
+
+import probnumdiffeq_jl_b200  # noqa: F401
+from probnumdiffeq_jl_b200 import lib, problems, tracer
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(name, n, seed, du0=0.0, dp=0.1):
+    pd = problems.PROBLEMS[name]
+    rng = np.random.default_rng(seed)
+    u0 = np.array(pd.u0, dtype=float)[None, :] * (1 + du0 * rng.uniform(-1, 1, (n, pd.d)))
+    p = np.array(pd.p, dtype=float)[None, :] * (1 + dp * rng.uniform(-1, 1, (n, pd.n_p)))
+    return pd, np.ascontiguousarray(u0), np.ascontiguousarray(p)
+
+
+def _gpu(pd, u0, p, q, *, builtin=True, **kw):
+    if builtin:
+        cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="builtin:" + pd.name, **kw)
+    else:
+        src = tracer.cuda_source(tracer.trace(pd.f, pd.d, pd.n_p), "UserProb")
+        cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="UserProb", rhs_src=src, **kw)
+    s = lib.Solver(cfg)
+    r = s.solve(u0, p)
+    n, d = u0.shape
+    out = dict(info=r.info, u=r.field(lib.F_U_FINAL).reshape(n, d), cov=r.field(lib.F_U_FINAL_COV).reshape(n, d, d),
+               naccept=r.field(lib.F_NACCEPT), nreject=r.field(lib.F_NREJECT), nf=r.field(lib.F_NF),
+               retcode=r.field(lib.F_RETCODE), loglik=r.field(lib.F_LOGLIK), t_end=r.field(lib.F_T_END),
+               diffusion=r.field(lib.F_DIFFUSION))
+    if r.has(lib.F_STEP_OFFSETS):
+        out.update(off=r.field(lib.F_STEP_OFFSETS), T=r.field(lib.F_T), U=r.field(lib.F_U).reshape(-1, d),
+                   C=r.field(lib.F_U_COV).reshape(-1, d, d), Df=r.field(lib.F_DIFFUSIONS))
+    if r.has(lib.F_X_FINAL):
+        D = pd.d * (q + 1)
+        out.update(x=r.field(lib.F_X_FINAL).reshape(n, D), xR=r.field(lib.F_X_FINAL_COVFAC).reshape(n, D, D))
+    r.free()
+    s.close()
+    return out
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b) / (np.abs(b) + 1e-300))
+
+
+def _relcov(a, b):
+    nb = np.linalg.norm(b, axis=(-2, -1))
+    ok = nb > 0
+    return np.max(np.linalg.norm(a - b, axis=(-2, -1))[ok] / nb[ok]) if ok.any() else 0.0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("calibrate", [True, False])
+def test_cfg1_fixed_steps_static_diffusion(oracle, calibrate):
+    """BASELINE cfg1: FitzHugh-Nagumo EK1(order=3), dt = 0.01 on [0, 20] (2000 steps), every step compared."""
+    pd, u0, p = _inputs("fitzhugh_nagumo", 3, 0, dp=0.05)
+    g = _gpu(pd, u0, p, 3, builtin=False, adaptive=False, dt=0.01, t0=0.0, t1=20.0, diffusion=lib.DIFF_FIXED,
+             calibrate=calibrate, save_everystep=True, save_state=True)
+    tr = tracer.trace(pd.f, pd.d, pd.n_p)
+    rhs = oracle.compile_rhs(tr, 3)
+    for i in range(u0.shape[0]):
+        o = oracle.solve(oracle.make_config(2, 3, 3, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=calibrate, smooth=False,
+                                            adaptive=False, dt=0.01, t0=0.0, t1=20.0, save_everystep=True,
+                                            cov_backend=oracle.COV_QR), rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"] == 2001
+        assert np.array_equal(g["T"][a:b], o["t"])
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < 1e-10   # calibrate_solution! applied to saved steps
+        assert _rel(g["Df"][a:b - 1], o["diffusions"][:-1]) < 1e-10
+        assert _relcov(g["cov"][i], o["pu_cov"][-1]) < 1e-10
+        assert g["loglik"][i] == pytest.approx(o["loglik"], rel=1e-10)
+        assert g["diffusion"][i] == pytest.approx(o["diffusions"][0], rel=1e-10)
+        # full state: x_filt mean and R'R
+        assert _rel(g["x"][i][:2], o["x_filt_mu"][-1][:2]) < 1e-10
+        Sg = g["xR"][i].T @ g["xR"][i]
+        So = o["x_filt_R"][-1].T @ o["x_filt_R"][-1]
+        assert np.linalg.norm(Sg - So) / np.linalg.norm(So) < 1e-10
+
+
+def test_cfg1_fixed_steps_dynamic_diffusion_and_teacher_forcing(oracle):
+    pd, u0, p = _inputs("fitzhugh_nagumo", 1, 1, dp=0.0)
+    tr = tracer.trace(pd.f, pd.d, pd.n_p)
+    rhs = oracle.compile_rhs(tr, 3)
+    kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC, smooth=False, adaptive=False, dt=0.01, t0=0.0, t1=20.0,
+              save_everystep=True, cov_backend=oracle.COV_QR)
+    o = oracle.solve(oracle.make_config(2, 3, 3, **kw), rhs, u0[0], p[0])
+    g = _gpu(pd, u0, p, 3, builtin=False, adaptive=False, dt=0.01, t0=0.0, t1=20.0, save_everystep=True)
+    assert np.array_equal(g["T"], o["t"])
+    assert _rel(g["U"], o["pu_mu"]) < 1e-9           # measured floor ~1e-10
+    assert _relcov(g["C"][1:], o["pu_cov"][1:]) < 1e-5  # floor 6e-7
+    assert _rel(g["Df"][:-1], o["diffusions"][:-1]) < 1e-4
+    # sigma^2 teacher forcing: the kernel consumes the oracle's sigma^2 sequence -> everything reaches 1e-10
+    sig = o["diffusions"][:-1]
+    o2 = oracle.solve(oracle.make_config(2, 3, 3, forced_diffusion=sig, **kw), rhs, u0[0], p[0])
+    g2 = _gpu(pd, u0, p, 3, builtin=False, adaptive=False, dt=0.01, t0=0.0, t1=20.0, save_everystep=True,
+              forced_diffusion=sig)
+    assert _rel(g2["U"], o2["pu_mu"]) < 1e-10
+    assert _relcov(g2["C"][1:], o2["pu_cov"][1:]) < 1e-10
+
+
+@pytest.mark.parametrize("name,q,t1", [("lotka_volterra", 3, 10.0), ("rober", 3, 100.0), ("fitzhugh_nagumo", 3, 20.0),
+                                       ("lotka_volterra", 5, 10.0), ("fitzhugh_nagumo", 2, 20.0)])
+def test_adaptive_nonstiff_identical_step_sequences(oracle, name, q, t1):
+    n = 24
+    pd, u0, p = _inputs(name, n, 2, du0=0.05 if name != "rober" else 0.0)
+    g = _gpu(pd, u0, p, q, builtin=(q == 3), adaptive=True, t0=0.0, t1=t1, save_everystep=True)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    cfg = oracle.make_config(pd.d, q, pd.n_p, alg=oracle.EK1, smooth=False, adaptive=True, t0=0.0, t1=t1, save_everystep=True,
+                             cov_backend=oracle.COV_QR)
+    for i in range(n):
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert g["naccept"][i] == o["naccept"] and g["nreject"][i] == o["nreject"] and g["nf"][i] == o["nf"]
+        assert g["retcode"][i] == 0 and o["retcode"] == "Success"
+        assert np.max(np.abs(g["T"][a:b] - o["t"])[1:] / o["t"][1:]) < 1e-7
+        assert g["T"][b - 1] == t1
+        scale = np.abs(o["pu_mu"]).max(axis=0)
+        assert np.max(np.abs(g["U"][a:b] - o["pu_mu"]) / scale) < 1e-8
+        assert _rel(g["u"][i], o["pu_mu"][-1]) < 1e-8 or np.max(np.abs(g["u"][i] - o["pu_mu"][-1]) / scale) < 1e-8
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < 1e-4
+
+
+@pytest.mark.parametrize("name,q,t1", [("vanderpol", 5, 2.0), ("orego", 3, 30.0)])
+def test_adaptive_stiff_step_teacher_forced(oracle, name, q, t1):
+    """Stiff trajectories are chaotic in the rounding: replay the oracle's accepted grid."""
+    pd, u0, p = _inputs(name, 1, 3, dp=0.0)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    o = oracle.solve(oracle.make_config(pd.d, q, pd.n_p, alg=oracle.EK1, smooth=False, adaptive=True, t0=0.0, t1=t1,
+                                        save_everystep=True, cov_backend=oracle.COV_QR), rhs, u0[0], p[0])
+    grid = o["t"][1:-1]
+    of = oracle.solve(oracle.make_config(pd.d, q, pd.n_p, alg=oracle.EK1, smooth=False, adaptive=False, dt=t1, t0=0.0, t1=t1,
+                                         save_everystep=True, cov_backend=oracle.COV_QR, tstops=grid), rhs, u0[0], p[0])
+    g = _gpu(pd, u0, p, q, builtin=False, adaptive=False, dt=t1, t0=0.0, t1=t1, save_everystep=True, tstops=grid)
+    assert np.array_equal(g["T"], of["t"]) and np.array_equal(of["t"], o["t"])
+    scale = np.abs(of["pu_mu"]).max(axis=0)
+    assert np.max(np.abs(g["U"] - of["pu_mu"]) / scale) < 1e-8
+    # free running: same order of work
+    gf = _gpu(pd, u0, p, q, adaptive=True, t0=0.0, t1=t1)
+    assert abs(int(gf["naccept"][0]) - o["naccept"]) <= 0.03 * o["naccept"]
+    assert gf["retcode"][0] == 0
+    assert np.max(np.abs(gf["u"][0] - o["pu_mu"][-1]) / scale) < 1e-3
+
+
+def test_nvrtc_and_ahead_of_time_kernels_agree():
+    pd, u0, p = _inputs("rober", 40, 4)
+    a = _gpu(pd, u0, p, 3, builtin=True, t0=0.0, t1=100.0)
+    b = _gpu(pd, u0, p, 3, builtin=False, t0=0.0, t1=100.0)
+    assert np.array_equal(a["naccept"], b["naccept"])
+    assert _rel(a["u"], b["u"]) < 1e-12
+
+
+@pytest.mark.parametrize("lanes", [2, 4, 8])
+def test_lane_group_sizes_agree(oracle, lanes):
+    pd, u0, p = _inputs("lotka_volterra", 13, 5, du0=0.1)   # 13: not a multiple of any group count
+    g = _gpu(pd, u0, p, 3, builtin=False, adaptive=True, t0=0.0, t1=10.0, lanes_per_traj=lanes)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    o = oracle.solve_ensemble(oracle.make_config(2, 3, 4, alg=oracle.EK1, smooth=False, adaptive=True, t0=0.0, t1=10.0,
+                                                 save_everystep=False, cov_backend=oracle.COV_QR), rhs, u0, p)
+    assert np.array_equal(g["naccept"], o["naccept"]) and np.array_equal(g["nreject"], o["nreject"])
+    assert _rel(g["u"], o["u_final"]) < 1e-8
+    assert g["info"].lanes_per_traj == lanes
+
+
+def test_edge_cases(oracle):
+    pd, u0, p = _inputs("lotka_volterra", 1, 6)
+    # single trajectory
+    g = _gpu(pd, u0, p, 3, t0=0.0, t1=10.0)
+    assert g["retcode"][0] == 0 and g["t_end"][0] == 10.0
+    # maxiters -> MaxIters retcode (sol.retcode), partial progress reported
+    g = _gpu(pd, u0, p, 3, t0=0.0, t1=10.0, maxiters=10)
+    assert lib.RETCODES[int(g["retcode"][0])] == "MaxIters" and g["t_end"][0] < 10.0
+    # user-provided initial dt with adaptive stepping, and tstops inside the interval
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    ts = np.array([2.5, 5.0, 7.5])
+    o = oracle.solve(oracle.make_config(2, 3, 4, alg=oracle.EK1, smooth=False, adaptive=True, dt=0.05, t0=0.0, t1=10.0, tstops=ts,
+                                        cov_backend=oracle.COV_QR), rhs, u0[0], p[0])
+    g = _gpu(pd, u0, p, 3, builtin=False, adaptive=True, dt=0.05, t0=0.0, t1=10.0, tstops=ts, save_everystep=True)
+    assert g["naccept"][0] == o["naccept"] and g["nreject"][0] == o["nreject"]
+    assert set(ts).issubset(set(g["T"]))
+    assert _rel(g["u"][0], o["pu_mu"][-1]) < 1e-8
+    # the host API mirror (solve(EnsembleProblem, EK1(), EnsembleB200()))
+    from probnumdiffeq_jl_b200 import api
+
+    prob = api.ODEProblem.from_library("lotka_volterra")
+    ens = api.EnsembleProblem(prob, prob_func=lambda pr, i, rep: api.remake(pr, u0=[1.0 + 0.01 * i, 1.0]))
+    sol = api.solve(ens, api.EK1(order=3, smooth=False), api.EnsembleB200(), trajectories=5)
+    assert len(sol) == 5 and sol.converged
+    assert all(len(s.t) == s.stats.naccept + 1 and s.t[-1] == 10.0 for s in sol.u)   # test/solution.jl:35-42
+    assert np.array_equal(sol[0].u[0], [1.0, 1.0]) and not sol[0].pu_cov[0].any()      # test/solution.jl:59-62
+
+
+def test_full_size_properties_rober_1m():
+    """BASELINE cfg5 at full size (2^20 trajectories): properties that need no oracle."""
+    n = 1 << 20
+    pd, u0, p = _inputs("rober", n, 3)
+    g = _gpu(pd, u0, p, 3, t0=0.0, t1=100.0)
+    assert np.all(g["retcode"] == 0) and np.all(g["t_end"] == 100.0)
+    # ROBER conserves u1 + u2 + u3 = 1 (linear invariant: the filter mean preserves it up to the tolerance)
+    assert np.max(np.abs(g["u"].sum(axis=1) - 1.0)) < 1e-6
+    assert np.all(np.linalg.eigvalsh(g["cov"]) > -1e-18)
+    # determinism + permutation equivariance: results do not depend on which warp / neighbours a trajectory gets
+    perm = np.random.default_rng(0).permutation(n)
+    g2 = _gpu(pd, u0[perm], p[perm], 3, t0=0.0, t1=100.0)
+    assert np.array_equal(g2["naccept"], g["naccept"][perm])
+    assert np.array_equal(g2["u"], g["u"][perm])
+    assert np.array_equal(g2["cov"], g["cov"][perm])
+    # identical inputs -> identical outputs
+    u0c = np.tile(u0[:1], (4096, 1))
+    pc = np.tile(p[:1], (4096, 1))
+    g3 = _gpu(pd, u0c, pc, 3, t0=0.0, t1=100.0)
+    assert np.all(g3["u"] == g3["u"][0]) and np.all(g3["naccept"] == g3["naccept"][0])
+    assert np.array_equal(g3["u"][0], g["u"][0])

@@ -1,0 +1,159 @@
+"""CPU-side checks of the product: the C-ABI library loads and exports every symbol include/pnode.h declares,
+argument errors mirror the reference's exceptions, NVRTC compiles traced right-hand sides for sm_100a without a
+device, and the device Taylor arithmetic (compiled for the host here) reproduces symbolic derivatives."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import sympy as sp
+
+import probnumdiffeq_jl_b200  # noqa: F401
+from probnumdiffeq_jl_b200 import lib, problems, tracer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(pnlib):
+    hdr = open(os.path.join(ROOT, "include", "pnode.h")).read()
+    declared = set(re.findall(r"^(?:int|void|double|int64_t|const char\*|const void\*)\s+(pnode_[a-z_]+)\s*\(", hdr, re.M))
+    assert declared, "no declarations found"
+    L = pnlib.load()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in pnode.h but not exported"
+    assert declared == set(pnlib.EXPORTS)
+    assert L.pnode_abi_version() == 1
+    # struct layout agreement between pnode.h and the ctypes mirror
+    src = '#include <stdio.h>\n#include "pnode.h"\nint main(){printf("%zu %zu", sizeof(pnode_config), sizeof(pnode_result_info));return 0;}'
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "s")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        a, b = map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split())
+    assert a == C.sizeof(pnlib.Config) and b == C.sizeof(pnlib.ResultInfo)
+
+
+def test_no_device_fails_loudly(pnlib):
+    if pnlib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    cfg = pnlib.make_config(d=3, q=3, n_p=3, rhs_name="builtin:rober", t0=0.0, t1=1.0)
+    with pytest.raises(pnlib.PnodeError) as e:
+        pnlib.Solver(cfg)
+    assert e.value.kind == "NoDevice"
+
+
+def _src(name="rober"):
+    pd = problems.PROBLEMS[name]
+    return pd, tracer.cuda_source(tracer.trace(pd.f, pd.d, pd.n_p), "UserProb")
+
+
+def test_argument_errors_mirror_reference(pnlib):
+    pd, src = _src()
+    base = dict(d=3, q=3, n_p=3, rhs_name="UserProb", rhs_src=src, t0=0.0, t1=1.0)
+
+    def err(**kw):
+        with pytest.raises(pnlib.PnodeError) as e:
+            pnlib.compile_check(pnlib.make_config(**{**base, **kw}))
+        return e.value
+
+    # test/errors_thrown.jl:6-16: adaptive=false without dt -> ArgumentError
+    assert err(adaptive=False, dt=0.0).kind == "ArgumentError"
+    # test/errors_thrown.jl:23-26 / src/checks.jl:18-20
+    assert err(smooth=True, save_everystep=False).kind == "ArgumentError"
+    assert err(q=0).kind == "ArgumentError"
+    assert err(t1=-1.0).kind == "ArgumentError"
+    assert err(lanes_per_traj=3).kind == "ArgumentError"
+    assert err(rhs_src=None).kind == "ArgumentError"
+    # src/algorithms.jl:101-110: Kronecker covariance only with the EK0
+    assert err(cov=pnlib.COV_KRONECKER).kind == "ArgumentError"
+    bad = pnlib.make_config(**base)
+    bad.struct_size = 8
+    with pytest.raises(pnlib.PnodeError):
+        pnlib.compile_check(bad)
+
+
+def test_nvrtc_compiles_traced_rhs_for_sm100a(pnlib):
+    pd, src = _src("vanderpol")
+    n = pnlib.compile_check(pnlib.make_config(d=2, q=5, n_p=1, rhs_name="UserProb", rhs_src=src, t0=0.0, t1=2.0))
+    assert n > 10_000
+    with pytest.raises(pnlib.PnodeError) as e:
+        pnlib.compile_check(pnlib.make_config(d=2, q=5, n_p=1, rhs_name="UserProb", rhs_src=src + "\n#error boom\n", t0=0.0, t1=2.0))
+    assert e.value.kind == "CompileError" and "boom" in str(e.value)
+
+
+def test_tracer_matches_python_rhs():
+    for name, pd in problems.PROBLEMS.items():
+        tr = tracer.trace(pd.f, pd.d, pd.n_p)
+        subs = {s: v for s, v in zip(tr.u, pd.u0)}
+        subs.update({s: v for s, v in zip(tr.p, pd.p)})
+        du = [0.0] * pd.d
+        pd.f(du, list(map(float, pd.u0)), list(map(float, pd.p)), 0.0)
+        got = [float(e.subs(subs)) for e in tr.f]
+        assert np.allclose(got, du, rtol=1e-13, atol=1e-300), name
+        assert "struct X" in tracer.cuda_source(tr, "X")
+
+
+_TAYLOR_MAIN = r"""
+#include <cmath>
+#include <cstdio>
+#define PN_HD inline
+#define __device__
+#define __forceinline__ inline
+#include "pn_taylor.cuh"
+%(problem)s
+int main() {
+  double u0[] = {%(u0)s};
+  double p[] = {%(p)s};
+  double out[(%(q)d + 1) * %(d)d];
+  pn_taylor_init<UserProb, %(q)d>(out, u0, p, %(t0)s);
+  for (int i = 0; i < (%(q)d + 1) * %(d)d; i++) printf("%%.17g\n", out[i]);
+  return 0;
+}
+"""
+
+
+def _device_taylor_on_host(f, d, n_p, u0, p, q, t0=0.0):
+    tr = tracer.trace(f, d, n_p)
+    src = _TAYLOR_MAIN % dict(problem=tracer.cuda_source(tr, "UserProb"), u0=",".join(map(repr, map(float, u0))),
+                              p=",".join(map(repr, map(float, p))) or "0.0", q=q, d=d, t0=repr(float(t0)))
+    with tempfile.TemporaryDirectory() as td:
+        c = os.path.join(td, "t.cpp")
+        open(c, "w").write(src)
+        exe = os.path.join(td, "t")
+        subprocess.run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "probnumdiffeq.jl_b200", "csrc", "kernels"), c, "-o", exe],
+                       check=True)
+        out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    return tr, np.array(list(map(float, out))).reshape(q + 1, d)
+
+
+def test_taylor_mode_init_matches_symbolic_derivatives(oracle):
+    """Product: truncated Taylor arithmetic (pn_taylor.cuh).  Oracle: symbolic Lie derivatives.  Two different
+    methods must give the same u^(k)(t0) (reference pin: test/state_init.jl:9-47)."""
+    for name, q in [("fitzhugh_nagumo", 5), ("vanderpol", 5), ("rober", 3), ("lotka_volterra", 4)]:
+        pd = problems.PROBLEMS[name]
+        tr, got = _device_taylor_on_host(pd.f, pd.d, pd.n_p, pd.u0, pd.p, q)
+        ys = oracle.symbolic_derivatives(tr, q)
+        subs = {s: v for s, v in zip(tr.u, pd.u0)}
+        subs.update({s: v for s, v in zip(tr.p, pd.p)})
+        want = np.array([[float(ys[k][i].subs(subs)) for i in range(pd.d)] for k in range(q + 1)])
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-12 * np.abs(want).max()), name
+
+
+def test_taylor_elementary_functions():
+    """exp / log / sin / cos / sqrt / tanh / pow recurrences against SymPy."""
+    def f(du, u, p, t):
+        du[0] = tracer.exp(-u[0]) * tracer.sin(u[1]) + tracer.sqrt(1 + u[0] ** 2) / (2 + tracer.cos(t))
+        du[1] = tracer.log(2 + u[1] ** 2) * tracer.tanh(u[0]) - (1 + u[0] ** 2) ** sp.Rational(-3, 2) * p[0]
+
+    u0, p, q = [0.3, -0.8], [1.7], 4
+    tr, got = _device_taylor_on_host(f, 2, 1, u0, p, q, t0=0.25)
+    from oracle import oracle as O
+
+    ys = O.symbolic_derivatives(tr, q)
+    subs = {tr.u[0]: u0[0], tr.u[1]: u0[1], tr.p[0]: p[0], tr.t: 0.25}
+    want = np.array([[float(ys[k][i].subs(subs)) for i in range(2)] for k in range(q + 1)])
+    assert np.allclose(got, want, rtol=1e-11, atol=1e-12)

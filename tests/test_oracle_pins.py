@@ -1,0 +1,334 @@
+"""Pin the CPU oracle against the reference's own known-answer values and formula identities.
+
+Every test cites the reference test (under /root/reference/test) whose assertion it restates.  These run
+on CPU (-m "not gpu").
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+from scipy.integrate import solve_ivp
+from scipy.stats import multivariate_normal
+
+import probnumdiffeq_jl_b200  # noqa: F401
+from probnumdiffeq_jl_b200 import problems, tracer
+
+dp = C.POINTER(C.c_double)
+
+
+def P(a):
+    return a.ctypes.data_as(dp)
+
+
+def F(a):  # numpy (row, col) matrix -> column-major buffer (Julia layout)
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def from_f(buf, shape):
+    return np.array(buf, dtype=np.float64).reshape(shape, order="F")
+
+
+# ----------------------------------------------------------------------------------------------------
+# test/core/priors.jl:49-192 -- IWP(d=2, q=2) golden matrices, h = 0.1, sigma = 0.1
+# ----------------------------------------------------------------------------------------------------
+def _iwp(oracle, q, h):
+    n = q + 1
+    L = oracle.lib()
+    A = np.zeros(n * n)
+    Lb = np.zeros(n * n)
+    L.oracle_iwp_preconditioned(q, P(A), P(Lb))
+    Ah = np.zeros(n * n)
+    Qh = np.zeros(n * n)
+    L.oracle_iwp_transition(q, C.c_double(h), P(Ah), P(Qh))
+    return (from_f(A, (n, n)), from_f(Lb, (n, n)), from_f(Ah, (n, n)), from_f(Qh, (n, n)))
+
+
+def test_iwp_golden_matrices(oracle):
+    h, sigma, d, q = 0.1, 0.1, 2, 2
+    A, Lb, Ah, QhR = _iwp(oracle, q, h)
+    # priors.jl:105-127 preconditioned
+    assert np.allclose(A, [[1, 2, 1], [0, 1, 1], [0, 0, 1]], rtol=0, atol=1e-15)
+    Qpre = Lb.T @ Lb
+    assert np.allclose(Qpre, [[1 / 5, 1 / 4, 1 / 3], [1 / 4, 1 / 3, 1 / 2], [1 / 3, 1 / 2, 1]], rtol=1e-14)
+    # priors.jl:86-103 vanilla transition
+    AH = np.array([[1, h, h**2 / 2], [0, 1, h], [0, 0, 1]])
+    QH = np.array([[h**5 / 20, h**4 / 8, h**3 / 6], [h**4 / 8, h**3 / 3, h**2 / 2], [h**3 / 6, h**2 / 2, h]])
+    assert np.allclose(Ah, AH, rtol=1e-14)
+    assert np.allclose(QhR.T @ QhR, QH, rtol=1e-13)
+    # dense derivative-major layout == PERM * blockdiag * PERM' (priors.jl:56-63): kron(B, I_d)
+    out = np.zeros((d * 3) * (d * 3))
+    oracle.lib().oracle_kron_identity(d, 3, 3, P(F(Ah).ravel(order="F")), P(out))
+    AhD = from_f(out, (6, 6))
+    PERM = np.array([[1, 0, 0, 0, 0, 0], [0, 0, 0, 1, 0, 0], [0, 1, 0, 0, 0, 0], [0, 0, 0, 0, 1, 0],
+                     [0, 0, 1, 0, 0, 0], [0, 0, 0, 0, 0, 1]], dtype=float)
+    blk = np.zeros((6, 6))
+    blk[:3, :3] = AH
+    blk[3:, 3:] = AH
+    assert np.allclose(AhD, PERM @ blk @ PERM.T, rtol=1e-14)
+    assert np.allclose(np.kron(Ah, np.eye(d)), AhD)  # test/core/kronecker.jl:10-19
+    # diffusion scaling (apply_diffusion, priors.jl:139-142): sigma^2 * Q
+    assert np.allclose((QhR * sigma).T @ (QhR * sigma), sigma**2 * QH, rtol=1e-13)
+
+
+@pytest.mark.parametrize("q", [1, 2, 3, 5, 8])
+def test_preconditioning_identities(oracle, q):
+    """test/core/preconditioning.jl:6-53: A_breve = P A(h) P^-1, Q_breve = P Q(h) P'."""
+    h = 0.37
+    n = q + 1
+    A, Lb, Ah, QhR = _iwp(oracle, q, h)
+    Pv = np.zeros(n)
+    PIv = np.zeros(n)
+    oracle.lib().oracle_preconditioner(q, C.c_double(h), P(Pv), P(PIv))
+    assert np.allclose(Pv * PIv, 1.0, rtol=1e-14)
+    from math import factorial
+
+    Atrue = np.array([[h ** (j - i) / factorial(j - i) if j >= i else 0.0 for j in range(n)] for i in range(n)])
+    Qtrue = np.array([[h ** (2 * q + 1 - i - j) / ((2 * q + 1 - i - j) * factorial(q - i) * factorial(q - j))
+                       for j in range(n)] for i in range(n)])
+    assert np.allclose(Ah, Atrue, rtol=1e-13)
+    assert np.allclose(QhR.T @ QhR, Qtrue, rtol=1e-10)
+    assert np.allclose(np.diag(Pv) @ Atrue @ np.diag(PIv), A, rtol=1e-12)
+    assert np.allclose(np.diag(Pv) @ Qtrue @ np.diag(Pv), Lb.T @ Lb, rtol=1e-9)
+    # preconditioning improves the conditioning (preconditioning.jl:33-38)
+    assert np.linalg.cond(Lb.T @ Lb) < np.linalg.cond(Qtrue) or q == 1
+
+
+# ----------------------------------------------------------------------------------------------------
+# test/core/filtering.jl -- predict / update / smooth against plain dense-matrix formulas
+# ----------------------------------------------------------------------------------------------------
+def _rand_setup(seed, D):
+    rng = np.random.default_rng(seed)
+    m = rng.random(D)
+    PR = np.triu(rng.random((D, D)))
+    A = rng.random((D, D))
+    QR = np.triu(rng.random((D, D)))
+    return rng, m, PR, A, QR
+
+
+@pytest.mark.parametrize("backend", [0, 1])
+@pytest.mark.parametrize("diffusion", [1.0, 0.3, 0.0])
+def test_predict_cov_vs_dense(oracle, backend, diffusion):
+    """filtering.jl:13-99: P_p = A P A' + s2 Q (incl. diffusion :70-90 and zero diffusion :92-99)."""
+    D = 6
+    _, m, PR, A, QR = _rand_setup(1, D)
+    Rout = np.zeros(D * D)
+    used = C.c_int(0)
+    oracle.lib().oracle_predict_cov(D, P(F(PR).ravel(order="F")), P(F(A).ravel(order="F")),
+                                    P(F(QR).ravel(order="F")), C.c_double(diffusion), backend, P(Rout), C.byref(used))
+    R = from_f(Rout, (D, D))
+    Pp = A @ (PR.T @ PR) @ A.T + diffusion * (QR.T @ QR)
+    assert np.allclose(R.T @ R, Pp, rtol=1e-12)
+    if diffusion != 0.0:
+        assert np.allclose(R, np.triu(R))  # upper triangular (Cholesky / QR)
+
+
+def test_triangularize_matches_numpy_qr(oracle):
+    """test/core/fast_linalg.jl: triangularize!(A) ~ qr(A).R up to row signs."""
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((15, 5))
+    buf = F(A).ravel(order="F").copy()
+    R = np.zeros(25)
+    oracle.lib().oracle_triangularize(15, 5, P(buf), P(R))
+    R = from_f(R, (5, 5))
+    Rnp = np.linalg.qr(A, mode="r")
+    assert np.allclose(np.abs(R), np.abs(Rnp), rtol=1e-12, atol=1e-13)
+    assert np.allclose(R.T @ R, A.T @ A, rtol=1e-12)
+
+
+def test_update_vs_dense(oracle):
+    """filtering.jl:121-243: K = P H' S^-1, m = m_p - K z, P = P_p - K S K' and the log-likelihood (:216)."""
+    D, d = 6, 2
+    rng, m, PR, _, _ = _rand_setup(3, D)
+    H = rng.random((d, D))
+    z = rng.random(d)
+    mu = np.zeros(D)
+    Rout = np.zeros(D * D)
+    ll = C.c_double(0)
+    rc = oracle.lib().oracle_update(D, d, P(m), P(F(PR).ravel(order="F")), P(z), P(F(H).ravel(order="F")),
+                                    P(mu), P(Rout), C.byref(ll))
+    assert rc == 0
+    Pp = PR.T @ PR
+    S = H @ Pp @ H.T
+    K = Pp @ H.T @ np.linalg.inv(S)
+    R = from_f(Rout, (D, D))
+    assert np.allclose(mu, m - K @ z, rtol=1e-11)
+    assert np.allclose(R.T @ R, Pp - K @ S @ K.T, rtol=1e-9, atol=1e-12)
+    assert np.isclose(ll.value, multivariate_normal(mean=np.zeros(d), cov=S).logpdf(z), rtol=1e-10)
+
+
+def test_update_zero_covariance_shortcut(oracle):
+    """filtering.jl:218-240 / update.jl:82-89."""
+    D, d = 4, 2
+    m = np.arange(D, dtype=float)
+    H = np.eye(d, D)
+    mu = np.zeros(D)
+    Rout = np.ones(D * D)
+    ll = C.c_double(0)
+    oracle.lib().oracle_update(D, d, P(m), P(np.zeros(D * D)), P(np.zeros(d)), P(F(H).ravel(order="F")), P(mu), P(Rout),
+                               C.byref(ll))
+    assert np.array_equal(mu, m) and not Rout.any() and ll.value == np.inf
+    oracle.lib().oracle_update(D, d, P(m), P(np.zeros(D * D)), P(np.ones(d)), P(F(H).ravel(order="F")), P(mu), P(Rout),
+                               C.byref(ll))
+    assert ll.value == -np.inf
+
+
+@pytest.mark.parametrize("diffusion", [1.0, 0.4])
+def test_backward_kernel_and_marginalize_vs_dense_rts(oracle, diffusion):
+    """filtering.jl:368-510: G = P A' (P_p)^-1, b = m - G m_p, Lambda = P - G P_p G'; smoothing step."""
+    D = 6
+    rng, m, PR, A, QR = _rand_setup(4, D)
+    Pm = PR.T @ PR
+    Q = diffusion * (QR.T @ QR)
+    m_p = A @ m
+    P_p = A @ Pm @ A.T + Q
+    Rp = np.zeros(D * D)
+    oracle.lib().oracle_predict_cov(D, P(F(PR).ravel(order="F")), P(F(A).ravel(order="F")), P(F(QR).ravel(order="F")),
+                                    C.c_double(diffusion), 1, P(Rp), None)
+    G = np.zeros(D * D)
+    b = np.zeros(D)
+    LR = np.zeros(2 * D * D)
+    oracle.lib().oracle_backward_kernel(D, P(m), P(F(PR).ravel(order="F")), P(m_p), P(Rp), P(F(A).ravel(order="F")),
+                                        P(F(QR).ravel(order="F")), C.c_double(diffusion), P(G), P(b), P(LR))
+    Gm = from_f(G, (D, D))
+    LRm = from_f(LR, (2 * D, D))
+    Gt = Pm @ A.T @ np.linalg.inv(P_p)
+    assert np.allclose(Gm, Gt, rtol=1e-8, atol=1e-10)
+    assert np.allclose(b, m - Gt @ m_p, rtol=1e-8, atol=1e-10)
+    assert np.allclose(LRm.T @ LRm, Pm - Gt @ P_p @ Gt.T, rtol=1e-7, atol=1e-9)
+    # smoothing towards x_next ~ N(m_s, P_s)
+    m_s = rng.random(D)
+    PsR = np.triu(rng.random((D, D)))
+    mu = np.zeros(D)
+    Rout = np.zeros(D * D)
+    oracle.lib().oracle_marginalize(D, P(m_s), P(F(PsR).ravel(order="F")), P(G), P(b), P(LR), P(mu), P(Rout))
+    R = from_f(Rout, (D, D))
+    Ps = PsR.T @ PsR
+    assert np.allclose(mu, m + Gt @ (m_s - m_p), rtol=1e-8)
+    assert np.allclose(R.T @ R, Pm + Gt @ (Ps - P_p) @ Gt.T, rtol=1e-7, atol=1e-9)
+
+
+# ----------------------------------------------------------------------------------------------------
+# end-to-end pins
+# ----------------------------------------------------------------------------------------------------
+def _lv(du, u, p, t):
+    problems.lotka_volterra(du, u, p, t)
+
+
+def _fitz(du, u, p, t):  # ODEProblemLibrary prob_ode_fitzhughnagumo (used by test/correctness.jl)
+    a, b, tinv, l = p
+    du[0] = u[0] - u[0] ** 3 / 3 - u[1] + l
+    du[1] = tinv * (u[0] + a - b * u[1])
+
+
+_CASES = {"lotkavolterra": (_lv, [1.0, 1.0], [1.5, 1.0, 3.0, 1.0]), "fitzhughnagumo": (_fitz, [1.0, 1.0], [0.7, 0.8, 1 / 12.5, 0.5])}
+
+
+def _truth(f, u0, p):
+    def fn(t, u):
+        du = [0.0, 0.0]
+        f(du, u, p, t)
+        return du
+
+    return solve_ivp(fn, (0, 1), u0, method="DOP853", rtol=1e-13, atol=1e-13).y[:, -1]
+
+
+# (alg, order, smooth, diffusion, threshold)  -- test/correctness.jl:12-56 (IWP rows this build covers)
+_CONSTANT = [(0, 2, 0, 0, 1e-5), (0, 3, 0, 0, 1e-8), (0, 5, 0, 0, 1e-10), (0, 3, 0, 1, 1e-7), (1, 2, 0, 0, 1e-7),
+             (1, 3, 0, 0, 1e-8), (1, 5, 0, 0, 1e-11), (1, 3, 0, 1, 1e-8), (0, 3, 1, 0, 1e-8), (0, 3, 1, 1, 2e-8),
+             (1, 3, 1, 0, 1e-8), (1, 3, 1, 1, 1e-8)]
+# test/correctness.jl:57-87
+_ADAPTIVE = [(0, 2, 2e-4), (0, 3, 1e-4), (0, 5, 1e-5), (0, 8, 2e-5), (1, 2, 2e-5), (1, 3, 1e-5), (1, 5, 1e-6), (1, 8, 5e-6)]
+
+
+@pytest.mark.parametrize("prob", list(_CASES))
+def test_correctness_constant_steps(oracle, prob):
+    f, u0, p = _CASES[prob]
+    ref = _truth(f, u0, p)
+    tr = tracer.trace(f, 2, 4)
+    for alg, q, smooth, diff, thr in _CONSTANT:
+        rhs = oracle.compile_rhs(tr, q)
+        for backend in (oracle.COV_REF, oracle.COV_QR):
+            cfg = oracle.make_config(2, q, 4, alg=alg, diffusion=diff, smooth=smooth, adaptive=False, dt=1e-2, t0=0, t1=1,
+                                     save_everystep=bool(smooth), cov_backend=backend)
+            s = oracle.solve(cfg, rhs, u0, p)
+            assert s["retcode"] == "Success"
+            assert np.mean(np.abs(s["pu_mu"][-1] - ref)) < thr, (prob, alg, q, smooth, diff, backend)
+
+
+@pytest.mark.parametrize("prob", list(_CASES))
+def test_correctness_adaptive(oracle, prob):
+    f, u0, p = _CASES[prob]
+    ref = _truth(f, u0, p)
+    tr = tracer.trace(f, 2, 4)
+    for alg, q, thr in _ADAPTIVE:
+        rhs = oracle.compile_rhs(tr, q)
+        s = oracle.solve(oracle.make_config(2, q, 4, alg=alg, smooth=True, adaptive=True, t0=0, t1=1), rhs, u0, p)
+        assert s["retcode"] == "Success"
+        assert np.mean(np.abs(s["pu_mu"][-1] - ref)) < thr, (prob, alg, q)
+        # test/solution.jl:35-46, 59-62
+        assert s["n"] == s["naccept"] + 1
+        assert s["t"][-1] == 1.0
+        assert np.array_equal(s["pu_mu"][0], u0) and not s["pu_R"][0].any()
+
+
+def test_exact_initialisation_linear_ode(oracle):
+    """test/state_init.jl:9-47: for u' = a u the derivatives are a^k u0 (q = 6)."""
+    a, u0v, q = -0.7, [1.3, -0.4], 6
+
+    def lin(du, u, p, t):
+        du[0] = p[0] * u[0]
+        du[1] = p[0] * u[1]
+
+    tr = tracer.trace(lin, 2, 1)
+    rhs = oracle.compile_rhs(tr, q)
+    s = oracle.solve(oracle.make_config(2, q, 1, adaptive=False, dt=0.1, t0=0, t1=0.1, smooth=False, save_everystep=True), rhs, u0v, [a])
+    x0 = s["x_filt_mu"][0].reshape(q + 1, 2)
+    for k in range(q + 1):
+        assert np.allclose(x0[k], a**k * np.array(u0v), rtol=1e-14)
+    assert not s["x_filt_R"][0].any()
+
+
+def test_smoothing_improves_interior_error(oracle):
+    """test/smoothing.jl:27-49: the smoothed solution is at least as accurate as the filtered one."""
+    f, u0, p = _CASES["lotkavolterra"]
+    tr = tracer.trace(f, 2, 4)
+    rhs = oracle.compile_rhs(tr, 3)
+
+    def fn(t, u):
+        du = [0.0, 0.0]
+        f(du, u, p, t)
+        return du
+
+    errs = {}
+    for smooth in (0, 1):
+        s = oracle.solve(oracle.make_config(2, 3, 4, alg=1, smooth=smooth, adaptive=False, dt=5e-2, t0=0, t1=1), rhs, u0, p)
+        ref = solve_ivp(fn, (0, 1), u0, method="DOP853", rtol=1e-13, atol=1e-13, t_eval=s["t"]).y.T
+        errs[smooth] = np.sqrt(np.mean((s["pu_mu"] - ref) ** 2))
+    assert errs[1] < errs[0]
+
+
+def test_cholesky_and_qr_backends_agree_under_fixed_diffusion(oracle):
+    """with FixedDiffusion the two covariance back-ends agree far below 1e-10."""
+    pd = problems.PROBLEMS["fitzhugh_nagumo"]
+    tr = tracer.trace(pd.f, 2, 3)
+    rhs = oracle.compile_rhs(tr, 3)
+    out = []
+    for be in (oracle.COV_REF, oracle.COV_QR):
+        out.append(oracle.solve(oracle.make_config(2, 3, 3, alg=1, diffusion=1, smooth=True, adaptive=False, dt=0.01, t0=0, t1=5,
+                                                   cov_backend=be), rhs, pd.u0, pd.p))
+    a, b = out
+    assert np.max(np.abs(a["pu_mu"] - b["pu_mu"]) / (np.abs(b["pu_mu"]) + 1e-300)) < 1e-11
+    assert np.max(np.linalg.norm(a["pu_cov"] - b["pu_cov"], axis=(1, 2))[1:] / np.linalg.norm(b["pu_cov"], axis=(1, 2))[1:]) < 1e-10
+    assert a["global_diffusion"] == pytest.approx(b["global_diffusion"], rel=1e-10)
+
+
+def test_global_diffusion_running_mle_quirk(oracle):
+    """calibration.jl:56-62: the divisor is the count before the step, so with two steps the
+    estimate equals the second increment."""
+    pd = problems.PROBLEMS["lotka_volterra"]
+    tr = tracer.trace(pd.f, 2, 4)
+    rhs = oracle.compile_rhs(tr, 2)
+    s1 = oracle.solve(oracle.make_config(2, 2, 4, alg=1, diffusion=1, calibrate=False, smooth=False, adaptive=False, dt=0.1, t0=0, t1=0.1), rhs, pd.u0, pd.p)
+    s2 = oracle.solve(oracle.make_config(2, 2, 4, alg=1, diffusion=1, calibrate=False, smooth=False, adaptive=False, dt=0.1, t0=0, t1=0.2), rhs, pd.u0, pd.p)
+    assert s1["global_diffusion"] != s2["global_diffusion"]
+    assert np.all(s2["diffusions"] == 1.0)  # set_diffusions! with calibrate=false
