@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rober", choices=sorted(WORKLOADS))
     ap.add_argument("--trajectories", type=int, default=0, help="trajectories per GPU (default: workload's BASELINE size)")
-    ap.add_argument("--cpu-sample", type=int, default=4096, help="trajectories per CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=65536, help="trajectories per CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
     args = ap.parse_args()

@@ -47,18 +47,23 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False) -> str:
+def build(force: bool = False, variant: str = "") -> str:
+    """variant "" : -ffp-contract=off (every product rounded; the default oracle).
+    variant "fma": -ffp-contract=fast, i.e. the *same* algorithm with fused multiply-adds -- used by the tests to measure
+    the rounding floor between two legitimate compilations of one algorithm."""
     src = os.path.join(_HERE, "pnode_oracle.c")
-    stamp_path = os.path.join(_HERE, "liboracle.stamp")
+    lib_path = _LIB_PATH if not variant else os.path.join(_HERE, f"liboracle_{variant}.so")
+    stamp_path = lib_path[:-3] + ".stamp"
     stamp = _stamp()
-    if not force and os.path.exists(_LIB_PATH) and os.path.exists(stamp_path) and open(stamp_path).read() == stamp:
-        return _LIB_PATH
-    cmd = ["gcc", "-O3", "-march=native", "-fno-fast-math", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared",
-           "-o", _LIB_PATH, src, "-lm"]
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp_path) and open(stamp_path).read() == stamp:
+        return lib_path
+    contract = "-ffp-contract=fast" if variant == "fma" else "-ffp-contract=off"
+    cmd = ["gcc", "-O3", "-march=native", "-mfma", "-fno-fast-math", contract, "-fopenmp", "-fPIC", "-shared",
+           "-o", lib_path, src, "-lm"]
     subprocess.run(cmd, check=True, cwd=_HERE)
-    with open(os.path.join(_HERE, "liboracle.stamp"), "w") as fh:
+    with open(stamp_path, "w") as fh:
         fh.write(stamp)
-    return _LIB_PATH
+    return lib_path
 
 
 class Config(C.Structure):
@@ -93,13 +98,19 @@ RHS_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINT
 TAYLOR_FN = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
                         C.c_int)
 
-_lib = None
+_libs = {}
+_variant = ""
+
+
+def use_variant(variant: str = "") -> None:
+    """Select which compilation of the oracle subsequent solve() calls use ("" or "fma")."""
+    global _variant
+    _variant = variant
 
 
 def lib():
-    global _lib
-    if _lib is None:
-        _lib = C.CDLL(build())
+    if _variant not in _libs:
+        _lib = C.CDLL(build(variant=_variant))
         dp = C.POINTER(C.c_double)
         _lib.oracle_solve.restype = C.c_int
         _lib.oracle_solve.argtypes = [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_void_p, dp, dp, C.POINTER(Traj)]
@@ -109,7 +120,8 @@ def lib():
             C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, dp, dp, C.c_int, dp, dp,
             C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), dp]
         _lib.oracle_max_threads.restype = C.c_int
-    return _lib
+        _libs[_variant] = _lib
+    return _libs[_variant]
 
 
 def _dp(a):
