@@ -13,6 +13,7 @@ struct PnParams {
     double t0, t1, dt0;
     double abstol, reltol, dtmin, dtmax;
     double beta1, beta2, qmin, qmax, gamma, qsteady_min, qsteady_max, qoldinit;
+    double qoldinit_pb2; /* qoldinit^beta2 (host-computed) */
     double initial_diffusion;
     long long maxiters;
     int calibrate;

@@ -43,10 +43,34 @@ PN_HD double pn_gbcast(double x, int src) {
     return __shfl_sync(0xffffffffu, x, src, G);
 }
 
-// Upper Cholesky of a symmetric M (row-major, only j >= i read) in place: M = U'U.  Returns false if a
-// pivot is not positive.
+// 1/x and 1/sqrt(x) from the MUFU seed (rcp.approx / rsqrt.approx: ~2^-23, full exponent range) plus two Newton
+// steps in FP64: <= 2 ulp, no slow-path branches.  The IEEE-rounded `1.0/x` and `sqrt(x)` each cost a
+// ~25-instruction sequence with a call on the slow path; the QR needs one of each per column.
+PN_HD double pn_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+PN_HD double pn_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double t = x * y;
+    double e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    t = x * y;
+    e = fma(-t, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    return y;
+}
+
+// Upper Cholesky of a symmetric M (row-major, only j >= i read) in place: M = U'U, inv[j] = 1/U[j][j].
+// Returns false if a pivot is not positive.
 template <int M_>
-PN_HD bool pn_chol(double (&A)[M_][M_]) {
+PN_HD bool pn_chol(double (&A)[M_][M_], double (&invd)[M_]) {
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < M_; j++) {
@@ -55,9 +79,10 @@ PN_HD bool pn_chol(double (&A)[M_][M_]) {
         for (int k = 0; k < M_; k++)
             if (k < j) s -= A[k][j] * A[k][j];
         if (!(s > 0.0)) ok = false;
-        double ujj = sqrt(s);
+        const double inv = pn_rsqrt(s);
+        const double ujj = s * inv;
         A[j][j] = ujj;
-        double inv = 1.0 / ujj;
+        invd[j] = inv;
 #pragma unroll
         for (int i = 0; i < M_; i++) {
             if (i <= j) continue;
@@ -72,20 +97,20 @@ PN_HD bool pn_chol(double (&A)[M_][M_]) {
 }
 // x <- (U'U)^{-1} x
 template <int M_>
-PN_HD void pn_chol_solve(const double (&U)[M_][M_], double (&x)[M_]) {
+PN_HD void pn_chol_solve(const double (&U)[M_][M_], const double (&invd)[M_], double (&x)[M_]) {
 #pragma unroll
     for (int a = 0; a < M_; a++) {
 #pragma unroll
         for (int k = 0; k < M_; k++)
             if (k < a) x[a] -= U[k][a] * x[k];
-        x[a] /= U[a][a];
+        x[a] *= invd[a];
     }
 #pragma unroll
     for (int a = M_ - 1; a >= 0; a--) {
 #pragma unroll
         for (int k = 0; k < M_; k++)
             if (k > a) x[a] -= U[a][k] * x[k];
-        x[a] /= U[a][a];
+        x[a] *= invd[a];
     }
 }
 
@@ -124,11 +149,12 @@ struct PnSmall {
             const double alpha = pn_gbcast<G>(x[ks], kl);
             /* branch-free on purpose: the shuffles below must be executed by the whole warp.
                A zero column (total == 0) gets gam = 0, i.e. H = I. */
-            const double nrm = sqrt(total);
+            const bool nz = total > 0.0;
+            const double nrm = nz ? total * pn_rsqrt(total) : 0.0;
             const double beta = -copysign(nrm, alpha);
             const double vk = alpha - beta;
             const double den = total + fabs(alpha) * nrm; /* = beta (beta - alpha) = v'v / 2 */
-            const double gam = (den > 0.0) ? 1.0 / den : 0.0;
+            const double gam = nz ? pn_rcp(den) : 0.0;
             if (gl == kl) x[ks] = vk;
             /* s_j = v' a_j over the group, j > k */
             double sj[D];
@@ -186,7 +212,7 @@ struct PnSmall {
         double R[RPL][D];      /* own rows of the right factor */
         double pr[NPA];
         double uprev[d];
-        double t = 0.0, dt = 0.0, dtcache = 0.0, qold = 0.0, loglik = 0.0, gdiff = 0.0, ldiff = 0.0;
+        double t = 0.0, dt = 0.0, dtcache = 0.0, qold = 0.0, qold_pb2 = 1.0, loglik = 0.0, gdiff = 0.0, ldiff = 0.0;
         long long traj = -1, naccept = 0, nreject = 0, nf = 0, iter = 0, tstop_idx = 0, save_pos = 0;
         int retcode = PN_RET_SUCCESS;
         bool have = false, queue_empty = false;
@@ -232,6 +258,7 @@ struct PnSmall {
                         gdiff = 0.0;
                         ldiff = 0.0;
                         qold = P.qoldinit;
+                        qold_pb2 = P.qoldinit_pb2;
                         retcode = PN_RET_SUCCESS;
                         dtcache = dt;
                         have = true;
@@ -250,12 +277,18 @@ struct PnSmall {
                     }
                 }
             }
+#ifdef PN_CTA_SYNC
+            /* keep the warps of a CTA in step: the two warps that share a scheduler then fetch the same
+               instruction lines (the unrolled loop body is ~100 KB, far beyond the L0 instruction cache) */
+            if (__syncthreads_or(have ? 1 : 0) == 0) break;
+#else
             if (__all_sync(FULL, !have)) break;
+#endif
 
             /* ============ (B) phase 1: attempt steps until one is accepted (no cross-lane traffic) ============ */
             bool finished = !have || !(t < P.t1);
             bool accept = false;
-            double h = 0.0, tstop = P.t1, EEst = 0.0, qq = 1.0, ediff = 0.0;
+            double h = 0.0, tstop = P.t1, EEst = 0.0, qq = 1.0, ediff = 0.0, lEE = 0.0;
             double hp[n], PIv[n], mup[D], z[d], J[d * d];
 #pragma unroll
             for (int k = 0; k < n; k++) hp[k] = (k == 0) ? 1.0 : 0.0;
@@ -348,12 +381,13 @@ struct PnSmall {
                     double zt[d];
 #pragma unroll
                     for (int a = 0; a < d; a++) zt[a] = z[a];
-                    const bool ok = pn_chol<d>(W);
-                    pn_chol_solve<d>(W, zt);
+                    double winv[d];
+                    const bool ok = pn_chol<d>(W, winv);
+                    pn_chol_solve<d>(W, winv, zt);
                     double qd = 0.0;
 #pragma unroll
                     for (int a = 0; a < d; a++) qd += z[a] * zt[a];
-                    ldiff = qd / (double)d;
+                    ldiff = qd * (1.0 / (double)d);
                     if (P.forced_diffusion && naccept < P.n_forced) ldiff = P.forced_diffusion[naccept];
                     if (!ok) {
                         retcode = PN_RET_UNSTABLE;
@@ -361,14 +395,15 @@ struct PnSmall {
                         break;
                     }
                     if (ADAPTIVE) {
+                        /* EEst^2 = mean_i (h sqrt(s2 W_ii) / sc_i)^2 : one rsqrt instead of d sqrt + d div */
                         double e2 = 0.0;
 #pragma unroll
                         for (int i = 0; i < d; i++) {
-                            const double e = h * sqrt(ldiff * wdiag[i]);
-                            const double r = e / (P.abstol + fmax(fabs(mup[i]), fabs(uprev[i])) * P.reltol);
-                            e2 += r * r;
+                            const double isc = pn_rcp(P.abstol + fmax(fabs(mup[i]), fabs(uprev[i])) * P.reltol);
+                            e2 += (ldiff * wdiag[i]) * (isc * isc);
                         }
-                        EEst = sqrt(e2 / (double)d);
+                        e2 = e2 * (h * h) * (1.0 / (double)d);
+                        EEst = (e2 > 0.0) ? e2 * pn_rsqrt(e2) : e2;
                         if (EEst != EEst) {
                             retcode = PN_RET_UNSTABLE;
                             finished = true;
@@ -382,9 +417,12 @@ struct PnSmall {
                     if (EEst == 0.0) {
                         qq = 1.0 / P.qmax;
                     } else {
-                        q11 = pow(EEst, P.beta1);
-                        qq = q11 / pow(qold, P.beta2);
-                        qq = fmax(1.0 / P.qmax, fmin(1.0 / P.qmin, qq / P.gamma));
+                        /* EEst^beta1 / qold^beta2 as exp(beta * log x); log(EEst) is reused for qold^beta2 of the
+                           next step (qold = max(EEst, qoldinit)), so a step costs one log and two exp */
+                        lEE = log(EEst);
+                        q11 = exp(P.beta1 * lEE);
+                        qq = q11 * pn_rcp(qold_pb2 * P.gamma);
+                        qq = fmax(1.0 / P.qmax, fmin(1.0 / P.qmin, qq));
                     }
                     if (!accept) { /* step_reject_controller! */
                         nreject++;
@@ -467,16 +505,21 @@ struct PnSmall {
 #pragma unroll
                     for (int a = 0; a < d; a++) S[a][a] = 1.0;
                 }
-                const bool okS = pn_chol<d>(S);
+                double sinv[d];
+                const bool okS = pn_chol<d>(S, sinv);
                 double zt[d];
 #pragma unroll
                 for (int a = 0; a < d; a++) zt[a] = z[a];
-                pn_chol_solve<d>(S, zt);
-                double quad = 0.0, logdet = 0.0;
+                pn_chol_solve<d>(S, sinv, zt);
+                double quad = 0.0, logdet = 0.0, dprod = 1.0;
 #pragma unroll
                 for (int a = 0; a < d; a++) {
                     quad += z[a] * zt[a];
-                    logdet += log(S[a][a]);
+                    dprod *= S[a][a];
+                    if ((a & 3) == 3 || a == d - 1) { /* one log per 4 Cholesky pivots */
+                        logdet += log(dprod);
+                        dprod = 1.0;
+                    }
                 }
                 if (accept) {
                     if (!okS) retcode = PN_RET_UNSTABLE;
@@ -488,7 +531,7 @@ struct PnSmall {
                     } else {
                         loglik += -0.5 * quad - 0.5 * (double)d * 1.8378770664093453 - logdet;
                         if (!DYNAMIC) { /* estimate_global_diffusion(::FixedDiffusion), calibration.jl:49-66 */
-                            const double inc = quad / (double)d;
+                            const double inc = quad * (1.0 / (double)d);
                             gdiff = (naccept == 0) ? inc : gdiff + (inc - gdiff) / (double)naccept;
                         }
                     }
@@ -500,7 +543,7 @@ struct PnSmall {
                     double v[d];
 #pragma unroll
                     for (int a = 0; a < d; a++) v[a] = C2[lr][a];
-                    pn_chol_solve<d>(S, v);
+                    pn_chol_solve<d>(S, sinv, v);
 #pragma unroll
                     for (int a = 0; a < d; a++) V[lr][a] = v[a];
                 }
@@ -532,6 +575,7 @@ struct PnSmall {
                     if (ADAPTIVE) {
                         if (P.qsteady_min <= qq && qq <= P.qsteady_max) qq = 1.0;
                         qold = fmax(EEst, P.qoldinit);
+                        qold_pb2 = (EEst > P.qoldinit) ? exp(P.beta2 * lEE) : P.qoldinit_pb2;
                         dtnew = dt / qq;
                     }
                     const double ttmp = t + h;

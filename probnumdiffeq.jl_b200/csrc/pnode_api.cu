@@ -113,7 +113,13 @@ static std::string cu_err(CUresult r) {
 }
 
 /* ---------------------------------------------------------------------------------------------- */
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
 struct Kernel {
+    int threads = PN_THREADS;
     const void* rt_fn = nullptr; /* nvcc-compiled (runtime API) */
     CUmodule mod = nullptr;      /* NVRTC-compiled */
     CUfunction drv_fn = nullptr;
@@ -188,7 +194,7 @@ static std::string kernel_key(const pnode_solver* s, int save) {
 
 /* NVRTC: user RHS + step kernels -> sm_100a CUBIN.  Needs no device. */
 static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_name, int q, int G, bool adaptive,
-                       bool dynamic, int save, std::vector<char>* cubin) {
+                       bool dynamic, int save, std::vector<char>* cubin, int threads = PN_THREADS, int min_blocks = 2) {
     std::string src;
     src += "#include \"pn_kernel_entry.cuh\"\n";
     src += rhs_src;
@@ -204,14 +210,28 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
     }
     if (nvrtcCreateProgram(&prog, src.c_str(), "pnode_user.cu", PN_N_EMBEDDED, hdr_src, hdr_name) != NVRTC_SUCCESS)
         return fail(PNODE_ERR_COMPILE, "nvrtcCreateProgram failed");
-    char dq[32], dg[32], da[32], dd[32], ds[32];
+    char dq[32], dg[32], da[32], dd[32], ds[32], dt[40], dm[40];
+    snprintf(dt, sizeof dt, "-DPN_THREADS=%d", threads);
+    snprintf(dm, sizeof dm, "-DPN_MIN_BLOCKS=%d", min_blocks);
     snprintf(dq, sizeof dq, "-DPN_Q=%d", q);
     snprintf(dg, sizeof dg, "-DPN_G=%d", G);
     snprintf(da, sizeof da, "-DPN_ADAPTIVE=%d", adaptive ? 1 : 0);
     snprintf(dd, sizeof dd, "-DPN_DYNAMIC=%d", dynamic ? 1 : 0);
     snprintf(ds, sizeof ds, "-DPN_SAVE=%d", save);
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", dq, dg, da, dd, ds};
-    nvrtcResult cr = nvrtcCompileProgram(prog, (int)(sizeof(opts) / sizeof(opts[0])), opts);
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", dq, dg, da, dd, ds, dt, dm};
+    std::vector<std::string> extra; /* developer knob: extra NVRTC options, space separated */
+    if (const char* e = getenv("PNODE_NVRTC_FLAGS")) {
+        std::string cur;
+        for (const char* c = e;; c++) {
+            if (*c == ' ' || *c == 0) {
+                if (!cur.empty()) extra.push_back(cur);
+                cur.clear();
+                if (!*c) break;
+            } else cur.push_back(*c);
+        }
+        for (auto& x : extra) opts.push_back(x.c_str());
+    }
+    nvrtcResult cr = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
     if (cr != NVRTC_SUCCESS) {
         size_t n = 0;
         nvrtcGetProgramLogSize(prog, &n);
@@ -239,15 +259,16 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
         src = "#include \"kernels/pn_builtin_problems.cuh\"\n";
         name = sn;
     }
+    out->threads = env_int("PNODE_THREADS", PN_THREADS);
     rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0,
-                     s->cfg.diffusion == PNODE_DIFF_DYNAMIC, save, &cubin);
+                     s->cfg.diffusion == PNODE_DIFF_DYNAMIC, save, &cubin, out->threads, env_int("PNODE_MIN_BLOCKS", 2));
     if (rc) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
     r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_entry");
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction: " + cu_err(r));
     int nblk = 0;
-    r = g_drv.Occupancy(&nblk, out->drv_fn, PN_THREADS, 0);
+    r = g_drv.Occupancy(&nblk, out->drv_fn, out->threads, 0);
     if (r != CUDA_SUCCESS || nblk < 1) return fail(PNODE_ERR_CUDA, "occupancy query failed: " + cu_err(r));
     out->blocks_per_sm = nblk;
     return 0;
@@ -256,7 +277,7 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
 static int get_kernel(pnode_solver* s, int save, Kernel* out) {
     if (out->valid()) return 0;
     auto t0 = std::chrono::steady_clock::now();
-    if (s->builtin) {
+    if (s->builtin && !env_int("PNODE_FORCE_NVRTC", 0)) {
         int n = 0;
         const PnBuiltinEntry* tab = pn_builtin_table(&n);
         std::string key = kernel_key(s, save);
@@ -270,9 +291,9 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
                 return 0;
             }
         }
-        if (!pn_builtin_struct_name(s->rhs_name.c_str()))
-            return fail(PNODE_ERR_ARGUMENT, "unknown built-in problem '" + s->rhs_name + "'");
     }
+    if (s->builtin && !pn_builtin_struct_name(s->rhs_name.c_str()))
+        return fail(PNODE_ERR_ARGUMENT, "unknown built-in problem '" + s->rhs_name + "'");
     int rc = compile_nvrtc(s, save, out);
     s->compile_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return rc;
@@ -363,6 +384,7 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     B.qsteady_min = cfg->qsteady_min > 0.0 ? cfg->qsteady_min : 1.0;
     B.qsteady_max = cfg->qsteady_max > 0.0 ? cfg->qsteady_max : 1.0;
     B.qoldinit = cfg->qoldinit > 0.0 ? cfg->qoldinit : 1e-4;
+    B.qoldinit_pb2 = std::pow(B.qoldinit, B.beta2);
     B.initial_diffusion = cfg->initial_diffusion > 0.0 ? cfg->initial_diffusion : 1.0;
     B.maxiters = cfg->maxiters > 0 ? cfg->maxiters : 1000000;
     B.calibrate = cfg->calibrate;
@@ -466,17 +488,17 @@ extern "C" void pnode_destroy(pnode_solver* s) {
 }
 
 static int launch(pnode_solver* s, Kernel& k, PnParams& P, int64_t n_traj) {
-    const int groups_per_block = PN_THREADS / s->G;
+    const int groups_per_block = k.threads / s->G;
     long long want = (n_traj + groups_per_block - 1) / groups_per_block;
     long long cap = (long long)s->n_sm * k.blocks_per_sm; /* persistent: a whole number of CTAs per SM */
     unsigned grid = (unsigned)std::max(1LL, std::min(want, cap));
     CUDA_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), s->stream));
     if (k.rt_fn) {
         void* args[] = {&P};
-        CUDA_TRY(cudaLaunchKernel(k.rt_fn, dim3(grid), dim3(PN_THREADS), args, 0, s->stream));
+        CUDA_TRY(cudaLaunchKernel(k.rt_fn, dim3(grid), dim3(k.threads), args, 0, s->stream));
     } else {
         void* args[] = {&P};
-        CUresult r = g_drv.LaunchKernel(k.drv_fn, grid, 1, 1, PN_THREADS, 1, 1, 0, (CUstream)s->stream, args, nullptr);
+        CUresult r = g_drv.LaunchKernel(k.drv_fn, grid, 1, 1, k.threads, 1, 1, 0, (CUstream)s->stream, args, nullptr);
         if (r != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuLaunchKernel: " + cu_err(r));
     }
     return 0;

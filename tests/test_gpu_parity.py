@@ -103,17 +103,23 @@ def test_cfg1_fixed_steps_dynamic_diffusion_and_teacher_forcing(oracle):
     tr = tracer.trace(pd.f, pd.d, pd.n_p)
     rhs = oracle.compile_rhs(tr, 3)
     kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC, smooth=False, adaptive=False, dt=0.01, t0=0.0, t1=20.0,
-              save_everystep=True, cov_backend=oracle.COV_QR)
-    o = oracle.solve(oracle.make_config(2, 3, 3, **kw), rhs, u0[0], p[0])
+              save_everystep=True)
+    o = oracle.solve(oracle.make_config(2, 3, 3, cov_backend=oracle.COV_QR, **kw), rhs, u0[0], p[0])
     g = _gpu(pd, u0, p, 3, builtin=False, adaptive=False, dt=0.01, t0=0.0, t1=20.0, save_everystep=True)
     assert np.array_equal(g["T"], o["t"])
     assert _rel(g["U"], o["pu_mu"]) < 1e-9           # measured floor ~1e-10
     assert _relcov(g["C"][1:], o["pu_cov"][1:]) < 1e-5  # floor 6e-7
-    # sigma^2 itself: single entries sit on zero crossings of z (relative floor ~0.25), so compare the sequence norm-wise
-    assert np.linalg.norm(g["Df"][:-1] - o["diffusions"][:-1]) / np.linalg.norm(o["diffusions"][:-1]) < 1e-5
+    # sigma^2 itself is rounding noise wherever z crosses zero (and at the first steps, where z is *only* rounding
+    # noise): compare the sequence norm-wise against the oracle's own floor under one-ulp perturbations
+    def m_sig(s_, b_):
+        return np.linalg.norm(s_["diffusions"][:-1] - b_["diffusions"][:-1]) / np.linalg.norm(b_["diffusions"][:-1])
+
+    kwq = dict(cov_backend=oracle.COV_QR, **kw)
+    fl = rounding.floor(oracle, rhs, 2, 3, 3, u0[0], p[0], kwq, o, m_sig)
+    assert m_sig(dict(diffusions=g["Df"]), o) < max(1e-6, 20 * fl)
     # sigma^2 teacher forcing: the kernel consumes the oracle's sigma^2 sequence -> everything reaches 1e-10
     sig = o["diffusions"][:-1]
-    o2 = oracle.solve(oracle.make_config(2, 3, 3, forced_diffusion=sig, **kw), rhs, u0[0], p[0])
+    o2 = oracle.solve(oracle.make_config(2, 3, 3, forced_diffusion=sig, cov_backend=oracle.COV_QR, **kw), rhs, u0[0], p[0])
     g2 = _gpu(pd, u0, p, 3, builtin=False, adaptive=False, dt=0.01, t0=0.0, t1=20.0, save_everystep=True,
               forced_diffusion=sig)
     assert _rel(g2["U"], o2["pu_mu"]) < 1e-10
