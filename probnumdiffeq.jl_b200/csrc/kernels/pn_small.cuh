@@ -121,6 +121,9 @@ struct PnSmall {
     static constexpr int D = d * n;
     static constexpr int RPL = (D + G - 1) / G; /* rows per lane, top and bottom block each */
     static constexpr int NPA = Prob::n_p > 0 ? Prob::n_p : 1;
+    /* H = [-J | I | 0 ...] touches the first 2d columns only and R^- is upper triangular, so R^- H' is zero in
+       rows >= 2d: row slots lr >= RU never enter the measurement update */
+    static constexpr int RU = (2 * d + G - 1) / G < RPL ? (2 * d + G - 1) / G : RPL;
 
     // Householder QR of the stack [Rt ; Bt] (2D x D) in place; on return Rt holds the upper-triangular
     // factor (row r on lane r % G), below-diagonal entries zeroed.  Bt is destroyed.
@@ -475,11 +478,11 @@ struct PnSmall {
                 }
                 qr_stack(R, B, gl);
 
-                /* C2 = R^- H' (row-local), S = C2'C2 */
-                double C2[RPL][d];
+                /* C2 = R^- H' (row-local; rows >= 2d are exactly zero, see RU), S = C2'C2 */
+                double C2[RU][d];
                 double S[d][d];
 #pragma unroll
-                for (int lr = 0; lr < RPL; lr++)
+                for (int lr = 0; lr < RU; lr++)
 #pragma unroll
                     for (int a = 0; a < d; a++) {
                         double s = R[lr][d + a];
@@ -494,7 +497,7 @@ struct PnSmall {
                         if (b < a) continue;
                         double s = 0.0;
 #pragma unroll
-                        for (int lr = 0; lr < RPL; lr++) s += C2[lr][a] * C2[lr][b];
+                        for (int lr = 0; lr < RU; lr++) s += C2[lr][a] * C2[lr][b];
                         S[a][b] = pn_gsum<G>(s);
                     }
                 double tr = 0.0;
@@ -537,9 +540,9 @@ struct PnSmall {
                     }
                 }
                 /* V = C2 S^-1 (row-local) ; K = R^-' V all-reduced ; mu = mu^- - K z ; R+ = R^- - C2 K' */
-                double V[RPL][d];
+                double V[RU][d];
 #pragma unroll
-                for (int lr = 0; lr < RPL; lr++) {
+                for (int lr = 0; lr < RU; lr++) {
                     double v[d];
 #pragma unroll
                     for (int a = 0; a < d; a++) v[a] = C2[lr][a];
@@ -554,7 +557,7 @@ struct PnSmall {
                     for (int a = 0; a < d; a++) {
                         double s = 0.0;
 #pragma unroll
-                        for (int lr = 0; lr < RPL; lr++) s += R[lr][c] * V[lr][a];
+                        for (int lr = 0; lr < RU; lr++) s += R[lr][c] * V[lr][a];
                         Kc[a] = pn_gsum<G>(s);
                     }
                     double s = mup[c];
@@ -562,7 +565,7 @@ struct PnSmall {
                     for (int a = 0; a < d; a++) s -= Kc[a] * z[a];
                     mu[c] = s;
 #pragma unroll
-                    for (int lr = 0; lr < RPL; lr++) {
+                    for (int lr = 0; lr < RU; lr++) {
                         double r = R[lr][c];
 #pragma unroll
                         for (int a = 0; a < d; a++) r -= C2[lr][a] * Kc[a];

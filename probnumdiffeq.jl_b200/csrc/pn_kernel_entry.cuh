@@ -2,14 +2,21 @@
 // (user-traced problems) builds.  One persistent launch solves the whole ensemble: the grid is sized to
 // a multiple of the SM count and groups pull trajectory indices from an atomic counter.
 #pragma once
-#include "kernels/pn_small.cuh"
 
+
+/* One 256-thread CTA per SM (8 warps, 2 per scheduler, ~255 registers each); the CTA re-synchronises once per
+   time-loop iteration (PN_CTA_SYNC) so that the two warps sharing a scheduler fetch the same instruction lines. */
 #ifndef PN_THREADS
-#define PN_THREADS 128
+#define PN_THREADS 256
 #endif
 #ifndef PN_MIN_BLOCKS
-#define PN_MIN_BLOCKS 2
+#define PN_MIN_BLOCKS 1
 #endif
+#ifndef PN_NO_CTA_SYNC
+#define PN_CTA_SYNC 1
+#endif
+
+#include "kernels/pn_small.cuh"
 
 template <class Prob, int Q, int G, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_small_kernel(const __grid_constant__ PnParams P) {

@@ -21,7 +21,7 @@
 #include "pn_builtin.h"
 #include "pn_embedded_sources.h" /* generated: kernel headers as strings for NVRTC */
 
-#define PN_THREADS 128
+#define PN_THREADS 256
 
 /* calibrate_solution! / set_diffusions! (src/integrator_utils.jl:46-88) for the per-step outputs of a
    FixedDiffusion solve: every saved covariance is scaled by the global MLE and sol.diffusions is overwritten. */
@@ -194,7 +194,7 @@ static std::string kernel_key(const pnode_solver* s, int save) {
 
 /* NVRTC: user RHS + step kernels -> sm_100a CUBIN.  Needs no device. */
 static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_name, int q, int G, bool adaptive,
-                       bool dynamic, int save, std::vector<char>* cubin, int threads = PN_THREADS, int min_blocks = 2) {
+                       bool dynamic, int save, std::vector<char>* cubin, int threads = PN_THREADS, int min_blocks = 1) {
     std::string src;
     src += "#include \"pn_kernel_entry.cuh\"\n";
     src += rhs_src;
@@ -261,7 +261,7 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
     }
     out->threads = env_int("PNODE_THREADS", PN_THREADS);
     rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0,
-                     s->cfg.diffusion == PNODE_DIFF_DYNAMIC, save, &cubin, out->threads, env_int("PNODE_MIN_BLOCKS", 2));
+                     s->cfg.diffusion == PNODE_DIFF_DYNAMIC, save, &cubin, out->threads, env_int("PNODE_MIN_BLOCKS", 1));
     if (rc) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
