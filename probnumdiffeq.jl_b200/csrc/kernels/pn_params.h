@@ -48,6 +48,5 @@ struct PnParams {
     double* s_diffusion;           /* [total]         */
     double* s_x_mean;              /* [total][D]      (smoothing only) */
     double* s_x_covfac;            /* [total][D][D]   (smoothing only) */
-    /* backward kernels for the smoother, one record per accepted step (index = saved point - 1 - traj) */
-    double* s_bk;                  /* [total - n_traj][PN_BK_RECORD(D)] */
+    double* s_h;                   /* [total] step size of the step k -> k+1 at slot k (smoothing only) */
 };

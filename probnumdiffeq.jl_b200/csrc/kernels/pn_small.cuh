@@ -274,6 +274,20 @@ struct PnSmall {
                                 for (int i = 0; i < d; i++) P.s_u_mean[save_pos * d + i] = mu[i];
 #pragma unroll
                                 for (int i = 0; i < d * d; i++) P.s_u_cov[save_pos * d * d + i] = 0.0;
+                                if (SAVE >= 2) {
+#pragma unroll
+                                    for (int c = 0; c < D; c++) P.s_x_mean[save_pos * D + c] = mu[c];
+                                }
+                            }
+                            if (SAVE >= 2 && P.step_offsets) {
+#pragma unroll
+                                for (int lr = 0; lr < RPL; lr++) {
+                                    const int row = lr * G + gl;
+                                    if (row < D) {
+#pragma unroll
+                                        for (int c = 0; c < D; c++) P.s_x_covfac[(save_pos * D + row) * D + c] = 0.0;
+                                    }
+                                }
                             }
                             save_pos += 1;
                         }
@@ -614,11 +628,26 @@ struct PnSmall {
                         }
                     if (wr && gl == 0) {
                         P.s_t[save_pos] = t;
-                        P.s_diffusion[save_pos - 1] = (ADAPTIVE || DYNAMIC) ? ldiff : P.initial_diffusion;
+                        P.s_diffusion[save_pos - 1] = (SAVE >= 2) ? ediff : ((ADAPTIVE || DYNAMIC) ? ldiff : P.initial_diffusion);
 #pragma unroll
                         for (int i = 0; i < d; i++) P.s_u_mean[save_pos * d + i] = mu[i];
 #pragma unroll
                         for (int i = 0; i < d * d; i++) P.s_u_cov[save_pos * d * d + i] = cv[i];
+                        if (SAVE >= 2) { /* what the smoother sweep needs: x_filt[k+1] and the step that produced it */
+                            P.s_h[save_pos - 1] = h;
+#pragma unroll
+                            for (int c = 0; c < D; c++) P.s_x_mean[save_pos * D + c] = mu[c];
+                        }
+                    }
+                    if (SAVE >= 2 && wr) {
+#pragma unroll
+                        for (int lr = 0; lr < RPL; lr++) {
+                            const int row = lr * G + gl;
+                            if (row < D) {
+#pragma unroll
+                                for (int c = 0; c < D; c++) P.s_x_covfac[(save_pos * D + row) * D + c] = R[lr][c];
+                            }
+                        }
                     }
                     if (accept) save_pos += 1;
                 }

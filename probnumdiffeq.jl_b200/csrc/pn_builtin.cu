@@ -4,6 +4,7 @@
 #include "pn_kernel_entry.cuh"
 #include "kernels/pn_builtin_problems.cuh"
 #include "pn_builtin.h"
+#include "kernels/pn_smooth.cuh"
 
 #define PN_ENTRY(NAME, PROB, Q, G, A, DY, S) \
     { "builtin:" NAME ":small:q" #Q ":g" #G ":a" #A ":dyn" #DY ":s" #S, \
@@ -41,3 +42,5 @@ extern "C" const PnBuiltinEntry* pn_builtin_table(int* count) {
     *count = (int)(sizeof(g_table) / sizeof(g_table[0]));
     return g_table;
 }
+
+extern "C" const void* pn_smooth_kernel_ptr(void) { return (const void*)&pn_smooth_kernel; }

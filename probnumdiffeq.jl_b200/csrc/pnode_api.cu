@@ -18,6 +18,8 @@
 
 #include "../../include/pnode.h"
 #include "kernels/pn_params.h"
+#define PN_SMOOTH_DECL_ONLY
+#include "kernels/pn_smooth.cuh"
 #include "pn_builtin.h"
 #include "pn_embedded_sources.h" /* generated: kernel headers as strings for NVRTC */
 
@@ -315,7 +317,6 @@ static int validate_config(const pnode_config* cfg) {
         return fail(PNODE_ERR_ARGUMENT, "If you set `save_everystep=false` also set `smooth=false` in the alg!"); /* checks.jl:18-20 */
     if (!(cfg->t1 > cfg->t0)) return fail(PNODE_ERR_ARGUMENT, "tspan must satisfy t1 > t0");
     if (!cfg->rhs_name) return fail(PNODE_ERR_ARGUMENT, "rhs_name is required");
-    if (cfg->smooth) return fail(PNODE_ERR_UNSUPPORTED, "smooth=true is not implemented yet in this build");
     const int D = cfg->d * (cfg->q + 1);
     int cov = cfg->cov;
     if (cov == PNODE_COV_AUTO) cov = PNODE_COV_DENSE; /* Kronecker fast path: see pn_kron (EK0) */
@@ -433,7 +434,7 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
     }
-    int rc = get_kernel(s, cfg->save_everystep ? 1 : 0, cfg->save_everystep ? &s->k_save : &s->k_final);
+    int rc = get_kernel(s, cfg->save_everystep ? (cfg->smooth ? 2 : 1) : 0, cfg->save_everystep ? &s->k_save : &s->k_final);
     if (rc) {
         pnode_destroy(s);
         return rc;
@@ -580,12 +581,61 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         P.s_u_mean = (double*)r->f[PNODE_F_U].d;
         P.s_u_cov = (double*)r->f[PNODE_F_U_COV].d;
         P.s_diffusion = (double*)r->f[PNODE_F_DIFFUSIONS].d;
+        double* d_h = nullptr;
+        if (s->cfg.smooth) {
+            if ((rc = alloc_field(r, PNODE_F_X, T * D * 8))) return rc;
+            if ((rc = alloc_field(r, PNODE_F_X_COVFAC, T * D * D * 8))) return rc;
+            CUDA_TRY(cudaMallocAsync((void**)&d_h, T * 8, s->stream));
+            CUDA_TRY(cudaMemsetAsync(d_h, 0, T * 8, s->stream));
+            P.s_x_mean = (double*)r->f[PNODE_F_X].d;
+            P.s_x_covfac = (double*)r->f[PNODE_F_X_COVFAC].d;
+            P.s_h = d_h;
+        }
         if ((rc = launch(s, s->k_save, P, n_traj))) return rc;
         launches = 2;
+        if (s->cfg.smooth) {
+            /* backward sweep: one warp per trajectory, records streamed back to front */
+            PnSmoothParams Q;
+            memset(&Q, 0, sizeof Q);
+            Q.n_traj = n_traj;
+            Q.d = d;
+            Q.q = s->cfg.q;
+            Q.dynamic = (s->cfg.diffusion == PNODE_DIFF_DYNAMIC);
+            Q.calibrate = s->cfg.calibrate;
+            Q.initial_diffusion = s->base.initial_diffusion;
+            Q.step_offsets = P.step_offsets;
+            Q.s_h = d_h;
+            Q.s_diffusion = P.s_diffusion;
+            Q.gdiff = P.diffusion;
+            Q.s_x_mean = P.s_x_mean;
+            Q.s_x_covfac = P.s_x_covfac;
+            Q.s_u_mean = P.s_u_mean;
+            Q.s_u_cov = P.s_u_cov;
+            memcpy(Q.L, s->base.L, sizeof Q.L);
+            Q.work_counter = s->d_counter;
+            const int n = s->cfg.q + 1;
+            const size_t per_warp = (size_t)(7 * D * D + 4 * D + 2 * n * n + 2 * n) * sizeof(double);
+            int warps = PN_SM_WARPS;
+            while (warps > 1 && per_warp * warps > 200 * 1024) warps--;
+            const size_t smem = per_warp * warps;
+            if (smem > 220 * 1024) return fail(PNODE_ERR_UNSUPPORTED, "state dimension too large for the shared-memory smoother");
+            const void* fn = pn_smooth_kernel_ptr();
+            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            int nblk = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, 32 * warps, smem));
+            if (nblk < 1) return fail(PNODE_ERR_CUDA, "smoother kernel does not fit on an SM");
+            long long want = (n_traj + warps - 1) / warps;
+            unsigned grid = (unsigned)std::max(1LL, std::min(want, (long long)s->n_sm * nblk));
+            CUDA_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), s->stream));
+            void* args[] = {&Q};
+            CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(32 * warps), args, smem, s->stream));
+            CUDA_TRY(cudaFreeAsync(d_h, s->stream));
+            launches = 3;
+        }
         if (s->cfg.diffusion == PNODE_DIFF_FIXED) {
             /* DIFFUSION holds sigma_hat^2 * initial (calibrate) or the constant initial diffusion */
             const double* scale = nullptr;
-            if (s->cfg.calibrate) {
+            if (s->cfg.calibrate && !s->cfg.smooth) { /* the smoother sweep already applied the calibration */
                 /* scale = sigma_hat^2 = diffusion / initial_diffusion; the kernel wrote diffusion = mle * initial */
                 scale = P.diffusion;
             }
@@ -596,7 +646,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             }
             pn_calibrate_saved<<<blocks, thr, 0, s->stream>>>((long long)T, (long long)N, P.step_offsets, scale,
                                                              P.diffusion, d * d, P.s_u_cov, P.s_diffusion);
-            launches = 3;
+            launches += 1;
         }
         r->info.total_saved = (int64_t)T;
     }

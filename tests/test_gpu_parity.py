@@ -275,3 +275,86 @@ def test_full_size_properties_rober_1m():
     g3 = _gpu(pd, u0c, pc, 3, t0=0.0, t1=100.0)
     assert np.all(g3["u"] == g3["u"][0]) and np.all(g3["naccept"] == g3["naccept"][0])
     assert np.array_equal(g3["u"][0], g["u"][0])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# smoother (BASELINE cfg1 / cfg3: filter + RTS smoother)
+# ------------------------------------------------------------------------------------------------------------------
+def _gpu_smooth(pd, u0, p, q, **kw):
+    src = tracer.cuda_source(tracer.trace(pd.f, pd.d, pd.n_p), "UserProb")
+    cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="UserProb", rhs_src=src, smooth=True, save_everystep=True,
+                          save_state=True, **kw)
+    s = lib.Solver(cfg)
+    r = s.solve(u0, p)
+    n, d = u0.shape
+    D = d * (q + 1)
+    out = dict(off=r.field(lib.F_STEP_OFFSETS), T=r.field(lib.F_T), U=r.field(lib.F_U).reshape(-1, d),
+               C=r.field(lib.F_U_COV).reshape(-1, d, d), X=r.field(lib.F_X).reshape(-1, D),
+               XR=r.field(lib.F_X_COVFAC).reshape(-1, D, D), Df=r.field(lib.F_DIFFUSIONS), naccept=r.field(lib.F_NACCEPT),
+               u=r.field(lib.F_U_FINAL).reshape(n, d), info=r.info)
+    r.free()
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("calibrate", [True, False])
+def test_cfg1_smoother_fixed_steps_static_diffusion(oracle, calibrate):
+    """BASELINE cfg1 with FixedDiffusion: smoothed means and covariances of all 2001 points, rtol 1e-10."""
+    pd, u0, p = _inputs("fitzhugh_nagumo", 2, 7, dp=0.05)
+    g = _gpu_smooth(pd, u0, p, 3, adaptive=False, dt=0.01, t0=0.0, t1=20.0, diffusion=lib.DIFF_FIXED, calibrate=calibrate)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    for i in range(u0.shape[0]):
+        o = oracle.solve(oracle.make_config(2, 3, 3, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=calibrate, smooth=True,
+                                            adaptive=False, dt=0.01, t0=0.0, t1=20.0, cov_backend=oracle.COV_QR), rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"] == 2001
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < 1e-10
+        assert not g["C"][a].any()                                   # exact initial value (test/solution.jl:59-62)
+        # full smoothed state: means norm-wise on the u-block, covariances as R'R
+        Sg = np.einsum("kra,krb->kab", g["XR"][a:b], g["XR"][a:b])
+        So = np.einsum("kra,krb->kab", o["x_smooth_R"], o["x_smooth_R"])
+        assert _relcov(Sg[1:], So[1:]) < 1e-9
+        # higher-derivative blocks of the state are conditioned much worse than the u-block (SURVEY.md H0)
+        assert _rel(g["X"][a:b], o["x_smooth_mu"]) < 1e-6
+        assert _rel(g["X"][a:b, :2], o["x_smooth_mu"][:, :2]) < 1e-10
+        assert _rel(g["Df"][a:b - 1], o["diffusions"][:-1]) < 1e-10
+
+
+def test_smoother_dynamic_diffusion_teacher_forced_and_free(oracle):
+    pd, u0, p = _inputs("fitzhugh_nagumo", 1, 8, dp=0.0)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC, smooth=True, adaptive=False, dt=0.01, t0=0.0, t1=20.0)
+    o = oracle.solve(oracle.make_config(2, 3, 3, cov_backend=oracle.COV_QR, **kw), rhs, u0[0], p[0])
+    g = _gpu_smooth(pd, u0, p, 3, adaptive=False, dt=0.01, t0=0.0, t1=20.0)
+    assert _rel(g["U"], o["pu_mu"]) < 1e-8       # measured oracle-vs-oracle floor 5e-10 (SURVEY.md H0)
+    assert _relcov(g["C"][1:], o["pu_cov"][1:]) < 1e-4  # floor 8e-7
+    sig = o["diffusions"][:-1]
+    o2 = oracle.solve(oracle.make_config(2, 3, 3, cov_backend=oracle.COV_QR, forced_diffusion=sig, **kw), rhs, u0[0], p[0])
+    g2 = _gpu_smooth(pd, u0, p, 3, adaptive=False, dt=0.01, t0=0.0, t1=20.0, forced_diffusion=sig)
+    # the forced sigma^2 sequence spans 40 orders of magnitude (its first entries are rounding noise, ~1e35), which
+    # degrades the conditioning of the smoothing gain: hold the kernel to 1e-10 or to the oracle's own floor
+    kwf = dict(cov_backend=oracle.COV_QR, forced_diffusion=sig, **kw)
+    fm = rounding.floor(oracle, rhs, 2, 3, 3, u0[0], p[0], kwf, o2, lambda s_, b_: _rel(s_["pu_mu"], b_["pu_mu"]), ulp_components=[])
+    fc = rounding.floor(oracle, rhs, 2, 3, 3, u0[0], p[0], kwf, o2, lambda s_, b_: _relcov(s_["pu_cov"][1:], b_["pu_cov"][1:]),
+                        ulp_components=[])
+    assert _rel(g2["U"], o2["pu_mu"]) < max(1e-10, 10 * fm), (fm,)
+    assert _relcov(g2["C"][1:], o2["pu_cov"][1:]) < max(1e-10, 10 * fc), (fc,)
+
+
+@pytest.mark.parametrize("name,q,t1", [("lotka_volterra", 3, 10.0), ("rober", 3, 100.0)])
+def test_smoother_adaptive(oracle, name, q, t1):
+    n = 6
+    pd, u0, p = _inputs(name, n, 9, du0=0.05 if name != "rober" else 0.0)
+    g = _gpu_smooth(pd, u0, p, q, adaptive=True, t0=0.0, t1=t1)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    for i in range(n):
+        o = oracle.solve(oracle.make_config(pd.d, q, pd.n_p, alg=oracle.EK1, smooth=True, adaptive=True, t0=0.0, t1=t1,
+                                            cov_backend=oracle.COV_QR), rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"]
+        scale = np.abs(o["pu_mu"]).max(axis=0)
+        dT = np.abs(g["T"][a:b] - o["t"])
+        du = np.abs(np.gradient(o["pu_mu"], o["t"], axis=0)).max(axis=0)
+        assert np.all(np.abs(g["U"][a:b] - o["pu_mu"]) <= 1e-7 * scale + 4.0 * du * dT[:, None])
+        assert np.max(np.abs(g["U"][b - 1] - o["pu_mu"][-1]) / scale) < 1e-8
