@@ -1,8 +1,10 @@
 // pn_params.h -- plain-old-data kernel parameter block shared by host (pnode_api.cu) and device code.
 // NVRTC-compatible: no standard headers.
-#pragma once
+#ifndef PN_PARAMS_H
+#define PN_PARAMS_H
 
 #define PN_MAX_N 12 /* q + 1 <= 12 */
+#define PN_INF (__longlong_as_double(0x7ff0000000000000LL))
 
 enum PnRetcode { PN_RET_SUCCESS = 0, PN_RET_MAXITERS = 1, PN_RET_DTLESSTHANMIN = 2, PN_RET_UNSTABLE = 3 };
 
@@ -50,3 +52,5 @@ struct PnParams {
     double* s_x_covfac;            /* [total][D][D]   (smoothing only) */
     double* s_h;                   /* [total] step size of the step k -> k+1 at slot k (smoothing only) */
 };
+
+#endif /* PN_PARAMS_H */

@@ -26,7 +26,8 @@
 // All arithmetic is FP64; tensor cores are not used (per-trajectory matrices are <= 32 x 32).
 //
 // NVRTC-compatible: no standard headers.
-#pragma once
+#ifndef PN_SMALL_CUH
+#define PN_SMALL_CUH
 #include "pn_params.h"
 #include "pn_taylor.cuh"
 
@@ -112,6 +113,47 @@ PN_HD void pn_chol_solve(const double (&U)[M_][M_], const double (&invd)[M_], do
             if (k > a) x[a] -= U[a][k] * x[k];
         x[a] *= invd[a];
     }
+}
+
+// ode_determine_initdt (OrdinaryDiffEqCore, Hairer-Wanner; restated from SURVEY.md A.6).  Two f evaluations.
+template <class Prob>
+PN_HD double pn_initial_dt(const PnParams& P, const double* u0, const double* pr) {
+    constexpr int d = Prob::d;
+    double dt;
+    double sk[d], f0[d], f1[d], u1[d];
+    const double epst = fabs(P.t0) > 0.0 ? (nextafter(fabs(P.t0), 1e300) - fabs(P.t0)) : 4.9406564584124654e-324;
+    const double dtmin = nextafter(fmax(P.dtmin, epst), 1e300);
+    const double smalldt = fmax(dtmin, 1e-6);
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+    Prob::template f<double>(f0, u0, pr, P.t0);
+#pragma unroll
+    for (int i = 0; i < d; i++) {
+        sk[i] = P.abstol + fabs(u0[i]) * P.reltol;
+        const double a = u0[i] / sk[i], b = f0[i] / sk[i];
+        d0 += a * a;
+        d1 += b * b;
+    }
+    d0 = sqrt(d0 / (double)d);
+    d1 = sqrt(d1 / (double)d);
+    double dta = (d0 < 1e-5 || d1 < 1e-5) ? smalldt : (d0 / d1) / 100.0;
+    dta = fmin(dta, P.dtmax);
+    if (dta < 10.0 * 2.220446049250313e-16) {
+        dt = fmax(smalldt, dtmin);
+    } else {
+#pragma unroll
+        for (int i = 0; i < d; i++) u1[i] = u0[i] + dta * f0[i];
+        Prob::template f<double>(f1, u1, pr, P.t0 + dta);
+#pragma unroll
+        for (int i = 0; i < d; i++) {
+            const double c = (f1[i] - f0[i]) / sk[i];
+            d2 += c * c;
+        }
+        d2 = sqrt(d2 / (double)d) / dta;
+        const double mx = fmax(d1, d2);
+        const double dtb = (mx <= 1e-15) ? fmax(1e-6, dta * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / (double)P.order);
+        dt = fmax(dtmin, fmin(fmin(100.0 * dta, dtb), P.dtmax));
+    }
+    return dt;
 }
 
 template <class Prob, int Q, int G, bool ADAPTIVE, bool DYNAMIC, int SAVE>
@@ -544,7 +586,7 @@ struct PnSmall {
                         bool zz = true;
 #pragma unroll
                         for (int a = 0; a < d; a++) zz = zz && (z[a] == 0.0);
-                        loglik += zz ? 1e308 * 10.0 : -1e308 * 10.0;
+                        loglik += zz ? PN_INF : -PN_INF;
                     } else {
                         loglik += -0.5 * quad - 0.5 * (double)d * 1.8378770664093453 - logdet;
                         if (!DYNAMIC) { /* estimate_global_diffusion(::FixedDiffusion), calibration.jl:49-66 */
@@ -735,42 +777,7 @@ struct PnSmall {
         pn_taylor_init<Prob, Q>(mu, u0, pr, P.t0);
         nf = Q;
         if (ADAPTIVE && !(P.dt0 > 0.0)) {
-            /* ode_determine_initdt (OrdinaryDiffEqCore) */
-            double sk[d], f0[d], f1[d], u1[d];
-            const double epst =
-                fabs(P.t0) > 0.0 ? (nextafter(fabs(P.t0), 1e300) - fabs(P.t0)) : 4.9406564584124654e-324;
-            const double dtmin = nextafter(fmax(P.dtmin, epst), 1e300);
-            const double smalldt = fmax(dtmin, 1e-6);
-            double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-            Prob::template f<double>(f0, u0, pr, P.t0);
-#pragma unroll
-            for (int i = 0; i < d; i++) {
-                sk[i] = P.abstol + fabs(u0[i]) * P.reltol;
-                const double a = u0[i] / sk[i], b = f0[i] / sk[i];
-                d0 += a * a;
-                d1 += b * b;
-            }
-            d0 = sqrt(d0 / (double)d);
-            d1 = sqrt(d1 / (double)d);
-            double dta = (d0 < 1e-5 || d1 < 1e-5) ? smalldt : (d0 / d1) / 100.0;
-            dta = fmin(dta, P.dtmax);
-            if (dta < 10.0 * 2.220446049250313e-16) {
-                dt = fmax(smalldt, dtmin);
-            } else {
-#pragma unroll
-                for (int i = 0; i < d; i++) u1[i] = u0[i] + dta * f0[i];
-                Prob::template f<double>(f1, u1, pr, P.t0 + dta);
-#pragma unroll
-                for (int i = 0; i < d; i++) {
-                    const double c = (f1[i] - f0[i]) / sk[i];
-                    d2 += c * c;
-                }
-                d2 = sqrt(d2 / (double)d) / dta;
-                const double mx = fmax(d1, d2);
-                const double dtb =
-                    (mx <= 1e-15) ? fmax(1e-6, dta * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / (double)P.order);
-                dt = fmax(dtmin, fmin(fmin(100.0 * dta, dtb), P.dtmax));
-            }
+            dt = pn_initial_dt<Prob>(P, u0, pr);
             nf += 2;
         } else {
             dt = P.dt0;
@@ -788,3 +795,5 @@ template <class Prob, int Q, int G, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 __device__ __forceinline__ void pn_small_entry(const PnParams& P) {
     PnSmall<Prob, Q, G, ADAPTIVE, DYNAMIC, SAVE>::run(P);
 }
+
+#endif /* PN_SMALL_CUH */

@@ -17,7 +17,8 @@
 // working set in shared memory; the arithmetic follows the reference formulas literally.
 //
 // NVRTC-compatible: no standard headers.
-#pragma once
+#ifndef PN_SMOOTH_CUH
+#define PN_SMOOTH_CUH
 #include "pn_params.h"
 
 struct PnSmoothParams {
@@ -259,3 +260,5 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
 }
 
 #endif /* PN_SMOOTH_DECL_ONLY */
+
+#endif /* PN_SMOOTH_CUH */

@@ -6,7 +6,8 @@
 // filter mean (after conditioning on them Sigma_0.R == 0 exactly).
 //
 // NVRTC-compatible: no standard headers.
-#pragma once
+#ifndef PN_TAYLOR_CUH
+#define PN_TAYLOR_CUH
 
 #ifndef PN_HD
 #define PN_HD __device__ __forceinline__
@@ -271,3 +272,5 @@ PN_HD void pn_taylor_init(double* out, const double* u0, const double* p, double
         for (int i = 0; i < d; i++) out[k * d + i] = U[i].c[k] * fact;
     }
 }
+
+#endif /* PN_TAYLOR_CUH */

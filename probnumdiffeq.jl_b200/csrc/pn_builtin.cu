@@ -10,7 +10,13 @@
     { "builtin:" NAME ":small:q" #Q ":g" #G ":a" #A ":dyn" #DY ":s" #S, \
       (const void*)&pn_small_kernel<PROB, Q, G, (A != 0), (DY != 0), S>, PROB::d, PROB::n_p }
 
+#define PN_ENTRY_KRON(NAME, PROB, Q, A, DY, S) \
+    { "builtin:" NAME ":kron:q" #Q ":g1:a" #A ":dyn" #DY ":s" #S, \
+      (const void*)&pn_kron_kernel<PROB, Q, (A != 0), (DY != 0), S>, PROB::d, PROB::n_p }
+
 static const PnBuiltinEntry g_table[] = {
+    /* cfg2: Lotka-Volterra EK0(order=3), adaptive, filter only, 1M trajectories */
+    PN_ENTRY_KRON("lotka_volterra", PnLotkaVolterra, 3, 1, 1, 0),
     /* cfg5: ROBER / OREGO stiff EK1(order=3), adaptive, filter only (bench.py headline) */
     PN_ENTRY("rober", PnRober, 3, 4, 1, 1, 0),
     PN_ENTRY("orego", PnOrego, 3, 4, 1, 1, 0),

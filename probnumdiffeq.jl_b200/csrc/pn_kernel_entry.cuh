@@ -22,3 +22,11 @@ template <class Prob, int Q, int G, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_small_kernel(const __grid_constant__ PnParams P) {
     pn_small_entry<Prob, Q, G, ADAPTIVE, DYNAMIC, SAVE>(P);
 }
+
+#include "kernels/pn_kron.cuh"
+
+/* EK0 / IsometricKronecker: one thread per trajectory */
+template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
+__global__ void __launch_bounds__(128) pn_kron_kernel(const __grid_constant__ PnParams P) {
+    pn_kron_entry<Prob, Q, ADAPTIVE, DYNAMIC, SAVE>(P);
+}

@@ -134,6 +134,7 @@ struct pnode_solver {
     std::string rhs_src, rhs_name;
     int D = 0, G = 4, n_sm = 0;
     bool builtin = false;
+    bool kron = false; /* EK0: IsometricKronecker layout, one thread per trajectory */
     Kernel k_final;  /* SAVE = 0 */
     Kernel k_save;   /* SAVE = 1 */
     cudaStream_t stream = nullptr;
@@ -189,20 +190,25 @@ static int auto_lanes(int D) {
 
 static std::string kernel_key(const pnode_solver* s, int save) {
     char buf[256];
-    snprintf(buf, sizeof buf, "%s:small:q%d:g%d:a%d:dyn%d:s%d", s->rhs_name.c_str(), s->cfg.q, s->G,
+    snprintf(buf, sizeof buf, "%s:%s:q%d:g%d:a%d:dyn%d:s%d", s->rhs_name.c_str(), s->kron ? "kron" : "small", s->cfg.q, s->G,
              s->cfg.adaptive ? 1 : 0, s->cfg.diffusion == PNODE_DIFF_DYNAMIC ? 1 : 0, save);
     return buf;
 }
 
 /* NVRTC: user RHS + step kernels -> sm_100a CUBIN.  Needs no device. */
 static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_name, int q, int G, bool adaptive,
-                       bool dynamic, int save, std::vector<char>* cubin, int threads = PN_THREADS, int min_blocks = 1) {
+                       bool dynamic, int save, std::vector<char>* cubin, int threads = PN_THREADS, int min_blocks = 1,
+                       bool kron = false) {
     std::string src;
     src += "#include \"pn_kernel_entry.cuh\"\n";
     src += rhs_src;
-    src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_entry(const __grid_constant__ "
-           "PnParams P) {\n  pn_small_entry<" +
-           struct_name + ", PN_Q, PN_G, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
+    if (kron)
+        src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS) pn_entry(const __grid_constant__ PnParams P) {\n"
+               "  pn_kron_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
+    else
+        src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_entry(const "
+               "__grid_constant__ PnParams P) {\n  pn_small_entry<" +
+               struct_name + ", PN_Q, PN_G, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
     nvrtcProgram prog;
     const char* hdr_src[PN_N_EMBEDDED];
     const char* hdr_name[PN_N_EMBEDDED];
@@ -261,9 +267,9 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
         src = "#include \"kernels/pn_builtin_problems.cuh\"\n";
         name = sn;
     }
-    out->threads = env_int("PNODE_THREADS", PN_THREADS);
+    out->threads = s->kron ? 128 : env_int("PNODE_THREADS", PN_THREADS);
     rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0,
-                     s->cfg.diffusion == PNODE_DIFF_DYNAMIC, save, &cubin, out->threads, env_int("PNODE_MIN_BLOCKS", 1));
+                     s->cfg.diffusion == PNODE_DIFF_DYNAMIC, save, &cubin, out->threads, env_int("PNODE_MIN_BLOCKS", 1), s->kron);
     if (rc) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
@@ -286,8 +292,9 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
         for (int i = 0; i < n; i++) {
             if (key == tab[i].key) {
                 out->rt_fn = tab[i].fn;
+                out->threads = s->kron ? 128 : PN_THREADS;
                 int nblk = 0;
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, out->rt_fn, PN_THREADS, 0));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, out->rt_fn, out->threads, 0));
                 if (nblk < 1) return fail(PNODE_ERR_CUDA, "kernel does not fit on an SM");
                 out->blocks_per_sm = nblk;
                 return 0;
@@ -322,8 +329,12 @@ static int validate_config(const pnode_config* cfg) {
     if (cov == PNODE_COV_AUTO) cov = PNODE_COV_DENSE; /* Kronecker fast path: see pn_kron (EK0) */
     if (cov == PNODE_COV_KRONECKER && cfg->alg != PNODE_EK0)
         return fail(PNODE_ERR_ARGUMENT, "IsometricKroneckerCovariance requires the EK0"); /* algorithms.jl:101-110 */
-    if (cfg->alg == PNODE_EK0) return fail(PNODE_ERR_UNSUPPORTED, "EK0 is not implemented yet in this build");
-    if (D > 32) return fail(PNODE_ERR_UNSUPPORTED, "D = d(q+1) > 32 needs the CTA-per-trajectory kernel (not in this build)");
+    if (cfg->alg == PNODE_EK0 && cov == PNODE_COV_DENSE && cfg->cov != PNODE_COV_AUTO)
+        return fail(PNODE_ERR_UNSUPPORTED, "EK0 with an IWP prior uses the IsometricKronecker layout (src/algorithms.jl:132-151)");
+    if (cfg->alg == PNODE_EK0 && cfg->q > 7)
+        return fail(PNODE_ERR_UNSUPPORTED, "EK0 thread-per-trajectory kernel supports order <= 7");
+    if (cfg->alg == PNODE_EK1 && D > 32)
+        return fail(PNODE_ERR_UNSUPPORTED, "D = d(q+1) > 32 needs the CTA-per-trajectory kernel (not in this build)");
     if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 2 && cfg->lanes_per_traj != 4 && cfg->lanes_per_traj != 8 &&
         cfg->lanes_per_traj != 16 && cfg->lanes_per_traj != 32)
         return fail(PNODE_ERR_ARGUMENT, "lanes_per_traj must be one of 0 (auto), 2, 4, 8, 16, 32");
@@ -343,7 +354,7 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     const int G = cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D);
     std::vector<char> cubin;
     rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, cfg->diffusion == PNODE_DIFF_DYNAMIC,
-                     cfg->save_everystep ? 1 : 0, &cubin);
+                     cfg->save_everystep ? (cfg->smooth ? 2 : 1) : 0, &cubin, PN_THREADS, 1, cfg->alg == PNODE_EK0);
     if (rc) return rc;
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
     return 0;
@@ -366,7 +377,8 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     if (!s->builtin) s->rhs_src = cfg->rhs_src;
     s->cfg.rhs_src = nullptr;
     s->cfg.rhs_name = nullptr;
-    s->G = cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D);
+    s->kron = (cfg->alg == PNODE_EK0);
+    s->G = s->kron ? 1 : (cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D));
     /* ---- constants ---- */
     PnParams& B = s->base;
     memset(&B, 0, sizeof B);
