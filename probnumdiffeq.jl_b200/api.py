@@ -246,3 +246,34 @@ def _unpack(res, n, d, save_everystep) -> List[ProbODESolution]:
             sols.append(ProbODESolution(np.array([te[i]]), uf[i:i + 1], cf[i:i + 1], None,
                                         Stats(int(nf[i]), int(na[i]), int(nr[i])), float(ll[i]), L.RETCODES[int(rc[i])]))
     return sols
+
+
+# ---- multi-GPU: trajectory sharding + optional NCCL statistics ---------------------------------------------------
+def shard_range(n_traj: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous trajectory range [lo, hi) of `rank`: floor split, remainder to the low ranks."""
+    base, rem = divmod(n_traj, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def ensemble_statistics(u_final: np.ndarray, group=None):
+    """Ensemble mean and covariance of the final solution values over ALL ranks.
+
+    The only collective of the whole path: one all-reduce (sum) of `1 + d + d*d` doubles (count, first and second
+    moments).  With `torch.distributed` initialised on the `nccl` backend the moments are reduced on the GPUs over
+    NVLink/NVSwitch; with `gloo` (CPU tests) on the host; without an initialised process group it is the local result."""
+    import torch
+    import torch.distributed as dist
+
+    u = np.ascontiguousarray(u_final, dtype=np.float64)
+    d = u.shape[1]
+    mom = np.concatenate([[float(u.shape[0])], u.sum(axis=0), (u.T @ u).ravel()])
+    if dist.is_available() and dist.is_initialized():
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.from_numpy(mom).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        mom = t.cpu().numpy()
+    n = mom[0]
+    mean = mom[1:1 + d] / n
+    cov = mom[1 + d:].reshape(d, d) / n - np.outer(mean, mean)
+    return int(n), mean, cov

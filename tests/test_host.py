@@ -19,7 +19,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol(pnlib):
     hdr = open(os.path.join(ROOT, "include", "pnode.h")).read()
-    declared = set(re.findall(r"^(?:int|void|double|int64_t|const char\*|const void\*)\s+(pnode_[a-z_]+)\s*\(", hdr, re.M))
+    declared = set(re.findall(r"^(?:int|void|double|int64_t|const char\*|const void\*)\s+(pnode_[a-z0-9_]+)\s*\(", hdr, re.M))
     assert declared, "no declarations found"
     L = pnlib.load()
     for name in sorted(declared):
