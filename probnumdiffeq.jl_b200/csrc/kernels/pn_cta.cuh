@@ -1,0 +1,535 @@
+// pn_cta.cuh -- CTA-per-trajectory ODE-filter kernel for large filter states (D = d(q+1) > 32, e.g. Pleiades
+// d = 28, q = 3, D = 112).  One 256-thread CTA owns one trajectory for its whole adaptive time loop; the right
+// factor R (D x D) is staged in shared memory (98 KB at D = 112) and never leaves the SM.
+//
+// Shared-memory budget: the dense 2D x D stack of predict_cov! (196 KB) does not fit next to the
+// update workspace, so the stack is never materialised:
+//   1. X = R Ah' in place (row-local, Ah = T (x) I_d),
+//   2. Householder QR of X in place  ->  upper-triangular R1,
+//   3. the process-noise block sqrt(s2) (L P^-1) (x) I_d is folded into R1 one derivative level at a time
+//      (a d x D batch, 25 KB): QR of [R1 ; batch] touches only the pivot row of R1 and the d batch rows per column.
+// The result has the same R'R as qr([R Ah' ; sqrt(s2) Qh.R]) of src/filtering/predict.jl:62-94.
+// The measurement update uses H = [-J | I | 0...]: R^- H' is zero in rows >= 2d, so K, S and the Joseph update only
+// touch the first 2d rows (src/filtering/update.jl:65-139).
+//
+// Everything is FP64 on the vector pipe; thread j owns column j in the QR updates (conflict-free shared-memory
+// access, the Householder vector is a broadcast read).
+//
+// NVRTC-compatible: no standard headers.
+#ifndef PN_CTA_CUH
+#define PN_CTA_CUH
+#include "pn_params.h"
+#include "pn_taylor.cuh"
+#include "pn_small.cuh" /* pn_initial_dt */
+
+#define PN_CTA_THREADS 256
+
+struct PnCtaShared {
+    double red[PN_CTA_THREADS / 32];
+    double hp[PN_MAX_N], PIv[PN_MAX_N];
+    double t, dt, h, tnew, tstop, EEst, qq, q11, lEE, qold, qold_pb2, ediff, ldiff, loglik, gdiff, dtcache;
+    double total, quad;
+    long long traj, naccept, nreject, nf, iter, tstop_idx, save_pos;
+    int retcode, accept, finished, okflag;
+};
+
+template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
+struct PnCta {
+    static constexpr int d = Prob::d;
+    static constexpr int n = Q + 1;
+    static constexpr int D = d * n;
+    static constexpr int NPA = Prob::n_p > 0 ? Prob::n_p : 1;
+    static constexpr int NT = PN_CTA_THREADS;
+    /* doubles of dynamic shared memory */
+    static constexpr int SM_DOUBLES = D * D + d * D + 2 * d * d /*C2*/ + 2 * d * d /*V*/ + D * d /*K*/ + d * d /*S*/ +
+                                      d * d /*J*/ + 3 * D /*mu,mup,tmp*/ + 4 * d /*z,zt,fu,uprev*/ + NPA +
+                                      (int)((sizeof(PnCtaShared) + 7) / 8);
+
+    static __device__ __forceinline__ double block_sum(double x, PnCtaShared* sh) {
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sh->red[threadIdx.x >> 5] = x;
+        __syncthreads();
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NT / 32; w++) s += sh->red[w];
+        return s;
+    }
+
+    // In-place upper Cholesky of the symmetric m x m matrix A (row-major, upper part read); inv diag in invd.
+    static __device__ void chol_sm(double* A, double* invd, int m, int* okflag) {
+        const int tid = threadIdx.x;
+        for (int j = 0; j < m; j++) {
+            __syncthreads();
+            const double s = A[j * m + j];
+            if (tid == 0 && !(s > 0.0)) *okflag = 0;
+            const double ujj = sqrt(s), inv = 1.0 / ujj;
+            __syncthreads();
+            for (int i = j + tid; i < m; i += NT) A[j * m + i] = (i == j) ? ujj : A[j * m + i] * inv;
+            if (tid == 0) invd[j] = inv;
+            __syncthreads();
+            /* trailing update A[i][k] -= U[j][i] U[j][k], j < i <= k */
+            const int rem = m - j - 1;
+            for (int e = tid; e < rem * rem; e += NT) {
+                const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+                if (k >= i) A[i * m + k] -= A[j * m + i] * A[j * m + k];
+            }
+        }
+        __syncthreads();
+    }
+    // x <- (U'U)^-1 x, serial (one thread), x in shared memory
+    static __device__ void chol_solve_serial(const double* U, const double* invd, double* x, int m) {
+        for (int a = 0; a < m; a++) {
+            double s = x[a];
+            for (int k = 0; k < a; k++) s -= U[k * m + a] * x[k];
+            x[a] = s * invd[a];
+        }
+        for (int a = m - 1; a >= 0; a--) {
+            double s = x[a];
+            for (int k = a + 1; k < m; k++) s -= U[a * m + k] * x[k];
+            x[a] = s * invd[a];
+        }
+    }
+
+    static __device__ void run(const PnParams& P) {
+        extern __shared__ double pn_cta_sm[];
+        const int tid = threadIdx.x;
+        double* R = pn_cta_sm;
+        double* Bt = R + D * D;
+        double* C2 = Bt + d * D;
+        double* V = C2 + 2 * d * d;
+        double* K = V + 2 * d * d;
+        double* S = K + D * d;
+        double* J = S + d * d;
+        double* mu = J + d * d;
+        double* mup = mu + D;
+        double* sinv = mup + D; /* D doubles of scratch: first d used as inverse Cholesky diagonal */
+        double* z = sinv + D;
+        double* zt = z + d;
+        double* fu = zt + d;
+        double* uprev = fu + d;
+        double* pr = uprev + d;
+        PnCtaShared* sh = (PnCtaShared*)(pr + NPA);
+
+        for (;;) {
+            /* ---- fetch ---- */
+            __syncthreads();
+            if (tid == 0) sh->traj = (long long)atomicAdd(P.work_counter, 1ULL);
+            __syncthreads();
+            const long long traj = sh->traj;
+            if (traj >= P.n_traj) break;
+            if (tid == 0) {
+                double u0[d], mu0[D], prr[NPA];
+                for (int i = 0; i < d; i++) u0[i] = P.u0[traj * d + i];
+                for (int i = 0; i < Prob::n_p; i++) prr[i] = P.p[traj * Prob::n_p + i];
+                pn_taylor_init<Prob, Q>(mu0, u0, prr, P.t0);
+                for (int c = 0; c < D; c++) mu[c] = mu0[c];
+                for (int i = 0; i < d; i++) uprev[i] = u0[i];
+                for (int i = 0; i < Prob::n_p; i++) pr[i] = prr[i];
+                sh->t = P.t0;
+                sh->nf = Q;
+                if (ADAPTIVE && !(P.dt0 > 0.0)) {
+                    sh->dt = pn_initial_dt<Prob>(P, u0, prr);
+                    sh->nf += 2;
+                } else {
+                    sh->dt = P.dt0;
+                }
+                sh->dtcache = sh->dt;
+                sh->naccept = sh->nreject = sh->iter = sh->tstop_idx = 0;
+                sh->loglik = sh->gdiff = sh->ldiff = 0.0;
+                sh->qold = P.qoldinit;
+                sh->qold_pb2 = P.qoldinit_pb2;
+                sh->retcode = PN_RET_SUCCESS;
+                sh->finished = 0;
+                sh->save_pos = 0;
+                if (SAVE >= 1) {
+                    long long sp = P.step_offsets ? P.step_offsets[traj] : 0;
+                    if (P.step_offsets) {
+                        P.s_t[sp] = P.t0;
+                        P.s_diffusion[sp] = 0.0;
+                        for (int i = 0; i < d; i++) P.s_u_mean[sp * d + i] = u0[i];
+                        for (int i = 0; i < d * d; i++) P.s_u_cov[sp * d * d + i] = 0.0;
+                    }
+                    sh->save_pos = sp + 1;
+                }
+            }
+            for (int e = tid; e < D * D; e += NT) R[e] = 0.0;
+            __syncthreads();
+
+            /* ---- adaptive time loop ---- */
+            while (!sh->finished) {
+                /* phase 1a: scalars (thread 0) */
+                if (tid == 0) {
+                    double t = sh->t, dt = sh->dt, tstop = P.t1;
+                    long long ti = sh->tstop_idx;
+                    while (ti < P.n_tstops && P.tstops[ti] <= t) ti++;
+                    if (ti < P.n_tstops && P.tstops[ti] < P.t1) tstop = P.tstops[ti];
+                    sh->tstop_idx = ti;
+                    sh->iter++;
+                    if (!(t < P.t1)) {
+                        sh->finished = 1;
+                    } else if (sh->iter > P.maxiters) {
+                        sh->retcode = PN_RET_MAXITERS;
+                        sh->finished = 1;
+                    } else {
+                        if (ADAPTIVE) {
+                            dt = fmin(dt, P.dtmax);
+                            dt = fmax(dt, P.dtmin);
+                            dt = fmin(dt, tstop - t);
+                        } else {
+                            dt = fmin(sh->dtcache, tstop - t);
+                        }
+                        if (dt != dt || !(t + dt > t) || (ADAPTIVE && dt <= P.dtmin)) {
+                            sh->retcode = PN_RET_DTLESSTHANMIN;
+                            sh->finished = 1;
+                        }
+                        sh->dt = dt;
+                        sh->h = dt;
+                        sh->tnew = t + dt;
+                        sh->tstop = tstop;
+                        sh->hp[0] = 1.0;
+                        for (int k = 1; k < n; k++) sh->hp[k] = sh->hp[k - 1] * dt / (double)k;
+                        const double sqh = sqrt(dt);
+                        for (int c = 0; c < n; c++) sh->PIv[c] = sh->hp[Q - c] * sqh;
+                    }
+                }
+                __syncthreads();
+                if (sh->finished) break;
+                const double h = sh->h;
+                /* predict_mean! */
+                for (int c = tid; c < D; c += NT) {
+                    const int j = c / d, i = c - j * d;
+                    double s = mu[c];
+                    for (int k = j + 1; k < n; k++) s += sh->hp[k - j] * mu[k * d + i];
+                    mup[c] = s;
+                }
+                __syncthreads();
+                /* measurement: f on one thread, J on another warp */
+                if (tid == 0) Prob::template f<double>(fu, mup, pr, sh->tnew);
+                if (tid == 32) Prob::jac(J, mup, pr, sh->tnew);
+                __syncthreads();
+                for (int i = tid; i < d; i += NT) z[i] = mup[d + i] - fu[i];
+                if (tid == 0) sh->nf += 1;
+                if (ADAPTIVE || DYNAMIC) {
+                    /* W = C'C, C[(m,i),a] = -LQ[m][0] J[a][i] + (i==a) LQ[m][1]   (calibration.jl:123-133) */
+                    for (int e = tid; e < d * d; e += NT) {
+                        const int a = e / d, b = e - a * d;
+                        if (b < a) continue;
+                        double s = 0.0;
+                        for (int m = 0; m < n; m++) {
+                            const double l0 = P.L[m * n + 0] * sh->PIv[0];
+                            const double l1 = (m >= 1) ? P.L[m * n + 1] * sh->PIv[1] : 0.0;
+                            for (int i = 0; i < d; i++) {
+                                const double ca = -l0 * J[a + d * i] + ((i == a) ? l1 : 0.0);
+                                const double cb = -l0 * J[b + d * i] + ((i == b) ? l1 : 0.0);
+                                s += ca * cb;
+                            }
+                        }
+                        S[a * d + b] = s;
+                    }
+                    __syncthreads();
+                    for (int i = tid; i < d; i += NT) {
+                        sinv[d + i] = S[i * d + i]; /* W_ii for the error estimate */
+                        zt[i] = z[i];
+                    }
+                    if (tid == 0) sh->okflag = 1;
+                    chol_sm(S, sinv, d, &sh->okflag);
+                    if (tid == 0) {
+                        chol_solve_serial(S, sinv, zt, d);
+                        double qd = 0.0;
+                        for (int a = 0; a < d; a++) qd += z[a] * zt[a];
+                        double ldiff = qd * (1.0 / (double)d);
+                        if (P.forced_diffusion && sh->naccept < P.n_forced) ldiff = P.forced_diffusion[sh->naccept];
+                        sh->ldiff = ldiff;
+                        if (!sh->okflag) {
+                            sh->retcode = PN_RET_UNSTABLE;
+                            sh->finished = 1;
+                        }
+                    }
+                    __syncthreads();
+                }
+                /* error estimate + controller (thread 0) */
+                if (tid == 0 && !sh->finished) {
+                    double EEst = 0.0, qq = 1.0, q11 = 0.0, lEE = 0.0;
+                    int accept = 1;
+                    if (ADAPTIVE) {
+                        double e2 = 0.0;
+                        for (int i = 0; i < d; i++) {
+                            const double isc = 1.0 / (P.abstol + fmax(fabs(mup[i]), fabs(uprev[i])) * P.reltol);
+                            e2 += (sh->ldiff * sinv[d + i]) * (isc * isc);
+                        }
+                        e2 = e2 * (h * h) * (1.0 / (double)d);
+                        EEst = (e2 > 0.0) ? sqrt(e2) : e2;
+                        if (EEst != EEst) {
+                            sh->retcode = PN_RET_UNSTABLE;
+                            sh->finished = 1;
+                        }
+                        if (EEst == 0.0) {
+                            qq = 1.0 / P.qmax;
+                        } else {
+                            lEE = log(EEst);
+                            q11 = exp(P.beta1 * lEE);
+                            qq = q11 / (sh->qold_pb2 * P.gamma);
+                            qq = fmax(1.0 / P.qmax, fmin(1.0 / P.qmin, qq));
+                        }
+                        accept = (EEst < 1.0) && !sh->finished;
+                        if (!accept && !sh->finished) {
+                            sh->nreject++;
+                            sh->dt = sh->dt / fmin(1.0 / P.qmin, q11 / P.gamma);
+                        }
+                    }
+                    sh->EEst = EEst;
+                    sh->qq = qq;
+                    sh->q11 = q11;
+                    sh->lEE = lEE;
+                    sh->accept = accept;
+                    double ediff = DYNAMIC ? sh->ldiff : P.initial_diffusion;
+                    if (P.forced_diffusion && sh->naccept < P.n_forced) ediff = P.forced_diffusion[sh->naccept];
+                    sh->ediff = ediff;
+                }
+                __syncthreads();
+                if (sh->finished) break;
+                if (!sh->accept) continue;
+
+                /* ================= phase 2 ================= */
+                /* 1. X = R Ah' in place (ascending j is safe) */
+                for (int r = tid; r < D; r += NT) {
+                    double* row = R + r * D;
+                    for (int i = 0; i < d; i++)
+                        for (int j = 0; j < n; j++) {
+                            double s = row[j * d + i];
+                            for (int k = j + 1; k < n; k++) s += sh->hp[k - j] * row[k * d + i];
+                            row[j * d + i] = s;
+                        }
+                }
+                __syncthreads();
+                /* 2. Householder QR of X in place */
+                for (int k = 0; k < D; k++) {
+                    double part = 0.0;
+                    for (int r = k + tid; r < D; r += NT) part += R[r * D + k] * R[r * D + k];
+                    const double total = block_sum(part, sh);
+                    const double alpha = R[k * D + k];
+                    if (total > 0.0) {
+                        const double nrm = sqrt(total);
+                        const double beta = -copysign(nrm, alpha);
+                        const double vk = alpha - beta;
+                        const double gam = 1.0 / (total + fabs(alpha) * nrm);
+                        for (int j = k + 1 + tid; j < D; j += NT) {
+                            double s = vk * R[k * D + j];
+                            for (int r = k + 1; r < D; r++) s += R[r * D + k] * R[r * D + j];
+                            s *= gam;
+                            R[k * D + j] -= s * vk;
+                            for (int r = k + 1; r < D; r++) R[r * D + j] -= s * R[r * D + k];
+                        }
+                        __syncthreads();
+                        for (int r = k + tid; r < D; r += NT) R[r * D + k] = (r == k) ? beta : 0.0;
+                    }
+                    __syncthreads();
+                }
+                /* 3. fold sqrt(s2) (L P^-1) (x) I_d into R, one derivative level (d rows) at a time */
+                {
+                    const double sd = (sh->ediff == 1.0) ? 1.0 : sqrt(sh->ediff);
+                    for (int m = 0; m < n; m++) {
+                        if (sh->ediff == 0.0) break; /* predict.jl:71-74: no process noise */
+                        for (int e = tid; e < d * D; e += NT) {
+                            const int i2 = e / D, c = e - i2 * D, j = c / d, ii = c - j * d;
+                            Bt[e] = (ii == i2 && j <= m) ? sd * P.L[m * n + j] * sh->PIv[j] : 0.0;
+                        }
+                        __syncthreads();
+                        for (int k = 0; k < D; k++) {
+                            /* column norm over {R[k][k]} U Bt[:,k] : one warp suffices (d <= 32 .. loop otherwise) */
+                            double part = 0.0;
+                            for (int i = tid; i < d; i += NT) part += Bt[i * D + k] * Bt[i * D + k];
+                            const double bsum = block_sum(part, sh);
+                            const double alpha = R[k * D + k];
+                            const double total = bsum + alpha * alpha;
+                            if (bsum > 0.0) {
+                                const double nrm = sqrt(total);
+                                const double beta = -copysign(nrm, alpha);
+                                const double vk = alpha - beta;
+                                const double gam = 1.0 / (total + fabs(alpha) * nrm);
+                                for (int j = k + 1 + tid; j < D; j += NT) {
+                                    double s = vk * R[k * D + j];
+                                    for (int i = 0; i < d; i++) s += Bt[i * D + k] * Bt[i * D + j];
+                                    s *= gam;
+                                    R[k * D + j] -= s * vk;
+                                    for (int i = 0; i < d; i++) Bt[i * D + j] -= s * Bt[i * D + k];
+                                }
+                                __syncthreads();
+                                if (tid == 0) R[k * D + k] = beta;
+                                for (int i = tid; i < d; i += NT) Bt[i * D + k] = 0.0;
+                            }
+                            __syncthreads();
+                        }
+                    }
+                }
+                /* 4. measurement update on the first 2d rows */
+                for (int e = tid; e < 2 * d * d; e += NT) {
+                    const int r = e / d, a = e - r * d;
+                    double s = R[r * D + d + a];
+                    for (int i = 0; i < d; i++) s -= R[r * D + i] * J[a + d * i];
+                    C2[e] = s;
+                }
+                __syncthreads();
+                for (int e = tid; e < d * d; e += NT) {
+                    const int a = e / d, b = e - a * d;
+                    if (b < a) continue;
+                    double s = 0.0;
+                    for (int r = 0; r < 2 * d; r++) s += C2[r * d + a] * C2[r * d + b];
+                    S[a * d + b] = s;
+                }
+                __syncthreads();
+                double trS = 0.0;
+                for (int a = tid; a < d; a += NT) trS += S[a * d + a];
+                trS = block_sum(trS, sh);
+                if (trS == 0.0) { /* Sigma^- H' == 0 : pass-through (update.jl:82-89) */
+                    for (int c = tid; c < D; c += NT) mu[c] = mup[c];
+                    if (tid == 0) {
+                        bool zz = true;
+                        for (int a = 0; a < d; a++) zz = zz && (z[a] == 0.0);
+                        sh->loglik += zz ? PN_INF : -PN_INF;
+                    }
+                    __syncthreads();
+                } else {
+                    if (tid == 0) sh->okflag = 1;
+                    for (int i = tid; i < d; i += NT) zt[i] = z[i];
+                    chol_sm(S, sinv, d, &sh->okflag);
+                    if (tid == 0) {
+                        chol_solve_serial(S, sinv, zt, d);
+                        double quad = 0.0, logdet = 0.0;
+                        for (int a = 0; a < d; a++) {
+                            quad += z[a] * zt[a];
+                            logdet += log(S[a * d + a]);
+                        }
+                        sh->loglik += -0.5 * quad - 0.5 * (double)d * 1.8378770664093453 - logdet;
+                        if (!DYNAMIC) {
+                            const double inc = quad * (1.0 / (double)d);
+                            sh->gdiff = (sh->naccept == 0) ? inc : sh->gdiff + (inc - sh->gdiff) / (double)sh->naccept;
+                        }
+                        if (!sh->okflag) sh->retcode = PN_RET_UNSTABLE;
+                    }
+                    /* V = C2 S^-1, one row per thread */
+                    for (int r = tid; r < 2 * d; r += NT) {
+                        double* x = V + r * d;
+                        for (int a = 0; a < d; a++) {
+                            double s = C2[r * d + a];
+                            for (int k = 0; k < a; k++) s -= S[k * d + a] * x[k];
+                            x[a] = s * sinv[a];
+                        }
+                        for (int a = d - 1; a >= 0; a--) {
+                            double s = x[a];
+                            for (int k = a + 1; k < d; k++) s -= S[a * d + k] * x[k];
+                            x[a] = s * sinv[a];
+                        }
+                    }
+                    __syncthreads();
+                    /* K = R^-' V */
+                    for (int e = tid; e < D * d; e += NT) {
+                        const int c = e / d, a = e - c * d;
+                        const int rmax = (c + 1 < 2 * d) ? c + 1 : 2 * d;
+                        double s = 0.0;
+                        for (int r = 0; r < rmax; r++) s += R[r * D + c] * V[r * d + a];
+                        K[e] = s;
+                    }
+                    __syncthreads();
+                    for (int c = tid; c < D; c += NT) {
+                        double s = mup[c];
+                        for (int a = 0; a < d; a++) s -= K[c * d + a] * z[a];
+                        mu[c] = s;
+                    }
+                    for (int e = tid; e < 2 * d * D; e += NT) {
+                        const int r = e / D, c = e - r * D;
+                        double s = R[e];
+                        for (int a = 0; a < d; a++) s -= C2[r * d + a] * K[c * d + a];
+                        R[e] = s;
+                    }
+                    __syncthreads();
+                }
+                /* loopfooter! accept (thread 0) */
+                if (tid == 0) {
+                    double dtnew = sh->dt, qq = sh->qq;
+                    if (ADAPTIVE) {
+                        if (P.qsteady_min <= qq && qq <= P.qsteady_max) qq = 1.0;
+                        sh->qold = fmax(sh->EEst, P.qoldinit);
+                        sh->qold_pb2 = (sh->EEst > P.qoldinit) ? exp(P.beta2 * sh->lEE) : P.qoldinit_pb2;
+                        dtnew = sh->dt / qq;
+                    }
+                    const double ttmp = sh->t + h;
+                    const double ref = fmax(fabs(sh->t), fabs(sh->tstop));
+                    const double epsref = nextafter(ref, 1e300) - ref;
+                    sh->t = (fabs(ttmp - sh->tstop) < 100.0 * epsref) ? sh->tstop : ttmp;
+                    sh->dt = dtnew;
+                    sh->naccept++;
+                    bool nanu = false;
+                    for (int i = 0; i < d; i++) {
+                        uprev[i] = mu[i];
+                        nanu = nanu || (mu[i] != mu[i]);
+                    }
+                    if (nanu) sh->retcode = PN_RET_UNSTABLE;
+                    if (sh->retcode != PN_RET_SUCCESS || !(sh->t < P.t1)) sh->finished = 1;
+                }
+                __syncthreads();
+                if (SAVE >= 1) {
+                    if (P.step_offsets) {
+                        const long long sp = sh->save_pos;
+                        for (int e = tid; e < d * d; e += NT) {
+                            const int a = e / d, b = e - a * d;
+                            double s = 0.0;
+                            for (int r = 0; r < D; r++) s += R[r * D + a] * R[r * D + b];
+                            P.s_u_cov[sp * d * d + e] = s;
+                        }
+                        for (int i = tid; i < d; i += NT) P.s_u_mean[sp * d + i] = mu[i];
+                        if (tid == 0) {
+                            P.s_t[sp] = sh->t;
+                            P.s_diffusion[sp - 1] = (ADAPTIVE || DYNAMIC) ? sh->ldiff : P.initial_diffusion;
+                        }
+                    }
+                    __syncthreads();
+                    if (tid == 0) sh->save_pos += 1;
+                    __syncthreads();
+                }
+            }
+            /* ---- postamble ---- */
+            __syncthreads();
+            double sc = 1.0, fd = sh->ldiff;
+            if (!DYNAMIC) {
+                if (P.calibrate && sh->naccept > 0) {
+                    sc = sh->gdiff;
+                    fd = sh->gdiff * P.initial_diffusion;
+                } else {
+                    fd = P.initial_diffusion;
+                }
+            }
+            for (int e = tid; e < d * d; e += NT) {
+                const int a = e / d, b = e - a * d;
+                double s = 0.0;
+                for (int r = 0; r < D; r++) s += R[r * D + a] * R[r * D + b];
+                P.u_cov[traj * d * d + e] = s * sc;
+            }
+            for (int i = tid; i < d; i += NT) P.u_mean[traj * d + i] = mu[i];
+            if (P.x_mean)
+                for (int c = tid; c < D; c += NT) P.x_mean[traj * D + c] = mu[c];
+            if (P.x_covfac) {
+                const double ss = sqrt(sc);
+                for (int e = tid; e < D * D; e += NT) P.x_covfac[traj * D * D + e] = R[e] * ss;
+            }
+            if (tid == 0) {
+                P.t_end[traj] = sh->t;
+                P.loglik[traj] = sh->loglik;
+                P.diffusion[traj] = fd;
+                P.dt_last[traj] = sh->dt;
+                P.naccept[traj] = sh->naccept;
+                P.nreject[traj] = sh->nreject;
+                P.nf[traj] = sh->nf;
+                P.retcode[traj] = sh->retcode;
+            }
+        }
+    }
+};
+
+template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
+__device__ __forceinline__ void pn_cta_entry(const PnParams& P) {
+    PnCta<Prob, Q, ADAPTIVE, DYNAMIC, SAVE>::run(P);
+}
+#endif /* PN_CTA_CUH */

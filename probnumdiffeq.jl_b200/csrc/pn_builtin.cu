@@ -14,7 +14,13 @@
     { "builtin:" NAME ":kron:q" #Q ":g1:a" #A ":dyn" #DY ":s" #S, \
       (const void*)&pn_kron_kernel<PROB, Q, (A != 0), (DY != 0), S>, PROB::d, PROB::n_p }
 
+#define PN_ENTRY_CTA(NAME, PROB, Q, A, DY, S) \
+    { "builtin:" NAME ":cta:q" #Q ":g256:a" #A ":dyn" #DY ":s" #S, \
+      (const void*)&pn_cta_kernel<PROB, Q, (A != 0), (DY != 0), S>, PROB::d, PROB::n_p }
+
 static const PnBuiltinEntry g_table[] = {
+    /* cfg4: Pleiades EK1(order=3), D = 112, adaptive, CTA per trajectory */
+    PN_ENTRY_CTA("pleiades", PnPleiades, 3, 1, 1, 0),
     /* cfg2: Lotka-Volterra EK0(order=3), adaptive, filter only, 1M trajectories */
     PN_ENTRY_KRON("lotka_volterra", PnLotkaVolterra, 3, 1, 1, 0),
     /* cfg5: ROBER / OREGO stiff EK1(order=3), adaptive, filter only (bench.py headline) */

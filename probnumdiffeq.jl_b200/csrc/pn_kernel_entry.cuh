@@ -30,3 +30,11 @@ template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 __global__ void __launch_bounds__(128) pn_kron_kernel(const __grid_constant__ PnParams P) {
     pn_kron_entry<Prob, Q, ADAPTIVE, DYNAMIC, SAVE>(P);
 }
+
+#include "kernels/pn_cta.cuh"
+
+/* large D (Pleiades, D = 112): one CTA per trajectory, R staged in shared memory */
+template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
+__global__ void __launch_bounds__(PN_CTA_THREADS, 1) pn_cta_kernel(const __grid_constant__ PnParams P) {
+    pn_cta_entry<Prob, Q, ADAPTIVE, DYNAMIC, SAVE>(P);
+}

@@ -20,6 +20,7 @@
 #include "kernels/pn_params.h"
 #define PN_SMOOTH_DECL_ONLY
 #include "kernels/pn_smooth.cuh"
+#include "kernels/pn_cta.cuh" /* PnCtaShared, PN_CTA_THREADS (templates are not instantiated here) */
 #include "pn_builtin.h"
 #include "pn_embedded_sources.h" /* generated: kernel headers as strings for NVRTC */
 
@@ -76,6 +77,7 @@ typedef CUresult (*fn_cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, 
                                       CUstream, void**, void**);
 typedef CUresult (*fn_cuOccupancy)(int*, CUfunction, int, size_t);
 typedef CUresult (*fn_cuGetErrorString)(CUresult, const char**);
+typedef CUresult (*fn_cuFuncSetAttribute)(CUfunction, CUfunction_attribute, int);
 struct DriverApi {
     fn_cuModuleLoadData ModuleLoadData = nullptr;
     fn_cuModuleUnload ModuleUnload = nullptr;
@@ -83,6 +85,7 @@ struct DriverApi {
     fn_cuLaunchKernel LaunchKernel = nullptr;
     fn_cuOccupancy Occupancy = nullptr;
     fn_cuGetErrorString GetErrorString = nullptr;
+    fn_cuFuncSetAttribute FuncSetAttribute = nullptr;
     bool ok = false;
 };
 static DriverApi g_drv;
@@ -98,6 +101,7 @@ static int load_driver() {
         {"cuLaunchKernel", (void**)&g_drv.LaunchKernel},
         {"cuOccupancyMaxActiveBlocksPerMultiprocessor", (void**)&g_drv.Occupancy},
         {"cuGetErrorString", (void**)&g_drv.GetErrorString},
+        {"cuFuncSetAttribute", (void**)&g_drv.FuncSetAttribute},
     };
     for (auto& s : syms) {
         cudaDriverEntryPointQueryResult qr;
@@ -135,6 +139,8 @@ struct pnode_solver {
     int D = 0, G = 4, n_sm = 0;
     bool builtin = false;
     bool kron = false; /* EK0: IsometricKronecker layout, one thread per trajectory */
+    bool cta = false;  /* EK1, D > 32: one CTA per trajectory, R in shared memory */
+    size_t smem = 0;   /* dynamic shared memory of the step kernel */
     Kernel k_final;  /* SAVE = 0 */
     Kernel k_save;   /* SAVE = 1 */
     cudaStream_t stream = nullptr;
@@ -190,7 +196,7 @@ static int auto_lanes(int D) {
 
 static std::string kernel_key(const pnode_solver* s, int save) {
     char buf[256];
-    snprintf(buf, sizeof buf, "%s:%s:q%d:g%d:a%d:dyn%d:s%d", s->rhs_name.c_str(), s->kron ? "kron" : "small", s->cfg.q, s->G,
+    snprintf(buf, sizeof buf, "%s:%s:q%d:g%d:a%d:dyn%d:s%d", s->rhs_name.c_str(), s->kron ? "kron" : (s->cta ? "cta" : "small"), s->cfg.q, s->G,
              s->cfg.adaptive ? 1 : 0, s->cfg.diffusion == PNODE_DIFF_DYNAMIC ? 1 : 0, save);
     return buf;
 }
@@ -198,11 +204,14 @@ static std::string kernel_key(const pnode_solver* s, int save) {
 /* NVRTC: user RHS + step kernels -> sm_100a CUBIN.  Needs no device. */
 static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_name, int q, int G, bool adaptive,
                        bool dynamic, int save, std::vector<char>* cubin, int threads = PN_THREADS, int min_blocks = 1,
-                       bool kron = false) {
+                       bool kron = false, bool cta = false) {
     std::string src;
     src += "#include \"pn_kernel_entry.cuh\"\n";
     src += rhs_src;
-    if (kron)
+    if (cta)
+        src += "\nextern \"C\" __global__ void __launch_bounds__(PN_CTA_THREADS, 1) pn_entry(const __grid_constant__ PnParams P) {\n"
+               "  pn_cta_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
+    else if (kron)
         src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS) pn_entry(const __grid_constant__ PnParams P) {\n"
                "  pn_kron_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
     else
@@ -267,16 +276,21 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
         src = "#include \"kernels/pn_builtin_problems.cuh\"\n";
         name = sn;
     }
-    out->threads = s->kron ? 128 : env_int("PNODE_THREADS", PN_THREADS);
+    out->threads = s->cta ? PN_CTA_THREADS : (s->kron ? 128 : env_int("PNODE_THREADS", PN_THREADS));
     rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0,
-                     s->cfg.diffusion == PNODE_DIFF_DYNAMIC, save, &cubin, out->threads, env_int("PNODE_MIN_BLOCKS", 1), s->kron);
+                     s->cfg.diffusion == PNODE_DIFF_DYNAMIC, save, &cubin, out->threads, env_int("PNODE_MIN_BLOCKS", 1), s->kron,
+                     s->cta);
     if (rc) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
     r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_entry");
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction: " + cu_err(r));
+    if (s->smem > 48 * 1024) {
+        r = g_drv.FuncSetAttribute(out->drv_fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->smem);
+        if (r != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuFuncSetAttribute(max dynamic smem): " + cu_err(r));
+    }
     int nblk = 0;
-    r = g_drv.Occupancy(&nblk, out->drv_fn, out->threads, 0);
+    r = g_drv.Occupancy(&nblk, out->drv_fn, out->threads, s->smem);
     if (r != CUDA_SUCCESS || nblk < 1) return fail(PNODE_ERR_CUDA, "occupancy query failed: " + cu_err(r));
     out->blocks_per_sm = nblk;
     return 0;
@@ -292,9 +306,11 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
         for (int i = 0; i < n; i++) {
             if (key == tab[i].key) {
                 out->rt_fn = tab[i].fn;
-                out->threads = s->kron ? 128 : PN_THREADS;
+                out->threads = s->cta ? PN_CTA_THREADS : (s->kron ? 128 : PN_THREADS);
+                if (s->smem > 48 * 1024)
+                    CUDA_TRY(cudaFuncSetAttribute(out->rt_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
                 int nblk = 0;
-                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, out->rt_fn, out->threads, 0));
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, out->rt_fn, out->threads, s->smem));
                 if (nblk < 1) return fail(PNODE_ERR_CUDA, "kernel does not fit on an SM");
                 out->blocks_per_sm = nblk;
                 return 0;
@@ -306,6 +322,13 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
     int rc = compile_nvrtc(s, save, out);
     s->compile_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return rc;
+}
+
+static size_t cta_smem_bytes(int d, int q, int n_p) {
+    const size_t n = q + 1, D = (size_t)d * n, npa = n_p > 0 ? n_p : 1;
+    const size_t dbl = D * D + d * D + 2 * d * d + 2 * d * d + D * d + d * d + d * d + 3 * D + 4 * d + npa +
+                       (sizeof(PnCtaShared) + 7) / 8;
+    return dbl * sizeof(double);
 }
 
 static int validate_config(const pnode_config* cfg) {
@@ -333,11 +356,16 @@ static int validate_config(const pnode_config* cfg) {
         return fail(PNODE_ERR_UNSUPPORTED, "EK0 with an IWP prior uses the IsometricKronecker layout (src/algorithms.jl:132-151)");
     if (cfg->alg == PNODE_EK0 && cfg->q > 7)
         return fail(PNODE_ERR_UNSUPPORTED, "EK0 thread-per-trajectory kernel supports order <= 7");
-    if (cfg->alg == PNODE_EK1 && D > 32)
-        return fail(PNODE_ERR_UNSUPPORTED, "D = d(q+1) > 32 needs the CTA-per-trajectory kernel (not in this build)");
     if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 2 && cfg->lanes_per_traj != 4 && cfg->lanes_per_traj != 8 &&
-        cfg->lanes_per_traj != 16 && cfg->lanes_per_traj != 32)
-        return fail(PNODE_ERR_ARGUMENT, "lanes_per_traj must be one of 0 (auto), 2, 4, 8, 16, 32");
+        cfg->lanes_per_traj != 16 && cfg->lanes_per_traj != 32 && cfg->lanes_per_traj != 256)
+        return fail(PNODE_ERR_ARGUMENT, "lanes_per_traj must be one of 0 (auto), 2, 4, 8, 16, 32, 256 (CTA per trajectory)");
+    if (cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256)) {
+        if (cta_smem_bytes(cfg->d, cfg->q, cfg->n_p) > 227 * 1024)
+            return fail(PNODE_ERR_UNSUPPORTED, "state dimension too large for the shared-memory CTA kernel");
+        if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 256)
+            return fail(PNODE_ERR_ARGUMENT, "D = d(q+1) > 32 runs one CTA per trajectory (lanes_per_traj 0 or 256)");
+        if (cfg->smooth) return fail(PNODE_ERR_UNSUPPORTED, "smoothing is not implemented for the CTA-per-trajectory kernel yet");
+    }
     const bool builtin = (std::string(cfg->rhs_name).rfind("builtin:", 0) == 0);
     if (!builtin && !cfg->rhs_src) return fail(PNODE_ERR_ARGUMENT, "rhs_src is required unless rhs_name is a builtin");
     return 0;
@@ -354,7 +382,8 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     const int G = cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D);
     std::vector<char> cubin;
     rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, cfg->diffusion == PNODE_DIFF_DYNAMIC,
-                     cfg->save_everystep ? (cfg->smooth ? 2 : 1) : 0, &cubin, PN_THREADS, 1, cfg->alg == PNODE_EK0);
+                     cfg->save_everystep ? (cfg->smooth ? 2 : 1) : 0, &cubin, PN_THREADS, 1, cfg->alg == PNODE_EK0,
+                     cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256));
     if (rc) return rc;
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
     return 0;
@@ -378,7 +407,9 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     s->cfg.rhs_src = nullptr;
     s->cfg.rhs_name = nullptr;
     s->kron = (cfg->alg == PNODE_EK0);
-    s->G = s->kron ? 1 : (cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D));
+    s->cta = !s->kron && (D > 32 || cfg->lanes_per_traj == 256);
+    s->smem = s->cta ? cta_smem_bytes(cfg->d, cfg->q, cfg->n_p) : 0;
+    s->G = s->kron ? 1 : (s->cta ? 256 : (cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D)));
     /* ---- constants ---- */
     PnParams& B = s->base;
     memset(&B, 0, sizeof B);
@@ -501,17 +532,17 @@ extern "C" void pnode_destroy(pnode_solver* s) {
 }
 
 static int launch(pnode_solver* s, Kernel& k, PnParams& P, int64_t n_traj) {
-    const int groups_per_block = k.threads / s->G;
+    const int groups_per_block = std::max(1, k.threads / s->G);
     long long want = (n_traj + groups_per_block - 1) / groups_per_block;
     long long cap = (long long)s->n_sm * k.blocks_per_sm; /* persistent: a whole number of CTAs per SM */
     unsigned grid = (unsigned)std::max(1LL, std::min(want, cap));
     CUDA_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), s->stream));
     if (k.rt_fn) {
         void* args[] = {&P};
-        CUDA_TRY(cudaLaunchKernel(k.rt_fn, dim3(grid), dim3(k.threads), args, 0, s->stream));
+        CUDA_TRY(cudaLaunchKernel(k.rt_fn, dim3(grid), dim3(k.threads), args, s->smem, s->stream));
     } else {
         void* args[] = {&P};
-        CUresult r = g_drv.LaunchKernel(k.drv_fn, grid, 1, 1, k.threads, 1, 1, 0, (CUstream)s->stream, args, nullptr);
+        CUresult r = g_drv.LaunchKernel(k.drv_fn, grid, 1, 1, k.threads, 1, 1, (unsigned)s->smem, (CUstream)s->stream, args, nullptr);
         if (r != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuLaunchKernel: " + cu_err(r));
     }
     return 0;

@@ -464,3 +464,63 @@ def test_full_size_properties_lv_ek0_1m():
     g2 = _gpu_ek0(pd, u0[perm], p[perm], 3, builtin=True, adaptive=True, t0=0.0, t1=10.0)
     assert np.array_equal(g2["u"], g["u"][perm]) and np.array_equal(g2["naccept"], g["naccept"][perm])
     print("EK0 cfg2 kernel ms", g["info"].kernel_ms, "steps/s", g["info"].total_accepted / (g["info"].kernel_ms * 1e-3))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CTA-per-trajectory kernel (BASELINE cfg4: Pleiades d = 28, D = 112)
+# ------------------------------------------------------------------------------------------------------------------
+def test_cta_kernel_matches_oracle_on_small_problems(oracle):
+    """The shared-memory CTA kernel is size-generic: run it on small problems where the oracle is fast."""
+    pd, u0, p = _inputs("fitzhugh_nagumo", 2, 14, dp=0.05)
+    g = _gpu(pd, u0, p, 3, builtin=False, adaptive=False, dt=0.01, t0=0.0, t1=5.0, diffusion=lib.DIFF_FIXED,
+             save_everystep=True, save_state=True, lanes_per_traj=256)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    for i in range(2):
+        o = oracle.solve(oracle.make_config(2, 3, 3, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, smooth=False, adaptive=False, dt=0.01,
+                                            t0=0.0, t1=5.0, save_everystep=True, cov_backend=oracle.COV_QR), rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"]
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < 1e-10
+        assert g["loglik"][i] == pytest.approx(o["loglik"], rel=1e-10)
+    pd, u0, p = _inputs("rober", 5, 15)
+    g = _gpu(pd, u0, p, 3, builtin=False, adaptive=True, t0=0.0, t1=100.0, lanes_per_traj=256)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    o = oracle.solve_ensemble(oracle.make_config(3, 3, 3, alg=oracle.EK1, smooth=False, adaptive=True, t0=0.0, t1=100.0,
+                                                 save_everystep=False, cov_backend=oracle.COV_QR), rhs, u0, p)
+    assert np.array_equal(g["naccept"], o["naccept"]) and np.array_equal(g["nreject"], o["nreject"])
+    assert _rel(g["u"], o["u_final"]) < 1e-8
+
+
+def test_cfg4_pleiades_cta_kernel(oracle):
+    """Pleiades first-order form (benchmarks/pleiades.jmd:35-61), EK1(order=3), D = 112, adaptive, filter only."""
+    n = 3
+    pd, u0, p = _inputs("pleiades", n, 2)
+    rng = np.random.default_rng(2)
+    u0[:, 14:] += 1e-3 * rng.uniform(-1, 1, (n, 14))      # perturb the initial positions (SURVEY.md section 8d cfg4)
+    p = np.zeros((n, 0))
+    g = _gpu(pd, u0, p, 3, builtin=True, adaptive=True, t0=0.0, t1=3.0, save_state=True)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    cfg = oracle.make_config(28, 3, 0, alg=oracle.EK1, smooth=False, adaptive=True, t0=0.0, t1=3.0, save_everystep=False,
+                             cov_backend=oracle.COV_QR)
+    assert np.all(g["retcode"] == 0) and np.all(g["t_end"] == 3.0)
+    for i in range(n):
+        o = oracle.solve(cfg, rhs, u0[i], [])
+        scale = np.abs(o["pu_mu"][-1]).max()
+        # ~600 adaptive steps of a 112-dimensional filter: the accept/reject pattern is compared with a small slack
+        assert abs(int(g["naccept"][i]) - o["naccept"]) <= 2 and abs(int(g["nreject"][i]) - o["nreject"]) <= 2, (g["naccept"][i], o["naccept"])
+        if g["naccept"][i] == o["naccept"] and g["nreject"][i] == o["nreject"]:
+            assert np.max(np.abs(g["u"][i] - o["pu_mu"][-1])) / scale < 1e-8
+        else:
+            assert np.max(np.abs(g["u"][i] - o["pu_mu"][-1])) / scale < 1e-4
+    # fixed steps + static diffusion: tight parity on the whole 112-dimensional state covariance
+    gf = _gpu(pd, u0[:1], p[:1], 3, builtin=False, adaptive=False, dt=0.01, t0=0.0, t1=0.5, diffusion=lib.DIFF_FIXED, save_state=True)
+    of = oracle.solve(oracle.make_config(28, 3, 0, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, smooth=False, adaptive=False, dt=0.01,
+                                         t0=0.0, t1=0.5, save_everystep=False, cov_backend=oracle.COV_QR), rhs, u0[0], [])
+    assert np.linalg.norm(gf["u"][0] - of["pu_mu"][-1]) / np.linalg.norm(of["pu_mu"][-1]) < 1e-10
+    assert _relcov(gf["cov"][0], of["pu_cov"][-1]) < 1e-10
+    Sg = gf["xR"][0].T @ gf["xR"][0]
+    So = of["x_filt_R"][-1].T @ of["x_filt_R"][-1]
+    assert np.linalg.norm(Sg - So) / np.linalg.norm(So) < 1e-10
+    assert gf["loglik"][0] == pytest.approx(of["loglik"], rel=1e-9)
+    print("pleiades cta kernel_ms", g["info"].kernel_ms, "accepted", g["info"].total_accepted)
