@@ -28,7 +28,7 @@ struct PnCtaShared {
     double red[PN_CTA_THREADS / 32];
     double hp[PN_MAX_N], PIv[PN_MAX_N];
     double t, dt, h, tnew, tstop, EEst, qq, q11, lEE, qold, qold_pb2, ediff, ldiff, loglik, gdiff, dtcache;
-    double total, quad;
+    double total, total2, quad;
     long long traj, naccept, nreject, nf, iter, tstop_idx, save_pos;
     int retcode, accept, finished, okflag;
 };
@@ -40,6 +40,8 @@ struct PnCta {
     static constexpr int D = d * n;
     static constexpr int NPA = Prob::n_p > 0 ? Prob::n_p : 1;
     static constexpr int NT = PN_CTA_THREADS;
+    /* threads that share one column in the Householder sweeps (adjacent lanes, power of two) */
+    static constexpr int TPC = (NT / D >= 8) ? 8 : (NT / D >= 4) ? 4 : (NT / D >= 2) ? 2 : 1;
     /* doubles of dynamic shared memory */
     static constexpr int SM_DOUBLES = D * D + d * D + 2 * d * d /*C2*/ + 2 * d * d /*V*/ + D * d /*K*/ + d * d /*S*/ +
                                       d * d /*J*/ + 3 * D /*mu,mup,tmp*/ + 4 * d /*z,zt,fu,uprev*/ + NPA +
@@ -304,64 +306,128 @@ struct PnCta {
                         }
                 }
                 __syncthreads();
-                /* 2. Householder QR of X in place */
-                for (int k = 0; k < D; k++) {
-                    double part = 0.0;
-                    for (int r = k + tid; r < D; r += NT) part += R[r * D + k] * R[r * D + k];
-                    const double total = block_sum(part, sh);
-                    const double alpha = R[k * D + k];
-                    if (total > 0.0) {
-                        const double nrm = sqrt(total);
-                        const double beta = -copysign(nrm, alpha);
-                        const double vk = alpha - beta;
-                        const double gam = 1.0 / (total + fabs(alpha) * nrm);
-                        for (int j = k + 1 + tid; j < D; j += NT) {
-                            double s = vk * R[k * D + j];
-                            for (int r = k + 1; r < D; r++) s += R[r * D + k] * R[r * D + j];
-                            s *= gam;
-                            R[k * D + j] -= s * vk;
-                            for (int r = k + 1; r < D; r++) R[r * D + j] -= s * R[r * D + k];
-                        }
+                /* 2.+3. Householder sweeps with ONE barrier per pivot.  TPC adjacent lanes share a column (rows
+                   interleaved); the owners of column k+1 compute its norm right after updating it, and the owners of
+                   column k-1 (idle by then) write its diagonal and clear its sub-diagonal. */
+                {
+                    const int col = tid / TPC, sub = tid % TPC;
+                    /* ---- sweep A: QR of X in place ---- */
+                    {
+                        double part = 0.0;
+                        if (col == 0)
+                            for (int r = sub; r < D; r += TPC) part += R[r * D] * R[r * D];
+#pragma unroll
+                        for (int o = TPC >> 1; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                        if (col == 0 && sub == 0) sh->total = part;
+                    }
+                    double beta_prev = 0.0;
+                    for (int k = 0; k < D; k++) {
                         __syncthreads();
-                        for (int r = k + tid; r < D; r += NT) R[r * D + k] = (r == k) ? beta : 0.0;
+                        const double total = sh->total;
+                        const double alpha = R[k * D + k];
+                        const bool nz = total > 0.0;
+                        const double nrm = nz ? sqrt(total) : 0.0;
+                        const double beta = nz ? -copysign(nrm, alpha) : alpha;
+                        const double vk = alpha - beta;
+                        const double gam = nz ? 1.0 / (total + fabs(alpha) * nrm) : 0.0;
+                        double s = 0.0;
+                        const bool mine = (col > k && col < D);
+                        if (mine) {
+                            for (int r = k + 1 + sub; r < D; r += TPC) s += R[r * D + k] * R[r * D + col];
+                            if (sub == 0) s += vk * R[k * D + col];
+                        }
+#pragma unroll
+                        for (int o = TPC >> 1; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                        s *= gam;
+                        double np = 0.0;
+                        if (mine) {
+                            const bool next = (col == k + 1);
+                            for (int r = k + 1 + sub; r < D; r += TPC) {
+                                const double v = R[r * D + col] - s * R[r * D + k];
+                                R[r * D + col] = v;
+                                if (next) np += v * v;
+                            }
+                            if (sub == 0) R[k * D + col] -= s * vk;
+                        }
+#pragma unroll
+                        for (int o = TPC >> 1; o >= 1; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
+                        if (col == k + 1 && sub == 0) sh->total2 = np;
+                        /* column k-1 is dead for everyone now: finish it */
+                        if (col == k - 1 && k >= 1) {
+                            for (int r = k + sub; r < D; r += TPC) R[r * D + col] = 0.0;
+                            if (sub == 0) R[(k - 1) * D + col] = beta_prev;
+                        }
+                        beta_prev = beta;
+                        __syncthreads();
+                        if (tid == 0) sh->total = sh->total2;
                     }
                     __syncthreads();
-                }
-                /* 3. fold sqrt(s2) (L P^-1) (x) I_d into R, one derivative level (d rows) at a time */
-                {
+                    if (tid == 0) R[(D - 1) * D + (D - 1)] = beta_prev;
+                    __syncthreads();
+
+                    /* ---- sweeps B: fold sqrt(s2) (U P^-1) (x) I_d into R, one derivative level (d rows) at a time.
+                       U is the *upper* triangular factor with U'U = L'L (host, pnode_api.cu): level m is zero in the
+                       columns of derivatives < m, so its sweep starts at pivot m*d. ---- */
                     const double sd = (sh->ediff == 1.0) ? 1.0 : sqrt(sh->ediff);
                     for (int m = 0; m < n; m++) {
                         if (sh->ediff == 0.0) break; /* predict.jl:71-74: no process noise */
+                        const int k0 = m * d;
                         for (int e = tid; e < d * D; e += NT) {
                             const int i2 = e / D, c = e - i2 * D, j = c / d, ii = c - j * d;
-                            Bt[e] = (ii == i2 && j <= m) ? sd * P.L[m * n + j] * sh->PIv[j] : 0.0;
+                            Bt[e] = (ii == i2 && j >= m) ? sd * P.U[m * n + j] * sh->PIv[j] : 0.0;
                         }
                         __syncthreads();
-                        for (int k = 0; k < D; k++) {
-                            /* column norm over {R[k][k]} U Bt[:,k] : one warp suffices (d <= 32 .. loop otherwise) */
+                        {
                             double part = 0.0;
-                            for (int i = tid; i < d; i += NT) part += Bt[i * D + k] * Bt[i * D + k];
-                            const double bsum = block_sum(part, sh);
+                            if (col == k0)
+                                for (int i = sub; i < d; i += TPC) part += Bt[i * D + k0] * Bt[i * D + k0];
+#pragma unroll
+                            for (int o = TPC >> 1; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                            if (col == k0 && sub == 0) sh->total = part;
+                        }
+                        double bprev = 0.0;
+                        bool have_prev = false;
+                        for (int k = k0; k < D; k++) {
+                            __syncthreads();
+                            const double bsum = sh->total;
                             const double alpha = R[k * D + k];
                             const double total = bsum + alpha * alpha;
-                            if (bsum > 0.0) {
-                                const double nrm = sqrt(total);
-                                const double beta = -copysign(nrm, alpha);
-                                const double vk = alpha - beta;
-                                const double gam = 1.0 / (total + fabs(alpha) * nrm);
-                                for (int j = k + 1 + tid; j < D; j += NT) {
-                                    double s = vk * R[k * D + j];
-                                    for (int i = 0; i < d; i++) s += Bt[i * D + k] * Bt[i * D + j];
-                                    s *= gam;
-                                    R[k * D + j] -= s * vk;
-                                    for (int i = 0; i < d; i++) Bt[i * D + j] -= s * Bt[i * D + k];
-                                }
-                                __syncthreads();
-                                if (tid == 0) R[k * D + k] = beta;
-                                for (int i = tid; i < d; i += NT) Bt[i * D + k] = 0.0;
+                            const bool nz = bsum > 0.0;
+                            const double nrm = nz ? sqrt(total) : 0.0;
+                            const double beta = nz ? -copysign(nrm, alpha) : alpha;
+                            const double vk = alpha - beta;
+                            const double gam = nz ? 1.0 / (total + fabs(alpha) * nrm) : 0.0;
+                            double s = 0.0;
+                            const bool mine = (col > k && col < D);
+                            if (mine) {
+                                for (int i = sub; i < d; i += TPC) s += Bt[i * D + k] * Bt[i * D + col];
+                                if (sub == 0) s += vk * R[k * D + col];
                             }
+#pragma unroll
+                            for (int o = TPC >> 1; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                            s *= gam;
+                            double np = 0.0;
+                            if (mine) {
+                                const bool next = (col == k + 1);
+                                for (int i = sub; i < d; i += TPC) {
+                                    const double v = Bt[i * D + col] - s * Bt[i * D + k];
+                                    Bt[i * D + col] = v;
+                                    if (next) np += v * v;
+                                }
+                                if (sub == 0) R[k * D + col] -= s * vk;
+                            }
+#pragma unroll
+                            for (int o = TPC >> 1; o >= 1; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
+                            if (col == k + 1 && sub == 0) sh->total2 = np;
+                            if (have_prev && col == k - 1 && sub == 0) R[(k - 1) * D + col] = bprev;
+                            bprev = beta;
+                            have_prev = true;
                             __syncthreads();
+                            if (tid == 0) sh->total = sh->total2;
                         }
+                        __syncthreads();
+                        if (tid == 0) R[(D - 1) * D + (D - 1)] = bprev;
+                        __syncthreads();
                     }
                 }
                 /* 4. measurement update on the first 2d rows */

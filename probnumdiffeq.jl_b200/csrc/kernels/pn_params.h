@@ -29,6 +29,10 @@ struct PnParams {
     unsigned long long* work_counter;
     /* IWP constants (src/priors/iwp.jl:74-108), row-major n x n, host-computed */
     double L[PN_MAX_N * PN_MAX_N];
+    /* upper-triangular U with U'U = L'L (Householder QR of L in extended precision on the host), row-major n x n:
+       an equivalent right factor of the same preconditioned process-noise covariance, used where an upper-triangular
+       noise block lets a sweep skip its leading zero columns */
+    double U[PN_MAX_N * PN_MAX_N];
     /* ---- per-trajectory outputs ---- */
     double* t_end;      /* [n_traj]       */
     double* u_mean;     /* [n_traj][d]    */

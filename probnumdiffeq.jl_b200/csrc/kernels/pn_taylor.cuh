@@ -22,6 +22,14 @@ PN_HD double pn_ipow(double x, int n) {
 }
 PN_HD double pn_sqrt(double x) { return sqrt(x); }
 PN_HD double pn_pow(double x, double r) { return pow(x, r); }
+// x^(k/2), k odd: sqrt(x)^k (k > 0) or (1/sqrt(x))^|k| -- replaces pow() in traced right-hand sides (e.g. r^-3)
+PN_HD double pn_pow_half(double x, int k) {
+    const double r = (k > 0) ? sqrt(x) : rsqrt(x);
+    const int m = (k > 0) ? k : -k;
+    double y = r;
+    for (int i = 1; i < m; i++) y *= r;
+    return y;
+}
 PN_HD double pn_exp(double x) { return exp(x); }
 PN_HD double pn_log(double x) { return log(x); }
 PN_HD double pn_sin(double x) { return sin(x); }
@@ -166,6 +174,8 @@ PN_HD PnTaylor<N> pn_pow(const PnTaylor<N>& a, double r) {
     }
     return p;
 }
+template <int N>
+PN_HD PnTaylor<N> pn_pow_half(const PnTaylor<N>& a, int k) { return pn_pow(a, 0.5 * (double)k); }
 template <int N>
 PN_HD PnTaylor<N> pn_exp(const PnTaylor<N>& a) {
     PnTaylor<N> e;

@@ -443,6 +443,33 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
                                  factorial_d(2 * q - c - m + 1);
             }
     }
+    {
+        /* U = qr(L).R in long double (U'U = L'L = Q_breve) */
+        const int n = cfg->q + 1;
+        long double A[PN_MAX_N][PN_MAX_N];
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) A[i][j] = (long double)B.L[i * n + j];
+        for (int k = 0; k < n; k++) {
+            long double tot = 0.0L;
+            for (int r = k; r < n; r++) tot += A[r][k] * A[r][k];
+            if (tot > 0.0L) {
+                const long double alpha = A[k][k], nrm = sqrtl(tot);
+                const long double beta = (alpha >= 0.0L) ? -nrm : nrm, vk = alpha - beta;
+                const long double gam = 1.0L / (tot + fabsl(alpha) * nrm);
+                for (int j = k + 1; j < n; j++) {
+                    long double sdot = vk * A[k][j];
+                    for (int r = k + 1; r < n; r++) sdot += A[r][k] * A[r][j];
+                    sdot *= gam;
+                    A[k][j] -= sdot * vk;
+                    for (int r = k + 1; r < n; r++) A[r][j] -= sdot * A[r][k];
+                }
+                A[k][k] = beta;
+                for (int r = k + 1; r < n; r++) A[r][k] = 0.0L;
+            }
+        }
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) B.U[i * n + j] = (j >= i) ? (double)A[i][j] : 0.0;
+    }
     /* ---- device ---- */
     int ndev = pnode_device_count();
     if (ndev <= 0) {

@@ -93,6 +93,8 @@ class _DevicePrinter(C99CodePrinter):
             return f"pn_sqrt({b})"
         if e == sp.Rational(-1, 2):
             return f"(1.0/pn_sqrt({b}))"
+        if e.is_Rational and int(e.q) == 2:
+            return f"pn_pow_half({b}, {int(e.p)})"   # x^(k/2) = sqrt(x)^k: no pow() call on the step path
         if e.is_Rational:
             return f"pn_pow({b}, {float(e)!r})"
         return f"pn_pow({b}, {self._print(e)})"
