@@ -29,6 +29,7 @@ struct PnCtaShared {
     double hp[PN_MAX_N], PIv[PN_MAX_N];
     double t, dt, h, tnew, tstop, EEst, qq, q11, lEE, qold, qold_pb2, ediff, ldiff, loglik, gdiff, dtcache;
     double total, total2, quad;
+    double hv[2][4]; /* Householder scalars {beta, vk, gam} of the current / next pivot */
     long long traj, naccept, nreject, nf, iter, tstop_idx, save_pos;
     int retcode, accept, finished, okflag;
 };
@@ -42,6 +43,7 @@ struct PnCta {
     static constexpr int NT = PN_CTA_THREADS;
     /* threads that share one column in the Householder sweeps (adjacent lanes, power of two) */
     static constexpr int TPC = (NT / D >= 8) ? 8 : (NT / D >= 4) ? 4 : (NT / D >= 2) ? 2 : 1;
+    static constexpr int NB = (d + TPC - 1) / TPC; /* batch rows per thread in the fold sweeps */
     /* doubles of dynamic shared memory */
     static constexpr int SM_DOUBLES = D * D + d * D + 2 * d * d /*C2*/ + 2 * d * d /*V*/ + D * d /*K*/ + d * d /*S*/ +
                                       d * d /*J*/ + 3 * D /*mu,mup,tmp*/ + 4 * d /*z,zt,fu,uprev*/ + NPA +
@@ -57,6 +59,15 @@ struct PnCta {
 #pragma unroll
         for (int w = 0; w < NT / 32; w++) s += sh->red[w];
         return s;
+    }
+
+    // beta, v_k = alpha - beta, gam = 2 / v'v of the reflector that maps (alpha, x) with |(alpha,x)|^2 = total onto beta e_1
+    static __device__ __forceinline__ void house_scalars(double* hv, double total, double alpha, bool nz) {
+        const double nrm = nz ? sqrt(total) : 0.0;
+        const double beta = nz ? -copysign(nrm, alpha) : alpha;
+        hv[0] = beta;
+        hv[1] = alpha - beta;
+        hv[2] = nz ? 1.0 / (total + fabs(alpha) * nrm) : 0.0;
     }
 
     // In-place upper Cholesky of the symmetric m x m matrix A (row-major, upper part read); inv diag in invd.
@@ -311,6 +322,9 @@ struct PnCta {
                    column k-1 (idle by then) write its diagonal and clear its sub-diagonal. */
                 {
                     const int col = tid / TPC, sub = tid % TPC;
+                    /* Householder scalars of pivot k live in sh->hv[k & 1] = {beta, vk, gam}: they are computed once, by
+                       the owner of the pivot column right after it has updated that column (double-buffered, so a
+                       pivot needs exactly one barrier). */
                     /* ---- sweep A: QR of X in place ---- */
                     {
                         double part = 0.0;
@@ -318,48 +332,77 @@ struct PnCta {
                             for (int r = sub; r < D; r += TPC) part += R[r * D] * R[r * D];
 #pragma unroll
                         for (int o = TPC >> 1; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                        if (col == 0 && sub == 0) sh->total = part;
+                        if (col == 0 && sub == 0) house_scalars(sh->hv[0], part, R[0], part > 0.0);
                     }
                     double beta_prev = 0.0;
                     for (int k = 0; k < D; k++) {
                         __syncthreads();
-                        const double total = sh->total;
-                        const double alpha = R[k * D + k];
-                        const bool nz = total > 0.0;
-                        const double nrm = nz ? sqrt(total) : 0.0;
-                        const double beta = nz ? -copysign(nrm, alpha) : alpha;
-                        const double vk = alpha - beta;
-                        const double gam = nz ? 1.0 / (total + fabs(alpha) * nrm) : 0.0;
+                        const double beta = sh->hv[k & 1][0], vk = sh->hv[k & 1][1], gam = sh->hv[k & 1][2];
                         double s = 0.0;
                         const bool mine = (col > k && col < D);
                         if (mine) {
-                            for (int r = k + 1 + sub; r < D; r += TPC) s += R[r * D + k] * R[r * D + col];
+                            /* loads are batched four rows at a time: the compiler cannot prove that column k and
+                               column col do not alias, so a plain loop serialises on the shared-memory latency */
+                            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                            int r = k + 1 + sub;
+                            for (; r + 3 * TPC < D; r += 4 * TPC) {
+                                const double v0 = R[r * D + k], v1 = R[(r + TPC) * D + k], v2 = R[(r + 2 * TPC) * D + k],
+                                             v3 = R[(r + 3 * TPC) * D + k];
+                                const double a0 = R[r * D + col], a1 = R[(r + TPC) * D + col], a2 = R[(r + 2 * TPC) * D + col],
+                                             a3 = R[(r + 3 * TPC) * D + col];
+                                s0 += v0 * a0;
+                                s1 += v1 * a1;
+                                s2 += v2 * a2;
+                                s3 += v3 * a3;
+                            }
+                            for (; r < D; r += TPC) s0 += R[r * D + k] * R[r * D + col];
+                            s = (s0 + s1) + (s2 + s3);
                             if (sub == 0) s += vk * R[k * D + col];
                         }
 #pragma unroll
                         for (int o = TPC >> 1; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                         s *= gam;
-                        double np = 0.0;
+                        double np = 0.0, anext = 0.0;
                         if (mine) {
                             const bool next = (col == k + 1);
-                            for (int r = k + 1 + sub; r < D; r += TPC) {
+                            int r = k + 1 + sub;
+                            for (; r + 3 * TPC < D; r += 4 * TPC) {
+                                const double v0 = R[r * D + k], v1 = R[(r + TPC) * D + k], v2 = R[(r + 2 * TPC) * D + k],
+                                             v3 = R[(r + 3 * TPC) * D + k];
+                                double a0 = R[r * D + col], a1 = R[(r + TPC) * D + col], a2 = R[(r + 2 * TPC) * D + col],
+                                       a3 = R[(r + 3 * TPC) * D + col];
+                                a0 -= s * v0;
+                                a1 -= s * v1;
+                                a2 -= s * v2;
+                                a3 -= s * v3;
+                                R[r * D + col] = a0;
+                                R[(r + TPC) * D + col] = a1;
+                                R[(r + 2 * TPC) * D + col] = a2;
+                                R[(r + 3 * TPC) * D + col] = a3;
+                                if (next) {
+                                    np += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+                                    if (r == k + 1) anext = a0;
+                                }
+                            }
+                            for (; r < D; r += TPC) {
                                 const double v = R[r * D + col] - s * R[r * D + k];
                                 R[r * D + col] = v;
-                                if (next) np += v * v;
+                                if (next) {
+                                    np += v * v;
+                                    if (r == k + 1) anext = v;
+                                }
                             }
                             if (sub == 0) R[k * D + col] -= s * vk;
                         }
 #pragma unroll
                         for (int o = TPC >> 1; o >= 1; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
-                        if (col == k + 1 && sub == 0) sh->total2 = np;
+                        if (col == k + 1 && sub == 0 && k + 1 < D) house_scalars(sh->hv[(k + 1) & 1], np, anext, np > 0.0);
                         /* column k-1 is dead for everyone now: finish it */
                         if (col == k - 1 && k >= 1) {
                             for (int r = k + sub; r < D; r += TPC) R[r * D + col] = 0.0;
                             if (sub == 0) R[(k - 1) * D + col] = beta_prev;
                         }
                         beta_prev = beta;
-                        __syncthreads();
-                        if (tid == 0) sh->total = sh->total2;
                     }
                     __syncthreads();
                     if (tid == 0) R[(D - 1) * D + (D - 1)] = beta_prev;
@@ -383,24 +426,33 @@ struct PnCta {
                                 for (int i = sub; i < d; i += TPC) part += Bt[i * D + k0] * Bt[i * D + k0];
 #pragma unroll
                             for (int o = TPC >> 1; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                            if (col == k0 && sub == 0) sh->total = part;
+                            if (col == k0 && sub == 0) {
+                                const double a0 = R[k0 * D + k0];
+                                house_scalars(sh->hv[k0 & 1], part + a0 * a0, a0, part > 0.0);
+                            }
                         }
                         double bprev = 0.0;
                         bool have_prev = false;
                         for (int k = k0; k < D; k++) {
                             __syncthreads();
-                            const double bsum = sh->total;
-                            const double alpha = R[k * D + k];
-                            const double total = bsum + alpha * alpha;
-                            const bool nz = bsum > 0.0;
-                            const double nrm = nz ? sqrt(total) : 0.0;
-                            const double beta = nz ? -copysign(nrm, alpha) : alpha;
-                            const double vk = alpha - beta;
-                            const double gam = nz ? 1.0 / (total + fabs(alpha) * nrm) : 0.0;
+                            const double beta = sh->hv[k & 1][0], vk = sh->hv[k & 1][1], gam = sh->hv[k & 1][2];
                             double s = 0.0;
                             const bool mine = (col > k && col < D);
+                            double bv[NB], ba[NB]; /* this thread's rows of batch columns k and col, kept in registers */
                             if (mine) {
-                                for (int i = sub; i < d; i += TPC) s += Bt[i * D + k] * Bt[i * D + col];
+#pragma unroll
+                                for (int ib = 0; ib < NB; ib++) {
+                                    const int i = sub + ib * TPC;
+                                    bv[ib] = (i < d) ? Bt[i * D + k] : 0.0;
+                                    ba[ib] = (i < d) ? Bt[i * D + col] : 0.0;
+                                }
+                                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                                for (int ib = 0; ib < NB; ib++) {
+                                    if (ib & 1) s1 += bv[ib] * ba[ib];
+                                    else s0 += bv[ib] * ba[ib];
+                                }
+                                s = s0 + s1;
                                 if (sub == 0) s += vk * R[k * D + col];
                             }
 #pragma unroll
@@ -409,21 +461,24 @@ struct PnCta {
                             double np = 0.0;
                             if (mine) {
                                 const bool next = (col == k + 1);
-                                for (int i = sub; i < d; i += TPC) {
-                                    const double v = Bt[i * D + col] - s * Bt[i * D + k];
-                                    Bt[i * D + col] = v;
+#pragma unroll
+                                for (int ib = 0; ib < NB; ib++) {
+                                    const int i = sub + ib * TPC;
+                                    const double v = ba[ib] - s * bv[ib];
+                                    if (i < d) Bt[i * D + col] = v;
                                     if (next) np += v * v;
                                 }
                                 if (sub == 0) R[k * D + col] -= s * vk;
                             }
 #pragma unroll
                             for (int o = TPC >> 1; o >= 1; o >>= 1) np += __shfl_xor_sync(0xffffffffu, np, o);
-                            if (col == k + 1 && sub == 0) sh->total2 = np;
+                            if (col == k + 1 && sub == 0 && k + 1 < D) {
+                                const double a1 = R[(k + 1) * D + (k + 1)];
+                                house_scalars(sh->hv[(k + 1) & 1], np + a1 * a1, a1, np > 0.0);
+                            }
                             if (have_prev && col == k - 1 && sub == 0) R[(k - 1) * D + col] = bprev;
                             bprev = beta;
                             have_prev = true;
-                            __syncthreads();
-                            if (tid == 0) sh->total = sh->total2;
                         }
                         __syncthreads();
                         if (tid == 0) R[(D - 1) * D + (D - 1)] = bprev;
