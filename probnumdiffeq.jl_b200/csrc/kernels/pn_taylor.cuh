@@ -24,7 +24,11 @@ PN_HD double pn_sqrt(double x) { return sqrt(x); }
 PN_HD double pn_pow(double x, double r) { return pow(x, r); }
 // x^(k/2), k odd: sqrt(x)^k (k > 0) or (1/sqrt(x))^|k| -- replaces pow() in traced right-hand sides (e.g. r^-3)
 PN_HD double pn_pow_half(double x, int k) {
+#ifdef __CUDA_ARCH__
     const double r = (k > 0) ? sqrt(x) : rsqrt(x);
+#else
+    const double r = (k > 0) ? sqrt(x) : 1.0 / sqrt(x);  // host build of the header (tests/test_host.py)
+#endif
     const int m = (k > 0) ? k : -k;
     double y = r;
     for (int i = 1; i < m; i++) y *= r;
