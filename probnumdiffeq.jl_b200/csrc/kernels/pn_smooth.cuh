@@ -36,6 +36,7 @@ struct PnSmoothParams {
     double* s_u_mean;              /* [total][d] out */
     double* s_u_cov;               /* [total][d][d] out */
     double L[PN_MAX_N * PN_MAX_N]; /* IWP left sqrt factor, row-major n x n */
+    double U[PN_MAX_N * PN_MAX_N]; /* upper-triangular right factor of the same covariance (pn_params.h) */
     unsigned long long* work_counter;
 };
 

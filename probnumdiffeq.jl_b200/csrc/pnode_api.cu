@@ -20,6 +20,7 @@
 #include "kernels/pn_params.h"
 #define PN_SMOOTH_DECL_ONLY
 #include "kernels/pn_smooth.cuh"
+#define PN_SMR_THREADS 256 /* pn_smooth_reg.cuh */
 #include "kernels/pn_cta.cuh" /* PnCtaShared, PN_CTA_THREADS (templates are not instantiated here) */
 #include "pn_builtin.h"
 #include "pn_embedded_sources.h" /* generated: kernel headers as strings for NVRTC */
@@ -143,6 +144,9 @@ struct pnode_solver {
     size_t smem = 0;   /* dynamic shared memory of the step kernel */
     Kernel k_final;  /* SAVE = 0 */
     Kernel k_save;   /* SAVE = 1 */
+    Kernel k_smooth; /* register-resident smoother sweep (pn_smooth_reg.cuh); invalid => shared-memory sweep */
+    int Gs = 0;      /* lanes per trajectory of the smoother sweep */
+    size_t smem_smooth = 0;
     cudaStream_t stream = nullptr;
     unsigned long long* d_counter = nullptr;
     double* d_tstops = nullptr;
@@ -194,11 +198,68 @@ static int auto_lanes(int D) {
     return 32;
 }
 
+/* lanes per trajectory of the register-resident smoother: the 2D x 2D sweep keeps 4 D ceil(D/G) doubles per lane */
+static int smooth_lanes(int D) {
+    const int cand[] = {2, 4, 8, 16, 32};
+    for (int g : cand) {
+        int rpl = (D + g - 1) / g;
+        if (4 * rpl * D <= 100) return g;
+    }
+    return 0; /* too large: shared-memory sweep (pn_smooth.cuh) */
+}
+/* must match PnSmoothReg<d,Q,G>::SMEM_BYTES */
+static size_t smooth_reg_smem_bytes(int d, int q, int G) {
+    const int D = d * (q + 1), RPL = (D + G - 1) / G, ROWS = RPL * G, LD = D | 1;
+    const int RAW = 2 * D * LD + ROWS * LD + 2 * D;
+    const int PHASE = (G >= 16) ? 0 : G;
+    const int REGION = ((RAW - PHASE + 15) / 16) * 16 + PHASE;
+    return (size_t)REGION * (PN_SMR_THREADS / G) * 8;
+}
+
 static std::string kernel_key(const pnode_solver* s, int save) {
     char buf[256];
     snprintf(buf, sizeof buf, "%s:%s:q%d:g%d:a%d:dyn%d:s%d", s->rhs_name.c_str(), s->kron ? "kron" : (s->cta ? "cta" : "small"), s->cfg.q, s->G,
              s->cfg.adaptive ? 1 : 0, s->cfg.diffusion == PNODE_DIFF_DYNAMIC ? 1 : 0, save);
     return buf;
+}
+
+static int nvrtc_compile(const std::string& src, std::vector<std::string> defs, std::vector<char>* cubin) {
+    nvrtcProgram prog;
+    const char* hdr_src[PN_N_EMBEDDED];
+    const char* hdr_name[PN_N_EMBEDDED];
+    for (int i = 0; i < PN_N_EMBEDDED; i++) {
+        hdr_src[i] = pn_embedded_sources[i].text;
+        hdr_name[i] = pn_embedded_sources[i].name;
+    }
+    if (nvrtcCreateProgram(&prog, src.c_str(), "pnode_user.cu", PN_N_EMBEDDED, hdr_src, hdr_name) != NVRTC_SUCCESS)
+        return fail(PNODE_ERR_COMPILE, "nvrtcCreateProgram failed");
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+    if (const char* e = getenv("PNODE_NVRTC_FLAGS")) { /* developer knob: extra NVRTC options, space separated */
+        std::string cur;
+        for (const char* c = e;; c++) {
+            if (*c == ' ' || *c == 0) {
+                if (!cur.empty()) defs.push_back(cur);
+                cur.clear();
+                if (!*c) break;
+            } else cur.push_back(*c);
+        }
+    }
+    for (auto& x : defs) opts.push_back(x.c_str());
+    nvrtcResult cr = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
+    if (cr != NVRTC_SUCCESS) {
+        size_t n = 0;
+        nvrtcGetProgramLogSize(prog, &n);
+        std::string log(n, '\0');
+        if (n) nvrtcGetProgramLog(prog, &log[0]);
+        nvrtcDestroyProgram(&prog);
+        return fail(PNODE_ERR_COMPILE, "NVRTC compilation failed:\n" + log);
+    }
+    size_t nb = 0;
+    nvrtcGetCUBINSize(prog, &nb);
+    cubin->resize(nb);
+    nvrtcGetCUBIN(prog, cubin->data());
+    nvrtcDestroyProgram(&prog);
+    return 0;
 }
 
 /* NVRTC: user RHS + step kernels -> sm_100a CUBIN.  Needs no device. */
@@ -218,51 +279,20 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
         src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_entry(const "
                "__grid_constant__ PnParams P) {\n  pn_small_entry<" +
                struct_name + ", PN_Q, PN_G, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
-    nvrtcProgram prog;
-    const char* hdr_src[PN_N_EMBEDDED];
-    const char* hdr_name[PN_N_EMBEDDED];
-    for (int i = 0; i < PN_N_EMBEDDED; i++) {
-        hdr_src[i] = pn_embedded_sources[i].text;
-        hdr_name[i] = pn_embedded_sources[i].name;
-    }
-    if (nvrtcCreateProgram(&prog, src.c_str(), "pnode_user.cu", PN_N_EMBEDDED, hdr_src, hdr_name) != NVRTC_SUCCESS)
-        return fail(PNODE_ERR_COMPILE, "nvrtcCreateProgram failed");
-    char dq[32], dg[32], da[32], dd[32], ds[32], dt[40], dm[40];
-    snprintf(dt, sizeof dt, "-DPN_THREADS=%d", threads);
-    snprintf(dm, sizeof dm, "-DPN_MIN_BLOCKS=%d", min_blocks);
-    snprintf(dq, sizeof dq, "-DPN_Q=%d", q);
-    snprintf(dg, sizeof dg, "-DPN_G=%d", G);
-    snprintf(da, sizeof da, "-DPN_ADAPTIVE=%d", adaptive ? 1 : 0);
-    snprintf(dd, sizeof dd, "-DPN_DYNAMIC=%d", dynamic ? 1 : 0);
-    snprintf(ds, sizeof ds, "-DPN_SAVE=%d", save);
-    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", dq, dg, da, dd, ds, dt, dm};
-    std::vector<std::string> extra; /* developer knob: extra NVRTC options, space separated */
-    if (const char* e = getenv("PNODE_NVRTC_FLAGS")) {
-        std::string cur;
-        for (const char* c = e;; c++) {
-            if (*c == ' ' || *c == 0) {
-                if (!cur.empty()) extra.push_back(cur);
-                cur.clear();
-                if (!*c) break;
-            } else cur.push_back(*c);
-        }
-        for (auto& x : extra) opts.push_back(x.c_str());
-    }
-    nvrtcResult cr = nvrtcCompileProgram(prog, (int)opts.size(), opts.data());
-    if (cr != NVRTC_SUCCESS) {
-        size_t n = 0;
-        nvrtcGetProgramLogSize(prog, &n);
-        std::string log(n, '\0');
-        if (n) nvrtcGetProgramLog(prog, &log[0]);
-        nvrtcDestroyProgram(&prog);
-        return fail(PNODE_ERR_COMPILE, "NVRTC compilation failed:\n" + log);
-    }
-    size_t nb = 0;
-    nvrtcGetCUBINSize(prog, &nb);
-    cubin->resize(nb);
-    nvrtcGetCUBIN(prog, cubin->data());
-    nvrtcDestroyProgram(&prog);
-    return 0;
+    auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
+    return nvrtc_compile(src, {def("PN_THREADS", threads), def("PN_MIN_BLOCKS", min_blocks), def("PN_Q", q), def("PN_G", G),
+                               def("PN_ADAPTIVE", adaptive ? 1 : 0), def("PN_DYNAMIC", dynamic ? 1 : 0), def("PN_SAVE", save)},
+                         cubin);
+}
+
+/* NVRTC: register-resident smoother sweep for (d, q, G); independent of the right-hand side. */
+static int nvrtc_smoother_cubin(int d, int q, int G, std::vector<char>* cubin) {
+    std::string src =
+        "#include \"kernels/pn_smooth_reg.cuh\"\n"
+        "extern \"C\" __global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_entry(const __grid_constant__ "
+        "PnSmoothParams P) {\n  pn_smooth_reg_entry<PN_SD, PN_SQ, PN_SG>(P);\n}\n";
+    auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
+    return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G)}, cubin);
 }
 
 static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
@@ -322,6 +352,44 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
     int rc = compile_nvrtc(s, save, out);
     s->compile_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return rc;
+}
+
+/* register-resident smoother: ahead-of-time instantiation if there is one, else NVRTC */
+static int get_smoother(pnode_solver* s) {
+    Kernel* out = &s->k_smooth;
+    if (out->valid()) return 0;
+    s->Gs = env_int("PNODE_SMOOTH_LANES", smooth_lanes(s->D));
+    if (s->Gs <= 0 || s->cta || env_int("PNODE_SMOOTH_GENERIC", 0)) return 0; /* shared-memory sweep */
+    s->smem_smooth = smooth_reg_smem_bytes(s->cfg.d, s->cfg.q, s->Gs);
+    if (s->smem_smooth > 227 * 1024) return 0;
+    auto t0 = std::chrono::steady_clock::now();
+    out->threads = PN_SMR_THREADS;
+    const void* fn = env_int("PNODE_FORCE_NVRTC", 0) ? nullptr : pn_smooth_reg_lookup(s->cfg.d, s->cfg.q, s->Gs);
+    if (fn) {
+        out->rt_fn = fn;
+        CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_smooth));
+        int nblk = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, out->threads, s->smem_smooth));
+        if (nblk < 1) return fail(PNODE_ERR_CUDA, "smoother kernel does not fit on an SM");
+        out->blocks_per_sm = nblk;
+        return 0;
+    }
+    int rc = load_driver();
+    if (rc) return rc;
+    std::vector<char> cubin;
+    if ((rc = nvrtc_smoother_cubin(s->cfg.d, s->cfg.q, s->Gs, &cubin))) return rc;
+    CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
+    if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
+    r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_smooth_entry");
+    if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction: " + cu_err(r));
+    r = g_drv.FuncSetAttribute(out->drv_fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->smem_smooth);
+    if (r != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuFuncSetAttribute(max dynamic smem): " + cu_err(r));
+    int nblk = 0;
+    r = g_drv.Occupancy(&nblk, out->drv_fn, out->threads, s->smem_smooth);
+    if (r != CUDA_SUCCESS || nblk < 1) return fail(PNODE_ERR_CUDA, "occupancy query failed: " + cu_err(r));
+    out->blocks_per_sm = nblk;
+    s->compile_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
 }
 
 static size_t cta_smem_bytes(int d, int q, int n_p) {
@@ -505,8 +573,11 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
         }
     }
     int rc = get_kernel(s, cfg->save_everystep ? (cfg->smooth ? 2 : 1) : 0, cfg->save_everystep ? &s->k_save : &s->k_final);
+    if (!rc && cfg->smooth) rc = get_smoother(s);
     if (rc) {
+        std::string keep = g_err;
         pnode_destroy(s);
+        g_err = keep;
         return rc;
     }
     *out = s;
@@ -549,7 +620,7 @@ extern "C" void pnode_destroy(pnode_solver* s) {
     if (!s) return;
     cudaSetDevice(s->cfg.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    for (Kernel* k : {&s->k_final, &s->k_save})
+    for (Kernel* k : {&s->k_final, &s->k_save, &s->k_smooth})
         if (k->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(k->mod);
     if (s->d_counter) cudaFree(s->d_counter);
     if (s->d_tstops) cudaFree(s->d_tstops);
@@ -683,22 +754,40 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             Q.s_u_cov = P.s_u_cov;
             memcpy(Q.L, s->base.L, sizeof Q.L);
             Q.work_counter = s->d_counter;
-            const int n = s->cfg.q + 1;
-            const size_t per_warp = (size_t)(7 * D * D + 4 * D + 2 * n * n + 2 * n) * sizeof(double);
-            int warps = PN_SM_WARPS;
-            while (warps > 1 && per_warp * warps > 200 * 1024) warps--;
-            const size_t smem = per_warp * warps;
-            if (smem > 220 * 1024) return fail(PNODE_ERR_UNSUPPORTED, "state dimension too large for the shared-memory smoother");
-            const void* fn = pn_smooth_kernel_ptr();
-            CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            int nblk = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, 32 * warps, smem));
-            if (nblk < 1) return fail(PNODE_ERR_CUDA, "smoother kernel does not fit on an SM");
-            long long want = (n_traj + warps - 1) / warps;
-            unsigned grid = (unsigned)std::max(1LL, std::min(want, (long long)s->n_sm * nblk));
-            CUDA_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), s->stream));
-            void* args[] = {&Q};
-            CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(32 * warps), args, smem, s->stream));
+            memcpy(Q.U, s->base.U, sizeof Q.U);
+            if (s->k_smooth.valid()) {
+                /* register-resident sweep: Gs lanes per trajectory, persistent, one CTA per SM */
+                Kernel& ks = s->k_smooth;
+                const int groups = ks.threads / s->Gs;
+                long long want = (n_traj + groups - 1) / groups;
+                unsigned grid = (unsigned)std::max(1LL, std::min(want, (long long)s->n_sm * ks.blocks_per_sm));
+                CUDA_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), s->stream));
+                void* args[] = {&Q};
+                if (ks.rt_fn) {
+                    CUDA_TRY(cudaLaunchKernel(ks.rt_fn, dim3(grid), dim3(ks.threads), args, s->smem_smooth, s->stream));
+                } else {
+                    CUresult cr = g_drv.LaunchKernel(ks.drv_fn, grid, 1, 1, ks.threads, 1, 1, (unsigned)s->smem_smooth,
+                                                     (CUstream)s->stream, args, nullptr);
+                    if (cr != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuLaunchKernel(smoother): " + cu_err(cr));
+                }
+            } else {
+                const int n = s->cfg.q + 1;
+                const size_t per_warp = (size_t)(7 * D * D + 4 * D + 2 * n * n + 2 * n) * sizeof(double);
+                int warps = PN_SM_WARPS;
+                while (warps > 1 && per_warp * warps > 200 * 1024) warps--;
+                const size_t smem = per_warp * warps;
+                if (smem > 220 * 1024) return fail(PNODE_ERR_UNSUPPORTED, "state dimension too large for the shared-memory smoother");
+                const void* fn = pn_smooth_kernel_ptr();
+                CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int nblk = 0;
+                CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, 32 * warps, smem));
+                if (nblk < 1) return fail(PNODE_ERR_CUDA, "smoother kernel does not fit on an SM");
+                long long want = (n_traj + warps - 1) / warps;
+                unsigned grid = (unsigned)std::max(1LL, std::min(want, (long long)s->n_sm * nblk));
+                CUDA_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), s->stream));
+                void* args[] = {&Q};
+                CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(32 * warps), args, smem, s->stream));
+            }
             CUDA_TRY(cudaFreeAsync(d_h, s->stream));
             launches = 3;
         }

@@ -360,6 +360,36 @@ def test_smoother_adaptive(oracle, name, q, t1):
         assert np.max(np.abs(g["U"][b - 1] - o["pu_mu"][-1]) / scale) < 1e-8
 
 
+def test_smoother_register_and_shared_memory_sweeps_agree(monkeypatch):
+    """The register-resident sweep (pn_smooth_reg.cuh: one joint QR, G never formed) and the shared-memory sweep
+    (pn_smooth.cuh: the reference formulas literally) smooth the same filtered records: ragged adaptive ensemble
+    (idle groups, different lengths per warp), BASELINE cfg3 shape (Van der Pol, order 5, D = 12)."""
+    n = 203
+    pd, u0, p = _inputs("vanderpol", n, 21, dp=0.2)
+    u0[:, 0] += 0.1 * np.random.default_rng(5).uniform(-1, 1, n)
+    g = _gpu_smooth(pd, u0, p, 5, adaptive=True, t0=0.0, t1=0.5)
+    monkeypatch.setenv("PNODE_SMOOTH_GENERIC", "1")
+    r = _gpu_smooth(pd, u0, p, 5, adaptive=True, t0=0.0, t1=0.5)
+    assert np.array_equal(g["off"], r["off"]) and np.array_equal(g["T"], r["T"])
+    assert len(set(np.diff(g["off"]))) > 3                          # ragged
+    scale = np.abs(r["U"]).max(axis=0)
+    assert np.max(np.abs(g["U"] - r["U"]) / scale) < 1e-9
+    assert _relcov(g["C"], r["C"]) < 1e-6
+    # (full-state covariances of this stiff order-5 problem have entries up to 1e20 in the high-derivative blocks;
+    #  they are compared on the non-stiff problem below)
+    monkeypatch.delenv("PNODE_SMOOTH_GENERIC")
+    pd, u0, p = _inputs("lotka_volterra", 37, 22, du0=0.05)
+    g = _gpu_smooth(pd, u0, p, 3, adaptive=True, t0=0.0, t1=10.0)
+    monkeypatch.setenv("PNODE_SMOOTH_GENERIC", "1")
+    r = _gpu_smooth(pd, u0, p, 3, adaptive=True, t0=0.0, t1=10.0)
+    assert np.array_equal(g["off"], r["off"])
+    assert _rel(g["U"], r["U"]) < 1e-10 and _relcov(g["C"], r["C"]) < 1e-9
+    Sg = np.einsum("kra,krb->kab", g["XR"], g["XR"])
+    Sr = np.einsum("kra,krb->kab", r["XR"], r["XR"])
+    assert _relcov(Sg, Sr) < 1e-8
+    assert _rel(g["X"], r["X"]) < 1e-8
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # EK0 / IsometricKronecker layout (BASELINE cfg2)
 # ------------------------------------------------------------------------------------------------------------------
