@@ -115,6 +115,93 @@ PN_HD void pn_chol_solve(const double (&U)[M_][M_], const double (&invd)[M_], do
     }
 }
 
+// Householder QR of the stack [Tt ; Bt], rows in registers: slot lr of lane gl holds row lr*G + gl of the block.
+// Columns 0..NE-1 are eliminated; columns NE..NC-1 only receive the reflections.  BOTUP: the first NE columns of
+// the bottom block are upper triangular (row r zero in columns < r), so bottom slot lr joins at column lr*G and
+// entries left of its first row are never touched.  On return Tt[:, 0:NE] is the upper-triangular factor (zeros
+// below the diagonal); if dinv != nullptr lane (k % G) stores 1/diag[k] (0 for a zero column) to dinv[k].
+// The j loop is chunked (JC columns at a time) to bound the number of live partial sums.
+template <int G, int RPL, int NC, int NE, bool BOTUP, int JC>
+PN_HD void pn_qr_rows(double (&Tt)[RPL][NC], double (&Bt)[RPL][NC], int gl, double* dinv) {
+#pragma unroll
+    for (int k = 0; k < NE; k++) {
+        const int ks = k / G, kl = k % G;
+        double x[RPL];
+        double part = 0.0;
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++) {
+            const int base = lr * G;
+            if (base + G - 1 < k) {
+                x[lr] = 0.0;
+            } else if (base >= k) {
+                x[lr] = Tt[lr][k];
+            } else {
+                x[lr] = (base + gl >= k) ? Tt[lr][k] : 0.0;
+            }
+            if (base + G - 1 >= k) part += x[lr] * x[lr];
+        }
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++)
+            if (!BOTUP || lr * G <= k) part += Bt[lr][k] * Bt[lr][k];
+        const double total = pn_gsum<G>(part);
+        const double alpha = pn_gbcast<G>(x[ks], kl);
+        const bool nz = total > 0.0;
+        const double rsq = pn_rsqrt(total);
+        const double nrm = nz ? total * rsq : 0.0;
+        const double beta = -copysign(nrm, alpha);
+        const double vk = alpha - beta;
+        const double den = total + fabs(alpha) * nrm; /* = v'v / 2 */
+        const double gam = nz ? pn_rcp(den) : 0.0;
+        if (dinv != nullptr && gl == kl) dinv[k] = nz ? -copysign(rsq, alpha) : 0.0;
+        if (gl == kl) x[ks] = vk;
+#pragma unroll
+        for (int j0 = 0; j0 < NC; j0 += JC) {
+            if (j0 + JC - 1 <= k) continue;
+            double sj[JC];
+#pragma unroll
+            for (int jj = 0; jj < JC; jj++) {
+                const int j = j0 + jj;
+                sj[jj] = 0.0;
+                if (j <= k || j >= NC) continue;
+                double s = 0.0;
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++)
+                    if (lr * G + G - 1 >= k) s += x[lr] * Tt[lr][j];
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++)
+                    if (!BOTUP || lr * G <= k) s += Bt[lr][k] * Bt[lr][j];
+                sj[jj] = s;
+            }
+#pragma unroll
+            for (int jj = 0; jj < JC; jj++) {
+                const int j = j0 + jj;
+                if (j <= k || j >= NC) continue;
+                sj[jj] = pn_gsum<G>(sj[jj]) * gam;
+            }
+#pragma unroll
+            for (int jj = 0; jj < JC; jj++) {
+                const int j = j0 + jj;
+                if (j <= k || j >= NC) continue;
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++)
+                    if (lr * G + G - 1 >= k) Tt[lr][j] -= sj[jj] * x[lr];
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++)
+                    if (!BOTUP || lr * G <= k) Bt[lr][j] -= sj[jj] * Bt[lr][k];
+            }
+        }
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++) {
+            const int base = lr * G;
+            if (base + G - 1 < k) continue;
+            const int row = base + gl;
+            if (row == k) Tt[lr][k] = beta;
+            else if (row > k) Tt[lr][k] = 0.0;
+        }
+    }
+}
+
+
 // ode_determine_initdt (OrdinaryDiffEqCore, Hairer-Wanner; restated from SURVEY.md A.6).  Two f evaluations.
 template <class Prob>
 PN_HD double pn_initial_dt(const PnParams& P, const double* u0, const double* pr) {
@@ -516,6 +603,7 @@ struct PnSmall {
                                 if (k > j) s += hp[k > j ? k - j : 0] * R[lr][k * d + i];
                             R[lr][j * d + i] = s;
                         }
+#ifdef PN_QR_LOWER_NOISE
                 /* bottom block: sqrt(s2) (L P^-1) (x) I_d, row (m,i) has L[m][c] PI[c] at column (c,i), c <= m */
                 {
                     const double sd = (ediff == 1.0) ? 1.0 : sqrt(ediff);
@@ -533,6 +621,30 @@ struct PnSmall {
                         }
                 }
                 qr_stack(R, B, gl);
+#else
+                /* bottom block: sqrt(s2) (U P^-1) (x) I_d with U'U = L'L upper triangular (pn_params.h): row (m,i) has
+                   U[m][c] PI[c] at column (c,i), c >= m, so the block is upper triangular and its rows join the
+                   Householder sweep one slot at a time */
+                {
+                    const double sd = (ediff == 1.0) ? 1.0 : sqrt(ediff);
+#pragma unroll
+                    for (int lr = 0; lr < RPL; lr++)
+#pragma unroll
+                        for (int c = 0; c < n; c++) {
+                            double usel = 0.0;
+#pragma unroll
+                            for (int m = 0; m < n; m++)
+                                if (m <= c) usel = (mB[lr] == m) ? P.U[m * n + c] : usel;
+                            const double val = usel * PIv[c] * sd;
+#pragma unroll
+                            for (int i = 0; i < d; i++) B[lr][c * d + i] = (iB[lr] == i) ? val : 0.0;
+                        }
+                }
+#ifndef PN_QR_JC
+#define PN_QR_JC D
+#endif
+                pn_qr_rows<G, RPL, D, D, true, PN_QR_JC>(R, B, gl, nullptr);
+#endif
 
                 /* C2 = R^- H' (row-local; rows >= 2d are exactly zero, see RU), S = C2'C2 */
                 double C2[RU][d];

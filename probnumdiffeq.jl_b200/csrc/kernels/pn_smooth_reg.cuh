@@ -45,93 +45,6 @@
 #define PN_SMR_THREADS 256
 #endif
 
-// Householder QR of the stack [Tt ; Bt], rows in registers: slot lr of lane gl holds row lr*G + gl of the block.
-// Columns 0..NE-1 are eliminated; columns NE..NC-1 only receive the reflections.  BOTUP: the first NE columns of
-// the bottom block are upper triangular (row r zero in columns < r), so bottom slot lr joins at column lr*G and
-// entries left of its first row are never touched.  On return Tt[:, 0:NE] is the upper-triangular factor (zeros
-// below the diagonal); if dinv != nullptr lane (k % G) stores 1/diag[k] (0 for a zero column) to dinv[k].
-// The j loop is chunked (JC columns at a time) to bound the number of live partial sums.
-template <int G, int RPL, int NC, int NE, bool BOTUP, int JC>
-PN_HD void pn_qr_rows(double (&Tt)[RPL][NC], double (&Bt)[RPL][NC], int gl, double* dinv) {
-#pragma unroll
-    for (int k = 0; k < NE; k++) {
-        const int ks = k / G, kl = k % G;
-        double x[RPL];
-        double part = 0.0;
-#pragma unroll
-        for (int lr = 0; lr < RPL; lr++) {
-            const int base = lr * G;
-            if (base + G - 1 < k) {
-                x[lr] = 0.0;
-            } else if (base >= k) {
-                x[lr] = Tt[lr][k];
-            } else {
-                x[lr] = (base + gl >= k) ? Tt[lr][k] : 0.0;
-            }
-            if (base + G - 1 >= k) part += x[lr] * x[lr];
-        }
-#pragma unroll
-        for (int lr = 0; lr < RPL; lr++)
-            if (!BOTUP || lr * G <= k) part += Bt[lr][k] * Bt[lr][k];
-        const double total = pn_gsum<G>(part);
-        const double alpha = pn_gbcast<G>(x[ks], kl);
-        const bool nz = total > 0.0;
-        const double rsq = pn_rsqrt(total);
-        const double nrm = nz ? total * rsq : 0.0;
-        const double beta = -copysign(nrm, alpha);
-        const double vk = alpha - beta;
-        const double den = total + fabs(alpha) * nrm; /* = v'v / 2 */
-        const double gam = nz ? pn_rcp(den) : 0.0;
-        if (dinv != nullptr && gl == kl) dinv[k] = nz ? -copysign(rsq, alpha) : 0.0;
-        if (gl == kl) x[ks] = vk;
-#pragma unroll
-        for (int j0 = 0; j0 < NC; j0 += JC) {
-            if (j0 + JC - 1 <= k) continue;
-            double sj[JC];
-#pragma unroll
-            for (int jj = 0; jj < JC; jj++) {
-                const int j = j0 + jj;
-                sj[jj] = 0.0;
-                if (j <= k || j >= NC) continue;
-                double s = 0.0;
-#pragma unroll
-                for (int lr = 0; lr < RPL; lr++)
-                    if (lr * G + G - 1 >= k) s += x[lr] * Tt[lr][j];
-#pragma unroll
-                for (int lr = 0; lr < RPL; lr++)
-                    if (!BOTUP || lr * G <= k) s += Bt[lr][k] * Bt[lr][j];
-                sj[jj] = s;
-            }
-#pragma unroll
-            for (int jj = 0; jj < JC; jj++) {
-                const int j = j0 + jj;
-                if (j <= k || j >= NC) continue;
-                sj[jj] = pn_gsum<G>(sj[jj]) * gam;
-            }
-#pragma unroll
-            for (int jj = 0; jj < JC; jj++) {
-                const int j = j0 + jj;
-                if (j <= k || j >= NC) continue;
-#pragma unroll
-                for (int lr = 0; lr < RPL; lr++)
-                    if (lr * G + G - 1 >= k) Tt[lr][j] -= sj[jj] * x[lr];
-#pragma unroll
-                for (int lr = 0; lr < RPL; lr++)
-                    if (!BOTUP || lr * G <= k) Bt[lr][j] -= sj[jj] * Bt[lr][k];
-            }
-        }
-#pragma unroll
-        for (int lr = 0; lr < RPL; lr++) {
-            const int base = lr * G;
-            if (base + G - 1 < k) continue;
-            const int row = base + gl;
-            if (row == k) Tt[lr][k] = beta;
-            else if (row > k) Tt[lr][k] = 0.0;
-        }
-    }
-}
-
-
 // Row of D doubles at p (16-byte aligned when D is even: record and row offsets are multiples of D doubles).
 template <int D_>
 PN_HD void pn_ld_row(const double* __restrict__ p, double (&dst)[D_], bool pred) {
