@@ -25,8 +25,8 @@ import sympy as sp
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
-EK0, EK1 = 0, 1
-DIFF_DYNAMIC, DIFF_FIXED = 0, 1
+EK0, EK1, DIAGONAL_EK1 = 0, 1, 2
+DIFF_DYNAMIC, DIFF_FIXED, DIFF_DYNAMIC_MV, DIFF_FIXED_MV = 0, 1, 2, 3
 COV_REF, COV_QR = 0, 1
 RET = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable"}
 
@@ -91,6 +91,7 @@ class Traj(C.Structure):
         ("x_smooth_mu", C.POINTER(C.c_double)), ("x_smooth_R", C.POINTER(C.c_double)),
         ("pu_mu", C.POINTER(C.c_double)), ("pu_R", C.POINTER(C.c_double)),
         ("bk_G", C.POINTER(C.c_double)), ("bk_b", C.POINTER(C.c_double)), ("bk_LR", C.POINTER(C.c_double)),
+        ("diffusions_mv", C.POINTER(C.c_double)), ("global_diffusion_mv", C.POINTER(C.c_double)),
     ]
 
 
@@ -266,9 +267,13 @@ def solve(cfg: Config, rhs: CompiledRHS, u0, p) -> dict:
         pu_mu=_arr(tr.pu_mu, (n, d)),
         pu_R=_arr(tr.pu_R, (n, d, D)).transpose(0, 2, 1).copy(),
     )
+    if tr.diffusions_mv:
+        out["diffusions_mv"] = _arr(tr.diffusions_mv, (n, d))
+        out["global_diffusion_mv"] = _arr(tr.global_diffusion_mv, (d,))
     if tr.x_smooth_mu:
         out["x_smooth_mu"] = _arr(tr.x_smooth_mu, (n, D))
         out["x_smooth_R"] = _arr(tr.x_smooth_R, (n, D, D)).transpose(0, 2, 1).copy()
+    if tr.bk_G:
         out["bk_G"] = _arr(tr.bk_G, (max(n - 1, 1), D, D))[: n - 1].transpose(0, 2, 1).copy()
         out["bk_b"] = _arr(tr.bk_b, (max(n - 1, 1), D))[: n - 1]
         out["bk_LR"] = _arr(tr.bk_LR, (max(n - 1, 1), D, 2 * D))[: n - 1].transpose(0, 2, 1).copy()

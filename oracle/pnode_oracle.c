@@ -427,8 +427,322 @@ static double initial_dt(const oracle_config* c, oracle_rhs_fn f, const double* 
     return fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
 }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* BlocksOfDiagonals layout (src/blocksofdiagonals.jl:15-52): d independent (q+1) x (q+1) factors, */
+/* block i <-> state indices i:d:D.  Selected for EK0 + multivariate diffusion and for DiagonalEK1 */
+/* (src/algorithms.jl:132-151).  The per-block routines are the generic ones above with N = q+1.   */
+/* ------------------------------------------------------------------------------------------ */
+static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, oracle_taylor_fn taylor,
+                        const double* u0, const double* p, oracle_traj* out) {
+    const int d = c->d, q = c->q, n = q + 1, D = d * n;
+    const int diag1 = (c->alg == ORACLE_DIAGONAL_EK1);
+    const int mv = (c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV);
+    const int dynamic = (c->diffusion == ORACLE_DIFF_DYNAMIC || c->diffusion == ORACLE_DIFF_DYNAMIC_MV);
+    memset(out, 0, sizeof(*out));
+    out->d = d; out->q = q; out->D = D; out->smooth = c->smooth; out->alg = c->alg;
+    out->global_diffusion = NAN;
+    if (d > 64 || n > 32) return -1;
+    if (c->alg == ORACLE_EK1) return -2; /* EK1 + MV diffusion is rejected by the reference (algorithms.jl:93-107) */
+    const size_t nn = (size_t)n * n, NB = nn * d; /* all blocks of one state */
+    double* Ah1 = (double*)malloc(sizeof(double) * nn);
+    double* Qh1 = (double*)malloc(sizeof(double) * nn);
+    double* mu = (double*)calloc(D, sizeof(double));
+    double* R = (double*)calloc(NB, sizeof(double));
+    double* mu_pred = (double*)calloc(D, sizeof(double));
+    double* R_pred = (double*)calloc(NB, sizeof(double));
+    double* mu_filt = (double*)calloc(D, sizeof(double));
+    double* R_filt = (double*)calloc(NB, sizeof(double));
+    double* H = (double*)calloc((size_t)d * n, sizeof(double)); /* block i: 1 x n at H + i*n */
+    double* J = (double*)calloc((size_t)d * d, sizeof(double));
+    double* G = (double*)malloc(sizeof(double) * NB);
+    double* bb = (double*)malloc(sizeof(double) * D);
+    double* LR = (double*)malloc(sizeof(double) * 2 * NB);
+    double* Qs = (double*)malloc(sizeof(double) * nn);
+    double z[64], fu[64], uprev[64], upred[64], err[64], HQH[64], Cq[32];
+    double local_diffusion[64], global_diffusion[64], default_diffusion[64], ediff[64];
+    for (int i = 0; i < d; i++) {
+        local_diffusion[i] = NAN;
+        global_diffusion[i] = NAN;
+        default_diffusion[i] = c->initial_diffusion;
+    }
+    dvec ts = {0}, diffs = {0}, xmu = {0}, xR = {0}, bG = {0}, bB = {0}, bL = {0};
+
+    taylor(mu, u0, p, c->t0, q);
+    out->nf += q;
+    for (int i = 0; i < d; i++) uprev[i] = mu[i];
+    double t = c->t0, dt;
+    if (c->adaptive && !(c->dt > 0.0)) {
+        dt = initial_dt(c, f, u0, p, q);
+        out->nf += 2;
+    } else {
+        dt = c->dt;
+    }
+    const double dtcache = dt;
+    double qold = c->qoldinit;
+    int64_t iter = 0, success_iter = 0, tstop_idx = 0;
+    int retcode = ORACLE_RET_SUCCESS;
+    double loglik_total = 0.0;
+    dvec_push(&ts, &t, 1);
+    dvec_push(&xmu, mu, D);
+    dvec_push(&xR, R, NB);
+
+    while (t < c->t1) {
+        double tstop = c->t1;
+        while (tstop_idx < c->n_tstops && c->tstops[tstop_idx] <= t) tstop_idx++;
+        if (tstop_idx < c->n_tstops && c->tstops[tstop_idx] < c->t1) tstop = c->tstops[tstop_idx];
+        iter++;
+        if (iter > c->maxiters) { retcode = ORACLE_RET_MAXITERS; break; }
+        if (c->adaptive) {
+            dt = fmin(dt, c->dtmax);
+            dt = fmax(dt, c->dtmin);
+            dt = fmin(dt, tstop - t);
+        } else {
+            dt = fmin(dtcache, tstop - t);
+        }
+        if (isnan(dt) || !(t + dt > t) || (c->adaptive && dt <= c->dtmin)) { retcode = ORACLE_RET_DTLESSTHANMIN; break; }
+        double tnew = t + dt;
+        oracle_iwp_transition(q, dt, Ah1, Qh1); /* every block shares Ah, Qh (iwp.jl:165-171 on the Blocks layout) */
+        for (int i = 0; i < d; i++) /* predict_mean! */
+            for (int r = 0; r < n; r++) {
+                double s = 0.0;
+                for (int k = 0; k < n; k++) s += AT(Ah1, r, k, n) * mu[k * d + i];
+                mu_pred[r * d + i] = s;
+            }
+        for (int i = 0; i < d; i++) upred[i] = mu_pred[i];
+        f(fu, upred, p, tnew);
+        out->nf += 1;
+        for (int i = 0; i < d; i++) z[i] = mu_pred[d + i] - fu[i];
+        /* calc_H! (derivative_utils.jl:1-33): EK0 H = E1; DiagonalEK1 H = E1 - Diagonal(diag(J)) E0 */
+        if (diag1) {
+            jac(J, upred, p, tnew);
+            out->njac += 1;
+        }
+        for (int i = 0; i < d; i++) {
+            double* Hi = H + (size_t)i * n;
+            for (int k = 0; k < n; k++) Hi[k] = 0.0;
+            Hi[1] = 1.0;
+            if (diag1) Hi[0] = -AT(J, i, i, d);
+        }
+        if (c->adaptive || dynamic) {
+            /* HQH block i = |Qh.R H_i'|^2 ; scalar: invquad(z, HQH)/d (calibration.jl:21-29,123-133);
+               multivariate: z_i^2 / Q11_i (local_diagonal_diffusion, calibration.jl:151-180) */
+            double qd = 0.0;
+            for (int i = 0; i < d; i++) {
+                const double* Hi = H + (size_t)i * n;
+                double e = 0.0;
+                for (int r = 0; r < n; r++) {
+                    double cq = 0.0;
+                    for (int k = 0; k < n; k++) cq += AT(Qh1, r, k, n) * Hi[k];
+                    e += cq * cq;
+                }
+                HQH[i] = e;
+                qd += z[i] * (z[i] / e);
+            }
+            for (int i = 0; i < d; i++) local_diffusion[i] = mv ? z[i] * z[i] / HQH[i] : qd / (double)d;
+        }
+        double EEst = 0.0;
+        if (c->adaptive) { /* estimate_errors! (perform_step.jl:240-259): block i of (Qh.R sqrt(s_i)) H_i' */
+            for (int i = 0; i < d; i++) {
+                const double* Hi = H + (size_t)i * n;
+                double s = sqrt(local_diffusion[i]);
+                for (size_t k = 0; k < nn; k++) Qs[k] = Qh1[k] * s;
+                double e = 0.0;
+                for (int r = 0; r < n; r++) {
+                    Cq[r] = 0.0;
+                    for (int k = 0; k < n; k++) Cq[r] += AT(Qs, r, k, n) * Hi[k];
+                    e += Cq[r] * Cq[r];
+                }
+                err[i] = sqrt(e) * dt;
+                err[i] = err[i] / (c->abstol + fmax(fabs(upred[i]), fabs(uprev[i])) * c->reltol);
+            }
+            EEst = rms_norm(err, d);
+            if (isnan(EEst)) { retcode = ORACLE_RET_UNSTABLE; break; }
+        }
+        int accept = (!c->adaptive) || (EEst < 1.0);
+        double q11 = 0.0, qq = 1.0;
+        if (c->adaptive) {
+            if (EEst == 0.0) {
+                qq = 1.0 / c->qmax;
+            } else {
+                q11 = pow(EEst, c->beta1);
+                qq = q11 / pow(qold, c->beta2);
+                qq = fmax(1.0 / c->qmax, fmin(1.0 / c->qmin, qq / c->gamma));
+            }
+        }
+        if (!accept) {
+            out->nreject++;
+            dt = dt / fmin(1.0 / c->qmin, q11 / c->gamma);
+            continue;
+        }
+        double ll_step = 0.0, S[64];
+        int ufail = 0;
+        for (int i = 0; i < d; i++) {
+            ediff[i] = dynamic ? local_diffusion[i] : default_diffusion[i];
+            const double* Hi = H + (size_t)i * n;
+            oracle_predict_cov(n, R + i * nn, Ah1, Qh1, ediff[i], c->cov_backend, R_pred + i * nn, NULL); /* predict.jl:120-141 */
+            if (c->smooth) /* markov_kernel.jl:274-323 */
+                backward_kernel_generic(n, 1, d, 0, mu + i, R + i * nn, mu_pred + i, R_pred + i * nn, Ah1, Qh1, ediff[i],
+                                        G + i * nn, bb + i, LR + i * 2 * nn);
+            double e = 0.0; /* S_i = |R^-_i H_i'|^2 (perform_step.jl:182-188) */
+            for (int r = 0; r < n; r++) {
+                double cq = 0.0;
+                for (int k = 0; k < n; k++) cq += AT(R_pred + i * nn, r, k, n) * Hi[k];
+                e += cq * cq;
+            }
+            S[i] = e;
+            double ll;
+            ufail |= update_generic(n, 1, 1, mu_pred + i, d, 0, R_pred + i * nn, z + i, 1, 0, Hi, mu_filt + i, R_filt + i * nn,
+                                    &ll); /* update.jl:197-239 */
+            ll_step += ll;
+        }
+        if (ufail) { retcode = ORACLE_RET_UNSTABLE; break; }
+        loglik_total += ll_step;
+        if (!dynamic) {
+            if (mv) { /* estimate_global_diffusion(::FixedMVDiffusion) (calibration.jl:88-107): z_j^2 / S[1,1] */
+                for (int j = 0; j < d; j++) {
+                    double inc = z[j] * z[j] / S[0];
+                    global_diffusion[j] = (success_iter == 0) ? inc : global_diffusion[j] + (inc - global_diffusion[j]) / (double)success_iter;
+                }
+            } else { /* FixedDiffusion: invquad(z, S)/d with S BlocksOfDiagonals (calibration.jl:21-29,49-66) */
+                double qd = 0.0;
+                for (int i = 0; i < d; i++) qd += z[i] * (z[i] / S[i]);
+                double inc = qd / (double)d;
+                double g = (success_iter == 0) ? inc : global_diffusion[0] + (inc - global_diffusion[0]) / (double)success_iter;
+                for (int j = 0; j < d; j++) global_diffusion[j] = g;
+            }
+        }
+        memcpy(mu, mu_filt, sizeof(double) * D);
+        memcpy(R, R_filt, sizeof(double) * NB);
+        double dtnew = dt;
+        if (c->adaptive) {
+            if (c->qsteady_min <= qq && qq <= c->qsteady_max) qq = 1.0;
+            qold = fmax(EEst, c->qoldinit);
+            dtnew = dt / qq;
+        }
+        double ttmp = t + dt;
+        double ref = fmax(fabs(t), fabs(tstop));
+        double epsref = nextafter(ref, INFINITY) - ref;
+        t = (fabs(ttmp - tstop) < 100.0 * epsref) ? tstop : ttmp;
+        dt = dtnew;
+        success_iter++;
+        out->naccept++;
+        int nanu = 0;
+        for (int i = 0; i < d; i++) {
+            uprev[i] = mu[i];
+            if (isnan(mu[i])) nanu = 1;
+        }
+        if (c->save_everystep) {
+            dvec_push(&ts, &t, 1);
+            dvec_push(&diffs, local_diffusion, d);
+            dvec_push(&xmu, mu, D);
+            dvec_push(&xR, R, NB);
+            if (c->smooth) {
+                dvec_push(&bG, G, NB);
+                dvec_push(&bB, bb, D);
+                dvec_push(&bL, LR, 2 * NB);
+            }
+        }
+        if (nanu) { retcode = ORACLE_RET_UNSTABLE; break; }
+    }
+    if (!c->save_everystep) {
+        dvec_push(&ts, &t, 1);
+        dvec_push(&diffs, local_diffusion, d);
+        dvec_push(&xmu, mu, D);
+        dvec_push(&xR, R, NB);
+    }
+    int64_t ns = (int64_t)ts.len;
+    out->n = ns;
+    out->retcode = retcode;
+    out->loglik = loglik_total;
+    out->global_diffusion = global_diffusion[0];
+    out->global_diffusion_mv = (double*)malloc(sizeof(double) * d);
+    memcpy(out->global_diffusion_mv, global_diffusion, sizeof(double) * d);
+    {
+        double pad[64];
+        for (int i = 0; i < d; i++) pad[i] = NAN;
+        while ((int64_t)diffs.len < ns * d) dvec_push(&diffs, pad, d);
+    }
+    if (!dynamic) {
+        if (c->calibrate && !isnan(global_diffusion[0])) { /* calibrate_solution!, apply_diffusion! on blocks */
+            for (int64_t k = 0; k < ns; k++)
+                for (int i = 0; i < d; i++) {
+                    diffs.p[k * d + i] = global_diffusion[i] * default_diffusion[i];
+                    double sm = sqrt(global_diffusion[i]);
+                    double* r = xR.p + (size_t)k * NB + i * nn;
+                    for (size_t e = 0; e < nn; e++) r[e] *= sm;
+                    if (c->smooth && k + 1 < ns) {
+                        double* l = bL.p + (size_t)k * 2 * NB + i * 2 * nn;
+                        for (size_t e = 0; e < 2 * nn; e++) l[e] *= sm;
+                    }
+                }
+        } else {
+            for (int64_t k = 0; k < ns; k++)
+                for (int i = 0; i < d; i++) diffs.p[k * d + i] = default_diffusion[i];
+        }
+    }
+    out->t = ts.p;
+    out->diffusions_mv = diffs.p;
+    out->diffusions = (double*)malloc(sizeof(double) * (size_t)ns);
+    for (int64_t k = 0; k < ns; k++) out->diffusions[k] = diffs.p[k * d];
+    out->x_filt_mu = xmu.p;
+    out->x_filt_R = (double*)calloc((size_t)ns * D * D, sizeof(double));
+    out->pu_mu = (double*)malloc(sizeof(double) * (size_t)ns * d);
+    out->pu_R = (double*)malloc(sizeof(double) * (size_t)ns * D * d);
+    /* dense form of a Blocks matrix: block i occupies rows/columns i:d:D (blocksofdiagonals.jl:44-52) */
+#define PN_BLOCKS_TO_DENSE(dst, src)                                                        \
+    for (int i = 0; i < d; i++)                                                             \
+        for (int cc = 0; cc < n; cc++)                                                      \
+            for (int r = 0; r < n; r++) AT(dst, r * d + i, cc * d + i, D) = AT((src) + i * nn, r, cc, n);
+    for (int64_t k = 0; k < ns; k++) {
+        double* dst = out->x_filt_R + (size_t)k * D * D;
+        PN_BLOCKS_TO_DENSE(dst, xR.p + (size_t)k * NB)
+    }
+    double* smu = NULL;
+    double* sR = NULL;
+    if (c->smooth && c->save_everystep) { /* smooth_solution! ; marginalize! Blocks (markov_kernel.jl:123-143) */
+        smu = (double*)malloc(sizeof(double) * (size_t)ns * D);
+        sR = (double*)malloc(sizeof(double) * (size_t)ns * NB);
+        memcpy(smu, xmu.p, sizeof(double) * (size_t)ns * D);
+        memcpy(sR, xR.p, sizeof(double) * (size_t)ns * NB);
+        for (int64_t k = ns - 2; k >= 0; k--) {
+            double dti = ts.p[k + 1] - ts.p[k];
+            if (dti == 0.0) {
+                memcpy(smu + (size_t)k * D, smu + (size_t)(k + 1) * D, sizeof(double) * D);
+                memcpy(sR + (size_t)k * NB, sR + (size_t)(k + 1) * NB, sizeof(double) * NB);
+                continue;
+            }
+            for (int i = 0; i < d; i++)
+                marginalize_generic(n, 1, d, 0, smu + (size_t)(k + 1) * D + i, sR + (size_t)(k + 1) * NB + i * nn,
+                                    bG.p + (size_t)k * NB + i * nn, bB.p + (size_t)k * D + i, bL.p + (size_t)k * 2 * NB + i * 2 * nn,
+                                    smu + (size_t)k * D + i, sR + (size_t)k * NB + i * nn);
+        }
+        out->x_smooth_mu = smu;
+        out->x_smooth_R = (double*)calloc((size_t)ns * D * D, sizeof(double));
+        for (int64_t k = 0; k < ns; k++) {
+            double* dst = out->x_smooth_R + (size_t)k * D * D;
+            PN_BLOCKS_TO_DENSE(dst, sR + (size_t)k * NB)
+        }
+    }
+#undef PN_BLOCKS_TO_DENSE
+    for (int64_t k = 0; k < ns; k++) {
+        const double* xm = (smu ? smu : xmu.p) + (size_t)k * D;
+        const double* xr = (smu ? out->x_smooth_R : out->x_filt_R) + (size_t)k * D * D;
+        for (int i = 0; i < d; i++) out->pu_mu[(size_t)k * d + i] = xm[i];
+        for (int i = 0; i < d; i++)
+            for (int r = 0; r < D; r++) out->pu_R[(size_t)k * D * d + (size_t)i * D + r] = AT(xr, r, i, D);
+    }
+    free(sR);
+    free(xR.p); free(bG.p); free(bB.p); free(bL.p);
+    free(Ah1); free(Qh1); free(mu); free(R); free(mu_pred); free(R_pred); free(mu_filt); free(R_filt);
+    free(H); free(J); free(G); free(bb); free(LR); free(Qs);
+    return 0;
+}
+
 int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, oracle_taylor_fn taylor,
                  const double* u0, const double* p, oracle_traj* out) {
+    if (c->alg == ORACLE_DIAGONAL_EK1 || c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV)
+        return solve_blocks(c, f, jac, taylor, u0, p, out);
     const int d = c->d, q = c->q, n = q + 1, D = d * n;
     const int kron = (c->alg == ORACLE_EK0);
     const int N = kron ? n : D;          /* size of the matrices the filter works on */
@@ -799,7 +1113,7 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
 void oracle_traj_free(oracle_traj* tr) {
     free(tr->t); free(tr->diffusions); free(tr->x_filt_mu); free(tr->x_filt_R);
     free(tr->x_smooth_mu); free(tr->x_smooth_R); free(tr->pu_mu); free(tr->pu_R);
-    free(tr->bk_G); free(tr->bk_b); free(tr->bk_LR);
+    free(tr->bk_G); free(tr->bk_b); free(tr->bk_LR); free(tr->diffusions_mv); free(tr->global_diffusion_mv);
     memset(tr, 0, sizeof(*tr));
 }
 

@@ -33,8 +33,8 @@ typedef void (*oracle_jac_fn)(double* J, const double* u, const double* p, doubl
 /* out[k*d + i] = d^k u_i / dt^k (t0), k = 0..q  (true derivatives, not Taylor coefficients) */
 typedef void (*oracle_taylor_fn)(double* out, const double* u, const double* p, double t, int q);
 
-enum { ORACLE_EK0 = 0, ORACLE_EK1 = 1 };
-enum { ORACLE_DIFF_DYNAMIC = 0, ORACLE_DIFF_FIXED = 1 };
+enum { ORACLE_EK0 = 0, ORACLE_EK1 = 1, ORACLE_DIAGONAL_EK1 = 2 /* BlocksOfDiagonals layout, src/algorithms.jl:343-393 */ };
+enum { ORACLE_DIFF_DYNAMIC = 0, ORACLE_DIFF_FIXED = 1, ORACLE_DIFF_DYNAMIC_MV = 2, ORACLE_DIFF_FIXED_MV = 3 /* src/diffusions/typedefs.jl */ };
 enum { ORACLE_COV_REF = 0 /* Gram+Cholesky, QR fallback (predict.jl:84-91) */, ORACLE_COV_QR = 1 };
 enum {
     ORACLE_RET_SUCCESS = 0,
@@ -86,6 +86,8 @@ typedef struct {
     double* bk_G;         /* [n-1][D*D] backward kernels (smooth only) */
     double* bk_b;         /* [n-1][D] */
     double* bk_LR;        /* [n-1][2D*D] col-major 2D x D */
+    double* diffusions_mv;      /* [n][d] per-component diffusions (BlocksOfDiagonals solves only, else NULL) */
+    double* global_diffusion_mv; /* [d] (BlocksOfDiagonals solves only, else NULL) */
 } oracle_traj;
 
 /* ---- component-level entry points (unit-tested against dense formulas) ---- */
