@@ -53,10 +53,17 @@ typedef enum pnode_status {
     PNODE_ERR_NO_DEVICE = -6
 } pnode_status;
 
-typedef enum pnode_alg { PNODE_EK0 = 0, PNODE_EK1 = 1 } pnode_alg;                         /* src/algorithms.jl:188-296 */
-typedef enum pnode_cov { PNODE_COV_AUTO = 0, PNODE_COV_DENSE = 1, PNODE_COV_KRONECKER = 2 } pnode_cov; /* src/covariance_structure.jl */
+typedef enum pnode_alg { PNODE_EK0 = 0, PNODE_EK1 = 1, PNODE_DIAGONAL_EK1 = 2 } pnode_alg; /* src/algorithms.jl:188-393 */
+/* src/covariance_structure.jl:1-63; AUTO follows covariance_structure(alg, prior, diffusion) src/algorithms.jl:132-151 */
+typedef enum pnode_cov { PNODE_COV_AUTO = 0, PNODE_COV_DENSE = 1, PNODE_COV_KRONECKER = 2, PNODE_COV_BLOCKS = 3 } pnode_cov;
 typedef enum pnode_prior { PNODE_PRIOR_IWP = 0 } pnode_prior;                              /* src/priors/iwp.jl */
-typedef enum pnode_diffusion { PNODE_DIFF_DYNAMIC = 0, PNODE_DIFF_FIXED = 1 } pnode_diffusion; /* src/diffusions/typedefs.jl */
+/* src/diffusions/typedefs.jl: DynamicDiffusion, FixedDiffusion, DynamicMVDiffusion, FixedMVDiffusion */
+typedef enum pnode_diffusion {
+    PNODE_DIFF_DYNAMIC = 0,
+    PNODE_DIFF_FIXED = 1,
+    PNODE_DIFF_DYNAMIC_MV = 2,
+    PNODE_DIFF_FIXED_MV = 3
+} pnode_diffusion;
 typedef enum pnode_retcode {
     PNODE_RET_SUCCESS = 0,
     PNODE_RET_MAXITERS = 1,
@@ -70,7 +77,8 @@ typedef struct pnode_config {
     int32_t device;            /* CUDA device ordinal */
     int32_t d, q, n_p;         /* ODE dimension, prior order (num_derivatives), parameters per trajectory */
     int32_t alg;               /* pnode_alg */
-    int32_t cov;               /* pnode_cov (AUTO: EK0 -> Kronecker, EK1 -> dense; src/algorithms.jl:132-151) */
+    int32_t cov;               /* pnode_cov (AUTO: EK0 + scalar diffusion -> Kronecker, EK0 + multivariate diffusion and
+                                  DiagonalEK1 -> blocks of diagonals, EK1 -> dense; src/algorithms.jl:132-151) */
     int32_t prior;             /* pnode_prior */
     int32_t diffusion;         /* pnode_diffusion */
     int32_t calibrate;         /* FixedDiffusion(calibrate=...) */
@@ -123,6 +131,9 @@ typedef enum pnode_field {
     PNODE_F_DIFFUSIONS = 16,   /* double [total]              sol.diffusions (slot k: step k -> k+1) */
     PNODE_F_X = 17,            /* double [total][D]           sol.x_filt / sol.x_smooth mean (save_state) */
     PNODE_F_X_COVFAC = 18,     /* double [total][D][D]        ... right factor            (save_state) */
+    /* multivariate diffusion models (Diagonal(sigma_1^2 .. sigma_d^2), src/diffusions/typedefs.jl) */
+    PNODE_F_DIFFUSION_MV = 19,  /* double [n_traj][d]         final / global diffusion per component */
+    PNODE_F_DIFFUSIONS_MV = 20, /* double [total][d]          sol.diffusions per component           */
     PNODE_F_COUNT
 } pnode_field;
 

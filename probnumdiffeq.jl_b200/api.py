@@ -5,6 +5,8 @@ Reference (Julia)                                         here (Python stand-in 
 ODEProblem(f, u0, tspan, p)                                ODEProblem(f, u0, tspan, p)
 EK0(; order, smooth, diffusionmodel) src/algorithms.jl:188  EK0(order=3, smooth=True, diffusionmodel=DynamicDiffusion())
 EK1(; order, smooth, diffusionmodel) src/algorithms.jl:250  EK1(...)
+DiagonalEK1(; ...)                   src/algorithms.jl:343  DiagonalEK1(...)   (BlocksOfDiagonals layout)
+DynamicMVDiffusion(), FixedMVDiffusion(...)  src/diffusions/typedefs.jl   same names (EK0 / DiagonalEK1)
 DynamicDiffusion(), FixedDiffusion(; initial_diffusion, calibrate)  src/diffusions/typedefs.jl   same names
 EnsembleProblem(prob; prob_func) (SciMLBase)               EnsembleProblem(prob, prob_func=...)
 solve(ensprob, alg, EnsembleThreads(); trajectories, ...)  solve(ensprob, alg, EnsembleB200(), trajectories=N, ...)
@@ -39,6 +41,19 @@ class FixedDiffusion:
 
 
 @dataclasses.dataclass(frozen=True)
+class DynamicMVDiffusion:
+    """Time-varying diagonal diffusion (src/diffusions/typedefs.jl); EK0 / DiagonalEK1 only."""
+    pass
+
+
+@dataclasses.dataclass(frozen=True)
+class FixedMVDiffusion:
+    """Time-fixed diagonal diffusion, optionally calibrated (src/diffusions/typedefs.jl); EK0 / DiagonalEK1 only."""
+    initial_diffusion: float = 1.0
+    calibrate: bool = True
+
+
+@dataclasses.dataclass(frozen=True)
 class IWP:
     """Integrated Wiener process prior (src/priors/iwp.jl)."""
     num_derivatives: int = 3
@@ -64,6 +79,11 @@ class EK0(_EK):
 class EK1(_EK):
     """Gaussian ODE filter with first-order linearisation (src/algorithms.jl:250-296)."""
     alg = _lib.EK1
+
+
+class DiagonalEK1(_EK):
+    """EK1 with a diagonal Jacobian approximation on the BlocksOfDiagonals layout (src/algorithms.jl:343-393)."""
+    alg = _lib.DIAGONAL_EK1
 
 
 @dataclasses.dataclass
@@ -142,7 +162,7 @@ class EnsembleSolution:
 
 def _check_alg(alg, adaptive, dt, save_everystep, dense):
     if not isinstance(alg, _EK):
-        raise ValueError("alg must be EK0(...) or EK1(...)")
+        raise ValueError("alg must be EK0(...), EK1(...) or DiagonalEK1(...)")
     if not adaptive and not (dt and dt > 0):
         # test/errors_thrown.jl:6-8
         raise ValueError("Fixed timestep methods require a choice of dt or choosing the tstops")
@@ -150,8 +170,15 @@ def _check_alg(alg, adaptive, dt, save_everystep, dense):
         raise RuntimeError("To use `dense=true` you need to set `smooth=true`!")  # src/checks.jl:15-17
     if not save_everystep and alg.smooth:
         raise RuntimeError("If you set `save_everystep=false` also set `smooth=false` in the alg!")  # checks.jl:18-20
-    if not isinstance(alg.diffusionmodel, (DynamicDiffusion, FixedDiffusion)):
+    if not isinstance(alg.diffusionmodel, (DynamicDiffusion, FixedDiffusion, DynamicMVDiffusion, FixedMVDiffusion)):
         raise ValueError("unsupported diffusion model")
+    if isinstance(alg, EK1):  # ekargcheck, src/algorithms.jl:93-107
+        if isinstance(alg.diffusionmodel, FixedMVDiffusion) and alg.diffusionmodel.calibrate:
+            raise ValueError("The `EK1` algorithm does not support automatic global calibration of multivariate diffusion "
+                             "models.")
+        if isinstance(alg.diffusionmodel, DynamicMVDiffusion):
+            raise ValueError("The `EK1` algorithm does not support automatic calibration of local multivariate diffusion "
+                             "models.")
 
 
 def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, abstol, reltol, save_everystep, maxiters,
@@ -166,6 +193,10 @@ def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, absto
               device=ens.device, lanes_per_traj=ens.lanes_per_traj, forced_diffusion=forced_diffusion)
     if isinstance(diff, FixedDiffusion):
         kw.update(diffusion=_lib.DIFF_FIXED, initial_diffusion=diff.initial_diffusion, calibrate=diff.calibrate)
+    elif isinstance(diff, FixedMVDiffusion):
+        kw.update(diffusion=_lib.DIFF_FIXED_MV, initial_diffusion=diff.initial_diffusion, calibrate=diff.calibrate)
+    elif isinstance(diff, DynamicMVDiffusion):
+        kw.update(diffusion=_lib.DIFF_DYNAMIC_MV)
     else:
         kw.update(diffusion=_lib.DIFF_DYNAMIC)
     if prob.builtin is not None:
@@ -233,7 +264,7 @@ def _unpack(res, n, d, save_everystep) -> List[ProbODESolution]:
         T = res.field(L.F_T)
         U = res.field(L.F_U).reshape(-1, d)
         Cv = res.field(L.F_U_COV).reshape(-1, d, d)
-        Df = res.field(L.F_DIFFUSIONS)
+        Df = res.field(L.F_DIFFUSIONS_MV).reshape(-1, d) if res.has(L.F_DIFFUSIONS_MV) else res.field(L.F_DIFFUSIONS)
         for i in range(n):
             a, b = off[i], off[i + 1]
             sols.append(ProbODESolution(T[a:b], U[a:b], Cv[a:b], Df[a:b - 1], Stats(int(nf[i]), int(na[i]), int(nr[i])),

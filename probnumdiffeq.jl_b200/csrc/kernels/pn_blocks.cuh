@@ -1,0 +1,421 @@
+// pn_blocks.cuh -- the BlocksOfDiagonals layout (src/blocksofdiagonals.jl:15-52): the D x D covariance factor is d
+// independent (q+1) x (q+1) blocks, block i <-> state indices i:d:D.  The reference selects it for the EK0 with a
+// multivariate diffusion and for the DiagonalEK1 (src/algorithms.jl:132-151, 343-393).
+//
+// One THREAD per trajectory, like pn_kron.cuh: the d factors, the 2n x n QR stack of the block being processed and
+// the n x d mean live in the thread's registers; the warp runs 32 independent adaptive time loops.
+//
+//   reference routine (file:line)                                       here (per thread, per block i)
+//   calc_H! DiagonalEK1      src/derivative_utils.jl:14-28               H_i = e_1' - J_ii e_0'   (EK0: H_i = e_1')
+//   local_scalar_diffusion   src/diffusions/calibration.jl:21-29,123-133 s2 = sum_i z_i^2 / HQH_i / d
+//   local_diagonal_diffusion src/diffusions/calibration.jl:151-180       s2_i = z_i^2 / HQH_i      (multivariate)
+//   estimate_errors! Blocks  src/perform_step.jl:240-259                 e_i = h sqrt(s2_i HQH_i)
+//   predict_cov! Blocks      src/filtering/predict.jl:120-141            QR of [R_i T' ; sqrt(s2_i) L P^-1]
+//   update! Blocks           src/filtering/update.jl:197-239             scalar S_i, K_i = R_i^-' c_i / S_i, ll = sum_i ll_i
+//   estimate_global_diffusion  src/diffusions/calibration.jl:49-66 (Fixed: invquad over blocks / d),
+//                              :88-107 (FixedMV: z_j^2 / S[1,1] -- the first block's S for every j, as written there)
+//   calibrate_solution!      src/integrator_utils.jl:46-65 + apply_diffusion! Blocks (apply_diffusion.jl:43-50)
+//
+// NVRTC-compatible: no standard headers.
+#ifndef PN_BLOCKS_CUH
+#define PN_BLOCKS_CUH
+#include "pn_params.h"
+#include "pn_taylor.cuh"
+#include "pn_small.cuh" /* pn_rcp, pn_rsqrt, pn_initial_dt */
+
+// thread-local Householder QR of [Rt ; Bt] (2n x n), Bt lower triangular; Rt returns upper triangular
+template <int n>
+PN_HD void pn_qr_local(double (&Rt)[n][n], double (&Bt)[n][n]) {
+#pragma unroll
+    for (int k = 0; k < n; k++) {
+        double total = 0.0;
+#pragma unroll
+        for (int r = 0; r < n; r++) {
+            if (r >= k) total += Rt[r][k] * Rt[r][k];
+            total += Bt[r][k] * Bt[r][k];
+        }
+        const double alpha = Rt[k][k];
+        const bool nz = total > 0.0;
+        const double nrm = nz ? total * pn_rsqrt(total) : 0.0;
+        const double beta = -copysign(nrm, alpha);
+        const double vk = alpha - beta;
+        const double gam = nz ? pn_rcp(total + fabs(alpha) * nrm) : 0.0;
+#pragma unroll
+        for (int j = 0; j < n; j++) {
+            if (j <= k) continue;
+            double s = vk * Rt[k][j];
+#pragma unroll
+            for (int r = 0; r < n; r++) {
+                if (r > k) s += Rt[r][k] * Rt[r][j];
+                s += Bt[r][k] * Bt[r][j];
+            }
+            s *= gam;
+            Rt[k][j] -= s * vk;
+#pragma unroll
+            for (int r = 0; r < n; r++) {
+                if (r > k) Rt[r][j] -= s * Rt[r][k];
+                Bt[r][j] -= s * Bt[r][k];
+            }
+        }
+        Rt[k][k] = beta;
+#pragma unroll
+        for (int r = 0; r < n; r++)
+            if (r > k) Rt[r][k] = 0.0;
+    }
+}
+
+template <class Prob, int Q, bool DIAG1, bool MV, bool ADAPTIVE, bool DYNAMIC, int SAVE>
+struct PnBlocks {
+    static constexpr int d = Prob::d;
+    static constexpr int n = Q + 1;
+    static constexpr int D = d * n;
+    static constexpr int NPA = Prob::n_p > 0 ? Prob::n_p : 1;
+
+    static __device__ void run(const PnParams& P) {
+        double M[n][d]; /* mean as n x d matrix: M[j][i] = mu[j*d + i] */
+        double RB[d][n][n];
+        double pr[NPA];
+        for (;;) {
+            const unsigned long long idx = atomicAdd(P.work_counter, 1ULL);
+            if ((long long)idx >= P.n_traj) break;
+            const long long traj = (long long)idx;
+            double t = P.t0, dt, loglik = 0.0, qold = P.qoldinit, qold_pb2 = P.qoldinit_pb2;
+            double gdiff[d], ldiff[d];
+#pragma unroll
+            for (int i = 0; i < d; i++) gdiff[i] = ldiff[i] = 0.0;
+            long long naccept = 0, nreject = 0, nf = Q, iter = 0, tstop_idx = 0, save_pos = 0;
+            int retcode = PN_RET_SUCCESS;
+            double uprev[d];
+            {
+                double u0[d], mu0[D];
+#pragma unroll
+                for (int i = 0; i < d; i++) u0[i] = P.u0[traj * d + i];
+#pragma unroll
+                for (int i = 0; i < Prob::n_p; i++) pr[i] = P.p[traj * Prob::n_p + i];
+                pn_taylor_init<Prob, Q>(mu0, u0, pr, P.t0);
+#pragma unroll
+                for (int j = 0; j < n; j++)
+#pragma unroll
+                    for (int i = 0; i < d; i++) M[j][i] = mu0[j * d + i];
+#pragma unroll
+                for (int i = 0; i < d; i++) uprev[i] = u0[i];
+                if (ADAPTIVE && !(P.dt0 > 0.0)) {
+                    dt = pn_initial_dt<Prob>(P, u0, pr);
+                    nf += 2;
+                } else {
+                    dt = P.dt0;
+                }
+            }
+            const double dtcache = dt;
+#pragma unroll
+            for (int i = 0; i < d; i++)
+#pragma unroll
+                for (int a = 0; a < n; a++)
+#pragma unroll
+                    for (int b = 0; b < n; b++) RB[i][a][b] = 0.0;
+            if (SAVE >= 1) {
+                save_pos = P.step_offsets ? P.step_offsets[traj] : 0;
+                if (P.step_offsets) {
+                    P.s_t[save_pos] = t;
+                    P.s_diffusion[save_pos] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < d; i++) {
+                        P.s_u_mean[save_pos * d + i] = M[0][i];
+                        if (P.s_diffusion_mv) P.s_diffusion_mv[save_pos * d + i] = 0.0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < d * d; i++) P.s_u_cov[save_pos * d * d + i] = 0.0;
+                    if (SAVE >= 2) save_state(P, save_pos, M, RB, 0.0, 0.0);
+                }
+                save_pos += 1;
+            }
+
+            while (t < P.t1 && retcode == PN_RET_SUCCESS) {
+                double tstop = P.t1;
+                while (tstop_idx < P.n_tstops && P.tstops[tstop_idx] <= t) tstop_idx++;
+                if (tstop_idx < P.n_tstops && P.tstops[tstop_idx] < P.t1) tstop = P.tstops[tstop_idx];
+                iter++;
+                if (iter > P.maxiters) {
+                    retcode = PN_RET_MAXITERS;
+                    break;
+                }
+                if (ADAPTIVE) {
+                    dt = fmin(dt, P.dtmax);
+                    dt = fmax(dt, P.dtmin);
+                    dt = fmin(dt, tstop - t);
+                } else {
+                    dt = fmin(dtcache, tstop - t);
+                }
+                const double h = dt;
+                if (h != h || !(t + h > t) || (ADAPTIVE && h <= P.dtmin)) {
+                    retcode = PN_RET_DTLESSTHANMIN;
+                    break;
+                }
+                const double tnew = t + h;
+                double hp[n], PIv[n];
+                hp[0] = 1.0;
+#pragma unroll
+                for (int k = 1; k < n; k++) hp[k] = hp[k - 1] * h / (double)k;
+                const double sqh = sqrt(h);
+#pragma unroll
+                for (int c = 0; c < n; c++) PIv[c] = hp[Q - c] * sqh;
+                double Mp[n][d];
+#pragma unroll
+                for (int j = 0; j < n; j++)
+#pragma unroll
+                    for (int i = 0; i < d; i++) {
+                        double s = M[j][i];
+#pragma unroll
+                        for (int k = 0; k < n; k++)
+                            if (k > j) s += hp[k > j ? k - j : 0] * M[k][i];
+                        Mp[j][i] = s;
+                    }
+                double fu[d], z[d], h0[d];
+                Prob::template f<double>(fu, Mp[0], pr, tnew);
+                nf += 1;
+#pragma unroll
+                for (int i = 0; i < d; i++) {
+                    z[i] = Mp[1][i] - fu[i];
+                    h0[i] = 0.0;
+                }
+                if (DIAG1) { /* H_i = e_1' - J_ii e_0' */
+                    double J[d * d];
+                    Prob::jac(J, Mp[0], pr, tnew);
+#pragma unroll
+                    for (int i = 0; i < d; i++) h0[i] = -J[i + d * i];
+                }
+                /* HQH_i = |Qh.R H_i'|^2, (Qh.R H_i')[m] = L[m][0] PI[0] h0_i + L[m][1] PI[1] */
+                double HQH[d];
+#pragma unroll
+                for (int i = 0; i < d; i++) {
+                    double e = 0.0;
+#pragma unroll
+                    for (int m = 0; m < n; m++) {
+                        const double cq = P.L[m * n + 0] * PIv[0] * h0[i] + ((m >= 1) ? P.L[m * n + 1] * PIv[1] : 0.0);
+                        e += cq * cq;
+                    }
+                    HQH[i] = e;
+                }
+                double EEst = 0.0, qq = 1.0, q11 = 0.0, lEE = 0.0;
+                if (ADAPTIVE || DYNAMIC) {
+                    double qd = 0.0;
+#pragma unroll
+                    for (int i = 0; i < d; i++) {
+                        const double r = z[i] * z[i] / HQH[i];
+                        ldiff[i] = r;
+                        qd += r;
+                    }
+                    if (!MV) {
+                        qd = qd / (double)d;
+#pragma unroll
+                        for (int i = 0; i < d; i++) ldiff[i] = qd;
+                    }
+                }
+                if (ADAPTIVE) {
+                    double e2 = 0.0;
+#pragma unroll
+                    for (int i = 0; i < d; i++) {
+                        const double isc = pn_rcp(P.abstol + fmax(fabs(Mp[0][i]), fabs(uprev[i])) * P.reltol);
+                        e2 += (ldiff[i] * HQH[i]) * (isc * isc);
+                    }
+                    e2 = e2 * (h * h) * (1.0 / (double)d);
+                    EEst = (e2 > 0.0) ? e2 * pn_rsqrt(e2) : e2;
+                    if (EEst != EEst) {
+                        retcode = PN_RET_UNSTABLE;
+                        break;
+                    }
+                    if (EEst == 0.0) {
+                        qq = 1.0 / P.qmax;
+                    } else {
+                        lEE = log(EEst);
+                        q11 = exp(P.beta1 * lEE);
+                        qq = q11 * pn_rcp(qold_pb2 * P.gamma);
+                        qq = fmax(1.0 / P.qmax, fmin(1.0 / P.qmin, qq));
+                    }
+                    if (!(EEst < 1.0)) { /* reject */
+                        nreject++;
+                        dt = dt / fmin(1.0 / P.qmin, q11 / P.gamma);
+                        continue;
+                    }
+                }
+                double ediff[d], S[d];
+                double llstep = 0.0;
+#pragma unroll
+                for (int i = 0; i < d; i++) {
+                    ediff[i] = DYNAMIC ? ldiff[i] : P.initial_diffusion;
+                    /* predict_cov! on block i */
+                    double Bt[n][n];
+                    const double sd = (ediff[i] == 1.0) ? 1.0 : sqrt(ediff[i]);
+#pragma unroll
+                    for (int r = 0; r < n; r++) {
+#pragma unroll
+                        for (int j = 0; j < n; j++) {
+                            double s = RB[i][r][j];
+#pragma unroll
+                            for (int k = 0; k < n; k++)
+                                if (k > j) s += hp[k > j ? k - j : 0] * RB[i][r][k];
+                            RB[i][r][j] = s;
+                        }
+#pragma unroll
+                        for (int c = 0; c < n; c++) Bt[r][c] = (c <= r) ? P.L[r * n + c] * PIv[c] * sd : 0.0;
+                    }
+                    pn_qr_local<n>(RB[i], Bt);
+                    /* update! on block i: c = R^- H_i' */
+                    double c1[n];
+                    double Si = 0.0;
+#pragma unroll
+                    for (int r = 0; r < n; r++) {
+                        c1[r] = RB[i][r][1] + h0[i] * RB[i][r][0];
+                        Si += c1[r] * c1[r];
+                    }
+                    S[i] = Si;
+                    if (Si == 0.0) { /* Sigma^- == 0: update.jl:82-89 */
+                        llstep += (z[i] == 0.0) ? PN_INF : -PN_INF;
+#pragma unroll
+                        for (int j = 0; j < n; j++) M[j][i] = Mp[j][i];
+                    } else {
+                        const double iS = pn_rcp(Si);
+                        llstep += -0.5 * z[i] * z[i] * iS - 0.5 * 1.8378770664093453 - 0.5 * log(Si);
+                        double K[n];
+#pragma unroll
+                        for (int c = 0; c < n; c++) {
+                            double s = 0.0;
+#pragma unroll
+                            for (int r = 0; r < n; r++) s += RB[i][r][c] * c1[r];
+                            K[c] = s * iS;
+                        }
+#pragma unroll
+                        for (int j = 0; j < n; j++) M[j][i] = Mp[j][i] - K[j] * z[i];
+#pragma unroll
+                        for (int r = 0; r < n; r++)
+#pragma unroll
+                            for (int c = 0; c < n; c++) RB[i][r][c] -= c1[r] * K[c];
+                    }
+                }
+                loglik += llstep;
+                if (!DYNAMIC) {
+                    if (MV) { /* calibration.jl:88-107: z_j^2 / S[1,1] */
+                        const double iS0 = 1.0 / S[0];
+#pragma unroll
+                        for (int j = 0; j < d; j++) {
+                            const double inc = z[j] * z[j] * iS0;
+                            gdiff[j] = (naccept == 0) ? inc : gdiff[j] + (inc - gdiff[j]) / (double)naccept;
+                        }
+                    } else {
+                        double qd = 0.0;
+#pragma unroll
+                        for (int i = 0; i < d; i++) qd += z[i] * (z[i] / S[i]);
+                        const double inc = qd / (double)d;
+                        const double g = (naccept == 0) ? inc : gdiff[0] + (inc - gdiff[0]) / (double)naccept;
+#pragma unroll
+                        for (int j = 0; j < d; j++) gdiff[j] = g;
+                    }
+                }
+                /* loopfooter! accept */
+                double dtnew = dt;
+                if (ADAPTIVE) {
+                    if (P.qsteady_min <= qq && qq <= P.qsteady_max) qq = 1.0;
+                    qold = fmax(EEst, P.qoldinit);
+                    qold_pb2 = (EEst > P.qoldinit) ? exp(P.beta2 * lEE) : P.qoldinit_pb2;
+                    dtnew = dt / qq;
+                }
+                const double ttmp = t + h;
+                const double ref = fmax(fabs(t), fabs(tstop));
+                const double epsref = nextafter(ref, 1e300) - ref;
+                t = (fabs(ttmp - tstop) < 100.0 * epsref) ? tstop : ttmp;
+                dt = dtnew;
+                naccept++;
+#pragma unroll
+                for (int i = 0; i < d; i++) {
+                    uprev[i] = M[0][i];
+                    if (M[0][i] != M[0][i]) retcode = PN_RET_UNSTABLE;
+                }
+                if (SAVE >= 1) {
+                    if (P.step_offsets) {
+                        P.s_t[save_pos] = t;
+                        P.s_diffusion[save_pos - 1] = (SAVE >= 2) ? ediff[0] : ((ADAPTIVE || DYNAMIC) ? ldiff[0] : P.initial_diffusion);
+#pragma unroll
+                        for (int i = 0; i < d; i++) {
+                            P.s_u_mean[save_pos * d + i] = M[0][i];
+                            if (P.s_diffusion_mv)
+                                P.s_diffusion_mv[(save_pos - 1) * d + i] =
+                                    (SAVE >= 2) ? ediff[i] : ((ADAPTIVE || DYNAMIC) ? ldiff[i] : P.initial_diffusion);
+                        }
+#pragma unroll
+                        for (int a = 0; a < d; a++) {
+                            double c0 = 0.0;
+#pragma unroll
+                            for (int r = 0; r < n; r++) c0 += RB[a][r][0] * RB[a][r][0];
+#pragma unroll
+                            for (int b = 0; b < d; b++) P.s_u_cov[save_pos * d * d + a * d + b] = (a == b) ? c0 : 0.0;
+                        }
+                        if (SAVE >= 2) save_state(P, save_pos, M, RB, h, 1.0);
+                    }
+                    save_pos += 1;
+                }
+            }
+            /* postamble */
+            P.t_end[traj] = t;
+#pragma unroll
+            for (int a = 0; a < d; a++) {
+                double sc = 1.0, fd = ldiff[a];
+                if (!DYNAMIC) {
+                    if (P.calibrate && naccept > 0) {
+                        sc = gdiff[a];
+                        fd = gdiff[a] * P.initial_diffusion;
+                    } else {
+                        fd = P.initial_diffusion;
+                    }
+                }
+                double c0 = 0.0;
+#pragma unroll
+                for (int r = 0; r < n; r++) c0 += RB[a][r][0] * RB[a][r][0];
+                P.u_mean[traj * d + a] = M[0][a];
+#pragma unroll
+                for (int b = 0; b < d; b++) P.u_cov[traj * d * d + a * d + b] = (a == b) ? c0 * sc : 0.0;
+                if (a == 0) P.diffusion[traj] = fd;
+                if (P.diffusion_mv) P.diffusion_mv[traj * d + a] = fd;
+                if (P.x_covfac) {
+                    const double ss = sqrt(sc);
+                    if (a == 0)
+                        for (int e = 0; e < D * D; e++) P.x_covfac[traj * D * D + e] = 0.0;
+#pragma unroll
+                    for (int r = 0; r < n; r++)
+#pragma unroll
+                        for (int c = 0; c < n; c++) P.x_covfac[(traj * D + r * d + a) * D + c * d + a] = RB[a][r][c] * ss;
+                }
+            }
+            P.loglik[traj] = loglik;
+            P.dt_last[traj] = dt;
+            P.naccept[traj] = naccept;
+            P.nreject[traj] = nreject;
+            P.nf[traj] = nf;
+            P.retcode[traj] = retcode;
+            if (P.x_mean) {
+#pragma unroll
+                for (int j = 0; j < n; j++)
+#pragma unroll
+                    for (int i = 0; i < d; i++) P.x_mean[traj * D + j * d + i] = M[j][i];
+            }
+        }
+    }
+
+    /* dense form of the Blocks state for the smoother sweep: block i occupies rows/columns i:d:D */
+    static PN_HD void save_state(const PnParams& P, long long pos, const double (&M)[n][d], const double (&RB)[d][n][n],
+                                 double h, double hvalid) {
+        if (hvalid != 0.0) P.s_h[pos - 1] = h;
+        for (int j = 0; j < n; j++)
+            for (int i = 0; i < d; i++) P.s_x_mean[pos * D + j * d + i] = M[j][i];
+        for (int e = 0; e < D * D; e++) P.s_x_covfac[pos * D * D + e] = 0.0;
+        for (int i = 0; i < d; i++)
+            for (int r = 0; r < n; r++)
+                for (int c = 0; c < n; c++) P.s_x_covfac[(pos * D + r * d + i) * D + c * d + i] = RB[i][r][c];
+    }
+};
+
+template <class Prob, int Q, bool DIAG1, bool MV, bool ADAPTIVE, bool DYNAMIC, int SAVE>
+__device__ __forceinline__ void pn_blocks_entry(const PnParams& P) {
+    PnBlocks<Prob, Q, DIAG1, MV, ADAPTIVE, DYNAMIC, SAVE>::run(P);
+}
+
+#endif /* PN_BLOCKS_CUH */

@@ -41,6 +41,7 @@ struct PnParams {
     double* x_covfac;   /* [n_traj][D][D] row-major right factor, Sigma = R'R (may be null) */
     double* loglik;     /* [n_traj] */
     double* diffusion;  /* [n_traj] final diffusion (global MLE for FixedDiffusion, last local otherwise) */
+    double* diffusion_mv; /* [n_traj][d] per-component diffusion (multivariate models; null otherwise) */
     double* dt_last;    /* [n_traj] */
     long long* naccept; /* [n_traj] */
     long long* nreject;
@@ -52,6 +53,7 @@ struct PnParams {
     double* s_u_mean;              /* [total][d]      */
     double* s_u_cov;               /* [total][d][d]   */
     double* s_diffusion;           /* [total]         */
+    double* s_diffusion_mv;        /* [total][d]      (multivariate diffusion models; null otherwise) */
     double* s_x_mean;              /* [total][D]      (smoothing only) */
     double* s_x_covfac;            /* [total][D][D]   (smoothing only) */
     double* s_h;                   /* [total] step size of the step k -> k+1 at slot k (smoothing only) */

@@ -31,6 +31,8 @@ struct PnSmoothParams {
     const double* s_h;             /* [total] h of the step k -> k+1 stored at slot k */
     const double* s_diffusion;     /* [total] */
     const double* gdiff;           /* [n_traj] global diffusion scale (calibrate) */
+    const double* s_diffusion_mv;  /* [total][d] per-component diffusions (multivariate models; null otherwise) */
+    const double* gdiff_mv;        /* [n_traj][d] per-component global scale (FixedMVDiffusion, calibrate)       */
     double* s_x_mean;              /* [total][D]    in: filtered, out: smoothed */
     double* s_x_covfac;            /* [total][D][D] in: filtered, out: smoothed (row-major right factor) */
     double* s_u_mean;              /* [total][d] out */

@@ -61,14 +61,16 @@ PN_HD void pn_ld_row(const double* __restrict__ p, double (&dst)[D_], bool pred)
         for (int c = 0; c < D_; c++) dst[c] = pred ? p[c] : 0.0;
     }
 }
-template <int D_>
-PN_HD void pn_st_row(double* __restrict__ p, const double (&src)[D_], double scale) {
+// column c = (j, i) is scaled by scv[i] (per-component calibration; a scalar model passes d equal entries)
+template <int D_, int d_>
+PN_HD void pn_st_row(double* __restrict__ p, const double (&src)[D_], const double (&scv)[d_]) {
     if (D_ % 2 == 0) {
 #pragma unroll
-        for (int c = 0; c < D_; c += 2) *reinterpret_cast<double2*>(p + c) = make_double2(src[c] * scale, src[c + 1] * scale);
+        for (int c = 0; c < D_; c += 2)
+            *reinterpret_cast<double2*>(p + c) = make_double2(src[c] * scv[c % d_], src[c + 1] * scv[(c + 1) % d_]);
     } else {
 #pragma unroll
-        for (int c = 0; c < D_; c++) p[c] = src[c] * scale;
+        for (int c = 0; c < D_; c++) p[c] = src[c] * scv[c % d_];
     }
 }
 
@@ -115,7 +117,9 @@ struct PnSmoothReg {
         }
 
         long long k = -1, a0 = 0;
-        double sc = 1.0;
+        double scv[d]; /* sqrt of the global calibration scale, per component */
+#pragma unroll
+        for (int i = 0; i < d; i++) scv[i] = 1.0;
         bool have = false, queue_empty = false;
 
         for (;;) {
@@ -134,7 +138,9 @@ struct PnSmoothReg {
                         got = true;
                         a0 = P.step_offsets[idx];
                         last = P.step_offsets[idx + 1] - 1;
-                        sc = (!P.dynamic && P.calibrate) ? sqrt(P.gdiff[idx]) : 1.0;
+#pragma unroll
+                        for (int i = 0; i < d; i++)
+                            scv[i] = (!P.dynamic && P.calibrate) ? sqrt(P.gdiff_mv ? P.gdiff_mv[idx * d + i] : P.gdiff[idx]) : 1.0;
                     }
                 }
                 double Rl[RPL][D];
@@ -153,7 +159,7 @@ struct PnSmoothReg {
                         double s = 0.0;
 #pragma unroll
                         for (int lr = 0; lr < RPL; lr++) s += Rl[lr][a] * Rl[lr][b];
-                        s = pn_gsum<G>(s) * (sc * sc);
+                        s = pn_gsum<G>(s) * (scv[a] * scv[b]);
                         cv[a * d + b] = s;
                         cv[b * d + a] = s;
                     }
@@ -163,7 +169,7 @@ struct PnSmoothReg {
                         const int row = lr * G + gl;
 #pragma unroll
                         for (int c = 0; c < D; c++) Sm[row * LD + c] = Rl[lr][c];
-                        if (sc != 1.0 && row < D) pn_st_row<D>(P.s_x_covfac + (last * D + row) * D, Rl[lr], sc);
+                        if (!P.dynamic && P.calibrate && row < D) pn_st_row<D, d>(P.s_x_covfac + (last * D + row) * D, Rl[lr], scv);
                     }
                     if (gl == 0) {
 #pragma unroll
@@ -192,7 +198,7 @@ struct PnSmoothReg {
                         const int row = lr * G + gl;
                         if (row < D) {
 #pragma unroll
-                            for (int c = 0; c < D; c++) P.s_x_covfac[(k * D + row) * D + c] = Sm[row * LD + c] * sc;
+                            for (int c = 0; c < D; c++) P.s_x_covfac[(k * D + row) * D + c] = Sm[row * LD + c] * scv[c % d];
                         }
                     }
                     if (gl == 0) {
@@ -242,9 +248,11 @@ struct PnSmoothReg {
                     }
                     /* bottom block: [ sd (U P^-1) (x) I_d | 0 ], upper triangular */
                     {
-                        const double sd = (ediff == 1.0) ? 1.0 : sqrt(ediff);
+                        const double sd0 = (ediff == 1.0) ? 1.0 : sqrt(ediff);
 #pragma unroll
                         for (int lr = 0; lr < RPL; lr++) {
+                            /* multivariate diffusion: row (m, i) of the noise factor carries sigma_i */
+                            const double sd = (P.s_diffusion_mv && P.dynamic && doit) ? sqrt(P.s_diffusion_mv[k * d + iB[lr]]) : sd0;
 #pragma unroll
                             for (int c = 0; c < n; c++) {
                                 double usel = 0.0;
@@ -347,7 +355,7 @@ struct PnSmoothReg {
                         double s = 0.0;
 #pragma unroll
                         for (int lr = 0; lr < RPL; lr++) s += St[lr][a] * St[lr][b];
-                        s = pn_gsum<G>(s) * (sc * sc);
+                        s = pn_gsum<G>(s) * (scv[a] * scv[b]);
                         cv[a * d + b] = s;
                         cv[b * d + a] = s;
                     }
@@ -357,7 +365,7 @@ struct PnSmoothReg {
                         const int row = lr * G + gl;
 #pragma unroll
                         for (int c = 0; c < D; c++) Sm[row * LD + c] = St[lr][c];
-                        if (row < D) pn_st_row<D>(P.s_x_covfac + (k * D + row) * D, St[lr], sc);
+                        if (row < D) pn_st_row<D, d>(P.s_x_covfac + (k * D + row) * D, St[lr], scv);
                     }
                     if (gl == 0) {
 #pragma unroll

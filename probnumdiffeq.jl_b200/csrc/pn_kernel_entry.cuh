@@ -31,6 +31,14 @@ __global__ void __launch_bounds__(128) pn_kron_kernel(const __grid_constant__ Pn
     pn_kron_entry<Prob, Q, ADAPTIVE, DYNAMIC, SAVE>(P);
 }
 
+#include "kernels/pn_blocks.cuh"
+
+/* BlocksOfDiagonals layout (EK0 + multivariate diffusion, DiagonalEK1): one thread per trajectory */
+template <class Prob, int Q, bool DIAG1, bool MV, bool ADAPTIVE, bool DYNAMIC, int SAVE>
+__global__ void __launch_bounds__(128) pn_blocks_kernel(const __grid_constant__ PnParams P) {
+    pn_blocks_entry<Prob, Q, DIAG1, MV, ADAPTIVE, DYNAMIC, SAVE>(P);
+}
+
 #include "kernels/pn_cta.cuh"
 
 /* large D (Pleiades, D = 112): one CTA per trajectory, R staged in shared memory */

@@ -32,7 +32,10 @@
 __global__ void pn_calibrate_saved(long long total, long long n_traj, const long long* __restrict__ off,
                                    const double* __restrict__ scale /* [n_traj] or null */,
                                    const double* __restrict__ diffusion /* [n_traj] */, int dd,
-                                   double* __restrict__ u_cov, double* __restrict__ s_diffusion) {
+                                   double* __restrict__ u_cov, double* __restrict__ s_diffusion, int d,
+                                   const double* __restrict__ scale_mv /* [n_traj][d] or null */,
+                                   const double* __restrict__ diffusion_mv /* [n_traj][d] or null */,
+                                   double* __restrict__ s_diffusion_mv /* [total][d] or null */) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= total) return;
     long long lo = 0, hi = n_traj; /* largest tr with off[tr] <= i */
@@ -40,11 +43,16 @@ __global__ void pn_calibrate_saved(long long total, long long n_traj, const long
         long long mid = (lo + hi) >> 1;
         if (off[mid] <= i) lo = mid; else hi = mid;
     }
-    if (scale) {
+    if (scale_mv) { /* apply_diffusion! on blocks (apply_diffusion.jl:43-50): component a scaled by sigma_a^2 */
+        for (int a = 0; a < d; a++)
+            for (int b = 0; b < d; b++) u_cov[i * dd + a * d + b] *= sqrt(scale_mv[lo * d + a] * scale_mv[lo * d + b]);
+    } else if (scale) {
         const double sc = scale[lo];
         for (int k = 0; k < dd; k++) u_cov[i * dd + k] *= sc;
     }
     s_diffusion[i] = diffusion[lo];
+    if (s_diffusion_mv)
+        for (int a = 0; a < d; a++) s_diffusion_mv[i * d + a] = diffusion_mv[lo * d + a];
 }
 
 /* FP64 roofline probe: 8 independent DFMA chains per thread (the denominator bench.py reports against;
@@ -140,6 +148,8 @@ struct pnode_solver {
     int D = 0, G = 4, n_sm = 0;
     bool builtin = false;
     bool kron = false; /* EK0: IsometricKronecker layout, one thread per trajectory */
+    bool blocks = false; /* BlocksOfDiagonals layout (EK0 + multivariate diffusion, DiagonalEK1), thread per trajectory */
+    bool mv = false;     /* multivariate (per-component) diffusion model */
     bool cta = false;  /* EK1, D > 32: one CTA per trajectory, R in shared memory */
     size_t smem = 0;   /* dynamic shared memory of the step kernel */
     Kernel k_final;  /* SAVE = 0 */
@@ -216,10 +226,15 @@ static size_t smooth_reg_smem_bytes(int d, int q, int G) {
     return (size_t)REGION * (PN_SMR_THREADS / G) * 8;
 }
 
+static bool is_dynamic(int diffusion) { return diffusion == PNODE_DIFF_DYNAMIC || diffusion == PNODE_DIFF_DYNAMIC_MV; }
+static bool is_mv(int diffusion) { return diffusion == PNODE_DIFF_DYNAMIC_MV || diffusion == PNODE_DIFF_FIXED_MV; }
+
 static std::string kernel_key(const pnode_solver* s, int save) {
     char buf[256];
-    snprintf(buf, sizeof buf, "%s:%s:q%d:g%d:a%d:dyn%d:s%d", s->rhs_name.c_str(), s->kron ? "kron" : (s->cta ? "cta" : "small"), s->cfg.q, s->G,
-             s->cfg.adaptive ? 1 : 0, s->cfg.diffusion == PNODE_DIFF_DYNAMIC ? 1 : 0, save);
+    const char* kind = s->blocks ? (s->cfg.alg == PNODE_DIAGONAL_EK1 ? (s->mv ? "blocks1mv" : "blocks1") : (s->mv ? "blocks0mv" : "blocks0"))
+                                 : (s->kron ? "kron" : (s->cta ? "cta" : "small"));
+    snprintf(buf, sizeof buf, "%s:%s:q%d:g%d:a%d:dyn%d:s%d", s->rhs_name.c_str(), kind, s->cfg.q, s->G, s->cfg.adaptive ? 1 : 0,
+             is_dynamic(s->cfg.diffusion) ? 1 : 0, save);
     return buf;
 }
 
@@ -265,11 +280,15 @@ static int nvrtc_compile(const std::string& src, std::vector<std::string> defs, 
 /* NVRTC: user RHS + step kernels -> sm_100a CUBIN.  Needs no device. */
 static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_name, int q, int G, bool adaptive,
                        bool dynamic, int save, std::vector<char>* cubin, int threads = PN_THREADS, int min_blocks = 1,
-                       bool kron = false, bool cta = false) {
+                       bool kron = false, bool cta = false, int blocks = 0 /* 0 no, 1 EK0, 2 DiagonalEK1 */, bool mv = false) {
     std::string src;
     src += "#include \"pn_kernel_entry.cuh\"\n";
     src += rhs_src;
-    if (cta)
+    if (blocks)
+        src += std::string("\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS) pn_entry(const __grid_constant__ PnParams P) {\n"
+               "  pn_blocks_entry<") + struct_name + ", PN_Q, " + (blocks == 2 ? "true" : "false") + ", " + (mv ? "true" : "false") +
+               ", (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
+    else if (cta)
         src += "\nextern \"C\" __global__ void __launch_bounds__(PN_CTA_THREADS, 1) pn_entry(const __grid_constant__ PnParams P) {\n"
                "  pn_cta_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
     else if (kron)
@@ -306,10 +325,10 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
         src = "#include \"kernels/pn_builtin_problems.cuh\"\n";
         name = sn;
     }
-    out->threads = s->cta ? PN_CTA_THREADS : (s->kron ? 128 : env_int("PNODE_THREADS", PN_THREADS));
-    rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0,
-                     s->cfg.diffusion == PNODE_DIFF_DYNAMIC, save, &cubin, out->threads, env_int("PNODE_MIN_BLOCKS", 1), s->kron,
-                     s->cta);
+    out->threads = s->cta ? PN_CTA_THREADS : ((s->kron || s->blocks) ? 128 : env_int("PNODE_THREADS", PN_THREADS));
+    rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0, is_dynamic(s->cfg.diffusion), save, &cubin, out->threads,
+                     env_int("PNODE_MIN_BLOCKS", 1), s->kron, s->cta,
+                     s->blocks ? (s->cfg.alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, s->mv);
     if (rc) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
@@ -336,7 +355,7 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
         for (int i = 0; i < n; i++) {
             if (key == tab[i].key) {
                 out->rt_fn = tab[i].fn;
-                out->threads = s->cta ? PN_CTA_THREADS : (s->kron ? 128 : PN_THREADS);
+                out->threads = s->cta ? PN_CTA_THREADS : ((s->kron || s->blocks) ? 128 : PN_THREADS);
                 if (s->smem > 48 * 1024)
                     CUDA_TRY(cudaFuncSetAttribute(out->rt_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
                 int nblk = 0;
@@ -399,6 +418,13 @@ static size_t cta_smem_bytes(int d, int q, int n_p) {
     return dbl * sizeof(double);
 }
 
+/* covariance_structure(alg, prior, diffusionmodel) (src/algorithms.jl:132-151) */
+static int resolve_layout(const pnode_config* cfg) {
+    if (cfg->alg == PNODE_EK0) return is_mv(cfg->diffusion) ? PNODE_COV_BLOCKS : PNODE_COV_KRONECKER;
+    if (cfg->alg == PNODE_DIAGONAL_EK1) return PNODE_COV_BLOCKS;
+    return PNODE_COV_DENSE;
+}
+
 static int validate_config(const pnode_config* cfg) {
     if (cfg->struct_size != (int32_t)sizeof(pnode_config))
         return fail(PNODE_ERR_ARGUMENT, "pnode_config.struct_size mismatch (ABI)");
@@ -406,9 +432,23 @@ static int validate_config(const pnode_config* cfg) {
     if (cfg->d < 1) return fail(PNODE_ERR_ARGUMENT, "We currently don't support scalar-valued problems (d >= 1 vector required)"); /* caches.jl:96-98 */
     if (cfg->q < 1 || cfg->q + 1 > PN_MAX_N) return fail(PNODE_ERR_ARGUMENT, "order must satisfy 1 <= order <= 11");
     if (cfg->prior != PNODE_PRIOR_IWP) return fail(PNODE_ERR_UNSUPPORTED, "only the IWP prior is implemented");
-    if (cfg->alg != PNODE_EK0 && cfg->alg != PNODE_EK1) return fail(PNODE_ERR_ARGUMENT, "Unknown algorithm"); /* derivative_utils.jl:31 */
-    if (cfg->diffusion != PNODE_DIFF_DYNAMIC && cfg->diffusion != PNODE_DIFF_FIXED)
-        return fail(PNODE_ERR_UNSUPPORTED, "only DynamicDiffusion and FixedDiffusion are implemented");
+    if (cfg->alg != PNODE_EK0 && cfg->alg != PNODE_EK1 && cfg->alg != PNODE_DIAGONAL_EK1)
+        return fail(PNODE_ERR_ARGUMENT, "Unknown algorithm"); /* derivative_utils.jl:31 */
+    if (cfg->diffusion < PNODE_DIFF_DYNAMIC || cfg->diffusion > PNODE_DIFF_FIXED_MV)
+        return fail(PNODE_ERR_ARGUMENT, "Unknown diffusion model");
+    if (cfg->alg == PNODE_EK1) { /* ekargcheck, src/algorithms.jl:93-107 */
+        if (cfg->diffusion == PNODE_DIFF_FIXED_MV && cfg->calibrate)
+            return fail(PNODE_ERR_ARGUMENT,
+                        "The `EK1` algorithm does not support automatic global calibration of multivariate diffusion models. "
+                        "Either use a scalar diffusion model, or set `calibrate=false` and calibrate manually by optimizing "
+                        "`sol.pnstats.log_likelihood`. Or use a different solve, like `EK0` or `DiagonalEK1`.");
+        if (cfg->diffusion == PNODE_DIFF_DYNAMIC_MV)
+            return fail(PNODE_ERR_ARGUMENT,
+                        "The `EK1` algorithm does not support automatic calibration of local multivariate diffusion models. "
+                        "Either use a scalar diffusion model, or use a different solve, like `EK0` or `DiagonalEK1`.");
+        if (cfg->diffusion == PNODE_DIFF_FIXED_MV)
+            return fail(PNODE_ERR_UNSUPPORTED, "EK1 with an uncalibrated multivariate diffusion is not implemented (dense layout)");
+    }
     if (!cfg->adaptive && !(cfg->dt > 0.0))
         return fail(PNODE_ERR_ARGUMENT, "Fixed timestep methods require a choice of dt or choosing the tstops"); /* test/errors_thrown.jl:6-8 */
     if (cfg->smooth && !cfg->save_everystep)
@@ -416,14 +456,22 @@ static int validate_config(const pnode_config* cfg) {
     if (!(cfg->t1 > cfg->t0)) return fail(PNODE_ERR_ARGUMENT, "tspan must satisfy t1 > t0");
     if (!cfg->rhs_name) return fail(PNODE_ERR_ARGUMENT, "rhs_name is required");
     const int D = cfg->d * (cfg->q + 1);
-    int cov = cfg->cov;
-    if (cov == PNODE_COV_AUTO) cov = PNODE_COV_DENSE; /* Kronecker fast path: see pn_kron (EK0) */
-    if (cov == PNODE_COV_KRONECKER && cfg->alg != PNODE_EK0)
+    const int layout = resolve_layout(cfg);
+    if (cfg->cov == PNODE_COV_KRONECKER && cfg->alg != PNODE_EK0)
         return fail(PNODE_ERR_ARGUMENT, "IsometricKroneckerCovariance requires the EK0"); /* algorithms.jl:101-110 */
-    if (cfg->alg == PNODE_EK0 && cov == PNODE_COV_DENSE && cfg->cov != PNODE_COV_AUTO)
-        return fail(PNODE_ERR_UNSUPPORTED, "EK0 with an IWP prior uses the IsometricKronecker layout (src/algorithms.jl:132-151)");
+    if (cfg->cov != PNODE_COV_AUTO && cfg->cov != layout)
+        return fail(PNODE_ERR_UNSUPPORTED,
+                    "only the covariance factorization the reference selects for this algorithm / diffusion model is implemented "
+                    "(covariance_structure, src/algorithms.jl:132-151)");
     if (cfg->alg == PNODE_EK0 && cfg->q > 7)
         return fail(PNODE_ERR_UNSUPPORTED, "EK0 thread-per-trajectory kernel supports order <= 7");
+    if (layout == PNODE_COV_BLOCKS) {
+        if (cfg->d * (cfg->q + 1) * (cfg->q + 1) > 160)
+            return fail(PNODE_ERR_UNSUPPORTED, "blocks-of-diagonals thread-per-trajectory kernel keeps d (q+1)^2 <= 160 doubles in registers");
+        if (cfg->n_forced > 0) return fail(PNODE_ERR_UNSUPPORTED, "forced_diffusion is a scalar-diffusion test hook");
+        if (cfg->smooth && smooth_lanes(D) == 0)
+            return fail(PNODE_ERR_UNSUPPORTED, "smoothing on the blocks-of-diagonals layout needs the register-resident sweep (D <= 24)");
+    }
     if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 2 && cfg->lanes_per_traj != 4 && cfg->lanes_per_traj != 8 &&
         cfg->lanes_per_traj != 16 && cfg->lanes_per_traj != 32 && cfg->lanes_per_traj != 256)
         return fail(PNODE_ERR_ARGUMENT, "lanes_per_traj must be one of 0 (auto), 2, 4, 8, 16, 32, 256 (CTA per trajectory)");
@@ -449,9 +497,11 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     const int D = cfg->d * (cfg->q + 1);
     const int G = cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D);
     std::vector<char> cubin;
-    rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, cfg->diffusion == PNODE_DIFF_DYNAMIC,
-                     cfg->save_everystep ? (cfg->smooth ? 2 : 1) : 0, &cubin, PN_THREADS, 1, cfg->alg == PNODE_EK0,
-                     cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256));
+    const int layout = resolve_layout(cfg);
+    rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, is_dynamic(cfg->diffusion),
+                     cfg->save_everystep ? (cfg->smooth ? 2 : 1) : 0, &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
+                     layout == PNODE_COV_KRONECKER, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256),
+                     layout == PNODE_COV_BLOCKS ? (cfg->alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, is_mv(cfg->diffusion));
     if (rc) return rc;
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
     return 0;
@@ -474,10 +524,12 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     if (!s->builtin) s->rhs_src = cfg->rhs_src;
     s->cfg.rhs_src = nullptr;
     s->cfg.rhs_name = nullptr;
-    s->kron = (cfg->alg == PNODE_EK0);
-    s->cta = !s->kron && (D > 32 || cfg->lanes_per_traj == 256);
+    s->kron = (resolve_layout(cfg) == PNODE_COV_KRONECKER);
+    s->blocks = (resolve_layout(cfg) == PNODE_COV_BLOCKS);
+    s->mv = is_mv(cfg->diffusion);
+    s->cta = !s->kron && !s->blocks && (D > 32 || cfg->lanes_per_traj == 256);
     s->smem = s->cta ? cta_smem_bytes(cfg->d, cfg->q, cfg->n_p) : 0;
-    s->G = s->kron ? 1 : (s->cta ? 256 : (cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D)));
+    s->G = (s->kron || s->blocks) ? 1 : (s->cta ? 256 : (cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D)));
     /* ---- constants ---- */
     PnParams& B = s->base;
     memset(&B, 0, sizeof B);
@@ -668,6 +720,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
     }
     if ((rc = alloc_field(r, PNODE_F_LOGLIK, N * 8))) return rc;
     if ((rc = alloc_field(r, PNODE_F_DIFFUSION, N * 8))) return rc;
+    if (s->mv && (rc = alloc_field(r, PNODE_F_DIFFUSION_MV, N * d * 8))) return rc;
     if ((rc = alloc_field(r, PNODE_F_DT_LAST, N * 8))) return rc;
     if ((rc = alloc_field(r, PNODE_F_NACCEPT, N * 8))) return rc;
     if ((rc = alloc_field(r, PNODE_F_NREJECT, N * 8))) return rc;
@@ -685,6 +738,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
     P.x_covfac = (double*)r->f[PNODE_F_X_FINAL_COVFAC].d;
     P.loglik = (double*)r->f[PNODE_F_LOGLIK].d;
     P.diffusion = (double*)r->f[PNODE_F_DIFFUSION].d;
+    P.diffusion_mv = (double*)r->f[PNODE_F_DIFFUSION_MV].d;
     P.dt_last = (double*)r->f[PNODE_F_DT_LAST].d;
     P.naccept = (long long*)r->f[PNODE_F_NACCEPT].d;
     P.nreject = (long long*)r->f[PNODE_F_NREJECT].d;
@@ -715,6 +769,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         if ((rc = alloc_field(r, PNODE_F_U, T * d * 8))) return rc;
         if ((rc = alloc_field(r, PNODE_F_U_COV, T * d * d * 8))) return rc;
         if ((rc = alloc_field(r, PNODE_F_DIFFUSIONS, T * 8))) return rc;
+        if (s->mv && (rc = alloc_field(r, PNODE_F_DIFFUSIONS_MV, T * d * 8))) return rc;
         CUDA_TRY(cudaMemcpyAsync(r->f[PNODE_F_STEP_OFFSETS].d, r->offsets.data(), (N + 1) * 8, cudaMemcpyHostToDevice,
                                  s->stream));
         P.step_offsets = (const long long*)r->f[PNODE_F_STEP_OFFSETS].d;
@@ -722,6 +777,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         P.s_u_mean = (double*)r->f[PNODE_F_U].d;
         P.s_u_cov = (double*)r->f[PNODE_F_U_COV].d;
         P.s_diffusion = (double*)r->f[PNODE_F_DIFFUSIONS].d;
+        P.s_diffusion_mv = (double*)r->f[PNODE_F_DIFFUSIONS_MV].d;
         double* d_h = nullptr;
         if (s->cfg.smooth) {
             if ((rc = alloc_field(r, PNODE_F_X, T * D * 8))) return rc;
@@ -741,7 +797,9 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             Q.n_traj = n_traj;
             Q.d = d;
             Q.q = s->cfg.q;
-            Q.dynamic = (s->cfg.diffusion == PNODE_DIFF_DYNAMIC);
+            Q.dynamic = is_dynamic(s->cfg.diffusion);
+            Q.s_diffusion_mv = P.s_diffusion_mv;
+            Q.gdiff_mv = P.diffusion_mv;
             Q.calibrate = s->cfg.calibrate;
             Q.initial_diffusion = s->base.initial_diffusion;
             Q.step_offsets = P.step_offsets;
@@ -791,7 +849,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             CUDA_TRY(cudaFreeAsync(d_h, s->stream));
             launches = 3;
         }
-        if (s->cfg.diffusion == PNODE_DIFF_FIXED) {
+        if (!is_dynamic(s->cfg.diffusion)) {
             /* DIFFUSION holds sigma_hat^2 * initial (calibrate) or the constant initial diffusion */
             const double* scale = nullptr;
             if (s->cfg.calibrate && !s->cfg.smooth) { /* the smoother sweep already applied the calibration */
@@ -803,8 +861,10 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             if (s->cfg.calibrate && s->base.initial_diffusion != 1.0) {
                 return fail(PNODE_ERR_UNSUPPORTED, "save_everystep with calibrate=true needs initial_diffusion == 1");
             }
-            pn_calibrate_saved<<<blocks, thr, 0, s->stream>>>((long long)T, (long long)N, P.step_offsets, scale,
-                                                             P.diffusion, d * d, P.s_u_cov, P.s_diffusion);
+            pn_calibrate_saved<<<blocks, thr, 0, s->stream>>>((long long)T, (long long)N, P.step_offsets, scale, P.diffusion,
+                                                             d * d, P.s_u_cov, P.s_diffusion, d,
+                                                             (scale && s->mv) ? P.diffusion_mv : nullptr, P.diffusion_mv,
+                                                             P.s_diffusion_mv);
             launches += 1;
         }
         r->info.total_saved = (int64_t)T;

@@ -15,10 +15,10 @@ from . import build as _build
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-EK0, EK1 = 0, 1
-COV_AUTO, COV_DENSE, COV_KRONECKER = 0, 1, 2
+EK0, EK1, DIAGONAL_EK1 = 0, 1, 2
+COV_AUTO, COV_DENSE, COV_KRONECKER, COV_BLOCKS = 0, 1, 2, 3
 PRIOR_IWP = 0
-DIFF_DYNAMIC, DIFF_FIXED = 0, 1
+DIFF_DYNAMIC, DIFF_FIXED, DIFF_DYNAMIC_MV, DIFF_FIXED_MV = 0, 1, 2, 3
 RETCODES = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable"}
 
 STATUS = {0: "OK", -1: "ArgumentError", -2: "DimensionMismatch", -3: "CompileError", -4: "CUDAError",
@@ -27,6 +27,7 @@ STATUS = {0: "OK", -1: "ArgumentError", -2: "DimensionMismatch", -3: "CompileErr
 # pnode_field
 F_T_END, F_U_FINAL, F_U_FINAL_COV, F_X_FINAL, F_X_FINAL_COVFAC, F_LOGLIK, F_DIFFUSION, F_DT_LAST = range(8)
 F_NACCEPT, F_NREJECT, F_NF, F_RETCODE, F_STEP_OFFSETS, F_T, F_U, F_U_COV, F_DIFFUSIONS, F_X, F_X_COVFAC = range(8, 19)
+F_DIFFUSION_MV, F_DIFFUSIONS_MV = 19, 20
 _FIELD_DTYPE = {F_NACCEPT: np.int64, F_NREJECT: np.int64, F_NF: np.int64, F_RETCODE: np.int32,
                 F_STEP_OFFSETS: np.int64}
 

@@ -482,6 +482,95 @@ def test_ek0_smoother(oracle):
         assert _relcov(Cv[a + 1:b], o["pu_cov"][1:]) < 1e-9
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# BlocksOfDiagonals layout: EK0 + multivariate diffusion, DiagonalEK1 (src/algorithms.jl:132-151)
+# ------------------------------------------------------------------------------------------------------------------
+def _gpu_blocks(pd, u0, p, q, alg, diffusion, **kw):
+    src = tracer.cuda_source(tracer.trace(pd.f, pd.d, pd.n_p), "UserProb")
+    cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="UserProb", rhs_src=src, alg=alg, diffusion=diffusion,
+                          save_everystep=True, save_state=True, **kw)
+    s = lib.Solver(cfg)
+    r = s.solve(u0, p)
+    n, d = u0.shape
+    D = d * (q + 1)
+    out = dict(off=r.field(lib.F_STEP_OFFSETS), T=r.field(lib.F_T), U=r.field(lib.F_U).reshape(-1, d),
+               C=r.field(lib.F_U_COV).reshape(-1, d, d), naccept=r.field(lib.F_NACCEPT), nreject=r.field(lib.F_NREJECT),
+               loglik=r.field(lib.F_LOGLIK), retcode=r.field(lib.F_RETCODE), xR=r.field(lib.F_X_FINAL_COVFAC).reshape(n, D, D),
+               x=r.field(lib.F_X_FINAL).reshape(n, D), cov=r.field(lib.F_U_FINAL_COV).reshape(n, d, d), Df=r.field(lib.F_DIFFUSIONS))
+    if r.has(lib.F_DIFFUSIONS_MV):
+        out.update(DfMV=r.field(lib.F_DIFFUSIONS_MV).reshape(-1, d), dMV=r.field(lib.F_DIFFUSION_MV).reshape(n, d))
+    if r.has(lib.F_X):
+        out.update(X=r.field(lib.F_X).reshape(-1, D), XR=r.field(lib.F_X_COVFAC).reshape(-1, D, D))
+    r.free()
+    s.close()
+    return out
+
+
+_BLOCKS_STATIC = [(lib.EK0, lib.DIFF_FIXED_MV, True), (lib.EK0, lib.DIFF_FIXED_MV, False), (lib.DIAGONAL_EK1, lib.DIFF_FIXED, True),
+                  (lib.DIAGONAL_EK1, lib.DIFF_FIXED, False), (lib.DIAGONAL_EK1, lib.DIFF_FIXED_MV, True)]
+
+
+@pytest.mark.parametrize("alg,diffusion,calibrate", _BLOCKS_STATIC)
+@pytest.mark.parametrize("smooth", [False, True])
+def test_blocks_fixed_steps_static_diffusion(oracle, alg, diffusion, calibrate, smooth):
+    """Static diffusion models on the BlocksOfDiagonals layout: every mean, covariance and diffusion of all 1001
+    points to 1e-10 (filter) / 1e-9 (smoother covariances), FitzHugh-Nagumo, dt = 0.01."""
+    pd, u0, p = _inputs("fitzhugh_nagumo", 2, 31, dp=0.05)
+    g = _gpu_blocks(pd, u0, p, 3, alg, diffusion, calibrate=calibrate, smooth=smooth, adaptive=False, dt=0.01, t0=0.0, t1=10.0)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    for i in range(u0.shape[0]):
+        o = oracle.solve(oracle.make_config(2, 3, 3, alg=alg, diffusion=diffusion, calibrate=calibrate, smooth=smooth, adaptive=False,
+                                            dt=0.01, t0=0.0, t1=10.0, cov_backend=oracle.COV_QR), rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"] == 1001 and g["retcode"][i] == 0
+        assert np.array_equal(g["T"][a:b], o["t"])
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < (1e-9 if smooth else 1e-10)
+        assert g["loglik"][i] == pytest.approx(o["loglik"], rel=1e-10)
+        if "DfMV" in g:
+            assert _rel(g["DfMV"][a:b - 1], o["diffusions_mv"][:-1]) < 1e-10
+            assert _rel(g["dMV"][i], o["diffusions_mv"][0]) < 1e-10
+        else:
+            assert _rel(g["Df"][a:b - 1], o["diffusions"][:-1]) < 1e-10
+        if smooth:
+            Sg = np.einsum("kra,krb->kab", g["XR"][a:b], g["XR"][a:b])
+            So = np.einsum("kra,krb->kab", o["x_smooth_R"], o["x_smooth_R"])
+            assert _relcov(Sg[1:], So[1:]) < 1e-9
+            assert _rel(g["X"][a:b, :2], o["x_smooth_mu"][:, :2]) < 1e-10
+        else:
+            Sg = g["xR"][i].T @ g["xR"][i]
+            So = o["x_filt_R"][-1].T @ o["x_filt_R"][-1]
+            assert np.linalg.norm(Sg - So) / np.linalg.norm(So) < 1e-10
+
+
+@pytest.mark.parametrize("alg,diffusion", [(lib.EK0, lib.DIFF_DYNAMIC_MV), (lib.DIAGONAL_EK1, lib.DIFF_DYNAMIC),
+                                           (lib.DIAGONAL_EK1, lib.DIFF_DYNAMIC_MV), (lib.EK0, lib.DIFF_FIXED_MV)])
+def test_blocks_adaptive_identical_step_sequences(oracle, alg, diffusion):
+    """Adaptive runs on the Blocks layout: identical accept/reject counts, step times to 1e-7, solutions rtol 1e-8."""
+    n = 12
+    pd, u0, p = _inputs("lotka_volterra", n, 33, du0=0.1)
+    g = _gpu_blocks(pd, u0, p, 3, alg, diffusion, adaptive=True, t0=0.0, t1=10.0)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    for i in range(n):
+        o = oracle.solve(oracle.make_config(2, 3, 4, alg=alg, diffusion=diffusion, smooth=False, adaptive=True, t0=0.0, t1=10.0,
+                                            cov_backend=oracle.COV_QR), rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert g["naccept"][i] == o["naccept"] and g["nreject"][i] == o["nreject"]
+        tol_t, tol_u = 1e-7, 1e-8
+        if diffusion == lib.DIFF_DYNAMIC_MV:
+            # sigma_i^2 = z_i^2 / HQH_i has no averaging over components: a residual component near a zero crossing moves
+            # its sigma_i^2 -- and through the error estimate the step size -- by O(1) per ulp.  Hold the kernel to the
+            # oracle's own rounding floor (fma / Cholesky-vs-QR / one-ulp variants with the same step pattern).
+            kwf = dict(alg=alg, diffusion=diffusion, smooth=False, adaptive=True, t0=0.0, t1=10.0, cov_backend=oracle.COV_QR)
+            ft = rounding.floor(oracle, rhs, 2, 3, 4, u0[i], p[i], kwf, o,
+                                lambda s_, b_: np.max(np.abs(s_["t"] - b_["t"]) / np.maximum(b_["t"], 1e-3)), ulp_components=[0, 3])
+            fu = rounding.floor(oracle, rhs, 2, 3, 4, u0[i], p[i], kwf, o, lambda s_, b_: _rel(s_["pu_mu"][-1], b_["pu_mu"][-1]),
+                                ulp_components=[0, 3])
+            tol_t, tol_u = max(tol_t, 20 * ft), max(tol_u, 20 * fu)
+        assert np.max(np.abs(g["T"][a:b] - o["t"]) / np.maximum(o["t"], 1e-3)) < tol_t
+        assert _rel(g["U"][b - 1], o["pu_mu"][-1]) < tol_u
+
+
 def test_full_size_properties_lv_ek0_1m():
     """BASELINE cfg2 at full size: 2^20 Lotka-Volterra trajectories, EK0(order=3), adaptive, filter only."""
     n = 1 << 20

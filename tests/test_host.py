@@ -70,6 +70,14 @@ def test_argument_errors_mirror_reference(pnlib):
     assert err(rhs_src=None).kind == "ArgumentError"
     # src/algorithms.jl:101-110: Kronecker covariance only with the EK0
     assert err(cov=pnlib.COV_KRONECKER).kind == "ArgumentError"
+    # ekargcheck (src/algorithms.jl:93-107; test/errors_thrown.jl:52-56): EK1 with multivariate diffusion models
+    assert err(diffusion=pnlib.DIFF_DYNAMIC_MV).kind == "ArgumentError"
+    assert err(diffusion=pnlib.DIFF_FIXED_MV, calibrate=True).kind == "ArgumentError"
+    assert err(alg=7).kind == "ArgumentError"
+    # the BlocksOfDiagonals kernels (EK0 + multivariate diffusion, DiagonalEK1) compile for sm_100a
+    for kw in (dict(alg=pnlib.EK0, diffusion=pnlib.DIFF_DYNAMIC_MV), dict(alg=pnlib.EK0, diffusion=pnlib.DIFF_FIXED_MV),
+               dict(alg=pnlib.DIAGONAL_EK1), dict(alg=pnlib.DIAGONAL_EK1, diffusion=pnlib.DIFF_FIXED, smooth=True, save_everystep=True)):
+        assert pnlib.compile_check(pnlib.make_config(**{**base, **kw})) > 10_000
     bad = pnlib.make_config(**base)
     bad.struct_size = 8
     with pytest.raises(pnlib.PnodeError):
