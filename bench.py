@@ -100,7 +100,8 @@ def cpu_reference_run(problem, q, t1, n_sample, seed, threads=0):
     rhs = O.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
     cfg = O.make_config(pd.d, q, pd.n_p, alg=O.EK1, smooth=False, adaptive=True, save_everystep=False, t0=0.0, t1=t1,
                         cov_backend=O.COV_REF)
-    nthr = threads or O.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: ask for the host's cores explicitly (affinity-aware)
+    nthr = threads or max(O.max_threads(), len(os.sched_getaffinity(0)))
     t = time.perf_counter()
     r = O.solve_ensemble(cfg, rhs, u0, p, n_threads=nthr)
     dt = time.perf_counter() - t

@@ -2,6 +2,12 @@
 // d = 28, q = 3, D = 112).  One 256-thread CTA owns one trajectory for its whole adaptive time loop; the right
 // factor R (D x D) is staged in shared memory (98 KB at D = 112) and never leaves the SM.
 //
+// predict_cov! follows the reference literally (src/filtering/predict.jl:84-91): the Gram matrix
+// M = X'X + s2 Qh (x) I_d of the stack is formed (register-tiled SYRK, upper triangle in packed storage) and
+// factorised by a right-looking Cholesky with ONE barrier per column (rows stay unscaled until the end, so a column
+// step only reads row j and writes rows > j); only if a pivot is not positive does it fall back to Householder QR
+// (`triangularize!`), exactly as the reference does.  The fallback avoids the dense 2D x D stack:
+//
 // Shared-memory budget: the dense 2D x D stack of predict_cov! (196 KB) does not fit next to the
 // update workspace, so the stack is never materialised:
 //   1. X = R Ah' in place (row-local, Ah = T (x) I_d),
@@ -30,8 +36,9 @@ struct PnCtaShared {
     double t, dt, h, tnew, tstop, EEst, qq, q11, lEE, qold, qold_pb2, ediff, ldiff, loglik, gdiff, dtcache;
     double total, total2, quad;
     double hv[2][4]; /* Householder scalars {beta, vk, gam} of the current / next pivot */
+    double Qn[PN_MAX_N * PN_MAX_N]; /* (P^-1 L'L P^-1)[c][c']: the 1-d process-noise covariance of this step */
     long long traj, naccept, nreject, nf, iter, tstop_idx, save_pos;
-    int retcode, accept, finished, okflag;
+    int retcode, accept, finished, okflag, chol_fail;
 };
 
 template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
@@ -45,9 +52,14 @@ struct PnCta {
     static constexpr int TPC = (NT / D >= 8) ? 8 : (NT / D >= 4) ? 4 : (NT / D >= 2) ? 2 : 1;
     static constexpr int NB = (d + TPC - 1) / TPC; /* batch rows per thread in the fold sweeps */
     /* doubles of dynamic shared memory */
-    static constexpr int SM_DOUBLES = D * D + d * D + 2 * d * d /*C2*/ + 2 * d * d /*V*/ + D * d /*K*/ + d * d /*S*/ +
-                                      d * d /*J*/ + 3 * D /*mu,mup,tmp*/ + 4 * d /*z,zt,fu,uprev*/ + NPA +
+    /* packed upper triangle of the Gram matrix; the region is shared with the fold batch Bt (d x D, QR fallback only)
+       and with the gain K (D x d, computed after the factor has been copied into R) */
+    static constexpr int MP = D * (D + 1) / 2;
+    static constexpr int UNI = (MP > 2 * d * D) ? MP : 2 * d * D;
+    static constexpr int SM_DOUBLES = D * D + UNI + 2 * d * d /*C2*/ + 2 * d * d /*V*/ + d * d /*S*/ + d * d /*J*/ +
+                                      3 * D /*mu,mup,tmp*/ + 4 * d /*z,zt,fu,uprev*/ + NPA +
                                       (int)((sizeof(PnCtaShared) + 7) / 8);
+    static __device__ __forceinline__ int pidx(int i, int j) { return i * D - (i * (i - 1)) / 2 + (j - i); } /* i <= j */
 
     static __device__ __forceinline__ double block_sum(double x, PnCtaShared* sh) {
 #pragma unroll
@@ -70,28 +82,114 @@ struct PnCta {
         hv[2] = nz ? 1.0 / (total + fabs(alpha) * nrm) : 0.0;
     }
 
-    // In-place upper Cholesky of the symmetric m x m matrix A (row-major, upper part read); inv diag in invd.
-    static __device__ void chol_sm(double* A, double* invd, int m, int* okflag) {
-        const int tid = threadIdx.x;
-        for (int j = 0; j < m; j++) {
+    // Blocked right-looking upper Cholesky A = U'U in shared memory, in place, panels of NBK columns, TWO barriers per
+    // panel.  PACKED: A holds the upper triangle row by row (row i starts at i*m - i(i-1)/2); else full row-major with
+    // leading dimension m (only the upper part is touched).  The NBK x NBK diagonal block is factorised redundantly by
+    // every thread in registers, so a failing pivot (<= 0: the reference's PosDefException, predict.jl:85-91) is seen
+    // by all threads at once and the return value is CTA-uniform.  invd (optional) receives 1 / U[j][j].
+    template <bool PACKED>
+    static __device__ bool chol_blocked(double* A, const int m, double* invd) {
+        constexpr int NBK = 4, TXW = 16, TYW = NT / TXW;
+        const int tid = threadIdx.x, ty = tid / TXW, tx = tid % TXW;
+        auto rowp = [&](int i) -> double* { return PACKED ? (A + i * m - (i * (i - 1)) / 2 - i) : (A + i * m); };
+        bool ok = true;
+        for (int jb = 0; jb < m; jb += NBK) {
+            const int nb = (m - jb < NBK) ? (m - jb) : NBK;
             __syncthreads();
-            const double s = A[j * m + j];
-            if (tid == 0 && !(s > 0.0)) *okflag = 0;
-            const double ujj = sqrt(s), inv = 1.0 / ujj;
+            double Ud[NBK][NBK], inv[NBK];
+#pragma unroll
+            for (int p = 0; p < NBK; p++)
+#pragma unroll
+                for (int q = 0; q < NBK; q++)
+                    Ud[p][q] = (p < nb && q < nb && q >= p) ? rowp(jb + p)[jb + q] : ((p == q) ? 1.0 : 0.0);
+#pragma unroll
+            for (int p = 0; p < NBK; p++) {
+                double sp = Ud[p][p];
+#pragma unroll
+                for (int r = 0; r < NBK; r++)
+                    if (r < p) sp -= Ud[r][p] * Ud[r][p];
+                if (!(sp > 0.0)) ok = false;
+                const double up = sqrt(sp), ip = 1.0 / up;
+                inv[p] = ip;
+                Ud[p][p] = up;
+#pragma unroll
+                for (int q = 0; q < NBK; q++) {
+                    if (q <= p) continue;
+                    double v = Ud[p][q];
+#pragma unroll
+                    for (int r = 0; r < NBK; r++)
+                        if (r < p) v -= Ud[r][p] * Ud[r][q];
+                    Ud[p][q] = v * ip;
+                }
+            }
+            if (!ok) break; /* uniform */
+            /* panel rows U[jb+p][k], k >= jb + nb: forward substitution with the diagonal block, column-local */
+            for (int k = jb + nb + tid; k < m; k += NT) {
+                double u[NBK];
+#pragma unroll
+                for (int p = 0; p < NBK; p++) {
+                    if (p < nb) {
+                        double v = rowp(jb + p)[k];
+#pragma unroll
+                        for (int r = 0; r < NBK; r++)
+                            if (r < p) v -= Ud[r][p] * u[r];
+                        u[p] = v * inv[p];
+                        rowp(jb + p)[k] = u[p];
+                    } else {
+                        u[p] = 0.0;
+                    }
+                }
+            }
             __syncthreads();
-            for (int i = j + tid; i < m; i += NT) A[j * m + i] = (i == j) ? ujj : A[j * m + i] * inv;
-            if (tid == 0) invd[j] = inv;
-            __syncthreads();
-            /* trailing update A[i][k] -= U[j][i] U[j][k], j < i <= k */
-            const int rem = m - j - 1;
-            for (int e = tid; e < rem * rem; e += NT) {
-                const int i = j + 1 + e / rem, k = j + 1 + e % rem;
-                if (k >= i) A[i * m + k] -= A[j * m + i] * A[j * m + k];
+            if (tid < NBK * NBK) { /* everybody has read the diagonal block: store its factor */
+                const int pp = tid / NBK, qq = tid % NBK;
+#pragma unroll
+                for (int p = 0; p < NBK; p++)
+#pragma unroll
+                    for (int q = 0; q < NBK; q++)
+                        if (p == pp && q == qq && p < nb && q < nb && q >= p) rowp(jb + p)[jb + q] = Ud[p][q];
+            }
+            if (invd != nullptr && tid < NBK) {
+#pragma unroll
+                for (int p = 0; p < NBK; p++)
+                    if (p == tid && p < nb) invd[jb + p] = inv[p];
+            }
+            /* trailing update with the nb finished rows */
+            for (int i = jb + nb + ty; i < m; i += TYW) {
+                double ui[NBK];
+#pragma unroll
+                for (int p = 0; p < NBK; p++) ui[p] = (p < nb) ? rowp(jb + p)[i] : 0.0;
+                double* ri = rowp(i);
+                for (int k = i + tx; k < m; k += TXW) {
+                    double sv = ri[k];
+#pragma unroll
+                    for (int p = 0; p < NBK; p++)
+                        if (p < nb) sv -= ui[p] * rowp(jb + p)[k];
+                    ri[k] = sv;
+                }
             }
         }
         __syncthreads();
+        return ok;
     }
-    // x <- (U'U)^-1 x, serial (one thread), x in shared memory
+    // x <- (U'U)^-1 x for m <= 32 by one warp (call with all 32 lanes of the warp): lane l holds x[l]; each solved
+    // entry is broadcast and eliminated from the remaining lanes (column-oriented substitution).
+    static __device__ void chol_solve_warp(const double* U, const double* invd, double* x, int m) {
+        const int lane = threadIdx.x & 31;
+        double xv = (lane < m) ? x[lane] : 0.0;
+        for (int a = 0; a < m; a++) { /* U' y = x */
+            const double ya = __shfl_sync(0xffffffffu, xv, a) * invd[a];
+            if (lane == a) xv = ya;
+            else if (lane > a && lane < m) xv -= U[a * m + lane] * ya;
+        }
+        for (int a = m - 1; a >= 0; a--) { /* U x = y */
+            const double xa = __shfl_sync(0xffffffffu, xv, a) * invd[a];
+            if (lane == a) xv = xa;
+            else if (lane < a) xv -= U[lane * m + a] * xa;
+        }
+        if (lane < m) x[lane] = xv;
+    }
+    // serial variant (one thread) for m > 32
     static __device__ void chol_solve_serial(const double* U, const double* invd, double* x, int m) {
         for (int a = 0; a < m; a++) {
             double s = x[a];
@@ -109,11 +207,12 @@ struct PnCta {
         extern __shared__ double pn_cta_sm[];
         const int tid = threadIdx.x;
         double* R = pn_cta_sm;
-        double* Bt = R + D * D;
-        double* C2 = Bt + d * D;
+        double* Mp = R + D * D; /* packed Gram matrix | Bt, K */
+        double* Bt = Mp;
+        double* K = Mp + d * D;
+        double* C2 = Mp + UNI;
         double* V = C2 + 2 * d * d;
-        double* K = V + 2 * d * d;
-        double* S = K + D * d;
+        double* S = V + 2 * d * d;
         double* J = S + d * d;
         double* mu = J + d * d;
         double* mup = mu + D;
@@ -246,10 +345,16 @@ struct PnCta {
                         sinv[d + i] = S[i * d + i]; /* W_ii for the error estimate */
                         zt[i] = z[i];
                     }
-                    if (tid == 0) sh->okflag = 1;
-                    chol_sm(S, sinv, d, &sh->okflag);
-                    if (tid == 0) {
+                    __syncthreads();
+                    const bool okW = chol_blocked<false>(S, d, sinv);
+                    if (d <= 32) {
+                        if (tid < 32) chol_solve_warp(S, sinv, zt, d);
+                    } else if (tid == 0) {
                         chol_solve_serial(S, sinv, zt, d);
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        sh->okflag = okW ? 1 : 0;
                         double qd = 0.0;
                         for (int a = 0; a < d; a++) qd += z[a] * zt[a];
                         double ldiff = qd * (1.0 / (double)d);
@@ -307,20 +412,108 @@ struct PnCta {
 
                 /* ================= phase 2 ================= */
                 /* 1. X = R Ah' in place (ascending j is safe) */
-                for (int r = tid; r < D; r += NT) {
-                    double* row = R + r * D;
-                    for (int i = 0; i < d; i++)
-                        for (int j = 0; j < n; j++) {
-                            double s = row[j * d + i];
-                            for (int k = j + 1; k < n; k++) s += sh->hp[k - j] * row[k * d + i];
-                            row[j * d + i] = s;
-                        }
+                for (int e = tid; e < D * d; e += NT) { /* one (row, component) pair per work item: conflict-free */
+                    const int r = e / d, i = e - r * d;
+                    double* row = R + r * D + i;
+                    double v[n];
+#pragma unroll
+                    for (int j = 0; j < n; j++) v[j] = row[j * d];
+#pragma unroll
+                    for (int j = 0; j < n; j++) {
+                        double s = v[j];
+#pragma unroll
+                        for (int k = 0; k < n; k++)
+                            if (k > j) s += sh->hp[k > j ? k - j : 0] * v[k];
+                        row[j * d] = s;
+                    }
                 }
                 __syncthreads();
-                /* 2.+3. Householder sweeps with ONE barrier per pivot.  TPC adjacent lanes share a column (rows
-                   interleaved); the owners of column k+1 compute its norm right after updating it, and the owners of
-                   column k-1 (idle by then) write its diagonal and clear its sub-diagonal. */
+                /* 2. Gram matrix + Cholesky (predict.jl:84-85) */
+                bool need_qr = true;
+#ifndef PN_CTA_QR_ONLY
                 {
+                    if (tid < n * n) { /* Qn = P^-1 (L'L) P^-1 */
+                        const int c = tid / n, c2 = tid - c * n;
+                        double acc = 0.0;
+                        for (int m = 0; m < n; m++) acc += P.L[m * n + c] * P.L[m * n + c2];
+                        sh->Qn[tid] = acc * sh->PIv[c] * sh->PIv[c2];
+                    }
+                    if (tid == 0) sh->chol_fail = 0;
+                    __syncthreads();
+                    const double ediff = sh->ediff;
+                    /* SYRK: 4 x 4 register tiles over the upper triangle of tiles */
+                    constexpr int TI = (D + 3) / 4;
+                    constexpr int NTILES = TI * (TI + 1) / 2;
+                    for (int e = tid; e < NTILES; e += NT) {
+                        int I = 0, rem = e;
+                        while (rem >= TI - I) {
+                            rem -= TI - I;
+                            I++;
+                        }
+                        const int J = I + rem;
+                        double acc[4][4];
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+#pragma unroll
+                            for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+                        const int ci = 4 * I, cj = 4 * J;
+                        if (D % 4 == 0) {
+#pragma unroll 2
+                            for (int r = 0; r < D; r++) {
+                                const double2 a01 = *reinterpret_cast<const double2*>(R + r * D + ci);
+                                const double2 a23 = *reinterpret_cast<const double2*>(R + r * D + ci + 2);
+                                const double2 b01 = *reinterpret_cast<const double2*>(R + r * D + cj);
+                                const double2 b23 = *reinterpret_cast<const double2*>(R + r * D + cj + 2);
+                                const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+                                const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                                for (int a = 0; a < 4; a++)
+#pragma unroll
+                                    for (int b = 0; b < 4; b++) acc[a][b] += av[a] * bv[b];
+                            }
+                        } else {
+                            for (int r = 0; r < D; r++) {
+                                double av[4], bv[4];
+#pragma unroll
+                                for (int a = 0; a < 4; a++) {
+                                    av[a] = (ci + a < D) ? R[r * D + ci + a] : 0.0;
+                                    bv[a] = (cj + a < D) ? R[r * D + cj + a] : 0.0;
+                                }
+#pragma unroll
+                                for (int a = 0; a < 4; a++)
+#pragma unroll
+                                    for (int b = 0; b < 4; b++) acc[a][b] += av[a] * bv[b];
+                            }
+                        }
+#pragma unroll
+                        for (int a = 0; a < 4; a++)
+#pragma unroll
+                            for (int b = 0; b < 4; b++) {
+                                const int gi = ci + a, gj = cj + b;
+                                if (gi <= gj && gj < D) {
+                                    const int ji = gi / d, jj = gj / d;
+                                    double v = acc[a][b];
+                                    if (gi - ji * d == gj - jj * d) v += ediff * sh->Qn[ji * n + jj]; /* predict.jl:79-83 */
+                                    Mp[pidx(gi, gj)] = v;
+                                }
+                            }
+                    }
+                    __syncthreads();
+                    const bool ok = chol_blocked<true>(Mp, D, nullptr);
+                    if (ok) { /* R^- = U: expand the packed factor into the dense one */
+                        for (int e = tid; e < D * D; e += NT) {
+                            const int i = e / D, k = e - i * D;
+                            R[e] = (k >= i) ? Mp[pidx(i, k)] : 0.0;
+                        }
+                        need_qr = false;
+                    }
+                    __syncthreads();
+                }
+#endif
+                /* 2'.+3'. fallback (predict.jl:90, triangularize!): Householder sweeps with ONE barrier per pivot.  TPC
+                   adjacent lanes share a column (rows interleaved); the owners of column k+1 compute its norm right after
+                   updating it, and the owners of column k-1 (idle by then) write its diagonal and clear its sub-diagonal. */
+                if (need_qr) {
                     const int col = tid / TPC, sub = tid % TPC;
                     /* Householder scalars of pivot k live in sh->hv[k & 1] = {beta, vk, gam}: they are computed once, by
                        the owner of the pivot column right after it has updated that column (double-buffered, so a
@@ -513,11 +706,17 @@ struct PnCta {
                     }
                     __syncthreads();
                 } else {
-                    if (tid == 0) sh->okflag = 1;
                     for (int i = tid; i < d; i += NT) zt[i] = z[i];
-                    chol_sm(S, sinv, d, &sh->okflag);
-                    if (tid == 0) {
+                    __syncthreads();
+                    const bool okS = chol_blocked<false>(S, d, sinv);
+                    if (d <= 32) {
+                        if (tid < 32) chol_solve_warp(S, sinv, zt, d);
+                    } else if (tid == 0) {
                         chol_solve_serial(S, sinv, zt, d);
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        sh->okflag = okS ? 1 : 0;
                         double quad = 0.0, logdet = 0.0;
                         for (int a = 0; a < d; a++) {
                             quad += z[a] * zt[a];
@@ -545,25 +744,52 @@ struct PnCta {
                         }
                     }
                     __syncthreads();
-                    /* K = R^-' V */
-                    for (int e = tid; e < D * d; e += NT) {
-                        const int c = e / d, a = e - c * d;
-                        const int rmax = (c + 1 < 2 * d) ? c + 1 : 2 * d;
-                        double s = 0.0;
-                        for (int r = 0; r < rmax; r++) s += R[r * D + c] * V[r * d + a];
-                        K[e] = s;
+                    /* K = R^-' V, stored transposed (Kt[a][c]); TA gains per thread so that a row entry of R^- is reused */
+                    {
+                        constexpr int TA = (d % 7 == 0) ? 7 : 4;
+                        constexpr int NAB = (d + TA - 1) / TA;
+                        for (int e = tid; e < D * NAB; e += NT) {
+                            const int ab = e / D, c = e - ab * D;
+                            const int rmax = (c + 1 < 2 * d) ? c + 1 : 2 * d;
+                            double acc[TA];
+#pragma unroll
+                            for (int t = 0; t < TA; t++) acc[t] = 0.0;
+                            for (int r = 0; r < rmax; r++) {
+                                const double rv = R[r * D + c];
+#pragma unroll
+                                for (int t = 0; t < TA; t++)
+                                    if (ab * TA + t < d) acc[t] += rv * V[r * d + ab * TA + t];
+                            }
+#pragma unroll
+                            for (int t = 0; t < TA; t++)
+                                if (ab * TA + t < d) K[(ab * TA + t) * D + c] = acc[t];
+                        }
                     }
                     __syncthreads();
                     for (int c = tid; c < D; c += NT) {
                         double s = mup[c];
-                        for (int a = 0; a < d; a++) s -= K[c * d + a] * z[a];
+                        for (int a = 0; a < d; a++) s -= K[a * D + c] * z[a];
                         mu[c] = s;
                     }
-                    for (int e = tid; e < 2 * d * D; e += NT) {
-                        const int r = e / D, c = e - r * D;
-                        double s = R[e];
-                        for (int a = 0; a < d; a++) s -= C2[r * d + a] * K[c * d + a];
-                        R[e] = s;
+                    /* R+ = R^- - C2 K' on the first 2d rows, TR rows per thread */
+                    {
+                        constexpr int TR = 4;
+                        constexpr int NRB = (2 * d + TR - 1) / TR;
+                        for (int e = tid; e < NRB * D; e += NT) {
+                            const int rb = e / D, c = e - rb * D;
+                            double acc[TR];
+#pragma unroll
+                            for (int t = 0; t < TR; t++) acc[t] = 0.0;
+                            for (int a = 0; a < d; a++) {
+                                const double kv = K[a * D + c];
+#pragma unroll
+                                for (int t = 0; t < TR; t++)
+                                    if (rb * TR + t < 2 * d) acc[t] += C2[(rb * TR + t) * d + a] * kv;
+                            }
+#pragma unroll
+                            for (int t = 0; t < TR; t++)
+                                if (rb * TR + t < 2 * d) R[(rb * TR + t) * D + c] -= acc[t];
+                        }
                     }
                     __syncthreads();
                 }

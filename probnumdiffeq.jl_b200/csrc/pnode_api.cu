@@ -413,8 +413,8 @@ static int get_smoother(pnode_solver* s) {
 
 static size_t cta_smem_bytes(int d, int q, int n_p) {
     const size_t n = q + 1, D = (size_t)d * n, npa = n_p > 0 ? n_p : 1;
-    const size_t dbl = D * D + d * D + 2 * d * d + 2 * d * d + D * d + d * d + d * d + 3 * D + 4 * d + npa +
-                       (sizeof(PnCtaShared) + 7) / 8;
+    const size_t mp = D * (D + 1) / 2, uni = mp > 2 * d * D ? mp : 2 * d * D; /* must match PnCta::SM_DOUBLES */
+    const size_t dbl = D * D + uni + 2 * d * d + 2 * d * d + d * d + d * d + 3 * D + 4 * d + npa + (sizeof(PnCtaShared) + 7) / 8;
     return dbl * sizeof(double);
 }
 

@@ -588,8 +588,13 @@ def test_full_size_properties_lv_ek0_1m():
 # ------------------------------------------------------------------------------------------------------------------
 # CTA-per-trajectory kernel (BASELINE cfg4: Pleiades d = 28, D = 112)
 # ------------------------------------------------------------------------------------------------------------------
-def test_cta_kernel_matches_oracle_on_small_problems(oracle):
-    """The shared-memory CTA kernel is size-generic: run it on small problems where the oracle is fast."""
+@pytest.mark.parametrize("qr_only", [False, True])
+def test_cta_kernel_matches_oracle_on_small_problems(oracle, monkeypatch, qr_only):
+    """The shared-memory CTA kernel is size-generic: run it on small problems where the oracle is fast.  Both
+    covariance-prediction routes of predict.jl:84-91 are covered: Gram + Cholesky (default) and the Householder
+    fallback `triangularize!` (forced with the developer flag PN_CTA_QR_ONLY)."""
+    if qr_only:
+        monkeypatch.setenv("PNODE_NVRTC_FLAGS", "-DPN_CTA_QR_ONLY")
     pd, u0, p = _inputs("fitzhugh_nagumo", 2, 14, dp=0.05)
     g = _gpu(pd, u0, p, 3, builtin=False, adaptive=False, dt=0.01, t0=0.0, t1=5.0, diffusion=lib.DIFF_FIXED,
              save_everystep=True, save_state=True, lanes_per_traj=256)
