@@ -286,7 +286,9 @@ def main():
             "gpu_launches": int(launches_t),
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture of this very
+                # command at its default size (profiles/r1g_pn_small_rober_1m_traffic.txt); null for other workloads / sizes
+                "traffic": 191.1e6 if (args.workload == "rober" and n == (1 << 20)) else None,
                 "peak_source": "measured live by pnode_measure_fp64_peak (DFMA probe); MEASURED_PEAKS.json has no FP64 figure",
                 "algorithmic_flops_per_accepted_step": f_acc, "algorithmic_flops_per_rejected_step": f_rej,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / dur / 1e9, "peak_gbs": hbm_peak,

@@ -28,6 +28,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 EK0, EK1, DIAGONAL_EK1 = 0, 1, 2
 DIFF_DYNAMIC, DIFF_FIXED, DIFF_DYNAMIC_MV, DIFF_FIXED_MV = 0, 1, 2, 3
 COV_REF, COV_QR = 0, 1
+PRIOR_IWP, PRIOR_IOUP = 0, 1
 RET = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable"}
 
 
@@ -77,6 +78,7 @@ class Config(C.Structure):
         ("gamma", C.c_double), ("qsteady_min", C.c_double), ("qsteady_max", C.c_double), ("qoldinit", C.c_double),
         ("tstops", C.POINTER(C.c_double)), ("n_tstops", C.c_int64),
         ("forced_diffusion", C.POINTER(C.c_double)), ("n_forced", C.c_int64),
+        ("prior", C.c_int32), ("reserved", C.c_int32), ("rate_parameter", C.c_double),
     ]
 
 
@@ -214,12 +216,14 @@ def compile_rhs(tr, q) -> CompiledRHS:
 def make_config(d, q, n_p, *, alg=EK1, diffusion=DIFF_DYNAMIC, calibrate=True, initial_diffusion=1.0, smooth=True,
                 adaptive=True, save_everystep=True, cov_backend=COV_REF, t0=0.0, t1=1.0, dt=0.0, abstol=1e-6,
                 reltol=1e-3, dtmin=0.0, dtmax=None, maxiters=1_000_000, beta1=None, beta2=None, qmin=0.2, qmax=10.0,
-                gamma=0.9, qsteady_min=1.0, qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None):
+                gamma=0.9, qsteady_min=1.0, qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None,
+                prior=PRIOR_IWP, rate_parameter=0.0):
     c = Config()
     c.d, c.q, c.n_p, c.alg = d, q, n_p, alg
     c.diffusion, c.calibrate, c.smooth, c.adaptive = diffusion, int(calibrate), int(smooth), int(adaptive)
     c.save_everystep, c.cov_backend, c.maxiters = int(save_everystep), cov_backend, int(maxiters)
     c.initial_diffusion = initial_diffusion
+    c.prior, c.rate_parameter = prior, float(rate_parameter)
     c.t0, c.t1, c.dt = t0, t1, dt
     c.abstol, c.reltol, c.dtmin = abstol, reltol, dtmin
     c.dtmax = (t1 - t0) if dtmax is None else dtmax

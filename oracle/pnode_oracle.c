@@ -150,6 +150,136 @@ void oracle_iwp_transition(int q, double h, double* Ah, double* QhR) {
         }
 }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* IOUP prior (src/priors/ioup.jl), scalar rate parameter                                      */
+/* ------------------------------------------------------------------------------------------ */
+
+/* Solve A X = B (A n x n, B n x m, column-major) by Gaussian elimination with partial pivoting; B <- X. */
+static void lu_solve(int n, int m, double* A, double* B) {
+    for (int k = 0; k < n; k++) {
+        int piv = k;
+        for (int i = k + 1; i < n; i++)
+            if (fabs(AT(A, i, k, n)) > fabs(AT(A, piv, k, n))) piv = i;
+        if (piv != k) {
+            for (int j = 0; j < n; j++) { double t = AT(A, k, j, n); AT(A, k, j, n) = AT(A, piv, j, n); AT(A, piv, j, n) = t; }
+            for (int j = 0; j < m; j++) { double t = AT(B, k, j, n); AT(B, k, j, n) = AT(B, piv, j, n); AT(B, piv, j, n) = t; }
+        }
+        for (int i = k + 1; i < n; i++) {
+            double f = AT(A, i, k, n) / AT(A, k, k, n);
+            if (f == 0.0) continue;
+            for (int j = k + 1; j < n; j++) AT(A, i, j, n) -= f * AT(A, k, j, n);
+            for (int j = 0; j < m; j++) AT(B, i, j, n) -= f * AT(B, k, j, n);
+        }
+    }
+    for (int j = 0; j < m; j++)
+        for (int i = n - 1; i >= 0; i--) {
+            double sacc = AT(B, i, j, n);
+            for (int k = i + 1; k < n; k++) sacc -= AT(A, i, k, n) * AT(B, k, j, n);
+            AT(B, i, j, n) = sacc / AT(A, i, i, n);
+        }
+}
+
+/* exp(M), M n x n column-major: scaling and squaring with the degree-13 Pade approximant (Higham 2005; what Julia's
+   `exp(::Matrix)` -- used by matrix_fraction_decomposition, src/priors/ltisde.jl:52-63 -- implements). */
+void oracle_expm(int n, const double* M, double* E) {
+    static const double b[14] = {64764752532480000.0, 32382376266240000.0, 7771770303897600.0, 1187353796428800.0,
+                                 129060195264000.0,   10559470521600.0,    670442572800.0,    33522128640.0,
+                                 1323241920.0,        40840800.0,          960960.0,          16380.0, 182.0, 1.0};
+    size_t nn = (size_t)n * n;
+    double nrm = 0.0; /* 1-norm */
+    for (int j = 0; j < n; j++) {
+        double c = 0.0;
+        for (int i = 0; i < n; i++) c += fabs(AT(M, i, j, n));
+        if (c > nrm) nrm = c;
+    }
+    int sq = 0;
+    if (nrm > 5.371920351148152) sq = (int)ceil(log2(nrm / 5.371920351148152));
+    if (sq < 0) sq = 0;
+    double sc = ldexp(1.0, -sq);
+    double* A = (double*)malloc(sizeof(double) * nn * 8);
+    double *A2 = A + nn, *A4 = A2 + nn, *A6 = A4 + nn, *U = A6 + nn, *V = U + nn, *T1 = V + nn, *T2 = T1 + nn;
+    for (size_t i = 0; i < nn; i++) A[i] = M[i] * sc;
+    gemm(n, n, n, 1.0, A, n, 0, A, n, 0, 0.0, A2, n);
+    gemm(n, n, n, 1.0, A2, n, 0, A2, n, 0, 0.0, A4, n);
+    gemm(n, n, n, 1.0, A4, n, 0, A2, n, 0, 0.0, A6, n);
+    /* U = A [A6 (b13 A6 + b11 A4 + b9 A2) + b7 A6 + b5 A4 + b3 A2 + b1 I] */
+    for (size_t i = 0; i < nn; i++) T1[i] = b[13] * A6[i] + b[11] * A4[i] + b[9] * A2[i];
+    gemm(n, n, n, 1.0, A6, n, 0, T1, n, 0, 0.0, T2, n);
+    for (size_t i = 0; i < nn; i++) T2[i] += b[7] * A6[i] + b[5] * A4[i] + b[3] * A2[i];
+    for (int i = 0; i < n; i++) AT(T2, i, i, n) += b[1];
+    gemm(n, n, n, 1.0, A, n, 0, T2, n, 0, 0.0, U, n);
+    /* V = A6 (b12 A6 + b10 A4 + b8 A2) + b6 A6 + b4 A4 + b2 A2 + b0 I */
+    for (size_t i = 0; i < nn; i++) T1[i] = b[12] * A6[i] + b[10] * A4[i] + b[8] * A2[i];
+    gemm(n, n, n, 1.0, A6, n, 0, T1, n, 0, 0.0, V, n);
+    for (size_t i = 0; i < nn; i++) V[i] += b[6] * A6[i] + b[4] * A4[i] + b[2] * A2[i];
+    for (int i = 0; i < n; i++) AT(V, i, i, n) += b[0];
+    /* (V - U) E = V + U */
+    for (size_t i = 0; i < nn; i++) { T1[i] = V[i] - U[i]; E[i] = V[i] + U[i]; }
+    lu_solve(n, n, T1, E);
+    for (int k = 0; k < sq; k++) {
+        gemm(n, n, n, 1.0, E, n, 0, E, n, 0, 0.0, T1, n);
+        memcpy(E, T1, sizeof(double) * nn);
+    }
+    free(A);
+}
+
+/* matrix_fraction_decomposition (src/priors/ltisde.jl:52-63): exp(dt [F LL'; 0 -F']) = [A *; 0 *], Q = Mexp[1:d, d+1:end] A'. */
+void oracle_matrix_fraction_decomposition(int n, const double* F, const double* Lvec /* n, dispersion column */, double dt,
+                                          double* A, double* Q) {
+    int m = 2 * n;
+    double* M = (double*)calloc((size_t)m * m, sizeof(double));
+    double* E = (double*)malloc(sizeof(double) * (size_t)m * m);
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) {
+            AT(M, i, j, m) = dt * AT(F, i, j, n);
+            AT(M, i, n + j, m) = dt * Lvec[i] * Lvec[j];
+            AT(M, n + i, n + j, m) = -dt * AT(F, j, i, n);
+        }
+    oracle_expm(m, M, E);
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) AT(A, i, j, n) = AT(E, i, j, m);
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) {
+            double sacc = 0.0;
+            for (int k = 0; k < n; k++) sacc += AT(E, i, n + k, m) * AT(A, j, k, n);
+            AT(Q, i, j, n) = sacc;
+        }
+    free(M);
+    free(E);
+}
+
+/* make_transition_matrices!(cache, ::IOUP, dt) (src/priors/ioup.jl:115-131), 1-d factors, scalar rate r:
+   the reference calls FiniteHorizonGramians.exp_and_gram_chol! (v0.2.1, third party, not vendored) on
+   F = shift + r e_q e_q', L = e_q over the horizon dt and then forms A = P Ah PI, Q = P Qh P.  The in-repo equivalent that
+   the reference's own tests pin it against is matrix_fraction_decomposition (test/core/priors.jl:29-32,266-272).  Here
+   the decomposition is evaluated in the *preconditioned* coordinates x~ = P x, where the SDE over tau = t/dt in [0, 1]
+   has the O(1) drift F~ = superdiag(q, q-1, ..., 1) + (r dt) e_q e_q' and dispersion e_q (for r = 0 this is exactly the
+   IWP's A_breve, Q_breve of iwp.jl:96-108), and mapped back: Ah = PI A~ P, Qh.R = chol(Q~).U PI (preconditioning
+   identities of test/core/priors.jl:220-223). */
+void oracle_ioup_transition(int q, double rate, double h, double* Ah, double* QhR) {
+    int n = q + 1;
+    double F[32 * 32], Lv[32], At[32 * 32], Qt[32 * 32], P[32], PI[32];
+    memset(F, 0, sizeof(F));
+    for (int j = 0; j < q; j++) AT(F, j, j + 1, n) = (double)(q - j);
+    AT(F, q, q, n) = rate * h;
+    for (int j = 0; j < n; j++) Lv[j] = (j == q) ? 1.0 : 0.0;
+    oracle_matrix_fraction_decomposition(n, F, Lv, 1.0, At, Qt);
+    for (int j = 0; j < n; j++) /* symmetrise before the factorisation */
+        for (int i = 0; i < j; i++) {
+            double v = 0.5 * (AT(Qt, i, j, n) + AT(Qt, j, i, n));
+            AT(Qt, i, j, n) = v;
+            AT(Qt, j, i, n) = v;
+        }
+    oracle_cholesky_upper(n, Qt);
+    oracle_preconditioner(q, h, P, PI);
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) {
+            AT(Ah, i, j, n) = PI[i] * (AT(At, i, j, n) * P[j]);
+            AT(QhR, i, j, n) = (i <= j) ? AT(Qt, i, j, n) * PI[j] : 0.0;
+        }
+}
+
 /* kron(B, I_d) (src/kronecker.jl:7): out[(r*d+i), (c*d+i)] = B[r,c]. */
 void oracle_kron_identity(int d, int n_rows, int n_cols, const double* B, double* out) {
     int M = n_rows * d, N = n_cols * d;
@@ -744,7 +874,8 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     if (c->alg == ORACLE_DIAGONAL_EK1 || c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV)
         return solve_blocks(c, f, jac, taylor, u0, p, out);
     const int d = c->d, q = c->q, n = q + 1, D = d * n;
-    const int kron = (c->alg == ORACLE_EK0);
+    /* covariance_structure (src/algorithms.jl:132-151): EK0 is Kronecker only with the IWP prior, else dense */
+    const int kron = (c->alg == ORACLE_EK0 && c->prior == ORACLE_PRIOR_IWP);
     const int N = kron ? n : D;          /* size of the matrices the filter works on */
     const int nrhs = kron ? d : 1;       /* mean handled as N x nrhs (update.jl:166-174) */
     const int rs = kron ? d : 1, cs = kron ? 1 : 0;
@@ -833,7 +964,8 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
 
         /* ---- perform_step! (src/perform_step.jl:79-154) ---- */
         double tnew = t + dt;                                  /* :85 */
-        oracle_iwp_transition(q, dt, Ah1, Qh1);                /* :87-99, make_transition_matrices! */
+        if (c->prior == ORACLE_PRIOR_IOUP) oracle_ioup_transition(q, c->rate_parameter, dt, Ah1, Qh1); /* ioup.jl:115-131 */
+        else oracle_iwp_transition(q, dt, Ah1, Qh1);           /* :87-99, make_transition_matrices! */
         if (kron) {
             memcpy(Ah, Ah1, sizeof(double) * NN);
             memcpy(QhR, Qh1, sizeof(double) * NN);
@@ -859,10 +991,12 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
         } else {
             memset(H, 0, sizeof(double) * (size_t)m * N);
             for (int i = 0; i < d; i++) AT(H, i, d + i, d) = 1.0;    /* H = E1 */
-            jac(J, upred, p, tnew);
-            out->njac += 1;
-            for (int a = 0; a < d; a++)
-                for (int i = 0; i < d; i++) AT(H, a, i, d) -= AT(J, a, i, d); /* H -= J * E0 (:13) */
+            if (c->alg == ORACLE_EK1) {
+                jac(J, upred, p, tnew);
+                out->njac += 1;
+                for (int a = 0; a < d; a++)
+                    for (int i = 0; i < d; i++) AT(H, a, i, d) -= AT(J, a, i, d); /* H -= J * E0 (:13) */
+            }
         }
         /* local diffusion (:110-112; calibration.jl:123-133, invquad :9-29) */
         int have_local = 0;

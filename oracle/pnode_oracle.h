@@ -35,6 +35,7 @@ typedef void (*oracle_taylor_fn)(double* out, const double* u, const double* p, 
 
 enum { ORACLE_EK0 = 0, ORACLE_EK1 = 1, ORACLE_DIAGONAL_EK1 = 2 /* BlocksOfDiagonals layout, src/algorithms.jl:343-393 */ };
 enum { ORACLE_DIFF_DYNAMIC = 0, ORACLE_DIFF_FIXED = 1, ORACLE_DIFF_DYNAMIC_MV = 2, ORACLE_DIFF_FIXED_MV = 3 /* src/diffusions/typedefs.jl */ };
+enum { ORACLE_PRIOR_IWP = 0, ORACLE_PRIOR_IOUP = 1 /* scalar rate parameter, src/priors/ioup.jl */ };
 enum { ORACLE_COV_REF = 0 /* Gram+Cholesky, QR fallback (predict.jl:84-91) */, ORACLE_COV_QR = 1 };
 enum {
     ORACLE_RET_SUCCESS = 0,
@@ -65,6 +66,9 @@ typedef struct {
        accepted step k (k = 0..n_forced-1); NULL = free running */
     const double* forced_diffusion;
     int64_t n_forced;
+    int32_t prior;          /* ORACLE_PRIOR_* */
+    int32_t reserved;
+    double rate_parameter;  /* IOUP: F[q,q] (src/priors/ioup.jl:66-79) */
 } oracle_config;
 
 /* One solved trajectory.  Arrays are owned by the struct; free with oracle_traj_free. */
@@ -94,6 +98,9 @@ typedef struct {
 void oracle_iwp_preconditioned(int q, double* A_breve /*n*n*/, double* L_breve /*n*n*/);
 void oracle_preconditioner(int q, double h, double* P /*n*/, double* PI /*n*/);
 void oracle_iwp_transition(int q, double h, double* Ah /*n*n*/, double* QhR /*n*n*/);
+void oracle_expm(int n, const double* M, double* E);
+void oracle_matrix_fraction_decomposition(int n, const double* F, const double* Lvec, double dt, double* A, double* Q);
+void oracle_ioup_transition(int q, double rate, double h, double* Ah /*n*n*/, double* QhR /*n*n upper*/);
 void oracle_kron_identity(int d, int n_rows, int n_cols, const double* B, double* out /* (n_rows*d) x (n_cols*d) */);
 int oracle_cholesky_upper(int n, double* M); /* in place; returns 0 on success */
 void oracle_triangularize(int m, int n, double* A /* m x n, in place */, double* Rout /* n x n */);

@@ -121,13 +121,49 @@ PN_HD void pn_chol_solve(const double (&U)[M_][M_], const double (&invd)[M_], do
 // entries left of its first row are never touched.  On return Tt[:, 0:NE] is the upper-triangular factor (zeros
 // below the diagonal); if dinv != nullptr lane (k % G) stores 1/diag[k] (0 for a zero column) to dinv[k].
 // The j loop is chunked (JC columns at a time) to bound the number of live partial sums.
+// Householder scalars of one pivot column
+struct PnHouse {
+    double beta, vk, gam, binv;
+};
+// norm, pivot broadcast and reflector scalars of column k of the stack (rows >= k of the top block, active bottom slots)
+template <int G, int RPL, int NC, bool BOTUP>
+PN_HD PnHouse pn_qr_house(const double (&Tt)[RPL][NC], const double (&Bt)[RPL][NC], int gl, int k) {
+    const int ks = k / G, kl = k % G;
+    double part = 0.0, xp = 0.0;
+#pragma unroll
+    for (int lr = 0; lr < RPL; lr++) {
+        const int base = lr * G;
+        if (base + G - 1 < k) continue;
+        const double xv = (base >= k) ? Tt[lr][k] : ((base + gl >= k) ? Tt[lr][k] : 0.0);
+        if (lr == ks) xp = xv;
+        part += xv * xv;
+    }
+#pragma unroll
+    for (int lr = 0; lr < RPL; lr++)
+        if (!BOTUP || lr * G <= k) part += Bt[lr][k] * Bt[lr][k];
+    const double total = pn_gsum<G>(part);
+    const double alpha = pn_gbcast<G>(xp, kl);
+    const bool nz = total > 0.0;
+    const double rsq = pn_rsqrt(total);
+    const double nrm = nz ? total * rsq : 0.0;
+    PnHouse h;
+    h.beta = -copysign(nrm, alpha);
+    h.vk = alpha - h.beta;
+    h.gam = nz ? pn_rcp(total + fabs(alpha) * nrm) : 0.0; /* 2 / v'v */
+    h.binv = nz ? -copysign(rsq, alpha) : 0.0;
+    return h;
+}
+
 template <int G, int RPL, int NC, int NE, bool BOTUP, int JC>
 PN_HD void pn_qr_rows(double (&Tt)[RPL][NC], double (&Bt)[RPL][NC], int gl, double* dinv) {
+    /* software-pipelined: the scalars of pivot k+1 (butterfly, rsqrt, rcp: a ~200-cycle dependent chain) are started
+       right after reflector k has updated column k+1, so the chain runs under the updates of columns k+2... */
+    PnHouse hs = pn_qr_house<G, RPL, NC, BOTUP>(Tt, Bt, gl, 0);
 #pragma unroll
     for (int k = 0; k < NE; k++) {
         const int ks = k / G, kl = k % G;
+        const PnHouse hk = hs;
         double x[RPL];
-        double part = 0.0;
 #pragma unroll
         for (int lr = 0; lr < RPL; lr++) {
             const int base = lr * G;
@@ -138,31 +174,37 @@ PN_HD void pn_qr_rows(double (&Tt)[RPL][NC], double (&Bt)[RPL][NC], int gl, doub
             } else {
                 x[lr] = (base + gl >= k) ? Tt[lr][k] : 0.0;
             }
-            if (base + G - 1 >= k) part += x[lr] * x[lr];
         }
+        if (dinv != nullptr && gl == kl) dinv[k] = hk.binv;
+        if (gl == kl) x[ks] = hk.vk;
+        /* column k+1 first, then the next pivot's scalars */
+        if (k + 1 < NC) {
+            const int j = k + 1;
+            double s = 0.0;
 #pragma unroll
-        for (int lr = 0; lr < RPL; lr++)
-            if (!BOTUP || lr * G <= k) part += Bt[lr][k] * Bt[lr][k];
-        const double total = pn_gsum<G>(part);
-        const double alpha = pn_gbcast<G>(x[ks], kl);
-        const bool nz = total > 0.0;
-        const double rsq = pn_rsqrt(total);
-        const double nrm = nz ? total * rsq : 0.0;
-        const double beta = -copysign(nrm, alpha);
-        const double vk = alpha - beta;
-        const double den = total + fabs(alpha) * nrm; /* = v'v / 2 */
-        const double gam = nz ? pn_rcp(den) : 0.0;
-        if (dinv != nullptr && gl == kl) dinv[k] = nz ? -copysign(rsq, alpha) : 0.0;
-        if (gl == kl) x[ks] = vk;
+            for (int lr = 0; lr < RPL; lr++)
+                if (lr * G + G - 1 >= k) s += x[lr] * Tt[lr][j];
+#pragma unroll
+            for (int lr = 0; lr < RPL; lr++)
+                if (!BOTUP || lr * G <= k) s += Bt[lr][k] * Bt[lr][j];
+            s = pn_gsum<G>(s) * hk.gam;
+#pragma unroll
+            for (int lr = 0; lr < RPL; lr++)
+                if (lr * G + G - 1 >= k) Tt[lr][j] -= s * x[lr];
+#pragma unroll
+            for (int lr = 0; lr < RPL; lr++)
+                if (!BOTUP || lr * G <= k) Bt[lr][j] -= s * Bt[lr][k];
+        }
+        if (k + 1 < NE) hs = pn_qr_house<G, RPL, NC, BOTUP>(Tt, Bt, gl, k + 1);
 #pragma unroll
         for (int j0 = 0; j0 < NC; j0 += JC) {
-            if (j0 + JC - 1 <= k) continue;
+            if (j0 + JC - 1 <= k + 1) continue;
             double sj[JC];
 #pragma unroll
             for (int jj = 0; jj < JC; jj++) {
                 const int j = j0 + jj;
                 sj[jj] = 0.0;
-                if (j <= k || j >= NC) continue;
+                if (j <= k + 1 || j >= NC) continue;
                 double s = 0.0;
 #pragma unroll
                 for (int lr = 0; lr < RPL; lr++)
@@ -175,13 +217,13 @@ PN_HD void pn_qr_rows(double (&Tt)[RPL][NC], double (&Bt)[RPL][NC], int gl, doub
 #pragma unroll
             for (int jj = 0; jj < JC; jj++) {
                 const int j = j0 + jj;
-                if (j <= k || j >= NC) continue;
-                sj[jj] = pn_gsum<G>(sj[jj]) * gam;
+                if (j <= k + 1 || j >= NC) continue;
+                sj[jj] = pn_gsum<G>(sj[jj]) * hk.gam;
             }
 #pragma unroll
             for (int jj = 0; jj < JC; jj++) {
                 const int j = j0 + jj;
-                if (j <= k || j >= NC) continue;
+                if (j <= k + 1 || j >= NC) continue;
 #pragma unroll
                 for (int lr = 0; lr < RPL; lr++)
                     if (lr * G + G - 1 >= k) Tt[lr][j] -= sj[jj] * x[lr];
@@ -195,12 +237,11 @@ PN_HD void pn_qr_rows(double (&Tt)[RPL][NC], double (&Bt)[RPL][NC], int gl, doub
             const int base = lr * G;
             if (base + G - 1 < k) continue;
             const int row = base + gl;
-            if (row == k) Tt[lr][k] = beta;
+            if (row == k) Tt[lr][k] = hk.beta;
             else if (row > k) Tt[lr][k] = 0.0;
         }
     }
 }
-
 
 // ode_determine_initdt (OrdinaryDiffEqCore, Hairer-Wanner; restated from SURVEY.md A.6).  Two f evaluations.
 template <class Prob>

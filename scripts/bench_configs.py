@@ -1,0 +1,71 @@
+"""Throughput of every BASELINE.json configuration on one GPU (device-event kernel time, inputs resident in HBM is not
+attempted here: this goes through the host-buffer C-ABI call and reports both the kernel time and the wall time).
+Writes one JSON line per configuration; used to fill the table in DESIGN.md / profiles/."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import probnumdiffeq_jl_b200  # noqa: F401
+from probnumdiffeq_jl_b200 import lib, problems
+
+PEAK = lib.measure_fp64_peak(0)
+
+
+def F_filt(D, d):
+    return (22 / 3) * D**3 + 8 * D * D * d + 6 * D * D + 6 * D * d * d + (2 / 3) * d**3
+
+
+def F_smooth(D, d):
+    return 10 * D**3 + (22 / 3) * D**3 + 2 * D * D * d + 2 * D * D
+
+
+def run(tag, name, n, q, t1, alg=lib.EK1, seed=0, reps=2, du0=0.0, dp=0.1, **kw):
+    pd = problems.PROBLEMS[name]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    u0 = np.array(pd.u0, dtype=float)[None, :] * (1 + du0 * rng.uniform(-1, 1, (n, pd.d)))
+    p = np.array(pd.p, dtype=float)[None, :] * (1 + dp * rng.uniform(-1, 1, (n, pd.n_p))) if pd.n_p else np.zeros((n, 0))
+    if name == "pleiades":
+        u0[:, 14:] += 1e-3 * rng.uniform(-1, 1, (n, 14))
+    cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="builtin:" + name, alg=alg, t0=0.0, t1=t1, **kw)
+    s = lib.Solver(cfg)
+    best = None
+    for _ in range(reps):
+        t = time.perf_counter()
+        r = s.solve(np.ascontiguousarray(u0), np.ascontiguousarray(p))
+        wall = time.perf_counter() - t
+        info = r.info
+        rc = r.field(lib.F_RETCODE)
+        rec = dict(kernel_ms=info.kernel_ms, wall_ms=wall * 1e3, accepted=int(info.total_accepted), rejected=int(info.total_rejected),
+                   launches=int(info.n_launches), ok=bool((rc == 0).all()))
+        r.free()
+        if best is None or rec["kernel_ms"] < best["kernel_ms"]:
+            best = rec
+    s.close()
+    D = pd.d * (q + 1)
+    fl = F_filt(D, pd.d) + (F_smooth(D, pd.d) if kw.get("smooth") else 0.0)
+    if alg == lib.EK0:
+        nn = q + 1
+        fl = (22 / 3) * nn**3 + 4 * nn * nn * pd.d
+    passes = 2 if kw.get("save_everystep") else 1   # the counting pass repeats the filter arithmetic
+    best.update(tag=tag, problem=name, n_traj=n, D=D, d=pd.d, steps_per_s_kernel=best["accepted"] / (best["kernel_ms"] * 1e-3),
+                steps_per_s_wall=best["accepted"] / (best["wall_ms"] * 1e-3),
+                algorithmic_tflops=best["accepted"] * fl / (best["kernel_ms"] * 1e-3) / 1e12, fp64_peak_tflops=PEAK,
+                note=f"{passes} filter pass(es) inside kernel_ms" if passes > 1 else "")
+    best["roofline_frac"] = best["algorithmic_tflops"] / PEAK
+    print(json.dumps(best), flush=True)
+
+
+which = sys.argv[1:] or ["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"]
+if "cfg1" in which:
+    run("cfg1 FHN EK1(3) dt=0.01 filter+smoother, 1 trajectory", "fitzhugh_nagumo", 1, 3, 20.0, adaptive=False, dt=0.01, smooth=True, save_everystep=True)
+    run("cfg1 shape, 65536 trajectories", "fitzhugh_nagumo", 65536, 3, 20.0, adaptive=False, dt=0.01, smooth=True, save_everystep=True, dp=0.05)
+if "cfg2" in which:
+    run("cfg2 LV EK0(3) adaptive filter only, 1M", "lotka_volterra", 1 << 20, 3, 10.0, alg=lib.EK0, du0=0.1)
+if "cfg3" in which:
+    run("cfg3 VdP mu=1e3 EK1(5) adaptive filter+smoother, 100k", "vanderpol", 100000, 5, 2.0, smooth=True, save_everystep=True, seed=1, dp=0.2)
+    run("cfg3 filter only", "vanderpol", 100000, 5, 2.0, seed=1, dp=0.2)
+if "cfg4" in which:
+    run("cfg4 Pleiades EK1(3) D=112 filter only, 16k", "pleiades", 16384, 3, 3.0, seed=2)
+if "cfg5" in which:
+    for n in (10_000, 100_000, 1_000_000, 4_000_000):
+        run(f"cfg5 ROBER EK1(3) adaptive filter only, {n}", "rober", n, 3, 100.0, seed=3)
+    run("cfg5 OREGO EK1(3) adaptive filter only, 131072", "orego", 131072, 3, 30.0, seed=3)

@@ -238,12 +238,16 @@ _CONSTANT = [(0, 2, 0, 0, 1e-5), (0, 3, 0, 0, 1e-8), (0, 5, 0, 0, 1e-10), (0, 3,
              (1, 3, 1, 0, 1e-8), (1, 3, 1, 1, 1e-8),
              # BlocksOfDiagonals layout: EK0 + FixedMV / DynamicMV diffusion (alg 0, diffusion 3 / 2) and DiagonalEK1 (alg 2)
              (0, 3, 0, 3, 1e-7), (0, 3, 0, 2, 1e-8), (2, 3, 0, 0, 1e-7), (2, 3, 0, 1, 1e-7),
-             (0, 3, 1, 3, 1e-7), (0, 3, 1, 2, 1e-8), (2, 3, 1, 0, 1e-7), (2, 3, 1, 1, 1e-7)]
+             (0, 3, 1, 3, 1e-7), (0, 3, 1, 2, 1e-8), (2, 3, 1, 0, 1e-7), (2, 3, 1, 1, 1e-7),
+             # IOUP(3, -1) prior rows (test/correctness.jl:50-51): alg + 10 marks the IOUP prior with rate -1
+             (10, 3, 1, 0, 2e-9), (11, 3, 1, 1, 1e-9)]
 # test/correctness.jl:57-87
 _ADAPTIVE = [(0, 2, 0, 2e-4), (0, 3, 0, 1e-4), (0, 5, 0, 1e-5), (0, 8, 0, 2e-5), (1, 2, 0, 2e-5), (1, 3, 0, 1e-5), (1, 5, 0, 1e-6),
              (1, 8, 0, 5e-6),
              # Blocks layout rows: EK0 + DynamicMV / FixedMV, DiagonalEK1 with Dynamic / Fixed diffusion
-             (0, 3, 2, 5e-5), (0, 3, 3, 1e-4), (2, 3, 0, 1e-4), (2, 3, 1, 1e-4)]
+             (0, 3, 2, 5e-5), (0, 3, 3, 1e-4), (2, 3, 0, 1e-4), (2, 3, 1, 1e-4),
+             # IOUP(3, -1) rows (test/correctness.jl:82-83)
+             (10, 3, 0, 1e-5), (11, 3, 1, 1e-5)]
 
 
 @pytest.mark.parametrize("prob", list(_CASES))
@@ -254,8 +258,9 @@ def test_correctness_constant_steps(oracle, prob):
     for alg, q, smooth, diff, thr in _CONSTANT:
         rhs = oracle.compile_rhs(tr, q)
         for backend in (oracle.COV_REF, oracle.COV_QR):
-            cfg = oracle.make_config(2, q, 4, alg=alg, diffusion=diff, smooth=smooth, adaptive=False, dt=1e-2, t0=0, t1=1,
-                                     save_everystep=bool(smooth), cov_backend=backend)
+            pk = dict(prior=oracle.PRIOR_IOUP, rate_parameter=-1.0) if alg >= 10 else {}
+            cfg = oracle.make_config(2, q, 4, alg=alg % 10, diffusion=diff, smooth=smooth, adaptive=False, dt=1e-2, t0=0, t1=1,
+                                     save_everystep=bool(smooth), cov_backend=backend, **pk)
             s = oracle.solve(cfg, rhs, u0, p)
             assert s["retcode"] == "Success"
             assert np.mean(np.abs(s["pu_mu"][-1] - ref)) < thr, (prob, alg, q, smooth, diff, backend)
@@ -268,7 +273,8 @@ def test_correctness_adaptive(oracle, prob):
     tr = tracer.trace(f, 2, 4)
     for alg, q, diff, thr in _ADAPTIVE:
         rhs = oracle.compile_rhs(tr, q)
-        s = oracle.solve(oracle.make_config(2, q, 4, alg=alg, diffusion=diff, smooth=True, adaptive=True, t0=0, t1=1), rhs, u0, p)
+        pk = dict(prior=oracle.PRIOR_IOUP, rate_parameter=-1.0) if alg >= 10 else {}
+        s = oracle.solve(oracle.make_config(2, q, 4, alg=alg % 10, diffusion=diff, smooth=True, adaptive=True, t0=0, t1=1, **pk), rhs, u0, p)
         assert s["retcode"] == "Success"
         assert np.mean(np.abs(s["pu_mu"][-1] - ref)) < thr, (prob, alg, q, diff)
         # test/solution.jl:35-46, 59-62
@@ -376,3 +382,49 @@ def test_blocks_layout_reduces_to_kronecker_and_dense(oracle):
                                          adaptive=False, dt=0.1, t0=0, t1=0.2), rhs, pd.u0, pd.p)
     assert s2["global_diffusion_mv"].shape == (2,) and s2["global_diffusion_mv"][0] != s2["global_diffusion_mv"][1]
     assert np.allclose(s2["diffusions_mv"], s2["global_diffusion_mv"][None, :])
+
+
+def test_ioup_transition_matrices(oracle):
+    """IOUP prior, scalar rate (src/priors/ioup.jl:66-79,115-131).  Pins: (a) rate 0 is the IWP (golden matrices above);
+    (b) the closed form of the LTI-SDE solution: Ah[:, q] = h^m phi_m(r h) (m = q - row, phi_m(z) = sum_k z^k/(k+m)!) and
+    Qh = int_0^h x(s) x(s)' ds with x the last column of exp(F s), integrated here with scipy.integrate.quad -- an
+    independent route from the oracle's matrix-fraction decomposition (src/priors/ltisde.jl:52-63);
+    (c) the reference's own consistency tests: A == PI A_breve P and Q == PI Q_breve PI (test/core/priors.jl:220-223)."""
+    import ctypes as C
+    import math
+    from scipy.integrate import quad
+
+    L = oracle.lib()
+    dp = C.POINTER(C.c_double)
+    L.oracle_ioup_transition.argtypes = [C.c_int, C.c_double, C.c_double, dp, dp]
+    L.oracle_iwp_transition.argtypes = [C.c_int, C.c_double, dp, dp]
+
+    def trans(fn, q, h, *a):
+        n = q + 1
+        A, R = np.zeros((n, n), order="F"), np.zeros((n, n), order="F")
+        fn(q, *a, h, A.ctypes.data_as(dp), R.ctypes.data_as(dp))
+        return A, R
+
+    def phi(m, z):
+        return sum(z**k / math.factorial(k + m) for k in range(60))
+
+    for q in (1, 2, 3, 5):
+        for h in (0.5, 0.01, 1.3):
+            A0, R0 = trans(L.oracle_ioup_transition, q, h, 0.0)
+            Ai, Ri = trans(L.oracle_iwp_transition, q, h)
+            assert np.allclose(A0, Ai, rtol=1e-13, atol=0)
+            assert np.allclose(R0.T @ R0, Ri.T @ Ri, rtol=1e-9, atol=0)
+            assert np.allclose(R0, np.triu(R0))
+            for r in (-1.0, -3.7, 0.8):
+                A, R = trans(L.oracle_ioup_transition, q, h, r)
+                x = lambda s_, a: s_ ** (q - a) * phi(q - a, r * s_)  # noqa: E731
+                for a in range(q + 1):
+                    assert A[a, q] == pytest.approx(x(h, a), rel=1e-12)
+                    for b in range(q):
+                        want = h ** (b - a) / math.factorial(b - a) if b >= a else 0.0
+                        assert A[a, b] == pytest.approx(want, rel=1e-12, abs=1e-300)
+                Q = R.T @ R
+                for a in range(q + 1):
+                    for b in range(a, q + 1):
+                        want = quad(lambda s_: x(s_, a) * x(s_, b), 0.0, h, epsabs=0, epsrel=1e-13)[0]
+                        assert Q[a, b] == pytest.approx(want, rel=1e-8 if q == 5 else 1e-10)
