@@ -56,7 +56,8 @@ typedef enum pnode_status {
 typedef enum pnode_alg { PNODE_EK0 = 0, PNODE_EK1 = 1, PNODE_DIAGONAL_EK1 = 2 } pnode_alg; /* src/algorithms.jl:188-393 */
 /* src/covariance_structure.jl:1-63; AUTO follows covariance_structure(alg, prior, diffusion) src/algorithms.jl:132-151 */
 typedef enum pnode_cov { PNODE_COV_AUTO = 0, PNODE_COV_DENSE = 1, PNODE_COV_KRONECKER = 2, PNODE_COV_BLOCKS = 3 } pnode_cov;
-typedef enum pnode_prior { PNODE_PRIOR_IWP = 0 } pnode_prior;                              /* src/priors/iwp.jl */
+/* src/priors/iwp.jl; src/priors/ioup.jl with a scalar rate parameter (IOUP(num_derivatives, rate)) */
+typedef enum pnode_prior { PNODE_PRIOR_IWP = 0, PNODE_PRIOR_IOUP = 1 } pnode_prior;
 /* src/diffusions/typedefs.jl: DynamicDiffusion, FixedDiffusion, DynamicMVDiffusion, FixedMVDiffusion */
 typedef enum pnode_diffusion {
     PNODE_DIFF_DYNAMIC = 0,
@@ -105,6 +106,8 @@ typedef struct pnode_config {
     /* test hook: sigma^2 used for accepted step k instead of the local estimate (host pointer, copied) */
     const double* forced_diffusion;
     int64_t n_forced;
+    /* IOUP prior: rate_parameter (F[q,q] of the SDE drift, src/priors/ioup.jl:66-79); ignored for the IWP */
+    double rate_parameter;
 } pnode_config;
 
 typedef struct pnode_solver pnode_solver;

@@ -60,11 +60,18 @@ class IWP:
 
 
 @dataclasses.dataclass(frozen=True)
+class IOUP:
+    """Integrated Ornstein-Uhlenbeck prior with a scalar rate parameter (src/priors/ioup.jl: IOUP(num_derivatives, rate))."""
+    num_derivatives: int = 3
+    rate_parameter: float = -1.0
+
+
+@dataclasses.dataclass(frozen=True)
 class _EK:
     order: int = 3
     smooth: bool = True
     diffusionmodel: object = DynamicDiffusion()
-    prior: Optional[IWP] = None
+    prior: Optional[object] = None   # IWP(q) or IOUP(q, rate)
 
     @property
     def q(self) -> int:
@@ -199,6 +206,8 @@ def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, absto
         kw.update(diffusion=_lib.DIFF_DYNAMIC_MV)
     else:
         kw.update(diffusion=_lib.DIFF_DYNAMIC)
+    if isinstance(alg.prior, IOUP):
+        kw.update(prior=_lib.PRIOR_IOUP, rate_parameter=alg.prior.rate_parameter)
     if prob.builtin is not None:
         kw.update(rhs_name="builtin:" + prob.builtin)
     else:

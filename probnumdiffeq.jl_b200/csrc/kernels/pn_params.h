@@ -33,6 +33,9 @@ struct PnParams {
        an equivalent right factor of the same preconditioned process-noise covariance, used where an upper-triangular
        noise block lets a sweep skip its leading zero columns */
     double U[PN_MAX_N * PN_MAX_N];
+    /* IOUP prior (src/priors/ioup.jl): scalar rate parameter, 16-point Gauss-Legendre rule on [0, 1] (host-computed) */
+    double rate;
+    double glx[16], glw[16];
     /* ---- per-trajectory outputs ---- */
     double* t_end;      /* [n_traj]       */
     double* u_mean;     /* [n_traj][d]    */

@@ -284,6 +284,16 @@ PN_HD double pn_initial_dt(const PnParams& P, const double* u0, const double* pr
     return dt;
 }
 
+#ifndef PN_IOUP
+#define PN_IOUP 0 /* 1: integrated Ornstein-Uhlenbeck prior with scalar rate P.rate (pn_ioup.cuh); 0: IWP */
+#endif
+#ifndef PN_EK0_DENSE
+#define PN_EK0_DENSE 0 /* 1: EK0 measurement (H = E1, no Jacobian) on the dense layout -- EK0 with a non-IWP prior */
+#endif
+#if PN_IOUP
+#include "pn_ioup.cuh"
+#endif
+
 template <class Prob, int Q, int G, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 struct PnSmall {
     static constexpr int d = Prob::d;
@@ -477,6 +487,15 @@ struct PnSmall {
             bool accept = false;
             double h = 0.0, tstop = P.t1, EEst = 0.0, qq = 1.0, ediff = 0.0, lEE = 0.0;
             double hp[n], PIv[n], mup[D], z[d], J[d * d];
+#if PN_IOUP
+            double tq[n], Uh[n][n]; /* last column of the 1-d transition matrix; upper factor of the 1-d process noise */
+#pragma unroll
+            for (int k = 0; k < n; k++) {
+                tq[k] = (k == Q) ? 1.0 : 0.0;
+#pragma unroll
+                for (int c = 0; c < n; c++) Uh[k][c] = 0.0;
+            }
+#endif
 #pragma unroll
             for (int k = 0; k < n; k++) hp[k] = (k == 0) ? 1.0 : 0.0;
 #pragma unroll
@@ -520,21 +539,37 @@ struct PnSmall {
                 const double sqh = sqrt(h);
 #pragma unroll
                 for (int c = 0; c < n; c++) PIv[c] = hp[Q - c] * sqh;
-                /* predict_mean!: mu^- = (T (x) I) mu, T[j][k] = h^(k-j)/(k-j)! */
+#if PN_IOUP
+                if (!pn_ioup_step<Q, G>(P.rate, P.glx, P.glw, h, gl, tq, Uh)) {
+                    retcode = PN_RET_UNSTABLE;
+                    finished = true;
+                    break;
+                }
+#endif
+                /* predict_mean!: mu^- = (T (x) I) mu, T[j][k] = h^(k-j)/(k-j)!  (IOUP: last column tq) */
 #pragma unroll
                 for (int j = 0; j < n; j++)
 #pragma unroll
                     for (int i = 0; i < d; i++) {
+#if PN_IOUP
+                        double s = (j == Q) ? tq[Q] * mu[j * d + i] : mu[j * d + i];
+#pragma unroll
+                        for (int k = 0; k < n; k++)
+                            if (k > j) s += ((k == Q) ? tq[j] : hp[k > j ? k - j : 0]) * mu[k * d + i];
+#else
                         double s = mu[j * d + i];
 #pragma unroll
                         for (int k = 0; k < n; k++)
                             if (k > j) s += hp[k > j ? k - j : 0] * mu[k * d + i];
+#endif
                         mup[j * d + i] = s;
                     }
                 /* measurement: z = E1 mu^- - f(E0 mu^-), J = df/du */
                 double fu[d];
                 Prob::template f<double>(fu, mup, pr, tnew);
+#if !PN_EK0_DENSE
                 Prob::jac(J, mup, pr, tnew);
+#endif
                 nf += 1;
 #pragma unroll
                 for (int i = 0; i < d; i++) z[i] = mup[d + i] - fu[i];
@@ -548,8 +583,15 @@ struct PnSmall {
                         for (int b = 0; b < d; b++) W[a][b] = 0.0;
 #pragma unroll
                     for (int m = 0; m < n; m++) {
+#if PN_IOUP
+                        /* Qh.R = Uh P^-1 (upper): column 0 lives in row 0, column 1 in rows 0 and 1 */
+                        if (m > 1) continue;
+                        const double l0 = (m == 0) ? Uh[0][0] * PIv[0] : 0.0;
+                        const double l1 = Uh[m][1] * PIv[1];
+#else
                         const double l0 = P.L[m * n + 0] * PIv[0];
                         const double l1 = (m >= 1) ? P.L[m * n + 1] * PIv[1] : 0.0;
+#endif
 #pragma unroll
                         for (int i = 0; i < d; i++) {
                             double c[d];
@@ -623,6 +665,10 @@ struct PnSmall {
                 /* identity step for groups that have nothing to commit: h = 0, no process noise, K = 0 */
 #pragma unroll
                 for (int k = 1; k < n; k++) hp[k] = 0.0;
+#if PN_IOUP
+#pragma unroll
+                for (int k = 0; k < n; k++) tq[k] = (k == Q) ? 1.0 : 0.0;
+#endif
 #pragma unroll
                 for (int c = 0; c < D; c++) mup[c] = mu[c];
                 ediff = 0.0;
@@ -638,10 +684,17 @@ struct PnSmall {
                     for (int i = 0; i < d; i++)
 #pragma unroll
                         for (int j = 0; j < n; j++) {
+#if PN_IOUP
+                            double s = (j == Q) ? tq[Q] * R[lr][j * d + i] : R[lr][j * d + i];
+#pragma unroll
+                            for (int k = 0; k < n; k++)
+                                if (k > j) s += ((k == Q) ? tq[j] : hp[k > j ? k - j : 0]) * R[lr][k * d + i];
+#else
                             double s = R[lr][j * d + i];
 #pragma unroll
                             for (int k = 0; k < n; k++)
                                 if (k > j) s += hp[k > j ? k - j : 0] * R[lr][k * d + i];
+#endif
                             R[lr][j * d + i] = s;
                         }
 #ifdef PN_QR_LOWER_NOISE
@@ -675,7 +728,11 @@ struct PnSmall {
                             double usel = 0.0;
 #pragma unroll
                             for (int m = 0; m < n; m++)
+#if PN_IOUP
+                                if (m <= c) usel = (mB[lr] == m) ? Uh[m][c] : usel;
+#else
                                 if (m <= c) usel = (mB[lr] == m) ? P.U[m * n + c] : usel;
+#endif
                             const double val = usel * PIv[c] * sd;
 #pragma unroll
                             for (int i = 0; i < d; i++) B[lr][c * d + i] = (iB[lr] == i) ? val : 0.0;

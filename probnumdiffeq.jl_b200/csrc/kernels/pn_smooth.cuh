@@ -39,6 +39,8 @@ struct PnSmoothParams {
     double* s_u_cov;               /* [total][d][d] out */
     double L[PN_MAX_N * PN_MAX_N]; /* IWP left sqrt factor, row-major n x n */
     double U[PN_MAX_N * PN_MAX_N]; /* upper-triangular right factor of the same covariance (pn_params.h) */
+    double rate;              /* IOUP prior: scalar rate parameter and the Gauss-Legendre rule (pn_ioup.cuh) */
+    double glx[16], glw[16];
     unsigned long long* work_counter;
 };
 

@@ -219,6 +219,10 @@ struct PnSmoothReg {
 #pragma unroll
                     for (int c = 0; c < n; c++) PIv[c] = hp[Q - c] * sqh;
                 }
+#if PN_IOUP
+                double tq[n], Uh[n][n];
+                pn_ioup_step<Q, G>(P.rate, P.glx, P.glw, hh, gl, tq, Uh);
+#endif
                 double Lf[RPL][D]; /* Lambda_f rows (bottom-right block after the sweep) */
                 {
                     double Tt[RPL][W], Bt[RPL][W];
@@ -239,10 +243,17 @@ struct PnSmoothReg {
                         for (int i = 0; i < d; i++)
 #pragma unroll
                             for (int j = 0; j < n; j++) {
+#if PN_IOUP
+                                double s = (j == Q) ? tq[Q] * Tt[lr][D + j * d + i] : Tt[lr][D + j * d + i];
+#pragma unroll
+                                for (int kk = 0; kk < n; kk++)
+                                    if (kk > j) s += ((kk == Q) ? tq[j] : hp[kk > j ? kk - j : 0]) * Tt[lr][D + kk * d + i];
+#else
                                 double s = Tt[lr][D + j * d + i];
 #pragma unroll
                                 for (int kk = 0; kk < n; kk++)
                                     if (kk > j) s += hp[kk > j ? kk - j : 0] * Tt[lr][D + kk * d + i];
+#endif
                                 Tt[lr][j * d + i] = s;
                             }
                     }
@@ -258,7 +269,11 @@ struct PnSmoothReg {
                                 double usel = 0.0;
 #pragma unroll
                                 for (int m = 0; m < n; m++)
+#if PN_IOUP
+                                    if (m <= c) usel = (mB[lr] == m) ? Uh[m][c] : usel;
+#else
                                     if (m <= c) usel = (mB[lr] == m) ? P.U[m * n + c] : usel;
+#endif
                                 const double val = usel * PIv[c] * sd;
 #pragma unroll
                                 for (int i = 0; i < d; i++) Bt[lr][c * d + i] = (iB[lr] == i) ? val : 0.0;
@@ -292,10 +307,17 @@ struct PnSmoothReg {
                 for (int j = 0; j < n; j++)
 #pragma unroll
                     for (int i = 0; i < d; i++) {
+#if PN_IOUP
+                        double s = (j == Q) ? tq[Q] * mu[j * d + i] : mu[j * d + i];
+#pragma unroll
+                        for (int kk = 0; kk < n; kk++)
+                            if (kk > j) s += ((kk == Q) ? tq[j] : hp[kk > j ? kk - j : 0]) * mu[kk * d + i];
+#else
                         double s = mu[j * d + i];
 #pragma unroll
                         for (int kk = 0; kk < n; kk++)
                             if (kk > j) s += hp[kk > j ? kk - j : 0] * mu[kk * d + i];
+#endif
                         w[j * d + i] = Ms[j * d + i] - s;
                     }
 #pragma unroll

@@ -280,7 +280,8 @@ static int nvrtc_compile(const std::string& src, std::vector<std::string> defs, 
 /* NVRTC: user RHS + step kernels -> sm_100a CUBIN.  Needs no device. */
 static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_name, int q, int G, bool adaptive,
                        bool dynamic, int save, std::vector<char>* cubin, int threads = PN_THREADS, int min_blocks = 1,
-                       bool kron = false, bool cta = false, int blocks = 0 /* 0 no, 1 EK0, 2 DiagonalEK1 */, bool mv = false) {
+                       bool kron = false, bool cta = false, int blocks = 0 /* 0 no, 1 EK0, 2 DiagonalEK1 */, bool mv = false,
+                       bool ioup = false, bool ek0_dense = false) {
     std::string src;
     src += "#include \"pn_kernel_entry.cuh\"\n";
     src += rhs_src;
@@ -300,18 +301,19 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
                struct_name + ", PN_Q, PN_G, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
     auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
     return nvrtc_compile(src, {def("PN_THREADS", threads), def("PN_MIN_BLOCKS", min_blocks), def("PN_Q", q), def("PN_G", G),
-                               def("PN_ADAPTIVE", adaptive ? 1 : 0), def("PN_DYNAMIC", dynamic ? 1 : 0), def("PN_SAVE", save)},
+                               def("PN_ADAPTIVE", adaptive ? 1 : 0), def("PN_DYNAMIC", dynamic ? 1 : 0), def("PN_SAVE", save),
+                               def("PN_IOUP", ioup ? 1 : 0), def("PN_EK0_DENSE", ek0_dense ? 1 : 0)},
                          cubin);
 }
 
 /* NVRTC: register-resident smoother sweep for (d, q, G); independent of the right-hand side. */
-static int nvrtc_smoother_cubin(int d, int q, int G, std::vector<char>* cubin) {
+static int nvrtc_smoother_cubin(int d, int q, int G, bool ioup, std::vector<char>* cubin) {
     std::string src =
         "#include \"kernels/pn_smooth_reg.cuh\"\n"
         "extern \"C\" __global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_entry(const __grid_constant__ "
         "PnSmoothParams P) {\n  pn_smooth_reg_entry<PN_SD, PN_SQ, PN_SG>(P);\n}\n";
     auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
-    return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G)}, cubin);
+    return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0)}, cubin);
 }
 
 static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
@@ -328,7 +330,8 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
     out->threads = s->cta ? PN_CTA_THREADS : ((s->kron || s->blocks) ? 128 : env_int("PNODE_THREADS", PN_THREADS));
     rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0, is_dynamic(s->cfg.diffusion), save, &cubin, out->threads,
                      env_int("PNODE_MIN_BLOCKS", 1), s->kron, s->cta,
-                     s->blocks ? (s->cfg.alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, s->mv);
+                     s->blocks ? (s->cfg.alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, s->mv, s->cfg.prior == PNODE_PRIOR_IOUP,
+                     s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks);
     if (rc) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
@@ -348,7 +351,7 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
 static int get_kernel(pnode_solver* s, int save, Kernel* out) {
     if (out->valid()) return 0;
     auto t0 = std::chrono::steady_clock::now();
-    if (s->builtin && !env_int("PNODE_FORCE_NVRTC", 0)) {
+    if (s->builtin && !env_int("PNODE_FORCE_NVRTC", 0) && s->cfg.prior == PNODE_PRIOR_IWP && !(s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks)) {
         int n = 0;
         const PnBuiltinEntry* tab = pn_builtin_table(&n);
         std::string key = kernel_key(s, save);
@@ -383,7 +386,8 @@ static int get_smoother(pnode_solver* s) {
     if (s->smem_smooth > 227 * 1024) return 0;
     auto t0 = std::chrono::steady_clock::now();
     out->threads = PN_SMR_THREADS;
-    const void* fn = env_int("PNODE_FORCE_NVRTC", 0) ? nullptr : pn_smooth_reg_lookup(s->cfg.d, s->cfg.q, s->Gs);
+    const bool ioup = (s->cfg.prior == PNODE_PRIOR_IOUP);
+    const void* fn = (env_int("PNODE_FORCE_NVRTC", 0) || ioup) ? nullptr : pn_smooth_reg_lookup(s->cfg.d, s->cfg.q, s->Gs);
     if (fn) {
         out->rt_fn = fn;
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_smooth));
@@ -396,7 +400,7 @@ static int get_smoother(pnode_solver* s) {
     int rc = load_driver();
     if (rc) return rc;
     std::vector<char> cubin;
-    if ((rc = nvrtc_smoother_cubin(s->cfg.d, s->cfg.q, s->Gs, &cubin))) return rc;
+    if ((rc = nvrtc_smoother_cubin(s->cfg.d, s->cfg.q, s->Gs, ioup, &cubin))) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
     r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_smooth_entry");
@@ -420,6 +424,7 @@ static size_t cta_smem_bytes(int d, int q, int n_p) {
 
 /* covariance_structure(alg, prior, diffusionmodel) (src/algorithms.jl:132-151) */
 static int resolve_layout(const pnode_config* cfg) {
+    if (cfg->alg == PNODE_EK0 && cfg->prior != PNODE_PRIOR_IWP) return PNODE_COV_DENSE; /* "other priors": dense */
     if (cfg->alg == PNODE_EK0) return is_mv(cfg->diffusion) ? PNODE_COV_BLOCKS : PNODE_COV_KRONECKER;
     if (cfg->alg == PNODE_DIAGONAL_EK1) return PNODE_COV_BLOCKS;
     return PNODE_COV_DENSE;
@@ -431,7 +436,15 @@ static int validate_config(const pnode_config* cfg) {
     /* ---- argument checks mirroring the reference's constructors ---- */
     if (cfg->d < 1) return fail(PNODE_ERR_ARGUMENT, "We currently don't support scalar-valued problems (d >= 1 vector required)"); /* caches.jl:96-98 */
     if (cfg->q < 1 || cfg->q + 1 > PN_MAX_N) return fail(PNODE_ERR_ARGUMENT, "order must satisfy 1 <= order <= 11");
-    if (cfg->prior != PNODE_PRIOR_IWP) return fail(PNODE_ERR_UNSUPPORTED, "only the IWP prior is implemented");
+    if (cfg->prior != PNODE_PRIOR_IWP && cfg->prior != PNODE_PRIOR_IOUP)
+        return fail(PNODE_ERR_UNSUPPORTED, "only the IWP and (scalar-rate) IOUP priors are implemented");
+    if (cfg->prior == PNODE_PRIOR_IOUP) {
+        if (cfg->alg == PNODE_DIAGONAL_EK1 || is_mv(cfg->diffusion))
+            return fail(PNODE_ERR_UNSUPPORTED, "the IOUP prior is implemented on the dense layout (EK0 / EK1 with a scalar diffusion)");
+        if (cfg->d * (cfg->q + 1) > 24)
+            return fail(PNODE_ERR_UNSUPPORTED, "the IOUP prior is implemented for D = d(q+1) <= 24 (register-resident kernels)");
+        if (cfg->lanes_per_traj == 256) return fail(PNODE_ERR_UNSUPPORTED, "the IOUP prior is not implemented in the CTA kernel");
+    }
     if (cfg->alg != PNODE_EK0 && cfg->alg != PNODE_EK1 && cfg->alg != PNODE_DIAGONAL_EK1)
         return fail(PNODE_ERR_ARGUMENT, "Unknown algorithm"); /* derivative_utils.jl:31 */
     if (cfg->diffusion < PNODE_DIFF_DYNAMIC || cfg->diffusion > PNODE_DIFF_FIXED_MV)
@@ -463,7 +476,7 @@ static int validate_config(const pnode_config* cfg) {
         return fail(PNODE_ERR_UNSUPPORTED,
                     "only the covariance factorization the reference selects for this algorithm / diffusion model is implemented "
                     "(covariance_structure, src/algorithms.jl:132-151)");
-    if (cfg->alg == PNODE_EK0 && cfg->q > 7)
+    if (layout == PNODE_COV_KRONECKER && cfg->q > 7)
         return fail(PNODE_ERR_UNSUPPORTED, "EK0 thread-per-trajectory kernel supports order <= 7");
     if (layout == PNODE_COV_BLOCKS) {
         if (cfg->d * (cfg->q + 1) * (cfg->q + 1) > 160)
@@ -501,7 +514,8 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, is_dynamic(cfg->diffusion),
                      cfg->save_everystep ? (cfg->smooth ? 2 : 1) : 0, &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
                      layout == PNODE_COV_KRONECKER, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256),
-                     layout == PNODE_COV_BLOCKS ? (cfg->alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, is_mv(cfg->diffusion));
+                     layout == PNODE_COV_BLOCKS ? (cfg->alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, is_mv(cfg->diffusion),
+                     cfg->prior == PNODE_PRIOR_IOUP, cfg->alg == PNODE_EK0 && layout == PNODE_COV_DENSE);
     if (rc) return rc;
     if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
     return 0;
@@ -589,6 +603,28 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
         }
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) B.U[i * n + j] = (j >= i) ? (double)A[i][j] : 0.0;
+    }
+    {
+        /* 16-point Gauss-Legendre rule on [0, 1] (Newton on the Legendre recurrence) for the IOUP process noise */
+        B.rate = cfg->rate_parameter;
+        const int m = 16;
+        for (int i = 0; i < m; i++) {
+            double x = std::cos(M_PI * (i + 0.75) / (m + 0.5)), dp = 1.0;
+            for (int it = 0; it < 100; it++) {
+                double p0 = 1.0, p1 = x;
+                for (int k = 2; k <= m; k++) {
+                    const double p2 = ((2.0 * k - 1.0) * x * p1 - (k - 1.0) * p0) / k;
+                    p0 = p1;
+                    p1 = p2;
+                }
+                dp = m * (x * p1 - p0) / (x * x - 1.0);
+                const double dx = p1 / dp;
+                x -= dx;
+                if (std::fabs(dx) < 1e-16) break;
+            }
+            B.glx[i] = 0.5 * (x + 1.0);
+            B.glw[i] = 1.0 / ((1.0 - x * x) * dp * dp); /* = (2 / ((1-x^2) P'^2)) / 2 */
+        }
     }
     /* ---- device ---- */
     int ndev = pnode_device_count();
@@ -813,6 +849,9 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             memcpy(Q.L, s->base.L, sizeof Q.L);
             Q.work_counter = s->d_counter;
             memcpy(Q.U, s->base.U, sizeof Q.U);
+            Q.rate = s->base.rate;
+            memcpy(Q.glx, s->base.glx, sizeof Q.glx);
+            memcpy(Q.glw, s->base.glw, sizeof Q.glw);
             if (s->k_smooth.valid()) {
                 /* register-resident sweep: Gs lanes per trajectory, persistent, one CTA per SM */
                 Kernel& ks = s->k_smooth;
@@ -829,6 +868,8 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                     if (cr != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuLaunchKernel(smoother): " + cu_err(cr));
                 }
             } else {
+                if (s->cfg.prior != PNODE_PRIOR_IWP)
+                    return fail(PNODE_ERR_UNSUPPORTED, "the shared-memory smoother sweep implements the IWP prior only");
                 const int n = s->cfg.q + 1;
                 const size_t per_warp = (size_t)(7 * D * D + 4 * D + 2 * n * n + 2 * n) * sizeof(double);
                 int warps = PN_SM_WARPS;

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 EK0, EK1, DIAGONAL_EK1 = 0, 1, 2
 COV_AUTO, COV_DENSE, COV_KRONECKER, COV_BLOCKS = 0, 1, 2, 3
-PRIOR_IWP = 0
+PRIOR_IWP, PRIOR_IOUP = 0, 1
 DIFF_DYNAMIC, DIFF_FIXED, DIFF_DYNAMIC_MV, DIFF_FIXED_MV = 0, 1, 2, 3
 RETCODES = {0: "Success", 1: "MaxIters", 2: "DtLessThanMin", 3: "Unstable"}
 
@@ -60,6 +60,7 @@ class Config(C.Structure):
         ("rhs_src", C.c_char_p), ("rhs_name", C.c_char_p),
         ("tstops", C.POINTER(C.c_double)), ("n_tstops", C.c_int64),
         ("forced_diffusion", C.POINTER(C.c_double)), ("n_forced", C.c_int64),
+        ("rate_parameter", C.c_double),
     ]
 
 
@@ -129,11 +130,13 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
                 initial_diffusion=1.0, smooth=False, adaptive=True, save_everystep=False, save_state=False,
                 lanes_per_traj=0, t0=0.0, t1=1.0, dt=0.0, abstol=1e-6, reltol=1e-3, dtmin=0.0, dtmax=0.0,
                 maxiters=1_000_000, beta1=0.0, beta2=0.0, qmin=0.2, qmax=10.0, gamma=0.9, qsteady_min=1.0,
-                qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None, device=0) -> Config:
+                qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None, device=0, prior=PRIOR_IWP,
+                rate_parameter=0.0) -> Config:
     c = Config()
     c.struct_size = C.sizeof(Config)
     c.device, c.d, c.q, c.n_p = device, d, q, n_p
-    c.alg, c.cov, c.prior, c.diffusion = alg, cov, PRIOR_IWP, diffusion
+    c.alg, c.cov, c.prior, c.diffusion = alg, cov, prior, diffusion
+    c.rate_parameter = float(rate_parameter)
     c.calibrate, c.smooth, c.adaptive = int(calibrate), int(smooth), int(adaptive)
     c.save_everystep, c.save_state, c.lanes_per_traj = int(save_everystep), int(save_state), lanes_per_traj
     c.maxiters, c.initial_diffusion = int(maxiters), float(initial_diffusion)

@@ -571,6 +571,77 @@ def test_blocks_adaptive_identical_step_sequences(oracle, alg, diffusion):
         assert _rel(g["U"][b - 1], o["pu_mu"][-1]) < tol_u
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# IOUP prior with a scalar rate parameter (src/priors/ioup.jl; test/correctness.jl:50-51,82-83 use IOUP(3, -1))
+# ------------------------------------------------------------------------------------------------------------------
+def _gpu_ioup(pd, u0, p, q, alg, rate, **kw):
+    src = tracer.cuda_source(tracer.trace(pd.f, pd.d, pd.n_p), "UserProb")
+    cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="UserProb", rhs_src=src, alg=alg, prior=lib.PRIOR_IOUP,
+                          rate_parameter=rate, save_everystep=True, save_state=True, **kw)
+    s = lib.Solver(cfg)
+    r = s.solve(u0, p)
+    n, d = u0.shape
+    D = d * (q + 1)
+    out = dict(off=r.field(lib.F_STEP_OFFSETS), T=r.field(lib.F_T), U=r.field(lib.F_U).reshape(-1, d),
+               C=r.field(lib.F_U_COV).reshape(-1, d, d), naccept=r.field(lib.F_NACCEPT), nreject=r.field(lib.F_NREJECT),
+               loglik=r.field(lib.F_LOGLIK), retcode=r.field(lib.F_RETCODE), Df=r.field(lib.F_DIFFUSIONS))
+    if r.has(lib.F_X):
+        out.update(X=r.field(lib.F_X).reshape(-1, D), XR=r.field(lib.F_X_COVFAC).reshape(-1, D, D))
+    r.free()
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("alg", [lib.EK0, lib.EK1])
+@pytest.mark.parametrize("smooth", [False, True])
+def test_ioup_fixed_steps_static_diffusion(oracle, alg, smooth):
+    """IOUP(3, -1) with FixedDiffusion, fixed steps: the per-step transition (Gauss-Legendre process noise + series /
+    recurrence for the phi functions on the device, matrix-fraction decomposition with a Pade exponential in the oracle)
+    and the dense EK0 measurement.  Means 1e-10; covariances 1e-9 (two independent routes to Qh)."""
+    pd, u0, p = _inputs("lotka_volterra", 2, 41, du0=0.05)
+    g = _gpu_ioup(pd, u0, p, 3, alg, -1.0, diffusion=lib.DIFF_FIXED, smooth=smooth, adaptive=False, dt=0.01, t0=0.0, t1=5.0)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    for i in range(u0.shape[0]):
+        o = oracle.solve(oracle.make_config(2, 3, 4, alg=alg, diffusion=oracle.DIFF_FIXED, smooth=smooth, adaptive=False, dt=0.01,
+                                            t0=0.0, t1=5.0, cov_backend=oracle.COV_QR, prior=oracle.PRIOR_IOUP, rate_parameter=-1.0),
+                         rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"] == 501 and g["retcode"][i] == 0
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < 1e-9
+        assert g["loglik"][i] == pytest.approx(o["loglik"], rel=1e-9)
+        assert _rel(g["Df"][a:b - 1], o["diffusions"][:-1]) < 1e-9
+        if smooth:
+            Sg = np.einsum("kra,krb->kab", g["XR"][a:b], g["XR"][a:b])
+            So = np.einsum("kra,krb->kab", o["x_smooth_R"], o["x_smooth_R"])
+            assert _relcov(Sg[1:], So[1:]) < 1e-8
+            assert _rel(g["X"][a:b, :2], o["x_smooth_mu"][:, :2]) < 1e-10
+
+
+@pytest.mark.parametrize("alg", [lib.EK0, lib.EK1])
+def test_ioup_adaptive_identical_step_sequences(oracle, alg):
+    n = 10
+    pd, u0, p = _inputs("lotka_volterra", n, 43, du0=0.1)
+    g = _gpu_ioup(pd, u0, p, 3, alg, -1.0, adaptive=True, t0=0.0, t1=10.0)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    for i in range(n):
+        o = oracle.solve(oracle.make_config(2, 3, 4, alg=alg, smooth=False, adaptive=True, t0=0.0, t1=10.0, cov_backend=oracle.COV_QR,
+                                            prior=oracle.PRIOR_IOUP, rate_parameter=-1.0), rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert g["naccept"][i] == o["naccept"] and g["nreject"][i] == o["nreject"]
+        assert np.max(np.abs(g["T"][a:b] - o["t"]) / np.maximum(o["t"], 1e-3)) < 1e-7
+        assert _rel(g["U"][b - 1], o["pu_mu"][-1]) < 1e-8
+
+
+def test_ioup_rate_zero_is_the_iwp():
+    """IOUP with rate 0 is the IWP (to_sde, src/priors/ioup.jl:66-79): the two code paths of the kernel agree."""
+    pd, u0, p = _inputs("lotka_volterra", 3, 45, du0=0.05)
+    a = _gpu_ioup(pd, u0, p, 3, lib.EK1, 0.0, diffusion=lib.DIFF_FIXED, adaptive=False, dt=0.02, t0=0.0, t1=4.0)
+    b = _gpu(pd, u0, p, 3, builtin=False, diffusion=lib.DIFF_FIXED, adaptive=False, dt=0.02, t0=0.0, t1=4.0, save_everystep=True)
+    assert _rel(a["U"], b["U"]) < 1e-11
+    assert _relcov(a["C"][1:], b["C"][1:]) < 1e-9
+
+
 def test_full_size_properties_lv_ek0_1m():
     """BASELINE cfg2 at full size: 2^20 Lotka-Volterra trajectories, EK0(order=3), adaptive, filter only."""
     n = 1 << 20
