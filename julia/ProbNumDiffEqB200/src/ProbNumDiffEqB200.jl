@@ -18,7 +18,14 @@ struct PnodeConfig
     qsteady_min::Float64; qsteady_max::Float64; qoldinit::Float64
     rhs_src::Cstring; rhs_name::Cstring
     tstops::Ptr{Float64}; n_tstops::Int64; forced_diffusion::Ptr{Float64}; n_forced::Int64
+    rate_parameter::Float64                      # IOUP(q, rate) prior; ignored for the IWP
 end
+
+# enum values of include/pnode.h
+alg_code(alg) = alg isa EK0 ? 0 : alg isa DiagonalEK1 ? 2 : 1
+prior_code(p) = p isa ProbNumDiffEq.IOUP ? 1 : 0
+rate_of(p) = p isa ProbNumDiffEq.IOUP ? Float64(p.rate_parameter) : 0.0
+diffusion_code(m) = m isa FixedMVDiffusion ? 3 : m isa DynamicMVDiffusion ? 2 : m isa FixedDiffusion ? 1 : 0
 
 check(rc) = rc == 0 || throw(ArgumentError(unsafe_string(ccall((:pnode_last_error, LIB), Cstring, ()))))
 
@@ -31,11 +38,11 @@ function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::ProbNumDi
     src = trace_to_cuda(ep.prob.f, d, n_p)            # Symbolics → "struct PnodeUserProblem { f<T>, jac }"
     GC.@preserve src begin
         cfg = Ref(PnodeConfig(sizeof(PnodeConfig), ens.device, d, ProbNumDiffEq.num_derivatives(alg.prior), n_p,
-                              alg isa EK0 ? 0 : 1, 0, 0, alg.diffusionmodel isa FixedDiffusion ? 1 : 0, 1,
+                              alg_code(alg), 0, prior_code(alg.prior), diffusion_code(alg.diffusionmodel), 1,
                               alg.smooth, adaptive, save_everystep, 0, 0, 0, 1_000_000, 1.0,
                               ep.prob.tspan[1], ep.prob.tspan[2], dt, abstol, reltol, 0.0, 0.0,
                               0, 0, 0.2, 10.0, 0.9, 1.0, 1.0, 1e-4,
-                              pointer(src), pointer("PnodeUserProblem"), C_NULL, 0, C_NULL, 0))
+                              pointer(src), pointer("PnodeUserProblem"), C_NULL, 0, C_NULL, 0, rate_of(alg.prior)))
         solver = Ref{Ptr{Cvoid}}()
         check(ccall((:pnode_create, LIB), Cint, (Ref{PnodeConfig}, Ref{Ptr{Cvoid}}), cfg, solver))
         res = Ref{Ptr{Cvoid}}()
