@@ -6,6 +6,12 @@
 #include "pn_builtin.h"
 #include "kernels/pn_smooth.cuh"
 #include "kernels/pn_smooth_reg.cuh"
+#include "kernels/pn_smooth_col.cuh"
+
+template <int d, int Q, int G>
+__global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_col_kernel(const __grid_constant__ PnSmoothParams P) {
+    pn_smooth_col_entry<d, Q, G>(P);
+}
 
 template <int d, int Q, int G>
 __global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_reg_kernel(const __grid_constant__ PnSmoothParams P) {
@@ -64,12 +70,14 @@ extern "C" const PnBuiltinEntry* pn_builtin_table(int* count) {
 extern "C" const void* pn_smooth_kernel_ptr(void) { return (const void*)&pn_smooth_kernel; }
 
 /* ahead-of-time instantiations of the register-resident smoother sweep (d, q, lanes): cfg1 FHN q=3, cfg3 VdP q=5 */
-extern "C" const void* pn_smooth_reg_lookup(int d, int q, int g) {
-    static const struct { int d, q, g; const void* fn; } tab[] = {
-        {2, 3, 4, (const void*)&pn_smooth_reg_kernel<2, 3, 4>},
-        {2, 5, 8, (const void*)&pn_smooth_reg_kernel<2, 5, 8>},
+extern "C" const void* pn_smooth_reg_lookup(int d, int q, int g, int column_distributed) {
+    static const struct { int d, q, g, col; const void* fn; } tab[] = {
+        {2, 3, 4, 0, (const void*)&pn_smooth_reg_kernel<2, 3, 4>},
+        {2, 5, 8, 0, (const void*)&pn_smooth_reg_kernel<2, 5, 8>},
+        {2, 3, 4, 1, (const void*)&pn_smooth_col_kernel<2, 3, 4>},
+        {2, 5, 8, 1, (const void*)&pn_smooth_col_kernel<2, 5, 8>},
     };
     for (auto& t : tab)
-        if (t.d == d && t.q == q && t.g == g) return t.fn;
+        if (t.d == d && t.q == q && t.g == g && t.col == column_distributed) return t.fn;
     return nullptr;
 }

@@ -229,6 +229,16 @@ static size_t smooth_reg_smem_bytes(int d, int q, int G) {
 static bool is_dynamic(int diffusion) { return diffusion == PNODE_DIFF_DYNAMIC || diffusion == PNODE_DIFF_DYNAMIC_MV; }
 static bool is_mv(int diffusion) { return diffusion == PNODE_DIFF_DYNAMIC_MV || diffusion == PNODE_DIFF_FIXED_MV; }
 
+/* must match PnSmoothCol<d,Q,G>::SMEM_BYTES */
+static size_t smooth_col_smem_bytes(int d, int q, int G) {
+    const int D = d * (q + 1), LD = D | 1;
+    const int off_rm = D * D + D + ((D * D + D) & 1);
+    const int RAW = off_rm + 2 * D * LD + 2 * D;
+    const int PHASE = (G >= 16) ? 0 : G;
+    const int REGION = ((RAW - PHASE + 15) / 16) * 16 + PHASE;
+    return (size_t)REGION * (PN_SMR_THREADS / G) * 8;
+}
+
 static std::string kernel_key(const pnode_solver* s, int save) {
     char buf[256];
     const char* kind = s->blocks ? (s->cfg.alg == PNODE_DIAGONAL_EK1 ? (s->mv ? "blocks1mv" : "blocks1") : (s->mv ? "blocks0mv" : "blocks0"))
@@ -307,11 +317,12 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
 }
 
 /* NVRTC: register-resident smoother sweep for (d, q, G); independent of the right-hand side. */
-static int nvrtc_smoother_cubin(int d, int q, int G, bool ioup, std::vector<char>* cubin) {
-    std::string src =
-        "#include \"kernels/pn_smooth_reg.cuh\"\n"
-        "extern \"C\" __global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_entry(const __grid_constant__ "
-        "PnSmoothParams P) {\n  pn_smooth_reg_entry<PN_SD, PN_SQ, PN_SG>(P);\n}\n";
+static int nvrtc_smoother_cubin(int d, int q, int G, bool ioup, bool col, std::vector<char>* cubin) {
+    std::string src = col ? "#include \"kernels/pn_smooth_col.cuh\"\n" : "#include \"kernels/pn_smooth_reg.cuh\"\n";
+    src += "extern \"C\" __global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_entry(const __grid_constant__ "
+           "PnSmoothParams P) {\n  ";
+    src += col ? "pn_smooth_col_entry" : "pn_smooth_reg_entry";
+    src += "<PN_SD, PN_SQ, PN_SG>(P);\n}\n";
     auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
     return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0)}, cubin);
 }
@@ -382,12 +393,14 @@ static int get_smoother(pnode_solver* s) {
     if (out->valid()) return 0;
     s->Gs = env_int("PNODE_SMOOTH_LANES", smooth_lanes(s->D));
     if (s->Gs <= 0 || s->cta || env_int("PNODE_SMOOTH_GENERIC", 0)) return 0; /* shared-memory sweep */
-    s->smem_smooth = smooth_reg_smem_bytes(s->cfg.d, s->cfg.q, s->Gs);
+    /* PNODE_SMOOTH_KIND: 1 (default) column-distributed sweep (pn_smooth_col.cuh), 0 row-distributed (pn_smooth_reg.cuh) */
+    const bool col = env_int("PNODE_SMOOTH_KIND", 1) != 0;
+    s->smem_smooth = col ? smooth_col_smem_bytes(s->cfg.d, s->cfg.q, s->Gs) : smooth_reg_smem_bytes(s->cfg.d, s->cfg.q, s->Gs);
     if (s->smem_smooth > 227 * 1024) return 0;
     auto t0 = std::chrono::steady_clock::now();
     out->threads = PN_SMR_THREADS;
     const bool ioup = (s->cfg.prior == PNODE_PRIOR_IOUP);
-    const void* fn = (env_int("PNODE_FORCE_NVRTC", 0) || ioup) ? nullptr : pn_smooth_reg_lookup(s->cfg.d, s->cfg.q, s->Gs);
+    const void* fn = (env_int("PNODE_FORCE_NVRTC", 0) || ioup) ? nullptr : pn_smooth_reg_lookup(s->cfg.d, s->cfg.q, s->Gs, col ? 1 : 0);
     if (fn) {
         out->rt_fn = fn;
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_smooth));
@@ -400,7 +413,7 @@ static int get_smoother(pnode_solver* s) {
     int rc = load_driver();
     if (rc) return rc;
     std::vector<char> cubin;
-    if ((rc = nvrtc_smoother_cubin(s->cfg.d, s->cfg.q, s->Gs, ioup, &cubin))) return rc;
+    if ((rc = nvrtc_smoother_cubin(s->cfg.d, s->cfg.q, s->Gs, ioup, col, &cubin))) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
     r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_smooth_entry");
