@@ -109,7 +109,7 @@ struct PnCta {
                 for (int r = 0; r < NBK; r++)
                     if (r < p) sp -= Ud[r][p] * Ud[r][p];
                 if (!(sp > 0.0)) ok = false;
-                const double up = sqrt(sp), ip = 1.0 / up;
+                const double ip = pn_rsqrt(sp), up = sp * ip; /* MUFU seed + 2 Newton steps: <= 2 ulp, no slow paths */
                 inv[p] = ip;
                 Ud[p][p] = up;
 #pragma unroll
@@ -729,19 +729,34 @@ struct PnCta {
                         }
                         if (!sh->okflag) sh->retcode = PN_RET_UNSTABLE;
                     }
-                    /* V = C2 S^-1, one row per thread */
-                    for (int r = tid; r < 2 * d; r += NT) {
-                        double* x = V + r * d;
-                        for (int a = 0; a < d; a++) {
-                            double s = C2[r * d + a];
-                            for (int k = 0; k < a; k++) s -= S[k * d + a] * x[k];
-                            x[a] = s * sinv[a];
+                    /* V = C2 S^-1 with the explicit inverse S^-1 = U^-1 U^-T: one thread per column of U^-1 (the only
+                       sequential part, <= d^2/2 dependent FMAs), then two small fully parallel products.  The
+                       Jacobian buffer is free by now and holds U^-1; S^-1 overwrites S. */
+                    __syncthreads();
+                    for (int b = tid; b < d; b += NT) { /* U x = e_b, x upper-triangular column b */
+                        double* x = J + b * d; /* J[b*d + a] = Uinv[a][b] (column b stored contiguously) */
+                        for (int a = d - 1; a > b; a--) x[a] = 0.0;
+                        x[b] = sinv[b];
+                        for (int a = b - 1; a >= 0; a--) {
+                            double sacc = 0.0;
+                            for (int k = a + 1; k <= b; k++) sacc -= S[a * d + k] * x[k];
+                            x[a] = sacc * sinv[a];
                         }
-                        for (int a = d - 1; a >= 0; a--) {
-                            double s = x[a];
-                            for (int k = a + 1; k < d; k++) s -= S[a * d + k] * x[k];
-                            x[a] = s * sinv[a];
-                        }
+                    }
+                    __syncthreads();
+                    for (int e = tid; e < d * d; e += NT) { /* S^-1[a][b] = sum_k Uinv[a][k] Uinv[b][k], k >= max(a, b) */
+                        const int a = e / d, b = e - a * d;
+                        const int k0 = a > b ? a : b;
+                        double sacc = 0.0;
+                        for (int k = k0; k < d; k++) sacc += J[k * d + a] * J[k * d + b];
+                        S[e] = sacc;
+                    }
+                    __syncthreads();
+                    for (int e = tid; e < 2 * d * d; e += NT) {
+                        const int r = e / d, a = e - r * d;
+                        double sacc = 0.0;
+                        for (int k = 0; k < d; k++) sacc += C2[r * d + k] * S[k * d + a];
+                        V[e] = sacc;
                     }
                     __syncthreads();
                     /* K = R^-' V, stored transposed (Kt[a][c]); TA gains per thread so that a row entry of R^- is reused */

@@ -97,7 +97,9 @@ struct PnSmoothCol {
     static constexpr int LD = D | 1;
     /* per-trajectory shared-memory region (doubles) */
     static constexpr int OFF_REC = 0;                    /* staged record: R (D x D row-major), mean (D)   */
-    static constexpr int OFF_RM = OFF_REC + D * D + D + ((D * D + D) & 1); /* R^- (strict upper part), D x LD */
+    static constexpr int RECSZ = D * D + D + ((D * D + D) & 1);
+    static constexpr bool ASYNC = (D % 2 == 0);          /* 16-byte cp.async staging needs even D */
+    static constexpr int OFF_RM = OFF_REC + (ASYNC ? 2 : 1) * RECSZ; /* R^- (strict upper part), D x LD; staging is double-buffered */
     static constexpr int OFF_SM = OFF_RM + D * LD;       /* R_s+       D x LD                              */
     static constexpr int OFF_DI = OFF_SM + D * LD;       /* 1/diag(R^-) D                                  */
     static constexpr int OFF_MS = OFF_DI + D;            /* mu_s+       D                                  */
@@ -137,6 +139,21 @@ struct PnSmoothCol {
         for (int c = gl; c < D; c += G) P.s_x_mean[k * D + c] = Ms[c];
     }
 
+    /* global -> shared copy of record k (factor + mean), 16 bytes per cp.async, G lanes cooperating */
+    static PN_HD void stage_async(const PnSmoothParams& P, long long k, double* buf, int gl) {
+        const double* src = P.s_x_covfac + k * D * D;
+        for (int e = 2 * gl; e < D * D; e += 2 * G) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + e);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + e) : "memory");
+        }
+        const double* srm = P.s_x_mean + k * D;
+        for (int c = 2 * gl; c < D; c += 2 * G) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + D * D + c);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(srm + c) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
     static __device__ void run(const PnSmoothParams& P, double* smem_all) {
         constexpr unsigned FULL = 0xffffffffu;
         const int lane = threadIdx.x & 31;
@@ -144,6 +161,7 @@ struct PnSmoothCol {
         const int leader = lane - gl;
         double* sm = smem_all + (size_t)(threadIdx.x / G) * REGION;
         double* Rec = sm + OFF_REC;
+        int cur = 0; /* staging buffer that holds (or is receiving) the record of the next step */
         double* Rm = sm + OFF_RM;
         double* Sm = sm + OFF_SM;
         double* Di = sm + OFF_DI;
@@ -187,6 +205,7 @@ struct PnSmoothCol {
                     if (gl == 0) write_pu(P, last, Sm, Ms, scv);
                     k = last - 1;
                     have = (k >= a0);
+                    if (ASYNC && have && P.s_h[k] != 0.0) stage_async(P, k, sm + OFF_REC + cur * RECSZ, gl);
                 }
                 __syncwarp();
             }
@@ -197,22 +216,28 @@ struct PnSmoothCol {
             const double h = active ? P.s_h[k] : 1.0;
             const bool copy = active && (h == 0.0); /* integrator_utils.jl:109-112 */
             const bool doit = active && !copy;
-            if (copy) write_record(P, k, Sm, Ms, scv, gl);
+            if (copy) {
+                write_record(P, k, Sm, Ms, scv, gl);
+                /* a copy step consumes no staged record: request the one of the next real step from here */
+                if (ASYNC && k > a0 && P.s_h[k - 1] != 0.0) stage_async(P, k - 1, sm + OFF_REC + cur * RECSZ, gl);
+            }
             __syncwarp();
             if (__any_sync(FULL, doit)) {
                 const double hh = doit ? h : 1.0;
                 const double ediff = doit ? (P.dynamic ? P.s_diffusion[k] : P.initial_diffusion) : 1.0;
-                /* stage the filtered record: coalesced 16-byte copies */
-                if (doit) {
+                /* the filtered record of this step was requested one step ago (cp.async, double-buffered); request the
+                   next one now so that its HBM / L2 latency hides under this step's arithmetic */
+                if (ASYNC) {
+                    Rec = sm + OFF_REC + cur * RECSZ;
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    if (!doit)
+                        for (int e = gl; e < D * D + D; e += G) Rec[e] = 0.0;
+                    if (doit && k > a0 && P.s_h[k - 1] != 0.0) stage_async(P, k - 1, sm + OFF_REC + (cur ^ 1) * RECSZ, gl);
+                    if (doit) cur ^= 1;
+                } else if (doit) {
                     const double* src = P.s_x_covfac + k * D * D;
-                    if ((D * D) % 2 == 0) {
-                        for (int e = 2 * gl; e < D * D; e += 2 * G)
-                            *reinterpret_cast<double2*>(Rec + e) = *reinterpret_cast<const double2*>(src + e);
-                    } else {
-                        for (int e = gl; e < D * D; e += G) Rec[e] = src[e];
-                    }
+                    for (int e = gl; e < D * D; e += G) Rec[e] = src[e];
                     for (int c = gl; c < D; c += G) Rec[D * D + c] = P.s_x_mean[k * D + c];
-                    if (k > a0) asm volatile("prefetch.global.L2 [%0];" ::"l"(src - D * D + gl * 16));
                 } else {
                     for (int e = gl; e < D * D + D; e += G) Rec[e] = 0.0;
                 }
@@ -290,6 +315,7 @@ struct PnSmoothCol {
                         A[D + r][s] = (left && ir == i) ? upj[mr] * sdv[ir] : 0.0;
                     }
                 }
+                pn_qr_cols<G, W, NS, D, 0, D, true>(A, gl, Di);
                 /* mean bookkeeping (replicated): delta = mu_s+ - Ah mu */
                 double delta[D];
 #pragma unroll
@@ -309,7 +335,6 @@ struct PnSmoothCol {
                         }
                         delta[j * d + i] = Ms[j * d + i] - s;
                     }
-                pn_qr_cols<G, W, NS, D, 0, D, true>(A, gl, Di);
                 /* publish the strict upper part of R^- */
 #pragma unroll
                 for (int s = 0; s < NS; s++) {

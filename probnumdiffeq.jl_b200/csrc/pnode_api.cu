@@ -232,7 +232,8 @@ static bool is_mv(int diffusion) { return diffusion == PNODE_DIFF_DYNAMIC_MV || 
 /* must match PnSmoothCol<d,Q,G>::SMEM_BYTES */
 static size_t smooth_col_smem_bytes(int d, int q, int G) {
     const int D = d * (q + 1), LD = D | 1;
-    const int off_rm = D * D + D + ((D * D + D) & 1);
+    const int recsz = D * D + D + ((D * D + D) & 1);
+    const int off_rm = ((D % 2 == 0) ? 2 : 1) * recsz;
     const int RAW = off_rm + 2 * D * LD + 2 * D;
     const int PHASE = (G >= 16) ? 0 : G;
     const int REGION = ((RAW - PHASE + 15) / 16) * 16 + PHASE;
