@@ -286,6 +286,74 @@ def solve(cfg: Config, rhs: CompiledRHS, u0, p) -> dict:
     return out
 
 
+def _transition_dense(cfg: Config, h: float):
+    """Dense Ah, Qh.R (D x D, numpy row/col indexing) of the configured prior for step h."""
+    L = lib()
+    d, q = cfg.d, cfg.q
+    n, D = q + 1, cfg.d * (cfg.q + 1)
+    dp = C.POINTER(C.c_double)
+    A1, Q1 = np.zeros(n * n), np.zeros(n * n)
+    if cfg.prior == PRIOR_IOUP:
+        L.oracle_ioup_transition.argtypes = [C.c_int, C.c_double, C.c_double, dp, dp]
+        L.oracle_ioup_transition(q, cfg.rate_parameter, h, _dp(A1), _dp(Q1))
+    else:
+        L.oracle_iwp_transition.argtypes = [C.c_int, C.c_double, dp, dp]
+        L.oracle_iwp_transition(q, h, _dp(A1), _dp(Q1))
+    L.oracle_kron_identity.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp]
+    Ah, Qh = np.zeros(D * D), np.zeros(D * D)
+    L.oracle_kron_identity(d, n, n, _dp(A1), _dp(Ah))
+    L.oracle_kron_identity(d, n, n, _dp(Q1), _dp(Qh))
+    return Ah, Qh  # column-major buffers
+
+
+def interpolate(cfg: Config, sol: dict, tval: float):
+    """Dense output `sol(t)` (src/solution.jl:330-398, `interpolate`): extrapolate the filtering estimate of the last saved
+    point before `tval` over h1 = tval - t[idx] (predict, src/filtering/predict.jl) and -- for a smoothed solution --
+    condition on the next smoothed estimate over h2 = t[idx+1] - tval (`smooth`, src/filtering/smooth.jl:43-65, which is
+    compute_backward_kernel! + marginalize!).  The reference evaluates the same formulas in preconditioned coordinates.
+    Works on the dense form of the state (also for the structured layouts).  Returns (u_mean [d], u_cov [d, d])."""
+    L = lib()
+    dp = C.POINTER(C.c_double)
+    L.oracle_predict_cov.argtypes = [C.c_int, dp, dp, dp, C.c_double, C.c_int, dp, C.POINTER(C.c_int)]
+    L.oracle_backward_kernel.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, C.c_double, dp, dp, dp]
+    L.oracle_marginalize.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp]
+    t = sol["t"]
+    d, D = sol["d"], sol["D"]
+    if tval < t[0]:
+        raise ValueError("Invalid t<t0")
+    smoothed = "x_smooth_mu" in sol
+    idx = int(np.sum(t <= tval)) - 1
+    if t[idx] == tval:
+        mu = (sol["x_smooth_mu"] if smoothed else sol["x_filt_mu"])[idx]
+        R = (sol["x_smooth_R"] if smoothed else sol["x_filt_R"])[idx]
+        return mu[:d].copy(), (R.T @ R)[:d, :d]
+    diffusion = float(sol["diffusions"][min(idx, len(t) - 1)])
+    colmajor = lambda M: np.asfortranarray(M).ravel(order="F").copy()  # noqa: E731
+    h1 = tval - t[idx]
+    Ah, Qh = _transition_dense(cfg, h1)
+    mu0 = np.ascontiguousarray(sol["x_filt_mu"][idx])
+    R0 = colmajor(sol["x_filt_R"][idx])
+    mu_p = (Ah.reshape((D, D), order="F") @ mu0).copy()
+    R_p = np.zeros(D * D)
+    L.oracle_predict_cov(D, _dp(R0), _dp(Ah), _dp(Qh), diffusion, COV_QR, _dp(R_p), None)
+    if not smoothed or tval >= t[-1]:
+        Rp = R_p.reshape((D, D), order="F")
+        return mu_p[:d], (Rp.T @ Rp)[:d, :d]
+    h2 = t[idx + 1] - tval
+    Ah2, Qh2 = _transition_dense(cfg, h2)
+    mu_pp = (Ah2.reshape((D, D), order="F") @ mu_p).copy()
+    R_pp = np.zeros(D * D)
+    L.oracle_predict_cov(D, _dp(R_p), _dp(Ah2), _dp(Qh2), diffusion, COV_QR, _dp(R_pp), None)
+    G, b, LR = np.zeros(D * D), np.zeros(D), np.zeros(2 * D * D)
+    L.oracle_backward_kernel(D, _dp(mu_p), _dp(R_p), _dp(mu_pp), _dp(R_pp), _dp(Ah2), _dp(Qh2), diffusion, _dp(G), _dp(b), _dp(LR))
+    mu_n = np.ascontiguousarray(sol["x_smooth_mu"][idx + 1])
+    R_n = colmajor(sol["x_smooth_R"][idx + 1])
+    mu_s, R_s = np.zeros(D), np.zeros(D * D)
+    L.oracle_marginalize(D, _dp(mu_n), _dp(R_n), _dp(G), _dp(b), _dp(LR), _dp(mu_s), _dp(R_s))
+    Rs = R_s.reshape((D, D), order="F")
+    return mu_s[:d], (Rs.T @ Rs)[:d, :d]
+
+
 def solve_ensemble(cfg: Config, rhs: CompiledRHS, u0, p, n_threads: int = 0) -> dict:
     u0 = np.ascontiguousarray(u0, dtype=np.float64)
     n_traj, d = u0.shape

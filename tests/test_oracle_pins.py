@@ -428,3 +428,39 @@ def test_ioup_transition_matrices(oracle):
                     for b in range(a, q + 1):
                         want = quad(lambda s_: x(s_, a) * x(s_, b), 0.0, h, epsabs=0, epsrel=1e-13)[0]
                         assert Q[a, b] == pytest.approx(want, rel=1e-8 if q == 5 else 1e-10)
+
+
+def test_dense_output_interpolation(oracle):
+    """`sol(t)` (src/solution.jl:330-398).  Reference pins: test/solution.jl:64-76 (monotone departure from u0, growing
+    variance, error for t < t0) and the dense L2 error of test/correctness.jl:113-119 (`appxtrue(sol, testsol)` evaluates
+    sol(t) between the saved points): EK1(order=3) adaptive < 1e-5, EK0(order=3) < 1e-4; plus continuity at the saved points."""
+    f, u0, p = _CASES["lotkavolterra"]
+    tr = tracer.trace(f, 2, 4)
+    rhs = oracle.compile_rhs(tr, 3)
+
+    def fn(t, u):
+        du = [0.0, 0.0]
+        f(du, u, p, t)
+        return du
+
+    for alg, smooth, thr in ((1, True, 1e-5), (0, True, 1e-4), (1, False, 1e-4)):  # last row: sanity only, not a reference pin
+        cfg = oracle.make_config(2, 3, 4, alg=alg, smooth=smooth, adaptive=True, t0=0, t1=1)
+        s = oracle.solve(cfg, rhs, u0, p)
+        ts = np.unique(np.concatenate([np.linspace(a, b, 12) for a, b in zip(s["t"][:-1], s["t"][1:])]))
+        ref = solve_ivp(fn, (0, 1), u0, method="DOP853", rtol=1e-13, atol=1e-13, t_eval=ts).y.T
+        got = np.array([oracle.interpolate(cfg, s, t)[0] for t in ts])
+        assert np.sqrt(np.mean((got - ref) ** 2)) < thr, (alg, smooth)
+        # test/solution.jl:64-76
+        m0, _ = oracle.interpolate(cfg, s, 0.0)
+        (m1, c1), (m2, c2) = oracle.interpolate(cfg, s, 1e-2), oracle.interpolate(cfg, s, 2e-2)
+        assert np.linalg.norm(m0 - m1) < np.linalg.norm(m0 - m2)
+        if not smooth:
+            assert np.all(np.diag(c1) < np.diag(c2))
+        with pytest.raises(ValueError):
+            oracle.interpolate(cfg, s, -1e-2)
+        # continuity: just after a saved point the interpolant is close to the saved value
+        k = len(s["t"]) // 2
+        mk, ck = oracle.interpolate(cfg, s, s["t"][k] + 1e-9)
+        assert np.allclose(mk, s["pu_mu"][k], rtol=1e-6)
+        if smooth:
+            assert np.allclose(ck, s["pu_cov"][k], rtol=1e-3, atol=1e-300)
