@@ -108,6 +108,10 @@ typedef struct pnode_config {
     int64_t n_forced;
     /* IOUP prior: rate_parameter (F[q,q] of the SDE drift, src/priors/ioup.jl:66-79); ignored for the IWP */
     double rate_parameter;
+    /* dense output sol(saveat) (src/solution.jl:330-398): ascending times in [t0, t1]; host pointer, copied at create.
+       Needs save_everystep; smoothed interpolation if smooth, else the filtering prediction */
+    const double* saveat;
+    int64_t n_saveat;
 } pnode_config;
 
 typedef struct pnode_solver pnode_solver;
@@ -137,6 +141,9 @@ typedef enum pnode_field {
     /* multivariate diffusion models (Diagonal(sigma_1^2 .. sigma_d^2), src/diffusions/typedefs.jl) */
     PNODE_F_DIFFUSION_MV = 19,  /* double [n_traj][d]         final / global diffusion per component */
     PNODE_F_DIFFUSIONS_MV = 20, /* double [total][d]          sol.diffusions per component           */
+    /* dense output on the saveat grid */
+    PNODE_F_SAVEAT_U = 21,      /* double [n_traj][n_saveat][d]      mean(sol(saveat[j]))            */
+    PNODE_F_SAVEAT_U_COV = 22,  /* double [n_traj][n_saveat][d][d]   Matrix(sol(saveat[j]).Sigma)    */
     PNODE_F_COUNT
 } pnode_field;
 

@@ -147,6 +147,9 @@ class ProbODESolution:
     stats: Stats
     log_likelihood: float
     retcode: str
+    saveat_t: Optional[np.ndarray] = None     # dense output on the requested grid: mean(sol(t)), Matrix(sol(t).Sigma)
+    saveat_u: Optional[np.ndarray] = None
+    saveat_cov: Optional[np.ndarray] = None
 
     @property
     def pu(self) -> List[Gaussian]:
@@ -189,7 +192,7 @@ def _check_alg(alg, adaptive, dt, save_everystep, dense):
 
 
 def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, abstol, reltol, save_everystep, maxiters,
-                dtmin, dtmax, tstops, save_state, forced_diffusion=None):
+                dtmin, dtmax, tstops, save_state, forced_diffusion=None, saveat=None):
     d, n_p = len(prob.u0), len(prob.p)
     if d < 1:
         raise RuntimeError("We currently don't support scalar-valued problems")  # src/caches.jl:96-98
@@ -197,7 +200,7 @@ def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, absto
     kw = dict(d=d, q=alg.q, n_p=n_p, alg=alg.alg, smooth=alg.smooth, adaptive=adaptive, dt=dt or 0.0,
               abstol=abstol, reltol=reltol, save_everystep=save_everystep, maxiters=maxiters, dtmin=dtmin,
               dtmax=dtmax or 0.0, t0=prob.tspan[0], t1=prob.tspan[1], tstops=tstops, save_state=save_state,
-              device=ens.device, lanes_per_traj=ens.lanes_per_traj, forced_diffusion=forced_diffusion)
+              device=ens.device, lanes_per_traj=ens.lanes_per_traj, forced_diffusion=forced_diffusion, saveat=saveat)
     if isinstance(diff, FixedDiffusion):
         kw.update(diffusion=_lib.DIFF_FIXED, initial_diffusion=diff.initial_diffusion, calibrate=diff.calibrate)
     elif isinstance(diff, FixedMVDiffusion):
@@ -222,7 +225,7 @@ _solver_cache = {}
 def solve(prob, alg, ensemblealg: Optional[EnsembleB200] = None, *, trajectories: Optional[int] = None,
           adaptive: bool = True, dt: Optional[float] = None, abstol: float = 1e-6, reltol: float = 1e-3,
           save_everystep: bool = True, dense: Optional[bool] = None, maxiters: int = 1_000_000, dtmin: float = 0.0,
-          dtmax: Optional[float] = None, tstops=None, save_state: bool = False, forced_diffusion=None):
+          dtmax: Optional[float] = None, tstops=None, save_state: bool = False, forced_diffusion=None, saveat=None):
     """`solve(prob, EK1())` for one trajectory, or `solve(EnsembleProblem(...), EK1(), EnsembleB200(); trajectories=N)`."""
     import time
 
@@ -249,12 +252,18 @@ def solve(prob, alg, ensemblealg: Optional[EnsembleB200] = None, *, trajectories
             p[i] = pi.p
     cfg = _config_for(base, alg, ens, adaptive=adaptive, dt=dt, abstol=abstol, reltol=reltol,
                       save_everystep=save_everystep, maxiters=maxiters, dtmin=dtmin, dtmax=dtmax, tstops=tstops,
-                      save_state=save_state, forced_diffusion=forced_diffusion)
+                      save_state=save_state, forced_diffusion=forced_diffusion, saveat=saveat)
     t0 = time.time()
     solver = _lib.Solver(cfg)
     try:
         res = solver.solve(u0, p)
         sols = _unpack(res, n, d, save_everystep)
+        if saveat is not None and len(saveat):
+            # dense output sol(saveat) evaluated on the device (src/solution.jl:330-398)
+            su = res.field(_lib.F_SAVEAT_U).reshape(n, len(saveat), d)
+            sc = res.field(_lib.F_SAVEAT_U_COV).reshape(n, len(saveat), d, d)
+            for i, sol_i in enumerate(sols):
+                sol_i.saveat_t, sol_i.saveat_u, sol_i.saveat_cov = np.asarray(saveat, dtype=float), su[i], sc[i]
         info = res.info
         res.free()
     finally:

@@ -21,6 +21,8 @@
 #define PN_SMOOTH_DECL_ONLY
 #include "kernels/pn_smooth.cuh"
 #define PN_SMR_THREADS 256 /* pn_smooth_reg.cuh */
+#define PN_DENSE_DECL_ONLY
+#include "kernels/pn_dense.cuh" /* PnDenseParams */
 #include "kernels/pn_cta.cuh" /* PnCtaShared, PN_CTA_THREADS (templates are not instantiated here) */
 #include "pn_builtin.h"
 #include "pn_embedded_sources.h" /* generated: kernel headers as strings for NVRTC */
@@ -53,6 +55,34 @@ __global__ void pn_calibrate_saved(long long total, long long n_traj, const long
     s_diffusion[i] = diffusion[lo];
     if (s_diffusion_mv)
         for (int a = 0; a < d; a++) s_diffusion_mv[i * d + a] = diffusion_mv[lo * d + a];
+}
+
+/* Dense output, smoothed solutions: record 1 of every virtual trajectory is x_smooth[idx+1] of its parent trajectory
+   (x_smooth[last] for a saveat point at or beyond the last saved time, with h2 = 0 so that the sweep copies it). */
+__global__ void pn_dense_gather(long long V, long long n_saveat, int D, const long long* __restrict__ off,
+                                const long long* __restrict__ v_idx, const double* __restrict__ s_x_mean,
+                                const double* __restrict__ s_x_covfac, double* __restrict__ v_mean, double* __restrict__ v_covfac) {
+    const long long per = (long long)D * D + D;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= V * per) return;
+    const long long v = i / per, e = i - v * per;
+    const long long tr = v / n_saveat;
+    const long long last = off[tr + 1] - 1;
+    long long rec = v_idx[v] + 1;
+    if (rec > last) rec = last;
+    if (e < (long long)D * D) v_covfac[(2 * v + 1) * (long long)D * D + e] = s_x_covfac[rec * (long long)D * D + e];
+    else v_mean[(2 * v + 1) * (long long)D + (e - (long long)D * D)] = s_x_mean[rec * (long long)D + (e - (long long)D * D)];
+}
+/* ... and the marginals of the records 0 (of the records 1 where h2 == 0: the sweep's copy rule) are the dense output */
+__global__ void pn_dense_collect(long long V, int d, const double* __restrict__ v_h, const double* __restrict__ vu_mean,
+                                 const double* __restrict__ vu_cov, double* __restrict__ out_u, double* __restrict__ out_cov) {
+    const long long per = (long long)d + (long long)d * d;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= V * per) return;
+    const long long v = i / per, e = i - v * per;
+    const long long src = (v_h[2 * v] == 0.0) ? 2 * v + 1 : 2 * v;
+    if (e < d) out_u[v * d + e] = vu_mean[src * d + e];
+    else out_cov[v * (long long)d * d + (e - d)] = vu_cov[src * (long long)d * d + (e - d)];
 }
 
 /* FP64 roofline probe: 8 independent DFMA chains per thread (the denominator bench.py reports against;
@@ -154,6 +184,10 @@ struct pnode_solver {
     size_t smem = 0;   /* dynamic shared memory of the step kernel */
     Kernel k_final;  /* SAVE = 0 */
     Kernel k_save;   /* SAVE = 1 */
+    Kernel k_dense;  /* dense-output predict kernel (pn_dense.cuh) */
+    int Gd = 0;      /* lanes per (trajectory, saveat point) pair */
+    double* d_saveat = nullptr;
+    int64_t n_saveat = 0;
     Kernel k_smooth; /* register-resident smoother sweep (pn_smooth_reg.cuh); invalid => shared-memory sweep */
     int Gs = 0;      /* lanes per trajectory of the smoother sweep */
     size_t smem_smooth = 0;
@@ -328,6 +362,16 @@ static int nvrtc_smoother_cubin(int d, int q, int G, bool ioup, bool col, std::v
     return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0)}, cubin);
 }
 
+/* NVRTC: dense-output predict kernel for (d, q, G) */
+static int nvrtc_dense_cubin(int d, int q, int G, bool ioup, std::vector<char>* cubin) {
+    std::string src =
+        "#include \"kernels/pn_dense.cuh\"\n"
+        "extern \"C\" __global__ void __launch_bounds__(256, 1) pn_dense_entry(const __grid_constant__ PnDenseParams P) {\n"
+        "  pn_dense_predict_entry<PN_SD, PN_SQ, PN_SG>(P);\n}\n";
+    auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
+    return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0)}, cubin);
+}
+
 static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
     int rc = load_driver();
     if (rc) return rc;
@@ -429,6 +473,28 @@ static int get_smoother(pnode_solver* s) {
     return 0;
 }
 
+static int get_dense(pnode_solver* s) {
+    Kernel* out = &s->k_dense;
+    if (out->valid()) return 0;
+    auto t0 = std::chrono::steady_clock::now();
+    s->Gd = auto_lanes(s->D);
+    out->threads = 256;
+    int rc = load_driver();
+    if (rc) return rc;
+    std::vector<char> cubin;
+    if ((rc = nvrtc_dense_cubin(s->cfg.d, s->cfg.q, s->Gd, s->cfg.prior == PNODE_PRIOR_IOUP, &cubin))) return rc;
+    CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
+    if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
+    r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_dense_entry");
+    if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction: " + cu_err(r));
+    int nblk = 0;
+    r = g_drv.Occupancy(&nblk, out->drv_fn, out->threads, 0);
+    if (r != CUDA_SUCCESS || nblk < 1) return fail(PNODE_ERR_CUDA, "occupancy query failed: " + cu_err(r));
+    out->blocks_per_sm = nblk;
+    s->compile_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
 static size_t cta_smem_bytes(int d, int q, int n_p) {
     const size_t n = q + 1, D = (size_t)d * n, npa = n_p > 0 ? n_p : 1;
     const size_t mp = D * (D + 1) / 2, uni = mp > 2 * d * D ? mp : 2 * d * D; /* must match PnCta::SM_DOUBLES */
@@ -509,6 +575,18 @@ static int validate_config(const pnode_config* cfg) {
             return fail(PNODE_ERR_ARGUMENT, "D = d(q+1) > 32 runs one CTA per trajectory (lanes_per_traj 0 or 256)");
         if (cfg->smooth) return fail(PNODE_ERR_UNSUPPORTED, "smoothing is not implemented for the CTA-per-trajectory kernel yet");
     }
+    if (cfg->n_saveat > 0) { /* dense output sol(saveat) */
+        if (!cfg->saveat) return fail(PNODE_ERR_ARGUMENT, "saveat is null but n_saveat > 0");
+        if (!cfg->save_everystep) return fail(PNODE_ERR_ARGUMENT, "saveat (dense output) needs save_everystep = true");
+        for (int64_t i = 0; i < cfg->n_saveat; i++) {
+            if (cfg->saveat[i] < cfg->t0) return fail(PNODE_ERR_ARGUMENT, "Invalid t<t0"); /* src/solution.jl:340-342 */
+            if (i > 0 && !(cfg->saveat[i] >= cfg->saveat[i - 1])) return fail(PNODE_ERR_ARGUMENT, "saveat must be ascending");
+        }
+        if (is_mv(cfg->diffusion)) return fail(PNODE_ERR_UNSUPPORTED, "dense output with multivariate diffusion models is not implemented");
+        if (D > 32) return fail(PNODE_ERR_UNSUPPORTED, "dense output is implemented for D = d(q+1) <= 32");
+        if (cfg->smooth && smooth_lanes(D) == 0)
+            return fail(PNODE_ERR_UNSUPPORTED, "dense output of smoothed solutions needs the register-resident sweep (D <= 24)");
+    }
     const bool builtin = (std::string(cfg->rhs_name).rfind("builtin:", 0) == 0);
     if (!builtin && !cfg->rhs_src) return fail(PNODE_ERR_ARGUMENT, "rhs_src is required unless rhs_name is a builtin");
     return 0;
@@ -526,7 +604,7 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     std::vector<char> cubin;
     const int layout = resolve_layout(cfg);
     rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, is_dynamic(cfg->diffusion),
-                     cfg->save_everystep ? (cfg->smooth ? 2 : 1) : 0, &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
+                     cfg->save_everystep ? ((cfg->smooth || cfg->n_saveat > 0) ? 2 : 1) : 0, &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
                      layout == PNODE_COV_KRONECKER, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256),
                      layout == PNODE_COV_BLOCKS ? (cfg->alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, is_mv(cfg->diffusion),
                      cfg->prior == PNODE_PRIOR_IOUP, cfg->alg == PNODE_EK0 && layout == PNODE_COV_DENSE);
@@ -674,8 +752,16 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
     }
-    int rc = get_kernel(s, cfg->save_everystep ? (cfg->smooth ? 2 : 1) : 0, cfg->save_everystep ? &s->k_save : &s->k_final);
+    if (cfg->n_saveat > 0) {
+        CUDA_TRY(cudaMalloc(&s->d_saveat, sizeof(double) * cfg->n_saveat));
+        CUDA_TRY(cudaMemcpy(s->d_saveat, cfg->saveat, sizeof(double) * cfg->n_saveat, cudaMemcpyHostToDevice));
+        s->n_saveat = cfg->n_saveat;
+    }
+    s->cfg.saveat = nullptr;
+    int rc = get_kernel(s, cfg->save_everystep ? ((cfg->smooth || cfg->n_saveat > 0) ? 2 : 1) : 0,
+                        cfg->save_everystep ? &s->k_save : &s->k_final);
     if (!rc && cfg->smooth) rc = get_smoother(s);
+    if (!rc && cfg->n_saveat > 0) rc = get_dense(s);
     if (rc) {
         std::string keep = g_err;
         pnode_destroy(s);
@@ -722,11 +808,12 @@ extern "C" void pnode_destroy(pnode_solver* s) {
     if (!s) return;
     cudaSetDevice(s->cfg.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    for (Kernel* k : {&s->k_final, &s->k_save, &s->k_smooth})
+    for (Kernel* k : {&s->k_final, &s->k_save, &s->k_smooth, &s->k_dense})
         if (k->mod && g_drv.ModuleUnload) g_drv.ModuleUnload(k->mod);
     if (s->d_counter) cudaFree(s->d_counter);
     if (s->d_tstops) cudaFree(s->d_tstops);
     if (s->d_forced) cudaFree(s->d_forced);
+    if (s->d_saveat) cudaFree(s->d_saveat);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -829,7 +916,9 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         P.s_diffusion = (double*)r->f[PNODE_F_DIFFUSIONS].d;
         P.s_diffusion_mv = (double*)r->f[PNODE_F_DIFFUSIONS_MV].d;
         double* d_h = nullptr;
-        if (s->cfg.smooth) {
+        const bool dense = s->n_saveat > 0;
+        const size_t V = N * (size_t)s->n_saveat;
+        if (s->cfg.smooth || dense) {
             if ((rc = alloc_field(r, PNODE_F_X, T * D * 8))) return rc;
             if ((rc = alloc_field(r, PNODE_F_X_COVFAC, T * D * D * 8))) return rc;
             CUDA_TRY(cudaMallocAsync((void**)&d_h, T * 8, s->stream));
@@ -840,37 +929,22 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         }
         if ((rc = launch(s, s->k_save, P, n_traj))) return rc;
         launches = 2;
-        if (s->cfg.smooth) {
-            /* backward sweep: one warp per trajectory, records streamed back to front */
-            PnSmoothParams Q;
-            memset(&Q, 0, sizeof Q);
-            Q.n_traj = n_traj;
+        /* the smoother sweep over a CSR of records (the real trajectories, or the two-point virtual ones of the dense output) */
+        auto launch_sweep = [&](PnSmoothParams& Q, long long ntraj) -> int {
             Q.d = d;
             Q.q = s->cfg.q;
-            Q.dynamic = is_dynamic(s->cfg.diffusion);
-            Q.s_diffusion_mv = P.s_diffusion_mv;
-            Q.gdiff_mv = P.diffusion_mv;
-            Q.calibrate = s->cfg.calibrate;
-            Q.initial_diffusion = s->base.initial_diffusion;
-            Q.step_offsets = P.step_offsets;
-            Q.s_h = d_h;
-            Q.s_diffusion = P.s_diffusion;
-            Q.gdiff = P.diffusion;
-            Q.s_x_mean = P.s_x_mean;
-            Q.s_x_covfac = P.s_x_covfac;
-            Q.s_u_mean = P.s_u_mean;
-            Q.s_u_cov = P.s_u_cov;
             memcpy(Q.L, s->base.L, sizeof Q.L);
-            Q.work_counter = s->d_counter;
             memcpy(Q.U, s->base.U, sizeof Q.U);
             Q.rate = s->base.rate;
             memcpy(Q.glx, s->base.glx, sizeof Q.glx);
             memcpy(Q.glw, s->base.glw, sizeof Q.glw);
+            Q.n_traj = ntraj;
+            Q.work_counter = s->d_counter;
             if (s->k_smooth.valid()) {
                 /* register-resident sweep: Gs lanes per trajectory, persistent, one CTA per SM */
                 Kernel& ks = s->k_smooth;
                 const int groups = ks.threads / s->Gs;
-                long long want = (n_traj + groups - 1) / groups;
+                long long want = (ntraj + groups - 1) / groups;
                 unsigned grid = (unsigned)std::max(1LL, std::min(want, (long long)s->n_sm * ks.blocks_per_sm));
                 CUDA_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), s->stream));
                 void* args[] = {&Q};
@@ -895,15 +969,119 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 int nblk = 0;
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, 32 * warps, smem));
                 if (nblk < 1) return fail(PNODE_ERR_CUDA, "smoother kernel does not fit on an SM");
-                long long want = (n_traj + warps - 1) / warps;
+                long long want = (ntraj + warps - 1) / warps;
                 unsigned grid = (unsigned)std::max(1LL, std::min(want, (long long)s->n_sm * nblk));
                 CUDA_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), s->stream));
                 void* args[] = {&Q};
                 CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(32 * warps), args, smem, s->stream));
             }
-            CUDA_TRY(cudaFreeAsync(d_h, s->stream));
-            launches = 3;
+            return 0;
+        };
+        /* dense output, first half: goal_pred = predict(x_filt[idx], h1) for every (trajectory, saveat point) pair; must run
+           before the sweep overwrites the filtered records with the smoothed ones */
+        PnDenseParams Dn;
+        memset(&Dn, 0, sizeof Dn);
+        double *v_mean = nullptr, *v_covfac = nullptr, *v_h = nullptr, *v_diff = nullptr, *vu_mean = nullptr, *vu_cov = nullptr;
+        long long *v_idx = nullptr, *v_off = nullptr;
+        if (dense) {
+            if ((rc = alloc_field(r, PNODE_F_SAVEAT_U, V * d * 8))) return rc;
+            if ((rc = alloc_field(r, PNODE_F_SAVEAT_U_COV, V * d * d * 8))) return rc;
+            Dn.n_traj = n_traj;
+            Dn.n_saveat = s->n_saveat;
+            Dn.saveat = s->d_saveat;
+            Dn.smooth = s->cfg.smooth;
+            Dn.calibrate_scale = (!is_dynamic(s->cfg.diffusion) && s->cfg.calibrate) ? 1 : 0;
+            Dn.step_offsets = P.step_offsets;
+            Dn.s_t = P.s_t;
+            Dn.s_h = d_h;
+            Dn.s_diffusion = P.s_diffusion;
+            Dn.s_x_mean = P.s_x_mean;
+            Dn.s_x_covfac = P.s_x_covfac;
+            Dn.gdiff = P.diffusion;
+            memcpy(Dn.U, s->base.U, sizeof Dn.U);
+            Dn.rate = s->base.rate;
+            memcpy(Dn.glx, s->base.glx, sizeof Dn.glx);
+            memcpy(Dn.glw, s->base.glw, sizeof Dn.glw);
+            Dn.out_u = (double*)r->f[PNODE_F_SAVEAT_U].d;
+            Dn.out_cov = (double*)r->f[PNODE_F_SAVEAT_U_COV].d;
+            if (s->cfg.smooth) {
+                CUDA_TRY(cudaMallocAsync((void**)&v_mean, 2 * V * D * 8, s->stream));
+                CUDA_TRY(cudaMallocAsync((void**)&v_covfac, 2 * V * D * D * 8, s->stream));
+                CUDA_TRY(cudaMallocAsync((void**)&v_h, 2 * V * 8, s->stream));
+                CUDA_TRY(cudaMallocAsync((void**)&v_diff, 2 * V * 8, s->stream));
+                CUDA_TRY(cudaMallocAsync((void**)&vu_mean, 2 * V * d * 8, s->stream));
+                CUDA_TRY(cudaMallocAsync((void**)&vu_cov, 2 * V * d * d * 8, s->stream));
+                CUDA_TRY(cudaMallocAsync((void**)&v_idx, V * 8, s->stream));
+                CUDA_TRY(cudaMallocAsync((void**)&v_off, (V + 1) * 8, s->stream));
+                Dn.v_idx = v_idx;
+                Dn.v_mean = v_mean;
+                Dn.v_covfac = v_covfac;
+                Dn.v_h = v_h;
+                Dn.v_diffusion = v_diff;
+            }
+            Kernel& kd = s->k_dense;
+            const int groups = kd.threads / s->Gd;
+            long long want = ((long long)V + groups - 1) / groups;
+            unsigned grid = (unsigned)std::max(1LL, std::min(want, (long long)s->n_sm * kd.blocks_per_sm * 4));
+            void* args[] = {&Dn};
+            CUresult cr = g_drv.LaunchKernel(kd.drv_fn, grid, 1, 1, kd.threads, 1, 1, 0, (CUstream)s->stream, args, nullptr);
+            if (cr != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuLaunchKernel(dense): " + cu_err(cr));
+            launches += 1;
         }
+        if (s->cfg.smooth) {
+            /* backward sweep over the real trajectories */
+            PnSmoothParams Q;
+            memset(&Q, 0, sizeof Q);
+            Q.dynamic = is_dynamic(s->cfg.diffusion);
+            Q.s_diffusion_mv = P.s_diffusion_mv;
+            Q.gdiff_mv = P.diffusion_mv;
+            Q.calibrate = s->cfg.calibrate;
+            Q.initial_diffusion = s->base.initial_diffusion;
+            Q.step_offsets = P.step_offsets;
+            Q.s_h = d_h;
+            Q.s_diffusion = P.s_diffusion;
+            Q.gdiff = P.diffusion;
+            Q.s_x_mean = P.s_x_mean;
+            Q.s_x_covfac = P.s_x_covfac;
+            Q.s_u_mean = P.s_u_mean;
+            Q.s_u_cov = P.s_u_cov;
+            if ((rc = launch_sweep(Q, n_traj))) return rc;
+            launches += 1;
+            if (dense) {
+                /* second half: smooth(goal_pred, x_smooth[idx+1], h2) == one backward step of the sweep on two-point
+                   virtual trajectories (records already carry the calibration scale; per-record diffusion) */
+                const int thr = 256;
+                const long long ng = (long long)V * ((long long)D * D + D);
+                pn_dense_gather<<<(unsigned)((ng + thr - 1) / thr), thr, 0, s->stream>>>((long long)V, s->n_saveat, D, P.step_offsets, v_idx,
+                                                                                        P.s_x_mean, P.s_x_covfac, v_mean, v_covfac);
+                std::vector<long long> voff(V + 1);
+                for (size_t i = 0; i <= V; i++) voff[i] = 2 * (long long)i;
+                CUDA_TRY(cudaMemcpyAsync(v_off, voff.data(), (V + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+                CUDA_TRY(cudaStreamSynchronize(s->stream)); /* voff is a stack-lifetime host buffer */
+                PnSmoothParams Qv;
+                memset(&Qv, 0, sizeof Qv);
+                Qv.dynamic = 1;
+                Qv.calibrate = 0;
+                Qv.initial_diffusion = s->base.initial_diffusion;
+                Qv.step_offsets = v_off;
+                Qv.s_h = v_h;
+                Qv.s_diffusion = v_diff;
+                Qv.gdiff = P.diffusion;
+                Qv.s_x_mean = v_mean;
+                Qv.s_x_covfac = v_covfac;
+                Qv.s_u_mean = vu_mean;
+                Qv.s_u_cov = vu_cov;
+                if ((rc = launch_sweep(Qv, (long long)V))) return rc;
+                const long long nc = (long long)V * (d + d * d);
+                pn_dense_collect<<<(unsigned)((nc + thr - 1) / thr), thr, 0, s->stream>>>((long long)V, d, v_h, vu_mean, vu_cov, Dn.out_u,
+                                                                                         Dn.out_cov);
+                launches += 3;
+                for (void* ptr : {(void*)v_mean, (void*)v_covfac, (void*)v_h, (void*)v_diff, (void*)vu_mean, (void*)vu_cov, (void*)v_idx,
+                                  (void*)v_off})
+                    CUDA_TRY(cudaFreeAsync(ptr, s->stream));
+            }
+        }
+        if (d_h) CUDA_TRY(cudaFreeAsync(d_h, s->stream));
         if (!is_dynamic(s->cfg.diffusion)) {
             /* DIFFUSION holds sigma_hat^2 * initial (calibrate) or the constant initial diffusion */
             const double* scale = nullptr;

@@ -27,7 +27,7 @@ STATUS = {0: "OK", -1: "ArgumentError", -2: "DimensionMismatch", -3: "CompileErr
 # pnode_field
 F_T_END, F_U_FINAL, F_U_FINAL_COV, F_X_FINAL, F_X_FINAL_COVFAC, F_LOGLIK, F_DIFFUSION, F_DT_LAST = range(8)
 F_NACCEPT, F_NREJECT, F_NF, F_RETCODE, F_STEP_OFFSETS, F_T, F_U, F_U_COV, F_DIFFUSIONS, F_X, F_X_COVFAC = range(8, 19)
-F_DIFFUSION_MV, F_DIFFUSIONS_MV = 19, 20
+F_DIFFUSION_MV, F_DIFFUSIONS_MV, F_SAVEAT_U, F_SAVEAT_U_COV = 19, 20, 21, 22
 _FIELD_DTYPE = {F_NACCEPT: np.int64, F_NREJECT: np.int64, F_NF: np.int64, F_RETCODE: np.int32,
                 F_STEP_OFFSETS: np.int64}
 
@@ -61,6 +61,7 @@ class Config(C.Structure):
         ("tstops", C.POINTER(C.c_double)), ("n_tstops", C.c_int64),
         ("forced_diffusion", C.POINTER(C.c_double)), ("n_forced", C.c_int64),
         ("rate_parameter", C.c_double),
+        ("saveat", C.POINTER(C.c_double)), ("n_saveat", C.c_int64),
     ]
 
 
@@ -131,7 +132,7 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
                 lanes_per_traj=0, t0=0.0, t1=1.0, dt=0.0, abstol=1e-6, reltol=1e-3, dtmin=0.0, dtmax=0.0,
                 maxiters=1_000_000, beta1=0.0, beta2=0.0, qmin=0.2, qmax=10.0, gamma=0.9, qsteady_min=1.0,
                 qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None, device=0, prior=PRIOR_IWP,
-                rate_parameter=0.0) -> Config:
+                rate_parameter=0.0, saveat=None) -> Config:
     c = Config()
     c.struct_size = C.sizeof(Config)
     c.device, c.d, c.q, c.n_p = device, d, q, n_p
@@ -155,6 +156,10 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
         a = np.ascontiguousarray(forced_diffusion, dtype=np.float64)
         keep.append(a)
         c.forced_diffusion, c.n_forced = a.ctypes.data_as(C.POINTER(C.c_double)), len(a)
+    if saveat is not None and len(saveat):
+        a = np.ascontiguousarray(saveat, dtype=np.float64)
+        keep.append(a)
+        c.saveat, c.n_saveat = a.ctypes.data_as(C.POINTER(C.c_double)), len(a)
     c._keep = keep
     return c
 

@@ -642,6 +642,63 @@ def test_ioup_rate_zero_is_the_iwp():
     assert _relcov(a["C"][1:], b["C"][1:]) < 1e-9
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# dense output sol(t) on a saveat grid (src/solution.jl:330-398)
+# ------------------------------------------------------------------------------------------------------------------
+def _gpu_dense(pd, u0, p, q, saveat, builtin=False, **kw):
+    src = tracer.cuda_source(tracer.trace(pd.f, pd.d, pd.n_p), "UserProb")
+    cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="UserProb", rhs_src=src, save_everystep=True, saveat=saveat, **kw)
+    s = lib.Solver(cfg)
+    r = s.solve(u0, p)
+    n, d = u0.shape
+    out = dict(U=r.field(lib.F_SAVEAT_U).reshape(n, len(saveat), d), C=r.field(lib.F_SAVEAT_U_COV).reshape(n, len(saveat), d, d),
+               off=r.field(lib.F_STEP_OFFSETS), T=r.field(lib.F_T), info=r.info)
+    r.free()
+    s.close()
+    return out
+
+
+@pytest.mark.parametrize("alg,smooth,diffusion,calibrate", [(lib.EK1, True, lib.DIFF_FIXED, True), (lib.EK1, False, lib.DIFF_FIXED, True),
+                                                            (lib.EK1, True, lib.DIFF_FIXED, False), (lib.EK0, True, lib.DIFF_FIXED, True),
+                                                            (lib.EK1, True, lib.DIFF_DYNAMIC, True)])
+def test_dense_output_on_saveat_grid(oracle, alg, smooth, diffusion, calibrate):
+    """sol(saveat) from the device against the oracle's `interpolate` on the same trajectory: grid points inside steps,
+    exactly on saved points (t = 0.4 is a multiple of dt), at t0 and at t1.  Static diffusion: means 1e-10,
+    covariances 1e-8; DynamicDiffusion: the rounding floor of SURVEY.md H0 (1e-8 / 1e-4)."""
+    pd, u0, p = _inputs("lotka_volterra", 2, 51, du0=0.05)
+    saveat = np.array([0.0, 0.013, 0.4, 0.77777, 1.23456, 2.0])
+    g = _gpu_dense(pd, u0, p, 3, saveat, alg=alg, smooth=smooth, diffusion=diffusion, calibrate=calibrate, adaptive=False, dt=0.02,
+                   t0=0.0, t1=2.0)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    static = diffusion == lib.DIFF_FIXED
+    for i in range(u0.shape[0]):
+        cfg = oracle.make_config(2, 3, 4, alg=alg, diffusion=diffusion, calibrate=calibrate, smooth=smooth, adaptive=False, dt=0.02,
+                                 t0=0.0, t1=2.0, cov_backend=oracle.COV_QR)
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        for j, t in enumerate(saveat):
+            m, c = oracle.interpolate(cfg, o, float(t))
+            assert _rel(g["U"][i, j], m) < (1e-10 if static else 1e-8), (i, j)
+            if np.linalg.norm(c) > 0:
+                assert np.linalg.norm(g["C"][i, j] - c) / np.linalg.norm(c) < (1e-8 if static else 1e-4), (i, j)
+            else:
+                assert not g["C"][i, j].any()
+
+
+def test_dense_output_adaptive_ensemble(oracle):
+    """Adaptive ensemble with ragged step counts, common saveat grid (what the NCCL ensemble statistics consume)."""
+    n = 40
+    pd, u0, p = _inputs("lotka_volterra", n, 53, du0=0.1)
+    saveat = np.linspace(0.0, 10.0, 17)
+    g = _gpu_dense(pd, u0, p, 3, saveat, alg=lib.EK1, smooth=True, adaptive=True, t0=0.0, t1=10.0)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    assert len(set(np.diff(g["off"]))) > 3
+    for i in (0, 7, 39):
+        cfg = oracle.make_config(2, 3, 4, alg=oracle.EK1, smooth=True, adaptive=True, t0=0.0, t1=10.0, cov_backend=oracle.COV_QR)
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        want = np.array([oracle.interpolate(cfg, o, float(t))[0] for t in saveat])
+        assert _rel(g["U"][i], want) < 1e-7
+
+
 def test_full_size_properties_lv_ek0_1m():
     """BASELINE cfg2 at full size: 2^20 Lotka-Volterra trajectories, EK0(order=3), adaptive, filter only."""
     n = 1 << 20
