@@ -305,24 +305,33 @@ def shard_range(n_traj: int, rank: int, world: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def ensemble_statistics(u_final: np.ndarray, group=None):
-    """Ensemble mean and covariance of the final solution values over ALL ranks.
+def ensemble_statistics(u: np.ndarray, group=None):
+    """Ensemble mean and covariance over ALL ranks of per-trajectory values `u`: shape (n, d) (e.g. the final solution
+    values) or (n, m, d) (the dense output on a common `saveat` grid of m points, `sol.saveat_u`).
 
-    The only collective of the whole path: one all-reduce (sum) of `1 + d + d*d` doubles (count, first and second
-    moments).  With `torch.distributed` initialised on the `nccl` backend the moments are reduced on the GPUs over
-    NVLink/NVSwitch; with `gloo` (CPU tests) on the host; without an initialised process group it is the local result."""
+    The only collective of the whole path: one all-reduce (sum) of `1 + m (d + d*d)` doubles (count, first and second
+    moments per grid point).  With `torch.distributed` initialised on the `nccl` backend the moments are reduced on the
+    GPUs over NVLink/NVSwitch; with `gloo` (CPU tests) on the host; without an initialised process group it is the local
+    result.  Returns (n_total, mean, cov) with mean (d,) / (m, d) and cov (d, d) / (m, d, d)."""
     import torch
     import torch.distributed as dist
 
-    u = np.ascontiguousarray(u_final, dtype=np.float64)
-    d = u.shape[1]
-    mom = np.concatenate([[float(u.shape[0])], u.sum(axis=0), (u.T @ u).ravel()])
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    grid = u.ndim == 3
+    if not grid:
+        u = u[:, None, :]
+    n_loc, m, d = u.shape
+    s1 = u.sum(axis=0)                                   # (m, d)
+    s2 = np.einsum("nma,nmb->mab", u, u)                 # (m, d, d)
+    mom = np.concatenate([[float(n_loc)], s1.ravel(), s2.ravel()])
     if dist.is_available() and dist.is_initialized():
         dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
         t = torch.from_numpy(mom).to(dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         mom = t.cpu().numpy()
     n = mom[0]
-    mean = mom[1:1 + d] / n
-    cov = mom[1 + d:].reshape(d, d) / n - np.outer(mean, mean)
+    mean = mom[1:1 + m * d].reshape(m, d) / n
+    cov = mom[1 + m * d:].reshape(m, d, d) / n - np.einsum("ma,mb->mab", mean, mean)
+    if not grid:
+        mean, cov = mean[0], cov[0]
     return int(n), mean, cov

@@ -31,7 +31,9 @@ def _worker(rank, world, port, n_traj, out_dir):
     u_all = rng.normal(size=(n_traj, 3))          # stands in for the per-trajectory final values
     lo, hi = api.shard_range(n_traj, rank, world)
     n, mean, cov = api.ensemble_statistics(u_all[lo:hi])
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), n=n, mean=mean, cov=cov, lo=lo, hi=hi)
+    g_all = rng.normal(size=(n_traj, 5, 2))       # ... and for the dense output on a common saveat grid of 5 points
+    _, gmean, gcov = api.ensemble_statistics(g_all[lo:hi])
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), n=n, mean=mean, cov=cov, lo=lo, hi=hi, gmean=gmean, gcov=gcov)
     dist.destroy_process_group()
 
 
@@ -60,3 +62,8 @@ def test_ensemble_statistics_allreduce_gloo_world2(tmp_path):
         assert int(r["n"]) == n_traj
         assert np.allclose(r["mean"], u_all.mean(axis=0), rtol=1e-12, atol=1e-14)
         assert np.allclose(r["cov"], np.cov(u_all.T, bias=True), rtol=1e-10, atol=1e-13)
+    g_all = rng.normal(size=(n_traj, 5, 2))
+    for r in res:
+        assert np.allclose(r["gmean"], g_all.mean(axis=0), rtol=1e-12, atol=1e-14)
+        for j in range(5):
+            assert np.allclose(r["gcov"][j], np.cov(g_all[:, j].T, bias=True), rtol=1e-10, atol=1e-13)
