@@ -85,6 +85,24 @@ __global__ void pn_dense_collect(long long V, int d, const double* __restrict__ 
     else out_cov[v * (long long)d * d + (e - d)] = vu_cov[src * (long long)d * d + (e - d)];
 }
 
+/* sol.stats totals of the ensemble: sum of naccept / nreject over the trajectories (two int64 instead of two arrays D2H) */
+__global__ void pn_sum_counts(long long n, const long long* __restrict__ a, const long long* __restrict__ b,
+                              unsigned long long* __restrict__ out) {
+    unsigned long long sa = 0, sb = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        sa += (unsigned long long)a[i];
+        sb += (unsigned long long)b[i];
+    }
+    for (int o = 16; o >= 1; o >>= 1) {
+        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, sa);
+        atomicAdd(out + 1, sb);
+    }
+}
+
 /* FP64 roofline probe: 8 independent DFMA chains per thread (the denominator bench.py reports against;
    MEASURED_PEAKS.json has no FP64 figure). */
 __global__ void pn_dfma_probe(double* out, int iters, double a, double b) {
@@ -1116,19 +1134,20 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
     r->info.q = s->cfg.q;
     r->info.D = D;
     r->info.lanes_per_traj = s->G;
-    /* totals (small D2H of the per-trajectory counters) */
+    /* totals: reduced on the device, 16 bytes D2H */
     {
-        std::vector<long long> a(N), b(N);
-        CUDA_TRY(cudaMemcpy(a.data(), P.naccept, N * 8, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(b.data(), P.nreject, N * 8, cudaMemcpyDeviceToHost));
-        long long sa = 0, sb = 0;
-        for (size_t i = 0; i < N; i++) {
-            sa += a[i];
-            sb += b[i];
-        }
-        r->info.total_accepted = sa;
-        r->info.total_rejected = sb;
-        r->info.d2h_bytes += (int64_t)(2 * N * 8);
+        unsigned long long* d_tot = nullptr;
+        CUDA_TRY(cudaMallocAsync((void**)&d_tot, 16, s->stream));
+        CUDA_TRY(cudaMemsetAsync(d_tot, 0, 16, s->stream));
+        const unsigned blocks = (unsigned)std::min<long long>(((long long)N + 255) / 256, 1024);
+        pn_sum_counts<<<blocks, 256, 0, s->stream>>>((long long)N, P.naccept, P.nreject, d_tot);
+        unsigned long long tot[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(tot, d_tot, 16, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        CUDA_TRY(cudaFreeAsync(d_tot, s->stream));
+        r->info.total_accepted = (int64_t)tot[0];
+        r->info.total_rejected = (int64_t)tot[1];
+        r->info.d2h_bytes += 16;
     }
     return 0;
 }

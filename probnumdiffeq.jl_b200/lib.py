@@ -196,6 +196,17 @@ class Result:
         _check(lib.pnode_result_copy(self._h, f, out.ctypes.data_as(C.c_void_p), nb))
         return out
 
+    def field_into(self, f, out: np.ndarray) -> np.ndarray:
+        """Copy a field into a caller-owned buffer (e.g. pinned host memory: full-rate D2H)."""
+        lib = load()
+        nb = lib.pnode_result_field_bytes(self._h, f)
+        if nb == 0:
+            raise KeyError(f"field {f} not produced")
+        if out.nbytes != nb or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("destination must be C-contiguous and exactly the size of the field")
+        _check(lib.pnode_result_copy(self._h, f, out.ctypes.data_as(C.c_void_p), nb))
+        return out
+
     def has(self, f) -> bool:
         return load().pnode_result_field_bytes(self._h, f) > 0
 
