@@ -1128,7 +1128,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     r->info.kernel_ms = ms;
-    r->info.n_launches = launches;
+    r->info.n_launches = launches + 1; /* + pn_sum_counts below */
     r->info.n_traj = n_traj;
     r->info.d = d;
     r->info.q = s->cfg.q;
