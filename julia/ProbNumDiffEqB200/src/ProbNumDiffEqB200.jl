@@ -19,6 +19,7 @@ struct PnodeConfig
     rhs_src::Cstring; rhs_name::Cstring
     tstops::Ptr{Float64}; n_tstops::Int64; forced_diffusion::Ptr{Float64}; n_forced::Int64
     rate_parameter::Float64                      # IOUP(q, rate) prior; ignored for the IWP
+    saveat::Ptr{Float64}; n_saveat::Int64        # dense output sol(saveat) evaluated on the device
 end
 
 # enum values of include/pnode.h
@@ -42,7 +43,7 @@ function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::ProbNumDi
                               alg.smooth, adaptive, save_everystep, 0, 0, 0, 1_000_000, 1.0,
                               ep.prob.tspan[1], ep.prob.tspan[2], dt, abstol, reltol, 0.0, 0.0,
                               0, 0, 0.2, 10.0, 0.9, 1.0, 1.0, 1e-4,
-                              pointer(src), pointer("PnodeUserProblem"), C_NULL, 0, C_NULL, 0, rate_of(alg.prior)))
+                              pointer(src), pointer("PnodeUserProblem"), C_NULL, 0, C_NULL, 0, rate_of(alg.prior), C_NULL, 0))
         solver = Ref{Ptr{Cvoid}}()
         check(ccall((:pnode_create, LIB), Cint, (Ref{PnodeConfig}, Ref{Ptr{Cvoid}}), cfg, solver))
         res = Ref{Ptr{Cvoid}}()
