@@ -331,7 +331,7 @@ struct PnBlocks {
                     if (M[0][i] != M[0][i]) retcode = PN_RET_UNSTABLE;
                 }
                 if (SAVE >= 1) {
-                    if (P.step_offsets) {
+                    if (P.step_offsets && save_pos < P.step_offsets[traj + 1]) {
                         P.s_t[save_pos] = t;
                         P.s_diffusion[save_pos - 1] = (SAVE >= 2) ? ediff[0] : ((ADAPTIVE || DYNAMIC) ? ldiff[0] : P.initial_diffusion);
 #pragma unroll

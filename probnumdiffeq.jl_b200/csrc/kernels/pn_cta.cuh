@@ -833,7 +833,7 @@ struct PnCta {
                 }
                 __syncthreads();
                 if (SAVE >= 1) {
-                    if (P.step_offsets) {
+                    if (P.step_offsets && sh->save_pos < P.step_offsets[traj + 1]) {
                         const long long sp = sh->save_pos;
                         for (int e = tid; e < d * d; e += NT) {
                             const int a = e / d, b = e - a * d;

@@ -286,7 +286,7 @@ struct PnKron {
                     if (M[0][i] != M[0][i]) retcode = PN_RET_UNSTABLE;
                 }
                 if (SAVE >= 1) {
-                    if (P.step_offsets) {
+                    if (P.step_offsets && save_pos < P.step_offsets[traj + 1]) {
                         double c0 = 0.0;
 #pragma unroll
                         for (int r = 0; r < n; r++) c0 += RB[r][0] * RB[r][0];

@@ -864,7 +864,8 @@ struct PnSmall {
                     if (!(t < P.t1)) finished = true;
                 }
                 if (SAVE >= 1) {
-                    const bool wr = accept && P.step_offsets;
+                    /* never write past this trajectory's CSR segment (the host-computed offsets are exact; belt and braces) */
+                    const bool wr = accept && P.step_offsets && save_pos < P.step_offsets[traj + 1];
                     double cv[d * d];
 #pragma unroll
                     for (int a = 0; a < d; a++)

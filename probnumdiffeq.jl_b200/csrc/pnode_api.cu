@@ -212,6 +212,7 @@ struct pnode_solver {
     cudaStream_t stream = nullptr;
     unsigned long long* d_counter = nullptr;
     double* d_tstops = nullptr;
+    std::vector<double> host_tstops;
     double* d_forced = nullptr;
     double compile_s = 0.0;
     PnParams base; /* constants filled at create */
@@ -753,6 +754,7 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     if (cfg->n_tstops > 0 && cfg->tstops) {
         CUDA_TRY(cudaMalloc(&s->d_tstops, sizeof(double) * cfg->n_tstops));
         CUDA_TRY(cudaMemcpy(s->d_tstops, cfg->tstops, sizeof(double) * cfg->n_tstops, cudaMemcpyHostToDevice));
+        s->host_tstops.assign(cfg->tstops, cfg->tstops + cfg->n_tstops);
         B.tstops = s->d_tstops;
         B.n_tstops = cfg->n_tstops;
     }
@@ -862,7 +864,9 @@ static int alloc_field(pnode_result* r, int field, size_t bytes) {
     return 0;
 }
 
-static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const double* d_p, pnode_result* r) {
+static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const double* d_p, pnode_result* r,
+                      bool force_count_pass, bool* need_count_pass) {
+    const std::vector<double>& host_tstops = s->host_tstops;
     const int d = s->cfg.d, D = s->D;
     const size_t N = (size_t)n_traj;
     int rc;
@@ -905,19 +909,48 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, s->stream));
     int64_t launches = 0;
+    long long fixed_steps_total = -1; /* >= 0: the counting pass was skipped and every trajectory was allotted this many steps in total */
     if (!s->cfg.save_everystep) {
         if ((rc = launch(s, s->k_final, P, n_traj))) return rc;
         launches = 1;
     } else {
-        /* pass 1: count accepted steps with the *same* binary (null step_offsets => no stores), so both
-           passes take bit-identical accept/reject decisions; pass 2 writes at exact CSR positions */
-        if ((rc = launch(s, s->k_save, P, n_traj))) return rc;
-        std::vector<long long> nacc(N);
-        CUDA_TRY(cudaMemcpyAsync(nacc.data(), P.naccept, N * 8, cudaMemcpyDeviceToHost, s->stream));
-        CUDA_TRY(cudaStreamSynchronize(s->stream));
         r->offsets.resize(N + 1);
         r->offsets[0] = 0;
-        for (size_t i = 0; i < N; i++) r->offsets[i + 1] = r->offsets[i] + nacc[i] + 1;
+        long long fixed_steps = -1;
+        if (!s->cfg.adaptive && !force_count_pass) {
+            /* fixed steps: the number of steps is a function of (t0, t1, dt, tstops) alone -- replay the kernels' time
+               bookkeeping (same IEEE operations) on the host and skip the counting pass.  A trajectory that stops early
+               (retcode != Success) is detected from the totals afterwards and the solve is repeated with the counting pass. */
+            double t = s->base.t0;
+            long long nst = 0, it = 0, ti = 0;
+            const double* ts = host_tstops.data();
+            const long long nts = (long long)host_tstops.size();
+            while (t < s->base.t1) {
+                double tstop = s->base.t1;
+                while (ti < nts && ts[ti] <= t) ti++;
+                if (ti < nts && ts[ti] < s->base.t1) tstop = ts[ti];
+                if (++it > s->base.maxiters) break;
+                const double dt = std::fmin(s->base.dt0, tstop - t);
+                if (dt != dt || !(t + dt > t)) break;
+                const double ttmp = t + dt;
+                const double ref = std::fmax(std::fabs(t), std::fabs(tstop));
+                const double epsref = std::nextafter(ref, 1e300) - ref;
+                t = (std::fabs(ttmp - tstop) < 100.0 * epsref) ? tstop : ttmp;
+                nst++;
+            }
+            fixed_steps = nst;
+            fixed_steps_total = nst * (long long)N;
+            for (size_t i = 0; i < N; i++) r->offsets[i + 1] = r->offsets[i] + nst + 1;
+        } else {
+            /* pass 1: count accepted steps with the *same* binary (null step_offsets => no stores), so both
+               passes take bit-identical accept/reject decisions; pass 2 writes at exact CSR positions */
+            if ((rc = launch(s, s->k_save, P, n_traj))) return rc;
+            launches += 1;
+            std::vector<long long> nacc(N);
+            CUDA_TRY(cudaMemcpyAsync(nacc.data(), P.naccept, N * 8, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            for (size_t i = 0; i < N; i++) r->offsets[i + 1] = r->offsets[i] + nacc[i] + 1;
+        }
         const size_t T = (size_t)r->offsets[N];
         if ((rc = alloc_field(r, PNODE_F_STEP_OFFSETS, (N + 1) * 8))) return rc;
         if ((rc = alloc_field(r, PNODE_F_T, T * 8))) return rc;
@@ -946,7 +979,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             P.s_h = d_h;
         }
         if ((rc = launch(s, s->k_save, P, n_traj))) return rc;
-        launches = 2;
+        launches += 1;
         /* the smoother sweep over a CSR of records (the real trajectories, or the two-point virtual ones of the dense output) */
         auto launch_sweep = [&](PnSmoothParams& Q, long long ntraj) -> int {
             Q.d = d;
@@ -1148,6 +1181,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         r->info.total_accepted = (int64_t)tot[0];
         r->info.total_rejected = (int64_t)tot[1];
         r->info.d2h_bytes += 16;
+        if (need_count_pass) *need_count_pass = (fixed_steps_total >= 0 && (long long)tot[0] != fixed_steps_total);
     }
     return 0;
 }
@@ -1183,7 +1217,18 @@ static int solve_common(pnode_solver* s, int64_t n_traj, const double* u0, const
         d_u0 = r->d_u0;
         d_p = r->d_p;
     }
-    int rc = solve_impl(s, n_traj, d_u0, d_p, r);
+    bool redo = false;
+    int rc = solve_impl(s, n_traj, d_u0, d_p, r, false, &redo);
+    if (!rc && redo) {
+        /* a fixed-step trajectory stopped early: repeat with the counting pass so that the CSR offsets are exact */
+        for (int i = 0; i < PNODE_F_COUNT; i++)
+            if (r->f[i].d) {
+                cudaFreeAsync(r->f[i].d, s->stream);
+                r->f[i] = Buf();
+            }
+        r->offsets.clear();
+        rc = solve_impl(s, n_traj, d_u0, d_p, r, true, nullptr);
+    }
     if (rc) {
         std::string keep = g_err;
         pnode_result_free(r);

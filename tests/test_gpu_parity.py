@@ -277,6 +277,40 @@ def test_full_size_properties_rober_1m():
     assert np.array_equal(g3["u"][0], g["u"][0])
 
 
+def test_fixed_steps_skip_the_counting_pass_and_fall_back_when_a_trajectory_fails():
+    """Fixed-step solves compute the CSR offsets on the host (no counting pass).  If a trajectory stops early the solve is
+    repeated with the counting pass: here the EK0 with dt = 0.02 is unstable on the stiff Van der Pol members (mu ~ 1e3)
+    of a mixed ensemble (Unstable retcode after a few steps) while the mild ones (mu ~ 1) finish."""
+    pd = problems.PROBLEMS["vanderpol"]
+    n = 12
+    u0 = np.tile(np.array(pd.u0, dtype=float), (n, 1))
+    p = np.ones((n, 1))
+    p[::3, 0] = 1e3
+    src = tracer.cuda_source(tracer.trace(pd.f, pd.d, pd.n_p), "UserProb")
+
+    def run(uu, pp):
+        cfg = lib.make_config(d=2, q=3, n_p=1, rhs_name="UserProb", rhs_src=src, alg=lib.EK0, adaptive=False, dt=0.02, t0=0.0,
+                              t1=4.0, save_everystep=True, smooth=True)
+        s = lib.Solver(cfg)
+        r = s.solve(uu, pp)
+        out = dict(off=r.field(lib.F_STEP_OFFSETS), na=r.field(lib.F_NACCEPT), rc=r.field(lib.F_RETCODE), T=r.field(lib.F_T),
+                   U=r.field(lib.F_U).reshape(-1, 2), nl=r.info.n_launches)
+        r.free()
+        s.close()
+        return out
+
+    g = run(u0, p)
+    assert np.array_equal(np.diff(g["off"]), g["na"] + 1)                  # exact CSR also for the failed members
+    bad = g["rc"] != 0
+    assert bad[::3].all() and not bad[1::3].any() and not bad[2::3].any()
+    ok = run(u0[~bad], p[~bad])                                            # no failure: single pass (one launch fewer)
+    assert ok["nl"] < g["nl"] and (ok["na"] == 200).all()
+    for j, i in enumerate(np.flatnonzero(~bad)):
+        a, b = g["off"][i], g["off"][i + 1]
+        a2, b2 = ok["off"][j], ok["off"][j + 1]
+        assert np.array_equal(g["T"][a:b], ok["T"][a2:b2]) and np.array_equal(g["U"][a:b], ok["U"][a2:b2])
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # smoother (BASELINE cfg1 / cfg3: filter + RTS smoother)
 # ------------------------------------------------------------------------------------------------------------------
