@@ -628,7 +628,20 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
                      layout == PNODE_COV_BLOCKS ? (cfg->alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, is_mv(cfg->diffusion),
                      cfg->prior == PNODE_PRIOR_IOUP, cfg->alg == PNODE_EK0 && layout == PNODE_COV_DENSE);
     if (rc) return rc;
-    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    int64_t total = (int64_t)cubin.size();
+    /* the smoother sweep and the dense-output kernel of this configuration compile from the same embedded headers */
+    if (cfg->smooth && smooth_lanes(D) > 0 && !(cfg->alg == PNODE_EK1 && D > 32)) {
+        std::vector<char> c2;
+        const bool col = env_int("PNODE_SMOOTH_KIND", 1) != 0;
+        if ((rc = nvrtc_smoother_cubin(cfg->d, cfg->q, smooth_lanes(D), cfg->prior == PNODE_PRIOR_IOUP, col, &c2))) return rc;
+        total += (int64_t)c2.size();
+    }
+    if (cfg->n_saveat > 0) {
+        std::vector<char> c3;
+        if ((rc = nvrtc_dense_cubin(cfg->d, cfg->q, auto_lanes(D), cfg->prior == PNODE_PRIOR_IOUP, &c3))) return rc;
+        total += (int64_t)c3.size();
+    }
+    if (cubin_bytes) *cubin_bytes = total;
     return 0;
 }
 

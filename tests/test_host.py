@@ -93,6 +93,27 @@ def test_nvrtc_compiles_traced_rhs_for_sm100a(pnlib):
     assert e.value.kind == "CompileError" and "boom" in str(e.value)
 
 
+def test_nvrtc_compiles_smoother_and_dense_output_kernels(pnlib, monkeypatch):
+    """The RTS sweeps (column- and row-distributed), the dense-output kernel and the IOUP variants compile for sm_100a
+    without a device (pnode_compile_check compiles every kernel the configuration needs)."""
+    pd, src = _src("vanderpol")
+    base = dict(d=2, q=5, n_p=1, rhs_name="UserProb", rhs_src=src, t0=0.0, t1=2.0, smooth=True, save_everystep=True)
+    step_only = pnlib.compile_check(pnlib.make_config(**{**base, "smooth": False}))
+    with_sweep = pnlib.compile_check(pnlib.make_config(**base))
+    assert with_sweep > step_only
+    monkeypatch.setenv("PNODE_SMOOTH_KIND", "0")
+    assert pnlib.compile_check(pnlib.make_config(**base)) > step_only
+    monkeypatch.delenv("PNODE_SMOOTH_KIND")
+    pd, src = _src("lotka_volterra")
+    kw = dict(d=2, q=3, n_p=4, rhs_name="UserProb", rhs_src=src, t0=0.0, t1=1.0, smooth=True, save_everystep=True,
+              saveat=[0.0, 0.5, 1.0])
+    assert pnlib.compile_check(pnlib.make_config(**kw)) > 10_000
+    assert pnlib.compile_check(pnlib.make_config(prior=pnlib.PRIOR_IOUP, rate_parameter=-1.0, **kw)) > 10_000
+    with pytest.raises(pnlib.PnodeError) as e:   # src/solution.jl:340-342
+        pnlib.compile_check(pnlib.make_config(**{**kw, "saveat": [-0.1, 0.5]}))
+    assert "Invalid t<t0" in str(e.value)
+
+
 def test_tracer_matches_python_rhs():
     for name, pd in problems.PROBLEMS.items():
         tr = tracer.trace(pd.f, pd.d, pd.n_p)
