@@ -424,6 +424,42 @@ def test_smoother_register_and_shared_memory_sweeps_agree(monkeypatch):
     assert _rel(g["X"], r["X"]) < 1e-8
 
 
+def test_smoother_properties_at_scale():
+    """BASELINE cfg3 shape (Van der Pol mu ~ 1e3, EK1 order 5, adaptive) on 20 000 trajectories / 11.6 M saved points:
+    size-independent properties of the RTS smoother -- identical time grids and final point with and without smoothing,
+    and a smoothed marginal variance that never exceeds the filtered one (conditioning on more data)."""
+    n = 20000
+    pd = problems.PROBLEMS["vanderpol"]
+    rng = np.random.default_rng(1)
+    u0 = np.tile(np.array(pd.u0, dtype=float), (n, 1))
+    u0[:, 0] += 0.1 * rng.uniform(-1, 1, n)
+    p = np.array(pd.p, dtype=float)[None, :] * (1 + 0.2 * rng.uniform(-1, 1, (n, 1)))
+    out = {}
+    for smooth in (False, True):
+        cfg = lib.make_config(d=2, q=5, n_p=1, rhs_name="builtin:vanderpol", adaptive=True, t0=0.0, t1=2.0, smooth=smooth,
+                              save_everystep=True)
+        s = lib.Solver(cfg)
+        r = s.solve(u0, p)
+        out[smooth] = dict(off=r.field(lib.F_STEP_OFFSETS), T=r.field(lib.F_T), U=r.field(lib.F_U).reshape(-1, 2),
+                           C=r.field(lib.F_U_COV).reshape(-1, 2, 2), rc=r.field(lib.F_RETCODE))
+        r.free()
+        s.close()
+    f, sm = out[False], out[True]
+    assert (f["rc"] == 0).all() and (sm["rc"] == 0).all()
+    assert np.array_equal(f["off"], sm["off"]) and np.array_equal(f["T"], sm["T"])
+    last = f["off"][1:] - 1
+    assert np.array_equal(f["U"][last], sm["U"][last])                       # x_smooth[N] = x_filt[N]
+    assert np.allclose(f["C"][last], sm["C"][last], rtol=1e-13, atol=0)
+    vf = np.einsum("kii->ki", f["C"])
+    vs = np.einsum("kii->ki", sm["C"])
+    assert np.isfinite(vs).all() and (vs >= 0).all()
+    assert np.all(vs <= vf * (1 + 1e-6) + 1e-300)
+    interior = np.ones(len(vf), dtype=bool)
+    interior[last] = False
+    interior[f["off"][:-1]] = False
+    assert np.mean(vs[interior] < vf[interior]) > 0.99                        # and it is a strict improvement almost everywhere
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # EK0 / IsometricKronecker layout (BASELINE cfg2)
 # ------------------------------------------------------------------------------------------------------------------
