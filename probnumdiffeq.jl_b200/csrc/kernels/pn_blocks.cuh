@@ -77,8 +77,8 @@ struct PnBlocks {
         double pr[NPA];
         for (;;) {
             const unsigned long long idx = atomicAdd(P.work_counter, 1ULL);
-            if ((long long)idx >= P.n_traj) break;
-            const long long traj = (long long)idx;
+            if ((long long)idx * P.traj_stride >= P.n_traj) break;
+            const long long traj = (long long)idx * P.traj_stride;
             double t = P.t0, dt, loglik = 0.0, qold = P.qoldinit, qold_pb2 = P.qoldinit_pb2;
             double gdiff[d], ldiff[d];
 #pragma unroll

@@ -227,7 +227,7 @@ struct PnCta {
         for (;;) {
             /* ---- fetch ---- */
             __syncthreads();
-            if (tid == 0) sh->traj = (long long)atomicAdd(P.work_counter, 1ULL);
+            if (tid == 0) sh->traj = (long long)atomicAdd(P.work_counter, 1ULL) * P.traj_stride;
             __syncthreads();
             const long long traj = sh->traj;
             if (traj >= P.n_traj) break;

@@ -26,6 +26,7 @@ struct PnDenseParams {
     int smooth;                    /* 1: fill the virtual trajectories; 0: write the filtering marginals directly */
     int calibrate_scale;           /* FixedDiffusion(calibrate=true): marginals / records are scaled by gdiff */
     const long long* step_offsets; /* [n_traj+1] */
+    const long long* counts;       /* [n_traj] or null (see PnSmoothParams) */
     const double* s_t;             /* [total] */
     const double* s_h;             /* [total] step k -> k+1 at slot k */
     const double* s_diffusion;     /* [total] diffusion used for step k -> k+1 at slot k */
@@ -75,7 +76,7 @@ struct PnDensePredict {
             const long long tr = act ? v / P.n_saveat : 0;
             const long long j = act ? v - tr * P.n_saveat : 0;
             const double tval = P.saveat[j];
-            const long long a0 = P.step_offsets[tr], last = P.step_offsets[tr + 1] - 1;
+            const long long a0 = P.step_offsets[tr], last = P.counts ? a0 + P.counts[tr] : P.step_offsets[tr + 1] - 1;
             /* idx: last saved point with t <= tval (binary search; t[a0] = t0 <= tval) */
             long long lo = a0, hi = last + 1;
             while (hi - lo > 1) {

@@ -72,8 +72,8 @@ struct PnKron {
         double pr[NPA];
         for (;;) {
             const unsigned long long idx = atomicAdd(P.work_counter, 1ULL);
-            if ((long long)idx >= P.n_traj) break;
-            const long long traj = (long long)idx;
+            if ((long long)idx * P.traj_stride >= P.n_traj) break;
+            const long long traj = (long long)idx * P.traj_stride;
             double t = P.t0, dt, loglik = 0.0, gdiff = 0.0, ldiff = 0.0, qold = P.qoldinit, qold_pb2 = P.qoldinit_pb2;
             long long naccept = 0, nreject = 0, nf = Q, iter = 0, tstop_idx = 0, save_pos = 0;
             int retcode = PN_RET_SUCCESS;

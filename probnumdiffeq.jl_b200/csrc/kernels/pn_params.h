@@ -25,6 +25,9 @@ struct PnParams {
     long long n_tstops;
     const double* forced_diffusion;
     long long n_forced;
+    /* work item idx of the queue is trajectory idx * traj_stride (1 for a normal solve; > 1 for the step-count pilot that
+       sizes the save buffers from a strided subsample of the ensemble) */
+    long long traj_stride;
     /* dynamic work queue */
     unsigned long long* work_counter;
     /* IWP constants (src/priors/iwp.jl:74-108), row-major n x n, host-computed */

@@ -415,10 +415,10 @@ struct PnSmall {
                 if (need && gl == 0) idx = atomicAdd(P.work_counter, 1ULL);
                 idx = __shfl_sync(FULL, idx, leader);
                 if (need) {
-                    if ((long long)idx >= P.n_traj) {
+                    if ((long long)idx * P.traj_stride >= P.n_traj) {
                         queue_empty = true;
                     } else {
-                        traj = (long long)idx;
+                        traj = (long long)idx * P.traj_stride;
                         {
                             InitOut io; /* lives in local memory; copied to registers below */
                             init_trajectory(P, traj, io);

@@ -28,6 +28,8 @@ struct PnSmoothParams {
     int calibrate;      /* FixedDiffusion(calibrate=true): scale factors by sqrt(global MLE) */
     double initial_diffusion;
     const long long* step_offsets; /* [n_traj+1] */
+    const long long* counts;       /* [n_traj] accepted steps per trajectory when the segments are over-allocated (pitch layout);
+                                      null: segment i is exactly [off[i], off[i+1]) */
     const double* s_h;             /* [total] h of the step k -> k+1 stored at slot k */
     const double* s_diffusion;     /* [total] */
     const double* gdiff;           /* [n_traj] global diffusion scale (calibrate) */
@@ -128,7 +130,7 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if ((long long)idx >= P.n_traj) break;
         const long long tr = (long long)idx;
-        const long long a0 = P.step_offsets[tr], a1 = P.step_offsets[tr + 1];
+        const long long a0 = P.step_offsets[tr], a1 = P.counts ? a0 + P.counts[tr] + 1 : P.step_offsets[tr + 1];
         const long long last = a1 - 1;
         const double sc = (!P.dynamic && P.calibrate) ? sqrt(P.gdiff[tr]) : 1.0;
         /* x_smooth[N] = x_filt[N] */

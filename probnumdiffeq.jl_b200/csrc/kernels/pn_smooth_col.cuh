@@ -188,7 +188,7 @@ struct PnSmoothCol {
                     } else {
                         got = true;
                         a0 = P.step_offsets[idx];
-                        last = P.step_offsets[idx + 1] - 1;
+                        last = P.counts ? a0 + P.counts[idx] : P.step_offsets[idx + 1] - 1;
 #pragma unroll
                         for (int i = 0; i < d; i++)
                             scv[i] = (!P.dynamic && P.calibrate) ? sqrt(P.gdiff_mv ? P.gdiff_mv[idx * d + i] : P.gdiff[idx]) : 1.0;

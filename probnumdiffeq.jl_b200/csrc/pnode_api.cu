@@ -57,17 +57,31 @@ __global__ void pn_calibrate_saved(long long total, long long n_traj, const long
         for (int a = 0; a < d; a++) s_diffusion_mv[i * d + a] = diffusion_mv[lo * d + a];
 }
 
+/* Over-allocated (pitch) layout -> exact CSR: element e of trajectory tr lives at (tr * pitch + e) in the work buffers */
+__global__ void pn_compact_saved(long long total, long long n_traj, const long long* __restrict__ off_exact, long long pitch,
+                                 int width, const double* __restrict__ src, double* __restrict__ dst) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total * width) return;
+    const long long e = i / width, w = i - e * width;
+    long long lo = 0, hi = n_traj;
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (off_exact[mid] <= e) lo = mid; else hi = mid;
+    }
+    dst[i] = src[(lo * pitch + (e - off_exact[lo])) * width + w];
+}
+
 /* Dense output, smoothed solutions: record 1 of every virtual trajectory is x_smooth[idx+1] of its parent trajectory
    (x_smooth[last] for a saveat point at or beyond the last saved time, with h2 = 0 so that the sweep copies it). */
 __global__ void pn_dense_gather(long long V, long long n_saveat, int D, const long long* __restrict__ off,
-                                const long long* __restrict__ v_idx, const double* __restrict__ s_x_mean,
+                                const long long* __restrict__ counts, const long long* __restrict__ v_idx, const double* __restrict__ s_x_mean,
                                 const double* __restrict__ s_x_covfac, double* __restrict__ v_mean, double* __restrict__ v_covfac) {
     const long long per = (long long)D * D + D;
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= V * per) return;
     const long long v = i / per, e = i - v * per;
     const long long tr = v / n_saveat;
-    const long long last = off[tr + 1] - 1;
+    const long long last = counts ? off[tr] + counts[tr] : off[tr + 1] - 1;
     long long rec = v_idx[v] + 1;
     if (rec > last) rec = last;
     if (e < (long long)D * D) v_covfac[(2 * v + 1) * (long long)D * D + e] = s_x_covfac[rec * (long long)D * D + e];
@@ -671,6 +685,7 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     /* ---- constants ---- */
     PnParams& B = s->base;
     memset(&B, 0, sizeof B);
+    B.traj_stride = 1;
     B.t0 = cfg->t0;
     B.t1 = cfg->t1;
     B.dt0 = cfg->dt;
@@ -930,6 +945,11 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         r->offsets.resize(N + 1);
         r->offsets[0] = 0;
         long long fixed_steps = -1;
+        const long long pilot_stride = 16;
+        long long pitch = 0;
+        bool pitch_mode = false;
+        std::vector<void*> work_bufs; /* pitch mode: internal buffers in the over-allocated layout */
+        const long long* d_counts = nullptr;
         if (!s->cfg.adaptive && !force_count_pass) {
             /* fixed steps: the number of steps is a function of (t0, t1, dt, tstops) alone -- replay the kernels' time
                bookkeeping (same IEEE operations) on the host and skip the counting pass.  A trajectory that stops early
@@ -954,6 +974,27 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             fixed_steps = nst;
             fixed_steps_total = nst * (long long)N;
             for (size_t i = 0; i < N; i++) r->offsets[i + 1] = r->offsets[i] + nst + 1;
+        } else if (!force_count_pass && !s->cfg.save_state && !env_int("PNODE_TWO_PASS", 0) && (long long)N >= 64LL * pilot_stride) {
+            /* adaptive steps, one full pass instead of two: a PILOT run of the same binary in counting mode on every
+               pilot_stride-th trajectory gives the step-count scale of the ensemble; every trajectory is allotted a segment
+               of pitch = margin * max_pilot (+ slack) saved points and the save pass writes into this over-allocated layout
+               (writes beyond a segment are dropped, the count goes on).  The small user-facing fields are compacted to the
+               exact CSR afterwards; the big state records stay internal.  If any trajectory overflows its segment the exact
+               counts are known by then and the solve is repeated with the counting-pass layout. */
+            PnParams Pp = P;
+            Pp.traj_stride = pilot_stride;
+            CUDA_TRY(cudaMemsetAsync(P.naccept, 0, N * 8, s->stream));
+            if ((rc = launch(s, s->k_save, Pp, (n_traj + pilot_stride - 1) / pilot_stride))) return rc;
+            launches += 1;
+            std::vector<long long> nacc(N);
+            CUDA_TRY(cudaMemcpyAsync(nacc.data(), P.naccept, N * 8, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            long long mx = 0;
+            for (size_t i = 0; i < N; i += (size_t)pilot_stride) mx = std::max(mx, nacc[i]);
+            const double margin = env_int("PNODE_PILOT_MARGIN_PCT", 125) / 100.0;
+            pitch = (long long)std::ceil((double)mx * margin) + 8 + 1;
+            pitch_mode = true;
+            for (size_t i = 0; i < N; i++) r->offsets[i + 1] = r->offsets[i] + pitch;
         } else {
             /* pass 1: count accepted steps with the *same* binary (null step_offsets => no stores), so both
                passes take bit-identical accept/reject decisions; pass 2 writes at exact CSR positions */
@@ -964,35 +1005,73 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             CUDA_TRY(cudaStreamSynchronize(s->stream));
             for (size_t i = 0; i < N; i++) r->offsets[i + 1] = r->offsets[i] + nacc[i] + 1;
         }
-        const size_t T = (size_t)r->offsets[N];
-        if ((rc = alloc_field(r, PNODE_F_STEP_OFFSETS, (N + 1) * 8))) return rc;
-        if ((rc = alloc_field(r, PNODE_F_T, T * 8))) return rc;
-        if ((rc = alloc_field(r, PNODE_F_U, T * d * 8))) return rc;
-        if ((rc = alloc_field(r, PNODE_F_U_COV, T * d * d * 8))) return rc;
-        if ((rc = alloc_field(r, PNODE_F_DIFFUSIONS, T * 8))) return rc;
-        if (s->mv && (rc = alloc_field(r, PNODE_F_DIFFUSIONS_MV, T * d * 8))) return rc;
-        CUDA_TRY(cudaMemcpyAsync(r->f[PNODE_F_STEP_OFFSETS].d, r->offsets.data(), (N + 1) * 8, cudaMemcpyHostToDevice,
-                                 s->stream));
-        P.step_offsets = (const long long*)r->f[PNODE_F_STEP_OFFSETS].d;
-        P.s_t = (double*)r->f[PNODE_F_T].d;
-        P.s_u_mean = (double*)r->f[PNODE_F_U].d;
-        P.s_u_cov = (double*)r->f[PNODE_F_U_COV].d;
-        P.s_diffusion = (double*)r->f[PNODE_F_DIFFUSIONS].d;
-        P.s_diffusion_mv = (double*)r->f[PNODE_F_DIFFUSIONS_MV].d;
+        const size_t T = (size_t)r->offsets[N]; /* points in the layout the kernels write (exact CSR, or N * pitch) */
+        /* exact layout: the kernels write the result fields directly; pitch layout: internal work buffers */
+        auto alloc_work = [&](int field, size_t bytes, void** out) -> int {
+            *out = nullptr;
+            if (bytes == 0) return 0;
+            if (!pitch_mode) {
+                int rc2 = alloc_field(r, field, bytes);
+                *out = r->f[field].d;
+                return rc2;
+            }
+            CUDA_TRY(cudaMallocAsync(out, bytes, s->stream));
+            work_bufs.push_back(*out);
+            return 0;
+        };
+        void *w_off = nullptr, *w_t = nullptr, *w_u = nullptr, *w_uc = nullptr, *w_df = nullptr, *w_dfmv = nullptr, *w_x = nullptr,
+             *w_xc = nullptr;
+        if ((rc = alloc_work(PNODE_F_STEP_OFFSETS, (N + 1) * 8, &w_off))) return rc;
+        if ((rc = alloc_work(PNODE_F_T, T * 8, &w_t))) return rc;
+        if ((rc = alloc_work(PNODE_F_U, T * d * 8, &w_u))) return rc;
+        if ((rc = alloc_work(PNODE_F_U_COV, T * d * d * 8, &w_uc))) return rc;
+        if ((rc = alloc_work(PNODE_F_DIFFUSIONS, T * 8, &w_df))) return rc;
+        if (s->mv && (rc = alloc_work(PNODE_F_DIFFUSIONS_MV, T * d * 8, &w_dfmv))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(w_off, r->offsets.data(), (N + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+        P.step_offsets = (const long long*)w_off;
+        P.s_t = (double*)w_t;
+        P.s_u_mean = (double*)w_u;
+        P.s_u_cov = (double*)w_uc;
+        P.s_diffusion = (double*)w_df;
+        P.s_diffusion_mv = (double*)w_dfmv;
         double* d_h = nullptr;
         const bool dense = s->n_saveat > 0;
         const size_t V = N * (size_t)s->n_saveat;
         if (s->cfg.smooth || dense) {
-            if ((rc = alloc_field(r, PNODE_F_X, T * D * 8))) return rc;
-            if ((rc = alloc_field(r, PNODE_F_X_COVFAC, T * D * D * 8))) return rc;
+            if ((rc = alloc_work(PNODE_F_X, T * D * 8, &w_x))) return rc;
+            if ((rc = alloc_work(PNODE_F_X_COVFAC, T * D * D * 8, &w_xc))) return rc;
             CUDA_TRY(cudaMallocAsync((void**)&d_h, T * 8, s->stream));
             CUDA_TRY(cudaMemsetAsync(d_h, 0, T * 8, s->stream));
-            P.s_x_mean = (double*)r->f[PNODE_F_X].d;
-            P.s_x_covfac = (double*)r->f[PNODE_F_X_COVFAC].d;
+            P.s_x_mean = (double*)w_x;
+            P.s_x_covfac = (double*)w_xc;
             P.s_h = d_h;
         }
         if ((rc = launch(s, s->k_save, P, n_traj))) return rc;
         launches += 1;
+        std::vector<long long> exact_off;
+        if (pitch_mode) {
+            /* the save pass counted every accepted step, stored or not: exact CSR offsets, overflow check */
+            std::vector<long long> nacc(N);
+            CUDA_TRY(cudaMemcpyAsync(nacc.data(), P.naccept, N * 8, cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            exact_off.resize(N + 1);
+            exact_off[0] = 0;
+            bool overflow = false;
+            for (size_t i = 0; i < N; i++) {
+                overflow = overflow || (nacc[i] + 1 > pitch);
+                exact_off[i + 1] = exact_off[i] + nacc[i] + 1;
+            }
+            if (overflow) { /* repeat with the counting-pass layout (solve_common) */
+                for (void* ptr : work_bufs) CUDA_TRY(cudaFreeAsync(ptr, s->stream));
+                if (d_h) CUDA_TRY(cudaFreeAsync(d_h, s->stream));
+                CUDA_TRY(cudaStreamSynchronize(s->stream));
+                cudaEventDestroy(e0);
+                cudaEventDestroy(e1);
+                if (need_count_pass) *need_count_pass = true;
+                return need_count_pass ? 0 : fail(PNODE_ERR_CUDA, "pilot segment overflow without a fallback");
+            }
+            d_counts = P.naccept;
+        }
         /* the smoother sweep over a CSR of records (the real trajectories, or the two-point virtual ones of the dense output) */
         auto launch_sweep = [&](PnSmoothParams& Q, long long ntraj) -> int {
             Q.d = d;
@@ -1056,6 +1135,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             Dn.smooth = s->cfg.smooth;
             Dn.calibrate_scale = (!is_dynamic(s->cfg.diffusion) && s->cfg.calibrate) ? 1 : 0;
             Dn.step_offsets = P.step_offsets;
+            Dn.counts = d_counts;
             Dn.s_t = P.s_t;
             Dn.s_h = d_h;
             Dn.s_diffusion = P.s_diffusion;
@@ -1102,6 +1182,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             Q.calibrate = s->cfg.calibrate;
             Q.initial_diffusion = s->base.initial_diffusion;
             Q.step_offsets = P.step_offsets;
+            Q.counts = d_counts;
             Q.s_h = d_h;
             Q.s_diffusion = P.s_diffusion;
             Q.gdiff = P.diffusion;
@@ -1116,7 +1197,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                    virtual trajectories (records already carry the calibration scale; per-record diffusion) */
                 const int thr = 256;
                 const long long ng = (long long)V * ((long long)D * D + D);
-                pn_dense_gather<<<(unsigned)((ng + thr - 1) / thr), thr, 0, s->stream>>>((long long)V, s->n_saveat, D, P.step_offsets, v_idx,
+                pn_dense_gather<<<(unsigned)((ng + thr - 1) / thr), thr, 0, s->stream>>>((long long)V, s->n_saveat, D, P.step_offsets, d_counts, v_idx,
                                                                                         P.s_x_mean, P.s_x_covfac, v_mean, v_covfac);
                 std::vector<long long> voff(V + 1);
                 for (size_t i = 0; i <= V; i++) voff[i] = 2 * (long long)i;
@@ -1164,7 +1245,28 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                                                              P.s_diffusion_mv);
             launches += 1;
         }
-        r->info.total_saved = (int64_t)T;
+        if (pitch_mode) {
+            /* user-facing fields: over-allocated layout -> exact CSR */
+            const size_t Te = (size_t)exact_off[N];
+            if ((rc = alloc_field(r, PNODE_F_STEP_OFFSETS, (N + 1) * 8))) return rc;
+            CUDA_TRY(cudaMemcpyAsync(r->f[PNODE_F_STEP_OFFSETS].d, exact_off.data(), (N + 1) * 8, cudaMemcpyHostToDevice, s->stream));
+            const long long* d_eoff = (const long long*)r->f[PNODE_F_STEP_OFFSETS].d;
+            struct { int field; int width; const void* src; } cp[] = {
+                {PNODE_F_T, 1, w_t}, {PNODE_F_U, d, w_u}, {PNODE_F_U_COV, d * d, w_uc}, {PNODE_F_DIFFUSIONS, 1, w_df},
+                {PNODE_F_DIFFUSIONS_MV, d, w_dfmv}};
+            for (auto& c : cp) {
+                if (!c.src) continue;
+                if ((rc = alloc_field(r, c.field, Te * c.width * 8))) return rc;
+                const long long ne = (long long)Te * c.width;
+                pn_compact_saved<<<(unsigned)((ne + 255) / 256), 256, 0, s->stream>>>((long long)Te, (long long)N, d_eoff, pitch, c.width,
+                                                                                     (const double*)c.src, (double*)r->f[c.field].d);
+                launches += 1;
+            }
+            CUDA_TRY(cudaStreamSynchronize(s->stream)); /* exact_off is a host buffer of this scope */
+            for (void* ptr : work_bufs) CUDA_TRY(cudaFreeAsync(ptr, s->stream));
+            r->offsets.assign(exact_off.begin(), exact_off.end());
+        }
+        r->info.total_saved = (int64_t)r->offsets[N];
     }
     CUDA_TRY(cudaEventRecord(e1, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));

@@ -424,6 +424,47 @@ def test_smoother_register_and_shared_memory_sweeps_agree(monkeypatch):
     assert _rel(g["X"], r["X"]) < 1e-8
 
 
+@pytest.mark.parametrize("smooth", [False, True])
+def test_pilot_sized_single_save_pass_equals_two_pass(monkeypatch, smooth):
+    """Adaptive save_everystep solves of >= 1024 trajectories size their segments from a pilot run and do ONE full pass;
+    the result must be bit-identical to the counting-pass layout (PNODE_TWO_PASS=1), also when the pilot's estimate is too
+    small and the solve falls back (PNODE_PILOT_MARGIN_PCT=50), and with dense output on a saveat grid."""
+    n = 2048
+    pd, u0, p = _inputs("lotka_volterra", n, 61, du0=0.3, dp=0.3)
+    saveat = np.linspace(0.0, 10.0, 5)
+
+    def run():
+        cfg = lib.make_config(d=2, q=3, n_p=4, rhs_name="builtin:lotka_volterra", adaptive=True, t0=0.0, t1=10.0, smooth=smooth,
+                              save_everystep=True, saveat=saveat)
+        s = lib.Solver(cfg)
+        r = s.solve(u0, p)
+        out = {f: r.field(f) for f in (lib.F_STEP_OFFSETS, lib.F_T, lib.F_U, lib.F_U_COV, lib.F_DIFFUSIONS, lib.F_NACCEPT,
+                                       lib.F_U_FINAL, lib.F_SAVEAT_U, lib.F_SAVEAT_U_COV)}
+        out["launches"] = r.info.n_launches
+        out["saved"] = r.info.total_saved
+        r.free()
+        s.close()
+        return out
+
+    a = run()
+    monkeypatch.setenv("PNODE_TWO_PASS", "1")
+    b = run()
+    monkeypatch.delenv("PNODE_TWO_PASS")
+    monkeypatch.setenv("PNODE_PILOT_MARGIN_PCT", "50")
+    c = run()
+    assert len(set(np.diff(a[lib.F_STEP_OFFSETS]))) > 5                     # ragged
+    assert a["saved"] == b["saved"] == c["saved"] == int(a[lib.F_NACCEPT].sum()) + n
+    used = np.ones(a["saved"], dtype=bool)
+    used[a[lib.F_STEP_OFFSETS][1:] - 1] = False      # sol.diffusions has one entry per STEP: the last slot of a segment is unused
+    for other in (b, c):
+        for f in a:
+            if f == lib.F_DIFFUSIONS:
+                assert np.array_equal(a[f][used], other[f][used])
+            elif f not in ("launches", "saved"):
+                assert np.array_equal(a[f], other[f]), f
+    assert c["launches"] == b["launches"] != a["launches"]                   # the fallback ended on the counting-pass layout
+
+
 def test_smoother_properties_at_scale():
     """BASELINE cfg3 shape (Van der Pol mu ~ 1e3, EK1 order 5, adaptive) on 20 000 trajectories / 11.6 M saved points:
     size-independent properties of the RTS smoother -- identical time grids and final point with and without smoothing,
