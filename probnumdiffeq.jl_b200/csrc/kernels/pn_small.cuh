@@ -897,8 +897,15 @@ struct PnSmall {
                         for (int lr = 0; lr < RPL; lr++) {
                             const int row = lr * G + gl;
                             if (row < D) {
+                                double* dst = P.s_x_covfac + (save_pos * D + row) * D;
+                                if (D % 2 == 0) { /* 16-byte stores: the row start is a multiple of D doubles */
 #pragma unroll
-                                for (int c = 0; c < D; c++) P.s_x_covfac[(save_pos * D + row) * D + c] = R[lr][c];
+                                    for (int c = 0; c < D; c += 2)
+                                        *reinterpret_cast<double2*>(dst + c) = make_double2(R[lr][c], R[lr][(c + 1 < D) ? c + 1 : c]);
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < D; c++) dst[c] = R[lr][c];
+                                }
                             }
                         }
                     }
