@@ -296,6 +296,9 @@ def main():
                 # command at its default size (profiles/r1g_pn_small_rober_1m_traffic.txt); null for other workloads / sizes
                 "traffic": 191.1e6 if (args.workload == "rober" and n == (1 << 20)) else None,
                 "peak_source": "measured live by pnode_measure_fp64_peak (DFMA probe); MEASURED_PEAKS.json has no FP64 figure",
+                # for reference: 64 DFMA / clk / SM x 148 SMs x sm_max_mhz (the DFMA probe reaches ~91 % of it)
+                "peak_nominal": 2.0 * 64 * 148 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12,
+                "frac_of_nominal": achieved / (2.0 * 64 * 148 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12),
                 "algorithmic_flops_per_accepted_step": f_acc, "algorithmic_flops_per_rejected_step": f_rej,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / dur / 1e9, "peak_gbs": hbm_peak,
                         "frac": alg_bytes / dur / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"},
