@@ -26,8 +26,13 @@ __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_small_kernel(con
 #include "kernels/pn_kron.cuh"
 
 /* EK0 / IsometricKronecker: one thread per trajectory */
+/* order <= 3: 4 CTAs of 128 threads per SM (<= 128 registers, 4 warps per scheduler): +9 % over the unconstrained 152
+   registers / 3 warps on cfg2; higher orders need the registers */
+#ifndef PN_KRON_MIN_BLOCKS
+#define PN_KRON_MIN_BLOCKS(Q) ((Q) <= 3 ? 4 : 1)
+#endif
 template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
-__global__ void __launch_bounds__(128) pn_kron_kernel(const __grid_constant__ PnParams P) {
+__global__ void __launch_bounds__(128, PN_KRON_MIN_BLOCKS(Q)) pn_kron_kernel(const __grid_constant__ PnParams P) {
     pn_kron_entry<Prob, Q, ADAPTIVE, DYNAMIC, SAVE>(P);
 }
 

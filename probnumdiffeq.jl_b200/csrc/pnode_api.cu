@@ -371,7 +371,7 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
         src += "\nextern \"C\" __global__ void __launch_bounds__(PN_CTA_THREADS, 1) pn_entry(const __grid_constant__ PnParams P) {\n"
                "  pn_cta_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
     else if (kron)
-        src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS) pn_entry(const __grid_constant__ PnParams P) {\n"
+        src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS, PN_KRON_MIN_BLOCKS(PN_Q)) pn_entry(const __grid_constant__ PnParams P) {\n"
                "  pn_kron_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
     else
         src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_entry(const "
