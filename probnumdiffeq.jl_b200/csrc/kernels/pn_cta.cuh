@@ -324,21 +324,25 @@ struct PnCta {
                 for (int i = tid; i < d; i += NT) z[i] = mup[d + i] - fu[i];
                 if (tid == 0) sh->nf += 1;
                 if (ADAPTIVE || DYNAMIC) {
-                    /* W = C'C, C[(m,i),a] = -LQ[m][0] J[a][i] + (i==a) LQ[m][1]   (calibration.jl:123-133) */
-                    for (int e = tid; e < d * d; e += NT) {
-                        const int a = e / d, b = e - a * d;
-                        if (b < a) continue;
-                        double s = 0.0;
+                    /* W = C'C, C[(m,i),a] = -LQ[m][0] J[a][i] + (i==a) LQ[m][1]   (calibration.jl:123-133); summed over m in
+                       closed form: W = alpha J J' - beta (J + J') + gamma I with alpha = sum LQ[m][0]^2, beta = sum LQ[m][0] LQ[m][1],
+                       gamma = sum LQ[m][1]^2 */
+                    {
+                        double al = 0.0, be = 0.0, ga = 0.0;
                         for (int m = 0; m < n; m++) {
                             const double l0 = P.L[m * n + 0] * sh->PIv[0];
                             const double l1 = (m >= 1) ? P.L[m * n + 1] * sh->PIv[1] : 0.0;
-                            for (int i = 0; i < d; i++) {
-                                const double ca = -l0 * J[a + d * i] + ((i == a) ? l1 : 0.0);
-                                const double cb = -l0 * J[b + d * i] + ((i == b) ? l1 : 0.0);
-                                s += ca * cb;
-                            }
+                            al += l0 * l0;
+                            be += l0 * l1;
+                            ga += l1 * l1;
                         }
-                        S[a * d + b] = s;
+                        for (int e = tid; e < d * d; e += NT) {
+                            const int a = e / d, b = e - a * d;
+                            if (b < a) continue;
+                            double jj = 0.0;
+                            for (int i = 0; i < d; i++) jj += J[a + d * i] * J[b + d * i];
+                            S[a * d + b] = al * jj - be * (J[a + d * b] + J[b + d * a]) + ((a == b) ? ga : 0.0);
+                        }
                     }
                     __syncthreads();
                     for (int i = tid; i < d; i += NT) {
