@@ -424,8 +424,8 @@ def test_smoother_register_and_shared_memory_sweeps_agree(monkeypatch):
     assert _rel(g["X"], r["X"]) < 1e-8
 
 
-@pytest.mark.parametrize("smooth", [False, True])
-def test_pilot_sized_single_save_pass_equals_two_pass(monkeypatch, smooth):
+@pytest.mark.parametrize("smooth,diffusion", [(False, lib.DIFF_DYNAMIC), (True, lib.DIFF_DYNAMIC), (True, lib.DIFF_FIXED)])
+def test_pilot_sized_single_save_pass_equals_two_pass(monkeypatch, smooth, diffusion):
     """Adaptive save_everystep solves of >= 1024 trajectories size their segments from a pilot run and do ONE full pass;
     the result must be bit-identical to the counting-pass layout (PNODE_TWO_PASS=1), also when the pilot's estimate is too
     small and the solve falls back (PNODE_PILOT_MARGIN_PCT=50), and with dense output on a saveat grid."""
@@ -435,7 +435,7 @@ def test_pilot_sized_single_save_pass_equals_two_pass(monkeypatch, smooth):
 
     def run():
         cfg = lib.make_config(d=2, q=3, n_p=4, rhs_name="builtin:lotka_volterra", adaptive=True, t0=0.0, t1=10.0, smooth=smooth,
-                              save_everystep=True, saveat=saveat)
+                              save_everystep=True, saveat=saveat, diffusion=diffusion)
         s = lib.Solver(cfg)
         r = s.solve(u0, p)
         out = {f: r.field(f) for f in (lib.F_STEP_OFFSETS, lib.F_T, lib.F_U, lib.F_U_COV, lib.F_DIFFUSIONS, lib.F_NACCEPT,
