@@ -13,6 +13,7 @@ test/state_init.jl:9-56).
 from __future__ import annotations
 
 import ctypes as C
+import fcntl
 import hashlib
 import os
 import subprocess
@@ -56,15 +57,22 @@ def build(force: bool = False, variant: str = "") -> str:
     lib_path = _LIB_PATH if not variant else os.path.join(_HERE, f"liboracle_{variant}.so")
     stamp_path = lib_path[:-3] + ".stamp"
     stamp = _stamp()
-    if not force and os.path.exists(lib_path) and os.path.exists(stamp_path) and open(stamp_path).read() == stamp:
-        return lib_path
-    contract = "-ffp-contract=fast" if variant == "fma" else "-ffp-contract=off"
-    cmd = ["gcc", "-O3", "-march=native", "-mfma", "-fno-fast-math", contract, "-fopenmp", "-fPIC", "-shared",
-           "-o", lib_path, src, "-lm"]
-    subprocess.run(cmd, check=True, cwd=_HERE)
-    with open(stamp_path, "w") as fh:
-        fh.write(stamp)
-    return lib_path
+    with open(lib_path[:-3] + ".lock", "w") as lock:  # several ranks / pytest-xdist workers may build at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and os.path.exists(lib_path) and os.path.exists(stamp_path) and open(stamp_path).read() == stamp:
+                return lib_path
+            contract = "-ffp-contract=fast" if variant == "fma" else "-ffp-contract=off"
+            tmp = lib_path + f".tmp{os.getpid()}"
+            cmd = ["gcc", "-O3", "-march=native", "-mfma", "-fno-fast-math", contract, "-fopenmp", "-fPIC", "-shared",
+                   "-o", tmp, src, "-lm"]
+            subprocess.run(cmd, check=True, cwd=_HERE)
+            os.replace(tmp, lib_path)
+            with open(stamp_path, "w") as fh:
+                fh.write(stamp)
+            return lib_path
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 class Config(C.Structure):

@@ -318,8 +318,29 @@ struct PnCta {
                 }
                 __syncthreads();
                 /* measurement: f on one thread, J on another warp */
-                if (tid == 0) Prob::template f<double>(fu, mup, pr, sh->tnew);
-                if (tid == 32) Prob::jac(J, mup, pr, sh->tnew);
+                /* f and J in Prob::jac_parts independent slices (rows a == k mod jac_parts), slice k on the first lane of warp k */
+                {
+                    constexpr int JP = Prob::jac_parts;
+                    static_assert(JP >= 1 && JP <= NT / 32, "jac_parts must not exceed the number of warps of the CTA");
+                    if (JP == 1) { /* default: f on one thread, J on a thread of another warp */
+                        if (tid == 0) Prob::template f<double>(fu, mup, pr, sh->tnew);
+                        if (tid == 32) Prob::jac(J, mup, pr, sh->tnew);
+                    }
+#define PN_CTA_RHS_SLICE(K)                                                              \
+    if (JP > 1 && JP > K && tid == 32 * K) {                                                  \
+        Prob::template f_part<(JP > K ? K : 0)>(fu, mup, pr, sh->tnew);                  \
+        Prob::template jac_part<(JP > K ? K : 0)>(J, mup, pr, sh->tnew);                 \
+    }
+                    PN_CTA_RHS_SLICE(0)
+                    PN_CTA_RHS_SLICE(1)
+                    PN_CTA_RHS_SLICE(2)
+                    PN_CTA_RHS_SLICE(3)
+                    PN_CTA_RHS_SLICE(4)
+                    PN_CTA_RHS_SLICE(5)
+                    PN_CTA_RHS_SLICE(6)
+                    PN_CTA_RHS_SLICE(7)
+#undef PN_CTA_RHS_SLICE
+                }
                 __syncthreads();
                 for (int i = tid; i < d; i += NT) z[i] = mup[d + i] - fu[i];
                 if (tid == 0) sh->nf += 1;

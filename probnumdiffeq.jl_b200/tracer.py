@@ -152,8 +152,11 @@ def _emit_block(exprs: Sequence[sp.Expr], targets: Sequence[str], scalar: str, p
     return "\n".join(lines)
 
 
-def cuda_source(tr: TracedRHS, struct_name: str = "PnodeUserProblem") -> str:
-    """CUDA C++ source defining ``struct <struct_name>`` with static ``d``, ``n_p``, ``f<T>`` and ``jac``.
+def cuda_source(tr: TracedRHS, struct_name: str = "PnodeUserProblem", jac_parts: int = 0) -> str:
+    """CUDA C++ source defining ``struct <struct_name>`` with static ``d``, ``n_p``, ``f<T>``, ``jac`` and
+    ``f_part<PART>`` / ``jac_part<PART>`` (``jac_parts`` independent slices of f and of the Jacobian, each with its own common
+    subexpressions, so that the CTA-per-trajectory kernel can evaluate a large right-hand side on several threads at once;
+    0 = automatic = 1: on Pleiades, d = 28, slices were slower than one thread each for f and J).
 
     This is the string handed to ``pnode_config.rhs_src`` and compiled by NVRTC for sm_100a together
     with the step kernels (csrc/kernels/*.cuh)."""
@@ -161,23 +164,70 @@ def cuda_source(tr: TracedRHS, struct_name: str = "PnodeUserProblem") -> str:
     rep = _subs_arrays(tr)
     fex = [e.xreplace(rep) for e in tr.f]
     J = tr.jacobian()
-    jex, jt = [], []
-    for i in range(tr.d):          # column i
-        for a in range(tr.d):      # row a
-            jex.append(J[a, i].xreplace(rep))
-            jt.append(f"J[{a + tr.d * i}]")
+    if jac_parts <= 0:
+        jac_parts = 1   # measured on Pleiades (d = 28): slicing f / J over the warps of the CTA kernel does not pay (i-cache)
     fbody = _emit_block(fex, [f"du[{i}]" for i in range(tr.d)], "T", pr, "x")
-    jbody = _emit_block(jex, jt, "double", pr, "y")
+    fparts = []
+    for k in range(jac_parts):
+        idx = [a for a in range(tr.d) if a % jac_parts == k]
+        body = _emit_block([fex[a] for a in idx], [f"du[{a}]" for a in idx], "double", pr, f"x{k}_").replace("\n    ", "\n      ")
+        fparts.append(f"    {'if' if k == 0 else 'else if'} constexpr (PART == {k}) {{\n  {body}\n    }}")
+    fpbody = "\n".join(fparts)
+    parts = []
+    for k in range(jac_parts):
+        jex, jt = [], []
+        for a in range(tr.d):          # row a: rows are dealt round-robin, a row shares the most subexpressions
+            if a % jac_parts != k:
+                continue
+            for i in range(tr.d):      # column i
+                jex.append(J[a, i].xreplace(rep))
+                jt.append(f"J[{a + tr.d * i}]")
+        body = _emit_block(jex, jt, "double", pr, f"y{k}_").replace("\n    ", "\n      ")
+        parts.append(f"    {'if' if k == 0 else 'else if'} constexpr (PART == {k}) {{\n  {body}\n    }}")
+    pbody = "\n".join(parts)
+    calls = "\n".join(f"    jac_part<{k}>(J, u, p, t);" for k in range(jac_parts))
     return f"""// generated by probnumdiffeq.jl_b200/tracer.py -- do not edit
 struct {struct_name} {{
   static constexpr int d = {tr.d};
   static constexpr int n_p = {tr.n_p};
+  static constexpr int jac_parts = {jac_parts};
   template <class T>
   __device__ __forceinline__ static void f(T* du, const T* u, const double* p, const T& t) {{
 {fbody}
   }}
+  // components a == PART (mod jac_parts) of f, double precision (the CTA-per-trajectory kernel spreads f and J over warps)
+  template <int PART>
+  __device__ __forceinline__ static void f_part(double* du, const double* u, const double* p, double t) {{
+{fpbody}
+  }}
+  // rows a == PART (mod jac_parts) of J (column-major, J[a + d*i] = d f_a / d u_i)
+  template <int PART>
+  __device__ __forceinline__ static void jac_part(double* J, const double* u, const double* p, double t) {{
+{pbody}
+  }}
   __device__ __forceinline__ static void jac(double* J, const double* u, const double* p, double t) {{
-{jbody}
+{calls}
   }}
 }};
 """
+
+
+BUILTIN_STRUCTS = {"fitzhugh_nagumo": "PnFitzHughNagumo", "lotka_volterra": "PnLotkaVolterra", "vanderpol": "PnVanDerPol",
+                   "rober": "PnRober", "orego": "PnOrego", "pleiades": "PnPleiades"}
+
+
+def builtin_header() -> str:
+    """csrc/kernels/pn_builtin_problems.cuh: the problems BASELINE.json names (problems.py), traced ahead of time."""
+    from . import problems
+
+    out = ["// pn_builtin_problems.cuh -- generated by probnumdiffeq.jl_b200/tracer.py from problems.py; do not edit.",
+           "// (regenerate: python scripts/gen_builtin_problems.py)",
+           '// Built-in right-hand sides named by BASELINE.json (rhs_name = "builtin:<name>").',
+           "#ifndef PN_BUILTIN_PROBLEMS_CUH", "#define PN_BUILTIN_PROBLEMS_CUH", '#include "pn_taylor.cuh"', ""]
+    for name, sname in BUILTIN_STRUCTS.items():
+        pd = problems.PROBLEMS[name]
+        src = cuda_source(trace(pd.f, pd.d, pd.n_p), sname)
+        out.append(f"// builtin:{name}")
+        out.append(src.split("\n", 1)[1])
+    out.append("#endif /* PN_BUILTIN_PROBLEMS_CUH */")
+    return "\n".join(out) + "\n"
