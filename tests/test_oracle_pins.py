@@ -464,3 +464,50 @@ def test_dense_output_interpolation(oracle):
         assert np.allclose(mk, s["pu_mu"][k], rtol=1e-6)
         if smooth:
             assert np.allclose(ck, s["pu_cov"][k], rtol=1e-3, atol=1e-300)
+
+
+def test_diffusion_models_accuracy(oracle):
+    """test/diffusions.jl:8-84: every diffusion model with the EK0 at dt = 1e-3 on FitzHugh-Nagumo reaches a final error
+    below 1e-5 (DynamicDiffusion, FixedDiffusion, FixedDiffusion(1e3, false), DynamicMVDiffusion, FixedMVDiffusion,
+    FixedMVDiffusion(initial, false))."""
+    f, u0, p = _CASES["fitzhughnagumo"]
+    ref = _truth(f, u0, p)
+    tr = tracer.trace(f, 2, 4)
+    rhs = oracle.compile_rhs(tr, 3)
+    for diff, kw in ((oracle.DIFF_DYNAMIC, {}), (oracle.DIFF_FIXED, {}), (oracle.DIFF_FIXED, dict(initial_diffusion=1e3, calibrate=False)),
+                     (oracle.DIFF_DYNAMIC_MV, {}), (oracle.DIFF_FIXED_MV, {}),
+                     (oracle.DIFF_FIXED_MV, dict(initial_diffusion=1.7, calibrate=False))):
+        s = oracle.solve(oracle.make_config(2, 3, 4, alg=oracle.EK0, diffusion=diff, smooth=False, adaptive=False, dt=1e-3, t0=0, t1=1,
+                                            save_everystep=False, **kw), rhs, u0, p)
+        assert s["retcode"] == "Success"
+        assert np.mean(np.abs(s["pu_mu"][-1] - ref)) < 1e-5, (diff, kw)
+
+
+def test_stiff_vanderpol(oracle):
+    """test/stiff_problem.jl:7-15: EK1(order=3) and DiagonalEK1(order=3), adaptive with default tolerances, on the stiff
+    Van der Pol problem (ODEProblemLibrary prob_ode_vanderpol_stiff, third party: mu = 1e6, u0 = (sqrt 3, 0) in (x, y) order,
+    t in [0, 1] as recalled) agree with an implicit reference solution to rtol 5e-3 at the end point and -- through the dense
+    output -- at t = 0.5."""
+    def vdp(du, u, p, t):
+        du[0] = u[1]
+        du[1] = p[0] * ((1 - u[0] * u[0]) * u[1] - u[0])
+
+    mu, u0 = 1e6, [np.sqrt(3.0), 0.0]
+
+    def fn(t, u):
+        return [u[1], mu * ((1 - u[0] ** 2) * u[1] - u[0])]
+
+    def jac(t, u):
+        return [[0.0, 1.0], [mu * (-2 * u[0] * u[1] - 1), mu * (1 - u[0] ** 2)]]
+
+    truth = solve_ivp(fn, (0, 1), u0, method="Radau", jac=jac, rtol=1e-10, atol=1e-12, dense_output=True)
+    tr = tracer.trace(vdp, 2, 1)
+    rhs = oracle.compile_rhs(tr, 3)
+    for alg in (oracle.EK1, oracle.DIAGONAL_EK1):
+        cfg = oracle.make_config(2, 3, 1, alg=alg, smooth=True, adaptive=True, t0=0, t1=1)
+        s = oracle.solve(cfg, rhs, u0, [mu])
+        assert s["retcode"] == "Success"
+        assert np.allclose(s["pu_mu"][-1], truth.y[:, -1], rtol=5e-3, atol=0) or \
+            np.linalg.norm(s["pu_mu"][-1] - truth.y[:, -1]) <= 5e-3 * np.linalg.norm(truth.y[:, -1])
+        m, _ = oracle.interpolate(cfg, s, 0.5)
+        assert np.linalg.norm(m - truth.sol(0.5)) <= 5e-3 * np.linalg.norm(truth.sol(0.5))
