@@ -511,3 +511,43 @@ def test_stiff_vanderpol(oracle):
             np.linalg.norm(s["pu_mu"][-1] - truth.y[:, -1]) <= 5e-3 * np.linalg.norm(truth.y[:, -1])
         m, _ = oracle.interpolate(cfg, s, 0.5)
         assert np.linalg.norm(m - truth.sol(0.5)) <= 5e-3 * np.linalg.norm(truth.sol(0.5))
+
+
+def test_ioup_damped_oscillator(oracle):
+    """test/ioup.jl:7-18,50-56: on u' = A u (A = [-a -2pi; 2pi -a], a = 0.1, t in [0, 2]) the adaptive EK1 with the IWP
+    reaches |error| < 1e-5 at the end point, and with the scalar-rate prior IOUP(3, -a) < 6e-6."""
+    a = 1e-1
+
+    def osc(du, u, p, t):
+        du[0] = -p[0] * u[0] - 2 * np.pi * u[1]
+        du[1] = 2 * np.pi * u[0] - p[0] * u[1]
+
+    tr = tracer.trace(osc, 2, 1)
+    rhs = oracle.compile_rhs(tr, 3)
+    A = np.array([[-a, -2 * np.pi], [2 * np.pi, -a]])
+    w, V = np.linalg.eig(A)
+    exact = np.real(V @ np.diag(np.exp(2.0 * w)) @ np.linalg.solve(V, np.array([1.0, 1.0])))
+    s = oracle.solve(oracle.make_config(2, 3, 1, alg=oracle.EK1, smooth=True, adaptive=True, t0=0, t1=2), rhs, [1.0, 1.0], [a])
+    assert np.linalg.norm(s["pu_mu"][-1] - exact) < 1e-5
+    s = oracle.solve(oracle.make_config(2, 3, 1, alg=oracle.EK1, smooth=True, adaptive=True, t0=0, t1=2, prior=oracle.PRIOR_IOUP,
+                                        rate_parameter=-a), rhs, [1.0, 1.0], [a])
+    assert np.linalg.norm(s["pu_mu"][-1] - exact) < 6e-6
+
+
+@pytest.mark.parametrize("q", [1, 2, 3, 4])
+def test_convergence_order(oracle, q):
+    """test/convergence.jl:19-28: on u' = 1.01 u, u0 = 1/2 the fixed-step EK0 of order q converges with order q + 1
+    (estimated from dt = 2^-7 ... 2^-4, tolerance 0.3 as in the reference, which runs it in BigFloat)."""
+    def lin(du, u, p, t):
+        du[0] = p[0] * u[0]
+
+    tr = tracer.trace(lin, 1, 1)
+    rhs = oracle.compile_rhs(tr, q)
+    dts = [0.5 ** k for k in (7, 6, 5, 4)]
+    errs = []
+    for dt in dts:
+        s = oracle.solve(oracle.make_config(1, q, 1, alg=oracle.EK0, smooth=False, adaptive=False, dt=dt, t0=0, t1=1, save_everystep=False),
+                         rhs, [0.5], [1.01])
+        errs.append(abs(s["pu_mu"][-1][0] - 0.5 * np.exp(1.01)))
+    orders = [np.log2(errs[i + 1] / errs[i]) for i in range(len(dts) - 1)]
+    assert abs(np.mean(orders) - (q + 1)) < 0.3, (errs, orders)
