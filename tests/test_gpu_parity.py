@@ -254,6 +254,35 @@ def test_edge_cases(oracle):
     assert np.array_equal(sol[0].u[0], [1.0, 1.0]) and not sol[0].pu_cov[0].any()      # test/solution.jl:59-62
 
 
+@pytest.mark.parametrize("alg", [lib.EK0, lib.EK1])
+def test_scalar_problem_convergence_orders(oracle, alg):
+    """test/convergence.jl:19-46 on the device: d = 1 (the smallest state the kernels are instantiated for), u' = 1.01 u,
+    orders 1..4, fixed steps 2^-7 ... 2^-4: convergence order q + 1 within 0.3 and agreement with the oracle."""
+    def lin(du, u, p, t):
+        du[0] = p[0] * u[0]
+
+    tr = tracer.trace(lin, 1, 1)
+    src = tracer.cuda_source(tr, "UserProb")
+    u0, p = np.array([[0.5]]), np.array([[1.01]])
+    for q in (1, 2, 3, 4):
+        rhs = oracle.compile_rhs(tr, q)
+        errs = []
+        for k in (7, 6, 5, 4):
+            dt = 0.5 ** k
+            cfg = lib.make_config(d=1, q=q, n_p=1, rhs_name="UserProb", rhs_src=src, alg=alg, adaptive=False, dt=dt, t0=0.0, t1=1.0)
+            s = lib.Solver(cfg)
+            r = s.solve(u0, p)
+            uf = r.field(lib.F_U_FINAL)[0]
+            r.free()
+            s.close()
+            o = oracle.solve(oracle.make_config(1, q, 1, alg=alg, smooth=False, adaptive=False, dt=dt, t0=0, t1=1, save_everystep=False,
+                                                cov_backend=oracle.COV_QR), rhs, [0.5], [1.01])
+            assert abs(uf - o["pu_mu"][-1][0]) <= 1e-9 * abs(uf)
+            errs.append(abs(uf - 0.5 * np.exp(1.01)))
+        orders = [np.log2(errs[i + 1] / errs[i]) for i in range(3)]
+        assert abs(np.mean(orders) - (q + 1)) < 0.3, (q, errs)
+
+
 def test_full_size_properties_rober_1m():
     """BASELINE cfg5 at full size (2^20 trajectories): properties that need no oracle."""
     n = 1 << 20
