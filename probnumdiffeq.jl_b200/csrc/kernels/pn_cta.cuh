@@ -30,6 +30,16 @@
 
 #define PN_CTA_THREADS 256
 
+/* number of independent slices the problem struct offers for f / J (tracer.py, jac_parts); 1 if it does not say */
+template <class P, class = void>
+struct PnJacParts {
+    static constexpr int value = 1;
+};
+template <class P>
+struct PnJacParts<P, decltype((void)P::jac_parts)> {
+    static constexpr int value = P::jac_parts;
+};
+
 struct PnCtaShared {
     double red[PN_CTA_THREADS / 32];
     double hp[PN_MAX_N], PIv[PN_MAX_N];
@@ -320,7 +330,7 @@ struct PnCta {
                 /* measurement: f on one thread, J on another warp */
                 /* f and J in Prob::jac_parts independent slices (rows a == k mod jac_parts), slice k on the first lane of warp k */
                 {
-                    constexpr int JP = Prob::jac_parts;
+                    constexpr int JP = PnJacParts<Prob>::value;
                     static_assert(JP >= 1 && JP <= NT / 32, "jac_parts must not exceed the number of warps of the CTA");
                     if (JP == 1) { /* default: f on one thread, J on a thread of another warp */
                         if (tid == 0) Prob::template f<double>(fu, mup, pr, sh->tnew);
@@ -331,6 +341,7 @@ struct PnCta {
         Prob::template f_part<(JP > K ? K : 0)>(fu, mup, pr, sh->tnew);                  \
         Prob::template jac_part<(JP > K ? K : 0)>(J, mup, pr, sh->tnew);                 \
     }
+                    if constexpr (JP > 1) {
                     PN_CTA_RHS_SLICE(0)
                     PN_CTA_RHS_SLICE(1)
                     PN_CTA_RHS_SLICE(2)
@@ -339,6 +350,7 @@ struct PnCta {
                     PN_CTA_RHS_SLICE(5)
                     PN_CTA_RHS_SLICE(6)
                     PN_CTA_RHS_SLICE(7)
+                    }
 #undef PN_CTA_RHS_SLICE
                 }
                 __syncthreads();

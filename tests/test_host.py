@@ -114,6 +114,25 @@ def test_nvrtc_compiles_smoother_and_dense_output_kernels(pnlib, monkeypatch):
     assert "Invalid t<t0" in str(e.value)
 
 
+def test_hand_written_problem_struct_compiles_for_every_kernel(pnlib):
+    """The ABI takes CUDA C++ source: a minimal struct (static d, n_p, f<T>, jac -- what the Julia host's Symbolics tracer
+    emits, without the optional f_part / jac_part slices) must compile for the group-per-trajectory, the
+    thread-per-trajectory and the CTA-per-trajectory kernels."""
+    src = """
+struct Mini {
+  static constexpr int d = 2; static constexpr int n_p = 1;
+  template <class T> __device__ __forceinline__ static void f(T* du, const T* u, const double* p, const T& t) {
+    du[0] = u[1]; du[1] = -p[0] * u[0];
+  }
+  __device__ __forceinline__ static void jac(double* J, const double* u, const double* p, double t) {
+    J[0] = 0.0; J[1] = -p[0]; J[2] = 1.0; J[3] = 0.0;
+  }
+};"""
+    base = dict(d=2, q=3, n_p=1, rhs_name="Mini", rhs_src=src, t0=0.0, t1=1.0)
+    for kw in (dict(), dict(alg=pnlib.EK0), dict(alg=pnlib.DIAGONAL_EK1), dict(lanes_per_traj=256)):
+        assert pnlib.compile_check(pnlib.make_config(**{**base, **kw})) > 10_000
+
+
 def test_tracer_matches_python_rhs():
     for name, pd in problems.PROBLEMS.items():
         tr = tracer.trace(pd.f, pd.d, pd.n_p)
