@@ -121,13 +121,16 @@ PN_HD void pn_chol_solve(const double (&U)[M_][M_], const double (&invd)[M_], do
 // entries left of its first row are never touched.  On return Tt[:, 0:NE] is the upper-triangular factor (zeros
 // below the diagonal); if dinv != nullptr lane (k % G) stores 1/diag[k] (0 for a zero column) to dinv[k].
 // The j loop is chunked (JC columns at a time) to bound the number of live partial sums.
+// live = false (per group): every reflector is the identity and the matrix is left untouched bit for bit -- the shuffles
+// still run for the whole warp; used for groups with nothing to commit, so that a trajectory's arithmetic never depends on
+// which other trajectories happen to share its warp.
 // Householder scalars of one pivot column
 struct PnHouse {
     double beta, vk, gam, binv;
 };
 // norm, pivot broadcast and reflector scalars of column k of the stack (rows >= k of the top block, active bottom slots)
 template <int G, int RPL, int NC, bool BOTUP>
-PN_HD PnHouse pn_qr_house(const double (&Tt)[RPL][NC], const double (&Bt)[RPL][NC], int gl, int k) {
+PN_HD PnHouse pn_qr_house(const double (&Tt)[RPL][NC], const double (&Bt)[RPL][NC], int gl, int k, bool live) {
     const int ks = k / G, kl = k % G;
     double part = 0.0, xp = 0.0;
 #pragma unroll
@@ -149,16 +152,16 @@ PN_HD PnHouse pn_qr_house(const double (&Tt)[RPL][NC], const double (&Bt)[RPL][N
     PnHouse h;
     h.beta = -copysign(nrm, alpha);
     h.vk = alpha - h.beta;
-    h.gam = nz ? pn_rcp(total + fabs(alpha) * nrm) : 0.0; /* 2 / v'v */
+    h.gam = (nz && live) ? pn_rcp(total + fabs(alpha) * nrm) : 0.0; /* 2 / v'v; 0: the reflector is the identity */
     h.binv = nz ? -copysign(rsq, alpha) : 0.0;
     return h;
 }
 
 template <int G, int RPL, int NC, int NE, bool BOTUP, int JC>
-PN_HD void pn_qr_rows(double (&Tt)[RPL][NC], double (&Bt)[RPL][NC], int gl, double* dinv) {
+PN_HD void pn_qr_rows(double (&Tt)[RPL][NC], double (&Bt)[RPL][NC], int gl, double* dinv, bool live = true) {
     /* software-pipelined: the scalars of pivot k+1 (butterfly, rsqrt, rcp: a ~200-cycle dependent chain) are started
        right after reflector k has updated column k+1, so the chain runs under the updates of columns k+2... */
-    PnHouse hs = pn_qr_house<G, RPL, NC, BOTUP>(Tt, Bt, gl, 0);
+    PnHouse hs = pn_qr_house<G, RPL, NC, BOTUP>(Tt, Bt, gl, 0, live);
 #pragma unroll
     for (int k = 0; k < NE; k++) {
         const int ks = k / G, kl = k % G;
@@ -195,7 +198,7 @@ PN_HD void pn_qr_rows(double (&Tt)[RPL][NC], double (&Bt)[RPL][NC], int gl, doub
             for (int lr = 0; lr < RPL; lr++)
                 if (!BOTUP || lr * G <= k) Bt[lr][j] -= s * Bt[lr][k];
         }
-        if (k + 1 < NE) hs = pn_qr_house<G, RPL, NC, BOTUP>(Tt, Bt, gl, k + 1);
+        if (k + 1 < NE) hs = pn_qr_house<G, RPL, NC, BOTUP>(Tt, Bt, gl, k + 1, live);
 #pragma unroll
         for (int j0 = 0; j0 < NC; j0 += JC) {
             if (j0 + JC - 1 <= k + 1) continue;
@@ -237,8 +240,12 @@ PN_HD void pn_qr_rows(double (&Tt)[RPL][NC], double (&Bt)[RPL][NC], int gl, doub
             const int base = lr * G;
             if (base + G - 1 < k) continue;
             const int row = base + gl;
-            if (row == k) Tt[lr][k] = hk.beta;
-            else if (row > k) Tt[lr][k] = 0.0;
+            { /* a group that is not live keeps its matrix bit for bit (gam = 0 above); selects, not branches: the
+                 predicated form made ptxas demote the row arrays to local memory */
+                const double keep = Tt[lr][k];
+                const double fin = (row == k) ? hk.beta : ((row > k) ? 0.0 : keep);
+                Tt[lr][k] = live ? fin : keep;
+            }
         }
     }
 }
@@ -507,7 +514,15 @@ struct PnSmall {
 #pragma unroll
             for (int i = 0; i < d * d; i++) J[i] = 0.0;
 
+            /* ONE attempt per iteration of the warp's loop: a group whose step is rejected sits out phase 2 (identity
+               step) and retries in the next iteration.  Retrying inside this phase instead (PN_RETRY_IN_PHASE1) keeps the
+               other groups of the warp waiting and -- worse -- lets the warps of the CTA drift apart in the ~100 KB
+               unrolled body: on OREGO (9 % rejections) a quarter of the issue slots were instruction-fetch stalls. */
+#ifdef PN_RETRY_IN_PHASE1
             while (!finished && !accept) {
+#else
+            for (int attempt = 0; attempt < 1 && !finished; attempt++) {
+#endif
                 double q11 = 0.0;
                 while (tstop_idx < P.n_tstops && P.tstops[tstop_idx] <= t) tstop_idx++;
                 tstop = P.t1;
@@ -675,7 +690,11 @@ struct PnSmall {
             }
 
             /* ============ (C) phase 2: covariance predict + update (warp-convergent) ============ */
-            if (__any_sync(FULL, accept)) {
+            /* Phase 2 runs in EVERY iteration, also for a warp in which no group accepted: a group without an accepted
+               step takes the identity step (R <- qr(R), same R'R), and it does so after each of ITS OWN rejections --
+               never depending on what the other trajectories of the warp did.  That keeps every trajectory's arithmetic
+               a function of its own history only (bit-reproducible runs; the counting and the save pass agree). */
+            {
                 double B[RPL][D];
                 /* top block: X = R Ah'  (row-local; ascending j is safe in place) */
 #pragma unroll
