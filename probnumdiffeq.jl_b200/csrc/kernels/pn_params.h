@@ -28,6 +28,10 @@ struct PnParams {
     /* work item idx of the queue is trajectory idx * traj_stride (1 for a normal solve; > 1 for the step-count pilot that
        sizes the save buffers from a strided subsample of the ensemble) */
     long long traj_stride;
+    /* initial states computed by pn_init_kernel before the step kernel starts (group-per-trajectory path): exact initial
+       derivatives mu0[n_traj][D] and the initial step dt0[n_traj]; null: the step kernel initialises in line */
+    const double* init_mu;
+    const double* init_dt;
     /* dynamic work queue */
     unsigned long long* work_counter;
     /* IWP constants (src/priors/iwp.jl:74-108), row-major n x n, host-computed */

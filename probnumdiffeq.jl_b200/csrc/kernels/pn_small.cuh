@@ -427,16 +427,17 @@ struct PnSmall {
                     } else {
                         traj = (long long)idx * P.traj_stride;
                         {
-                            InitOut io; /* lives in local memory; copied to registers below */
-                            init_trajectory(P, traj, io);
+                            /* initial state: computed for the whole ensemble by pn_init_kernel before this kernel started
+                               (TaylorModeInit + initial step; one thread per trajectory, off the persistent loop's
+                               critical path -- in line it cost ~3 % of the ROBER run and a local-memory frame) */
 #pragma unroll
-                            for (int c = 0; c < D; c++) mu[c] = io.mu[c];
+                            for (int c = 0; c < D; c++) mu[c] = P.init_mu[traj * D + c];
 #pragma unroll
-                            for (int i = 0; i < NPA; i++) pr[i] = io.pr[i];
+                            for (int i = 0; i < NPA; i++) pr[i] = (i < Prob::n_p) ? P.p[traj * Prob::n_p + i] : 0.0;
 #pragma unroll
-                            for (int i = 0; i < d; i++) uprev[i] = io.mu[i];
-                            dt = io.dt;
-                            nf = io.nf;
+                            for (int i = 0; i < d; i++) uprev[i] = mu[i];
+                            dt = P.init_dt[traj];
+                            nf = Q + ((ADAPTIVE && !(P.dt0 > 0.0)) ? 2 : 0);
                             t = P.t0;
                         }
 #pragma unroll
@@ -993,40 +994,30 @@ struct PnSmall {
         }
     }
 
-    /* initial state + initial step (cold path, once per trajectory) */
-    struct InitOut {
-        double mu[D];
-        double pr[NPA];
-        double dt;
-        long long nf;
-    };
-    static __device__ __noinline__ void init_trajectory(const PnParams& P, long long traj, InitOut& io) {
-        double u0[d];
-        double mu[D], pr[NPA], dt;
-        long long nf;
+};
+
+// Initial state + initial step of every trajectory, one thread each (launched before the persistent step kernel):
+// exact initial derivatives (TaylorModeInit, autodiffinit.jl:52-67; Sigma0.R = 0) and
+// ode_determine_initdt (when adaptive and no dt is given).
+template <class Prob, int Q, bool ADAPTIVE>
+__device__ __forceinline__ void pn_init_entry(const PnParams& P, double* init_mu, double* init_dt) {
+    constexpr int d = Prob::d, D = d * (Q + 1), NPA = Prob::n_p > 0 ? Prob::n_p : 1;
+    for (long long traj = blockIdx.x * (long long)blockDim.x + threadIdx.x; traj < P.n_traj;
+         traj += (long long)gridDim.x * blockDim.x) {
+        double u0[d], mu[D], pr[NPA];
 #pragma unroll
         for (int i = 0; i < NPA; i++) pr[i] = 0.0;
 #pragma unroll
         for (int i = 0; i < d; i++) u0[i] = P.u0[traj * d + i];
 #pragma unroll
         for (int i = 0; i < Prob::n_p; i++) pr[i] = P.p[traj * Prob::n_p + i];
-        /* exact initial derivatives (TaylorModeInit, autodiffinit.jl:52-67); Sigma0.R = 0 */
         pn_taylor_init<Prob, Q>(mu, u0, pr, P.t0);
-        nf = Q;
-        if (ADAPTIVE && !(P.dt0 > 0.0)) {
-            dt = pn_initial_dt<Prob>(P, u0, pr);
-            nf += 2;
-        } else {
-            dt = P.dt0;
-        }
+        const double dt = (ADAPTIVE && !(P.dt0 > 0.0)) ? pn_initial_dt<Prob>(P, u0, pr) : P.dt0;
 #pragma unroll
-        for (int c = 0; c < D; c++) io.mu[c] = mu[c];
-#pragma unroll
-        for (int i = 0; i < NPA; i++) io.pr[i] = pr[i];
-        io.dt = dt;
-        io.nf = nf;
+        for (int c = 0; c < D; c++) init_mu[traj * D + c] = mu[c];
+        init_dt[traj] = dt;
     }
-};
+}
 
 template <class Prob, int Q, int G, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 __device__ __forceinline__ void pn_small_entry(const PnParams& P) {

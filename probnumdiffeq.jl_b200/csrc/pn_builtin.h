@@ -3,6 +3,7 @@ struct PnBuiltinEntry {
     const char* key;
     const void* fn;
     int d, n_p;
+    const void* init_fn; /* pn_init_kernel of the same (problem, order, adaptive) for the group-per-trajectory path, else null */
 };
 extern "C" const PnBuiltinEntry* pn_builtin_table(int* count);
 extern "C" const char* pn_builtin_struct_name(const char* name);

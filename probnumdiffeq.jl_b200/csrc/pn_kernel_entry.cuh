@@ -23,6 +23,11 @@ __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_small_kernel(con
     pn_small_entry<Prob, Q, G, ADAPTIVE, DYNAMIC, SAVE>(P);
 }
 
+template <class Prob, int Q, bool ADAPTIVE>
+__global__ void __launch_bounds__(128) pn_init_kernel(const __grid_constant__ PnParams P, double* init_mu, double* init_dt) {
+    pn_init_entry<Prob, Q, ADAPTIVE>(P, init_mu, init_dt);
+}
+
 #include "kernels/pn_kron.cuh"
 
 /* EK0 / IsometricKronecker: one thread per trajectory */

@@ -198,6 +198,8 @@ static int env_int(const char* name, int dflt) {
 struct Kernel {
     int threads = PN_THREADS;
     const void* rt_fn = nullptr; /* nvcc-compiled (runtime API) */
+    const void* rt_init = nullptr; /* pn_init_kernel (group-per-trajectory path) */
+    CUfunction drv_init = nullptr;
     CUmodule mod = nullptr;      /* NVRTC-compiled */
     CUfunction drv_fn = nullptr;
     int blocks_per_sm = 1;
@@ -228,6 +230,9 @@ struct pnode_solver {
     double* d_tstops = nullptr;
     std::vector<double> host_tstops;
     double* d_forced = nullptr;
+    double* d_init_mu = nullptr; /* pn_init_kernel outputs, grown on demand */
+    double* d_init_dt = nullptr;
+    size_t init_cap = 0;
     double compile_s = 0.0;
     PnParams base; /* constants filled at create */
 };
@@ -376,7 +381,9 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
     else
         src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_entry(const "
                "__grid_constant__ PnParams P) {\n  pn_small_entry<" +
-               struct_name + ", PN_Q, PN_G, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
+               struct_name + ", PN_Q, PN_G, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n"
+               "extern \"C\" __global__ void __launch_bounds__(128) pn_init(const __grid_constant__ PnParams P, double* init_mu, "
+               "double* init_dt) {\n  pn_init_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0)>(P, init_mu, init_dt);\n}\n";
     auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
     return nvrtc_compile(src, {def("PN_THREADS", threads), def("PN_MIN_BLOCKS", min_blocks), def("PN_Q", q), def("PN_G", G),
                                def("PN_ADAPTIVE", adaptive ? 1 : 0), def("PN_DYNAMIC", dynamic ? 1 : 0), def("PN_SAVE", save),
@@ -426,6 +433,10 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
     r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_entry");
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction: " + cu_err(r));
+    if (!s->kron && !s->blocks && !s->cta) {
+        r = g_drv.ModuleGetFunction(&out->drv_init, out->mod, "pn_init");
+        if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction(pn_init): " + cu_err(r));
+    }
     if (s->smem > 48 * 1024) {
         r = g_drv.FuncSetAttribute(out->drv_fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->smem);
         if (r != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuFuncSetAttribute(max dynamic smem): " + cu_err(r));
@@ -447,6 +458,7 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
         for (int i = 0; i < n; i++) {
             if (key == tab[i].key) {
                 out->rt_fn = tab[i].fn;
+                out->rt_init = tab[i].init_fn;
                 out->threads = s->cta ? PN_CTA_THREADS : ((s->kron || s->blocks) ? 128 : PN_THREADS);
                 if (s->smem > 48 * 1024)
                     CUDA_TRY(cudaFuncSetAttribute(out->rt_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
@@ -862,11 +874,41 @@ extern "C" void pnode_destroy(pnode_solver* s) {
     if (s->d_tstops) cudaFree(s->d_tstops);
     if (s->d_forced) cudaFree(s->d_forced);
     if (s->d_saveat) cudaFree(s->d_saveat);
+    if (s->d_init_mu) cudaFreeAsync(s->d_init_mu, s->stream);
+    if (s->d_init_dt) cudaFreeAsync(s->d_init_dt, s->stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
 
+/* pn_init_kernel: initial derivatives + initial step of every trajectory into the solver's init buffers */
+static int launch_init(pnode_solver* s, Kernel& k, PnParams& P) {
+    if (!k.rt_init && !k.drv_init) return 0;
+    const size_t N = (size_t)P.n_traj;
+    if (s->init_cap < N) {
+        if (s->d_init_mu) CUDA_TRY(cudaFreeAsync(s->d_init_mu, s->stream));
+        if (s->d_init_dt) CUDA_TRY(cudaFreeAsync(s->d_init_dt, s->stream));
+        CUDA_TRY(cudaMallocAsync((void**)&s->d_init_mu, N * s->D * 8, s->stream));
+        CUDA_TRY(cudaMallocAsync((void**)&s->d_init_dt, N * 8, s->stream));
+        s->init_cap = N;
+    }
+    const unsigned grid = (unsigned)std::min<size_t>((N + 127) / 128, (size_t)s->n_sm * 16);
+    void* args[] = {&P, &s->d_init_mu, &s->d_init_dt};
+    if (k.rt_init) {
+        CUDA_TRY(cudaLaunchKernel(k.rt_init, dim3(grid), dim3(128), args, 0, s->stream));
+    } else {
+        CUresult r = g_drv.LaunchKernel(k.drv_init, grid, 1, 1, 128, 1, 1, 0, (CUstream)s->stream, args, nullptr);
+        if (r != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuLaunchKernel(pn_init): " + cu_err(r));
+    }
+    P.init_mu = s->d_init_mu;
+    P.init_dt = s->d_init_dt;
+    return 0;
+}
+
 static int launch(pnode_solver* s, Kernel& k, PnParams& P, int64_t n_traj) {
+    if (!P.init_mu && (k.rt_init || k.drv_init)) {
+        int rci = launch_init(s, k, P);
+        if (rci) return rci;
+    }
     const int groups_per_block = std::max(1, k.threads / s->G);
     long long want = (n_traj + groups_per_block - 1) / groups_per_block;
     long long cap = (long long)s->n_sm * k.blocks_per_sm; /* persistent: a whole number of CTAs per SM */
@@ -937,10 +979,18 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
     CUDA_TRY(cudaEventCreate(&e1));
     CUDA_TRY(cudaEventRecord(e0, s->stream));
     int64_t launches = 0;
+    {
+        /* group-per-trajectory path: initial states of the whole ensemble first (inside the timed region) */
+        Kernel& kmain = s->cfg.save_everystep ? s->k_save : s->k_final;
+        if (kmain.rt_init || kmain.drv_init) {
+            if ((rc = launch_init(s, kmain, P))) return rc;
+            launches += 1;
+        }
+    }
     long long fixed_steps_total = -1; /* >= 0: the counting pass was skipped and every trajectory was allotted this many steps in total */
     if (!s->cfg.save_everystep) {
         if ((rc = launch(s, s->k_final, P, n_traj))) return rc;
-        launches = 1;
+        launches += 1;
     } else {
         r->offsets.resize(N + 1);
         r->offsets[0] = 0;
