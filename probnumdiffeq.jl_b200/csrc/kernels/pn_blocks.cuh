@@ -87,24 +87,17 @@ struct PnBlocks {
             int retcode = PN_RET_SUCCESS;
             double uprev[d];
             {
-                double u0[d], mu0[D];
-#pragma unroll
-                for (int i = 0; i < d; i++) u0[i] = P.u0[traj * d + i];
+                /* initial state from pn_init_kernel (pre-pass over the whole ensemble: TaylorModeInit + initial step) */
 #pragma unroll
                 for (int i = 0; i < Prob::n_p; i++) pr[i] = P.p[traj * Prob::n_p + i];
-                pn_taylor_init<Prob, Q>(mu0, u0, pr, P.t0);
 #pragma unroll
                 for (int j = 0; j < n; j++)
 #pragma unroll
-                    for (int i = 0; i < d; i++) M[j][i] = mu0[j * d + i];
+                    for (int i = 0; i < d; i++) M[j][i] = P.init_mu[traj * D + j * d + i];
 #pragma unroll
-                for (int i = 0; i < d; i++) uprev[i] = u0[i];
-                if (ADAPTIVE && !(P.dt0 > 0.0)) {
-                    dt = pn_initial_dt<Prob>(P, u0, pr);
-                    nf += 2;
-                } else {
-                    dt = P.dt0;
-                }
+                for (int i = 0; i < d; i++) uprev[i] = M[0][i];
+                dt = P.init_dt[traj];
+                if (ADAPTIVE && !(P.dt0 > 0.0)) nf += 2;
             }
             const double dtcache = dt;
 #pragma unroll

@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_reg_kernel(const 
 
 #define PN_ENTRY_KRON(NAME, PROB, Q, A, DY, S) \
     { "builtin:" NAME ":kron:q" #Q ":g1:a" #A ":dyn" #DY ":s" #S, \
-      (const void*)&pn_kron_kernel<PROB, Q, (A != 0), (DY != 0), S>, PROB::d, PROB::n_p, nullptr }
+      (const void*)&pn_kron_kernel<PROB, Q, (A != 0), (DY != 0), S>, PROB::d, PROB::n_p, \
+      (const void*)&pn_init_kernel<PROB, Q, (A != 0)> }
 
 #define PN_ENTRY_CTA(NAME, PROB, Q, A, DY, S) \
     { "builtin:" NAME ":cta:q" #Q ":g256:a" #A ":dyn" #DY ":s" #S, \

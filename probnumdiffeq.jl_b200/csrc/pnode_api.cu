@@ -381,8 +381,9 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
     else
         src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_entry(const "
                "__grid_constant__ PnParams P) {\n  pn_small_entry<" +
-               struct_name + ", PN_Q, PN_G, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n"
-               "extern \"C\" __global__ void __launch_bounds__(128) pn_init(const __grid_constant__ PnParams P, double* init_mu, "
+               struct_name + ", PN_Q, PN_G, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
+    if (!cta) /* every path but the CTA kernel takes its initial states from the pre-pass */
+        src += "extern \"C\" __global__ void __launch_bounds__(128) pn_init(const __grid_constant__ PnParams P, double* init_mu, "
                "double* init_dt) {\n  pn_init_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0)>(P, init_mu, init_dt);\n}\n";
     auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
     return nvrtc_compile(src, {def("PN_THREADS", threads), def("PN_MIN_BLOCKS", min_blocks), def("PN_Q", q), def("PN_G", G),
@@ -433,7 +434,7 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
     r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_entry");
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction: " + cu_err(r));
-    if (!s->kron && !s->blocks && !s->cta) {
+    if (!s->cta) {
         r = g_drv.ModuleGetFunction(&out->drv_init, out->mod, "pn_init");
         if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction(pn_init): " + cu_err(r));
     }
