@@ -87,6 +87,7 @@ class Config(C.Structure):
         ("tstops", C.POINTER(C.c_double)), ("n_tstops", C.c_int64),
         ("forced_diffusion", C.POINTER(C.c_double)), ("n_forced", C.c_int64),
         ("prior", C.c_int32), ("reserved", C.c_int32), ("rate_parameter", C.c_double),
+        ("mass_matrix", C.POINTER(C.c_double)),
     ]
 
 
@@ -225,7 +226,7 @@ def make_config(d, q, n_p, *, alg=EK1, diffusion=DIFF_DYNAMIC, calibrate=True, i
                 adaptive=True, save_everystep=True, cov_backend=COV_REF, t0=0.0, t1=1.0, dt=0.0, abstol=1e-6,
                 reltol=1e-3, dtmin=0.0, dtmax=None, maxiters=1_000_000, beta1=None, beta2=None, qmin=0.2, qmax=10.0,
                 gamma=0.9, qsteady_min=1.0, qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None,
-                prior=PRIOR_IWP, rate_parameter=0.0):
+                prior=PRIOR_IWP, rate_parameter=0.0, mass_matrix=None):
     c = Config()
     c.d, c.q, c.n_p, c.alg = d, q, n_p, alg
     c.diffusion, c.calibrate, c.smooth, c.adaptive = diffusion, int(calibrate), int(smooth), int(adaptive)
@@ -248,6 +249,11 @@ def make_config(d, q, n_p, *, alg=EK1, diffusion=DIFF_DYNAMIC, calibrate=True, i
         fd = np.ascontiguousarray(forced_diffusion, dtype=np.float64)
         keep.append(fd)
         c.forced_diffusion, c.n_forced = _dp(fd), len(fd)
+    if mass_matrix is not None:
+        mm = np.asfortranarray(np.asarray(mass_matrix, dtype=np.float64).reshape(d, d))  # column-major for the C side
+        mm = np.ascontiguousarray(mm.T).reshape(-1)                                      # = column-major bytes of M
+        keep.append(mm)
+        c.mass_matrix = _dp(mm)
     c._keep = keep
     return c
 

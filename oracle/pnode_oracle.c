@@ -532,13 +532,51 @@ static double rms_norm(const double* x, int n) { /* ODE_DEFAULT_NORM (DiffEqBase
 }
 
 /* ode_determine_initdt (OrdinaryDiffEqCore, 3rd party; restated from SURVEY.md A.6 -- parity unpinned). */
-static double initial_dt(const oracle_config* c, oracle_rhs_fn f, const double* u0, const double* p, int order) {
+/* Mass matrix M (column-major d x d).  `singular`: Gaussian elimination with partial pivoting meets an exactly zero pivot
+   (ArrayInterface.issingular = !issuccess(lu(M))).  `MMinv` = inverse of MM = M (+ 1e-20 I if any diagonal entry of M is zero,
+   src/initialization/autodiffinit.jl:20-31).  Conditioning the standard-normal initial state on E_0 x = u0 and
+   MM E_o x = df_o, o = 1..q (autodiffinit.jl:33-47, common.jl:122-139) gives the mean blocks MM^-1 df_o and a covariance
+   that is zero up to rounding; the restatement takes it as exactly zero, as for M = I. */
+static void mass_setup(int d, const double* M, double* MMinv, int* singular) {
+    double A[64 * 64], B[64 * 64];
+    memcpy(A, M, sizeof(double) * d * d);
+    *singular = 0;
+    for (int k = 0; k < d && !*singular; k++) {
+        int piv = k;
+        for (int i = k + 1; i < d; i++)
+            if (fabs(AT(A, i, k, d)) > fabs(AT(A, piv, k, d))) piv = i;
+        if (AT(A, piv, k, d) == 0.0) { *singular = 1; break; }
+        if (piv != k)
+            for (int j = 0; j < d; j++) { double t = AT(A, k, j, d); AT(A, k, j, d) = AT(A, piv, j, d); AT(A, piv, j, d) = t; }
+        for (int i = k + 1; i < d; i++) {
+            double f = AT(A, i, k, d) / AT(A, k, k, d);
+            for (int j = k + 1; j < d; j++) AT(A, i, j, d) -= f * AT(A, k, j, d);
+        }
+    }
+    memcpy(A, M, sizeof(double) * d * d);
+    int zero_diag = 0;
+    for (int i = 0; i < d; i++) zero_diag |= (AT(M, i, i, d) == 0.0);
+    if (zero_diag)
+        for (int i = 0; i < d; i++) AT(A, i, i, d) += 1e-20;
+    memset(B, 0, sizeof(double) * d * d);
+    for (int i = 0; i < d; i++) AT(B, i, i, d) = 1.0;
+    lu_solve(d, d, A, B);
+    memcpy(MMinv, B, sizeof(double) * d * d);
+}
+
+/* With a mass matrix M != I the initial step is max(smalldt, dtmin) = 1e-6 and no f evaluation is counted:
+   a singular M makes the integrator a DAE integrator (`isdae`, early return); for a non-singular M upstream solves
+   M \ f0 through `integrator.alg.linsolve` inside a try block, a field the EK algorithms do not have, so the catch
+   branch returns the same value.  (3rd party, recalled; consistent with test/mass_matrix.jl:15-16 -- rtol 1e-10 with
+   M = -100 I -- which the Hairer-Wanner step of 0.1 would miss by four orders of magnitude with this restatement.) */
+static double initial_dt(const oracle_config* c, oracle_rhs_fn f, const double* u0, const double* p, int order, int mass) {
     int d = c->d;
     double sk[64], tmp[64], f0[64], f1[64], u1[64];
     double t = c->t0;
     double dtmax = c->dtmax;
     double dtmin = nextafter(fmax(c->dtmin, nextafter(fabs(t), INFINITY) - fabs(t)), INFINITY);
     double smalldt = fmax(dtmin, 1e-6);
+    if (mass) return fmax(smalldt, dtmin);
     for (int i = 0; i < d; i++) sk[i] = c->abstol + fabs(u0[i]) * c->reltol;
     for (int i = 0; i < d; i++) tmp[i] = u0[i] / sk[i];
     double d0 = rms_norm(tmp, d);
@@ -603,7 +641,7 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
     for (int i = 0; i < d; i++) uprev[i] = mu[i];
     double t = c->t0, dt;
     if (c->adaptive && !(c->dt > 0.0)) {
-        dt = initial_dt(c, f, u0, p, q);
+        dt = initial_dt(c, f, u0, p, q, 0);
         out->nf += 2;
     } else {
         dt = c->dt;
@@ -871,6 +909,10 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
 
 int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, oracle_taylor_fn taylor,
                  const double* u0, const double* p, oracle_traj* out) {
+    /* mass matrices: restated for EK1 on the dense layout only (EK0 + Kronecker: ArgumentError in the reference,
+       caches.jl:111-118) */
+    if (c->mass_matrix && (c->alg != ORACLE_EK1 || c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV))
+        return -2;
     if (c->alg == ORACLE_DIAGONAL_EK1 || c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV)
         return solve_blocks(c, f, jac, taylor, u0, p, out);
     const int d = c->d, q = c->q, n = q + 1, D = d * n;
@@ -916,13 +958,29 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     taylor(mu, u0, p, c->t0, q);
     out->nf += q; /* autodiffinit.jl:17 */
     for (int i = 0; i < d; i++) uprev[i] = mu[i];
+    const double* Mm = c->mass_matrix;
+    double* MMinv = NULL;
+    int m_singular = 0;
+    if (Mm) {
+        MMinv = (double*)malloc(sizeof(double) * d * d);
+        mass_setup(d, Mm, MMinv, &m_singular);
+        (void)m_singular;
+        for (int o = 1; o <= q; o++) { /* x_o = MM^-1 df_o */
+            for (int a = 0; a < d; a++) {
+                double sacc = 0.0;
+                for (int i = 0; i < d; i++) sacc += AT(MMinv, a, i, d) * mu[o * d + i];
+                z[a] = sacc;
+            }
+            for (int a = 0; a < d; a++) mu[o * d + a] = z[a];
+        }
+    }
 
     double t = c->t0;
     double dt;
     const int order = q; /* alg_order (src/alg_utils.jl:45) */
     if (c->adaptive && !(c->dt > 0.0)) {
-        dt = initial_dt(c, f, u0, p, order);
-        out->nf += 2;
+        dt = initial_dt(c, f, u0, p, order, Mm != NULL);
+        if (!Mm) out->nf += 2;
     } else {
         dt = c->dt;
     }
@@ -985,12 +1043,21 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
         f(fu, upred, p, tnew);
         out->nf += 1;
         for (int i = 0; i < d; i++) z[i] = mu_pred[d + i] - fu[i];
+        if (Mm) /* z = M E1 mu_pred - f (measurement_models.jl:18) */
+            for (int a = 0; a < d; a++) {
+                double sacc = 0.0;
+                for (int i = 0; i < d; i++) sacc += AT(Mm, a, i, d) * mu_pred[d + i];
+                z[a] = sacc - fu[a];
+            }
         /* calc_H! (derivative_utils.jl:1-33) */
         if (kron) {
             for (int k = 0; k < N; k++) H[k] = (k == 1) ? 1.0 : 0.0; /* E1.B = e_1' (projection.jl:20-29) */
         } else {
             memset(H, 0, sizeof(double) * (size_t)m * N);
             for (int i = 0; i < d; i++) AT(H, i, d + i, d) = 1.0;    /* H = E1 */
+            if (Mm) /* H = M E1 (derivative_utils.jl:43-50) */
+                for (int a = 0; a < d; a++)
+                    for (int i = 0; i < d; i++) AT(H, a, d + i, d) = AT(Mm, a, i, d);
             if (c->alg == ORACLE_EK1) {
                 jac(J, upred, p, tnew);
                 out->njac += 1;
@@ -1240,7 +1307,7 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     free(xR.p); free(bG.p); free(bB.p); free(bL.p);
     free(Ah1); free(Qh1); free(Ah); free(QhR); free(mu); free(R); free(mu_pred); free(R_pred);
     free(mu_filt); free(R_filt); free(H); free(J); free(Cq); free(W); free(G); free(bb); free(LR);
-    free(Rdense); free(tmpDD);
+    free(Rdense); free(tmpDD); free(MMinv);
     return 0;
 }
 

@@ -69,6 +69,9 @@ typedef struct {
     int32_t prior;          /* ORACLE_PRIOR_* */
     int32_t reserved;
     double rate_parameter;  /* IOUP: F[q,q] (src/priors/ioup.jl:66-79) */
+    /* constant mass matrix M (d x d, column-major) of M u' = f(u,p,t); NULL = identity.  z = M E1 x - f
+       (src/measurement_models.jl:11-20), H = M E1 - J E0 (src/derivative_utils.jl:1-53).  EK1 (dense) only. */
+    const double* mass_matrix;
 } oracle_config;
 
 /* One solved trajectory.  Arrays are owned by the struct; free with oracle_traj_free. */

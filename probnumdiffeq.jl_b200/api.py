@@ -100,9 +100,13 @@ class ODEProblem:
     tspan: Tuple[float, float]
     p: Sequence[float] = ()
     builtin: Optional[str] = None   # name in problems.PROBLEMS -> ahead-of-time kernels when available
+    mass_matrix: Optional[Sequence[Sequence[float]]] = None   # ODEFunction(f; mass_matrix=M): M u' = f(u, p, t), d x d, may be singular
 
     @staticmethod
     def from_library(name: str) -> "ODEProblem":
+        if name in _problems.MASS_MATRIX_PROBLEMS:
+            pd = _problems.MASS_MATRIX_PROBLEMS[name]
+            return ODEProblem(pd.f, list(pd.u0), tuple(pd.tspan), list(pd.p), mass_matrix=pd.mass_matrix)
         pd = _problems.PROBLEMS[name]
         return ODEProblem(pd.f, list(pd.u0), tuple(pd.tspan), list(pd.p), builtin=name)
 
@@ -211,6 +215,16 @@ def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, absto
         kw.update(diffusion=_lib.DIFF_DYNAMIC)
     if isinstance(alg.prior, IOUP):
         kw.update(prior=_lib.PRIOR_IOUP, rate_parameter=alg.prior.rate_parameter)
+    if prob.mass_matrix is not None:
+        M = np.asarray(prob.mass_matrix, dtype=float)
+        if M.shape != (d, d):
+            raise ValueError("mass_matrix must be d x d")  # DimensionMismatch
+        if not np.array_equal(M, np.eye(d)):
+            if isinstance(alg, EK0) and isinstance(alg.prior, IWP) and not isinstance(diff, (FixedMVDiffusion, DynamicMVDiffusion)):
+                # src/caches.jl:111-118 (the reference lets a UniformScaling through; a matrix argument is never one)
+                raise ValueError("The selected algorithm uses an efficient Kronecker-factorized implementation which is "
+                                 "incompatible with the provided mass matrix. Try using the `EK1` instead.")
+            kw.update(mass_matrix=M)
     if prob.builtin is not None:
         kw.update(rhs_name="builtin:" + prob.builtin)
     else:

@@ -297,6 +297,11 @@ PN_HD double pn_initial_dt(const PnParams& P, const double* u0, const double* pr
 #ifndef PN_EK0_DENSE
 #define PN_EK0_DENSE 0 /* 1: EK0 measurement (H = E1, no Jacobian) on the dense layout -- EK0 with a non-IWP prior */
 #endif
+#ifndef PN_MASS
+#define PN_MASS 0 /* 1: mass matrix M u' = f; the generated source defines constexpr pn_mass(a,i) = M[a][i] and
+                     pn_mass_inv(a,i) = (M + 1e-20 I if M has a zero diagonal entry)^-1 (autodiffinit.jl:20-31), so zero
+                     entries fold away at compile time.  z = M E1 x - f, H = M E1 - J E0. */
+#endif
 #if PN_IOUP
 #include "pn_ioup.cuh"
 #endif
@@ -437,7 +442,7 @@ struct PnSmall {
 #pragma unroll
                             for (int i = 0; i < d; i++) uprev[i] = mu[i];
                             dt = P.init_dt[traj];
-                            nf = Q + ((ADAPTIVE && !(P.dt0 > 0.0)) ? 2 : 0);
+                            nf = Q + ((ADAPTIVE && !(P.dt0 > 0.0) && !PN_MASS) ? 2 : 0);
                             t = P.t0;
                         }
 #pragma unroll
@@ -587,8 +592,19 @@ struct PnSmall {
                 Prob::jac(J, mup, pr, tnew);
 #endif
                 nf += 1;
+#if PN_MASS
+#pragma unroll
+                for (int a = 0; a < d; a++) { /* z = M E1 mu^- - f (measurement_models.jl:18) */
+                    double sm = 0.0;
+#pragma unroll
+                    for (int i = 0; i < d; i++)
+                        if (pn_mass(a, i) != 0.0) sm += pn_mass(a, i) * mup[d + i];
+                    z[a] = sm - fu[a];
+                }
+#else
 #pragma unroll
                 for (int i = 0; i < d; i++) z[i] = mup[d + i] - fu[i];
+#endif
 
                 if (ADAPTIVE || DYNAMIC) {
                     /* C[(m,i),a] = (Qh.R H')[(m,i),a] = -LQ[m][0] J[a][i] + LQ[m][1] (i==a) ; W = C'C */
@@ -612,7 +628,11 @@ struct PnSmall {
                         for (int i = 0; i < d; i++) {
                             double c[d];
 #pragma unroll
+#if PN_MASS
+                            for (int a = 0; a < d; a++) c[a] = -l0 * J[a + d * i] + ((pn_mass(a, i) != 0.0) ? l1 * pn_mass(a, i) : 0.0);
+#else
                             for (int a = 0; a < d; a++) c[a] = -l0 * J[a + d * i] + ((i == a) ? l1 : 0.0);
+#endif
 #pragma unroll
                             for (int a = 0; a < d; a++)
 #pragma unroll
@@ -771,7 +791,14 @@ struct PnSmall {
                 for (int lr = 0; lr < RU; lr++)
 #pragma unroll
                     for (int a = 0; a < d; a++) {
+#if PN_MASS
+                        double s = 0.0; /* H = [-J | M | 0] */
+#pragma unroll
+                        for (int i = 0; i < d; i++)
+                            if (pn_mass(a, i) != 0.0) s += R[lr][d + i] * pn_mass(a, i);
+#else
                         double s = R[lr][d + a];
+#endif
 #pragma unroll
                         for (int i = 0; i < d; i++) s -= R[lr][i] * J[a + d * i];
                         C2[lr][a] = accept ? s : 0.0;
@@ -1012,7 +1039,33 @@ __device__ __forceinline__ void pn_init_entry(const PnParams& P, double* init_mu
 #pragma unroll
         for (int i = 0; i < Prob::n_p; i++) pr[i] = P.p[traj * Prob::n_p + i];
         pn_taylor_init<Prob, Q>(mu, u0, pr, P.t0);
+#if PN_MASS
+        /* conditioning on MM E_o x = d^o/dt^o of u' = f(u), o >= 1 (autodiffinit.jl:33-47): x_o = MM^-1 df_o */
+#pragma unroll
+        for (int o = 1; o <= Q; o++) {
+            double xo[d];
+#pragma unroll
+            for (int a = 0; a < d; a++) {
+                double sm = 0.0;
+#pragma unroll
+                for (int i = 0; i < d; i++)
+                    if (pn_mass_inv(a, i) != 0.0) sm += pn_mass_inv(a, i) * mu[o * d + i];
+                xo[a] = sm;
+            }
+#pragma unroll
+            for (int a = 0; a < d; a++) mu[o * d + a] = xo[a];
+        }
+        /* initial step with a mass matrix: max(smalldt, dtmin) (see oracle initial_dt; ode_determine_initdt's isdae /
+           failed-linsolve branches) */
+        double dt = P.dt0;
+        if (ADAPTIVE && !(P.dt0 > 0.0)) {
+            const double epst = fabs(P.t0) > 0.0 ? (nextafter(fabs(P.t0), 1e300) - fabs(P.t0)) : 4.9406564584124654e-324;
+            const double dtmin = nextafter(fmax(P.dtmin, epst), 1e300);
+            dt = fmax(fmax(dtmin, 1e-6), dtmin);
+        }
+#else
         const double dt = (ADAPTIVE && !(P.dt0 > 0.0)) ? pn_initial_dt<Prob>(P, u0, pr) : P.dt0;
+#endif
 #pragma unroll
         for (int c = 0; c < D; c++) init_mu[traj * D + c] = mu[c];
         init_dt[traj] = dt;

@@ -234,6 +234,7 @@ struct pnode_solver {
     double* d_init_dt = nullptr;
     size_t init_cap = 0;
     double compile_s = 0.0;
+    std::string mass_src; /* generated preamble (PN_MASS, pn_mass, pn_mass_inv) when the problem has a mass matrix */
     PnParams base; /* constants filled at create */
 };
 
@@ -364,8 +365,8 @@ static int nvrtc_compile(const std::string& src, std::vector<std::string> defs, 
 static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_name, int q, int G, bool adaptive,
                        bool dynamic, int save, std::vector<char>* cubin, int threads = PN_THREADS, int min_blocks = 1,
                        bool kron = false, bool cta = false, int blocks = 0 /* 0 no, 1 EK0, 2 DiagonalEK1 */, bool mv = false,
-                       bool ioup = false, bool ek0_dense = false) {
-    std::string src;
+                       bool ioup = false, bool ek0_dense = false, const std::string& preamble = std::string()) {
+    std::string src = preamble;
     src += "#include \"pn_kernel_entry.cuh\"\n";
     src += rhs_src;
     if (blocks)
@@ -390,6 +391,69 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
                                def("PN_ADAPTIVE", adaptive ? 1 : 0), def("PN_DYNAMIC", dynamic ? 1 : 0), def("PN_SAVE", save),
                                def("PN_IOUP", ioup ? 1 : 0), def("PN_EK0_DENSE", ek0_dense ? 1 : 0)},
                          cubin);
+}
+
+/* Mass matrix M (d x d row-major) -> generated preamble: PN_MASS, constexpr pn_mass(a,i) = M[a][i] and pn_mass_inv(a,i) =
+   MM^-1[a][i] with MM = M (+ 1e-20 I if M has a zero diagonal entry; src/initialization/autodiffinit.jl:20-31).  The entries
+   are compile-time constants of the NVRTC build, so the zeros of M cost nothing.  Empty string for M = identity / null. */
+static int mass_preamble(const double* M, int d, std::string* out) {
+    out->clear();
+    if (!M) return 0;
+    bool identity = true;
+    for (int a = 0; a < d; a++)
+        for (int i = 0; i < d; i++) {
+            if (!std::isfinite(M[a * d + i])) return fail(PNODE_ERR_ARGUMENT, "mass_matrix has a non-finite entry");
+            if (M[a * d + i] != (a == i ? 1.0 : 0.0)) identity = false;
+        }
+    if (identity) return 0;
+    std::vector<double> A(M, M + (size_t)d * d), Inv((size_t)d * d, 0.0);
+    bool zero_diag = false;
+    for (int i = 0; i < d; i++) zero_diag |= (M[i * d + i] == 0.0);
+    for (int i = 0; i < d; i++) {
+        if (zero_diag) A[i * d + i] += 1e-20;
+        Inv[i * d + i] = 1.0;
+    }
+    for (int k = 0; k < d; k++) { /* Gauss-Jordan with partial pivoting */
+        int piv = k;
+        for (int r = k + 1; r < d; r++)
+            if (std::fabs(A[r * d + k]) > std::fabs(A[piv * d + k])) piv = r;
+        if (A[piv * d + k] == 0.0)
+            return fail(PNODE_ERR_ARGUMENT, "mass_matrix: M (+ 1e-20 I) is singular -- the initial derivatives are undefined "
+                                            "(SingularException in the reference's initial conditioning)");
+        if (piv != k)
+            for (int c = 0; c < d; c++) {
+                std::swap(A[k * d + c], A[piv * d + c]);
+                std::swap(Inv[k * d + c], Inv[piv * d + c]);
+            }
+        const double pv = A[k * d + k];
+        for (int c = 0; c < d; c++) {
+            A[k * d + c] /= pv;
+            Inv[k * d + c] /= pv;
+        }
+        for (int r = 0; r < d; r++) {
+            if (r == k) continue;
+            const double f = A[r * d + k];
+            if (f == 0.0) continue;
+            for (int c = 0; c < d; c++) {
+                A[r * d + c] -= f * A[k * d + c];
+                Inv[r * d + c] -= f * Inv[k * d + c];
+            }
+        }
+    }
+    auto table = [&](const char* name, const double* T) {
+        std::string t = std::string("__host__ __device__ constexpr double ") + name + "(int a, int i) {\n  return ";
+        char buf[96];
+        for (int a = 0; a < d; a++)
+            for (int i = 0; i < d; i++) {
+                if (T[a * d + i] == 0.0) continue;
+                snprintf(buf, sizeof buf, "(a == %d && i == %d) ? %.17g : ", a, i, T[a * d + i]);
+                t += buf;
+            }
+        t += "0.0;\n}\n";
+        return t;
+    };
+    *out = "#define PN_MASS 1\n" + table("pn_mass", M) + table("pn_mass_inv", Inv.data());
+    return 0;
 }
 
 /* NVRTC: register-resident smoother sweep for (d, q, G); independent of the right-hand side. */
@@ -428,7 +492,7 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
     rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0, is_dynamic(s->cfg.diffusion), save, &cubin, out->threads,
                      env_int("PNODE_MIN_BLOCKS", 1), s->kron, s->cta,
                      s->blocks ? (s->cfg.alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, s->mv, s->cfg.prior == PNODE_PRIOR_IOUP,
-                     s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks);
+                     s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks, s->mass_src);
     if (rc) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
@@ -452,7 +516,8 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
 static int get_kernel(pnode_solver* s, int save, Kernel* out) {
     if (out->valid()) return 0;
     auto t0 = std::chrono::steady_clock::now();
-    if (s->builtin && !env_int("PNODE_FORCE_NVRTC", 0) && s->cfg.prior == PNODE_PRIOR_IWP && !(s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks)) {
+    if (s->builtin && !env_int("PNODE_FORCE_NVRTC", 0) && s->cfg.prior == PNODE_PRIOR_IWP && s->mass_src.empty() &&
+        !(s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks)) {
         int n = 0;
         const PnBuiltinEntry* tab = pn_builtin_table(&n);
         std::string key = kernel_key(s, save);
@@ -633,6 +698,21 @@ static int validate_config(const pnode_config* cfg) {
         if (cfg->smooth && smooth_lanes(D) == 0)
             return fail(PNODE_ERR_UNSUPPORTED, "dense output of smoothed solutions needs the register-resident sweep (D <= 24)");
     }
+    if (cfg->mass_matrix) {
+        std::string pre;
+        int mrc = mass_preamble(cfg->mass_matrix, cfg->d, &pre);
+        if (mrc) return mrc;
+        if (!pre.empty()) { /* M != I */
+            if (layout == PNODE_COV_KRONECKER) /* src/caches.jl:111-118 (a matrix argument is never a UniformScaling) */
+                return fail(PNODE_ERR_ARGUMENT,
+                            "The selected algorithm uses an efficient Kronecker-factorized implementation which is incompatible "
+                            "with the provided mass matrix. Try using the `EK1` instead.");
+            if (cfg->alg != PNODE_EK1 || layout != PNODE_COV_DENSE)
+                return fail(PNODE_ERR_UNSUPPORTED, "mass matrices are implemented for the EK1 on the dense layout");
+            if (D > 32 || cfg->lanes_per_traj == 256)
+                return fail(PNODE_ERR_UNSUPPORTED, "mass matrices are implemented for D = d(q+1) <= 32 (register-resident kernel)");
+        }
+    }
     const bool builtin = (std::string(cfg->rhs_name).rfind("builtin:", 0) == 0);
     if (!builtin && !cfg->rhs_src) return fail(PNODE_ERR_ARGUMENT, "rhs_src is required unless rhs_name is a builtin");
     return 0;
@@ -649,11 +729,13 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     const int G = cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D);
     std::vector<char> cubin;
     const int layout = resolve_layout(cfg);
+    std::string mass_src;
+    if ((rc = mass_preamble(cfg->mass_matrix, cfg->d, &mass_src))) return rc;
     rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, is_dynamic(cfg->diffusion),
                      cfg->save_everystep ? ((cfg->smooth || cfg->n_saveat > 0) ? 2 : 1) : 0, &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
                      layout == PNODE_COV_KRONECKER, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256),
                      layout == PNODE_COV_BLOCKS ? (cfg->alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, is_mv(cfg->diffusion),
-                     cfg->prior == PNODE_PRIOR_IOUP, cfg->alg == PNODE_EK0 && layout == PNODE_COV_DENSE);
+                     cfg->prior == PNODE_PRIOR_IOUP, cfg->alg == PNODE_EK0 && layout == PNODE_COV_DENSE, mass_src);
     if (rc) return rc;
     int64_t total = (int64_t)cubin.size();
     /* the smoother sweep and the dense-output kernel of this configuration compile from the same embedded headers */
@@ -689,6 +771,8 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     if (!s->builtin) s->rhs_src = cfg->rhs_src;
     s->cfg.rhs_src = nullptr;
     s->cfg.rhs_name = nullptr;
+    mass_preamble(cfg->mass_matrix, cfg->d, &s->mass_src); /* validated above */
+    s->cfg.mass_matrix = nullptr;
     s->kron = (resolve_layout(cfg) == PNODE_COV_KRONECKER);
     s->blocks = (resolve_layout(cfg) == PNODE_COV_BLOCKS);
     s->mv = is_mv(cfg->diffusion);

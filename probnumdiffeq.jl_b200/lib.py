@@ -62,6 +62,7 @@ class Config(C.Structure):
         ("forced_diffusion", C.POINTER(C.c_double)), ("n_forced", C.c_int64),
         ("rate_parameter", C.c_double),
         ("saveat", C.POINTER(C.c_double)), ("n_saveat", C.c_int64),
+        ("mass_matrix", C.POINTER(C.c_double)),
     ]
 
 
@@ -132,7 +133,7 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
                 lanes_per_traj=0, t0=0.0, t1=1.0, dt=0.0, abstol=1e-6, reltol=1e-3, dtmin=0.0, dtmax=0.0,
                 maxiters=1_000_000, beta1=0.0, beta2=0.0, qmin=0.2, qmax=10.0, gamma=0.9, qsteady_min=1.0,
                 qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None, device=0, prior=PRIOR_IWP,
-                rate_parameter=0.0, saveat=None) -> Config:
+                rate_parameter=0.0, saveat=None, mass_matrix=None) -> Config:
     c = Config()
     c.struct_size = C.sizeof(Config)
     c.device, c.d, c.q, c.n_p = device, d, q, n_p
@@ -160,6 +161,10 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
         a = np.ascontiguousarray(saveat, dtype=np.float64)
         keep.append(a)
         c.saveat, c.n_saveat = a.ctypes.data_as(C.POINTER(C.c_double)), len(a)
+    if mass_matrix is not None:
+        a = np.ascontiguousarray(np.asarray(mass_matrix, dtype=np.float64).reshape(d, d))
+        keep.append(a)
+        c.mass_matrix = a.ctypes.data_as(C.POINTER(C.c_double))
     c._keep = keep
     return c
 

@@ -7,7 +7,7 @@ functions are plain Python working on floats *and* on SymPy symbols, so they can
 from __future__ import annotations
 
 import dataclasses
-from typing import Callable, Sequence, Tuple
+from typing import Callable, Optional, Sequence, Tuple
 
 
 @dataclasses.dataclass
@@ -17,6 +17,7 @@ class ProblemDef:
     u0: Sequence[float]
     p: Sequence[float]
     tspan: Tuple[float, float]
+    mass_matrix: Optional[Sequence[Sequence[float]]] = None   # M of M u' = f (None = identity)
 
     @property
     def d(self) -> int:
@@ -54,6 +55,15 @@ def rober(du, u, p, t):
     du[0] = -k1 * u[0] + k3 * u[1] * u[2]
     du[1] = k1 * u[0] - k3 * u[1] * u[2] - k2 * u[1] ** 2
     du[2] = k2 * u[1] ** 2
+
+
+def rober_dae(du, u, p, t):
+    """ROBER as the reference benchmarks it: mass-matrix DAE, M = Diagonal([1, 1, 0]), third row the algebraic constraint
+    (benchmarks/rober.jmd:37-46; test/mass_matrix.jl:64-79)."""
+    k1, k2, k3 = p[0], p[1], p[2]
+    du[0] = -k1 * u[0] + k3 * u[1] * u[2]
+    du[1] = k1 * u[0] - k3 * u[1] * u[2] - k2 * u[1] ** 2
+    du[2] = u[0] + u[1] + u[2] - 1
 
 
 def orego(du, u, p, t):
@@ -106,4 +116,10 @@ PROBLEMS = {
         [],
         (0.0, 3.0),
     ),
+}
+
+# Mass-matrix problems: traced and compiled at run time (the ahead-of-time kernel table holds ODE-form problems only).
+MASS_MATRIX_PROBLEMS = {
+    "rober_dae": ProblemDef("rober_dae", rober_dae, [1.0, 0.0, 0.0], [0.04, 3e7, 1e4], (0.0, 1e5),
+                            mass_matrix=[[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 0.0]]),
 }

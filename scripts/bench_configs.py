@@ -19,16 +19,22 @@ def F_smooth(D, d):
 
 
 def run(tag, name, n, q, t1, alg=lib.EK1, seed=0, reps=2, du0=0.0, dp=0.1, **kw):
-    pd = problems.PROBLEMS[name]
+    pd = problems.PROBLEMS.get(name) or problems.MASS_MATRIX_PROBLEMS[name]
     rng = np.random.Generator(np.random.PCG64(seed))
     u0 = np.array(pd.u0, dtype=float)[None, :] * (1 + du0 * rng.uniform(-1, 1, (n, pd.d)))
     p = np.array(pd.p, dtype=float)[None, :] * (1 + dp * rng.uniform(-1, 1, (n, pd.n_p))) if pd.n_p else np.zeros((n, 0))
     if name == "pleiades":
         u0[:, 14:] += 1e-3 * rng.uniform(-1, 1, (n, 14))
-    cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="builtin:" + name, alg=alg, t0=0.0, t1=t1, **kw)
+    if pd.mass_matrix is not None:   # mass-matrix problems are traced and NVRTC-compiled (M baked into the kernel)
+        from probnumdiffeq_jl_b200 import tracer
+        src = tracer.cuda_source(tracer.trace(pd.f, pd.d, pd.n_p), "UserProb")
+        cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="UserProb", rhs_src=src, alg=alg, t0=0.0, t1=t1,
+                              mass_matrix=pd.mass_matrix, **kw)
+    else:
+        cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="builtin:" + name, alg=alg, t0=0.0, t1=t1, **kw)
     s = lib.Solver(cfg)
     best = None
-    for _ in range(reps):
+    for _ in range(reps + (1 if pd.mass_matrix is not None else 0)):   # first call of an NVRTC solver compiles
         t = time.perf_counter()
         r = s.solve(np.ascontiguousarray(u0), np.ascontiguousarray(p))
         wall = time.perf_counter() - t
@@ -69,3 +75,6 @@ if "cfg5" in which:
     for n in (10_000, 100_000, 1_000_000, 4_000_000):
         run(f"cfg5 ROBER EK1(3) adaptive filter only, {n}", "rober", n, 3, 100.0, seed=3)
     run("cfg5 OREGO EK1(3) adaptive filter only, 131072", "orego", 131072, 3, 30.0, seed=3)
+if "cfg5dae" in which:   # ROBER as the reference benchmarks it: mass-matrix DAE form (benchmarks/rober.jmd:37-46)
+    for n in (100_000, 1_000_000):
+        run(f"cfg5 ROBER-DAE (M = diag(1,1,0)) EK1(3) adaptive filter only, {n}", "rober_dae", n, 3, 100.0, seed=3)

@@ -916,3 +916,135 @@ def test_cfg4_pleiades_cta_kernel(oracle):
     assert np.linalg.norm(Sg - So) / np.linalg.norm(So) < 1e-10
     assert gf["loglik"][0] == pytest.approx(of["loglik"], rel=1e-9)
     print("pleiades cta kernel_ms", g["info"].kernel_ms, "accepted", g["info"].total_accepted)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# mass-matrix problems M u' = f: z = M E1 x - f, H = M E1 - J E0
+# ------------------------------------------------------------------------------------------------------------------
+def _mass_inputs(n, seed, dp=0.1):
+    pd = problems.MASS_MATRIX_PROBLEMS["rober_dae"]
+    rng = np.random.default_rng(seed)
+    u0 = np.tile(np.array(pd.u0, dtype=float), (n, 1))
+    p = np.array(pd.p, dtype=float)[None, :] * (1 + dp * rng.uniform(-1, 1, (n, pd.n_p)))
+    return pd, np.ascontiguousarray(u0), np.ascontiguousarray(p)
+
+
+@pytest.mark.parametrize("t1", [1e-2, 10.0])
+def test_mass_matrix_rober_dae_adaptive(oracle, t1):
+    """ROBER as the reference benchmarks it (benchmarks/rober.jmd:37-46; test/mass_matrix.jl:64-88): singular
+    M = Diagonal([1, 1, 0]), adaptive EK1(order=3).  The algebraic row makes the early residuals pure cancellation
+    (z_3 = 1 - sum(u^-) ~ 1e-14 with 1e-16 rounding noise, sigma^2 ~ 1e16), so the free-running step sequence carries
+    percent-level rounding noise in ANY two implementations -- the same situation as the stiff problems above, and the same
+    protocol: (i) the kernel replays the oracle's accepted grid and stays within the oracle-vs-oracle floor, (ii) with
+    sigma^2 forced as well it reaches 1e-8, (iii) free running: same work, same end point norm-wise to 1e-8 (Julia
+    `isapprox`, what test/mass_matrix.jl asserts), first step 1e-6, constraint satisfied on every saved point."""
+    n = 8
+    pd, u0, p = _mass_inputs(n, 61)
+    M = np.array(pd.mass_matrix)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    # (iii) free running ensemble
+    g = _gpu(pd, u0, p, 3, builtin=False, adaptive=True, t0=0.0, t1=t1, save_everystep=True, mass_matrix=M)
+    kwo = dict(alg=oracle.EK1, smooth=False, adaptive=True, t0=0.0, t1=t1, save_everystep=True, cov_backend=oracle.COV_QR,
+               mass_matrix=M)
+    cfg = oracle.make_config(3, 3, 3, **kwo)
+    sols = []
+    for i in range(n):
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        sols.append(o)
+        a, b = g["off"][i], g["off"][i + 1]
+        assert g["retcode"][i] == 0 and o["retcode"] == "Success"
+        assert abs(int(g["naccept"][i]) - o["naccept"]) <= max(2, 0.03 * o["naccept"]), i
+        assert g["nf"][i] == 3 + g["naccept"][i] + g["nreject"][i]        # no f evaluations in the initial-step choice
+        assert g["T"][a + 1] - g["T"][a] == o["t"][1] - o["t"][0] == 1e-6   # initial step with a mass matrix
+        assert g["T"][b - 1] == t1
+        assert np.linalg.norm(g["u"][i] - o["pu_mu"][-1]) <= 1e-8 * np.linalg.norm(o["pu_mu"][-1]), i
+        assert np.max(np.abs(g["U"][a:b].sum(axis=1) - 1.0)) < 1e-9
+    # (i) step-teacher-forced, (ii) sigma^2 forced as well
+    for i in (0, 6):
+        o = sols[i]
+        grid = o["t"][1:-1]
+        kw = dict(alg=oracle.EK1, smooth=False, adaptive=False, dt=t1, t0=0.0, t1=t1, save_everystep=True, tstops=grid,
+                  cov_backend=oracle.COV_QR, mass_matrix=M)
+        of = oracle.solve(oracle.make_config(3, 3, 3, **kw), rhs, u0[i], p[i])
+        gi = _gpu(pd, u0[i:i + 1], p[i:i + 1], 3, builtin=False, adaptive=False, dt=t1, t0=0.0, t1=t1, save_everystep=True,
+                  tstops=grid, mass_matrix=M)
+        assert np.array_equal(gi["T"], of["t"]) and np.array_equal(of["t"], o["t"])
+        scale = np.abs(of["pu_mu"]).max(axis=0)
+
+        def m_mean(s_, b_):
+            return np.max(np.abs(s_["pu_mu"] - b_["pu_mu"]) / scale)
+
+        fl = rounding.floor(oracle, rhs, 3, 3, 3, u0[i], p[i], kw, of, m_mean)
+        err = np.max(np.abs(gi["U"] - of["pu_mu"]) / scale)
+        assert err < max(1e-8, 10.0 * fl), (i, err, fl)
+        sig = of["diffusions"][:-1]
+        kwf = dict(forced_diffusion=sig, **kw)
+        of2 = oracle.solve(oracle.make_config(3, 3, 3, **kwf), rhs, u0[i], p[i])
+        g2 = _gpu(pd, u0[i:i + 1], p[i:i + 1], 3, builtin=False, adaptive=False, dt=t1, t0=0.0, t1=t1, save_everystep=True,
+                  tstops=grid, forced_diffusion=sig, mass_matrix=M)
+        fl2 = rounding.floor(oracle, rhs, 3, 3, 3, u0[i], p[i], kwf, of2, m_mean)
+        fc2 = rounding.floor(oracle, rhs, 3, 3, 3, u0[i], p[i], kwf, of2,
+                             lambda s_, b_: _relcov(s_["pu_cov"][1:], b_["pu_cov"][1:]))
+        assert np.max(np.abs(g2["U"] - of2["pu_mu"]) / scale) < max(1e-8, 10.0 * fl2), (i, fl2)
+        assert _relcov(g2["C"][1:], of2["pu_cov"][1:]) < max(1e-8, 10.0 * fc2), (i, fc2)
+    if t1 == 1e-2:   # test/mass_matrix.jl:81-82 (nominal parameters): implicit reference solution, rtol 1e-8
+        from scipy.integrate import solve_ivp
+        k1, k2, k3 = pd.p
+        ref = solve_ivp(lambda t, u: [-k1 * u[0] + k3 * u[1] * u[2], k1 * u[0] - k3 * u[1] * u[2] - k2 * u[1] ** 2, k2 * u[1] ** 2],
+                        (0, t1), pd.u0, method="Radau", rtol=1e-12, atol=1e-14).y[:, -1]
+        g1 = _gpu(pd, u0[:1], np.array([pd.p]), 3, builtin=False, adaptive=True, t0=0.0, t1=t1, mass_matrix=M)
+        assert np.linalg.norm(g1["u"][0] - ref) <= 1e-8 * np.linalg.norm(ref)
+
+
+@pytest.mark.parametrize("smooth", [False, True])
+def test_mass_matrix_general_fixed_steps_static_diffusion(oracle, smooth):
+    """A dense, non-symmetric, non-singular M on fixed steps with FixedDiffusion: filter (and smoother) means and
+    covariances of every saved point against the oracle, rtol 1e-10; plus the dense output on a saveat grid."""
+    pd, u0, p = _mass_inputs(3, 62)
+    u0 = u0 + np.array([0.0, 0.1, 0.2])
+    p = p * np.array([1.0, 1e-6, 1e-3])
+    M = np.array([[1.0, 0.2, 0.0], [0.0, 1.0, 0.0], [0.1, 0.0, 0.5]])
+    kw = dict(adaptive=False, dt=1e-3, t0=0.0, t1=0.2, diffusion=lib.DIFF_FIXED, calibrate=True, mass_matrix=M)
+    saveat = np.array([0.0, 0.0123, 0.1, 0.2])
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    cfg = oracle.make_config(3, 3, 3, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=True, smooth=smooth, adaptive=False,
+                             dt=1e-3, t0=0.0, t1=0.2, cov_backend=oracle.COV_QR, mass_matrix=M)
+    if smooth:
+        g = _gpu_smooth(pd, u0, p, 3, **kw)
+    else:
+        g = _gpu(pd, u0, p, 3, builtin=False, save_everystep=True, **kw)
+    gd = _gpu_dense(pd, u0, p, 3, saveat, smooth=smooth, **kw)
+    for i in range(u0.shape[0]):
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"] == 201
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < 1e-9
+        for j, t in enumerate(saveat):
+            m, c = oracle.interpolate(cfg, o, float(t))
+            assert _rel(gd["U"][i, j], m) < 1e-10, (i, j)
+            if np.linalg.norm(c) > 0:
+                assert np.linalg.norm(gd["C"][i, j] - c) / np.linalg.norm(c) < 1e-8, (i, j)
+
+
+def test_mass_matrix_uniform_scaling_and_errors(oracle):
+    """test/mass_matrix.jl:7-17: M = -100 I, f(u) = u: adaptive EK1(order=3) end point against exp(-t/100), rtol 1e-10;
+    EK0 on the Kronecker layout raises the reference's ArgumentError (src/caches.jl:111-118)."""
+    def vf(du, u, p, t):
+        du[0] = u[0]
+        du[1] = u[1]
+
+    pd = problems.ProblemDef("vf", vf, [1.0, 2.0], [], (0.0, 1.0))
+    u0 = np.array([[1.0, 2.0], [0.5, -1.0]])
+    p = np.zeros((2, 0))
+    M = -100.0 * np.eye(2)
+    g = _gpu(pd, u0, p, 3, builtin=False, adaptive=True, t0=0.0, t1=1.0, mass_matrix=M)
+    assert np.allclose(g["u"], u0 * np.exp(-0.01), rtol=1e-10, atol=0)
+    rhs = oracle.compile_rhs(tracer.trace(vf, 2, 0), 3)
+    o = oracle.solve(oracle.make_config(2, 3, 0, alg=oracle.EK1, smooth=False, adaptive=True, t0=0.0, t1=1.0, cov_backend=oracle.COV_QR,
+                                        mass_matrix=M), rhs, u0[0], [])
+    assert abs(int(g["naccept"][0]) - o["naccept"]) <= 2 and g["nf"][0] == 3 + g["naccept"][0] + g["nreject"][0]
+    assert _rel(g["u"][0], o["pu_mu"][-1]) < 1e-10
+    with pytest.raises(lib.PnodeError) as e:
+        _gpu(pd, u0, p, 3, builtin=False, alg=lib.EK0, adaptive=True, t0=0.0, t1=1.0, mass_matrix=M)
+    assert e.value.kind == "ArgumentError"

@@ -205,3 +205,25 @@ def test_taylor_elementary_functions():
     subs = {tr.u[0]: u0[0], tr.u[1]: u0[1], tr.p[0]: p[0], tr.t: 0.25}
     want = np.array([[float(ys[k][i].subs(subs)) for i in range(2)] for k in range(q + 1)])
     assert np.allclose(got, want, rtol=1e-11, atol=1e-12)
+
+
+def test_mass_matrix_kernels_compile_and_argument_checks(pnlib):
+    """Mass-matrix problems (src/measurement_models.jl:11-20, src/derivative_utils.jl:43-50): the EK1 step kernel with M
+    baked in compiles for sm_100a; EK0 on the Kronecker layout raises the reference's ArgumentError (src/caches.jl:111-118);
+    an identity M is the plain path; a matrix whose initial conditioning is singular is rejected."""
+    pd, src = _src("rober")
+    base = dict(d=3, q=3, n_p=3, rhs_name="UserProb", rhs_src=src, t0=0.0, t1=1e-2)
+    plain = pnlib.compile_check(pnlib.make_config(**base))
+    assert pnlib.compile_check(pnlib.make_config(mass_matrix=np.eye(3), **base)) == plain
+    assert pnlib.compile_check(pnlib.make_config(mass_matrix=np.diag([1.0, 1.0, 0.0]), **base)) > 10_000
+    assert pnlib.compile_check(pnlib.make_config(mass_matrix=[[1, 0.2, 0], [0, 1, 0], [0.1, 0, 0.5]], smooth=True,
+                                                 save_everystep=True, saveat=[0.0, 5e-3], **base)) > 10_000
+    with pytest.raises(pnlib.PnodeError) as e:
+        pnlib.compile_check(pnlib.make_config(mass_matrix=-100 * np.eye(3), alg=pnlib.EK0, **base))
+    assert e.value.kind == "ArgumentError" and "incompatible with the provided mass matrix" in str(e.value)
+    with pytest.raises(pnlib.PnodeError) as e:
+        pnlib.compile_check(pnlib.make_config(mass_matrix=-100 * np.eye(3), alg=pnlib.DIAGONAL_EK1, **base))
+    assert e.value.kind == "Unsupported"
+    with pytest.raises(pnlib.PnodeError) as e:
+        pnlib.compile_check(pnlib.make_config(mass_matrix=[[1, 1, 0], [1, 1, 0], [0, 0, 1]], **base))
+    assert e.value.kind == "ArgumentError"

@@ -4,6 +4,7 @@ Every test cites the reference test (under /root/reference/test) whose assertion
 on CPU (-m "not gpu").
 """
 import ctypes as C
+import math
 
 import numpy as np
 import pytest
@@ -551,3 +552,95 @@ def test_convergence_order(oracle, q):
         errs.append(abs(s["pu_mu"][-1][0] - 0.5 * np.exp(1.01)))
     orders = [np.log2(errs[i + 1] / errs[i]) for i in range(len(dts) - 1)]
     assert abs(np.mean(orders) - (q + 1)) < 0.3, (errs, orders)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# mass-matrix problems  M u' = f(u, p, t)  (reference test/mass_matrix.jl)
+# ---------------------------------------------------------------------------------------------------------------------
+def _rober_dae(du, u, p, t):
+    du[0] = -p[0] * u[0] + p[2] * u[1] * u[2]
+    du[1] = p[0] * u[0] - p[2] * u[1] * u[2] - p[1] * u[1] * u[1]
+    du[2] = u[0] + u[1] + u[2] - 1.0
+
+
+def _rober_truth(t1, p=(0.04, 3e7, 1e4)):
+    k1, k2, k3 = p
+
+    def fn(t, u):
+        return [-k1 * u[0] + k3 * u[1] * u[2], k1 * u[0] - k3 * u[1] * u[2] - k2 * u[1] ** 2, k2 * u[1] ** 2]
+
+    def jac(t, u):
+        return [[-k1, k3 * u[2], k3 * u[1]], [k1, -k3 * u[2] - 2 * k2 * u[1], -k3 * u[1]], [0.0, 2 * k2 * u[1], 0.0]]
+
+    return solve_ivp(fn, (0, t1), [1.0, 0.0, 0.0], method="Radau", jac=jac, rtol=1e-12, atol=1e-14).y[:, -1]
+
+
+def test_mass_matrix_uniform_scaling(oracle):
+    """test/mass_matrix.jl:7-17: M = -100 I, f(u) = u on [0, 1]: the adaptive EK1(order=3) end point agrees with the exact
+    solution exp(-t/100) to rtol 1e-10; :19-52: the fixed-step EK1 (dt = 1e-2, N = 10 components) to rtol 1e-7."""
+    def vf(du, u, p, t):
+        for i in range(len(du)):
+            du[i] = u[i]
+
+    tr = tracer.trace(vf, 1, 0)
+    rhs = oracle.compile_rhs(tr, 3)
+    s = oracle.solve(oracle.make_config(1, 3, 0, alg=oracle.EK1, smooth=True, adaptive=True, t0=0, t1=1,
+                                        mass_matrix=[[-100.0]]), rhs, [1.0], [])
+    assert s["retcode"] == "Success"
+    assert abs(s["pu_mu"][-1][0] - np.exp(-0.01)) <= 1e-10 * np.exp(-0.01)
+    assert abs((s["t"][1] - s["t"][0]) - 1e-6) < 1e-18
+    # the reference conditions the initial state on MM E_o x = d^o/dt^o of u' = f(u) (autodiffinit.jl:33-47): x_o = df_o / M
+    assert np.allclose(s["x_filt_mu"][0], [1.0, -0.01, -0.01, -0.01], rtol=1e-15, atol=0)
+    N = 10
+    tr = tracer.trace(vf, N, 0)
+    rhs = oracle.compile_rhs(tr, 3)
+    s = oracle.solve(oracle.make_config(N, 3, 0, alg=oracle.EK1, smooth=False, adaptive=False, dt=1e-2, t0=0, t1=1,
+                                        save_everystep=False, mass_matrix=-100.0 * np.eye(N)), rhs, np.ones(N), [])
+    assert np.allclose(s["pu_mu"][-1], np.exp(-0.01), rtol=1e-7, atol=0)
+    # EK0 on the Kronecker layout with a mass matrix: not restated (ArgumentError in the reference unless M is a UniformScaling)
+    with pytest.raises(Exception):
+        oracle.solve(oracle.make_config(N, 3, 0, alg=oracle.EK0, smooth=False, adaptive=False, dt=1e-2, t0=0, t1=1,
+                                        mass_matrix=-100.0 * np.eye(N)), rhs, np.ones(N), [])
+
+
+def test_mass_matrix_robertson_dae(oracle):
+    """test/mass_matrix.jl:64-88: Robertson in mass-matrix form, M = Diagonal([1, 1, 0]), t in [0, 1e-2]: the adaptive
+    EK1(order=3) end point agrees with an implicit reference solution to rtol 1e-8 (norm-wise, Julia's isapprox)."""
+    ref = _rober_truth(1e-2)
+    tr = tracer.trace(_rober_dae, 3, 3)
+    rhs = oracle.compile_rhs(tr, 3)
+    cfg = oracle.make_config(3, 3, 3, alg=oracle.EK1, smooth=True, adaptive=True, t0=0, t1=1e-2, mass_matrix=np.diag([1.0, 1.0, 0.0]))
+    s = oracle.solve(cfg, rhs, [1.0, 0.0, 0.0], [0.04, 3e7, 1e4])
+    assert s["retcode"] == "Success"
+    assert np.linalg.norm(s["pu_mu"][-1] - ref) <= 1e-8 * np.linalg.norm(ref)
+    # a mass matrix != I: initial step = max(1e-6, dtmin) (see oracle initial_dt)
+    assert abs((s["t"][1] - s["t"][0]) - 1e-6) < 1e-18
+    # the algebraic constraint holds along the whole solution
+    assert np.max(np.abs(s["pu_mu"].sum(axis=1) - 1.0)) < 1e-10
+
+
+def test_mass_matrix_measurement(oracle):
+    """test/core/measurement_models.jl:35-45: z = M E1 x - f(E0 x).  Checked through the first step of a solve with forced
+    unit diffusion: with Sigma0 = 0 the filter mean after one step satisfies H (mu^- - K z) with z = M E1 mu^- - f -- here the
+    residual of the updated mean M E1 mu - f(E0 mu^-) - J E0 (mu - mu^-) vanishes to rounding."""
+    tr = tracer.trace(_rober_dae, 3, 3)
+    rhs = oracle.compile_rhs(tr, 3)
+    M = np.array([[1.0, 0.2, 0.0], [0.0, 1.0, 0.0], [0.1, 0.0, 0.5]])
+    p = [0.04, 3e1, 1e1]
+    u0 = [1.0, 0.1, 0.2]
+    cfg = oracle.make_config(3, 3, 3, alg=oracle.EK1, smooth=True, adaptive=False, dt=1e-3, t0=0, t1=1e-3, mass_matrix=M)
+    s = oracle.solve(cfg, rhs, u0, p)
+    d = 3
+    mu0, mu1 = s["x_filt_mu"][0], s["x_filt_mu"][1]
+    # initial state: M x_1 = f(u0)
+    f0 = np.zeros(3); _rober_dae(f0, np.array(u0), p, 0.0)
+    assert np.allclose(M @ mu0[d:2 * d], f0, rtol=1e-13, atol=1e-15)
+    # predicted mean (IWP Taylor step), linearisation point and the updated mean's residual
+    h = 1e-3
+    T = np.array([[h ** (k - j) / math.factorial(k - j) if k >= j else 0.0 for k in range(4)] for j in range(4)])
+    mup = np.kron(T, np.eye(d)) @ mu0
+    fu = np.zeros(3); _rober_dae(fu, mup[:d], p, h)
+    u = mup[:d]
+    J = np.array([[-p[0], p[2] * u[2], p[2] * u[1]], [p[0], -p[2] * u[2] - 2 * p[1] * u[1], -p[2] * u[1]], [1.0, 1.0, 1.0]])
+    res = M @ mu1[d:2 * d] - fu - J @ (mu1[:d] - mup[:d])
+    assert np.max(np.abs(res)) < 1e-12
