@@ -1,6 +1,6 @@
 # See INTEGRATION.md. Host-side binding of include/pnode.h (unexecuted: no Julia in the build image).
 module ProbNumDiffEqB200
-using ProbNumDiffEq, SciMLBase, Symbolics
+using ProbNumDiffEq, SciMLBase, Symbolics, LinearAlgebra
 const LIB = "libpnode_cuda"
 
 struct EnsembleB200 <: SciMLBase.EnsembleAlgorithm
@@ -20,12 +20,15 @@ struct PnodeConfig
     tstops::Ptr{Float64}; n_tstops::Int64; forced_diffusion::Ptr{Float64}; n_forced::Int64
     rate_parameter::Float64                      # IOUP(q, rate) prior; ignored for the IWP
     saveat::Ptr{Float64}; n_saveat::Int64        # dense output sol(saveat) evaluated on the device
+    mass_matrix::Ptr{Float64}                    # d × d row-major, C_NULL = identity (ODEFunction(f; mass_matrix=M))
 end
 
 # enum values of include/pnode.h
 alg_code(alg) = alg isa EK0 ? 0 : alg isa DiagonalEK1 ? 2 : 1
 prior_code(p) = p isa ProbNumDiffEq.IOUP ? 1 : 0
 rate_of(p) = p isa ProbNumDiffEq.IOUP ? Float64(p.rate_parameter) : 0.0
+# row-major copy of a constant mass matrix; `nothing` for I (UniformScaling λI becomes the dense λ·I)
+mass_of(f, d) = f.mass_matrix === LinearAlgebra.I ? nothing : collect(transpose(Matrix{Float64}(f.mass_matrix * LinearAlgebra.I(d))))
 diffusion_code(m) = m isa FixedMVDiffusion ? 3 : m isa DynamicMVDiffusion ? 2 : m isa FixedDiffusion ? 1 : 0
 
 check(rc) = rc == 0 || throw(ArgumentError(unsafe_string(ccall((:pnode_last_error, LIB), Cstring, ()))))
@@ -37,13 +40,15 @@ function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::ProbNumDi
     u0 = reduce(hcat, (p.u0 for p in probs))          # d × N column-major == [N][d] row-major
     ps = reduce(hcat, (collect(p.p) for p in probs))
     src = trace_to_cuda(ep.prob.f, d, n_p)            # Symbolics → "struct PnodeUserProblem { f<T>, jac }"
-    GC.@preserve src begin
+    mm = mass_of(ep.prob.f, d)
+    GC.@preserve src mm begin
         cfg = Ref(PnodeConfig(sizeof(PnodeConfig), ens.device, d, ProbNumDiffEq.num_derivatives(alg.prior), n_p,
                               alg_code(alg), 0, prior_code(alg.prior), diffusion_code(alg.diffusionmodel), 1,
                               alg.smooth, adaptive, save_everystep, 0, 0, 0, 1_000_000, 1.0,
                               ep.prob.tspan[1], ep.prob.tspan[2], dt, abstol, reltol, 0.0, 0.0,
                               0, 0, 0.2, 10.0, 0.9, 1.0, 1.0, 1e-4,
-                              pointer(src), pointer("PnodeUserProblem"), C_NULL, 0, C_NULL, 0, rate_of(alg.prior), C_NULL, 0))
+                              pointer(src), pointer("PnodeUserProblem"), C_NULL, 0, C_NULL, 0, rate_of(alg.prior), C_NULL, 0,
+                              mm === nothing ? Ptr{Float64}(C_NULL) : pointer(mm)))
         solver = Ref{Ptr{Cvoid}}()
         check(ccall((:pnode_create, LIB), Cint, (Ref{PnodeConfig}, Ref{Ptr{Cvoid}}), cfg, solver))
         res = Ref{Ptr{Cvoid}}()
