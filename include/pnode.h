@@ -115,8 +115,9 @@ typedef struct pnode_config {
     /* constant mass matrix M of  M u' = f(u, p, t)  (`ODEFunction(f; mass_matrix=M)`): d x d, row-major, host pointer,
        copied at create; NULL = identity.  Measurement z = M E1 x - f(E0 x) (src/measurement_models.jl:11-20),
        H = M E1 - J E0 (src/derivative_utils.jl:1-53), initial derivatives as src/initialization/autodiffinit.jl:20-47.
-       May be singular (index-1 DAEs).  EK1 on the dense layout (D <= 32); anything else is rejected:
-       EK0 -> PNODE_ERR_ARGUMENT with the reference's message (src/caches.jl:111-118). */
+       May be singular (index-1 DAEs).  EK1 on the dense layout (D <= 32): any M; DiagonalEK1 / EK0 with a multivariate
+       diffusion (blocks layout): diagonal M; EK0 on the Kronecker layout: M = lambda I only, otherwise
+       PNODE_ERR_ARGUMENT with the reference's message (src/caches.jl:111-118). */
     const double* mass_matrix;
 } pnode_config;
 

@@ -639,10 +639,17 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
     taylor(mu, u0, p, c->t0, q);
     out->nf += q;
     for (int i = 0; i < d; i++) uprev[i] = mu[i];
+    const double* Mm = c->mass_matrix; /* diagonal (checked by the caller) */
+    if (Mm) {
+        int zero_diag = 0;
+        for (int i = 0; i < d; i++) zero_diag |= (AT(Mm, i, i, d) == 0.0);
+        for (int o = 1; o <= q; o++) /* x_o = MM^-1 df_o, MM = M (+ 1e-20 I) (autodiffinit.jl:20-47) */
+            for (int i = 0; i < d; i++) mu[o * d + i] = (1.0 / (AT(Mm, i, i, d) + (zero_diag ? 1e-20 : 0.0))) * mu[o * d + i];
+    }
     double t = c->t0, dt;
     if (c->adaptive && !(c->dt > 0.0)) {
-        dt = initial_dt(c, f, u0, p, q, 0);
-        out->nf += 2;
+        dt = initial_dt(c, f, u0, p, q, Mm != NULL);
+        if (!Mm) out->nf += 2;
     } else {
         dt = c->dt;
     }
@@ -680,8 +687,8 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
         for (int i = 0; i < d; i++) upred[i] = mu_pred[i];
         f(fu, upred, p, tnew);
         out->nf += 1;
-        for (int i = 0; i < d; i++) z[i] = mu_pred[d + i] - fu[i];
-        /* calc_H! (derivative_utils.jl:1-33): EK0 H = E1; DiagonalEK1 H = E1 - Diagonal(diag(J)) E0 */
+        for (int i = 0; i < d; i++) z[i] = (Mm ? AT(Mm, i, i, d) : 1.0) * mu_pred[d + i] - fu[i];
+        /* calc_H! (derivative_utils.jl:1-53): EK0 H = M E1; DiagonalEK1 H = M E1 - Diagonal(diag(J)) E0 */
         if (diag1) {
             jac(J, upred, p, tnew);
             out->njac += 1;
@@ -689,7 +696,7 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
         for (int i = 0; i < d; i++) {
             double* Hi = H + (size_t)i * n;
             for (int k = 0; k < n; k++) Hi[k] = 0.0;
-            Hi[1] = 1.0;
+            Hi[1] = Mm ? AT(Mm, i, i, d) : 1.0;
             if (diag1) Hi[0] = -AT(J, i, i, d);
         }
         if (c->adaptive || dynamic) {
@@ -909,10 +916,23 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
 
 int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, oracle_taylor_fn taylor,
                  const double* u0, const double* p, oracle_traj* out) {
-    /* mass matrices: restated for EK1 on the dense layout only (EK0 + Kronecker: ArgumentError in the reference,
-       caches.jl:111-118) */
-    if (c->mass_matrix && (c->alg != ORACLE_EK1 || c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV))
-        return -2;
+    /* mass matrices: EK1 on the dense layout takes any M; the Kronecker layout (EK0 + IWP + scalar diffusion) only a
+       UniformScaling (ArgumentError otherwise, caches.jl:111-118; H = lambda E1, derivative_utils.jl:45-47); the
+       BlocksOfDiagonals layout is restated for diagonal M */
+    if (c->mass_matrix) {
+        const double* M = c->mass_matrix;
+        int diagonal = 1, uniform = 1, zero_diag = 0;
+        for (int a = 0; a < c->d; a++)
+            for (int i = 0; i < c->d; i++) {
+                if (a != i && AT(M, a, i, c->d) != 0.0) diagonal = 0;
+                if (a == i && AT(M, a, i, c->d) != M[0]) uniform = 0;
+                if (a == i && AT(M, a, i, c->d) == 0.0) zero_diag = 1;
+            }
+        const int blocks_layout = (c->alg == ORACLE_DIAGONAL_EK1 || c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV);
+        if (blocks_layout && (!diagonal || (c->alg == ORACLE_EK0 && zero_diag))) return -2;
+        if (!blocks_layout && c->alg == ORACLE_EK0 && c->prior == ORACLE_PRIOR_IWP && !(diagonal && uniform && !zero_diag)) return -2;
+        if (!blocks_layout && c->alg == ORACLE_EK0 && c->prior != ORACLE_PRIOR_IWP) return -2;
+    }
     if (c->alg == ORACLE_DIAGONAL_EK1 || c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV)
         return solve_blocks(c, f, jac, taylor, u0, p, out);
     const int d = c->d, q = c->q, n = q + 1, D = d * n;
@@ -1043,7 +1063,7 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
         f(fu, upred, p, tnew);
         out->nf += 1;
         for (int i = 0; i < d; i++) z[i] = mu_pred[d + i] - fu[i];
-        if (Mm) /* z = M E1 mu_pred - f (measurement_models.jl:18) */
+        if (Mm) /* z = M E1 mu_pred - f (measurement_models.jl:18); on the Kronecker layout M = lambda I */
             for (int a = 0; a < d; a++) {
                 double sacc = 0.0;
                 for (int i = 0; i < d; i++) sacc += AT(Mm, a, i, d) * mu_pred[d + i];
@@ -1051,7 +1071,7 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
             }
         /* calc_H! (derivative_utils.jl:1-33) */
         if (kron) {
-            for (int k = 0; k < N; k++) H[k] = (k == 1) ? 1.0 : 0.0; /* E1.B = e_1' (projection.jl:20-29) */
+            for (int k = 0; k < N; k++) H[k] = (k == 1) ? (Mm ? Mm[0] : 1.0) : 0.0; /* E1.B = e_1' (projection.jl:20-29), times lambda */
         } else {
             memset(H, 0, sizeof(double) * (size_t)m * N);
             for (int i = 0; i < d; i++) AT(H, i, d + i, d) = 1.0;    /* H = E1 */

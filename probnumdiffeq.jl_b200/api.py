@@ -220,8 +220,10 @@ def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, absto
         if M.shape != (d, d):
             raise ValueError("mass_matrix must be d x d")  # DimensionMismatch
         if not np.array_equal(M, np.eye(d)):
-            if isinstance(alg, EK0) and isinstance(alg.prior, IWP) and not isinstance(diff, (FixedMVDiffusion, DynamicMVDiffusion)):
-                # src/caches.jl:111-118 (the reference lets a UniformScaling through; a matrix argument is never one)
+            uniform = np.array_equal(M, M[0, 0] * np.eye(d)) and M[0, 0] != 0.0
+            if isinstance(alg, EK0) and isinstance(alg.prior, IWP) and not isinstance(diff, (FixedMVDiffusion, DynamicMVDiffusion)) \
+                    and not uniform:
+                # src/caches.jl:111-118: only a UniformScaling (here: M == lambda I) passes on the Kronecker layout
                 raise ValueError("The selected algorithm uses an efficient Kronecker-factorized implementation which is "
                                  "incompatible with the provided mass matrix. Try using the `EK1` instead.")
             kw.update(mass_matrix=M)

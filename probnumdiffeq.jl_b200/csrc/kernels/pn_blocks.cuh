@@ -97,7 +97,7 @@ struct PnBlocks {
 #pragma unroll
                 for (int i = 0; i < d; i++) uprev[i] = M[0][i];
                 dt = P.init_dt[traj];
-                if (ADAPTIVE && !(P.dt0 > 0.0)) nf += 2;
+                if (ADAPTIVE && !(P.dt0 > 0.0) && !PN_MASS) nf += 2;
             }
             const double dtcache = dt;
 #pragma unroll
@@ -168,7 +168,11 @@ struct PnBlocks {
                 nf += 1;
 #pragma unroll
                 for (int i = 0; i < d; i++) {
+#if PN_MASS
+                    z[i] = pn_mass(i, i) * Mp[1][i] - fu[i]; /* diagonal M: H_i = M_ii e_1' - J_ii e_0' */
+#else
                     z[i] = Mp[1][i] - fu[i];
+#endif
                     h0[i] = 0.0;
                 }
                 if (DIAG1) { /* H_i = e_1' - J_ii e_0' */
@@ -184,7 +188,11 @@ struct PnBlocks {
                     double e = 0.0;
 #pragma unroll
                     for (int m = 0; m < n; m++) {
+#if PN_MASS
+                        const double cq = P.L[m * n + 0] * PIv[0] * h0[i] + ((m >= 1) ? P.L[m * n + 1] * PIv[1] * pn_mass(i, i) : 0.0);
+#else
                         const double cq = P.L[m * n + 0] * PIv[0] * h0[i] + ((m >= 1) ? P.L[m * n + 1] * PIv[1] : 0.0);
+#endif
                         e += cq * cq;
                     }
                     HQH[i] = e;
@@ -258,7 +266,11 @@ struct PnBlocks {
                     double Si = 0.0;
 #pragma unroll
                     for (int r = 0; r < n; r++) {
+#if PN_MASS
+                        c1[r] = RB[i][r][1] * pn_mass(i, i) + h0[i] * RB[i][r][0];
+#else
                         c1[r] = RB[i][r][1] + h0[i] * RB[i][r][0];
+#endif
                         Si += c1[r] * c1[r];
                     }
                     S[i] = Si;

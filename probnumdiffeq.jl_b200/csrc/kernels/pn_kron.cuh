@@ -89,7 +89,7 @@ struct PnKron {
 #pragma unroll
                 for (int i = 0; i < d; i++) uprev[i] = M[0][i];
                 dt = P.init_dt[traj];
-                if (ADAPTIVE && !(P.dt0 > 0.0)) nf += 2;
+                if (ADAPTIVE && !(P.dt0 > 0.0) && !PN_MASS) nf += 2;
             }
             const double dtcache = dt;
 #pragma unroll
@@ -157,14 +157,22 @@ struct PnKron {
                 double zz = 0.0;
 #pragma unroll
                 for (int i = 0; i < d; i++) {
+#if PN_MASS
+                    z[i] = pn_mass(0, 0) * Mp[1][i] - fu[i]; /* M = lambda I: H.B = lambda e_1' (derivative_utils.jl:45-47) */
+#else
                     z[i] = Mp[1][i] - fu[i];
+#endif
                     zz += z[i] * z[i];
                 }
                 /* W.B = |Qh.R.B[:,1]|^2 */
                 double Wb = 0.0;
 #pragma unroll
                 for (int m = 1; m < n; m++) {
+#if PN_MASS
+                    const double l1 = P.L[m * n + 1] * PIv[1] * pn_mass(0, 0);
+#else
                     const double l1 = P.L[m * n + 1] * PIv[1];
+#endif
                     Wb += l1 * l1;
                 }
                 double EEst = 0.0, qq = 1.0, q11 = 0.0, lEE = 0.0;
@@ -226,7 +234,11 @@ struct PnKron {
                 double S = 0.0;
 #pragma unroll
                 for (int r = 0; r < n; r++) {
+#if PN_MASS
+                    c1[r] = RB[r][1] * pn_mass(0, 0);
+#else
                     c1[r] = RB[r][1];
+#endif
                     S += c1[r] * c1[r];
                 }
                 if (S == 0.0) { /* Sigma^- == 0: update.jl:82-89 */

@@ -703,14 +703,33 @@ static int validate_config(const pnode_config* cfg) {
         int mrc = mass_preamble(cfg->mass_matrix, cfg->d, &pre);
         if (mrc) return mrc;
         if (!pre.empty()) { /* M != I */
-            if (layout == PNODE_COV_KRONECKER) /* src/caches.jl:111-118 (a matrix argument is never a UniformScaling) */
-                return fail(PNODE_ERR_ARGUMENT,
-                            "The selected algorithm uses an efficient Kronecker-factorized implementation which is incompatible "
-                            "with the provided mass matrix. Try using the `EK1` instead.");
-            if (cfg->alg != PNODE_EK1 || layout != PNODE_COV_DENSE)
-                return fail(PNODE_ERR_UNSUPPORTED, "mass matrices are implemented for the EK1 on the dense layout");
-            if (D > 32 || cfg->lanes_per_traj == 256)
-                return fail(PNODE_ERR_UNSUPPORTED, "mass matrices are implemented for D = d(q+1) <= 32 (register-resident kernel)");
+            const int d = cfg->d;
+            const double* M = cfg->mass_matrix;
+            bool diagonal = true, uniform = true, zero_on_diag = false;
+            for (int a = 0; a < d; a++)
+                for (int i = 0; i < d; i++) {
+                    if (a != i && M[a * d + i] != 0.0) diagonal = false;
+                    if (a == i && M[a * d + i] != M[0]) uniform = false;
+                    if (a == i && M[a * d + i] == 0.0) zero_on_diag = true;
+                }
+            uniform = uniform && diagonal;
+            if (layout == PNODE_COV_KRONECKER) {
+                /* src/caches.jl:111-118: only a UniformScaling passes (H = lambda E1, derivative_utils.jl:45-47) */
+                if (!uniform || zero_on_diag)
+                    return fail(PNODE_ERR_ARGUMENT,
+                                "The selected algorithm uses an efficient Kronecker-factorized implementation which is incompatible "
+                                "with the provided mass matrix. Try using the `EK1` instead.");
+            } else if (layout == PNODE_COV_BLOCKS) {
+                if (!diagonal)
+                    return fail(PNODE_ERR_UNSUPPORTED, "the blocks-of-diagonals layout (DiagonalEK1, EK0 with multivariate diffusion) takes diagonal mass matrices only");
+                if (cfg->alg == PNODE_EK0 && zero_on_diag)
+                    return fail(PNODE_ERR_ARGUMENT, "the EK0 cannot solve problems with a singular mass matrix (H_i = M_ii e_1' vanishes); use the EK1 or the DiagonalEK1");
+            } else {
+                if (cfg->alg != PNODE_EK1)
+                    return fail(PNODE_ERR_UNSUPPORTED, "mass matrices on the dense layout are implemented for the EK1");
+                if (D > 32 || cfg->lanes_per_traj == 256)
+                    return fail(PNODE_ERR_UNSUPPORTED, "mass matrices are implemented for D = d(q+1) <= 32 (register-resident kernel)");
+            }
         }
     }
     const bool builtin = (std::string(cfg->rhs_name).rfind("builtin:", 0) == 0);

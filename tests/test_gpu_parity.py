@@ -1045,6 +1045,57 @@ def test_mass_matrix_uniform_scaling_and_errors(oracle):
                                         mass_matrix=M), rhs, u0[0], [])
     assert abs(int(g["naccept"][0]) - o["naccept"]) <= 2 and g["nf"][0] == 3 + g["naccept"][0] + g["nreject"][0]
     assert _rel(g["u"][0], o["pu_mu"][-1]) < 1e-10
-    with pytest.raises(lib.PnodeError) as e:
-        _gpu(pd, u0, p, 3, builtin=False, alg=lib.EK0, adaptive=True, t0=0.0, t1=1.0, mass_matrix=M)
+    with pytest.raises(lib.PnodeError) as e:   # not a UniformScaling
+        _gpu(pd, u0, p, 3, builtin=False, alg=lib.EK0, adaptive=True, t0=0.0, t1=1.0, mass_matrix=np.diag([1.0, 2.0]))
     assert e.value.kind == "ArgumentError"
+
+
+@pytest.mark.parametrize("alg,diffusion", [(lib.EK0, lib.DIFF_FIXED), (lib.EK0, lib.DIFF_FIXED_MV), (lib.DIAGONAL_EK1, lib.DIFF_FIXED)])
+@pytest.mark.parametrize("smooth", [False, True])
+def test_mass_matrix_structured_layouts_fixed_steps(oracle, alg, diffusion, smooth):
+    """test/mass_matrix.jl:19-52 ("Kronecker working"): M = lambda I with the EK0 (Kronecker layout), and diagonal M on the
+    BlocksOfDiagonals layout (EK0 + FixedMV, DiagonalEK1); fixed steps, static diffusion: every saved mean and covariance
+    to 1e-10 against the oracle, and the end point against the exact solution of lambda u' = -u."""
+    def vf(du, u, p, t):
+        du[0] = -p[0] * u[0]
+        du[1] = -p[1] * u[1] + 0.1 * u[0]
+
+    pd = problems.ProblemDef("vf", vf, [1.0, 2.0], [1.0, 0.5], (0.0, 1.0))
+    u0 = np.array([[1.0, 2.0], [0.5, -1.0]])
+    p = np.array([[1.0, 0.5], [1.3, 0.7]])
+    kron = (alg == lib.EK0 and diffusion == lib.DIFF_FIXED)
+    M = -3.0 * np.eye(2) if kron else np.diag([-3.0, 0.5])
+    g = _gpu_blocks(pd, u0, p, 3, alg, diffusion, calibrate=True, smooth=smooth, adaptive=False, dt=0.01, t0=0.0, t1=1.0,
+                    mass_matrix=M)
+    rhs = oracle.compile_rhs(tracer.trace(vf, 2, 2), 3)
+    for i in range(2):
+        o = oracle.solve(oracle.make_config(2, 3, 2, alg=alg, diffusion=diffusion, calibrate=True, smooth=smooth, adaptive=False,
+                                            dt=0.01, t0=0.0, t1=1.0, cov_backend=oracle.COV_QR, mass_matrix=M), rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"] == 101 and g["retcode"][i] == 0
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < (1e-9 if smooth else 1e-10)
+        assert g["loglik"][i] == pytest.approx(o["loglik"], rel=1e-10)
+        # the initial higher derivatives are those of u' = f(u) divided by M (autodiffinit.jl:33-47), hence only 1e-4
+        assert abs(g["U"][b - 1, 0] - u0[i, 0] * np.exp(-p[i, 0] / M[0, 0])) < 1e-4 * abs(u0[i, 0])
+
+
+def test_mass_matrix_rober_dae_diagonal_ek1(oracle):
+    """test/mass_matrix.jl:87-88: DiagonalEK1(order=3) on the Robertson DAE, rtol 1e-8 against an implicit reference
+    solution; step counts as the oracle's (free running, see test_mass_matrix_rober_dae_adaptive for the protocol)."""
+    from scipy.integrate import solve_ivp
+    pd = problems.MASS_MATRIX_PROBLEMS["rober_dae"]
+    M = np.array(pd.mass_matrix)
+    k1, k2, k3 = pd.p
+    ref = solve_ivp(lambda t, u: [-k1 * u[0] + k3 * u[1] * u[2], k1 * u[0] - k3 * u[1] * u[2] - k2 * u[1] ** 2, k2 * u[1] ** 2],
+                    (0, 1e-2), pd.u0, method="Radau", rtol=1e-12, atol=1e-14).y[:, -1]
+    u0, p = np.array([pd.u0]), np.array([pd.p])
+    g = _gpu_blocks(pd, u0, p, 3, lib.DIAGONAL_EK1, lib.DIFF_DYNAMIC, adaptive=True, t0=0.0, t1=1e-2, mass_matrix=M)
+    assert g["retcode"][0] == 0
+    assert np.linalg.norm(g["U"][-1] - ref) <= 1e-8 * np.linalg.norm(ref)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 3, 3), 3)
+    o = oracle.solve(oracle.make_config(3, 3, 3, alg=oracle.DIAGONAL_EK1, smooth=False, adaptive=True, t0=0.0, t1=1e-2,
+                                        cov_backend=oracle.COV_QR, mass_matrix=M), rhs, u0[0], p[0])
+    assert abs(int(g["naccept"][0]) - o["naccept"]) <= 2
+    assert g["T"][1] - g["T"][0] == 1e-6
+    assert np.linalg.norm(g["U"][-1] - o["pu_mu"][-1]) <= 1e-8 * np.linalg.norm(o["pu_mu"][-1])

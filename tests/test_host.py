@@ -218,12 +218,19 @@ def test_mass_matrix_kernels_compile_and_argument_checks(pnlib):
     assert pnlib.compile_check(pnlib.make_config(mass_matrix=np.diag([1.0, 1.0, 0.0]), **base)) > 10_000
     assert pnlib.compile_check(pnlib.make_config(mass_matrix=[[1, 0.2, 0], [0, 1, 0], [0.1, 0, 0.5]], smooth=True,
                                                  save_everystep=True, saveat=[0.0, 5e-3], **base)) > 10_000
+    # EK0 / Kronecker: only a UniformScaling (M == lambda I) passes; DiagonalEK1 / blocks: diagonal M
+    assert pnlib.compile_check(pnlib.make_config(mass_matrix=-100 * np.eye(3), alg=pnlib.EK0, **base)) > 10_000
+    assert pnlib.compile_check(pnlib.make_config(mass_matrix=np.diag([1.0, 1.0, 0.0]), alg=pnlib.DIAGONAL_EK1, **base)) > 10_000
+    for M in (np.diag([1.0, 2.0, 3.0]), np.diag([1.0, 1.0, 0.0]), [[1, 0.2, 0], [0, 1, 0], [0, 0, 1]]):
+        with pytest.raises(pnlib.PnodeError) as e:
+            pnlib.compile_check(pnlib.make_config(mass_matrix=M, alg=pnlib.EK0, **base))
+        assert e.value.kind == "ArgumentError" and "incompatible with the provided mass matrix" in str(e.value)
     with pytest.raises(pnlib.PnodeError) as e:
-        pnlib.compile_check(pnlib.make_config(mass_matrix=-100 * np.eye(3), alg=pnlib.EK0, **base))
-    assert e.value.kind == "ArgumentError" and "incompatible with the provided mass matrix" in str(e.value)
-    with pytest.raises(pnlib.PnodeError) as e:
-        pnlib.compile_check(pnlib.make_config(mass_matrix=-100 * np.eye(3), alg=pnlib.DIAGONAL_EK1, **base))
+        pnlib.compile_check(pnlib.make_config(mass_matrix=[[1, 0.2, 0], [0, 1, 0], [0, 0, 1]], alg=pnlib.DIAGONAL_EK1, **base))
     assert e.value.kind == "Unsupported"
+    with pytest.raises(pnlib.PnodeError) as e:   # EK0 + multivariate diffusion (blocks) with a singular M
+        pnlib.compile_check(pnlib.make_config(mass_matrix=np.diag([1.0, 1.0, 0.0]), alg=pnlib.EK0, diffusion=pnlib.DIFF_DYNAMIC_MV, **base))
+    assert e.value.kind == "ArgumentError"
     with pytest.raises(pnlib.PnodeError) as e:
         pnlib.compile_check(pnlib.make_config(mass_matrix=[[1, 1, 0], [1, 1, 0], [0, 0, 1]], **base))
     assert e.value.kind == "ArgumentError"

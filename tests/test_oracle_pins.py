@@ -594,13 +594,14 @@ def test_mass_matrix_uniform_scaling(oracle):
     N = 10
     tr = tracer.trace(vf, N, 0)
     rhs = oracle.compile_rhs(tr, 3)
-    s = oracle.solve(oracle.make_config(N, 3, 0, alg=oracle.EK1, smooth=False, adaptive=False, dt=1e-2, t0=0, t1=1,
-                                        save_everystep=False, mass_matrix=-100.0 * np.eye(N)), rhs, np.ones(N), [])
-    assert np.allclose(s["pu_mu"][-1], np.exp(-0.01), rtol=1e-7, atol=0)
-    # EK0 on the Kronecker layout with a mass matrix: not restated (ArgumentError in the reference unless M is a UniformScaling)
+    for alg in (oracle.EK1, oracle.EK0, oracle.DIAGONAL_EK1):   # :19-52 "Kronecker working": s1, s0, s1diag
+        s = oracle.solve(oracle.make_config(N, 3, 0, alg=alg, smooth=False, adaptive=False, dt=1e-2, t0=0, t1=1,
+                                            save_everystep=False, mass_matrix=-100.0 * np.eye(N)), rhs, np.ones(N), [])
+        assert np.allclose(s["pu_mu"][-1], np.exp(-0.01), rtol=1e-7, atol=0), alg
+    # EK0 on the Kronecker layout with a mass matrix that is not a UniformScaling: ArgumentError (src/caches.jl:111-118)
     with pytest.raises(Exception):
         oracle.solve(oracle.make_config(N, 3, 0, alg=oracle.EK0, smooth=False, adaptive=False, dt=1e-2, t0=0, t1=1,
-                                        mass_matrix=-100.0 * np.eye(N)), rhs, np.ones(N), [])
+                                        mass_matrix=np.diag(np.arange(1.0, N + 1))), rhs, np.ones(N), [])
 
 
 def test_mass_matrix_robertson_dae(oracle):
@@ -617,6 +618,14 @@ def test_mass_matrix_robertson_dae(oracle):
     assert abs((s["t"][1] - s["t"][0]) - 1e-6) < 1e-18
     # the algebraic constraint holds along the whole solution
     assert np.max(np.abs(s["pu_mu"].sum(axis=1) - 1.0)) < 1e-10
+    # :87-88 DiagonalEK1(order=3), same threshold; :90 EK0 -> ArgumentError
+    s = oracle.solve(oracle.make_config(3, 3, 3, alg=oracle.DIAGONAL_EK1, smooth=True, adaptive=True, t0=0, t1=1e-2,
+                                        mass_matrix=np.diag([1.0, 1.0, 0.0])), rhs, [1.0, 0.0, 0.0], [0.04, 3e7, 1e4])
+    assert s["retcode"] == "Success"
+    assert np.linalg.norm(s["pu_mu"][-1] - ref) <= 1e-8 * np.linalg.norm(ref)
+    with pytest.raises(Exception):
+        oracle.solve(oracle.make_config(3, 3, 3, alg=oracle.EK0, smooth=True, adaptive=True, t0=0, t1=1e-2,
+                                        mass_matrix=np.diag([1.0, 1.0, 0.0])), rhs, [1.0, 0.0, 0.0], [0.04, 3e7, 1e4])
 
 
 def test_mass_matrix_measurement(oracle):
