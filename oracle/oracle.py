@@ -88,6 +88,7 @@ class Config(C.Structure):
         ("forced_diffusion", C.POINTER(C.c_double)), ("n_forced", C.c_int64),
         ("prior", C.c_int32), ("reserved", C.c_int32), ("rate_parameter", C.c_double),
         ("mass_matrix", C.POINTER(C.c_double)),
+        ("second_order", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -226,8 +227,9 @@ def make_config(d, q, n_p, *, alg=EK1, diffusion=DIFF_DYNAMIC, calibrate=True, i
                 adaptive=True, save_everystep=True, cov_backend=COV_REF, t0=0.0, t1=1.0, dt=0.0, abstol=1e-6,
                 reltol=1e-3, dtmin=0.0, dtmax=None, maxiters=1_000_000, beta1=None, beta2=None, qmin=0.2, qmax=10.0,
                 gamma=0.9, qsteady_min=1.0, qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None,
-                prior=PRIOR_IWP, rate_parameter=0.0, mass_matrix=None):
+                prior=PRIOR_IWP, rate_parameter=0.0, mass_matrix=None, second_order=False):
     c = Config()
+    c.second_order = int(second_order)
     c.d, c.q, c.n_p, c.alg = d, q, n_p, alg
     c.diffusion, c.calibrate, c.smooth, c.adaptive = diffusion, int(calibrate), int(smooth), int(adaptive)
     c.save_everystep, c.cov_backend, c.maxiters = int(save_everystep), cov_backend, int(maxiters)
@@ -275,6 +277,7 @@ def solve(cfg: Config, rhs: CompiledRHS, u0, p) -> dict:
     if rc != 0:
         raise RuntimeError(f"oracle_solve failed rc={rc}")
     n, d, D = tr.n, tr.d, tr.D
+    du = 2 * d if cfg.second_order else d   # sol.u = (du, u) for second-order problems (SolProj = [E1; E0])
     out = dict(
         n=n, d=d, q=tr.q, D=D, retcode=RET[tr.retcode], naccept=tr.naccept, nreject=tr.nreject, nf=tr.nf,
         njac=tr.njac, loglik=tr.loglik, global_diffusion=tr.global_diffusion,
@@ -282,8 +285,8 @@ def solve(cfg: Config, rhs: CompiledRHS, u0, p) -> dict:
         x_filt_mu=_arr(tr.x_filt_mu, (n, D)),
         # stored column-major D x D -> numpy [k, col, row]; transpose to [k, row, col]
         x_filt_R=_arr(tr.x_filt_R, (n, D, D)).transpose(0, 2, 1).copy(),
-        pu_mu=_arr(tr.pu_mu, (n, d)),
-        pu_R=_arr(tr.pu_R, (n, d, D)).transpose(0, 2, 1).copy(),
+        pu_mu=_arr(tr.pu_mu, (n, du)),
+        pu_R=_arr(tr.pu_R, (n, du, D)).transpose(0, 2, 1).copy(),
     )
     if tr.diffusions_mv:
         out["diffusions_mv"] = _arr(tr.diffusions_mv, (n, d))
@@ -333,6 +336,8 @@ def interpolate(cfg: Config, sol: dict, tval: float):
     L.oracle_marginalize.argtypes = [C.c_int, dp, dp, dp, dp, dp, dp, dp]
     t = sol["t"]
     d, D = sol["d"], sol["D"]
+    # SolProj: E0, or [E1; E0] for second-order problems (src/caches.jl:126)
+    sel = np.r_[d:2 * d, 0:d] if cfg.second_order else np.arange(d)
     if tval < t[0]:
         raise ValueError("Invalid t<t0")
     smoothed = "x_smooth_mu" in sol
@@ -340,7 +345,7 @@ def interpolate(cfg: Config, sol: dict, tval: float):
     if t[idx] == tval:
         mu = (sol["x_smooth_mu"] if smoothed else sol["x_filt_mu"])[idx]
         R = (sol["x_smooth_R"] if smoothed else sol["x_filt_R"])[idx]
-        return mu[:d].copy(), (R.T @ R)[:d, :d]
+        return mu[sel].copy(), (R.T @ R)[np.ix_(sel, sel)]
     diffusion = float(sol["diffusions"][min(idx, len(t) - 1)])
     colmajor = lambda M: np.asfortranarray(M).ravel(order="F").copy()  # noqa: E731
     h1 = tval - t[idx]
@@ -352,7 +357,7 @@ def interpolate(cfg: Config, sol: dict, tval: float):
     L.oracle_predict_cov(D, _dp(R0), _dp(Ah), _dp(Qh), diffusion, COV_QR, _dp(R_p), None)
     if not smoothed or tval >= t[-1]:
         Rp = R_p.reshape((D, D), order="F")
-        return mu_p[:d], (Rp.T @ Rp)[:d, :d]
+        return mu_p[sel], (Rp.T @ Rp)[np.ix_(sel, sel)]
     h2 = t[idx + 1] - tval
     Ah2, Qh2 = _transition_dense(cfg, h2)
     mu_pp = (Ah2.reshape((D, D), order="F") @ mu_p).copy()
@@ -365,7 +370,7 @@ def interpolate(cfg: Config, sol: dict, tval: float):
     mu_s, R_s = np.zeros(D), np.zeros(D * D)
     L.oracle_marginalize(D, _dp(mu_n), _dp(R_n), _dp(G), _dp(b), _dp(LR), _dp(mu_s), _dp(R_s))
     Rs = R_s.reshape((D, D), order="F")
-    return mu_s[:d], (Rs.T @ Rs)[:d, :d]
+    return mu_s[sel], (Rs.T @ Rs)[np.ix_(sel, sel)]
 
 
 def solve_ensemble(cfg: Config, rhs: CompiledRHS, u0, p, n_threads: int = 0) -> dict:

@@ -570,7 +570,7 @@ static void mass_setup(int d, const double* M, double* MMinv, int* singular) {
    branch returns the same value.  (3rd party, recalled; consistent with test/mass_matrix.jl:15-16 -- rtol 1e-10 with
    M = -100 I -- which the Hairer-Wanner step of 0.1 would miss by four orders of magnitude with this restatement.) */
 static double initial_dt(const oracle_config* c, oracle_rhs_fn f, const double* u0, const double* p, int order, int mass) {
-    int d = c->d;
+    int d = c->second_order ? 2 * c->d : c->d; /* the ArrayPartition (du, u) of a second-order problem */
     double sk[64], tmp[64], f0[64], f1[64], u1[64];
     double t = c->t0;
     double dtmax = c->dtmax;
@@ -605,6 +605,7 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
                         const double* u0, const double* p, oracle_traj* out) {
     const int d = c->d, q = c->q, n = q + 1, D = d * n;
     const int diag1 = (c->alg == ORACLE_DIAGONAL_EK1);
+    const int so = 0, du = d; /* second-order problems are not restated on this layout */
     const int mv = (c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV);
     const int dynamic = (c->diffusion == ORACLE_DIFF_DYNAMIC || c->diffusion == ORACLE_DIFF_DYNAMIC_MV);
     memset(out, 0, sizeof(*out));
@@ -862,8 +863,8 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
     for (int64_t k = 0; k < ns; k++) out->diffusions[k] = diffs.p[k * d];
     out->x_filt_mu = xmu.p;
     out->x_filt_R = (double*)calloc((size_t)ns * D * D, sizeof(double));
-    out->pu_mu = (double*)malloc(sizeof(double) * (size_t)ns * d);
-    out->pu_R = (double*)malloc(sizeof(double) * (size_t)ns * D * d);
+    out->pu_mu = (double*)malloc(sizeof(double) * (size_t)ns * du);
+    out->pu_R = (double*)malloc(sizeof(double) * (size_t)ns * D * du);
     /* dense form of a Blocks matrix: block i occupies rows/columns i:d:D (blocksofdiagonals.jl:44-52) */
 #define PN_BLOCKS_TO_DENSE(dst, src)                                                        \
     for (int i = 0; i < d; i++)                                                             \
@@ -903,9 +904,11 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
     for (int64_t k = 0; k < ns; k++) {
         const double* xm = (smu ? smu : xmu.p) + (size_t)k * D;
         const double* xr = (smu ? out->x_smooth_R : out->x_filt_R) + (size_t)k * D * D;
-        for (int i = 0; i < d; i++) out->pu_mu[(size_t)k * d + i] = xm[i];
-        for (int i = 0; i < d; i++)
-            for (int r = 0; r < D; r++) out->pu_R[(size_t)k * D * d + (size_t)i * D + r] = AT(xr, r, i, D);
+        for (int j = 0; j < du; j++) { /* SolProj row j selects state entry sc: E0 rows, or (E1; E0) for second order */
+            const int sc = so ? (j < d ? d + j : j - d) : j;
+            out->pu_mu[(size_t)k * du + j] = xm[sc];
+            for (int r = 0; r < D; r++) out->pu_R[(size_t)k * D * du + (size_t)j * D + r] = AT(xr, r, sc, D);
+        }
     }
     free(sR);
     free(xR.p); free(bG.p); free(bB.p); free(bL.p);
@@ -919,6 +922,9 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     /* mass matrices: EK1 on the dense layout takes any M; the Kronecker layout (EK0 + IWP + scalar diffusion) only a
        UniformScaling (ArgumentError otherwise, caches.jl:111-118; H = lambda E1, derivative_utils.jl:45-47); the
        BlocksOfDiagonals layout is restated for diagonal M */
+    if (c->second_order && (c->mass_matrix || c->q < 2 || c->alg == ORACLE_DIAGONAL_EK1 ||
+                            c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV))
+        return -2; /* second-order problems: restated for EK0 (Kronecker / dense) and EK1 with scalar diffusions */
     if (c->mass_matrix) {
         const double* M = c->mass_matrix;
         int diagonal = 1, uniform = 1, zero_diag = 0;
@@ -945,7 +951,10 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     memset(out, 0, sizeof(*out));
     out->d = d; out->q = q; out->D = D; out->smooth = c->smooth; out->alg = c->alg;
     out->global_diffusion = NAN;
-    if (d > 64 || n > 32) return -1;
+    const int so = c->second_order ? 1 : 0;
+    const int du = so ? 2 * d : d;       /* length of sol.u: (du, u) for second-order problems */
+    const int e1 = so ? 2 : 1;           /* the measured derivative: E2 x for second-order problems, E1 x otherwise */
+    if (du > 64 || n > 32) return -1;
 
     /* --- work buffers (EKCache, src/caches.jl:198-214) --- */
     size_t NN = (size_t)N * N;
@@ -960,7 +969,7 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     double* mu_filt = (double*)calloc(D, sizeof(double));
     double* R_filt = (double*)calloc(NN, sizeof(double));
     double* H = (double*)calloc((size_t)m * N, sizeof(double));
-    double* J = (double*)calloc((size_t)d * d, sizeof(double));
+    double* J = (double*)calloc((size_t)du * du, sizeof(double));
     double* Cq = (double*)malloc(sizeof(double) * (size_t)N * m);
     double* W = (double*)malloc(sizeof(double) * (size_t)m * m);
     double* G = (double*)malloc(sizeof(double) * NN);
@@ -975,9 +984,19 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     /* --- initial state: exact Taylor-mode derivatives, Sigma0.R == 0 exactly
        (src/initialization/autodiffinit.jl:1-47 + common.jl:122-139; SURVEY H7;
         test/solution.jl:59-62 asserts iszero(pu[1].Sigma.R)) --- */
-    taylor(mu, u0, p, c->t0, q);
+    if (so) { /* derivatives of the first-order form; the state takes the u-part (autodiffinit.jl:34-37: df.x[2]) */
+        double* t2 = (double*)malloc(sizeof(double) * (size_t)du * n);
+        taylor(t2, u0, p, c->t0, q);
+        for (int o = 0; o <= q; o++)
+            for (int i = 0; i < d; i++) mu[o * d + i] = t2[o * du + d + i];
+        free(t2);
+    } else {
+        taylor(mu, u0, p, c->t0, q);
+    }
     out->nf += q; /* autodiffinit.jl:17 */
-    for (int i = 0; i < d; i++) uprev[i] = mu[i];
+    /* error scaling uses integ.u / integ.uprev, for second-order problems their first partition du = E1 x
+       (perform_step.jl:204-216) */
+    for (int i = 0; i < d; i++) uprev[i] = so ? mu[d + i] : mu[i];
     const double* Mm = c->mass_matrix;
     double* MMinv = NULL;
     int m_singular = 0;
@@ -1059,10 +1078,12 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
                 mu_pred[r * rs + cc * cs] = s;
             }
         for (int i = 0; i < d; i++) upred[i] = mu_pred[i];     /* integ.u = E0 mu_pred (:103-104) */
+        if (so) /* integ.u = SolProj mu_pred = (E1 mu_pred, E0 mu_pred) */
+            for (int i = 0; i < d; i++) { upred[i] = mu_pred[d + i]; upred[d + i] = mu_pred[i]; }
         /* evaluate_ode! (:107, :167-180): z = E1 mu_pred - f(E0 mu_pred) (measurement_models.jl:11-20) */
         f(fu, upred, p, tnew);
         out->nf += 1;
-        for (int i = 0; i < d; i++) z[i] = mu_pred[d + i] - fu[i];
+        for (int i = 0; i < d; i++) z[i] = mu_pred[e1 * d + i] - fu[i]; /* second order: E2 x - f1(E1 x, E0 x) (:38-48) */
         if (Mm) /* z = M E1 mu_pred - f (measurement_models.jl:18); on the Kronecker layout M = lambda I */
             for (int a = 0; a < d; a++) {
                 double sacc = 0.0;
@@ -1071,16 +1092,23 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
             }
         /* calc_H! (derivative_utils.jl:1-33) */
         if (kron) {
-            for (int k = 0; k < N; k++) H[k] = (k == 1) ? (Mm ? Mm[0] : 1.0) : 0.0; /* E1.B = e_1' (projection.jl:20-29), times lambda */
+            for (int k = 0; k < N; k++) H[k] = (k == e1) ? (Mm ? Mm[0] : 1.0) : 0.0; /* E1.B = e_1' (projection.jl:20-29), times lambda; second order: E2 (derivative_utils.jl:39-41) */
         } else {
             memset(H, 0, sizeof(double) * (size_t)m * N);
-            for (int i = 0; i < d; i++) AT(H, i, d + i, d) = 1.0;    /* H = E1 */
+            for (int i = 0; i < d; i++) AT(H, i, e1 * d + i, d) = 1.0;    /* H = E1 (second order: E2) */
             if (Mm) /* H = M E1 (derivative_utils.jl:43-50) */
                 for (int a = 0; a < d; a++)
                     for (int i = 0; i < d; i++) AT(H, a, d + i, d) = AT(Mm, a, i, d);
             if (c->alg == ORACLE_EK1) {
                 jac(J, upred, p, tnew);
                 out->njac += 1;
+                if (so) { /* H -= ddu[1:d, :] * SolProj, SolProj = [E1; E0] (:12-13): J is the 2d x 2d Jacobian of the first-order form */
+                    for (int a = 0; a < d; a++)
+                        for (int i = 0; i < d; i++) {
+                            AT(H, a, d + i, d) -= AT(J, a, i, du);     /* d f1_a / d du_i -> E1 columns */
+                            AT(H, a, i, d) -= AT(J, a, d + i, du);     /* d f1_a / d u_i  -> E0 columns */
+                        }
+                } else
                 for (int a = 0; a < d; a++)
                     for (int i = 0; i < d; i++) AT(H, a, i, d) -= AT(J, a, i, d); /* H -= J * E0 (:13) */
             }
@@ -1214,7 +1242,7 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
         out->naccept++;
         int nanu = 0;
         for (int i = 0; i < d; i++) {
-            uprev[i] = mu[i]; /* update_uprev! (integrator_utils.jl:173-183) */
+            uprev[i] = so ? mu[d + i] : mu[i]; /* update_uprev! (integrator_utils.jl:173-183) */
             if (isnan(mu[i])) nanu = 1;
         }
         /* savevalues! (integrator_utils.jl:143-171) */
@@ -1267,8 +1295,8 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     out->diffusions = diffs.p;
     out->x_filt_mu = xmu.p;
     out->x_filt_R = (double*)malloc(sizeof(double) * (size_t)ns * D * D);
-    out->pu_mu = (double*)malloc(sizeof(double) * (size_t)ns * d);
-    out->pu_R = (double*)malloc(sizeof(double) * (size_t)ns * D * d);
+    out->pu_mu = (double*)malloc(sizeof(double) * (size_t)ns * du);
+    out->pu_R = (double*)malloc(sizeof(double) * (size_t)ns * D * du);
     for (int64_t k = 0; k < ns; k++) {
         double* dst = out->x_filt_R + (size_t)k * D * D;
         if (kron) oracle_kron_identity(d, n, n, xR.p + (size_t)k * NN, dst);
@@ -1319,9 +1347,11 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     for (int64_t k = 0; k < ns; k++) {
         const double* xm = (smu ? smu : xmu.p) + (size_t)k * D;
         const double* xr = (smu ? out->x_smooth_R : out->x_filt_R) + (size_t)k * D * D;
-        for (int i = 0; i < d; i++) out->pu_mu[(size_t)k * d + i] = xm[i];
-        for (int i = 0; i < d; i++)
-            for (int r = 0; r < D; r++) out->pu_R[(size_t)k * D * d + (size_t)i * D + r] = AT(xr, r, i, D);
+        for (int j = 0; j < du; j++) { /* SolProj row j selects state entry sc: E0 rows, or (E1; E0) for second order */
+            const int sc = so ? (j < d ? d + j : j - d) : j;
+            out->pu_mu[(size_t)k * du + j] = xm[sc];
+            for (int r = 0; r < D; r++) out->pu_R[(size_t)k * D * du + (size_t)j * D + r] = AT(xr, r, sc, D);
+        }
     }
     free(sR);
     free(xR.p); free(bG.p); free(bB.p); free(bL.p);

@@ -72,6 +72,13 @@ typedef struct {
     /* constant mass matrix M (d x d, column-major) of M u' = f(u,p,t); NULL = identity.  z = M E1 x - f
        (src/measurement_models.jl:11-20), H = M E1 - J E0 (src/derivative_utils.jl:1-53).  EK1 (dense) only. */
     const double* mass_matrix;
+    /* SecondOrderODEProblem(f1, du0, u0, tspan, p): d = length(u) positions, the state models u and its q derivatives,
+       z = E2 x - f1(E1 x, E0 x) (src/measurement_models.jl:29-49), H = E2 - J_du E1 - J_u E0 (EK1; EK0: E2;
+       src/derivative_utils.jl:1-53), SolProj = [E1; E0] (src/caches.jl:126).  The rhs callbacks are those of the
+       first-order form F([du; u]) = [f1(du, u); du] of dimension 2d (what the DynamicalODEFunction evaluates on the
+       ArrayPartition); u0 holds (du0, u0); pu_* have 2d entries in SolProj order (du, u). */
+    int32_t second_order;
+    int32_t reserved1;
 } oracle_config;
 
 /* One solved trajectory.  Arrays are owned by the struct; free with oracle_traj_free. */

@@ -653,3 +653,76 @@ def test_mass_matrix_measurement(oracle):
     J = np.array([[-p[0], p[2] * u[2], p[2] * u[1]], [p[0], -p[2] * u[2] - 2 * p[1] * u[1], -p[2] * u[1]], [1.0, 1.0, 1.0]])
     res = M @ mu1[d:2 * d] - fu - J @ (mu1[:d] - mup[:d])
     assert np.max(np.abs(res)) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# second-order ODEs  u'' = f1(u', u, p, t)  (reference test/secondorderode.jl)
+# ---------------------------------------------------------------------------------------------------------------------
+def _twobody_first_order(du, u, p, t):
+    """First-order form F([du; u]) = [f1(du, u); du] of twobody2 (test/secondorderode.jl:15-19): x = (v1, v2, r1, r2)."""
+    r3 = (u[2] * u[2] + u[3] * u[3]) ** 1.5
+    du[0] = -u[2] / r3
+    du[1] = -u[3] / r3
+    du[2] = u[0]
+    du[3] = u[1]
+
+
+def _twobody_truth(ts):
+    def fn(t, x):
+        r3 = (x[2] ** 2 + x[3] ** 2) ** 1.5
+        return [-x[2] / r3, -x[3] / r3, x[0], x[1]]
+
+    s = solve_ivp(fn, (0, 0.1), [0.0, 2.0, 0.4, 0.0], method="DOP853", rtol=1e-13, atol=1e-13, dense_output=True)
+    return np.array([s.sol(t) for t in ts])
+
+
+def test_second_order_twobody(oracle):
+    """test/secondorderode.jl:29-52: two-body problem as SecondOrderODEProblem (du0 = (0, 2), u0 = (0.4, 0), t in [0, 0.1]),
+    default tolerances: sol.u[end] (= (du, u)) and the dense output at t = 0.1/pi agree with an accurate solution to
+    rtol 1e-3 -- EK0, EK1, EK1 + FixedDiffusion."""
+    tr = tracer.trace(_twobody_first_order, 4, 0)
+    rhs = oracle.compile_rhs(tr, 3)
+    want = _twobody_truth([0.1, 0.1 / np.pi])
+    for alg, diff in ((oracle.EK0, oracle.DIFF_DYNAMIC), (oracle.EK1, oracle.DIFF_DYNAMIC), (oracle.EK1, oracle.DIFF_FIXED)):
+        cfg = oracle.make_config(2, 3, 0, alg=alg, diffusion=diff, smooth=True, adaptive=True, t0=0, t1=0.1, second_order=True)
+        s = oracle.solve(cfg, rhs, [0.0, 2.0, 0.4, 0.0], [])
+        assert s["retcode"] == "Success" and s["pu_mu"].shape[1] == 4
+        assert np.array_equal(s["pu_mu"][0], [0.0, 2.0, 0.4, 0.0])      # test/solution.jl:59-62: exact initial values
+        assert not s["pu_cov"][0].any()
+        assert np.linalg.norm(s["pu_mu"][-1] - want[0]) <= 1e-3 * np.linalg.norm(want[0]), alg
+        m, c = oracle.interpolate(cfg, s, 0.1 / np.pi)
+        assert np.linalg.norm(m - want[1]) <= 1e-3 * np.linalg.norm(want[1]), alg
+        assert c.shape == (4, 4) and np.all(np.linalg.eigvalsh(c) > -1e-18)
+        # sol.stats.nf (test/stats.jl:31-50): q (initialisation) + 2 (initial step) + one per attempted step
+        assert s["nf"] == 3 + 2 + s["naccept"] + s["nreject"]
+
+
+def test_second_order_measurement_and_state_layout(oracle):
+    """test/core/measurement_models.jl:57-90: z = E2 x - f1(E1 x, E0 x).  One fixed step from the exact initial state
+    (Sigma0 = 0): the updated mean satisfies the linearised measurement, and the state holds u, u', u'', u''' with
+    u'' = f1(u', u) at t0 (test/state_init.jl)."""
+    def vdp2(du, u, p, t):   # first-order form of test/solution.jl:12-22: x = (du, u)
+        du[0] = p[0] * ((1 - u[1] * u[1]) * u[0] - u[1])
+        du[1] = u[0]
+
+    tr = tracer.trace(vdp2, 2, 1)
+    rhs = oracle.compile_rhs(tr, 3)
+    mu_p, h = 1.3, 1e-2
+    for alg in (oracle.EK0, oracle.EK1):
+        cfg = oracle.make_config(1, 3, 1, alg=alg, smooth=False, adaptive=False, dt=h, t0=0, t1=h, second_order=True)
+        s = oracle.solve(cfg, rhs, [0.5, 2.0], [mu_p])
+        x0, x1 = s["x_filt_mu"][0], s["x_filt_mu"][1]
+        f1 = lambda v, u: mu_p * ((1 - u * u) * v - u)  # noqa: E731
+        assert x0[0] == 2.0 and x0[1] == 0.5 and x0[2] == pytest.approx(f1(0.5, 2.0), rel=1e-15)
+        # third derivative: d/dt f1 = df1/dv * u'' + df1/du * u'
+        d3 = mu_p * (1 - 4.0) * x0[2] + mu_p * (-2 * 2.0 * 0.5 - 1) * 0.5
+        assert x0[3] == pytest.approx(d3, rel=1e-14)
+        T = np.array([[h ** (k - j) / math.factorial(k - j) if k >= j else 0.0 for k in range(4)] for j in range(4)])
+        xp = T @ x0
+        z = xp[2] - f1(xp[1], xp[0])
+        if alg == oracle.EK1:   # H = E2 - J_du E1 - J_u E0: the update zeroes the linearised residual
+            Jv, Ju = mu_p * (1 - xp[0] ** 2), mu_p * (-2 * xp[0] * xp[1] - 1)
+            assert abs(z + (x1[2] - xp[2]) - Jv * (x1[1] - xp[1]) - Ju * (x1[0] - xp[0])) < 1e-12
+        else:                   # H = E2: the updated second derivative equals f1 at the predicted point
+            assert abs(x1[2] - f1(xp[1], xp[0])) < 1e-12
+        assert np.array_equal(s["pu_mu"][1], [x1[1], x1[0]])   # sol.u = (du, u)
