@@ -119,6 +119,15 @@ typedef struct pnode_config {
        diffusion (blocks layout): diagonal M; EK0 on the Kronecker layout: M = lambda I only, otherwise
        PNODE_ERR_ARGUMENT with the reference's message (src/caches.jl:111-118). */
     const double* mass_matrix;
+    /* SecondOrderODEProblem(f1, du0, u0, tspan, p)  (src/measurement_models.jl:29-49, src/caches.jl:100-126): 1 = `d` is the
+       number of positions u; the state models u and its q >= 2 derivatives (D = d(q+1)); z = E2 x - f1(E1 x, E0 x);
+       H = E2 (EK0) or E2 - J_du E1 - J_u E0 (EK1).  rhs_src / rhs_name describe the FIRST-ORDER FORM of dimension 2d,
+       F([du; u]) = [f1(du, u); du] (what the reference's DynamicalODEFunction evaluates on ArrayPartition(du, u)); the
+       kernels use its first d rows.  u0 is [n_traj][2d] = (du0, u0); every U field has 2d entries per point in the
+       reference's sol.u order (du, u), every U_COV field (2d)^2.  EK0 (Kronecker layout) and EK1 (dense, D <= 32),
+       IWP prior, scalar diffusion models. */
+    int32_t second_order;
+    int32_t reserved1;
 } pnode_config;
 
 typedef struct pnode_solver pnode_solver;

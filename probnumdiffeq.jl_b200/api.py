@@ -101,6 +101,7 @@ class ODEProblem:
     p: Sequence[float] = ()
     builtin: Optional[str] = None   # name in problems.PROBLEMS -> ahead-of-time kernels when available
     mass_matrix: Optional[Sequence[Sequence[float]]] = None   # ODEFunction(f; mass_matrix=M): M u' = f(u, p, t), d x d, may be singular
+    second_order: bool = False      # built by SecondOrderODEProblem: f is the first-order form on (du, u), u0 = (du0, u0)
 
     @staticmethod
     def from_library(name: str) -> "ODEProblem":
@@ -109,6 +110,25 @@ class ODEProblem:
             return ODEProblem(pd.f, list(pd.u0), tuple(pd.tspan), list(pd.p), mass_matrix=pd.mass_matrix)
         pd = _problems.PROBLEMS[name]
         return ODEProblem(pd.f, list(pd.u0), tuple(pd.tspan), list(pd.p), builtin=name)
+
+
+def SecondOrderODEProblem(f1: Callable, du0: Sequence[float], u0: Sequence[float], tspan: Tuple[float, float],
+                          p: Sequence[float] = ()) -> ODEProblem:
+    """`SecondOrderODEProblem(f1, du0, u0, tspan, p)` with the in-place signature `f1(ddu, du, u, p, t)`.  The filter models
+    u and its derivatives and measures `E2 x - f1(E1 x, E0 x)` (src/measurement_models.jl:29-49); `sol.u` holds
+    `(du, u)` as the reference's ArrayPartition does (SolProj = [E1; E0], src/caches.jl:126)."""
+    d = len(u0)
+    if len(du0) != d:
+        raise ValueError("du0 and u0 must have the same length")  # DimensionMismatch
+
+    def first_order_form(dx, x, p_, t):   # F([du; u]) = [f1(du, u); du], what DynamicalODEFunction evaluates
+        ddu = [0] * d
+        f1(ddu, x[:d], x[d:], p_, t)
+        for i in range(d):
+            dx[i] = ddu[i]
+            dx[d + i] = x[i]
+
+    return ODEProblem(first_order_form, list(du0) + list(u0), tuple(tspan), list(p), second_order=True)
 
 
 def remake(prob: ODEProblem, **kw) -> ODEProblem:
@@ -200,8 +220,11 @@ def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, absto
     d, n_p = len(prob.u0), len(prob.p)
     if d < 1:
         raise RuntimeError("We currently don't support scalar-valued problems")  # src/caches.jl:96-98
+    dim_rhs = d
+    if prob.second_order:
+        d = d // 2   # positions; the traced right-hand side keeps the first-order form of dimension 2d
     diff = alg.diffusionmodel
-    kw = dict(d=d, q=alg.q, n_p=n_p, alg=alg.alg, smooth=alg.smooth, adaptive=adaptive, dt=dt or 0.0,
+    kw = dict(second_order=prob.second_order, d=d, q=alg.q, n_p=n_p, alg=alg.alg, smooth=alg.smooth, adaptive=adaptive, dt=dt or 0.0,
               abstol=abstol, reltol=reltol, save_everystep=save_everystep, maxiters=maxiters, dtmin=dtmin,
               dtmax=dtmax or 0.0, t0=prob.tspan[0], t1=prob.tspan[1], tstops=tstops, save_state=save_state,
               device=ens.device, lanes_per_traj=ens.lanes_per_traj, forced_diffusion=forced_diffusion, saveat=saveat)
@@ -230,7 +253,7 @@ def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, absto
     if prob.builtin is not None:
         kw.update(rhs_name="builtin:" + prob.builtin)
     else:
-        tr = _tracer.trace(prob.f, d, n_p)
+        tr = _tracer.trace(prob.f, dim_rhs, n_p)
         kw.update(rhs_name="PnodeUserProblem", rhs_src=_tracer.cuda_source(tr, "PnodeUserProblem"))
     return _lib.make_config(**kw)
 

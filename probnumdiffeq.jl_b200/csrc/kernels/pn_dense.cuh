@@ -193,24 +193,25 @@ struct PnDensePredict {
                     }
                 }
             } else {
-                double cv[d * d];
+                constexpr int DU = PN_SECOND ? 2 * d : d; /* sol(t) = SolProj x: (E1; E0) rows for second-order problems */
+                double cv[DU * DU];
 #pragma unroll
-                for (int a = 0; a < d; a++)
+                for (int a = 0; a < DU; a++)
 #pragma unroll
-                    for (int b = 0; b < d; b++) {
+                    for (int b = 0; b < DU; b++) {
                         if (b < a) continue;
                         double s = 0.0;
 #pragma unroll
-                        for (int lr = 0; lr < RPL; lr++) s += R[lr][a] * R[lr][b];
+                        for (int lr = 0; lr < RPL; lr++) s += R[lr][pn_solcol<d>(a)] * R[lr][pn_solcol<d>(b)];
                         s = pn_gsum<G>(s) * g;
-                        cv[a * d + b] = s;
-                        cv[b * d + a] = s;
+                        cv[a * DU + b] = s;
+                        cv[b * DU + a] = s;
                     }
                 if (act && gl == 0) {
 #pragma unroll
-                    for (int i = 0; i < d; i++) P.out_u[v * d + i] = mup[i];
+                    for (int i = 0; i < DU; i++) P.out_u[v * DU + i] = mup[pn_solcol<d>(i)];
 #pragma unroll
-                    for (int i = 0; i < d * d; i++) P.out_cov[v * d * d + i] = cv[i];
+                    for (int i = 0; i < DU * DU; i++) P.out_cov[v * DU * DU + i] = cv[i];
                 }
             }
         }

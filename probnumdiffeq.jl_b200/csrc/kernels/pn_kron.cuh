@@ -21,7 +21,11 @@
 
 template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 struct PnKron {
-    static constexpr int d = Prob::d;
+    static constexpr int DP = Prob::d;                  /* dimension of the right-hand side */
+    static constexpr int d = PN_SECOND ? DP / 2 : DP;   /* second-order problems (PN_SECOND, see pn_small.cuh): positions */
+    static constexpr int DU = DP;                       /* length of sol.u = (du, u) */
+    static constexpr int E1B = PN_SECOND ? 2 : 1;       /* H.B = e_2' (derivative_utils.jl:39-41) / e_1' */
+    static constexpr int SB = PN_SECOND ? 1 : 0;        /* block the error estimate is scaled with (du / u) */
     static constexpr int n = Q + 1;
     static constexpr int D = d * n;
     static constexpr int NPA = Prob::n_p > 0 ? Prob::n_p : 1;
@@ -66,6 +70,35 @@ struct PnKron {
         }
     }
 
+    /* sol.u = SolProj x and its covariance: E0 rows (c00 I), or (E1; E0) rows for second-order problems
+       ([c11 I, c10 I; c10 I, c00 I]); cjk = sum_r RB[r][j] RB[r][k] */
+    static __device__ __forceinline__ void write_pu(double* um, double* uc, const double (&M)[n][d], const double (&RB)[n][n], double sc) {
+        double c00 = 0.0, c01 = 0.0, c11 = 0.0;
+#pragma unroll
+        for (int r = 0; r < n; r++) {
+            c00 += RB[r][0] * RB[r][0];
+            if (PN_SECOND) {
+                c01 += RB[r][0] * RB[r][1];
+                c11 += RB[r][1] * RB[r][1];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DU; j++) um[j] = PN_SECOND ? (j < d ? M[1][j < d ? j : 0] : M[0][j >= d ? j - d : 0]) : M[0][j < d ? j : 0];
+#pragma unroll
+        for (int a = 0; a < DU; a++)
+#pragma unroll
+            for (int b = 0; b < DU; b++) {
+                double v = 0.0;
+                if (PN_SECOND) {
+                    const int ia = a % d, ib = b % d;
+                    if (ia == ib) v = (a < d && b < d) ? c11 : ((a >= d && b >= d) ? c00 : c01);
+                } else {
+                    v = (a == b) ? c00 : 0.0;
+                }
+                uc[a * DU + b] = v * sc;
+            }
+    }
+
     static __device__ void run(const PnParams& P) {
         double M[n][d];   /* mean as n x d matrix: M[j][i] = mu[j*d + i] */
         double RB[n][n];
@@ -87,7 +120,7 @@ struct PnKron {
 #pragma unroll
                     for (int i = 0; i < d; i++) M[j][i] = P.init_mu[traj * D + j * d + i];
 #pragma unroll
-                for (int i = 0; i < d; i++) uprev[i] = M[0][i];
+                for (int i = 0; i < d; i++) uprev[i] = M[SB][i];
                 dt = P.init_dt[traj];
                 if (ADAPTIVE && !(P.dt0 > 0.0) && !PN_MASS) nf += 2;
             }
@@ -101,10 +134,7 @@ struct PnKron {
                 if (P.step_offsets) {
                     P.s_t[save_pos] = t;
                     P.s_diffusion[save_pos] = 0.0;
-#pragma unroll
-                    for (int i = 0; i < d; i++) P.s_u_mean[save_pos * d + i] = M[0][i];
-#pragma unroll
-                    for (int i = 0; i < d * d; i++) P.s_u_cov[save_pos * d * d + i] = 0.0;
+                    write_pu(P.s_u_mean + save_pos * DU, P.s_u_cov + save_pos * DU * DU, M, RB, 1.0);
                     if (SAVE >= 2) save_state(P, save_pos, M, RB, 0.0, 0.0);
                 }
                 save_pos += 1;
@@ -151,8 +181,18 @@ struct PnKron {
                             if (k > j) s += hp[k > j ? k - j : 0] * M[k][i];
                         Mp[j][i] = s;
                     }
+#if PN_SECOND
+                double fu[DP], z[d], x2[DP];
+#pragma unroll
+                for (int i = 0; i < d; i++) {
+                    x2[i] = Mp[1][i]; /* (du, u) */
+                    x2[d + i] = Mp[0][i];
+                }
+                Prob::template f<double>(fu, x2, pr, tnew);
+#else
                 double fu[d], z[d];
                 Prob::template f<double>(fu, Mp[0], pr, tnew);
+#endif
                 nf += 1;
                 double zz = 0.0;
 #pragma unroll
@@ -160,18 +200,18 @@ struct PnKron {
 #if PN_MASS
                     z[i] = pn_mass(0, 0) * Mp[1][i] - fu[i]; /* M = lambda I: H.B = lambda e_1' (derivative_utils.jl:45-47) */
 #else
-                    z[i] = Mp[1][i] - fu[i];
+                    z[i] = Mp[E1B][i] - fu[i];
 #endif
                     zz += z[i] * z[i];
                 }
                 /* W.B = |Qh.R.B[:,1]|^2 */
                 double Wb = 0.0;
 #pragma unroll
-                for (int m = 1; m < n; m++) {
+                for (int m = E1B; m < n; m++) {
 #if PN_MASS
                     const double l1 = P.L[m * n + 1] * PIv[1] * pn_mass(0, 0);
 #else
-                    const double l1 = P.L[m * n + 1] * PIv[1];
+                    const double l1 = P.L[m * n + E1B] * PIv[E1B];
 #endif
                     Wb += l1 * l1;
                 }
@@ -185,7 +225,7 @@ struct PnKron {
                     double e2 = 0.0;
 #pragma unroll
                     for (int i = 0; i < d; i++) {
-                        const double isc = pn_rcp(P.abstol + fmax(fabs(Mp[0][i]), fabs(uprev[i])) * P.reltol);
+                        const double isc = pn_rcp(P.abstol + fmax(fabs(Mp[SB][i]), fabs(uprev[i])) * P.reltol);
                         e2 += isc * isc;
                     }
                     e2 = e2 * e2c * (1.0 / (double)d);
@@ -237,7 +277,7 @@ struct PnKron {
 #if PN_MASS
                     c1[r] = RB[r][1] * pn_mass(0, 0);
 #else
-                    c1[r] = RB[r][1];
+                    c1[r] = RB[r][E1B];
 #endif
                     S += c1[r] * c1[r];
                 }
@@ -287,22 +327,14 @@ struct PnKron {
                 naccept++;
 #pragma unroll
                 for (int i = 0; i < d; i++) {
-                    uprev[i] = M[0][i];
+                    uprev[i] = M[SB][i];
                     if (M[0][i] != M[0][i]) retcode = PN_RET_UNSTABLE;
                 }
                 if (SAVE >= 1) {
                     if (P.step_offsets && save_pos < P.step_offsets[traj + 1]) {
-                        double c0 = 0.0;
-#pragma unroll
-                        for (int r = 0; r < n; r++) c0 += RB[r][0] * RB[r][0];
                         P.s_t[save_pos] = t;
                         P.s_diffusion[save_pos - 1] = (SAVE >= 2) ? ediff : ((ADAPTIVE || DYNAMIC) ? ldiff : P.initial_diffusion);
-#pragma unroll
-                        for (int i = 0; i < d; i++) P.s_u_mean[save_pos * d + i] = M[0][i];
-#pragma unroll
-                        for (int a = 0; a < d; a++)
-#pragma unroll
-                            for (int b = 0; b < d; b++) P.s_u_cov[save_pos * d * d + a * d + b] = (a == b) ? c0 : 0.0;
+                        write_pu(P.s_u_mean + save_pos * DU, P.s_u_cov + save_pos * DU * DU, M, RB, 1.0);
                         if (SAVE >= 2) save_state(P, save_pos, M, RB, h, 1.0);
                     }
                     save_pos += 1;
@@ -318,16 +350,8 @@ struct PnKron {
                     fd = P.initial_diffusion;
                 }
             }
-            double c0 = 0.0;
-#pragma unroll
-            for (int r = 0; r < n; r++) c0 += RB[r][0] * RB[r][0];
             P.t_end[traj] = t;
-#pragma unroll
-            for (int i = 0; i < d; i++) P.u_mean[traj * d + i] = M[0][i];
-#pragma unroll
-            for (int a = 0; a < d; a++)
-#pragma unroll
-                for (int b = 0; b < d; b++) P.u_cov[traj * d * d + a * d + b] = (a == b) ? c0 * sc : 0.0;
+            write_pu(P.u_mean + traj * DU, P.u_cov + traj * DU * DU, M, RB, sc);
             P.loglik[traj] = loglik;
             P.diffusion[traj] = fd;
             P.dt_last[traj] = dt;

@@ -297,6 +297,18 @@ PN_HD double pn_initial_dt(const PnParams& P, const double* u0, const double* pr
 #ifndef PN_EK0_DENSE
 #define PN_EK0_DENSE 0 /* 1: EK0 measurement (H = E1, no Jacobian) on the dense layout -- EK0 with a non-IWP prior */
 #endif
+#ifndef PN_SECOND
+#define PN_SECOND 0 /* 1: SecondOrderODEProblem.  Prob is the first-order form F([du; u]) = [f1(du, u); du] of dimension
+                       2d (what the reference's DynamicalODEFunction evaluates on ArrayPartition(du, u)); the state models
+                       the d positions u and their q derivatives, z = E2 x - f1(E1 x, E0 x) (measurement_models.jl:29-49),
+                       H = E2 - J_du E1 - J_u E0 (derivative_utils.jl:1-53), sol.u = SolProj x = (E1 x, E0 x)
+                       (caches.jl:126); error scaling uses the du partition (perform_step.jl:204-216). */
+#endif
+/* SolProj row j -> state entry: E0 rows, or [E1; E0] for second-order problems */
+template <int d>
+PN_HD constexpr int pn_solcol(int j) {
+    return PN_SECOND ? (j < d ? d + j : j - d) : j;
+}
 #ifndef PN_MASS
 #define PN_MASS 0 /* 1: mass matrix M u' = f; the generated source defines constexpr pn_mass(a,i) = M[a][i] and
                      pn_mass_inv(a,i) = (M + 1e-20 I if M has a zero diagonal entry)^-1 (autodiffinit.jl:20-31), so zero
@@ -308,14 +320,17 @@ PN_HD double pn_initial_dt(const PnParams& P, const double* u0, const double* pr
 
 template <class Prob, int Q, int G, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 struct PnSmall {
-    static constexpr int d = Prob::d;
+    static constexpr int DP = Prob::d;                       /* dimension of the right-hand side */
+    static constexpr int d = PN_SECOND ? DP / 2 : DP;        /* modelled components (positions for second-order problems) */
+    static constexpr int DU = DP;                            /* length of sol.u */
+    static constexpr int E1B = PN_SECOND ? 2 : 1;            /* derivative block the measurement reads (E2 / E1) */
     static constexpr int n = Q + 1;
     static constexpr int D = d * n;
     static constexpr int RPL = (D + G - 1) / G; /* rows per lane, top and bottom block each */
     static constexpr int NPA = Prob::n_p > 0 ? Prob::n_p : 1;
     /* H = [-J | I | 0 ...] touches the first 2d columns only and R^- is upper triangular, so R^- H' is zero in
        rows >= 2d: row slots lr >= RU never enter the measurement update */
-    static constexpr int RU = (2 * d + G - 1) / G < RPL ? (2 * d + G - 1) / G : RPL;
+    static constexpr int RU = ((E1B + 1) * d + G - 1) / G < RPL ? ((E1B + 1) * d + G - 1) / G : RPL;
 
     // Householder QR of the stack [Rt ; Bt] (2D x D) in place; on return Rt holds the upper-triangular
     // factor (row r on lane r % G), below-diagonal entries zeroed.  Bt is destroyed.
@@ -440,7 +455,7 @@ struct PnSmall {
 #pragma unroll
                             for (int i = 0; i < NPA; i++) pr[i] = (i < Prob::n_p) ? P.p[traj * Prob::n_p + i] : 0.0;
 #pragma unroll
-                            for (int i = 0; i < d; i++) uprev[i] = mu[i];
+                            for (int i = 0; i < d; i++) uprev[i] = mu[pn_solcol<d>(i)];
                             dt = P.init_dt[traj];
                             nf = Q + ((ADAPTIVE && !(P.dt0 > 0.0) && !PN_MASS) ? 2 : 0);
                             t = P.t0;
@@ -464,9 +479,9 @@ struct PnSmall {
                                 P.s_t[save_pos] = t;
                                 P.s_diffusion[save_pos] = 0.0;
 #pragma unroll
-                                for (int i = 0; i < d; i++) P.s_u_mean[save_pos * d + i] = mu[i];
+                                for (int i = 0; i < DU; i++) P.s_u_mean[save_pos * DU + i] = mu[pn_solcol<d>(i)];
 #pragma unroll
-                                for (int i = 0; i < d * d; i++) P.s_u_cov[save_pos * d * d + i] = 0.0;
+                                for (int i = 0; i < DU * DU; i++) P.s_u_cov[save_pos * DU * DU + i] = 0.0;
                                 if (SAVE >= 2) {
 #pragma unroll
                                     for (int c = 0; c < D; c++) P.s_x_mean[save_pos * D + c] = mu[c];
@@ -500,6 +515,11 @@ struct PnSmall {
             bool accept = false;
             double h = 0.0, tstop = P.t1, EEst = 0.0, qq = 1.0, ediff = 0.0, lEE = 0.0;
             double hp[n], PIv[n], mup[D], z[d], J[d * d];
+#if PN_SECOND
+            double Jv[d * d]; /* d f1 / d du; J holds d f1 / d u */
+#pragma unroll
+            for (int i = 0; i < d * d; i++) Jv[i] = 0.0;
+#endif
 #if PN_IOUP
             double tq[n], Uh[n][n]; /* last column of the 1-d transition matrix; upper factor of the 1-d process noise */
 #pragma unroll
@@ -586,10 +606,33 @@ struct PnSmall {
                         mup[j * d + i] = s;
                     }
                 /* measurement: z = E1 mu^- - f(E0 mu^-), J = df/du */
+#if PN_SECOND
+                double fu[DP], x2[DP];
+#pragma unroll
+                for (int i = 0; i < d; i++) {
+                    x2[i] = mup[d + i]; /* (du, u) = (E1 mu^-, E0 mu^-) */
+                    x2[d + i] = mup[i];
+                }
+                Prob::template f<double>(fu, x2, pr, tnew);
+#if !PN_EK0_DENSE
+                {
+                    double J2[DP * DP];
+                    Prob::jac(J2, x2, pr, tnew);
+#pragma unroll
+                    for (int a = 0; a < d; a++)
+#pragma unroll
+                        for (int i = 0; i < d; i++) {
+                            Jv[a + d * i] = J2[a + DP * i];
+                            J[a + d * i] = J2[a + DP * (d + i)];
+                        }
+                }
+#endif
+#else
                 double fu[d];
                 Prob::template f<double>(fu, mup, pr, tnew);
 #if !PN_EK0_DENSE
                 Prob::jac(J, mup, pr, tnew);
+#endif
 #endif
                 nf += 1;
 #if PN_MASS
@@ -603,7 +646,7 @@ struct PnSmall {
                 }
 #else
 #pragma unroll
-                for (int i = 0; i < d; i++) z[i] = mup[d + i] - fu[i];
+                for (int i = 0; i < d; i++) z[i] = mup[E1B * d + i] - fu[i];
 #endif
 
                 if (ADAPTIVE || DYNAMIC) {
@@ -623,6 +666,9 @@ struct PnSmall {
 #else
                         const double l0 = P.L[m * n + 0] * PIv[0];
                         const double l1 = (m >= 1) ? P.L[m * n + 1] * PIv[1] : 0.0;
+#if PN_SECOND
+                        const double l2 = (m >= 2) ? P.L[m * n + 2] * PIv[2] : 0.0;
+#endif
 #endif
 #pragma unroll
                         for (int i = 0; i < d; i++) {
@@ -630,6 +676,8 @@ struct PnSmall {
 #pragma unroll
 #if PN_MASS
                             for (int a = 0; a < d; a++) c[a] = -l0 * J[a + d * i] + ((pn_mass(a, i) != 0.0) ? l1 * pn_mass(a, i) : 0.0);
+#elif PN_SECOND
+                            for (int a = 0; a < d; a++) c[a] = -l0 * J[a + d * i] - l1 * Jv[a + d * i] + ((i == a) ? l2 : 0.0);
 #else
                             for (int a = 0; a < d; a++) c[a] = -l0 * J[a + d * i] + ((i == a) ? l1 : 0.0);
 #endif
@@ -664,7 +712,7 @@ struct PnSmall {
                         double e2 = 0.0;
 #pragma unroll
                         for (int i = 0; i < d; i++) {
-                            const double isc = pn_rcp(P.abstol + fmax(fabs(mup[i]), fabs(uprev[i])) * P.reltol);
+                            const double isc = pn_rcp(P.abstol + fmax(fabs(mup[pn_solcol<d>(i)]), fabs(uprev[i])) * P.reltol);
                             e2 += (ldiff * wdiag[i]) * (isc * isc);
                         }
                         e2 = e2 * (h * h) * (1.0 / (double)d);
@@ -797,10 +845,14 @@ struct PnSmall {
                         for (int i = 0; i < d; i++)
                             if (pn_mass(a, i) != 0.0) s += R[lr][d + i] * pn_mass(a, i);
 #else
-                        double s = R[lr][d + a];
+                        double s = R[lr][E1B * d + a];
 #endif
 #pragma unroll
                         for (int i = 0; i < d; i++) s -= R[lr][i] * J[a + d * i];
+#if PN_SECOND
+#pragma unroll
+                        for (int i = 0; i < d; i++) s -= R[lr][d + i] * Jv[a + d * i];
+#endif
                         C2[lr][a] = accept ? s : 0.0;
                     }
 #pragma unroll
@@ -903,7 +955,7 @@ struct PnSmall {
                     bool nanu = false;
 #pragma unroll
                     for (int i = 0; i < d; i++) {
-                        uprev[i] = mu[i];
+                        uprev[i] = mu[pn_solcol<d>(i)];
                         nanu = nanu || (mu[i] != mu[i]);
                     }
                     if (nanu) retcode = PN_RET_UNSTABLE;
@@ -913,26 +965,26 @@ struct PnSmall {
                 if (SAVE >= 1) {
                     /* never write past this trajectory's CSR segment (the host-computed offsets are exact; belt and braces) */
                     const bool wr = accept && P.step_offsets && save_pos < P.step_offsets[traj + 1];
-                    double cv[d * d];
+                    double cv[DU * DU];
 #pragma unroll
-                    for (int a = 0; a < d; a++)
+                    for (int a = 0; a < DU; a++)
 #pragma unroll
-                        for (int b = 0; b < d; b++) {
+                        for (int b = 0; b < DU; b++) {
                         if (b < a) continue;
                             double s = 0.0;
 #pragma unroll
-                            for (int lr = 0; lr < RPL; lr++) s += R[lr][a] * R[lr][b];
+                            for (int lr = 0; lr < RPL; lr++) s += R[lr][pn_solcol<d>(a)] * R[lr][pn_solcol<d>(b)];
                             s = pn_gsum<G>(s);
-                            cv[a * d + b] = s;
-                            cv[b * d + a] = s;
+                            cv[a * DU + b] = s;
+                            cv[b * DU + a] = s;
                         }
                     if (wr && gl == 0) {
                         P.s_t[save_pos] = t;
                         P.s_diffusion[save_pos - 1] = (SAVE >= 2) ? ediff : ((ADAPTIVE || DYNAMIC) ? ldiff : P.initial_diffusion);
 #pragma unroll
-                        for (int i = 0; i < d; i++) P.s_u_mean[save_pos * d + i] = mu[i];
+                        for (int i = 0; i < DU; i++) P.s_u_mean[save_pos * DU + i] = mu[pn_solcol<d>(i)];
 #pragma unroll
-                        for (int i = 0; i < d * d; i++) P.s_u_cov[save_pos * d * d + i] = cv[i];
+                        for (int i = 0; i < DU * DU; i++) P.s_u_cov[save_pos * DU * DU + i] = cv[i];
                         if (SAVE >= 2) { /* what the smoother sweep needs: x_filt[k+1] and the step that produced it */
                             P.s_h[save_pos - 1] = h;
 #pragma unroll
@@ -972,26 +1024,26 @@ struct PnSmall {
                         fd = P.initial_diffusion;
                     }
                 }
-                double cv[d * d];
+                double cv[DU * DU];
 #pragma unroll
-                for (int a = 0; a < d; a++)
+                for (int a = 0; a < DU; a++)
 #pragma unroll
-                    for (int b = 0; b < d; b++) {
+                    for (int b = 0; b < DU; b++) {
                         if (b < a) continue;
                         double s = 0.0;
 #pragma unroll
-                        for (int lr = 0; lr < RPL; lr++) s += R[lr][a] * R[lr][b];
+                        for (int lr = 0; lr < RPL; lr++) s += R[lr][pn_solcol<d>(a)] * R[lr][pn_solcol<d>(b)];
                         s = pn_gsum<G>(s) * sc;
-                        cv[a * d + b] = s;
-                        cv[b * d + a] = s;
+                        cv[a * DU + b] = s;
+                        cv[b * DU + a] = s;
                     }
                 if (fin) {
                     if (gl == 0) {
                         P.t_end[traj] = t;
 #pragma unroll
-                        for (int i = 0; i < d; i++) P.u_mean[traj * d + i] = mu[i];
+                        for (int i = 0; i < DU; i++) P.u_mean[traj * DU + i] = mu[pn_solcol<d>(i)];
 #pragma unroll
-                        for (int i = 0; i < d * d; i++) P.u_cov[traj * d * d + i] = cv[i];
+                        for (int i = 0; i < DU * DU; i++) P.u_cov[traj * DU * DU + i] = cv[i];
                         P.loglik[traj] = loglik;
                         P.diffusion[traj] = fd;
                         P.dt_last[traj] = dt;
@@ -1028,17 +1080,28 @@ struct PnSmall {
 // ode_determine_initdt (when adaptive and no dt is given).
 template <class Prob, int Q, bool ADAPTIVE>
 __device__ __forceinline__ void pn_init_entry(const PnParams& P, double* init_mu, double* init_dt) {
-    constexpr int d = Prob::d, D = d * (Q + 1), NPA = Prob::n_p > 0 ? Prob::n_p : 1;
+    constexpr int DP = Prob::d, d = PN_SECOND ? DP / 2 : DP, D = d * (Q + 1), NPA = Prob::n_p > 0 ? Prob::n_p : 1;
     for (long long traj = blockIdx.x * (long long)blockDim.x + threadIdx.x; traj < P.n_traj;
          traj += (long long)gridDim.x * blockDim.x) {
-        double u0[d], mu[D], pr[NPA];
+        double u0[DP], mu[D], pr[NPA];
 #pragma unroll
         for (int i = 0; i < NPA; i++) pr[i] = 0.0;
 #pragma unroll
-        for (int i = 0; i < d; i++) u0[i] = P.u0[traj * d + i];
+        for (int i = 0; i < DP; i++) u0[i] = P.u0[traj * DP + i];
 #pragma unroll
         for (int i = 0; i < Prob::n_p; i++) pr[i] = P.p[traj * Prob::n_p + i];
+#if PN_SECOND
+        { /* derivatives of the first-order form (du, u); the state takes the u-part (autodiffinit.jl:34-37) */
+            double mu2[DP * (Q + 1)];
+            pn_taylor_init<Prob, Q>(mu2, u0, pr, P.t0);
+#pragma unroll
+            for (int o = 0; o <= Q; o++)
+#pragma unroll
+                for (int i = 0; i < d; i++) mu[o * d + i] = mu2[o * DP + d + i];
+        }
+#else
         pn_taylor_init<Prob, Q>(mu, u0, pr, P.t0);
+#endif
 #if PN_MASS
         /* conditioning on MM E_o x = d^o/dt^o of u' = f(u), o >= 1 (autodiffinit.jl:33-47): x_o = MM^-1 df_o */
 #pragma unroll

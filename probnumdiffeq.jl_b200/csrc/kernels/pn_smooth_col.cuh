@@ -111,18 +111,22 @@ struct PnSmoothCol {
 
     /* u-block of Sigma = S'S from the shared-memory factor (all D rows: the factor of the last point is dense) */
     static PN_HD void write_pu(const PnSmoothParams& P, long long k, const double* Sm, const double* Ms, const double (&scv)[d]) {
+        /* sol.pu = SolProj x: E0 rows, or (E1; E0) rows for second-order problems (PN_SECOND, pn_small.cuh) */
+        constexpr int DU = PN_SECOND ? 2 * d : d;
 #pragma unroll
-        for (int a = 0; a < d; a++) {
-            P.s_u_mean[k * d + a] = Ms[a];
+        for (int a = 0; a < DU; a++) {
+            const int ca = pn_solcol<d>(a);
+            P.s_u_mean[k * DU + a] = Ms[ca];
 #pragma unroll
-            for (int b = 0; b < d; b++) {
+            for (int b = 0; b < DU; b++) {
                 if (b < a) continue;
+                const int cb = pn_solcol<d>(b);
                 double s = 0.0;
 #pragma unroll
-                for (int r = 0; r < D; r++) s += Sm[r * LD + a] * Sm[r * LD + b];
-                s *= scv[a] * scv[b];
-                P.s_u_cov[k * d * d + a * d + b] = s;
-                P.s_u_cov[k * d * d + b * d + a] = s;
+                for (int r = 0; r < D; r++) s += Sm[r * LD + ca] * Sm[r * LD + cb];
+                s *= scv[ca % d] * scv[cb % d];
+                P.s_u_cov[k * DU * DU + a * DU + b] = s;
+                P.s_u_cov[k * DU * DU + b * DU + a] = s;
             }
         }
     }

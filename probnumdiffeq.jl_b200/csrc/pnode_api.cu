@@ -457,24 +457,24 @@ static int mass_preamble(const double* M, int d, std::string* out) {
 }
 
 /* NVRTC: register-resident smoother sweep for (d, q, G); independent of the right-hand side. */
-static int nvrtc_smoother_cubin(int d, int q, int G, bool ioup, bool col, std::vector<char>* cubin) {
+static int nvrtc_smoother_cubin(int d, int q, int G, bool ioup, bool col, std::vector<char>* cubin, bool second = false) {
     std::string src = col ? "#include \"kernels/pn_smooth_col.cuh\"\n" : "#include \"kernels/pn_smooth_reg.cuh\"\n";
     src += "extern \"C\" __global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_entry(const __grid_constant__ "
            "PnSmoothParams P) {\n  ";
     src += col ? "pn_smooth_col_entry" : "pn_smooth_reg_entry";
     src += "<PN_SD, PN_SQ, PN_SG>(P);\n}\n";
     auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
-    return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0)}, cubin);
+    return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0), def("PN_SECOND", second ? 1 : 0)}, cubin);
 }
 
 /* NVRTC: dense-output predict kernel for (d, q, G) */
-static int nvrtc_dense_cubin(int d, int q, int G, bool ioup, std::vector<char>* cubin) {
+static int nvrtc_dense_cubin(int d, int q, int G, bool ioup, std::vector<char>* cubin, bool second = false) {
     std::string src =
         "#include \"kernels/pn_dense.cuh\"\n"
         "extern \"C\" __global__ void __launch_bounds__(256, 1) pn_dense_entry(const __grid_constant__ PnDenseParams P) {\n"
         "  pn_dense_predict_entry<PN_SD, PN_SQ, PN_SG>(P);\n}\n";
     auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
-    return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0)}, cubin);
+    return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0), def("PN_SECOND", second ? 1 : 0)}, cubin);
 }
 
 static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
@@ -556,7 +556,7 @@ static int get_smoother(pnode_solver* s) {
     auto t0 = std::chrono::steady_clock::now();
     out->threads = PN_SMR_THREADS;
     const bool ioup = (s->cfg.prior == PNODE_PRIOR_IOUP);
-    const void* fn = (env_int("PNODE_FORCE_NVRTC", 0) || ioup) ? nullptr : pn_smooth_reg_lookup(s->cfg.d, s->cfg.q, s->Gs, col ? 1 : 0);
+    const void* fn = (env_int("PNODE_FORCE_NVRTC", 0) || ioup || s->cfg.second_order) ? nullptr : pn_smooth_reg_lookup(s->cfg.d, s->cfg.q, s->Gs, col ? 1 : 0);
     if (fn) {
         out->rt_fn = fn;
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_smooth));
@@ -569,7 +569,7 @@ static int get_smoother(pnode_solver* s) {
     int rc = load_driver();
     if (rc) return rc;
     std::vector<char> cubin;
-    if ((rc = nvrtc_smoother_cubin(s->cfg.d, s->cfg.q, s->Gs, ioup, col, &cubin))) return rc;
+    if ((rc = nvrtc_smoother_cubin(s->cfg.d, s->cfg.q, s->Gs, ioup, col, &cubin, s->cfg.second_order != 0))) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
     r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_smooth_entry");
@@ -593,7 +593,7 @@ static int get_dense(pnode_solver* s) {
     int rc = load_driver();
     if (rc) return rc;
     std::vector<char> cubin;
-    if ((rc = nvrtc_dense_cubin(s->cfg.d, s->cfg.q, s->Gd, s->cfg.prior == PNODE_PRIOR_IOUP, &cubin))) return rc;
+    if ((rc = nvrtc_dense_cubin(s->cfg.d, s->cfg.q, s->Gd, s->cfg.prior == PNODE_PRIOR_IOUP, &cubin, s->cfg.second_order != 0))) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
     r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_dense_entry");
@@ -698,6 +698,16 @@ static int validate_config(const pnode_config* cfg) {
         if (cfg->smooth && smooth_lanes(D) == 0)
             return fail(PNODE_ERR_UNSUPPORTED, "dense output of smoothed solutions needs the register-resident sweep (D <= 24)");
     }
+    if (cfg->second_order) { /* SecondOrderODEProblem */
+        if (cfg->q < 2) return fail(PNODE_ERR_ARGUMENT, "second-order problems need order >= 2 (the measurement reads the second derivative)");
+        if (cfg->mass_matrix) return fail(PNODE_ERR_ARGUMENT, "second-order problems take no mass matrix (derivative_utils.jl:39-41 asserts mass_matrix === I)");
+        if (cfg->prior != PNODE_PRIOR_IWP) return fail(PNODE_ERR_UNSUPPORTED, "second-order problems are implemented for the IWP prior");
+        if (layout == PNODE_COV_BLOCKS) return fail(PNODE_ERR_UNSUPPORTED, "second-order problems are implemented for the EK0 (Kronecker layout) and the EK1 (dense layout)");
+        if (layout == PNODE_COV_DENSE && (D > 32 || cfg->lanes_per_traj == 256))
+            return fail(PNODE_ERR_UNSUPPORTED, "second-order problems on the dense layout are implemented for D = d(q+1) <= 32");
+        if (cfg->smooth && (smooth_lanes(D) == 0 || env_int("PNODE_SMOOTH_KIND", 1) == 0 || env_int("PNODE_SMOOTH_GENERIC", 0)))
+            return fail(PNODE_ERR_UNSUPPORTED, "smoothing of second-order problems needs the column-distributed register sweep (D <= 24)");
+    }
     if (cfg->mass_matrix) {
         std::string pre;
         int mrc = mass_preamble(cfg->mass_matrix, cfg->d, &pre);
@@ -750,6 +760,7 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     const int layout = resolve_layout(cfg);
     std::string mass_src;
     if ((rc = mass_preamble(cfg->mass_matrix, cfg->d, &mass_src))) return rc;
+    if (cfg->second_order) mass_src = "#define PN_SECOND 1\n" + mass_src;
     rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, is_dynamic(cfg->diffusion),
                      cfg->save_everystep ? ((cfg->smooth || cfg->n_saveat > 0) ? 2 : 1) : 0, &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
                      layout == PNODE_COV_KRONECKER, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256),
@@ -761,12 +772,12 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     if (cfg->smooth && smooth_lanes(D) > 0 && !(cfg->alg == PNODE_EK1 && D > 32)) {
         std::vector<char> c2;
         const bool col = env_int("PNODE_SMOOTH_KIND", 1) != 0;
-        if ((rc = nvrtc_smoother_cubin(cfg->d, cfg->q, smooth_lanes(D), cfg->prior == PNODE_PRIOR_IOUP, col, &c2))) return rc;
+        if ((rc = nvrtc_smoother_cubin(cfg->d, cfg->q, smooth_lanes(D), cfg->prior == PNODE_PRIOR_IOUP, col, &c2, cfg->second_order != 0))) return rc;
         total += (int64_t)c2.size();
     }
     if (cfg->n_saveat > 0) {
         std::vector<char> c3;
-        if ((rc = nvrtc_dense_cubin(cfg->d, cfg->q, auto_lanes(D), cfg->prior == PNODE_PRIOR_IOUP, &c3))) return rc;
+        if ((rc = nvrtc_dense_cubin(cfg->d, cfg->q, auto_lanes(D), cfg->prior == PNODE_PRIOR_IOUP, &c3, cfg->second_order != 0))) return rc;
         total += (int64_t)c3.size();
     }
     if (cubin_bytes) *cubin_bytes = total;
@@ -791,6 +802,7 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     s->cfg.rhs_src = nullptr;
     s->cfg.rhs_name = nullptr;
     mass_preamble(cfg->mass_matrix, cfg->d, &s->mass_src); /* validated above */
+    if (cfg->second_order) s->mass_src = "#define PN_SECOND 1\n" + s->mass_src; /* generated preamble of the step kernels */
     s->cfg.mass_matrix = nullptr;
     s->kron = (resolve_layout(cfg) == PNODE_COV_KRONECKER);
     s->blocks = (resolve_layout(cfg) == PNODE_COV_BLOCKS);
@@ -1042,11 +1054,12 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                       bool force_count_pass, bool* need_count_pass) {
     const std::vector<double>& host_tstops = s->host_tstops;
     const int d = s->cfg.d, D = s->D;
+    const int du = s->cfg.second_order ? 2 * d : d; /* length of sol.u: (du, u) for second-order problems */
     const size_t N = (size_t)n_traj;
     int rc;
     if ((rc = alloc_field(r, PNODE_F_T_END, N * 8))) return rc;
-    if ((rc = alloc_field(r, PNODE_F_U_FINAL, N * d * 8))) return rc;
-    if ((rc = alloc_field(r, PNODE_F_U_FINAL_COV, N * d * d * 8))) return rc;
+    if ((rc = alloc_field(r, PNODE_F_U_FINAL, N * du * 8))) return rc;
+    if ((rc = alloc_field(r, PNODE_F_U_FINAL_COV, N * du * du * 8))) return rc;
     if (s->cfg.save_state) {
         if ((rc = alloc_field(r, PNODE_F_X_FINAL, N * D * 8))) return rc;
         if ((rc = alloc_field(r, PNODE_F_X_FINAL_COVFAC, N * D * D * 8))) return rc;
@@ -1177,8 +1190,8 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
              *w_xc = nullptr;
         if ((rc = alloc_work(PNODE_F_STEP_OFFSETS, (N + 1) * 8, &w_off))) return rc;
         if ((rc = alloc_work(PNODE_F_T, T * 8, &w_t))) return rc;
-        if ((rc = alloc_work(PNODE_F_U, T * d * 8, &w_u))) return rc;
-        if ((rc = alloc_work(PNODE_F_U_COV, T * d * d * 8, &w_uc))) return rc;
+        if ((rc = alloc_work(PNODE_F_U, T * du * 8, &w_u))) return rc;
+        if ((rc = alloc_work(PNODE_F_U_COV, T * du * du * 8, &w_uc))) return rc;
         if ((rc = alloc_work(PNODE_F_DIFFUSIONS, T * 8, &w_df))) return rc;
         if (s->mv && (rc = alloc_work(PNODE_F_DIFFUSIONS_MV, T * d * 8, &w_dfmv))) return rc;
         CUDA_TRY(cudaMemcpyAsync(w_off, r->offsets.data(), (N + 1) * 8, cudaMemcpyHostToDevice, s->stream));
@@ -1281,8 +1294,8 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         double *v_mean = nullptr, *v_covfac = nullptr, *v_h = nullptr, *v_diff = nullptr, *vu_mean = nullptr, *vu_cov = nullptr;
         long long *v_idx = nullptr, *v_off = nullptr;
         if (dense) {
-            if ((rc = alloc_field(r, PNODE_F_SAVEAT_U, V * d * 8))) return rc;
-            if ((rc = alloc_field(r, PNODE_F_SAVEAT_U_COV, V * d * d * 8))) return rc;
+            if ((rc = alloc_field(r, PNODE_F_SAVEAT_U, V * du * 8))) return rc;
+            if ((rc = alloc_field(r, PNODE_F_SAVEAT_U_COV, V * du * du * 8))) return rc;
             Dn.n_traj = n_traj;
             Dn.n_saveat = s->n_saveat;
             Dn.saveat = s->d_saveat;
@@ -1307,8 +1320,8 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 CUDA_TRY(cudaMallocAsync((void**)&v_covfac, 2 * V * D * D * 8, s->stream));
                 CUDA_TRY(cudaMallocAsync((void**)&v_h, 2 * V * 8, s->stream));
                 CUDA_TRY(cudaMallocAsync((void**)&v_diff, 2 * V * 8, s->stream));
-                CUDA_TRY(cudaMallocAsync((void**)&vu_mean, 2 * V * d * 8, s->stream));
-                CUDA_TRY(cudaMallocAsync((void**)&vu_cov, 2 * V * d * d * 8, s->stream));
+                CUDA_TRY(cudaMallocAsync((void**)&vu_mean, 2 * V * du * 8, s->stream));
+                CUDA_TRY(cudaMallocAsync((void**)&vu_cov, 2 * V * du * du * 8, s->stream));
                 CUDA_TRY(cudaMallocAsync((void**)&v_idx, V * 8, s->stream));
                 CUDA_TRY(cudaMallocAsync((void**)&v_off, (V + 1) * 8, s->stream));
                 Dn.v_idx = v_idx;
@@ -1371,8 +1384,8 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 Qv.s_u_mean = vu_mean;
                 Qv.s_u_cov = vu_cov;
                 if ((rc = launch_sweep(Qv, (long long)V))) return rc;
-                const long long nc = (long long)V * (d + d * d);
-                pn_dense_collect<<<(unsigned)((nc + thr - 1) / thr), thr, 0, s->stream>>>((long long)V, d, v_h, vu_mean, vu_cov, Dn.out_u,
+                const long long nc = (long long)V * (du + du * du);
+                pn_dense_collect<<<(unsigned)((nc + thr - 1) / thr), thr, 0, s->stream>>>((long long)V, du, v_h, vu_mean, vu_cov, Dn.out_u,
                                                                                          Dn.out_cov);
                 launches += 3;
                 for (void* ptr : {(void*)v_mean, (void*)v_covfac, (void*)v_h, (void*)v_diff, (void*)vu_mean, (void*)vu_cov, (void*)v_idx,
@@ -1394,7 +1407,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 return fail(PNODE_ERR_UNSUPPORTED, "save_everystep with calibrate=true needs initial_diffusion == 1");
             }
             pn_calibrate_saved<<<blocks, thr, 0, s->stream>>>((long long)T, (long long)N, P.step_offsets, scale, P.diffusion,
-                                                             d * d, P.s_u_cov, P.s_diffusion, d,
+                                                             du * du, P.s_u_cov, P.s_diffusion, d,
                                                              (scale && s->mv) ? P.diffusion_mv : nullptr, P.diffusion_mv,
                                                              P.s_diffusion_mv);
             launches += 1;
@@ -1406,7 +1419,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             CUDA_TRY(cudaMemcpyAsync(r->f[PNODE_F_STEP_OFFSETS].d, exact_off.data(), (N + 1) * 8, cudaMemcpyHostToDevice, s->stream));
             const long long* d_eoff = (const long long*)r->f[PNODE_F_STEP_OFFSETS].d;
             struct { int field; int width; const void* src; } cp[] = {
-                {PNODE_F_T, 1, w_t}, {PNODE_F_U, d, w_u}, {PNODE_F_U_COV, d * d, w_uc}, {PNODE_F_DIFFUSIONS, 1, w_df},
+                {PNODE_F_T, 1, w_t}, {PNODE_F_U, du, w_u}, {PNODE_F_U_COV, du * du, w_uc}, {PNODE_F_DIFFUSIONS, 1, w_df},
                 {PNODE_F_DIFFUSIONS_MV, d, w_dfmv}};
             for (auto& c : cp) {
                 if (!c.src) continue;
@@ -1469,7 +1482,7 @@ static int solve_common(pnode_solver* s, int64_t n_traj, const double* u0, const
     memset(&r->info, 0, sizeof r->info);
     const double *d_u0 = u0, *d_p = p;
     if (!device_inputs) {
-        const size_t bu = (size_t)n_traj * s->cfg.d * 8, bp = (size_t)n_traj * std::max(s->cfg.n_p, 0) * 8;
+        const size_t bu = (size_t)n_traj * s->cfg.d * (s->cfg.second_order ? 2 : 1) * 8, bp = (size_t)n_traj * std::max(s->cfg.n_p, 0) * 8;
         auto t0 = std::chrono::steady_clock::now();
         cudaError_t e = cudaMallocAsync((void**)&r->d_u0, bu, s->stream);
         if (e == cudaSuccess && bp) e = cudaMallocAsync((void**)&r->d_p, bp, s->stream);

@@ -63,6 +63,7 @@ class Config(C.Structure):
         ("rate_parameter", C.c_double),
         ("saveat", C.POINTER(C.c_double)), ("n_saveat", C.c_int64),
         ("mass_matrix", C.POINTER(C.c_double)),
+        ("second_order", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -133,8 +134,9 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
                 lanes_per_traj=0, t0=0.0, t1=1.0, dt=0.0, abstol=1e-6, reltol=1e-3, dtmin=0.0, dtmax=0.0,
                 maxiters=1_000_000, beta1=0.0, beta2=0.0, qmin=0.2, qmax=10.0, gamma=0.9, qsteady_min=1.0,
                 qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None, device=0, prior=PRIOR_IWP,
-                rate_parameter=0.0, saveat=None, mass_matrix=None) -> Config:
+                rate_parameter=0.0, saveat=None, mass_matrix=None, second_order=False) -> Config:
     c = Config()
+    c.second_order = int(second_order)
     c.struct_size = C.sizeof(Config)
     c.device, c.d, c.q, c.n_p = device, d, q, n_p
     c.alg, c.cov, c.prior, c.diffusion = alg, cov, prior, diffusion

@@ -1099,3 +1099,100 @@ def test_mass_matrix_rober_dae_diagonal_ek1(oracle):
     assert abs(int(g["naccept"][0]) - o["naccept"]) <= 2
     assert g["T"][1] - g["T"][0] == 1e-6
     assert np.linalg.norm(g["U"][-1] - o["pu_mu"][-1]) <= 1e-8 * np.linalg.norm(o["pu_mu"][-1])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# second-order problems u'' = f1(u', u): z = E2 x - f1(E1 x, E0 x), sol.u = (du, u)
+# ------------------------------------------------------------------------------------------------------------------
+def _twobody_first_order(du, u, p, t):
+    """First-order form F([du; u]) = [f1(du, u); du] of test/secondorderode.jl:15-19 with a gravitational parameter p[0]."""
+    r3 = (u[2] * u[2] + u[3] * u[3]) ** 1.5
+    du[0] = -p[0] * u[2] / r3
+    du[1] = -p[0] * u[3] / r3
+    du[2] = u[0]
+    du[3] = u[1]
+
+
+def _gpu_second(u0, p, q, *, smooth=False, saveat=None, **kw):
+    src = tracer.cuda_source(tracer.trace(_twobody_first_order, 4, 1), "UserProb")
+    cfg = lib.make_config(d=2, q=q, n_p=1, rhs_name="UserProb", rhs_src=src, second_order=True, smooth=smooth, save_everystep=True,
+                          save_state=True, saveat=saveat, **kw)
+    s = lib.Solver(cfg)
+    r = s.solve(u0, p)
+    n, D = u0.shape[0], 2 * (q + 1)
+    out = dict(off=r.field(lib.F_STEP_OFFSETS), T=r.field(lib.F_T), U=r.field(lib.F_U).reshape(-1, 4), C=r.field(lib.F_U_COV).reshape(-1, 4, 4),
+               u=r.field(lib.F_U_FINAL).reshape(n, 4), cov=r.field(lib.F_U_FINAL_COV).reshape(n, 4, 4), naccept=r.field(lib.F_NACCEPT),
+               nreject=r.field(lib.F_NREJECT), nf=r.field(lib.F_NF), retcode=r.field(lib.F_RETCODE), loglik=r.field(lib.F_LOGLIK),
+               Df=r.field(lib.F_DIFFUSIONS))
+    if r.has(lib.F_X):
+        out.update(X=r.field(lib.F_X).reshape(-1, D), XR=r.field(lib.F_X_COVFAC).reshape(-1, D, D))
+    if saveat is not None:
+        out.update(SU=r.field(lib.F_SAVEAT_U).reshape(n, len(saveat), 4), SC=r.field(lib.F_SAVEAT_U_COV).reshape(n, len(saveat), 4, 4))
+    r.free()
+    s.close()
+    return out
+
+
+def _second_inputs(n, seed):
+    rng = np.random.default_rng(seed)
+    u0 = np.array([0.0, 2.0, 0.4, 0.0])[None, :] * (1 + 0.05 * rng.uniform(-1, 1, (n, 4)))   # (du0, u0)
+    p = 1.0 + 0.1 * rng.uniform(-1, 1, (n, 1))
+    return np.ascontiguousarray(u0), np.ascontiguousarray(p)
+
+
+@pytest.mark.parametrize("alg", [lib.EK1, lib.EK0])
+@pytest.mark.parametrize("smooth", [False, True])
+def test_second_order_fixed_steps_static_diffusion(oracle, alg, smooth):
+    """Two-body problem as a SecondOrderODEProblem, fixed steps, FixedDiffusion: every saved sol.u = (du, u), its 4 x 4
+    covariance, the diffusions and the log-likelihood against the oracle at 1e-10 (smoother covariances 1e-9); the dense
+    output on a saveat grid at 1e-10 / 1e-8."""
+    u0, p = _second_inputs(3, 71)
+    saveat = np.array([0.0, 0.0123, 0.05, 0.1])
+    kw = dict(alg=alg, adaptive=False, dt=1e-3, t0=0.0, t1=0.1, diffusion=lib.DIFF_FIXED, calibrate=True)
+    g = _gpu_second(u0, p, 3, smooth=smooth, saveat=saveat, **kw)
+    rhs = oracle.compile_rhs(tracer.trace(_twobody_first_order, 4, 1), 3)
+    cfg = oracle.make_config(2, 3, 1, alg=alg, diffusion=oracle.DIFF_FIXED, calibrate=True, smooth=smooth, adaptive=False, dt=1e-3,
+                             t0=0.0, t1=0.1, cov_backend=oracle.COV_QR, second_order=True)
+    for i in range(3):
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"] == 101 and g["retcode"][i] == 0
+        assert np.array_equal(g["U"][a], u0[i]) and not g["C"][a].any()        # exact initial values (test/solution.jl:59-62)
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < (1e-9 if smooth else 1e-10)
+        assert g["loglik"][i] == pytest.approx(o["loglik"], rel=1e-10)
+        assert _rel(g["Df"][a:b - 1], o["diffusions"][:-1]) < 1e-10
+        assert g["nf"][i] == o["nf"]
+        for j, t in enumerate(saveat):
+            m, c = oracle.interpolate(cfg, o, float(t))
+            assert _rel(g["SU"][i, j], m) < 1e-10, (i, j)
+            if np.linalg.norm(c) > 0:
+                assert np.linalg.norm(g["SC"][i, j] - c) / np.linalg.norm(c) < 1e-8, (i, j)
+
+
+@pytest.mark.parametrize("alg", [lib.EK1, lib.EK0])
+def test_second_order_adaptive(oracle, alg):
+    """test/secondorderode.jl:29-52 on an ensemble: adaptive EK0 / EK1 (default tolerances, smoothing), identical
+    accept / reject / nf counts as the oracle, end points 1e-8; sol.u[end] and sol(T/pi) within rtol 1e-3 of an accurate
+    solution (the reference's own assertion)."""
+    from scipy.integrate import solve_ivp
+    n = 12
+    u0, p = _second_inputs(n, 72)
+    tq = 0.1 / np.pi
+    g = _gpu_second(u0, p, 3, smooth=True, saveat=np.array([tq]), alg=alg, adaptive=True, t0=0.0, t1=0.1)
+    rhs = oracle.compile_rhs(tracer.trace(_twobody_first_order, 4, 1), 3)
+    cfg = oracle.make_config(2, 3, 1, alg=alg, smooth=True, adaptive=True, t0=0.0, t1=0.1, cov_backend=oracle.COV_QR, second_order=True)
+    for i in range(n):
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert g["retcode"][i] == 0 and o["retcode"] == "Success"
+        assert g["naccept"][i] == o["naccept"] and g["nreject"][i] == o["nreject"] and g["nf"][i] == o["nf"], i
+        assert np.max(np.abs(g["T"][a:b] - o["t"])[1:] / o["t"][1:]) < 2e-6
+        assert np.linalg.norm(g["U"][b - 1] - o["pu_mu"][-1]) <= 1e-8 * np.linalg.norm(o["pu_mu"][-1])
+        m, _ = oracle.interpolate(cfg, o, tq)
+        assert np.linalg.norm(g["SU"][i, 0] - m) <= 1e-7 * np.linalg.norm(m)
+        mu_i = p[i, 0]
+        tr = solve_ivp(lambda t, x: [-mu_i * x[2] / (x[2] ** 2 + x[3] ** 2) ** 1.5, -mu_i * x[3] / (x[2] ** 2 + x[3] ** 2) ** 1.5, x[0], x[1]],
+                       (0, 0.1), u0[i], method="DOP853", rtol=1e-12, atol=1e-12, dense_output=True)
+        assert np.linalg.norm(g["U"][b - 1] - tr.y[:, -1]) <= 1e-3 * np.linalg.norm(tr.y[:, -1])
+        assert np.linalg.norm(g["SU"][i, 0] - tr.sol(tq)) <= 1e-3 * np.linalg.norm(tr.sol(tq))

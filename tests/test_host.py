@@ -234,3 +234,29 @@ def test_mass_matrix_kernels_compile_and_argument_checks(pnlib):
     with pytest.raises(pnlib.PnodeError) as e:
         pnlib.compile_check(pnlib.make_config(mass_matrix=[[1, 1, 0], [1, 1, 0], [0, 0, 1]], **base))
     assert e.value.kind == "ArgumentError"
+
+
+def _twobody_first_order(du, u, p, t):
+    r3 = (u[2] * u[2] + u[3] * u[3]) ** 1.5
+    du[0] = -u[2] / r3
+    du[1] = -u[3] / r3
+    du[2] = u[0]
+    du[3] = u[1]
+
+
+def test_second_order_kernels_compile_and_argument_checks(pnlib):
+    """SecondOrderODEProblem path (src/measurement_models.jl:29-49): the step kernels (EK1 dense, EK0 Kronecker), the
+    smoother sweep and the dense-output kernel compile with PN_SECOND for sm_100a; unsupported combinations are rejected."""
+    src = tracer.cuda_source(tracer.trace(_twobody_first_order, 4, 0), "UserProb")
+    base = dict(d=2, q=3, n_p=0, rhs_name="UserProb", rhs_src=src, t0=0.0, t1=0.1, second_order=True)
+    for alg in (pnlib.EK1, pnlib.EK0):
+        a = pnlib.compile_check(pnlib.make_config(alg=alg, **base))
+        b = pnlib.compile_check(pnlib.make_config(alg=alg, smooth=True, save_everystep=True, saveat=[0.0, 0.03, 0.1], **base))
+        assert b > a > 10_000
+    for kw, kind in ((dict(q=1), "ArgumentError"), (dict(alg=pnlib.DIAGONAL_EK1), "Unsupported"),
+                     (dict(alg=pnlib.EK0, diffusion=pnlib.DIFF_DYNAMIC_MV), "Unsupported"),
+                     (dict(mass_matrix=2 * np.eye(2)), "ArgumentError"),
+                     (dict(prior=pnlib.PRIOR_IOUP, rate_parameter=-1.0), "Unsupported")):
+        with pytest.raises(pnlib.PnodeError) as e:
+            pnlib.compile_check(pnlib.make_config(**{**base, **kw}))
+        assert e.value.kind == kind, kw
