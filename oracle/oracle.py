@@ -397,3 +397,65 @@ def solve_ensemble(cfg: Config, rhs: CompiledRHS, u0, p, n_threads: int = 0) -> 
 
 def max_threads() -> int:
     return lib().oracle_max_threads()
+
+
+def fenrir_data_loglik(cfg: Config, sol: dict, data_t, data_u, observation_matrix=None, observation_noise_cov=1.0) -> float:
+    """Fenrir data log-likelihood (src/data_likelihoods/fenrir.jl:30-137, `fit_pnsolution_to_data!`) of a solution computed
+    with smooth=True (the backward kernels are saved) whose time grid contains every `data_t` (the reference adds them to
+    tstops, :46-48).  The reference stops the integrator with `step!` -- no postamble, i.e. no smoothing and no
+    calibration -- so the sweep starts from the *filtering* estimates and, for FixedDiffusion, from uncalibrated kernels:
+    call the oracle with calibrate=False.
+
+    Backward over the saved points: x_post[N] = x_filt[N]; x_post[i] = marginalize(x_post[i+1], K_i) (:100-108); at a data
+    time a Kalman update with observation matrix proj * SolProj and noise R (:110-123, `measure_and_update!` :127-137,
+    `update!(...; R)` src/filtering/update.jl:65-139 with the QR route of :132-136), accumulating its log-likelihood.
+    Returns -inf if the solve did not succeed (:55-59)."""
+    if sol["retcode"] != "Success":
+        return -np.inf
+    if "bk_G" not in sol:
+        raise ValueError("fenrir only works with smoothing. Set `smooth=true`.")   # fenrir.jl:42-44
+    d, D = sol["d"], sol["D"]
+    sel = np.r_[d:2 * d, 0:d] if cfg.second_order else np.arange(d)
+    solproj = np.eye(D)[sel]
+    data_t = np.asarray(data_t, dtype=float)
+    data_u = np.asarray(data_u, dtype=float).reshape(len(data_t), -1)
+    o = data_u.shape[1]
+    proj = np.eye(len(sel)) if observation_matrix is None else np.asarray(observation_matrix, dtype=float).reshape(o, len(sel))
+    H = proj @ solproj
+    cov = np.asarray(observation_noise_cov, dtype=float)
+    Rn = np.sqrt(float(cov)) * np.eye(o) if cov.ndim == 0 else np.linalg.cholesky(cov.reshape(o, o)).T   # cov2psdmatrix
+
+    def update(m, R, u):
+        z = H @ m - u
+        C = R @ H.T
+        Sr = np.linalg.qr(np.vstack([C, Rn]), mode="r")              # make_obscov_sqrt
+        S = Sr.T @ Sr
+        K = np.linalg.solve(S, (R.T @ C).T).T
+        ll = -0.5 * z @ np.linalg.solve(S, z) - 0.5 * o * np.log(2 * np.pi) - np.sum(np.log(np.abs(np.diag(Sr))))
+        m2 = m - K @ z
+        R2 = R @ (np.eye(D) - K @ H).T
+        R3 = np.linalg.qr(np.vstack([R2, (K @ Rn.T).T]), mode="r")
+        return m2, R3, ll
+
+    t = sol["t"]
+    n = len(t)
+    m, R = sol["x_filt_mu"][-1].copy(), sol["x_filt_R"][-1].copy()
+    LL = 0.0
+    data_idx = len(data_t) - 1
+    if t[-1] in data_t:
+        m, R, ll = update(m, R, data_u[-1])
+        LL += ll
+        data_idx -= 1
+    for i in range(n - 2, -1, -1):
+        if t[i] == t[i + 1]:
+            continue
+        G, b, LR = sol["bk_G"][i], sol["bk_b"][i], sol["bk_LR"][i]
+        m = G @ m + b
+        R = np.linalg.qr(np.vstack([R @ G.T, LR]), mode="r")
+        if data_idx >= 0 and t[i] == data_t[data_idx]:
+            m, R, ll = update(m, R, data_u[data_idx])
+            if not np.isinf(ll):
+                LL += ll
+            data_idx -= 1
+    assert data_idx == -1, "every data time must be a saved time point"
+    return float(LL)

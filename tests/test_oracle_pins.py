@@ -726,3 +726,71 @@ def test_second_order_measurement_and_state_layout(oracle):
         else:                   # H = E2: the updated second derivative equals f1 at the predicted point
             assert abs(x1[2] - f1(xp[1], xp[0])) < 1e-12
         assert np.array_equal(s["pu_mu"][1], [x1[1], x1[0]])   # sol.u = (du, u)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Fenrir data log-likelihood (reference src/data_likelihoods/fenrir.jl, test/data_likelihoods.jl)
+# ---------------------------------------------------------------------------------------------------------------------
+def _joint_data_loglik(sol, data_t, data_u, H, Rcov):
+    """Independent evaluation: the PN posterior is the Gaussian Markov chain x_N ~ N(m_N, P_N), x_i | x_{i+1} ~
+    N(G_i x_{i+1} + b_i, Lambda_i).  Build the joint Gaussian of the observed states explicitly and evaluate the data's
+    log-density with scipy -- what test/data_likelihoods.jl checks by comparing fenrir with the forward (filtering / dalton)
+    evaluations of the same marginal likelihood."""
+    t = sol["t"]
+    n = len(t)
+    D = sol["D"]
+    m = [None] * n
+    P = [None] * n
+    m[-1] = sol["x_filt_mu"][-1]
+    P[-1] = sol["x_filt_R"][-1].T @ sol["x_filt_R"][-1]
+    for i in range(n - 2, -1, -1):
+        G, b, LR = sol["bk_G"][i], sol["bk_b"][i], sol["bk_LR"][i]
+        m[i] = G @ m[i + 1] + b
+        P[i] = G @ P[i + 1] @ G.T + LR.T @ LR
+    idx = [int(np.where(t == tv)[0][0]) for tv in data_t]
+    o = H.shape[0]
+    mean = np.concatenate([H @ m[i] for i in idx])
+    cov = np.zeros((o * len(idx), o * len(idx)))
+    for a, ia in enumerate(idx):
+        for b_, ib in enumerate(idx):
+            lo, hi = min(ia, ib), max(ia, ib)
+            C = P[hi]
+            for k in range(hi - 1, lo - 1, -1):   # Cov(x_lo, x_hi) = G_lo ... G_{hi-1} P_hi
+                C = sol["bk_G"][k] @ C
+            if ia > ib:
+                C = C.T
+            cov[a * o:(a + 1) * o, b_ * o:(b_ + 1) * o] = H @ C @ H.T + (Rcov if a == b_ else 0.0)
+    return multivariate_normal(mean=mean, cov=cov, allow_singular=False).logpdf(np.concatenate(data_u))
+
+
+@pytest.mark.parametrize("alg_name,diffusion", [("EK1", "dynamic"), ("EK1", "fixed"), ("EK0", "dynamic")])
+def test_fenrir_data_loglik_matches_the_joint_gaussian(oracle, alg_name, diffusion):
+    """test/data_likelihoods.jl:17-60: Lotka-Volterra, two noisy observations (sigma = 0.5) at t = 5 and t = 10, fixed steps
+    dt = 2e-2; the Fenrir log-likelihood equals the log-density of the data under the PN posterior (rtol 1e-6, the
+    tolerance of the reference's fenrir-vs-dalton-vs-filtering comparison); also with partial observations H = [1 0]."""
+    pd = problems.PROBLEMS["lotka_volterra"]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 2, 4), 3)
+    rng = np.random.default_rng(5)
+    data_t = np.array([5.0, 10.0])
+    truth = solve_ivp(lambda t, u: [1.5 * u[0] - u[0] * u[1], -3 * u[1] + u[0] * u[1]], (0, 10), [1.0, 1.0], rtol=1e-10, atol=1e-10,
+                      t_eval=data_t).y.T
+    sigma = 0.5
+    data_u = truth + sigma * rng.standard_normal(truth.shape)
+    alg = oracle.EK1 if alg_name == "EK1" else oracle.EK0
+    diff = oracle.DIFF_DYNAMIC if diffusion == "dynamic" else oracle.DIFF_FIXED
+    cfg = oracle.make_config(2, 3, 4, alg=alg, diffusion=diff, calibrate=False, smooth=True, adaptive=False, dt=2e-2, t0=0, t1=10,
+                             tstops=data_t, cov_backend=oracle.COV_QR)
+    s = oracle.solve(cfg, rhs, pd.u0, pd.p)
+    assert all(tv in s["t"] for tv in data_t)
+    ll = oracle.fenrir_data_loglik(cfg, s, data_t, data_u, observation_noise_cov=sigma ** 2)
+    want = _joint_data_loglik(s, data_t, data_u, np.eye(8)[:2], sigma ** 2 * np.eye(2))
+    assert ll == pytest.approx(want, rel=1e-6)
+    # the likelihood is informative: data shifted far from the solution is much less likely
+    assert oracle.fenrir_data_loglik(cfg, s, data_t, data_u + 3.0, observation_noise_cov=sigma ** 2) < ll - 10
+    # partial observations (test/data_likelihoods.jl:62-73) and a full noise covariance (:86-110)
+    Hp = np.array([[1.0, 0.0]])
+    llp = oracle.fenrir_data_loglik(cfg, s, data_t, data_u[:, :1], observation_matrix=Hp, observation_noise_cov=sigma ** 2)
+    assert llp == pytest.approx(_joint_data_loglik(s, data_t, data_u[:, :1], Hp @ np.eye(8)[:2], sigma ** 2 * np.eye(1)), rel=1e-6)
+    Rm = np.array([[sigma ** 2, 0.05], [0.05, 2 * sigma ** 2]])
+    llm = oracle.fenrir_data_loglik(cfg, s, data_t, data_u, observation_noise_cov=Rm)
+    assert llm == pytest.approx(_joint_data_loglik(s, data_t, data_u, np.eye(8)[:2], Rm), rel=1e-6)
