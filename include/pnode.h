@@ -128,6 +128,20 @@ typedef struct pnode_config {
        IWP prior, scalar diffusion models. */
     int32_t second_order;
     int32_t reserved1;
+    /* Fenrir data log-likelihood, `fenrir_data_loglik(prob, alg; data=(t, u), observation_matrix, observation_noise_cov)`
+       (src/data_likelihoods/fenrir.jl:30-137).  n_data > 0: the data times are added to tstops (:46), the solve keeps the
+       filtering estimates (the reference stops with `step!`: no smoothing, no calibration), and a backward pass fits the
+       PN posterior to the data (fit_pnsolution_to_data!, :68-125), one log-likelihood per trajectory in
+       PNODE_F_FENRIR_LOGLIK (-Inf for a trajectory whose solve did not succeed, :55-59).  Needs smooth = 1
+       (ArgumentError otherwise, :42-44).  One data set for the whole ensemble (parameter sweeps). */
+    const double* data_t;             /* [n_data] ascending, in [t0, t1]; host pointer, copied at create            */
+    int64_t n_data;
+    const double* data_u;             /* [n_data][n_obs]                                                            */
+    int32_t n_obs;                    /* length of one observation                                                  */
+    int32_t reserved2;
+    const double* observation_matrix; /* [n_obs][len(sol.u)] row-major; NULL = identity (n_obs == len(sol.u))        */
+    const double* observation_noise_cov; /* [n_obs][n_obs] symmetric positive definite; NULL = observation_noise_var * I */
+    double observation_noise_var;
 } pnode_config;
 
 typedef struct pnode_solver pnode_solver;
@@ -160,6 +174,7 @@ typedef enum pnode_field {
     /* dense output on the saveat grid */
     PNODE_F_SAVEAT_U = 21,      /* double [n_traj][n_saveat][d]      mean(sol(saveat[j]))            */
     PNODE_F_SAVEAT_U_COV = 22,  /* double [n_traj][n_saveat][d][d]   Matrix(sol(saveat[j]).Sigma)    */
+    PNODE_F_FENRIR_LOGLIK = 23, /* double [n_traj]  Fenrir data log-likelihood (config data_t / data_u) */
     PNODE_F_COUNT
 } pnode_field;
 

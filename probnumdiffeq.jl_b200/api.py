@@ -216,7 +216,7 @@ def _check_alg(alg, adaptive, dt, save_everystep, dense):
 
 
 def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, abstol, reltol, save_everystep, maxiters,
-                dtmin, dtmax, tstops, save_state, forced_diffusion=None, saveat=None):
+                dtmin, dtmax, tstops, save_state, forced_diffusion=None, saveat=None, fenrir=None):
     d, n_p = len(prob.u0), len(prob.p)
     if d < 1:
         raise RuntimeError("We currently don't support scalar-valued problems")  # src/caches.jl:96-98
@@ -250,6 +250,8 @@ def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, absto
                 raise ValueError("The selected algorithm uses an efficient Kronecker-factorized implementation which is "
                                  "incompatible with the provided mass matrix. Try using the `EK1` instead.")
             kw.update(mass_matrix=M)
+    if fenrir is not None:
+        kw.update(**fenrir)
     if prob.builtin is not None:
         kw.update(rhs_name="builtin:" + prob.builtin)
     else:
@@ -309,6 +311,47 @@ def solve(prob, alg, ensemblealg: Optional[EnsembleB200] = None, *, trajectories
         solver.close()
     out = EnsembleSolution(sols, time.time() - t0, all(s.retcode == "Success" for s in sols), info)
     return out.u[0] if single else out
+
+
+def fenrir_data_loglik(prob, alg, ensemblealg: Optional[EnsembleB200] = None, *, data, observation_noise_cov,
+                       observation_matrix=None, trajectories: Optional[int] = None, adaptive: bool = True,
+                       dt: Optional[float] = None, abstol: float = 1e-6, reltol: float = 1e-3, maxiters: int = 1_000_000,
+                       dtmin: float = 0.0, dtmax: Optional[float] = None, tstops=None):
+    """`fenrir_data_loglik(prob, alg; data=(t, u), observation_matrix, observation_noise_cov, kwargs...)`
+    (src/data_likelihoods/fenrir.jl:30-66): the Fenrir approximate log-likelihood of `data` -- a pair (t, u) -- under the PN
+    posterior of the ODE solution.  For an `EnsembleProblem` (a parameter sweep against ONE data set) it returns one value
+    per trajectory; the solves and the backward passes of the whole ensemble run on the device."""
+    if not alg.smooth:
+        raise ValueError("fenrir only works with smoothing. Set `smooth=true`.")   # fenrir.jl:42-44
+    ens = ensemblealg or EnsembleB200()
+    single = isinstance(prob, ODEProblem)
+    eprob = EnsembleProblem(prob) if single else prob
+    n = 1 if single else trajectories
+    if n is None or n < 1:
+        raise ValueError("trajectories must be a positive integer")
+    _check_alg(alg, adaptive, dt, True, False)
+    base = eprob.prob
+    d, n_p = len(base.u0), len(base.p)
+    u0 = np.empty((n, d))
+    p = np.empty((n, max(n_p, 0)))
+    for i in range(n):
+        pi = eprob.prob_func(base, i, 0) if eprob.prob_func else base
+        u0[i] = pi.u0
+        if n_p:
+            p[i] = pi.p
+    data_t, data_u = data
+    fen = dict(data_t=np.asarray(data_t, dtype=float), data_u=np.asarray(data_u, dtype=float),
+               observation_matrix=observation_matrix, observation_noise_cov=observation_noise_cov)
+    cfg = _config_for(base, alg, ens, adaptive=adaptive, dt=dt, abstol=abstol, reltol=reltol, save_everystep=True,
+                      maxiters=maxiters, dtmin=dtmin, dtmax=dtmax, tstops=tstops, save_state=False, fenrir=fen)
+    solver = _lib.Solver(cfg)
+    try:
+        res = solver.solve(u0, p)
+        ll = res.field(_lib.F_FENRIR_LOGLIK).copy()
+        res.free()
+    finally:
+        solver.close()
+    return float(ll[0]) if single else ll
 
 
 def _unpack(res, n, d, save_everystep) -> List[ProbODESolution]:

@@ -44,7 +44,22 @@ struct PnSmoothParams {
     double rate;              /* IOUP prior: scalar rate parameter and the Gauss-Legendre rule (pn_ioup.cuh) */
     double glx[16], glw[16];
     unsigned long long* work_counter;
+    /* Fenrir data log-likelihood (src/data_likelihoods/fenrir.jl:68-137, fit_pnsolution_to_data!): a non-null fenrir_ll
+       turns the shared-memory sweep into the backward pass that starts from the filtering estimates, marginalizes with the
+       backward kernels and, at every data time, applies a Kalman update with observation matrix obs_H and noise factor
+       obs_Rn, accumulating its log-likelihood.  Nothing is written back to the records in that mode. */
+    const double* s_t;      /* [total] saved times */
+    const double* data_t;   /* [n_data] ascending; every entry is a saved time of every trajectory (tstops) */
+    const double* data_u;   /* [n_data][n_obs] */
+    const double* obs_H;    /* [n_obs][D] row-major: proj * SolProj */
+    const double* obs_Rn;   /* [n_obs][n_obs] row-major right factor of the observation-noise covariance */
+    long long n_data;
+    int n_obs;
+    const int* retcode;     /* [n_traj] return codes of the solve: -Inf unless Success (fenrir.jl:55-59) */
+    double* fenrir_ll;      /* [n_traj] out */
 };
+/* extra shared-memory doubles per warp in Fenrir mode (host and kernel must agree) */
+#define PN_FENRIR_EXTRA(D, o) (3 * (D) * (o) + ((D) + (o)) * (o) + 4 * (o))
 
 #define PN_SM_WARPS 4
 
@@ -103,12 +118,94 @@ __device__ void pn_sm_rdiv_chol(double* B, int rows, const double* U, int D, int
     __syncwarp();
 }
 
+// measure_and_update! (fenrir.jl:127-137) + update!(...; R) (src/filtering/update.jl:65-139, QR route :132-136) on the
+// posterior (mus, Rs) in shared memory; returns the log-likelihood of the observation u (same value on all lanes).
+__device__ double pn_sm_fenrir_update(const PnSmoothParams& P, const double* u, double* mus, double* Rs, double* Xs, double* F, int D,
+                                      int lane) {
+    const int o = P.n_obs;
+    double* Cb = F;                 /* D x o   C = R H'                  */
+    double* Kb = Cb + D * o;        /* D x o   K                         */
+    double* K1 = Kb + D * o;        /* D x o   K Rn'                     */
+    double* Sb = K1 + D * o;        /* (D + o) x o stack -> S.R          */
+    double* z = Sb + (D + o) * o;   /* o                                 */
+    double* zt = z + o;             /* o                                 */
+    double nrm = 0.0;
+    for (int i = lane; i < D * D; i += 32) nrm += fabs(Rs[i]);
+    nrm = pn_warp_sum(nrm);
+    for (int a = lane; a < o; a += 32) {
+        double sacc = 0.0;
+        for (int c = 0; c < D; c++) sacc += P.obs_H[a * D + c] * mus[c];
+        z[a] = sacc - u[a];
+        zt[a] = z[a];
+    }
+    __syncwarp();
+    if (nrm == 0.0) { /* update.jl:82-89: Sigma == 0 -> copy, +-Inf */
+        double nz = 0.0;
+        for (int a = 0; a < o; a++) nz += fabs(z[a]);
+        return (nz == 0.0) ? PN_INF : -PN_INF;
+    }
+    for (int i = lane; i < D * o; i += 32) {
+        const int r = i / o, a = i % o;
+        double sacc = 0.0;
+        for (int c = 0; c < D; c++) sacc += Rs[r * D + c] * P.obs_H[a * D + c];
+        Cb[i] = sacc;
+        Sb[i] = sacc;
+    }
+    for (int i = lane; i < o * o; i += 32) Sb[D * o + i] = P.obs_Rn[i];
+    __syncwarp();
+    pn_sm_qr(Sb, D + o, o, lane); /* make_obscov_sqrt: S.R = qr([R H'; Rn]).R */
+    for (int i = lane; i < D * o; i += 32) {
+        const int c = i / o, a = i % o;
+        double sacc = 0.0;
+        for (int r = 0; r < D; r++) sacc += Rs[r * D + c] * Cb[r * o + a];
+        Kb[i] = sacc;
+    }
+    __syncwarp();
+    pn_sm_rdiv_chol(Kb, D, Sb, o, lane); /* K = Sigma H' S^-1 */
+    pn_sm_rdiv_chol(zt, 1, Sb, o, lane); /* S^-1 z            */
+    double quad = 0.0, logdet = 0.0;
+    for (int a = 0; a < o; a++) {
+        quad += z[a] * zt[a];
+        logdet += log(fabs(Sb[a * o + a]));
+    }
+    const double ll = -0.5 * quad - 0.5 * (double)o * 1.8378770664093453 - logdet;
+    for (int i = lane; i < D * o; i += 32) {
+        const int c = i / o, a = i % o;
+        double sacc = 0.0;
+        for (int b = 0; b < o; b++) sacc += Kb[c * o + b] * P.obs_Rn[a * o + b];
+        K1[i] = sacc; /* (K Rn')[c][a] */
+    }
+    /* stack [ R (I - K H)' ; (K Rn')' ] */
+    for (int i = lane; i < D * D; i += 32) {
+        const int r = i / D, c = i % D;
+        double sacc = Rs[i];
+        for (int a = 0; a < o; a++) sacc -= Cb[r * o + a] * Kb[c * o + a];
+        Xs[i] = sacc;
+    }
+    __syncwarp();
+    for (int i = lane; i < o * D; i += 32) {
+        const int a = i / D, c = i % D;
+        Xs[D * D + i] = K1[c * o + a];
+    }
+    for (int c = lane; c < D; c += 32) {
+        double sacc = mus[c];
+        for (int a = 0; a < o; a++) sacc -= Kb[c * o + a] * z[a];
+        mus[c] = sacc;
+    }
+    __syncwarp();
+    pn_sm_qr(Xs, D + o, D, lane);
+    for (int i = lane; i < D * D; i += 32) Rs[i] = Xs[i];
+    __syncwarp();
+    return ll;
+}
+
 __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __grid_constant__ PnSmoothParams P) {
     extern __shared__ double pn_sm_shared[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int d = P.d, q = P.q, n = q + 1, D = d * n, DD = D * D;
     /* per-warp workspace */
-    const int per_warp = 7 * DD + 4 * D + 2 * n * n + 2 * n;
+    const bool fen = P.fenrir_ll != nullptr;
+    const int per_warp = 7 * DD + 4 * D + 2 * n * n + 2 * n + (fen ? PN_FENRIR_EXTRA(D, P.n_obs) : 0);
     double* W = pn_sm_shared + (size_t)warp * per_warp;
     double* Rk = W;            /* D x D  filtered factor at k                 */
     double* Xs = Rk + DD;      /* 3D x D stack; first used as 2D x D predict  */
@@ -123,6 +220,7 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
     double* LQ = T1 + n * n;   /* n x n: (L P^-1)                          */
     double* hp = LQ + n * n;   /* n */
     double* PIv = hp + n;      /* n */
+    double* Fw = PIv + n;      /* Fenrir workspace (fen only) */
 
     for (;;) {
         unsigned long long idx = 0;
@@ -137,15 +235,23 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
         for (int i = lane; i < DD; i += 32) Rs[i] = P.s_x_covfac[last * DD + i];
         for (int i = lane; i < D; i += 32) mus[i] = P.s_x_mean[last * D + i];
         __syncwarp();
+        double LL = 0.0;
+        long long data_idx = P.n_data - 1;
+        if (fen && data_idx >= 0 && P.s_t[last] == P.data_t[data_idx]) { /* fenrir.jl:87-97 */
+            LL += pn_sm_fenrir_update(P, P.data_u + data_idx * P.n_obs, mus, Rs, Xs, Fw, D, lane);
+            data_idx--;
+        }
         /* outputs of the last point (calibrated) */
+        if (!fen)
         for (int i = lane; i < d * d; i += 32) {
             const int a = i / d, b = i % d;
             double s = 0.0;
             for (int r = 0; r < D; r++) s += Rs[r * D + a] * Rs[r * D + b];
             P.s_u_cov[last * d * d + i] = s * sc * sc;
         }
+        if (!fen)
         for (int i = lane; i < d; i += 32) P.s_u_mean[last * d + i] = mus[i];
-        if (sc != 1.0)
+        if (sc != 1.0 && !fen)
             for (int i = lane; i < DD; i += 32) P.s_x_covfac[last * DD + i] = Rs[i] * sc;
         __syncwarp();
 
@@ -168,6 +274,7 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
             }
             __syncwarp();
             if (h == 0.0) { /* integrator_utils.jl:109-112: x_smooth[k] = x_smooth[k+1] */
+                if (fen) continue; /* fenrir.jl:103-106 */
                 for (int i = lane; i < DD; i += 32) P.s_x_covfac[k * DD + i] = Rs[i] * sc;
                 for (int i = lane; i < D; i += 32) P.s_x_mean[k * D + i] = mus[i];
             } else {
@@ -245,14 +352,22 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
                 for (int i = lane; i < DD; i += 32) {
                     const double v = Xs[i];
                     Rs[i] = v;
-                    P.s_x_covfac[k * DD + i] = v * sc;
+                    if (!fen) P.s_x_covfac[k * DD + i] = v * sc;
                 }
                 for (int i = lane; i < D; i += 32) {
                     mus[i] = mup[i];
-                    P.s_x_mean[k * D + i] = mup[i];
+                    if (!fen) P.s_x_mean[k * D + i] = mup[i];
                 }
             }
             __syncwarp();
+            if (fen) { /* fenrir.jl:110-123: data update at this time point */
+                if (data_idx >= 0 && P.s_t[k] == P.data_t[data_idx]) {
+                    const double ll = pn_sm_fenrir_update(P, P.data_u + data_idx * P.n_obs, mus, Rs, Xs, Fw, D, lane);
+                    if (ll - ll == 0.0) LL += ll; /* !isinf */
+                    data_idx--;
+                }
+                continue;
+            }
             /* pu[k] = SolProj x_smooth[k]  (integrator_utils.jl:117-118) */
             for (int i = lane; i < d * d; i += 32) {
                 const int a = i / d, b = i % d;
@@ -262,6 +377,10 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
             }
             for (int i = lane; i < d; i += 32) P.s_u_mean[k * d + i] = mus[i];
             __syncwarp();
+        }
+        if (fen && lane == 0) {
+            const bool ok = (!P.retcode || P.retcode[tr] == PN_RET_SUCCESS) && data_idx < 0;
+            P.fenrir_ll[tr] = ok ? LL : -PN_INF;
         }
     }
 }

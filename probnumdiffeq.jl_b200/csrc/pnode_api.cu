@@ -234,6 +234,10 @@ struct pnode_solver {
     double* d_init_dt = nullptr;
     size_t init_cap = 0;
     double compile_s = 0.0;
+    /* Fenrir data log-likelihood: device copies of the data set and the observation model */
+    double *d_data_t = nullptr, *d_data_u = nullptr, *d_obs_H = nullptr, *d_obs_Rn = nullptr;
+    int64_t n_data = 0;
+    int n_obs = 0;
     std::string mass_src; /* generated preamble (PN_MASS, pn_mass, pn_mass_inv) when the problem has a mass matrix */
     PnParams base; /* constants filled at create */
 };
@@ -698,6 +702,24 @@ static int validate_config(const pnode_config* cfg) {
         if (cfg->smooth && smooth_lanes(D) == 0)
             return fail(PNODE_ERR_UNSUPPORTED, "dense output of smoothed solutions needs the register-resident sweep (D <= 24)");
     }
+    if (cfg->n_data > 0) { /* fenrir_data_loglik */
+        if (!cfg->smooth) return fail(PNODE_ERR_ARGUMENT, "fenrir only works with smoothing. Set `smooth=true`."); /* fenrir.jl:42-44 */
+        if (!cfg->data_t || !cfg->data_u || cfg->n_obs < 1) return fail(PNODE_ERR_ARGUMENT, "data_t / data_u / n_obs are required with n_data > 0");
+        const int dul = cfg->second_order ? 2 * cfg->d : cfg->d;
+        if (!cfg->observation_matrix && cfg->n_obs != dul)
+            return fail(PNODE_ERR_ARGUMENT, "without an observation_matrix every observation must have length(sol.u) entries"); /* DimensionMismatch */
+        if (cfg->n_obs > D) return fail(PNODE_ERR_ARGUMENT, "n_obs must not exceed the state dimension");
+        for (int64_t i = 0; i < cfg->n_data; i++) {
+            if (!(cfg->data_t[i] >= cfg->t0 && cfg->data_t[i] <= cfg->t1)) return fail(PNODE_ERR_ARGUMENT, "data.t must lie in tspan");
+            if (i > 0 && !(cfg->data_t[i] > cfg->data_t[i - 1])) return fail(PNODE_ERR_ARGUMENT, "data.t must be strictly ascending");
+        }
+        if (!cfg->observation_noise_cov && !(cfg->observation_noise_var > 0.0))
+            return fail(PNODE_ERR_ARGUMENT, "observation_noise_cov must be positive (definite)");
+        if (cfg->prior != PNODE_PRIOR_IWP || is_mv(cfg->diffusion))
+            return fail(PNODE_ERR_UNSUPPORTED, "the Fenrir backward pass is implemented for the IWP prior with scalar diffusion models");
+        if (cfg->n_saveat > 0) return fail(PNODE_ERR_UNSUPPORTED, "saveat and a Fenrir data set cannot be combined (the records stay filtering estimates)");
+        if (D > 32) return fail(PNODE_ERR_UNSUPPORTED, "the Fenrir backward pass is implemented for D = d(q+1) <= 32");
+    }
     if (cfg->second_order) { /* SecondOrderODEProblem */
         if (cfg->q < 2) return fail(PNODE_ERR_ARGUMENT, "second-order problems need order >= 2 (the measurement reads the second derivative)");
         if (cfg->mass_matrix) return fail(PNODE_ERR_ARGUMENT, "second-order problems take no mass matrix (derivative_utils.jl:39-41 asserts mass_matrix === I)");
@@ -907,12 +929,62 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     CUDA_TRY(cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
-    if (cfg->n_tstops > 0 && cfg->tstops) {
-        CUDA_TRY(cudaMalloc(&s->d_tstops, sizeof(double) * cfg->n_tstops));
-        CUDA_TRY(cudaMemcpy(s->d_tstops, cfg->tstops, sizeof(double) * cfg->n_tstops, cudaMemcpyHostToDevice));
-        s->host_tstops.assign(cfg->tstops, cfg->tstops + cfg->n_tstops);
-        B.tstops = s->d_tstops;
-        B.n_tstops = cfg->n_tstops;
+    {
+        /* tstops = union(data.t, tstops) (fenrir.jl:46) */
+        std::vector<double> ts;
+        if (cfg->n_tstops > 0 && cfg->tstops) ts.assign(cfg->tstops, cfg->tstops + cfg->n_tstops);
+        if (cfg->n_data > 0) {
+            ts.insert(ts.end(), cfg->data_t, cfg->data_t + cfg->n_data);
+            std::sort(ts.begin(), ts.end());
+            ts.erase(std::unique(ts.begin(), ts.end()), ts.end());
+        }
+        if (!ts.empty()) {
+            CUDA_TRY(cudaMalloc(&s->d_tstops, sizeof(double) * ts.size()));
+            CUDA_TRY(cudaMemcpy(s->d_tstops, ts.data(), sizeof(double) * ts.size(), cudaMemcpyHostToDevice));
+            s->host_tstops = ts;
+            B.tstops = s->d_tstops;
+            B.n_tstops = (long long)ts.size();
+        }
+    }
+    if (cfg->n_data > 0) {
+        const int o = cfg->n_obs, dul = cfg->second_order ? 2 * cfg->d : cfg->d;
+        s->n_data = cfg->n_data;
+        s->n_obs = o;
+        /* state2data_projmat = proj * SolProj (fenrir.jl:85): o x D, SolProj = E0 rows or (E1; E0) rows */
+        std::vector<double> H((size_t)o * D, 0.0), Rn((size_t)o * o, 0.0);
+        for (int a = 0; a < o; a++)
+            for (int j = 0; j < dul; j++) {
+                const double pv = cfg->observation_matrix ? cfg->observation_matrix[a * dul + j] : (a == j ? 1.0 : 0.0);
+                const int sc = cfg->second_order ? (j < cfg->d ? cfg->d + j : j - cfg->d) : j;
+                H[(size_t)a * D + sc] = pv;
+            }
+        if (cfg->observation_noise_cov) { /* cov2psdmatrix(::AbstractMatrix): upper Cholesky factor (ProbNumDiffEq.jl:72-73) */
+            std::vector<double> A(cfg->observation_noise_cov, cfg->observation_noise_cov + (size_t)o * o);
+            for (int j = 0; j < o; j++) {
+                double dsum = A[j * o + j];
+                for (int k = 0; k < j; k++) dsum -= Rn[k * o + j] * Rn[k * o + j];
+                if (!(dsum > 0.0)) {
+                    delete s;
+                    return fail(PNODE_ERR_ARGUMENT, "observation_noise_cov is not positive definite"); /* PosDefException */
+                }
+                Rn[j * o + j] = std::sqrt(dsum);
+                for (int i = j + 1; i < o; i++) {
+                    double v = A[j * o + i];
+                    for (int k = 0; k < j; k++) v -= Rn[k * o + j] * Rn[k * o + i];
+                    Rn[j * o + i] = v / Rn[j * o + j];
+                }
+            }
+        } else {
+            for (int a = 0; a < o; a++) Rn[a * o + a] = std::sqrt(cfg->observation_noise_var);
+        }
+        CUDA_TRY(cudaMalloc(&s->d_data_t, sizeof(double) * cfg->n_data));
+        CUDA_TRY(cudaMalloc(&s->d_data_u, sizeof(double) * cfg->n_data * o));
+        CUDA_TRY(cudaMalloc(&s->d_obs_H, sizeof(double) * H.size()));
+        CUDA_TRY(cudaMalloc(&s->d_obs_Rn, sizeof(double) * Rn.size()));
+        CUDA_TRY(cudaMemcpy(s->d_data_t, cfg->data_t, sizeof(double) * cfg->n_data, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(s->d_data_u, cfg->data_u, sizeof(double) * cfg->n_data * o, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(s->d_obs_H, H.data(), sizeof(double) * H.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(s->d_obs_Rn, Rn.data(), sizeof(double) * Rn.size(), cudaMemcpyHostToDevice));
     }
     if (cfg->n_forced > 0 && cfg->forced_diffusion) {
         CUDA_TRY(cudaMalloc(&s->d_forced, sizeof(double) * cfg->n_forced));
@@ -934,6 +1006,7 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
         s->n_saveat = cfg->n_saveat;
     }
     s->cfg.saveat = nullptr;
+    s->cfg.data_t = s->cfg.data_u = s->cfg.observation_matrix = s->cfg.observation_noise_cov = nullptr;
     int rc = get_kernel(s, cfg->save_everystep ? ((cfg->smooth || cfg->n_saveat > 0) ? 2 : 1) : 0,
                         cfg->save_everystep ? &s->k_save : &s->k_final);
     if (!rc && cfg->smooth) rc = get_smoother(s);
@@ -990,6 +1063,8 @@ extern "C" void pnode_destroy(pnode_solver* s) {
     if (s->d_tstops) cudaFree(s->d_tstops);
     if (s->d_forced) cudaFree(s->d_forced);
     if (s->d_saveat) cudaFree(s->d_saveat);
+    for (double* ptr : {s->d_data_t, s->d_data_u, s->d_obs_H, s->d_obs_Rn})
+        if (ptr) cudaFree(ptr);
     if (s->d_init_mu) cudaFreeAsync(s->d_init_mu, s->stream);
     if (s->d_init_dt) cudaFreeAsync(s->d_init_dt, s->stream);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -1250,7 +1325,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             memcpy(Q.glw, s->base.glw, sizeof Q.glw);
             Q.n_traj = ntraj;
             Q.work_counter = s->d_counter;
-            if (s->k_smooth.valid()) {
+            if (s->k_smooth.valid() && !Q.fenrir_ll) {
                 /* register-resident sweep: Gs lanes per trajectory, persistent, one CTA per SM */
                 Kernel& ks = s->k_smooth;
                 const int groups = ks.threads / s->Gs;
@@ -1269,7 +1344,8 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 if (s->cfg.prior != PNODE_PRIOR_IWP)
                     return fail(PNODE_ERR_UNSUPPORTED, "the shared-memory smoother sweep implements the IWP prior only");
                 const int n = s->cfg.q + 1;
-                const size_t per_warp = (size_t)(7 * D * D + 4 * D + 2 * n * n + 2 * n) * sizeof(double);
+                const size_t per_warp =
+                    (size_t)(7 * D * D + 4 * D + 2 * n * n + 2 * n + (Q.fenrir_ll ? PN_FENRIR_EXTRA(D, Q.n_obs) : 0)) * sizeof(double);
                 int warps = PN_SM_WARPS;
                 while (warps > 1 && per_warp * warps > 200 * 1024) warps--;
                 const size_t smem = per_warp * warps;
@@ -1357,6 +1433,21 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             Q.s_x_covfac = P.s_x_covfac;
             Q.s_u_mean = P.s_u_mean;
             Q.s_u_cov = P.s_u_cov;
+            if (s->n_data > 0) {
+                /* Fenrir: the backward pass fits the PN posterior to the data instead of smoothing; the records and the
+                   U fields stay the filtering estimates, uncalibrated (the reference stops with step!, no postamble) */
+                if ((rc = alloc_field(r, PNODE_F_FENRIR_LOGLIK, N * 8))) return rc;
+                Q.calibrate = 0;
+                Q.s_t = P.s_t;
+                Q.data_t = s->d_data_t;
+                Q.data_u = s->d_data_u;
+                Q.obs_H = s->d_obs_H;
+                Q.obs_Rn = s->d_obs_Rn;
+                Q.n_data = s->n_data;
+                Q.n_obs = s->n_obs;
+                Q.retcode = (const int*)r->f[PNODE_F_RETCODE].d;
+                Q.fenrir_ll = (double*)r->f[PNODE_F_FENRIR_LOGLIK].d;
+            }
             if ((rc = launch_sweep(Q, n_traj))) return rc;
             launches += 1;
             if (dense) {

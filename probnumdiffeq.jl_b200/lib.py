@@ -28,6 +28,7 @@ STATUS = {0: "OK", -1: "ArgumentError", -2: "DimensionMismatch", -3: "CompileErr
 F_T_END, F_U_FINAL, F_U_FINAL_COV, F_X_FINAL, F_X_FINAL_COVFAC, F_LOGLIK, F_DIFFUSION, F_DT_LAST = range(8)
 F_NACCEPT, F_NREJECT, F_NF, F_RETCODE, F_STEP_OFFSETS, F_T, F_U, F_U_COV, F_DIFFUSIONS, F_X, F_X_COVFAC = range(8, 19)
 F_DIFFUSION_MV, F_DIFFUSIONS_MV, F_SAVEAT_U, F_SAVEAT_U_COV = 19, 20, 21, 22
+F_FENRIR_LOGLIK = 23
 _FIELD_DTYPE = {F_NACCEPT: np.int64, F_NREJECT: np.int64, F_NF: np.int64, F_RETCODE: np.int32,
                 F_STEP_OFFSETS: np.int64}
 
@@ -64,6 +65,10 @@ class Config(C.Structure):
         ("saveat", C.POINTER(C.c_double)), ("n_saveat", C.c_int64),
         ("mass_matrix", C.POINTER(C.c_double)),
         ("second_order", C.c_int32), ("reserved1", C.c_int32),
+        ("data_t", C.POINTER(C.c_double)), ("n_data", C.c_int64), ("data_u", C.POINTER(C.c_double)),
+        ("n_obs", C.c_int32), ("reserved2", C.c_int32),
+        ("observation_matrix", C.POINTER(C.c_double)), ("observation_noise_cov", C.POINTER(C.c_double)),
+        ("observation_noise_var", C.c_double),
     ]
 
 
@@ -134,7 +139,8 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
                 lanes_per_traj=0, t0=0.0, t1=1.0, dt=0.0, abstol=1e-6, reltol=1e-3, dtmin=0.0, dtmax=0.0,
                 maxiters=1_000_000, beta1=0.0, beta2=0.0, qmin=0.2, qmax=10.0, gamma=0.9, qsteady_min=1.0,
                 qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None, device=0, prior=PRIOR_IWP,
-                rate_parameter=0.0, saveat=None, mass_matrix=None, second_order=False) -> Config:
+                rate_parameter=0.0, saveat=None, mass_matrix=None, second_order=False, data_t=None, data_u=None,
+                observation_matrix=None, observation_noise_cov=None) -> Config:
     c = Config()
     c.second_order = int(second_order)
     c.struct_size = C.sizeof(Config)
@@ -163,6 +169,23 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
         a = np.ascontiguousarray(saveat, dtype=np.float64)
         keep.append(a)
         c.saveat, c.n_saveat = a.ctypes.data_as(C.POINTER(C.c_double)), len(a)
+    if data_t is not None and len(data_t):   # Fenrir data log-likelihood
+        dp_ = C.POINTER(C.c_double)
+        a = np.ascontiguousarray(data_t, dtype=np.float64)
+        b = np.ascontiguousarray(np.asarray(data_u, dtype=np.float64).reshape(len(a), -1))
+        keep += [a, b]
+        c.data_t, c.n_data, c.data_u, c.n_obs = a.ctypes.data_as(dp_), len(a), b.ctypes.data_as(dp_), b.shape[1]
+        if observation_matrix is not None:
+            h = np.ascontiguousarray(np.asarray(observation_matrix, dtype=np.float64).reshape(b.shape[1], -1))
+            keep.append(h)
+            c.observation_matrix = h.ctypes.data_as(dp_)
+        cov = np.asarray(observation_noise_cov, dtype=np.float64)
+        if cov.ndim == 0:
+            c.observation_noise_var = float(cov)
+        else:
+            cv = np.ascontiguousarray(cov.reshape(b.shape[1], b.shape[1]))
+            keep.append(cv)
+            c.observation_noise_cov = cv.ctypes.data_as(dp_)
     if mass_matrix is not None:
         a = np.ascontiguousarray(np.asarray(mass_matrix, dtype=np.float64).reshape(d, d))
         keep.append(a)

@@ -78,3 +78,32 @@ if "cfg5" in which:
 if "cfg5dae" in which:   # ROBER as the reference benchmarks it: mass-matrix DAE form (benchmarks/rober.jmd:37-46)
     for n in (100_000, 1_000_000):
         run(f"cfg5 ROBER-DAE (M = diag(1,1,0)) EK1(3) adaptive filter only, {n}", "rober_dae", n, 3, 100.0, seed=3)
+if "fenrir" in which:   # Fenrir data log-likelihood of a parameter sweep against one data set (src/data_likelihoods/fenrir.jl)
+    from probnumdiffeq_jl_b200 import tracer as _tr
+    pd = problems.PROBLEMS["lotka_volterra"]
+    for n in (16_384, 131_072):
+        rng = np.random.Generator(np.random.PCG64(7))
+        u0 = np.tile(np.array(pd.u0, dtype=float), (n, 1))
+        p = np.array(pd.p, dtype=float)[None, :] * (1 + 0.1 * rng.uniform(-1, 1, (n, pd.n_p)))
+        data_t = np.linspace(0.5, 10.0, 20)
+        data_u = 1.0 + rng.uniform(0, 2, (20, 2))
+        src = _tr.cuda_source(_tr.trace(pd.f, 2, 4), "UserProb")
+        cfg = lib.make_config(d=2, q=3, n_p=4, rhs_name="UserProb", rhs_src=src, smooth=True, save_everystep=True, t0=0.0, t1=10.0,
+                              data_t=data_t, data_u=data_u, observation_noise_cov=0.25)
+        s = lib.Solver(cfg)
+        best = None
+        for _ in range(3):
+            t = time.perf_counter()
+            r = s.solve(np.ascontiguousarray(u0), np.ascontiguousarray(p))
+            wall = time.perf_counter() - t
+            info = r.info
+            ll = r.field(lib.F_FENRIR_LOGLIK)
+            rec = dict(kernel_ms=info.kernel_ms, wall_ms=wall * 1e3, accepted=int(info.total_accepted), launches=int(info.n_launches),
+                       ok=bool(np.isfinite(ll).all()))
+            r.free()
+            if best is None or rec["kernel_ms"] < best["kernel_ms"]:
+                best = rec
+        s.close()
+        best.update(tag=f"Fenrir log-likelihood, LV EK1(3) adaptive, 20 observations, {n} parameter sets", n_traj=n,
+                    loglik_per_s_kernel=n / (best["kernel_ms"] * 1e-3), steps_per_s_kernel=best["accepted"] / (best["kernel_ms"] * 1e-3))
+        print(json.dumps(best), flush=True)

@@ -1196,3 +1196,101 @@ def test_second_order_adaptive(oracle, alg):
                        (0, 0.1), u0[i], method="DOP853", rtol=1e-12, atol=1e-12, dense_output=True)
         assert np.linalg.norm(g["U"][b - 1] - tr.y[:, -1]) <= 1e-3 * np.linalg.norm(tr.y[:, -1])
         assert np.linalg.norm(g["SU"][i, 0] - tr.sol(tq)) <= 1e-3 * np.linalg.norm(tr.sol(tq))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Fenrir data log-likelihood over an ensemble of parameters (src/data_likelihoods/fenrir.jl)
+# ------------------------------------------------------------------------------------------------------------------
+def _gpu_fenrir(pd, u0, p, q, data_t, data_u, *, second_order=False, f=None, **kw):
+    fn = f or pd.f
+    dim = u0.shape[1]
+    src = tracer.cuda_source(tracer.trace(fn, dim, p.shape[1]), "UserProb")
+    cfg = lib.make_config(d=dim // 2 if second_order else dim, q=q, n_p=p.shape[1], rhs_name="UserProb", rhs_src=src, smooth=True,
+                          save_everystep=True, second_order=second_order, data_t=data_t, data_u=data_u, **kw)
+    s = lib.Solver(cfg)
+    r = s.solve(u0, p)
+    out = dict(ll=r.field(lib.F_FENRIR_LOGLIK), off=r.field(lib.F_STEP_OFFSETS), T=r.field(lib.F_T), retcode=r.field(lib.F_RETCODE),
+               U=r.field(lib.F_U).reshape(-1, dim))
+    r.free()
+    s.close()
+    return out
+
+
+def _lv_data(rng, sigma, data_t):
+    from scipy.integrate import solve_ivp
+    truth = solve_ivp(lambda t, u: [1.5 * u[0] - u[0] * u[1], -3 * u[1] + u[0] * u[1]], (0, 10), [1.0, 1.0], rtol=1e-10, atol=1e-10,
+                      t_eval=data_t).y.T
+    return truth + sigma * rng.standard_normal(truth.shape)
+
+
+@pytest.mark.parametrize("alg,diffusion", [(lib.EK1, lib.DIFF_DYNAMIC), (lib.EK1, lib.DIFF_FIXED), (lib.EK0, lib.DIFF_DYNAMIC)])
+def test_fenrir_fixed_steps(oracle, alg, diffusion):
+    """test/data_likelihoods.jl:17-60 over an ensemble of parameters: Lotka-Volterra, noisy observations, fixed steps
+    dt = 2e-2 with the data times as tstops; the device's backward pass against the oracle's fit_pnsolution_to_data!
+    (rtol 1e-8; the reference compares its three likelihood evaluations at 1e-6); full and partial observations, scalar and
+    matrix noise covariances; the maximum over the sweep sits at the data-generating parameters."""
+    rng = np.random.default_rng(81)
+    sigma = 0.5
+    data_t = np.array([2.5, 5.0, 7.5, 10.0])
+    data_u = _lv_data(rng, sigma, data_t)
+    n = 9
+    pd, u0, p = _inputs("lotka_volterra", n, 82, dp=0.0)
+    p[:, 0] = 1.5 * (1 + np.linspace(-0.2, 0.2, n))     # sweep of the first rate constant, the middle one is the truth
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 2, 4), 3)
+    Rm = np.array([[sigma ** 2, 0.05], [0.05, 2 * sigma ** 2]])
+    cases = [dict(), dict(observation_matrix=np.array([[1.0, 0.0]])), dict(observation_noise_cov=Rm)]
+    for case in cases:
+        H = case.get("observation_matrix")
+        du_ = data_u if H is None else data_u @ H.T
+        cov = case.get("observation_noise_cov", sigma ** 2)
+        g = _gpu_fenrir(pd, u0, p, 3, data_t, du_, alg=alg, diffusion=diffusion, calibrate=False, adaptive=False, dt=2e-2, t0=0.0,
+                        t1=10.0, observation_matrix=H, observation_noise_cov=cov)
+        cfg = oracle.make_config(2, 3, 4, alg=alg, diffusion=diffusion, calibrate=False, smooth=True, adaptive=False, dt=2e-2, t0=0.0,
+                                 t1=10.0, tstops=data_t, cov_backend=oracle.COV_QR)
+        want = np.array([oracle.fenrir_data_loglik(cfg, oracle.solve(cfg, rhs, u0[i], p[i]), data_t, du_, observation_matrix=H,
+                                                   observation_noise_cov=cov) for i in range(n)])
+        assert np.all(g["retcode"] == 0)
+        assert np.allclose(g["ll"], want, rtol=1e-8, atol=0), (case.keys(), np.max(np.abs(g["ll"] / want - 1)))
+        if not case:
+            assert int(np.argmax(g["ll"])) in (n // 2 - 1, n // 2, n // 2 + 1)
+            # the U fields stay the filtering estimates (the reference's step! skips the postamble): same as a filter-only solve
+            gf = _gpu(pd, u0[:1], p[:1], 3, builtin=False, alg=alg, diffusion=diffusion, calibrate=False, adaptive=False, dt=2e-2,
+                      t0=0.0, t1=10.0, save_everystep=True, tstops=data_t)
+            assert np.array_equal(g["U"][g["off"][0]:g["off"][1]], gf["U"])
+
+
+def test_fenrir_adaptive_and_second_order(oracle):
+    """Adaptive steps (ragged step counts, data times hit through tstops) and a second-order problem (observation matrix
+    applied to sol.u = (du, u): positions only) against the oracle, rtol 1e-6; a failed solve gives -Inf (fenrir.jl:55-59)."""
+    rng = np.random.default_rng(83)
+    sigma = 0.1
+    data_t = np.array([3.0, 6.0, 10.0])
+    data_u = _lv_data(rng, sigma, data_t)
+    n = 6
+    pd, u0, p = _inputs("lotka_volterra", n, 84, dp=0.05)
+    g = _gpu_fenrir(pd, u0, p, 3, data_t, data_u, alg=lib.EK1, adaptive=True, t0=0.0, t1=10.0, observation_noise_cov=sigma ** 2)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 2, 4), 3)
+    cfg = oracle.make_config(2, 3, 4, alg=oracle.EK1, smooth=True, adaptive=True, t0=0.0, t1=10.0, tstops=data_t, cov_backend=oracle.COV_QR)
+    want = np.array([oracle.fenrir_data_loglik(cfg, oracle.solve(cfg, rhs, u0[i], p[i]), data_t, data_u, observation_noise_cov=sigma ** 2)
+                     for i in range(n)])
+    assert len(set(np.diff(g["off"]))) > 1
+    assert np.allclose(g["ll"], want, rtol=1e-6, atol=0), np.max(np.abs(g["ll"] / want - 1))
+    gm = _gpu_fenrir(pd, u0, p, 3, data_t, data_u, alg=lib.EK1, adaptive=True, t0=0.0, t1=10.0, observation_noise_cov=sigma ** 2,
+                     maxiters=20)
+    assert np.all(gm["retcode"] != 0) and np.all(np.isneginf(gm["ll"]))
+    # second-order two-body problem, positions observed
+    u2, p2 = _second_inputs(4, 85)
+    dt2 = np.array([0.05, 0.1])
+    from scipy.integrate import solve_ivp
+    tr = solve_ivp(lambda t, x: [-x[2] / (x[2] ** 2 + x[3] ** 2) ** 1.5, -x[3] / (x[2] ** 2 + x[3] ** 2) ** 1.5, x[0], x[1]], (0, 0.1),
+                   [0.0, 2.0, 0.4, 0.0], rtol=1e-12, atol=1e-12, t_eval=dt2).y.T
+    Hpos = np.hstack([np.zeros((2, 2)), np.eye(2)])
+    obs = tr @ Hpos.T + 1e-3 * rng.standard_normal((2, 2))
+    g2 = _gpu_fenrir(None, u2, p2, 3, dt2, obs, second_order=True, f=_twobody_first_order, alg=lib.EK1, adaptive=False, dt=1e-3, t0=0.0,
+                     t1=0.1, diffusion=lib.DIFF_FIXED, calibrate=False, observation_matrix=Hpos, observation_noise_cov=1e-6)
+    rhs2 = oracle.compile_rhs(tracer.trace(_twobody_first_order, 4, 1), 3)
+    cfg2 = oracle.make_config(2, 3, 1, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, smooth=True, adaptive=False, dt=1e-3,
+                              t0=0.0, t1=0.1, tstops=dt2, cov_backend=oracle.COV_QR, second_order=True)
+    want2 = np.array([oracle.fenrir_data_loglik(cfg2, oracle.solve(cfg2, rhs2, u2[i], p2[i]), dt2, obs, observation_matrix=Hpos,
+                                                observation_noise_cov=1e-6) for i in range(4)])
+    assert np.allclose(g2["ll"], want2, rtol=1e-7, atol=0), np.max(np.abs(g2["ll"] / want2 - 1))

@@ -260,3 +260,29 @@ def test_second_order_kernels_compile_and_argument_checks(pnlib):
         with pytest.raises(pnlib.PnodeError) as e:
             pnlib.compile_check(pnlib.make_config(**{**base, **kw}))
         assert e.value.kind == kind, kw
+
+
+def test_fenrir_configuration_checks(pnlib):
+    """fenrir_data_loglik (src/data_likelihoods/fenrir.jl:30-66): needs smoothing (ArgumentError, :42-44), a consistent data
+    set and a positive (definite) observation noise; unsupported combinations are named."""
+    pd, src = _src("lotka_volterra")
+    base = dict(d=2, q=3, n_p=4, rhs_name="UserProb", rhs_src=src, t0=0.0, t1=2.0, smooth=True, save_everystep=True,
+                data_t=[1.0, 2.0], data_u=[[1.0, 1.0], [2.0, 2.0]], observation_noise_cov=0.25)
+    assert pnlib.compile_check(pnlib.make_config(**base)) > 10_000
+    assert pnlib.compile_check(pnlib.make_config(**{**base, "observation_noise_cov": [[0.25, 0.01], [0.01, 0.5]]})) > 10_000
+
+    def err(**kw):
+        with pytest.raises(pnlib.PnodeError) as e:
+            pnlib.compile_check(pnlib.make_config(**{**base, **kw}))
+        return e.value
+
+    e = err(smooth=False)
+    assert e.kind == "ArgumentError" and "fenrir only works with smoothing" in str(e)
+    assert err(data_t=[2.0, 1.0]).kind == "ArgumentError"
+    assert err(data_t=[1.0, 3.0]).kind == "ArgumentError"
+    assert err(observation_noise_cov=0.0).kind == "ArgumentError"
+    assert err(data_u=[[1.0], [2.0]]).kind == "ArgumentError"                      # partial data without an observation matrix
+    assert pnlib.compile_check(pnlib.make_config(**{**base, "data_u": [[1.0], [2.0]], "observation_matrix": [[1.0, 0.0]]})) > 10_000
+    assert err(saveat=[0.5]).kind == "Unsupported"
+    assert err(prior=pnlib.PRIOR_IOUP, rate_parameter=-1.0).kind == "Unsupported"
+    assert err(alg=pnlib.EK0, diffusion=pnlib.DIFF_DYNAMIC_MV).kind == "Unsupported"
