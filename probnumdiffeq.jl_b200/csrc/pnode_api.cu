@@ -461,14 +461,16 @@ static int mass_preamble(const double* M, int d, std::string* out) {
 }
 
 /* NVRTC: register-resident smoother sweep for (d, q, G); independent of the right-hand side. */
-static int nvrtc_smoother_cubin(int d, int q, int G, bool ioup, bool col, std::vector<char>* cubin, bool second = false) {
+static int nvrtc_smoother_cubin(int d, int q, int G, bool ioup, bool col, std::vector<char>* cubin, bool second = false,
+                                bool fenrir = false) {
     std::string src = col ? "#include \"kernels/pn_smooth_col.cuh\"\n" : "#include \"kernels/pn_smooth_reg.cuh\"\n";
     src += "extern \"C\" __global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_entry(const __grid_constant__ "
            "PnSmoothParams P) {\n  ";
     src += col ? "pn_smooth_col_entry" : "pn_smooth_reg_entry";
     src += "<PN_SD, PN_SQ, PN_SG>(P);\n}\n";
     auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
-    return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0), def("PN_SECOND", second ? 1 : 0)}, cubin);
+    return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0), def("PN_SECOND", second ? 1 : 0),
+                               def("PN_FENRIR", fenrir ? 1 : 0)}, cubin);
 }
 
 /* NVRTC: dense-output predict kernel for (d, q, G) */
@@ -560,7 +562,7 @@ static int get_smoother(pnode_solver* s) {
     auto t0 = std::chrono::steady_clock::now();
     out->threads = PN_SMR_THREADS;
     const bool ioup = (s->cfg.prior == PNODE_PRIOR_IOUP);
-    const void* fn = (env_int("PNODE_FORCE_NVRTC", 0) || ioup || s->cfg.second_order) ? nullptr : pn_smooth_reg_lookup(s->cfg.d, s->cfg.q, s->Gs, col ? 1 : 0);
+    const void* fn = (env_int("PNODE_FORCE_NVRTC", 0) || ioup || s->cfg.second_order || s->n_data > 0) ? nullptr : pn_smooth_reg_lookup(s->cfg.d, s->cfg.q, s->Gs, col ? 1 : 0);
     if (fn) {
         out->rt_fn = fn;
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_smooth));
@@ -573,7 +575,7 @@ static int get_smoother(pnode_solver* s) {
     int rc = load_driver();
     if (rc) return rc;
     std::vector<char> cubin;
-    if ((rc = nvrtc_smoother_cubin(s->cfg.d, s->cfg.q, s->Gs, ioup, col, &cubin, s->cfg.second_order != 0))) return rc;
+    if ((rc = nvrtc_smoother_cubin(s->cfg.d, s->cfg.q, s->Gs, ioup, col, &cubin, s->cfg.second_order != 0, s->n_data > 0))) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
     r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_smooth_entry");
@@ -794,7 +796,7 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     if (cfg->smooth && smooth_lanes(D) > 0 && !(cfg->alg == PNODE_EK1 && D > 32)) {
         std::vector<char> c2;
         const bool col = env_int("PNODE_SMOOTH_KIND", 1) != 0;
-        if ((rc = nvrtc_smoother_cubin(cfg->d, cfg->q, smooth_lanes(D), cfg->prior == PNODE_PRIOR_IOUP, col, &c2, cfg->second_order != 0))) return rc;
+        if ((rc = nvrtc_smoother_cubin(cfg->d, cfg->q, smooth_lanes(D), cfg->prior == PNODE_PRIOR_IOUP, col, &c2, cfg->second_order != 0, cfg->n_data > 0))) return rc;
         total += (int64_t)c2.size();
     }
     if (cfg->n_saveat > 0) {
@@ -1325,7 +1327,11 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             memcpy(Q.glw, s->base.glw, sizeof Q.glw);
             Q.n_traj = ntraj;
             Q.work_counter = s->d_counter;
-            if (s->k_smooth.valid() && !Q.fenrir_ll) {
+            /* Fenrir mode: the column-distributed register sweep carries the data updates; the row-distributed variant and
+               observation vectors longer than sol.u go through the shared-memory sweep (PNODE_FENRIR_GENERIC=1 forces it) */
+            const int du_ = s->cfg.second_order ? 2 * d : d;
+            const bool fen_reg = env_int("PNODE_SMOOTH_KIND", 1) != 0 && Q.n_obs <= du_ && !env_int("PNODE_FENRIR_GENERIC", 0);
+            if (s->k_smooth.valid() && (!Q.fenrir_ll || fen_reg)) {
                 /* register-resident sweep: Gs lanes per trajectory, persistent, one CTA per SM */
                 Kernel& ks = s->k_smooth;
                 const int groups = ks.threads / s->Gs;
