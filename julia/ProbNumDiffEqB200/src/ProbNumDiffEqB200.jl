@@ -21,6 +21,9 @@ struct PnodeConfig
     rate_parameter::Float64                      # IOUP(q, rate) prior; ignored for the IWP
     saveat::Ptr{Float64}; n_saveat::Int64        # dense output sol(saveat) evaluated on the device
     mass_matrix::Ptr{Float64}                    # d × d row-major, C_NULL = identity (ODEFunction(f; mass_matrix=M))
+    second_order::Int32; reserved1::Int32        # SecondOrderODEProblem: rhs is the first-order form on (du, u)
+    data_t::Ptr{Float64}; n_data::Int64; data_u::Ptr{Float64}; n_obs::Int32; reserved2::Int32   # fenrir_data_loglik
+    observation_matrix::Ptr{Float64}; observation_noise_cov::Ptr{Float64}; observation_noise_var::Float64
 end
 
 # enum values of include/pnode.h
@@ -48,7 +51,8 @@ function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::ProbNumDi
                               ep.prob.tspan[1], ep.prob.tspan[2], dt, abstol, reltol, 0.0, 0.0,
                               0, 0, 0.2, 10.0, 0.9, 1.0, 1.0, 1e-4,
                               pointer(src), pointer("PnodeUserProblem"), C_NULL, 0, C_NULL, 0, rate_of(alg.prior), C_NULL, 0,
-                              mm === nothing ? Ptr{Float64}(C_NULL) : pointer(mm)))
+                              mm === nothing ? Ptr{Float64}(C_NULL) : pointer(mm),
+                              0, 0, C_NULL, 0, C_NULL, 0, 0, C_NULL, C_NULL, 0.0))   # first-order problem, no data set
         solver = Ref{Ptr{Cvoid}}()
         check(ccall((:pnode_create, LIB), Cint, (Ref{PnodeConfig}, Ref{Ptr{Cvoid}}), cfg, solver))
         res = Ref{Ptr{Cvoid}}()
