@@ -110,6 +110,8 @@ struct PnKron {
             double t = P.t0, dt, loglik = 0.0, gdiff = 0.0, ldiff = 0.0, qold = P.qoldinit, qold_pb2 = P.qoldinit_pb2;
             long long naccept = 0, nreject = 0, nf = Q, iter = 0, tstop_idx = 0, save_pos = 0;
             int retcode = PN_RET_SUCCESS;
+            double lgm = 1.0; /* lazily accumulated sum of log S (pn_logacc_mul, pn_small.cuh) */
+            int lge = 0;
             double uprev[d];
             {
                 /* initial state from pn_init_kernel (pre-pass over the whole ensemble: TaylorModeInit + initial step) */
@@ -289,7 +291,8 @@ struct PnKron {
                         for (int i = 0; i < d; i++) M[j][i] = Mp[j][i];
                 } else {
                     const double iS = pn_rcp(S);
-                    loglik += -0.5 * zz * iS - 0.5 * (double)d * 1.8378770664093453 - 0.5 * log(S);
+                    loglik += -0.5 * zz * iS - 0.5 * (double)d * 1.8378770664093453;
+                    if (!pn_logacc_mul(lgm, lge, S)) loglik -= 0.5 * log(S);
                     if (!DYNAMIC) {
                         const double inc = zz * iS * (1.0 / (double)d);
                         gdiff = (naccept == 0) ? inc : gdiff + (inc - gdiff) / (double)naccept;
@@ -352,7 +355,7 @@ struct PnKron {
             }
             P.t_end[traj] = t;
             write_pu(P.u_mean + traj * DU, P.u_cov + traj * DU * DU, M, RB, sc);
-            P.loglik[traj] = loglik;
+            P.loglik[traj] = loglik - 0.5 * pn_logacc_value(lgm, lge);
             P.diffusion[traj] = fd;
             P.dt_last[traj] = dt;
             P.naccept[traj] = naccept;
