@@ -18,6 +18,7 @@ class ProblemDef:
     p: Sequence[float]
     tspan: Tuple[float, float]
     mass_matrix: Optional[Sequence[Sequence[float]]] = None   # M of M u' = f (None = identity)
+    second_order: bool = False   # f is the first-order form F([du; u]) = [f1(du, u); du] of a SecondOrderODEProblem, u0 = (du0, u0)
 
     @property
     def d(self) -> int:
@@ -64,6 +65,16 @@ def rober_dae(du, u, p, t):
     du[0] = -k1 * u[0] + k3 * u[1] * u[2]
     du[1] = k1 * u[0] - k3 * u[1] * u[2] - k2 * u[1] ** 2
     du[2] = u[0] + u[1] + u[2] - 1
+
+
+def twobody_first_order(du, u, p, t):
+    """Two-body problem of test/secondorderode.jl:15-19 (with a gravitational parameter p[0]) in the first-order form of a
+    SecondOrderODEProblem: x = (v1, v2, r1, r2)."""
+    r3 = (u[2] * u[2] + u[3] * u[3]) ** 1.5
+    du[0] = -p[0] * u[2] / r3
+    du[1] = -p[0] * u[3] / r3
+    du[2] = u[0]
+    du[3] = u[1]
 
 
 def orego(du, u, p, t):
@@ -123,3 +134,15 @@ MASS_MATRIX_PROBLEMS = {
     "rober_dae": ProblemDef("rober_dae", rober_dae, [1.0, 0.0, 0.0], [0.04, 3e7, 1e4], (0.0, 1e5),
                             mass_matrix=[[1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 0.0]]),
 }
+
+# Second-order problems (SecondOrderODEProblem): `d` of the solver is len(u0) // 2
+SECOND_ORDER_PROBLEMS = {
+    "twobody": ProblemDef("twobody", twobody_first_order, [0.0, 2.0, 0.4, 0.0], [1.0], (0.0, 0.1), second_order=True),
+}
+
+
+def lookup(name: str) -> ProblemDef:
+    for table in (PROBLEMS, MASS_MATRIX_PROBLEMS, SECOND_ORDER_PROBLEMS):
+        if name in table:
+            return table[name]
+    raise KeyError(name)

@@ -60,6 +60,17 @@ CASES = {
     "oracle_lv_ek1_q3_ioup_fixed": ("lotka_volterra", 3, dict(alg=1, diffusion=1, calibrate=True, smooth=True, adaptive=False, dt=0.02, t0=0.0, t1=4.0,
                                                                prior=1, rate_parameter=-1.0)),
     "oracle_rober_ek1_q3_adaptive": ("rober", 3, dict(alg=1, diffusion=0, smooth=False, adaptive=True, t0=0.0, t1=100.0)),
+    # mass matrix (dense, non-symmetric), second-order problem, Fenrir data log-likelihood
+    "oracle_robermass_ek1_q3_fixed_smooth": ("rober_dae", 3, dict(alg=1, diffusion=1, calibrate=True, smooth=True, adaptive=False, dt=1e-3, t0=0.0,
+                                                                  t1=0.2, mass_matrix=[[1.0, 0.2, 0.0], [0.0, 1.0, 0.0], [0.1, 0.0, 0.5]]),
+                                             [1.0, 0.1, 0.2], [0.04, 30.0, 10.0]),
+    "oracle_twobody2_ek1_q3_fixed_smooth": ("twobody", 3, dict(alg=1, diffusion=1, calibrate=True, smooth=True, adaptive=False, dt=1e-3, t0=0.0,
+                                                               t1=0.1, second_order=True)),
+    "oracle_lv_ek1_q3_fenrir": ("lotka_volterra", 3, dict(alg=1, diffusion=1, calibrate=False, smooth=True, adaptive=False, dt=0.02, t0=0.0,
+                                                          t1=10.0, tstops=[2.5, 5.0, 7.5, 10.0])),
+}
+FENRIR_DATA = {  # data set of the Fenrir fixture: times, observations (seeded noise around the solution), noise variance
+    "oracle_lv_ek1_q3_fenrir": dict(data_t=[2.5, 5.0, 7.5, 10.0], sigma=0.5, seed=7),
 }
 
 
@@ -68,13 +79,24 @@ def oracle_cases():
     from probnumdiffeq_jl_b200 import problems, tracer
     from oracle import oracle as O
 
-    for name, (prob, q, kw) in CASES.items():
-        pd = problems.PROBLEMS[prob]
+    for name, case in CASES.items():
+        prob, q, kw = case[:3]
+        pd = problems.lookup(prob)
         rhs = O.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
-        u0 = np.array(pd.u0, dtype=float)
-        p = np.array(pd.p, dtype=float)
-        s = O.solve(O.make_config(pd.d, q, pd.n_p, cov_backend=O.COV_QR, **kw), rhs, u0, p)
-        keep = dict(problem=prob, q=q, config=json.dumps(kw), u0=u0, p=p, t=s["t"], pu_mu=s["pu_mu"], pu_cov=s["pu_cov"],
+        u0 = np.array(case[3] if len(case) > 3 else pd.u0, dtype=float)
+        p = np.array(case[4] if len(case) > 4 else pd.p, dtype=float)
+        d_model = pd.d // 2 if kw.get("second_order") else pd.d
+        cfg = O.make_config(d_model, q, pd.n_p, cov_backend=O.COV_QR, **kw)
+        s = O.solve(cfg, rhs, u0, p)
+        extra = {}
+        if name in FENRIR_DATA:
+            fd = FENRIR_DATA[name]
+            t = np.array(fd["data_t"])
+            idx = [int(np.where(s["t"] == tv)[0][0]) for tv in t]
+            obs = s["pu_mu"][idx] + fd["sigma"] * np.random.default_rng(fd["seed"]).standard_normal((len(t), pd.d))
+            extra = dict(data_t=t, data_u=obs, noise_var=fd["sigma"] ** 2,
+                         fenrir_ll=O.fenrir_data_loglik(cfg, s, t, obs, observation_noise_cov=fd["sigma"] ** 2))
+        keep = dict(**extra, problem=prob, q=q, config=json.dumps(kw), u0=u0, p=p, t=s["t"], pu_mu=s["pu_mu"], pu_cov=s["pu_cov"],
                     diffusions=s.get("diffusions_mv", s["diffusions"]), loglik=s["loglik"], naccept=s["naccept"], nreject=s["nreject"])
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **keep)
         print(name, s["retcode"], s["n"], "points")
