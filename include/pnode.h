@@ -124,8 +124,8 @@ typedef struct pnode_config {
        H = E2 (EK0) or E2 - J_du E1 - J_u E0 (EK1).  rhs_src / rhs_name describe the FIRST-ORDER FORM of dimension 2d,
        F([du; u]) = [f1(du, u); du] (what the reference's DynamicalODEFunction evaluates on ArrayPartition(du, u)); the
        kernels use its first d rows.  u0 is [n_traj][2d] = (du0, u0); every U field has 2d entries per point in the
-       reference's sol.u order (du, u), every U_COV field (2d)^2.  EK0 (Kronecker layout) and EK1 (dense, D <= 32),
-       IWP prior, scalar diffusion models. */
+       reference's sol.u order (du, u), every U_COV field (2d)^2.  EK0, DiagonalEK1 and EK1 (dense, D <= 32) with
+       every diffusion model the first-order path supports; IWP prior. */
     int32_t second_order;
     int32_t reserved1;
     /* Fenrir data log-likelihood, `fenrir_data_loglik(prob, alg; data=(t, u), observation_matrix, observation_noise_cov)`

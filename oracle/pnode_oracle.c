@@ -605,13 +605,13 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
                         const double* u0, const double* p, oracle_traj* out) {
     const int d = c->d, q = c->q, n = q + 1, D = d * n;
     const int diag1 = (c->alg == ORACLE_DIAGONAL_EK1);
-    const int so = 0, du = d; /* second-order problems are not restated on this layout */
+    const int so = c->second_order ? 1 : 0, du = so ? 2 * d : d, e1 = so ? 2 : 1; /* second-order problems: see oracle_solve */
     const int mv = (c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV);
     const int dynamic = (c->diffusion == ORACLE_DIFF_DYNAMIC || c->diffusion == ORACLE_DIFF_DYNAMIC_MV);
     memset(out, 0, sizeof(*out));
     out->d = d; out->q = q; out->D = D; out->smooth = c->smooth; out->alg = c->alg;
     out->global_diffusion = NAN;
-    if (d > 64 || n > 32) return -1;
+    if (du > 64 || n > 32) return -1;
     if (c->alg == ORACLE_EK1) return -2; /* EK1 + MV diffusion is rejected by the reference (algorithms.jl:93-107) */
     const size_t nn = (size_t)n * n, NB = nn * d; /* all blocks of one state */
     double* Ah1 = (double*)malloc(sizeof(double) * nn);
@@ -623,7 +623,7 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
     double* mu_filt = (double*)calloc(D, sizeof(double));
     double* R_filt = (double*)calloc(NB, sizeof(double));
     double* H = (double*)calloc((size_t)d * n, sizeof(double)); /* block i: 1 x n at H + i*n */
-    double* J = (double*)calloc((size_t)d * d, sizeof(double));
+    double* J = (double*)calloc((size_t)du * du, sizeof(double));
     double* G = (double*)malloc(sizeof(double) * NB);
     double* bb = (double*)malloc(sizeof(double) * D);
     double* LR = (double*)malloc(sizeof(double) * 2 * NB);
@@ -637,9 +637,17 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
     }
     dvec ts = {0}, diffs = {0}, xmu = {0}, xR = {0}, bG = {0}, bB = {0}, bL = {0};
 
-    taylor(mu, u0, p, c->t0, q);
+    if (so) {
+        double* t2 = (double*)malloc(sizeof(double) * (size_t)du * n);
+        taylor(t2, u0, p, c->t0, q);
+        for (int o = 0; o <= q; o++)
+            for (int i = 0; i < d; i++) mu[o * d + i] = t2[o * du + d + i];
+        free(t2);
+    } else {
+        taylor(mu, u0, p, c->t0, q);
+    }
     out->nf += q;
-    for (int i = 0; i < d; i++) uprev[i] = mu[i];
+    for (int i = 0; i < d; i++) uprev[i] = so ? mu[d + i] : mu[i];
     const double* Mm = c->mass_matrix; /* diagonal (checked by the caller) */
     if (Mm) {
         int zero_diag = 0;
@@ -686,9 +694,11 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
                 mu_pred[r * d + i] = s;
             }
         for (int i = 0; i < d; i++) upred[i] = mu_pred[i];
+        if (so)
+            for (int i = 0; i < d; i++) { upred[i] = mu_pred[d + i]; upred[d + i] = mu_pred[i]; }
         f(fu, upred, p, tnew);
         out->nf += 1;
-        for (int i = 0; i < d; i++) z[i] = (Mm ? AT(Mm, i, i, d) : 1.0) * mu_pred[d + i] - fu[i];
+        for (int i = 0; i < d; i++) z[i] = (Mm ? AT(Mm, i, i, d) : 1.0) * mu_pred[e1 * d + i] - fu[i];
         /* calc_H! (derivative_utils.jl:1-53): EK0 H = M E1; DiagonalEK1 H = M E1 - Diagonal(diag(J)) E0 */
         if (diag1) {
             jac(J, upred, p, tnew);
@@ -697,8 +707,12 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
         for (int i = 0; i < d; i++) {
             double* Hi = H + (size_t)i * n;
             for (int k = 0; k < n; k++) Hi[k] = 0.0;
-            Hi[1] = Mm ? AT(Mm, i, i, d) : 1.0;
-            if (diag1) Hi[0] = -AT(J, i, i, d);
+            Hi[e1] = Mm ? AT(Mm, i, i, d) : 1.0;
+            if (diag1 && !so) Hi[0] = -AT(J, i, i, d);
+            if (diag1 && so) { /* ddu_diag = [Jdu_ii Ju_ii] on the (E1; E0) rows of block i (derivative_utils.jl:20-27) */
+                Hi[1] = -AT(J, i, i, du);
+                Hi[0] = -AT(J, i, d + i, du);
+            }
         }
         if (c->adaptive || dynamic) {
             /* HQH block i = |Qh.R H_i'|^2 ; scalar: invquad(z, HQH)/d (calibration.jl:21-29,123-133);
@@ -805,7 +819,7 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
         out->naccept++;
         int nanu = 0;
         for (int i = 0; i < d; i++) {
-            uprev[i] = mu[i];
+            uprev[i] = so ? mu[d + i] : mu[i];
             if (isnan(mu[i])) nanu = 1;
         }
         if (c->save_everystep) {
@@ -922,9 +936,7 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     /* mass matrices: EK1 on the dense layout takes any M; the Kronecker layout (EK0 + IWP + scalar diffusion) only a
        UniformScaling (ArgumentError otherwise, caches.jl:111-118; H = lambda E1, derivative_utils.jl:45-47); the
        BlocksOfDiagonals layout is restated for diagonal M */
-    if (c->second_order && (c->mass_matrix || c->q < 2 || c->alg == ORACLE_DIAGONAL_EK1 ||
-                            c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV))
-        return -2; /* second-order problems: restated for EK0 (Kronecker / dense) and EK1 with scalar diffusions */
+    if (c->second_order && (c->mass_matrix || c->q < 2)) return -2;
     if (c->mass_matrix) {
         const double* M = c->mass_matrix;
         int diagonal = 1, uniform = 1, zero_diag = 0;

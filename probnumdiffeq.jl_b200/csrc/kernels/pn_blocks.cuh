@@ -66,10 +66,46 @@ PN_HD void pn_qr_local(double (&Rt)[n][n], double (&Bt)[n][n]) {
 
 template <class Prob, int Q, bool DIAG1, bool MV, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 struct PnBlocks {
-    static constexpr int d = Prob::d;
+    static constexpr int DP = Prob::d;                  /* dimension of the right-hand side */
+    static constexpr int d = PN_SECOND ? DP / 2 : DP;   /* second-order problems (PN_SECOND, pn_small.cuh): positions */
+    static constexpr int DU = DP;                       /* length of sol.u = (du, u) */
+    static constexpr int E1B = PN_SECOND ? 2 : 1;       /* H_i = e_2' - Jdu_ii e_1' - Ju_ii e_0' (derivative_utils.jl:14-28) / e_1' - J_ii e_0' */
+    static constexpr int SB = PN_SECOND ? 1 : 0;        /* block the error estimate is scaled with (du / u) */
     static constexpr int n = Q + 1;
     static constexpr int D = d * n;
     static constexpr int NPA = Prob::n_p > 0 ? Prob::n_p : 1;
+
+    /* sol.u = SolProj x and its covariance, component-wise scaled by sc[a]: E0 rows, or (E1; E0) rows for second-order
+       problems (component a couples its du and u entries only) */
+    static __device__ __forceinline__ void write_pu(double* um, double* uc, const double (&M)[n][d], const double (&RB)[d][n][n],
+                                                    const double* sc) {
+#pragma unroll
+        for (int i = 0; i < DU * DU; i++) uc[i] = 0.0;
+#pragma unroll
+        for (int a = 0; a < d; a++) {
+            double c00 = 0.0, c01 = 0.0, c11 = 0.0;
+#pragma unroll
+            for (int r = 0; r < n; r++) {
+                c00 += RB[a][r][0] * RB[a][r][0];
+                if (PN_SECOND) {
+                    c01 += RB[a][r][0] * RB[a][r][1];
+                    c11 += RB[a][r][1] * RB[a][r][1];
+                }
+            }
+            const double s = sc ? sc[a] : 1.0;
+            if (PN_SECOND) {
+                um[a] = M[1][a];
+                um[d + a] = M[0][a];
+                uc[a * DU + a] = c11 * s;
+                uc[a * DU + d + a] = c01 * s;
+                uc[(d + a) * DU + a] = c01 * s;
+                uc[(d + a) * DU + d + a] = c00 * s;
+            } else {
+                um[a] = M[0][a];
+                uc[a * DU + a] = c00 * s;
+            }
+        }
+    }
 
     static __device__ void run(const PnParams& P) {
         double M[n][d]; /* mean as n x d matrix: M[j][i] = mu[j*d + i] */
@@ -95,7 +131,7 @@ struct PnBlocks {
 #pragma unroll
                     for (int i = 0; i < d; i++) M[j][i] = P.init_mu[traj * D + j * d + i];
 #pragma unroll
-                for (int i = 0; i < d; i++) uprev[i] = M[0][i];
+                for (int i = 0; i < d; i++) uprev[i] = M[SB][i];
                 dt = P.init_dt[traj];
                 if (ADAPTIVE && !(P.dt0 > 0.0) && !PN_MASS) nf += 2;
             }
@@ -112,12 +148,9 @@ struct PnBlocks {
                     P.s_t[save_pos] = t;
                     P.s_diffusion[save_pos] = 0.0;
 #pragma unroll
-                    for (int i = 0; i < d; i++) {
-                        P.s_u_mean[save_pos * d + i] = M[0][i];
+                    for (int i = 0; i < d; i++)
                         if (P.s_diffusion_mv) P.s_diffusion_mv[save_pos * d + i] = 0.0;
-                    }
-#pragma unroll
-                    for (int i = 0; i < d * d; i++) P.s_u_cov[save_pos * d * d + i] = 0.0;
+                    write_pu(P.s_u_mean + save_pos * DU, P.s_u_cov + save_pos * DU * DU, M, RB, nullptr);
                     if (SAVE >= 2) save_state(P, save_pos, M, RB, 0.0, 0.0);
                 }
                 save_pos += 1;
@@ -163,23 +196,44 @@ struct PnBlocks {
                             if (k > j) s += hp[k > j ? k - j : 0] * M[k][i];
                         Mp[j][i] = s;
                     }
+#if PN_SECOND
+                double fu[DP], z[d], h0[d], h1[d], x2[DP];
+#pragma unroll
+                for (int i = 0; i < d; i++) {
+                    x2[i] = Mp[1][i]; /* (du, u) */
+                    x2[d + i] = Mp[0][i];
+                    h1[i] = 0.0;
+                }
+                Prob::template f<double>(fu, x2, pr, tnew);
+#else
                 double fu[d], z[d], h0[d];
                 Prob::template f<double>(fu, Mp[0], pr, tnew);
+#endif
                 nf += 1;
 #pragma unroll
                 for (int i = 0; i < d; i++) {
 #if PN_MASS
                     z[i] = pn_mass(i, i) * Mp[1][i] - fu[i]; /* diagonal M: H_i = M_ii e_1' - J_ii e_0' */
 #else
-                    z[i] = Mp[1][i] - fu[i];
+                    z[i] = Mp[E1B][i] - fu[i];
 #endif
                     h0[i] = 0.0;
                 }
                 if (DIAG1) { /* H_i = e_1' - J_ii e_0' */
+#if PN_SECOND
+                    double J2[DP * DP]; /* ddu_diag = [Jdu_ii Ju_ii] times the (E1; E0) rows of block i (derivative_utils.jl:20-27) */
+                    Prob::jac(J2, x2, pr, tnew);
+#pragma unroll
+                    for (int i = 0; i < d; i++) {
+                        h1[i] = -J2[i + DP * i];
+                        h0[i] = -J2[i + DP * (d + i)];
+                    }
+#else
                     double J[d * d];
                     Prob::jac(J, Mp[0], pr, tnew);
 #pragma unroll
                     for (int i = 0; i < d; i++) h0[i] = -J[i + d * i];
+#endif
                 }
                 /* HQH_i = |Qh.R H_i'|^2, (Qh.R H_i')[m] = L[m][0] PI[0] h0_i + L[m][1] PI[1] */
                 double HQH[d];
@@ -190,6 +244,9 @@ struct PnBlocks {
                     for (int m = 0; m < n; m++) {
 #if PN_MASS
                         const double cq = P.L[m * n + 0] * PIv[0] * h0[i] + ((m >= 1) ? P.L[m * n + 1] * PIv[1] * pn_mass(i, i) : 0.0);
+#elif PN_SECOND
+                        const double cq = P.L[m * n + 0] * PIv[0] * h0[i] + ((m >= 1) ? P.L[m * n + 1] * PIv[1] * h1[i] : 0.0) +
+                                          ((m >= 2) ? P.L[m * n + 2] * PIv[2] : 0.0);
 #else
                         const double cq = P.L[m * n + 0] * PIv[0] * h0[i] + ((m >= 1) ? P.L[m * n + 1] * PIv[1] : 0.0);
 #endif
@@ -216,7 +273,7 @@ struct PnBlocks {
                     double e2 = 0.0;
 #pragma unroll
                     for (int i = 0; i < d; i++) {
-                        const double isc = pn_rcp(P.abstol + fmax(fabs(Mp[0][i]), fabs(uprev[i])) * P.reltol);
+                        const double isc = pn_rcp(P.abstol + fmax(fabs(Mp[SB][i]), fabs(uprev[i])) * P.reltol);
                         e2 += (ldiff[i] * HQH[i]) * (isc * isc);
                     }
                     e2 = e2 * (h * h) * (1.0 / (double)d);
@@ -268,6 +325,8 @@ struct PnBlocks {
                     for (int r = 0; r < n; r++) {
 #if PN_MASS
                         c1[r] = RB[i][r][1] * pn_mass(i, i) + h0[i] * RB[i][r][0];
+#elif PN_SECOND
+                        c1[r] = RB[i][r][2] + h1[i] * RB[i][r][1] + h0[i] * RB[i][r][0];
 #else
                         c1[r] = RB[i][r][1] + h0[i] * RB[i][r][0];
 #endif
@@ -332,7 +391,7 @@ struct PnBlocks {
                 naccept++;
 #pragma unroll
                 for (int i = 0; i < d; i++) {
-                    uprev[i] = M[0][i];
+                    uprev[i] = M[SB][i];
                     if (M[0][i] != M[0][i]) retcode = PN_RET_UNSTABLE;
                 }
                 if (SAVE >= 1) {
@@ -341,19 +400,11 @@ struct PnBlocks {
                         P.s_diffusion[save_pos - 1] = (SAVE >= 2) ? ediff[0] : ((ADAPTIVE || DYNAMIC) ? ldiff[0] : P.initial_diffusion);
 #pragma unroll
                         for (int i = 0; i < d; i++) {
-                            P.s_u_mean[save_pos * d + i] = M[0][i];
                             if (P.s_diffusion_mv)
                                 P.s_diffusion_mv[(save_pos - 1) * d + i] =
                                     (SAVE >= 2) ? ediff[i] : ((ADAPTIVE || DYNAMIC) ? ldiff[i] : P.initial_diffusion);
                         }
-#pragma unroll
-                        for (int a = 0; a < d; a++) {
-                            double c0 = 0.0;
-#pragma unroll
-                            for (int r = 0; r < n; r++) c0 += RB[a][r][0] * RB[a][r][0];
-#pragma unroll
-                            for (int b = 0; b < d; b++) P.s_u_cov[save_pos * d * d + a * d + b] = (a == b) ? c0 : 0.0;
-                        }
+                        write_pu(P.s_u_mean + save_pos * DU, P.s_u_cov + save_pos * DU * DU, M, RB, nullptr);
                         if (SAVE >= 2) save_state(P, save_pos, M, RB, h, 1.0);
                     }
                     save_pos += 1;
@@ -361,6 +412,7 @@ struct PnBlocks {
             }
             /* postamble */
             P.t_end[traj] = t;
+            double scs[d];
 #pragma unroll
             for (int a = 0; a < d; a++) {
                 double sc = 1.0, fd = ldiff[a];
@@ -372,12 +424,7 @@ struct PnBlocks {
                         fd = P.initial_diffusion;
                     }
                 }
-                double c0 = 0.0;
-#pragma unroll
-                for (int r = 0; r < n; r++) c0 += RB[a][r][0] * RB[a][r][0];
-                P.u_mean[traj * d + a] = M[0][a];
-#pragma unroll
-                for (int b = 0; b < d; b++) P.u_cov[traj * d * d + a * d + b] = (a == b) ? c0 * sc : 0.0;
+                scs[a] = sc;
                 if (a == 0) P.diffusion[traj] = fd;
                 if (P.diffusion_mv) P.diffusion_mv[traj * d + a] = fd;
                 if (P.x_covfac) {
@@ -390,6 +437,7 @@ struct PnBlocks {
                         for (int c = 0; c < n; c++) P.x_covfac[(traj * D + r * d + a) * D + c * d + a] = RB[a][r][c] * ss;
                 }
             }
+            write_pu(P.u_mean + traj * DU, P.u_cov + traj * DU * DU, M, RB, scs);
             P.loglik[traj] = loglik;
             P.dt_last[traj] = dt;
             P.naccept[traj] = naccept;

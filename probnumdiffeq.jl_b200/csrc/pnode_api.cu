@@ -46,8 +46,11 @@ __global__ void pn_calibrate_saved(long long total, long long n_traj, const long
         if (off[mid] <= i) lo = mid; else hi = mid;
     }
     if (scale_mv) { /* apply_diffusion! on blocks (apply_diffusion.jl:43-50): component a scaled by sigma_a^2 */
-        for (int a = 0; a < d; a++)
-            for (int b = 0; b < d; b++) u_cov[i * dd + a * d + b] *= sqrt(scale_mv[lo * d + a] * scale_mv[lo * d + b]);
+        /* sol.u has du = dd / du entries per point: d, or (du, u) = 2d for second-order problems (component = index mod d) */
+        int du = 1;
+        while (du * du < dd) du++;
+        for (int a = 0; a < du; a++)
+            for (int b = 0; b < du; b++) u_cov[i * dd + a * du + b] *= sqrt(scale_mv[lo * d + a % d] * scale_mv[lo * d + b % d]);
     } else if (scale) {
         const double sc = scale[lo];
         for (int k = 0; k < dd; k++) u_cov[i * dd + k] *= sc;
@@ -726,7 +729,6 @@ static int validate_config(const pnode_config* cfg) {
         if (cfg->q < 2) return fail(PNODE_ERR_ARGUMENT, "second-order problems need order >= 2 (the measurement reads the second derivative)");
         if (cfg->mass_matrix) return fail(PNODE_ERR_ARGUMENT, "second-order problems take no mass matrix (derivative_utils.jl:39-41 asserts mass_matrix === I)");
         if (cfg->prior != PNODE_PRIOR_IWP) return fail(PNODE_ERR_UNSUPPORTED, "second-order problems are implemented for the IWP prior");
-        if (layout == PNODE_COV_BLOCKS) return fail(PNODE_ERR_UNSUPPORTED, "second-order problems are implemented for the EK0 (Kronecker layout) and the EK1 (dense layout)");
         if (layout == PNODE_COV_DENSE && (D > 32 || cfg->lanes_per_traj == 256))
             return fail(PNODE_ERR_UNSUPPORTED, "second-order problems on the dense layout are implemented for D = d(q+1) <= 32");
         if (cfg->smooth && (smooth_lanes(D) == 0 || env_int("PNODE_SMOOTH_KIND", 1) == 0 || env_int("PNODE_SMOOTH_GENERIC", 0)))

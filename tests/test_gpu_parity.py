@@ -1294,3 +1294,47 @@ def test_fenrir_adaptive_and_second_order(oracle):
     want2 = np.array([oracle.fenrir_data_loglik(cfg2, oracle.solve(cfg2, rhs2, u2[i], p2[i]), dt2, obs, observation_matrix=Hpos,
                                                 observation_noise_cov=1e-6) for i in range(4)])
     assert np.allclose(g2["ll"], want2, rtol=1e-7, atol=0), np.max(np.abs(g2["ll"] / want2 - 1))
+
+
+@pytest.mark.parametrize("alg,diffusion", [(lib.DIAGONAL_EK1, lib.DIFF_FIXED), (lib.EK0, lib.DIFF_FIXED_MV), (lib.DIAGONAL_EK1, lib.DIFF_FIXED_MV)])
+@pytest.mark.parametrize("smooth", [False, True])
+def test_second_order_blocks_layout_fixed_steps(oracle, alg, diffusion, smooth):
+    """Second-order problems on the BlocksOfDiagonals layout (DiagonalEK1: H_i = e_2' - Jdu_ii e_1' - Ju_ii e_0',
+    src/derivative_utils.jl:14-28; EK0 with multivariate diffusion): fixed steps, static diffusion, every saved
+    sol.u = (du, u) with its covariance against the oracle at 1e-10 / 1e-9."""
+    u0, p = _second_inputs(2, 91)
+    kw = dict(alg=alg, adaptive=False, dt=1e-3, t0=0.0, t1=0.1, diffusion=diffusion, calibrate=True)
+    g = _gpu_second(u0, p, 3, smooth=smooth, **kw)
+    rhs = oracle.compile_rhs(tracer.trace(_twobody_first_order, 4, 1), 3)
+    cfg = oracle.make_config(2, 3, 1, alg=alg, diffusion=diffusion, calibrate=True, smooth=smooth, adaptive=False, dt=1e-3, t0=0.0, t1=0.1,
+                             cov_backend=oracle.COV_QR, second_order=True)
+    for i in range(2):
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"] == 101 and g["retcode"][i] == 0
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < (1e-9 if smooth else 1e-10)
+        assert g["loglik"][i] == pytest.approx(o["loglik"], rel=1e-10)
+        assert _relcov(g["cov"][i][None], o["pu_cov"][-1][None]) < (1e-9 if smooth else 1e-10)
+
+
+@pytest.mark.parametrize("alg,diffusion", [(lib.DIAGONAL_EK1, lib.DIFF_DYNAMIC), (lib.EK0, lib.DIFF_DYNAMIC_MV), (lib.DIAGONAL_EK1, lib.DIFF_DYNAMIC_MV)])
+def test_second_order_blocks_layout_adaptive(oracle, alg, diffusion):
+    """test/secondorderode.jl:30-52, the DiagonalEK1 / multivariate-diffusion rows: adaptive, identical accept / reject /
+    nf counts as the oracle, end point 1e-8, and rtol 1e-3 against an accurate solution."""
+    from scipy.integrate import solve_ivp
+    n = 6
+    u0, p = _second_inputs(n, 92)
+    g = _gpu_second(u0, p, 3, smooth=True, alg=alg, diffusion=diffusion, adaptive=True, t0=0.0, t1=0.1)
+    rhs = oracle.compile_rhs(tracer.trace(_twobody_first_order, 4, 1), 3)
+    cfg = oracle.make_config(2, 3, 1, alg=alg, diffusion=diffusion, smooth=True, adaptive=True, t0=0.0, t1=0.1, cov_backend=oracle.COV_QR,
+                             second_order=True)
+    for i in range(n):
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert g["naccept"][i] == o["naccept"] and g["nreject"][i] == o["nreject"] and g["nf"][i] == o["nf"], i
+        assert np.linalg.norm(g["U"][b - 1] - o["pu_mu"][-1]) <= 1e-8 * np.linalg.norm(o["pu_mu"][-1])
+        mu_i = p[i, 0]
+        tr = solve_ivp(lambda t, x: [-mu_i * x[2] / (x[2] ** 2 + x[3] ** 2) ** 1.5, -mu_i * x[3] / (x[2] ** 2 + x[3] ** 2) ** 1.5, x[0], x[1]],
+                       (0, 0.1), u0[i], method="DOP853", rtol=1e-12, atol=1e-12)
+        assert np.linalg.norm(g["U"][b - 1] - tr.y[:, -1]) <= 1e-3 * np.linalg.norm(tr.y[:, -1])

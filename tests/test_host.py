@@ -253,8 +253,9 @@ def test_second_order_kernels_compile_and_argument_checks(pnlib):
         a = pnlib.compile_check(pnlib.make_config(alg=alg, **base))
         b = pnlib.compile_check(pnlib.make_config(alg=alg, smooth=True, save_everystep=True, saveat=[0.0, 0.03, 0.1], **base))
         assert b > a > 10_000
-    for kw, kind in ((dict(q=1), "ArgumentError"), (dict(alg=pnlib.DIAGONAL_EK1), "Unsupported"),
-                     (dict(alg=pnlib.EK0, diffusion=pnlib.DIFF_DYNAMIC_MV), "Unsupported"),
+    for kw in (dict(alg=pnlib.DIAGONAL_EK1), dict(alg=pnlib.EK0, diffusion=pnlib.DIFF_DYNAMIC_MV)):   # blocks layout
+        assert pnlib.compile_check(pnlib.make_config(**{**base, **kw})) > 10_000
+    for kw, kind in ((dict(q=1), "ArgumentError"),
                      (dict(mass_matrix=2 * np.eye(2)), "ArgumentError"),
                      (dict(prior=pnlib.PRIOR_IOUP, rate_parameter=-1.0), "Unsupported")):
         with pytest.raises(pnlib.PnodeError) as e:

@@ -679,11 +679,14 @@ def _twobody_truth(ts):
 def test_second_order_twobody(oracle):
     """test/secondorderode.jl:29-52: two-body problem as SecondOrderODEProblem (du0 = (0, 2), u0 = (0.4, 0), t in [0, 0.1]),
     default tolerances: sol.u[end] (= (du, u)) and the dense output at t = 0.1/pi agree with an accurate solution to
-    rtol 1e-3 -- EK0, EK1, EK1 + FixedDiffusion."""
+    rtol 1e-3 -- every algorithm / diffusion-model pair of the reference's list."""
     tr = tracer.trace(_twobody_first_order, 4, 0)
     rhs = oracle.compile_rhs(tr, 3)
     want = _twobody_truth([0.1, 0.1 / np.pi])
-    for alg, diff in ((oracle.EK0, oracle.DIFF_DYNAMIC), (oracle.EK1, oracle.DIFF_DYNAMIC), (oracle.EK1, oracle.DIFF_FIXED)):
+    for alg, diff in ((oracle.EK0, oracle.DIFF_DYNAMIC), (oracle.EK1, oracle.DIFF_DYNAMIC), (oracle.EK1, oracle.DIFF_FIXED),
+                      (oracle.EK0, oracle.DIFF_FIXED_MV), (oracle.EK0, oracle.DIFF_DYNAMIC_MV), (oracle.DIAGONAL_EK1, oracle.DIFF_DYNAMIC),
+                      (oracle.DIAGONAL_EK1, oracle.DIFF_FIXED), (oracle.DIAGONAL_EK1, oracle.DIFF_FIXED_MV),
+                      (oracle.DIAGONAL_EK1, oracle.DIFF_DYNAMIC_MV)):   # the algorithm list of test/secondorderode.jl:30-43
         cfg = oracle.make_config(2, 3, 0, alg=alg, diffusion=diff, smooth=True, adaptive=True, t0=0, t1=0.1, second_order=True)
         s = oracle.solve(cfg, rhs, [0.0, 2.0, 0.4, 0.0], [])
         assert s["retcode"] == "Success" and s["pu_mu"].shape[1] == 4
