@@ -273,7 +273,9 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        alg_bytes = n * (8 * (d + pd.n_p) + 8 * (d + d * d) + 8 * 5 + 3 * 8 + 4)
+        # per trajectory: u0, p (read by the init pre-pass), the pre-pass' initial state mu0[D] + dt0 (read by the step kernel),
+        # final mean / covariance, five doubles and three counters + retcode
+        alg_bytes = n * (8 * (d + pd.n_p) + 8 * (D + 1) + 8 * (d + d * d) + 8 * 5 + 3 * 8 + 4)
         line = {
             "metric": METRIC, "value": acc_t / wall_m, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall_m / args.steps, "higher_is_better": True,
@@ -293,8 +295,9 @@ def main():
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture of this very
-                # command at its default size (profiles/r1g_pn_small_rober_1m_traffic.txt); null for other workloads / sizes
-                "traffic": 191.1e6 if (args.workload == "rober" and n == (1 << 20)) else None,
+                # command at its default size (profiles/r1r_pn_small_rober_summary.txt: 146.9 MB read + 123.3 MB written, the
+                # write side includes the L2 write-back of the init pre-pass' buffers); null for other workloads / sizes
+                "traffic": 270.2e6 if (args.workload == "rober" and n == (1 << 20)) else None,
                 "peak_source": "measured live by pnode_measure_fp64_peak (DFMA probe); MEASURED_PEAKS.json has no FP64 figure",
                 # for reference: 64 DFMA / clk / SM x 148 SMs x sm_max_mhz (the DFMA probe reaches ~91 % of it)
                 "peak_nominal": 2.0 * 64 * 148 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12,
