@@ -968,7 +968,7 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
                 double dsum = A[j * o + j];
                 for (int k = 0; k < j; k++) dsum -= Rn[k * o + j] * Rn[k * o + j];
                 if (!(dsum > 0.0)) {
-                    delete s;
+                    pnode_destroy(s);
                     return fail(PNODE_ERR_ARGUMENT, "observation_noise_cov is not positive definite"); /* PosDefException */
                 }
                 Rn[j * o + j] = std::sqrt(dsum);

@@ -1338,3 +1338,47 @@ def test_second_order_blocks_layout_adaptive(oracle, alg, diffusion):
         tr = solve_ivp(lambda t, x: [-mu_i * x[2] / (x[2] ** 2 + x[3] ** 2) ** 1.5, -mu_i * x[3] / (x[2] ** 2 + x[3] ** 2) ** 1.5, x[0], x[1]],
                        (0, 0.1), u0[i], method="DOP853", rtol=1e-12, atol=1e-12)
         assert np.linalg.norm(g["U"][b - 1] - tr.y[:, -1]) <= 1e-3 * np.linalg.norm(tr.y[:, -1])
+
+
+def test_new_paths_at_scale_agree_with_small_runs(oracle):
+    """Size-independent property for the mass-matrix, second-order and Fenrir paths: a large adaptive ensemble goes through
+    the pilot-sized single save pass (over-allocated segments + compaction), a small one through the counting pass; the
+    first trajectories of the large run must equal the small run bit for bit (every trajectory's arithmetic depends on
+    its own history only), and every trajectory of the large run must succeed."""
+    n_big, n_small = 4096, 6
+    # mass matrix (ROBER DAE)
+    pd, u0, p = _mass_inputs(n_big, 101)
+    M = np.array(pd.mass_matrix)
+    kw = dict(builtin=False, adaptive=True, t0=0.0, t1=1.0, save_everystep=True, mass_matrix=M)
+    big, small = _gpu(pd, u0, p, 3, **kw), _gpu(pd, u0[:n_small], p[:n_small], 3, **kw)
+    assert np.all(big["retcode"] == 0) and big["info"].total_saved == big["off"][-1]
+    e = small["off"][-1]
+    assert np.array_equal(big["off"][:n_small + 1], small["off"]) and np.array_equal(big["T"][:e], small["T"])
+    assert np.array_equal(big["U"][:e], small["U"]) and np.array_equal(big["C"][:e], small["C"])
+    assert np.max(np.abs(big["U"].sum(axis=1) - 1.0)) < 1e-9          # the algebraic constraint, every point of every trajectory
+    # second-order problem, smoothed, with dense output
+    u2, p2 = _second_inputs(n_big, 102)
+    sv = np.array([0.02, 0.1 / np.pi, 0.1])
+    kw2 = dict(smooth=True, saveat=sv, alg=lib.EK1, adaptive=True, t0=0.0, t1=0.1)
+    b2, s2 = _gpu_second(u2, p2, 3, **kw2), _gpu_second(u2[:n_small], p2[:n_small], 3, **kw2)
+    e = s2["off"][-1]
+    assert np.all(b2["retcode"] == 0) and np.array_equal(b2["off"][:n_small + 1], s2["off"])
+    assert np.array_equal(b2["U"][:e], s2["U"]) and np.array_equal(b2["C"][:e], s2["C"])
+    assert np.array_equal(b2["SU"][:n_small], s2["SU"]) and np.array_equal(b2["SC"][:n_small], s2["SC"])
+    # energy of the two-body problem along the smoothed solution: conserved to solver accuracy
+    E = 0.5 * (b2["U"][:, 0] ** 2 + b2["U"][:, 1] ** 2) - np.repeat(p2[:, 0], np.diff(b2["off"])) / np.hypot(b2["U"][:, 2], b2["U"][:, 3])
+    E0 = np.repeat(E[b2["off"][:-1]], np.diff(b2["off"]))
+    assert np.max(np.abs(E - E0) / np.abs(E0)) < 2e-2      # default tolerances (reltol 1e-3): measured 6e-3
+    # Fenrir log-likelihoods of a parameter sweep
+    rng = np.random.default_rng(103)
+    data_t = np.array([2.0, 4.0, 6.0, 8.0, 10.0])
+    data_u = _lv_data(rng, 0.2, data_t)
+    pdl, u0l, pl = _inputs("lotka_volterra", n_big, 104, dp=0.1)
+    kwf = dict(alg=lib.EK1, adaptive=True, t0=0.0, t1=10.0, observation_noise_cov=0.04)
+    bf, sf = _gpu_fenrir(pdl, u0l, pl, 3, data_t, data_u, **kwf), _gpu_fenrir(pdl, u0l[:n_small], pl[:n_small], 3, data_t, data_u, **kwf)
+    assert np.all(bf["retcode"] == 0) and np.all(np.isfinite(bf["ll"]))
+    assert np.array_equal(bf["ll"][:n_small], sf["ll"])
+    # the data were generated at the nominal parameters: the likelihood decreases with the distance from them
+    dist = np.linalg.norm(pl / np.array(pdl.p) - 1.0, axis=1)
+    near, far = bf["ll"][dist < 0.05], bf["ll"][dist > 0.12]
+    assert near.size > 10 and far.size > 10 and np.median(near) > np.median(far)
