@@ -1382,3 +1382,18 @@ def test_new_paths_at_scale_agree_with_small_runs(oracle):
     dist = np.linalg.norm(pl / np.array(pdl.p) - 1.0, axis=1)
     near, far = bf["ll"][dist < 0.05], bf["ll"][dist > 0.12]
     assert near.size > 10 and far.size > 10 and np.median(near) > np.median(far)
+
+
+def test_fenrir_register_and_shared_memory_sweeps_agree(monkeypatch):
+    """The Fenrir backward pass exists twice: in the column-distributed register sweep (default) and in the shared-memory
+    warp-per-trajectory sweep (fallback for observation vectors longer than sol.u; PNODE_FENRIR_GENERIC=1).  Same
+    formulas, different reduction orders: the log-likelihoods agree to 1e-9."""
+    rng = np.random.default_rng(111)
+    data_t = np.array([1.0, 2.5, 4.0, 10.0])
+    data_u = _lv_data(rng, 0.3, data_t)
+    pd, u0, p = _inputs("lotka_volterra", 40, 112, dp=0.1)
+    kw = dict(alg=lib.EK1, adaptive=True, t0=0.0, t1=10.0, observation_noise_cov=np.array([[0.09, 0.01], [0.01, 0.2]]))
+    a = _gpu_fenrir(pd, u0, p, 3, data_t, data_u, **kw)
+    monkeypatch.setenv("PNODE_FENRIR_GENERIC", "1")
+    b = _gpu_fenrir(pd, u0, p, 3, data_t, data_u, **kw)
+    assert np.all(np.isfinite(a["ll"])) and np.allclose(a["ll"], b["ll"], rtol=1e-9, atol=0)
