@@ -89,6 +89,8 @@ class Config(C.Structure):
         ("prior", C.c_int32), ("reserved", C.c_int32), ("rate_parameter", C.c_double),
         ("mass_matrix", C.POINTER(C.c_double)),
         ("second_order", C.c_int32), ("reserved1", C.c_int32),
+        ("data_t", C.POINTER(C.c_double)), ("n_data", C.c_int64), ("data_u", C.POINTER(C.c_double)),
+        ("n_obs", C.c_int32), ("reserved2", C.c_int32), ("obs_H", C.POINTER(C.c_double)), ("obs_Rn", C.POINTER(C.c_double)),
     ]
 
 
@@ -104,6 +106,7 @@ class Traj(C.Structure):
         ("pu_mu", C.POINTER(C.c_double)), ("pu_R", C.POINTER(C.c_double)),
         ("bk_G", C.POINTER(C.c_double)), ("bk_b", C.POINTER(C.c_double)), ("bk_LR", C.POINTER(C.c_double)),
         ("diffusions_mv", C.POINTER(C.c_double)), ("global_diffusion_mv", C.POINTER(C.c_double)),
+        ("data_loglik", C.c_double),
     ]
 
 
@@ -227,7 +230,8 @@ def make_config(d, q, n_p, *, alg=EK1, diffusion=DIFF_DYNAMIC, calibrate=True, i
                 adaptive=True, save_everystep=True, cov_backend=COV_REF, t0=0.0, t1=1.0, dt=0.0, abstol=1e-6,
                 reltol=1e-3, dtmin=0.0, dtmax=None, maxiters=1_000_000, beta1=None, beta2=None, qmin=0.2, qmax=10.0,
                 gamma=0.9, qsteady_min=1.0, qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None,
-                prior=PRIOR_IWP, rate_parameter=0.0, mass_matrix=None, second_order=False):
+                prior=PRIOR_IWP, rate_parameter=0.0, mass_matrix=None, second_order=False, data=None,
+                observation_matrix=None, observation_noise_cov=None):
     c = Config()
     c.second_order = int(second_order)
     c.d, c.q, c.n_p, c.alg = d, q, n_p, alg
@@ -251,6 +255,24 @@ def make_config(d, q, n_p, *, alg=EK1, diffusion=DIFF_DYNAMIC, calibrate=True, i
         fd = np.ascontiguousarray(forced_diffusion, dtype=np.float64)
         keep.append(fd)
         c.forced_diffusion, c.n_forced = _dp(fd), len(fd)
+    if data is not None:   # DataUpdateCallback: (t, u), the times join the tstops (filtering.jl:24)
+        dt_, du_ = np.ascontiguousarray(data[0], dtype=np.float64), np.asarray(data[1], dtype=np.float64)
+        du_ = np.ascontiguousarray(du_.reshape(len(dt_), -1))
+        o, D = du_.shape[1], d * (q + 1)
+        sel = np.r_[d:2 * d, 0:d] if second_order else np.arange(d)
+        proj = np.eye(len(sel)) if observation_matrix is None else np.asarray(observation_matrix, dtype=np.float64).reshape(o, len(sel))
+        Hs = np.ascontiguousarray((proj @ np.eye(D)[sel]).T).reshape(-1)           # column-major bytes of the o x D matrix
+        cov = np.asarray(observation_noise_cov, dtype=np.float64)
+        Rn = np.sqrt(float(cov)) * np.eye(o) if cov.ndim == 0 else np.linalg.cholesky(cov.reshape(o, o)).T
+        Rn = np.ascontiguousarray(Rn.T).reshape(-1)
+        keep += [dt_, du_, Hs, Rn]
+        c.data_t, c.n_data, c.data_u, c.n_obs, c.obs_H, c.obs_Rn = _dp(dt_), len(dt_), _dp(du_), o, _dp(Hs), _dp(Rn)
+        tstops = np.union1d(dt_, [] if tstops is None else np.asarray(tstops, dtype=np.float64))
+        tstops = tstops[(tstops > t0) & (tstops < t1)]
+        if len(tstops):
+            ts = np.ascontiguousarray(tstops, dtype=np.float64)
+            keep.append(ts)
+            c.tstops, c.n_tstops = _dp(ts), len(ts)
     if mass_matrix is not None:
         mm = np.asfortranarray(np.asarray(mass_matrix, dtype=np.float64).reshape(d, d))  # column-major for the C side
         mm = np.ascontiguousarray(mm.T).reshape(-1)                                      # = column-major bytes of M
@@ -280,7 +302,7 @@ def solve(cfg: Config, rhs: CompiledRHS, u0, p) -> dict:
     du = 2 * d if cfg.second_order else d   # sol.u = (du, u) for second-order problems (SolProj = [E1; E0])
     out = dict(
         n=n, d=d, q=tr.q, D=D, retcode=RET[tr.retcode], naccept=tr.naccept, nreject=tr.nreject, nf=tr.nf,
-        njac=tr.njac, loglik=tr.loglik, global_diffusion=tr.global_diffusion,
+        njac=tr.njac, loglik=tr.loglik, global_diffusion=tr.global_diffusion, data_loglik=tr.data_loglik,
         t=_arr(tr.t, (n,)), diffusions=_arr(tr.diffusions, (n,)),
         x_filt_mu=_arr(tr.x_filt_mu, (n, D)),
         # stored column-major D x D -> numpy [k, col, row]; transpose to [k, row, col]

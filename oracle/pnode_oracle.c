@@ -931,12 +931,73 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
     return 0;
 }
 
+/* DataUpdateCallback affect! (src/callbacks/dataupdate.jl:48-82): condition the filter state (mu, R) on the observation
+   u = H x + eps, eps ~ N(0, Rn'Rn): obs_cov factor make_obscov_sqrt = qr([R H'; Rn]).R (:86-87), then
+   update!(...; R) (src/filtering/update.jl:65-139) with the QR route of :132-136.  Returns the log-likelihood. */
+static double data_update(int D, int o, const double* H /* o x D */, const double* Rn /* o x o */, const double* u, double* mu,
+                          double* R) {
+    double* z = (double*)malloc(sizeof(double) * o);
+    double* zt = (double*)malloc(sizeof(double) * o);
+    double* Cm = (double*)malloc(sizeof(double) * D * o);
+    double* St = (double*)malloc(sizeof(double) * (D + o) * o);
+    double* Sr = (double*)malloc(sizeof(double) * o * o);
+    double* K = (double*)malloc(sizeof(double) * D * o);
+    double* Mc = (double*)malloc(sizeof(double) * D * D);
+    double* R2 = (double*)malloc(sizeof(double) * (D + o) * D);
+    double* K1 = (double*)malloc(sizeof(double) * D * o);
+    double ll;
+    for (int a = 0; a < o; a++) {
+        double sacc = 0.0;
+        for (int c = 0; c < D; c++) sacc += AT(H, a, c, o) * mu[c];
+        z[a] = sacc - u[a];
+        zt[a] = z[a];
+    }
+    if (all_zero(R, (size_t)D * D)) { /* update.jl:82-89 */
+        ll = all_zero(z, (size_t)o) ? INFINITY : -INFINITY;
+    } else {
+        gemm(D, o, D, 1.0, R, D, 0, H, o, 1, 0.0, Cm, D);           /* R H' */
+        for (int a = 0; a < o; a++) {
+            for (int r = 0; r < D; r++) AT(St, r, a, D + o) = AT(Cm, r, a, D);
+            for (int b = 0; b < o; b++) AT(St, D + b, a, D + o) = AT(Rn, b, a, o);
+        }
+        oracle_triangularize(D + o, o, St, Sr);                     /* S = Sr'Sr */
+        gemm(D, o, D, 1.0, R, D, 1, Cm, D, 0, 0.0, K, D);           /* Sigma H' */
+        rdiv_chol_upper(D, o, K, Sr);                               /* K = Sigma H' S^-1 */
+        rdiv_chol_upper(1, o, zt, Sr);                              /* z' S^-1 */
+        double quad = 0.0, logdet = 0.0;
+        for (int a = 0; a < o; a++) {
+            quad += z[a] * zt[a];
+            logdet += 2.0 * log(fabs(AT(Sr, a, a, o)));
+        }
+        ll = -0.5 * quad - 0.5 * (double)o * log(2.0 * M_PI) - 0.5 * logdet;
+        for (int c = 0; c < D; c++)
+            for (int a = 0; a < o; a++) mu[c] -= AT(K, c, a, D) * z[a];
+        gemm(D, D, o, -1.0, K, D, 0, H, o, 0, 0.0, Mc, D);          /* I - K H */
+        for (int i = 0; i < D; i++) AT(Mc, i, i, D) += 1.0;
+        gemm(D, o, o, 1.0, K, D, 0, Rn, o, 1, 0.0, K1, D);          /* K Rn' */
+        for (int c = 0; c < D; c++) {
+            for (int r = 0; r < D; r++) {
+                double sacc = 0.0;
+                for (int l = 0; l < D; l++) sacc += AT(R, r, l, D) * AT(Mc, c, l, D); /* R (I - K H)' */
+                AT(R2, r, c, D + o) = sacc;
+            }
+            for (int a = 0; a < o; a++) AT(R2, D + a, c, D + o) = AT(K1, c, a, D);
+        }
+        oracle_triangularize(D + o, D, R2, R);
+    }
+    free(z); free(zt); free(Cm); free(St); free(Sr); free(K); free(Mc); free(R2); free(K1);
+    return ll;
+}
+
 int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, oracle_taylor_fn taylor,
                  const double* u0, const double* p, oracle_traj* out) {
     /* mass matrices: EK1 on the dense layout takes any M; the Kronecker layout (EK0 + IWP + scalar diffusion) only a
        UniformScaling (ArgumentError otherwise, caches.jl:111-118; H = lambda E1, derivative_utils.jl:45-47); the
        BlocksOfDiagonals layout is restated for diagonal M */
     if (c->second_order && (c->mass_matrix || c->q < 2)) return -2;
+    if (c->n_data > 0 && (c->alg == ORACLE_DIAGONAL_EK1 || c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV ||
+                          (c->alg == ORACLE_EK0 && c->prior == ORACLE_PRIOR_IWP)))
+        return -2; /* data updates in the forward pass: restated on the dense layout */
     if (c->mass_matrix) {
         const double* M = c->mass_matrix;
         int diagonal = 1, uniform = 1, zero_diag = 0;
@@ -1257,6 +1318,9 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
             uprev[i] = so ? mu[d + i] : mu[i]; /* update_uprev! (integrator_utils.jl:173-183) */
             if (isnan(mu[i])) nanu = 1;
         }
+        /* PresetTimeCallback at the data times (dataupdate.jl:83): condition the state on the observation */
+        for (int64_t j = 0; j < c->n_data; j++)
+            if (c->data_t[j] == t) out->data_loglik += data_update(D, c->n_obs, c->obs_H, c->obs_Rn, c->data_u + j * c->n_obs, mu, R);
         /* savevalues! (integrator_utils.jl:143-171) */
         if (c->save_everystep) {
             dvec_push(&ts, &t, 1);

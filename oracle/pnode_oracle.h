@@ -79,6 +79,17 @@ typedef struct {
        ArrayPartition); u0 holds (du0, u0); pu_* have 2d entries in SolProj order (du, u). */
     int32_t second_order;
     int32_t reserved1;
+    /* DataUpdateCallback (src/callbacks/dataupdate.jl:39-84) as used by filtering_data_loglik
+       (src/data_likelihoods/filtering.jl): whenever an accepted step ends on a data time the filter state is updated on
+       the observation y = Hx + eps, eps ~ N(0, Rn'Rn), and the update's log-likelihood is accumulated in
+       oracle_traj.data_loglik.  The caller puts the data times into tstops.  Dense layout only. */
+    const double* data_t;   /* [n_data] */
+    int64_t n_data;
+    const double* data_u;   /* [n_data][n_obs] */
+    int32_t n_obs;
+    int32_t reserved2;
+    const double* obs_H;    /* n_obs x D, column-major: observation_matrix * SolProj */
+    const double* obs_Rn;   /* n_obs x n_obs, column-major upper factor of the observation-noise covariance */
 } oracle_config;
 
 /* One solved trajectory.  Arrays are owned by the struct; free with oracle_traj_free. */
@@ -102,6 +113,7 @@ typedef struct {
     double* bk_LR;        /* [n-1][2D*D] col-major 2D x D */
     double* diffusions_mv;      /* [n][d] per-component diffusions (BlocksOfDiagonals solves only, else NULL) */
     double* global_diffusion_mv; /* [d] (BlocksOfDiagonals solves only, else NULL) */
+    double data_loglik;   /* sum of the data updates' log-likelihoods (DataUpdateLogLikelihood); 0 without a data set */
 } oracle_traj;
 
 /* ---- component-level entry points (unit-tested against dense formulas) ---- */

@@ -797,3 +797,33 @@ def test_fenrir_data_loglik_matches_the_joint_gaussian(oracle, alg_name, diffusi
     Rm = np.array([[sigma ** 2, 0.05], [0.05, 2 * sigma ** 2]])
     llm = oracle.fenrir_data_loglik(cfg, s, data_t, data_u, observation_noise_cov=Rm)
     assert llm == pytest.approx(_joint_data_loglik(s, data_t, data_u, np.eye(8)[:2], Rm), rel=1e-6)
+
+
+@pytest.mark.parametrize("diffusion", ["dynamic", "fixed"])
+def test_filtering_and_fenrir_data_likelihoods_agree(oracle, diffusion):
+    """test/data_likelihoods.jl:17-60 (`compare_data_likelihoods`): the data log-likelihood computed by updating on the
+    data inside the forward pass (filtering_data_loglik: DataUpdateCallback, src/callbacks/dataupdate.jl:39-84, smooth =
+    false) equals the Fenrir value (backward pass over the saved kernels, smooth = true) to rtol 1e-6 -- EK1, fixed steps
+    dt = 2e-2, Lotka-Volterra, observations with sigma = 0.5 at t = 5 and t = 10; also with partial observations
+    (:62-73) and a matrix noise covariance (:86-110)."""
+    pd = problems.PROBLEMS["lotka_volterra"]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 2, 4), 3)
+    rng = np.random.default_rng(11)
+    data_t = np.array([5.0, 10.0])
+    truth = solve_ivp(lambda t, u: [1.5 * u[0] - u[0] * u[1], -3 * u[1] + u[0] * u[1]], (0, 10), [1.0, 1.0], rtol=1e-10, atol=1e-10,
+                      t_eval=data_t).y.T
+    sigma = 0.5
+    data_u = truth + sigma * rng.standard_normal(truth.shape)
+    diff = oracle.DIFF_DYNAMIC if diffusion == "dynamic" else oracle.DIFF_FIXED
+    base = dict(alg=oracle.EK1, diffusion=diff, calibrate=False, adaptive=False, dt=2e-2, t0=0, t1=10, cov_backend=oracle.COV_QR)
+    Rm = np.array([[sigma ** 2, 0.05], [0.05, 2 * sigma ** 2]])
+    for H, cov in ((None, sigma ** 2), (np.array([[1.0, 0.0]]), sigma ** 2), (None, Rm)):
+        du_ = data_u if H is None else data_u @ H.T
+        cfg_s = oracle.make_config(2, 3, 4, smooth=True, tstops=data_t, **base)
+        fen = oracle.fenrir_data_loglik(cfg_s, oracle.solve(cfg_s, rhs, pd.u0, pd.p), data_t, du_, observation_matrix=H,
+                                        observation_noise_cov=cov)
+        cfg_f = oracle.make_config(2, 3, 4, smooth=False, save_everystep=False, data=(data_t, du_), observation_matrix=H,
+                                   observation_noise_cov=cov, **base)
+        s = oracle.solve(cfg_f, rhs, pd.u0, pd.p)
+        assert s["retcode"] == "Success"
+        assert s["data_loglik"] == pytest.approx(fen, rel=1e-6)
