@@ -357,6 +357,9 @@ struct PnSmoothCol {
                 }
                 __syncwarp();
             }
+            /* (Fenrir build: ncu, profiles/r1t, shows 49 % of the samples at this barrier -- the other warps wait for a warp's
+               single-lane data update.  Dropping the lockstep for a warp-level exit test was measured 45 % SLOWER (the
+               warps drift apart in the unrolled body, instruction fetch); the remedy is a group-cooperative update.) */
             if (__syncthreads_or(((have || !queue_empty) ? 1 : 0)) == 0) break;
 
             /* ===== (B) one backward step for every group that has one ===== */
