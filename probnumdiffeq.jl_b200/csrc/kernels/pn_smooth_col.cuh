@@ -90,129 +90,9 @@ PN_HD void pn_qr_cols(double (&A)[NROW][NS], int gl, double* dinv) {
 #ifndef PN_FENRIR
 #define PN_FENRIR 0 /* 1: build the sweep with the Fenrir data updates (NVRTC builds of solvers that carry a data set) */
 #endif
-// Fenrir data update (src/data_likelihoods/fenrir.jl:127-137 measure_and_update!, src/filtering/update.jl:65-139 with the QR
-// route of :132-136) on the posterior (Ms, Sm) of one trajectory in shared memory, executed by ONE lane of the group: data
-// points are rare compared with steps (tens against hundreds), so the update stays off the register-resident step path
-// and needs no shared-memory scratch (its work arrays are a local-memory frame that only this cold path touches).
-// Returns the log-likelihood of the observation.
-template <int D, int LD, int OMAX>
-__device__ __noinline__ double pn_fenrir_update_serial(const double* __restrict__ H, const double* __restrict__ Rn,
-                                                       const double* __restrict__ u, int o, double* Sm, double* Ms) {
-    double Cb[D][OMAX], Kb[D][OMAX], Sb[D + OMAX][OMAX], Ex[OMAX][D], z[OMAX], zt[OMAX];
-    double nrm = 0.0;
-    for (int r = 0; r < D; r++)
-        for (int c = 0; c < D; c++) nrm += fabs(Sm[r * LD + c]);
-    for (int a = 0; a < o; a++) {
-        double sacc = 0.0;
-        for (int c = 0; c < D; c++) sacc += H[a * D + c] * Ms[c];
-        z[a] = sacc - u[a];
-        zt[a] = z[a];
-    }
-    if (nrm == 0.0) { /* update.jl:82-89 */
-        double nz = 0.0;
-        for (int a = 0; a < o; a++) nz += fabs(z[a]);
-        return (nz == 0.0) ? PN_INF : -PN_INF;
-    }
-    for (int r = 0; r < D; r++)
-        for (int a = 0; a < o; a++) {
-            double sacc = 0.0;
-            for (int c = 0; c < D; c++) sacc += Sm[r * LD + c] * H[a * D + c];
-            Cb[r][a] = sacc;
-            Sb[r][a] = sacc;
-        }
-    for (int a = 0; a < o; a++)
-        for (int b = 0; b < o; b++) Sb[D + a][b] = Rn[a * o + b];
-    /* S.R = qr([C; Rn]).R */
-    for (int k = 0; k < o; k++) {
-        double total = 0.0;
-        for (int r = k; r < D + o; r++) total += Sb[r][k] * Sb[r][k];
-        if (total > 0.0) {
-            const double alpha = Sb[k][k], nr = sqrt(total), beta = -copysign(nr, alpha), vk = alpha - beta;
-            const double gam = 1.0 / (total + fabs(alpha) * nr);
-            for (int j = k + 1; j < o; j++) {
-                double sj = vk * Sb[k][j];
-                for (int r = k + 1; r < D + o; r++) sj += Sb[r][k] * Sb[r][j];
-                sj *= gam;
-                Sb[k][j] -= sj * vk;
-                for (int r = k + 1; r < D + o; r++) Sb[r][j] -= sj * Sb[r][k];
-            }
-            Sb[k][k] = beta;
-        }
-    }
-    /* K = Sigma H' S^-1, row by row: x U = b, y U' = x (U = S.R upper) */
-    for (int c = 0; c < D; c++) {
-        for (int a = 0; a < o; a++) {
-            double sacc = 0.0;
-            for (int r = 0; r < D; r++) sacc += Sm[r * LD + c] * Cb[r][a];
-            Kb[c][a] = sacc;
-        }
-        for (int a = 0; a < o; a++) {
-            double sacc = Kb[c][a];
-            for (int b = 0; b < a; b++) sacc -= Kb[c][b] * Sb[b][a];
-            Kb[c][a] = sacc / Sb[a][a];
-        }
-        for (int a = o - 1; a >= 0; a--) {
-            double sacc = Kb[c][a];
-            for (int b = a + 1; b < o; b++) sacc -= Kb[c][b] * Sb[a][b];
-            Kb[c][a] = sacc / Sb[a][a];
-        }
-    }
-    for (int a = 0; a < o; a++) {
-        double sacc = zt[a];
-        for (int b = 0; b < a; b++) sacc -= zt[b] * Sb[b][a];
-        zt[a] = sacc / Sb[a][a];
-    }
-    for (int a = o - 1; a >= 0; a--) {
-        double sacc = zt[a];
-        for (int b = a + 1; b < o; b++) sacc -= zt[b] * Sb[a][b];
-        zt[a] = sacc / Sb[a][a];
-    }
-    double quad = 0.0, logdet = 0.0;
-    for (int a = 0; a < o; a++) {
-        quad += z[a] * zt[a];
-        logdet += log(fabs(Sb[a][a]));
-    }
-    const double ll = -0.5 * quad - 0.5 * (double)o * 1.8378770664093453 - logdet;
-    /* mean, and the stack [ R (I - K H)' ; (K Rn')' ] -> in place in Sm plus o extra rows */
-    for (int c = 0; c < D; c++) {
-        double sacc = Ms[c];
-        for (int a = 0; a < o; a++) sacc -= Kb[c][a] * z[a];
-        Ms[c] = sacc;
-    }
-    for (int r = 0; r < D; r++)
-        for (int c = 0; c < D; c++) {
-            double sacc = Sm[r * LD + c];
-            for (int a = 0; a < o; a++) sacc -= Cb[r][a] * Kb[c][a];
-            Sm[r * LD + c] = sacc;
-        }
-    for (int a = 0; a < o; a++)
-        for (int c = 0; c < D; c++) {
-            double sacc = 0.0;
-            for (int b = 0; b < o; b++) sacc += Kb[c][b] * Rn[a * o + b];
-            Ex[a][c] = sacc;
-        }
-    for (int k = 0; k < D; k++) {
-        double total = 0.0;
-        for (int r = k; r < D; r++) total += Sm[r * LD + k] * Sm[r * LD + k];
-        for (int a = 0; a < o; a++) total += Ex[a][k] * Ex[a][k];
-        if (total > 0.0) {
-            const double alpha = Sm[k * LD + k], nr = sqrt(total), beta = -copysign(nr, alpha), vk = alpha - beta;
-            const double gam = 1.0 / (total + fabs(alpha) * nr);
-            for (int j = k + 1; j < D; j++) {
-                double sj = vk * Sm[k * LD + j];
-                for (int r = k + 1; r < D; r++) sj += Sm[r * LD + k] * Sm[r * LD + j];
-                for (int a = 0; a < o; a++) sj += Ex[a][k] * Ex[a][j];
-                sj *= gam;
-                Sm[k * LD + j] -= sj * vk;
-                for (int r = k + 1; r < D; r++) Sm[r * LD + j] -= sj * Sm[r * LD + k];
-                for (int a = 0; a < o; a++) Ex[a][j] -= sj * Ex[a][k];
-            }
-            Sm[k * LD + k] = beta;
-        }
-        for (int r = k + 1; r < D; r++) Sm[r * LD + k] = 0.0;
-    }
-    return ll;
-}
+// Fenrir data update on the posterior (Ms, Sm) of one trajectory in shared memory: executed by ONE lane of the group (data
+// points are rare compared with steps), work arrays in a local-memory frame that only this cold path touches.
+#include "pn_fenrir_update.cuh"
 
 template <int d, int Q, int G>
 struct PnSmoothCol {
@@ -359,7 +239,8 @@ struct PnSmoothCol {
             }
             /* (Fenrir build: ncu, profiles/r1t, shows 49 % of the samples at this barrier -- the other warps wait for a warp's
                single-lane data update.  Dropping the lockstep for a warp-level exit test was measured 45 % SLOWER (the
-               warps drift apart in the unrolled body, instruction fetch); the remedy is a group-cooperative update.) */
+               warps drift apart in the unrolled body, instruction fetch); the remedy was a cheaper update -- the pre-array
+               form of pn_fenrir_update.cuh, 2.3x on the whole call -- and, next, a group-cooperative one.) */
             if (__syncthreads_or(((have || !queue_empty) ? 1 : 0)) == 0) break;
 
             /* ===== (B) one backward step for every group that has one ===== */

@@ -287,3 +287,59 @@ def test_fenrir_configuration_checks(pnlib):
     assert err(saveat=[0.5]).kind == "Unsupported"
     assert err(prior=pnlib.PRIOR_IOUP, rate_parameter=-1.0).kind == "Unsupported"
     assert err(alg=pnlib.EK0, diffusion=pnlib.DIFF_DYNAMIC_MV).kind == "Unsupported"
+
+
+def test_fenrir_update_header_against_reference_formulas(tmp_path):
+    """csrc/kernels/pn_fenrir_update.cuh is plain C++: compile it with g++ and compare the single-thread data update (one
+    orthogonal transformation of the pre-array) with the reference's formulas -- make_obscov_sqrt
+    (src/callbacks/dataupdate.jl:86-87), update!(...; R) (src/filtering/update.jl:65-139) -- on random inputs: mean,
+    covariance R'R and log-likelihood, full / partial observations, triangular and dense prior factors, Sigma == 0."""
+    hdr = os.path.join(os.path.dirname(lib.__file__), "csrc", "kernels")
+    src = tmp_path / "fen.cpp"
+    src.write_text('#include <math.h>\n#define PN_FEN_FN\n#define PN_FEN_INF INFINITY\n#include "pn_fenrir_update.cuh"\n'
+                   'extern "C" double upd_8_2(const double* H, const double* Rn, const double* u, int o, double* Sm, double* Ms) {\n'
+                   '  return pn_fenrir_update_serial<8, 9, 2>(H, Rn, u, o, Sm, Ms);\n}\n'
+                   'extern "C" double upd_12_4(const double* H, const double* Rn, const double* u, int o, double* Sm, double* Ms) {\n'
+                   '  return pn_fenrir_update_serial<12, 13, 4>(H, Rn, u, o, Sm, Ms);\n}\n')
+    so = tmp_path / "fen.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-I", hdr, "-o", str(so), str(src)], check=True)
+    L = C.CDLL(str(so))
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(0)
+    for fn, D, LD, o, dense in ((L.upd_8_2, 8, 9, 2, False), (L.upd_8_2, 8, 9, 1, True), (L.upd_12_4, 12, 13, 4, False),
+                                (L.upd_12_4, 12, 13, 3, True)):
+        fn.restype = C.c_double
+        fn.argtypes = [dp, dp, dp, C.c_int, dp, dp]
+        R = rng.standard_normal((D, D)) * 1e-2
+        if not dense:
+            R = np.triu(R)
+        m = rng.standard_normal(D)
+        H = np.ascontiguousarray(rng.standard_normal((o, D)))
+        Rn = np.ascontiguousarray(np.triu(rng.standard_normal((o, o))) + 2 * np.eye(o))
+        u = rng.standard_normal(o)
+        # reference formulas
+        z = H @ m - u
+        Cm = R @ H.T
+        Sr = np.linalg.qr(np.vstack([Cm, Rn]), mode="r")
+        S = Sr.T @ Sr
+        K = np.linalg.solve(S, (R.T @ Cm).T).T
+        ll = -0.5 * z @ np.linalg.solve(S, z) - 0.5 * o * np.log(2 * np.pi) - np.sum(np.log(np.abs(np.diag(Sr))))
+        m_ref = m - K @ z
+        R2 = R @ (np.eye(D) - K @ H).T
+        R3 = np.linalg.qr(np.vstack([R2, (K @ Rn.T).T]), mode="r")
+        Sm = np.zeros((D, LD))
+        Sm[:, :D] = R
+        Ms = m.copy()
+        got = fn(H.ctypes.data_as(dp), Rn.ctypes.data_as(dp), u.ctypes.data_as(dp), o, Sm.ctypes.data_as(dp), Ms.ctypes.data_as(dp))
+        assert got == pytest.approx(ll, rel=1e-12)
+        assert np.allclose(Ms, m_ref, rtol=1e-12, atol=1e-15)
+        Sg, Sw = Sm[:, :D].T @ Sm[:, :D], R3.T @ R3
+        assert np.linalg.norm(Sg - Sw) / np.linalg.norm(Sw) < 1e-12
+        assert not Sm[:, D:].any()
+    # Sigma == 0: +Inf if the residual is zero, -Inf otherwise, state untouched (update.jl:82-89)
+    Sm, Ms = np.zeros((8, 9)), np.arange(8.0)
+    H = np.ascontiguousarray(np.eye(8)[:2])
+    Rn = np.ascontiguousarray(np.eye(2))
+    for u, want in ((np.array([0.0, 1.0]), np.inf), (np.array([0.5, 1.0]), -np.inf)):
+        got = L.upd_8_2(H.ctypes.data_as(dp), Rn.ctypes.data_as(dp), u.ctypes.data_as(dp), 2, Sm.ctypes.data_as(dp), Ms.ctypes.data_as(dp))
+        assert got == want and np.array_equal(Ms, np.arange(8.0))
