@@ -133,7 +133,9 @@ typedef struct pnode_config {
        filtering estimates (the reference stops with `step!`: no smoothing, no calibration), and a backward pass fits the
        PN posterior to the data (fit_pnsolution_to_data!, :68-125), one log-likelihood per trajectory in
        PNODE_F_FENRIR_LOGLIK (-Inf for a trajectory whose solve did not succeed, :55-59).  Needs smooth = 1
-       (ArgumentError otherwise, :42-44).  One data set for the whole ensemble (parameter sweeps). */
+       (ArgumentError otherwise, :42-44).  One data set for the whole ensemble (parameter sweeps).  The value is the dense
+       formula; with the EK0 the reference's Kronecker update omits the factor d of log det S (update.jl:147 quirk), see
+       DESIGN.md section 5. */
     const double* data_t;             /* [n_data] ascending, in [t0, t1]; host pointer, copied at create            */
     int64_t n_data;
     const double* data_u;             /* [n_data][n_obs]                                                            */

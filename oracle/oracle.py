@@ -421,7 +421,8 @@ def max_threads() -> int:
     return lib().oracle_max_threads()
 
 
-def fenrir_data_loglik(cfg: Config, sol: dict, data_t, data_u, observation_matrix=None, observation_noise_cov=1.0) -> float:
+def fenrir_data_loglik(cfg: Config, sol: dict, data_t, data_u, observation_matrix=None, observation_noise_cov=1.0,
+                       kronecker_logdet_quirk: bool = False) -> float:
     """Fenrir data log-likelihood (src/data_likelihoods/fenrir.jl:30-137, `fit_pnsolution_to_data!`) of a solution computed
     with smooth=True (the backward kernels are saved) whose time grid contains every `data_t` (the reference adds them to
     tstops, :46-48).  The reference stops the integrator with `step!` -- no postamble, i.e. no smoothing and no
@@ -431,7 +432,13 @@ def fenrir_data_loglik(cfg: Config, sol: dict, data_t, data_u, observation_matri
     Backward over the saved points: x_post[N] = x_filt[N]; x_post[i] = marginalize(x_post[i+1], K_i) (:100-108); at a data
     time a Kalman update with observation matrix proj * SolProj and noise R (:110-123, `measure_and_update!` :127-137,
     `update!(...; R)` src/filtering/update.jl:65-139 with the QR route of :132-136), accumulating its log-likelihood.
-    Returns -inf if the solve did not succeed (:55-59)."""
+    Returns -inf if the solve did not succeed (:55-59).
+
+    `kronecker_logdet_quirk`: on the IsometricKronecker layout (EK0 + IWP + scalar diffusion; full observations and
+    isotropic noise only) the reference's data update runs on the n x n factors (update.jl:151-195) and its log-density
+    takes `logdet` of the 1 x 1 factor of S WITHOUT multiplying by d -- the quirk of update.jl:147 that the solver's own
+    log-likelihood has as well.  False (default) evaluates the dense formula, which is also what the product returns for the
+    EK0 (documented deviation); True reproduces the reference's EK0 value: log det S / n_obs."""
     if sol["retcode"] != "Success":
         return -np.inf
     if "bk_G" not in sol:
@@ -453,7 +460,10 @@ def fenrir_data_loglik(cfg: Config, sol: dict, data_t, data_u, observation_matri
         Sr = np.linalg.qr(np.vstack([C, Rn]), mode="r")              # make_obscov_sqrt
         S = Sr.T @ Sr
         K = np.linalg.solve(S, (R.T @ C).T).T
-        ll = -0.5 * z @ np.linalg.solve(S, z) - 0.5 * o * np.log(2 * np.pi) - np.sum(np.log(np.abs(np.diag(Sr))))
+        half_logdet = np.sum(np.log(np.abs(np.diag(Sr))))
+        if kronecker_logdet_quirk:
+            half_logdet /= o
+        ll = -0.5 * z @ np.linalg.solve(S, z) - 0.5 * o * np.log(2 * np.pi) - half_logdet
         m2 = m - K @ z
         R2 = R @ (np.eye(D) - K @ H).T
         R3 = np.linalg.qr(np.vstack([R2, (K @ Rn.T).T]), mode="r")
