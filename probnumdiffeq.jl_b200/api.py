@@ -244,7 +244,8 @@ def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, absto
             raise ValueError("mass_matrix must be d x d")  # DimensionMismatch
         if not np.array_equal(M, np.eye(d)):
             uniform = np.array_equal(M, M[0, 0] * np.eye(d)) and M[0, 0] != 0.0
-            if isinstance(alg, EK0) and isinstance(alg.prior, IWP) and not isinstance(diff, (FixedMVDiffusion, DynamicMVDiffusion)) \
+            if isinstance(alg, EK0) and (alg.prior is None or isinstance(alg.prior, IWP)) \
+                    and not isinstance(diff, (FixedMVDiffusion, DynamicMVDiffusion)) \
                     and not uniform:
                 # src/caches.jl:111-118: only a UniformScaling (here: M == lambda I) passes on the Kronecker layout
                 raise ValueError("The selected algorithm uses an efficient Kronecker-factorized implementation which is "

@@ -343,3 +343,25 @@ def test_fenrir_update_header_against_reference_formulas(tmp_path):
     for u, want in ((np.array([0.0, 1.0]), np.inf), (np.array([0.5, 1.0]), -np.inf)):
         got = L.upd_8_2(H.ctypes.data_as(dp), Rn.ctypes.data_as(dp), u.ctypes.data_as(dp), 2, Sm.ctypes.data_as(dp), Ms.ctypes.data_as(dp))
         assert got == want and np.array_equal(Ms, np.arange(8.0))
+
+
+def test_python_mirror_argument_errors_of_the_new_entry_points():
+    """api.SecondOrderODEProblem / api.fenrir_data_loglik raise before any device work, like the reference's constructors."""
+    from probnumdiffeq_jl_b200 import api
+
+    with pytest.raises(ValueError):   # DimensionMismatch
+        api.SecondOrderODEProblem(lambda ddu, du, u, p, t: None, [0.0], [1.0, 2.0], (0.0, 1.0))
+    prob = api.ODEProblem.from_library("lotka_volterra")
+    with pytest.raises(ValueError) as e:   # src/data_likelihoods/fenrir.jl:42-44
+        api.fenrir_data_loglik(prob, api.EK1(order=3, smooth=False), data=([1.0], [[1.0, 1.0]]), observation_noise_cov=0.1)
+    assert "fenrir only works with smoothing" in str(e.value)
+    two = api.SecondOrderODEProblem(lambda ddu, du, u, p, t: [ddu.__setitem__(0, -u[0])], [0.0], [1.0], (0.0, 1.0))
+    assert two.second_order and two.u0 == [0.0, 1.0]
+    dx = [0, 0]
+    two.f(dx, [0.5, 2.0], [], 0.0)     # first-order form F([du; u]) = [f1(du, u); du]
+    assert dx == [-2.0, 0.5]
+    dae = api.ODEProblem.from_library("rober_dae")
+    with pytest.raises(ValueError) as e:   # src/caches.jl:111-118
+        api._config_for(dae, api.EK0(order=3), api.EnsembleB200(), adaptive=True, dt=None, abstol=1e-6, reltol=1e-3, save_everystep=True,
+                        maxiters=10 ** 6, dtmin=0.0, dtmax=None, tstops=None, save_state=False)
+    assert "incompatible with the provided mass matrix" in str(e.value)
