@@ -601,6 +601,7 @@ static double initial_dt(const oracle_config* c, oracle_rhs_fn f, const double* 
 /* block i <-> state indices i:d:D.  Selected for EK0 + multivariate diffusion and for DiagonalEK1 */
 /* (src/algorithms.jl:132-151).  The per-block routines are the generic ones above with N = q+1.   */
 /* ------------------------------------------------------------------------------------------ */
+static double data_update_factor(int n, int nc, int rs, const double* u, int us, double sn, double* mu, double* R);
 static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, oracle_taylor_fn taylor,
                         const double* u0, const double* p, oracle_traj* out) {
     const int d = c->d, q = c->q, n = q + 1, D = d * n;
@@ -822,6 +823,11 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
             uprev[i] = so ? mu[d + i] : mu[i];
             if (isnan(mu[i])) nanu = 1;
         }
+        /* DataUpdateCallback on the blocks (update.jl:197-239): one scalar observation per block */
+        for (int64_t j = 0; j < c->n_data; j++)
+            if (c->data_t[j] == t)
+                for (int i = 0; i < d; i++)
+                    out->data_loglik += data_update_factor(n, 1, d, c->data_u + j * c->n_obs + i, 1, AT(c->obs_Rn, i, i, d), mu + i, R + i * nn);
         if (c->save_everystep) {
             dvec_push(&ts, &t, 1);
             dvec_push(&diffs, local_diffusion, d);
@@ -913,6 +919,21 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
             double* dst = out->x_smooth_R + (size_t)k * D * D;
             PN_BLOCKS_TO_DENSE(dst, sR + (size_t)k * NB)
         }
+        /* dense-form backward kernels for inspection (block i <-> indices i:d:, also in the 2D x D factor of Lambda) */
+        int64_t nk = ns - 1;
+        out->bk_G = (double*)calloc((size_t)(nk > 0 ? nk : 1) * D * D, sizeof(double));
+        out->bk_b = (double*)malloc(sizeof(double) * (size_t)(nk > 0 ? nk : 1) * D);
+        out->bk_LR = (double*)calloc((size_t)(nk > 0 ? nk : 1) * 2 * D * D, sizeof(double));
+        for (int64_t k = 0; k < nk; k++) {
+            double* Gd = out->bk_G + (size_t)k * D * D;
+            double* Ld = out->bk_LR + (size_t)k * 2 * D * D;
+            PN_BLOCKS_TO_DENSE(Gd, bG.p + (size_t)k * NB)
+            for (int i = 0; i < d; i++)
+                for (int cc = 0; cc < n; cc++)
+                    for (int r = 0; r < 2 * n; r++)
+                        AT(Ld, r * d + i, cc * d + i, 2 * D) = AT(bL.p + (size_t)k * 2 * NB + (size_t)i * 2 * nn, r, cc, 2 * n);
+            memcpy(out->bk_b + (size_t)k * D, bB.p + (size_t)k * D, sizeof(double) * D);
+        }
     }
 #undef PN_BLOCKS_TO_DENSE
     for (int64_t k = 0; k < ns; k++) {
@@ -929,6 +950,51 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
     free(Ah1); free(Qh1); free(mu); free(R); free(mu_pred); free(R_pred); free(mu_filt); free(R_filt);
     free(H); free(J); free(G); free(bb); free(LR); free(Qs);
     return 0;
+}
+
+/* The same data update on ONE n x n factor with the mean handled as an n x nc matrix (column c at mu[r*rs + c]):
+   the Kronecker layout (nc = d: update.jl:151-195, with the log-density of the 1 x 1 factor -- logdet is NOT multiplied by
+   d, the quirk of update.jl:147) and one block of the BlocksOfDiagonals layout (nc = 1: update.jl:197-239).  Observation
+   row e_0' (full observations of the solution), noise standard deviation sn.  Returns the log-likelihood. */
+static double data_update_factor(int n, int nc, int rs, const double* u, int us, double sn, double* mu, double* R) {
+    double f[32], K[32], z[64];
+    double* St = (double*)malloc(sizeof(double) * (n + 1) * n);
+    double s2 = sn * sn, quad = 0.0, ll;
+    for (int r = 0; r < n; r++) { f[r] = AT(R, r, 0, n); s2 += f[r] * f[r]; } /* R H' with H = e_0' */
+    for (int c = 0; c < nc; c++) z[c] = mu[c] - u[c * us];
+    if (all_zero(R, (size_t)n * n)) { /* update.jl:82-89 */
+        ll = all_zero(z, (size_t)nc) ? INFINITY : -INFINITY;
+        free(St);
+        return ll;
+    }
+    for (int k = 0; k < n; k++) {
+        double sacc = 0.0;
+        for (int r = 0; r < n; r++) sacc += AT(R, r, k, n) * f[r];
+        K[k] = sacc / s2;
+    }
+    for (int c = 0; c < nc; c++) quad += z[c] * z[c] / s2;
+    ll = -0.5 * quad - 0.5 * (double)nc * log(2.0 * M_PI) - 0.5 * log(s2);
+    for (int r = 0; r < n; r++)
+        for (int c = 0; c < nc; c++) mu[r * rs + c] -= K[r] * z[c];
+    for (int k = 0; k < n; k++) {
+        for (int r = 0; r < n; r++) AT(St, r, k, n + 1) = AT(R, r, k, n) - f[r] * K[k]; /* R (I - K H)' */
+        AT(St, n, k, n + 1) = sn * K[k];                                                 /* (K Rn')'    */
+    }
+    oracle_triangularize(n + 1, n, St, R);
+    free(St);
+    return ll;
+}
+
+/* observation model check for the structured layouts: observation_matrix = I (obs_H = E0) and a diagonal noise factor */
+static int data_model_is_componentwise(const oracle_config* c, int D) {
+    if (c->n_obs != c->d) return 0;
+    for (int a = 0; a < c->d; a++) {
+        for (int k = 0; k < D; k++)
+            if (AT(c->obs_H, a, k, c->d) != ((k == a) ? 1.0 : 0.0)) return 0;
+        for (int b = 0; b < c->d; b++)
+            if (a != b && AT(c->obs_Rn, a, b, c->d) != 0.0) return 0;
+    }
+    return 1;
 }
 
 /* DataUpdateCallback affect! (src/callbacks/dataupdate.jl:48-82): condition the filter state (mu, R) on the observation
@@ -995,9 +1061,16 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
        UniformScaling (ArgumentError otherwise, caches.jl:111-118; H = lambda E1, derivative_utils.jl:45-47); the
        BlocksOfDiagonals layout is restated for diagonal M */
     if (c->second_order && (c->mass_matrix || c->q < 2)) return -2;
+    if (c->n_data > 0 && (c->second_order || c->mass_matrix) && c->alg != ORACLE_EK1) return -2;
     if (c->n_data > 0 && (c->alg == ORACLE_DIAGONAL_EK1 || c->diffusion == ORACLE_DIFF_DYNAMIC_MV || c->diffusion == ORACLE_DIFF_FIXED_MV ||
-                          (c->alg == ORACLE_EK0 && c->prior == ORACLE_PRIOR_IWP)))
-        return -2; /* data updates in the forward pass: restated on the dense layout */
+                          (c->alg == ORACLE_EK0 && c->prior == ORACLE_PRIOR_IWP))) {
+        /* structured layouts: full observations with component-wise noise only ("Partial observations only work with the
+           EK1 right now", dataupdate.jl:69-71); the Kronecker layout additionally needs isotropic noise */
+        if (!data_model_is_componentwise(c, c->d * (c->q + 1))) return -2;
+        if (c->alg == ORACLE_EK0 && c->diffusion != ORACLE_DIFF_DYNAMIC_MV && c->diffusion != ORACLE_DIFF_FIXED_MV)
+            for (int a = 1; a < c->d; a++)
+                if (AT(c->obs_Rn, a, a, c->d) != c->obs_Rn[0]) return -2;
+    }
     if (c->mass_matrix) {
         const double* M = c->mass_matrix;
         int diagonal = 1, uniform = 1, zero_diag = 0;
@@ -1320,7 +1393,10 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
         }
         /* PresetTimeCallback at the data times (dataupdate.jl:83): condition the state on the observation */
         for (int64_t j = 0; j < c->n_data; j++)
-            if (c->data_t[j] == t) out->data_loglik += data_update(D, c->n_obs, c->obs_H, c->obs_Rn, c->data_u + j * c->n_obs, mu, R);
+            if (c->data_t[j] == t) {
+                if (kron) out->data_loglik += data_update_factor(n, d, d, c->data_u + j * c->n_obs, 1, c->obs_Rn[0], mu, R);
+                else out->data_loglik += data_update(D, c->n_obs, c->obs_H, c->obs_Rn, c->data_u + j * c->n_obs, mu, R);
+            }
         /* savevalues! (integrator_utils.jl:143-171) */
         if (c->save_everystep) {
             dvec_push(&ts, &t, 1);

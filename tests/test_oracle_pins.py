@@ -863,3 +863,38 @@ def test_second_order_pleiades(oracle):
         assert res[so][1] < 5e-2
     assert res[True][1] < res[False][1]              # more accurate ...
     assert res[True][0] < 0.4 * res[False][0]        # ... and (far) cheaper per step: D = 56 instead of 112
+
+
+@pytest.mark.parametrize("alg_name,diffusion", [("EK0", "dynamic"), ("EK0", "fixed"), ("EK0", "fixed_mv"), ("EK0", "dynamic_mv"),
+                                                ("DiagonalEK1", "dynamic"), ("DiagonalEK1", "fixed"), ("DiagonalEK1", "fixed_mv")])
+def test_filtering_and_fenrir_agree_on_the_structured_layouts(oracle, alg_name, diffusion):
+    """The EK0 / DiagonalEK1 rows of `compare_data_likelihoods` (test/data_likelihoods.jl:31-60): data updates on the
+    Kronecker factors (update.jl:151-195) and on the blocks (update.jl:197-239) in the forward pass against Fenrir's backward
+    pass, rtol 1e-6.  On the Kronecker layout both carry the reference's log-determinant quirk (update.jl:147: logdet of the
+    1 x 1 factor, not multiplied by d), which is what `kronecker_logdet_quirk=True` evaluates."""
+    pd = problems.PROBLEMS["lotka_volterra"]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 2, 4), 3)
+    rng = np.random.default_rng(13)
+    data_t = np.array([5.0, 10.0])
+    truth = solve_ivp(lambda t, u: [1.5 * u[0] - u[0] * u[1], -3 * u[1] + u[0] * u[1]], (0, 10), [1.0, 1.0], rtol=1e-10, atol=1e-10,
+                      t_eval=data_t).y.T
+    sigma = 0.5
+    data_u = truth + sigma * rng.standard_normal(truth.shape)
+    alg = oracle.EK0 if alg_name == "EK0" else oracle.DIAGONAL_EK1
+    diff = dict(dynamic=oracle.DIFF_DYNAMIC, fixed=oracle.DIFF_FIXED, fixed_mv=oracle.DIFF_FIXED_MV, dynamic_mv=oracle.DIFF_DYNAMIC_MV)[diffusion]
+    base = dict(alg=alg, diffusion=diff, calibrate=False, adaptive=False, dt=2e-2, t0=0, t1=10, cov_backend=oracle.COV_QR)
+    kron = alg_name == "EK0" and diffusion in ("dynamic", "fixed")
+    cfg_s = oracle.make_config(2, 3, 4, smooth=True, tstops=data_t, **base)
+    fen = oracle.fenrir_data_loglik(cfg_s, oracle.solve(cfg_s, rhs, pd.u0, pd.p), data_t, data_u, observation_noise_cov=sigma ** 2,
+                                    kronecker_logdet_quirk=kron)
+    cfg_f = oracle.make_config(2, 3, 4, smooth=False, save_everystep=False, data=(data_t, data_u), observation_noise_cov=sigma ** 2, **base)
+    s = oracle.solve(cfg_f, rhs, pd.u0, pd.p)
+    assert s["retcode"] == "Success"
+    assert s["data_loglik"] == pytest.approx(fen, rel=1e-6)
+    if kron:   # the dense formula differs by (d - 1)/2 * sum_j log S_j
+        dense = oracle.fenrir_data_loglik(cfg_s, oracle.solve(cfg_s, rhs, pd.u0, pd.p), data_t, data_u, observation_noise_cov=sigma ** 2)
+        assert abs(dense - fen) > 0.1
+        # partial observations are EK1-only in the reference (dataupdate.jl:69-71)
+        with pytest.raises(Exception):
+            oracle.solve(oracle.make_config(2, 3, 4, smooth=False, save_everystep=False, data=(data_t, data_u[:, :1]),
+                                            observation_matrix=[[1.0, 0.0]], observation_noise_cov=sigma ** 2, **base), rhs, pd.u0, pd.p)
