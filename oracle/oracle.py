@@ -477,7 +477,8 @@ def fenrir_data_loglik(cfg: Config, sol: dict, data_t, data_u, observation_matri
     if t[-1] in data_t:
         m, R, ll = update(m, R, data_u[-1])
         LL += ll
-        data_idx -= 1
+    data_idx -= 1   # unconditional (fenrir.jl:99, `data_idx = length(data.u) - 1`): a last observation that does not sit at
+    #                 sol.t[end] is skipped by the reference
     for i in range(n - 2, -1, -1):
         if t[i] == t[i + 1]:
             continue

@@ -293,6 +293,14 @@ void oracle_kron_identity(int d, int n_rows, int n_cols, const double* B, double
 /* filtering components (generic size N; EK1 dense: N = D, EK0 Kronecker: N = q+1 on factors)  */
 /* ------------------------------------------------------------------------------------------ */
 
+/* how often predict_cov!'s Cholesky (predict.jl:85) succeeded / fell back to triangularize! (:90); diagnostics only */
+static long long g_cov_total = 0, g_cov_fallback = 0;
+void oracle_cov_stats(long long* total, long long* fallback, int reset) {
+    if (total) *total = g_cov_total;
+    if (fallback) *fallback = g_cov_fallback;
+    if (reset) g_cov_total = g_cov_fallback = 0;
+}
+
 /* predict_cov! (src/filtering/predict.jl:62-94). */
 void oracle_predict_cov(int N, const double* R, const double* Ah, const double* QhR, double diffusion, int backend,
                         double* Rout, int* used_qr) {
@@ -316,6 +324,10 @@ void oracle_predict_cov(int N, const double* R, const double* Ah, const double* 
         gemm(N, N, 2 * N, 1.0, S, 2 * N, 1, S, 2 * N, 0, 0.0, M, N); /* :84 */
         ok = (oracle_cholesky_upper(N, M) == 0);                     /* :85 */
         if (ok) memcpy(Rout, M, sizeof(double) * N * N);
+#pragma omp atomic
+        g_cov_total += 1;
+#pragma omp atomic
+        g_cov_fallback += ok ? 0 : 1;
     }
     if (!ok) { /* :90 */
         oracle_triangularize(2 * N, N, S, Rout);
@@ -591,7 +603,7 @@ static double initial_dt(const oracle_config* c, oracle_rhs_fn f, const double* 
     for (int i = 0; i < d; i++) tmp[i] = (f1[i] - f0[i]) / sk[i];
     double d2 = rms_norm(tmp, d) / dt0;
     double mx = fmax(d1, d2);
-    double dt1 = (mx <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / (double)order);
+    double dt1 = (mx <= 1e-15) ? fmax(smalldt, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / (double)order);
     return fmax(dtmin, fmin(fmin(100.0 * dt0, dt1), dtmax));
 }
 

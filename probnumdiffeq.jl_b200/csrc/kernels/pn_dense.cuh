@@ -32,7 +32,8 @@ struct PnDenseParams {
     const double* s_diffusion;     /* [total] diffusion used for step k -> k+1 at slot k */
     const double* s_x_mean;        /* [total][D] filtered */
     const double* s_x_covfac;      /* [total][D][D] filtered */
-    const double* gdiff;           /* [n_traj] */
+    const double* gdiff;           /* [n_traj] sigma_hat^2 * initial_diffusion */
+    double initial_diffusion;      /* the covariance scale of calibrate_solution! is gdiff / initial_diffusion */
     double U[PN_MAX_N * PN_MAX_N];
     double rate;
     double glx[16], glw[16];
@@ -170,7 +171,7 @@ struct PnDensePredict {
                 }
             }
             pn_qr_rows<G, RPL, D, D, true, D>(R, B, gl, nullptr);
-            const double g = (P.calibrate_scale && act) ? P.gdiff[tr] : 1.0;
+            const double g = (P.calibrate_scale && act) ? P.gdiff[tr] / P.initial_diffusion : 1.0;
             if (P.smooth) {
                 if (act) {
                     if (gl == 0) {

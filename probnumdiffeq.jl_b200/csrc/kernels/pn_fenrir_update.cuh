@@ -27,9 +27,11 @@
 
 // Posterior mean Ms[D] and right factor Sm (D rows, leading dimension LD) are updated in place on the observation u[o] with
 // observation matrix H (o x D row-major) and noise right factor Rn (o x o row-major, upper triangular).  Returns the
-// log-likelihood of the observation; +-Inf without touching the state if Sigma == 0 (update.jl:82-89).
+// log-likelihood of the observation; +-Inf without touching the state if Sigma == 0 (update.jl:82-89).  kron_logdet: the
+// reference's value on the IsometricKronecker layout (log det S / o, see PnSmoothParams::kron_logdet).
 template <int D, int LD, int OMAX>
-PN_FEN_FN double pn_fenrir_update_serial(const double* H, const double* Rn, const double* u, int o, double* Sm, double* Ms) {
+PN_FEN_FN double pn_fenrir_update_serial(const double* H, const double* Rn, const double* u, int o, double* Sm, double* Ms,
+                                         bool kron_logdet = false) {
     double Top[OMAX][OMAX + D]; /* rows 0..o-1 of the pre-array: [Rn | 0] -> [S.R | Kb] */
     double Cb[D][OMAX];         /* left block of the bottom rows: R H' -> 0               */
     double z[OMAX], w[OMAX];
@@ -99,6 +101,8 @@ PN_FEN_FN double pn_fenrir_update_serial(const double* H, const double* Rn, cons
         for (int a = 0; a < o; a++) sacc -= Top[a][o + c] * w[a];
         Ms[c] = sacc;
     }
+    /* IsometricKronecker layout: logdet of the 1 x 1 factor of S = s I, not multiplied by d (update.jl:140-148, 182-194) */
+    if (kron_logdet) logdet /= (double)o;
     return -0.5 * quad - 0.5 * (double)o * 1.8378770664093453 - logdet;
 }
 

@@ -285,7 +285,7 @@ PN_HD double pn_initial_dt(const PnParams& P, const double* u0, const double* pr
         }
         d2 = sqrt(d2 / (double)d) / dta;
         const double mx = fmax(d1, d2);
-        const double dtb = (mx <= 1e-15) ? fmax(1e-6, dta * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / (double)P.order);
+        const double dtb = (mx <= 1e-15) ? fmax(smalldt, dta * 1e-3) : pow(10.0, -(2.0 + log10(mx)) / (double)P.order);
         dt = fmax(dtmin, fmin(fmin(100.0 * dta, dtb), P.dtmax));
     }
     return dt;
@@ -346,77 +346,6 @@ struct PnSmall {
     /* H = [-J | I | 0 ...] touches the first 2d columns only and R^- is upper triangular, so R^- H' is zero in
        rows >= 2d: row slots lr >= RU never enter the measurement update */
     static constexpr int RU = ((E1B + 1) * d + G - 1) / G < RPL ? ((E1B + 1) * d + G - 1) / G : RPL;
-
-    // Householder QR of the stack [Rt ; Bt] (2D x D) in place; on return Rt holds the upper-triangular
-    // factor (row r on lane r % G), below-diagonal entries zeroed.  Bt is destroyed.
-    static PN_HD void qr_stack(double (&Rt)[RPL][D], double (&Bt)[RPL][D], int gl) {
-#pragma unroll
-        for (int k = 0; k < D; k++) {
-            const int ks = k / G;  /* slot of the pivot row */
-            const int kl = k % G;  /* lane of the pivot row */
-            double x[RPL];
-            double part = 0.0;
-#pragma unroll
-            for (int lr = 0; lr < RPL; lr++) {
-                const int base = lr * G;
-                if (base + G - 1 < k) {
-                    x[lr] = 0.0; /* finished rows */
-                } else if (base >= k) {
-                    x[lr] = Rt[lr][k];
-                } else {
-                    x[lr] = (base + gl >= k) ? Rt[lr][k] : 0.0;
-                }
-                part += x[lr] * x[lr];
-            }
-#pragma unroll
-            for (int lr = 0; lr < RPL; lr++) part += Bt[lr][k] * Bt[lr][k];
-            const double total = pn_gsum<G>(part);
-            const double alpha = pn_gbcast<G>(x[ks], kl);
-            /* branch-free on purpose: the shuffles below must be executed by the whole warp.
-               A zero column (total == 0) gets gam = 0, i.e. H = I. */
-            const bool nz = total > 0.0;
-            const double nrm = nz ? total * pn_rsqrt(total) : 0.0;
-            const double beta = -copysign(nrm, alpha);
-            const double vk = alpha - beta;
-            const double den = total + fabs(alpha) * nrm; /* = beta (beta - alpha) = v'v / 2 */
-            const double gam = nz ? pn_rcp(den) : 0.0;
-            if (gl == kl) x[ks] = vk;
-            /* s_j = v' a_j over the group, j > k */
-            double sj[D];
-#pragma unroll
-            for (int j = 0; j < D; j++) {
-                if (j <= k) continue;
-                double s = 0.0;
-#pragma unroll
-                for (int lr = 0; lr < RPL; lr++)
-                    if (lr * G + G - 1 >= k) s += x[lr] * Rt[lr][j];
-#pragma unroll
-                for (int lr = 0; lr < RPL; lr++) s += Bt[lr][k] * Bt[lr][j];
-                sj[j] = s;
-            }
-#pragma unroll
-            for (int j = 0; j < D; j++)
-                if (j > k) sj[j] = pn_gsum<G>(sj[j]) * gam;
-#pragma unroll
-            for (int j = 0; j < D; j++) {
-                if (j <= k) continue;
-#pragma unroll
-                for (int lr = 0; lr < RPL; lr++)
-                    if (lr * G + G - 1 >= k) Rt[lr][j] -= sj[j] * x[lr];
-#pragma unroll
-                for (int lr = 0; lr < RPL; lr++) Bt[lr][j] -= sj[j] * Bt[lr][k];
-            }
-            /* column k: beta on the pivot, zeros below */
-#pragma unroll
-            for (int lr = 0; lr < RPL; lr++) {
-                const int base = lr * G;
-                if (base + G - 1 < k) continue;
-                const int row = base + gl;
-                if (row == k) Rt[lr][k] = beta;
-                else if (row > k) Rt[lr][k] = 0.0;
-            }
-        }
-    }
 
     static __device__ void run(const PnParams& P) {
         constexpr unsigned FULL = 0xffffffffu;
@@ -556,14 +485,9 @@ struct PnSmall {
             for (int i = 0; i < d * d; i++) J[i] = 0.0;
 
             /* ONE attempt per iteration of the warp's loop: a group whose step is rejected sits out phase 2 (identity
-               step) and retries in the next iteration.  Retrying inside this phase instead (PN_RETRY_IN_PHASE1) keeps the
-               other groups of the warp waiting and -- worse -- lets the warps of the CTA drift apart in the ~100 KB
-               unrolled body: on OREGO (9 % rejections) a quarter of the issue slots were instruction-fetch stalls. */
-#ifdef PN_RETRY_IN_PHASE1
-            while (!finished && !accept) {
-#else
+               step) and retries in the next iteration.  (Retrying inside this phase kept the other groups of the warp
+               waiting and let the warps of the CTA drift apart in the ~100 KB unrolled body: measured slower, git history.) */
             for (int attempt = 0; attempt < 1 && !finished; attempt++) {
-#endif
                 double q11 = 0.0;
                 while (tstop_idx < P.n_tstops && P.tstops[tstop_idx] <= t) tstop_idx++;
                 tstop = P.t1;
@@ -800,25 +724,6 @@ struct PnSmall {
 #endif
                             R[lr][j * d + i] = s;
                         }
-#ifdef PN_QR_LOWER_NOISE
-                /* bottom block: sqrt(s2) (L P^-1) (x) I_d, row (m,i) has L[m][c] PI[c] at column (c,i), c <= m */
-                {
-                    const double sd = (ediff == 1.0) ? 1.0 : sqrt(ediff);
-#pragma unroll
-                    for (int lr = 0; lr < RPL; lr++)
-#pragma unroll
-                        for (int c = 0; c < n; c++) {
-                            double lsel = 0.0;
-#pragma unroll
-                            for (int m = 0; m < n; m++)
-                                if (m >= c) lsel = (mB[lr] == m) ? P.L[m * n + c] : lsel;
-                            const double val = lsel * PIv[c] * sd;
-#pragma unroll
-                            for (int i = 0; i < d; i++) B[lr][c * d + i] = (iB[lr] == i) ? val : 0.0;
-                        }
-                }
-                qr_stack(R, B, gl);
-#else
                 /* bottom block: sqrt(s2) (U P^-1) (x) I_d with U'U = L'L upper triangular (pn_params.h): row (m,i) has
                    U[m][c] PI[c] at column (c,i), c >= m, so the block is upper triangular and its rows join the
                    Householder sweep one slot at a time */
@@ -845,7 +750,6 @@ struct PnSmall {
 #define PN_QR_JC D
 #endif
                 pn_qr_rows<G, RPL, D, D, true, PN_QR_JC>(R, B, gl, nullptr);
-#endif
 
                 /* C2 = R^- H' (row-local; rows >= 2d are exactly zero, see RU), S = C2'C2 */
                 double C2[RU][d];

@@ -32,7 +32,8 @@ struct PnSmoothParams {
                                       null: segment i is exactly [off[i], off[i+1]) */
     const double* s_h;             /* [total] h of the step k -> k+1 stored at slot k */
     const double* s_diffusion;     /* [total] */
-    const double* gdiff;           /* [n_traj] global diffusion scale (calibrate) */
+    const double* gdiff;           /* [n_traj] calibrated diffusion sigma_hat^2 * initial_diffusion (sol.diffusions); the covariance
+                                      scale of calibrate_solution! is gdiff / initial_diffusion (integrator_utils.jl:46-57) */
     const double* s_diffusion_mv;  /* [total][d] per-component diffusions (multivariate models; null otherwise) */
     const double* gdiff_mv;        /* [n_traj][d] per-component global scale (FixedMVDiffusion, calibrate)       */
     double* s_x_mean;              /* [total][D]    in: filtered, out: smoothed */
@@ -57,6 +58,9 @@ struct PnSmoothParams {
     int n_obs;
     const int* retcode;     /* [n_traj] return codes of the solve: -Inf unless Success (fenrir.jl:55-59) */
     double* fenrir_ll;      /* [n_traj] out */
+    int kron_logdet;        /* 1: IsometricKronecker layout (EK0 + IWP + scalar diffusion): the reference's data update runs on the
+                               n x n factors and takes logdet of the 1 x 1 factor of S without the factor d (update.jl:140-148,
+                               182-194) -- log det S / n_obs instead of log det S */
 };
 /* extra shared-memory doubles per warp in Fenrir mode (host and kernel must agree) */
 #define PN_FENRIR_EXTRA(D, o) (3 * (D) * (o) + ((D) + (o)) * (o) + 4 * (o))
@@ -168,6 +172,7 @@ __device__ double pn_sm_fenrir_update(const PnSmoothParams& P, const double* u, 
         quad += z[a] * zt[a];
         logdet += log(fabs(Sb[a * o + a]));
     }
+    if (P.kron_logdet) logdet /= (double)o;
     const double ll = -0.5 * quad - 0.5 * (double)o * 1.8378770664093453 - logdet;
     for (int i = lane; i < D * o; i += 32) {
         const int c = i / o, a = i % o;
@@ -230,17 +235,16 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
         const long long tr = (long long)idx;
         const long long a0 = P.step_offsets[tr], a1 = P.counts ? a0 + P.counts[tr] + 1 : P.step_offsets[tr + 1];
         const long long last = a1 - 1;
-        const double sc = (!P.dynamic && P.calibrate) ? sqrt(P.gdiff[tr]) : 1.0;
+        const double sc = (!P.dynamic && P.calibrate) ? sqrt(P.gdiff[tr] / P.initial_diffusion) : 1.0;
         /* x_smooth[N] = x_filt[N] */
         for (int i = lane; i < DD; i += 32) Rs[i] = P.s_x_covfac[last * DD + i];
         for (int i = lane; i < D; i += 32) mus[i] = P.s_x_mean[last * D + i];
         __syncwarp();
         double LL = 0.0;
         long long data_idx = P.n_data - 1;
-        if (fen && data_idx >= 0 && P.s_t[last] == P.data_t[data_idx]) { /* fenrir.jl:87-97 */
+        if (fen && data_idx >= 0 && P.s_t[last] == P.data_t[data_idx]) /* fenrir.jl:87-97 */
             LL += pn_sm_fenrir_update(P, P.data_u + data_idx * P.n_obs, mus, Rs, Xs, Fw, D, lane);
-            data_idx--;
-        }
+        data_idx--; /* unconditional (fenrir.jl:99): a last observation that is not at sol.t[end] is skipped, as in the reference */
         /* outputs of the last point (calibrated) */
         if (!fen)
         for (int i = lane; i < d * d; i += 32) {
@@ -363,7 +367,7 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
             if (fen) { /* fenrir.jl:110-123: data update at this time point */
                 if (data_idx >= 0 && P.s_t[k] == P.data_t[data_idx]) {
                     const double ll = pn_sm_fenrir_update(P, P.data_u + data_idx * P.n_obs, mus, Rs, Xs, Fw, D, lane);
-                    if (ll - ll == 0.0) LL += ll; /* !isinf */
+                    if (!(ll == PN_INF || ll == -PN_INF)) LL += ll; /* !isinf(ll): a NaN propagates (fenrir.jl:118-120) */
                     data_idx--;
                 }
                 continue;

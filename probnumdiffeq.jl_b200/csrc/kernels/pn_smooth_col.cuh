@@ -207,7 +207,7 @@ struct PnSmoothCol {
                         last = P.counts ? a0 + P.counts[idx] : P.step_offsets[idx + 1] - 1;
 #pragma unroll
                         for (int i = 0; i < d; i++)
-                            scv[i] = (!P.dynamic && P.calibrate) ? sqrt(P.gdiff_mv ? P.gdiff_mv[idx * d + i] : P.gdiff[idx]) : 1.0;
+                            scv[i] = (!P.dynamic && P.calibrate) ? sqrt((P.gdiff_mv ? P.gdiff_mv[idx * d + i] : P.gdiff[idx]) / P.initial_diffusion) : 1.0;
                         for (int e = gl; e < D * D; e += G) {
                             const int r = e / D, c = e - r * D;
                             Sm[r * LD + c] = P.s_x_covfac[last * D * D + e];
@@ -222,9 +222,11 @@ struct PnSmoothCol {
                     LL = 0.0;
                     if (P.s_t[last] == P.data_t[data_idx]) { /* fenrir.jl:87-97 */
                         if (gl == 0)
-                            LL += pn_fenrir_update_serial<D, LD, OMAX>(P.obs_H, P.obs_Rn, P.data_u + data_idx * P.n_obs, P.n_obs, Sm, Ms);
-                        data_idx--;
+                            LL += pn_fenrir_update_serial<D, LD, OMAX>(P.obs_H, P.obs_Rn, P.data_u + data_idx * P.n_obs, P.n_obs, Sm, Ms,
+                                                                       P.kron_logdet != 0);
                     }
+                    data_idx--; /* unconditional, as fenrir.jl:99 (`data_idx = length(data.u) - 1`): a last observation that is
+                                   not at sol.t[end] is skipped by the reference, and so it is here */
                 }
                 if (got) {
                     if (!P.dynamic && P.calibrate && !fen) write_record(P, last, Sm, Ms, scv, gl);
@@ -440,8 +442,9 @@ struct PnSmoothCol {
                 }
                 if (doit && fen && data_idx >= 0 && P.s_t[k] == P.data_t[data_idx]) { /* fenrir.jl:110-123 */
                     if (gl == 0) {
-                        const double ll = pn_fenrir_update_serial<D, LD, OMAX>(P.obs_H, P.obs_Rn, P.data_u + data_idx * P.n_obs, P.n_obs, Sm, Ms);
-                        if (ll - ll == 0.0) LL += ll; /* !isinf */
+                        const double ll = pn_fenrir_update_serial<D, LD, OMAX>(P.obs_H, P.obs_Rn, P.data_u + data_idx * P.n_obs, P.n_obs, Sm, Ms,
+                                                                               P.kron_logdet != 0);
+                        if (!(ll == PN_INF || ll == -PN_INF)) LL += ll; /* !isinf(ll): a NaN propagates, as in fenrir.jl:118-120 */
                     }
                     data_idx--;
                 }

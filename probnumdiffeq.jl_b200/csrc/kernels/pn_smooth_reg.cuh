@@ -140,7 +140,7 @@ struct PnSmoothReg {
                         last = P.counts ? a0 + P.counts[idx] : P.step_offsets[idx + 1] - 1;
 #pragma unroll
                         for (int i = 0; i < d; i++)
-                            scv[i] = (!P.dynamic && P.calibrate) ? sqrt(P.gdiff_mv ? P.gdiff_mv[idx * d + i] : P.gdiff[idx]) : 1.0;
+                            scv[i] = (!P.dynamic && P.calibrate) ? sqrt((P.gdiff_mv ? P.gdiff_mv[idx * d + i] : P.gdiff[idx]) / P.initial_diffusion) : 1.0;
                     }
                 }
                 double Rl[RPL][D];

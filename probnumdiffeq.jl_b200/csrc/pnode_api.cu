@@ -32,7 +32,7 @@
 /* calibrate_solution! / set_diffusions! (src/integrator_utils.jl:46-88) for the per-step outputs of a
    FixedDiffusion solve: every saved covariance is scaled by the global MLE and sol.diffusions is overwritten. */
 __global__ void pn_calibrate_saved(long long total, long long n_traj, const long long* __restrict__ off,
-                                   const double* __restrict__ scale /* [n_traj] or null */,
+                                   const double* __restrict__ scale /* [n_traj] or null: sigma_hat^2 * initial_diffusion */, double scale_mul /* 1 / initial_diffusion */,
                                    const double* __restrict__ diffusion /* [n_traj] */, int dd,
                                    double* __restrict__ u_cov, double* __restrict__ s_diffusion, int d,
                                    const double* __restrict__ scale_mv /* [n_traj][d] or null */,
@@ -50,14 +50,31 @@ __global__ void pn_calibrate_saved(long long total, long long n_traj, const long
         int du = 1;
         while (du * du < dd) du++;
         for (int a = 0; a < du; a++)
-            for (int b = 0; b < du; b++) u_cov[i * dd + a * du + b] *= sqrt(scale_mv[lo * d + a % d] * scale_mv[lo * d + b % d]);
+            for (int b = 0; b < du; b++) u_cov[i * dd + a * du + b] *= sqrt(scale_mv[lo * d + a % d] * scale_mv[lo * d + b % d]) * scale_mul;
     } else if (scale) {
-        const double sc = scale[lo];
+        const double sc = scale[lo] * scale_mul;
         for (int k = 0; k < dd; k++) u_cov[i * dd + k] *= sc;
     }
     s_diffusion[i] = diffusion[lo];
     if (s_diffusion_mv)
         for (int a = 0; a < d; a++) s_diffusion_mv[i * d + a] = diffusion_mv[lo * d + a];
+}
+
+/* ... and the saved filter states of a filter-only solve (save_state): right factors scaled by sqrt(sigma_hat^2), column c
+   belongs to component c mod d for the multivariate models (apply_diffusion.jl:35-104) */
+__global__ void pn_calibrate_saved_state(long long total, long long n_traj, const long long* __restrict__ off,
+                                         const double* __restrict__ scale, double scale_mul, const double* __restrict__ scale_mv, int D,
+                                         int d, double* __restrict__ x_covfac) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= total * D * D) return;
+    const long long e = i / ((long long)D * D);
+    const int c = (int)(i % D);
+    long long lo = 0, hi = n_traj;
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (off[mid] <= e) lo = mid; else hi = mid;
+    }
+    x_covfac[i] *= sqrt((scale_mv ? scale_mv[lo * d + c % d] : scale[lo]) * scale_mul);
 }
 
 /* Over-allocated (pitch) layout -> exact CSR: element e of trajectory tr lives at (tr * pitch + e) in the work buffers */
@@ -622,6 +639,13 @@ static size_t cta_smem_bytes(int d, int q, int n_p) {
     return dbl * sizeof(double);
 }
 
+/* SAVE template level of the step kernel: 0 final values only, 1 per-step sol.t / sol.u / sol.pu, 2 additionally the filter
+   state per step (what the smoother sweep, the dense output and save_state = sol.x_filt need) */
+static int save_level(const pnode_config* cfg, bool cta) {
+    if (!cfg->save_everystep) return 0;
+    return (cfg->smooth || cfg->n_saveat > 0 || (cfg->save_state && !cta)) ? 2 : 1;
+}
+
 /* covariance_structure(alg, prior, diffusionmodel) (src/algorithms.jl:132-151) */
 static int resolve_layout(const pnode_config* cfg) {
     if (cfg->alg == PNODE_EK0 && cfg->prior != PNODE_PRIOR_IWP) return PNODE_COV_DENSE; /* "other priors": dense */
@@ -694,6 +718,8 @@ static int validate_config(const pnode_config* cfg) {
         if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 256)
             return fail(PNODE_ERR_ARGUMENT, "D = d(q+1) > 32 runs one CTA per trajectory (lanes_per_traj 0 or 256)");
         if (cfg->smooth) return fail(PNODE_ERR_UNSUPPORTED, "smoothing is not implemented for the CTA-per-trajectory kernel yet");
+        if (cfg->save_everystep && cfg->save_state)
+            return fail(PNODE_ERR_UNSUPPORTED, "save_state with save_everystep (sol.x_filt of every step) is not implemented for the CTA-per-trajectory kernel");
     }
     if (cfg->n_saveat > 0) { /* dense output sol(saveat) */
         if (!cfg->saveat) return fail(PNODE_ERR_ARGUMENT, "saveat is null but n_saveat > 0");
@@ -722,6 +748,30 @@ static int validate_config(const pnode_config* cfg) {
             return fail(PNODE_ERR_ARGUMENT, "observation_noise_cov must be positive (definite)");
         if (cfg->prior != PNODE_PRIOR_IWP || is_mv(cfg->diffusion))
             return fail(PNODE_ERR_UNSUPPORTED, "the Fenrir backward pass is implemented for the IWP prior with scalar diffusion models");
+        if (layout != PNODE_COV_DENSE) {
+            /* the structured layouts carry the data update on their factors: full observations only
+               (src/callbacks/dataupdate.jl:69-71) and a noise covariance of the layout's own shape
+               (to_factorized_matrix, src/covariance_structure.jl:46-58: isotropic for Kronecker, diagonal for blocks) */
+            bool ident = (cfg->n_obs == dul);
+            if (ident && cfg->observation_matrix)
+                for (int a = 0; a < dul; a++)
+                    for (int j = 0; j < dul; j++) ident = ident && (cfg->observation_matrix[a * dul + j] == (a == j ? 1.0 : 0.0));
+            if (!ident) return fail(PNODE_ERR_ARGUMENT, "Partial observations only work with the EK1 right now");
+            if (cfg->observation_noise_cov) {
+                const double* C = cfg->observation_noise_cov;
+                bool diag = true, iso = true;
+                for (int a = 0; a < dul; a++)
+                    for (int j = 0; j < dul; j++) {
+                        if (a != j && C[a * dul + j] != 0.0) diag = false;
+                        if (a == j && C[a * dul + j] != C[0]) iso = false;
+                    }
+                if (!diag || (layout == PNODE_COV_KRONECKER && !iso))
+                    return fail(PNODE_ERR_ARGUMENT,
+                                layout == PNODE_COV_KRONECKER
+                                    ? "observation_noise_cov must be a scalar or a multiple of the identity for the EK0 (Kronecker-factorized covariances); use the EK1 for a matrix-valued noise covariance"
+                                    : "observation_noise_cov must be a scalar or a diagonal matrix for the block-diagonal covariance layout; use the EK1 for a full noise covariance");
+            }
+        }
         if (cfg->n_saveat > 0) return fail(PNODE_ERR_UNSUPPORTED, "saveat and a Fenrir data set cannot be combined (the records stay filtering estimates)");
         if (D > 32) return fail(PNODE_ERR_UNSUPPORTED, "the Fenrir backward pass is implemented for D = d(q+1) <= 32");
     }
@@ -788,7 +838,7 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     if ((rc = mass_preamble(cfg->mass_matrix, cfg->d, &mass_src))) return rc;
     if (cfg->second_order) mass_src = "#define PN_SECOND 1\n" + mass_src;
     rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, is_dynamic(cfg->diffusion),
-                     cfg->save_everystep ? ((cfg->smooth || cfg->n_saveat > 0) ? 2 : 1) : 0, &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
+                     save_level(cfg, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256)), &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
                      layout == PNODE_COV_KRONECKER, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256),
                      layout == PNODE_COV_BLOCKS ? (cfg->alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, is_mv(cfg->diffusion),
                      cfg->prior == PNODE_PRIOR_IOUP, cfg->alg == PNODE_EK0 && layout == PNODE_COV_DENSE, mass_src);
@@ -929,10 +979,19 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
         delete s;
         return fail(PNODE_ERR_ARGUMENT, "invalid device ordinal");
     }
-    CUDA_TRY(cudaSetDevice(cfg->device));
-    CUDA_TRY(cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
+    /* from here on a failure must release what the half-built solver already owns (stream, device buffers) */
+#define CUDA_TRY_S(expr)                                                                                 \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) {                                                                         \
+            pnode_destroy(s);                                                                            \
+            return fail(PNODE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+        }                                                                                                \
+    } while (0)
+    CUDA_TRY_S(cudaSetDevice(cfg->device));
+    CUDA_TRY_S(cudaDeviceGetAttribute(&s->n_sm, cudaDevAttrMultiProcessorCount, cfg->device));
+    CUDA_TRY_S(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_TRY_S(cudaMalloc(&s->d_counter, sizeof(unsigned long long)));
     {
         /* tstops = union(data.t, tstops) (fenrir.jl:46) */
         std::vector<double> ts;
@@ -943,8 +1002,8 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
             ts.erase(std::unique(ts.begin(), ts.end()), ts.end());
         }
         if (!ts.empty()) {
-            CUDA_TRY(cudaMalloc(&s->d_tstops, sizeof(double) * ts.size()));
-            CUDA_TRY(cudaMemcpy(s->d_tstops, ts.data(), sizeof(double) * ts.size(), cudaMemcpyHostToDevice));
+            CUDA_TRY_S(cudaMalloc(&s->d_tstops, sizeof(double) * ts.size()));
+            CUDA_TRY_S(cudaMemcpy(s->d_tstops, ts.data(), sizeof(double) * ts.size(), cudaMemcpyHostToDevice));
             s->host_tstops = ts;
             B.tstops = s->d_tstops;
             B.n_tstops = (long long)ts.size();
@@ -981,18 +1040,18 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
         } else {
             for (int a = 0; a < o; a++) Rn[a * o + a] = std::sqrt(cfg->observation_noise_var);
         }
-        CUDA_TRY(cudaMalloc(&s->d_data_t, sizeof(double) * cfg->n_data));
-        CUDA_TRY(cudaMalloc(&s->d_data_u, sizeof(double) * cfg->n_data * o));
-        CUDA_TRY(cudaMalloc(&s->d_obs_H, sizeof(double) * H.size()));
-        CUDA_TRY(cudaMalloc(&s->d_obs_Rn, sizeof(double) * Rn.size()));
-        CUDA_TRY(cudaMemcpy(s->d_data_t, cfg->data_t, sizeof(double) * cfg->n_data, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(s->d_data_u, cfg->data_u, sizeof(double) * cfg->n_data * o, cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(s->d_obs_H, H.data(), sizeof(double) * H.size(), cudaMemcpyHostToDevice));
-        CUDA_TRY(cudaMemcpy(s->d_obs_Rn, Rn.data(), sizeof(double) * Rn.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY_S(cudaMalloc(&s->d_data_t, sizeof(double) * cfg->n_data));
+        CUDA_TRY_S(cudaMalloc(&s->d_data_u, sizeof(double) * cfg->n_data * o));
+        CUDA_TRY_S(cudaMalloc(&s->d_obs_H, sizeof(double) * H.size()));
+        CUDA_TRY_S(cudaMalloc(&s->d_obs_Rn, sizeof(double) * Rn.size()));
+        CUDA_TRY_S(cudaMemcpy(s->d_data_t, cfg->data_t, sizeof(double) * cfg->n_data, cudaMemcpyHostToDevice));
+        CUDA_TRY_S(cudaMemcpy(s->d_data_u, cfg->data_u, sizeof(double) * cfg->n_data * o, cudaMemcpyHostToDevice));
+        CUDA_TRY_S(cudaMemcpy(s->d_obs_H, H.data(), sizeof(double) * H.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY_S(cudaMemcpy(s->d_obs_Rn, Rn.data(), sizeof(double) * Rn.size(), cudaMemcpyHostToDevice));
     }
     if (cfg->n_forced > 0 && cfg->forced_diffusion) {
-        CUDA_TRY(cudaMalloc(&s->d_forced, sizeof(double) * cfg->n_forced));
-        CUDA_TRY(cudaMemcpy(s->d_forced, cfg->forced_diffusion, sizeof(double) * cfg->n_forced, cudaMemcpyHostToDevice));
+        CUDA_TRY_S(cudaMalloc(&s->d_forced, sizeof(double) * cfg->n_forced));
+        CUDA_TRY_S(cudaMemcpy(s->d_forced, cfg->forced_diffusion, sizeof(double) * cfg->n_forced, cudaMemcpyHostToDevice));
         B.forced_diffusion = s->d_forced;
         B.n_forced = cfg->n_forced;
     }
@@ -1005,14 +1064,14 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
         }
     }
     if (cfg->n_saveat > 0) {
-        CUDA_TRY(cudaMalloc(&s->d_saveat, sizeof(double) * cfg->n_saveat));
-        CUDA_TRY(cudaMemcpy(s->d_saveat, cfg->saveat, sizeof(double) * cfg->n_saveat, cudaMemcpyHostToDevice));
+        CUDA_TRY_S(cudaMalloc(&s->d_saveat, sizeof(double) * cfg->n_saveat));
+        CUDA_TRY_S(cudaMemcpy(s->d_saveat, cfg->saveat, sizeof(double) * cfg->n_saveat, cudaMemcpyHostToDevice));
         s->n_saveat = cfg->n_saveat;
     }
     s->cfg.saveat = nullptr;
     s->cfg.data_t = s->cfg.data_u = s->cfg.observation_matrix = s->cfg.observation_noise_cov = nullptr;
-    int rc = get_kernel(s, cfg->save_everystep ? ((cfg->smooth || cfg->n_saveat > 0) ? 2 : 1) : 0,
-                        cfg->save_everystep ? &s->k_save : &s->k_final);
+#undef CUDA_TRY_S
+    int rc = get_kernel(s, save_level(cfg, s->cta), cfg->save_everystep ? &s->k_save : &s->k_final);
     if (!rc && cfg->smooth) rc = get_smoother(s);
     if (!rc && cfg->n_saveat > 0) rc = get_dense(s);
     if (rc) {
@@ -1129,6 +1188,28 @@ static int alloc_field(pnode_result* r, int field, size_t bytes) {
     return 0;
 }
 
+/* Temporaries of one solve_impl call (timing events, work buffers): released on every exit path, early returns included */
+struct SolveScope {
+    cudaStream_t st;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<void*> bufs;
+    explicit SolveScope(cudaStream_t stream) : st(stream) {}
+    void track(void* ptr) {
+        if (ptr) bufs.push_back(ptr);
+    }
+    void release(void* ptr) { /* free now */
+        auto it = std::find(bufs.begin(), bufs.end(), ptr);
+        if (it == bufs.end()) return;
+        bufs.erase(it);
+        cudaFreeAsync(ptr, st);
+    }
+    ~SolveScope() {
+        for (void* ptr : bufs) cudaFreeAsync(ptr, st);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
+
 static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const double* d_p, pnode_result* r,
                       bool force_count_pass, bool* need_count_pass) {
     const std::vector<double>& host_tstops = s->host_tstops;
@@ -1170,9 +1251,10 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
     P.nf = (long long*)r->f[PNODE_F_NF].d;
     P.retcode = (int*)r->f[PNODE_F_RETCODE].d;
 
-    cudaEvent_t e0, e1;
-    CUDA_TRY(cudaEventCreate(&e0));
-    CUDA_TRY(cudaEventCreate(&e1));
+    SolveScope scope(s->stream);
+    CUDA_TRY(cudaEventCreate(&scope.e0));
+    CUDA_TRY(cudaEventCreate(&scope.e1));
+    cudaEvent_t e0 = scope.e0, e1 = scope.e1;
     CUDA_TRY(cudaEventRecord(e0, s->stream));
     int64_t launches = 0;
     {
@@ -1263,6 +1345,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             }
             CUDA_TRY(cudaMallocAsync(out, bytes, s->stream));
             work_bufs.push_back(*out);
+            scope.track(*out);
             return 0;
         };
         void *w_off = nullptr, *w_t = nullptr, *w_u = nullptr, *w_uc = nullptr, *w_df = nullptr, *w_dfmv = nullptr, *w_x = nullptr,
@@ -1283,10 +1366,11 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         double* d_h = nullptr;
         const bool dense = s->n_saveat > 0;
         const size_t V = N * (size_t)s->n_saveat;
-        if (s->cfg.smooth || dense) {
+        if (s->cfg.smooth || dense || s->cfg.save_state) { /* save_state without smoothing: sol.x_filt */
             if ((rc = alloc_work(PNODE_F_X, T * D * 8, &w_x))) return rc;
             if ((rc = alloc_work(PNODE_F_X_COVFAC, T * D * D * 8, &w_xc))) return rc;
             CUDA_TRY(cudaMallocAsync((void**)&d_h, T * 8, s->stream));
+            scope.track(d_h);
             CUDA_TRY(cudaMemsetAsync(d_h, 0, T * 8, s->stream));
             P.s_x_mean = (double*)w_x;
             P.s_x_covfac = (double*)w_xc;
@@ -1308,11 +1392,9 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 exact_off[i + 1] = exact_off[i] + nacc[i] + 1;
             }
             if (overflow) { /* repeat with the counting-pass layout (solve_common) */
-                for (void* ptr : work_bufs) CUDA_TRY(cudaFreeAsync(ptr, s->stream));
-                if (d_h) CUDA_TRY(cudaFreeAsync(d_h, s->stream));
+                for (void* ptr : work_bufs) scope.release(ptr);
+                if (d_h) scope.release(d_h);
                 CUDA_TRY(cudaStreamSynchronize(s->stream));
-                cudaEventDestroy(e0);
-                cudaEventDestroy(e1);
                 if (need_count_pass) *need_count_pass = true;
                 return need_count_pass ? 0 : fail(PNODE_ERR_CUDA, "pilot segment overflow without a fallback");
             }
@@ -1393,6 +1475,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             Dn.s_x_mean = P.s_x_mean;
             Dn.s_x_covfac = P.s_x_covfac;
             Dn.gdiff = P.diffusion;
+            Dn.initial_diffusion = s->base.initial_diffusion;
             memcpy(Dn.U, s->base.U, sizeof Dn.U);
             Dn.rate = s->base.rate;
             memcpy(Dn.glx, s->base.glx, sizeof Dn.glx);
@@ -1401,13 +1484,21 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             Dn.out_cov = (double*)r->f[PNODE_F_SAVEAT_U_COV].d;
             if (s->cfg.smooth) {
                 CUDA_TRY(cudaMallocAsync((void**)&v_mean, 2 * V * D * 8, s->stream));
+                scope.track(v_mean);
                 CUDA_TRY(cudaMallocAsync((void**)&v_covfac, 2 * V * D * D * 8, s->stream));
+                scope.track(v_covfac);
                 CUDA_TRY(cudaMallocAsync((void**)&v_h, 2 * V * 8, s->stream));
+                scope.track(v_h);
                 CUDA_TRY(cudaMallocAsync((void**)&v_diff, 2 * V * 8, s->stream));
+                scope.track(v_diff);
                 CUDA_TRY(cudaMallocAsync((void**)&vu_mean, 2 * V * du * 8, s->stream));
+                scope.track(vu_mean);
                 CUDA_TRY(cudaMallocAsync((void**)&vu_cov, 2 * V * du * du * 8, s->stream));
+                scope.track(vu_cov);
                 CUDA_TRY(cudaMallocAsync((void**)&v_idx, V * 8, s->stream));
+                scope.track(v_idx);
                 CUDA_TRY(cudaMallocAsync((void**)&v_off, (V + 1) * 8, s->stream));
+                scope.track(v_off);
                 Dn.v_idx = v_idx;
                 Dn.v_mean = v_mean;
                 Dn.v_covfac = v_covfac;
@@ -1455,6 +1546,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 Q.n_obs = s->n_obs;
                 Q.retcode = (const int*)r->f[PNODE_F_RETCODE].d;
                 Q.fenrir_ll = (double*)r->f[PNODE_F_FENRIR_LOGLIK].d;
+                Q.kron_logdet = s->kron ? 1 : 0; /* the reference's Kronecker log-density (update.jl:140-148, 182-194) */
             }
             if ((rc = launch_sweep(Q, n_traj))) return rc;
             launches += 1;
@@ -1489,10 +1581,10 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 launches += 3;
                 for (void* ptr : {(void*)v_mean, (void*)v_covfac, (void*)v_h, (void*)v_diff, (void*)vu_mean, (void*)vu_cov, (void*)v_idx,
                                   (void*)v_off})
-                    CUDA_TRY(cudaFreeAsync(ptr, s->stream));
+                    scope.release(ptr);
             }
         }
-        if (d_h) CUDA_TRY(cudaFreeAsync(d_h, s->stream));
+        if (d_h) scope.release(d_h);
         if (!is_dynamic(s->cfg.diffusion)) {
             /* DIFFUSION holds sigma_hat^2 * initial (calibrate) or the constant initial diffusion */
             const double* scale = nullptr;
@@ -1502,14 +1594,18 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             }
             const int thr = 256;
             const unsigned blocks = (unsigned)((T + thr - 1) / thr);
-            if (s->cfg.calibrate && s->base.initial_diffusion != 1.0) {
-                return fail(PNODE_ERR_UNSUPPORTED, "save_everystep with calibrate=true needs initial_diffusion == 1");
-            }
-            pn_calibrate_saved<<<blocks, thr, 0, s->stream>>>((long long)T, (long long)N, P.step_offsets, scale, P.diffusion,
+            pn_calibrate_saved<<<blocks, thr, 0, s->stream>>>((long long)T, (long long)N, P.step_offsets, scale, 1.0 / s->base.initial_diffusion, P.diffusion,
                                                              du * du, P.s_u_cov, P.s_diffusion, d,
                                                              (scale && s->mv) ? P.diffusion_mv : nullptr, P.diffusion_mv,
                                                              P.s_diffusion_mv);
             launches += 1;
+            if (scale && P.s_x_covfac && !pitch_mode) { /* sol.x_filt of a filter-only solve: apply_diffusion! on every saved factor */
+                const long long ne = (long long)T * D * D;
+                pn_calibrate_saved_state<<<(unsigned)((ne + thr - 1) / thr), thr, 0, s->stream>>>((long long)T, (long long)N, P.step_offsets, scale,
+                                                                                                1.0 / s->base.initial_diffusion,
+                                                                                                s->mv ? P.diffusion_mv : nullptr, D, d, P.s_x_covfac);
+                launches += 1;
+            }
         }
         if (pitch_mode) {
             /* user-facing fields: over-allocated layout -> exact CSR */
@@ -1529,7 +1625,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 launches += 1;
             }
             CUDA_TRY(cudaStreamSynchronize(s->stream)); /* exact_off is a host buffer of this scope */
-            for (void* ptr : work_bufs) CUDA_TRY(cudaFreeAsync(ptr, s->stream));
+            for (void* ptr : work_bufs) scope.release(ptr);
             r->offsets.assign(exact_off.begin(), exact_off.end());
         }
         r->info.total_saved = (int64_t)r->offsets[N];
@@ -1539,8 +1635,6 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
     CUDA_TRY(cudaGetLastError());
     float ms = 0.f;
     CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     r->info.kernel_ms = ms;
     r->info.n_launches = launches + 1; /* + pn_sum_counts below */
     r->info.n_traj = n_traj;
@@ -1552,13 +1646,14 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
     {
         unsigned long long* d_tot = nullptr;
         CUDA_TRY(cudaMallocAsync((void**)&d_tot, 16, s->stream));
+        scope.track(d_tot);
         CUDA_TRY(cudaMemsetAsync(d_tot, 0, 16, s->stream));
         const unsigned blocks = (unsigned)std::min<long long>(((long long)N + 255) / 256, 1024);
         pn_sum_counts<<<blocks, 256, 0, s->stream>>>((long long)N, P.naccept, P.nreject, d_tot);
         unsigned long long tot[2] = {0, 0};
         CUDA_TRY(cudaMemcpyAsync(tot, d_tot, 16, cudaMemcpyDeviceToHost, s->stream));
         CUDA_TRY(cudaStreamSynchronize(s->stream));
-        CUDA_TRY(cudaFreeAsync(d_tot, s->stream));
+        scope.release(d_tot);
         r->info.total_accepted = (int64_t)tot[0];
         r->info.total_rejected = (int64_t)tot[1];
         r->info.d2h_bytes += 16;

@@ -287,6 +287,16 @@ def test_fenrir_configuration_checks(pnlib):
     assert err(saveat=[0.5]).kind == "Unsupported"
     assert err(prior=pnlib.PRIOR_IOUP, rate_parameter=-1.0).kind == "Unsupported"
     assert err(alg=pnlib.EK0, diffusion=pnlib.DIFF_DYNAMIC_MV).kind == "Unsupported"
+    # structured layouts: the reference's data update runs on the factors -- full observations only
+    # (src/callbacks/dataupdate.jl:69-71) and a noise covariance of the layout's own shape (covariance_structure.jl:46-58)
+    for alg in (pnlib.EK0, pnlib.DIAGONAL_EK1):
+        assert pnlib.compile_check(pnlib.make_config(**{**base, "alg": alg})) > 10_000
+        e = err(alg=alg, data_u=[[1.0], [2.0]], observation_matrix=[[1.0, 0.0]])
+        assert e.kind == "ArgumentError" and "Partial observations only work with the EK1 right now" in str(e)
+        assert err(alg=alg, observation_noise_cov=[[0.25, 0.01], [0.01, 0.5]]).kind == "ArgumentError"
+    assert err(alg=pnlib.EK0, observation_noise_cov=[[0.25, 0.0], [0.0, 0.5]]).kind == "ArgumentError"       # not isotropic
+    assert pnlib.compile_check(pnlib.make_config(**{**base, "alg": pnlib.EK0, "observation_noise_cov": [[0.25, 0.0], [0.0, 0.25]]})) > 10_000
+    assert pnlib.compile_check(pnlib.make_config(**{**base, "alg": pnlib.DIAGONAL_EK1, "observation_noise_cov": [[0.25, 0.0], [0.0, 0.5]]})) > 10_000
 
 
 def test_fenrir_update_header_against_reference_formulas(tmp_path):

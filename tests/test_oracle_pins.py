@@ -799,6 +799,24 @@ def test_fenrir_data_loglik_matches_the_joint_gaussian(oracle, alg_name, diffusi
     assert llm == pytest.approx(_joint_data_loglik(s, data_t, data_u, np.eye(8)[:2], Rm), rel=1e-6)
 
 
+def test_fenrir_skips_a_last_observation_that_is_not_at_the_end_point(oracle):
+    """fit_pnsolution_to_data! (src/data_likelihoods/fenrir.jl:87-99): the end-point update happens only if sol.t[end] is a
+    data time, and `data_idx = length(data.u) - 1` is set UNCONDITIONALLY afterwards -- so when data.t[end] < sol.t[end] the
+    reference never folds the last observation in.  The restatement does the same: the value equals the joint-Gaussian
+    log-density of all observations but the last one."""
+    pd = problems.PROBLEMS["lotka_volterra"]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 2, 4), 3)
+    rng = np.random.default_rng(6)
+    data_t = np.array([2.5, 5.0, 7.5])
+    data_u = np.array([[1.0, 1.0]]) + 0.3 * rng.standard_normal((3, 2))
+    cfg = oracle.make_config(2, 3, 4, alg=oracle.EK1, calibrate=False, smooth=True, adaptive=False, dt=2e-2, t0=0, t1=10, tstops=data_t,
+                             cov_backend=oracle.COV_QR)
+    s = oracle.solve(cfg, rhs, pd.u0, pd.p)
+    ll = oracle.fenrir_data_loglik(cfg, s, data_t, data_u, observation_noise_cov=0.09)
+    want = _joint_data_loglik(s, data_t[:-1], data_u[:-1], np.eye(8)[:2], 0.09 * np.eye(2))
+    assert ll == pytest.approx(want, rel=1e-6)
+
+
 @pytest.mark.parametrize("diffusion", ["dynamic", "fixed"])
 def test_filtering_and_fenrir_data_likelihoods_agree(oracle, diffusion):
     """test/data_likelihoods.jl:17-60 (`compare_data_likelihoods`): the data log-likelihood computed by updating on the
