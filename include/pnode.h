@@ -168,7 +168,8 @@ typedef enum pnode_field {
     PNODE_F_U = 14,            /* double [total][d]           sol.u  (smoothed if smooth) */
     PNODE_F_U_COV = 15,        /* double [total][d][d]        Matrix(sol.pu.Sigma)       */
     PNODE_F_DIFFUSIONS = 16,   /* double [total]              sol.diffusions (slot k: step k -> k+1) */
-    PNODE_F_X = 17,            /* double [total][D]           sol.x_filt / sol.x_smooth mean (save_state) */
+    PNODE_F_X = 17,            /* double [total][D]           sol.x_filt / sol.x_smooth mean (save_state; not produced by the
+                                  CTA-per-trajectory kernel, D > 32, which returns the final state only) */
     PNODE_F_X_COVFAC = 18,     /* double [total][D][D]        ... right factor            (save_state) */
     /* multivariate diffusion models (Diagonal(sigma_1^2 .. sigma_d^2), src/diffusions/typedefs.jl) */
     PNODE_F_DIFFUSION_MV = 19,  /* double [n_traj][d]         final / global diffusion per component */
@@ -219,6 +220,17 @@ int pnode_solve_ensemble(pnode_solver* s, int64_t n_traj, const double* u0, cons
    pnode_result_copy.  Used to time the kernels without staging. */
 int pnode_solve_ensemble_device(pnode_solver* s, int64_t n_traj, const double* d_u0, const double* d_p,
                                 pnode_result** out);
+
+/* One ensemble over several devices of one node (replaces the reference's single-process
+   EnsembleThreads loop, SciMLBase `solve(::EnsembleProblem, alg, ensemblealg; trajectories)`): solvers[i] -- created from the
+   same configuration with `device` = the i-th GPU -- solves the contiguous trajectory range pnode_shard_range(n_traj, i,
+   n_solvers) on its own host thread and stream; there is no exchange between the shards.  results[i] receives shard i
+   (concatenate in shard order: saved-point offsets of shard i are relative to that shard).  On failure nothing is returned
+   and the first failing shard's message is in pnode_last_error(). */
+int pnode_solve_ensemble_sharded(pnode_solver* const* solvers, int32_t n_solvers, int64_t n_traj, const double* u0,
+                                 const double* p, pnode_result** results /* [n_solvers] */);
+/* [lo, hi) of shard `shard` out of `n_shards`: floor split, the remainder goes to the low shards. */
+void pnode_shard_range(int64_t n_traj, int32_t shard, int32_t n_shards, int64_t* lo, int64_t* hi);
 
 int pnode_result_info_get(const pnode_result* r, pnode_result_info* info);
 /* Bytes needed for a field (0 if the field was not produced). */

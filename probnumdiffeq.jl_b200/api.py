@@ -143,9 +143,27 @@ class EnsembleProblem:
 
 @dataclasses.dataclass(frozen=True)
 class EnsembleB200:
-    """Ensemble algorithm: all trajectories in one persistent-kernel launch on a B200."""
+    """Ensemble algorithm: all trajectories in one persistent-kernel launch per B200.
+
+    `devices` (a tuple of device ordinals, or "all") shards the ensemble over several GPUs of the node: contiguous trajectory
+    ranges (`shard_range`), one solver + host thread + stream per device inside the library
+    (`pnode_solve_ensemble_sharded`), no exchange between the shards; the solutions come back concatenated in trajectory order
+    (SURVEY.md section 8e).  Default: the single device `device`."""
     device: int = 0
     lanes_per_traj: int = 0
+    devices: object = None
+
+    def device_list(self) -> Tuple[int, ...]:
+        if self.devices is None:
+            return (self.device,)
+        if isinstance(self.devices, str):
+            if self.devices != "all":
+                raise ValueError('devices must be a sequence of device ordinals or "all"')
+            return tuple(range(max(_lib.device_count(), 1)))
+        devs = tuple(int(x) for x in self.devices)
+        if not devs or len(set(devs)) != len(devs):
+            raise ValueError("devices must be a non-empty sequence of distinct device ordinals")
+        return devs
 
 
 @dataclasses.dataclass
@@ -296,21 +314,32 @@ def solve(prob, alg, ensemblealg: Optional[EnsembleB200] = None, *, trajectories
                       save_everystep=save_everystep, maxiters=maxiters, dtmin=dtmin, dtmax=dtmax, tstops=tstops,
                       save_state=save_state, forced_diffusion=forced_diffusion, saveat=saveat)
     t0 = time.time()
-    solver = _lib.Solver(cfg)
+    devs = ens.device_list()
+    if len(devs) > n:
+        devs = devs[:n]
+    solvers = []
     try:
-        res = solver.solve(u0, p)
-        sols = _unpack(res, n, d, save_everystep)
-        if saveat is not None and len(saveat):
-            # dense output sol(saveat) evaluated on the device (src/solution.jl:330-398)
-            su = res.field(_lib.F_SAVEAT_U).reshape(n, len(saveat), d)
-            sc = res.field(_lib.F_SAVEAT_U_COV).reshape(n, len(saveat), d, d)
-            for i, sol_i in enumerate(sols):
-                sol_i.saveat_t, sol_i.saveat_u, sol_i.saveat_cov = np.asarray(saveat, dtype=float), su[i], sc[i]
-        info = res.info
-        res.free()
+        for dev in devs:   # one solver (kernels, stream, work queue) per device, same configuration
+            cfg.device = dev
+            solvers.append(_lib.Solver(cfg))
+        results = [solvers[0].solve(u0, p)] if len(solvers) == 1 else _lib.solve_sharded(solvers, u0, p)
+        sols, infos = [], []
+        for k, res in enumerate(results):   # shard k holds the trajectories shard_range(n, k, len(devs)), in order
+            lo, hi = _lib.shard_range(n, k, len(results))
+            part = _unpack(res, hi - lo, d, save_everystep)
+            if saveat is not None and len(saveat):
+                # dense output sol(saveat) evaluated on the device (src/solution.jl:330-398)
+                su = res.field(_lib.F_SAVEAT_U).reshape(hi - lo, len(saveat), d)
+                sc = res.field(_lib.F_SAVEAT_U_COV).reshape(hi - lo, len(saveat), d, d)
+                for i, sol_i in enumerate(part):
+                    sol_i.saveat_t, sol_i.saveat_u, sol_i.saveat_cov = np.asarray(saveat, dtype=float), su[i], sc[i]
+            sols += part
+            infos.append(res.info)
+            res.free()
     finally:
-        solver.close()
-    out = EnsembleSolution(sols, time.time() - t0, all(s.retcode == "Success" for s in sols), info)
+        for sv in solvers:
+            sv.close()
+    out = EnsembleSolution(sols, time.time() - t0, all(s.retcode == "Success" for s in sols), infos[0] if len(infos) == 1 else infos)
     return out.u[0] if single else out
 
 

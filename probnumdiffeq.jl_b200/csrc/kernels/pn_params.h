@@ -16,6 +16,7 @@ struct PnParams {
     double abstol, reltol, dtmin, dtmax;
     double beta1, beta2, qmin, qmax, gamma, qsteady_min, qsteady_max, qoldinit;
     double qoldinit_pb2; /* qoldinit^beta2 (host-computed) */
+    double inv_qmax, inv_qmin, inv_gamma; /* 1/qmax, 1/qmin, 1/gamma (host-computed, IEEE divisions) */
     double initial_diffusion;
     long long maxiters;
     int calibrate;
@@ -40,6 +41,9 @@ struct PnParams {
        an equivalent right factor of the same preconditioned process-noise covariance, used where an upper-triangular
        noise block lets a sweep skip its leading zero columns */
     double U[PN_MAX_N * PN_MAX_N];
+    /* Qb = L'L, the preconditioned IWP process-noise covariance itself (iwp.jl:84-108), row-major n x n: the Gram + Cholesky
+       route of predict_cov! (predict.jl:84-85) adds s2 (P^-1 Qb P^-1) (x) I_d to X'X */
+    double Qb[PN_MAX_N * PN_MAX_N];
     /* IOUP prior (src/priors/ioup.jl): scalar rate parameter, 16-point Gauss-Legendre rule on [0, 1] (host-computed) */
     double rate;
     double glx[16], glw[16];

@@ -68,6 +68,20 @@ PN_HD double pn_rsqrt(double x) {
     return y;
 }
 
+#ifndef PN_FAST_SCALAR
+#define PN_FAST_SCALAR 1 /* 1: the scalar bookkeeping of a step (powers of h, controller factors, eps(t)) multiplies by reciprocals
+                            (pn_rcp / host-computed constants) instead of IEEE divisions and takes eps from the exponent field:
+                            <= 2 ulp per quantity, ~250 fewer instructions and several ~100-cycle dependent chains per step;
+                            0: the literal divisions / nextafter of round 1 */
+#endif
+/* nextafter(x, +inf) - x for finite x > 0: the spacing of the doubles in x's binade, 2^(e - 52), from the exponent field
+   (exact; subnormal / huge arguments take the library route) */
+__device__ __forceinline__ double pn_ulp_above(double x) {
+    const int ex = (__double2hiint(x) >> 20) & 0x7ff;
+    if (ex > 52 && ex < 0x7ff) return __hiloint2double((ex - 52) << 20, 0);
+    return nextafter(x, 1e300) - x;
+}
+
 // Upper Cholesky of a symmetric M (row-major, only j >= i read) in place: M = U'U, inv[j] = 1/U[j][j].
 // Returns false if a pivot is not positive.
 template <int M_>
@@ -250,6 +264,158 @@ PN_HD void pn_qr_rows(double (&Tt)[RPL][NC], double (&Bt)[RPL][NC], int gl, doub
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// predict_cov! on the reference's own route (filtering/predict.jl:84-85): M = X'X + s2 Qh, Sigma^-.R = cholesky(M).U, with
+// triangularize! only when the factorisation fails (:90).  X = R Ah' is row-distributed in registers; the Gram matrix
+// needs every row on every lane, so the rows are published once in the group's shared-memory exchange region and each
+// lane streams all of them (16-byte broadcast loads) into the accumulators of ITS rows of M -- no cross-lane reduction,
+// and X leaves the registers for the duration of the factorisation.  Arithmetic per lane at D = 12, G = 4: 288 DFMA
+// (Gram) + ~250 (Cholesky) against ~1030 for the Householder sweep of the 2D x D stack.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef PN_PREDICT_CHOL
+#define PN_PREDICT_CHOL 1 /* 0: always triangularize! (Householder QR of the stack, the round-1 kernel) */
+#endif
+/* doubles per group of the exchange region: D*D rounded so that the 32/G groups of a warp start 16 bytes apart modulo the
+   128 bytes of banks (their broadcast loads do not collide) */
+template <int D>
+PN_HD constexpr int pn_xs_doubles() {
+    return ((D * D + 15) / 16) * 16 + 2;
+}
+
+#ifndef PN_R_IN_SMEM
+#define PN_R_IN_SMEM 0 /* 1 (needs PN_PREDICT_CHOL): the filtered factor lives in the group's exchange region BETWEEN iterations and is
+                          loaded at the start of phase 2, so the registers of R are free during phase 1 (f, J, sigma^2, controller) */
+#endif
+/* own rows of a row-cyclic D x D matrix <-> the group's exchange region (row-major) */
+template <int G, int RPL, int D>
+PN_HD void pn_rows_store(double* sx, const double (&R)[RPL][D], int gl) {
+#pragma unroll
+    for (int lr = 0; lr < RPL; lr++) {
+        const int row = lr * G + gl;
+        if (row < D) {
+            double* dst = sx + row * D;
+            if constexpr (D % 2 == 0) {
+#pragma unroll
+                for (int c = 0; c < D; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(R[lr][c], R[lr][c + 1]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < D; c++) dst[c] = R[lr][c];
+            }
+        }
+    }
+}
+template <int G, int RPL, int D>
+PN_HD void pn_rows_load(const double* sx, double (&R)[RPL][D], int gl) {
+#pragma unroll
+    for (int lr = 0; lr < RPL; lr++) {
+        const int row = lr * G + gl;
+        const double* src = sx + (row < D ? row : 0) * D;
+        if constexpr (D % 2 == 0) {
+#pragma unroll
+            for (int c = 0; c < D; c += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(src + c);
+                R[lr][c] = (row < D) ? v.x : 0.0;
+                R[lr][c + 1] = (row < D) ? v.y : 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; c++) R[lr][c] = (row < D) ? src[c] : 0.0;
+        }
+    }
+}
+
+// Right-looking Cholesky of the row-cyclic symmetric M (slot lr of lane gl holds row lr*G + gl; entries j >= row valid, the
+// rest is never read).  On return R holds the upper-triangular factor in the same distribution (zeros left of the
+// diagonal) and the function tells whether every pivot was positive.  The pivot row is broadcast with shuffles; a lane's
+// element of the pivot column is, by symmetry, one of the broadcast values (selected by its lane index).
+template <int G, int RPL, int D>
+PN_HD bool pn_chol_rows(double (&Mw)[RPL][D], double (&R)[RPL][D], int gl) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+        const int ks = k / G, kl = k % G;
+        double rk[D];
+#pragma unroll
+        for (int j = 0; j < D; j++) rk[j] = (j >= k) ? pn_gbcast<G>(Mw[ks][j], kl) : 0.0;
+        ok = ok && (rk[k] > 0.0);
+        const double pinv = pn_rcp(rk[k]);
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++) {
+            const int base = lr * G;
+            if (base + G - 1 <= k) continue; /* every row of this slot is finished */
+            double mik = 0.0;                /* M[row][k] = M[k][row] */
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                if (base + g > k && base + g < D) mik = (gl == g) ? rk[base + g] : mik;
+            const double f = mik * pinv;
+#pragma unroll
+            for (int j = 0; j < D; j++)
+                if (j >= base && j > k) Mw[lr][j] = fma(-f, rk[j], Mw[lr][j]);
+        }
+    }
+    /* U[row][j] = M[row][j] / sqrt(pivot of the row), pivot = M[row][row] as left by the eliminations before it */
+#pragma unroll
+    for (int lr = 0; lr < RPL; lr++) {
+        const int base = lr * G;
+        double piv = 1.0;
+#pragma unroll
+        for (int g = 0; g < G; g++)
+            if (base + g < D) piv = (gl == g) ? Mw[lr][base + g] : piv;
+        const double ri = pn_rsqrt(piv);
+#pragma unroll
+        for (int j = 0; j < D; j++) R[lr][j] = (j >= base + gl && base + gl < D) ? Mw[lr][j] * ri : 0.0;
+    }
+    return ok;
+}
+
+// triangularize! (fast_linalg.jl:70-79) of the stack [X ; B] for ONE trajectory, executed by a single lane on the group's
+// exchange region: the cold path of predict_cov! (predict.jl:90), taken when the Cholesky factorisation of the Gram matrix
+// fails or the diffusion is exactly zero.  X (D x D row-major in shared memory) is reduced in place by Householder
+// reflections, then the rows of the upper-triangular noise block B (brow(m, c) = entry of row (m, i) at column (c, i)) are
+// folded in one at a time with Givens rotations.  Not inlined: its local-memory frame belongs to this path only.
+template <int D, int d, int n>
+__device__ __noinline__ void pn_triangularize_serial(double* X, const double* bfac /* n x n row-major, upper */) {
+    for (int k = 0; k < D; k++) {
+        double tot = 0.0;
+        for (int r = k; r < D; r++) tot += X[r * D + k] * X[r * D + k];
+        if (tot > 0.0) {
+            const double alpha = X[k * D + k], nrm = sqrt(tot), beta = -copysign(nrm, alpha), vk = alpha - beta;
+            const double gam = 1.0 / (tot + fabs(alpha) * nrm);
+            for (int j = k + 1; j < D; j++) {
+                double sj = vk * X[k * D + j];
+                for (int r = k + 1; r < D; r++) sj += X[r * D + k] * X[r * D + j];
+                sj *= gam;
+                X[k * D + j] -= sj * vk;
+                for (int r = k + 1; r < D; r++) X[r * D + j] -= sj * X[r * D + k];
+            }
+            X[k * D + k] = beta;
+        }
+        for (int r = k + 1; r < D; r++) X[r * D + k] = 0.0;
+    }
+    double b[D];
+    for (int m = 0; m < n; m++)
+        for (int i = 0; i < d; i++) {
+            for (int c = 0; c < D; c++) b[c] = 0.0;
+            bool any = false;
+            for (int c = m; c < n; c++) {
+                b[c * d + i] = bfac[m * n + c];
+                any = any || (b[c * d + i] != 0.0);
+            }
+            if (!any) continue;
+            for (int j = m * d + i; j < D; j++) { /* rotate (X[j][j:], b[j:]) so that b[j] vanishes */
+                const double a = X[j * D + j], bb = b[j];
+                if (bb == 0.0) continue;
+                const double rr = sqrt(a * a + bb * bb), cs = a / rr, sn = bb / rr;
+                for (int c = j; c < D; c++) {
+                    const double xv = X[j * D + c], bv = b[c];
+                    X[j * D + c] = cs * xv + sn * bv;
+                    b[c] = cs * bv - sn * xv;
+                }
+            }
+        }
+}
+
 // ode_determine_initdt (OrdinaryDiffEqCore, Hairer-Wanner; restated from SURVEY.md A.6).  Two f evaluations.
 template <class Prob>
 PN_HD double pn_initial_dt(const PnParams& P, const double* u0, const double* pr) {
@@ -347,11 +513,13 @@ struct PnSmall {
        rows >= 2d: row slots lr >= RU never enter the measurement update */
     static constexpr int RU = ((E1B + 1) * d + G - 1) / G < RPL ? ((E1B + 1) * d + G - 1) / G : RPL;
 
-    static __device__ void run(const PnParams& P) {
+    static constexpr int XS = pn_xs_doubles<D>(); /* exchange region per group, doubles */
+    static __device__ void run(const PnParams& P, double* smem) {
         constexpr unsigned FULL = 0xffffffffu;
         const int lane = threadIdx.x & 31;
         const int gl = lane % G;
         const int leader = lane - gl;
+        double* const sx = smem + (size_t)(threadIdx.x / G) * XS; /* this group's exchange region (PN_PREDICT_CHOL) */
 
         /* bottom-block row bookkeeping: slot lr holds stack row D + rb, rb = lr*G + gl = m*d + i */
         int mB[RPL], iB[RPL];
@@ -408,6 +576,9 @@ struct PnSmall {
                         for (int lr = 0; lr < RPL; lr++)
 #pragma unroll
                             for (int c = 0; c < D; c++) R[lr][c] = 0.0;
+#if PN_R_IN_SMEM && PN_PREDICT_CHOL
+                        pn_rows_store<G, RPL, D>(sx, R, gl); /* Sigma_0.R = 0 */
+#endif
                         naccept = nreject = iter = tstop_idx = 0;
                         loglik = 0.0;
                         gdiff = 0.0;
@@ -515,8 +686,13 @@ struct PnSmall {
                 /* hp[k] = h^k/k! ; PIv[c] = h^(q-c+1/2)/(q-c)!  (preconditioning.jl:45-54) */
                 hp[0] = 1.0;
 #pragma unroll
+#if PN_FAST_SCALAR
+                for (int k = 1; k < n; k++) hp[k] = hp[k - 1] * h * (1.0 / (double)k);
+                const double sqh = h * pn_rsqrt(h);
+#else
                 for (int k = 1; k < n; k++) hp[k] = hp[k - 1] * h / (double)k;
                 const double sqh = sqrt(h);
+#endif
 #pragma unroll
                 for (int c = 0; c < n; c++) PIv[c] = hp[Q - c] * sqh;
 #if PN_IOUP
@@ -595,6 +771,23 @@ struct PnSmall {
                     for (int a = 0; a < d; a++)
 #pragma unroll
                         for (int b = 0; b < d; b++) W[a][b] = 0.0;
+#if PN_FAST_SCALAR && !PN_IOUP && !PN_MASS && !PN_SECOND
+                    /* closed form of the same W = H Qh H' with Qh = (P^-1 Qb P^-1) (x) I_d, H = [-J | I | 0]:
+                       W = qh00 J J' - qh01 (J + J') + qh11 I  (3x fewer multiply-adds than summing C'C over the n derivative rows) */
+                    {
+                        const double w00 = P.Qb[0] * PIv[0] * PIv[0], w01 = P.Qb[1] * PIv[0] * PIv[1], w11 = P.Qb[n + 1] * PIv[1] * PIv[1];
+#pragma unroll
+                        for (int a = 0; a < d; a++)
+#pragma unroll
+                            for (int b = 0; b < d; b++) {
+                                if (b < a) continue;
+                                double jj = 0.0;
+#pragma unroll
+                                for (int i = 0; i < d; i++) jj += J[a + d * i] * J[b + d * i];
+                                W[a][b] = w00 * jj - w01 * (J[a + d * b] + J[b + d * a]) + ((a == b) ? w11 : 0.0);
+                            }
+                    }
+#else
 #pragma unroll
                     for (int m = 0; m < n; m++) {
 #if PN_IOUP
@@ -627,6 +820,7 @@ struct PnSmall {
                                     if (b >= a) W[a][b] += c[a] * c[b];
                         }
                     }
+#endif
                     double wdiag[d];
 #pragma unroll
                     for (int a = 0; a < d; a++) wdiag[a] = W[a][a];
@@ -667,18 +861,22 @@ struct PnSmall {
                 if (ADAPTIVE) {
                     /* stepsize_controller!(::PIController) (OrdinaryDiffEqCore) */
                     if (EEst == 0.0) {
-                        qq = 1.0 / P.qmax;
+                        qq = P.inv_qmax;
                     } else {
                         /* EEst^beta1 / qold^beta2 as exp(beta * log x); log(EEst) is reused for qold^beta2 of the
                            next step (qold = max(EEst, qoldinit)), so a step costs one log and two exp */
                         lEE = log(EEst);
                         q11 = exp(P.beta1 * lEE);
                         qq = q11 * pn_rcp(qold_pb2 * P.gamma);
-                        qq = fmax(1.0 / P.qmax, fmin(1.0 / P.qmin, qq));
+                        qq = fmax(P.inv_qmax, fmin(P.inv_qmin, qq));
                     }
                     if (!accept) { /* step_reject_controller! */
                         nreject++;
-                        dt = dt / fmin(1.0 / P.qmin, q11 / P.gamma);
+#if PN_FAST_SCALAR
+                        dt = dt * pn_rcp(fmin(P.inv_qmin, q11 * P.inv_gamma));
+#else
+                        dt = dt / fmin(P.inv_qmin, q11 / P.gamma);
+#endif
                     }
                 }
                 ediff = DYNAMIC ? ldiff : P.initial_diffusion;
@@ -704,6 +902,10 @@ struct PnSmall {
                a function of its own history only (bit-reproducible runs; the counting and the save pass agree). */
             {
                 double B[RPL][D];
+#if PN_R_IN_SMEM && PN_PREDICT_CHOL
+                __syncwarp();
+                pn_rows_load<G, RPL, D>(sx, R, gl); /* the filtered factor of the previous iteration */
+#endif
                 /* top block: X = R Ah'  (row-local; ascending j is safe in place) */
 #pragma unroll
                 for (int lr = 0; lr < RPL; lr++)
@@ -724,6 +926,100 @@ struct PnSmall {
 #endif
                             R[lr][j * d + i] = s;
                         }
+#if PN_PREDICT_CHOL
+                /* predict_cov! (predict.jl:75-92): M = X'X + s2 Qh, R^- = cholesky(M).U; triangularize! if that fails.
+                   Groups without an accepted step keep their factor bit for bit (h = 0 made X = R above). */
+                {
+                    (void)B;
+                    /* (1) publish the own rows of X */
+                    pn_rows_store<G, RPL, D>(sx, R, gl);
+                    __syncwarp();
+                    /* (2) accumulators of the own rows start from s2 Qh = s2 (P^-1 Qb P^-1) (x) I_d, Qb = L'L (iwp.jl:74-108):
+                       row (m,i) has s2 PI[m] Qb[m][c] PI[c] at column (c,i) */
+                    double Mw[RPL][D];
+#pragma unroll
+                    for (int lr = 0; lr < RPL; lr++) {
+                        double pim = 0.0; /* s2 PI[m] of the own row (m, i) */
+#pragma unroll
+                        for (int m = 0; m < n; m++) pim = (mB[lr] == m) ? PIv[m] * ediff : pim;
+#pragma unroll
+                        for (int c = 0; c < n; c++) {
+#if PN_IOUP
+                            double qsel = 0.0; /* Qb = Uh'Uh */
+#pragma unroll
+                            for (int m = 0; m < n; m++) {
+                                double qmc = 0.0;
+#pragma unroll
+                                for (int r = 0; r < n; r++)
+                                    if (r <= m && r <= c) qmc += Uh[r][m] * Uh[r][c];
+                                qsel = (mB[lr] == m) ? qmc : qsel;
+                            }
+#else
+                            const double qsel = (mB[lr] < n) ? P.Qb[mB[lr] * n + c] : 0.0; /* constant-bank load, run-time row */
+#endif
+                            const double val = qsel * pim * PIv[c];
+#pragma unroll
+                            for (int i = 0; i < d; i++) Mw[lr][c * d + i] = (iB[lr] == i) ? val : 0.0;
+                        }
+                    }
+                    /* (3) Gram matrix: stream every row of X from the exchange region */
+#ifndef PN_GRAM_UNROLL
+#define PN_GRAM_UNROLL 2
+#endif
+#define PN_STR2(x) #x
+#define PN_PRAGMA_UNROLL(k) _Pragma(PN_STR2(unroll k))
+                    PN_PRAGMA_UNROLL(PN_GRAM_UNROLL)
+                    for (int r = 0; r < D; r++) {
+                        double xr[D], xo[RPL];
+                        const double* src = sx + r * D;
+                        if constexpr (D % 2 == 0) {
+#pragma unroll
+                            for (int c = 0; c < D; c += 2) {
+                                const double2 v = *reinterpret_cast<const double2*>(src + c);
+                                xr[c] = v.x;
+                                xr[c + 1] = v.y;
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < D; c++) xr[c] = src[c];
+                        }
+#pragma unroll
+                        for (int lr = 0; lr < RPL; lr++) xo[lr] = (lr * G + gl < D) ? src[lr * G + gl] : 0.0;
+#pragma unroll
+                        for (int lr = 0; lr < RPL; lr++)
+#pragma unroll
+                            for (int j = 0; j < D; j++)
+                                if (j >= lr * G) Mw[lr][j] = fma(xo[lr], xr[j], Mw[lr][j]);
+                    }
+                    /* (4) factorise; idle groups and zero diffusion (predict.jl:71-74 keeps X, which the update below needs
+                       in triangular form) do not count as failures of the Cholesky route */
+                    bool ok = pn_chol_rows<G, RPL, D>(Mw, R, gl);
+#ifdef PN_FORCE_CHOL_FAIL
+                    ok = ok && ((naccept % PN_FORCE_CHOL_FAIL) != 0); /* test hook: exercise the fallback on every N-th step */
+#endif
+                    const bool redo = accept && (!ok || ediff == 0.0);
+                    if (__any_sync(FULL, redo)) { /* predict.jl:90: triangularize!(stack) -- cold path, one lane per trajectory */
+                        if (redo && gl == 0) {
+                            double bf[n * n]; /* sqrt(s2) (U P^-1): the noise block's n x n factor */
+                            const double sd = (ediff == 1.0) ? 1.0 : sqrt(ediff);
+#pragma unroll
+                            for (int m = 0; m < n; m++)
+#pragma unroll
+                                for (int c = 0; c < n; c++) /* (unrolled: a run-time index would demote PIv to local memory) */
+#if PN_IOUP
+                                    bf[m * n + c] = (c >= m) ? Uh[m][c] * PIv[c] * sd : 0.0;
+#else
+                                    bf[m * n + c] = (c >= m) ? P.U[m * n + c] * PIv[c] * sd : 0.0;
+#endif
+                            pn_triangularize_serial<D, d, n>(sx, bf);
+                        }
+                        __syncwarp();
+                    }
+                    if (redo || !accept) /* take the factor from the exchange region: the fallback's result / the untouched X = R */
+                        pn_rows_load<G, RPL, D>(sx, R, gl);
+                    __syncwarp(); /* the region is rewritten in the next iteration */
+                }
+#else
                 /* bottom block: sqrt(s2) (U P^-1) (x) I_d with U'U = L'L upper triangular (pn_params.h): row (m,i) has
                    U[m][c] PI[c] at column (c,i), c >= m, so the block is upper triangular and its rows join the
                    Householder sweep one slot at a time */
@@ -751,6 +1047,7 @@ struct PnSmall {
 #endif
                 pn_qr_rows<G, RPL, D, D, true, PN_QR_JC>(R, B, gl, nullptr);
 
+#endif /* PN_PREDICT_CHOL */
                 /* C2 = R^- H' (row-local; rows >= 2d are exactly zero, see RU), S = C2'C2 */
                 double C2[RU][d];
                 double S[d][d];
@@ -857,6 +1154,9 @@ struct PnSmall {
                         R[lr][c] = r;
                     }
                 }
+#if PN_R_IN_SMEM && PN_PREDICT_CHOL
+                if (accept) pn_rows_store<G, RPL, D>(sx, R, gl); /* x_filt.Sigma.R for the next iteration (idle groups: the region still holds it) */
+#endif
                 if (accept) {
                     /* loopfooter! accept branch (OrdinaryDiffEqCore) */
                     double dtnew = dt;
@@ -864,11 +1164,19 @@ struct PnSmall {
                         if (P.qsteady_min <= qq && qq <= P.qsteady_max) qq = 1.0;
                         qold = fmax(EEst, P.qoldinit);
                         qold_pb2 = (EEst > P.qoldinit) ? exp(P.beta2 * lEE) : P.qoldinit_pb2;
+#if PN_FAST_SCALAR
+                        dtnew = dt * pn_rcp(qq);
+#else
                         dtnew = dt / qq;
+#endif
                     }
                     const double ttmp = t + h;
                     const double ref = fmax(fabs(t), fabs(tstop));
+#if PN_FAST_SCALAR
+                    const double epsref = pn_ulp_above(ref);
+#else
                     const double epsref = nextafter(ref, 1e300) - ref;
+#endif
                     t = (fabs(ttmp - tstop) < 100.0 * epsref) ? tstop : ttmp;
                     dt = dtnew;
                     naccept++;
@@ -1057,7 +1365,8 @@ __device__ __forceinline__ void pn_init_entry(const PnParams& P, double* init_mu
 
 template <class Prob, int Q, int G, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 __device__ __forceinline__ void pn_small_entry(const PnParams& P) {
-    PnSmall<Prob, Q, G, ADAPTIVE, DYNAMIC, SAVE>::run(P);
+    extern __shared__ double pn_small_shared[]; /* (PN_THREADS / G) exchange regions of pn_xs_doubles<D>() doubles */
+    PnSmall<Prob, Q, G, ADAPTIVE, DYNAMIC, SAVE>::run(P, pn_small_shared);
 }
 
 #endif /* PN_SMALL_CUH */

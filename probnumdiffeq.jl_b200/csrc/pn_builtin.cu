@@ -38,12 +38,12 @@ static const PnBuiltinEntry g_table[] = {
     /* cfg2: Lotka-Volterra EK0(order=3), adaptive, filter only, 1M trajectories */
     PN_ENTRY_KRON("lotka_volterra", PnLotkaVolterra, 3, 1, 1, 0),
     /* cfg5: ROBER / OREGO stiff EK1(order=3), adaptive, filter only (bench.py headline) */
-    PN_ENTRY("rober", PnRober, 3, 4, 1, 1, 0),
-    PN_ENTRY("orego", PnOrego, 3, 4, 1, 1, 0),
+    PN_ENTRY("rober", PnRober, 3, 2, 1, 1, 0),
+    PN_ENTRY("orego", PnOrego, 3, 2, 1, 1, 0),
     /* cfg1: FitzHugh-Nagumo EK1(order=3) */
     PN_ENTRY("fitzhugh_nagumo", PnFitzHughNagumo, 3, 2, 1, 1, 0),
     /* cfg3: Van der Pol EK1(order=5) */
-    PN_ENTRY("vanderpol", PnVanDerPol, 5, 4, 1, 1, 0),
+    PN_ENTRY("vanderpol", PnVanDerPol, 5, 2, 1, 1, 0),
     /* Lotka-Volterra through the dense EK1 path */
     PN_ENTRY("lotka_volterra", PnLotkaVolterra, 3, 2, 1, 1, 0),
 };

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pnode.h"
@@ -295,12 +296,26 @@ static double factorial_d(int k) {
     return f;
 }
 
-static int auto_lanes(int D) {
-    /* registers per lane ~ 2 * 2 * D * ceil(D/G) (stack) must stay below ~150 doubles-worth */
+/* lanes per trajectory of the register-resident Householder sweeps (dense-output kernel; the step kernel when built with
+   PN_PREDICT_CHOL=0): the 2D x D stack keeps 2 D ceil(D/G) doubles per lane */
+static int auto_lanes_qr(int D) {
     const int cand[] = {2, 4, 8, 16, 32};
     for (int g : cand) {
         int rpl = (D + g - 1) / g;
         if (2 * rpl * D <= 80) return g;
+    }
+    return 32;
+}
+/* lanes per trajectory of the step kernel (Gram + Cholesky predict): a lane keeps its D ceil(D/G) entries of the factor and
+   about half as many accumulators of the Gram matrix; the scalar part of a step (f, J, sigma^2, controller) is replicated
+   in the group, so fewer lanes mean less replicated work: D = 12 runs 2 lanes (measured 2.06e9 against 1.45e9 steps/s
+   with 4 on ROBER, profiles/r2c_variants.jsonl) */
+static int auto_lanes(int D) {
+    if (env_int("PNODE_QR_LANES", 0)) return auto_lanes_qr(D);
+    const int cand[] = {2, 4, 8, 16, 32};
+    for (int g : cand) {
+        int rpl = (D + g - 1) / g;
+        if (rpl * D <= 72) return g;
     }
     return 32;
 }
@@ -321,6 +336,13 @@ static size_t smooth_reg_smem_bytes(int d, int q, int G) {
     const int PHASE = (G >= 16) ? 0 : G;
     const int REGION = ((RAW - PHASE + 15) / 16) * 16 + PHASE;
     return (size_t)REGION * (PN_SMR_THREADS / G) * 8;
+}
+
+/* group-per-trajectory kernel: threads per CTA (the ahead-of-time instantiations are built for PN_THREADS) and the dynamic
+   shared memory of its per-group exchange regions (must match pn_xs_doubles<D>() in pn_small.cuh) */
+static size_t small_smem_bytes(int D, int G, int threads) {
+    const size_t xs = ((size_t)(D * D + 15) / 16) * 16 + 2;
+    return (size_t)(threads / G) * xs * sizeof(double);
 }
 
 static bool is_dynamic(int diffusion) { return diffusion == PNODE_DIFF_DYNAMIC || diffusion == PNODE_DIFF_DYNAMIC_MV; }
@@ -515,6 +537,11 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
         name = sn;
     }
     out->threads = s->cta ? PN_CTA_THREADS : ((s->kron || s->blocks) ? 128 : env_int("PNODE_THREADS", PN_THREADS));
+    if (!s->cta && !s->kron && !s->blocks) {
+        /* one exchange region per group: large states with few lanes per trajectory run smaller CTAs */
+        while (out->threads > 32 && small_smem_bytes(s->D, s->G, out->threads) > 200 * 1024) out->threads /= 2;
+        s->smem = small_smem_bytes(s->D, s->G, out->threads);
+    }
     rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0, is_dynamic(s->cfg.diffusion), save, &cubin, out->threads,
                      env_int("PNODE_MIN_BLOCKS", 1), s->kron, s->cta,
                      s->blocks ? (s->cfg.alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, s->mv, s->cfg.prior == PNODE_PRIOR_IOUP,
@@ -552,6 +579,7 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
                 out->rt_fn = tab[i].fn;
                 out->rt_init = tab[i].init_fn;
                 out->threads = s->cta ? PN_CTA_THREADS : ((s->kron || s->blocks) ? 128 : PN_THREADS);
+                if (!s->cta && !s->kron && !s->blocks) s->smem = small_smem_bytes(s->D, s->G, out->threads);
                 if (s->smem > 48 * 1024)
                     CUDA_TRY(cudaFuncSetAttribute(out->rt_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
                 int nblk = 0;
@@ -614,7 +642,7 @@ static int get_dense(pnode_solver* s) {
     Kernel* out = &s->k_dense;
     if (out->valid()) return 0;
     auto t0 = std::chrono::steady_clock::now();
-    s->Gd = auto_lanes(s->D);
+    s->Gd = auto_lanes_qr(s->D);
     out->threads = 256;
     int rc = load_driver();
     if (rc) return rc;
@@ -718,8 +746,6 @@ static int validate_config(const pnode_config* cfg) {
         if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 256)
             return fail(PNODE_ERR_ARGUMENT, "D = d(q+1) > 32 runs one CTA per trajectory (lanes_per_traj 0 or 256)");
         if (cfg->smooth) return fail(PNODE_ERR_UNSUPPORTED, "smoothing is not implemented for the CTA-per-trajectory kernel yet");
-        if (cfg->save_everystep && cfg->save_state)
-            return fail(PNODE_ERR_UNSUPPORTED, "save_state with save_everystep (sol.x_filt of every step) is not implemented for the CTA-per-trajectory kernel");
     }
     if (cfg->n_saveat > 0) { /* dense output sol(saveat) */
         if (!cfg->saveat) return fail(PNODE_ERR_ARGUMENT, "saveat is null but n_saveat > 0");
@@ -853,7 +879,7 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     }
     if (cfg->n_saveat > 0) {
         std::vector<char> c3;
-        if ((rc = nvrtc_dense_cubin(cfg->d, cfg->q, auto_lanes(D), cfg->prior == PNODE_PRIOR_IOUP, &c3, cfg->second_order != 0))) return rc;
+        if ((rc = nvrtc_dense_cubin(cfg->d, cfg->q, auto_lanes_qr(D), cfg->prior == PNODE_PRIOR_IOUP, &c3, cfg->second_order != 0))) return rc;
         total += (int64_t)c3.size();
     }
     if (cubin_bytes) *cubin_bytes = total;
@@ -884,8 +910,8 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     s->blocks = (resolve_layout(cfg) == PNODE_COV_BLOCKS);
     s->mv = is_mv(cfg->diffusion);
     s->cta = !s->kron && !s->blocks && (D > 32 || cfg->lanes_per_traj == 256);
-    s->smem = s->cta ? cta_smem_bytes(cfg->d, cfg->q, cfg->n_p) : 0;
     s->G = (s->kron || s->blocks) ? 1 : (s->cta ? 256 : (cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D)));
+    s->smem = s->cta ? cta_smem_bytes(cfg->d, cfg->q, cfg->n_p) : 0; /* group-per-trajectory kernel: set with its thread count in get_kernel */
     /* ---- constants ---- */
     PnParams& B = s->base;
     memset(&B, 0, sizeof B);
@@ -906,6 +932,9 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     B.qsteady_max = cfg->qsteady_max > 0.0 ? cfg->qsteady_max : 1.0;
     B.qoldinit = cfg->qoldinit > 0.0 ? cfg->qoldinit : 1e-4;
     B.qoldinit_pb2 = std::pow(B.qoldinit, B.beta2);
+    B.inv_qmax = 1.0 / B.qmax;
+    B.inv_qmin = 1.0 / B.qmin;
+    B.inv_gamma = 1.0 / B.gamma;
     B.initial_diffusion = cfg->initial_diffusion > 0.0 ? cfg->initial_diffusion : 1.0;
     B.maxiters = cfg->maxiters > 0 ? cfg->maxiters : 1000000;
     B.calibrate = cfg->calibrate;
@@ -918,6 +947,16 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
                 double fq = factorial_d(q - c);
                 B.L[m * n + c] = std::sqrt((double)(2 * q - 2 * m + 1)) * (fq * fq) / factorial_d(m - c) /
                                  factorial_d(2 * q - c - m + 1);
+            }
+    }
+    {
+        /* Qb = L'L accumulated in long double */
+        const int n = cfg->q + 1;
+        for (int a = 0; a < n; a++)
+            for (int b = 0; b < n; b++) {
+                long double acc = 0.0L;
+                for (int m = 0; m < n; m++) acc += (long double)B.L[m * n + a] * (long double)B.L[m * n + b];
+                B.Qb[a * n + b] = (double)acc;
             }
     }
     {
@@ -1356,6 +1395,9 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         if ((rc = alloc_work(PNODE_F_U_COV, T * du * du * 8, &w_uc))) return rc;
         if ((rc = alloc_work(PNODE_F_DIFFUSIONS, T * 8, &w_df))) return rc;
         if (s->mv && (rc = alloc_work(PNODE_F_DIFFUSIONS_MV, T * d * 8, &w_dfmv))) return rc;
+        /* slot k of a trajectory's diffusions belongs to the step k -> k+1: its last slot is never written, keep it defined */
+        CUDA_TRY(cudaMemsetAsync(w_df, 0, T * 8, s->stream));
+        if (w_dfmv) CUDA_TRY(cudaMemsetAsync(w_dfmv, 0, T * d * 8, s->stream));
         CUDA_TRY(cudaMemcpyAsync(w_off, r->offsets.data(), (N + 1) * 8, cudaMemcpyHostToDevice, s->stream));
         P.step_offsets = (const long long*)w_off;
         P.s_t = (double*)w_t;
@@ -1366,7 +1408,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         double* d_h = nullptr;
         const bool dense = s->n_saveat > 0;
         const size_t V = N * (size_t)s->n_saveat;
-        if (s->cfg.smooth || dense || s->cfg.save_state) { /* save_state without smoothing: sol.x_filt */
+        if (s->cfg.smooth || dense || (s->cfg.save_state && !s->cta)) { /* save_state without smoothing: sol.x_filt (group / thread kernels) */
             if ((rc = alloc_work(PNODE_F_X, T * D * 8, &w_x))) return rc;
             if ((rc = alloc_work(PNODE_F_X_COVFAC, T * D * D * 8, &w_xc))) return rc;
             CUDA_TRY(cudaMallocAsync((void**)&d_h, T * 8, s->stream));
@@ -1722,6 +1764,50 @@ extern "C" int pnode_solve_ensemble(pnode_solver* s, int64_t n_traj, const doubl
 extern "C" int pnode_solve_ensemble_device(pnode_solver* s, int64_t n_traj, const double* d_u0, const double* d_p,
                                            pnode_result** out) {
     return solve_common(s, n_traj, d_u0, d_p, true, out);
+}
+
+extern "C" void pnode_shard_range(int64_t n_traj, int32_t shard, int32_t n_shards, int64_t* lo, int64_t* hi) {
+    const int64_t base = n_traj / n_shards, rem = n_traj % n_shards;
+    const int64_t l = shard * base + std::min<int64_t>(shard, rem);
+    if (lo) *lo = l;
+    if (hi) *hi = l + base + (shard < rem ? 1 : 0);
+}
+
+extern "C" int pnode_solve_ensemble_sharded(pnode_solver* const* solvers, int32_t n_solvers, int64_t n_traj, const double* u0,
+                                            const double* p, pnode_result** results) {
+    if (!solvers || !results || n_solvers < 1) return fail(PNODE_ERR_ARGUMENT, "null argument");
+    if (n_traj < n_solvers) return fail(PNODE_ERR_ARGUMENT, "trajectories must be at least the number of devices");
+    for (int i = 0; i < n_solvers; i++) {
+        results[i] = nullptr;
+        if (!solvers[i]) return fail(PNODE_ERR_ARGUMENT, "null solver");
+        for (int j = 0; j < i; j++)
+            if (solvers[j] == solvers[i]) return fail(PNODE_ERR_ARGUMENT, "a pnode_solver is not thread-safe: pass one solver per device");
+        if (solvers[i]->cfg.d != solvers[0]->cfg.d || solvers[i]->cfg.n_p != solvers[0]->cfg.n_p ||
+            solvers[i]->cfg.second_order != solvers[0]->cfg.second_order)
+            return fail(PNODE_ERR_DIMENSION, "the solvers of one sharded solve must share the problem dimensions");
+    }
+    const int dim = solvers[0]->cfg.d * (solvers[0]->cfg.second_order ? 2 : 1), n_p = std::max(solvers[0]->cfg.n_p, 0);
+    std::vector<int> rcs((size_t)n_solvers, 0);
+    std::vector<std::string> errs((size_t)n_solvers);
+    std::vector<std::thread> threads;
+    for (int i = 0; i < n_solvers; i++)
+        threads.emplace_back([&, i]() { /* one host thread (and the solver's own stream) per device */
+            int64_t lo = 0, hi = 0;
+            pnode_shard_range(n_traj, i, n_solvers, &lo, &hi);
+            rcs[i] = solve_common(solvers[i], hi - lo, u0 + lo * dim, p ? p + lo * n_p : nullptr, false, &results[i]);
+            if (rcs[i]) errs[i] = g_err; /* thread-local */
+        });
+    for (auto& t : threads) t.join();
+    for (int i = 0; i < n_solvers; i++)
+        if (rcs[i]) {
+            for (int j = 0; j < n_solvers; j++)
+                if (results[j]) {
+                    pnode_result_free(results[j]);
+                    results[j] = nullptr;
+                }
+            return fail(rcs[i], "shard " + std::to_string(i) + ": " + errs[i]);
+        }
+    return 0;
 }
 
 extern "C" int pnode_result_info_get(const pnode_result* r, pnode_result_info* info) {

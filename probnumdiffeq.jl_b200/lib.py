@@ -36,7 +36,7 @@ EXPORTS = [
     "pnode_device_count", "pnode_last_error", "pnode_abi_version", "pnode_create", "pnode_destroy",
     "pnode_compile_check", "pnode_compile_seconds", "pnode_solve_ensemble", "pnode_solve_ensemble_device",
     "pnode_result_info_get", "pnode_result_field_bytes", "pnode_result_copy", "pnode_result_device_ptr",
-    "pnode_result_free", "pnode_measure_fp64_peak",
+    "pnode_result_free", "pnode_measure_fp64_peak", "pnode_solve_ensemble_sharded", "pnode_shard_range",
 ]
 
 
@@ -121,6 +121,10 @@ def load():
     lib.pnode_result_free.argtypes = [vp]
     lib.pnode_measure_fp64_peak.restype = C.c_int
     lib.pnode_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.pnode_solve_ensemble_sharded.restype = C.c_int
+    lib.pnode_solve_ensemble_sharded.argtypes = [C.POINTER(vp), C.c_int32, C.c_int64, dp, dp, C.POINTER(vp)]
+    lib.pnode_shard_range.restype = None
+    lib.pnode_shard_range.argtypes = [C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 
@@ -192,6 +196,27 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
         c.mass_matrix = a.ctypes.data_as(C.POINTER(C.c_double))
     c._keep = keep
     return c
+
+
+def shard_range(n_traj: int, shard: int, n_shards: int):
+    """[lo, hi) of `shard` (pnode_shard_range: floor split, remainder to the low shards)."""
+    lo, hi = C.c_int64(0), C.c_int64(0)
+    load().pnode_shard_range(n_traj, shard, n_shards, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+def solve_sharded(solvers, u0: np.ndarray, p: np.ndarray):
+    """One ensemble over several devices (pnode_solve_ensemble_sharded): `solvers[i]` -- one per device, same configuration --
+    solves the contiguous range shard_range(n, i, len(solvers)) on its own host thread inside the library.  Returns the
+    per-shard Results in shard order."""
+    u0 = np.ascontiguousarray(u0, dtype=np.float64)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    k = len(solvers)
+    hs = (C.c_void_p * k)(*[s._h for s in solvers])
+    rs = (C.c_void_p * k)()
+    dp = C.POINTER(C.c_double)
+    _check(load().pnode_solve_ensemble_sharded(hs, k, u0.shape[0], u0.ctypes.data_as(dp), p.ctypes.data_as(dp) if p.size else None, rs))
+    return [Result(C.c_void_p(rs[i]), solvers[i]) for i in range(k)]
 
 
 def measure_fp64_peak(device: int = 0) -> float:

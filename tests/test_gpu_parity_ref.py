@@ -138,7 +138,7 @@ def test_cfg3_vdp_q5_smoother_vs_oracle(oracle, monkeypatch, kind, t1):
     for forced, k in ((True, 10.0), (False, 20.0)):
         kw = dict(base, forced_diffusion=sig) if forced else dict(base)
         g = _gpu_smooth(pd, u0, p, 5, adaptive=False, dt=t1, t0=0.0, t1=t1, tstops=grid, **({"forced_diffusion": sig} if forced else {}))
-        assert g["info"].lanes_per_traj == 4                       # filter <.,5,4>; the sweep runs 8 lanes per trajectory
+        assert g["info"].lanes_per_traj == 2                       # filter <.,5,2>; the sweep runs 8 lanes per trajectory
         for backend in (oracle.COV_QR, oracle.COV_REF):
             kwb = dict(kw, cov_backend=backend)
             ob = oracle.solve(oracle.make_config(2, 5, 1, **kwb), rhs, u0[0], p[0])
@@ -151,28 +151,36 @@ def test_cfg3_vdp_q5_smoother_vs_oracle(oracle, monkeypatch, kind, t1):
 
 
 def test_cfg3_vdp_q5_smoother_adaptive_ensemble_vs_oracle(oracle):
-    """Free-running adaptive cfg3 ensemble (ragged lengths, idle groups in the sweep's warps): every trajectory whose
-    accept/reject pattern matches the oracle's is compared on its smoothed means; all of them on the end point."""
+    """Free-running adaptive cfg3 ensemble (ragged lengths, idle groups in the sweep's warps).  The stiff Van der Pol step
+    pattern is rounding-sensitive: the oracle itself changes its number of steps under rounding-level
+    perturbations (tests/floor.py: the other covariance back-end, fused multiply-adds, ONE ulp on one initial derivative) on
+    most of these trajectories.  So: every trajectory must end within 1e-5 of the oracle and take a number of steps inside
+    the oracle's own envelope (+-1); trajectories whose envelope is a single value must reproduce it (one miss allowed);
+    and wherever the step count equals the oracle's, the smoothed means are compared point by point."""
+    import floor as F
     n = 12
     pd, u0, p = _inputs("vanderpol", n, 106, dp=0.2)
     u0[:, 0] += 0.1 * np.random.default_rng(7).uniform(-1, 1, n)
     g = _gpu_smooth(pd, u0, p, 5, adaptive=True, t0=0.0, t1=0.5)
     rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 5)
-    cfg = oracle.make_config(2, 5, 1, alg=oracle.EK1, smooth=True, adaptive=True, t0=0.0, t1=0.5, save_everystep=True,
-                             cov_backend=oracle.COV_QR)
-    same = 0
+    kw = dict(alg=oracle.EK1, smooth=True, adaptive=True, t0=0.0, t1=0.5, save_everystep=True, cov_backend=oracle.COV_REF)
+    same = stable = stable_hit = 0
     for i in range(n):
-        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        o = oracle.solve(oracle.make_config(2, 5, 1, **kw), rhs, u0[i], p[i])
+        env = {o["n"]} | {s["n"] for _, s in F.variants(oracle, rhs, 2, 5, 1, u0[i], p[i], kw)}
         a, b = g["off"][i], g["off"][i + 1]
         scale = np.abs(o["pu_mu"]).max(axis=0)
-        assert abs((b - a) - o["n"]) <= max(2, 0.03 * o["n"])
+        assert min(env) - 1 <= b - a <= max(env) + 1, (i, b - a, sorted(env))
         assert np.max(np.abs(g["U"][b - 1] - o["pu_mu"][-1]) / scale) < 1e-5
+        if len(env) == 1:
+            stable += 1
+            stable_hit += int(b - a == o["n"])
         if b - a == o["n"]:   # same accept pattern; the step times drift by rounding through sigma^2 (oracle QR-vs-Cholesky: <= 4e-3)
             same += 1
             dT = np.abs(g["T"][a:b] - o["t"])
             du = np.abs(np.gradient(o["pu_mu"], o["t"], axis=0)).max(axis=0)
             assert np.all(np.abs(g["U"][a:b] - o["pu_mu"]) <= 1e-6 * scale + 4.0 * du * dT[:, None])
-    assert same >= n // 2
+    assert stable_hit >= stable - 1 and same >= 1, (same, stable, stable_hit)
 
 
 # ------------------------------------------------------------------------------------------------------------------
