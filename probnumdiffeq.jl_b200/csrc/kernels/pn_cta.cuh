@@ -28,7 +28,23 @@
 #include "pn_taylor.cuh"
 #include "pn_small.cuh" /* pn_initial_dt */
 
-#define PN_CTA_THREADS 256
+#ifndef PN_CTA_THREADS
+#define PN_CTA_THREADS 256 /* threads per CTA (one trajectory); the host may build with 512 */
+#endif
+#ifndef PN_CTA_MIN_BLOCKS
+#define PN_CTA_MIN_BLOCKS 1 /* resident CTAs per SM the register allocation must allow (mid-sized states, e.g. D = 56, fit several) */
+#endif
+
+/* doubles of dynamic shared memory of the CTA kernel (host and device use this one formula):
+   d modelled components, n = q + 1, dp = dimension of the right-hand side (2d for second-order problems), hb = number of
+   d-column blocks the measurement matrix H touches (2; 3 for second-order problems), mass: M is staged in shared memory */
+__host__ __device__ constexpr long long pn_cta_sm_doubles(int d, int n, int dp, int hb, int npa, bool mass, int shared_struct_bytes) {
+    const long long D = (long long)d * n, MP = D * (D + 1) / 2, UNI = (MP > 2 * d * D) ? MP : 2 * d * D, NR = (long long)hb * d;
+    return D * D + UNI + NR * d /*C2*/ + NR * d /*V*/ + (long long)d * d /*S*/ +
+           (hb == 3 ? (long long)dp * dp : (long long)d * d) /*J (second order: the Jacobian of the first-order form)*/ +
+           (mass ? (long long)d * d : 0) /*M*/ + 3 * D /*mu,mup,tmp*/ + 3 * d /*z,zt,uprev*/ + 2 * dp /*fu,x2*/ + npa +
+           (shared_struct_bytes + 7) / 8;
+}
 
 /* number of independent slices the problem struct offers for f / J (tracer.py, jac_parts); 1 if it does not say */
 template <class P, class = void>
@@ -49,11 +65,19 @@ struct PnCtaShared {
     double Qn[PN_MAX_N * PN_MAX_N]; /* (P^-1 L'L P^-1)[c][c']: the 1-d process-noise covariance of this step */
     long long traj, naccept, nreject, nf, iter, tstop_idx, save_pos;
     int retcode, accept, finished, okflag, chol_fail;
+    double cinv[4]; /* reciprocal pivots of the current panel (gram_chol_tiles) */
 };
+#define PN_CTA_TS 18 /* doubles between consecutive 4 x 4 tiles of the tile-packed factor: 144 bytes, so that the eight lanes of a
+                        quarter warp reading consecutive tiles with 16-byte loads hit distinct bank groups */
 
 template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 struct PnCta {
-    static constexpr int d = Prob::d;
+    static constexpr int DP = Prob::d;                 /* dimension of the right-hand side */
+    static constexpr int d = PN_SECOND ? DP / 2 : DP;  /* modelled components (positions for second-order problems) */
+    static constexpr int DU = DP;                      /* length of sol.u: (du, u) for second-order problems */
+    static constexpr int E1B = PN_SECOND ? 2 : 1;      /* derivative block the measurement reads (E2 / E1) */
+    static constexpr int HB = E1B + 1;                 /* d-column blocks H touches: H = [-J | M | 0..] or [-J_u | -J_du | I | 0..] */
+    static constexpr int NR = HB * d;                  /* R^- is upper triangular, so R^- H' vanishes in rows >= NR */
     static constexpr int n = Q + 1;
     static constexpr int D = d * n;
     static constexpr int NPA = Prob::n_p > 0 ? Prob::n_p : 1;
@@ -66,9 +90,8 @@ struct PnCta {
        and with the gain K (D x d, computed after the factor has been copied into R) */
     static constexpr int MP = D * (D + 1) / 2;
     static constexpr int UNI = (MP > 2 * d * D) ? MP : 2 * d * D;
-    static constexpr int SM_DOUBLES = D * D + UNI + 2 * d * d /*C2*/ + 2 * d * d /*V*/ + d * d /*S*/ + d * d /*J*/ +
-                                      3 * D /*mu,mup,tmp*/ + 4 * d /*z,zt,fu,uprev*/ + NPA +
-                                      (int)((sizeof(PnCtaShared) + 7) / 8);
+    static constexpr int JS = PN_SECOND ? DP * DP : d * d; /* Jacobian buffer (second order: of the first-order form) */
+    static constexpr int SM_DOUBLES = (int)pn_cta_sm_doubles(d, n, DP, HB, NPA, PN_MASS != 0, (int)sizeof(PnCtaShared));
     static __device__ __forceinline__ int pidx(int i, int j) { return i * D - (i * (i - 1)) / 2 + (j - i); } /* i <= j */
 
     static __device__ __forceinline__ double block_sum(double x, PnCtaShared* sh) {
@@ -182,6 +205,175 @@ struct PnCta {
         __syncthreads();
         return ok;
     }
+    // ----------------------------------------------------------------------------------------------------------------
+    // Gram matrix + Cholesky on 4 x 4 register tiles (predict.jl:84-85 for the D x D factor; the d x d matrices S and W use
+    // the same routine).  Tile (I, J), I <= J, of the symmetric M x M matrix belongs to thread e % NT (e = row-major index over
+    // the upper triangle of tiles) for the whole routine and lives in its REGISTERS: the Gram phase accumulates it from the
+    // rows of A (two 32-byte operands per 16 multiply-adds), and the right-looking factorisation updates it in place; a tile
+    // is written to shared memory once, when its tile row becomes the panel.  Per panel: the owner of the diagonal tile
+    // factorises it (4 pivots) and publishes it with the reciprocal pivots; barrier; the owners of the panel row solve their
+    // own tiles against it and publish them; barrier; every owner below subtracts U_PI' U_PJ (two tiles read, 64 FMAs).  Two
+    // barriers per 4 columns, no read-modify-write traffic on shared memory.
+    //   A      rows x M row-major (leading dimension M) or nullptr (no Gram phase: tiles start from init alone)
+    //   init   (gi, gj) -> value added to entry (gi, gj), gi <= gj
+    //   Tp     tile-packed result: tile (I, J) at Tp + tix(I, J) * PN_CTA_TS, row-major 4 x 4 (upper triangle of U)
+    //   invd   optional: 1 / U[j][j]
+    // Returns false (CTA-uniform) as soon as a pivot is not positive (the reference's PosDefException, predict.jl:85-91);
+    // Tp is then incomplete.
+    // ----------------------------------------------------------------------------------------------------------------
+    template <int M>
+    static __device__ __forceinline__ int tix(int I, int J) {
+        constexpr int TI = (M + 3) / 4;
+        return I * TI - (I * (I - 1)) / 2 + (J - I);
+    }
+    template <int M, class Init>
+    static __device__ bool gram_chol_tiles(const double* A, int rows, double* Tp, double* invd, PnCtaShared* sh, Init init) {
+        constexpr int TI = (M + 3) / 4, NTILES = TI * (TI + 1) / 2, TPT = (NTILES + NT - 1) / NT, TS = PN_CTA_TS;
+        constexpr bool ALIGNED = (M % 4 == 0);
+        const int tid = threadIdx.x;
+        int tI[TPT], tJ[TPT];
+        double acc[TPT][4][4];
+#pragma unroll
+        for (int k = 0; k < TPT; k++) {
+            int e = tid + k * NT, I = 0;
+            if (e >= NTILES) e = -1;
+            int rem = e;
+            while (e >= 0 && rem >= TI - I) {
+                rem -= TI - I;
+                I++;
+            }
+            tI[k] = (e >= 0) ? I : -1;
+            tJ[k] = (e >= 0) ? I + rem : -1;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[k][a][b] = 0.0;
+        }
+        if (A != nullptr) {
+#pragma unroll 2
+            for (int r = 0; r < rows; r++) {
+                const double* row = A + r * M;
+#pragma unroll
+                for (int k = 0; k < TPT; k++) {
+                    if (tI[k] < 0) continue;
+                    double av[4], bv[4];
+                    if constexpr (ALIGNED) {
+                        const double2 a01 = *reinterpret_cast<const double2*>(row + 4 * tI[k]);
+                        const double2 a23 = *reinterpret_cast<const double2*>(row + 4 * tI[k] + 2);
+                        const double2 b01 = *reinterpret_cast<const double2*>(row + 4 * tJ[k]);
+                        const double2 b23 = *reinterpret_cast<const double2*>(row + 4 * tJ[k] + 2);
+                        av[0] = a01.x, av[1] = a01.y, av[2] = a23.x, av[3] = a23.y;
+                        bv[0] = b01.x, bv[1] = b01.y, bv[2] = b23.x, bv[3] = b23.y;
+                    } else {
+#pragma unroll
+                        for (int a = 0; a < 4; a++) {
+                            av[a] = (4 * tI[k] + a < M) ? row[4 * tI[k] + a] : 0.0;
+                            bv[a] = (4 * tJ[k] + a < M) ? row[4 * tJ[k] + a] : 0.0;
+                        }
+                    }
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++) acc[k][a][b] = fma(av[a], bv[b], acc[k][a][b]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < TPT; k++) {
+            if (tI[k] < 0) continue;
+#pragma unroll
+            for (int a = 0; a < 4; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int gi = 4 * tI[k] + a, gj = 4 * tJ[k] + b;
+                    if (gi < M && gj < M) {
+                        if (gi <= gj) acc[k][a][b] += init(gi, gj);
+                    } else {
+                        acc[k][a][b] = (gi == gj) ? 1.0 : 0.0; /* padding of the last tile row / column: identity */
+                    }
+                }
+        }
+        /* diagonal tile of a panel: factor in registers, publish U_PP (upper, zeros below) and the reciprocal pivots */
+        auto factor_diag = [&](int k, int P) {
+            double inv[4];
+            const bool ok = pn_chol<4>(acc[k], inv);
+            double* dst = Tp + tix<M>(P, P) * TS;
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
+                *reinterpret_cast<double2*>(dst + 4 * a) = make_double2(a <= 0 ? acc[k][a][0] : 0.0, a <= 1 ? acc[k][a][1] : 0.0);
+                *reinterpret_cast<double2*>(dst + 4 * a + 2) = make_double2(a <= 2 ? acc[k][a][2] : 0.0, acc[k][a][3]);
+                sh->cinv[a] = inv[a];
+                if (invd != nullptr && 4 * P + a < M) invd[4 * P + a] = inv[a];
+            }
+            if (!ok) sh->chol_fail = 1;
+        };
+        if (tid == 0) sh->chol_fail = 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TPT; k++)
+            if (tI[k] == 0 && tJ[k] == 0) factor_diag(k, 0);
+        bool ok = true;
+        for (int P = 0; P < TI; P++) {
+            __syncthreads(); /* U_PP, cinv, chol_fail of panel P are visible */
+            if (sh->chol_fail) {
+                ok = false;
+                break;
+            }
+            /* panel row: U_PJ = U_PP^-T M_PJ, solved in the owner's registers */
+#pragma unroll
+            for (int k = 0; k < TPT; k++) {
+                if (tI[k] != P || tJ[k] == P) continue;
+                const double* dg = Tp + tix<M>(P, P) * TS;
+                const double u01 = dg[1], u02 = dg[2], u03 = dg[3], u12 = dg[6], u13 = dg[7], u23 = dg[11];
+                const double i0 = sh->cinv[0], i1 = sh->cinv[1], i2 = sh->cinv[2], i3 = sh->cinv[3];
+                double* dst = Tp + tix<M>(P, tJ[k]) * TS;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const double x0 = acc[k][0][b] * i0;
+                    const double x1 = (acc[k][1][b] - u01 * x0) * i1;
+                    const double x2 = (acc[k][2][b] - u02 * x0 - u12 * x1) * i2;
+                    const double x3 = (acc[k][3][b] - u03 * x0 - u13 * x1 - u23 * x2) * i3;
+                    acc[k][0][b] = x0, acc[k][1][b] = x1, acc[k][2][b] = x2, acc[k][3][b] = x3;
+                }
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                    *reinterpret_cast<double2*>(dst + 4 * a) = make_double2(acc[k][a][0], acc[k][a][1]);
+                    *reinterpret_cast<double2*>(dst + 4 * a + 2) = make_double2(acc[k][a][2], acc[k][a][3]);
+                }
+            }
+            if (P + 1 == TI) break;
+            __syncthreads(); /* the panel row is visible */
+#pragma unroll
+            for (int k = 0; k < TPT; k++) {
+                if (tI[k] <= P) continue; /* also skips unused slots (-1) */
+                const double* pi = Tp + tix<M>(P, tI[k]) * TS;
+                const double* pj = Tp + tix<M>(P, tJ[k]) * TS;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const double2 a01 = *reinterpret_cast<const double2*>(pi + 4 * q), a23 = *reinterpret_cast<const double2*>(pi + 4 * q + 2);
+                    const double2 b01 = *reinterpret_cast<const double2*>(pj + 4 * q), b23 = *reinterpret_cast<const double2*>(pj + 4 * q + 2);
+                    const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+                    const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                    for (int a = 0; a < 4; a++)
+#pragma unroll
+                        for (int b = 0; b < 4; b++) acc[k][a][b] = fma(-av[a], bv[b], acc[k][a][b]);
+                }
+                if (tI[k] == P + 1 && tJ[k] == P + 1) factor_diag(k, P + 1);
+            }
+        }
+        __syncthreads();
+        return ok;
+    }
+    /* tile-packed upper factor -> dense row-major M x M (zeros below the diagonal) */
+    template <int M>
+    static __device__ void expand_tiles(const double* Tp, double* out) {
+        for (int e = threadIdx.x; e < M * M; e += NT) {
+            const int i = e / M, k = e - i * M;
+            out[e] = (k >= i) ? Tp[tix<M>(i >> 2, k >> 2) * PN_CTA_TS + (i & 3) * 4 + (k & 3)] : 0.0;
+        }
+    }
+
     // x <- (U'U)^-1 x for m <= 32 by one warp (call with all 32 lanes of the warp): lane l holds x[l]; each solved
     // entry is broadcast and eliminated from the remaining lanes (column-oriented substitution).
     static __device__ void chol_solve_warp(const double* U, const double* invd, double* x, int m) {
@@ -221,18 +413,33 @@ struct PnCta {
         double* Bt = Mp;
         double* K = Mp + d * D;
         double* C2 = Mp + UNI;
-        double* V = C2 + 2 * d * d;
-        double* S = V + 2 * d * d;
+        double* V = C2 + NR * d;
+        double* S = V + NR * d;
         double* J = S + d * d;
-        double* mu = J + d * d;
+        double* Mm = J + JS; /* mass matrix (PN_MASS) */
+        double* mu = Mm + (PN_MASS ? d * d : 0);
         double* mup = mu + D;
         double* sinv = mup + D; /* D doubles of scratch: first d used as inverse Cholesky diagonal */
         double* z = sinv + D;
         double* zt = z + d;
-        double* fu = zt + d;
-        double* uprev = fu + d;
-        double* pr = uprev + d;
+        double* uprev = zt + d;
+        double* fu = uprev + d;
+        double* x2 = fu + DP;
+        double* pr = x2 + DP;
         PnCtaShared* sh = (PnCtaShared*)(pr + NPA);
+        /* entries of H's column blocks (as used in W = H Qh H' and C2 = R^- H'):
+           first order  H = [-J | M | 0 ...]   (M = I without a mass matrix; measurement_models.jl:11-20, derivative_utils.jl:1-33)
+           second order H = [-J_u | -J_du | I | 0 ...]   (measurement_models.jl:29-49, derivative_utils.jl:35-53) */
+        auto Ju = [&](int a, int i) -> double { return PN_SECOND ? J[a + DP * (d + i)] : J[a + d * i]; }; /* d f / d u */
+        auto Jd = [&](int a, int i) -> double { return PN_SECOND ? J[a + DP * i] : 0.0; };                /* d f1 / d du */
+        auto Hb = [&](int b, int a, int i) -> double {
+            if (b == 0) return -Ju(a, i);
+            if (PN_SECOND) return (b == 1) ? -Jd(a, i) : ((a == i) ? 1.0 : 0.0);
+            return PN_MASS ? Mm[a * d + i] : ((a == i) ? 1.0 : 0.0);
+        };
+#if PN_MASS
+        for (int e = tid; e < d * d; e += NT) Mm[e] = pn_mass(e / d, e % d);
+#endif
 
         for (;;) {
             /* ---- fetch ---- */
@@ -241,22 +448,16 @@ struct PnCta {
             __syncthreads();
             const long long traj = sh->traj;
             if (traj >= P.n_traj) break;
+            /* initial state and first step: computed for the whole ensemble by pn_init_kernel (TaylorModeInit incl. the
+               second-order / mass-matrix conditioning, ode_determine_initdt) before this kernel started */
+            for (int c = tid; c < D; c += NT) mu[c] = P.init_mu[traj * D + c];
+            for (int i = tid; i < Prob::n_p; i += NT) pr[i] = P.p[traj * Prob::n_p + i];
+            __syncthreads();
+            for (int i = tid; i < d; i += NT) uprev[i] = mu[pn_solcol<d>(i)];
             if (tid == 0) {
-                double u0[d], mu0[D], prr[NPA];
-                for (int i = 0; i < d; i++) u0[i] = P.u0[traj * d + i];
-                for (int i = 0; i < Prob::n_p; i++) prr[i] = P.p[traj * Prob::n_p + i];
-                pn_taylor_init<Prob, Q>(mu0, u0, prr, P.t0);
-                for (int c = 0; c < D; c++) mu[c] = mu0[c];
-                for (int i = 0; i < d; i++) uprev[i] = u0[i];
-                for (int i = 0; i < Prob::n_p; i++) pr[i] = prr[i];
                 sh->t = P.t0;
-                sh->nf = Q;
-                if (ADAPTIVE && !(P.dt0 > 0.0)) {
-                    sh->dt = pn_initial_dt<Prob>(P, u0, prr);
-                    sh->nf += 2;
-                } else {
-                    sh->dt = P.dt0;
-                }
+                sh->dt = P.init_dt[traj];
+                sh->nf = Q + ((ADAPTIVE && !(P.dt0 > 0.0) && !PN_MASS) ? 2 : 0);
                 sh->dtcache = sh->dt;
                 sh->naccept = sh->nreject = sh->iter = sh->tstop_idx = 0;
                 sh->loglik = sh->gdiff = sh->ldiff = 0.0;
@@ -270,8 +471,8 @@ struct PnCta {
                     if (P.step_offsets) {
                         P.s_t[sp] = P.t0;
                         P.s_diffusion[sp] = 0.0;
-                        for (int i = 0; i < d; i++) P.s_u_mean[sp * d + i] = u0[i];
-                        for (int i = 0; i < d * d; i++) P.s_u_cov[sp * d * d + i] = 0.0;
+                        for (int i = 0; i < DU; i++) P.s_u_mean[sp * DU + i] = mu[pn_solcol<d>(i)];
+                        for (int i = 0; i < DU * DU; i++) P.s_u_cov[sp * DU * DU + i] = 0.0;
                     }
                     sh->save_pos = sp + 1;
                 }
@@ -327,19 +528,28 @@ struct PnCta {
                     mup[c] = s;
                 }
                 __syncthreads();
-                /* measurement: f on one thread, J on another warp */
-                /* f and J in Prob::jac_parts independent slices (rows a == k mod jac_parts), slice k on the first lane of warp k */
+                /* measurement: f on one thread, J on a thread of another warp (or in Prob::jac_parts independent slices,
+                   slice k on the first lane of warp k) */
+                const double* xin = mup;
+#if PN_SECOND
+                for (int i = tid; i < d; i += NT) { /* (du, u) = (E1 mu^-, E0 mu^-) */
+                    x2[i] = mup[d + i];
+                    x2[d + i] = mup[i];
+                }
+                __syncthreads();
+                xin = x2;
+#endif
                 {
                     constexpr int JP = PnJacParts<Prob>::value;
                     static_assert(JP >= 1 && JP <= NT / 32, "jac_parts must not exceed the number of warps of the CTA");
-                    if (JP == 1) { /* default: f on one thread, J on a thread of another warp */
-                        if (tid == 0) Prob::template f<double>(fu, mup, pr, sh->tnew);
-                        if (tid == 32) Prob::jac(J, mup, pr, sh->tnew);
+                    if (JP == 1) {
+                        if (tid == 0) Prob::template f<double>(fu, xin, pr, sh->tnew);
+                        if (tid == 32) Prob::jac(J, xin, pr, sh->tnew);
                     }
 #define PN_CTA_RHS_SLICE(K)                                                              \
     if (JP > 1 && JP > K && tid == 32 * K) {                                                  \
-        Prob::template f_part<(JP > K ? K : 0)>(fu, mup, pr, sh->tnew);                  \
-        Prob::template jac_part<(JP > K ? K : 0)>(J, mup, pr, sh->tnew);                 \
+        Prob::template f_part<(JP > K ? K : 0)>(fu, xin, pr, sh->tnew);                  \
+        Prob::template jac_part<(JP > K ? K : 0)>(J, xin, pr, sh->tnew);                 \
     }
                     if constexpr (JP > 1) {
                     PN_CTA_RHS_SLICE(0)
@@ -354,13 +564,21 @@ struct PnCta {
 #undef PN_CTA_RHS_SLICE
                 }
                 __syncthreads();
-                for (int i = tid; i < d; i += NT) z[i] = mup[d + i] - fu[i];
+                for (int a = tid; a < d; a += NT) {
+#if PN_MASS
+                    double sm = 0.0; /* z = M E1 mu^- - f (measurement_models.jl:18) */
+                    for (int i = 0; i < d; i++) sm += Mm[a * d + i] * mup[d + i];
+                    z[a] = sm - fu[a];
+#else
+                    z[a] = mup[E1B * d + a] - fu[a];
+#endif
+                }
                 if (tid == 0) sh->nf += 1;
                 if (ADAPTIVE || DYNAMIC) {
                     /* W = C'C, C[(m,i),a] = -LQ[m][0] J[a][i] + (i==a) LQ[m][1]   (calibration.jl:123-133); summed over m in
                        closed form: W = alpha J J' - beta (J + J') + gamma I with alpha = sum LQ[m][0]^2, beta = sum LQ[m][0] LQ[m][1],
                        gamma = sum LQ[m][1]^2 */
-                    {
+                    if (!PN_SECOND && !PN_MASS) {
                         double al = 0.0, be = 0.0, ga = 0.0;
                         for (int m = 0; m < n; m++) {
                             const double l0 = P.L[m * n + 0] * sh->PIv[0];
@@ -375,6 +593,27 @@ struct PnCta {
                             double jj = 0.0;
                             for (int i = 0; i < d; i++) jj += J[a + d * i] * J[b + d * i];
                             S[a * d + b] = al * jj - be * (J[a + d * b] + J[b + d * a]) + ((a == b) ? ga : 0.0);
+                        }
+                    } else {
+                        /* general form: W = sum_{b1,b2} qh[b1][b2] H_b1 H_b2', qh = P^-1 (L'L) P^-1 restricted to the HB blocks of H */
+                        double qh[HB][HB];
+                        for (int b1 = 0; b1 < HB; b1++)
+                            for (int b2 = 0; b2 < HB; b2++) {
+                                double acc = 0.0;
+                                for (int m = 0; m < n; m++) acc += P.L[m * n + b1] * P.L[m * n + b2];
+                                qh[b1][b2] = acc * sh->PIv[b1] * sh->PIv[b2];
+                            }
+                        for (int e = tid; e < d * d; e += NT) {
+                            const int a = e / d, b = e - a * d;
+                            if (b < a) continue;
+                            double w = 0.0;
+                            for (int b1 = 0; b1 < HB; b1++)
+                                for (int b2 = 0; b2 < HB; b2++) {
+                                    double acc = 0.0;
+                                    for (int i = 0; i < d; i++) acc += Hb(b1, a, i) * Hb(b2, b, i);
+                                    w += qh[b1][b2] * acc;
+                                }
+                            S[a * d + b] = w;
                         }
                     }
                     __syncthreads();
@@ -411,7 +650,7 @@ struct PnCta {
                     if (ADAPTIVE) {
                         double e2 = 0.0;
                         for (int i = 0; i < d; i++) {
-                            const double isc = 1.0 / (P.abstol + fmax(fabs(mup[i]), fabs(uprev[i])) * P.reltol);
+                            const double isc = 1.0 / (P.abstol + fmax(fabs(mup[pn_solcol<d>(i)]), fabs(uprev[i])) * P.reltol);
                             e2 += (sh->ldiff * sinv[d + i]) * (isc * isc);
                         }
                         e2 = e2 * (h * h) * (1.0 / (double)d);
@@ -715,11 +954,17 @@ struct PnCta {
                         __syncthreads();
                     }
                 }
-                /* 4. measurement update on the first 2d rows */
-                for (int e = tid; e < 2 * d * d; e += NT) {
+                /* 4. measurement update on the first NR rows: C2 = R^- H' */
+                for (int e = tid; e < NR * d; e += NT) {
                     const int r = e / d, a = e - r * d;
-                    double s = R[r * D + d + a];
-                    for (int i = 0; i < d; i++) s -= R[r * D + i] * J[a + d * i];
+                    double s = 0.0;
+                    if (!PN_SECOND && !PN_MASS) {
+                        s = R[r * D + d + a];
+                        for (int i = 0; i < d; i++) s -= R[r * D + i] * J[a + d * i];
+                    } else {
+                        for (int b = 0; b < HB; b++)
+                            for (int i = 0; i < d; i++) s += R[r * D + b * d + i] * Hb(b, a, i);
+                    }
                     C2[e] = s;
                 }
                 __syncthreads();
@@ -727,7 +972,7 @@ struct PnCta {
                     const int a = e / d, b = e - a * d;
                     if (b < a) continue;
                     double s = 0.0;
-                    for (int r = 0; r < 2 * d; r++) s += C2[r * d + a] * C2[r * d + b];
+                    for (int r = 0; r < NR; r++) s += C2[r * d + a] * C2[r * d + b];
                     S[a * d + b] = s;
                 }
                 __syncthreads();
@@ -789,7 +1034,7 @@ struct PnCta {
                         S[e] = sacc;
                     }
                     __syncthreads();
-                    for (int e = tid; e < 2 * d * d; e += NT) {
+                    for (int e = tid; e < NR * d; e += NT) {
                         const int r = e / d, a = e - r * d;
                         double sacc = 0.0;
                         for (int k = 0; k < d; k++) sacc += C2[r * d + k] * S[k * d + a];
@@ -802,7 +1047,7 @@ struct PnCta {
                         constexpr int NAB = (d + TA - 1) / TA;
                         for (int e = tid; e < D * NAB; e += NT) {
                             const int ab = e / D, c = e - ab * D;
-                            const int rmax = (c + 1 < 2 * d) ? c + 1 : 2 * d;
+                            const int rmax = (c + 1 < NR) ? c + 1 : NR;
                             double acc[TA];
 #pragma unroll
                             for (int t = 0; t < TA; t++) acc[t] = 0.0;
@@ -823,10 +1068,10 @@ struct PnCta {
                         for (int a = 0; a < d; a++) s -= K[a * D + c] * z[a];
                         mu[c] = s;
                     }
-                    /* R+ = R^- - C2 K' on the first 2d rows, TR rows per thread */
+                    /* R+ = R^- - C2 K' on the first NR rows, TR rows per thread */
                     {
                         constexpr int TR = 4;
-                        constexpr int NRB = (2 * d + TR - 1) / TR;
+                        constexpr int NRB = (NR + TR - 1) / TR;
                         for (int e = tid; e < NRB * D; e += NT) {
                             const int rb = e / D, c = e - rb * D;
                             double acc[TR];
@@ -836,11 +1081,11 @@ struct PnCta {
                                 const double kv = K[a * D + c];
 #pragma unroll
                                 for (int t = 0; t < TR; t++)
-                                    if (rb * TR + t < 2 * d) acc[t] += C2[(rb * TR + t) * d + a] * kv;
+                                    if (rb * TR + t < NR) acc[t] += C2[(rb * TR + t) * d + a] * kv;
                             }
 #pragma unroll
                             for (int t = 0; t < TR; t++)
-                                if (rb * TR + t < 2 * d) R[(rb * TR + t) * D + c] -= acc[t];
+                                if (rb * TR + t < NR) R[(rb * TR + t) * D + c] -= acc[t];
                         }
                     }
                     __syncthreads();
@@ -862,7 +1107,7 @@ struct PnCta {
                     sh->naccept++;
                     bool nanu = false;
                     for (int i = 0; i < d; i++) {
-                        uprev[i] = mu[i];
+                        uprev[i] = mu[pn_solcol<d>(i)];
                         nanu = nanu || (mu[i] != mu[i]);
                     }
                     if (nanu) sh->retcode = PN_RET_UNSTABLE;
@@ -872,13 +1117,13 @@ struct PnCta {
                 if (SAVE >= 1) {
                     if (P.step_offsets && sh->save_pos < P.step_offsets[traj + 1]) {
                         const long long sp = sh->save_pos;
-                        for (int e = tid; e < d * d; e += NT) {
-                            const int a = e / d, b = e - a * d;
+                        for (int e = tid; e < DU * DU; e += NT) {
+                            const int a = pn_solcol<d>(e / DU), b = pn_solcol<d>(e % DU);
                             double s = 0.0;
                             for (int r = 0; r < D; r++) s += R[r * D + a] * R[r * D + b];
-                            P.s_u_cov[sp * d * d + e] = s;
+                            P.s_u_cov[sp * DU * DU + e] = s;
                         }
-                        for (int i = tid; i < d; i += NT) P.s_u_mean[sp * d + i] = mu[i];
+                        for (int i = tid; i < DU; i += NT) P.s_u_mean[sp * DU + i] = mu[pn_solcol<d>(i)];
                         if (tid == 0) {
                             P.s_t[sp] = sh->t;
                             P.s_diffusion[sp - 1] = (ADAPTIVE || DYNAMIC) ? sh->ldiff : P.initial_diffusion;
@@ -900,13 +1145,13 @@ struct PnCta {
                     fd = P.initial_diffusion;
                 }
             }
-            for (int e = tid; e < d * d; e += NT) {
-                const int a = e / d, b = e - a * d;
+            for (int e = tid; e < DU * DU; e += NT) {
+                const int a = pn_solcol<d>(e / DU), b = pn_solcol<d>(e % DU);
                 double s = 0.0;
                 for (int r = 0; r < D; r++) s += R[r * D + a] * R[r * D + b];
-                P.u_cov[traj * d * d + e] = s * sc;
+                P.u_cov[traj * DU * DU + e] = s * sc;
             }
-            for (int i = tid; i < d; i += NT) P.u_mean[traj * d + i] = mu[i];
+            for (int i = tid; i < DU; i += NT) P.u_mean[traj * DU + i] = mu[pn_solcol<d>(i)];
             if (P.x_mean)
                 for (int c = tid; c < D; c += NT) P.x_mean[traj * D + c] = mu[c];
             if (P.x_covfac) {

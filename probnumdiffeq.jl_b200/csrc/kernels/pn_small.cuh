@@ -534,7 +534,7 @@ struct PnSmall {
         double R[RPL][D];      /* own rows of the right factor */
         double pr[NPA];
         double uprev[d];
-        double t = 0.0, dt = 0.0, dtcache = 0.0, qold = 0.0, qold_pb2 = 1.0, loglik = 0.0, gdiff = 0.0, ldiff = 0.0;
+        double t = 0.0, dt = 0.0, dtcache = 0.0, qold_pb2 = 1.0, loglik = 0.0, gdiff = 0.0, ldiff = 0.0;
         long long traj = -1, naccept = 0, nreject = 0, nf = 0, iter = 0, tstop_idx = 0, save_pos = 0;
         int retcode = PN_RET_SUCCESS;
         bool have = false, queue_empty = false;
@@ -583,7 +583,6 @@ struct PnSmall {
                         loglik = 0.0;
                         gdiff = 0.0;
                         ldiff = 0.0;
-                        qold = P.qoldinit;
                         qold_pb2 = P.qoldinit_pb2;
                         retcode = PN_RET_SUCCESS;
                         dtcache = dt;
@@ -890,10 +889,37 @@ struct PnSmall {
 #pragma unroll
                 for (int k = 0; k < n; k++) tq[k] = (k == Q) ? 1.0 : 0.0;
 #endif
-#pragma unroll
-                for (int c = 0; c < D; c++) mup[c] = mu[c];
                 ediff = 0.0;
             }
+            /* from here on one mean vector is live: the predicted mean of an accepted attempt, else the filtered mean (the
+               update below subtracts K z with K = 0 for groups that commit nothing) */
+#pragma unroll
+            for (int c = 0; c < D; c++) mu[c] = accept ? mup[c] : mu[c];
+            double t_next = t;
+            if (accept) {
+                /* loopfooter! accept branch (OrdinaryDiffEqCore), scalar part: everything that does not depend on
+                   the covariance update is settled here, so that the controller's temporaries are dead during phase 2 */
+                double dtnew = dt;
+                if (ADAPTIVE) {
+                    if (P.qsteady_min <= qq && qq <= P.qsteady_max) qq = 1.0;
+                    qold_pb2 = (EEst > P.qoldinit) ? exp(P.beta2 * lEE) : P.qoldinit_pb2; /* qold = max(EEst, qoldinit), kept as qold^beta2 */
+#if PN_FAST_SCALAR
+                    dtnew = dt * pn_rcp(qq);
+#else
+                    dtnew = dt / qq;
+#endif
+                }
+                const double ttmp = t + h;
+                const double ref = fmax(fabs(t), fabs(tstop));
+#if PN_FAST_SCALAR
+                const double epsref = pn_ulp_above(ref);
+#else
+                const double epsref = nextafter(ref, 1e300) - ref;
+#endif
+                t_next = (fabs(ttmp - tstop) < 100.0 * epsref) ? tstop : ttmp;
+                dt = dtnew;
+            }
+            t = t_next;
 
             /* ============ (C) phase 2: covariance predict + update (warp-convergent) ============ */
             /* Phase 2 runs in EVERY iteration, also for a warp in which no group accepted: a group without an accepted
@@ -937,6 +963,42 @@ struct PnSmall {
                     /* (2) accumulators of the own rows start from s2 Qh = s2 (P^-1 Qb P^-1) (x) I_d, Qb = L'L (iwp.jl:74-108):
                        row (m,i) has s2 PI[m] Qb[m][c] PI[c] at column (c,i) */
                     double Mw[RPL][D];
+                    if constexpr (G <= 4) {
+                        /* few lanes: the (derivative, component) pair of an own row is one of G compile-time alternatives, so the
+                           row of s2 Qh is picked with G selects per entry from the n(n+1)/2 distinct values qh[m][c] */
+                        double qh[n][n];
+#pragma unroll
+                        for (int m = 0; m < n; m++)
+#pragma unroll
+                            for (int c = 0; c < n; c++) {
+                                if (c < m) continue;
+#if PN_IOUP
+                                double qmc = 0.0; /* Qb = Uh'Uh */
+#pragma unroll
+                                for (int r = 0; r < n; r++)
+                                    if (r <= m) qmc += Uh[r][m] * Uh[r][c];
+#else
+                                const double qmc = P.Qb[m * n + c];
+#endif
+                                qh[m][c] = qmc * (PIv[m] * ediff) * PIv[c];
+                            }
+#pragma unroll
+                        for (int lr = 0; lr < RPL; lr++)
+#pragma unroll
+                            for (int j = 0; j < D; j++) {
+                                if (j < lr * G) continue; /* never read (pn_chol_rows) */
+                                double v = 0.0;
+#pragma unroll
+                                for (int g = 0; g < G; g++) {
+                                    const int rb = lr * G + g;
+                                    if (rb < D && (rb % d) == (j % d)) {
+                                        const int m = rb / d, c = j / d;
+                                        v = (gl == g) ? qh[m < c ? m : c][m < c ? c : m] : v;
+                                    }
+                                }
+                                Mw[lr][j] = v;
+                            }
+                    } else {
 #pragma unroll
                     for (int lr = 0; lr < RPL; lr++) {
                         double pim = 0.0; /* s2 PI[m] of the own row (m, i) */
@@ -961,6 +1023,7 @@ struct PnSmall {
 #pragma unroll
                             for (int i = 0; i < d; i++) Mw[lr][c * d + i] = (iB[lr] == i) ? val : 0.0;
                         }
+                    }
                     }
                     /* (3) Gram matrix: stream every row of X from the exchange region */
 #ifndef PN_GRAM_UNROLL
@@ -1142,7 +1205,7 @@ struct PnSmall {
                         for (int lr = 0; lr < RU; lr++) s += R[lr][c] * V[lr][a];
                         Kc[a] = pn_gsum<G>(s);
                     }
-                    double s = mup[c];
+                    double s = mu[c];
 #pragma unroll
                     for (int a = 0; a < d; a++) s -= Kc[a] * z[a];
                     mu[c] = s;
@@ -1158,27 +1221,7 @@ struct PnSmall {
                 if (accept) pn_rows_store<G, RPL, D>(sx, R, gl); /* x_filt.Sigma.R for the next iteration (idle groups: the region still holds it) */
 #endif
                 if (accept) {
-                    /* loopfooter! accept branch (OrdinaryDiffEqCore) */
-                    double dtnew = dt;
-                    if (ADAPTIVE) {
-                        if (P.qsteady_min <= qq && qq <= P.qsteady_max) qq = 1.0;
-                        qold = fmax(EEst, P.qoldinit);
-                        qold_pb2 = (EEst > P.qoldinit) ? exp(P.beta2 * lEE) : P.qoldinit_pb2;
-#if PN_FAST_SCALAR
-                        dtnew = dt * pn_rcp(qq);
-#else
-                        dtnew = dt / qq;
-#endif
-                    }
-                    const double ttmp = t + h;
-                    const double ref = fmax(fabs(t), fabs(tstop));
-#if PN_FAST_SCALAR
-                    const double epsref = pn_ulp_above(ref);
-#else
-                    const double epsref = nextafter(ref, 1e300) - ref;
-#endif
-                    t = (fabs(ttmp - tstop) < 100.0 * epsref) ? tstop : ttmp;
-                    dt = dtnew;
+                    /* loopfooter! accept branch, the part that needs the updated mean (the scalars were settled before phase 2) */
                     naccept++;
                     bool nanu = false;
 #pragma unroll

@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_reg_kernel(const 
 
 #define PN_ENTRY_CTA(NAME, PROB, Q, A, DY, S) \
     { "builtin:" NAME ":cta:q" #Q ":g256:a" #A ":dyn" #DY ":s" #S, \
-      (const void*)&pn_cta_kernel<PROB, Q, (A != 0), (DY != 0), S>, PROB::d, PROB::n_p, nullptr }
+      (const void*)&pn_cta_kernel<PROB, Q, (A != 0), (DY != 0), S>, PROB::d, PROB::n_p, \
+      (const void*)&pn_init_kernel<PROB, Q, (A != 0)> }
 
 static const PnBuiltinEntry g_table[] = {
     /* cfg4: Pleiades EK1(order=3), D = 112, adaptive, CTA per trajectory */

@@ -4,15 +4,18 @@
 #pragma once
 
 
-/* One 256-thread CTA per SM (8 warps, 2 per scheduler, ~255 registers each); the CTA re-synchronises once per
-   time-loop iteration (PN_CTA_SYNC) so that the two warps sharing a scheduler fetch the same instruction lines. */
+/* One 256-thread CTA per SM (8 warps, 2 per scheduler, ~255 registers each).  The warps of a CTA run free: the two warps
+   that share a scheduler drift into different phases of the time loop (the scalar, latency-bound first phase of one overlaps
+   the FMA-dense Gram / Cholesky phase of the other): ROBER 2.39e9 -> 2.63e9 steps/s, OREGO 2.05e9 -> 2.32e9
+   (profiles/r2f_variants.jsonl).  PN_USE_CTA_SYNC re-synchronises the CTA once per iteration instead, which paid while the
+   unrolled loop body (Householder sweep, ~100 KB) thrashed the instruction cache (round 1). */
 #ifndef PN_THREADS
 #define PN_THREADS 256
 #endif
 #ifndef PN_MIN_BLOCKS
 #define PN_MIN_BLOCKS 1
 #endif
-#ifndef PN_NO_CTA_SYNC
+#ifdef PN_USE_CTA_SYNC
 #define PN_CTA_SYNC 1
 #endif
 
@@ -53,6 +56,6 @@ __global__ void __launch_bounds__(128) pn_blocks_kernel(const __grid_constant__ 
 
 /* large D (Pleiades, D = 112): one CTA per trajectory, R staged in shared memory */
 template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
-__global__ void __launch_bounds__(PN_CTA_THREADS, 1) pn_cta_kernel(const __grid_constant__ PnParams P) {
+__global__ void __launch_bounds__(PN_CTA_THREADS, PN_CTA_MIN_BLOCKS) pn_cta_kernel(const __grid_constant__ PnParams P) {
     pn_cta_entry<Prob, Q, ADAPTIVE, DYNAMIC, SAVE>(P);
 }

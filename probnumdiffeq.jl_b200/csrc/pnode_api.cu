@@ -420,7 +420,7 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
                "  pn_blocks_entry<") + struct_name + ", PN_Q, " + (blocks == 2 ? "true" : "false") + ", " + (mv ? "true" : "false") +
                ", (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
     else if (cta)
-        src += "\nextern \"C\" __global__ void __launch_bounds__(PN_CTA_THREADS, 1) pn_entry(const __grid_constant__ PnParams P) {\n"
+        src += "\nextern \"C\" __global__ void __launch_bounds__(PN_CTA_THREADS, PN_CTA_MIN_BLOCKS) pn_entry(const __grid_constant__ PnParams P) {\n"
                "  pn_cta_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
     else if (kron)
         src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS, PN_KRON_MIN_BLOCKS(PN_Q)) pn_entry(const __grid_constant__ PnParams P) {\n"
@@ -429,11 +429,11 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
         src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS, PN_MIN_BLOCKS) pn_entry(const "
                "__grid_constant__ PnParams P) {\n  pn_small_entry<" +
                struct_name + ", PN_Q, PN_G, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
-    if (!cta) /* every path but the CTA kernel takes its initial states from the pre-pass */
-        src += "extern \"C\" __global__ void __launch_bounds__(128) pn_init(const __grid_constant__ PnParams P, double* init_mu, "
+    /* every step kernel takes its initial states from the pre-pass */
+    src += "extern \"C\" __global__ void __launch_bounds__(128) pn_init(const __grid_constant__ PnParams P, double* init_mu, "
                "double* init_dt) {\n  pn_init_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0)>(P, init_mu, init_dt);\n}\n";
     auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
-    return nvrtc_compile(src, {def("PN_THREADS", threads), def("PN_MIN_BLOCKS", min_blocks), def("PN_Q", q), def("PN_G", G),
+    return nvrtc_compile(src, {def(cta ? "PN_CTA_THREADS" : "PN_THREADS", threads), def(cta ? "PN_CTA_MIN_BLOCKS" : "PN_MIN_BLOCKS", min_blocks), def("PN_Q", q), def("PN_G", G),
                                def("PN_ADAPTIVE", adaptive ? 1 : 0), def("PN_DYNAMIC", dynamic ? 1 : 0), def("PN_SAVE", save),
                                def("PN_IOUP", ioup ? 1 : 0), def("PN_EK0_DENSE", ek0_dense ? 1 : 0)},
                          cubin);
@@ -525,6 +525,18 @@ static int nvrtc_dense_cubin(int d, int q, int G, bool ioup, std::vector<char>* 
     return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0), def("PN_SECOND", second ? 1 : 0)}, cubin);
 }
 
+static size_t cta_smem_bytes(int d, int q, int n_p, bool second_order = false, bool mass = false) {
+    return (size_t)pn_cta_sm_doubles(d, q + 1, second_order ? 2 * d : d, second_order ? 3 : 2, n_p > 0 ? n_p : 1, mass,
+                                     (int)sizeof(PnCtaShared)) * sizeof(double);
+}
+/* threads per CTA and resident CTAs per SM of the CTA-per-trajectory kernel: states that leave room for several CTAs in
+   shared memory run two (registers <= 128 per thread); the ahead-of-time instantiations use the compiled-in defaults */
+static void cta_shape(size_t smem, int* threads, int* min_blocks) {
+    *threads = env_int("PNODE_CTA_THREADS", PN_CTA_THREADS);
+    *min_blocks = env_int("PNODE_CTA_MIN_BLOCKS", (2 * smem + 4096 <= 227 * 1024) ? 2 : 1);
+    if (*threads * *min_blocks > 1024) *min_blocks = 1024 / *threads;
+}
+
 static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
     int rc = load_driver();
     if (rc) return rc;
@@ -536,14 +548,19 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
         src = "#include \"kernels/pn_builtin_problems.cuh\"\n";
         name = sn;
     }
-    out->threads = s->cta ? PN_CTA_THREADS : ((s->kron || s->blocks) ? 128 : env_int("PNODE_THREADS", PN_THREADS));
+    out->threads = (s->kron || s->blocks) ? 128 : env_int("PNODE_THREADS", PN_THREADS);
+    int min_blocks = env_int("PNODE_MIN_BLOCKS", 1);
+    if (s->cta) {
+        cta_shape(s->smem, &out->threads, &min_blocks);
+        s->G = out->threads; /* one CTA per trajectory */
+    }
     if (!s->cta && !s->kron && !s->blocks) {
         /* one exchange region per group: large states with few lanes per trajectory run smaller CTAs */
         while (out->threads > 32 && small_smem_bytes(s->D, s->G, out->threads) > 200 * 1024) out->threads /= 2;
         s->smem = small_smem_bytes(s->D, s->G, out->threads);
     }
     rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0, is_dynamic(s->cfg.diffusion), save, &cubin, out->threads,
-                     env_int("PNODE_MIN_BLOCKS", 1), s->kron, s->cta,
+                     min_blocks, s->kron, s->cta,
                      s->blocks ? (s->cfg.alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, s->mv, s->cfg.prior == PNODE_PRIOR_IOUP,
                      s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks, s->mass_src);
     if (rc) return rc;
@@ -551,10 +568,8 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
     r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_entry");
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction: " + cu_err(r));
-    if (!s->cta) {
-        r = g_drv.ModuleGetFunction(&out->drv_init, out->mod, "pn_init");
-        if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction(pn_init): " + cu_err(r));
-    }
+    r = g_drv.ModuleGetFunction(&out->drv_init, out->mod, "pn_init");
+    if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleGetFunction(pn_init): " + cu_err(r));
     if (s->smem > 48 * 1024) {
         r = g_drv.FuncSetAttribute(out->drv_fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)s->smem);
         if (r != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuFuncSetAttribute(max dynamic smem): " + cu_err(r));
@@ -579,6 +594,7 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
                 out->rt_fn = tab[i].fn;
                 out->rt_init = tab[i].init_fn;
                 out->threads = s->cta ? PN_CTA_THREADS : ((s->kron || s->blocks) ? 128 : PN_THREADS);
+                if (s->cta) s->G = out->threads;
                 if (!s->cta && !s->kron && !s->blocks) s->smem = small_smem_bytes(s->D, s->G, out->threads);
                 if (s->smem > 48 * 1024)
                     CUDA_TRY(cudaFuncSetAttribute(out->rt_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
@@ -660,13 +676,6 @@ static int get_dense(pnode_solver* s) {
     return 0;
 }
 
-static size_t cta_smem_bytes(int d, int q, int n_p) {
-    const size_t n = q + 1, D = (size_t)d * n, npa = n_p > 0 ? n_p : 1;
-    const size_t mp = D * (D + 1) / 2, uni = mp > 2 * d * D ? mp : 2 * d * D; /* must match PnCta::SM_DOUBLES */
-    const size_t dbl = D * D + uni + 2 * d * d + 2 * d * d + d * d + d * d + 3 * D + 4 * d + npa + (sizeof(PnCtaShared) + 7) / 8;
-    return dbl * sizeof(double);
-}
-
 /* SAVE template level of the step kernel: 0 final values only, 1 per-step sol.t / sol.u / sol.pu, 2 additionally the filter
    state per step (what the smoother sweep, the dense output and save_state = sol.x_filt need) */
 static int save_level(const pnode_config* cfg, bool cta) {
@@ -741,7 +750,7 @@ static int validate_config(const pnode_config* cfg) {
         cfg->lanes_per_traj != 16 && cfg->lanes_per_traj != 32 && cfg->lanes_per_traj != 256)
         return fail(PNODE_ERR_ARGUMENT, "lanes_per_traj must be one of 0 (auto), 2, 4, 8, 16, 32, 256 (CTA per trajectory)");
     if (cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256)) {
-        if (cta_smem_bytes(cfg->d, cfg->q, cfg->n_p) > 227 * 1024)
+        if (cta_smem_bytes(cfg->d, cfg->q, cfg->n_p, cfg->second_order != 0, cfg->mass_matrix != nullptr) > 227 * 1024)
             return fail(PNODE_ERR_UNSUPPORTED, "state dimension too large for the shared-memory CTA kernel");
         if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 256)
             return fail(PNODE_ERR_ARGUMENT, "D = d(q+1) > 32 runs one CTA per trajectory (lanes_per_traj 0 or 256)");
@@ -805,8 +814,8 @@ static int validate_config(const pnode_config* cfg) {
         if (cfg->q < 2) return fail(PNODE_ERR_ARGUMENT, "second-order problems need order >= 2 (the measurement reads the second derivative)");
         if (cfg->mass_matrix) return fail(PNODE_ERR_ARGUMENT, "second-order problems take no mass matrix (derivative_utils.jl:39-41 asserts mass_matrix === I)");
         if (cfg->prior != PNODE_PRIOR_IWP) return fail(PNODE_ERR_UNSUPPORTED, "second-order problems are implemented for the IWP prior");
-        if (layout == PNODE_COV_DENSE && (D > 32 || cfg->lanes_per_traj == 256))
-            return fail(PNODE_ERR_UNSUPPORTED, "second-order problems on the dense layout are implemented for D = d(q+1) <= 32");
+        if (layout == PNODE_COV_DENSE && cfg->alg != PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256))
+            return fail(PNODE_ERR_UNSUPPORTED, "second-order problems with the EK0 on the dense layout are implemented for D = d(q+1) <= 32");
         if (cfg->smooth && (smooth_lanes(D) == 0 || env_int("PNODE_SMOOTH_KIND", 1) == 0 || env_int("PNODE_SMOOTH_GENERIC", 0)))
             return fail(PNODE_ERR_UNSUPPORTED, "smoothing of second-order problems needs the column-distributed register sweep (D <= 24)");
     }
@@ -839,8 +848,6 @@ static int validate_config(const pnode_config* cfg) {
             } else {
                 if (cfg->alg != PNODE_EK1)
                     return fail(PNODE_ERR_UNSUPPORTED, "mass matrices on the dense layout are implemented for the EK1");
-                if (D > 32 || cfg->lanes_per_traj == 256)
-                    return fail(PNODE_ERR_UNSUPPORTED, "mass matrices are implemented for D = d(q+1) <= 32 (register-resident kernel)");
             }
         }
     }
@@ -911,7 +918,7 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     s->mv = is_mv(cfg->diffusion);
     s->cta = !s->kron && !s->blocks && (D > 32 || cfg->lanes_per_traj == 256);
     s->G = (s->kron || s->blocks) ? 1 : (s->cta ? 256 : (cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D)));
-    s->smem = s->cta ? cta_smem_bytes(cfg->d, cfg->q, cfg->n_p) : 0; /* group-per-trajectory kernel: set with its thread count in get_kernel */
+    s->smem = s->cta ? cta_smem_bytes(cfg->d, cfg->q, cfg->n_p, cfg->second_order != 0, !s->mass_src.empty() && s->mass_src.find("PN_MASS") != std::string::npos) : 0; /* group-per-trajectory kernel: set with its thread count in get_kernel */
     /* ---- constants ---- */
     PnParams& B = s->base;
     memset(&B, 0, sizeof B);

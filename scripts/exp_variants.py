@@ -2,7 +2,7 @@
 compile-time switches / CTA sizes (PNODE_NVRTC_FLAGS, PNODE_THREADS, PNODE_MIN_BLOCKS), timed with the solver's device
 events and checked against the first variant (accept / reject counts identical, end points to 1e-8).
 
-    python scripts/exp_variants.py rober 262144 100.0 3 "name|threads|flags[|lanes]" ...
+    python scripts/exp_variants.py rober 262144 100.0 3 "name|threads|flags[|lanes[|min_blocks]]" ...
 
 One JSON line per variant (profiles/r2*_variants.jsonl)."""
 import json, os, sys
@@ -23,7 +23,8 @@ def main():
     ref = None
     for var in variants:
         vname, threads, flags = var[:3]
-        lanes = int(var[3]) if len(var) > 3 else 0
+        lanes = int(var[3]) if len(var) > 3 and var[3] else 0
+        os.environ["PNODE_MIN_BLOCKS"] = var[4] if len(var) > 4 and var[4] else "1"
         os.environ["PNODE_FORCE_NVRTC"] = "1"
         os.environ["PNODE_THREADS"] = threads
         os.environ["PNODE_NVRTC_FLAGS"] = flags
