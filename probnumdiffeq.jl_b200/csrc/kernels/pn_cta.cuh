@@ -38,12 +38,19 @@
 /* doubles of dynamic shared memory of the CTA kernel (host and device use this one formula):
    d modelled components, n = q + 1, dp = dimension of the right-hand side (2d for second-order problems), hb = number of
    d-column blocks the measurement matrix H touches (2; 3 for second-order problems), mass: M is staged in shared memory */
+__host__ __device__ constexpr long long pn_cta_ev(long long x) { return (x + 1) & ~1LL; } /* keep every buffer 16-byte aligned */
+/* doubles of the tile-packed upper factor of an M x M matrix (4 x 4 tiles, PN_CTA_TS = 18 doubles apart) */
+__host__ __device__ constexpr long long pn_cta_tiles(long long M) { return ((M + 3) / 4) * ((M + 3) / 4 + 1) / 2 * 18; }
+__host__ __device__ constexpr long long pn_cta_uni(int d, int n) {
+    const long long D = (long long)d * n, tp = pn_cta_tiles(D), bk = pn_cta_ev(d * D) + d * D; /* tile-packed factor | fold batch + gain */
+    return pn_cta_ev(tp > bk ? tp : bk);
+}
 __host__ __device__ constexpr long long pn_cta_sm_doubles(int d, int n, int dp, int hb, int npa, bool mass, int shared_struct_bytes) {
-    const long long D = (long long)d * n, MP = D * (D + 1) / 2, UNI = (MP > 2 * d * D) ? MP : 2 * d * D, NR = (long long)hb * d;
-    return D * D + UNI + NR * d /*C2*/ + NR * d /*V*/ + (long long)d * d /*S*/ +
-           (hb == 3 ? (long long)dp * dp : (long long)d * d) /*J (second order: the Jacobian of the first-order form)*/ +
-           (mass ? (long long)d * d : 0) /*M*/ + 3 * D /*mu,mup,tmp*/ + 3 * d /*z,zt,uprev*/ + 2 * dp /*fu,x2*/ + npa +
-           (shared_struct_bytes + 7) / 8;
+    const long long D = (long long)d * n, NR = (long long)hb * d;
+    return pn_cta_ev(D * D) + pn_cta_uni(d, n) + pn_cta_ev(NR * d) /*C2*/ + pn_cta_ev(pn_cta_tiles(d)) /*tile-packed factor of S, W*/ +
+           pn_cta_ev((long long)d * d) /*S*/ + pn_cta_ev(hb == 3 ? (long long)dp * dp : (long long)d * d) /*J (second order: of the first-order form)*/ +
+           pn_cta_ev(mass ? (long long)d * d : 0) /*M*/ + pn_cta_ev(3 * D) /*mu,mup,tmp*/ + pn_cta_ev(3 * d) /*z,zt,uprev*/ +
+           pn_cta_ev(2 * dp) /*fu,x2*/ + pn_cta_ev(npa) + (shared_struct_bytes + 7) / 8;
 }
 
 /* number of independent slices the problem struct offers for f / J (tracer.py, jac_parts); 1 if it does not say */
@@ -57,7 +64,7 @@ struct PnJacParts<P, decltype((void)P::jac_parts)> {
 };
 
 struct PnCtaShared {
-    double red[PN_CTA_THREADS / 32];
+    double red[32]; /* one slot per warp; sized for 1024 threads so that host and NVRTC builds agree on sizeof */
     double hp[PN_MAX_N], PIv[PN_MAX_N];
     double t, dt, h, tnew, tstop, EEst, qq, q11, lEE, qold, qold_pb2, ediff, ldiff, loglik, gdiff, dtcache;
     double total, total2, quad;
@@ -88,11 +95,9 @@ struct PnCta {
     /* doubles of dynamic shared memory */
     /* packed upper triangle of the Gram matrix; the region is shared with the fold batch Bt (d x D, QR fallback only)
        and with the gain K (D x d, computed after the factor has been copied into R) */
-    static constexpr int MP = D * (D + 1) / 2;
-    static constexpr int UNI = (MP > 2 * d * D) ? MP : 2 * d * D;
+    static constexpr int UNI = (int)pn_cta_uni(d, n);
     static constexpr int JS = PN_SECOND ? DP * DP : d * d; /* Jacobian buffer (second order: of the first-order form) */
     static constexpr int SM_DOUBLES = (int)pn_cta_sm_doubles(d, n, DP, HB, NPA, PN_MASS != 0, (int)sizeof(PnCtaShared));
-    static __device__ __forceinline__ int pidx(int i, int j) { return i * D - (i * (i - 1)) / 2 + (j - i); } /* i <= j */
 
     static __device__ __forceinline__ double block_sum(double x, PnCtaShared* sh) {
 #pragma unroll
@@ -115,96 +120,6 @@ struct PnCta {
         hv[2] = nz ? 1.0 / (total + fabs(alpha) * nrm) : 0.0;
     }
 
-    // Blocked right-looking upper Cholesky A = U'U in shared memory, in place, panels of NBK columns, TWO barriers per
-    // panel.  PACKED: A holds the upper triangle row by row (row i starts at i*m - i(i-1)/2); else full row-major with
-    // leading dimension m (only the upper part is touched).  The NBK x NBK diagonal block is factorised redundantly by
-    // every thread in registers, so a failing pivot (<= 0: the reference's PosDefException, predict.jl:85-91) is seen
-    // by all threads at once and the return value is CTA-uniform.  invd (optional) receives 1 / U[j][j].
-    template <bool PACKED>
-    static __device__ bool chol_blocked(double* A, const int m, double* invd) {
-        constexpr int NBK = 4, TXW = 16, TYW = NT / TXW;
-        const int tid = threadIdx.x, ty = tid / TXW, tx = tid % TXW;
-        auto rowp = [&](int i) -> double* { return PACKED ? (A + i * m - (i * (i - 1)) / 2 - i) : (A + i * m); };
-        bool ok = true;
-        for (int jb = 0; jb < m; jb += NBK) {
-            const int nb = (m - jb < NBK) ? (m - jb) : NBK;
-            __syncthreads();
-            double Ud[NBK][NBK], inv[NBK];
-#pragma unroll
-            for (int p = 0; p < NBK; p++)
-#pragma unroll
-                for (int q = 0; q < NBK; q++)
-                    Ud[p][q] = (p < nb && q < nb && q >= p) ? rowp(jb + p)[jb + q] : ((p == q) ? 1.0 : 0.0);
-#pragma unroll
-            for (int p = 0; p < NBK; p++) {
-                double sp = Ud[p][p];
-#pragma unroll
-                for (int r = 0; r < NBK; r++)
-                    if (r < p) sp -= Ud[r][p] * Ud[r][p];
-                if (!(sp > 0.0)) ok = false;
-                const double ip = pn_rsqrt(sp), up = sp * ip; /* MUFU seed + 2 Newton steps: <= 2 ulp, no slow paths */
-                inv[p] = ip;
-                Ud[p][p] = up;
-#pragma unroll
-                for (int q = 0; q < NBK; q++) {
-                    if (q <= p) continue;
-                    double v = Ud[p][q];
-#pragma unroll
-                    for (int r = 0; r < NBK; r++)
-                        if (r < p) v -= Ud[r][p] * Ud[r][q];
-                    Ud[p][q] = v * ip;
-                }
-            }
-            if (!ok) break; /* uniform */
-            /* panel rows U[jb+p][k], k >= jb + nb: forward substitution with the diagonal block, column-local */
-            for (int k = jb + nb + tid; k < m; k += NT) {
-                double u[NBK];
-#pragma unroll
-                for (int p = 0; p < NBK; p++) {
-                    if (p < nb) {
-                        double v = rowp(jb + p)[k];
-#pragma unroll
-                        for (int r = 0; r < NBK; r++)
-                            if (r < p) v -= Ud[r][p] * u[r];
-                        u[p] = v * inv[p];
-                        rowp(jb + p)[k] = u[p];
-                    } else {
-                        u[p] = 0.0;
-                    }
-                }
-            }
-            __syncthreads();
-            if (tid < NBK * NBK) { /* everybody has read the diagonal block: store its factor */
-                const int pp = tid / NBK, qq = tid % NBK;
-#pragma unroll
-                for (int p = 0; p < NBK; p++)
-#pragma unroll
-                    for (int q = 0; q < NBK; q++)
-                        if (p == pp && q == qq && p < nb && q < nb && q >= p) rowp(jb + p)[jb + q] = Ud[p][q];
-            }
-            if (invd != nullptr && tid < NBK) {
-#pragma unroll
-                for (int p = 0; p < NBK; p++)
-                    if (p == tid && p < nb) invd[jb + p] = inv[p];
-            }
-            /* trailing update with the nb finished rows */
-            for (int i = jb + nb + ty; i < m; i += TYW) {
-                double ui[NBK];
-#pragma unroll
-                for (int p = 0; p < NBK; p++) ui[p] = (p < nb) ? rowp(jb + p)[i] : 0.0;
-                double* ri = rowp(i);
-                for (int k = i + tx; k < m; k += TXW) {
-                    double sv = ri[k];
-#pragma unroll
-                    for (int p = 0; p < NBK; p++)
-                        if (p < nb) sv -= ui[p] * rowp(jb + p)[k];
-                    ri[k] = sv;
-                }
-            }
-        }
-        __syncthreads();
-        return ok;
-    }
     // ----------------------------------------------------------------------------------------------------------------
     // Gram matrix + Cholesky on 4 x 4 register tiles (predict.jl:84-85 for the D x D factor; the d x d matrices S and W use
     // the same routine).  Tile (I, J), I <= J, of the symmetric M x M matrix belongs to thread e % NT (e = row-major index over
@@ -405,28 +320,63 @@ struct PnCta {
         }
     }
 
+    // K' <- S^-1 K' column by column (one thread per column of the d x D matrix at K), mu = mu^- - K z.  S holds the upper
+    // Cholesky factor, invd its reciprocal diagonal.  Column-oriented substitution in registers: per pivot one dependent
+    // multiply and one level of independent FMAs; the factor is read as shared-memory broadcasts.  Not inlined: the routine
+    // wants d + d^2/2-ish registers of its own, which the surrounding kernel cannot spare.
+    static __device__ __forceinline__ void gain_columns(double* K, const volatile double* S, const double* invd, const double* mup, double* mu,
+                                                     const double* z) {
+        for (int c = threadIdx.x; c < D; c += NT) {
+            double x[d];
+#pragma unroll
+            for (int a = 0; a < d; a++) x[a] = K[a * D + c];
+#pragma unroll
+            for (int a = 0; a < d; a++) { /* U' y = b */
+                x[a] *= invd[a];
+#pragma unroll
+                for (int j = 0; j < d; j++)
+                    if (j > a) x[j] = fma(-S[a * d + j], x[a], x[j]);
+            }
+#pragma unroll
+            for (int a = d - 1; a >= 0; a--) { /* U k = y */
+                double acc = x[a];
+#pragma unroll
+                for (int j = 0; j < d; j++)
+                    if (j > a) acc = fma(-S[a * d + j], x[j], acc);
+                x[a] = acc * invd[a];
+            }
+            double m = mup[c];
+#pragma unroll
+            for (int a = 0; a < d; a++) {
+                K[a * D + c] = x[a];
+                m = fma(-x[a], z[a], m);
+            }
+            mu[c] = m; /* mu = mu^- - K z (update.jl:115) */
+        }
+    }
+
     static __device__ void run(const PnParams& P) {
-        extern __shared__ double pn_cta_sm[];
+        extern __shared__ __align__(16) double pn_cta_sm[];
         const int tid = threadIdx.x;
         double* R = pn_cta_sm;
-        double* Mp = R + D * D; /* packed Gram matrix | Bt, K */
+        double* Mp = R + pn_cta_ev(D * D); /* tile-packed factor of the Gram matrix | Bt, K */
         double* Bt = Mp;
-        double* K = Mp + d * D;
+        double* K = Mp + pn_cta_ev(d * D);
         double* C2 = Mp + UNI;
-        double* V = C2 + NR * d;
-        double* S = V + NR * d;
-        double* J = S + d * d;
-        double* Mm = J + JS; /* mass matrix (PN_MASS) */
-        double* mu = Mm + (PN_MASS ? d * d : 0);
+        double* Ts = C2 + pn_cta_ev(NR * d); /* tile-packed factors of the d x d matrices W and S */
+        double* S = Ts + pn_cta_ev(pn_cta_tiles(d));
+        double* J = S + pn_cta_ev(d * d);
+        double* Mm = J + pn_cta_ev(JS); /* mass matrix (PN_MASS) */
+        double* mu = Mm + pn_cta_ev(PN_MASS ? d * d : 0);
         double* mup = mu + D;
         double* sinv = mup + D; /* D doubles of scratch: first d used as inverse Cholesky diagonal */
-        double* z = sinv + D;
+        double* z = sinv + D + (pn_cta_ev(3 * D) - 3 * D);
         double* zt = z + d;
         double* uprev = zt + d;
-        double* fu = uprev + d;
+        double* fu = uprev + d + (pn_cta_ev(3 * d) - 3 * d);
         double* x2 = fu + DP;
         double* pr = x2 + DP;
-        PnCtaShared* sh = (PnCtaShared*)(pr + NPA);
+        PnCtaShared* sh = (PnCtaShared*)(pr + pn_cta_ev(NPA));
         /* entries of H's column blocks (as used in W = H Qh H' and C2 = R^- H'):
            first order  H = [-J | M | 0 ...]   (M = I without a mass matrix; measurement_models.jl:11-20, derivative_utils.jl:1-33)
            second order H = [-J_u | -J_du | I | 0 ...]   (measurement_models.jl:29-49, derivative_utils.jl:35-53) */
@@ -622,7 +572,9 @@ struct PnCta {
                         zt[i] = z[i];
                     }
                     __syncthreads();
-                    const bool okW = chol_blocked<false>(S, d, sinv);
+                    const bool okW = gram_chol_tiles<d>(nullptr, 0, Ts, sinv, sh, [&](int gi, int gj) -> double { return S[gi * d + gj]; });
+                    expand_tiles<d>(Ts, S);
+                    __syncthreads();
                     if (d <= 32) {
                         if (tid < 32) chol_solve_warp(S, sinv, zt, d);
                     } else if (tid == 0) {
@@ -714,73 +666,15 @@ struct PnCta {
                         for (int m = 0; m < n; m++) acc += P.L[m * n + c] * P.L[m * n + c2];
                         sh->Qn[tid] = acc * sh->PIv[c] * sh->PIv[c2];
                     }
-                    if (tid == 0) sh->chol_fail = 0;
                     __syncthreads();
                     const double ediff = sh->ediff;
-                    /* SYRK: 4 x 4 register tiles over the upper triangle of tiles */
-                    constexpr int TI = (D + 3) / 4;
-                    constexpr int NTILES = TI * (TI + 1) / 2;
-                    for (int e = tid; e < NTILES; e += NT) {
-                        int I = 0, rem = e;
-                        while (rem >= TI - I) {
-                            rem -= TI - I;
-                            I++;
-                        }
-                        const int J = I + rem;
-                        double acc[4][4];
-#pragma unroll
-                        for (int a = 0; a < 4; a++)
-#pragma unroll
-                            for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
-                        const int ci = 4 * I, cj = 4 * J;
-                        if (D % 4 == 0) {
-#pragma unroll 2
-                            for (int r = 0; r < D; r++) {
-                                const double2 a01 = *reinterpret_cast<const double2*>(R + r * D + ci);
-                                const double2 a23 = *reinterpret_cast<const double2*>(R + r * D + ci + 2);
-                                const double2 b01 = *reinterpret_cast<const double2*>(R + r * D + cj);
-                                const double2 b23 = *reinterpret_cast<const double2*>(R + r * D + cj + 2);
-                                const double av[4] = {a01.x, a01.y, a23.x, a23.y};
-                                const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-                                for (int a = 0; a < 4; a++)
-#pragma unroll
-                                    for (int b = 0; b < 4; b++) acc[a][b] += av[a] * bv[b];
-                            }
-                        } else {
-                            for (int r = 0; r < D; r++) {
-                                double av[4], bv[4];
-#pragma unroll
-                                for (int a = 0; a < 4; a++) {
-                                    av[a] = (ci + a < D) ? R[r * D + ci + a] : 0.0;
-                                    bv[a] = (cj + a < D) ? R[r * D + cj + a] : 0.0;
-                                }
-#pragma unroll
-                                for (int a = 0; a < 4; a++)
-#pragma unroll
-                                    for (int b = 0; b < 4; b++) acc[a][b] += av[a] * bv[b];
-                            }
-                        }
-#pragma unroll
-                        for (int a = 0; a < 4; a++)
-#pragma unroll
-                            for (int b = 0; b < 4; b++) {
-                                const int gi = ci + a, gj = cj + b;
-                                if (gi <= gj && gj < D) {
-                                    const int ji = gi / d, jj = gj / d;
-                                    double v = acc[a][b];
-                                    if (gi - ji * d == gj - jj * d) v += ediff * sh->Qn[ji * n + jj]; /* predict.jl:79-83 */
-                                    Mp[pidx(gi, gj)] = v;
-                                }
-                            }
-                    }
-                    __syncthreads();
-                    const bool ok = chol_blocked<true>(Mp, D, nullptr);
-                    if (ok) { /* R^- = U: expand the packed factor into the dense one */
-                        for (int e = tid; e < D * D; e += NT) {
-                            const int i = e / D, k = e - i * D;
-                            R[e] = (k >= i) ? Mp[pidx(i, k)] : 0.0;
-                        }
+                    /* M = X'X + s2 Qh (x) I_d (predict.jl:79-85), factorised tile by tile in registers */
+                    const bool ok = gram_chol_tiles<D>(R, D, Mp, nullptr, sh, [&](int gi, int gj) -> double {
+                        const int ji = gi / d, jj = gj / d;
+                        return (gi - ji * d == gj - jj * d) ? ediff * sh->Qn[ji * n + jj] : 0.0;
+                    });
+                    if (ok) { /* R^- = U: expand the tile-packed factor into the dense one */
+                        expand_tiles<D>(Mp, R);
                         need_qr = false;
                     }
                     __syncthreads();
@@ -968,16 +862,12 @@ struct PnCta {
                     C2[e] = s;
                 }
                 __syncthreads();
-                for (int e = tid; e < d * d; e += NT) {
-                    const int a = e / d, b = e - a * d;
-                    if (b < a) continue;
-                    double s = 0.0;
-                    for (int r = 0; r < NR; r++) s += C2[r * d + a] * C2[r * d + b];
-                    S[a * d + b] = s;
-                }
-                __syncthreads();
+                /* S = C2'C2 = U_S'U_S (perform_step.jl:182-188, update.jl:100): Gram + Cholesky on register tiles; the
+                   tile-packed factor goes to Ts */
+                const bool okS = gram_chol_tiles<d>(C2, NR, Ts, sinv, sh, [](int, int) -> double { return 0.0; });
+                /* a singular S is either Sigma^- H' == 0 (pass-through, update.jl:82-89) or a breakdown */
                 double trS = 0.0;
-                for (int a = tid; a < d; a += NT) trS += S[a * d + a];
+                for (int e = tid; e < NR * d; e += NT) trS += C2[e] * C2[e];
                 trS = block_sum(trS, sh);
                 if (trS == 0.0) { /* Sigma^- H' == 0 : pass-through (update.jl:82-89) */
                     for (int c = tid; c < D; c += NT) mu[c] = mup[c];
@@ -988,60 +878,14 @@ struct PnCta {
                     }
                     __syncthreads();
                 } else {
+                    expand_tiles<d>(Ts, S);
                     for (int i = tid; i < d; i += NT) zt[i] = z[i];
                     __syncthreads();
-                    const bool okS = chol_blocked<false>(S, d, sinv);
-                    if (d <= 32) {
-                        if (tid < 32) chol_solve_warp(S, sinv, zt, d);
-                    } else if (tid == 0) {
-                        chol_solve_serial(S, sinv, zt, d);
-                    }
-                    __syncthreads();
-                    if (tid == 0) {
-                        sh->okflag = okS ? 1 : 0;
-                        double quad = 0.0, logdet = 0.0;
-                        for (int a = 0; a < d; a++) {
-                            quad += z[a] * zt[a];
-                            logdet += log(S[a * d + a]);
-                        }
-                        sh->loglik += -0.5 * quad - 0.5 * (double)d * 1.8378770664093453 - logdet;
-                        if (!DYNAMIC) {
-                            const double inc = quad * (1.0 / (double)d);
-                            sh->gdiff = (sh->naccept == 0) ? inc : sh->gdiff + (inc - sh->gdiff) / (double)sh->naccept;
-                        }
-                        if (!sh->okflag) sh->retcode = PN_RET_UNSTABLE;
-                    }
-                    /* V = C2 S^-1 with the explicit inverse S^-1 = U^-1 U^-T: one thread per column of U^-1 (the only
-                       sequential part, <= d^2/2 dependent FMAs), then two small fully parallel products.  The
-                       Jacobian buffer is free by now and holds U^-1; S^-1 overwrites S. */
-                    __syncthreads();
-                    for (int b = tid; b < d; b += NT) { /* U x = e_b, x upper-triangular column b */
-                        double* x = J + b * d; /* J[b*d + a] = Uinv[a][b] (column b stored contiguously) */
-                        for (int a = d - 1; a > b; a--) x[a] = 0.0;
-                        x[b] = sinv[b];
-                        for (int a = b - 1; a >= 0; a--) {
-                            double sacc = 0.0;
-                            for (int k = a + 1; k <= b; k++) sacc -= S[a * d + k] * x[k];
-                            x[a] = sacc * sinv[a];
-                        }
-                    }
-                    __syncthreads();
-                    for (int e = tid; e < d * d; e += NT) { /* S^-1[a][b] = sum_k Uinv[a][k] Uinv[b][k], k >= max(a, b) */
-                        const int a = e / d, b = e - a * d;
-                        const int k0 = a > b ? a : b;
-                        double sacc = 0.0;
-                        for (int k = k0; k < d; k++) sacc += J[k * d + a] * J[k * d + b];
-                        S[e] = sacc;
-                    }
-                    __syncthreads();
-                    for (int e = tid; e < NR * d; e += NT) {
-                        const int r = e / d, a = e - r * d;
-                        double sacc = 0.0;
-                        for (int k = 0; k < d; k++) sacc += C2[r * d + k] * S[k * d + a];
-                        V[e] = sacc;
-                    }
-                    __syncthreads();
-                    /* K = R^-' V, stored transposed (Kt[a][c]); TA gains per thread so that a row entry of R^- is reused */
+                    /* K' = S^-1 (C2' R^-)  (update.jl:100-109: K = Sigma^-.R' (Sigma^-.R H') / chol(S)).  First Bm = C2' R^- (d x D,
+                       stored where the gain goes), TA rows per thread so that an entry of R^- is reused; then one thread per
+                       column solves U_S' U_S k = b in registers (column-oriented substitution: one dependent multiply and one
+                       level of independent FMAs per pivot), the factor read as shared-memory broadcasts.  Warp 0 meanwhile
+                       solves for z (log-likelihood) on its own. */
                     {
                         constexpr int TA = (d % 7 == 0) ? 7 : 4;
                         constexpr int NAB = (d + TA - 1) / TA;
@@ -1055,7 +899,7 @@ struct PnCta {
                                 const double rv = R[r * D + c];
 #pragma unroll
                                 for (int t = 0; t < TA; t++)
-                                    if (ab * TA + t < d) acc[t] += rv * V[r * d + ab * TA + t];
+                                    if (ab * TA + t < d) acc[t] += rv * C2[r * d + ab * TA + t];
                             }
 #pragma unroll
                             for (int t = 0; t < TA; t++)
@@ -1063,11 +907,30 @@ struct PnCta {
                         }
                     }
                     __syncthreads();
-                    for (int c = tid; c < D; c += NT) {
-                        double s = mup[c];
-                        for (int a = 0; a < d; a++) s -= K[a * D + c] * z[a];
-                        mu[c] = s;
+                    if (tid >= NT - 32) { /* last warp: z solve + log-likelihood bookkeeping */
+                        if (d <= 32) {
+                            chol_solve_warp(S, sinv, zt, d);
+                        } else if (tid == NT - 32) {
+                            chol_solve_serial(S, sinv, zt, d);
+                        }
+                        __syncwarp();
+                        if (tid == NT - 32) {
+                            sh->okflag = okS ? 1 : 0;
+                            double quad = 0.0, logdet = 0.0;
+                            for (int a = 0; a < d; a++) {
+                                quad += z[a] * zt[a];
+                                logdet += log(S[a * d + a]);
+                            }
+                            sh->loglik += -0.5 * quad - 0.5 * (double)d * 1.8378770664093453 - logdet;
+                            if (!DYNAMIC) {
+                                const double inc = quad * (1.0 / (double)d);
+                                sh->gdiff = (sh->naccept == 0) ? inc : sh->gdiff + (inc - sh->gdiff) / (double)sh->naccept;
+                            }
+                            if (!sh->okflag) sh->retcode = PN_RET_UNSTABLE;
+                        }
                     }
+                    gain_columns(K, S, sinv, mup, mu, z);
+                    __syncthreads();
                     /* R+ = R^- - C2 K' on the first NR rows, TR rows per thread */
                     {
                         constexpr int TR = 4;

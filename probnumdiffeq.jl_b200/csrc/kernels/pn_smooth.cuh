@@ -58,6 +58,8 @@ struct PnSmoothParams {
     int n_obs;
     const int* retcode;     /* [n_traj] return codes of the solve: -Inf unless Success (fenrir.jl:55-59) */
     double* fenrir_ll;      /* [n_traj] out */
+    int write_x;            /* 1: the smoothed state records (s_x_mean, s_x_covfac) are somebody's input or output (save_state, dense
+                               output); 0: a sweep may leave the records alone and only emit sol.u / sol.pu -- a third of its HBM bytes */
     int kron_logdet;        /* 1: IsometricKronecker layout (EK0 + IWP + scalar diffusion): the reference's data update runs on the
                                n x n factors and takes logdet of the 1 x 1 factor of S without the factor d (update.jl:140-148,
                                182-194) -- log det S / n_obs instead of log det S */

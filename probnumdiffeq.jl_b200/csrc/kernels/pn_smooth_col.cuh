@@ -229,7 +229,7 @@ struct PnSmoothCol {
                                    not at sol.t[end] is skipped by the reference, and so it is here */
                 }
                 if (got) {
-                    if (!P.dynamic && P.calibrate && !fen) write_record(P, last, Sm, Ms, scv, gl);
+                    if (!P.dynamic && P.calibrate && !fen && P.write_x) write_record(P, last, Sm, Ms, scv, gl);
                     if (gl == 0 && !fen) write_pu(P, last, Sm, Ms, scv);
                     k = last - 1;
                     have = (k >= a0);
@@ -251,7 +251,7 @@ struct PnSmoothCol {
             const bool copy = active && (h == 0.0); /* integrator_utils.jl:109-112 */
             const bool doit = active && !copy;
             if (copy) {
-                if (!fen) write_record(P, k, Sm, Ms, scv, gl);
+                if (!fen && P.write_x) write_record(P, k, Sm, Ms, scv, gl);
                 /* a copy step consumes no staged record: request the one of the next real step from here */
                 if (ASYNC && k > a0 && P.s_h[k - 1] != 0.0) stage_async(P, k - 1, sm + OFF_REC + cur * RECSZ, gl);
             }
@@ -437,7 +437,7 @@ struct PnSmoothCol {
                 }
                 __syncwarp();
                 if (doit && !fen) {
-                    write_record(P, k, Sm, Ms, scv, gl);
+                    if (P.write_x) write_record(P, k, Sm, Ms, scv, gl);
                     if (gl == 0) write_pu(P, k, Sm, Ms, scv);
                 }
                 if (doit && fen && data_idx >= 0 && P.s_t[k] == P.data_t[data_idx]) { /* fenrir.jl:110-123 */

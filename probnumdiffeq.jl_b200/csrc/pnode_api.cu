@@ -1581,6 +1581,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             Q.s_x_covfac = P.s_x_covfac;
             Q.s_u_mean = P.s_u_mean;
             Q.s_u_cov = P.s_u_cov;
+            Q.write_x = (s->cfg.save_state || dense) ? 1 : 0; /* sol.x_smooth asked for, or the dense output reads the smoothed records */
             if (s->n_data > 0) {
                 /* Fenrir: the backward pass fits the PN posterior to the data instead of smoothing; the records and the
                    U fields stay the filtering estimates, uncalibrated (the reference stops with step!, no postamble) */

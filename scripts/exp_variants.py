@@ -19,7 +19,10 @@ def main():
     rng = np.random.default_rng(3)
     u0 = np.tile(np.array(pd.u0, dtype=float), (n, 1))
     p = np.array(pd.p, dtype=float)[None, :] * (1 + 0.1 * rng.uniform(-1, 1, (n, pd.n_p)))
+    if name == "pleiades":   # initial positions perturbed by 1e-3
+        u0[:, 14:] += 1e-3 * rng.uniform(-1, 1, (n, 14))
     smooth = os.environ.get("EXP_SMOOTH", "0") == "1"
+    second = os.environ.get("EXP_SECOND", "0") == "1"   # the problem's first-order form as a SecondOrderODEProblem
     ref = None
     for var in variants:
         vname, threads, flags = var[:3]
@@ -27,9 +30,13 @@ def main():
         os.environ["PNODE_MIN_BLOCKS"] = var[4] if len(var) > 4 and var[4] else "1"
         os.environ["PNODE_FORCE_NVRTC"] = "1"
         os.environ["PNODE_THREADS"] = threads
+        os.environ["PNODE_CTA_THREADS"] = threads          # CTA-per-trajectory kernel (D > 32)
+        os.environ["PNODE_CTA_MIN_BLOCKS"] = var[4] if len(var) > 4 and var[4] else ""
+        if not os.environ["PNODE_CTA_MIN_BLOCKS"]:
+            del os.environ["PNODE_CTA_MIN_BLOCKS"]
         os.environ["PNODE_NVRTC_FLAGS"] = flags
         try:
-            cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="builtin:" + name, t0=0.0, t1=t1, smooth=smooth, save_everystep=smooth, lanes_per_traj=lanes)
+            cfg = lib.make_config(d=pd.d // 2 if second else pd.d, second_order=second, q=q, n_p=pd.n_p, rhs_name="builtin:" + name, t0=0.0, t1=t1, smooth=smooth, save_everystep=smooth, lanes_per_traj=lanes)
             s = lib.Solver(cfg)
             best = None
             for _ in range(3):
