@@ -144,6 +144,16 @@ typedef struct pnode_config {
     const double* observation_matrix; /* [n_obs][len(sol.u)] row-major; NULL = identity (n_obs == len(sol.u))        */
     const double* observation_noise_cov; /* [n_obs][n_obs] symmetric positive definite; NULL = observation_noise_var * I */
     double observation_noise_var;
+    /* EK0 / EK1 / DiagonalEK1(pn_observation_noise = R) (src/algorithms.jl:195-393; cov2psdmatrix, src/caches.jl:175-178): the ODE
+       residual z = 0 is observed with noise covariance R.  The measurement covariance gains R (src/perform_step.jl:182-188) and the
+       filtered covariance K R K', re-factorised by Cholesky with triangularize! as the fallback (src/filtering/update.jl:125-136).
+       pn_observation_noise: [d][d] row-major symmetric positive definite, host pointer, copied at create; NULL with
+       pn_observation_noise_var > 0: R = var * I (a Number / UniformScaling); both unset: noise-free.  As in ekargcheck
+       (src/algorithms.jl:78-130): not with FixedDiffusion(calibrate = true) / FixedMVDiffusion(calibrate = true); the Kronecker
+       layout (EK0 + scalar diffusion) takes isotropic R only, the blocks layout (DiagonalEK1, EK0 + multivariate diffusion)
+       diagonal R only -- PNODE_ERR_ARGUMENT with the reference's messages. */
+    const double* pn_observation_noise;
+    double pn_observation_noise_var;
 } pnode_config;
 
 typedef struct pnode_solver pnode_solver;

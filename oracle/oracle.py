@@ -91,6 +91,7 @@ class Config(C.Structure):
         ("second_order", C.c_int32), ("reserved1", C.c_int32),
         ("data_t", C.POINTER(C.c_double)), ("n_data", C.c_int64), ("data_u", C.POINTER(C.c_double)),
         ("n_obs", C.c_int32), ("reserved2", C.c_int32), ("obs_H", C.POINTER(C.c_double)), ("obs_Rn", C.POINTER(C.c_double)),
+        ("pn_obs_Rn", C.POINTER(C.c_double)),
     ]
 
 
@@ -231,7 +232,7 @@ def make_config(d, q, n_p, *, alg=EK1, diffusion=DIFF_DYNAMIC, calibrate=True, i
                 reltol=1e-3, dtmin=0.0, dtmax=None, maxiters=1_000_000, beta1=None, beta2=None, qmin=0.2, qmax=10.0,
                 gamma=0.9, qsteady_min=1.0, qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None,
                 prior=PRIOR_IWP, rate_parameter=0.0, mass_matrix=None, second_order=False, data=None,
-                observation_matrix=None, observation_noise_cov=None):
+                observation_matrix=None, observation_noise_cov=None, pn_observation_noise=None):
     c = Config()
     c.second_order = int(second_order)
     c.d, c.q, c.n_p, c.alg = d, q, n_p, alg
@@ -273,6 +274,13 @@ def make_config(d, q, n_p, *, alg=EK1, diffusion=DIFF_DYNAMIC, calibrate=True, i
             ts = np.ascontiguousarray(tstops, dtype=np.float64)
             keep.append(ts)
             c.tstops, c.n_tstops = _dp(ts), len(ts)
+    if pn_observation_noise is not None:
+        # cov2psdmatrix (src/covariance_structure.jl): a number / UniformScaling x -> sqrt(x) I, a matrix -> cholesky(M).U
+        cov = np.asarray(pn_observation_noise, dtype=np.float64)
+        Rn = np.sqrt(float(cov)) * np.eye(d) if cov.ndim == 0 else (np.diag(np.sqrt(cov)) if cov.ndim == 1 else np.linalg.cholesky(cov.reshape(d, d)).T)
+        Rn = np.ascontiguousarray(Rn.T).reshape(-1)   # column-major bytes
+        keep.append(Rn)
+        c.pn_obs_Rn = _dp(Rn)
     if mass_matrix is not None:
         mm = np.asfortranarray(np.asarray(mass_matrix, dtype=np.float64).reshape(d, d))  # column-major for the C side
         mm = np.ascontiguousarray(mm.T).reshape(-1)                                      # = column-major bytes of M

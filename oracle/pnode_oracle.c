@@ -370,7 +370,7 @@ static void rdiv_chol_upper(int m, int n, double* B, const double* U) {
    Returns 0 ok, 1 if S is not positive definite (Julia would throw PosDefException). */
 static int update_generic(int N, int m, int nrhs, const double* mu_p, int rs, int cs, const double* R_p,
                           const double* z, int zs_a, int zs_c, const double* H /* m x N */, double* mu_out,
-                          double* R_out, double* loglik) {
+                          double* R_out, double* loglik, const double* Rn /* m x m upper factor of pn_observation_noise, or NULL */) {
     if (all_zero(R_p, (size_t)N * N)) { /* :82-89 */
         for (int r = 0; r < N; r++)
             for (int c = 0; c < nrhs; c++) mu_out[r * rs + c * cs] = mu_p[r * rs + c * cs];
@@ -390,6 +390,8 @@ static int update_generic(int N, int m, int nrhs, const double* mu_p, int rs, in
     gemm(N, m, N, 1.0, R_p, N, 0, H, m, 1, 0.0, K1, N);  /* C_Dxd = R_p H'  (perform_step.jl:183, update.jl:101) */
     gemm(m, m, N, 1.0, K1, N, 1, K1, N, 0, 0.0, S, m);   /* S = C' C        (perform_step.jl:184) */
     gemm(N, m, N, 1.0, R_p, N, 1, K1, N, 0, 0.0, K, N);  /* K2 = R_p' K1    (update.jl:102) */
+    if (Rn) /* + R.R'R.R (perform_step.jl:185-187) */
+        gemm(m, m, m, 1.0, Rn, m, 1, Rn, m, 0, 1.0, S, m);
     double logdet;
     int fail = 0;
     if (m == 1) { /* S_chol = S[1] (update.jl:108) */
@@ -433,6 +435,22 @@ static int update_generic(int N, int m, int nrhs, const double* mu_p, int rs, in
     gemm(N, N, m, -1.0, K, N, 0, H, m, 0, 0.0, Mc, N);
     for (int i = 0; i < N; i++) AT(Mc, i, i, N) += 1.0;
     gemm(N, N, N, 1.0, R_p, N, 0, Mc, N, 1, 0.0, R_out, N);
+    if (Rn) { /* update.jl:125-136: Sigma = R_out'R_out + K R K'; cholesky, or triangularize!([R_out; (K R.R')']) if it fails */
+        gemm(N, m, m, 1.0, K, N, 0, Rn, m, 1, 0.0, K1, N);          /* K1 = K R.R' */
+        gemm(N, N, N, 1.0, R_out, N, 1, R_out, N, 0, 0.0, Mc, N);
+        gemm(N, N, m, 1.0, K1, N, 0, K1, N, 1, 1.0, Mc, N);
+        if (oracle_cholesky_upper(N, Mc) == 0) {
+            memcpy(R_out, Mc, sizeof(double) * N * N);
+        } else {
+            double* St = (double*)malloc(sizeof(double) * (N + m) * N);
+            for (int c = 0; c < N; c++) {
+                for (int r = 0; r < N; r++) AT(St, r, c, N + m) = AT(R_out, r, c, N);
+                for (int a = 0; a < m; a++) AT(St, N + a, c, N + m) = AT(K1, c, a, N);
+            }
+            oracle_triangularize(N + m, N, St, R_out);
+            free(St);
+        }
+    }
     free(K1);
     free(K);
     free(S);
@@ -443,7 +461,7 @@ static int update_generic(int N, int m, int nrhs, const double* mu_p, int rs, in
 
 int oracle_update(int D, int d, const double* mu_p, const double* R_p, const double* z, const double* H,
                   double* mu_out, double* R_out, double* loglik) {
-    return update_generic(D, d, 1, mu_p, 1, 0, R_p, z, 1, 0, H, mu_out, R_out, loglik);
+    return update_generic(D, d, 1, mu_p, 1, 0, R_p, z, 1, 0, H, mu_out, R_out, loglik, NULL);
 }
 
 /* compute_backward_kernel! (src/filtering/markov_kernel.jl:190-235; Kronecker :237-272). */
@@ -795,8 +813,12 @@ static int solve_blocks(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn j
             }
             S[i] = e;
             double ll;
+            /* blocks layout: the observation noise is Diagonal (to_factorized_matrix, covariance_structure.jl:46-58), block i takes
+               the 1 x 1 factor R.R[i][i] */
+            const double rni = c->pn_obs_Rn ? c->pn_obs_Rn[(size_t)i * d + i] : 0.0;
+            if (c->pn_obs_Rn) S[i] += rni * rni;
             ufail |= update_generic(n, 1, 1, mu_pred + i, d, 0, R_pred + i * nn, z + i, 1, 0, Hi, mu_filt + i, R_filt + i * nn,
-                                    &ll); /* update.jl:197-239 */
+                                    &ll, c->pn_obs_Rn ? &rni : NULL); /* update.jl:197-239 */
             ll_step += ll;
         }
         if (ufail) { retcode = ORACLE_RET_UNSTABLE; break; }
@@ -1351,13 +1373,15 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
         if (c->smooth)                                                               /* :126-131 */
             backward_kernel_generic(N, nrhs, rs, cs, mu, R, mu_pred, R_pred, Ah, QhR, ediff, G, bb, LR);
         double ll;
-        int ufail = update_generic(N, m, nrhs, mu_pred, rs, cs, R_pred, z, 1, 1, H, mu_filt, R_filt, &ll); /* :134-138 */
+        /* Kronecker layout: isotropic observation noise, the factor of the 1 x 1 left Kronecker factor is R.R[0][0] */
+        int ufail = update_generic(N, m, nrhs, mu_pred, rs, cs, R_pred, z, 1, 1, H, mu_filt, R_filt, &ll, c->pn_obs_Rn); /* :134-138 */
         if (ufail) { retcode = ORACLE_RET_UNSTABLE; break; }
         loglik_total += ll;                                                          /* :142-143 */
         if (!dynamic) { /* estimate_global_diffusion(::FixedDiffusion) (calibration.jl:49-66) */
             /* invquad(z, S) / d with S = measurement covariance from the predicted state */
             gemm(N, m, N, 1.0, R_pred, N, 0, H, m, 1, 0.0, Cq, N);
             gemm(m, m, N, 1.0, Cq, N, 1, Cq, N, 0, 0.0, W, m);
+            if (c->pn_obs_Rn) gemm(m, m, m, 1.0, c->pn_obs_Rn, m, 1, c->pn_obs_Rn, m, 0, 1.0, W, m); /* measurement.Sigma includes R */
             double inc;
             if (kron) {
                 double zz = 0.0;

@@ -90,6 +90,10 @@ typedef struct {
     int32_t reserved2;
     const double* obs_H;    /* n_obs x D, column-major: observation_matrix * SolProj */
     const double* obs_Rn;   /* n_obs x n_obs, column-major upper factor of the observation-noise covariance */
+    /* EK0/EK1(pn_observation_noise = R) (src/algorithms.jl:188-393, src/caches.jl:175-178): d x d column-major upper factor R.R of
+       the noise covariance the ODE measurement z = 0 is observed with; NULL = noise-free.  S += R.R'R.R
+       (src/perform_step.jl:182-188) and the filtered covariance gains K R K' (src/filtering/update.jl:125-136). */
+    const double* pn_obs_Rn;
 } oracle_config;
 
 /* One solved trajectory.  Arrays are owned by the struct; free with oracle_traj_free. */

@@ -72,6 +72,9 @@ class _EK:
     smooth: bool = True
     diffusionmodel: object = DynamicDiffusion()
     prior: Optional[object] = None   # IWP(q) or IOUP(q, rate)
+    # observation noise of the ODE measurement z = 0 (src/algorithms.jl:195-393): a number (R = x I), a 1-d array (Diagonal) or a
+    # d x d covariance matrix; the layout rules of ekargcheck (src/algorithms.jl:78-130) are checked by the library
+    pn_observation_noise: Optional[object] = None
 
     @property
     def q(self) -> int:
@@ -256,6 +259,8 @@ def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, absto
         kw.update(diffusion=_lib.DIFF_DYNAMIC)
     if isinstance(alg.prior, IOUP):
         kw.update(prior=_lib.PRIOR_IOUP, rate_parameter=alg.prior.rate_parameter)
+    if alg.pn_observation_noise is not None:
+        kw.update(pn_observation_noise=alg.pn_observation_noise)
     if prob.mass_matrix is not None:
         M = np.asarray(prob.mass_matrix, dtype=float)
         if M.shape != (d, d):

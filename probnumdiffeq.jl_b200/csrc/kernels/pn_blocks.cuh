@@ -338,6 +338,10 @@ struct PnBlocks {
 #pragma unroll
                         for (int j = 0; j < n; j++) M[j][i] = Mp[j][i];
                     } else {
+#if PN_OBSN
+                        Si += pn_obsn_cov(i, i); /* diagonal pn_observation_noise: block i's 1 x 1 factor (perform_step.jl:185-187) */
+                        S[i] = Si;
+#endif
                         const double iS = pn_rcp(Si);
                         llstep += -0.5 * z[i] * z[i] * iS - 0.5 * 1.8378770664093453 - 0.5 * log(Si);
                         double K[n];
@@ -354,6 +358,17 @@ struct PnBlocks {
                         for (int r = 0; r < n; r++)
 #pragma unroll
                             for (int c = 0; c < n; c++) RB[i][r][c] -= c1[r] * K[c];
+#if PN_OBSN
+                        { /* update.jl:125-136 on block i: qr([R+ ; sqrt(r_i) K']) */
+                            double Bn[n][n];
+                            const double sr = sqrt(pn_obsn_cov(i, i));
+#pragma unroll
+                            for (int r = 0; r < n; r++)
+#pragma unroll
+                                for (int c = 0; c < n; c++) Bn[r][c] = (r == 0) ? sr * K[c] : 0.0;
+                            pn_qr_local<n>(RB[i], Bn);
+                        }
+#endif
                     }
                 }
                 loglik += llstep;

@@ -290,6 +290,9 @@ struct PnKron {
 #pragma unroll
                         for (int i = 0; i < d; i++) M[j][i] = Mp[j][i];
                 } else {
+#if PN_OBSN
+                    S += pn_obsn_cov(0, 0); /* isotropic pn_observation_noise: the 1 x 1 left Kronecker factor of R (perform_step.jl:185-187) */
+#endif
                     const double iS = pn_rcp(S);
                     loglik += -0.5 * zz * iS - 0.5 * (double)d * 1.8378770664093453;
                     if (!pn_logacc_mul(lgm, lge, S)) loglik -= 0.5 * log(S);
@@ -313,6 +316,17 @@ struct PnKron {
                     for (int r = 0; r < n; r++)
 #pragma unroll
                         for (int c = 0; c < n; c++) RB[r][c] -= c1[r] * K[c];
+#if PN_OBSN
+                    { /* update.jl:125-136 on the factor: Sigma = R+'R+ + K r K', here as qr([R+ ; sqrt(r) K']) */
+                        double Bn[n][n];
+                        const double sr = sqrt(pn_obsn_cov(0, 0));
+#pragma unroll
+                        for (int r = 0; r < n; r++)
+#pragma unroll
+                            for (int c = 0; c < n; c++) Bn[r][c] = (r == 0) ? sr * K[c] : 0.0;
+                        qr_stack(RB, Bn);
+                    }
+#endif
                 }
                 /* loopfooter! accept */
                 double dtnew = dt;

@@ -325,6 +325,40 @@ PN_HD void pn_rows_load(const double* sx, double (&R)[RPL][D], int gl) {
     }
 }
 
+// Own rows of X'X added to the accumulators Mw (entries j >= lr*G of slot lr): every row of X is streamed from the group's
+// exchange region (16-byte broadcast loads), no cross-lane reduction.
+#ifndef PN_GRAM_UNROLL
+#define PN_GRAM_UNROLL 2
+#endif
+#define PN_STR2(x) #x
+#define PN_PRAGMA_UNROLL(k) _Pragma(PN_STR2(unroll k))
+template <int G, int RPL, int D>
+PN_HD void pn_gram_rows(const double* sx, double (&Mw)[RPL][D], int gl) {
+    PN_PRAGMA_UNROLL(PN_GRAM_UNROLL)
+    for (int r = 0; r < D; r++) {
+        double xr[D], xo[RPL];
+        const double* src = sx + r * D;
+        if constexpr (D % 2 == 0) {
+#pragma unroll
+            for (int c = 0; c < D; c += 2) {
+                const double2 v = *reinterpret_cast<const double2*>(src + c);
+                xr[c] = v.x;
+                xr[c + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; c++) xr[c] = src[c];
+        }
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++) xo[lr] = (lr * G + gl < D) ? src[lr * G + gl] : 0.0;
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++)
+#pragma unroll
+            for (int j = 0; j < D; j++)
+                if (j >= lr * G) Mw[lr][j] = fma(xo[lr], xr[j], Mw[lr][j]);
+    }
+}
+
 // Right-looking Cholesky of the row-cyclic symmetric M (slot lr of lane gl holds row lr*G + gl; entries j >= row valid, the
 // rest is never read).  On return R holds the upper-triangular factor in the same distribution (zeros left of the
 // diagonal) and the function tells whether every pivot was positive.  The pivot row is broadcast with shuffles; a lane's
@@ -374,8 +408,8 @@ PN_HD bool pn_chol_rows(double (&Mw)[RPL][D], double (&R)[RPL][D], int gl) {
 // fails or the diffusion is exactly zero.  X (D x D row-major in shared memory) is reduced in place by Householder
 // reflections, then the rows of the upper-triangular noise block B (brow(m, c) = entry of row (m, i) at column (c, i)) are
 // folded in one at a time with Givens rotations.  Not inlined: its local-memory frame belongs to this path only.
-template <int D, int d, int n>
-__device__ __noinline__ void pn_triangularize_serial(double* X, const double* bfac /* n x n row-major, upper */) {
+template <int D>
+__device__ __noinline__ void pn_house_serial(double* X) {
     for (int k = 0; k < D; k++) {
         double tot = 0.0;
         for (int r = k; r < D; r++) tot += X[r * D + k] * X[r * D + k];
@@ -393,6 +427,24 @@ __device__ __noinline__ void pn_triangularize_serial(double* X, const double* bf
         }
         for (int r = k + 1; r < D; r++) X[r * D + k] = 0.0;
     }
+}
+/* fold the dense row b (entries left of j0 zero) into the upper-triangular X with Givens rotations; b is destroyed */
+template <int D>
+__device__ __forceinline__ void pn_givens_fold(double* X, double* b, int j0) {
+    for (int j = j0; j < D; j++) { /* rotate (X[j][j:], b[j:]) so that b[j] vanishes */
+        const double a = X[j * D + j], bb = b[j];
+        if (bb == 0.0) continue;
+        const double rr = sqrt(a * a + bb * bb), cs = a / rr, sn = bb / rr;
+        for (int c = j; c < D; c++) {
+            const double xv = X[j * D + c], bv = b[c];
+            X[j * D + c] = cs * xv + sn * bv;
+            b[c] = cs * bv - sn * xv;
+        }
+    }
+}
+template <int D, int d, int n>
+__device__ __noinline__ void pn_triangularize_serial(double* X, const double* bfac /* n x n row-major, upper */) {
+    pn_house_serial<D>(X);
     double b[D];
     for (int m = 0; m < n; m++)
         for (int i = 0; i < d; i++) {
@@ -403,17 +455,15 @@ __device__ __noinline__ void pn_triangularize_serial(double* X, const double* bf
                 any = any || (b[c * d + i] != 0.0);
             }
             if (!any) continue;
-            for (int j = m * d + i; j < D; j++) { /* rotate (X[j][j:], b[j:]) so that b[j] vanishes */
-                const double a = X[j * D + j], bb = b[j];
-                if (bb == 0.0) continue;
-                const double rr = sqrt(a * a + bb * bb), cs = a / rr, sn = bb / rr;
-                for (int c = j; c < D; c++) {
-                    const double xv = X[j * D + c], bv = b[c];
-                    X[j * D + c] = cs * xv + sn * bv;
-                    b[c] = cs * bv - sn * xv;
-                }
-            }
+            pn_givens_fold<D>(X, b, m * d + i);
         }
+}
+/* triangularize!([X ; E]) with NE dense extra rows E (row-major NE x D, destroyed): the fallback of the observation-noise
+   update (update.jl:133-135, [x_out.Sigma.R ; (K R.R')']) */
+template <int D, int NE>
+__device__ __noinline__ void pn_triangularize_serial_dense(double* X, double* E) {
+    pn_house_serial<D>(X);
+    for (int a = 0; a < NE; a++) pn_givens_fold<D>(X, E + a * D, 0);
 }
 
 // ode_determine_initdt (OrdinaryDiffEqCore, Hairer-Wanner; restated from SURVEY.md A.6).  Two f evaluations.
@@ -490,6 +540,11 @@ template <int d>
 PN_HD constexpr int pn_solcol(int j) {
     return PN_SECOND ? (j < d ? d + j : j - d) : j;
 }
+#ifndef PN_OBSN
+#define PN_OBSN 0 /* 1: EK0/EK1(pn_observation_noise = R): the generated source defines constexpr pn_obsn_cov(a,b) = (R.R'R.R)[a][b] and
+                     pn_obsn_rt(a,b) = R.R[a][b] (cov2psdmatrix, caches.jl:175-178).  S += R (perform_step.jl:185-187), the filtered
+                     covariance gains K R K' and is re-factorised (update.jl:125-136). */
+#endif
 #ifndef PN_MASS
 #define PN_MASS 0 /* 1: mass matrix M u' = f; the generated source defines constexpr pn_mass(a,i) = M[a][i] and
                      pn_mass_inv(a,i) = (M + 1e-20 I if M has a zero diagonal entry)^-1 (autodiffinit.jl:20-31), so zero
@@ -1026,34 +1081,7 @@ struct PnSmall {
                     }
                     }
                     /* (3) Gram matrix: stream every row of X from the exchange region */
-#ifndef PN_GRAM_UNROLL
-#define PN_GRAM_UNROLL 2
-#endif
-#define PN_STR2(x) #x
-#define PN_PRAGMA_UNROLL(k) _Pragma(PN_STR2(unroll k))
-                    PN_PRAGMA_UNROLL(PN_GRAM_UNROLL)
-                    for (int r = 0; r < D; r++) {
-                        double xr[D], xo[RPL];
-                        const double* src = sx + r * D;
-                        if constexpr (D % 2 == 0) {
-#pragma unroll
-                            for (int c = 0; c < D; c += 2) {
-                                const double2 v = *reinterpret_cast<const double2*>(src + c);
-                                xr[c] = v.x;
-                                xr[c + 1] = v.y;
-                            }
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < D; c++) xr[c] = src[c];
-                        }
-#pragma unroll
-                        for (int lr = 0; lr < RPL; lr++) xo[lr] = (lr * G + gl < D) ? src[lr * G + gl] : 0.0;
-#pragma unroll
-                        for (int lr = 0; lr < RPL; lr++)
-#pragma unroll
-                            for (int j = 0; j < D; j++)
-                                if (j >= lr * G) Mw[lr][j] = fma(xo[lr], xr[j], Mw[lr][j]);
-                    }
+                    pn_gram_rows<G, RPL, D>(sx, Mw, gl);
                     /* (4) factorise; idle groups and zero diffusion (predict.jl:71-74 keeps X, which the update below needs
                        in triangular form) do not count as failures of the Cholesky route */
                     bool ok = pn_chol_rows<G, RPL, D>(Mw, R, gl);
@@ -1152,6 +1180,14 @@ struct PnSmall {
 #pragma unroll
                     for (int a = 0; a < d; a++) S[a][a] = 1.0;
                 }
+#if PN_OBSN
+#pragma unroll
+                for (int a = 0; a < d; a++) /* compute_measurement_covariance!: + R.R'R.R (perform_step.jl:185-187) */
+#pragma unroll
+                    for (int b = 0; b < d; b++)
+                        if (b >= a && pn_obsn_cov(a, b) != 0.0) S[a][b] += passthrough ? 0.0 : pn_obsn_cov(a, b);
+                double K1all[D][d]; /* K R.R' (update.jl:128) */
+#endif
                 double sinv[d];
                 const bool okS = pn_chol<d>(S, sinv);
                 double zt[d];
@@ -1209,6 +1245,16 @@ struct PnSmall {
 #pragma unroll
                     for (int a = 0; a < d; a++) s -= Kc[a] * z[a];
                     mu[c] = s;
+#if PN_OBSN
+#pragma unroll
+                    for (int a = 0; a < d; a++) {
+                        double k1 = 0.0;
+#pragma unroll
+                        for (int b = 0; b < d; b++)
+                            if (pn_obsn_rt(a, b) != 0.0) k1 += Kc[b] * pn_obsn_rt(a, b);
+                        K1all[c][a] = k1;
+                    }
+#endif
 #pragma unroll
                     for (int lr = 0; lr < RU; lr++) {
                         double r = R[lr][c];
@@ -1217,6 +1263,53 @@ struct PnSmall {
                         R[lr][c] = r;
                     }
                 }
+#if PN_OBSN
+                {
+                    /* update.jl:125-136: Sigma = R+'R+ + K R K' = cholesky(...).U, triangularize!([R+ ; (K R.R')']) if that fails.  Same
+                       machinery as predict_cov!: own rows published, Gram matrix streamed, row-cyclic Cholesky.  Groups that commit
+                       nothing (or passed the prediction through, update.jl:82-89) keep their factor bit for bit. */
+                    pn_rows_store<G, RPL, D>(sx, R, gl);
+                    __syncwarp();
+                    double Mw[RPL][D];
+#pragma unroll
+                    for (int lr = 0; lr < RPL; lr++) {
+                        double k1o[d]; /* own row of K R.R' */
+#pragma unroll
+                        for (int a = 0; a < d; a++) {
+                            double v = 0.0;
+#pragma unroll
+                            for (int g = 0; g < G; g++)
+                                if (lr * G + g < D) v = (gl == g) ? K1all[lr * G + g < D ? lr * G + g : 0][a] : v;
+                            k1o[a] = v;
+                        }
+#pragma unroll
+                        for (int j = 0; j < D; j++) {
+                            if (j < lr * G) continue;
+                            double v = 0.0;
+#pragma unroll
+                            for (int a = 0; a < d; a++) v += k1o[a] * K1all[j][a];
+                            Mw[lr][j] = v;
+                        }
+                    }
+                    pn_gram_rows<G, RPL, D>(sx, Mw, gl);
+                    const bool okn = pn_chol_rows<G, RPL, D>(Mw, R, gl);
+                    const bool live = accept && !passthrough;
+                    const bool redo = live && !okn;
+                    if (__any_sync(FULL, redo)) {
+                        if (redo && gl == 0) {
+                            double E[d * D];
+#pragma unroll
+                            for (int a = 0; a < d; a++)
+#pragma unroll
+                                for (int c = 0; c < D; c++) E[a * D + c] = K1all[c][a];
+                            pn_triangularize_serial_dense<D, d>(sx, E);
+                        }
+                        __syncwarp();
+                    }
+                    if (redo || !live) pn_rows_load<G, RPL, D>(sx, R, gl);
+                    __syncwarp();
+                }
+#endif
 #if PN_R_IN_SMEM && PN_PREDICT_CHOL
                 if (accept) pn_rows_store<G, RPL, D>(sx, R, gl); /* x_filt.Sigma.R for the next iteration (idle groups: the region still holds it) */
 #endif

@@ -525,15 +525,66 @@ static int nvrtc_dense_cubin(int d, int q, int G, bool ioup, std::vector<char>* 
     return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0), def("PN_SECOND", second ? 1 : 0)}, cubin);
 }
 
+/* pn_observation_noise (d x d row-major covariance, or var * I) -> generated preamble: PN_OBSN, constexpr pn_obsn_cov(a,b) = R[a][b]
+   and pn_obsn_rt(a,b) = R.R[a][b], the upper Cholesky factor (cov2psdmatrix: a Number / UniformScaling x -> sqrt(x) I, a matrix ->
+   cholesky(M).U; src/caches.jl:175-178).  Empty string without noise. */
+static bool has_obsn(const pnode_config* cfg) { return cfg->pn_observation_noise != nullptr || cfg->pn_observation_noise_var > 0.0; }
+static int obsn_preamble(const pnode_config* cfg, std::string* out) {
+    out->clear();
+    if (!has_obsn(cfg)) return 0;
+    const int d = cfg->d;
+    std::vector<double> Cv((size_t)d * d, 0.0), U((size_t)d * d, 0.0);
+    for (int a = 0; a < d; a++)
+        for (int b = 0; b < d; b++)
+            Cv[a * d + b] = cfg->pn_observation_noise ? cfg->pn_observation_noise[a * d + b] : (a == b ? cfg->pn_observation_noise_var : 0.0);
+    for (int a = 0; a < d; a++)
+        for (int b = 0; b < d; b++) {
+            if (!std::isfinite(Cv[a * d + b])) return fail(PNODE_ERR_ARGUMENT, "pn_observation_noise has a non-finite entry");
+            if (std::fabs(Cv[a * d + b] - Cv[b * d + a]) > 1e-12 * (std::fabs(Cv[a * d + b]) + std::fabs(Cv[b * d + a])))
+                return fail(PNODE_ERR_ARGUMENT, "pn_observation_noise must be symmetric");
+        }
+    for (int j = 0; j < d; j++) { /* upper Cholesky Cv = U'U */
+        double sacc = Cv[j * d + j];
+        for (int k = 0; k < j; k++) sacc -= U[k * d + j] * U[k * d + j];
+        if (!(sacc > 0.0)) return fail(PNODE_ERR_ARGUMENT, "pn_observation_noise must be positive definite (PosDefException in cov2psdmatrix)");
+        U[j * d + j] = std::sqrt(sacc);
+        for (int i = j + 1; i < d; i++) {
+            double v = Cv[j * d + i];
+            for (int k = 0; k < j; k++) v -= U[k * d + j] * U[k * d + i];
+            U[j * d + i] = v / U[j * d + j];
+        }
+    }
+    auto table = [&](const char* name, const double* T) {
+        std::string t = std::string("__host__ __device__ constexpr double ") + name + "(int a, int i) {\n  return ";
+        char buf[96];
+        for (int a = 0; a < d; a++)
+            for (int i = 0; i < d; i++) {
+                if (T[a * d + i] == 0.0) continue;
+                snprintf(buf, sizeof buf, "(a == %d && i == %d) ? %.17g : ", a, i, T[a * d + i]);
+                t += buf;
+            }
+        t += "0.0;\n}\n";
+        return t;
+    };
+    *out = "#define PN_OBSN 1\n" + table("pn_obsn_cov", Cv.data()) + table("pn_obsn_rt", U.data());
+    return 0;
+}
+
 static size_t cta_smem_bytes(int d, int q, int n_p, bool second_order = false, bool mass = false) {
     return (size_t)pn_cta_sm_doubles(d, q + 1, second_order ? 2 * d : d, second_order ? 3 : 2, n_p > 0 ? n_p : 1, mass,
                                      (int)sizeof(PnCtaShared)) * sizeof(double);
 }
-/* threads per CTA and resident CTAs per SM of the CTA-per-trajectory kernel: states that leave room for several CTAs in
-   shared memory run two (registers <= 128 per thread); the ahead-of-time instantiations use the compiled-in defaults */
+/* threads per CTA and resident CTAs per SM of the CTA-per-trajectory kernel.  A step is a chain of short phases separated by
+   barriers (4-column Cholesky panels, single-thread f / J), so several small CTAs per SM beat one large one wherever shared
+   memory allows: measured on Pleiades as 14 second-order equations (D = 56, profiles/r2i_cta_variants.jsonl) 4 x 128 threads
+   6.6e6 steps/s, 2 x 256 5.6e6, 1 x 512 3.1e6; at D = 112 only one CTA fits and 256 = 512 threads.  The ahead-of-time
+   instantiations use the compiled-in defaults (256 threads, one CTA). */
 static void cta_shape(size_t smem, int* threads, int* min_blocks) {
-    *threads = env_int("PNODE_CTA_THREADS", PN_CTA_THREADS);
-    *min_blocks = env_int("PNODE_CTA_MIN_BLOCKS", (2 * smem + 4096 <= 227 * 1024) ? 2 : 1);
+    const size_t budget = 227 * 1024, per = smem + 1024; /* + the per-CTA reservation */
+    int nb = (4 * per <= budget) ? 4 : (2 * per <= budget) ? 2 : 1;
+    int th = (nb == 4) ? 128 : 256;
+    *threads = env_int("PNODE_CTA_THREADS", th);
+    *min_blocks = env_int("PNODE_CTA_MIN_BLOCKS", nb);
     if (*threads * *min_blocks > 1024) *min_blocks = 1024 / *threads;
 }
 
@@ -851,6 +902,37 @@ static int validate_config(const pnode_config* cfg) {
             }
         }
     }
+    if (cfg->pn_observation_noise_var < 0.0) return fail(PNODE_ERR_ARGUMENT, "pn_observation_noise must be positive (semi)definite");
+    if (has_obsn(cfg)) { /* ekargcheck (src/algorithms.jl:78-130) */
+        if (!is_dynamic(cfg->diffusion) && cfg->calibrate)
+            return fail(PNODE_ERR_ARGUMENT,
+                        "Automatic calibration of global diffusion models is not possible when using observation noise. If you want to "
+                        "calibrate a global diffusion parameter, do so setting `calibrate=false` and optimizing `sol.pnstats.log_likelihood` manually.");
+        if (cfg->pn_observation_noise) {
+            const int d = cfg->d;
+            const double* Cn = cfg->pn_observation_noise;
+            bool diag = true, iso = true;
+            for (int a = 0; a < d; a++)
+                for (int j = 0; j < d; j++) {
+                    if (a != j && Cn[a * d + j] != 0.0) diag = false;
+                    if (a == j && Cn[a * d + j] != Cn[0]) iso = false;
+                }
+            if (layout == PNODE_COV_KRONECKER && !(diag && iso))
+                return fail(PNODE_ERR_ARGUMENT,
+                            "The supplied `pn_observation_noise` is not compatible with the chosen `IsometricKroneckerCovariance` "
+                            "factorization. Try one of `BlockDiagonalCovariance` or `DenseCovariance` instead!");
+            if (layout == PNODE_COV_BLOCKS && !diag)
+                return fail(PNODE_ERR_ARGUMENT,
+                            "The supplied `pn_observation_noise` is not compatible with the chosen `BlockDiagonalCovariance` factorization. "
+                            "Try `DenseCovariance` instead!");
+        }
+        std::string pre;
+        int orc = obsn_preamble(cfg, &pre);
+        if (orc) return orc;
+        if (layout == PNODE_COV_DENSE && (D > 32 || cfg->lanes_per_traj == 256))
+            return fail(PNODE_ERR_UNSUPPORTED, "pn_observation_noise is implemented for D = d(q+1) <= 32 on the dense layout");
+        if (cfg->n_data > 0) return fail(PNODE_ERR_UNSUPPORTED, "pn_observation_noise and a Fenrir data set cannot be combined yet");
+    }
     const bool builtin = (std::string(cfg->rhs_name).rfind("builtin:", 0) == 0);
     if (!builtin && !cfg->rhs_src) return fail(PNODE_ERR_ARGUMENT, "rhs_src is required unless rhs_name is a builtin");
     return 0;
@@ -870,6 +952,11 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     std::string mass_src;
     if ((rc = mass_preamble(cfg->mass_matrix, cfg->d, &mass_src))) return rc;
     if (cfg->second_order) mass_src = "#define PN_SECOND 1\n" + mass_src;
+    {
+        std::string obs_src;
+        if ((rc = obsn_preamble(cfg, &obs_src))) return rc;
+        mass_src = obs_src + mass_src;
+    }
     rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, is_dynamic(cfg->diffusion),
                      save_level(cfg, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256)), &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
                      layout == PNODE_COV_KRONECKER, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256),
@@ -912,7 +999,13 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     s->cfg.rhs_name = nullptr;
     mass_preamble(cfg->mass_matrix, cfg->d, &s->mass_src); /* validated above */
     if (cfg->second_order) s->mass_src = "#define PN_SECOND 1\n" + s->mass_src; /* generated preamble of the step kernels */
+    {
+        std::string obs_src;
+        obsn_preamble(cfg, &obs_src); /* validated above */
+        s->mass_src = obs_src + s->mass_src;
+    }
     s->cfg.mass_matrix = nullptr;
+    s->cfg.pn_observation_noise = nullptr;
     s->kron = (resolve_layout(cfg) == PNODE_COV_KRONECKER);
     s->blocks = (resolve_layout(cfg) == PNODE_COV_BLOCKS);
     s->mv = is_mv(cfg->diffusion);

@@ -69,6 +69,7 @@ class Config(C.Structure):
         ("n_obs", C.c_int32), ("reserved2", C.c_int32),
         ("observation_matrix", C.POINTER(C.c_double)), ("observation_noise_cov", C.POINTER(C.c_double)),
         ("observation_noise_var", C.c_double),
+        ("pn_observation_noise", C.POINTER(C.c_double)), ("pn_observation_noise_var", C.c_double),
     ]
 
 
@@ -144,7 +145,7 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
                 maxiters=1_000_000, beta1=0.0, beta2=0.0, qmin=0.2, qmax=10.0, gamma=0.9, qsteady_min=1.0,
                 qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None, device=0, prior=PRIOR_IWP,
                 rate_parameter=0.0, saveat=None, mass_matrix=None, second_order=False, data_t=None, data_u=None,
-                observation_matrix=None, observation_noise_cov=None) -> Config:
+                observation_matrix=None, observation_noise_cov=None, pn_observation_noise=None) -> Config:
     c = Config()
     c.second_order = int(second_order)
     c.struct_size = C.sizeof(Config)
@@ -190,6 +191,15 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
             cv = np.ascontiguousarray(cov.reshape(b.shape[1], b.shape[1]))
             keep.append(cv)
             c.observation_noise_cov = cv.ctypes.data_as(dp_)
+    if pn_observation_noise is not None:
+        # a Number / UniformScaling, a Diagonal (1-d array) or a d x d covariance matrix (cov2psdmatrix)
+        cov = np.asarray(pn_observation_noise, dtype=np.float64)
+        if cov.ndim == 0:
+            c.pn_observation_noise_var = float(cov)
+        else:
+            cv = np.ascontiguousarray(np.diag(cov) if cov.ndim == 1 else cov.reshape(d, d))
+            keep.append(cv)
+            c.pn_observation_noise = cv.ctypes.data_as(C.POINTER(C.c_double))
     if mass_matrix is not None:
         a = np.ascontiguousarray(np.asarray(mass_matrix, dtype=np.float64).reshape(d, d))
         keep.append(a)

@@ -375,3 +375,35 @@ def test_python_mirror_argument_errors_of_the_new_entry_points():
         api._config_for(dae, api.EK0(order=3), api.EnsembleB200(), adaptive=True, dt=None, abstol=1e-6, reltol=1e-3, save_everystep=True,
                         maxiters=10 ** 6, dtmin=0.0, dtmax=None, tstops=None, save_state=False)
     assert "incompatible with the provided mass matrix" in str(e.value)
+
+
+def test_pn_observation_noise_argument_errors_and_compilation(pnlib):
+    """ekargcheck (src/algorithms.jl:78-130) for `pn_observation_noise`, and the three noise-aware step kernels compile for
+    sm_100a (test/observation_noise.jl's compatibility table: EK0 isotropic only, DiagonalEK1 diagonal only, EK1 anything)."""
+    import numpy as np
+    pd, src = _src("lotka_volterra")
+    base = dict(d=2, q=3, n_p=4, rhs_name="UserProb", rhs_src=src, t0=0.0, t1=1.0)
+    full, diag = np.array([[0.1, 0.01], [0.01, 0.1]]), np.array([0.1, 0.2])
+
+    def err(**kw):
+        with pytest.raises(pnlib.PnodeError) as e:
+            pnlib.compile_check(pnlib.make_config(**{**base, **kw}))
+        return e.value
+
+    e = err(diffusion=pnlib.DIFF_FIXED, calibrate=True, pn_observation_noise=0.1)
+    assert e.kind == "ArgumentError" and "Automatic calibration of global diffusion models is not possible" in str(e)
+    e = err(alg=pnlib.EK0, pn_observation_noise=diag)
+    assert e.kind == "ArgumentError" and "IsometricKroneckerCovariance" in str(e)
+    e = err(alg=pnlib.EK0, pn_observation_noise=full)
+    assert e.kind == "ArgumentError" and "IsometricKroneckerCovariance" in str(e)
+    e = err(alg=pnlib.DIAGONAL_EK1, pn_observation_noise=full)
+    assert e.kind == "ArgumentError" and "BlockDiagonalCovariance" in str(e)
+    assert err(pn_observation_noise=np.array([[0.1, 0.2], [0.2, 0.1]])).kind == "ArgumentError"      # not positive definite
+    assert err(pn_observation_noise=np.array([[0.1, 0.02], [0.01, 0.1]])).kind == "ArgumentError"    # not symmetric
+    assert err(pn_observation_noise=-1.0).kind == "ArgumentError"
+    plain = pnlib.compile_check(pnlib.make_config(**base))
+    for kw in (dict(pn_observation_noise=0.1), dict(pn_observation_noise=diag), dict(pn_observation_noise=full),
+               dict(alg=pnlib.EK0, pn_observation_noise=0.1), dict(alg=pnlib.EK0, pn_observation_noise=np.array([0.1, 0.1])),
+               dict(alg=pnlib.DIAGONAL_EK1, pn_observation_noise=diag), dict(alg=pnlib.EK0, diffusion=pnlib.DIFF_DYNAMIC_MV, pn_observation_noise=diag)):
+        assert pnlib.compile_check(pnlib.make_config(**{**base, **kw})) > 10_000
+    assert pnlib.compile_check(pnlib.make_config(**{**base, "pn_observation_noise": full})) > plain   # the second Gram + Cholesky

@@ -916,3 +916,68 @@ def test_filtering_and_fenrir_agree_on_the_structured_layouts(oracle, alg_name, 
         with pytest.raises(Exception):
             oracle.solve(oracle.make_config(2, 3, 4, smooth=False, save_everystep=False, data=(data_t, data_u[:, :1]),
                                             observation_matrix=[[1.0, 0.0]], observation_noise_cov=sigma ** 2, **base), rhs, pd.u0, pd.p)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# pn_observation_noise (src/algorithms.jl:188-393 keyword; src/perform_step.jl:182-188; src/filtering/update.jl:125-136)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("noise", [0.1, np.array([0.1, 0.2]), np.array([[0.1, 0.01], [0.01, 0.1]])])
+def test_pn_observation_noise_step_is_the_classical_kalman_update(oracle, noise):
+    """Every filter step of an EK1 solve with `pn_observation_noise = R` against the textbook formulas evaluated with numpy on
+    the dense covariances: S = H Sigma^- H' + R, K = Sigma^- H' S^-1, mu = mu^- - K z, Sigma = Sigma^- - K S K' (which equals the
+    Joseph form + K R K' of update.jl:118-136), log-likelihood N(z; 0, S).  R: a number, a Diagonal, a full matrix
+    (test/observation_noise.jl's list for the EK1)."""
+    pd = problems.PROBLEMS["lotka_volterra"]
+    tr = tracer.trace(pd.f, 2, 4)
+    rhs = oracle.compile_rhs(tr, 3)
+    u0, p = np.array(pd.u0, dtype=float), np.array(pd.p, dtype=float)
+    cfg = oracle.make_config(2, 3, 4, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, smooth=False, adaptive=False, dt=0.05,
+                             t0=0.0, t1=1.0, pn_observation_noise=noise)
+    s = oracle.solve(cfg, rhs, u0, p)
+    assert s["retcode"] == "Success" and s["n"] == 21
+    Rcov = noise * np.eye(2) if np.ndim(noise) == 0 else (np.diag(noise) if np.ndim(noise) == 1 else noise)
+    D = 8
+    Ah, Qh = oracle._transition_dense(cfg, 0.05)
+    Ah, Qh = Ah.reshape((D, D), order="F"), Qh.reshape((D, D), order="F")
+    ll = 0.0
+    for k in range(20):
+        mu, R = s["x_filt_mu"][k], s["x_filt_R"][k]
+        mp, Sp = Ah @ mu, Ah @ (R.T @ R) @ Ah.T + Qh.T @ Qh
+        du = np.zeros(2)
+        pd.f(du, mp[:2], p, s["t"][k + 1])
+        x, y = mp[:2]
+        J = np.array([[p[0] - p[1] * y, -p[1] * x], [p[3] * y, -p[2] + p[3] * x]])
+        H = np.hstack([-J, np.eye(2), np.zeros((2, 4))])
+        z = mp[2:4] - du
+        S = H @ Sp @ H.T + Rcov
+        K = Sp @ H.T @ np.linalg.inv(S)
+        mu_new, S_new = mp - K @ z, Sp - K @ S @ K.T
+        Rn = s["x_filt_R"][k + 1]
+        assert np.allclose(s["x_filt_mu"][k + 1], mu_new, rtol=1e-9, atol=1e-12)
+        assert np.linalg.norm(Rn.T @ Rn - S_new) <= 1e-8 * np.linalg.norm(S_new)
+        assert np.allclose(np.tril(Rn, -1), 0.0)                       # cholesky(...).U / triangularize!: upper triangular
+        ll += -0.5 * z @ np.linalg.solve(S, z) - np.log(2 * np.pi) - 0.5 * np.linalg.slogdet(S)[1]
+    assert s["loglik"] == pytest.approx(ll, rel=1e-8)
+
+
+def test_pn_observation_noise_structured_layouts_and_limits(oracle):
+    """test/observation_noise.jl: isotropic noise with the EK0 (Kronecker), diagonal noise with the DiagonalEK1 (blocks), anything
+    with the EK1.  An isotropic R gives the same solution on the Kronecker / blocks / dense layouts where they coincide (EK0), and
+    R -> 0 recovers the noise-free solve."""
+    pd = problems.PROBLEMS["lotka_volterra"]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 2, 4), 3)
+    u0, p = np.array(pd.u0, dtype=float), np.array(pd.p, dtype=float)
+    base = dict(calibrate=False, smooth=False, adaptive=False, dt=0.02, t0=0.0, t1=1.0)
+    ek0 = oracle.solve(oracle.make_config(2, 3, 4, alg=oracle.EK0, diffusion=oracle.DIFF_FIXED, pn_observation_noise=0.1, **base), rhs, u0, p)
+    ek0mv = oracle.solve(oracle.make_config(2, 3, 4, alg=oracle.EK0, diffusion=oracle.DIFF_FIXED_MV, pn_observation_noise=np.array([0.1, 0.1]), **base), rhs, u0, p)
+    assert ek0["retcode"] == ek0mv["retcode"] == "Success"
+    assert np.allclose(ek0["pu_mu"], ek0mv["pu_mu"], rtol=1e-10) and np.allclose(ek0["pu_cov"], ek0mv["pu_cov"], rtol=1e-8, atol=1e-300)
+    d1 = oracle.solve(oracle.make_config(2, 3, 4, alg=oracle.DIAGONAL_EK1, diffusion=oracle.DIFF_FIXED, pn_observation_noise=np.array([0.1, 0.2]), **base), rhs, u0, p)
+    assert d1["retcode"] == "Success"
+    free = oracle.solve(oracle.make_config(2, 3, 4, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, **base), rhs, u0, p)
+    tiny = oracle.solve(oracle.make_config(2, 3, 4, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, pn_observation_noise=1e-30, **base), rhs, u0, p)
+    noisy = oracle.solve(oracle.make_config(2, 3, 4, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, pn_observation_noise=0.1, **base), rhs, u0, p)
+    assert np.allclose(free["pu_mu"], tiny["pu_mu"], rtol=1e-9)
+    # a noisy "observation" of the ODE residual is trusted less: the solution departs from the noise-free one, its covariance grows
+    assert not np.allclose(free["pu_mu"], noisy["pu_mu"], rtol=1e-6)
+    assert np.all(np.trace(noisy["pu_cov"][1:], axis1=1, axis2=2) > np.trace(free["pu_cov"][1:], axis1=1, axis2=2))
