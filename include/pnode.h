@@ -140,7 +140,12 @@ typedef struct pnode_config {
     int64_t n_data;
     const double* data_u;             /* [n_data][n_obs]                                                            */
     int32_t n_obs;                    /* length of one observation                                                  */
-    int32_t reserved2;
+    int32_t data_forward;             /* 0: Fenrir (backward pass, above).  1: DataUpdateCallback (src/callbacks/dataupdate.jl:39-84)
+                                         as used by filtering_data_loglik / dalton_data_loglik (src/data_likelihoods/filtering.jl,
+                                         dalton.jl): whenever an accepted step ends on a data time the FILTER state is updated on
+                                         y = H x + eps, eps ~ N(0, R), before it is saved, and the updates' log-likelihoods are
+                                         summed per trajectory in PNODE_F_DATA_LOGLIK (DataUpdateLogLikelihood.ll).  smooth is free.
+                                         Dense layout (EK1, D <= 32); partial observations and matrix noise allowed. */
     const double* observation_matrix; /* [n_obs][len(sol.u)] row-major; NULL = identity (n_obs == len(sol.u))        */
     const double* observation_noise_cov; /* [n_obs][n_obs] symmetric positive definite; NULL = observation_noise_var * I */
     double observation_noise_var;
@@ -188,6 +193,7 @@ typedef enum pnode_field {
     PNODE_F_SAVEAT_U = 21,      /* double [n_traj][n_saveat][d]      mean(sol(saveat[j]))            */
     PNODE_F_SAVEAT_U_COV = 22,  /* double [n_traj][n_saveat][d][d]   Matrix(sol(saveat[j]).Sigma)    */
     PNODE_F_FENRIR_LOGLIK = 23, /* double [n_traj]  Fenrir data log-likelihood (config data_t / data_u) */
+    PNODE_F_DATA_LOGLIK = 24,   /* double [n_traj]  sum of the forward data updates' log-likelihoods (data_forward = 1) */
     PNODE_F_COUNT
 } pnode_field;
 

@@ -389,6 +389,83 @@ def fenrir_data_loglik(prob, alg, ensemblealg: Optional[EnsembleB200] = None, *,
     return float(ll[0]) if single else ll
 
 
+def _ensemble_inputs(prob, trajectories):
+    single = isinstance(prob, ODEProblem)
+    eprob = EnsembleProblem(prob) if single else prob
+    n = 1 if single else trajectories
+    if n is None or n < 1:
+        raise ValueError("trajectories must be a positive integer")
+    base = eprob.prob
+    d, n_p = len(base.u0), len(base.p)
+    u0 = np.empty((n, d))
+    p = np.empty((n, max(n_p, 0)))
+    for i in range(n):
+        pi = eprob.prob_func(base, i, 0) if eprob.prob_func else base
+        u0[i] = pi.u0
+        if n_p:
+            p[i] = pi.p
+    return single, base, n, u0, p
+
+
+def _forward_data_solve(prob, alg, ens, *, data, observation_noise_cov, observation_matrix, trajectories, with_data, adaptive, dt, abstol,
+                        reltol, maxiters, dtmin, dtmax, tstops):
+    """One ensemble solve with save_everystep=false and tstops = union(data.t, tstops); with `with_data` the DataUpdateCallback is
+    active.  Returns (data log-likelihoods, PN log-likelihoods, single)."""
+    single, base, n, u0, p = _ensemble_inputs(prob, trajectories)
+    data_t, data_u = np.asarray(data[0], dtype=float), np.asarray(data[1], dtype=float)
+    alg_f = dataclasses.replace(alg, smooth=False)   # the reference only warns that smoothing is wasted here; save_everystep=false
+    _check_alg(alg_f, adaptive, dt, False, False)
+    if with_data:
+        extra = dict(data_t=data_t, data_u=data_u, observation_matrix=observation_matrix, observation_noise_cov=observation_noise_cov,
+                     data_forward=True)
+        ts = tstops
+    else:
+        extra = None
+        ts = np.union1d(data_t, [] if tstops is None else np.asarray(tstops, dtype=float))
+        ts = ts[(ts > base.tspan[0]) & (ts < base.tspan[1])]
+    cfg = _config_for(base, alg_f, ens, adaptive=adaptive, dt=dt, abstol=abstol, reltol=reltol, save_everystep=False, maxiters=maxiters,
+                      dtmin=dtmin, dtmax=dtmax, tstops=ts, save_state=False, fenrir=extra)
+    solver = _lib.Solver(cfg)
+    try:
+        res = solver.solve(u0, p)
+        dll = res.field(_lib.F_DATA_LOGLIK).copy() if with_data else np.zeros(n)
+        pll = res.field(_lib.F_LOGLIK).copy()
+        res.free()
+    finally:
+        solver.close()
+    return dll, pll, single
+
+
+def filtering_data_loglik(prob, alg, ensemblealg: Optional[EnsembleB200] = None, *, data, observation_noise_cov, observation_matrix=None,
+                          trajectories: Optional[int] = None, adaptive: bool = True, dt: Optional[float] = None, abstol: float = 1e-6,
+                          reltol: float = 1e-3, maxiters: int = 1_000_000, dtmin: float = 0.0, dtmax: Optional[float] = None, tstops=None):
+    """`filtering_data_loglik(prob, alg; data=(t, u), observation_matrix, observation_noise_cov, kwargs...)`
+    (src/data_likelihoods/filtering.jl): the data are conditioned on during the FORWARD pass (`DataUpdateCallback`,
+    src/callbacks/dataupdate.jl:39-84) and the updates' log-likelihoods are summed.  One value per trajectory for an
+    `EnsembleProblem` (a parameter sweep against one data set)."""
+    ens = ensemblealg or EnsembleB200()
+    dll, _, single = _forward_data_solve(prob, alg, ens, data=data, observation_noise_cov=observation_noise_cov,
+                                         observation_matrix=observation_matrix, trajectories=trajectories, with_data=True, adaptive=adaptive,
+                                         dt=dt, abstol=abstol, reltol=reltol, maxiters=maxiters, dtmin=dtmin, dtmax=dtmax, tstops=tstops)
+    return float(dll[0]) if single else dll
+
+
+def dalton_data_loglik(prob, alg, ensemblealg: Optional[EnsembleB200] = None, *, data, observation_noise_cov, observation_matrix=None,
+                       trajectories: Optional[int] = None, adaptive: Optional[bool] = None, dt: Optional[float] = None, abstol: float = 1e-6,
+                       reltol: float = 1e-3, maxiters: int = 1_000_000, dtmin: float = 0.0, dtmax: Optional[float] = None, tstops=None):
+    """`dalton_data_loglik` (src/data_likelihoods/dalton.jl:23-78): data log-likelihood of the solve WITH data updates, plus the PN
+    log-likelihood of that solve, minus the PN log-likelihood of the same solve WITHOUT data (both through the data times)."""
+    if adaptive is None:
+        raise ValueError("`dalton_nll` only works with fixed step sizes. Set `adaptive=false`.")   # dalton.jl:41-44 (keyword must be passed)
+    ens = ensemblealg or EnsembleB200()
+    kw = dict(data=data, observation_noise_cov=observation_noise_cov, observation_matrix=observation_matrix, trajectories=trajectories,
+              adaptive=adaptive, dt=dt, abstol=abstol, reltol=reltol, maxiters=maxiters, dtmin=dtmin, dtmax=dtmax, tstops=tstops)
+    dll, pll_with, single = _forward_data_solve(prob, alg, ens, with_data=True, **kw)
+    _, pll_without, _ = _forward_data_solve(prob, alg, ens, with_data=False, **kw)
+    out = dll + pll_with - pll_without
+    return float(out[0]) if single else out
+
+
 def _unpack(res, n, d, save_everystep) -> List[ProbODESolution]:
     L = _lib
     na, nr, nf = res.field(L.F_NACCEPT), res.field(L.F_NREJECT), res.field(L.F_NF)

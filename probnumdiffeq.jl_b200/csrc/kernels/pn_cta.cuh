@@ -423,11 +423,17 @@ struct PnCta {
                         P.s_diffusion[sp] = 0.0;
                         for (int i = 0; i < DU; i++) P.s_u_mean[sp * DU + i] = mu[pn_solcol<d>(i)];
                         for (int i = 0; i < DU * DU; i++) P.s_u_cov[sp * DU * DU + i] = 0.0;
+                        if (SAVE >= 2)
+                            for (int c = 0; c < D; c++) P.s_x_mean[sp * D + c] = mu[c];
                     }
                     sh->save_pos = sp + 1;
                 }
             }
             for (int e = tid; e < D * D; e += NT) R[e] = 0.0;
+            if (SAVE >= 2 && P.step_offsets) { /* Sigma_0.R = 0 */
+                double* dst = P.s_x_covfac + P.step_offsets[traj] * (long long)D * D;
+                for (int e = tid; e < D * D; e += NT) dst[e] = 0.0;
+            }
             __syncthreads();
 
             /* ---- adaptive time loop ---- */
@@ -989,7 +995,13 @@ struct PnCta {
                         for (int i = tid; i < DU; i += NT) P.s_u_mean[sp * DU + i] = mu[pn_solcol<d>(i)];
                         if (tid == 0) {
                             P.s_t[sp] = sh->t;
-                            P.s_diffusion[sp - 1] = (ADAPTIVE || DYNAMIC) ? sh->ldiff : P.initial_diffusion;
+                            P.s_diffusion[sp - 1] = (SAVE >= 2) ? sh->ediff : ((ADAPTIVE || DYNAMIC) ? sh->ldiff : P.initial_diffusion);
+                            if (SAVE >= 2) P.s_h[sp - 1] = h;
+                        }
+                        if (SAVE >= 2) { /* what the smoother sweep needs: x_filt[k+1] (D^2 + D doubles, coalesced) */
+                            double* dst = P.s_x_covfac + sp * (long long)D * D;
+                            for (int e = tid; e < D * D; e += NT) dst[e] = R[e];
+                            for (int c = tid; c < D; c += NT) P.s_x_mean[sp * D + c] = mu[c];
                         }
                     }
                     __syncthreads();

@@ -47,6 +47,12 @@ struct PnParams {
     /* IOUP prior (src/priors/ioup.jl): scalar rate parameter, 16-point Gauss-Legendre rule on [0, 1] (host-computed) */
     double rate;
     double glx[16], glw[16];
+    /* forward data updates (DataUpdateCallback, src/callbacks/dataupdate.jl:39-84; kernels built with PN_DATA): observation times
+       (all of them are tstops), observations [n_data][PN_DATA_O], and the per-trajectory sum of the updates' log-likelihoods */
+    const double* data_t;
+    const double* data_u;
+    long long n_data;
+    double* data_loglik; /* [n_traj] */
     /* ---- per-trajectory outputs ---- */
     double* t_end;      /* [n_traj]       */
     double* u_mean;     /* [n_traj][d]    */

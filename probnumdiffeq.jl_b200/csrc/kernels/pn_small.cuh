@@ -545,6 +545,11 @@ PN_HD constexpr int pn_solcol(int j) {
                      pn_obsn_rt(a,b) = R.R[a][b] (cov2psdmatrix, caches.jl:175-178).  S += R (perform_step.jl:185-187), the filtered
                      covariance gains K R K' and is re-factorised (update.jl:125-136). */
 #endif
+#ifndef PN_DATA
+#define PN_DATA 0 /* 1: forward data updates at the observation times (DataUpdateCallback, src/callbacks/dataupdate.jl:39-84, as used by
+                     filtering_data_loglik / dalton_data_loglik): the generated source defines PN_DATA_O = length of an observation and
+                     constexpr pn_data_H(a,c) = (observation_matrix * SolProj)[a][c], pn_data_cov(a,b) = R[a][b], pn_data_rt(a,b) = R.R[a][b] */
+#endif
 #ifndef PN_MASS
 #define PN_MASS 0 /* 1: mass matrix M u' = f; the generated source defines constexpr pn_mass(a,i) = M[a][i] and
                      pn_mass_inv(a,i) = (M + 1e-20 I if M has a zero diagonal entry)^-1 (autodiffinit.jl:20-31), so zero
@@ -569,6 +574,170 @@ struct PnSmall {
     static constexpr int RU = ((E1B + 1) * d + G - 1) / G < RPL ? ((E1B + 1) * d + G - 1) / G : RPL;
 
     static constexpr int XS = pn_xs_doubles<D>(); /* exchange region per group, doubles */
+
+    // update.jl:125-136: Sigma = R'R + K1 K1' (K1 = K R.R', D x O) re-factorised as cholesky(...).U, triangularize!([R ; K1']) if that
+    // fails.  Same machinery as predict_cov!: own rows published, Gram matrix streamed, row-cyclic Cholesky.  Groups with
+    // live = false keep their factor bit for bit.  Warp-convergent (full-mask shuffles).
+    template <int O>
+    static PN_HD void noise_refactor(double* sx, double (&R)[RPL][D], const double (&K1all)[D][O], bool live, int gl) {
+        constexpr unsigned FULL = 0xffffffffu;
+        pn_rows_store<G, RPL, D>(sx, R, gl);
+        __syncwarp();
+        double Mw[RPL][D];
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++) {
+            double k1o[O]; /* own row of K1 */
+#pragma unroll
+            for (int a = 0; a < O; a++) {
+                double v = 0.0;
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    if (lr * G + g < D) v = (gl == g) ? K1all[lr * G + g < D ? lr * G + g : 0][a] : v;
+                k1o[a] = v;
+            }
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                if (j < lr * G) continue;
+                double v = 0.0;
+#pragma unroll
+                for (int a = 0; a < O; a++) v += k1o[a] * K1all[j][a];
+                Mw[lr][j] = v;
+            }
+        }
+        pn_gram_rows<G, RPL, D>(sx, Mw, gl);
+        const bool okn = pn_chol_rows<G, RPL, D>(Mw, R, gl);
+        const bool redo = live && !okn;
+        if (__any_sync(FULL, redo)) {
+            if (redo && gl == 0) {
+                double E[O * D];
+#pragma unroll
+                for (int a = 0; a < O; a++)
+#pragma unroll
+                    for (int c = 0; c < D; c++) E[a * D + c] = K1all[c][a];
+                pn_triangularize_serial_dense<D, O>(sx, E);
+            }
+            __syncwarp();
+        }
+        if (redo || !live) pn_rows_load<G, RPL, D>(sx, R, gl);
+        __syncwarp();
+    }
+
+#if PN_DATA
+    // One Kalman update of (mu, R) on the observation y = H x + eps, eps ~ N(0, R_obs), for every group with live = true
+    // (DataUpdateCallback's affect!, dataupdate.jl:47-80: obs_cov = (R H')'(R H') + R_obs, update!(...; R = R_obs)); returns the
+    // update's log-likelihood (pn_logpdf!, update.jl:140-148; +-Inf for a zero predicted covariance, :82-89).  H, R_obs and its
+    // factor are compile-time tables of the NVRTC build (zeros fold away).  Warp-convergent.
+    static PN_HD double data_update(double* sx, double (&mu)[D], double (&R)[RPL][D], const double* y, bool live, int gl) {
+        constexpr int O = PN_DATA_O;
+        double zd[O];
+#pragma unroll
+        for (int a = 0; a < O; a++) {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; c++)
+                if (pn_data_H(a, c) != 0.0) s += pn_data_H(a, c) * mu[c];
+            zd[a] = s - (live ? y[a] : 0.0);
+        }
+        double C2[RPL][O], S[O][O];
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++)
+#pragma unroll
+            for (int a = 0; a < O; a++) {
+                double s = 0.0;
+#pragma unroll
+                for (int c = 0; c < D; c++)
+                    if (pn_data_H(a, c) != 0.0) s += R[lr][c] * pn_data_H(a, c);
+                C2[lr][a] = live ? s : 0.0;
+            }
+#pragma unroll
+        for (int a = 0; a < O; a++)
+#pragma unroll
+            for (int b = 0; b < O; b++) {
+                if (b < a) continue;
+                double s = 0.0;
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++) s += C2[lr][a] * C2[lr][b];
+                S[a][b] = pn_gsum<G>(s);
+            }
+        /* iszero(Sigma.R) (update.jl:82): all rows of R, not only R H' */
+        double rr = 0.0;
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++)
+#pragma unroll
+            for (int c = 0; c < D; c++) rr += R[lr][c] * R[lr][c];
+        rr = pn_gsum<G>(rr);
+        const bool zero_cov = (rr == 0.0);
+        const bool act = live && !zero_cov;
+#pragma unroll
+        for (int a = 0; a < O; a++)
+#pragma unroll
+            for (int b = 0; b < O; b++)
+                if (b >= a) S[a][b] = act ? S[a][b] + pn_data_cov(a, b) : ((a == b) ? 1.0 : 0.0);
+        double sinv[O];
+        pn_chol<O>(S, sinv);
+        double zt[O];
+#pragma unroll
+        for (int a = 0; a < O; a++) zt[a] = zd[a];
+        pn_chol_solve<O>(S, sinv, zt);
+        double quad = 0.0, logdet = 0.0;
+#pragma unroll
+        for (int a = 0; a < O; a++) {
+            quad += zd[a] * zt[a];
+            logdet += log(S[a][a]);
+        }
+        double ll = 0.0;
+        if (live) {
+            bool zz = true;
+#pragma unroll
+            for (int a = 0; a < O; a++) zz = zz && (zd[a] == 0.0);
+            ll = zero_cov ? (zz ? PN_INF : -PN_INF) : (-0.5 * quad - 0.5 * (double)O * 1.8378770664093453 - logdet);
+        }
+        double V[RPL][O];
+#pragma unroll
+        for (int lr = 0; lr < RPL; lr++) {
+            double v[O];
+#pragma unroll
+            for (int a = 0; a < O; a++) v[a] = act ? C2[lr][a] : 0.0;
+            pn_chol_solve<O>(S, sinv, v);
+#pragma unroll
+            for (int a = 0; a < O; a++) V[lr][a] = v[a];
+        }
+        double K1all[D][O];
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+            double Kc[O];
+#pragma unroll
+            for (int a = 0; a < O; a++) {
+                double s = 0.0;
+#pragma unroll
+                for (int lr = 0; lr < RPL; lr++) s += R[lr][c] * V[lr][a];
+                Kc[a] = pn_gsum<G>(s);
+            }
+            double s = mu[c];
+#pragma unroll
+            for (int a = 0; a < O; a++) s -= Kc[a] * zd[a];
+            mu[c] = act ? s : mu[c];
+#pragma unroll
+            for (int lr = 0; lr < RPL; lr++) {
+                double r = R[lr][c];
+#pragma unroll
+                for (int a = 0; a < O; a++) r -= C2[lr][a] * Kc[a];
+                R[lr][c] = act ? r : R[lr][c];
+            }
+#pragma unroll
+            for (int a = 0; a < O; a++) {
+                double k1 = 0.0;
+#pragma unroll
+                for (int b = 0; b < O; b++)
+                    if (pn_data_rt(a, b) != 0.0) k1 += Kc[b] * pn_data_rt(a, b);
+                K1all[c][a] = k1;
+            }
+        }
+        noise_refactor<O>(sx, R, K1all, act, gl);
+        return ll;
+    }
+#endif
+
     static __device__ void run(const PnParams& P, double* smem) {
         constexpr unsigned FULL = 0xffffffffu;
         const int lane = threadIdx.x & 31;
@@ -593,6 +762,10 @@ struct PnSmall {
         long long traj = -1, naccept = 0, nreject = 0, nf = 0, iter = 0, tstop_idx = 0, save_pos = 0;
         int retcode = PN_RET_SUCCESS;
         bool have = false, queue_empty = false;
+#if PN_DATA
+        long long data_idx = 0; /* next observation (the data times are tstops, so every one of them is hit exactly) */
+        double data_ll = 0.0;   /* DataUpdateLogLikelihood.ll */
+#endif
 #pragma unroll
         for (int lr = 0; lr < RPL; lr++)
 #pragma unroll
@@ -635,6 +808,11 @@ struct PnSmall {
                         pn_rows_store<G, RPL, D>(sx, R, gl); /* Sigma_0.R = 0 */
 #endif
                         naccept = nreject = iter = tstop_idx = 0;
+#if PN_DATA
+                        data_idx = 0;
+                        data_ll = 0.0;
+                        while (data_idx < P.n_data && P.data_t[data_idx] <= P.t0) data_idx++; /* PresetTimeCallback: t0 is not a step end */
+#endif
                         loglik = 0.0;
                         gdiff = 0.0;
                         ldiff = 0.0;
@@ -1264,51 +1442,9 @@ struct PnSmall {
                     }
                 }
 #if PN_OBSN
-                {
-                    /* update.jl:125-136: Sigma = R+'R+ + K R K' = cholesky(...).U, triangularize!([R+ ; (K R.R')']) if that fails.  Same
-                       machinery as predict_cov!: own rows published, Gram matrix streamed, row-cyclic Cholesky.  Groups that commit
-                       nothing (or passed the prediction through, update.jl:82-89) keep their factor bit for bit. */
-                    pn_rows_store<G, RPL, D>(sx, R, gl);
-                    __syncwarp();
-                    double Mw[RPL][D];
-#pragma unroll
-                    for (int lr = 0; lr < RPL; lr++) {
-                        double k1o[d]; /* own row of K R.R' */
-#pragma unroll
-                        for (int a = 0; a < d; a++) {
-                            double v = 0.0;
-#pragma unroll
-                            for (int g = 0; g < G; g++)
-                                if (lr * G + g < D) v = (gl == g) ? K1all[lr * G + g < D ? lr * G + g : 0][a] : v;
-                            k1o[a] = v;
-                        }
-#pragma unroll
-                        for (int j = 0; j < D; j++) {
-                            if (j < lr * G) continue;
-                            double v = 0.0;
-#pragma unroll
-                            for (int a = 0; a < d; a++) v += k1o[a] * K1all[j][a];
-                            Mw[lr][j] = v;
-                        }
-                    }
-                    pn_gram_rows<G, RPL, D>(sx, Mw, gl);
-                    const bool okn = pn_chol_rows<G, RPL, D>(Mw, R, gl);
-                    const bool live = accept && !passthrough;
-                    const bool redo = live && !okn;
-                    if (__any_sync(FULL, redo)) {
-                        if (redo && gl == 0) {
-                            double E[d * D];
-#pragma unroll
-                            for (int a = 0; a < d; a++)
-#pragma unroll
-                                for (int c = 0; c < D; c++) E[a * D + c] = K1all[c][a];
-                            pn_triangularize_serial_dense<D, d>(sx, E);
-                        }
-                        __syncwarp();
-                    }
-                    if (redo || !live) pn_rows_load<G, RPL, D>(sx, R, gl);
-                    __syncwarp();
-                }
+                /* update.jl:125-136: + K R K'.  Groups that commit nothing (or passed the prediction through, update.jl:82-89) keep their
+                   factor bit for bit. */
+                noise_refactor<d>(sx, R, K1all, accept && !passthrough, gl);
 #endif
 #if PN_R_IN_SMEM && PN_PREDICT_CHOL
                 if (accept) pn_rows_store<G, RPL, D>(sx, R, gl); /* x_filt.Sigma.R for the next iteration (idle groups: the region still holds it) */
@@ -1326,6 +1462,16 @@ struct PnSmall {
                     if (retcode != PN_RET_SUCCESS) finished = true;
                     if (!(t < P.t1)) finished = true;
                 }
+#if PN_DATA
+                {
+                    /* PresetTimeCallback at the data times (dataupdate.jl:83): condition the filtered state on the observation before it
+                       is saved (callbacks run before savevalues!); uprev keeps the value from before the update (update_uprev! copies
+                       integ.u, which the callback does not touch) */
+                    const bool du = accept && data_idx < P.n_data && t == P.data_t[data_idx];
+                    if (__any_sync(FULL, du)) data_ll += data_update(sx, mu, R, P.data_u + (du ? data_idx : 0) * PN_DATA_O, du, gl);
+                    if (du) data_idx++;
+                }
+#endif
                 if (SAVE >= 1) {
                     /* never write past this trajectory's CSR segment (the host-computed offsets are exact; belt and braces) */
                     const bool wr = accept && P.step_offsets && save_pos < P.step_offsets[traj + 1];
@@ -1409,6 +1555,9 @@ struct PnSmall {
 #pragma unroll
                         for (int i = 0; i < DU * DU; i++) P.u_cov[traj * DU * DU + i] = cv[i];
                         P.loglik[traj] = loglik;
+#if PN_DATA
+                        if (P.data_loglik) P.data_loglik[traj] = data_ll;
+#endif
                         P.diffusion[traj] = fd;
                         P.dt_last[traj] = dt;
                         P.naccept[traj] = naccept;

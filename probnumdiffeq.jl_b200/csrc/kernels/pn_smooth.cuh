@@ -58,6 +58,9 @@ struct PnSmoothParams {
     int n_obs;
     const int* retcode;     /* [n_traj] return codes of the solve: -Inf unless Success (fenrir.jl:55-59) */
     double* fenrir_ll;      /* [n_traj] out */
+    double* workspace;      /* null: the warp-per-trajectory sweep keeps its work matrices in shared memory (D <= 56); else a global buffer
+                               of gridDim.x * PN_SM_WARPS * per_warp doubles (large states, e.g. Pleiades D = 112: 7 D^2 doubles per
+                               warp do not fit in shared memory; the buffer stays L2-resident) */
     int write_x;            /* 1: the smoothed state records (s_x_mean, s_x_covfac) are somebody's input or output (save_state, dense
                                output); 0: a sweep may leave the records alone and only emit sol.u / sol.pu -- a third of its HBM bytes */
     int kron_logdet;        /* 1: IsometricKronecker layout (EK0 + IWP + scalar diffusion): the reference's data update runs on the
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
     /* per-warp workspace */
     const bool fen = P.fenrir_ll != nullptr;
     const int per_warp = 7 * DD + 4 * D + 2 * n * n + 2 * n + (fen ? PN_FENRIR_EXTRA(D, P.n_obs) : 0);
-    double* W = pn_sm_shared + (size_t)warp * per_warp;
+    double* W = P.workspace ? P.workspace + ((size_t)blockIdx.x * PN_SM_WARPS + warp) * per_warp : pn_sm_shared + (size_t)warp * per_warp;
     double* Rk = W;            /* D x D  filtered factor at k                 */
     double* Xs = Rk + DD;      /* 3D x D stack; first used as 2D x D predict  */
     double* Gm = Xs + 3 * DD;  /* D x D  smoothing gain                       */

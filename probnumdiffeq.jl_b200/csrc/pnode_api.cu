@@ -257,6 +257,8 @@ struct pnode_solver {
     double compile_s = 0.0;
     /* Fenrir data log-likelihood: device copies of the data set and the observation model */
     double *d_data_t = nullptr, *d_data_u = nullptr, *d_obs_H = nullptr, *d_obs_Rn = nullptr;
+    bool data_forward = false; /* the data set drives forward updates in the step kernel (DataUpdateCallback) instead of the Fenrir pass */
+    bool fenrir() const { return n_data > 0 && !data_forward; }
     int64_t n_data = 0;
     int n_obs = 0;
     std::string mass_src; /* generated preamble (PN_MASS, pn_mass, pn_mass_inv) when the problem has a mass matrix */
@@ -525,6 +527,67 @@ static int nvrtc_dense_cubin(int d, int q, int G, bool ioup, std::vector<char>* 
     return nvrtc_compile(src, {def("PN_SD", d), def("PN_SQ", q), def("PN_SG", G), def("PN_IOUP", ioup ? 1 : 0), def("PN_SECOND", second ? 1 : 0)}, cubin);
 }
 
+/* Observation model of a data set: H = observation_matrix * SolProj (o x D, fenrir.jl:85 / dataupdate.jl:60-61; SolProj = E0 rows, or
+   (E1; E0) rows for second-order problems), the noise covariance R (o x o) and its upper Cholesky factor R.R (cov2psdmatrix). */
+static int build_obs_model(const pnode_config* cfg, int D, std::vector<double>* H, std::vector<double>* Cv, std::vector<double>* Rn) {
+    const int o = cfg->n_obs, dul = cfg->second_order ? 2 * cfg->d : cfg->d;
+    H->assign((size_t)o * D, 0.0);
+    Cv->assign((size_t)o * o, 0.0);
+    Rn->assign((size_t)o * o, 0.0);
+    for (int a = 0; a < o; a++)
+        for (int j = 0; j < dul; j++) {
+            const double pv = cfg->observation_matrix ? cfg->observation_matrix[a * dul + j] : (a == j ? 1.0 : 0.0);
+            const int sc = cfg->second_order ? (j < cfg->d ? cfg->d + j : j - cfg->d) : j;
+            (*H)[(size_t)a * D + sc] = pv;
+        }
+    if (cfg->observation_noise_cov) { /* cov2psdmatrix(::AbstractMatrix): upper Cholesky factor (ProbNumDiffEq.jl:72-73) */
+        Cv->assign(cfg->observation_noise_cov, cfg->observation_noise_cov + (size_t)o * o);
+        for (int j = 0; j < o; j++) {
+            double dsum = (*Cv)[j * o + j];
+            for (int k = 0; k < j; k++) dsum -= (*Rn)[k * o + j] * (*Rn)[k * o + j];
+            if (!(dsum > 0.0)) return fail(PNODE_ERR_ARGUMENT, "observation_noise_cov is not positive definite"); /* PosDefException */
+            (*Rn)[j * o + j] = std::sqrt(dsum);
+            for (int i = j + 1; i < o; i++) {
+                double v = (*Cv)[j * o + i];
+                for (int k = 0; k < j; k++) v -= (*Rn)[k * o + j] * (*Rn)[k * o + i];
+                (*Rn)[j * o + i] = v / (*Rn)[j * o + j];
+            }
+        }
+    } else {
+        for (int a = 0; a < o; a++) {
+            (*Cv)[a * o + a] = cfg->observation_noise_var;
+            (*Rn)[a * o + a] = std::sqrt(cfg->observation_noise_var);
+        }
+    }
+    return 0;
+}
+/* `__host__ __device__ constexpr double name(int a, int i)` returning T[a][i] of a rows x cols table (zeros are left out, so
+   they fold away in the unrolled kernels) */
+static std::string constexpr_table(const char* name, const double* T, int rows, int cols) {
+    std::string t = std::string("__host__ __device__ constexpr double ") + name + "(int a, int i) {\n  return ";
+    char buf[96];
+    for (int a = 0; a < rows; a++)
+        for (int i = 0; i < cols; i++) {
+            if (T[(size_t)a * cols + i] == 0.0) continue;
+            snprintf(buf, sizeof buf, "(a == %d && i == %d) ? %.17g : ", a, i, T[(size_t)a * cols + i]);
+            t += buf;
+        }
+    t += "0.0;\n}\n";
+    return t;
+}
+/* forward data updates (data_forward = 1) -> generated preamble: PN_DATA, PN_DATA_O, pn_data_H, pn_data_cov, pn_data_rt */
+static int data_preamble(const pnode_config* cfg, std::string* out) {
+    out->clear();
+    if (!(cfg->n_data > 0 && cfg->data_forward)) return 0;
+    const int D = cfg->d * (cfg->q + 1);
+    std::vector<double> H, Cv, Rn;
+    int rc = build_obs_model(cfg, D, &H, &Cv, &Rn);
+    if (rc) return rc;
+    *out = "#define PN_DATA 1\n#define PN_DATA_O " + std::to_string(cfg->n_obs) + "\n" + constexpr_table("pn_data_H", H.data(), cfg->n_obs, D) +
+           constexpr_table("pn_data_cov", Cv.data(), cfg->n_obs, cfg->n_obs) + constexpr_table("pn_data_rt", Rn.data(), cfg->n_obs, cfg->n_obs);
+    return 0;
+}
+
 /* pn_observation_noise (d x d row-major covariance, or var * I) -> generated preamble: PN_OBSN, constexpr pn_obsn_cov(a,b) = R[a][b]
    and pn_obsn_rt(a,b) = R.R[a][b], the upper Cholesky factor (cov2psdmatrix: a Number / UniformScaling x -> sqrt(x) I, a matrix ->
    cholesky(M).U; src/caches.jl:175-178).  Empty string without noise. */
@@ -677,7 +740,7 @@ static int get_smoother(pnode_solver* s) {
     auto t0 = std::chrono::steady_clock::now();
     out->threads = PN_SMR_THREADS;
     const bool ioup = (s->cfg.prior == PNODE_PRIOR_IOUP);
-    const void* fn = (env_int("PNODE_FORCE_NVRTC", 0) || ioup || s->cfg.second_order || s->n_data > 0) ? nullptr : pn_smooth_reg_lookup(s->cfg.d, s->cfg.q, s->Gs, col ? 1 : 0);
+    const void* fn = (env_int("PNODE_FORCE_NVRTC", 0) || ioup || s->cfg.second_order || s->fenrir()) ? nullptr : pn_smooth_reg_lookup(s->cfg.d, s->cfg.q, s->Gs, col ? 1 : 0);
     if (fn) {
         out->rt_fn = fn;
         CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_smooth));
@@ -690,7 +753,7 @@ static int get_smoother(pnode_solver* s) {
     int rc = load_driver();
     if (rc) return rc;
     std::vector<char> cubin;
-    if ((rc = nvrtc_smoother_cubin(s->cfg.d, s->cfg.q, s->Gs, ioup, col, &cubin, s->cfg.second_order != 0, s->n_data > 0))) return rc;
+    if ((rc = nvrtc_smoother_cubin(s->cfg.d, s->cfg.q, s->Gs, ioup, col, &cubin, s->cfg.second_order != 0, s->fenrir()))) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
     r = g_drv.ModuleGetFunction(&out->drv_fn, out->mod, "pn_smooth_entry");
@@ -805,7 +868,10 @@ static int validate_config(const pnode_config* cfg) {
             return fail(PNODE_ERR_UNSUPPORTED, "state dimension too large for the shared-memory CTA kernel");
         if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 256)
             return fail(PNODE_ERR_ARGUMENT, "D = d(q+1) > 32 runs one CTA per trajectory (lanes_per_traj 0 or 256)");
-        if (cfg->smooth) return fail(PNODE_ERR_UNSUPPORTED, "smoothing is not implemented for the CTA-per-trajectory kernel yet");
+        if (cfg->smooth && cfg->prior != PNODE_PRIOR_IWP)
+            return fail(PNODE_ERR_UNSUPPORTED, "smoothing with the CTA-per-trajectory kernel implements the IWP prior");
+        if (cfg->smooth && cfg->second_order)
+            return fail(PNODE_ERR_UNSUPPORTED, "smoothing of second-order problems needs the column-distributed register sweep (D <= 24)");
     }
     if (cfg->n_saveat > 0) { /* dense output sol(saveat) */
         if (!cfg->saveat) return fail(PNODE_ERR_ARGUMENT, "saveat is null but n_saveat > 0");
@@ -819,8 +885,9 @@ static int validate_config(const pnode_config* cfg) {
         if (cfg->smooth && smooth_lanes(D) == 0)
             return fail(PNODE_ERR_UNSUPPORTED, "dense output of smoothed solutions needs the register-resident sweep (D <= 24)");
     }
-    if (cfg->n_data > 0) { /* fenrir_data_loglik */
-        if (!cfg->smooth) return fail(PNODE_ERR_ARGUMENT, "fenrir only works with smoothing. Set `smooth=true`."); /* fenrir.jl:42-44 */
+    if (cfg->n_data > 0) { /* fenrir_data_loglik (backward pass), or DataUpdateCallback (forward updates) */
+        if (!cfg->data_forward && !cfg->smooth)
+            return fail(PNODE_ERR_ARGUMENT, "fenrir only works with smoothing. Set `smooth=true`."); /* fenrir.jl:42-44 */
         if (!cfg->data_t || !cfg->data_u || cfg->n_obs < 1) return fail(PNODE_ERR_ARGUMENT, "data_t / data_u / n_obs are required with n_data > 0");
         const int dul = cfg->second_order ? 2 * cfg->d : cfg->d;
         if (!cfg->observation_matrix && cfg->n_obs != dul)
@@ -832,9 +899,22 @@ static int validate_config(const pnode_config* cfg) {
         }
         if (!cfg->observation_noise_cov && !(cfg->observation_noise_var > 0.0))
             return fail(PNODE_ERR_ARGUMENT, "observation_noise_cov must be positive (definite)");
-        if (cfg->prior != PNODE_PRIOR_IWP || is_mv(cfg->diffusion))
+        if (cfg->data_forward) {
+            /* dataupdate.jl:69-71: "Partial observations only work with the EK1 right now"; here the forward updates are built into
+               the dense-layout step kernel */
+            if (layout != PNODE_COV_DENSE) {
+                if (cfg->n_obs != dul) return fail(PNODE_ERR_ARGUMENT, "Partial observations only work with the EK1 right now");
+                return fail(PNODE_ERR_UNSUPPORTED, "forward data updates (DataUpdateCallback) are implemented for the EK1 on the dense layout; "
+                                                   "fenrir_data_loglik serves the EK0 and the DiagonalEK1");
+            }
+            if (D > 32 || cfg->lanes_per_traj == 256)
+                return fail(PNODE_ERR_UNSUPPORTED, "forward data updates are implemented for D = d(q+1) <= 32");
+            if (cfg->prior != PNODE_PRIOR_IWP) return fail(PNODE_ERR_UNSUPPORTED, "forward data updates are implemented for the IWP prior");
+            std::vector<double> Hh, Cc, Rr;
+            if (int orc = build_obs_model(cfg, D, &Hh, &Cc, &Rr)) return orc;
+        } else if (cfg->prior != PNODE_PRIOR_IWP || is_mv(cfg->diffusion))
             return fail(PNODE_ERR_UNSUPPORTED, "the Fenrir backward pass is implemented for the IWP prior with scalar diffusion models");
-        if (layout != PNODE_COV_DENSE) {
+        if (!cfg->data_forward && layout != PNODE_COV_DENSE) {
             /* the structured layouts carry the data update on their factors: full observations only
                (src/callbacks/dataupdate.jl:69-71) and a noise covariance of the layout's own shape
                (to_factorized_matrix, src/covariance_structure.jl:46-58: isotropic for Kronecker, diagonal for blocks) */
@@ -858,8 +938,9 @@ static int validate_config(const pnode_config* cfg) {
                                     : "observation_noise_cov must be a scalar or a diagonal matrix for the block-diagonal covariance layout; use the EK1 for a full noise covariance");
             }
         }
-        if (cfg->n_saveat > 0) return fail(PNODE_ERR_UNSUPPORTED, "saveat and a Fenrir data set cannot be combined (the records stay filtering estimates)");
-        if (D > 32) return fail(PNODE_ERR_UNSUPPORTED, "the Fenrir backward pass is implemented for D = d(q+1) <= 32");
+        if (!cfg->data_forward && cfg->n_saveat > 0)
+            return fail(PNODE_ERR_UNSUPPORTED, "saveat and a Fenrir data set cannot be combined (the records stay filtering estimates)");
+        if (!cfg->data_forward && D > 32) return fail(PNODE_ERR_UNSUPPORTED, "the Fenrir backward pass is implemented for D = d(q+1) <= 32");
     }
     if (cfg->second_order) { /* SecondOrderODEProblem */
         if (cfg->q < 2) return fail(PNODE_ERR_ARGUMENT, "second-order problems need order >= 2 (the measurement reads the second derivative)");
@@ -931,7 +1012,8 @@ static int validate_config(const pnode_config* cfg) {
         if (orc) return orc;
         if (layout == PNODE_COV_DENSE && (D > 32 || cfg->lanes_per_traj == 256))
             return fail(PNODE_ERR_UNSUPPORTED, "pn_observation_noise is implemented for D = d(q+1) <= 32 on the dense layout");
-        if (cfg->n_data > 0) return fail(PNODE_ERR_UNSUPPORTED, "pn_observation_noise and a Fenrir data set cannot be combined yet");
+        if (cfg->n_data > 0 && !cfg->data_forward)
+            return fail(PNODE_ERR_UNSUPPORTED, "pn_observation_noise and a Fenrir data set cannot be combined yet");
     }
     const bool builtin = (std::string(cfg->rhs_name).rfind("builtin:", 0) == 0);
     if (!builtin && !cfg->rhs_src) return fail(PNODE_ERR_ARGUMENT, "rhs_src is required unless rhs_name is a builtin");
@@ -953,9 +1035,10 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     if ((rc = mass_preamble(cfg->mass_matrix, cfg->d, &mass_src))) return rc;
     if (cfg->second_order) mass_src = "#define PN_SECOND 1\n" + mass_src;
     {
-        std::string obs_src;
+        std::string obs_src, data_src;
         if ((rc = obsn_preamble(cfg, &obs_src))) return rc;
-        mass_src = obs_src + mass_src;
+        if ((rc = data_preamble(cfg, &data_src))) return rc;
+        mass_src = obs_src + data_src + mass_src;
     }
     rc = nvrtc_cubin(cfg->rhs_src, cfg->rhs_name, cfg->q, G, cfg->adaptive != 0, is_dynamic(cfg->diffusion),
                      save_level(cfg, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256)), &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
@@ -968,7 +1051,7 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     if (cfg->smooth && smooth_lanes(D) > 0 && !(cfg->alg == PNODE_EK1 && D > 32)) {
         std::vector<char> c2;
         const bool col = env_int("PNODE_SMOOTH_KIND", 1) != 0;
-        if ((rc = nvrtc_smoother_cubin(cfg->d, cfg->q, smooth_lanes(D), cfg->prior == PNODE_PRIOR_IOUP, col, &c2, cfg->second_order != 0, cfg->n_data > 0))) return rc;
+        if ((rc = nvrtc_smoother_cubin(cfg->d, cfg->q, smooth_lanes(D), cfg->prior == PNODE_PRIOR_IOUP, col, &c2, cfg->second_order != 0, cfg->n_data > 0 && !cfg->data_forward))) return rc;
         total += (int64_t)c2.size();
     }
     if (cfg->n_saveat > 0) {
@@ -1000,9 +1083,11 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     mass_preamble(cfg->mass_matrix, cfg->d, &s->mass_src); /* validated above */
     if (cfg->second_order) s->mass_src = "#define PN_SECOND 1\n" + s->mass_src; /* generated preamble of the step kernels */
     {
-        std::string obs_src;
+        std::string obs_src, data_src;
         obsn_preamble(cfg, &obs_src); /* validated above */
-        s->mass_src = obs_src + s->mass_src;
+        data_preamble(cfg, &data_src);
+        s->mass_src = obs_src + data_src + s->mass_src;
+        s->data_forward = (cfg->n_data > 0 && cfg->data_forward);
     }
     s->cfg.mass_matrix = nullptr;
     s->cfg.pn_observation_noise = nullptr;
@@ -1152,32 +1237,10 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
         const int o = cfg->n_obs, dul = cfg->second_order ? 2 * cfg->d : cfg->d;
         s->n_data = cfg->n_data;
         s->n_obs = o;
-        /* state2data_projmat = proj * SolProj (fenrir.jl:85): o x D, SolProj = E0 rows or (E1; E0) rows */
-        std::vector<double> H((size_t)o * D, 0.0), Rn((size_t)o * o, 0.0);
-        for (int a = 0; a < o; a++)
-            for (int j = 0; j < dul; j++) {
-                const double pv = cfg->observation_matrix ? cfg->observation_matrix[a * dul + j] : (a == j ? 1.0 : 0.0);
-                const int sc = cfg->second_order ? (j < cfg->d ? cfg->d + j : j - cfg->d) : j;
-                H[(size_t)a * D + sc] = pv;
-            }
-        if (cfg->observation_noise_cov) { /* cov2psdmatrix(::AbstractMatrix): upper Cholesky factor (ProbNumDiffEq.jl:72-73) */
-            std::vector<double> A(cfg->observation_noise_cov, cfg->observation_noise_cov + (size_t)o * o);
-            for (int j = 0; j < o; j++) {
-                double dsum = A[j * o + j];
-                for (int k = 0; k < j; k++) dsum -= Rn[k * o + j] * Rn[k * o + j];
-                if (!(dsum > 0.0)) {
-                    pnode_destroy(s);
-                    return fail(PNODE_ERR_ARGUMENT, "observation_noise_cov is not positive definite"); /* PosDefException */
-                }
-                Rn[j * o + j] = std::sqrt(dsum);
-                for (int i = j + 1; i < o; i++) {
-                    double v = A[j * o + i];
-                    for (int k = 0; k < j; k++) v -= Rn[k * o + j] * Rn[k * o + i];
-                    Rn[j * o + i] = v / Rn[j * o + j];
-                }
-            }
-        } else {
-            for (int a = 0; a < o; a++) Rn[a * o + a] = std::sqrt(cfg->observation_noise_var);
+        std::vector<double> H, Cv, Rn;
+        if (int orc = build_obs_model(cfg, D, &H, &Cv, &Rn)) {
+            pnode_destroy(s);
+            return orc;
         }
         CUDA_TRY_S(cudaMalloc(&s->d_data_t, sizeof(double) * cfg->n_data));
         CUDA_TRY_S(cudaMalloc(&s->d_data_u, sizeof(double) * cfg->n_data * o));
@@ -1364,6 +1427,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
         if ((rc = alloc_field(r, PNODE_F_X_FINAL_COVFAC, N * D * D * 8))) return rc;
     }
     if ((rc = alloc_field(r, PNODE_F_LOGLIK, N * 8))) return rc;
+    if (s->data_forward && (rc = alloc_field(r, PNODE_F_DATA_LOGLIK, N * 8))) return rc;
     if ((rc = alloc_field(r, PNODE_F_DIFFUSION, N * 8))) return rc;
     if (s->mv && (rc = alloc_field(r, PNODE_F_DIFFUSION_MV, N * d * 8))) return rc;
     if ((rc = alloc_field(r, PNODE_F_DT_LAST, N * 8))) return rc;
@@ -1382,6 +1446,12 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
     P.x_mean = (double*)r->f[PNODE_F_X_FINAL].d;
     P.x_covfac = (double*)r->f[PNODE_F_X_FINAL_COVFAC].d;
     P.loglik = (double*)r->f[PNODE_F_LOGLIK].d;
+    if (s->data_forward) { /* DataUpdateCallback: the step kernel conditions on the observations as it passes their times */
+        P.data_t = s->d_data_t;
+        P.data_u = s->d_data_u;
+        P.n_data = s->n_data;
+        P.data_loglik = (double*)r->f[PNODE_F_DATA_LOGLIK].d;
+    }
     P.diffusion = (double*)r->f[PNODE_F_DIFFUSION].d;
     P.diffusion_mv = (double*)r->f[PNODE_F_DIFFUSION_MV].d;
     P.dt_last = (double*)r->f[PNODE_F_DT_LAST].d;
@@ -1579,19 +1649,30 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 const size_t per_warp =
                     (size_t)(7 * D * D + 4 * D + 2 * n * n + 2 * n + (Q.fenrir_ll ? PN_FENRIR_EXTRA(D, Q.n_obs) : 0)) * sizeof(double);
                 int warps = PN_SM_WARPS;
-                while (warps > 1 && per_warp * warps > 200 * 1024) warps--;
-                const size_t smem = per_warp * warps;
-                if (smem > 220 * 1024) return fail(PNODE_ERR_UNSUPPORTED, "state dimension too large for the shared-memory smoother");
                 const void* fn = pn_smooth_kernel_ptr();
-                CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                /* states whose work matrices (7 D^2 doubles per warp) do not fit in shared memory -- Pleiades, D = 112: 0.7 MB --
+                   sweep out of a global workspace that stays L2-resident (filter + smoother) */
+                const bool global_ws = per_warp > 200 * 1024;
+                while (!global_ws && warps > 1 && per_warp * warps > 200 * 1024) warps--;
+                const size_t smem = global_ws ? 0 : per_warp * warps;
+                if (!global_ws) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int nblk = 0;
                 CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nblk, fn, 32 * warps, smem));
                 if (nblk < 1) return fail(PNODE_ERR_CUDA, "smoother kernel does not fit on an SM");
+                if (global_ws) nblk = std::min(nblk, 2); /* 8 warps per SM x 0.7 MB: the working set of the whole grid stays below L2 */
                 long long want = (ntraj + warps - 1) / warps;
                 unsigned grid = (unsigned)std::max(1LL, std::min(want, (long long)s->n_sm * nblk));
+                double* ws = nullptr;
+                if (global_ws) {
+                    if (warps != PN_SM_WARPS) return fail(PNODE_ERR_CUDA, "workspace indexing assumes PN_SM_WARPS warps per CTA");
+                    CUDA_TRY(cudaMallocAsync((void**)&ws, (size_t)grid * warps * per_warp, s->stream));
+                    scope.track(ws);
+                }
+                Q.workspace = ws;
                 CUDA_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(unsigned long long), s->stream));
                 void* args[] = {&Q};
                 CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(32 * warps), args, smem, s->stream));
+                if (ws) scope.release(ws);
             }
             return 0;
         };
@@ -1675,7 +1756,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             Q.s_u_mean = P.s_u_mean;
             Q.s_u_cov = P.s_u_cov;
             Q.write_x = (s->cfg.save_state || dense) ? 1 : 0; /* sol.x_smooth asked for, or the dense output reads the smoothed records */
-            if (s->n_data > 0) {
+            if (s->fenrir()) {
                 /* Fenrir: the backward pass fits the PN posterior to the data instead of smoothing; the records and the
                    U fields stay the filtering estimates, uncalibrated (the reference stops with step!, no postamble) */
                 if ((rc = alloc_field(r, PNODE_F_FENRIR_LOGLIK, N * 8))) return rc;

@@ -29,6 +29,7 @@ F_T_END, F_U_FINAL, F_U_FINAL_COV, F_X_FINAL, F_X_FINAL_COVFAC, F_LOGLIK, F_DIFF
 F_NACCEPT, F_NREJECT, F_NF, F_RETCODE, F_STEP_OFFSETS, F_T, F_U, F_U_COV, F_DIFFUSIONS, F_X, F_X_COVFAC = range(8, 19)
 F_DIFFUSION_MV, F_DIFFUSIONS_MV, F_SAVEAT_U, F_SAVEAT_U_COV = 19, 20, 21, 22
 F_FENRIR_LOGLIK = 23
+F_DATA_LOGLIK = 24
 _FIELD_DTYPE = {F_NACCEPT: np.int64, F_NREJECT: np.int64, F_NF: np.int64, F_RETCODE: np.int32,
                 F_STEP_OFFSETS: np.int64}
 
@@ -66,7 +67,7 @@ class Config(C.Structure):
         ("mass_matrix", C.POINTER(C.c_double)),
         ("second_order", C.c_int32), ("reserved1", C.c_int32),
         ("data_t", C.POINTER(C.c_double)), ("n_data", C.c_int64), ("data_u", C.POINTER(C.c_double)),
-        ("n_obs", C.c_int32), ("reserved2", C.c_int32),
+        ("n_obs", C.c_int32), ("data_forward", C.c_int32),
         ("observation_matrix", C.POINTER(C.c_double)), ("observation_noise_cov", C.POINTER(C.c_double)),
         ("observation_noise_var", C.c_double),
         ("pn_observation_noise", C.POINTER(C.c_double)), ("pn_observation_noise_var", C.c_double),
@@ -145,9 +146,10 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
                 maxiters=1_000_000, beta1=0.0, beta2=0.0, qmin=0.2, qmax=10.0, gamma=0.9, qsteady_min=1.0,
                 qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None, device=0, prior=PRIOR_IWP,
                 rate_parameter=0.0, saveat=None, mass_matrix=None, second_order=False, data_t=None, data_u=None,
-                observation_matrix=None, observation_noise_cov=None, pn_observation_noise=None) -> Config:
+                observation_matrix=None, observation_noise_cov=None, pn_observation_noise=None, data_forward=False) -> Config:
     c = Config()
     c.second_order = int(second_order)
+    c.data_forward = int(data_forward)
     c.struct_size = C.sizeof(Config)
     c.device, c.d, c.q, c.n_p = device, d, q, n_p
     c.alg, c.cov, c.prior, c.diffusion = alg, cov, prior, diffusion

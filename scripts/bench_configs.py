@@ -18,7 +18,7 @@ def F_smooth(D, d):
     return 10 * D**3 + (22 / 3) * D**3 + 2 * D * D * d + 2 * D * D
 
 
-def run(tag, name, n, q, t1, alg=lib.EK1, seed=0, reps=2, du0=0.0, dp=0.1, **kw):
+def run(tag, name, n, q, t1, alg=lib.EK1, seed=0, reps=2, du0=0.0, dp=0.1, second=False, **kw):
     pd = problems.PROBLEMS.get(name) or problems.MASS_MATRIX_PROBLEMS[name]
     rng = np.random.Generator(np.random.PCG64(seed))
     u0 = np.array(pd.u0, dtype=float)[None, :] * (1 + du0 * rng.uniform(-1, 1, (n, pd.d)))
@@ -31,7 +31,8 @@ def run(tag, name, n, q, t1, alg=lib.EK1, seed=0, reps=2, du0=0.0, dp=0.1, **kw)
         cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="UserProb", rhs_src=src, alg=alg, t0=0.0, t1=t1,
                               mass_matrix=pd.mass_matrix, **kw)
     else:
-        cfg = lib.make_config(d=pd.d, q=q, n_p=pd.n_p, rhs_name="builtin:" + name, alg=alg, t0=0.0, t1=t1, **kw)
+        cfg = lib.make_config(d=pd.d // 2 if second else pd.d, second_order=second, q=q, n_p=pd.n_p, rhs_name="builtin:" + name, alg=alg,
+                              t0=0.0, t1=t1, **kw)
     s = lib.Solver(cfg)
     best = None
     for _ in range(reps + (1 if pd.mass_matrix is not None else 0)):   # first call of an NVRTC solver compiles
@@ -46,8 +47,9 @@ def run(tag, name, n, q, t1, alg=lib.EK1, seed=0, reps=2, du0=0.0, dp=0.1, **kw)
         if best is None or rec["kernel_ms"] < best["kernel_ms"]:
             best = rec
     s.close()
-    D = pd.d * (q + 1)
-    fl = F_filt(D, pd.d) + (F_smooth(D, pd.d) if kw.get("smooth") else 0.0)
+    dm = pd.d // 2 if second else pd.d
+    D = dm * (q + 1)
+    fl = F_filt(D, dm) + (F_smooth(D, pd.d) if kw.get("smooth") else 0.0)
     if alg == lib.EK0:
         nn = q + 1
         fl = (22 / 3) * nn**3 + 4 * nn * nn * pd.d
@@ -71,8 +73,13 @@ if "cfg3" in which:
     run("cfg3 filter only", "vanderpol", 100000, 5, 2.0, seed=1, dp=0.2)
 if "cfg4" in which:
     run("cfg4 Pleiades EK1(3) D=112 filter only, 16k", "pleiades", 16384, 3, 3.0, seed=2)
+    run("cfg4 Pleiades as 14 second-order equations (benchmarks/pleiades.jmd prob2), EK1(3) D=56 filter only, 16k", "pleiades", 16384, 3, 3.0,
+        seed=2, second=True)
+    # filter + smoother at D = 112: 100 KB of filter record per step -- 512 trajectories x ~770 record slots = 40 GB on one GPU
+    # (16 384 trajectories need ~1 TB: trajectory-sharded over 8 GPUs by storage, in chunks)
+    run("cfg4 Pleiades EK1(3) D=112 filter+smoother, 512 trajectories", "pleiades", 512, 3, 3.0, seed=2, smooth=True, save_everystep=True, reps=1)
 if "cfg5" in which:
-    for n in (10_000, 100_000, 1_000_000, 4_000_000):
+    for n in (10_000, 100_000, 1_000_000, 10_000_000):
         run(f"cfg5 ROBER EK1(3) adaptive filter only, {n}", "rober", n, 3, 100.0, seed=3)
     run("cfg5 OREGO EK1(3) adaptive filter only, 131072", "orego", 131072, 3, 30.0, seed=3)
 if "cfg5dae" in which:   # ROBER as the reference benchmarks it: mass-matrix DAE form (benchmarks/rober.jmd:37-46)

@@ -131,3 +131,48 @@ def test_pleiades_as_14_second_order_equations_d56(oracle):
     per1 = g1["info"].kernel_ms / g1["info"].total_accepted
     print(f"pleiades second-order D=56: {1e3 / per2:.3e} steps/s; first-order D=112: {1e3 / per1:.3e} steps/s")
     assert np.all(g2["retcode"] == 0) and per2 < 0.5 * per1
+
+
+def test_cta_kernel_with_smoothing_small_and_pleiades_d112(oracle):
+    """Filter + smoother for states beyond the register sweeps (SURVEY.md section 8d cfg4 asks for both numbers): the CTA kernel
+    saves its filter records, the warp-per-trajectory sweep (reference formulas literally, pn_smooth.cuh) runs them backwards --
+    out of shared memory for mid-sized states, out of an L2-resident global workspace for Pleiades (D = 112, 7 D^2 doubles per
+    warp).  Fixed steps + FixedDiffusion: smoothed means 1e-10, covariances 1e-9 against the oracle, every saved point."""
+    from test_gpu_parity import _gpu_smooth
+    pd, u0, p = _inputs("fitzhugh_nagumo", 2, 181, dp=0.05)
+    kw = dict(adaptive=False, dt=0.01, t0=0.0, t1=2.0, diffusion=lib.DIFF_FIXED, calibrate=True)
+    g = _gpu_smooth(pd, u0, p, 3, lanes_per_traj=256, **kw)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    cfg = oracle.make_config(2, 3, 3, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=True, smooth=True, adaptive=False, dt=0.01,
+                             t0=0.0, t1=2.0, cov_backend=oracle.COV_REF)
+    for i in range(2):
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"] == 201
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < 1e-9
+    n = 2
+    pd, u0, _ = _inputs("pleiades", n, 2)
+    u0[:, 14:] += 1e-3 * np.random.default_rng(2).uniform(-1, 1, (n, 14))
+    p = np.zeros((n, 0))
+    kw = dict(adaptive=False, dt=0.01, t0=0.0, t1=0.3, diffusion=lib.DIFF_FIXED, calibrate=True)
+    g = _gpu_smooth(pd, u0, p, 3, **kw)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 28, 0), 3)
+    cfg = oracle.make_config(28, 3, 0, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=True, smooth=True, adaptive=False, dt=0.01,
+                             t0=0.0, t1=0.3, cov_backend=oracle.COV_REF)
+    for i in range(n):
+        o = oracle.solve(cfg, rhs, u0[i], [])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"] == 31
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < 1e-9
+    # adaptive ensemble: ragged lengths through the pilot-sized save pass; smoothed end point = filtered end point
+    m = 64
+    _, U0, _ = _inputs("pleiades", m, 5)
+    U0[:, 14:] += 1e-3 * np.random.default_rng(5).uniform(-1, 1, (m, 14))
+    gs = _gpu_smooth(pd, U0, np.zeros((m, 0)), 3, adaptive=True, t0=0.0, t1=1.0)
+    gf = _gpu(pd, U0, np.zeros((m, 0)), 3, builtin=False, adaptive=True, t0=0.0, t1=1.0)
+    ends = gs["off"][1:] - 1
+    assert np.array_equal(np.diff(gs["off"]) - 1, gf["naccept"])
+    assert _rel(gs["U"][ends], gf["u"]) < 1e-12
+    print("pleiades D=112 filter+smoother, 64 trajectories to t=1: kernel_ms", gs["info"].kernel_ms, "steps", int(gf["naccept"].sum()))
