@@ -64,6 +64,24 @@ def committed_ncu(workload, n):
     return tab.get(f"{workload}:{n}")
 
 
+def executed_flops_per_accepted_step(workload):
+    """Executed FP64 operations (2 DFMA + DMUL + DADD, predicated-on thread instructions counted by ncu) per accepted step of the
+    dominant kernel, from the committed capture of this workload that carries its own accepted-step count (any ensemble size: the
+    per-step count does not depend on it).  Rejected attempts and the identity steps of finished groups are inside the count."""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_captures.json")))
+    except Exception:
+        return None, None
+    best = None
+    for key, e in tab.items():
+        if key.split(":")[0] == workload and e.get("accepted_steps"):
+            if best is None or e["accepted_steps"] > best[1]["accepted_steps"]:
+                best = (key, e)
+    if best is None:
+        return None, None
+    return best[1]["executed"]["fp64_flops"] / best[1]["accepted_steps"], best[0]
+
+
 def make_inputs(problem, n, seed):
     from probnumdiffeq_jl_b200 import problems
 
@@ -333,6 +351,8 @@ def main():
         if smooth:
             alg_bytes += (acc / args.steps) * 8 * (2 * (D * D + D + 2) + 1 + d + d * d)
         cap = committed_ncu(args.workload, n)
+        ex_per_step, ex_key = executed_flops_per_accepted_step(args.workload)
+        executed_tflops = (acc / args.steps) * ex_per_step / dur / 1e12 if ex_per_step else None
         line = {
             "metric": METRIC, "value": acc_t / wall_m, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall_m / args.steps, "higher_is_better": True,
@@ -363,6 +383,12 @@ def main():
                 # reference's own Gram + Cholesky route and uses the Kronecker / triangular structure, so it EXECUTES fewer FP64
                 # operations than that: the executed count and the FP64-pipe utilisation below come from the ncu capture
                 "executed": cap.get("executed") if cap else None,
+                # what the FP64 pipe really does: executed FP64 operations per accepted step (ncu capture `executed_from`) x the
+                # accepted steps of THIS run / the CUDA-event duration of THIS run.  `frac` above can exceed 1 because its numerator
+                # credits the dense-operand count of SURVEY.md section 8d (17 658 FLOP per step at D = 12) while the kernel uses the
+                # structure of Ah, Qh and H; `frac_executed` is the pipe-level figure and is the one to judge the kernel by.
+                "executed_flops_per_accepted_step": ex_per_step, "executed_from": ex_key,
+                "executed_tflops": executed_tflops, "frac_executed": executed_tflops / fp64_peak if executed_tflops else None,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / dur / 1e9, "peak_gbs": hbm_peak,
                         "frac": alg_bytes / dur / 1e9 / hbm_peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback"},
             },

@@ -1,6 +1,6 @@
 """Summarise an .ncu-rep: key raw metrics, stall reasons, top source lines.
 
-    ncu_summary.py rep [out_prefix [capture_key]]
+    ncu_summary.py rep [out_prefix [capture_key [accepted_steps]]]
 
 With `capture_key` ("workload:trajectories", e.g. "rober:1048576") the numbers bench.py cannot measure itself -- DRAM bytes of the
 kernel, FP64-pipe utilisation, executed FP64 operations -- are stored under that key in profiles/ncu_captures.json, from where
@@ -70,6 +70,9 @@ if len(sys.argv) > 3:
                      "note": "ncu --set full capture (serialised, cold cache): shares and counts, not a timing"}}
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_captures.json")
     tab = json.load(open(path)) if os.path.exists(path) else {}
+    if len(sys.argv) > 4:   # accepted steps of the captured launch (from the run's own bench line): executed FLOPs per step
+        entry["accepted_steps"] = float(sys.argv[4])
+        entry["executed"]["fp64_flops_per_accepted_step"] = flops / float(sys.argv[4])
     tab[sys.argv[3]] = entry
     json.dump(tab, open(path, "w"), indent=1, sort_keys=True)
     print("\nstored", sys.argv[3], "->", path)
