@@ -56,7 +56,7 @@ typedef enum pnode_status {
 typedef enum pnode_alg { PNODE_EK0 = 0, PNODE_EK1 = 1, PNODE_DIAGONAL_EK1 = 2 } pnode_alg; /* src/algorithms.jl:188-393 */
 /* src/covariance_structure.jl:1-63; AUTO follows covariance_structure(alg, prior, diffusion) src/algorithms.jl:132-151 */
 typedef enum pnode_cov { PNODE_COV_AUTO = 0, PNODE_COV_DENSE = 1, PNODE_COV_KRONECKER = 2, PNODE_COV_BLOCKS = 3 } pnode_cov;
-/* src/priors/iwp.jl; src/priors/ioup.jl with a scalar rate parameter (IOUP(num_derivatives, rate)) */
+/* src/priors/iwp.jl; src/priors/ioup.jl (scalar rate_parameter, or rate_matrix / update_rate_parameter below) */
 typedef enum pnode_prior { PNODE_PRIOR_IWP = 0, PNODE_PRIOR_IOUP = 1 } pnode_prior;
 /* src/diffusions/typedefs.jl: DynamicDiffusion, FixedDiffusion, DynamicMVDiffusion, FixedMVDiffusion */
 typedef enum pnode_diffusion {
@@ -159,6 +159,16 @@ typedef struct pnode_config {
        diagonal R only -- PNODE_ERR_ARGUMENT with the reference's messages. */
     const double* pn_observation_noise;
     double pn_observation_noise_var;
+    /* IOUP(num_derivatives, rate_parameter::Union{AbstractVector,AbstractMatrix}) (src/priors/ioup.jl:81-113): [d][d] row-major rate
+       matrix of the SDE drift, F[q-block, q-block] = rate (a vector rate is passed as its diagonal matrix, as to_sde does); host
+       pointer, copied at create; NULL = the scalar rate_parameter.  IOUP(num_derivatives; update_rate_parameter = true)
+       (RosenbrockExpEK, src/algorithms.jl:438-459): update_rate_parameter = 1 sets the rate to the Jacobian J(uprev, t) before every
+       step (src/perform_step.jl:88-96); rate_matrix must then be NULL ("Do not manually set the `rate_parameter` ...",
+       src/caches.jl:139-149) and the EK1 is required (the Jacobian is the traced one).  Both run on the general-prior path
+       (one warp per trajectory, dense transition pairs; filter and smoother; EK0 and EK1 with scalar diffusion models). */
+    const double* rate_matrix;
+    int32_t update_rate_parameter;
+    int32_t reserved2;
 } pnode_config;
 
 typedef struct pnode_solver pnode_solver;

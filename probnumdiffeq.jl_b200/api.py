@@ -61,9 +61,33 @@ class IWP:
 
 @dataclasses.dataclass(frozen=True)
 class IOUP:
-    """Integrated Ornstein-Uhlenbeck prior with a scalar rate parameter (src/priors/ioup.jl: IOUP(num_derivatives, rate))."""
+    """Integrated Ornstein-Uhlenbeck prior (src/priors/ioup.jl): `IOUP(num_derivatives, rate_parameter)` with a number, a length-d
+    vector or a d x d matrix, or `IOUP(num_derivatives, update_rate_parameter=True)` (rate := Jacobian before every step,
+    src/perform_step.jl:88-96; the rate must then be left unset, src/caches.jl:139-149)."""
     num_derivatives: int = 3
-    rate_parameter: float = -1.0
+    rate_parameter: object = None
+    update_rate_parameter: bool = False
+
+    def __post_init__(self):
+        if self.rate_parameter is None and not self.update_rate_parameter:
+            raise TypeError("IOUP(num_derivatives; update_rate_parameter) needs update_rate_parameter=True when no rate is given")  # ioup.jl:51-54
+        if self.rate_parameter is not None and self.update_rate_parameter:
+            raise ValueError("Do not manually set the `rate_parameter` of the IOUP prior when using the `update_rate_parameter=true` option."
+                             "Reset the prior and try again.")  # caches.jl:139-149
+
+    def __hash__(self):
+        r = self.rate_parameter
+        return hash((self.num_derivatives, None if r is None else np.asarray(r, dtype=float).tobytes(), self.update_rate_parameter))
+
+
+def ExpEK(*, L, order=3, **kw):
+    """`ExpEK(; L, order=3, kwargs...) = EK0(; prior=IOUP(order, L), kwargs...)` (src/algorithms.jl:405-425)."""
+    return EK0(prior=IOUP(order, L), **kw)
+
+
+def RosenbrockExpEK(*, order=3, **kw):
+    """`RosenbrockExpEK(; order=3, kwargs...) = EK1(; prior=IOUP(order, update_rate_parameter=true), kwargs...)` (src/algorithms.jl:438-459)."""
+    return EK1(prior=IOUP(order, update_rate_parameter=True), **kw)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -258,7 +282,8 @@ def _config_for(prob: ODEProblem, alg, ens: EnsembleB200, *, adaptive, dt, absto
     else:
         kw.update(diffusion=_lib.DIFF_DYNAMIC)
     if isinstance(alg.prior, IOUP):
-        kw.update(prior=_lib.PRIOR_IOUP, rate_parameter=alg.prior.rate_parameter)
+        kw.update(prior=_lib.PRIOR_IOUP, rate_parameter=alg.prior.rate_parameter if alg.prior.rate_parameter is not None else 0.0,
+                  update_rate_parameter=alg.prior.update_rate_parameter)
     if alg.pn_observation_noise is not None:
         kw.update(pn_observation_noise=alg.pn_observation_noise)
     if prob.mass_matrix is not None:

@@ -53,6 +53,12 @@ struct PnParams {
     const double* data_u;
     long long n_data;
     double* data_loglik; /* [n_traj] */
+    /* general-prior filter (pn_gen.cuh): IOUP with a vector / matrix rate parameter (d x d row-major device array; null: rate I_d),
+       Rosenbrock-style rate update (rate := J(uprev, t), perform_step.jl:88-96), per-warp workspace (null: shared memory) */
+    const double* rate_matrix;
+    int update_rate;
+    double* gen_workspace;
+    double* s_rate; /* [total][d][d] rate matrix of the step k -> k+1 at slot k (smoothing with update_rate only; null otherwise) */
     /* ---- per-trajectory outputs ---- */
     double* t_end;      /* [n_traj]       */
     double* u_mean;     /* [n_traj][d]    */

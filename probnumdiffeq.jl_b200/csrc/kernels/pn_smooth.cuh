@@ -20,6 +20,9 @@
 #ifndef PN_SMOOTH_CUH
 #define PN_SMOOTH_CUH
 #include "pn_params.h"
+#ifndef PN_SMOOTH_DECL_ONLY
+#include "pn_lti.cuh"
+#endif
 
 struct PnSmoothParams {
     long long n_traj;
@@ -63,10 +66,17 @@ struct PnSmoothParams {
                                warp do not fit in shared memory; the buffer stays L2-resident) */
     int write_x;            /* 1: the smoothed state records (s_x_mean, s_x_covfac) are somebody's input or output (save_state, dense
                                output); 0: a sweep may leave the records alone and only emit sol.u / sol.pu -- a third of its HBM bytes */
+    /* general LTI prior (IOUP with a vector / matrix rate, or the Jacobian-updated rate; pn_lti.cuh): the transition of a step is a
+       dense pair (Ah, Qh.R) recomputed from (h, rate matrix); shared-memory sweep only */
+    int gen_prior;
+    const double* rate_matrix; /* [d][d] row-major (null: rate I_d) */
+    const double* s_rate;      /* [total][d][d] per-step rate matrices saved by the filter (update_rate_parameter); null: rate_matrix */
     int kron_logdet;        /* 1: IsometricKronecker layout (EK0 + IWP + scalar diffusion): the reference's data update runs on the
                                n x n factors and takes logdet of the 1 x 1 factor of S without the factor d (update.jl:140-148,
                                182-194) -- log det S / n_obs instead of log det S */
 };
+/* extra doubles per warp with a general prior (host and kernel must agree) */
+#define PN_SMOOTH_GEN_EXTRA(D, d, n) (2 * (D) * (D) + 2 * (d) * (d) + (n))
 /* extra shared-memory doubles per warp in Fenrir mode (host and kernel must agree) */
 #define PN_FENRIR_EXTRA(D, o) (3 * (D) * (o) + ((D) + (o)) * (o) + 4 * (o))
 
@@ -215,7 +225,8 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
     const int d = P.d, q = P.q, n = q + 1, D = d * n, DD = D * D;
     /* per-warp workspace */
     const bool fen = P.fenrir_ll != nullptr;
-    const int per_warp = 7 * DD + 4 * D + 2 * n * n + 2 * n + (fen ? PN_FENRIR_EXTRA(D, P.n_obs) : 0);
+    const int fen_extra = fen ? PN_FENRIR_EXTRA(D, P.n_obs) : 0;
+    const int per_warp = 7 * DD + 4 * D + 2 * n * n + 2 * n + fen_extra + (P.gen_prior ? PN_SMOOTH_GEN_EXTRA(D, d, n) : 0);
     double* W = P.workspace ? P.workspace + ((size_t)blockIdx.x * PN_SM_WARPS + warp) * per_warp : pn_sm_shared + (size_t)warp * per_warp;
     double* Rk = W;            /* D x D  filtered factor at k                 */
     double* Xs = Rk + DD;      /* 3D x D stack; first used as 2D x D predict  */
@@ -231,6 +242,12 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
     double* hp = LQ + n * n;   /* n */
     double* PIv = hp + n;      /* n */
     double* Fw = PIv + n;      /* Fenrir workspace (fen only) */
+    double* Ahd = Fw + fen_extra; /* general prior: dense Ah, Qh.R, rate matrix, h * rate, diagonal of P^-1 */
+    double* Qcd = Ahd + DD;
+    double* Rmg = Qcd + DD;
+    double* Zmg = Rmg + d * d;
+    double* PIg = Zmg + d * d;
+    const bool gen = P.gen_prior != 0;
 
     for (;;) {
         unsigned long long idx = 0;
@@ -282,6 +299,12 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
                 LQ[i] = (c <= r) ? P.L[r * n + c] * PIv[c] : 0.0;
             }
             __syncwarp();
+            if (gen && h != 0.0) { /* dense transition of this step (Xs, Gm are free here) */
+                for (int i = lane; i < d * d; i += 32)
+                    Rmg[i] = P.s_rate ? P.s_rate[k * d * d + i] : (P.rate_matrix ? P.rate_matrix[i] : ((i / d == i % d) ? P.rate : 0.0));
+                __syncwarp();
+                pn_gen_transition(Ahd, Qcd, Rmg, h, d, n, Xs, Xs + DD, Xs + 2 * DD, Gm, Zmg, PIg, lane);
+            }
             if (h == 0.0) { /* integrator_utils.jl:109-112: x_smooth[k] = x_smooth[k+1] */
                 if (fen) continue; /* fenrir.jl:103-106 */
                 for (int i = lane; i < DD; i += 32) P.s_x_covfac[k * DD + i] = Rs[i] * sc;
@@ -292,6 +315,13 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
                 for (int i = lane; i < DD; i += 32) {
                     const int r = i / D, c = i % D, j = c / d, ii = c % d;
                     double s = 0.0;
+                    if (gen) {
+                        for (int kk = 0; kk < D; kk++) s += Rk[r * D + kk] * Ahd[c * D + kk];
+                        Xs[i] = s;
+                        Tm[i] = s;
+                        Xs[DD + i] = sd * Qcd[i];
+                        continue;
+                    }
                     for (int jj = j; jj < n; jj++) s += T1[j * n + jj] * Rk[r * D + jj * d + ii];
                     Xs[i] = s;
                     Tm[i] = s; /* keep X for G */
@@ -302,6 +332,9 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
                 for (int i = lane; i < D; i += 32) {
                     const int j = i / d, ii = i % d;
                     double s = 0.0;
+                    if (gen)
+                        for (int kk = 0; kk < D; kk++) s += Ahd[i * D + kk] * muk[kk];
+                    else
                     for (int jj = j; jj < n; jj++) s += T1[j * n + jj] * muk[jj * d + ii];
                     mup[i] = s;
                 }
@@ -331,6 +364,9 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
                 for (int i = lane; i < DD; i += 32) {
                     const int c = i / D, a = i % D, j = c / d, ii = c % d;
                     double s = 0.0;
+                    if (gen)
+                        for (int kk = 0; kk < D; kk++) s += Gm[a * D + kk] * Ahd[kk * D + c];
+                    else
                     for (int jj = 0; jj <= j; jj++) s += Gm[a * D + jj * d + ii] * T1[jj * n + j];
                     Tm[i] = ((a == c) ? 1.0 : 0.0) - s;
                 }
@@ -345,6 +381,9 @@ __global__ void __launch_bounds__(32 * PN_SM_WARPS) pn_smooth_kernel(const __gri
                     }
                     const int m = r / d, i2 = r % d;
                     double s2 = 0.0;
+                    if (gen)
+                        for (int kk = r; kk < D; kk++) s2 += Qcd[r * D + kk] * Gm[a * D + kk];
+                    else
                     for (int j = 0; j <= m; j++) s2 += LQ[m * n + j] * Gm[a * D + j * d + i2];
                     Xs[i] = s0;
                     Xs[DD + i] = s1;

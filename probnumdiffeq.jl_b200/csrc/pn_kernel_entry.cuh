@@ -59,3 +59,11 @@ template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 __global__ void __launch_bounds__(PN_CTA_THREADS, PN_CTA_MIN_BLOCKS) pn_cta_kernel(const __grid_constant__ PnParams P) {
     pn_cta_entry<Prob, Q, ADAPTIVE, DYNAMIC, SAVE>(P);
 }
+
+#include "kernels/pn_gen.cuh"
+
+/* general dense transition pairs (IOUP with a vector / matrix / Jacobian-updated rate): one warp per trajectory */
+template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
+__global__ void __launch_bounds__(32 * PN_GEN_WARPS) pn_gen_kernel(const __grid_constant__ PnParams P) {
+    pn_gen_entry<Prob, Q, ADAPTIVE, DYNAMIC, SAVE>(P);
+}

@@ -21,6 +21,8 @@
 #include "kernels/pn_params.h"
 #define PN_SMOOTH_DECL_ONLY
 #include "kernels/pn_smooth.cuh"
+#define PN_LTI_DECL_ONLY
+#include "kernels/pn_lti.cuh" /* PN_GEN_WARPS, pn_gen_ws_doubles */
 #define PN_SMR_THREADS 256 /* pn_smooth_reg.cuh */
 #define PN_DENSE_DECL_ONLY
 #include "kernels/pn_dense.cuh" /* PnDenseParams */
@@ -236,6 +238,10 @@ struct pnode_solver {
     bool blocks = false; /* BlocksOfDiagonals layout (EK0 + multivariate diffusion, DiagonalEK1), thread per trajectory */
     bool mv = false;     /* multivariate (per-component) diffusion model */
     bool cta = false;  /* EK1, D > 32: one CTA per trajectory, R in shared memory */
+    bool gen = false;  /* general-prior path (pn_gen.cuh): IOUP with a vector / matrix / Jacobian-updated rate, one warp per trajectory */
+    double* d_rate = nullptr;   /* [d][d] rate matrix */
+    double* d_gen_ws = nullptr; /* per-warp workspace when it does not fit in shared memory */
+    size_t gen_ws_doubles = 0;  /* per warp */
     size_t smem = 0;   /* dynamic shared memory of the step kernel */
     Kernel k_final;  /* SAVE = 0 */
     Kernel k_save;   /* SAVE = 1 */
@@ -413,11 +419,14 @@ static int nvrtc_compile(const std::string& src, std::vector<std::string> defs, 
 static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_name, int q, int G, bool adaptive,
                        bool dynamic, int save, std::vector<char>* cubin, int threads = PN_THREADS, int min_blocks = 1,
                        bool kron = false, bool cta = false, int blocks = 0 /* 0 no, 1 EK0, 2 DiagonalEK1 */, bool mv = false,
-                       bool ioup = false, bool ek0_dense = false, const std::string& preamble = std::string()) {
+                       bool ioup = false, bool ek0_dense = false, const std::string& preamble = std::string(), bool gen = false) {
     std::string src = preamble;
     src += "#include \"pn_kernel_entry.cuh\"\n";
     src += rhs_src;
-    if (blocks)
+    if (gen)
+        src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS) pn_entry(const __grid_constant__ PnParams P) {\n"
+               "  pn_gen_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
+    else if (blocks)
         src += std::string("\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS) pn_entry(const __grid_constant__ PnParams P) {\n"
                "  pn_blocks_entry<") + struct_name + ", PN_Q, " + (blocks == 2 ? "true" : "false") + ", " + (mv ? "true" : "false") +
                ", (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
@@ -437,9 +446,15 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
     auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
     return nvrtc_compile(src, {def(cta ? "PN_CTA_THREADS" : "PN_THREADS", threads), def(cta ? "PN_CTA_MIN_BLOCKS" : "PN_MIN_BLOCKS", min_blocks), def("PN_Q", q), def("PN_G", G),
                                def("PN_ADAPTIVE", adaptive ? 1 : 0), def("PN_DYNAMIC", dynamic ? 1 : 0), def("PN_SAVE", save),
-                               def("PN_IOUP", ioup ? 1 : 0), def("PN_EK0_DENSE", ek0_dense ? 1 : 0)},
+                               def("PN_IOUP", (ioup && !gen) ? 1 : 0), def("PN_EK0_DENSE", ek0_dense ? 1 : 0)},
                          cubin);
 }
+
+/* general-prior path: IOUP with a rate matrix (vector rates arrive as diagonal matrices) or the Jacobian-updated rate */
+static bool is_gen(const pnode_config* cfg) {
+    return cfg->prior == PNODE_PRIOR_IOUP && (cfg->rate_matrix != nullptr || cfg->update_rate_parameter != 0);
+}
+static size_t gen_ws_doubles(int d, int q) { return (size_t)pn_gen_ws_doubles(d, q + 1); }
 
 /* Mass matrix M (d x d row-major) -> generated preamble: PN_MASS, constexpr pn_mass(a,i) = M[a][i] and pn_mass_inv(a,i) =
    MM^-1[a][i] with MM = M (+ 1e-20 I if M has a zero diagonal entry; src/initialization/autodiffinit.jl:20-31).  The entries
@@ -668,7 +683,9 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
         cta_shape(s->smem, &out->threads, &min_blocks);
         s->G = out->threads; /* one CTA per trajectory */
     }
-    if (!s->cta && !s->kron && !s->blocks) {
+    if (s->gen) {
+        out->threads = 32 * PN_GEN_WARPS;
+    } else if (!s->cta && !s->kron && !s->blocks) {
         /* one exchange region per group: large states with few lanes per trajectory run smaller CTAs */
         while (out->threads > 32 && small_smem_bytes(s->D, s->G, out->threads) > 200 * 1024) out->threads /= 2;
         s->smem = small_smem_bytes(s->D, s->G, out->threads);
@@ -676,7 +693,7 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
     rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0, is_dynamic(s->cfg.diffusion), save, &cubin, out->threads,
                      min_blocks, s->kron, s->cta,
                      s->blocks ? (s->cfg.alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, s->mv, s->cfg.prior == PNODE_PRIOR_IOUP,
-                     s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks, s->mass_src);
+                     s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks, s->mass_src, s->gen);
     if (rc) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
@@ -732,7 +749,7 @@ static int get_smoother(pnode_solver* s) {
     Kernel* out = &s->k_smooth;
     if (out->valid()) return 0;
     s->Gs = env_int("PNODE_SMOOTH_LANES", smooth_lanes(s->D));
-    if (s->Gs <= 0 || s->cta || env_int("PNODE_SMOOTH_GENERIC", 0)) return 0; /* shared-memory sweep */
+    if (s->Gs <= 0 || s->cta || s->gen || env_int("PNODE_SMOOTH_GENERIC", 0)) return 0; /* shared-memory sweep */
     /* PNODE_SMOOTH_KIND: 1 (default) column-distributed sweep (pn_smooth_col.cuh), 0 row-distributed (pn_smooth_reg.cuh) */
     const bool col = env_int("PNODE_SMOOTH_KIND", 1) != 0;
     s->smem_smooth = col ? smooth_col_smem_bytes(s->cfg.d, s->cfg.q, s->Gs) : smooth_reg_smem_bytes(s->cfg.d, s->cfg.q, s->Gs);
@@ -816,9 +833,30 @@ static int validate_config(const pnode_config* cfg) {
     if (cfg->prior == PNODE_PRIOR_IOUP) {
         if (cfg->alg == PNODE_DIAGONAL_EK1 || is_mv(cfg->diffusion))
             return fail(PNODE_ERR_UNSUPPORTED, "the IOUP prior is implemented on the dense layout (EK0 / EK1 with a scalar diffusion)");
-        if (cfg->d * (cfg->q + 1) > 24)
-            return fail(PNODE_ERR_UNSUPPORTED, "the IOUP prior is implemented for D = d(q+1) <= 24 (register-resident kernels)");
-        if (cfg->lanes_per_traj == 256) return fail(PNODE_ERR_UNSUPPORTED, "the IOUP prior is not implemented in the CTA kernel");
+        if (cfg->update_rate_parameter && cfg->rate_matrix)
+            return fail(PNODE_ERR_ARGUMENT, "Do not manually set the `rate_parameter` of the IOUP prior when using the "
+                                            "`update_rate_parameter=true` option.Reset the prior and try again."); /* caches.jl:139-149 */
+        if (cfg->update_rate_parameter && cfg->alg != PNODE_EK1)
+            return fail(PNODE_ERR_UNSUPPORTED, "update_rate_parameter takes the rate from the traced Jacobian: EK1 only (RosenbrockExpEK)");
+        if (is_gen(cfg)) {
+            /* general-prior path: one warp per trajectory, dense transition pairs */
+            if (cfg->rate_matrix)
+                for (int i = 0; i < cfg->d * cfg->d; i++)
+                    if (!std::isfinite(cfg->rate_matrix[i])) return fail(PNODE_ERR_ARGUMENT, "rate_parameter has a non-finite entry");
+            if (cfg->d * (cfg->q + 1) > 64)
+                return fail(PNODE_ERR_UNSUPPORTED, "IOUP priors with a vector / matrix / updated rate are implemented for D = d(q+1) <= 64");
+            if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 32)
+                return fail(PNODE_ERR_ARGUMENT, "IOUP priors with a vector / matrix / updated rate run one warp per trajectory (lanes_per_traj 0 or 32)");
+            if (cfg->n_saveat > 0) return fail(PNODE_ERR_UNSUPPORTED, "dense output is not implemented for IOUP priors with a vector / matrix / updated rate");
+            if (cfg->mass_matrix || cfg->second_order || cfg->n_data > 0 || has_obsn(cfg))
+                return fail(PNODE_ERR_UNSUPPORTED, "IOUP priors with a vector / matrix / updated rate: plain first-order ODEs without mass matrix, data or observation noise");
+        } else {
+            if (cfg->d * (cfg->q + 1) > 24)
+                return fail(PNODE_ERR_UNSUPPORTED, "the scalar-rate IOUP prior is implemented for D = d(q+1) <= 24 (register-resident kernels); pass the rate as a vector for larger states");
+            if (cfg->lanes_per_traj == 256) return fail(PNODE_ERR_UNSUPPORTED, "the IOUP prior is not implemented in the CTA kernel");
+        }
+    } else if (cfg->rate_matrix || cfg->update_rate_parameter) {
+        return fail(PNODE_ERR_ARGUMENT, "rate_matrix / update_rate_parameter belong to the IOUP prior");
     }
     if (cfg->alg != PNODE_EK0 && cfg->alg != PNODE_EK1 && cfg->alg != PNODE_DIAGONAL_EK1)
         return fail(PNODE_ERR_ARGUMENT, "Unknown algorithm"); /* derivative_utils.jl:31 */
@@ -863,7 +901,7 @@ static int validate_config(const pnode_config* cfg) {
     if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 2 && cfg->lanes_per_traj != 4 && cfg->lanes_per_traj != 8 &&
         cfg->lanes_per_traj != 16 && cfg->lanes_per_traj != 32 && cfg->lanes_per_traj != 256)
         return fail(PNODE_ERR_ARGUMENT, "lanes_per_traj must be one of 0 (auto), 2, 4, 8, 16, 32, 256 (CTA per trajectory)");
-    if (cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256)) {
+    if (!is_gen(cfg) && cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256)) {
         if (cta_smem_bytes(cfg->d, cfg->q, cfg->n_p, cfg->second_order != 0, cfg->mass_matrix != nullptr) > 227 * 1024)
             return fail(PNODE_ERR_UNSUPPORTED, "state dimension too large for the shared-memory CTA kernel");
         if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 256)
@@ -1044,9 +1082,13 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
                      save_level(cfg, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256)), &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
                      layout == PNODE_COV_KRONECKER, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256),
                      layout == PNODE_COV_BLOCKS ? (cfg->alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, is_mv(cfg->diffusion),
-                     cfg->prior == PNODE_PRIOR_IOUP, cfg->alg == PNODE_EK0 && layout == PNODE_COV_DENSE, mass_src);
+                     cfg->prior == PNODE_PRIOR_IOUP, cfg->alg == PNODE_EK0 && layout == PNODE_COV_DENSE, mass_src, is_gen(cfg));
     if (rc) return rc;
     int64_t total = (int64_t)cubin.size();
+    if (is_gen(cfg)) { /* the smoother of this path is the ahead-of-time shared-memory sweep */
+        if (cubin_bytes) *cubin_bytes = total;
+        return 0;
+    }
     /* the smoother sweep and the dense-output kernel of this configuration compile from the same embedded headers */
     if (cfg->smooth && smooth_lanes(D) > 0 && !(cfg->alg == PNODE_EK1 && D > 32)) {
         std::vector<char> c2;
@@ -1094,8 +1136,14 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     s->kron = (resolve_layout(cfg) == PNODE_COV_KRONECKER);
     s->blocks = (resolve_layout(cfg) == PNODE_COV_BLOCKS);
     s->mv = is_mv(cfg->diffusion);
-    s->cta = !s->kron && !s->blocks && (D > 32 || cfg->lanes_per_traj == 256);
-    s->G = (s->kron || s->blocks) ? 1 : (s->cta ? 256 : (cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D)));
+    s->gen = is_gen(cfg);
+    s->cta = !s->gen && !s->kron && !s->blocks && (D > 32 || cfg->lanes_per_traj == 256);
+    s->G = (s->kron || s->blocks) ? 1 : (s->gen ? 32 : (s->cta ? 256 : (cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D))));
+    if (s->gen) {
+        s->gen_ws_doubles = gen_ws_doubles(cfg->d, cfg->q);
+        const size_t bytes = s->gen_ws_doubles * PN_GEN_WARPS * sizeof(double);
+        s->smem = bytes <= 200 * 1024 ? bytes : 0; /* 0: global workspace (allocated below) */
+    } else
     s->smem = s->cta ? cta_smem_bytes(cfg->d, cfg->q, cfg->n_p, cfg->second_order != 0, !s->mass_src.empty() && s->mass_src.find("PN_MASS") != std::string::npos) : 0; /* group-per-trajectory kernel: set with its thread count in get_kernel */
     /* ---- constants ---- */
     PnParams& B = s->base;
@@ -1270,10 +1318,25 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
         CUDA_TRY_S(cudaMemcpy(s->d_saveat, cfg->saveat, sizeof(double) * cfg->n_saveat, cudaMemcpyHostToDevice));
         s->n_saveat = cfg->n_saveat;
     }
+    if (s->gen) {
+        B.update_rate = cfg->update_rate_parameter;
+        if (cfg->rate_matrix) {
+            CUDA_TRY_S(cudaMalloc(&s->d_rate, sizeof(double) * cfg->d * cfg->d));
+            CUDA_TRY_S(cudaMemcpy(s->d_rate, cfg->rate_matrix, sizeof(double) * cfg->d * cfg->d, cudaMemcpyHostToDevice));
+            B.rate_matrix = s->d_rate;
+        }
+    }
+    s->cfg.rate_matrix = nullptr;
     s->cfg.saveat = nullptr;
     s->cfg.data_t = s->cfg.data_u = s->cfg.observation_matrix = s->cfg.observation_noise_cov = nullptr;
 #undef CUDA_TRY_S
     int rc = get_kernel(s, save_level(cfg, s->cta), cfg->save_everystep ? &s->k_save : &s->k_final);
+    if (!rc && s->gen && s->smem == 0) { /* per-warp workspace of the general-prior filter: one slot per resident warp of the persistent grid */
+        Kernel& kk = cfg->save_everystep ? s->k_save : s->k_final;
+        const size_t slots = (size_t)s->n_sm * kk.blocks_per_sm * PN_GEN_WARPS;
+        if (cudaMalloc(&s->d_gen_ws, slots * s->gen_ws_doubles * sizeof(double)) != cudaSuccess) rc = fail(PNODE_ERR_CUDA, "cudaMalloc(general-prior workspace)");
+        s->base.gen_workspace = s->d_gen_ws;
+    }
     if (!rc && cfg->smooth) rc = get_smoother(s);
     if (!rc && cfg->n_saveat > 0) rc = get_dense(s);
     if (rc) {
@@ -1328,6 +1391,8 @@ extern "C" void pnode_destroy(pnode_solver* s) {
     if (s->d_tstops) cudaFree(s->d_tstops);
     if (s->d_forced) cudaFree(s->d_forced);
     if (s->d_saveat) cudaFree(s->d_saveat);
+    if (s->d_rate) cudaFree(s->d_rate);
+    if (s->d_gen_ws) cudaFree(s->d_gen_ws);
     for (double* ptr : {s->d_data_t, s->d_data_u, s->d_obs_H, s->d_obs_Rn})
         if (ptr) cudaFree(ptr);
     if (s->d_init_mu) cudaFreeAsync(s->d_init_mu, s->stream);
@@ -1587,6 +1652,12 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             P.s_x_mean = (double*)w_x;
             P.s_x_covfac = (double*)w_xc;
             P.s_h = d_h;
+            if (s->gen && s->base.update_rate && s->cfg.smooth) { /* the backward kernel of a step needs the rate it was taken with */
+                double* d_sr = nullptr;
+                CUDA_TRY(cudaMallocAsync((void**)&d_sr, T * d * d * 8, s->stream));
+                scope.track(d_sr);
+                P.s_rate = d_sr;
+            }
         }
         if ((rc = launch(s, s->k_save, P, n_traj))) return rc;
         launches += 1;
@@ -1643,11 +1714,17 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                     if (cr != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuLaunchKernel(smoother): " + cu_err(cr));
                 }
             } else {
-                if (s->cfg.prior != PNODE_PRIOR_IWP)
-                    return fail(PNODE_ERR_UNSUPPORTED, "the shared-memory smoother sweep implements the IWP prior only");
+                if (s->cfg.prior != PNODE_PRIOR_IWP && !s->gen)
+                    return fail(PNODE_ERR_UNSUPPORTED, "the shared-memory smoother sweep implements the IWP prior and the general-rate IOUP only");
                 const int n = s->cfg.q + 1;
+                if (s->gen) { /* dense transition pairs recomputed per step (pn_lti.cuh) */
+                    Q.gen_prior = 1;
+                    Q.rate_matrix = s->d_rate;
+                    Q.s_rate = P.s_rate;
+                }
                 const size_t per_warp =
-                    (size_t)(7 * D * D + 4 * D + 2 * n * n + 2 * n + (Q.fenrir_ll ? PN_FENRIR_EXTRA(D, Q.n_obs) : 0)) * sizeof(double);
+                    (size_t)(7 * D * D + 4 * D + 2 * n * n + 2 * n + (Q.fenrir_ll ? PN_FENRIR_EXTRA(D, Q.n_obs) : 0) +
+                             (s->gen ? PN_SMOOTH_GEN_EXTRA(D, d, n) : 0)) * sizeof(double);
                 int warps = PN_SM_WARPS;
                 const void* fn = pn_smooth_kernel_ptr();
                 /* states whose work matrices (7 D^2 doubles per warp) do not fit in shared memory -- Pleiades, D = 112: 0.7 MB --

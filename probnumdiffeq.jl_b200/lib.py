@@ -71,6 +71,7 @@ class Config(C.Structure):
         ("observation_matrix", C.POINTER(C.c_double)), ("observation_noise_cov", C.POINTER(C.c_double)),
         ("observation_noise_var", C.c_double),
         ("pn_observation_noise", C.POINTER(C.c_double)), ("pn_observation_noise_var", C.c_double),
+        ("rate_matrix", C.POINTER(C.c_double)), ("update_rate_parameter", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -146,14 +147,18 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
                 maxiters=1_000_000, beta1=0.0, beta2=0.0, qmin=0.2, qmax=10.0, gamma=0.9, qsteady_min=1.0,
                 qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None, device=0, prior=PRIOR_IWP,
                 rate_parameter=0.0, saveat=None, mass_matrix=None, second_order=False, data_t=None, data_u=None,
-                observation_matrix=None, observation_noise_cov=None, pn_observation_noise=None, data_forward=False) -> Config:
+                observation_matrix=None, observation_noise_cov=None, pn_observation_noise=None, data_forward=False,
+                update_rate_parameter=False) -> Config:
+    """`rate_parameter`: a number, a length-d vector or a d x d matrix (IOUP, src/priors/ioup.jl:81-101)."""
     c = Config()
+    rate_arr = np.asarray(rate_parameter, dtype=np.float64) if rate_parameter is not None else np.asarray(0.0)
+    c.update_rate_parameter = int(update_rate_parameter)
     c.second_order = int(second_order)
     c.data_forward = int(data_forward)
     c.struct_size = C.sizeof(Config)
     c.device, c.d, c.q, c.n_p = device, d, q, n_p
     c.alg, c.cov, c.prior, c.diffusion = alg, cov, prior, diffusion
-    c.rate_parameter = float(rate_parameter)
+    c.rate_parameter = float(rate_arr) if rate_arr.ndim == 0 else 0.0
     c.calibrate, c.smooth, c.adaptive = int(calibrate), int(smooth), int(adaptive)
     c.save_everystep, c.save_state, c.lanes_per_traj = int(save_everystep), int(save_state), lanes_per_traj
     c.maxiters, c.initial_diffusion = int(maxiters), float(initial_diffusion)
@@ -206,6 +211,12 @@ def make_config(*, d, q, n_p, rhs_name, rhs_src=None, alg=EK1, cov=COV_AUTO, dif
         a = np.ascontiguousarray(np.asarray(mass_matrix, dtype=np.float64).reshape(d, d))
         keep.append(a)
         c.mass_matrix = a.ctypes.data_as(C.POINTER(C.c_double))
+    if rate_arr.ndim >= 1:   # vector rate -> Diagonal(r), matrix rate as is (to_sde, ioup.jl:85-93)
+        if rate_arr.ndim == 1 and rate_arr.shape[0] != d or rate_arr.ndim == 2 and rate_arr.shape != (d, d):
+            raise ValueError("rate_parameter must be a number, a vector of length d or a d x d matrix")
+        a = np.ascontiguousarray(np.diag(rate_arr) if rate_arr.ndim == 1 else rate_arr)
+        keep.append(a)
+        c.rate_matrix = a.ctypes.data_as(C.POINTER(C.c_double))
     c._keep = keep
     return c
 
