@@ -92,6 +92,7 @@ class Config(C.Structure):
         ("data_t", C.POINTER(C.c_double)), ("n_data", C.c_int64), ("data_u", C.POINTER(C.c_double)),
         ("n_obs", C.c_int32), ("reserved2", C.c_int32), ("obs_H", C.POINTER(C.c_double)), ("obs_Rn", C.POINTER(C.c_double)),
         ("pn_obs_Rn", C.POINTER(C.c_double)),
+        ("rate_matrix", C.POINTER(C.c_double)), ("update_rate_parameter", C.c_int32), ("reserved3", C.c_int32),
     ]
 
 
@@ -232,14 +233,17 @@ def make_config(d, q, n_p, *, alg=EK1, diffusion=DIFF_DYNAMIC, calibrate=True, i
                 reltol=1e-3, dtmin=0.0, dtmax=None, maxiters=1_000_000, beta1=None, beta2=None, qmin=0.2, qmax=10.0,
                 gamma=0.9, qsteady_min=1.0, qsteady_max=1.0, qoldinit=1e-4, tstops=None, forced_diffusion=None,
                 prior=PRIOR_IWP, rate_parameter=0.0, mass_matrix=None, second_order=False, data=None,
-                observation_matrix=None, observation_noise_cov=None, pn_observation_noise=None):
+                observation_matrix=None, observation_noise_cov=None, pn_observation_noise=None, update_rate_parameter=False):
+    """`rate_parameter` (IOUP): a number, a length-d vector (Diagonal) or a d x d matrix (src/priors/ioup.jl:81-101)."""
     c = Config()
+    rate_arr = np.asarray(0.0 if rate_parameter is None else rate_parameter, dtype=np.float64)
+    c.update_rate_parameter = int(update_rate_parameter)
     c.second_order = int(second_order)
     c.d, c.q, c.n_p, c.alg = d, q, n_p, alg
     c.diffusion, c.calibrate, c.smooth, c.adaptive = diffusion, int(calibrate), int(smooth), int(adaptive)
     c.save_everystep, c.cov_backend, c.maxiters = int(save_everystep), cov_backend, int(maxiters)
     c.initial_diffusion = initial_diffusion
-    c.prior, c.rate_parameter = prior, float(rate_parameter)
+    c.prior, c.rate_parameter = prior, (float(rate_arr) if rate_arr.ndim == 0 else 0.0)
     c.t0, c.t1, c.dt = t0, t1, dt
     c.abstol, c.reltol, c.dtmin = abstol, reltol, dtmin
     c.dtmax = (t1 - t0) if dtmax is None else dtmax
@@ -248,6 +252,10 @@ def make_config(d, q, n_p, *, alg=EK1, diffusion=DIFF_DYNAMIC, calibrate=True, i
     c.qmin, c.qmax, c.gamma = qmin, qmax, gamma
     c.qsteady_min, c.qsteady_max, c.qoldinit = qsteady_min, qsteady_max, qoldinit
     keep = []
+    if rate_arr.ndim >= 1:
+        rm = np.asfortranarray(np.diag(rate_arr) if rate_arr.ndim == 1 else rate_arr.reshape(d, d))
+        keep.append(rm)
+        c.rate_matrix = rm.ctypes.data_as(C.POINTER(C.c_double))
     if tstops is not None and len(tstops):
         ts = np.ascontiguousarray(tstops, dtype=np.float64)
         keep.append(ts)

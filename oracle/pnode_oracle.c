@@ -280,6 +280,70 @@ void oracle_ioup_transition(int q, double rate, double h, double* Ah, double* Qh
         }
 }
 
+/* matrix_fraction_decomposition (src/priors/ltisde.jl:52-63) with a general dispersion: LLt = L L' (n x n). */
+static void mfd_general(int n, const double* F, const double* LLt, double dt, double* A, double* Q) {
+    int m = 2 * n;
+    double* M = (double*)calloc((size_t)m * m, sizeof(double));
+    double* E = (double*)malloc(sizeof(double) * (size_t)m * m);
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) {
+            AT(M, i, j, m) = dt * AT(F, i, j, n);
+            AT(M, i, n + j, m) = dt * AT(LLt, i, j, n);
+            AT(M, n + i, n + j, m) = -dt * AT(F, j, i, n);
+        }
+    oracle_expm(m, M, E);
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) AT(A, i, j, n) = AT(E, i, j, m);
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < n; i++) {
+            double sacc = 0.0;
+            for (int k = 0; k < n; k++) sacc += AT(E, i, n + k, m) * AT(A, j, k, n);
+            AT(Q, i, j, n) = sacc;
+        }
+    free(M);
+    free(E);
+}
+
+/* make_transition_matrices!(cache, ::IOUP, dt) (src/priors/ioup.jl:115-131) for a vector / matrix rate parameter: to_sde
+   (ioup.jl:81-101) gives F = kron(shift, I_d) with F[q-block, q-block] = R and L = kron(e_q, I_d) in the derivative-major state
+   ordering; the discretisation is the matrix fraction decomposition the reference's own tests pin exp_and_gram_chol! against
+   (test/core/priors.jl:29-32, 229-272), evaluated as in oracle_ioup_transition in the preconditioned coordinates:
+   F~ = kron(superdiag(q, ..., 1), I_d) + kron(e_q e_q', R dt), dispersion kron(e_q, I_d), horizon 1. */
+int oracle_ioup_transition_matrix(int d, int q, const double* rate, double h, double* Ah, double* QhR) {
+    int n = q + 1, D = d * n;
+    size_t DD = (size_t)D * D;
+    double* F = (double*)calloc(DD, sizeof(double));
+    double* LLt = (double*)calloc(DD, sizeof(double));
+    double* At = (double*)malloc(sizeof(double) * DD);
+    double* Qt = (double*)malloc(sizeof(double) * DD);
+    double P[32], PI[32];
+    for (int a = 0; a < q; a++)
+        for (int i = 0; i < d; i++) AT(F, a * d + i, (a + 1) * d + i, D) = (double)(q - a);
+    for (int i = 0; i < d; i++) {
+        for (int j = 0; j < d; j++) AT(F, q * d + i, q * d + j, D) = AT(rate, i, j, d) * h;
+        AT(LLt, q * d + i, q * d + i, D) = 1.0;
+    }
+    mfd_general(D, F, LLt, 1.0, At, Qt);
+    for (int j = 0; j < D; j++)
+        for (int i = 0; i < j; i++) {
+            double v = 0.5 * (AT(Qt, i, j, D) + AT(Qt, j, i, D));
+            AT(Qt, i, j, D) = v;
+            AT(Qt, j, i, D) = v;
+        }
+    int rc = oracle_cholesky_upper(D, Qt);
+    oracle_preconditioner(q, h, P, PI);
+    for (int j = 0; j < D; j++)
+        for (int i = 0; i < D; i++) {
+            AT(Ah, i, j, D) = PI[i / d] * (AT(At, i, j, D) * P[j / d]);
+            AT(QhR, i, j, D) = (i <= j) ? AT(Qt, i, j, D) * PI[j / d] : 0.0;
+        }
+    free(F);
+    free(LLt);
+    free(At);
+    free(Qt);
+    return rc == 0 ? 0 : -1;
+}
+
 /* kron(B, I_d) (src/kronecker.jl:7): out[(r*d+i), (c*d+i)] = B[r,c]. */
 void oracle_kron_identity(int d, int n_rows, int n_cols, const double* B, double* out) {
     int M = n_rows * d, N = n_cols * d;
@@ -1158,6 +1222,7 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     double* Rdense = (double*)malloc(sizeof(double) * (size_t)D * D);
     double* tmpDD = (double*)malloc(sizeof(double) * (size_t)2 * D * D);
     double z[64], zt[64], fu[64], uprev[64], upred[64], err[64];
+    double* rate_now = (double*)calloc((size_t)d * d + 1, sizeof(double));
 
     dvec ts = {0}, diffs = {0}, xmu = {0}, xR = {0}, bG = {0}, bB = {0}, bL = {0};
 
@@ -1241,9 +1306,21 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
 
         /* ---- perform_step! (src/perform_step.jl:79-154) ---- */
         double tnew = t + dt;                                  /* :85 */
-        if (c->prior == ORACLE_PRIOR_IOUP) oracle_ioup_transition(q, c->rate_parameter, dt, Ah1, Qh1); /* ioup.jl:115-131 */
+        const int gen_rate = (c->prior == ORACLE_PRIOR_IOUP) && (c->rate_matrix || c->update_rate_parameter);
+        if (gen_rate) {
+            if (c->update_rate_parameter) { /* :88-96: calc_J!(rate, integ, cache, false) -- the Jacobian at (uprev, t) */
+                jac(J, uprev, p, t);
+                out->njac += 1;
+                memcpy(rate_now, J, sizeof(double) * d * d);
+            } else {
+                memcpy(rate_now, c->rate_matrix, sizeof(double) * d * d);
+            }
+            if (oracle_ioup_transition_matrix(d, q, rate_now, dt, Ah, QhR) != 0) { retcode = ORACLE_RET_UNSTABLE; break; }
+        } else if (c->prior == ORACLE_PRIOR_IOUP) oracle_ioup_transition(q, c->rate_parameter, dt, Ah1, Qh1); /* ioup.jl:115-131 */
         else oracle_iwp_transition(q, dt, Ah1, Qh1);           /* :87-99, make_transition_matrices! */
-        if (kron) {
+        if (gen_rate) {
+            /* dense pair already in place */
+        } else if (kron) {
             memcpy(Ah, Ah1, sizeof(double) * NN);
             memcpy(QhR, Qh1, sizeof(double) * NN);
         } else {
@@ -1545,7 +1622,7 @@ int oracle_solve(const oracle_config* c, oracle_rhs_fn f, oracle_jac_fn jac, ora
     free(xR.p); free(bG.p); free(bB.p); free(bL.p);
     free(Ah1); free(Qh1); free(Ah); free(QhR); free(mu); free(R); free(mu_pred); free(R_pred);
     free(mu_filt); free(R_filt); free(H); free(J); free(Cq); free(W); free(G); free(bb); free(LR);
-    free(Rdense); free(tmpDD); free(MMinv);
+    free(Rdense); free(tmpDD); free(MMinv); free(rate_now);
     return 0;
 }
 

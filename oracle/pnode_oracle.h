@@ -94,6 +94,12 @@ typedef struct {
        the noise covariance the ODE measurement z = 0 is observed with; NULL = noise-free.  S += R.R'R.R
        (src/perform_step.jl:182-188) and the filtered covariance gains K R K' (src/filtering/update.jl:125-136). */
     const double* pn_obs_Rn;
+    /* IOUP(num_derivatives, rate_parameter::Union{AbstractVector,AbstractMatrix}) (src/priors/ioup.jl:81-113): d x d COLUMN-major
+       rate matrix (a vector rate as Diagonal(r), as to_sde does); NULL = the scalar rate_parameter.  update_rate_parameter = 1:
+       the rate is set to the Jacobian J(uprev, t) before every step (src/perform_step.jl:88-96, RosenbrockExpEK). */
+    const double* rate_matrix;
+    int32_t update_rate_parameter;
+    int32_t reserved3;
 } oracle_config;
 
 /* One solved trajectory.  Arrays are owned by the struct; free with oracle_traj_free. */
@@ -127,6 +133,8 @@ void oracle_iwp_transition(int q, double h, double* Ah /*n*n*/, double* QhR /*n*
 void oracle_expm(int n, const double* M, double* E);
 void oracle_matrix_fraction_decomposition(int n, const double* F, const double* Lvec, double dt, double* A, double* Q);
 void oracle_ioup_transition(int q, double rate, double h, double* Ah /*n*n*/, double* QhR /*n*n upper*/);
+/* the same for a d x d column-major rate matrix: dense D x D column-major Ah and Qh.R; returns -1 if Qh is not positive definite */
+int oracle_ioup_transition_matrix(int d, int q, const double* rate, double h, double* Ah, double* QhR);
 void oracle_kron_identity(int d, int n_rows, int n_cols, const double* B, double* out /* (n_rows*d) x (n_cols*d) */);
 int oracle_cholesky_upper(int n, double* M); /* in place; returns 0 on success */
 void oracle_triangularize(int m, int n, double* A /* m x n, in place */, double* Rout /* n x n */);

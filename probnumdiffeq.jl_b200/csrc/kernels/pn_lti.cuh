@@ -26,7 +26,7 @@
 
 /* doubles of per-warp workspace (host and kernel must agree) */
 __host__ __device__ constexpr int pn_gen_ws_doubles(int d, int n) {
-    return 9 * (d * n) * (d * n) + 6 * (d * n) + 3 * (d * n) * d + 6 * d * d + 8 * d + 4 * n + 16;
+    return 10 * (d * n) * (d * n) + 6 * (d * n) + 3 * (d * n) * d + 6 * d * d + 8 * d + 4 * n + 16;
 }
 
 #ifndef PN_LTI_DECL_ONLY

@@ -1333,6 +1333,7 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     int rc = get_kernel(s, save_level(cfg, s->cta), cfg->save_everystep ? &s->k_save : &s->k_final);
     if (!rc && s->gen && s->smem == 0) { /* per-warp workspace of the general-prior filter: one slot per resident warp of the persistent grid */
         Kernel& kk = cfg->save_everystep ? s->k_save : s->k_final;
+        kk.blocks_per_sm = std::min(kk.blocks_per_sm, 2); /* keep the working set of the grid near the L2 capacity */
         const size_t slots = (size_t)s->n_sm * kk.blocks_per_sm * PN_GEN_WARPS;
         if (cudaMalloc(&s->d_gen_ws, slots * s->gen_ws_doubles * sizeof(double)) != cudaSuccess) rc = fail(PNODE_ERR_CUDA, "cudaMalloc(general-prior workspace)");
         s->base.gen_workspace = s->d_gen_ws;

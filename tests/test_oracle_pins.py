@@ -241,14 +241,26 @@ _CONSTANT = [(0, 2, 0, 0, 1e-5), (0, 3, 0, 0, 1e-8), (0, 5, 0, 0, 1e-10), (0, 3,
              (0, 3, 0, 3, 1e-7), (0, 3, 0, 2, 1e-8), (2, 3, 0, 0, 1e-7), (2, 3, 0, 1, 1e-7),
              (0, 3, 1, 3, 1e-7), (0, 3, 1, 2, 1e-8), (2, 3, 1, 0, 1e-7), (2, 3, 1, 1, 1e-7),
              # IOUP(3, -1) prior rows (test/correctness.jl:50-51): alg + 10 marks the IOUP prior with rate -1
-             (10, 3, 1, 0, 2e-9), (11, 3, 1, 1, 1e-9)]
+             (10, 3, 1, 0, 2e-9), (11, 3, 1, 1, 1e-9),
+             # EK1(prior=IOUP(3, update_rate_parameter=true), smooth=true) (test/correctness.jl:53): alg 21
+             (21, 3, 1, 0, 1e-9)]
 # test/correctness.jl:57-87
 _ADAPTIVE = [(0, 2, 0, 2e-4), (0, 3, 0, 1e-4), (0, 5, 0, 1e-5), (0, 8, 0, 2e-5), (1, 2, 0, 2e-5), (1, 3, 0, 1e-5), (1, 5, 0, 1e-6),
              (1, 8, 0, 5e-6),
              # Blocks layout rows: EK0 + DynamicMV / FixedMV, DiagonalEK1 with Dynamic / Fixed diffusion
              (0, 3, 2, 5e-5), (0, 3, 3, 1e-4), (2, 3, 0, 1e-4), (2, 3, 1, 1e-4),
              # IOUP(3, -1) rows (test/correctness.jl:82-83)
-             (10, 3, 0, 1e-5), (11, 3, 1, 1e-5)]
+             (10, 3, 0, 1e-5), (11, 3, 1, 1e-5),
+             # EK1(prior=IOUP(3, update_rate_parameter=true), smooth=true) (test/correctness.jl:84)
+             (21, 3, 0, 2e-5)]
+
+
+def _prior_kw(oracle, alg):
+    if alg >= 20:
+        return dict(prior=oracle.PRIOR_IOUP, rate_parameter=None, update_rate_parameter=True)
+    if alg >= 10:
+        return dict(prior=oracle.PRIOR_IOUP, rate_parameter=-1.0)
+    return {}
 
 
 @pytest.mark.parametrize("prob", list(_CASES))
@@ -259,7 +271,7 @@ def test_correctness_constant_steps(oracle, prob):
     for alg, q, smooth, diff, thr in _CONSTANT:
         rhs = oracle.compile_rhs(tr, q)
         for backend in (oracle.COV_REF, oracle.COV_QR):
-            pk = dict(prior=oracle.PRIOR_IOUP, rate_parameter=-1.0) if alg >= 10 else {}
+            pk = _prior_kw(oracle, alg)
             cfg = oracle.make_config(2, q, 4, alg=alg % 10, diffusion=diff, smooth=smooth, adaptive=False, dt=1e-2, t0=0, t1=1,
                                      save_everystep=bool(smooth), cov_backend=backend, **pk)
             s = oracle.solve(cfg, rhs, u0, p)
@@ -274,7 +286,7 @@ def test_correctness_adaptive(oracle, prob):
     tr = tracer.trace(f, 2, 4)
     for alg, q, diff, thr in _ADAPTIVE:
         rhs = oracle.compile_rhs(tr, q)
-        pk = dict(prior=oracle.PRIOR_IOUP, rate_parameter=-1.0) if alg >= 10 else {}
+        pk = _prior_kw(oracle, alg)
         s = oracle.solve(oracle.make_config(2, q, 4, alg=alg % 10, diffusion=diff, smooth=True, adaptive=True, t0=0, t1=1, **pk), rhs, u0, p)
         assert s["retcode"] == "Success"
         assert np.mean(np.abs(s["pu_mu"][-1] - ref)) < thr, (prob, alg, q, diff)
@@ -533,6 +545,82 @@ def test_ioup_damped_oscillator(oracle):
     s = oracle.solve(oracle.make_config(2, 3, 1, alg=oracle.EK1, smooth=True, adaptive=True, t0=0, t1=2, prior=oracle.PRIOR_IOUP,
                                         rate_parameter=-a), rhs, [1.0, 1.0], [a])
     assert np.linalg.norm(s["pu_mu"][-1] - exact) < 6e-6
+
+
+def test_ioup_rate_types_and_rate_update(oracle):
+    """test/ioup.jl:20-56 on the same damped oscillator: (a) adaptive EK1 with IOUP(3, A + 1e-3 noise) needs fewer f evaluations
+    than the IWP and ends within 2e-5; with the exact rate matrix A fewer still and within 5e-10 (:22-31); (b) fixed steps dt = 0.1
+    with FixedDiffusion: the error falls with the order 1, 2, 3, 5 (:34-46); (c) the four ways of writing the rate -a -- number,
+    vector, diagonal matrix, -a I -- all end within 6e-6 (:48-55) and, being the same SDE, agree with each other to rounding (the
+    scalar and the matrix path discretise with differently sized matrix exponentials); (d) the Jacobian-updated rate
+    (RosenbrockExpEK) reproduces the exact-rate run on this linear problem, where J = A at every step."""
+    a = 1e-1
+
+    def osc(du, u, p, t):
+        du[0] = -p[0] * u[0] - 2 * np.pi * u[1]
+        du[1] = 2 * np.pi * u[0] - p[0] * u[1]
+
+    tr = tracer.trace(osc, 2, 1)
+    A = np.array([[-a, -2 * np.pi], [2 * np.pi, -a]])
+    w, V = np.linalg.eig(A)
+    exact = np.real(V @ np.diag(np.exp(2.0 * w)) @ np.linalg.solve(V, np.array([1.0, 1.0])))
+    rhs = oracle.compile_rhs(tr, 3)
+
+    def run(q=3, rhs_=rhs, **kw):
+        kw.setdefault("adaptive", True)
+        s = oracle.solve(oracle.make_config(2, q, 1, alg=oracle.EK1, smooth=False, save_everystep=False, t0=0, t1=2, **kw), rhs_, [1.0, 1.0], [a])
+        assert s["retcode"] == "Success"
+        return s, np.linalg.norm(s["pu_mu"][-1] - exact)
+
+    iwp, e_iwp = run()
+    A_noisy = A + 1e-3 * np.random.default_rng(42).standard_normal((2, 2))
+    noisy, e_noisy = run(prior=oracle.PRIOR_IOUP, rate_parameter=A_noisy)
+    exact_rate, e_exact = run(prior=oracle.PRIOR_IOUP, rate_parameter=A)
+    assert e_iwp < 1e-5 and noisy["nf"] < iwp["nf"] and e_noisy < 2e-5
+    assert exact_rate["nf"] < noisy["nf"] and e_exact < 5e-10
+    last = 1.0
+    for q in (1, 2, 3, 5):
+        _, e = run(q=q, rhs_=oracle.compile_rhs(tr, q), prior=oracle.PRIOR_IOUP, rate_parameter=A_noisy, diffusion=oracle.DIFF_FIXED,
+                   adaptive=False, dt=1e-1)
+        assert e < last
+        last = e
+    ends = []
+    for r in (-a, [-a, -a], [[-a, 0.0], [0.0, -a]], -a * np.eye(2)):
+        s, e = run(prior=oracle.PRIOR_IOUP, rate_parameter=r)
+        assert e < 6e-6
+        ends.append((s["pu_mu"][-1], s["naccept"], s["nreject"]))
+    for u, na, nr in ends[1:]:
+        assert (na, nr) == ends[0][1:] and np.allclose(u, ends[0][0], rtol=1e-11, atol=0)
+    upd, e_upd = run(prior=oracle.PRIOR_IOUP, rate_parameter=None, update_rate_parameter=True)
+    assert upd["naccept"] == exact_rate["naccept"] and np.allclose(upd["pu_mu"][-1], exact_rate["pu_mu"][-1], rtol=1e-13)
+    assert upd["njac"] == 2 * upd["naccept"] + 2 * upd["nreject"]   # one Jacobian for the rate, one for H, per attempt
+
+
+def test_ioup_matrix_transition_against_scipy(oracle):
+    """make_transition_matrices!(::IOUP) for a matrix rate (src/priors/ioup.jl:81-131) against an independent evaluation: A = expm(F h)
+    and Q = int_0^h expm(F s) L L' expm(F s)' ds by scipy quadrature, for the SDE of test/core/priors.jl:229-262 (d = 2, q = 2, random
+    rate matrix, derivative-major state ordering)."""
+    from scipy.integrate import quad_vec
+    from scipy.linalg import expm
+    d, q, h = 2, 2, 0.3
+    n, D = q + 1, d * (q + 1)
+    r = np.random.default_rng(5).standard_normal((d, d))
+    F = np.kron(np.diag(np.ones(q), 1), np.eye(d))
+    F[-d:, -d:] = r
+    Lm = np.kron(np.eye(n)[:, [q]], np.eye(d))
+    A_true = expm(F * h)
+    Q_true = quad_vec(lambda s: expm(F * s) @ Lm @ Lm.T @ expm(F * s).T, 0.0, h, epsabs=1e-15, epsrel=1e-13)[0]
+    L = oracle.lib()
+    dp = C.POINTER(C.c_double)
+    L.oracle_ioup_transition_matrix.argtypes = [C.c_int, C.c_int, dp, C.c_double, dp, dp]
+    L.oracle_ioup_transition_matrix.restype = C.c_int
+    rf = np.asfortranarray(r)
+    Ah, QR = np.zeros(D * D), np.zeros(D * D)
+    assert L.oracle_ioup_transition_matrix(d, q, rf.ctypes.data_as(dp), h, Ah.ctypes.data_as(dp), QR.ctypes.data_as(dp)) == 0
+    Ah, QR = Ah.reshape(D, D).T, QR.reshape(D, D).T
+    assert np.allclose(Ah, A_true, rtol=1e-12, atol=1e-14)
+    assert np.allclose(QR.T @ QR, Q_true, rtol=1e-10, atol=1e-18)
+    assert np.allclose(QR, np.triu(QR))
 
 
 @pytest.mark.parametrize("q", [1, 2, 3, 4])
