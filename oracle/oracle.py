@@ -388,6 +388,13 @@ def interpolate(cfg: Config, sol: dict, tval: float):
     colmajor = lambda M: np.asfortranarray(M).ravel(order="F").copy()  # noqa: E731
     h1 = tval - t[idx]
     Ah, Qh = _transition_dense(cfg, h1)
+    mv = None
+    if cfg.diffusion in (DIFF_DYNAMIC_MV, DIFF_FIXED_MV) and "diffusions_mv" in sol:
+        # sol.diffusions[idx] is a Diagonal: apply_diffusion scales block i of Qh by sigma_i^2, i.e. the columns of the dense right factor
+        # Qh.R (derivative-major ordering) by sigma_(c mod d); the scalar `diffusion` passed on is then 1
+        mv = np.sqrt(np.tile(np.asarray(sol["diffusions_mv"][min(idx, len(t) - 1)], dtype=float), D // d))
+        Qh = colmajor(Qh.reshape((D, D), order="F") * mv[None, :])
+        diffusion = 1.0
     mu0 = np.ascontiguousarray(sol["x_filt_mu"][idx])
     R0 = colmajor(sol["x_filt_R"][idx])
     mu_p = (Ah.reshape((D, D), order="F") @ mu0).copy()
@@ -398,6 +405,8 @@ def interpolate(cfg: Config, sol: dict, tval: float):
         return mu_p[sel], (Rp.T @ Rp)[np.ix_(sel, sel)]
     h2 = t[idx + 1] - tval
     Ah2, Qh2 = _transition_dense(cfg, h2)
+    if mv is not None:
+        Qh2 = colmajor(Qh2.reshape((D, D), order="F") * mv[None, :])
     mu_pp = (Ah2.reshape((D, D), order="F") @ mu_p).copy()
     R_pp = np.zeros(D * D)
     L.oracle_predict_cov(D, _dp(R_p), _dp(Ah2), _dp(Qh2), diffusion, COV_QR, _dp(R_pp), None)

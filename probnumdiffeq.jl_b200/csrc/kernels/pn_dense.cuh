@@ -43,6 +43,11 @@ struct PnDenseParams {
     double* v_covfac;    /* [2V][D][D] */
     double* v_h;         /* [2V] slot 2v: h2 */
     double* v_diffusion; /* [2V] slot 2v */
+    /* multivariate diffusion models (DynamicMVDiffusion / FixedMVDiffusion on the blocks layout): per-component diffusions of the saved
+       steps, per-component calibration scale, per-component diffusion of the virtual steps; null for the scalar models */
+    const double* s_diffusion_mv; /* [total][d] */
+    const double* gdiff_mv;       /* [n_traj][d] */
+    double* v_diffusion_mv;       /* [2V][d] slot 2v */
     /* direct outputs (smooth == 0) */
     double* out_u;       /* [V][d]    */
     double* out_cov;     /* [V][d][d] */
@@ -86,7 +91,14 @@ struct PnDensePredict {
             }
             const long long rec = lo;
             const double h1 = act ? tval - P.s_t[rec] : 0.0;
-            const double ediff = (last > a0) ? P.s_diffusion[(rec < last) ? rec : last - 1] : 0.0;
+            const long long dslot = (rec < last) ? rec : last - 1;
+            const double ediff = (last > a0) ? P.s_diffusion[dslot] : 0.0;
+            double edc[d], gc[d]; /* per-component diffusion and calibration scale (all equal for the scalar models) */
+#pragma unroll
+            for (int i = 0; i < d; i++) {
+                edc[i] = (P.s_diffusion_mv && last > a0) ? P.s_diffusion_mv[dslot * d + i] : ediff;
+                gc[i] = (P.calibrate_scale && act) ? (P.gdiff_mv ? P.gdiff_mv[tr * d + i] : P.gdiff[tr]) / P.initial_diffusion : 1.0;
+            }
             const double h2 = (rec < last) ? P.s_t[rec + 1] - tval : 0.0;
             double hp[n], PIv[n];
             hp[0] = 1.0;
@@ -131,7 +143,6 @@ struct PnDensePredict {
                     mup[jj * d + i] = s;
                 }
             double R[RPL][D], B[RPL][D];
-            const double sd = (ediff == 1.0) ? 1.0 : sqrt(ediff);
 #pragma unroll
             for (int lr = 0; lr < RPL; lr++) {
                 const int row = lr * G + gl;
@@ -165,31 +176,42 @@ struct PnDensePredict {
 #else
                         if (m <= c) usel = (mB[lr] == m) ? P.U[m * n + c] : usel;
 #endif
-                    const double val = usel * PIv[c] * sd;
+                    double sdr = 0.0; /* sqrt of the diffusion of the row's component */
+#pragma unroll
+                    for (int i = 0; i < d; i++) sdr = (iB[lr] == i) ? ((edc[i] == 1.0) ? 1.0 : sqrt(edc[i])) : sdr;
+                    const double val = usel * PIv[c] * sdr;
 #pragma unroll
                     for (int i = 0; i < d; i++) B[lr][c * d + i] = (iB[lr] == i) ? val : 0.0;
                 }
             }
             pn_qr_rows<G, RPL, D, D, true, D>(R, B, gl, nullptr);
-            const double g = (P.calibrate_scale && act) ? P.gdiff[tr] / P.initial_diffusion : 1.0;
             if (P.smooth) {
                 if (act) {
                     if (gl == 0) {
                         P.v_idx[v] = rec;
                         P.v_h[2 * v] = h2;
                         P.v_h[2 * v + 1] = 0.0;
-                        P.v_diffusion[2 * v] = ediff * g;
+                        P.v_diffusion[2 * v] = ediff * gc[0];
                         P.v_diffusion[2 * v + 1] = 0.0;
+                        if (P.v_diffusion_mv) {
+#pragma unroll
+                            for (int i = 0; i < d; i++) {
+                                P.v_diffusion_mv[2 * v * d + i] = edc[i] * gc[i];
+                                P.v_diffusion_mv[(2 * v + 1) * d + i] = 0.0;
+                            }
+                        }
 #pragma unroll
                         for (int c = 0; c < D; c++) P.v_mean[2 * v * D + c] = mup[c];
                     }
-                    const double sg = sqrt(g);
+                    double sg[d];
+#pragma unroll
+                    for (int i = 0; i < d; i++) sg[i] = sqrt(gc[i]);
 #pragma unroll
                     for (int lr = 0; lr < RPL; lr++) {
                         const int row = lr * G + gl;
                         if (row < D) {
 #pragma unroll
-                            for (int c = 0; c < D; c++) P.v_covfac[(2 * v * D + row) * D + c] = R[lr][c] * sg;
+                            for (int c = 0; c < D; c++) P.v_covfac[(2 * v * D + row) * D + c] = R[lr][c] * sg[c % d];
                         }
                     }
                 }
@@ -204,7 +226,7 @@ struct PnDensePredict {
                         double s = 0.0;
 #pragma unroll
                         for (int lr = 0; lr < RPL; lr++) s += R[lr][pn_solcol<d>(a)] * R[lr][pn_solcol<d>(b)];
-                        s = pn_gsum<G>(s) * g;
+                        s = pn_gsum<G>(s) * sqrt(gc[pn_solcol<d>(a) % d] * gc[pn_solcol<d>(b) % d]);
                         cv[a * DU + b] = s;
                         cv[b * DU + a] = s;
                     }

@@ -918,7 +918,6 @@ static int validate_config(const pnode_config* cfg) {
             if (cfg->saveat[i] < cfg->t0) return fail(PNODE_ERR_ARGUMENT, "Invalid t<t0"); /* src/solution.jl:340-342 */
             if (i > 0 && !(cfg->saveat[i] >= cfg->saveat[i - 1])) return fail(PNODE_ERR_ARGUMENT, "saveat must be ascending");
         }
-        if (is_mv(cfg->diffusion)) return fail(PNODE_ERR_UNSUPPORTED, "dense output with multivariate diffusion models is not implemented");
         if (D > 32) return fail(PNODE_ERR_UNSUPPORTED, "dense output is implemented for D = d(q+1) <= 32");
         if (cfg->smooth && smooth_lanes(D) == 0)
             return fail(PNODE_ERR_UNSUPPORTED, "dense output of smoothed solutions needs the register-resident sweep (D <= 24)");
@@ -1758,7 +1757,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
            before the sweep overwrites the filtered records with the smoothed ones */
         PnDenseParams Dn;
         memset(&Dn, 0, sizeof Dn);
-        double *v_mean = nullptr, *v_covfac = nullptr, *v_h = nullptr, *v_diff = nullptr, *vu_mean = nullptr, *vu_cov = nullptr;
+        double *v_mean = nullptr, *v_covfac = nullptr, *v_h = nullptr, *v_diff = nullptr, *vu_mean = nullptr, *vu_cov = nullptr, *v_diff_mv = nullptr;
         long long *v_idx = nullptr, *v_off = nullptr;
         if (dense) {
             if ((rc = alloc_field(r, PNODE_F_SAVEAT_U, V * du * 8))) return rc;
@@ -1776,6 +1775,8 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             Dn.s_x_mean = P.s_x_mean;
             Dn.s_x_covfac = P.s_x_covfac;
             Dn.gdiff = P.diffusion;
+            Dn.s_diffusion_mv = s->mv ? P.s_diffusion_mv : nullptr;
+            Dn.gdiff_mv = s->mv ? P.diffusion_mv : nullptr;
             Dn.initial_diffusion = s->base.initial_diffusion;
             memcpy(Dn.U, s->base.U, sizeof Dn.U);
             Dn.rate = s->base.rate;
@@ -1805,6 +1806,11 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 Dn.v_covfac = v_covfac;
                 Dn.v_h = v_h;
                 Dn.v_diffusion = v_diff;
+                if (s->mv) {
+                    CUDA_TRY(cudaMallocAsync((void**)&v_diff_mv, 2 * V * d * 8, s->stream));
+                    scope.track(v_diff_mv);
+                    Dn.v_diffusion_mv = v_diff_mv;
+                }
             }
             Kernel& kd = s->k_dense;
             const int groups = kd.threads / s->Gd;
@@ -1871,6 +1877,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                 Qv.step_offsets = v_off;
                 Qv.s_h = v_h;
                 Qv.s_diffusion = v_diff;
+                Qv.s_diffusion_mv = v_diff_mv;
                 Qv.gdiff = P.diffusion;
                 Qv.s_x_mean = v_mean;
                 Qv.s_x_covfac = v_covfac;
@@ -1882,7 +1889,7 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
                                                                                          Dn.out_cov);
                 launches += 3;
                 for (void* ptr : {(void*)v_mean, (void*)v_covfac, (void*)v_h, (void*)v_diff, (void*)vu_mean, (void*)vu_cov, (void*)v_idx,
-                                  (void*)v_off})
+                                  (void*)v_off, (void*)v_diff_mv})
                     scope.release(ptr);
             }
         }

@@ -838,6 +838,32 @@ def test_dense_output_on_saveat_grid(oracle, alg, smooth, diffusion, calibrate):
                 assert not g["C"][i, j].any()
 
 
+@pytest.mark.parametrize("alg,smooth,diffusion,calibrate", [(lib.EK0, True, lib.DIFF_FIXED_MV, True), (lib.EK0, False, lib.DIFF_FIXED_MV, True),
+                                                            (lib.DIAGONAL_EK1, True, lib.DIFF_FIXED_MV, False), (lib.EK0, True, lib.DIFF_DYNAMIC_MV, True)])
+def test_dense_output_multivariate_diffusions(oracle, alg, smooth, diffusion, calibrate):
+    """sol(saveat) with the multivariate diffusion models (blocks layout): `diffusions[idx]` is a Diagonal and scales block i of Qh
+    (src/solution.jl:351, apply_diffusion on BlocksOfDiagonals); FixedMVDiffusion: 1e-10 / 1e-8, DynamicMVDiffusion: the rounding floor
+    of the scalar dynamic case (1e-8 / 1e-4)."""
+    pd, u0, p = _inputs("lotka_volterra", 2, 52, du0=0.05)
+    saveat = np.array([0.0, 0.013, 0.4, 0.77777, 1.23456, 2.0])
+    g = _gpu_dense(pd, u0, p, 3, saveat, alg=alg, smooth=smooth, diffusion=diffusion, calibrate=calibrate, adaptive=False, dt=0.02,
+                   t0=0.0, t1=2.0)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    static = diffusion == lib.DIFF_FIXED_MV
+    for i in range(u0.shape[0]):
+        cfg = oracle.make_config(2, 3, 4, alg=alg, diffusion=diffusion, calibrate=calibrate, smooth=smooth, adaptive=False, dt=0.02,
+                                 t0=0.0, t1=2.0, cov_backend=oracle.COV_QR)
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        assert not np.allclose(o["diffusions_mv"][1, 0], o["diffusions_mv"][1, 1], rtol=1e-3)   # the components really differ
+        for j, t in enumerate(saveat):
+            m, c = oracle.interpolate(cfg, o, float(t))
+            assert _rel(g["U"][i, j], m) < (1e-10 if static else 1e-8), (i, j)
+            if np.linalg.norm(c) > 0:
+                assert np.linalg.norm(g["C"][i, j] - c) / np.linalg.norm(c) < (1e-8 if static else 1e-4), (i, j)
+            else:
+                assert not g["C"][i, j].any()
+
+
 def test_dense_output_adaptive_ensemble(oracle):
     """Adaptive ensemble with ragged step counts, common saveat grid (what the NCCL ensemble statistics consume)."""
     n = 40
