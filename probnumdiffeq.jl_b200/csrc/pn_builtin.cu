@@ -7,6 +7,7 @@
 #include "kernels/pn_smooth.cuh"
 #include "kernels/pn_smooth_reg.cuh"
 #include "kernels/pn_smooth_col.cuh"
+#include "kernels/pn_dense_gen.cuh"
 
 template <int d, int Q, int G>
 __global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_col_kernel(const __grid_constant__ PnSmoothParams P) {
@@ -71,6 +72,7 @@ extern "C" const PnBuiltinEntry* pn_builtin_table(int* count) {
 }
 
 extern "C" const void* pn_smooth_kernel_ptr(void) { return (const void*)&pn_smooth_kernel; }
+extern "C" const void* pn_dense_gen_kernel_ptr(void) { return (const void*)&pn_dense_gen_kernel; }
 
 /* ahead-of-time instantiations of the register-resident smoother sweep (d, q, lanes): cfg1 FHN q=3, cfg3 VdP q=5 */
 extern "C" const void* pn_smooth_reg_lookup(int d, int q, int g, int column_distributed) {

@@ -26,6 +26,7 @@
 #define PN_SMR_THREADS 256 /* pn_smooth_reg.cuh */
 #define PN_DENSE_DECL_ONLY
 #include "kernels/pn_dense.cuh" /* PnDenseParams */
+#include "kernels/pn_dense_gen.cuh" /* PN_DENSE_GEN_WS */
 #include "kernels/pn_cta.cuh" /* PnCtaShared, PN_CTA_THREADS (templates are not instantiated here) */
 #include "pn_builtin.h"
 #include "pn_embedded_sources.h" /* generated: kernel headers as strings for NVRTC */
@@ -789,6 +790,13 @@ static int get_dense(pnode_solver* s) {
     Kernel* out = &s->k_dense;
     if (out->valid()) return 0;
     auto t0 = std::chrono::steady_clock::now();
+    if (s->D > 32) { /* warp-per-pair predict kernel (ahead-of-time, size-generic) */
+        s->Gd = 32;
+        out->threads = 32 * PN_SM_WARPS;
+        out->rt_fn = pn_dense_gen_kernel_ptr();
+        out->blocks_per_sm = 2;
+        return 0;
+    }
     s->Gd = auto_lanes_qr(s->D);
     out->threads = 256;
     int rc = load_driver();
@@ -918,9 +926,12 @@ static int validate_config(const pnode_config* cfg) {
             if (cfg->saveat[i] < cfg->t0) return fail(PNODE_ERR_ARGUMENT, "Invalid t<t0"); /* src/solution.jl:340-342 */
             if (i > 0 && !(cfg->saveat[i] >= cfg->saveat[i - 1])) return fail(PNODE_ERR_ARGUMENT, "saveat must be ascending");
         }
-        if (D > 32) return fail(PNODE_ERR_UNSUPPORTED, "dense output is implemented for D = d(q+1) <= 32");
-        if (cfg->smooth && smooth_lanes(D) == 0)
-            return fail(PNODE_ERR_UNSUPPORTED, "dense output of smoothed solutions needs the register-resident sweep (D <= 24)");
+        if (D > 32 || (cfg->smooth && smooth_lanes(D) == 0)) {
+            /* beyond the register kernels: warp-per-pair predict (pn_dense_gen.cuh) + the shared-memory sweep */
+            if (cfg->prior != PNODE_PRIOR_IWP || cfg->second_order || is_mv(cfg->diffusion) || layout != PNODE_COV_DENSE)
+                return fail(PNODE_ERR_UNSUPPORTED, "dense output for D = d(q+1) > 32 (smoothed: > 24) is implemented for first-order problems, the IWP prior "
+                                                   "and scalar diffusion models on the dense layout");
+        }
     }
     if (cfg->n_data > 0) { /* fenrir_data_loglik (backward pass), or DataUpdateCallback (forward updates) */
         if (!cfg->data_forward && !cfg->smooth)
@@ -1815,10 +1826,28 @@ static int solve_impl(pnode_solver* s, int64_t n_traj, const double* d_u0, const
             Kernel& kd = s->k_dense;
             const int groups = kd.threads / s->Gd;
             long long want = ((long long)V + groups - 1) / groups;
+            if (kd.rt_fn) { /* D > 32: warp per pair, workspace in shared memory or (Pleiades: 0.2 MB per warp) in a global buffer */
+                const int n = s->cfg.q + 1;
+                const size_t per_warp = (size_t)PN_DENSE_GEN_WS(D, n) * sizeof(double);
+                const bool global_ws = per_warp * PN_SM_WARPS > 200 * 1024;
+                const size_t smem = global_ws ? 0 : per_warp * PN_SM_WARPS;
+                if (!global_ws && smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kd.rt_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                unsigned grid = (unsigned)std::max(1LL, std::min(want, (long long)s->n_sm * (global_ws ? 2 : 1)));
+                double* ws = nullptr;
+                if (global_ws) {
+                    CUDA_TRY(cudaMallocAsync((void**)&ws, (size_t)grid * PN_SM_WARPS * per_warp, s->stream));
+                    scope.track(ws);
+                }
+                int dd = d, qq = s->cfg.q;
+                void* args[] = {&Dn, &dd, &qq, &ws};
+                CUDA_TRY(cudaLaunchKernel(kd.rt_fn, dim3(grid), dim3(kd.threads), args, smem, s->stream));
+                if (ws) scope.release(ws);
+            } else {
             unsigned grid = (unsigned)std::max(1LL, std::min(want, (long long)s->n_sm * kd.blocks_per_sm * 4));
             void* args[] = {&Dn};
             CUresult cr = g_drv.LaunchKernel(kd.drv_fn, grid, 1, 1, kd.threads, 1, 1, 0, (CUstream)s->stream, args, nullptr);
             if (cr != CUDA_SUCCESS) return fail(PNODE_ERR_CUDA, "cuLaunchKernel(dense): " + cu_err(cr));
+            }
             launches += 1;
         }
         if (s->cfg.smooth) {

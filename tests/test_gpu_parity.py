@@ -854,7 +854,8 @@ def test_dense_output_multivariate_diffusions(oracle, alg, smooth, diffusion, ca
         cfg = oracle.make_config(2, 3, 4, alg=alg, diffusion=diffusion, calibrate=calibrate, smooth=smooth, adaptive=False, dt=0.02,
                                  t0=0.0, t1=2.0, cov_backend=oracle.COV_QR)
         o = oracle.solve(cfg, rhs, u0[i], p[i])
-        assert not np.allclose(o["diffusions_mv"][1, 0], o["diffusions_mv"][1, 1], rtol=1e-3)   # the components really differ
+        if calibrate or not static:
+            assert not np.allclose(o["diffusions_mv"][1, 0], o["diffusions_mv"][1, 1], rtol=1e-3)   # the components really differ
         for j, t in enumerate(saveat):
             m, c = oracle.interpolate(cfg, o, float(t))
             assert _rel(g["U"][i, j], m) < (1e-10 if static else 1e-8), (i, j)
