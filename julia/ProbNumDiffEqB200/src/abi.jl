@@ -54,12 +54,15 @@ struct PnodeConfig
     n_data::Int64
     data_u::Ptr{Float64}
     n_obs::Int32
-    reserved2::Int32
+    data_forward::Int32                # 0: Fenrir backward pass; 1: DataUpdateCallback (forward updates at the data times)
     observation_matrix::Ptr{Float64}
     observation_noise_cov::Ptr{Float64}
     observation_noise_var::Float64
     pn_observation_noise::Ptr{Float64}
     pn_observation_noise_var::Float64
+    rate_matrix::Ptr{Float64}          # IOUP with a vector / matrix rate: d x d row-major (NULL: scalar rate_parameter)
+    update_rate_parameter::Int32       # IOUP(q; update_rate_parameter=true): rate := Jacobian before every step
+    reserved2::Int32
 end
 
 # struct pnode_result_info

@@ -21,10 +21,22 @@ end
 
 alg_code(alg) = alg isa ProbNumDiffEq.EK0 ? PNODE_EK0 : alg isa ProbNumDiffEq.DiagonalEK1 ? PNODE_DIAGONAL_EK1 : PNODE_EK1
 prior_code(p) = p isa ProbNumDiffEq.IOUP ? PNODE_PRIOR_IOUP : PNODE_PRIOR_IWP
-function rate_of(p)
-    p isa ProbNumDiffEq.IOUP || return 0.0
-    p.rate_parameter isa Number || throw(ArgumentError("EnsembleB200 supports the IOUP prior with a scalar rate parameter"))
-    return Float64(p.rate_parameter)
+"""
+`(scalar rate, row-major d x d rate matrix or nothing, update flag)` of the prior (src/priors/ioup.jl:33-101): a Number stays a
+number, a vector becomes `Diagonal(r)` and a matrix is passed as is -- exactly what `to_sde` builds --, and
+`IOUP(q; update_rate_parameter=true)` (rate_parameter === missing) asks the library for the Jacobian-updated rate.
+"""
+function rate_of(p, d::Int)
+    p isa ProbNumDiffEq.IOUP || return (0.0, nothing, 0)
+    r = p.rate_parameter
+    if p.update_rate_parameter
+        ismissing(r) || throw(ArgumentError("Do not manually set the `rate_parameter` of the IOUP prior when using the `update_rate_parameter=true` option.Reset the prior and try again."))
+        return (0.0, nothing, 1)
+    end
+    r isa Number && return (Float64(r), nothing, 0)
+    R = r isa AbstractVector ? Matrix{Float64}(LinearAlgebra.Diagonal(r)) : Matrix{Float64}(r)
+    size(R) == (d, d) || throw(DimensionMismatch("the IOUP rate parameter must be a number, a vector of length $d or a $d x $d matrix"))
+    return (0.0, collect(vec(permutedims(R))), 0)        # row-major for the C side
 end
 function diffusion_fields(m)
     m isa ProbNumDiffEq.FixedMVDiffusion && return (PNODE_DIFF_FIXED_MV, m.calibrate ? 1 : 0, Float64(first(m.initial_diffusion)))
@@ -75,23 +87,24 @@ function make_config(prob, alg, device::Integer, lanes::Integer; adaptive, dt, a
     name = "PnodeUserProblem"
     mm = second ? nothing : mass_of(prob.f, d)
     noise, noise_var = obsnoise_of(alg.pn_observation_noise, d)
+    rate, rate_mat, rate_update = rate_of(alg.prior, d)
     ts = tstops === nothing ? Float64[] : sort!(collect(Float64, tstops))
     sa = saveat === nothing ? Float64[] : collect(Float64, saveat)
     data_t, data_u, n_obs, obs_H, obs_cov, obs_var = Float64[], Float64[], 0, nothing, nothing, 0.0
     if fenrir !== nothing
         data_t, data_u, n_obs, obs_H, obs_cov, obs_var = fenrir
     end
-    keep = Any[src, name, mm, noise, ts, sa, data_t, data_u, obs_H, obs_cov]
+    keep = Any[src, name, mm, noise, ts, sa, data_t, data_u, obs_H, obs_cov, rate_mat]
     cfg = PnodeConfig(
         sizeof(PnodeConfig), device, d, q, n_p, alg_code(alg), 0 #= PNODE_COV_AUTO =#, prior_code(alg.prior), diffusion, calibrate,
         alg.smooth ? 1 : 0, adaptive ? 1 : 0, save_everystep ? 1 : 0, save_state ? 1 : 0, lanes, 0, maxiters, initial_diffusion,
         prob.tspan[1], prob.tspan[2], dt, abstol, reltol, dtmin, dtmax,
         beta1, beta2, qmin, qmax, gamma, qsteady_min, qsteady_max, qoldinit,
         Base.unsafe_convert(Cstring, src), Base.unsafe_convert(Cstring, name),
-        ptr_or_null(ts), length(ts), Ptr{Float64}(C_NULL), 0, rate_of(alg.prior), ptr_or_null(sa), length(sa),
+        ptr_or_null(ts), length(ts), Ptr{Float64}(C_NULL), 0, rate, ptr_or_null(sa), length(sa),
         ptr_or_null(mm), second ? 1 : 0, 0,
         ptr_or_null(data_t), length(data_t), ptr_or_null(data_u), n_obs, 0, ptr_or_null(obs_H), ptr_or_null(obs_cov), obs_var,
-        ptr_or_null(noise), noise_var)
+        ptr_or_null(noise), noise_var, ptr_or_null(rate_mat), rate_update, 0)
     return ConfigBundle(Ref(cfg), keep)
 end
 

@@ -176,3 +176,46 @@ def test_cta_kernel_with_smoothing_small_and_pleiades_d112(oracle):
     assert np.array_equal(np.diff(gs["off"]) - 1, gf["naccept"])
     assert _rel(gs["U"][ends], gf["u"]) < 1e-12
     print("pleiades D=112 filter+smoother, 64 trajectories to t=1: kernel_ms", gs["info"].kernel_ms, "steps", int(gf["naccept"].sum()))
+
+
+@pytest.mark.parametrize("smooth", [True, False])
+def test_dense_output_beyond_the_register_kernels(oracle, smooth):
+    """sol(saveat) (src/solution.jl:330-398) where the dense-output register kernels end (D > 32): warp-per-pair predict
+    (pn_dense_gen.cuh) + one backward step of the shared-memory sweep on the two-point virtual trajectories.  Pleiades, D = 112, fixed
+    steps, FixedDiffusion (calibrated): against the oracle's `interpolate` at grid points inside steps, on saved points, at t0 and t1;
+    and Lotka-Volterra, order 6, forced onto the CTA filter (lanes_per_traj = 256): register predict kernel, shared-memory sweep."""
+    from test_gpu_parity import _gpu_dense
+    n = 2
+    pd, u0, _ = _inputs("pleiades", n, 7)
+    u0[:, 14:] += 1e-3 * np.random.default_rng(7).uniform(-1, 1, (n, 14))
+    p = np.zeros((n, 0))
+    saveat = np.array([0.0, 0.0042, 0.05, 0.1234, 0.2])
+    kw = dict(adaptive=False, dt=0.01, t0=0.0, t1=0.2, diffusion=lib.DIFF_FIXED, calibrate=True)
+    g = _gpu_dense(pd, u0, p, 3, saveat, smooth=smooth, **kw)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 28, 0), 3)
+    cfg = oracle.make_config(28, 3, 0, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=True, smooth=smooth, adaptive=False, dt=0.01,
+                             t0=0.0, t1=0.2, cov_backend=oracle.COV_REF)
+    for i in range(n):
+        o = oracle.solve(cfg, rhs, u0[i], [])
+        for j, t in enumerate(saveat):
+            m, c = oracle.interpolate(cfg, o, float(t))
+            assert _rel(g["U"][i, j], m) < 1e-10, (i, j)
+            if np.linalg.norm(c) > 0:
+                assert np.linalg.norm(g["C"][i, j] - c) / np.linalg.norm(c) < 1e-8, (i, j)
+            else:
+                assert not g["C"][i, j].any()
+    # CTA filter + register predict + shared-memory sweep over the virtual trajectories
+    pd, u0, p = _inputs("lotka_volterra", 2, 8, du0=0.05)
+    saveat = np.array([0.0, 0.013, 0.4, 0.77777, 1.0])
+    kw = dict(adaptive=False, dt=0.02, t0=0.0, t1=1.0, diffusion=lib.DIFF_FIXED, calibrate=True)
+    g = _gpu_dense(pd, u0, p, 6, saveat, smooth=smooth, lanes_per_traj=256, **kw)
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 6)
+    cfg = oracle.make_config(2, 6, 4, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=True, smooth=smooth, adaptive=False, dt=0.02,
+                             t0=0.0, t1=1.0, cov_backend=oracle.COV_REF)
+    for i in range(2):
+        o = oracle.solve(cfg, rhs, u0[i], p[i])
+        for j, t in enumerate(saveat):
+            m, c = oracle.interpolate(cfg, o, float(t))
+            assert _rel(g["U"][i, j], m) < 1e-10, (i, j)
+            if np.linalg.norm(c) > 0:
+                assert np.linalg.norm(g["C"][i, j] - c) / np.linalg.norm(c) < 1e-7, (i, j)

@@ -407,3 +407,26 @@ def test_pn_observation_noise_argument_errors_and_compilation(pnlib):
                dict(alg=pnlib.DIAGONAL_EK1, pn_observation_noise=diag), dict(alg=pnlib.EK0, diffusion=pnlib.DIFF_DYNAMIC_MV, pn_observation_noise=diag)):
         assert pnlib.compile_check(pnlib.make_config(**{**base, **kw})) > 10_000
     assert pnlib.compile_check(pnlib.make_config(**{**base, "pn_observation_noise": full})) > plain   # the second Gram + Cholesky
+
+
+def test_config_struct_is_the_same_in_header_python_and_julia():
+    """`pnode_config` is declared three times -- include/pnode.h (the ABI), lib.Config (ctypes) and PnodeConfig in the Julia host
+    (julia/ProbNumDiffEqB200/src/abi.jl): same field names in the same order, and the ctypes size equals what the library checks."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "pnode.h")).read()
+    body = hdr[hdr.index("typedef struct pnode_config {"):hdr.index("} pnode_config;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = []
+    for stmt in body[body.index("{") + 1:].split(";"):
+        m = re.match(r"\s*(?:const\s+)?(?:char|double|int32_t|int64_t)\s*\*?\s*(.+)$", stmt.strip(), flags=re.S)
+        if m:
+            c_fields += [n.strip().lstrip("*").strip() for n in m.group(1).split(",")]
+    py_fields = [f[0] for f in lib.Config._fields_]
+    jl = open(os.path.join(root, "julia", "ProbNumDiffEqB200", "src", "abi.jl")).read()
+    jl_body = jl[jl.index("struct PnodeConfig"):]
+    jl_body = jl_body[:jl_body.index("\nend")]
+    jl_fields = re.findall(r"^\s*(\w+)::", jl_body, flags=re.M)
+    assert c_fields == py_fields
+    assert c_fields == jl_fields
+    assert len(c_fields) > 50
