@@ -85,6 +85,13 @@ if "cfg5" in which:
 if "cfg5dae" in which:   # ROBER as the reference benchmarks it: mass-matrix DAE form (benchmarks/rober.jmd:37-46)
     for n in (100_000, 1_000_000):
         run(f"cfg5 ROBER-DAE (M = diag(1,1,0)) EK1(3) adaptive filter only, {n}", "rober_dae", n, 3, 100.0, seed=3)
+if "ioup" in which:   # IOUP priors: scalar rate on the register kernels, matrix / Jacobian-updated rate on the general-prior path (pn_gen.cuh)
+    run("IOUP(3, -1) scalar rate, LV EK1 adaptive filter only, 262144 (register kernels)", "lotka_volterra", 262144, 3, 10.0, du0=0.1,
+        prior=lib.PRIOR_IOUP, rate_parameter=-1.0)
+    run("IOUP(3, 2x2 matrix rate), LV EK1 adaptive filter only, 65536 (general-prior path, warp per trajectory)", "lotka_volterra", 65536, 3, 10.0,
+        du0=0.1, prior=lib.PRIOR_IOUP, rate_parameter=np.array([[-1.0, 0.3], [-0.2, -0.5]]))
+    run("RosenbrockExpEK (IOUP(3, update_rate_parameter=true)), LV EK1 adaptive filter only, 65536", "lotka_volterra", 65536, 3, 10.0, du0=0.1,
+        prior=lib.PRIOR_IOUP, rate_parameter=None, update_rate_parameter=True)
 if "fenrir" in which:   # Fenrir data log-likelihood of a parameter sweep against one data set (src/data_likelihoods/fenrir.jl)
     from probnumdiffeq_jl_b200 import tracer as _tr
     pd = problems.PROBLEMS["lotka_volterra"]
