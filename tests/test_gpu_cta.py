@@ -210,12 +210,18 @@ def test_dense_output_beyond_the_register_kernels(oracle, smooth):
     kw = dict(adaptive=False, dt=0.02, t0=0.0, t1=1.0, diffusion=lib.DIFF_FIXED, calibrate=True)
     g = _gpu_dense(pd, u0, p, 6, saveat, smooth=smooth, lanes_per_traj=256, **kw)
     rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 6)
-    cfg = oracle.make_config(2, 6, 4, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=True, smooth=smooth, adaptive=False, dt=0.02,
-                             t0=0.0, t1=1.0, cov_backend=oracle.COV_REF)
+    okw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=True, smooth=smooth, adaptive=False, dt=0.02, t0=0.0, t1=1.0)
+    cfg = oracle.make_config(2, 6, 4, cov_backend=oracle.COV_REF, **okw)
+    cfg_qr = oracle.make_config(2, 6, 4, cov_backend=oracle.COV_QR, **okw)
     for i in range(2):
         o = oracle.solve(cfg, rhs, u0[i], p[i])
+        o_qr = oracle.solve(cfg_qr, rhs, u0[i], p[i])
         for j, t in enumerate(saveat):
             m, c = oracle.interpolate(cfg, o, float(t))
+            _, c_qr = oracle.interpolate(cfg_qr, o_qr, float(t))
             assert _rel(g["U"][i, j], m) < 1e-10, (i, j)
             if np.linalg.norm(c) > 0:
-                assert np.linalg.norm(g["C"][i, j] - c) / np.linalg.norm(c) < 1e-7, (i, j)
+                # order 6: the 7 x 7 preconditioned process-noise matrix has condition number 5e8, the covariances (1e-25 here) carry a
+                # relative rounding floor of ~1e-7 -- measured from the oracle's two covariance back-ends in place
+                floor = np.linalg.norm(c_qr - c) / np.linalg.norm(c)
+                assert np.linalg.norm(g["C"][i, j] - c) / np.linalg.norm(c) < max(1e-8, 20 * floor), (i, j, floor)
