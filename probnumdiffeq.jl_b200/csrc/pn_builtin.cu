@@ -34,7 +34,18 @@ __global__ void __launch_bounds__(PN_SMR_THREADS, 1) pn_smooth_reg_kernel(const 
       (const void*)&pn_cta_kernel<PROB, Q, (A != 0), (DY != 0), S>, PROB::d, PROB::n_p, \
       (const void*)&pn_init_kernel<PROB, Q, (A != 0)> }
 
+#define PN_ENTRY_THREAD(NAME, PROB, Q, A, DY) \
+    { "builtin:" NAME ":thread:q" #Q ":g1:a" #A ":dyn" #DY ":s0", \
+      (const void*)&pn_thread_kernel<PROB, Q, (A != 0), (DY != 0)>, PROB::d, PROB::n_p, \
+      (const void*)&pn_init_kernel<PROB, Q, (A != 0)> }
+
 static const PnBuiltinEntry g_table[] = {
+    /* filter-only solves of small states: one thread per trajectory (pn_thread.cuh) -- cfg5 (bench.py headline), cfg1 / cfg3 filter halves */
+    PN_ENTRY_THREAD("rober", PnRober, 3, 1, 1),
+    PN_ENTRY_THREAD("orego", PnOrego, 3, 1, 1),
+    PN_ENTRY_THREAD("fitzhugh_nagumo", PnFitzHughNagumo, 3, 1, 1),
+    PN_ENTRY_THREAD("vanderpol", PnVanDerPol, 5, 1, 1),
+    PN_ENTRY_THREAD("lotka_volterra", PnLotkaVolterra, 3, 1, 1),
     /* cfg4: Pleiades EK1(order=3), D = 112, adaptive, CTA per trajectory */
     PN_ENTRY_CTA("pleiades", PnPleiades, 3, 1, 1, 0),
     /* cfg2: Lotka-Volterra EK0(order=3), adaptive, filter only, 1M trajectories */

@@ -67,3 +67,11 @@ template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC, int SAVE>
 __global__ void __launch_bounds__(32 * PN_GEN_WARPS) pn_gen_kernel(const __grid_constant__ PnParams P) {
     pn_gen_entry<Prob, Q, ADAPTIVE, DYNAMIC, SAVE>(P);
 }
+
+#include "kernels/pn_thread.cuh"
+
+/* small states, filter only: one thread per trajectory, Gram matrix in registers, factor packed in shared memory */
+template <class Prob, int Q, bool ADAPTIVE, bool DYNAMIC>
+__global__ void __launch_bounds__(PN_THREAD_NT, PN_THREAD_MINB) pn_thread_kernel(const __grid_constant__ PnParams P) {
+    pn_thread_entry<Prob, Q, ADAPTIVE, DYNAMIC>(P);
+}

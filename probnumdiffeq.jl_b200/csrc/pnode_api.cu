@@ -23,6 +23,7 @@
 #include "kernels/pn_smooth.cuh"
 #define PN_LTI_DECL_ONLY
 #include "kernels/pn_lti.cuh" /* PN_GEN_WARPS, pn_gen_ws_doubles */
+#define PN_THREAD_NT 256 /* pn_thread.cuh: threads per CTA of the ahead-of-time instantiations */
 #define PN_SMR_THREADS 256 /* pn_smooth_reg.cuh */
 #define PN_DENSE_DECL_ONLY
 #include "kernels/pn_dense.cuh" /* PnDenseParams */
@@ -239,6 +240,7 @@ struct pnode_solver {
     bool blocks = false; /* BlocksOfDiagonals layout (EK0 + multivariate diffusion, DiagonalEK1), thread per trajectory */
     bool mv = false;     /* multivariate (per-component) diffusion model */
     bool cta = false;  /* EK1, D > 32: one CTA per trajectory, R in shared memory */
+    bool thread = false; /* small states, filter only: one thread per trajectory (pn_thread.cuh) */
     bool gen = false;  /* general-prior path (pn_gen.cuh): IOUP with a vector / matrix / Jacobian-updated rate, one warp per trajectory */
     double* d_rate = nullptr;   /* [d][d] rate matrix */
     double* d_gen_ws = nullptr; /* per-warp workspace when it does not fit in shared memory */
@@ -354,6 +356,11 @@ static size_t small_smem_bytes(int D, int G, int threads) {
     return (size_t)(threads / G) * xs * sizeof(double);
 }
 
+/* pn_thread.cuh::pn_thread_sm_doubles: packed factor + mean, doubles per thread */
+static size_t thread_sm_doubles(int d, int n) {
+    const int D = d * n;
+    return (size_t)(2 * d * D + (D - 2 * d) * (D - 2 * d + 1) / 2 + D);
+}
 static bool is_dynamic(int diffusion) { return diffusion == PNODE_DIFF_DYNAMIC || diffusion == PNODE_DIFF_DYNAMIC_MV; }
 static bool is_mv(int diffusion) { return diffusion == PNODE_DIFF_DYNAMIC_MV || diffusion == PNODE_DIFF_FIXED_MV; }
 
@@ -371,7 +378,7 @@ static size_t smooth_col_smem_bytes(int d, int q, int G) {
 static std::string kernel_key(const pnode_solver* s, int save) {
     char buf[256];
     const char* kind = s->blocks ? (s->cfg.alg == PNODE_DIAGONAL_EK1 ? (s->mv ? "blocks1mv" : "blocks1") : (s->mv ? "blocks0mv" : "blocks0"))
-                                 : (s->kron ? "kron" : (s->cta ? "cta" : "small"));
+                                 : (s->kron ? "kron" : (s->cta ? "cta" : (s->thread ? "thread" : "small")));
     snprintf(buf, sizeof buf, "%s:%s:q%d:g%d:a%d:dyn%d:s%d", s->rhs_name.c_str(), kind, s->cfg.q, s->G, s->cfg.adaptive ? 1 : 0,
              is_dynamic(s->cfg.diffusion) ? 1 : 0, save);
     return buf;
@@ -420,11 +427,14 @@ static int nvrtc_compile(const std::string& src, std::vector<std::string> defs, 
 static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_name, int q, int G, bool adaptive,
                        bool dynamic, int save, std::vector<char>* cubin, int threads = PN_THREADS, int min_blocks = 1,
                        bool kron = false, bool cta = false, int blocks = 0 /* 0 no, 1 EK0, 2 DiagonalEK1 */, bool mv = false,
-                       bool ioup = false, bool ek0_dense = false, const std::string& preamble = std::string(), bool gen = false) {
+                       bool ioup = false, bool ek0_dense = false, const std::string& preamble = std::string(), bool gen = false, bool thread = false) {
     std::string src = preamble;
     src += "#include \"pn_kernel_entry.cuh\"\n";
     src += rhs_src;
-    if (gen)
+    if (thread)
+        src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREAD_NT, PN_THREAD_MINB) pn_entry(const __grid_constant__ PnParams P) {\n"
+               "  pn_thread_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0)>(P);\n}\n";
+    else if (gen)
         src += "\nextern \"C\" __global__ void __launch_bounds__(PN_THREADS) pn_entry(const __grid_constant__ PnParams P) {\n"
                "  pn_gen_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0), (PN_DYNAMIC != 0), PN_SAVE>(P);\n}\n";
     else if (blocks)
@@ -446,6 +456,7 @@ static int nvrtc_cubin(const std::string& rhs_src, const std::string& struct_nam
                "double* init_dt) {\n  pn_init_entry<" + struct_name + ", PN_Q, (PN_ADAPTIVE != 0)>(P, init_mu, init_dt);\n}\n";
     auto def = [](const char* name, int v) { return std::string("-D") + name + "=" + std::to_string(v); };
     return nvrtc_compile(src, {def(cta ? "PN_CTA_THREADS" : "PN_THREADS", threads), def(cta ? "PN_CTA_MIN_BLOCKS" : "PN_MIN_BLOCKS", min_blocks), def("PN_Q", q), def("PN_G", G),
+                               def("PN_THREAD_NT", thread ? threads : 256), def("PN_THREAD_MINB", thread ? min_blocks : 1),
                                def("PN_ADAPTIVE", adaptive ? 1 : 0), def("PN_DYNAMIC", dynamic ? 1 : 0), def("PN_SAVE", save),
                                def("PN_IOUP", (ioup && !gen) ? 1 : 0), def("PN_EK0_DENSE", ek0_dense ? 1 : 0)},
                          cubin);
@@ -684,7 +695,12 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
         cta_shape(s->smem, &out->threads, &min_blocks);
         s->G = out->threads; /* one CTA per trajectory */
     }
-    if (s->gen) {
+    if (s->thread) {
+        out->threads = 256;
+        while (out->threads > 32 && thread_sm_doubles(s->cfg.d, s->cfg.q + 1) * out->threads * 8 > 227 * 1024) out->threads /= 2;
+        s->smem = thread_sm_doubles(s->cfg.d, s->cfg.q + 1) * out->threads * 8;
+        min_blocks = 1;
+    } else if (s->gen) {
         out->threads = 32 * PN_GEN_WARPS;
     } else if (!s->cta && !s->kron && !s->blocks) {
         /* one exchange region per group: large states with few lanes per trajectory run smaller CTAs */
@@ -694,7 +710,7 @@ static int compile_nvrtc(pnode_solver* s, int save, Kernel* out) {
     rc = nvrtc_cubin(src, name, s->cfg.q, s->G, s->cfg.adaptive != 0, is_dynamic(s->cfg.diffusion), save, &cubin, out->threads,
                      min_blocks, s->kron, s->cta,
                      s->blocks ? (s->cfg.alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, s->mv, s->cfg.prior == PNODE_PRIOR_IOUP,
-                     s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks, s->mass_src, s->gen);
+                     s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks, s->mass_src, s->gen, s->thread);
     if (rc) return rc;
     CUresult r = g_drv.ModuleLoadData(&out->mod, cubin.data());
     if (r != CUDA_SUCCESS) return fail(PNODE_ERR_COMPILE, "cuModuleLoadData: " + cu_err(r));
@@ -717,7 +733,8 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
     if (out->valid()) return 0;
     auto t0 = std::chrono::steady_clock::now();
     if (s->builtin && !env_int("PNODE_FORCE_NVRTC", 0) && s->cfg.prior == PNODE_PRIOR_IWP && s->mass_src.empty() &&
-        !(s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks)) {
+        !(s->cfg.alg == PNODE_EK0 && !s->kron && !s->blocks) &&
+        !(s->thread && thread_sm_doubles(s->cfg.d, s->cfg.q + 1) * PN_THREAD_NT * 8 > 227 * 1024) /* CTA size of the ahead-of-time build */) {
         int n = 0;
         const PnBuiltinEntry* tab = pn_builtin_table(&n);
         std::string key = kernel_key(s, save);
@@ -727,6 +744,10 @@ static int get_kernel(pnode_solver* s, int save, Kernel* out) {
                 out->rt_init = tab[i].init_fn;
                 out->threads = s->cta ? PN_CTA_THREADS : ((s->kron || s->blocks) ? 128 : PN_THREADS);
                 if (s->cta) s->G = out->threads;
+                if (s->thread) {
+                    out->threads = PN_THREAD_NT;
+                    s->smem = thread_sm_doubles(s->cfg.d, s->cfg.q + 1) * PN_THREAD_NT * 8;
+                } else
                 if (!s->cta && !s->kron && !s->blocks) s->smem = small_smem_bytes(s->D, s->G, out->threads);
                 if (s->smem > 48 * 1024)
                     CUDA_TRY(cudaFuncSetAttribute(out->rt_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem));
@@ -830,6 +851,17 @@ static int resolve_layout(const pnode_config* cfg) {
     return PNODE_COV_DENSE;
 }
 
+/* pn_thread.cuh: EK1, IWP, plain first-order ODE, filter only, small state */
+static bool thread_eligible(const pnode_config* cfg) {
+    const int D = cfg->d * (cfg->q + 1);
+    return cfg->alg == PNODE_EK1 && cfg->prior == PNODE_PRIOR_IWP && !cfg->save_everystep && !cfg->mass_matrix && !cfg->second_order &&
+           cfg->n_data == 0 && !has_obsn(cfg) && cfg->q >= 1 && D <= 16 && (cfg->lanes_per_traj == 0 || cfg->lanes_per_traj == 1);
+}
+
+static bool use_thread(const pnode_config* cfg) {
+    return thread_eligible(cfg) && (cfg->lanes_per_traj == 1 || (env_int("PNODE_THREAD_KERNEL", 1) != 0 && cfg->d * (cfg->q + 1) <= 12));
+}
+
 static int validate_config(const pnode_config* cfg) {
     if (cfg->struct_size != (int32_t)sizeof(pnode_config))
         return fail(PNODE_ERR_ARGUMENT, "pnode_config.struct_size mismatch (ABI)");
@@ -906,9 +938,12 @@ static int validate_config(const pnode_config* cfg) {
         if (cfg->smooth && smooth_lanes(D) == 0)
             return fail(PNODE_ERR_UNSUPPORTED, "smoothing on the blocks-of-diagonals layout needs the register-resident sweep (D <= 24)");
     }
-    if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 2 && cfg->lanes_per_traj != 4 && cfg->lanes_per_traj != 8 &&
+    if (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 1 && cfg->lanes_per_traj != 2 && cfg->lanes_per_traj != 4 && cfg->lanes_per_traj != 8 &&
         cfg->lanes_per_traj != 16 && cfg->lanes_per_traj != 32 && cfg->lanes_per_traj != 256)
-        return fail(PNODE_ERR_ARGUMENT, "lanes_per_traj must be one of 0 (auto), 2, 4, 8, 16, 32, 256 (CTA per trajectory)");
+        return fail(PNODE_ERR_ARGUMENT, "lanes_per_traj must be one of 0 (auto), 1 (thread per trajectory), 2, 4, 8, 16, 32, 256 (CTA per trajectory)");
+    if (cfg->lanes_per_traj == 1 && !thread_eligible(cfg))
+        return fail(PNODE_ERR_UNSUPPORTED, "lanes_per_traj = 1 (thread per trajectory) serves the EK1 with the IWP prior on first-order problems, "
+                                           "filter only (save_everystep = 0), D = d(q+1) <= 16");
     if (!is_gen(cfg) && cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256)) {
         if (cta_smem_bytes(cfg->d, cfg->q, cfg->n_p, cfg->second_order != 0, cfg->mass_matrix != nullptr) > 227 * 1024)
             return fail(PNODE_ERR_UNSUPPORTED, "state dimension too large for the shared-memory CTA kernel");
@@ -1092,7 +1127,7 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
                      save_level(cfg, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256)), &cubin, layout == PNODE_COV_DENSE ? PN_THREADS : 128, 1,
                      layout == PNODE_COV_KRONECKER, cfg->alg == PNODE_EK1 && (D > 32 || cfg->lanes_per_traj == 256),
                      layout == PNODE_COV_BLOCKS ? (cfg->alg == PNODE_DIAGONAL_EK1 ? 2 : 1) : 0, is_mv(cfg->diffusion),
-                     cfg->prior == PNODE_PRIOR_IOUP, cfg->alg == PNODE_EK0 && layout == PNODE_COV_DENSE, mass_src, is_gen(cfg));
+                     cfg->prior == PNODE_PRIOR_IOUP, cfg->alg == PNODE_EK0 && layout == PNODE_COV_DENSE, mass_src, is_gen(cfg), use_thread(cfg));
     if (rc) return rc;
     int64_t total = (int64_t)cubin.size();
     if (is_gen(cfg)) { /* the smoother of this path is the ahead-of-time shared-memory sweep */
@@ -1147,8 +1182,10 @@ extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
     s->blocks = (resolve_layout(cfg) == PNODE_COV_BLOCKS);
     s->mv = is_mv(cfg->diffusion);
     s->gen = is_gen(cfg);
+    /* thread per trajectory: on request (lanes_per_traj = 1), or automatically where it is the faster mapping (PNODE_THREAD_KERNEL=0: off) */
+    s->thread = use_thread(cfg);
     s->cta = !s->gen && !s->kron && !s->blocks && (D > 32 || cfg->lanes_per_traj == 256);
-    s->G = (s->kron || s->blocks) ? 1 : (s->gen ? 32 : (s->cta ? 256 : (cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D))));
+    s->G = (s->kron || s->blocks || s->thread) ? 1 : (s->gen ? 32 : (s->cta ? 256 : (cfg->lanes_per_traj > 0 ? cfg->lanes_per_traj : auto_lanes(D))));
     if (s->gen) {
         s->gen_ws_doubles = gen_ws_doubles(cfg->d, cfg->q);
         const size_t bytes = s->gen_ws_doubles * PN_GEN_WARPS * sizeof(double);
