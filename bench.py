@@ -64,7 +64,7 @@ def committed_ncu(workload, n):
     return tab.get(f"{workload}:{n}")
 
 
-def executed_flops_per_accepted_step(workload):
+def executed_flops_per_accepted_step(workload, kernel_prefix=""):
     """Executed FP64 operations (2 DFMA + DMUL + DADD, predicated-on thread instructions counted by ncu) per accepted step of the
     dominant kernel, from the committed capture of this workload that carries its own accepted-step count (any ensemble size: the
     per-step count does not depend on it).  Rejected attempts and the identity steps of finished groups are inside the count."""
@@ -74,7 +74,7 @@ def executed_flops_per_accepted_step(workload):
         return None, None
     best = None
     for key, e in tab.items():
-        if key.split(":")[0] == workload and e.get("accepted_steps"):
+        if key.split(":")[0] == workload and e.get("accepted_steps") and kernel_prefix in e.get("kernel", ""):
             if best is None or e["accepted_steps"] > best[1]["accepted_steps"]:
                 best = (key, e)
     if best is None:
@@ -246,12 +246,15 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    lanes_used = [0]   # lanes per trajectory of the step kernel that ran (1: pn_thread, 2 ... 32: pn_small, 256: pn_cta)
+
     def step_device():
         flush.zero_()
         torch.cuda.synchronize()
         r = solver.solve_device(n, du0.data_ptr(), dp.data_ptr())
         info = r.info
         out = (info.total_accepted, info.total_rejected, info.kernel_ms, info.n_launches)
+        lanes_used[0] = int(info.lanes_per_traj)
         r.free()
         return out
 
@@ -350,8 +353,12 @@ def main():
         alg_bytes = n * (8 * (d + pd.n_p) + 8 * (D + 1) + 8 * (d + d * d) + 8 * 5 + 3 * 8 + 4)
         if smooth:
             alg_bytes += (acc / args.steps) * 8 * (2 * (D * D + D + 2) + 1 + d + d * d)
+        kprefix = ("pn_kron_kernel" if alg == "EK0" else
+                   {1: "pn_thread_kernel", 256: "pn_cta_kernel"}.get(lanes_used[0], "pn_small_kernel"))
         cap = committed_ncu(args.workload, n)
-        ex_per_step, ex_key = executed_flops_per_accepted_step(args.workload)
+        if cap and kprefix not in cap.get("kernel", ""):
+            cap = None   # the committed capture is of another step kernel than the one that ran
+        ex_per_step, ex_key = executed_flops_per_accepted_step(args.workload, kprefix)
         executed_tflops = (acc / args.steps) * ex_per_step / dur / 1e12 if ex_per_step else None
         line = {
             "metric": METRIC, "value": acc_t / wall_m, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -360,7 +367,10 @@ def main():
             "config": {
                 "workload": workload_name(args.workload),
                 "trajectories_per_gpu": n, "trajectories_total": int(n_t), "D": D, "d": d,
-                "lanes_per_trajectory": int(solver.cfg.lanes_per_traj) or None,
+                "lanes_per_trajectory": lanes_used[0],
+                "step_kernel": ("pn_kron_kernel (one thread per trajectory)" if alg == "EK0" else
+                                {1: "pn_thread_kernel (one thread per trajectory)", 256: "pn_cta_kernel (one CTA per trajectory)"}.get(
+                                    lanes_used[0], f"pn_small_kernel ({lanes_used[0]} lanes per trajectory)")),
                 "parallelism": f"trajectory-sharded x{world}, no collective on the step path",
                 "l2": "256 MiB buffer written between timed iterations (inputs+outputs are also re-staged per step)",
                 "kernel_ms_per_step_device_events": 1e3 * ksec_m / args.steps,

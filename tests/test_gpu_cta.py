@@ -221,7 +221,8 @@ def test_dense_output_beyond_the_register_kernels(oracle, smooth):
             _, c_qr = oracle.interpolate(cfg_qr, o_qr, float(t))
             assert _rel(g["U"][i, j], m) < 1e-10, (i, j)
             if np.linalg.norm(c) > 0:
-                # order 6: the 7 x 7 preconditioned process-noise matrix has condition number 5e8, the covariances (1e-25 here) carry a
-                # relative rounding floor of ~1e-7 -- measured from the oracle's two covariance back-ends in place
+                # order 6: the 7 x 7 preconditioned process-noise matrix has condition number 5e8, so the covariances (1e-25 here) carry a
+                # relative rounding floor of eps * cond ~ 1e-7 (measured: 1.4e-7 against the oracle, 7e-9 ... 1e-7 between the oracle's own
+                # two covariance back-ends); the bound is ten times that
                 floor = np.linalg.norm(c_qr - c) / np.linalg.norm(c)
-                assert np.linalg.norm(g["C"][i, j] - c) / np.linalg.norm(c) < max(1e-8, 20 * floor), (i, j, floor)
+                assert np.linalg.norm(g["C"][i, j] - c) / np.linalg.norm(c) < max(1e-6, 20 * floor), (i, j, floor)
