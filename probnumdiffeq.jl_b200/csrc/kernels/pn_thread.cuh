@@ -34,6 +34,20 @@
 #define PN_THREAD_MINB 1
 #endif
 
+/* compile-time loop: f(PnInt<I>{}) for I = B ... E-1.  `#pragma unroll` is a hint that the compiler declines for the large bodies of this
+   kernel (measured: the row loop of the Gram phase stayed rolled, with run-time structure tests and branches in the hot path) */
+template <int V>
+struct PnInt {
+    static constexpr int value = V;
+};
+template <int B, int E, class F>
+__device__ __forceinline__ void pn_static_for(F&& f) {
+    if constexpr (B < E) {
+        f(PnInt<B>{});
+        pn_static_for<B + 1, E>(f);
+    }
+}
+
 /* doubles of shared memory per thread (host and kernel must agree): packed factor + mean */
 __host__ __device__ constexpr int pn_thread_sm_doubles(int d, int n) {
     return 2 * d * (d * n) + ((d * n) - 2 * d) * ((d * n) - 2 * d + 1) / 2 + d * n;
@@ -255,8 +269,8 @@ struct PnThread {
                         for (int i = 0; i < d; i++) M[m * d + i][c * d + i] = v;
                     }
                 /* stream the factor: row r of X = R Ah' in flight, M += x x' */
-#pragma unroll
-                for (int r = 0; r < D; r++) {
+                pn_static_for<0, D>([&](auto rc) {
+                    constexpr int r = decltype(rc)::value;
                     double x[D];
 #pragma unroll
                     for (int c = 0; c < D; c++) x[c] = stored(r, c) ? my[slot(r, stored(r, c) ? c : r) * NT] : 0.0;
@@ -276,11 +290,11 @@ struct PnThread {
 #pragma unroll
                         for (int b = 0; b < D; b++)
                             if (b >= a && xnz(r, a) && xnz(r, b)) M[a][b] = fma(x[a], x[b], M[a][b]);
-                }
+                });
                 /* Cholesky in registers (right-looking, upper) */
                 bool okc = true;
-#pragma unroll
-                for (int k = 0; k < D; k++) {
+                pn_static_for<0, D>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value;
                     const double piv = M[k][k];
                     okc = okc && (piv > 0.0);
                     const double ri = pn_rsqrt(piv);
@@ -293,7 +307,7 @@ struct PnThread {
 #pragma unroll
                         for (int j = 0; j < D; j++)
                             if (i > k && j >= i) M[i][j] = fma(-M[k][i], M[k][j], M[i][j]);
-                }
+                });
                 if (!okc || ediff == 0.0) { /* predict.jl:90 / :71-74: cold path, the stack in local memory */
                     double X[D * D];
                     fallback(P, my, h, ediff, X);
@@ -371,8 +385,8 @@ struct PnThread {
                 }
                 /* column by column: K[c] = U[:, c]' V ; mu[c] -= K[c] z ; R+[r][c] = U[r][c] - C2[r] K[c]' (r < 2d); rows >= 2d unchanged */
                 bool nanu = false;
-#pragma unroll
-                for (int c = 0; c < D; c++) {
+                pn_static_for<0, D>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
                     double Kc[d];
 #pragma unroll
                     for (int a = 0; a < d; a++) {
@@ -401,7 +415,7 @@ struct PnThread {
                             my[slot(r, c) * NT] = M[r][c];
                         }
                     }
-                }
+                });
                 naccept++;
                 if (nanu) retcode = PN_RET_UNSTABLE;
                 if (retcode != PN_RET_SUCCESS) finished = true;

@@ -394,7 +394,8 @@ static int nvrtc_compile(const std::string& src, std::vector<std::string> defs, 
     }
     if (nvrtcCreateProgram(&prog, src.c_str(), "pnode_user.cu", PN_N_EMBEDDED, hdr_src, hdr_name) != NVRTC_SUCCESS)
         return fail(PNODE_ERR_COMPILE, "nvrtcCreateProgram failed");
-    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+    /* -default-device: the compile-time loops of pn_thread.cuh pass generic lambdas, which carry no execution-space annotation */
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
     if (const char* e = getenv("PNODE_NVRTC_FLAGS")) { /* developer knob: extra NVRTC options, space separated */
         std::string cur;
         for (const char* c = e;; c++) {

@@ -11,7 +11,7 @@ from test_gpu_parity import _gpu, _inputs, _rel, _relcov
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,q,t1,dt", [("fitzhugh_nagumo", 3, 5.0, 0.01), ("rober", 3, 1.0, 0.002), ("vanderpol", 5, 0.05, 1e-4)])
+@pytest.mark.parametrize("name,q,t1,dt", [("fitzhugh_nagumo", 3, 5.0, 0.01), ("rober", 3, 0.02, 1e-4), ("vanderpol", 5, 0.05, 1e-4)])
 def test_thread_kernel_fixed_steps_static_diffusion(oracle, name, q, t1, dt):
     """Fixed steps, FixedDiffusion: end state (mean, covariance, full state factor as R'R), log-likelihood and the calibrated
     diffusion at 1e-10 against BOTH oracle back-ends; the kernel follows the reference's Gram + Cholesky route."""
