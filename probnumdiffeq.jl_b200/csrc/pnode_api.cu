@@ -852,10 +852,18 @@ static int resolve_layout(const pnode_config* cfg) {
     return PNODE_COV_DENSE;
 }
 
+/* M == I (or no mass matrix at all): the ODE kernels apply */
+static bool mass_is_identity(const pnode_config* cfg) {
+    if (!cfg->mass_matrix) return true;
+    for (int a = 0; a < cfg->d; a++)
+        for (int i = 0; i < cfg->d; i++)
+            if (cfg->mass_matrix[a * cfg->d + i] != (a == i ? 1.0 : 0.0)) return false;
+    return true;
+}
 /* pn_thread.cuh: EK1, IWP, plain first-order ODE, filter only, small state */
 static bool thread_eligible(const pnode_config* cfg) {
     const int D = cfg->d * (cfg->q + 1);
-    return cfg->alg == PNODE_EK1 && cfg->prior == PNODE_PRIOR_IWP && !cfg->save_everystep && !cfg->mass_matrix && !cfg->second_order &&
+    return cfg->alg == PNODE_EK1 && cfg->prior == PNODE_PRIOR_IWP && !cfg->save_everystep && mass_is_identity(cfg) && !cfg->second_order &&
            cfg->n_data == 0 && !has_obsn(cfg) && cfg->q >= 1 && D <= 16 && (cfg->lanes_per_traj == 0 || cfg->lanes_per_traj == 1);
 }
 
