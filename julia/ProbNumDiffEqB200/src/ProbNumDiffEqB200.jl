@@ -8,7 +8,7 @@
 #   trace.jl     Symbolics trace of f -> CUDA C++ `struct PnodeUserProblem { f<T>, jac }` (the printer of tracer.py)
 #   solve.jl     keyword mapping, `__solve`, multi-GPU sharding
 #   solution.jl  `B200ODESolution` with the field names of ProbNumDiffEq.ProbODESolution (src/solution.jl:33-56)
-#   fenrir.jl    `fenrir_data_loglik` over an ensemble of parameters
+#   fenrir.jl    `fenrir_data_loglik`, `filtering_data_loglik`, `dalton_data_loglik` over an ensemble of parameters
 module ProbNumDiffEqB200
 
 using LinearAlgebra

@@ -108,6 +108,7 @@ const PNODE_F_DIFFUSIONS_MV = 20
 const PNODE_F_SAVEAT_U = 21
 const PNODE_F_SAVEAT_U_COV = 22
 const PNODE_F_FENRIR_LOGLIK = 23
+const PNODE_F_DATA_LOGLIK = 24
 
 # enum pnode_alg / pnode_prior / pnode_diffusion / pnode_retcode, status codes
 const PNODE_EK0, PNODE_EK1, PNODE_DIAGONAL_EK1 = 0, 1, 2

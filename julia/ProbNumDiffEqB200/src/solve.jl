@@ -76,7 +76,8 @@ struct ConfigBundle
 end
 
 function make_config(prob, alg, device::Integer, lanes::Integer; adaptive, dt, abstol, reltol, save_everystep, save_state, maxiters, dtmin,
-                     dtmax, tstops, saveat, beta1, beta2, qmin, qmax, gamma, qsteady_min, qsteady_max, qoldinit, fenrir=nothing)
+                     dtmax, tstops, saveat, beta1, beta2, qmin, qmax, gamma, qsteady_min, qsteady_max, qoldinit, fenrir=nothing,
+                     data_forward=false, smooth=alg.smooth)
     second = prob.f isa SciMLBase.DynamicalODEFunction
     dim = length(prob.u0)
     d = second ? dim ÷ 2 : dim
@@ -97,13 +98,13 @@ function make_config(prob, alg, device::Integer, lanes::Integer; adaptive, dt, a
     keep = Any[src, name, mm, noise, ts, sa, data_t, data_u, obs_H, obs_cov, rate_mat]
     cfg = PnodeConfig(
         sizeof(PnodeConfig), device, d, q, n_p, alg_code(alg), 0 #= PNODE_COV_AUTO =#, prior_code(alg.prior), diffusion, calibrate,
-        alg.smooth ? 1 : 0, adaptive ? 1 : 0, save_everystep ? 1 : 0, save_state ? 1 : 0, lanes, 0, maxiters, initial_diffusion,
+        smooth ? 1 : 0, adaptive ? 1 : 0, save_everystep ? 1 : 0, save_state ? 1 : 0, lanes, 0, maxiters, initial_diffusion,
         prob.tspan[1], prob.tspan[2], dt, abstol, reltol, dtmin, dtmax,
         beta1, beta2, qmin, qmax, gamma, qsteady_min, qsteady_max, qoldinit,
         Base.unsafe_convert(Cstring, src), Base.unsafe_convert(Cstring, name),
         ptr_or_null(ts), length(ts), Ptr{Float64}(C_NULL), 0, rate, ptr_or_null(sa), length(sa),
         ptr_or_null(mm), second ? 1 : 0, 0,
-        ptr_or_null(data_t), length(data_t), ptr_or_null(data_u), n_obs, 0, ptr_or_null(obs_H), ptr_or_null(obs_cov), obs_var,
+        ptr_or_null(data_t), length(data_t), ptr_or_null(data_u), n_obs, data_forward ? 1 : 0, ptr_or_null(obs_H), ptr_or_null(obs_cov), obs_var,
         ptr_or_null(noise), noise_var, ptr_or_null(rate_mat), rate_update, 0)
     return ConfigBundle(Ref(cfg), keep)
 end
