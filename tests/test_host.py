@@ -430,3 +430,33 @@ def test_config_struct_is_the_same_in_header_python_and_julia():
     assert c_fields == py_fields
     assert c_fields == jl_fields
     assert len(c_fields) > 50
+
+
+def test_field_ids_and_enums_agree_between_header_and_julia():
+    """Every `const PNODE_* = n` of the Julia binding has the value the header's enums give it (field ids, algorithm / prior / diffusion /
+    covariance codes, error codes)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "pnode.h")).read(), flags=re.S)
+    c_vals = {}
+    for body in re.findall(r"enum\s*\w*\s*\{(.*?)\}", hdr, flags=re.S):
+        nxt = 0
+        for item in body.split(","):
+            item = item.strip()
+            if not item:
+                continue
+            m = re.match(r"(\w+)\s*(?:=\s*(-?\d+))?$", item)
+            assert m, item
+            nxt = int(m.group(2)) if m.group(2) is not None else nxt
+            c_vals[m.group(1)] = nxt
+            nxt += 1
+    jl = open(os.path.join(root, "julia", "ProbNumDiffEqB200", "src", "abi.jl")).read()
+    jl_vals = {}
+    for names, vals in re.findall(r"^const\s+((?:PNODE_\w+\s*,\s*)*PNODE_\w+)\s*=\s*([-\d\s,]+)$", jl, flags=re.M):
+        ns = [x.strip() for x in names.split(",")]
+        vs = [int(x) for x in vals.split(",")]
+        assert len(ns) == len(vs), names
+        jl_vals.update(zip(ns, vs))
+    assert len(jl_vals) > 30
+    for k, v in jl_vals.items():
+        assert k in c_vals, k
+        assert c_vals[k] == v, (k, v, c_vals[k])
