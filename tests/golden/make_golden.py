@@ -59,6 +59,11 @@ CASES = {
     "oracle_lv_diagek1_q3_fixedmv": ("lotka_volterra", 3, dict(alg=2, diffusion=3, calibrate=True, smooth=True, adaptive=False, dt=0.02, t0=0.0, t1=4.0)),
     "oracle_lv_ek1_q3_ioup_fixed": ("lotka_volterra", 3, dict(alg=1, diffusion=1, calibrate=True, smooth=True, adaptive=False, dt=0.02, t0=0.0, t1=4.0,
                                                                prior=1, rate_parameter=-1.0)),
+    # IOUP with a matrix rate, and with the Jacobian-updated rate (RosenbrockExpEK): the general-prior path
+    "oracle_lv_ek1_q3_ioup_matrix_fixed": ("lotka_volterra", 3, dict(alg=1, diffusion=1, calibrate=True, smooth=True, adaptive=False, dt=0.02, t0=0.0,
+                                                                      t1=4.0, prior=1, rate_parameter=[[-1.0, 0.3], [-0.2, -0.5]])),
+    "oracle_fhn_ek1_q3_ioup_rateupdate_fixed": ("fitzhugh_nagumo", 3, dict(alg=1, diffusion=1, calibrate=True, smooth=True, adaptive=False, dt=0.02,
+                                                                           t0=0.0, t1=2.0, prior=1, rate_parameter=None, update_rate_parameter=True)),
     "oracle_rober_ek1_q3_adaptive": ("rober", 3, dict(alg=1, diffusion=0, smooth=False, adaptive=True, t0=0.0, t1=100.0)),
     # mass matrix (dense, non-symmetric), second-order problem, Fenrir data log-likelihood
     "oracle_robermass_ek1_q3_fixed_smooth": ("rober_dae", 3, dict(alg=1, diffusion=1, calibrate=True, smooth=True, adaptive=False, dt=1e-3, t0=0.0,
@@ -74,12 +79,14 @@ FENRIR_DATA = {  # data set of the Fenrir fixture: times, observations (seeded n
 }
 
 
-def oracle_cases():
+def oracle_cases(only=None):
     import probnumdiffeq_jl_b200  # noqa: F401
     from probnumdiffeq_jl_b200 import problems, tracer
     from oracle import oracle as O
 
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         prob, q, kw = case[:3]
         pd = problems.lookup(prob)
         rhs = O.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
@@ -103,6 +110,9 @@ def oracle_cases():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:   # regenerate the named oracle fixtures only
+        oracle_cases(set(sys.argv[1:]))
+        sys.exit(0)
     if os.path.exists(REF):
         json.dump(parse_reference_constants(), open(os.path.join(HERE, "reference_iwp_d2_q2.json"), "w"), indent=1)
         print("reference_iwp_d2_q2.json")
