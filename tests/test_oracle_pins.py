@@ -596,6 +596,35 @@ def test_ioup_rate_types_and_rate_update(oracle):
     assert upd["njac"] == 2 * upd["naccept"] + 2 * upd["nreject"]   # one Jacobian for the rate, one for H, per attempt
 
 
+def test_exponential_integrators_linear_ode(oracle):
+    """test/exponential_integrators.jl:6-41 in full: u' = p u, p = -1, u0 = 1, t in [0, 10], default tolerances, adaptive steps,
+    smoothing on (the defaults of `solve(prob, alg)`).  ExpEK(L = p) is EK0 with IOUP(3, p), RosenbrockExpEK is EK1 with
+    IOUP(3, update_rate_parameter = true) (src/algorithms.jl:425, :458-459).  The reference asserts absolute end-point errors
+    (1e-7, 1e-9, 2e-10, 2e-12), their ordering, and that both exponential integrators take fewer steps and fewer f evaluations
+    than EK0 / EK1.  The thresholds sit within a factor of 2.5 of what the restatement produces, so they pin the adaptive
+    path (error estimate, PI controller, initial step) and not only the filter algebra."""
+
+    def lin(du, u, p, t):
+        du[0] = p[0] * u[0]
+
+    rhs = oracle.compile_rhs(tracer.trace(lin, 1, 1), 3)
+    uend = math.exp(-10.0)
+
+    def run(**kw):
+        s = oracle.solve(oracle.make_config(1, 3, 1, smooth=True, adaptive=True, t0=0, t1=10, **kw), rhs, [1.0], [-1.0])
+        assert s["retcode"] == "Success"
+        return abs(s["pu_mu"][-1][0] - uend), s["n"], s["nf"]
+
+    e0, n0, nf0 = run(alg=oracle.EK0)
+    e1, n1, nf1 = run(alg=oracle.EK1)
+    ee, ne, nfe = run(alg=oracle.EK0, prior=oracle.PRIOR_IOUP, rate_parameter=-1.0)
+    er, nr, nfr = run(alg=oracle.EK1, prior=oracle.PRIOR_IOUP, rate_parameter=None, update_rate_parameter=True)
+    assert e0 < 1e-7 and e1 < 1e-9 and ee < 2e-10 and er < 2e-12
+    assert er < ee < e1 < e0
+    assert ne < n0 and nfe < nf0 and ne < n1 and nfe < nf1
+    assert nr < n0 and nfr < nf0 and nr < n1 and nfr < nf1
+
+
 def test_ioup_matrix_transition_against_scipy(oracle):
     """make_transition_matrices!(::IOUP) for a matrix rate (src/priors/ioup.jl:81-131) against an independent evaluation: A = expm(F h)
     and Q = int_0^h expm(F s) L L' expm(F s)' ds by scipy quadrature, for the SDE of test/core/priors.jl:229-262 (d = 2, q = 2, random
