@@ -878,7 +878,7 @@ static int validate_config(const pnode_config* cfg) {
     if (cfg->d < 1) return fail(PNODE_ERR_ARGUMENT, "We currently don't support scalar-valued problems (d >= 1 vector required)"); /* caches.jl:96-98 */
     if (cfg->q < 1 || cfg->q + 1 > PN_MAX_N) return fail(PNODE_ERR_ARGUMENT, "order must satisfy 1 <= order <= 11");
     if (cfg->prior != PNODE_PRIOR_IWP && cfg->prior != PNODE_PRIOR_IOUP)
-        return fail(PNODE_ERR_UNSUPPORTED, "only the IWP and (scalar-rate) IOUP priors are implemented");
+        return fail(PNODE_ERR_UNSUPPORTED, "only the IWP and IOUP priors are implemented");
     if (cfg->prior == PNODE_PRIOR_IOUP) {
         if (cfg->alg == PNODE_DIAGONAL_EK1 || is_mv(cfg->diffusion))
             return fail(PNODE_ERR_UNSUPPORTED, "the IOUP prior is implemented on the dense layout (EK0 / EK1 with a scalar diffusion)");
@@ -901,7 +901,7 @@ static int validate_config(const pnode_config* cfg) {
                 return fail(PNODE_ERR_UNSUPPORTED, "IOUP priors with a vector / matrix / updated rate: plain first-order ODEs without mass matrix, data or observation noise");
         } else {
             if (cfg->d * (cfg->q + 1) > 24)
-                return fail(PNODE_ERR_UNSUPPORTED, "the scalar-rate IOUP prior is implemented for D = d(q+1) <= 24 (register-resident kernels); pass the rate as a vector for larger states");
+                return fail(PNODE_ERR_UNSUPPORTED, "the scalar-rate IOUP prior is implemented for D = d(q+1) <= 24 on the register-resident kernels and, for plain first-order problems without dense output, up to D = 64 on the general-prior path");
             if (cfg->lanes_per_traj == 256) return fail(PNODE_ERR_UNSUPPORTED, "the IOUP prior is not implemented in the CTA kernel");
         }
     } else if (cfg->rate_matrix || cfg->update_rate_parameter) {
@@ -1112,8 +1112,36 @@ static int validate_config(const pnode_config* cfg) {
     return 0;
 }
 
+/* A scalar-rate IOUP beyond the register-resident kernels (24 < D <= 64): IOUP(q, r) is the SDE of IOUP(q, r I) (test/ioup.jl:48-55 runs
+   the four spellings against the same threshold), so the configuration is handed to the general-prior path with the rate matrix r I.
+   Only where that path serves the rest of the configuration; otherwise the original configuration goes on and validate_config names
+   what is missing. */
+struct RatePromotion {
+    pnode_config cfg;
+    std::vector<double> iso;
+};
+static const pnode_config* promote_scalar_rate(const pnode_config* cfg, RatePromotion* w) {
+    if (!cfg || cfg->struct_size != (int32_t)sizeof(pnode_config)) return cfg;
+    if (cfg->prior != PNODE_PRIOR_IOUP || cfg->rate_matrix || cfg->update_rate_parameter || cfg->d < 1 || cfg->q < 1) return cfg;
+    const int D = cfg->d * (cfg->q + 1);
+    if (D <= 24 || D > 64) return cfg;
+    if (cfg->n_saveat > 0 || cfg->mass_matrix || cfg->second_order || cfg->n_data > 0 || has_obsn(cfg) ||
+        (cfg->lanes_per_traj != 0 && cfg->lanes_per_traj != 32))
+        return cfg;
+    w->cfg = *cfg;
+    w->iso.assign((size_t)cfg->d * cfg->d, 0.0);
+    for (int i = 0; i < cfg->d; i++) w->iso[(size_t)i * cfg->d + i] = cfg->rate_parameter;
+    w->cfg.rate_matrix = w->iso.data();
+    return &w->cfg;
+}
+
+static int compile_check_impl(const pnode_config* cfg, int64_t* cubin_bytes);
 /* Validate + NVRTC-compile only (no device needed).  Used by host-side tests and to pre-warm caches. */
 extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes) {
+    RatePromotion promoted;
+    return compile_check_impl(promote_scalar_rate(cfg, &promoted), cubin_bytes);
+}
+static int compile_check_impl(const pnode_config* cfg, int64_t* cubin_bytes) {
     if (!cfg) return fail(PNODE_ERR_ARGUMENT, "null argument");
     int rc = validate_config(cfg);
     if (rc) return rc;
@@ -1159,7 +1187,12 @@ extern "C" int pnode_compile_check(const pnode_config* cfg, int64_t* cubin_bytes
     return 0;
 }
 
+static int create_impl(const pnode_config* cfg, pnode_solver** out);
 extern "C" int pnode_create(const pnode_config* cfg, pnode_solver** out) {
+    RatePromotion promoted; /* the rate matrix is copied to the device inside create_impl: nothing of `promoted` outlives the call */
+    return create_impl(promote_scalar_rate(cfg, &promoted), out);
+}
+static int create_impl(const pnode_config* cfg, pnode_solver** out) {
     if (!cfg || !out) return fail(PNODE_ERR_ARGUMENT, "null argument");
     *out = nullptr;
     {

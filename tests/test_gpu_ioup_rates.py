@@ -137,6 +137,38 @@ def test_exact_rate_matrix_on_the_linear_oscillator_and_api(oracle):
         api.IOUP(3, A, update_rate_parameter=True)
 
 
+def test_exponential_integrators_scalar_problem(oracle):
+    """test/exponential_integrators.jl:6-41 through the Python mirror of the reference API, on the device: u' = p u (d = 1, the smallest
+    state: D = 4), p = -1, t in [0, 10], default tolerances, adaptive steps, smoothing on.  EK0 runs on the Kronecker layout, EK1 on the
+    dense one, ExpEK(L = p) on the scalar-rate IOUP kernels, RosenbrockExpEK on the general-prior path.  The reference's own assertions
+    (end-point errors 1e-7 / 1e-9 / 2e-10 / 2e-12, their ordering, fewer steps and f evaluations for the exponential integrators) and
+    parity with the oracle (same accept / reject counts, same nf, end point 1e-8 of the solution scale)."""
+
+    def lin(du, u, p, t):
+        du[0] = p[0] * u[0]
+
+    prob = api.ODEProblem(lin, [1.0], (0.0, 10.0), [-1.0])
+    rhs = oracle.compile_rhs(tracer.trace(lin, 1, 1), 3)
+    uend = np.exp(-10.0)
+    res = {}
+    for name, alg, okw in (("ek0", api.EK0(order=3), dict(alg=oracle.EK0)), ("ek1", api.EK1(order=3), dict(alg=oracle.EK1)),
+                           ("exp", api.ExpEK(L=-1.0, order=3), dict(alg=oracle.EK0, prior=oracle.PRIOR_IOUP, rate_parameter=-1.0)),
+                           ("ros", api.RosenbrockExpEK(order=3),
+                            dict(alg=oracle.EK1, prior=oracle.PRIOR_IOUP, rate_parameter=None, update_rate_parameter=True))):
+        sol = api.solve(prob, alg)
+        o = oracle.solve(oracle.make_config(1, 3, 1, smooth=True, adaptive=True, t0=0, t1=10, **okw), rhs, [1.0], [-1.0])
+        assert sol.retcode == "Success" and o["retcode"] == "Success"
+        assert (sol.stats.naccept, sol.stats.nreject, sol.stats.nf) == (o["naccept"], o["nreject"], o["nf"]), name
+        assert len(sol.t) == o["n"] and sol.t[-1] == 10.0
+        # smoothed trajectory against the oracle on the scale of the solution (u decays from 1 to 4.5e-5)
+        assert np.max(np.abs(np.asarray(sol.u)[:, 0] - o["pu_mu"][:, 0])) < 1e-8, name
+        res[name] = (abs(sol.u[-1][0] - uend), len(sol.t), sol.stats.nf)
+    (e0, n0, nf0), (e1, n1, nf1), (ee, ne, nfe), (er, nr, nfr) = res["ek0"], res["ek1"], res["exp"], res["ros"]
+    assert e0 < 1e-7 and e1 < 1e-9 and ee < 2e-10 and er < 2e-12
+    assert er < ee < e1 < e0
+    assert ne < n0 and nfe < nf0 and ne < n1 and nfe < nf1 and nr < n0 and nfr < nf0 and nr < n1 and nfr < nf1
+
+
 def test_large_state_through_the_global_workspace(oracle):
     """D = d(q+1) = 28 * 2 = 56 (Pleiades, order 1): the per-warp workspace (10 D^2 doubles and change, 0.3 MB) does not fit in shared
     memory and the filter runs out of a global buffer; diagonal rate, fixed steps, static diffusion, every point against the oracle."""
@@ -148,6 +180,26 @@ def test_large_state_through_the_global_workspace(oracle):
     for i in range(2):
         o = oracle.solve(oracle.make_config(28, 1, 0, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, smooth=False, adaptive=False,
                                             dt=0.01, t0=0.0, t1=0.1, cov_backend=oracle.COV_REF, prior=oracle.PRIOR_IOUP, rate_parameter=rate),
+                         rhs, u0[i], p[i])
+        a, b = g["off"][i], g["off"][i + 1]
+        assert b - a == o["n"] == 11 and g["retcode"][i] == 0
+        assert _rel(g["U"][a:b], o["pu_mu"]) < 1e-10
+        assert _relcov(g["C"][a + 1:b], o["pu_cov"][1:]) < 1e-9
+
+
+def test_scalar_rate_beyond_the_register_kernels(oracle):
+    """IOUP(1, r) on Pleiades (D = 56 > 24, the limit of the register-resident scalar-rate kernels): the library hands the same SDE to
+    the general-prior path as IOUP(1, r I) (pnode_api.cu::promote_scalar_rate; test/ioup.jl:48-55).  Against the oracle's scalar-rate
+    discretisation, fixed steps, static diffusion, every point; and bit-identical to the solve that spells the rate as r I."""
+    pd, u0, p = _inputs("pleiades", 2, 506, du0=1e-3)
+    kw = dict(adaptive=False, dt=0.01, t0=0.0, t1=0.1, diffusion=lib.DIFF_FIXED, calibrate=False, prior=lib.PRIOR_IOUP)
+    g = _gpu(pd, u0, p, 1, builtin=False, save_everystep=True, rate_parameter=-0.5, **kw)
+    gm = _gpu(pd, u0, p, 1, builtin=False, save_everystep=True, rate_parameter=-0.5 * np.eye(28), **kw)
+    assert np.array_equal(g["U"], gm["U"]) and np.array_equal(g["C"], gm["C"])
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 1)
+    for i in range(2):
+        o = oracle.solve(oracle.make_config(28, 1, 0, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, smooth=False, adaptive=False,
+                                            dt=0.01, t0=0.0, t1=0.1, cov_backend=oracle.COV_REF, prior=oracle.PRIOR_IOUP, rate_parameter=-0.5),
                          rhs, u0[i], p[i])
         a, b = g["off"][i], g["off"][i + 1]
         assert b - a == o["n"] == 11 and g["retcode"][i] == 0

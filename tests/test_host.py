@@ -460,3 +460,15 @@ def test_field_ids_and_enums_agree_between_header_and_julia():
     for k, v in jl_vals.items():
         assert k in c_vals, k
         assert c_vals[k] == v, (k, v, c_vals[k])
+
+
+def test_scalar_rate_ioup_beyond_the_register_kernels_goes_to_the_general_path(pnlib):
+    """IOUP(q, r) with 24 < D <= 64 compiles (as IOUP(q, r I) on the general-prior path, pnode_api.cu::promote_scalar_rate); beyond
+    D = 64, or with dense output, the error names the limits."""
+    pd, src = _src("pleiades")
+    kw = dict(d=28, n_p=0, rhs_name="UserProb", rhs_src=src, t0=0.0, t1=0.1, prior=pnlib.PRIOR_IOUP, rate_parameter=-0.5)
+    assert pnlib.compile_check(pnlib.make_config(q=1, **kw)) > 10_000
+    for bad in (dict(q=3), dict(q=1, smooth=True, save_everystep=True, saveat=[0.0, 0.05])):
+        with pytest.raises(pnlib.PnodeError) as e:
+            pnlib.compile_check(pnlib.make_config(**{**kw, **bad}))
+        assert "up to D = 64 on the general-prior path" in str(e.value)
