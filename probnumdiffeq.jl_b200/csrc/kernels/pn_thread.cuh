@@ -33,6 +33,12 @@
 #ifndef PN_THREAD_MINB
 #define PN_THREAD_MINB 1
 #endif
+#ifndef PN_THREAD_EARLY_GRAM
+#define PN_THREAD_EARLY_GRAM 0 /* 1: X'X of the factor is accumulated during the attempt, next to the scalar chain mean -> f, J -> sigma^2 ->
+                                  error estimate (independent work for the same warp); s2 Qh is added once the attempt is accepted -- the order
+                                  of the reference's stacked product (predict.jl:75-85: factor rows first, noise rows after).  A rejected
+                                  attempt then wastes its Gram phase. */
+#endif
 
 /* compile-time loop: f(PnInt<I>{}) for I = B ... E-1.  `#pragma unroll` is a hint that the compiler declines for the large bodies of this
    kernel (measured: the row loop of the Gram phase stayed rolled, with run-time structure tests and branches in the hot path) */
@@ -68,6 +74,32 @@ struct PnThread {
     static __device__ __forceinline__ constexpr bool stored(int r, int c) { return r < RU || c >= r; }
     /* X = R Ah' : entry (r, (j, i)) = sum_{k >= j} T[j][k] R[r][(k, i)] is structurally zero iff no k >= j has a stored entry */
     static __device__ __forceinline__ constexpr bool xnz(int r, int col) { return r < RU || (Q * d + (col % d)) >= r; }
+
+    /* stream the factor: row r of X = R Ah' in flight, M += x x' (upper triangle) */
+    static __device__ __forceinline__ void gram_rows(const double* my, const double (&hp)[n], double (&M)[D][D]) {
+        pn_static_for<0, D>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            double x[D];
+#pragma unroll
+            for (int c = 0; c < D; c++) x[c] = stored(r, c) ? my[slot(r, stored(r, c) ? c : r) * NT] : 0.0;
+#pragma unroll
+            for (int i = 0; i < d; i++)
+#pragma unroll
+                for (int j = 0; j < n; j++) {
+                    if (!xnz(r, j * d + i)) continue;
+                    double s = stored(r, j * d + i) ? x[j * d + i] : 0.0;
+#pragma unroll
+                    for (int k = 0; k < n; k++)
+                        if (k > j && stored(r, k * d + i)) s += hp[k > j ? k - j : 0] * x[k * d + i];
+                    x[j * d + i] = s;
+                }
+#pragma unroll
+            for (int a = 0; a < D; a++)
+#pragma unroll
+                for (int b = 0; b < D; b++)
+                    if (b >= a && xnz(r, a) && xnz(r, b)) M[a][b] = fma(x[a], x[b], M[a][b]);
+        });
+    }
 
     static __device__ void run(const PnParams& P, double* smem) {
         double* const my = smem + threadIdx.x;                  /* slot s at my[s * NT] */
@@ -108,6 +140,13 @@ struct PnThread {
             bool accept = false;
             double h = 0.0, tstop = P.t1, EEst = 0.0, qq = 1.0, ediff = 0.0, lEE = 0.0;
             double hp[n], PIv[n], z[d], J[d * d];
+#if PN_THREAD_EARLY_GRAM
+            double M[D][D]; /* upper triangle: X'X of this attempt -> (accepted) Gram matrix -> predicted factor U */
+#pragma unroll
+            for (int a = 0; a < D; a++)
+#pragma unroll
+                for (int b = 0; b < D; b++) M[a][b] = 0.0;
+#endif
 #pragma unroll
             for (int k = 0; k < n; k++) hp[k] = (k == 0) ? 1.0 : 0.0;
 #pragma unroll
@@ -147,6 +186,9 @@ struct PnThread {
                 const double sqh = h * pn_rsqrt(h);
 #pragma unroll
                 for (int c = 0; c < n; c++) PIv[c] = hp[Q - c] * sqh;
+#if PN_THREAD_EARLY_GRAM
+                gram_rows(my, hp, M); /* independent of everything below up to the accept decision */
+#endif
                 /* predict_mean!: mu^- = (T (x) I) mu */
                 double mup[D];
 #pragma unroll
@@ -253,11 +295,13 @@ struct PnThread {
                 dt = dtnew;
 
                 /* ============ (C) covariance predict + update ============ */
+#if !PN_THREAD_EARLY_GRAM
                 double M[D][D]; /* upper triangle: Gram matrix -> predicted factor U */
 #pragma unroll
                 for (int a = 0; a < D; a++)
 #pragma unroll
                     for (int b = 0; b < D; b++) M[a][b] = 0.0;
+#endif
                 /* s2 Qh = s2 (P^-1 Qb P^-1) (x) I_d */
 #pragma unroll
                 for (int m = 0; m < n; m++)
@@ -266,31 +310,11 @@ struct PnThread {
                         if (c < m) continue;
                         const double v = P.Qb[m * n + c] * (PIv[m] * ediff) * PIv[c];
 #pragma unroll
-                        for (int i = 0; i < d; i++) M[m * d + i][c * d + i] = v;
+                        for (int i = 0; i < d; i++) M[m * d + i][c * d + i] = PN_THREAD_EARLY_GRAM ? M[m * d + i][c * d + i] + v : v;
                     }
-                /* stream the factor: row r of X = R Ah' in flight, M += x x' */
-                pn_static_for<0, D>([&](auto rc) {
-                    constexpr int r = decltype(rc)::value;
-                    double x[D];
-#pragma unroll
-                    for (int c = 0; c < D; c++) x[c] = stored(r, c) ? my[slot(r, stored(r, c) ? c : r) * NT] : 0.0;
-#pragma unroll
-                    for (int i = 0; i < d; i++)
-#pragma unroll
-                        for (int j = 0; j < n; j++) {
-                            if (!xnz(r, j * d + i)) continue;
-                            double s = stored(r, j * d + i) ? x[j * d + i] : 0.0;
-#pragma unroll
-                            for (int k = 0; k < n; k++)
-                                if (k > j && stored(r, k * d + i)) s += hp[k > j ? k - j : 0] * x[k * d + i];
-                            x[j * d + i] = s;
-                        }
-#pragma unroll
-                    for (int a = 0; a < D; a++)
-#pragma unroll
-                        for (int b = 0; b < D; b++)
-                            if (b >= a && xnz(r, a) && xnz(r, b)) M[a][b] = fma(x[a], x[b], M[a][b]);
-                });
+#if !PN_THREAD_EARLY_GRAM
+                gram_rows(my, hp, M);
+#endif
                 /* Cholesky in registers (right-looking, upper) */
                 bool okc = true;
                 pn_static_for<0, D>([&](auto kc) {
