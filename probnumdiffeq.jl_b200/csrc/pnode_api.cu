@@ -938,11 +938,13 @@ static int validate_config(const pnode_config* cfg) {
         return fail(PNODE_ERR_UNSUPPORTED,
                     "only the covariance factorization the reference selects for this algorithm / diffusion model is implemented "
                     "(covariance_structure, src/algorithms.jl:132-151)");
-    if (layout == PNODE_COV_KRONECKER && cfg->q > 7)
-        return fail(PNODE_ERR_UNSUPPORTED, "EK0 thread-per-trajectory kernel supports order <= 7");
+    /* pn_kron.cuh keeps the n x n factor and the n x d mean in one thread; beyond order 7 they no longer fit the register file and the
+       compiler places them in thread-local memory (L1-resident): slower per step, same arithmetic (test/correctness.jl runs EK0(order=8)) */
     if (layout == PNODE_COV_BLOCKS) {
-        if (cfg->d * (cfg->q + 1) * (cfg->q + 1) > 160)
-            return fail(PNODE_ERR_UNSUPPORTED, "blocks-of-diagonals thread-per-trajectory kernel keeps d (q+1)^2 <= 160 doubles in registers");
+        /* pn_blocks.cuh keeps the d factors of n x n in one thread: registers up to about 160 doubles, thread-local memory beyond (e.g.
+           Pleiades with the DiagonalEK1: 448 doubles); the bound keeps compile time and the local-memory footprint of a launch in check */
+        if (cfg->d * (cfg->q + 1) * (cfg->q + 1) > 512)
+            return fail(PNODE_ERR_UNSUPPORTED, "the blocks-of-diagonals thread-per-trajectory kernel is built for d (q+1)^2 <= 512 doubles of factors per trajectory");
         if (cfg->n_forced > 0) return fail(PNODE_ERR_UNSUPPORTED, "forced_diffusion is a scalar-diffusion test hook");
         if (cfg->smooth && smooth_lanes(D) == 0)
             return fail(PNODE_ERR_UNSUPPORTED, "smoothing on the blocks-of-diagonals layout needs the register-resident sweep (D <= 24)");

@@ -472,3 +472,18 @@ def test_scalar_rate_ioup_beyond_the_register_kernels_goes_to_the_general_path(p
         with pytest.raises(pnlib.PnodeError) as e:
             pnlib.compile_check(pnlib.make_config(**{**kw, **bad}))
         assert "up to D = 64 on the general-prior path" in str(e.value)
+
+
+def test_structured_layouts_beyond_the_register_budget_compile(pnlib):
+    """EK0 at order 8 / 11 (Kronecker layout) and the blocks layout at d = 28 (DiagonalEK1, EK0 + DynamicMVDiffusion on Pleiades) compile:
+    the factors then live in thread-local memory.  Beyond d (q+1)^2 = 512 the blocks kernel says so."""
+    pd, src = _src("lotka_volterra")
+    for q in (8, 11):
+        assert pnlib.compile_check(pnlib.make_config(d=2, q=q, n_p=4, rhs_name="UserProb", rhs_src=src, t0=0.0, t1=1.0, alg=pnlib.EK0)) > 10_000
+    pd, src = _src("pleiades")
+    kw = dict(d=28, n_p=0, rhs_name="UserProb", rhs_src=src, t0=0.0, t1=0.1)
+    assert pnlib.compile_check(pnlib.make_config(q=3, alg=pnlib.DIAGONAL_EK1, **kw)) > 10_000
+    assert pnlib.compile_check(pnlib.make_config(q=3, alg=pnlib.EK0, diffusion=pnlib.DIFF_DYNAMIC_MV, **kw)) > 10_000
+    with pytest.raises(pnlib.PnodeError) as e:
+        pnlib.compile_check(pnlib.make_config(q=5, alg=pnlib.DIAGONAL_EK1, **kw))
+    assert e.value.kind == "Unsupported" and "512" in str(e.value)
