@@ -227,7 +227,9 @@ const char* pnode_last_error(void);
 /* ABI version of this header. */
 int pnode_abi_version(void);
 
-/* Validate the configuration, compile (NVRTC, sm_100a) or look up the kernels, allocate the work queue. */
+/* Validate the configuration, compile (NVRTC, sm_100a) or look up the kernels, allocate the work queue.  NVRTC results are cached per
+   process (key: generated program text + compile-time options), so a second solver of the same right-hand side and compile-time
+   configuration -- another tspan, tolerance, ensemble -- does not compile again (PNODE_NVRTC_CACHE=0 turns the cache off). */
 int pnode_create(const pnode_config* cfg, pnode_solver** out);
 void pnode_destroy(pnode_solver* s);
 /* Validate the configuration and run NVRTC only (no device needed); *cubin_bytes = size of the sm_100a CUBIN

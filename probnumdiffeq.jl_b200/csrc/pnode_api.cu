@@ -384,7 +384,45 @@ static std::string kernel_key(const pnode_solver* s, int save) {
     return buf;
 }
 
+/* Process-wide cache of NVRTC results, keyed by the complete input of a compilation (program text + every option; the embedded headers
+   are fixed per build of this library).  Creating a second solver for the same right-hand side and configuration -- every call of the host
+   mirrors' `solve` does -- then costs a lookup instead of seconds of compile time.  PNODE_NVRTC_CACHE=0 turns it off. */
+#include <map>
+#include <mutex>
+static std::mutex g_cubin_mutex;
+static std::map<std::string, std::vector<char>> g_cubin_cache;
+static size_t g_cubin_cache_bytes = 0;
+static int nvrtc_compile_uncached(const std::string& src, std::vector<std::string> defs, std::vector<char>* cubin);
 static int nvrtc_compile(const std::string& src, std::vector<std::string> defs, std::vector<char>* cubin) {
+    const char* off = getenv("PNODE_NVRTC_CACHE");
+    if (off && atoi(off) == 0) return nvrtc_compile_uncached(src, defs, cubin);
+    std::string key;
+    for (auto& x : defs) {
+        key += x;
+        key.push_back('\n');
+    }
+    if (const char* e = getenv("PNODE_NVRTC_FLAGS")) key += e;
+    key.push_back('\0');
+    key += src;
+    {
+        std::lock_guard<std::mutex> lk(g_cubin_mutex);
+        auto it = g_cubin_cache.find(key);
+        if (it != g_cubin_cache.end()) {
+            *cubin = it->second;
+            return 0;
+        }
+    }
+    int rc = nvrtc_compile_uncached(src, defs, cubin);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_cubin_mutex);
+    if (g_cubin_cache_bytes + cubin->size() > ((size_t)512 << 20)) { /* bound the footprint: start over */
+        g_cubin_cache.clear();
+        g_cubin_cache_bytes = 0;
+    }
+    if (g_cubin_cache.emplace(key, *cubin).second) g_cubin_cache_bytes += cubin->size();
+    return 0;
+}
+static int nvrtc_compile_uncached(const std::string& src, std::vector<std::string> defs, std::vector<char>* cubin) {
     nvrtcProgram prog;
     const char* hdr_src[PN_N_EMBEDDED];
     const char* hdr_name[PN_N_EMBEDDED];

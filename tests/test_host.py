@@ -487,3 +487,25 @@ def test_structured_layouts_beyond_the_register_budget_compile(pnlib):
     with pytest.raises(pnlib.PnodeError) as e:
         pnlib.compile_check(pnlib.make_config(q=5, alg=pnlib.DIAGONAL_EK1, **kw))
     assert e.value.kind == "Unsupported" and "512" in str(e.value)
+
+
+def test_nvrtc_results_are_cached_per_process(pnlib, monkeypatch):
+    """A second solver for the same right-hand side and compile-time configuration does not compile again (pnode_api.cu::nvrtc_compile):
+    run-time parameters (tspan, tolerances) are not part of the key, compile-time ones (order) are; PNODE_NVRTC_CACHE=0 turns it off."""
+    import time
+    pd, src = _src("orego")
+    kw = dict(d=3, n_p=3, rhs_name="UserProb", rhs_src=src + "\n// cache test\n", t0=0.0)
+
+    def timed(**extra):
+        t = time.perf_counter()
+        n = pnlib.compile_check(pnlib.make_config(**{**kw, **extra}))
+        return n, time.perf_counter() - t
+
+    n1, cold = timed(q=3, t1=1.0)
+    n2, warm = timed(q=3, t1=2.0, abstol=1e-8)
+    assert n1 == n2 and warm < 0.2 * cold
+    n3, other = timed(q=2, t1=1.0)
+    assert n3 != n1 and other > 5 * warm
+    monkeypatch.setenv("PNODE_NVRTC_CACHE", "0")
+    n4, off = timed(q=3, t1=1.0)
+    assert n4 == n1 and off > 5 * warm
