@@ -15,15 +15,15 @@ Field-compatible stand-in for `ProbNumDiffEq.ProbODESolution`: `u, pu, t, x_filt
 stats, retcode`.  `pu[k]` and the entries of `x_filt` / `x_smooth` are `ProbNumDiffEq.Gaussian`s with `PSDMatrix` covariances
 (`Σ.R` is the right factor the library returns).
 """
-struct B200ODESolution{uType,puType,tType,xType,diffType,P,A,S} <: SciMLBase.AbstractODESolution{Float64,2,uType}
+struct B200ODESolution{uType,puType,tType,xfType,xsType,diffType,P,A,S} <: SciMLBase.AbstractODESolution{Float64,2,uType}
     u::uType
     pu::puType
     u_analytic::Nothing
     errors::Nothing
     t::tType
     k::Nothing
-    x_filt::xType
-    x_smooth::xType
+    x_filt::xfType      # Vector of Gaussians, or `nothing`: the library returns ONE state record per point (smoothed if alg.smooth)
+    x_smooth::xsType
     diffusions::diffType
     backward_kernels::Nothing
     pnstats::B200PNStats

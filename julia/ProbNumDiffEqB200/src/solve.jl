@@ -38,8 +38,18 @@ function rate_of(p, d::Int)
     size(R) == (d, d) || throw(DimensionMismatch("the IOUP rate parameter must be a number, a vector of length $d or a $d x $d matrix"))
     return (0.0, collect(vec(permutedims(R))), 0)        # row-major for the C side
 end
+"`initial_diffusion` of a FixedMVDiffusion (a number, a vector or a Diagonal, src/diffusions/typedefs.jl:83-99) as the ONE number the ABI takes."
+function uniform_initial_diffusion(x)
+    x isa Number && return Float64(x)
+    v = x isa LinearAlgebra.Diagonal ? x.diag : x
+    (x isa AbstractMatrix && !(x isa LinearAlgebra.Diagonal)) && throw(ArgumentError(
+        "Invalid `initial_diffusion`. The `FixedMVDiffusion` assumes a dense diagonal diffusion model. So, pass either a Number, a Vector, or a `Diagonal` matrix!"))
+    all(==(first(v)), v) || throw(ArgumentError("libpnode_cuda takes one initial diffusion for all components: a FixedMVDiffusion with " *
+                                                "different per-component initial values is not supported by EnsembleB200"))
+    return Float64(first(v))
+end
 function diffusion_fields(m)
-    m isa ProbNumDiffEq.FixedMVDiffusion && return (PNODE_DIFF_FIXED_MV, m.calibrate ? 1 : 0, Float64(first(m.initial_diffusion)))
+    m isa ProbNumDiffEq.FixedMVDiffusion && return (PNODE_DIFF_FIXED_MV, m.calibrate ? 1 : 0, uniform_initial_diffusion(m.initial_diffusion))
     m isa ProbNumDiffEq.DynamicMVDiffusion && return (PNODE_DIFF_DYNAMIC_MV, 0, 1.0)
     m isa ProbNumDiffEq.FixedDiffusion && return (PNODE_DIFF_FIXED, m.calibrate ? 1 : 0, Float64(m.initial_diffusion))
     return (PNODE_DIFF_DYNAMIC, 0, 1.0)
@@ -109,26 +119,33 @@ function make_config(prob, alg, device::Integer, lanes::Integer; adaptive, dt, a
     return ConfigBundle(Ref(cfg), keep)
 end
 
-"Checks the reference performs before a solve starts (src/checks.jl, src/caches.jl:96-98, test/errors_thrown.jl)."
-function check_problem(prob, alg; adaptive, dt, save_everystep)
-    length(prob.u0) >= 1 || error("We currently don't support scalar-valued problems")
+"""
+Checks the reference performs before a solve starts, with its exception types and messages: `ErrorException`s of src/checks.jl:1-21 and
+src/caches.jl:96-98, the `ArgumentError` for fixed steps without `dt` (raised upstream; test/errors_thrown.jl:6-8).
+"""
+function check_problem(prob, alg; adaptive, dt, save_everystep, dense)
     prob.u0 isa Number && error("We currently don't support scalar-valued problems")
+    if prob.f isa SciMLBase.DynamicalODEFunction && !(prob.problem_type isa SciMLBase.SecondOrderODEProblem)
+        error("The given problem is a `DynamicalODEProblem`, but not a `SecondOrderODEProblem`.\n" *
+              "This can not be handled by ProbNumDiffEq.jl right now. Please check if the\n" *
+              "problem can be formulated as a second order ODE. If not, please open a new\ngithub issue!")
+    end
+    (dense && !alg.smooth) && error("To use `dense=true` you need to set `smooth=true`!")
+    (!save_everystep && alg.smooth) && error("If you set `save_everystep=false` also set `smooth=false` in the alg!")
     (!adaptive && !(dt > 0)) && throw(ArgumentError("Fixed timestep methods require a choice of dt or choosing the tstops"))
-    (alg.smooth && !save_everystep) &&
-        throw(ArgumentError("If you do not want to save everystep, set `smooth=false` in the solver"))
     return nothing
 end
 
 function SciMLBase.__solve(ep::SciMLBase.AbstractEnsembleProblem, alg::ProbNumDiffEq.AbstractEK, ens::EnsembleB200;
                            trajectories::Integer, adaptive=true, dt=0.0, abstol=1e-6, reltol=1e-3, save_everystep=true,
-                           save_state=false, maxiters=1_000_000, dtmin=0.0, dtmax=0.0, tstops=nothing, saveat=nothing,
+                           dense=save_everystep && alg.smooth, save_state=false, maxiters=1_000_000, dtmin=0.0, dtmax=0.0, tstops=nothing, saveat=nothing,
                            beta1=0.0, beta2=0.0, qmin=0.2, qmax=10.0, gamma=0.9, qsteady_min=1.0, qsteady_max=1.0, qoldinit=1e-4,
                            kwargs...)
     t_start = time()
     N = Int(trajectories)
     probs = [ep.prob_func(deepcopy(ep.prob), i, 1) for i in 1:N]
     prob = ep.prob
-    check_problem(prob, alg; adaptive, dt, save_everystep)
+    check_problem(prob, alg; adaptive, dt, save_everystep, dense)
     second = prob.f isa SciMLBase.DynamicalODEFunction
     dsol = length(prob.u0)                               # length of sol.u: (du, u) for second-order problems
     d = second ? dsol ÷ 2 : dsol
