@@ -208,6 +208,59 @@ def test_backward_kernel_and_marginalize_vs_dense_rts(oracle, diffusion):
     assert np.allclose(R.T @ R, Pm + Gt @ (Ps - P_p) @ Gt.T, rtol=1e-7, atol=1e-9)
 
 
+@pytest.mark.parametrize("D,d", [(2, 1), (4, 1), (8, 2), (12, 3), (9, 3), (28, 7)])
+def test_filter_identities_over_state_shapes(oracle, D, d):
+    """The identities of test/core/filtering.jl (predict :13-99, update :121-243, backward kernel and smoothing step :368-510) on random
+    inputs for the state shapes of the configurations this repository runs -- the smallest (one component, order 1), the BASELINE
+    shapes D = 8 and 12, an odd shape, and a D = 28 state -- with both covariance back-ends."""
+    rng, m, PR, A, QR = _rand_setup(100 + D, D)
+    L = oracle.lib()
+    Pm = PR.T @ PR
+    for diffusion in (1.0, 0.37):
+        P_p = A @ Pm @ A.T + diffusion * (QR.T @ QR)
+        Rps = []
+        for backend in (0, 1):
+            Rp = np.zeros(D * D)
+            L.oracle_predict_cov(D, P(F(PR).ravel(order="F")), P(F(A).ravel(order="F")), P(F(QR).ravel(order="F")), C.c_double(diffusion),
+                                 backend, P(Rp), None)
+            R = from_f(Rp, (D, D))
+            assert np.allclose(R.T @ R, P_p, rtol=1e-10, atol=1e-12 * np.abs(P_p).max())
+            assert np.allclose(R, np.triu(R))
+            Rps.append(Rp)
+        # update with a random measurement matrix (d x D)
+        H = rng.random((d, D))
+        z = rng.random(d)
+        mu = np.zeros(D)
+        Rout = np.zeros(D * D)
+        ll = C.c_double(0)
+        m_p = A @ m
+        assert L.oracle_update(D, d, P(m_p), P(Rps[0]), P(z), P(F(H).ravel(order="F")), P(mu), P(Rout), C.byref(ll)) == 0
+        S = H @ P_p @ H.T
+        K = P_p @ H.T @ np.linalg.inv(S)
+        R = from_f(Rout, (D, D))
+        assert np.allclose(mu, m_p - K @ z, rtol=1e-9, atol=1e-11)
+        assert np.allclose(R.T @ R, P_p - K @ S @ K.T, rtol=1e-8, atol=1e-10 * np.abs(P_p).max())
+        assert np.isclose(ll.value, multivariate_normal(mean=np.zeros(d), cov=S).logpdf(z), rtol=1e-9)
+        # backward kernel + one smoothing step
+        G = np.zeros(D * D)
+        b = np.zeros(D)
+        LR = np.zeros(2 * D * D)
+        L.oracle_backward_kernel(D, P(m), P(F(PR).ravel(order="F")), P(m_p), P(Rps[1]), P(F(A).ravel(order="F")), P(F(QR).ravel(order="F")),
+                                 C.c_double(diffusion), P(G), P(b), P(LR))
+        Gt = Pm @ A.T @ np.linalg.inv(P_p)
+        scale = np.abs(Gt).max()
+        assert np.allclose(from_f(G, (D, D)), Gt, rtol=1e-6, atol=1e-8 * scale)
+        LRm = from_f(LR, (2 * D, D))
+        assert np.allclose(LRm.T @ LRm, Pm - Gt @ P_p @ Gt.T, rtol=1e-5, atol=1e-7 * np.abs(Pm).max() * max(1.0, scale * scale))
+        m_s = rng.random(D)
+        PsR = np.triu(rng.random((D, D)))
+        L.oracle_marginalize(D, P(m_s), P(F(PsR).ravel(order="F")), P(G), P(b), P(LR), P(mu), P(Rout))
+        R = from_f(Rout, (D, D))
+        want = Pm + Gt @ (PsR.T @ PsR - P_p) @ Gt.T
+        assert np.allclose(mu, m + Gt @ (m_s - m_p), rtol=1e-6, atol=1e-8 * scale)
+        assert np.allclose(R.T @ R, want, rtol=1e-5, atol=1e-7 * np.abs(want).max())
+
+
 # ----------------------------------------------------------------------------------------------------
 # end-to-end pins
 # ----------------------------------------------------------------------------------------------------
