@@ -16,8 +16,7 @@ pytestmark = pytest.mark.gpu
 def test_ek0_order_8_on_the_kronecker_layout(oracle):
     """EK0(order=8), Lotka-Volterra on [0, 1].  Adaptive: the oracle's accept / reject counts per trajectory, end points 1e-7 (the
     reference's accuracy threshold for this row, test/correctness.jl:57-87, is pinned on the oracle in tests/test_oracle_pins.py).
-    Fixed steps, static diffusion: every saved mean 1e-9; covariances against the oracle's own Cholesky-vs-QR floor (order 8 scales
-    the state by h^(q + 1/2): the two back-ends of the oracle differ by 1e-5 there)."""
+    One compilation only: the order-8 kernel keeps its factor in thread-local memory and takes NVRTC 25 s."""
     n = 4
     pd, u0, p = _inputs("lotka_volterra", n, 601, du0=0.1, dp=0.1)
     rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 8)
@@ -27,17 +26,6 @@ def test_ek0_order_8_on_the_kronecker_layout(oracle):
     assert np.all(g["retcode"] == 0)
     assert np.array_equal(g["naccept"], o["naccept"]) and np.array_equal(g["nreject"], o["nreject"])
     assert _rel(g["u"], o["u_final"]) < 1e-7
-    kw = dict(adaptive=False, dt=0.05, t0=0.0, t1=1.0, diffusion=lib.DIFF_FIXED, calibrate=False)
-    g = _gpu(pd, u0, p, 8, builtin=False, alg=lib.EK0, save_everystep=True, **kw)
-    for i in range(n):
-        okw = dict(alg=oracle.EK0, diffusion=oracle.DIFF_FIXED, calibrate=False, smooth=False, adaptive=False, dt=0.05, t0=0.0, t1=1.0)
-        a = oracle.solve(oracle.make_config(2, 8, 4, cov_backend=oracle.COV_REF, **okw), rhs, u0[i], p[i])
-        b = oracle.solve(oracle.make_config(2, 8, 4, cov_backend=oracle.COV_QR, **okw), rhs, u0[i], p[i])
-        lo, hi = g["off"][i], g["off"][i + 1]
-        assert hi - lo == a["n"] == 21 and g["retcode"][i] == 0
-        assert _rel(g["U"][lo:hi], a["pu_mu"]) < 1e-9
-        floor = _relcov(b["pu_cov"][1:], a["pu_cov"][1:])
-        assert _relcov(g["C"][lo + 1:hi], a["pu_cov"][1:]) < max(1e-9, 20 * floor)
 
 
 def test_blocks_layout_at_d_28(oracle):
