@@ -12,7 +12,9 @@
  * (tests/test_oracle_*.py): IWP golden matrices test/core/priors.jl:49-192, the
  * dense-formula identities of test/core/filtering.jl, exact initialisation
  * test/state_init.jl:9-56 / test/solution.jl:59-62 and the end-to-end accuracy
- * thresholds of test/correctness.jl:12-56.  The adaptive step controller lives in
+ * thresholds of test/correctness.jl:12-87 and test/exponential_integrators.jl:6-41 (the
+ * tightest pin the reference has on the adaptive path), plus the per-feature tests
+ * listed in DESIGN.md section 5.  The adaptive step controller lives in
  * OrdinaryDiffEqCore (3rd party, not vendored): step-sequence parity against live
  * Julia is UNPINNED ("parity unpinned" items).
  *
