@@ -32,7 +32,7 @@ def _to_mp(M):
 
 
 def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=None, second_order=False, obs_noise=None, diag_jac=False,
-                          mv=False):
+                          mv=False, dense_ts=None):
     """Returns numpy arrays: filtered / smoothed means [N+1, D] and covariances [N+1, D, D], local diffusions [N], the running MLE of the
     global diffusion, the log-likelihood, and the log-likelihood with the scalar (Kronecker-factor) log-determinant.
 
@@ -72,14 +72,15 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
     sub = dict(zip(xs, [sp.Rational(str(x)) for x in u0]))
     m = mp.matrix([mp.mpf(sp.N(e.subs(sub), 80)) for dk in derivs[:n] for e in dk])
     h = mp.mpf(str(h))
-    if rate is None:
-        A1, Q1 = mp.matrix(n, n), mp.matrix(n, n)
-        for i in range(n):
-            for j in range(n):
-                A1[i, j] = h ** (j - i) / mp.factorial(j - i) if j >= i else 0
-                Q1[i, j] = h ** (2 * q + 1 - i - j) / ((2 * q + 1 - i - j) * mp.factorial(q - i) * mp.factorial(q - j))
-        A, Q = _kron_identity(A1, d), _kron_identity(Q1, d)
-    else:                                                # dx = F x dt + L dW, F = shift (x) I + e_q e_q' (x) rate, L = e_q (x) I
+    def transition(h):
+        if rate is None:
+            A1, Q1 = mp.matrix(n, n), mp.matrix(n, n)
+            for i in range(n):
+                for j in range(n):
+                    A1[i, j] = h ** (j - i) / mp.factorial(j - i) if j >= i else 0
+                    Q1[i, j] = h ** (2 * q + 1 - i - j) / ((2 * q + 1 - i - j) * mp.factorial(q - i) * mp.factorial(q - j))
+            return _kron_identity(A1, d), _kron_identity(Q1, d)
+        # dx = F x dt + L dW, F = shift (x) I + e_q e_q' (x) rate, L = e_q (x) I
         F = mp.zeros(D, D)
         for jj in range(q):
             for a in range(d):
@@ -94,8 +95,10 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
         blk = mp.zeros(2 * D, 2 * D)
         blk[:D, :D], blk[:D, D:], blk[D:, D:] = -F * h, LLt * h, F.T * h
         E = mp.expm(blk)
-        A = E[D:, D:].T
-        Q = A * E[:D, D:]
+        At = E[D:, D:].T
+        return At, At * E[:D, D:]
+
+    A, Q = transition(h)
     sel = lambda k: _kron_identity(mp.matrix([[1 if c == k else 0 for c in range(n)]]), d)
     E0, E1 = sel(0), sel(1)
     E2 = sel(2) if second_order else None
@@ -155,7 +158,25 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
         sP[k] = fP[k] + G * (sP[k + 1] - pP[k]) * G.T
     vec = lambda x: np.array([float(v) for v in x])
     mat = lambda M: np.array([[float(M[i, j]) for j in range(M.cols)] for i in range(M.rows)])
-    return dict(fm=np.array([vec(x) for x in fm]), fP=np.array([mat(x) for x in fP]), sm=np.array([vec(x) for x in sm]),
+    dense = {}
+    if dense_ts is not None:
+        # sol(t) (src/solution.jl:330-398): predict the filtering estimate of the last saved point over h1 with that interval's diffusion, then
+        # one smoothing step against the next smoothed estimate over h2
+        dm, dP = [], []
+        for tv in dense_ts:
+            tv = mp.mpf(str(tv))
+            k = int(mp.floor(tv / h))
+            h1, h2 = tv - k * h, (k + 1) * h - tv
+            A1_, Q1_ = transition(h1)
+            A2_, Q2_ = transition(h2)
+            sk = sig[k]
+            m_p, P_p = A1_ * fm[k], A1_ * fP[k] * A1_.T + sk * Q1_
+            m_2, P_2 = A2_ * m_p, A2_ * P_p * A2_.T + sk * Q2_
+            G = P_p * A2_.T * P_2 ** -1
+            dm.append(m_p + G * (sm[k + 1] - m_2))
+            dP.append(P_p + G * (sP[k + 1] - P_2) * G.T)
+        dense = dict(dm=np.array([vec(x) for x in dm]), dP=np.array([mat(x) for x in dP]))
+    return dict(**dense, fm=np.array([vec(x) for x in fm]), fP=np.array([mat(x) for x in fP]), sm=np.array([vec(x) for x in sm]),
                 sP=np.array([mat(x) for x in sP]), sig=np.array([vec(x) if isinstance(x, list) else float(x) for x in sig]), gd=float(gd),
                 gd_mv=vec(gd_mv), ll=float(ll), ll_kron=float(ll_kron))
 
@@ -334,3 +355,21 @@ def test_blocks_layout_trajectories(oracle):
     assert np.max(np.abs(s["pu_mu"] - ref["sm"][:, :2])) < 1e-10
     want = ref["sP"][1:, :2, :2] * np.sqrt(np.outer(ref["gd_mv"], ref["gd_mv"]))[None]
     assert _relc(s["pu_cov"][1:], want) < 1e-8
+
+
+@pytest.mark.parametrize("dynamic", [False, True], ids=["fixed", "dynamic"])
+def test_dense_output(oracle, dynamic):
+    """sol(t) between the saved points (src/solution.jl:330-398, src/filtering/smooth.jl:43-65) against the 60-digit evaluation of the same
+    two-stage formula: means 1e-9, covariances 1e-6 (dynamic diffusion) / 1e-8."""
+    mp.mp.dps = 60
+    f, u0, p, q, h, N = problems.lotka_volterra, [1.0, 1.0], [1.5, 1.0, 3.0, 1.0], 3, "0.02", 30
+    ts = ["0.005", "0.031", "0.3", "0.4137", "0.59"]
+    ref = dense_filter_smoother(f, u0, p, q, h, N, True, dynamic, dense_ts=ts)
+    rhs = oracle.compile_rhs(tracer.trace(f, 2, 4), q)
+    cfg = oracle.make_config(2, q, 4, alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC if dynamic else oracle.DIFF_FIXED, calibrate=False, smooth=True,
+                             adaptive=False, dt=float(h), t0=0.0, t1=float(h) * N, save_everystep=True)
+    s = oracle.solve(cfg, rhs, u0, p)
+    for k, tv in enumerate(ts):
+        mu, cov = oracle.interpolate(cfg, s, float(tv))
+        assert np.max(np.abs(mu - ref["dm"][k, :2])) < 1e-9
+        assert np.linalg.norm(cov - ref["dP"][k, :2, :2]) / np.linalg.norm(ref["dP"][k, :2, :2]) < (1e-6 if dynamic else 1e-8)
