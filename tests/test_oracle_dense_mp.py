@@ -32,7 +32,7 @@ def _to_mp(M):
 
 
 def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=None, second_order=False, obs_noise=None, diag_jac=False,
-                          mv=False, dense_ts=None):
+                          mv=False, dense_ts=None, tols=None):
     """Returns numpy arrays: filtered / smoothed means [N+1, D] and covariances [N+1, D, D], local diffusions [N], the running MLE of the
     global diffusion, the log-likelihood, and the log-likelihood with the scalar (Kronecker-factor) log-determinant.
 
@@ -71,7 +71,12 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
         derivs = [derivs[0]] + [Minv * dk for dk in derivs[1:]]
     sub = dict(zip(xs, [sp.Rational(str(x)) for x in u0]))
     m = mp.matrix([mp.mpf(sp.N(e.subs(sub), 80)) for dk in derivs[:n] for e in dk])
-    h = mp.mpf(str(h))
+    hs = None
+    if isinstance(h, (list, tuple, np.ndarray)):      # variable steps: one transition pair per step (exact binary values of the doubles)
+        hs = [mp.mpf(float(x)) for x in h]
+        h = hs[0]
+    else:
+        h = mp.mpf(str(h))
     def transition(h):
         if rate is None:
             A1, Q1 = mp.matrix(n, n), mp.matrix(n, n)
@@ -99,6 +104,7 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
         return At, At * E[:D, D:]
 
     A, Q = transition(h)
+    As = []
     sel = lambda k: _kron_identity(mp.matrix([[1 if c == k else 0 for c in range(n)]]), d)
     E0, E1 = sel(0), sel(1)
     E2 = sel(2) if second_order else None
@@ -110,7 +116,11 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
     fm, fP, pm, pP, sig = [m.copy()], [P.copy()], [], [], []
     ll = ll_kron = gd = mp.mpf(0)
     gd_mv = [mp.mpf(0)] * d
+    eest = []
     for k in range(nsteps):
+        if hs is not None:
+            A, Q = transition(hs[k])
+        As.append(A)
         mpred = A * m
         if second_order:
             xin = list(E1 * mpred) + list(E0 * mpred)
@@ -126,6 +136,15 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
                 Jx = mp.diag([Jx[a, a] for a in range(d)])
             H = lhs - Jx * E0 if ek1 else lhs
         W = H * Q * H.T
+        if tols is not None:
+            # local error estimate (src/perform_step.jl:199-247): e_i = h sqrt(sigma^2_loc W_ii), scaled by abstol + max(|u^-_i|, |uprev_i|) reltol, RMS over i
+            s2l = (z.T * mp.lu_solve(W, z))[0] / d
+            hk = hs[k] if hs is not None else h
+            acc = mp.mpf(0)
+            for a in range(d):
+                sc = tols[0] + max(abs((E0 * mpred)[a]), abs((E0 * m)[a])) * tols[1]
+                acc += (hk * mp.sqrt(s2l * W[a, a]) / sc) ** 2
+            eest.append(mp.sqrt(acc / d))
         if mv and dynamic:
             s2 = [z[a] ** 2 / W[a, a] for a in range(d)]
             Qs = mp.zeros(D, D)
@@ -153,7 +172,7 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
     sm, sP = [None] * (nsteps + 1), [None] * (nsteps + 1)
     sm[nsteps], sP[nsteps] = fm[nsteps], fP[nsteps]
     for k in range(nsteps - 1, -1, -1):
-        G = fP[k] * A.T * pP[k] ** -1 if k > 0 else mp.zeros(D, D)      # P_0 = 0: G = 0, the initial state stays exact
+        G = fP[k] * As[k].T * pP[k] ** -1 if k > 0 else mp.zeros(D, D)      # P_0 = 0: G = 0, the initial state stays exact
         sm[k] = fm[k] + G * (sm[k + 1] - pm[k])
         sP[k] = fP[k] + G * (sP[k + 1] - pP[k]) * G.T
     vec = lambda x: np.array([float(v) for v in x])
@@ -176,6 +195,7 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
             dm.append(m_p + G * (sm[k + 1] - m_2))
             dP.append(P_p + G * (sP[k + 1] - P_2) * G.T)
         dense = dict(dm=np.array([vec(x) for x in dm]), dP=np.array([mat(x) for x in dP]))
+    dense["eest"] = np.array([float(x) for x in eest])
     return dict(**dense, fm=np.array([vec(x) for x in fm]), fP=np.array([mat(x) for x in fP]), sm=np.array([vec(x) for x in sm]),
                 sP=np.array([mat(x) for x in sP]), sig=np.array([vec(x) if isinstance(x, list) else float(x) for x in sig]), gd=float(gd),
                 gd_mv=vec(gd_mv), ll=float(ll), ll_kron=float(ll_kron))
@@ -373,3 +393,30 @@ def test_dense_output(oracle, dynamic):
         mu, cov = oracle.interpolate(cfg, s, float(tv))
         assert np.max(np.abs(mu - ref["dm"][k, :2])) < 1e-9
         assert np.linalg.norm(cov - ref["dP"][k, :2, :2]) / np.linalg.norm(ref["dP"][k, :2, :2]) < (1e-6 if dynamic else 1e-8)
+
+
+def test_variable_steps_teacher_forced(oracle):
+    """The accepted step sequence of an ADAPTIVE oracle solve, replayed by the 60-digit filter / smoother with one transition pair per step: pins the
+    variable-step algebra (preconditioner and transition matrices recomputed per step, src/perform_step.jl:37-50) independently of the step-size
+    controller, which is third-party code restated from SURVEY.md A.6."""
+    mp.mp.dps = 60
+    f, u0, p, q = problems.lotka_volterra, [1.0, 1.0], [1.5, 1.0, 3.0, 1.0], 3
+    rhs = oracle.compile_rhs(tracer.trace(f, 2, 4), q)
+    s = oracle.solve(oracle.make_config(2, q, 4, alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC, smooth=True, adaptive=True, t0=0.0, t1=3.0), rhs, u0, p)
+    assert s["retcode"] == "Success" and 20 < s["naccept"] < 200 and np.ptp(np.diff(s["t"])) > 1e-3      # genuinely variable steps
+    hs = np.diff(s["t"])
+    ref = dense_filter_smoother(f, u0, p, q, hs, len(hs), True, True, tols=(1e-6, 1e-3))
+    # every accepted step has an error estimate below one, and -- no attempt of this solve was rejected -- each step size is the proposal of
+    # the PI controller (OrdinaryDiffEqCore, restated in SURVEY.md A.6: q = EEst^b1 / qold^b2 / gamma clamped to [1/qmax, 1/qmin], b1 = 7/(10 order),
+    # b2 = 2/(5 order), qold = max(EEst_prev, 1e-4)) evaluated here from the 60-digit error estimates; the last step is clipped to the end point
+    E = ref["eest"]
+    assert s["nreject"] == 0 and np.all(E < 1.0)
+    b1, b2, qold = 0.7 / q, 0.4 / q, 1e-4
+    for k in range(len(hs) - 2):
+        fac = min(1.0 / 0.2, max(1.0 / 10.0, E[k] ** b1 / qold ** b2 / 0.9))
+        qold = max(E[k], 1e-4)
+        assert hs[k + 1] == pytest.approx(hs[k] / fac, rel=1e-6), k
+    # the oracle accumulates t += h in floating point; the replay uses the differences of its saved times, so the two step sequences agree to an ulp
+    assert np.max(np.abs(s["diffusions"][:len(hs)] - ref["sig"]) / ref["sig"]) < 1e-5
+    assert np.max(np.abs(s["pu_mu"] - ref["sm"][:, :2])) < 1e-8
+    assert _relc(s["pu_cov"][1:], ref["sP"][1:, :2, :2]) < 1e-5
