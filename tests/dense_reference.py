@@ -23,10 +23,11 @@ def _to_mp(M):
 
 
 def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=None, second_order=False, obs_noise=None, diag_jac=False,
-                          mv=False, dense_ts=None, tols=None):
+                          mv=False, dense_ts=None, tols=None, rate_update=False):
     """Returns numpy arrays: filtered / smoothed means [N+1, D] and covariances [N+1, D, D], local diffusions [N], the running MLE of the
     global diffusion, the log-likelihood, and the log-likelihood with the scalar (Kronecker-factor) log-determinant.
 
+    rate_update   IOUP(q, update_rate_parameter=true) (RosenbrockExpEK): the rate matrix is re-set to the Jacobian before every step
     rate          IOUP prior with this d x d rate matrix (src/priors/ioup.jl:66-101): transition pair from the matrix exponential of the Van Loan
                   block matrix, in plain coordinates
     mass          nonsingular mass matrix M: z = M E1 x - f(E0 x), H = M E1 - J E0 (src/measurement_models.jl:11-20); initial state as the
@@ -68,7 +69,7 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
         h = hs[0]
     else:
         h = mp.mpf(str(h))
-    def transition(h):
+    def transition(h, rate=rate):
         if rate is None:
             A1, Q1 = mp.matrix(n, n), mp.matrix(n, n)
             for i in range(n):
@@ -81,7 +82,7 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
         for jj in range(q):
             for a in range(d):
                 F[jj * d + a, (jj + 1) * d + a] = 1
-        Rm = _to_mp(rate)
+        Rm = rate if isinstance(rate, mp.matrix) else _to_mp(rate)
         for a in range(d):
             for b in range(d):
                 F[q * d + a, q * d + b] = Rm[a, b]
@@ -111,6 +112,8 @@ def dense_filter_smoother(f, u0, p, q, h, nsteps, ek1, dynamic, rate=None, mass=
     for k in range(nsteps):
         if hs is not None:
             A, Q = transition(hs[k])
+        if rate_update:      # src/perform_step.jl:88-96: the rate parameter is the Jacobian at the last filtered mean, before every step
+            A, Q = transition(hs[k] if hs is not None else h, rate=mp.matrix(J_l(list(E0 * m))))
         As.append(A)
         mpred = A * m
         if second_order:

@@ -238,3 +238,18 @@ def test_variable_steps_teacher_forced(oracle):
     assert np.max(np.abs(s["diffusions"][:len(hs)] - ref["sig"]) / ref["sig"]) < 1e-5
     assert np.max(np.abs(s["pu_mu"] - ref["sm"][:, :2])) < 1e-8
     assert _relc(s["pu_cov"][1:], ref["sP"][1:, :2, :2]) < 1e-5
+
+
+def test_rosenbrock_exp_ek_trajectory(oracle):
+    """EK1(prior = IOUP(3, update_rate_parameter = true)) = RosenbrockExpEK (src/algorithms.jl:458-459, src/perform_step.jl:88-96): before every step
+    the rate parameter becomes the Jacobian at the last filtered mean and the transition pair is rebuilt; the smoother uses each step's own pair."""
+    mp.mp.dps = 120
+    f, u0, p, q, h, N = problems.lotka_volterra, [1.0, 1.0], [1.5, 1.0, 3.0, 1.0], 3, "0.02", 40
+    ref = dense_filter_smoother(f, u0, p, q, h, N, True, False, rate=np.zeros((2, 2)), rate_update=True)
+    rhs = oracle.compile_rhs(tracer.trace(f, 2, 4), q)
+    kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, adaptive=False, dt=float(h), t0=0.0, t1=float(h) * N, save_everystep=True,
+              prior=oracle.PRIOR_IOUP, rate_parameter=None, update_rate_parameter=True)
+    _check(oracle.solve(oracle.make_config(2, q, 4, smooth=False, **kw), rhs, u0, p), ref, 2, None)
+    s = oracle.solve(oracle.make_config(2, q, 4, smooth=True, **kw), rhs, u0, p)
+    assert np.max(np.abs(s["pu_mu"] - ref["sm"][:, :2])) < 1e-10
+    assert _relc(s["pu_cov"][1:], ref["sP"][1:, :2, :2]) < 1e-8
