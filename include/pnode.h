@@ -115,7 +115,7 @@ typedef struct pnode_config {
     /* constant mass matrix M of  M u' = f(u, p, t)  (`ODEFunction(f; mass_matrix=M)`): d x d, row-major, host pointer,
        copied at create; NULL = identity.  Measurement z = M E1 x - f(E0 x) (src/measurement_models.jl:11-20),
        H = M E1 - J E0 (src/derivative_utils.jl:1-53), initial derivatives as src/initialization/autodiffinit.jl:20-47.
-       May be singular (index-1 DAEs).  EK1 on the dense layout (D <= 32): any M; DiagonalEK1 / EK0 with a multivariate
+       May be singular (index-1 DAEs).  EK1 on the dense layout (register kernels for D <= 32, the CTA-per-trajectory kernel beyond): any M; DiagonalEK1 / EK0 with a multivariate
        diffusion (blocks layout): diagonal M; EK0 on the Kronecker layout: M = lambda I only, otherwise
        PNODE_ERR_ARGUMENT with the reference's message (src/caches.jl:111-118). */
     const double* mass_matrix;
@@ -124,7 +124,8 @@ typedef struct pnode_config {
        H = E2 (EK0) or E2 - J_du E1 - J_u E0 (EK1).  rhs_src / rhs_name describe the FIRST-ORDER FORM of dimension 2d,
        F([du; u]) = [f1(du, u); du] (what the reference's DynamicalODEFunction evaluates on ArrayPartition(du, u)); the
        kernels use its first d rows.  u0 is [n_traj][2d] = (du0, u0); every U field has 2d entries per point in the
-       reference's sol.u order (du, u), every U_COV field (2d)^2.  EK0, DiagonalEK1 and EK1 (dense, D <= 32) with
+       reference's sol.u order (du, u), every U_COV field (2d)^2.  EK0, DiagonalEK1 and EK1 (dense; D > 32 on the CTA-per-trajectory kernel:
+       Pleiades as 14 second-order equations, D = 56; smoothing of second-order problems needs D <= 24) with
        every diffusion model the first-order path supports; IWP prior. */
     int32_t second_order;
     int32_t reserved1;
