@@ -87,7 +87,8 @@ typedef struct pnode_config {
     int32_t adaptive;          /* solve(...; adaptive) */
     int32_t save_everystep;    /* solve(...; save_everystep) */
     int32_t save_state;        /* also return the full filter state (x_filt / x_smooth) not only pu */
-    int32_t lanes_per_traj;    /* 0 = auto; else 2,4,8,16,32 lanes cooperating on one trajectory */
+    int32_t lanes_per_traj;    /* 0 = auto; 1 = one thread per trajectory (EK1, IWP, filter only, D <= 16); 2,4,8,16,32 lanes cooperating on one
+                                  trajectory; 256 = one CTA per trajectory (the automatic choice for the EK1 with D > 32) */
     int32_t reserved0;
     int64_t maxiters;
     double initial_diffusion;
@@ -106,7 +107,8 @@ typedef struct pnode_config {
     /* test hook: sigma^2 used for accepted step k instead of the local estimate (host pointer, copied) */
     const double* forced_diffusion;
     int64_t n_forced;
-    /* IOUP prior: rate_parameter (F[q,q] of the SDE drift, src/priors/ioup.jl:66-79); ignored for the IWP */
+    /* IOUP prior: rate_parameter (F[q,q] of the SDE drift, src/priors/ioup.jl:66-79); ignored for the IWP.  Register-resident kernels for
+       D <= 24; larger states (D <= 64) run as the rate matrix rate_parameter * I on the general-prior path (see rate_matrix) */
     double rate_parameter;
     /* dense output sol(saveat) (src/solution.jl:330-398): ascending times in [t0, t1]; host pointer, copied at create.
        Needs save_everystep; smoothed interpolation if smooth, else the filtering prediction */
