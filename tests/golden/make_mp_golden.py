@@ -3,7 +3,7 @@
     python tests/golden/make_mp_golden.py        ->  tests/golden/mp_*.npz   (a few seconds per case)
 
 Fixed steps, FixedDiffusion(calibrate=false), so every number is a deterministic function of (problem, u0, p, order, dt): filtered and smoothed
-solution means / covariances (sol.u, sol.pu) at every step and the log-likelihood.  tests/test_golden_mp.py compares the oracle (CPU leg) and the
+solution means / covariances (sol.u, sol.pu) at every step and the log-likelihood.  tests/test_zz_golden_mp.py compares the oracle (CPU leg) and the
 CUDA path through the C ABI (GPU leg) with them."""
 import json
 import os
