@@ -509,3 +509,26 @@ def test_nvrtc_results_are_cached_per_process(pnlib, monkeypatch):
     monkeypatch.setenv("PNODE_NVRTC_CACHE", "0")
     n4, off = timed(q=3, t1=1.0)
     assert n4 == n1 and off > 5 * warm
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm; the oracle port on the host cores) on a small sample: one JSON line with the
+    keys of the bench contract, `impl: reference`, the e2e object equal to the line's value, and the same metric / unit / workload names the
+    GPU arm prints."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-sample", "512"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert line["unit"] == "accepted trajectory-steps/s" and "rober" in line["config"]["workload"]
+    assert line["value"] > 0 and line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
