@@ -49,7 +49,11 @@ PN_HD double pn_gbcast(double x, int src) {
 // ~25-instruction sequence with a call on the slow path; the QR needs one of each per column.
 PN_HD double pn_rcp(double x) {
     double r;
+#ifdef PN_HOST_EMULATION /* tests/emulation: the kernel headers compiled for the host; a seed of the same accuracy */
+    r = pn_host_seed_rcp(x);
+#else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
@@ -58,7 +62,11 @@ PN_HD double pn_rcp(double x) {
 }
 PN_HD double pn_rsqrt(double x) {
     double y;
+#ifdef PN_HOST_EMULATION
+    y = pn_host_seed_rsqrt(x);
+#else
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#endif
     double t = x * y;
     double e = fma(-t, y, 1.0);
     y = fma(0.5 * y, e, y);

@@ -1,0 +1,152 @@
+"""The headline kernel's SOURCE on the CPU: csrc/kernels/pn_thread.cuh (one thread per trajectory: Gram matrix in registers, packed factor,
+in-register Cholesky, update, controller -- DESIGN.md section 4.0) is compiled for the host with g++ under tests/emulation/cuda_shim.h and run on
+single trajectories.  The kernel gives a whole trajectory to one thread and exchanges nothing with other threads, so a warp of one is a faithful
+execution of its arithmetic (the hardware reciprocal / reciprocal-square-root seeds are replaced by seeds of the same 23-bit accuracy; products
+and sums are not contracted into FMAs here, so the agreement with the device is to rounding, not bit for bit).
+
+Checked against the oracle (fixed steps 1e-10, adaptive: identical accept / reject counts) and against the extended-precision fixtures
+(tests/golden/mp_*.npz).  This runs in the CPU suite: a logic error in the kernel shows up without a GPU.  It is not a product path -- nothing in
+probnumdiffeq.jl_b200/ can reach it, and the library still refuses to create a solver without a device."""
+import ctypes as C
+import json
+import os
+import subprocess
+import tempfile
+from math import factorial, sqrt
+
+import numpy as np
+import pytest
+
+import probnumdiffeq_jl_b200  # noqa: F401
+from probnumdiffeq_jl_b200 import problems, tracer
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(HERE), "probnumdiffeq.jl_b200", "csrc")
+GOLD = os.path.join(HERE, "golden")
+STRUCT = {"rober": "PnRober", "fitzhugh_nagumo": "PnFitzHughNagumo", "vanderpol": "PnVanDerPol", "lotka_volterra": "PnLotkaVolterra",
+          "orego": "PnOrego"}
+dp = C.POINTER(C.c_double)
+
+
+def _build(problem, q, adaptive, dynamic):
+    out = os.path.join(tempfile.gettempdir(), f"pn_emu_{os.getuid()}", f"{problem}_q{q}_a{int(adaptive)}_d{int(dynamic)}.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = os.path.join(HERE, "emulation", "pn_thread_host.cpp")
+    deps = [src, os.path.join(HERE, "emulation", "cuda_shim.h")] + [os.path.join(CSRC, "kernels", f) for f in
+                                                                     ("pn_thread.cuh", "pn_small.cuh", "pn_params.h", "pn_builtin_problems.cuh")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-I", CSRC, f"-DPN_EMU_PROBLEM={STRUCT[problem]}",
+                        f"-DPN_EMU_Q={q}", f"-DPN_EMU_ADAPTIVE={int(adaptive)}", f"-DPN_EMU_DYNAMIC={int(dynamic)}", src, "-o", out], check=True)
+    lib = C.CDLL(out)
+    lib.pn_emu_solve.restype = None
+    return lib
+
+
+def _iwp_constants(q):
+    """L of src/priors/iwp.jl:84-92 (lower triangular), Qb = L'L, and an upper-triangular U with U'U = L'L -- computed here, not taken from
+    pnode_api.cu."""
+    n = q + 1
+    L = np.zeros((n, n))
+    for m in range(n):
+        for c in range(m + 1):
+            L[m, c] = sqrt(2 * q - 2 * m + 1) * factorial(q - c) ** 2 / factorial(m - c) / factorial(2 * q - c - m + 1)
+    return L, np.triu(np.linalg.qr(L, mode="r")), L.T @ L
+
+
+def _run(problem, q, u_init, p, *, t1, dt, adaptive=False, dynamic=False, calibrate=False, abstol=1e-6, reltol=1e-3, forced=None):
+    lib = _build(problem, q, adaptive, dynamic)
+    d, n = lib.pn_emu_d(), q + 1
+    D = d * n
+    L, U, Qb = _iwp_constants(q)
+    scal = np.array([0.0, t1, dt, abstol, reltol, 0.0, t1, 0.7 / q, 0.4 / q, 0.2, 10.0, 0.9, 1.0, 1.0, 1e-4, 1.0])
+    um, uc, xm, xr = np.zeros(d), np.zeros(d * d), np.zeros(D), np.zeros(D * D)
+    so, cnt = np.zeros(4), np.zeros(4, dtype=np.int64)
+    mu0 = np.ascontiguousarray(u_init, dtype=float)
+    pp = np.ascontiguousarray(p if len(p) else [0.0], dtype=float)
+    fd = None if forced is None else np.ascontiguousarray(forced, dtype=float)
+    A = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    lib.pn_emu_solve(A(scal), int(calibrate), A(np.ascontiguousarray(L.ravel())), A(np.ascontiguousarray(U.ravel())),
+                     A(np.ascontiguousarray(Qb.ravel())), A(mu0), A(pp), A(um), A(uc), A(xm), A(xr), A(so), cnt.ctypes.data_as(C.POINTER(C.c_longlong)),
+                     A(fd) if fd is not None else None, C.c_longlong(0 if fd is None else len(fd)))
+    return dict(u=um, cov=uc.reshape(d, d), x=xm, xR=xr.reshape(D, D), t_end=so[0], loglik=so[1], diffusion=so[2], dt_last=so[3],
+                naccept=int(cnt[0]), nreject=int(cnt[1]), nf=int(cnt[2]), retcode=int(cnt[3]))
+
+
+def _rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / np.linalg.norm(b)
+
+
+@pytest.mark.parametrize("problem,q,t1,dt", [("fitzhugh_nagumo", 3, 2.0, 0.01), ("rober", 3, 0.08, 1e-3), ("vanderpol", 5, 0.006, 1e-4),
+                                             ("lotka_volterra", 3, 2.0, 0.02)])
+@pytest.mark.parametrize("dynamic", [False, True])
+def test_fixed_steps_against_the_oracle(oracle, problem, q, t1, dt, dynamic):
+    """Fixed steps; FixedDiffusion(calibrate=false): end state (all derivatives), covariance, log-likelihood at 1e-10.  DynamicDiffusion: the local
+    diffusions are ratios of rounding-sensitive residuals, so means 1e-8 and covariances 1e-4 -- the bounds of the GPU tests."""
+    pd = problems.PROBLEMS[problem]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    o = oracle.solve(oracle.make_config(pd.d, q, pd.n_p, alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC if dynamic else oracle.DIFF_FIXED, calibrate=False,
+                                        smooth=False, adaptive=False, dt=dt, t0=0.0, t1=t1, save_everystep=True, cov_backend=oracle.COV_REF),
+                     rhs, pd.u0, pd.p)
+    o2 = oracle.solve(oracle.make_config(pd.d, q, pd.n_p, alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC if dynamic else oracle.DIFF_FIXED, calibrate=False,
+                                         smooth=False, adaptive=False, dt=dt, t0=0.0, t1=t1, save_everystep=True, cov_backend=oracle.COV_QR),
+                      rhs, pd.u0, pd.p)
+    k = _run(problem, q, o["x_filt_mu"][0], pd.p, t1=t1, dt=dt, dynamic=dynamic)
+    assert k["retcode"] == 0 and k["naccept"] == o["naccept"] and k["t_end"] == o["t"][-1]
+    So = o["x_filt_R"][-1].T @ o["x_filt_R"][-1]
+    So2 = o2["x_filt_R"][-1].T @ o2["x_filt_R"][-1]
+    # the highest derivatives of a stiff problem (Van der Pol: x^(5) ~ 4e9) carry the rounding of the whole run: the full state and its covariance are
+    # compared against the oracle's own floor (its two covariance back-ends), the solution components at the fixed bound
+    fx, fS = _rel(o2["x_filt_mu"][-1], o["x_filt_mu"][-1]), _rel(So2, So)
+    assert _rel(k["u"], o["pu_mu"][-1]) < (1e-8 if dynamic else 1e-10)
+    assert _rel(k["x"], o["x_filt_mu"][-1]) < max(1e-8 if dynamic else 1e-10, 20 * fx)
+    assert _rel(k["cov"], o["pu_cov"][-1]) < (1e-4 if dynamic else 1e-9)
+    assert _rel(k["xR"].T @ k["xR"], So) < max(1e-4 if dynamic else 1e-9, 20 * fS)
+    assert k["loglik"] == pytest.approx(o["loglik"], rel=1e-6 if dynamic else 1e-10)
+
+
+@pytest.mark.parametrize("name", ["mp_fhn_ek1_q3", "mp_rober_ek1_q3", "mp_vdp_ek1_q5"])
+def test_fixed_steps_against_the_extended_precision_fixtures(oracle, name):
+    """The same kernel source against trajectories that depend on neither the oracle nor the kernels (tests/golden/make_mp_golden.py)."""
+    z = np.load(os.path.join(GOLD, name + ".npz"), allow_pickle=False)
+    c = json.loads(str(z["config"]))
+    pd = problems.PROBLEMS[c["problem"]]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), c["q"])
+    x0 = oracle.solve(oracle.make_config(pd.d, c["q"], pd.n_p, adaptive=False, dt=c["dt"], t0=0.0, t1=c["dt"], smooth=False, save_everystep=True),
+                      rhs, z["u0"], z["p"])["x_filt_mu"][0]          # exact initial derivatives (symbolic)
+    k = _run(c["problem"], c["q"], x0, z["p"], t1=c["t1"], dt=c["dt"])
+    assert k["retcode"] == 0 and k["naccept"] == c["steps"]
+    assert _rel(k["u"], z["filt_u"][-1]) < 1e-10
+    assert _rel(k["cov"], z["filt_cov"][-1]) < 1e-8
+    assert k["loglik"] == pytest.approx(float(z["loglik"]), rel=1e-10)
+
+
+@pytest.mark.parametrize("problem,q,t1,dt0", [("rober", 3, 10.0, 1e-4), ("lotka_volterra", 3, 5.0, 1e-2), ("orego", 3, 1.0, 1e-4)])
+def test_adaptive_steps_against_the_oracle(oracle, problem, q, t1, dt0):
+    """Adaptive steps from a given first step (error estimate, PI controller, reject path -- the kernel's own scalar phase with its reciprocal-based
+    bookkeeping, PN_FAST_SCALAR): the oracle's accept / reject counts, end point 1e-8."""
+    pd = problems.PROBLEMS[problem]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    o = oracle.solve(oracle.make_config(pd.d, q, pd.n_p, alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC, smooth=False, adaptive=True, dt=dt0, t0=0.0, t1=t1,
+                                        save_everystep=True, cov_backend=oracle.COV_REF), rhs, pd.u0, pd.p)
+    k = _run(problem, q, o["x_filt_mu"][0], pd.p, t1=t1, dt=dt0, adaptive=True, dynamic=True)
+    assert k["retcode"] == 0 and o["retcode"] == "Success"
+    assert (k["naccept"], k["nreject"]) == (o["naccept"], o["nreject"])
+    assert k["t_end"] == t1
+    assert _rel(k["u"], o["pu_mu"][-1]) < 1e-8
+
+
+def test_zero_diffusion_takes_the_triangularize_route(oracle):
+    """predict.jl:71-74 / :90 (the CPU twin of tests/test_gpu_thread.py::test_thread_kernel_zero_diffusion_takes_the_triangularize_route): with zero
+    diffusion, forced on every third accepted step through the kernel's test hook, the Gram + Cholesky route does not apply and the kernel's cold
+    path -- Householder triangularisation of the stack in local memory -- runs; everything still agrees with the oracle at 1e-10."""
+    pd = problems.PROBLEMS["lotka_volterra"]
+    nst = 100
+    forced = np.where(np.arange(nst) % 3 == 2, 0.0, 1.0 + 0.1 * np.arange(nst))
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), 3)
+    o = oracle.solve(oracle.make_config(2, 3, 4, alg=oracle.EK1, smooth=False, save_everystep=True, cov_backend=oracle.COV_REF, adaptive=False, dt=0.02,
+                                        t0=0.0, t1=2.0, forced_diffusion=forced), rhs, pd.u0, pd.p)
+    k = _run("lotka_volterra", 3, o["x_filt_mu"][0], pd.p, t1=2.0, dt=0.02, dynamic=True, forced=forced)
+    assert k["retcode"] == 0 and k["naccept"] == o["naccept"] == nst
+    assert _rel(k["u"], o["pu_mu"][-1]) < 1e-10
+    assert _rel(k["cov"], o["pu_cov"][-1]) < 1e-9
+    assert k["loglik"] == pytest.approx(o["loglik"], rel=1e-9)
