@@ -1,11 +1,13 @@
-// pn_thread_host.cpp -- the thread-per-trajectory step kernel (csrc/kernels/pn_thread.cuh: the headline kernel of bench.py) compiled for the
-// host under cuda_shim.h and run on one trajectory.  PN_EMU_PROBLEM / PN_EMU_Q / PN_EMU_ADAPTIVE / PN_EMU_DYNAMIC select the instantiation at
+// pn_thread_host.cpp -- the thread-per-trajectory step kernels (csrc/kernels/pn_thread.cuh: the headline kernel of bench.py; pn_kron.cuh and
+// pn_blocks.cuh: the structured layouts) compiled for the host under cuda_shim.h and run on one trajectory.  PN_EMU_PROBLEM / PN_EMU_Q / PN_EMU_ADAPTIVE / PN_EMU_DYNAMIC select the instantiation at
 // compile time, as the NVRTC build does.  The caller (tests/test_kernel_host_emulation.py) passes the host-side constants of PnParams computed
 // independently of pnode_api.cu (IWP factor L, its upper twin U, Qb = L'L, controller constants) and the initial state, and compares the
 // outputs with the oracle and with the extended-precision fixtures.  Test infrastructure: nothing in the product includes this file.
 #include "cuda_shim.h"
 #define PN_THREAD_NT 1
 #include "kernels/pn_thread.cuh"
+#include "kernels/pn_kron.cuh"   /* PN_EMU_KERNEL 1: EK0 on the IsometricKronecker layout, one thread per trajectory */
+#include "kernels/pn_blocks.cuh" /* PN_EMU_KERNEL 2: BlocksOfDiagonals layout (PN_EMU_DIAG1: DiagonalEK1, else EK0; PN_EMU_MV: multivariate diffusion) */
 #include "kernels/pn_builtin_problems.cuh"
 #ifdef PN_EMU_USER_SOURCE
 #include PN_EMU_USER_SOURCE
@@ -19,6 +21,15 @@ double pn_thread_shared[8192];
 #ifndef PN_EMU_DYNAMIC
 #define PN_EMU_DYNAMIC 0
 #endif
+#ifndef PN_EMU_KERNEL
+#define PN_EMU_KERNEL 0
+#endif
+#ifndef PN_EMU_DIAG1
+#define PN_EMU_DIAG1 0
+#endif
+#ifndef PN_EMU_MV
+#define PN_EMU_MV 0
+#endif
 
 extern "C" int pn_emu_d(void) { return PN_EMU_PROBLEM::d; }
 extern "C" int pn_emu_n_p(void) { return PN_EMU_PROBLEM::n_p; }
@@ -30,7 +41,7 @@ extern "C" int pn_emu_q(void) { return PN_EMU_Q; }
 // counts  : naccept, nreject, nf, retcode                                                                              (4 x int64)
 extern "C" void pn_emu_solve(const double* scal_in, int calibrate, const double* L, const double* U, const double* Qb, const double* init_mu,
                              const double* p, double* u_mean, double* u_cov, double* x_mean, double* x_covfac, double* scal_out,
-                             long long* counts, const double* forced_diffusion, long long n_forced) {
+                             long long* counts, const double* forced_diffusion, long long n_forced, double* diffusion_mv) {
     constexpr int n = PN_EMU_Q + 1;
     PnParams P;
     std::memset(&P, 0, sizeof P);
@@ -60,6 +71,13 @@ extern "C" void pn_emu_solve(const double* scal_in, int calibrate, const double*
     P.t_end = &scal_out[0], P.loglik = &scal_out[1], P.diffusion = &scal_out[2], P.dt_last = &scal_out[3];
     P.u_mean = u_mean, P.u_cov = u_cov, P.x_mean = x_mean, P.x_covfac = x_covfac;
     P.naccept = &naccept, P.nreject = &nreject, P.nf = &nf, P.retcode = &retcode;
+    P.diffusion_mv = diffusion_mv;
+#if PN_EMU_KERNEL == 0
     pn_thread_entry<PN_EMU_PROBLEM, PN_EMU_Q, (PN_EMU_ADAPTIVE != 0), (PN_EMU_DYNAMIC != 0)>(P);
+#elif PN_EMU_KERNEL == 1
+    pn_kron_entry<PN_EMU_PROBLEM, PN_EMU_Q, (PN_EMU_ADAPTIVE != 0), (PN_EMU_DYNAMIC != 0), 0>(P);
+#else
+    pn_blocks_entry<PN_EMU_PROBLEM, PN_EMU_Q, (PN_EMU_DIAG1 != 0), (PN_EMU_MV != 0), (PN_EMU_ADAPTIVE != 0), (PN_EMU_DYNAMIC != 0), 0>(P);
+#endif
     counts[0] = naccept, counts[1] = nreject, counts[2] = nf, counts[3] = retcode;
 }

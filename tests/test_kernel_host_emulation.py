@@ -23,20 +23,25 @@ from probnumdiffeq_jl_b200 import problems, tracer
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "probnumdiffeq.jl_b200", "csrc")
 GOLD = os.path.join(HERE, "golden")
-STRUCT = {"rober": "PnRober", "fitzhugh_nagumo": "PnFitzHughNagumo", "vanderpol": "PnVanDerPol", "lotka_volterra": "PnLotkaVolterra",
+STRUCT = {"pleiades": "PnPleiades", "rober": "PnRober", "fitzhugh_nagumo": "PnFitzHughNagumo", "vanderpol": "PnVanDerPol", "lotka_volterra": "PnLotkaVolterra",
           "orego": "PnOrego"}
 dp = C.POINTER(C.c_double)
 
 
-def _build(problem, q, adaptive, dynamic):
-    out = os.path.join(tempfile.gettempdir(), f"pn_emu_{os.getuid()}", f"{problem}_q{q}_a{int(adaptive)}_d{int(dynamic)}.so")
+KERNELS = {"thread": (0, 0, 0), "kron": (1, 0, 0), "blocks_ek0_mv": (2, 0, 1), "blocks_diag1": (2, 1, 0)}   # PN_EMU_KERNEL, _DIAG1, _MV
+
+
+def _build(problem, q, adaptive, dynamic, kernel="thread"):
+    kk, diag1, mv = KERNELS[kernel]
+    out = os.path.join(tempfile.gettempdir(), f"pn_emu_{os.getuid()}", f"{kernel}_{problem}_q{q}_a{int(adaptive)}_d{int(dynamic)}.so")
     os.makedirs(os.path.dirname(out), exist_ok=True)
     src = os.path.join(HERE, "emulation", "pn_thread_host.cpp")
     deps = [src, os.path.join(HERE, "emulation", "cuda_shim.h")] + [os.path.join(CSRC, "kernels", f) for f in
-                                                                     ("pn_thread.cuh", "pn_small.cuh", "pn_params.h", "pn_builtin_problems.cuh")]
+                                                                     ("pn_thread.cuh", "pn_kron.cuh", "pn_blocks.cuh", "pn_small.cuh", "pn_params.h", "pn_builtin_problems.cuh")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
         subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-ffp-contract=off", "-I", CSRC, f"-DPN_EMU_PROBLEM={STRUCT[problem]}",
-                        f"-DPN_EMU_Q={q}", f"-DPN_EMU_ADAPTIVE={int(adaptive)}", f"-DPN_EMU_DYNAMIC={int(dynamic)}", src, "-o", out], check=True)
+                        f"-DPN_EMU_Q={q}", f"-DPN_EMU_ADAPTIVE={int(adaptive)}", f"-DPN_EMU_DYNAMIC={int(dynamic)}", f"-DPN_EMU_KERNEL={kk}",
+                        f"-DPN_EMU_DIAG1={diag1}", f"-DPN_EMU_MV={mv}", src, "-o", out], check=True)
     lib = C.CDLL(out)
     lib.pn_emu_solve.restype = None
     return lib
@@ -53,22 +58,22 @@ def _iwp_constants(q):
     return L, np.triu(np.linalg.qr(L, mode="r")), L.T @ L
 
 
-def _run(problem, q, u_init, p, *, t1, dt, adaptive=False, dynamic=False, calibrate=False, abstol=1e-6, reltol=1e-3, forced=None):
-    lib = _build(problem, q, adaptive, dynamic)
+def _run(problem, q, u_init, p, *, t1, dt, adaptive=False, dynamic=False, calibrate=False, abstol=1e-6, reltol=1e-3, forced=None, kernel="thread"):
+    lib = _build(problem, q, adaptive, dynamic, kernel)
     d, n = lib.pn_emu_d(), q + 1
     D = d * n
     L, U, Qb = _iwp_constants(q)
     scal = np.array([0.0, t1, dt, abstol, reltol, 0.0, t1, 0.7 / q, 0.4 / q, 0.2, 10.0, 0.9, 1.0, 1.0, 1e-4, 1.0])
     um, uc, xm, xr = np.zeros(d), np.zeros(d * d), np.zeros(D), np.zeros(D * D)
-    so, cnt = np.zeros(4), np.zeros(4, dtype=np.int64)
+    so, cnt, dmv = np.zeros(4), np.zeros(4, dtype=np.int64), np.zeros(d)
     mu0 = np.ascontiguousarray(u_init, dtype=float)
     pp = np.ascontiguousarray(p if len(p) else [0.0], dtype=float)
     fd = None if forced is None else np.ascontiguousarray(forced, dtype=float)
     A = lambda a: a.ctypes.data_as(dp)  # noqa: E731
     lib.pn_emu_solve(A(scal), int(calibrate), A(np.ascontiguousarray(L.ravel())), A(np.ascontiguousarray(U.ravel())),
                      A(np.ascontiguousarray(Qb.ravel())), A(mu0), A(pp), A(um), A(uc), A(xm), A(xr), A(so), cnt.ctypes.data_as(C.POINTER(C.c_longlong)),
-                     A(fd) if fd is not None else None, C.c_longlong(0 if fd is None else len(fd)))
-    return dict(u=um, cov=uc.reshape(d, d), x=xm, xR=xr.reshape(D, D), t_end=so[0], loglik=so[1], diffusion=so[2], dt_last=so[3],
+                     A(fd) if fd is not None else None, C.c_longlong(0 if fd is None else len(fd)), A(dmv))
+    return dict(diffusion_mv=dmv, u=um, cov=uc.reshape(d, d), x=xm, xR=xr.reshape(D, D), t_end=so[0], loglik=so[1], diffusion=so[2], dt_last=so[3],
                 naccept=int(cnt[0]), nreject=int(cnt[1]), nf=int(cnt[2]), retcode=int(cnt[3]))
 
 
@@ -150,3 +155,62 @@ def test_zero_diffusion_takes_the_triangularize_route(oracle):
     assert _rel(k["u"], o["pu_mu"][-1]) < 1e-10
     assert _rel(k["cov"], o["pu_cov"][-1]) < 1e-9
     assert k["loglik"] == pytest.approx(o["loglik"], rel=1e-9)
+
+
+# ---- the structured layouts: pn_kron.cuh (EK0, IsometricKronecker) and pn_blocks.cuh (BlocksOfDiagonals), also one thread per trajectory ----
+@pytest.mark.parametrize("q", [3, 8])
+def test_kron_kernel_orders(oracle, q):
+    """EK0 on the Kronecker layout at order 3 and 8 (beyond order 7 the device build keeps the factor in thread-local memory; the arithmetic is
+    the same code; the oracle's symbolic initial derivatives make order 11 too slow for the suite): fixed steps with static diffusion against the oracle -- means 1e-9, covariance against the oracle's own Cholesky-vs-QR floor (order
+    q scales the state by h^(q + 1/2)), the log-likelihood with the reference's Kronecker log-determinant -- and an adaptive run: accept / reject counts."""
+    pd = problems.PROBLEMS["lotka_volterra"]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    kw = dict(alg=oracle.EK0, diffusion=oracle.DIFF_FIXED, calibrate=False, smooth=False, adaptive=False, dt=0.05, t0=0.0, t1=1.0, save_everystep=True)
+    o = oracle.solve(oracle.make_config(2, q, 4, cov_backend=oracle.COV_REF, **kw), rhs, pd.u0, pd.p)
+    o2 = oracle.solve(oracle.make_config(2, q, 4, cov_backend=oracle.COV_QR, **kw), rhs, pd.u0, pd.p)
+    k = _run("lotka_volterra", q, o["x_filt_mu"][0], pd.p, t1=1.0, dt=0.05, kernel="kron")
+    assert k["retcode"] == 0 and k["naccept"] == o["naccept"] == 20
+    assert _rel(k["u"], o["pu_mu"][-1]) < 1e-9
+    assert _rel(k["cov"], o["pu_cov"][-1]) < max(1e-9, 20 * _rel(o2["pu_cov"][-1], o["pu_cov"][-1]))
+    assert k["loglik"] == pytest.approx(o["loglik"], rel=1e-8)
+    if True:
+        o = oracle.solve(oracle.make_config(2, q, 4, alg=oracle.EK0, diffusion=oracle.DIFF_DYNAMIC, smooth=False, adaptive=True, dt=1e-2, t0=0.0, t1=1.0,
+                                            save_everystep=True, cov_backend=oracle.COV_REF), rhs, pd.u0, pd.p)
+        k = _run("lotka_volterra", q, o["x_filt_mu"][0], pd.p, t1=1.0, dt=1e-2, adaptive=True, dynamic=True, kernel="kron")
+        assert k["retcode"] == 0 and k["t_end"] == 1.0
+        if q == 3:
+            assert (k["naccept"], k["nreject"]) == (o["naccept"], o["nreject"])
+            assert _rel(k["u"], o["pu_mu"][-1]) < 1e-7
+        else:
+            # order 8: a quarter of the attempts is rejected and the controller's exponent 7 / (10 q) moves the step size by a few per cent per step, so one
+            # accept / reject decision that falls the other way at rounding level (this build has no FMA contraction, the device has) changes every count
+            # after it; both runs are valid solves: same end point within the solver tolerance, step counts of the same size
+            assert _rel(k["u"], o["pu_mu"][-1]) < 1e-4 and 0.5 * o["naccept"] < k["naccept"] < 2 * o["naccept"]
+
+
+@pytest.mark.parametrize("problem,q,t1,dt", [("lotka_volterra", 3, 1.0, 0.02), ("lotka_volterra", 8, 0.5, 0.05), ("pleiades", 3, 0.1, 0.01)])
+def test_blocks_kernel_shapes(oracle, problem, q, t1, dt):
+    """The blocks layout from the register-resident shape (d (q+1)^2 = 32) to those that live in thread-local memory on the device (162, and
+    Pleiades: 448): DiagonalEK1 with FixedDiffusion, fixed steps -- means 1e-10 / covariance 1e-9 / log-likelihood 1e-9 (order 8: the oracle's own
+    floor) -- and the EK0 with DynamicMVDiffusion, adaptive: the oracle's step counts and per-component diffusions."""
+    pd = problems.PROBLEMS[problem]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    kw = dict(alg=oracle.DIAGONAL_EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, smooth=False, adaptive=False, dt=dt, t0=0.0, t1=t1, save_everystep=True)
+    o = oracle.solve(oracle.make_config(pd.d, q, pd.n_p, cov_backend=oracle.COV_REF, **kw), rhs, pd.u0, pd.p)
+    o2 = oracle.solve(oracle.make_config(pd.d, q, pd.n_p, cov_backend=oracle.COV_QR, **kw), rhs, pd.u0, pd.p)
+    k = _run(problem, q, o["x_filt_mu"][0], pd.p, t1=t1, dt=dt, kernel="blocks_diag1")
+    assert k["retcode"] == 0 and k["naccept"] == o["naccept"]
+    assert _rel(k["u"], o["pu_mu"][-1]) < 1e-10
+    assert _rel(k["cov"], o["pu_cov"][-1]) < max(1e-9, 20 * _rel(o2["pu_cov"][-1], o["pu_cov"][-1]))
+    # order 8 with the uncalibrated unit diffusion: the log-likelihood (-9.5e8) is z' S^-1 z with a residual z that is a cancellation of O(1) terms; the
+    # kernel's preconditioned arithmetic and the oracle's round z differently in the 9th digit
+    assert k["loglik"] == pytest.approx(o["loglik"], rel=1e-9 if q <= 3 else 1e-7)
+    # first step of the adaptive run: at order 8 a step of dt / 10 = 0.005 puts the residual z ~ h^8 below the rounding level of f, so the per-component
+    # diffusion of that step is rounding noise (a 1-ulp change of u0 moves the oracle's own value by 4x) and every later step size with it; start at dt
+    dt0 = dt / 10 if q <= 3 else dt
+    o = oracle.solve(oracle.make_config(pd.d, q, pd.n_p, alg=oracle.EK0, diffusion=oracle.DIFF_DYNAMIC_MV, smooth=False, adaptive=True, dt=dt0, t0=0.0,
+                                        t1=t1, save_everystep=True, cov_backend=oracle.COV_REF), rhs, pd.u0, pd.p)
+    k = _run(problem, q, o["x_filt_mu"][0], pd.p, t1=t1, dt=dt0, adaptive=True, dynamic=True, kernel="blocks_ek0_mv")
+    assert (k["naccept"], k["nreject"], k["retcode"]) == (o["naccept"], o["nreject"], 0)
+    assert _rel(k["u"], o["pu_mu"][-1]) < 1e-8
+    assert _rel(k["diffusion_mv"], o["diffusions_mv"][o["naccept"] - 1]) < 1e-5
