@@ -153,16 +153,21 @@ struct PnSmoothCol {
     /* global -> shared copy of record k (factor + mean), 16 bytes per cp.async, G lanes cooperating */
     static PN_HD void stage_async(const PnSmoothParams& P, long long k, double* buf, int gl) {
         const double* src = P.s_x_covfac + k * D * D;
+        const double* srm = P.s_x_mean + k * D;
+#ifdef PN_HOST_EMULATION /* tests/emulation: the copy lands at once -- the earliest moment the hardware allows */
+        for (int e = 2 * gl; e < D * D; e += 2 * G) buf[e] = src[e], buf[e + 1] = src[e + 1];
+        for (int c = 2 * gl; c < D; c += 2 * G) buf[D * D + c] = srm[c], buf[D * D + c + 1] = srm[c + 1];
+#else
         for (int e = 2 * gl; e < D * D; e += 2 * G) {
             const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + e);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src + e) : "memory");
         }
-        const double* srm = P.s_x_mean + k * D;
         for (int c = 2 * gl; c < D; c += 2 * G) {
             const unsigned sa = (unsigned)__cvta_generic_to_shared(buf + D * D + c);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(srm + c) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
     }
 
     static __device__ void run(const PnSmoothParams& P, double* smem_all) {
@@ -263,7 +268,9 @@ struct PnSmoothCol {
                    next one now so that its HBM / L2 latency hides under this step's arithmetic */
                 if (ASYNC) {
                     Rec = sm + OFF_REC + cur * RECSZ;
+#ifndef PN_HOST_EMULATION
                     asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
                     if (!doit)
                         for (int e = gl; e < D * D + D; e += G) Rec[e] = 0.0;
                     if (doit && k > a0 && P.s_h[k - 1] != 0.0) stage_async(P, k - 1, sm + OFF_REC + (cur ^ 1) * RECSZ, gl);

@@ -237,7 +237,9 @@ struct PnSmoothReg {
 #pragma unroll
                             for (int c = 0; c < D; c++) Tt[lr][D + c] = rr[c];
                             /* next record towards L2 while this one is processed */
+#ifndef PN_HOST_EMULATION
                             if (ld && k > a0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.s_x_covfac + ((k - 1) * D + row) * D));
+#endif
                         }
 #pragma unroll
                         for (int i = 0; i < d; i++)

@@ -1,7 +1,15 @@
 // cuda_shim.h -- just enough of the CUDA C++ dialect to compile the kernel headers of probnumdiffeq.jl_b200/csrc/kernels for the HOST
-// with g++, one "thread" per process: execution-space qualifiers vanish, threadIdx is 0, warp collectives are the identity on a warp of
-// one, atomics are plain operations.  Only kernels that give a whole trajectory to ONE thread (pn_thread.cuh, the headline kernel)
-// are meaningful under this shim; the group / CTA kernels exchange data between lanes and are checked on the device only.
+// with g++.  Two modes:
+//   default       one "thread" per process: execution-space qualifiers vanish, threadIdx is 0, warp collectives are the identity on a
+//                 warp of one, atomics are plain operations.  For the kernels that give a whole trajectory to ONE thread (pn_thread.cuh,
+//                 the headline kernel; pn_kron.cuh, pn_blocks.cuh).
+//   PN_SHIM_WARP  one WARP: every lane is a host thread (threadIdx is thread_local), the warp collectives (__shfl*_sync, __any / __all /
+//                 __ballot_sync, __syncwarp; __syncthreads* for a CTA of that one warp) exchange through a slot array between two
+//                 pthread barriers, atomics are real atomics, "shared memory" is one array all lanes see.  For the group kernels
+//                 (pn_small.cuh, pn_smooth_col.cuh, pn_smooth_reg.cuh: G lanes per trajectory).  Because every cross-lane hand-over goes
+//                 through a pthread barrier, ThreadSanitizer (-fsanitize=thread) sees exactly the ordering the device guarantees at
+//                 __syncwarp / shuffle points and reports any shared-memory access pair that is not separated by one: a host-side
+//                 racecheck of the exchange protocol (compute-sanitizer is closed on the GPU pool).
 // Test infrastructure (tests/test_kernel_host_emulation.py); nothing in the product includes it.
 #pragma once
 #include <cmath>
@@ -23,13 +31,85 @@
 struct PnShimDim3 {
     unsigned x, y, z;
 };
+#ifdef PN_SHIM_WARP
+#include <pthread.h>
+extern thread_local PnShimDim3 threadIdx; /* set by the lane's host thread (pn_warp_host.cpp) */
+extern PnShimDim3 blockDim;               /* {lanes, 1, 1} */
+static const PnShimDim3 blockIdx{0, 0, 0}, gridDim{1, 1, 1};
+struct PnShimWarp {
+    pthread_barrier_t bar;
+    uint64_t slot[32];
+    int lanes; /* host threads in the warp: a multiple of the group size, <= 32 (lanes that do not exist never take part) */
+};
+extern PnShimWarp pn_shim_warp;
+static inline void pn_shim_barrier() { pthread_barrier_wait(&pn_shim_warp.bar); }
+#else
 static const PnShimDim3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
+#endif
 
 struct double2 {
     double x, y;
 };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
+#ifdef PN_SHIM_WARP
+/* publish -> barrier -> read the source lane's slot -> barrier (the second one keeps a fast lane's next publish off a slow lane's read) */
+template <class T>
+static inline T pn_shim_exchange(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffles move at most 64 bits here");
+    const int lane = threadIdx.x & 31;
+    uint64_t b = 0;
+    std::memcpy(&b, &v, sizeof(T));
+    pn_shim_warp.slot[lane] = b;
+    pn_shim_barrier();
+    const uint64_t r = pn_shim_warp.slot[(src_lane >= 0 && src_lane < pn_shim_warp.lanes) ? src_lane : lane];
+    pn_shim_barrier();
+    T o;
+    std::memcpy(&o, &r, sizeof(T));
+    return o;
+}
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+    const int lane = threadIdx.x & 31;
+    return pn_shim_exchange(v, (lane & ~(width - 1)) | (src & (width - 1)));
+}
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) {
+    const int lane = threadIdx.x & 31, s = lane ^ m;
+    return pn_shim_exchange(v, ((s & ~(width - 1)) == (lane & ~(width - 1))) ? s : lane);
+}
+template <class T>
+static inline T __shfl_down_sync(unsigned, T v, int dlt, int width = 32) {
+    const int lane = threadIdx.x & 31, s = lane + dlt;
+    return pn_shim_exchange(v, ((s & ~(width - 1)) == (lane & ~(width - 1))) ? s : lane);
+}
+template <class T>
+static inline T __shfl_up_sync(unsigned, T v, int dlt, int width = 32) {
+    const int lane = threadIdx.x & 31, s = lane - dlt;
+    return pn_shim_exchange(v, (s >= 0 && (s & ~(width - 1)) == (lane & ~(width - 1))) ? s : lane);
+}
+#ifdef PN_SHIM_DROP_SYNCWARP /* negative control of the race check: without the kernels' __syncwarp()s ThreadSanitizer must report */
+static inline void __syncwarp(unsigned = 0xffffffffu) {}
+#else
+static inline void __syncwarp(unsigned = 0xffffffffu) { pn_shim_barrier(); }
+#endif
+static inline unsigned __ballot_sync(unsigned, int p) {
+    const int lane = threadIdx.x & 31;
+    pn_shim_warp.slot[lane] = p ? 1u : 0u;
+    pn_shim_barrier();
+    unsigned m = 0;
+    for (int l = 0; l < pn_shim_warp.lanes; l++) m |= (unsigned)pn_shim_warp.slot[l] << l;
+    pn_shim_barrier();
+    return m;
+}
+static inline int __any_sync(unsigned k, int p) { return __ballot_sync(k, p) != 0u; }
+static inline int __all_sync(unsigned k, int p) { return __ballot_sync(k, !p) == 0u; }
+static inline unsigned __activemask() { return pn_shim_warp.lanes >= 32 ? 0xffffffffu : ((1u << pn_shim_warp.lanes) - 1u); }
+/* the CTA is this one warp */
+static inline void __syncthreads() { pn_shim_barrier(); }
+static inline int __syncthreads_or(int p) { return __any_sync(0xffffffffu, p); }
+static inline int __syncthreads_and(int p) { return __all_sync(0xffffffffu, p); }
+#else
 template <class T>
 static inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
 template <class T>
@@ -46,6 +126,7 @@ static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 static inline int __any_sync(unsigned, int p) { return p; }
 static inline int __all_sync(unsigned, int p) { return p; }
 static inline unsigned __activemask() { return 1u; }
+#endif
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline void __threadfence() {}
@@ -53,6 +134,10 @@ static inline void __threadfence_block() {}
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
 
+#ifdef PN_SHIM_WARP
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+#else
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
     const unsigned long long o = *p;
     *p = o + v;
@@ -68,6 +153,7 @@ static inline double atomicAdd(double* p, double v) {
     *p = o + v;
     return o;
 }
+#endif
 
 static inline int __double2hiint(double x) {
     int64_t b;

@@ -1,0 +1,190 @@
+// pn_warp_host.cpp -- the group-per-trajectory kernels (csrc/kernels/pn_small.cuh: the step kernel of the saving / smoothing solves;
+// pn_smooth_col.cuh and pn_smooth_reg.cuh: the register-resident RTS sweeps) compiled for the host under cuda_shim.h in PN_SHIM_WARP mode and
+// run as ONE WARP of host threads: every lane is a pthread, shuffles / votes / __syncwarp go through pthread barriers, the kernels' shared
+// memory is one array all lanes see.  32 / G trajectories are in flight at a time and the groups pull more from the kernels' own atomic work
+// queue.  PN_EMU_PROBLEM / PN_EMU_Q / PN_EMU_G / PN_EMU_GS / PN_EMU_ADAPTIVE / PN_EMU_DYNAMIC select the instantiation at compile time, as
+// the NVRTC build does.  Built with -fsanitize=thread the same program is a racecheck of the kernels' shared-memory protocol.
+// The caller (tests/test_kernel_host_emulation.py) computes the host-side constants of the parameter blocks independently of pnode_api.cu and
+// compares the outputs with the oracle.  Test infrastructure: nothing in the product includes this file.
+#define PN_SHIM_WARP 1
+#include "cuda_shim.h"
+#include <vector>
+
+thread_local PnShimDim3 threadIdx{0, 0, 0};
+PnShimDim3 blockDim{32, 1, 1};
+PnShimWarp pn_shim_warp;
+
+#ifndef PN_EMU_G
+#define PN_EMU_G 4
+#endif
+#ifndef PN_EMU_GS
+#define PN_EMU_GS 8
+#endif
+#define PN_THREADS 32     /* one warp is the CTA */
+#define PN_SMR_THREADS 32
+#include "kernels/pn_small.cuh"
+#include "kernels/pn_smooth_col.cuh"
+#include "kernels/pn_smooth_reg.cuh"
+#include "kernels/pn_builtin_problems.cuh"
+
+#ifndef PN_EMU_ADAPTIVE
+#define PN_EMU_ADAPTIVE 0
+#endif
+#ifndef PN_EMU_DYNAMIC
+#define PN_EMU_DYNAMIC 0
+#endif
+#ifndef PN_EMU_SAVE
+#define PN_EMU_SAVE 2
+#endif
+
+alignas(16) double pn_small_shared[32768];
+alignas(16) double pn_smc_shared[32768];
+alignas(16) double pn_smr_shared[32768];
+
+extern "C" int pn_emu_d(void) { return PN_EMU_PROBLEM::d; }
+extern "C" int pn_emu_n_p(void) { return PN_EMU_PROBLEM::n_p; }
+extern "C" int pn_emu_q(void) { return PN_EMU_Q; }
+extern "C" int pn_emu_g(void) { return PN_EMU_G; }
+extern "C" int pn_emu_gs(void) { return PN_EMU_GS; }
+
+template <class F>
+static void run_warp(int lanes, F body) {
+    pn_shim_warp.lanes = lanes;
+    blockDim.x = (unsigned)lanes;
+    pthread_barrier_init(&pn_shim_warp.bar, nullptr, (unsigned)lanes);
+    struct Arg {
+        F* body;
+        int lane;
+    };
+    std::vector<pthread_t> th(lanes);
+    std::vector<Arg> args(lanes);
+    for (int l = 0; l < lanes; l++) {
+        args[l] = Arg{&body, l};
+        pthread_create(&th[l], nullptr, [](void* a) -> void* {
+            Arg* x = (Arg*)a;
+            threadIdx.x = (unsigned)x->lane;
+            (*x->body)();
+            return nullptr;
+        }, &args[l]);
+    }
+    for (int l = 0; l < lanes; l++) pthread_join(th[l], nullptr);
+    pthread_barrier_destroy(&pn_shim_warp.bar);
+}
+
+// scal_in : as pn_thread_host.cpp (16 doubles).  Per-trajectory inputs: init_mu [n_traj][D], init_dt [n_traj], p [n_traj][n_p].
+// Per-trajectory outputs: u_mean [n_traj][d], u_cov [n_traj][d][d], scal_out [n_traj][4] (t_end, loglik, diffusion, dt_last), counts
+// [n_traj][4] (naccept, nreject, nf, retcode).  With PN_EMU_SAVE >= 1 the CSR records (offsets [n_traj + 1]; s_t, s_u_mean, s_u_cov,
+// s_diffusion; with SAVE = 2 also s_x_mean, s_x_covfac, s_h) are written; smooth = 1 / 2 then runs the column- / row-distributed sweep
+// over them (in place, like the product: the records and s_u_mean / s_u_cov become the smoothed ones).
+extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* scal_in, int calibrate, const double* L, const double* U,
+                                  const double* Qb, const double* init_mu, const double* init_dt, const double* p, double* u_mean,
+                                  double* u_cov, double* scal_out, long long* counts, const long long* offsets, double* s_t,
+                                  double* s_u_mean, double* s_u_cov, double* s_diffusion, double* s_x_mean, double* s_x_covfac, double* s_h,
+                                  int smooth, int write_x) {
+    constexpr int n = PN_EMU_Q + 1;
+    PnParams P;
+    std::memset(&P, 0, sizeof P);
+    unsigned long long counter = 0;
+    std::vector<double> t_end(n_traj), loglik(n_traj), diffusion(n_traj), dt_last(n_traj);
+    std::vector<long long> naccept(n_traj), nreject(n_traj), nf(n_traj);
+    std::vector<int> retcode(n_traj, -1);
+    P.n_traj = n_traj;
+    P.p = p;
+    P.t0 = scal_in[0], P.t1 = scal_in[1], P.dt0 = scal_in[2];
+    P.abstol = scal_in[3], P.reltol = scal_in[4], P.dtmin = scal_in[5], P.dtmax = scal_in[6];
+    P.beta1 = scal_in[7], P.beta2 = scal_in[8], P.qmin = scal_in[9], P.qmax = scal_in[10], P.gamma = scal_in[11];
+    P.qsteady_min = scal_in[12], P.qsteady_max = scal_in[13], P.qoldinit = scal_in[14];
+    P.qoldinit_pb2 = std::pow(P.qoldinit, P.beta2);
+    P.inv_qmax = 1.0 / P.qmax, P.inv_qmin = 1.0 / P.qmin, P.inv_gamma = 1.0 / P.gamma;
+    P.initial_diffusion = scal_in[15];
+    P.maxiters = 1000000;
+    P.calibrate = calibrate;
+    P.order = PN_EMU_Q;
+    P.traj_stride = 1;
+    P.init_mu = init_mu;
+    P.init_dt = init_dt;
+    P.work_counter = &counter;
+    for (int i = 0; i < n * n; i++) P.L[i] = L[i], P.U[i] = U[i], P.Qb[i] = Qb[i];
+    P.t_end = t_end.data(), P.loglik = loglik.data(), P.diffusion = diffusion.data(), P.dt_last = dt_last.data();
+    P.u_mean = u_mean, P.u_cov = u_cov;
+    P.naccept = naccept.data(), P.nreject = nreject.data(), P.nf = nf.data(), P.retcode = retcode.data();
+    if (PN_EMU_SAVE >= 1) {
+        P.step_offsets = offsets;
+        P.s_t = s_t, P.s_u_mean = s_u_mean, P.s_u_cov = s_u_cov, P.s_diffusion = s_diffusion;
+        if (PN_EMU_SAVE >= 2) P.s_x_mean = s_x_mean, P.s_x_covfac = s_x_covfac, P.s_h = s_h;
+    }
+    run_warp(lanes, [&]() { pn_small_entry<PN_EMU_PROBLEM, PN_EMU_Q, PN_EMU_G, (PN_EMU_ADAPTIVE != 0), (PN_EMU_DYNAMIC != 0), PN_EMU_SAVE>(P); });
+    for (long long i = 0; i < n_traj; i++) {
+        scal_out[4 * i + 0] = t_end[i], scal_out[4 * i + 1] = loglik[i], scal_out[4 * i + 2] = diffusion[i], scal_out[4 * i + 3] = dt_last[i];
+        counts[4 * i + 0] = naccept[i], counts[4 * i + 1] = nreject[i], counts[4 * i + 2] = nf[i], counts[4 * i + 3] = retcode[i];
+    }
+#if PN_EMU_SAVE >= 2
+    if (smooth) {
+        PnSmoothParams S;
+        std::memset(&S, 0, sizeof S);
+        counter = 0;
+        S.n_traj = n_traj;
+        S.d = PN_EMU_PROBLEM::d, S.q = PN_EMU_Q;
+        S.dynamic = (PN_EMU_DYNAMIC != 0);
+        S.calibrate = calibrate;
+        S.initial_diffusion = P.initial_diffusion;
+        S.step_offsets = offsets;
+        S.s_h = s_h, S.s_diffusion = s_diffusion, S.gdiff = diffusion.data();
+        S.s_x_mean = s_x_mean, S.s_x_covfac = s_x_covfac, S.s_u_mean = s_u_mean, S.s_u_cov = s_u_cov;
+        for (int i = 0; i < n * n; i++) S.L[i] = L[i], S.U[i] = U[i];
+        S.work_counter = &counter;
+        S.write_x = write_x;
+        if (smooth == 1)
+            run_warp(lanes, [&]() { pn_smooth_col_entry<PN_EMU_PROBLEM::d, PN_EMU_Q, PN_EMU_GS>(S); });
+        else
+            run_warp(lanes, [&]() { pn_smooth_reg_entry<PN_EMU_PROBLEM::d, PN_EMU_Q, PN_EMU_GS>(S); });
+    }
+#endif
+}
+
+#ifdef PN_EMU_MAIN
+// Stand-alone form for ThreadSanitizer (a sanitized library cannot be loaded into an unsanitized python): reads one ensemble from a file of
+// doubles written by the test -- N, lanes, smooth, write_x, saved points per trajectory, scal_in[16], L, U, Qb, init_mu, init_dt, p -- runs the
+// step kernel and the sweep, prints a checksum.  ThreadSanitizer's report (and its exit code 66) is the result.
+#include <cstdio>
+int main(int argc, char** argv) {
+    if (argc < 2) return 2;
+    FILE* f = std::fopen(argv[1], "rb");
+    if (!f) return 2;
+    std::vector<double> in;
+    double buf[1024];
+    size_t got;
+    while ((got = std::fread(buf, 8, 1024, f)) > 0) in.insert(in.end(), buf, buf + got);
+    std::fclose(f);
+    constexpr int n = PN_EMU_Q + 1, d = PN_EMU_PROBLEM::d, D = d * n, np_ = PN_EMU_PROBLEM::n_p;
+    const double* c = in.data();
+    const long long N = (long long)c[0];
+    const int lanes = (int)c[1], smooth = (int)c[2], write_x = (int)c[3];
+    const long long ns = (long long)c[4];
+    c += 5;
+    const double* scal = c;
+    c += 16;
+    const double *L = c, *U = c + n * n, *Qb = c + 2 * n * n;
+    c += 3 * n * n;
+    const double* init_mu = c;
+    c += N * D;
+    const double* init_dt = c;
+    c += N;
+    const double* p = c;
+    c += N * (np_ > 0 ? np_ : 1);
+    if (c - in.data() != (long long)in.size()) return 3;
+    std::vector<long long> off(N + 1), counts(4 * N);
+    for (long long i = 0; i <= N; i++) off[i] = i * ns;
+    const long long T = off[N];
+    std::vector<double> um(N * d), uc(N * d * d), so(4 * N), s_t(T), s_u(T * d), s_c(T * d * d), s_df(T), s_x(T * D), s_xr(T * D * D), s_h(T);
+    pn_emu_warp_solve(N, lanes, scal, 0, L, U, Qb, init_mu, init_dt, p, um.data(), uc.data(), so.data(), counts.data(), off.data(), s_t.data(),
+                      s_u.data(), s_c.data(), s_df.data(), s_x.data(), s_xr.data(), s_h.data(), smooth, write_x);
+    double sum = 0.0;
+    for (double v : um) sum += v;
+    for (double v : s_u) sum += v;
+    long long acc = 0;
+    for (long long i = 0; i < N; i++) acc += counts[4 * i];
+    std::printf("accepted %lld checksum %.17g\n", acc, sum);
+    return 0;
+}
+#endif

@@ -214,3 +214,152 @@ def test_blocks_kernel_shapes(oracle, problem, q, t1, dt):
     assert (k["naccept"], k["nreject"], k["retcode"]) == (o["naccept"], o["nreject"], 0)
     assert _rel(k["u"], o["pu_mu"][-1]) < 1e-8
     assert _rel(k["diffusion_mv"], o["diffusions_mv"][o["naccept"] - 1]) < 1e-5
+
+
+# ---- the group-per-trajectory kernels as ONE WARP of host threads (cuda_shim.h, PN_SHIM_WARP): pn_small.cuh, pn_smooth_col.cuh, pn_smooth_reg.cuh ----
+def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False):
+    out = os.path.join(tempfile.gettempdir(), f"pn_emu_{os.getuid()}",
+                       f"warp_{problem}_q{q}_g{G}_gs{GS}_a{int(adaptive)}_d{int(dynamic)}_s{save}{'_tsan' if tsan else ''}" + (".exe" if tsan else ".so"))
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    src = os.path.join(HERE, "emulation", "pn_warp_host.cpp")
+    deps = [src, os.path.join(HERE, "emulation", "cuda_shim.h")] + [os.path.join(CSRC, "kernels", f) for f in
+                                                                     ("pn_small.cuh", "pn_smooth_col.cuh", "pn_smooth_reg.cuh", "pn_smooth.cuh", "pn_params.h",
+                                                                      "pn_builtin_problems.cuh")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
+        mode = ["-fsanitize=thread", "-g", "-DPN_EMU_MAIN=1"] if tsan else ["-fPIC", "-shared"]
+        subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", *mode, "-I", CSRC, f"-DPN_EMU_PROBLEM={STRUCT[problem]}", f"-DPN_EMU_Q={q}",
+                        f"-DPN_EMU_G={G}", f"-DPN_EMU_GS={GS}", f"-DPN_EMU_ADAPTIVE={int(adaptive)}", f"-DPN_EMU_DYNAMIC={int(dynamic)}",
+                        f"-DPN_EMU_SAVE={save}", src, "-o", out, "-lpthread"], check=True)
+    return out
+
+
+def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False, dynamic=False, calibrate=False, save=2, smooth=0, write_x=1, lanes=32,
+              abstol=1e-6, reltol=1e-3):
+    lib = C.CDLL(_build_warp(problem, q, G, GS, adaptive, dynamic, save))
+    lib.pn_emu_warp_solve.restype = None
+    d, n = lib.pn_emu_d(), q + 1
+    D = d * n
+    N = len(init_mu)
+    L, U, Qb = _iwp_constants(q)
+    scal = np.array([0.0, t1, dt, abstol, reltol, 0.0, t1, 0.7 / q, 0.4 / q, 0.2, 10.0, 0.9, 1.0, 1.0, 1e-4, 1.0])
+    off = np.ascontiguousarray(offsets, dtype=np.int64)
+    T = int(off[-1])
+    o = dict(u=np.zeros((N, d)), cov=np.zeros((N, d, d)), scal=np.zeros((N, 4)), counts=np.zeros((N, 4), dtype=np.int64), s_t=np.full(T, np.nan),
+             s_u=np.full((T, d), np.nan), s_cov=np.full((T, d, d), np.nan), s_diff=np.full(T, np.nan), s_x=np.full((T, D), np.nan),
+             s_xR=np.full((T, D, D), np.nan), s_h=np.zeros(T))
+    mu0 = np.ascontiguousarray(init_mu, dtype=float)
+    dt0 = np.full(N, float(dt))
+    pp = np.ascontiguousarray(ps, dtype=float)
+    A = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    I = lambda a: a.ctypes.data_as(C.POINTER(C.c_longlong))  # noqa: E731
+    lib.pn_emu_warp_solve(C.c_longlong(N), int(lanes), A(scal), int(calibrate), A(np.ascontiguousarray(L.ravel())), A(np.ascontiguousarray(U.ravel())),
+                          A(np.ascontiguousarray(Qb.ravel())), A(mu0), A(dt0), A(pp), A(o["u"]), A(o["cov"]), A(o["scal"]), I(o["counts"]), I(off),
+                          A(o["s_t"]), A(o["s_u"]), A(o["s_cov"]), A(o["s_diff"]), A(o["s_x"]), A(o["s_xR"]), A(o["s_h"]), int(smooth), int(write_x))
+    return o
+
+
+def _ensemble(pd, N, seed=0):
+    rng = np.random.default_rng(seed)
+    u0 = np.array(pd.u0, dtype=float)[None, :] * (1.0 + 0.05 * rng.standard_normal((N, pd.d)))
+    p = np.array(pd.p, dtype=float)[None, :] * (1.0 + 0.05 * rng.standard_normal((N, pd.n_p)))
+    return u0, p
+
+
+@pytest.mark.parametrize("problem,q,G,GS,t1,dt,N", [("fitzhugh_nagumo", 3, 4, 8, 1.0, 0.05, 11), ("vanderpol", 5, 8, 8, 0.01, 2.5e-4, 6)])
+@pytest.mark.parametrize("sweep", [1, 2])
+def test_group_step_kernel_and_register_sweeps_as_a_warp(oracle, problem, q, G, GS, t1, dt, N, sweep):
+    """pn_small.cuh (saving pass, SAVE = 2) and the register-resident sweeps pn_smooth_col.cuh (sweep 1, the default) / pn_smooth_reg.cuh (sweep 2) on the
+    BASELINE shapes cfg1 (FitzHugh-Nagumo, EK1(3), G = 4 / 8) and cfg3 (Van der Pol, EK1(5): the instantiation <d = 2, q = 5, G = 8>), run as one
+    warp of 32 host threads over an ensemble larger than the 32 / G groups (so the groups pull from the work queue and drain raggedly), fixed steps,
+    FixedDiffusion without calibration: every filtered and smoothed mean 1e-10 against the oracle, covariances against the oracle's own
+    Cholesky-vs-QR floor, and the log-likelihood."""
+    pd = problems.PROBLEMS[problem]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N)
+    kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, adaptive=False, dt=dt, t0=0.0, t1=t1, save_everystep=True)
+    of, os_, os2 = [], [], []
+    for i in range(N):
+        of.append(oracle.solve(oracle.make_config(pd.d, q, pd.n_p, smooth=False, cov_backend=oracle.COV_REF, **kw), rhs, u0[i], p[i]))
+        os_.append(oracle.solve(oracle.make_config(pd.d, q, pd.n_p, smooth=True, cov_backend=oracle.COV_REF, **kw), rhs, u0[i], p[i]))
+        os2.append(oracle.solve(oracle.make_config(pd.d, q, pd.n_p, smooth=True, cov_backend=oracle.COV_QR, **kw), rhs, u0[i], p[i]))
+    ns = of[0]["n"]
+    off = np.arange(N + 1) * ns
+    mu0 = np.array([o["x_filt_mu"][0] for o in of])
+    kf = _run_warp(problem, q, G, GS, mu0, p, off, t1=t1, dt=dt, smooth=0)
+    ks = _run_warp(problem, q, G, GS, mu0, p, off, t1=t1, dt=dt, smooth=sweep)
+    for i in range(N):
+        sl = slice(off[i], off[i + 1])
+        assert tuple(kf["counts"][i]) == (ns - 1, 0, of[i]["nf"], 0)
+        assert np.allclose(kf["s_t"][sl], of[i]["t"], rtol=0, atol=1e-13)
+        assert _rel(kf["s_u"][sl], of[i]["pu_mu"]) < 1e-10 and _rel(kf["s_x"][sl], of[i]["x_filt_mu"]) < 1e-10
+        assert _rel(kf["s_cov"][sl][1:], of[i]["pu_cov"][1:]) < 1e-9
+        assert kf["scal"][i, 1] == pytest.approx(of[i]["loglik"], rel=1e-10)
+        assert _rel(ks["s_u"][sl], os_[i]["pu_mu"]) < 1e-10
+        floor = _rel(os2[i]["pu_cov"][1:], os_[i]["pu_cov"][1:])
+        assert _rel(ks["s_cov"][sl][1:], os_[i]["pu_cov"][1:]) < max(1e-9, 20 * floor)
+        # the smoothed state records (write_x): means, and the factors through R'R
+        assert _rel(ks["s_x"][sl], os_[i]["x_smooth_mu"]) < 1e-9
+
+
+def test_group_step_kernel_adaptive_ragged_ensemble(oracle):
+    """pn_small.cuh, adaptive with DynamicDiffusion, nothing saved, on ROBER (G = 4: eight trajectories in flight, 19 in the queue with different
+    parameters and therefore different step counts): per-trajectory accept / reject / nf counts identical with the oracle's, end states 1e-8."""
+    pd = problems.PROBLEMS["rober"]
+    q, N = 3, 19
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N, seed=3)
+    u0[:] = np.array(pd.u0)[None, :]
+    oo = [oracle.solve(oracle.make_config(pd.d, q, pd.n_p, alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC, smooth=False, adaptive=True, dt=1e-4, t0=0.0, t1=10.0,
+                                          save_everystep=True, cov_backend=oracle.COV_REF), rhs, u0[i], p[i]) for i in range(N)]
+    mu0 = np.array([o["x_filt_mu"][0] for o in oo])
+    k = _run_warp("rober", q, 4, 8, mu0, p, np.arange(N + 1), t1=10.0, dt=1e-4, adaptive=True, dynamic=True, save=0)
+    assert len({o["naccept"] for o in oo}) > 3  # ragged
+    for i in range(N):
+        assert tuple(k["counts"][i]) == (oo[i]["naccept"], oo[i]["nreject"], oo[i]["nf"], 0)
+        assert k["scal"][i, 0] == 10.0
+        assert _rel(k["u"][i], oo[i]["pu_mu"][-1]) < 1e-8
+        assert k["scal"][i, 1] == pytest.approx(oo[i]["loglik"], rel=1e-8)
+
+
+def _tsan_run(problem, q, G, GS, *, N, t1, dt, adaptive, dynamic, save, smooth, oracle, drop_syncwarp=False, lanes=32):
+    pd = problems.PROBLEMS[problem]
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N, seed=5)
+    kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC if dynamic else oracle.DIFF_FIXED, calibrate=False, adaptive=False, dt=dt, t0=0.0, t1=t1,
+              save_everystep=True, smooth=False)
+    oo = [oracle.solve(oracle.make_config(pd.d, q, pd.n_p, **kw), rhs, u0[i], p[i]) for i in range(N)]
+    L, U, Qb = _iwp_constants(q)
+    scal = np.array([0.0, t1, dt, 1e-6, 1e-3, 0.0, t1, 0.7 / q, 0.4 / q, 0.2, 10.0, 0.9, 1.0, 1.0, 1e-4, 1.0])
+    blob = np.concatenate([[N, lanes, smooth, 1, oo[0]["n"] if save else 1], scal, L.ravel(), U.ravel(), Qb.ravel(),
+                           np.array([o["x_filt_mu"][0] for o in oo]).ravel(), np.full(N, dt), p.ravel()]).astype(np.float64)
+    exe = _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=True)
+    if drop_syncwarp:
+        exe2 = exe.replace(".exe", "_nosync.exe")
+        if not os.path.exists(exe2) or os.path.getmtime(exe2) < os.path.getmtime(exe):
+            subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fsanitize=thread", "-g", "-DPN_EMU_MAIN=1", "-DPN_SHIM_DROP_SYNCWARP=1", "-I", CSRC,
+                            f"-DPN_EMU_PROBLEM={STRUCT[problem]}", f"-DPN_EMU_Q={q}", f"-DPN_EMU_G={G}", f"-DPN_EMU_GS={GS}",
+                            f"-DPN_EMU_ADAPTIVE={int(adaptive)}", f"-DPN_EMU_DYNAMIC={int(dynamic)}", f"-DPN_EMU_SAVE={save}",
+                            os.path.join(HERE, "emulation", "pn_warp_host.cpp"), "-o", exe2, "-lpthread"], check=True)
+        exe = exe2
+    path = os.path.join(os.path.dirname(exe), f"tsan_in_{problem}_{q}_{save}_{smooth}.bin")
+    blob.tofile(path)
+    r = subprocess.run([exe, path], capture_output=True, text=True, timeout=900, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0"))
+    return r, sum(o["naccept"] for o in oo)
+
+
+@pytest.mark.parametrize("problem,q,G,GS,t1,dt,smooth", [("fitzhugh_nagumo", 3, 4, 8, 0.5, 0.05, 1), ("fitzhugh_nagumo", 3, 4, 8, 0.5, 0.05, 2),
+                                                       ("vanderpol", 5, 8, 8, 2.5e-3, 2.5e-4, 1)])
+def test_threadsanitizer_racecheck_of_the_exchange_protocol(oracle, problem, q, G, GS, t1, dt, smooth):
+    """Racecheck on the host (compute-sanitizer is closed on the GPU pool): the step kernel (saving pass: Gram + Cholesky through the group's exchange
+    region) and the register sweeps (record staging with cp.async double buffering, smoothed-record write-back) as one warp of host threads under
+    ThreadSanitizer.  Every cross-lane ordering the device guarantees (shuffles, votes, __syncwarp) is a pthread barrier, so a shared- or global-memory
+    access pair of two lanes that the kernel does not separate by one of them is reported.  Clean run: exit code 0, no report, all steps accepted."""
+    r, nacc = _tsan_run(problem, q, G, GS, N=9, t1=t1, dt=dt, adaptive=False, dynamic=False, save=2, smooth=smooth, oracle=oracle)
+    assert "ThreadSanitizer" not in r.stderr, r.stderr[:4000]
+    assert r.returncode == 0 and f"accepted {nacc} " in r.stdout
+
+
+def test_threadsanitizer_sees_a_missing_syncwarp(oracle):
+    """Negative control: the same program with the kernels' __syncwarp() calls compiled out must be reported as racy (the check has teeth)."""
+    r, _ = _tsan_run("fitzhugh_nagumo", 3, 4, 8, N=9, t1=0.5, dt=0.05, adaptive=False, dynamic=False, save=2, smooth=1, oracle=oracle, drop_syncwarp=True)
+    assert "ThreadSanitizer: data race" in r.stderr and r.returncode != 0
