@@ -3,10 +3,11 @@
 //   default       one "thread" per process: execution-space qualifiers vanish, threadIdx is 0, warp collectives are the identity on a
 //                 warp of one, atomics are plain operations.  For the kernels that give a whole trajectory to ONE thread (pn_thread.cuh,
 //                 the headline kernel; pn_kron.cuh, pn_blocks.cuh).
-//   PN_SHIM_WARP  one WARP: every lane is a host thread (threadIdx is thread_local), the warp collectives (__shfl*_sync, __any / __all /
-//                 __ballot_sync, __syncwarp; __syncthreads* for a CTA of that one warp) exchange through a slot array between two
-//                 pthread barriers, atomics are real atomics, "shared memory" is one array all lanes see.  For the group kernels
-//                 (pn_small.cuh, pn_smooth_col.cuh, pn_smooth_reg.cuh: G lanes per trajectory).  Because every cross-lane hand-over goes
+//   PN_SHIM_WARP  one CTA of one or more WARPS: every lane is a host thread (threadIdx is thread_local), the warp collectives (__shfl*_sync,
+//                 __any / __all / __ballot_sync, __syncwarp) exchange through a per-warp slot array between two pthread barriers of that
+//                 warp, __syncthreads* are barriers over the CTA, atomics are real atomics, "shared memory" is one array all lanes see.
+//                 For the group kernels (pn_small.cuh, pn_smooth_col.cuh, pn_smooth_reg.cuh: G lanes per trajectory, one warp) and the
+//                 CTA-per-trajectory kernel (pn_cta.cuh, 256 threads).  Because every cross-lane hand-over goes
 //                 through a pthread barrier, ThreadSanitizer (-fsanitize=thread) sees exactly the ordering the device guarantees at
 //                 __syncwarp / shuffle points and reports any shared-memory access pair that is not separated by one: a host-side
 //                 racecheck of the exchange protocol (compute-sanitizer is closed on the GPU pool).
@@ -26,7 +27,7 @@
 #define __grid_constant__
 #define __restrict__
 #define __shared__
-#define __align__(x) alignas(x)
+#define __align__(x) __attribute__((aligned(x)))
 
 struct PnShimDim3 {
     unsigned x, y, z;
@@ -41,8 +42,16 @@ struct PnShimWarp {
     uint64_t slot[32];
     int lanes; /* host threads in the warp: a multiple of the group size, <= 32 (lanes that do not exist never take part) */
 };
-extern PnShimWarp pn_shim_warp;
+struct PnShimCta { /* a CTA of up to 32 warps: warp collectives stay inside a warp, __syncthreads* span the CTA */
+    PnShimWarp warp[32];
+    pthread_barrier_t bar;
+    int vote[1024];
+    int threads;
+};
+extern PnShimCta pn_shim_cta;
+#define pn_shim_warp (pn_shim_cta.warp[threadIdx.x >> 5])
 static inline void pn_shim_barrier() { pthread_barrier_wait(&pn_shim_warp.bar); }
+static inline void pn_shim_cta_barrier() { pthread_barrier_wait(&pn_shim_cta.bar); }
 #else
 static const PnShimDim3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
 #endif
@@ -105,10 +114,17 @@ static inline unsigned __ballot_sync(unsigned, int p) {
 static inline int __any_sync(unsigned k, int p) { return __ballot_sync(k, p) != 0u; }
 static inline int __all_sync(unsigned k, int p) { return __ballot_sync(k, !p) == 0u; }
 static inline unsigned __activemask() { return pn_shim_warp.lanes >= 32 ? 0xffffffffu : ((1u << pn_shim_warp.lanes) - 1u); }
-/* the CTA is this one warp */
-static inline void __syncthreads() { pn_shim_barrier(); }
-static inline int __syncthreads_or(int p) { return __any_sync(0xffffffffu, p); }
-static inline int __syncthreads_and(int p) { return __all_sync(0xffffffffu, p); }
+static inline void __syncthreads() { pn_shim_cta_barrier(); }
+static inline int pn_shim_cta_count(int p) {
+    pn_shim_cta.vote[threadIdx.x] = p ? 1 : 0;
+    pn_shim_cta_barrier();
+    int c = 0;
+    for (int t = 0; t < pn_shim_cta.threads; t++) c += pn_shim_cta.vote[t];
+    pn_shim_cta_barrier();
+    return c;
+}
+static inline int __syncthreads_or(int p) { return pn_shim_cta_count(p) != 0; }
+static inline int __syncthreads_and(int p) { return pn_shim_cta_count(p) == pn_shim_cta.threads; }
 #else
 template <class T>
 static inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }

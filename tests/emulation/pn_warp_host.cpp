@@ -12,7 +12,7 @@
 
 thread_local PnShimDim3 threadIdx{0, 0, 0};
 PnShimDim3 blockDim{32, 1, 1};
-PnShimWarp pn_shim_warp;
+PnShimCta pn_shim_cta;
 
 #ifndef PN_EMU_G
 #define PN_EMU_G 4
@@ -22,9 +22,16 @@ PnShimWarp pn_shim_warp;
 #endif
 #define PN_THREADS 32     /* one warp is the CTA */
 #define PN_SMR_THREADS 32
+#ifndef PN_EMU_KERNEL
+#define PN_EMU_KERNEL 0 /* 0: pn_small.cuh (G lanes per trajectory, one warp); 1: pn_cta.cuh (one CTA of PN_CTA_THREADS threads per trajectory) */
+#endif
 #include "kernels/pn_small.cuh"
 #include "kernels/pn_smooth_col.cuh"
 #include "kernels/pn_smooth_reg.cuh"
+#if PN_EMU_KERNEL == 1
+#include "kernels/pn_cta.cuh"
+alignas(16) double pn_cta_sm[65536];
+#endif
 #include "kernels/pn_builtin_problems.cuh"
 
 #ifndef PN_EMU_ADAPTIVE
@@ -48,27 +55,33 @@ extern "C" int pn_emu_g(void) { return PN_EMU_G; }
 extern "C" int pn_emu_gs(void) { return PN_EMU_GS; }
 
 template <class F>
-static void run_warp(int lanes, F body) {
-    pn_shim_warp.lanes = lanes;
-    blockDim.x = (unsigned)lanes;
-    pthread_barrier_init(&pn_shim_warp.bar, nullptr, (unsigned)lanes);
+static void run_warp(int threads, F body) { /* a CTA of `threads` host threads: ceil(threads / 32) warps */
+    const int warps = (threads + 31) / 32;
+    pn_shim_cta.threads = threads;
+    blockDim.x = (unsigned)threads;
+    pthread_barrier_init(&pn_shim_cta.bar, nullptr, (unsigned)threads);
+    for (int w = 0; w < warps; w++) {
+        pn_shim_cta.warp[w].lanes = (threads - 32 * w < 32) ? threads - 32 * w : 32;
+        pthread_barrier_init(&pn_shim_cta.warp[w].bar, nullptr, (unsigned)pn_shim_cta.warp[w].lanes);
+    }
     struct Arg {
         F* body;
-        int lane;
+        int tid;
     };
-    std::vector<pthread_t> th(lanes);
-    std::vector<Arg> args(lanes);
-    for (int l = 0; l < lanes; l++) {
+    std::vector<pthread_t> th(threads);
+    std::vector<Arg> args(threads);
+    for (int l = 0; l < threads; l++) {
         args[l] = Arg{&body, l};
         pthread_create(&th[l], nullptr, [](void* a) -> void* {
             Arg* x = (Arg*)a;
-            threadIdx.x = (unsigned)x->lane;
+            threadIdx.x = (unsigned)x->tid;
             (*x->body)();
             return nullptr;
         }, &args[l]);
     }
-    for (int l = 0; l < lanes; l++) pthread_join(th[l], nullptr);
-    pthread_barrier_destroy(&pn_shim_warp.bar);
+    for (int l = 0; l < threads; l++) pthread_join(th[l], nullptr);
+    pthread_barrier_destroy(&pn_shim_cta.bar);
+    for (int w = 0; w < warps; w++) pthread_barrier_destroy(&pn_shim_cta.warp[w].bar);
 }
 
 // scal_in : as pn_thread_host.cpp (16 doubles).  Per-trajectory inputs: init_mu [n_traj][D], init_dt [n_traj], p [n_traj][n_p].
@@ -113,12 +126,17 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
         P.s_t = s_t, P.s_u_mean = s_u_mean, P.s_u_cov = s_u_cov, P.s_diffusion = s_diffusion;
         if (PN_EMU_SAVE >= 2) P.s_x_mean = s_x_mean, P.s_x_covfac = s_x_covfac, P.s_h = s_h;
     }
+#if PN_EMU_KERNEL == 1
+    (void)lanes;
+    run_warp(PN_CTA_THREADS, [&]() { pn_cta_entry<PN_EMU_PROBLEM, PN_EMU_Q, (PN_EMU_ADAPTIVE != 0), (PN_EMU_DYNAMIC != 0), PN_EMU_SAVE>(P); });
+#else
     run_warp(lanes, [&]() { pn_small_entry<PN_EMU_PROBLEM, PN_EMU_Q, PN_EMU_G, (PN_EMU_ADAPTIVE != 0), (PN_EMU_DYNAMIC != 0), PN_EMU_SAVE>(P); });
+#endif
     for (long long i = 0; i < n_traj; i++) {
         scal_out[4 * i + 0] = t_end[i], scal_out[4 * i + 1] = loglik[i], scal_out[4 * i + 2] = diffusion[i], scal_out[4 * i + 3] = dt_last[i];
         counts[4 * i + 0] = naccept[i], counts[4 * i + 1] = nreject[i], counts[4 * i + 2] = nf[i], counts[4 * i + 3] = retcode[i];
     }
-#if PN_EMU_SAVE >= 2
+#if PN_EMU_SAVE >= 2 && PN_EMU_KERNEL == 0
     if (smooth) {
         PnSmoothParams S;
         std::memset(&S, 0, sizeof S);

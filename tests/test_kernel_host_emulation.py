@@ -217,25 +217,25 @@ def test_blocks_kernel_shapes(oracle, problem, q, t1, dt):
 
 
 # ---- the group-per-trajectory kernels as ONE WARP of host threads (cuda_shim.h, PN_SHIM_WARP): pn_small.cuh, pn_smooth_col.cuh, pn_smooth_reg.cuh ----
-def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False):
+def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False, cta=False):
     out = os.path.join(tempfile.gettempdir(), f"pn_emu_{os.getuid()}",
-                       f"warp_{problem}_q{q}_g{G}_gs{GS}_a{int(adaptive)}_d{int(dynamic)}_s{save}{'_tsan' if tsan else ''}" + (".exe" if tsan else ".so"))
+                       f"{'cta' if cta else 'warp'}_{problem}_q{q}_g{G}_gs{GS}_a{int(adaptive)}_d{int(dynamic)}_s{save}{'_tsan' if tsan else ''}" + (".exe" if tsan else ".so"))
     os.makedirs(os.path.dirname(out), exist_ok=True)
     src = os.path.join(HERE, "emulation", "pn_warp_host.cpp")
     deps = [src, os.path.join(HERE, "emulation", "cuda_shim.h")] + [os.path.join(CSRC, "kernels", f) for f in
-                                                                     ("pn_small.cuh", "pn_smooth_col.cuh", "pn_smooth_reg.cuh", "pn_smooth.cuh", "pn_params.h",
-                                                                      "pn_builtin_problems.cuh")]
+                                                                     ("pn_small.cuh", "pn_cta.cuh", "pn_smooth_col.cuh", "pn_smooth_reg.cuh", "pn_smooth.cuh",
+                                                                      "pn_params.h", "pn_builtin_problems.cuh")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
         mode = ["-fsanitize=thread", "-g", "-DPN_EMU_MAIN=1"] if tsan else ["-fPIC", "-shared"]
         subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", *mode, "-I", CSRC, f"-DPN_EMU_PROBLEM={STRUCT[problem]}", f"-DPN_EMU_Q={q}",
                         f"-DPN_EMU_G={G}", f"-DPN_EMU_GS={GS}", f"-DPN_EMU_ADAPTIVE={int(adaptive)}", f"-DPN_EMU_DYNAMIC={int(dynamic)}",
-                        f"-DPN_EMU_SAVE={save}", src, "-o", out, "-lpthread"], check=True)
+                        f"-DPN_EMU_SAVE={save}", f"-DPN_EMU_KERNEL={int(cta)}", src, "-o", out, "-lpthread"], check=True)
     return out
 
 
 def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False, dynamic=False, calibrate=False, save=2, smooth=0, write_x=1, lanes=32,
-              abstol=1e-6, reltol=1e-3):
-    lib = C.CDLL(_build_warp(problem, q, G, GS, adaptive, dynamic, save))
+              abstol=1e-6, reltol=1e-3, cta=False):
+    lib = C.CDLL(_build_warp(problem, q, G, GS, adaptive, dynamic, save, cta=cta))
     lib.pn_emu_warp_solve.restype = None
     d, n = lib.pn_emu_d(), q + 1
     D = d * n
@@ -321,18 +321,21 @@ def test_group_step_kernel_adaptive_ragged_ensemble(oracle):
         assert k["scal"][i, 1] == pytest.approx(oo[i]["loglik"], rel=1e-8)
 
 
-def _tsan_run(problem, q, G, GS, *, N, t1, dt, adaptive, dynamic, save, smooth, oracle, drop_syncwarp=False, lanes=32):
+def _tsan_run(problem, q, G, GS, *, N, t1, dt, adaptive, dynamic, save, smooth, oracle, drop_syncwarp=False, lanes=32, cta=False):
     pd = problems.PROBLEMS[problem]
     rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
     u0, p = _ensemble(pd, N, seed=5)
-    kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC if dynamic else oracle.DIFF_FIXED, calibrate=False, adaptive=False, dt=dt, t0=0.0, t1=t1,
+    if pd.n_p == 0:
+        p = np.zeros((N, 1))
+    kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC if dynamic else oracle.DIFF_FIXED, calibrate=False, adaptive=adaptive, dt=dt, t0=0.0, t1=t1,
               save_everystep=True, smooth=False)
-    oo = [oracle.solve(oracle.make_config(pd.d, q, pd.n_p, **kw), rhs, u0[i], p[i]) for i in range(N)]
+    assert not (adaptive and save)  # ragged CSR segments are not laid out here
+    oo = [oracle.solve(oracle.make_config(pd.d, q, pd.n_p, **kw), rhs, u0[i], p[i] if pd.n_p else []) for i in range(N)]
     L, U, Qb = _iwp_constants(q)
     scal = np.array([0.0, t1, dt, 1e-6, 1e-3, 0.0, t1, 0.7 / q, 0.4 / q, 0.2, 10.0, 0.9, 1.0, 1.0, 1e-4, 1.0])
     blob = np.concatenate([[N, lanes, smooth, 1, oo[0]["n"] if save else 1], scal, L.ravel(), U.ravel(), Qb.ravel(),
                            np.array([o["x_filt_mu"][0] for o in oo]).ravel(), np.full(N, dt), p.ravel()]).astype(np.float64)
-    exe = _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=True)
+    exe = _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=True, cta=cta)
     if drop_syncwarp:
         exe2 = exe.replace(".exe", "_nosync.exe")
         if not os.path.exists(exe2) or os.path.getmtime(exe2) < os.path.getmtime(exe):
@@ -363,3 +366,47 @@ def test_threadsanitizer_sees_a_missing_syncwarp(oracle):
     """Negative control: the same program with the kernels' __syncwarp() calls compiled out must be reported as racy (the check has teeth)."""
     r, _ = _tsan_run("fitzhugh_nagumo", 3, 4, 8, N=9, t1=0.5, dt=0.05, adaptive=False, dynamic=False, save=2, smooth=1, oracle=oracle, drop_syncwarp=True)
     assert "ThreadSanitizer: data race" in r.stderr and r.returncode != 0
+
+
+# ---- the CTA-per-trajectory kernel (pn_cta.cuh: D > 32, Pleiades D = 112) as a CTA of 256 host threads ----
+def test_cta_kernel_pleiades_as_256_host_threads(oracle):
+    """pn_cta.cuh on Pleiades EK1(3), D = 112 (BASELINE cfg4): Gram + blocked Cholesky on register tiles out of shared memory, a chain of
+    __syncthreads() per step.  Three trajectories through the work queue, fixed steps with FixedDiffusion: end state 1e-10 / covariance 1e-9 /
+    log-likelihood 1e-9 against the oracle (the reference's route, COV_REF); adaptive with DynamicDiffusion: the oracle's accept / reject counts."""
+    pd = problems.PROBLEMS["pleiades"]
+    q, N = 3, 3
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N, seed=7)
+    p = np.zeros((N, 1))
+    kw = dict(alg=oracle.EK1, smooth=False, t0=0.0, save_everystep=True, cov_backend=oracle.COV_REF)
+    oo = [oracle.solve(oracle.make_config(pd.d, q, pd.n_p, diffusion=oracle.DIFF_FIXED, calibrate=False, adaptive=False, dt=0.01, t1=0.06, **kw), rhs, u0[i], [])
+          for i in range(N)]
+    mu0 = np.array([o["x_filt_mu"][0] for o in oo])
+    k = _run_warp("pleiades", q, 4, 8, mu0, p, np.arange(N + 1), t1=0.06, dt=0.01, save=0, cta=True)
+    for i in range(N):
+        assert tuple(k["counts"][i]) == (oo[i]["naccept"], 0, oo[i]["nf"], 0)
+        assert _rel(k["u"][i], oo[i]["pu_mu"][-1]) < 1e-10
+        assert _rel(k["cov"][i], oo[i]["pu_cov"][-1]) < 1e-9
+        assert k["scal"][i, 1] == pytest.approx(oo[i]["loglik"], rel=1e-9)
+    oa = [oracle.solve(oracle.make_config(pd.d, q, pd.n_p, diffusion=oracle.DIFF_DYNAMIC, adaptive=True, dt=1e-3, t1=0.3, **kw), rhs, u0[i], []) for i in range(N)]
+    k = _run_warp("pleiades", q, 4, 8, mu0, p, np.arange(N + 1), t1=0.3, dt=1e-3, adaptive=True, dynamic=True, save=0, cta=True)
+    for i in range(N):
+        assert tuple(k["counts"][i]) == (oa[i]["naccept"], oa[i]["nreject"], oa[i]["nf"], 0)
+        assert _rel(k["u"][i], oa[i]["pu_mu"][-1]) < 1e-8
+
+
+def test_threadsanitizer_racecheck_of_the_cta_kernel(oracle):
+    """pn_cta.cuh (Pleiades, D = 112) as a CTA of 256 host threads under ThreadSanitizer: every hand-over between threads of the step (panel
+    factorisation -> trailing update, C2 / S / gain, the scalar bookkeeping in PnCtaShared) must be separated by one of the kernel's __syncthreads()."""
+    r, nacc = _tsan_run("pleiades", 3, 4, 8, N=2, t1=0.03, dt=0.01, adaptive=False, dynamic=False, save=0, smooth=0, oracle=oracle, cta=True)
+    assert "ThreadSanitizer" not in r.stderr, r.stderr[:4000]
+    assert r.returncode == 0 and f"accepted {nacc} " in r.stdout
+
+
+@pytest.mark.parametrize("problem,cta,N,t1,dt", [("rober", False, 11, 1.0, 1e-4), ("pleiades", True, 2, 0.1, 1e-3)])
+def test_threadsanitizer_racecheck_adaptive(oracle, problem, cta, N, t1, dt):
+    """The adaptive route (rejected attempts, the controller, DynamicDiffusion; ROBER on pn_small: a ragged ensemble draining through the work queue;
+    Pleiades on pn_cta) under ThreadSanitizer: clean, and the total of accepted steps is the oracle's."""
+    r, nacc = _tsan_run(problem, 3, 4, 8, N=N, t1=t1, dt=dt, adaptive=True, dynamic=True, save=0, smooth=0, oracle=oracle, cta=cta)
+    assert "ThreadSanitizer" not in r.stderr, r.stderr[:4000]
+    assert r.returncode == 0 and f"accepted {nacc} " in r.stdout
