@@ -8,6 +8,7 @@
 // compares the outputs with the oracle.  Test infrastructure: nothing in the product includes this file.
 #define PN_SHIM_WARP 1
 #include "cuda_shim.h"
+#include <cstdlib>
 #include <vector>
 
 thread_local PnShimDim3 threadIdx{0, 0, 0};
@@ -26,6 +27,7 @@ PnShimCta pn_shim_cta;
 #define PN_EMU_KERNEL 0 /* 0: pn_small.cuh (G lanes per trajectory, one warp); 1: pn_cta.cuh (one CTA of PN_CTA_THREADS threads per trajectory) */
 #endif
 #include "kernels/pn_small.cuh"
+#include "kernels/pn_smooth.cuh" /* the warp-per-trajectory sweep (shared memory up to D = 56, a global workspace beyond: Pleiades D = 112) */
 #include "kernels/pn_smooth_col.cuh"
 #include "kernels/pn_smooth_reg.cuh"
 #if PN_EMU_KERNEL == 1
@@ -47,6 +49,7 @@ alignas(16) double pn_cta_sm[65536];
 alignas(16) double pn_small_shared[32768];
 alignas(16) double pn_smc_shared[32768];
 alignas(16) double pn_smr_shared[32768];
+alignas(16) double pn_sm_shared[32768];
 
 extern "C" int pn_emu_d(void) { return PN_EMU_PROBLEM::d; }
 extern "C" int pn_emu_n_p(void) { return PN_EMU_PROBLEM::n_p; }
@@ -136,7 +139,7 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
         scal_out[4 * i + 0] = t_end[i], scal_out[4 * i + 1] = loglik[i], scal_out[4 * i + 2] = diffusion[i], scal_out[4 * i + 3] = dt_last[i];
         counts[4 * i + 0] = naccept[i], counts[4 * i + 1] = nreject[i], counts[4 * i + 2] = nf[i], counts[4 * i + 3] = retcode[i];
     }
-#if PN_EMU_SAVE >= 2 && PN_EMU_KERNEL == 0
+#if PN_EMU_SAVE >= 2
     if (smooth) {
         PnSmoothParams S;
         std::memset(&S, 0, sizeof S);
@@ -152,10 +155,25 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
         for (int i = 0; i < n * n; i++) S.L[i] = L[i], S.U[i] = U[i];
         S.work_counter = &counter;
         S.write_x = write_x;
-        if (smooth == 1)
+        if (smooth == 3) { /* pn_smooth_kernel: PN_SM_WARPS warps per CTA, one trajectory per warp; work matrices in shared memory when the four
+                              warps' share fits the device's 200 KB, else in a global workspace -- the product's rule (pnode_api.cu launch_sweep) */
+            constexpr int D = PN_EMU_PROBLEM::d * n;
+            const size_t per_warp = 7 * D * D + 4 * D + 2 * n * n + 2 * n;
+            std::vector<double> ws;
+            if (per_warp * 8 > 200 * 1024) {
+                ws.resize(per_warp * PN_SM_WARPS);
+                S.workspace = ws.data();
+            } else if (per_warp * PN_SM_WARPS > sizeof pn_sm_shared / 8) {
+                std::abort();
+            }
+            run_warp(32 * PN_SM_WARPS, [&]() { pn_smooth_kernel(S); });
+        }
+#if PN_EMU_KERNEL == 0
+        else if (smooth == 1)
             run_warp(lanes, [&]() { pn_smooth_col_entry<PN_EMU_PROBLEM::d, PN_EMU_Q, PN_EMU_GS>(S); });
         else
             run_warp(lanes, [&]() { pn_smooth_reg_entry<PN_EMU_PROBLEM::d, PN_EMU_Q, PN_EMU_GS>(S); });
+#endif
     }
 #endif
 }
