@@ -34,6 +34,13 @@ PnShimCta pn_shim_cta;
 #include "kernels/pn_cta.cuh"
 alignas(16) double pn_cta_sm[65536];
 #endif
+#if PN_EMU_KERNEL == 2 /* pn_gen.cuh: general LTI prior (IOUP with a vector / matrix / Jacobian-updated rate), one warp per trajectory */
+#include "kernels/pn_gen.cuh"
+alignas(16) double pn_gen_shared[65536];
+#endif
+static const double* g_rate_matrix = nullptr; /* [d][d] row-major (PN_EMU_KERNEL 2) */
+static int g_update_rate = 0;
+extern "C" void pn_emu_set_rate(const double* rate, int update_rate) { g_rate_matrix = rate, g_update_rate = update_rate; }
 #include "kernels/pn_builtin_problems.cuh"
 
 #ifndef PN_EMU_ADAPTIVE
@@ -129,7 +136,12 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
         P.s_t = s_t, P.s_u_mean = s_u_mean, P.s_u_cov = s_u_cov, P.s_diffusion = s_diffusion;
         if (PN_EMU_SAVE >= 2) P.s_x_mean = s_x_mean, P.s_x_covfac = s_x_covfac, P.s_h = s_h;
     }
-#if PN_EMU_KERNEL == 1
+#if PN_EMU_KERNEL == 2
+    (void)lanes;
+    P.rate_matrix = g_rate_matrix, P.update_rate = g_update_rate;
+    if (pn_gen_ws_doubles(PN_EMU_PROBLEM::d, n) * PN_GEN_WARPS > (int)(sizeof pn_gen_shared / 8)) std::abort();
+    run_warp(32 * PN_GEN_WARPS, [&]() { pn_gen_entry<PN_EMU_PROBLEM, PN_EMU_Q, (PN_EMU_ADAPTIVE != 0), (PN_EMU_DYNAMIC != 0), PN_EMU_SAVE>(P); });
+#elif PN_EMU_KERNEL == 1
     (void)lanes;
     run_warp(PN_CTA_THREADS, [&]() { pn_cta_entry<PN_EMU_PROBLEM, PN_EMU_Q, (PN_EMU_ADAPTIVE != 0), (PN_EMU_DYNAMIC != 0), PN_EMU_SAVE>(P); });
 #else
@@ -155,10 +167,13 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
         for (int i = 0; i < n * n; i++) S.L[i] = L[i], S.U[i] = U[i];
         S.work_counter = &counter;
         S.write_x = write_x;
+#if PN_EMU_KERNEL == 2
+        S.gen_prior = 1, S.rate_matrix = g_rate_matrix;
+#endif
         if (smooth == 3) { /* pn_smooth_kernel: PN_SM_WARPS warps per CTA, one trajectory per warp; work matrices in shared memory when the four
                               warps' share fits the device's 200 KB, else in a global workspace -- the product's rule (pnode_api.cu launch_sweep) */
             constexpr int D = PN_EMU_PROBLEM::d * n;
-            const size_t per_warp = 7 * D * D + 4 * D + 2 * n * n + 2 * n;
+            const size_t per_warp = 7 * D * D + 4 * D + 2 * n * n + 2 * n + (S.gen_prior ? PN_SMOOTH_GEN_EXTRA(D, PN_EMU_PROBLEM::d, n) : 0);
             std::vector<double> ws;
             if (per_warp * 8 > 200 * 1024) {
                 ws.resize(per_warp * PN_SM_WARPS);

@@ -217,9 +217,10 @@ def test_blocks_kernel_shapes(oracle, problem, q, t1, dt):
 
 
 # ---- the group-per-trajectory kernels as ONE WARP of host threads (cuda_shim.h, PN_SHIM_WARP): pn_small.cuh, pn_smooth_col.cuh, pn_smooth_reg.cuh ----
-def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False, cta=False):
+def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False, cta=False, defs=()):
+    tag = "".join("_" + x.replace("=", "") for x in defs)
     out = os.path.join(tempfile.gettempdir(), f"pn_emu_{os.getuid()}",
-                       f"{'cta' if cta else 'warp'}_{problem}_q{q}_g{G}_gs{GS}_a{int(adaptive)}_d{int(dynamic)}_s{save}{'_tsan' if tsan else ''}" + (".exe" if tsan else ".so"))
+                       f"{('warp', 'cta', 'gen')[int(cta)]}_{problem}_q{q}_g{G}_gs{GS}_a{int(adaptive)}_d{int(dynamic)}_s{save}{tag}{'_tsan' if tsan else ''}" + (".exe" if tsan else ".so"))
     os.makedirs(os.path.dirname(out), exist_ok=True)
     src = os.path.join(HERE, "emulation", "pn_warp_host.cpp")
     deps = [src, os.path.join(HERE, "emulation", "cuda_shim.h")] + [os.path.join(CSRC, "kernels", f) for f in
@@ -229,16 +230,21 @@ def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False, cta=Fals
         mode = ["-fsanitize=thread", "-g", "-DPN_EMU_MAIN=1"] if tsan else ["-fPIC", "-shared"]
         subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", *mode, "-I", CSRC, f"-DPN_EMU_PROBLEM={STRUCT[problem]}", f"-DPN_EMU_Q={q}",
                         f"-DPN_EMU_G={G}", f"-DPN_EMU_GS={GS}", f"-DPN_EMU_ADAPTIVE={int(adaptive)}", f"-DPN_EMU_DYNAMIC={int(dynamic)}",
-                        f"-DPN_EMU_SAVE={save}", f"-DPN_EMU_KERNEL={int(cta)}", src, "-o", out, "-lpthread"], check=True)
+                        f"-DPN_EMU_SAVE={save}", f"-DPN_EMU_KERNEL={int(cta)}", *["-D" + x for x in defs], src, "-o", out, "-lpthread"], check=True)
     return out
 
 
 def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False, dynamic=False, calibrate=False, save=2, smooth=0, write_x=1, lanes=32,
-              abstol=1e-6, reltol=1e-3, cta=False):
-    lib = C.CDLL(_build_warp(problem, q, G, GS, adaptive, dynamic, save, cta=cta))
+              abstol=1e-6, reltol=1e-3, cta=False, defs=(), rate=None, update_rate=False):
+    lib = C.CDLL(_build_warp(problem, q, G, GS, adaptive, dynamic, save, cta=cta, defs=defs))
     lib.pn_emu_warp_solve.restype = None
-    d, n = lib.pn_emu_d(), q + 1
-    D = d * n
+    if rate is not None:
+        rate = np.ascontiguousarray(rate, dtype=float)
+        lib.pn_emu_set_rate(rate.ctypes.data_as(dp), int(update_rate))
+    elif update_rate:
+        lib.pn_emu_set_rate(None, 1)
+    d, n = lib.pn_emu_d(), q + 1            # d: length of sol.u (for a second-order problem (du, u): twice the modelled dimension)
+    D = len(init_mu[0])
     N = len(init_mu)
     L, U, Qb = _iwp_constants(q)
     scal = np.array([0.0, t1, dt, abstol, reltol, 0.0, t1, 0.7 / q, 0.4 / q, 0.2, 10.0, 0.9, 1.0, 1.0, 1e-4, 1.0])
@@ -443,3 +449,67 @@ def test_cta_kernel_saving_pass_and_large_state_sweep(oracle):
         assert _rel(ks["s_u"][sl], os_[i]["pu_mu"]) < 1e-10
         assert _rel(ks["s_cov"][sl][1:], os_[i]["pu_cov"][1:]) < max(1e-9, 20 * _rel(os2[i]["pu_cov"][1:], os_[i]["pu_cov"][1:]))
         assert _rel(ks["s_x"][sl], os_[i]["x_smooth_mu"]) < max(1e-9, 20 * _rel(os2[i]["x_smooth_mu"], os_[i]["x_smooth_mu"]))
+
+
+def test_cta_kernel_pleiades_as_14_second_order_equations(oracle):
+    """pn_cta.cuh built with PN_SECOND (benchmarks/pleiades.jmd's own form: SecondOrderODEProblem, d = 14, D = 56; H = [-J_u | -J_du | I | 0],
+    measurement_models.jl:29-49) as 256 host threads: fixed steps 1e-10 on sol.u = (du, u) / 1e-9 on its covariance / log-likelihood, and the
+    adaptive run's accept / reject counts, against the oracle's second-order route."""
+    pd = problems.PROBLEMS["pleiades"]
+    q, N = 3, 3
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 28, 0), q)
+    u0, _ = _ensemble(pd, N, seed=13)
+    p = np.zeros((N, 1))
+    kw = dict(alg=oracle.EK1, smooth=False, t0=0.0, save_everystep=True, cov_backend=oracle.COV_REF, second_order=True)
+    oo = [oracle.solve(oracle.make_config(14, q, 0, diffusion=oracle.DIFF_FIXED, calibrate=False, adaptive=False, dt=0.01, t1=0.06, **kw), rhs, u0[i], [])
+          for i in range(N)]
+    mu0 = np.array([o["x_filt_mu"][0] for o in oo])
+    assert mu0.shape == (N, 56)
+    k = _run_warp("pleiades", q, 4, 8, mu0, p, np.arange(N + 1), t1=0.06, dt=0.01, save=0, cta=True, defs=("PN_SECOND=1",))
+    for i in range(N):
+        assert tuple(k["counts"][i]) == (oo[i]["naccept"], 0, oo[i]["nf"], 0)
+        assert _rel(k["u"][i], oo[i]["pu_mu"][-1]) < 1e-10
+        assert _rel(k["cov"][i], oo[i]["pu_cov"][-1]) < 1e-9
+        assert k["scal"][i, 1] == pytest.approx(oo[i]["loglik"], rel=1e-9)
+    oa = [oracle.solve(oracle.make_config(14, q, 0, diffusion=oracle.DIFF_DYNAMIC, adaptive=True, dt=1e-3, t1=0.3, **kw), rhs, u0[i], []) for i in range(N)]
+    k = _run_warp("pleiades", q, 4, 8, mu0, p, np.arange(N + 1), t1=0.3, dt=1e-3, adaptive=True, dynamic=True, save=0, cta=True, defs=("PN_SECOND=1",))
+    for i in range(N):
+        assert tuple(k["counts"][i]) == (oa[i]["naccept"], oa[i]["nreject"], oa[i]["nf"], 0)
+        assert _rel(k["u"][i], oa[i]["pu_mu"][-1]) < 1e-8
+
+
+@pytest.mark.parametrize("rate,update", [(np.array([[-1.0, 0.3], [-0.2, -0.5]]), False), (np.diag([-1.0, -0.4]), False), (None, True)])
+def test_general_prior_kernel_ioup_rates(oracle, rate, update):
+    """pn_gen.cuh + pn_lti.cuh (IOUP with a matrix rate, a vector rate as its diagonal matrix, and the Jacobian-updated rate of the
+    RosenbrockExpEK; src/priors/ioup.jl:81-131, perform_step.jl:88-96) as four warps of host threads, one trajectory per warp: fixed steps with
+    FixedDiffusion against the oracle (whose transition pairs come from a Pade exponential of the Van Loan block matrix, not from scaling and
+    doubling) -- every filtered point 1e-10 / covariance 1e-9 / log-likelihood 1e-9, and with a constant rate the smoothed points through
+    pn_smooth.cuh's dense-transition mode."""
+    pd = problems.PROBLEMS["lotka_volterra"]
+    q, N, dt, t1 = 3, 6, 0.02, 0.4
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N, seed=17)
+    okw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, adaptive=False, dt=dt, t0=0.0, t1=t1, prior=oracle.PRIOR_IOUP,
+               cov_backend=oracle.COV_REF, save_everystep=True)
+    if update:
+        okw["update_rate_parameter"] = True
+    else:
+        okw["rate_parameter"] = rate if rate[0, 1] != 0 else np.diag(rate).copy()
+    of = [oracle.solve(oracle.make_config(2, q, 4, smooth=False, **okw), rhs, u0[i], p[i]) for i in range(N)]
+    ns = of[0]["n"]
+    off = np.arange(N + 1) * ns
+    mu0 = np.array([o["x_filt_mu"][0] for o in of])
+    kf = _run_warp("lotka_volterra", q, 4, 8, mu0, p, off, t1=t1, dt=dt, save=2, smooth=0, cta=2, rate=rate, update_rate=update)
+    for i in range(N):
+        sl = slice(off[i], off[i + 1])
+        assert tuple(kf["counts"][i][[0, 1, 3]]) == (ns - 1, 0, 0)
+        assert _rel(kf["s_u"][sl], of[i]["pu_mu"]) < 1e-10
+        assert _rel(kf["s_cov"][sl][1:], of[i]["pu_cov"][1:]) < 1e-9
+        assert kf["scal"][i, 1] == pytest.approx(of[i]["loglik"], rel=1e-9)
+    if not update:
+        os_ = [oracle.solve(oracle.make_config(2, q, 4, smooth=True, **okw), rhs, u0[i], p[i]) for i in range(N)]
+        ks = _run_warp("lotka_volterra", q, 4, 8, mu0, p, off, t1=t1, dt=dt, save=2, smooth=3, cta=2, rate=rate)
+        for i in range(N):
+            sl = slice(off[i], off[i + 1])
+            assert _rel(ks["s_u"][sl], os_[i]["pu_mu"]) < 1e-10
+            assert _rel(ks["s_cov"][sl][1:], os_[i]["pu_cov"][1:]) < 1e-9
