@@ -39,6 +39,8 @@ extern PnShimDim3 blockDim;               /* {lanes, 1, 1} */
 static const PnShimDim3 blockIdx{0, 0, 0}, gridDim{1, 1, 1};
 struct PnShimWarp {
     pthread_barrier_t bar;
+    pthread_barrier_t sub[4][16]; /* barriers of the aligned lane groups of 2, 4, 8, 16 lanes: collectives with a group mask (a subset of the warp
+                                     that calls from divergent code, e.g. pn_ioup.cuh's butterflies in the retry phase) synchronise the group only */
     uint64_t slot[32];
     int lanes; /* host threads in the warp: a multiple of the group size, <= 32 (lanes that do not exist never take part) */
 };
@@ -50,7 +52,18 @@ struct PnShimCta { /* a CTA of up to 32 warps: warp collectives stay inside a wa
 };
 extern PnShimCta pn_shim_cta;
 #define pn_shim_warp (pn_shim_cta.warp[threadIdx.x >> 5])
-static inline void pn_shim_barrier() { pthread_barrier_wait(&pn_shim_warp.bar); }
+static inline void pn_shim_barrier(unsigned mask = 0xffffffffu) {
+    PnShimWarp& w = pn_shim_warp;
+    const unsigned all = w.lanes >= 32 ? 0xffffffffu : ((1u << w.lanes) - 1u);
+    if ((mask & all) == all) {
+        pthread_barrier_wait(&w.bar);
+        return;
+    }
+    const int sz = __builtin_popcount(mask), first = __builtin_ctz(mask);
+    const int lg = __builtin_ctz((unsigned)sz) - 1;
+    if ((sz & (sz - 1)) || sz < 2 || sz > 16 || first % sz || mask != (((1u << sz) - 1u) << first) || !((mask >> (threadIdx.x & 31)) & 1u)) __builtin_trap();
+    pthread_barrier_wait(&w.sub[lg][first / sz]);
+}
 static inline void pn_shim_cta_barrier() { pthread_barrier_wait(&pn_shim_cta.bar); }
 #else
 static const PnShimDim3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0}, blockDim{1, 1, 1}, gridDim{1, 1, 1};
@@ -64,43 +77,43 @@ static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #ifdef PN_SHIM_WARP
 /* publish -> barrier -> read the source lane's slot -> barrier (the second one keeps a fast lane's next publish off a slow lane's read) */
 template <class T>
-static inline T pn_shim_exchange(T v, int src_lane) {
+static inline T pn_shim_exchange(unsigned mask, T v, int src_lane) {
     static_assert(sizeof(T) <= 8, "shuffles move at most 64 bits here");
     const int lane = threadIdx.x & 31;
     uint64_t b = 0;
     std::memcpy(&b, &v, sizeof(T));
     pn_shim_warp.slot[lane] = b;
-    pn_shim_barrier();
+    pn_shim_barrier(mask);
     const uint64_t r = pn_shim_warp.slot[(src_lane >= 0 && src_lane < pn_shim_warp.lanes) ? src_lane : lane];
-    pn_shim_barrier();
+    pn_shim_barrier(mask);
     T o;
     std::memcpy(&o, &r, sizeof(T));
     return o;
 }
 template <class T>
-static inline T __shfl_sync(unsigned, T v, int src, int width = 32) {
+static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
     const int lane = threadIdx.x & 31;
-    return pn_shim_exchange(v, (lane & ~(width - 1)) | (src & (width - 1)));
+    return pn_shim_exchange(mask, v, (lane & ~(width - 1)) | (src & (width - 1)));
 }
 template <class T>
-static inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) {
+static inline T __shfl_xor_sync(unsigned mask, T v, int m, int width = 32) {
     const int lane = threadIdx.x & 31, s = lane ^ m;
-    return pn_shim_exchange(v, ((s & ~(width - 1)) == (lane & ~(width - 1))) ? s : lane);
+    return pn_shim_exchange(mask, v, ((s & ~(width - 1)) == (lane & ~(width - 1))) ? s : lane);
 }
 template <class T>
-static inline T __shfl_down_sync(unsigned, T v, int dlt, int width = 32) {
+static inline T __shfl_down_sync(unsigned mask, T v, int dlt, int width = 32) {
     const int lane = threadIdx.x & 31, s = lane + dlt;
-    return pn_shim_exchange(v, ((s & ~(width - 1)) == (lane & ~(width - 1))) ? s : lane);
+    return pn_shim_exchange(mask, v, ((s & ~(width - 1)) == (lane & ~(width - 1))) ? s : lane);
 }
 template <class T>
-static inline T __shfl_up_sync(unsigned, T v, int dlt, int width = 32) {
+static inline T __shfl_up_sync(unsigned mask, T v, int dlt, int width = 32) {
     const int lane = threadIdx.x & 31, s = lane - dlt;
-    return pn_shim_exchange(v, (s >= 0 && (s & ~(width - 1)) == (lane & ~(width - 1))) ? s : lane);
+    return pn_shim_exchange(mask, v, (s >= 0 && (s & ~(width - 1)) == (lane & ~(width - 1))) ? s : lane);
 }
 #ifdef PN_SHIM_DROP_SYNCWARP /* negative control of the race check: without the kernels' __syncwarp()s ThreadSanitizer must report */
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 #else
-static inline void __syncwarp(unsigned = 0xffffffffu) { pn_shim_barrier(); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { pn_shim_barrier(mask); }
 #endif
 static inline unsigned __ballot_sync(unsigned, int p) {
     const int lane = threadIdx.x & 31;

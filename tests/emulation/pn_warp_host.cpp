@@ -41,6 +41,11 @@ alignas(16) double pn_gen_shared[65536];
 static const double* g_rate_matrix = nullptr; /* [d][d] row-major (PN_EMU_KERNEL 2) */
 static int g_update_rate = 0;
 extern "C" void pn_emu_set_rate(const double* rate, int update_rate) { g_rate_matrix = rate, g_update_rate = update_rate; }
+static double g_rate = 0.0, g_glx[16], g_glw[16]; /* scalar-rate IOUP of the register kernels (built with PN_IOUP=1): rate, Gauss-Legendre rule on [0, 1] */
+extern "C" void pn_emu_set_ioup(double rate, const double* glx, const double* glw) {
+    g_rate = rate;
+    for (int i = 0; i < 16; i++) g_glx[i] = glx[i], g_glw[i] = glw[i];
+}
 #include "kernels/pn_builtin_problems.cuh"
 
 #ifndef PN_EMU_ADAPTIVE
@@ -73,6 +78,8 @@ static void run_warp(int threads, F body) { /* a CTA of `threads` host threads: 
     for (int w = 0; w < warps; w++) {
         pn_shim_cta.warp[w].lanes = (threads - 32 * w < 32) ? threads - 32 * w : 32;
         pthread_barrier_init(&pn_shim_cta.warp[w].bar, nullptr, (unsigned)pn_shim_cta.warp[w].lanes);
+        for (int lg = 0; lg < 4; lg++)
+            for (int g = 0; g < (32 >> (lg + 1)); g++) pthread_barrier_init(&pn_shim_cta.warp[w].sub[lg][g], nullptr, 2u << lg);
     }
     struct Arg {
         F* body;
@@ -91,7 +98,11 @@ static void run_warp(int threads, F body) { /* a CTA of `threads` host threads: 
     }
     for (int l = 0; l < threads; l++) pthread_join(th[l], nullptr);
     pthread_barrier_destroy(&pn_shim_cta.bar);
-    for (int w = 0; w < warps; w++) pthread_barrier_destroy(&pn_shim_cta.warp[w].bar);
+    for (int w = 0; w < warps; w++) {
+        pthread_barrier_destroy(&pn_shim_cta.warp[w].bar);
+        for (int lg = 0; lg < 4; lg++)
+            for (int g = 0; g < (32 >> (lg + 1)); g++) pthread_barrier_destroy(&pn_shim_cta.warp[w].sub[lg][g]);
+    }
 }
 
 // scal_in : as pn_thread_host.cpp (16 doubles).  Per-trajectory inputs: init_mu [n_traj][D], init_dt [n_traj], p [n_traj][n_p].
@@ -128,6 +139,8 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
     P.init_dt = init_dt;
     P.work_counter = &counter;
     for (int i = 0; i < n * n; i++) P.L[i] = L[i], P.U[i] = U[i], P.Qb[i] = Qb[i];
+    P.rate = g_rate;
+    for (int i = 0; i < 16; i++) P.glx[i] = g_glx[i], P.glw[i] = g_glw[i];
     P.t_end = t_end.data(), P.loglik = loglik.data(), P.diffusion = diffusion.data(), P.dt_last = dt_last.data();
     P.u_mean = u_mean, P.u_cov = u_cov;
     P.naccept = naccept.data(), P.nreject = nreject.data(), P.nf = nf.data(), P.retcode = retcode.data();
@@ -167,6 +180,8 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
         for (int i = 0; i < n * n; i++) S.L[i] = L[i], S.U[i] = U[i];
         S.work_counter = &counter;
         S.write_x = write_x;
+        S.rate = g_rate;
+        for (int i = 0; i < 16; i++) S.glx[i] = g_glx[i], S.glw[i] = g_glw[i];
 #if PN_EMU_KERNEL == 2
         S.gen_prior = 1, S.rate_matrix = g_rate_matrix;
 #endif

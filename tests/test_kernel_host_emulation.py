@@ -20,6 +20,9 @@ import pytest
 import probnumdiffeq_jl_b200  # noqa: F401
 from probnumdiffeq_jl_b200 import problems, tracer
 
+# a warp / CTA of host threads that disagrees about its collectives deadlocks instead of failing: bound every test
+pytestmark = pytest.mark.timeout(600)
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(HERE), "probnumdiffeq.jl_b200", "csrc")
 GOLD = os.path.join(HERE, "golden")
@@ -235,7 +238,7 @@ def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False, cta=Fals
 
 
 def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False, dynamic=False, calibrate=False, save=2, smooth=0, write_x=1, lanes=32,
-              abstol=1e-6, reltol=1e-3, cta=False, defs=(), rate=None, update_rate=False):
+              abstol=1e-6, reltol=1e-3, cta=False, defs=(), rate=None, update_rate=False, ioup_rate=None):
     lib = C.CDLL(_build_warp(problem, q, G, GS, adaptive, dynamic, save, cta=cta, defs=defs))
     lib.pn_emu_warp_solve.restype = None
     if rate is not None:
@@ -243,6 +246,10 @@ def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False
         lib.pn_emu_set_rate(rate.ctypes.data_as(dp), int(update_rate))
     elif update_rate:
         lib.pn_emu_set_rate(None, 1)
+    if ioup_rate is not None:  # scalar-rate IOUP of the register kernels (defs must hold PN_IOUP=1): 16-point Gauss-Legendre rule on [0, 1]
+        x, w = np.polynomial.legendre.leggauss(16)
+        lib.pn_emu_set_ioup.argtypes = [C.c_double, dp, dp]
+        lib.pn_emu_set_ioup(float(ioup_rate), np.ascontiguousarray(0.5 * (x + 1)).ctypes.data_as(dp), np.ascontiguousarray(0.5 * w).ctypes.data_as(dp))
     d, n = lib.pn_emu_d(), q + 1            # d: length of sol.u (for a second-order problem (du, u): twice the modelled dimension)
     D = len(init_mu[0])
     N = len(init_mu)
@@ -513,3 +520,30 @@ def test_general_prior_kernel_ioup_rates(oracle, rate, update):
             sl = slice(off[i], off[i + 1])
             assert _rel(ks["s_u"][sl], os_[i]["pu_mu"]) < 1e-10
             assert _rel(ks["s_cov"][sl][1:], os_[i]["pu_cov"][1:]) < 1e-9
+
+
+@pytest.mark.parametrize("sweep", [1, 2])
+def test_scalar_rate_ioup_on_the_register_kernels(oracle, sweep):
+    """IOUP(3, -1) (src/priors/ioup.jl; pn_ioup.cuh: phi-functions + 16-point Gauss-Legendre per step inside pn_small.cuh and the sweeps, PN_IOUP=1)
+    as a warp of host threads: filtered and smoothed points (column- and row-distributed register sweeps; the warp-per-trajectory sweep serves the
+    IWP and the general-prior path only, pnode_api.cu launch_sweep) 1e-10 / 1e-9 against the oracle's Van Loan route, Lotka-Volterra, fixed steps."""
+    pd = problems.PROBLEMS["lotka_volterra"]
+    q, N, dt, t1 = 3, 9, 0.02, 0.4
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N, seed=19)
+    okw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, adaptive=False, dt=dt, t0=0.0, t1=t1, prior=oracle.PRIOR_IOUP,
+               rate_parameter=-1.0, cov_backend=oracle.COV_REF, save_everystep=True)
+    of = [oracle.solve(oracle.make_config(2, q, 4, smooth=False, **okw), rhs, u0[i], p[i]) for i in range(N)]
+    os_ = [oracle.solve(oracle.make_config(2, q, 4, smooth=True, **okw), rhs, u0[i], p[i]) for i in range(N)]
+    ns = of[0]["n"]
+    off = np.arange(N + 1) * ns
+    mu0 = np.array([o["x_filt_mu"][0] for o in of])
+    kf = _run_warp("lotka_volterra", q, 4, 8, mu0, p, off, t1=t1, dt=dt, save=2, smooth=0, defs=("PN_IOUP=1",), ioup_rate=-1.0)
+    ks = _run_warp("lotka_volterra", q, 4, 8, mu0, p, off, t1=t1, dt=dt, save=2, smooth=sweep, defs=("PN_IOUP=1",), ioup_rate=-1.0)
+    for i in range(N):
+        sl = slice(off[i], off[i + 1])
+        assert _rel(kf["s_u"][sl], of[i]["pu_mu"]) < 1e-10
+        assert _rel(kf["s_cov"][sl][1:], of[i]["pu_cov"][1:]) < 1e-9
+        assert kf["scal"][i, 1] == pytest.approx(of[i]["loglik"], rel=1e-9)
+        assert _rel(ks["s_u"][sl], os_[i]["pu_mu"]) < 1e-10
+        assert _rel(ks["s_cov"][sl][1:], os_[i]["pu_cov"][1:]) < 1e-9
