@@ -206,15 +206,30 @@ void oracle_user_taylor(double* out, const double* u, const double* p, double t,
 
 
 _rhs_cache = {}
+_C_SOURCE_VERSION = 1  # bump when c_source / symbolic_derivatives change (invalidates the on-disk text cache)
 
 
 def compile_rhs(tr, q) -> CompiledRHS:
-    src = c_source(tr, q)
-    key = hashlib.sha1(src.encode()).hexdigest()[:16]
-    if key in _rhs_cache:
-        return _rhs_cache[key]
+    # the symbolic Lie derivatives dominate (Pleiades at order 3: 20 s): cache the generated C text per (traced expressions, q),
+    # in the process and on disk next to the compiled libraries
     tmp = os.path.join(tempfile.gettempdir(), f"pnode_oracle_rhs_{os.getuid()}")
     os.makedirs(tmp, exist_ok=True)
+    tkey = hashlib.sha1((sp.srepr(list(tr.f)) + sp.srepr(list(tr.u)) + sp.srepr(list(tr.p)) + f"|{q}|{_C_SOURCE_VERSION}").encode()).hexdigest()[:20]
+    if tkey in _rhs_cache:
+        return _rhs_cache[tkey]
+    spath = os.path.join(tmp, f"src_{tkey}.c")
+    if os.path.exists(spath):
+        with open(spath) as fh:
+            src = fh.read()
+    else:
+        src = c_source(tr, q)
+        with open(spath + f".{os.getpid()}", "w") as fh:
+            fh.write(src)
+        os.replace(spath + f".{os.getpid()}", spath)
+    key = hashlib.sha1(src.encode()).hexdigest()[:16]
+    if key in _rhs_cache:
+        _rhs_cache[tkey] = _rhs_cache[key]
+        return _rhs_cache[key]
     cpath = os.path.join(tmp, f"rhs_{key}.c")
     so = os.path.join(tmp, f"rhs_{key}.so")
     if not os.path.exists(so):
@@ -223,7 +238,7 @@ def compile_rhs(tr, q) -> CompiledRHS:
         subprocess.run(["gcc", "-O2", "-fno-fast-math", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, cpath,
                         "-lm"], check=True)
     r = CompiledRHS(so, tr.d, tr.n_p, q)
-    _rhs_cache[key] = r
+    _rhs_cache[key] = _rhs_cache[tkey] = r
     return r
 
 
