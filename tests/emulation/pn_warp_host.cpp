@@ -41,6 +41,16 @@ alignas(16) double pn_gen_shared[65536];
 static const double* g_rate_matrix = nullptr; /* [d][d] row-major (PN_EMU_KERNEL 2) */
 static int g_update_rate = 0;
 extern "C" void pn_emu_set_rate(const double* rate, int update_rate) { g_rate_matrix = rate, g_update_rate = update_rate; }
+/* Fenrir mode of the sweeps (built with PN_FENRIR=1 for the column sweep): observations, observation model, output [n_traj] */
+static const double *g_data_t = nullptr, *g_data_u = nullptr, *g_obs_H = nullptr, *g_obs_Rn = nullptr;
+static double* g_fenrir_ll = nullptr;
+static long long g_n_data = 0;
+static int g_n_obs = 0, g_kron_logdet = 0;
+extern "C" void pn_emu_set_fenrir(const double* data_t, const double* data_u, long long n_data, int n_obs, const double* obs_H, const double* obs_Rn,
+                                  double* fenrir_ll, int kron_logdet) {
+    g_data_t = data_t, g_data_u = data_u, g_n_data = n_data, g_n_obs = n_obs, g_obs_H = obs_H, g_obs_Rn = obs_Rn, g_fenrir_ll = fenrir_ll;
+    g_kron_logdet = kron_logdet;
+}
 static double g_rate = 0.0, g_glx[16], g_glw[16]; /* scalar-rate IOUP of the register kernels (built with PN_IOUP=1): rate, Gauss-Legendre rule on [0, 1] */
 extern "C" void pn_emu_set_ioup(double rate, const double* glx, const double* glw) {
     g_rate = rate;
@@ -182,13 +192,19 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
         S.write_x = write_x;
         S.rate = g_rate;
         for (int i = 0; i < 16; i++) S.glx[i] = g_glx[i], S.glw[i] = g_glw[i];
+        if (g_fenrir_ll) { /* pnode_api.cu solve_impl: uncalibrated, the records stay the filtering estimates */
+            S.calibrate = 0;
+            S.s_t = s_t, S.data_t = g_data_t, S.data_u = g_data_u, S.obs_H = g_obs_H, S.obs_Rn = g_obs_Rn, S.n_data = g_n_data, S.n_obs = g_n_obs;
+            S.retcode = retcode.data(), S.fenrir_ll = g_fenrir_ll, S.kron_logdet = g_kron_logdet;
+        }
 #if PN_EMU_KERNEL == 2
         S.gen_prior = 1, S.rate_matrix = g_rate_matrix;
 #endif
         if (smooth == 3) { /* pn_smooth_kernel: PN_SM_WARPS warps per CTA, one trajectory per warp; work matrices in shared memory when the four
                               warps' share fits the device's 200 KB, else in a global workspace -- the product's rule (pnode_api.cu launch_sweep) */
             constexpr int D = PN_EMU_PROBLEM::d * n;
-            const size_t per_warp = 7 * D * D + 4 * D + 2 * n * n + 2 * n + (S.gen_prior ? PN_SMOOTH_GEN_EXTRA(D, PN_EMU_PROBLEM::d, n) : 0);
+            const size_t per_warp = 7 * D * D + 4 * D + 2 * n * n + 2 * n + (S.gen_prior ? PN_SMOOTH_GEN_EXTRA(D, PN_EMU_PROBLEM::d, n) : 0) +
+                                    (S.fenrir_ll ? PN_FENRIR_EXTRA(D, S.n_obs) : 0);
             std::vector<double> ws;
             if (per_warp * 8 > 200 * 1024) {
                 ws.resize(per_warp * PN_SM_WARPS);

@@ -238,7 +238,7 @@ def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False, cta=Fals
 
 
 def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False, dynamic=False, calibrate=False, save=2, smooth=0, write_x=1, lanes=32,
-              abstol=1e-6, reltol=1e-3, cta=False, defs=(), rate=None, update_rate=False, ioup_rate=None):
+              abstol=1e-6, reltol=1e-3, cta=False, defs=(), rate=None, update_rate=False, ioup_rate=None, fenrir=None):
     lib = C.CDLL(_build_warp(problem, q, G, GS, adaptive, dynamic, save, cta=cta, defs=defs))
     lib.pn_emu_warp_solve.restype = None
     if rate is not None:
@@ -246,6 +246,14 @@ def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False
         lib.pn_emu_set_rate(rate.ctypes.data_as(dp), int(update_rate))
     elif update_rate:
         lib.pn_emu_set_rate(None, 1)
+    keep = []
+    if fenrir is not None:  # (data_t, data_u [n_data][n_obs], H [n_obs][D], Rn [n_obs][n_obs]) -> o["fenrir_ll"]
+        ft, fu, fH, fR = [np.ascontiguousarray(a, dtype=float) for a in fenrir]
+        fll = np.full(len(init_mu), np.nan)
+        keep += [ft, fu, fH, fR, fll]
+        lib.pn_emu_set_fenrir.argtypes = [dp, dp, C.c_longlong, C.c_int, dp, dp, dp, C.c_int]
+        lib.pn_emu_set_fenrir(ft.ctypes.data_as(dp), fu.ctypes.data_as(dp), len(ft), fu.shape[1], fH.ctypes.data_as(dp), fR.ctypes.data_as(dp),
+                              fll.ctypes.data_as(dp), 0)
     if ioup_rate is not None:  # scalar-rate IOUP of the register kernels (defs must hold PN_IOUP=1): 16-point Gauss-Legendre rule on [0, 1]
         x, w = np.polynomial.legendre.leggauss(16)
         lib.pn_emu_set_ioup.argtypes = [C.c_double, dp, dp]
@@ -268,6 +276,8 @@ def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False
     lib.pn_emu_warp_solve(C.c_longlong(N), int(lanes), A(scal), int(calibrate), A(np.ascontiguousarray(L.ravel())), A(np.ascontiguousarray(U.ravel())),
                           A(np.ascontiguousarray(Qb.ravel())), A(mu0), A(dt0), A(pp), A(o["u"]), A(o["cov"]), A(o["scal"]), I(o["counts"]), I(off),
                           A(o["s_t"]), A(o["s_u"]), A(o["s_cov"]), A(o["s_diff"]), A(o["s_x"]), A(o["s_xR"]), A(o["s_h"]), int(smooth), int(write_x))
+    if fenrir is not None:
+        o["fenrir_ll"] = keep[4]
     return o
 
 
@@ -547,3 +557,29 @@ def test_scalar_rate_ioup_on_the_register_kernels(oracle, sweep):
         assert kf["scal"][i, 1] == pytest.approx(of[i]["loglik"], rel=1e-9)
         assert _rel(ks["s_u"][sl], os_[i]["pu_mu"]) < 1e-10
         assert _rel(ks["s_cov"][sl][1:], os_[i]["pu_cov"][1:]) < 1e-9
+
+
+@pytest.mark.parametrize("sweep,data_k", [(1, [10, 20]), (3, [10, 20]), (1, [5, 15]), (3, [5, 15])])
+def test_fenrir_backward_pass_as_a_warp(oracle, sweep, data_k):
+    """fenrir_data_loglik (src/data_likelihoods/fenrir.jl:68-137): the backward pass with data updates inside the column sweep (pn_smooth_col.cuh built
+    with PN_FENRIR, pn_fenrir_update.cuh: sweep 1) and inside the warp-per-trajectory sweep (pn_smooth.cuh: sweep 3) on FitzHugh-Nagumo EK1(3),
+    observations of both components with noise variance 0.25: the oracle's value at 1e-10 per trajectory -- with the last observation at the final time
+    and with it before the final time (fenrir.jl:87-99: the sweep then starts at the second to last observation)."""
+    pd = problems.PROBLEMS["fitzhugh_nagumo"]
+    q, N, dt, t1 = 3, 9, 0.05, 1.0
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N, seed=23)
+    data_u = np.array([[1.9, 0.2], [1.7, 0.6]])
+    cfg = oracle.make_config(2, q, pd.n_p, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, adaptive=False, dt=dt, t0=0.0, t1=t1,
+                             save_everystep=True, smooth=True, cov_backend=oracle.COV_REF)
+    sols = [oracle.solve(cfg, rhs, u0[i], p[i]) for i in range(N)]
+    data_t = sols[0]["t"][data_k]  # grid points of the fixed-step solve (the reference makes the data times tstops)
+    want = [oracle.fenrir_data_loglik(cfg, s, data_t, data_u, observation_noise_cov=0.25) for s in sols]
+    ns = sols[0]["n"]
+    off = np.arange(N + 1) * ns
+    mu0 = np.array([s["x_filt_mu"][0] for s in sols])
+    H = np.eye(8)[:2]
+    k = _run_warp("fitzhugh_nagumo", q, 4, 8, mu0, p, off, t1=t1, dt=dt, save=2, smooth=sweep, defs=("PN_FENRIR=1",),
+                  fenrir=(data_t, data_u, H, 0.5 * np.eye(2)))
+    assert np.all(np.isfinite(want))
+    assert np.allclose(k["fenrir_ll"], want, rtol=1e-10, atol=0)
