@@ -254,6 +254,26 @@ int main(int argc, char** argv) {
     c += N;
     const double* p = c;
     c += N * (np_ > 0 ? np_ : 1);
+    /* optional tagged sections: 1 rate matrix (update flag, d x d) | 2 scalar-rate IOUP (rate, glx[16], glw[16]) | 3 Fenrir (n_data, n_obs, data_t,
+       data_u, H [n_obs][D], Rn [n_obs][n_obs]) */
+    std::vector<double> fll(N, 0.0);
+    while (c - in.data() < (long long)in.size()) {
+        const int tag = (int)*c++;
+        if (tag == 1) {
+            pn_emu_set_rate(c[1] < 0 ? nullptr : c + 2, (int)c[0]);
+            c += 2 + d * d;
+        } else if (tag == 2) {
+            pn_emu_set_ioup(c[0], c + 1, c + 17);
+            c += 33;
+        } else if (tag == 3) {
+            const long long nd = (long long)c[0];
+            const int no = (int)c[1];
+            pn_emu_set_fenrir(c + 2, c + 2 + nd, nd, no, c + 2 + nd + nd * no, c + 2 + nd + nd * no + (long long)no * D, fll.data(), 0);
+            c += 2 + nd + nd * no + (long long)no * D + no * no;
+        } else {
+            return 3;
+        }
+    }
     if (c - in.data() != (long long)in.size()) return 3;
     std::vector<long long> off(N + 1), counts(4 * N);
     for (long long i = 0; i <= N; i++) off[i] = i * ns;
@@ -263,6 +283,7 @@ int main(int argc, char** argv) {
                       s_u.data(), s_c.data(), s_df.data(), s_x.data(), s_xr.data(), s_h.data(), smooth, write_x);
     double sum = 0.0;
     for (double v : um) sum += v;
+    for (double v : fll) sum += v;
     for (double v : s_u) sum += v;
     long long acc = 0;
     for (long long i = 0; i < N; i++) acc += counts[4 * i];

@@ -345,21 +345,23 @@ def test_group_step_kernel_adaptive_ragged_ensemble(oracle):
         assert k["scal"][i, 1] == pytest.approx(oo[i]["loglik"], rel=1e-8)
 
 
-def _tsan_run(problem, q, G, GS, *, N, t1, dt, adaptive, dynamic, save, smooth, oracle, drop_syncwarp=False, lanes=32, cta=False):
+def _tsan_run(problem, q, G, GS, *, N, t1, dt, adaptive, dynamic, save, smooth, oracle, drop_syncwarp=False, lanes=32, cta=False, defs=(), okw=None,
+              extra=()):
     pd = problems.PROBLEMS[problem]
     rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
     u0, p = _ensemble(pd, N, seed=5)
     if pd.n_p == 0:
         p = np.zeros((N, 1))
     kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC if dynamic else oracle.DIFF_FIXED, calibrate=False, adaptive=adaptive, dt=dt, t0=0.0, t1=t1,
-              save_everystep=True, smooth=False)
+              save_everystep=True, smooth=False, **(okw or {}))
     assert not (adaptive and save)  # ragged CSR segments are not laid out here
     oo = [oracle.solve(oracle.make_config(pd.d, q, pd.n_p, **kw), rhs, u0[i], p[i] if pd.n_p else []) for i in range(N)]
     L, U, Qb = _iwp_constants(q)
     scal = np.array([0.0, t1, dt, 1e-6, 1e-3, 0.0, t1, 0.7 / q, 0.4 / q, 0.2, 10.0, 0.9, 1.0, 1.0, 1e-4, 1.0])
     blob = np.concatenate([[N, lanes, smooth, 1, oo[0]["n"] if save else 1], scal, L.ravel(), U.ravel(), Qb.ravel(),
-                           np.array([o["x_filt_mu"][0] for o in oo]).ravel(), np.full(N, dt), p.ravel()]).astype(np.float64)
-    exe = _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=True, cta=cta)
+                           np.array([o["x_filt_mu"][0] for o in oo]).ravel(), np.full(N, dt), p.ravel(),
+                           *[np.asarray(e, dtype=float).ravel() for e in extra]]).astype(np.float64)
+    exe = _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=True, cta=cta, defs=defs)
     if drop_syncwarp:
         exe2 = exe.replace(".exe", "_nosync.exe")
         if not os.path.exists(exe2) or os.path.getmtime(exe2) < os.path.getmtime(exe):
@@ -368,7 +370,7 @@ def _tsan_run(problem, q, G, GS, *, N, t1, dt, adaptive, dynamic, save, smooth, 
                             f"-DPN_EMU_ADAPTIVE={int(adaptive)}", f"-DPN_EMU_DYNAMIC={int(dynamic)}", f"-DPN_EMU_SAVE={save}",
                             os.path.join(HERE, "emulation", "pn_warp_host.cpp"), "-o", exe2, "-lpthread"], check=True)
         exe = exe2
-    path = os.path.join(os.path.dirname(exe), f"tsan_in_{problem}_{q}_{save}_{smooth}.bin")
+    path = os.path.join(os.path.dirname(exe), f"tsan_in_{problem}_{q}_{save}_{smooth}_{int(cta)}{len(extra)}.bin")
     blob.tofile(path)
     r = subprocess.run([exe, path], capture_output=True, text=True, timeout=900, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0"))
     return r, sum(o["naccept"] for o in oo)
@@ -583,3 +585,21 @@ def test_fenrir_backward_pass_as_a_warp(oracle, sweep, data_k):
                   fenrir=(data_t, data_u, H, 0.5 * np.eye(2)))
     assert np.all(np.isfinite(want))
     assert np.allclose(k["fenrir_ll"], want, rtol=1e-10, atol=0)
+
+
+def test_threadsanitizer_racecheck_general_prior_ioup_and_fenrir(oracle):
+    """The remaining lane-exchanging builds under ThreadSanitizer: pn_gen + pn_lti with the Jacobian-updated rate and with a matrix rate followed by the
+    dense-transition sweep; pn_small + the column sweep with PN_IOUP; the Fenrir backward pass in the column sweep.  All clean."""
+    rate = np.array([[-1.0, 0.3], [-0.2, -0.5]])
+    common = dict(N=6, t1=0.2, dt=0.02, adaptive=False, dynamic=False, oracle=oracle)
+    runs = [
+        _tsan_run("lotka_volterra", 3, 4, 8, save=2, smooth=0, cta=2, okw=dict(prior=oracle.PRIOR_IOUP, update_rate_parameter=True), extra=([1, 1, -1], np.zeros(4)), **common),
+        _tsan_run("lotka_volterra", 3, 4, 8, save=2, smooth=3, cta=2, okw=dict(prior=oracle.PRIOR_IOUP, rate_parameter=rate), extra=([1, 0, 1], rate), **common),
+        _tsan_run("lotka_volterra", 3, 4, 8, save=2, smooth=1, defs=("PN_IOUP=1",), okw=dict(prior=oracle.PRIOR_IOUP, rate_parameter=-1.0),
+                  extra=([2, -1.0], 0.5 * (np.polynomial.legendre.leggauss(16)[0] + 1), 0.5 * np.polynomial.legendre.leggauss(16)[1]), **common),
+        _tsan_run("fitzhugh_nagumo", 3, 4, 8, save=2, smooth=1, defs=("PN_FENRIR=1",),
+                  extra=([3, 2, 2], [0.1, 0.2], [[1.9, 0.2], [1.7, 0.6]], np.eye(8)[:2], 0.5 * np.eye(2)), **common),
+    ]
+    for r, nacc in runs:
+        assert "ThreadSanitizer" not in r.stderr, r.stderr[:4000]
+        assert r.returncode == 0 and f"accepted {nacc} " in r.stdout, (r.returncode, r.stdout, r.stderr[:2000])
