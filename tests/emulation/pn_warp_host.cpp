@@ -57,6 +57,9 @@ extern "C" void pn_emu_set_ioup(double rate, const double* glx, const double* gl
     for (int i = 0; i < 16; i++) g_glx[i] = glx[i], g_glw[i] = glw[i];
 }
 #include "kernels/pn_builtin_problems.cuh"
+#ifdef PN_EMU_USER_SOURCE /* a traced right-hand side (tracer.cuda_source), as the NVRTC build appends it */
+#include PN_EMU_USER_SOURCE
+#endif
 
 #ifndef PN_EMU_ADAPTIVE
 #define PN_EMU_ADAPTIVE 0

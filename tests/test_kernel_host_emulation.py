@@ -220,8 +220,35 @@ def test_blocks_kernel_shapes(oracle, problem, q, t1, dt):
 
 
 # ---- the group-per-trajectory kernels as ONE WARP of host threads (cuda_shim.h, PN_SHIM_WARP): pn_small.cuh, pn_smooth_col.cuh, pn_smooth_reg.cuh ----
-def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False, cta=False, defs=()):
+def _table(name, T):
+    """constexpr lookup table in the form pnode_api.cu generates for the NVRTC build (mass_preamble / obsn_preamble)"""
+    T = np.asarray(T, dtype=float)
+    body = "".join(f"(a == {a} && i == {i}) ? {float(T[a, i])!r} : " for a in range(T.shape[0]) for i in range(T.shape[1]) if T[a, i] != 0.0)
+    return f"constexpr double {name}(int a, int i) {{\n  return {body}0.0;\n}}\n"
+
+
+def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False, cta=False, defs=(), preamble=None):
     tag = "".join("_" + x.replace("=", "") for x in defs)
+    pre = []
+    if preamble is not None:  # generated source that precedes the kernel headers (what pnode_api.cu prepends to the NVRTC program)
+        import hashlib
+        h = hashlib.sha1(preamble.encode()).hexdigest()[:10]
+        tag += "_pre" + h
+        ppath = os.path.join(tempfile.gettempdir(), f"pn_emu_{os.getuid()}", f"preamble_{h}.h")
+        os.makedirs(os.path.dirname(ppath), exist_ok=True)
+        if not os.path.exists(ppath):
+            with open(ppath, "w") as fh:
+                fh.write(preamble)
+        pre = ["-include", ppath]
+    if problem not in STRUCT:  # a traced problem of the library (mass-matrix / second-order tables): generated source, struct UserProb
+        pdef = problems.lookup(problem)
+        upath = os.path.join(tempfile.gettempdir(), f"pn_emu_{os.getuid()}", f"user_{problem}.cuh")
+        os.makedirs(os.path.dirname(upath), exist_ok=True)
+        text = tracer.cuda_source(tracer.trace(pdef.f, len(pdef.u0), len(pdef.p)), "UserProb")
+        if not os.path.exists(upath) or open(upath).read() != text:
+            with open(upath, "w") as fh:
+                fh.write(text)
+        pre += [f'-DPN_EMU_USER_SOURCE="{upath}"']
     out = os.path.join(tempfile.gettempdir(), f"pn_emu_{os.getuid()}",
                        f"{('warp', 'cta', 'gen')[int(cta)]}_{problem}_q{q}_g{G}_gs{GS}_a{int(adaptive)}_d{int(dynamic)}_s{save}{tag}{'_tsan' if tsan else ''}" + (".exe" if tsan else ".so"))
     os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -231,15 +258,15 @@ def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False, cta=Fals
                                                                       "pn_params.h", "pn_builtin_problems.cuh")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(f) for f in deps):
         mode = ["-fsanitize=thread", "-g", "-DPN_EMU_MAIN=1"] if tsan else ["-fPIC", "-shared"]
-        subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", *mode, "-I", CSRC, f"-DPN_EMU_PROBLEM={STRUCT[problem]}", f"-DPN_EMU_Q={q}",
+        subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", *mode, "-I", CSRC, f"-DPN_EMU_PROBLEM={STRUCT.get(problem, 'UserProb')}", f"-DPN_EMU_Q={q}",
                         f"-DPN_EMU_G={G}", f"-DPN_EMU_GS={GS}", f"-DPN_EMU_ADAPTIVE={int(adaptive)}", f"-DPN_EMU_DYNAMIC={int(dynamic)}",
-                        f"-DPN_EMU_SAVE={save}", f"-DPN_EMU_KERNEL={int(cta)}", *["-D" + x for x in defs], src, "-o", out, "-lpthread"], check=True)
+                        f"-DPN_EMU_SAVE={save}", f"-DPN_EMU_KERNEL={int(cta)}", *["-D" + x for x in defs], *pre, src, "-o", out, "-lpthread"], check=True)
     return out
 
 
 def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False, dynamic=False, calibrate=False, save=2, smooth=0, write_x=1, lanes=32,
-              abstol=1e-6, reltol=1e-3, cta=False, defs=(), rate=None, update_rate=False, ioup_rate=None, fenrir=None):
-    lib = C.CDLL(_build_warp(problem, q, G, GS, adaptive, dynamic, save, cta=cta, defs=defs))
+              abstol=1e-6, reltol=1e-3, cta=False, defs=(), rate=None, update_rate=False, ioup_rate=None, fenrir=None, preamble=None):
+    lib = C.CDLL(_build_warp(problem, q, G, GS, adaptive, dynamic, save, cta=cta, defs=defs, preamble=preamble))
     lib.pn_emu_warp_solve.restype = None
     if rate is not None:
         rate = np.ascontiguousarray(rate, dtype=float)
@@ -603,3 +630,44 @@ def test_threadsanitizer_racecheck_general_prior_ioup_and_fenrir(oracle):
     for r, nacc in runs:
         assert "ThreadSanitizer" not in r.stderr, r.stderr[:4000]
         assert r.returncode == 0 and f"accepted {nacc} " in r.stdout, (r.returncode, r.stdout, r.stderr[:2000])
+
+
+def test_observation_noise_and_mass_matrix_builds_as_a_warp(oracle):
+    """Two generated-preamble builds of pn_small.cuh as a warp of host threads.  PN_OBSN: `pn_observation_noise = 0.01 I` in the step update
+    (S += R, Joseph term K R K' re-factorised; src/filtering/update.jl:125-136, perform_step.jl:185-187) on FitzHugh-Nagumo.  PN_MASS: ROBER as the
+    index-1 DAE the reference benchmarks (M = diag(1, 1, 0), H = [-J | M | 0]; measurement_models.jl:11-20), adaptive with DynamicDiffusion.  Tables as
+    pnode_api.cu generates them; against the oracle: fixed steps 1e-10 / 1e-9, adaptive accept / reject counts."""
+    pd = problems.PROBLEMS["fitzhugh_nagumo"]
+    q, N, dt, t1 = 3, 9, 0.05, 1.0
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N, seed=29)
+    Rn = 0.01 * np.eye(2)
+    oo = [oracle.solve(oracle.make_config(2, q, pd.n_p, alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, adaptive=False, dt=dt, t0=0.0, t1=t1,
+                                          save_everystep=True, smooth=False, cov_backend=oracle.COV_REF, pn_observation_noise=Rn), rhs, u0[i], p[i])
+          for i in range(N)]
+    ns = oo[0]["n"]
+    off = np.arange(N + 1) * ns
+    pre = "#define PN_OBSN 1\n" + _table("pn_obsn_cov", Rn) + _table("pn_obsn_rt", np.linalg.cholesky(Rn).T)
+    k = _run_warp("fitzhugh_nagumo", q, 4, 8, np.array([o["x_filt_mu"][0] for o in oo]), p, off, t1=t1, dt=dt, save=2, preamble=pre)
+    for i in range(N):
+        sl = slice(off[i], off[i + 1])
+        assert _rel(k["s_u"][sl], oo[i]["pu_mu"]) < 1e-10
+        assert _rel(k["s_cov"][sl][1:], oo[i]["pu_cov"][1:]) < 1e-9
+        assert k["scal"][i, 1] == pytest.approx(oo[i]["loglik"], rel=1e-9)
+
+    pd = problems.lookup("rober_dae")
+    N = 10
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 3, 3), q)
+    rng = np.random.default_rng(31)
+    p = np.array(pd.p)[None, :] * (1.0 + 0.05 * rng.standard_normal((N, 3)))
+    u0 = np.tile(np.array(pd.u0, dtype=float), (N, 1))
+    M = np.array(pd.mass_matrix)
+    oo = [oracle.solve(oracle.make_config(3, q, 3, alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC, adaptive=True, dt=1e-4, t0=0.0, t1=10.0,
+                                          save_everystep=True, smooth=False, cov_backend=oracle.COV_REF, mass_matrix=M), rhs, u0[i], p[i]) for i in range(N)]
+    assert all(o["retcode"] == "Success" and o["naccept"] > 5 for o in oo)
+    pre = "#define PN_MASS 1\n" + _table("pn_mass", M) + _table("pn_mass_inv", np.linalg.inv(M + 1e-20 * np.eye(3)))
+    k = _run_warp("rober_dae", q, 4, 8, np.array([o["x_filt_mu"][0] for o in oo]), p, np.arange(N + 1), t1=10.0, dt=1e-4, adaptive=True, dynamic=True, save=0,
+                  preamble=pre)
+    for i in range(N):
+        assert tuple(k["counts"][i][[0, 1, 3]]) == (oo[i]["naccept"], oo[i]["nreject"], 0)
+        assert _rel(k["u"][i], oo[i]["pu_mu"][-1]) < 1e-8
