@@ -51,6 +51,13 @@ extern "C" void pn_emu_set_fenrir(const double* data_t, const double* data_u, lo
     g_data_t = data_t, g_data_u = data_u, g_n_data = n_data, g_n_obs = n_obs, g_obs_H = obs_H, g_obs_Rn = obs_Rn, g_fenrir_ll = fenrir_ll;
     g_kron_logdet = kron_logdet;
 }
+/* forward data updates (DataUpdateCallback; pn_small.cuh built with a PN_DATA preamble): observations, which are tstops, and the output [n_traj] */
+static const double *g_fwd_t = nullptr, *g_fwd_u = nullptr;
+static long long g_fwd_n = 0;
+static double* g_fwd_ll = nullptr;
+extern "C" void pn_emu_set_data(const double* data_t, const double* data_u, long long n_data, double* data_loglik) {
+    g_fwd_t = data_t, g_fwd_u = data_u, g_fwd_n = n_data, g_fwd_ll = data_loglik;
+}
 static double g_rate = 0.0, g_glx[16], g_glw[16]; /* scalar-rate IOUP of the register kernels (built with PN_IOUP=1): rate, Gauss-Legendre rule on [0, 1] */
 extern "C" void pn_emu_set_ioup(double rate, const double* glx, const double* glw) {
     g_rate = rate;
@@ -152,6 +159,10 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
     P.init_dt = init_dt;
     P.work_counter = &counter;
     for (int i = 0; i < n * n; i++) P.L[i] = L[i], P.U[i] = U[i], P.Qb[i] = Qb[i];
+    if (g_fwd_ll) {
+        P.data_t = g_fwd_t, P.data_u = g_fwd_u, P.n_data = g_fwd_n, P.data_loglik = g_fwd_ll;
+        P.tstops = g_fwd_t, P.n_tstops = g_fwd_n; /* filtering.jl:24: the data times are tstops (those at t1 are harmless) */
+    }
     P.rate = g_rate;
     for (int i = 0; i < 16; i++) P.glx[i] = g_glx[i], P.glw[i] = g_glw[i];
     P.t_end = t_end.data(), P.loglik = loglik.data(), P.diffusion = diffusion.data(), P.dt_last = dt_last.data();

@@ -265,7 +265,7 @@ def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False, cta=Fals
 
 
 def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False, dynamic=False, calibrate=False, save=2, smooth=0, write_x=1, lanes=32,
-              abstol=1e-6, reltol=1e-3, cta=False, defs=(), rate=None, update_rate=False, ioup_rate=None, fenrir=None, preamble=None):
+              abstol=1e-6, reltol=1e-3, cta=False, defs=(), rate=None, update_rate=False, ioup_rate=None, fenrir=None, preamble=None, data=None):
     lib = C.CDLL(_build_warp(problem, q, G, GS, adaptive, dynamic, save, cta=cta, defs=defs, preamble=preamble))
     lib.pn_emu_warp_solve.restype = None
     if rate is not None:
@@ -281,6 +281,12 @@ def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False
         lib.pn_emu_set_fenrir.argtypes = [dp, dp, C.c_longlong, C.c_int, dp, dp, dp, C.c_int]
         lib.pn_emu_set_fenrir(ft.ctypes.data_as(dp), fu.ctypes.data_as(dp), len(ft), fu.shape[1], fH.ctypes.data_as(dp), fR.ctypes.data_as(dp),
                               fll.ctypes.data_as(dp), 0)
+    if data is not None:  # forward data updates: (data_t, data_u [n_data][n_obs]) -> o["data_ll"]; the build needs a PN_DATA preamble
+        dt_, du_ = [np.ascontiguousarray(a, dtype=float) for a in data]
+        dll = np.full(len(init_mu), np.nan)
+        keep += [dt_, du_, dll]
+        lib.pn_emu_set_data.argtypes = [dp, dp, C.c_longlong, dp]
+        lib.pn_emu_set_data(dt_.ctypes.data_as(dp), du_.ctypes.data_as(dp), len(dt_), dll.ctypes.data_as(dp))
     if ioup_rate is not None:  # scalar-rate IOUP of the register kernels (defs must hold PN_IOUP=1): 16-point Gauss-Legendre rule on [0, 1]
         x, w = np.polynomial.legendre.leggauss(16)
         lib.pn_emu_set_ioup.argtypes = [C.c_double, dp, dp]
@@ -305,6 +311,8 @@ def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False
                           A(o["s_t"]), A(o["s_u"]), A(o["s_cov"]), A(o["s_diff"]), A(o["s_x"]), A(o["s_xR"]), A(o["s_h"]), int(smooth), int(write_x))
     if fenrir is not None:
         o["fenrir_ll"] = keep[4]
+    if data is not None:
+        o["data_ll"] = dll
     return o
 
 
@@ -671,3 +679,25 @@ def test_observation_noise_and_mass_matrix_builds_as_a_warp(oracle):
     for i in range(N):
         assert tuple(k["counts"][i][[0, 1, 3]]) == (oo[i]["naccept"], oo[i]["nreject"], 0)
         assert _rel(k["u"][i], oo[i]["pu_mu"][-1]) < 1e-8
+
+
+def test_forward_data_updates_as_a_warp(oracle):
+    """filtering_data_loglik's forward pass (DataUpdateCallback, src/callbacks/dataupdate.jl:39-84; pn_small.cuh built with the PN_DATA preamble
+    pnode_api.cu generates): adaptive EK1(3) with DynamicDiffusion on FitzHugh-Nagumo, observations of both components at t = 0.5 and t = 1 (the first
+    one a tstop inside the interval), noise variance 0.25 -- accept / reject counts and the sum of the updates' log-likelihoods against the oracle."""
+    pd = problems.PROBLEMS["fitzhugh_nagumo"]
+    q, N, t1 = 3, 10, 1.0
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N, seed=37)
+    data_t, data_u = np.array([0.5, 1.0]), np.array([[1.9, 0.2], [1.7, 0.6]])
+    oo = [oracle.solve(oracle.make_config(2, q, pd.n_p, alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC, adaptive=True, dt=1e-2, t0=0.0, t1=t1, smooth=False,
+                                          save_everystep=True, cov_backend=oracle.COV_REF, data=(data_t, data_u), observation_noise_cov=0.25), rhs, u0[i], p[i])
+          for i in range(N)]
+    pre = ("#define PN_DATA 1\n#define PN_DATA_O 2\n" + _table("pn_data_H", np.eye(8)[:2]) + _table("pn_data_cov", 0.25 * np.eye(2)) +
+           _table("pn_data_rt", 0.5 * np.eye(2)))
+    k = _run_warp("fitzhugh_nagumo", q, 4, 8, np.array([o["x_filt_mu"][0] for o in oo]), p, np.arange(N + 1), t1=t1, dt=1e-2, adaptive=True, dynamic=True,
+                  save=0, preamble=pre, data=(data_t, data_u))
+    for i in range(N):
+        assert tuple(k["counts"][i][[0, 1, 3]]) == (oo[i]["naccept"], oo[i]["nreject"], 0)
+        assert k["data_ll"][i] == pytest.approx(oo[i]["data_loglik"], rel=1e-9)
+        assert _rel(k["u"][i], oo[i]["pu_mu"][-1]) < 1e-9
