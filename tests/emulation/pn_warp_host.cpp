@@ -30,6 +30,10 @@ PnShimCta pn_shim_cta;
 #include "kernels/pn_smooth.cuh" /* the warp-per-trajectory sweep (shared memory up to D = 56, a global workspace beyond: Pleiades D = 112) */
 #include "kernels/pn_smooth_col.cuh"
 #include "kernels/pn_smooth_reg.cuh"
+#include "kernels/pn_dense.cuh" /* dense output sol(t) on a saveat grid: register predict per (trajectory, grid point) pair */
+#ifndef PN_EMU_GD
+#define PN_EMU_GD 2 /* lanes per pair of the dense-output kernel (pnode_api.cu auto_lanes_qr(D)) */
+#endif
 #if PN_EMU_KERNEL == 1
 #include "kernels/pn_cta.cuh"
 alignas(16) double pn_cta_sm[65536];
@@ -57,6 +61,13 @@ static long long g_fwd_n = 0;
 static double* g_fwd_ll = nullptr;
 extern "C" void pn_emu_set_data(const double* data_t, const double* data_u, long long n_data, double* data_loglik) {
     g_fwd_t = data_t, g_fwd_u = data_u, g_fwd_n = n_data, g_fwd_ll = data_loglik;
+}
+/* dense output of a filter-only solve (solution.jl:330-398 without the smoothing half): grid, outputs [n_traj][n_saveat][d] and [..][d][d] */
+static const double* g_saveat = nullptr;
+static long long g_n_saveat = 0;
+static double *g_dense_u = nullptr, *g_dense_cov = nullptr;
+extern "C" void pn_emu_set_saveat(const double* saveat, long long n, double* out_u, double* out_cov) {
+    g_saveat = saveat, g_n_saveat = n, g_dense_u = out_u, g_dense_cov = out_cov;
 }
 static double g_rate = 0.0, g_glx[16], g_glw[16]; /* scalar-rate IOUP of the register kernels (built with PN_IOUP=1): rate, Gauss-Legendre rule on [0, 1] */
 extern "C" void pn_emu_set_ioup(double rate, const double* glx, const double* glw) {
@@ -188,6 +199,24 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
         scal_out[4 * i + 0] = t_end[i], scal_out[4 * i + 1] = loglik[i], scal_out[4 * i + 2] = diffusion[i], scal_out[4 * i + 3] = dt_last[i];
         counts[4 * i + 0] = naccept[i], counts[4 * i + 1] = nreject[i], counts[4 * i + 2] = nf[i], counts[4 * i + 3] = retcode[i];
     }
+#if PN_EMU_SAVE >= 2 && PN_EMU_KERNEL == 0
+    if (g_saveat && !smooth) { /* pnode_api.cu solve_impl, dense && !smooth: the predict kernel writes the filtering marginals directly */
+        PnDenseParams Dn;
+        std::memset(&Dn, 0, sizeof Dn);
+        Dn.n_traj = n_traj, Dn.n_saveat = g_n_saveat, Dn.saveat = g_saveat;
+        Dn.smooth = 0;
+        Dn.calibrate_scale = (calibrate && !(PN_EMU_DYNAMIC != 0)) ? 1 : 0;
+        Dn.step_offsets = offsets;
+        Dn.s_t = s_t, Dn.s_h = s_h, Dn.s_diffusion = s_diffusion, Dn.s_x_mean = s_x_mean, Dn.s_x_covfac = s_x_covfac;
+        Dn.gdiff = diffusion.data();
+        Dn.initial_diffusion = P.initial_diffusion;
+        for (int i = 0; i < n * n; i++) Dn.U[i] = U[i];
+        Dn.rate = g_rate;
+        for (int i = 0; i < 16; i++) Dn.glx[i] = g_glx[i], Dn.glw[i] = g_glw[i];
+        Dn.out_u = g_dense_u, Dn.out_cov = g_dense_cov;
+        run_warp(lanes, [&]() { pn_dense_predict_entry<PN_EMU_PROBLEM::d, PN_EMU_Q, PN_EMU_GD>(Dn); });
+    }
+#endif
 #if PN_EMU_SAVE >= 2
     if (smooth) {
         PnSmoothParams S;

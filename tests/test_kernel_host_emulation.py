@@ -265,7 +265,7 @@ def _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=False, cta=Fals
 
 
 def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False, dynamic=False, calibrate=False, save=2, smooth=0, write_x=1, lanes=32,
-              abstol=1e-6, reltol=1e-3, cta=False, defs=(), rate=None, update_rate=False, ioup_rate=None, fenrir=None, preamble=None, data=None):
+              abstol=1e-6, reltol=1e-3, cta=False, defs=(), rate=None, update_rate=False, ioup_rate=None, fenrir=None, preamble=None, data=None, saveat=None):
     lib = C.CDLL(_build_warp(problem, q, G, GS, adaptive, dynamic, save, cta=cta, defs=defs, preamble=preamble))
     lib.pn_emu_warp_solve.restype = None
     if rate is not None:
@@ -287,6 +287,13 @@ def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False
         keep += [dt_, du_, dll]
         lib.pn_emu_set_data.argtypes = [dp, dp, C.c_longlong, dp]
         lib.pn_emu_set_data(dt_.ctypes.data_as(dp), du_.ctypes.data_as(dp), len(dt_), dll.ctypes.data_as(dp))
+    if saveat is not None:  # dense output of a filter-only solve -> o["dense_u"] [N][n_saveat][d], o["dense_cov"]
+        sa = np.ascontiguousarray(saveat, dtype=float)
+        dd_ = lib.pn_emu_d()
+        du_out, dc_out = np.full((len(init_mu), len(sa), dd_), np.nan), np.full((len(init_mu), len(sa), dd_, dd_), np.nan)
+        keep += [sa, du_out, dc_out]
+        lib.pn_emu_set_saveat.argtypes = [dp, C.c_longlong, dp, dp]
+        lib.pn_emu_set_saveat(sa.ctypes.data_as(dp), len(sa), du_out.ctypes.data_as(dp), dc_out.ctypes.data_as(dp))
     if ioup_rate is not None:  # scalar-rate IOUP of the register kernels (defs must hold PN_IOUP=1): 16-point Gauss-Legendre rule on [0, 1]
         x, w = np.polynomial.legendre.leggauss(16)
         lib.pn_emu_set_ioup.argtypes = [C.c_double, dp, dp]
@@ -313,6 +320,8 @@ def _run_warp(problem, q, G, GS, init_mu, ps, offsets, *, t1, dt, adaptive=False
         o["fenrir_ll"] = keep[4]
     if data is not None:
         o["data_ll"] = dll
+    if saveat is not None:
+        o["dense_u"], o["dense_cov"] = du_out, dc_out
     return o
 
 
@@ -701,3 +710,30 @@ def test_forward_data_updates_as_a_warp(oracle):
         assert tuple(k["counts"][i][[0, 1, 3]]) == (oo[i]["naccept"], oo[i]["nreject"], 0)
         assert k["data_ll"][i] == pytest.approx(oo[i]["data_loglik"], rel=1e-9)
         assert _rel(k["u"][i], oo[i]["pu_mu"][-1]) < 1e-9
+
+
+@pytest.mark.parametrize("dynamic,calibrate", [(False, False), (False, True), (True, False)])
+def test_dense_output_kernel_as_a_warp(oracle, dynamic, calibrate):
+    """sol(t) of a filter-only solve on a saveat grid (src/solution.jl:330-398: predict from the last saved point; pn_dense.cuh, G = 2 lanes per
+    (trajectory, grid point) pair): FitzHugh-Nagumo EK1(3), fixed steps, grid points between, on and after saved points -- FixedDiffusion with and
+    without calibration (the marginals are scaled by the global MLE), DynamicDiffusion -- against the oracle's `interpolate`, 1e-10 / 1e-9."""
+    pd = problems.PROBLEMS["fitzhugh_nagumo"]
+    q, N, dt, t1 = 3, 7, 0.05, 1.0
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N, seed=41)
+    cfg = oracle.make_config(2, q, pd.n_p, alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC if dynamic else oracle.DIFF_FIXED, calibrate=calibrate, adaptive=False,
+                             dt=dt, t0=0.0, t1=t1, save_everystep=True, smooth=False, cov_backend=oracle.COV_REF)
+    sols = [oracle.solve(cfg, rhs, u0[i], p[i]) for i in range(N)]
+    ns = sols[0]["n"]
+    off = np.arange(N + 1) * ns
+    grid = np.concatenate([[0.0, 0.013, 0.31, 0.5 * (sols[0]["t"][7] + sols[0]["t"][8])], sols[0]["t"][[3, 11]], [0.987, 1.0]])
+    k = _run_warp("fitzhugh_nagumo", q, 4, 8, np.array([s["x_filt_mu"][0] for s in sols]), p, off, t1=t1, dt=dt, dynamic=dynamic, calibrate=calibrate, save=2,
+                  saveat=grid)
+    for i in range(N):
+        for j, tv in enumerate(grid):
+            um, uc = oracle.interpolate(cfg, sols[i], float(tv))
+            assert _rel(k["dense_u"][i, j], um) < 1e-10
+            if tv > 0:
+                assert _rel(k["dense_cov"][i, j], uc) < 1e-9
+            else:
+                assert np.all(k["dense_cov"][i, j] == 0.0)
