@@ -298,7 +298,7 @@ int main(int argc, char** argv) {
     const double* p = c;
     c += N * (np_ > 0 ? np_ : 1);
     /* optional tagged sections: 1 rate matrix (update flag, d x d) | 2 scalar-rate IOUP (rate, glx[16], glw[16]) | 3 Fenrir (n_data, n_obs, data_t,
-       data_u, H [n_obs][D], Rn [n_obs][n_obs]) */
+       data_u, H [n_obs][D], Rn [n_obs][n_obs]) | 4 forward data updates (n_data, n_obs, data_t, data_u) */
     std::vector<double> fll(N, 0.0);
     while (c - in.data() < (long long)in.size()) {
         const int tag = (int)*c++;
@@ -313,6 +313,11 @@ int main(int argc, char** argv) {
             const int no = (int)c[1];
             pn_emu_set_fenrir(c + 2, c + 2 + nd, nd, no, c + 2 + nd + nd * no, c + 2 + nd + nd * no + (long long)no * D, fll.data(), 0);
             c += 2 + nd + nd * no + (long long)no * D + no * no;
+        } else if (tag == 4) { /* forward data updates: n_data, n_obs, data_t, data_u */
+            const long long nd = (long long)c[0];
+            const int no = (int)c[1];
+            pn_emu_set_data(c + 2, c + 2 + nd, nd, fll.data());
+            c += 2 + nd + nd * no;
         } else {
             return 3;
         }

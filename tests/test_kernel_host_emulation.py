@@ -390,10 +390,12 @@ def test_group_step_kernel_adaptive_ragged_ensemble(oracle):
 
 
 def _tsan_run(problem, q, G, GS, *, N, t1, dt, adaptive, dynamic, save, smooth, oracle, drop_syncwarp=False, lanes=32, cta=False, defs=(), okw=None,
-              extra=()):
-    pd = problems.PROBLEMS[problem]
+              extra=(), preamble=None, p_override=None):
+    pd = problems.lookup(problem)
     rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
     u0, p = _ensemble(pd, N, seed=5)
+    if p_override is not None:
+        u0, p = p_override
     if pd.n_p == 0:
         p = np.zeros((N, 1))
     kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC if dynamic else oracle.DIFF_FIXED, calibrate=False, adaptive=adaptive, dt=dt, t0=0.0, t1=t1,
@@ -405,12 +407,12 @@ def _tsan_run(problem, q, G, GS, *, N, t1, dt, adaptive, dynamic, save, smooth, 
     blob = np.concatenate([[N, lanes, smooth, 1, oo[0]["n"] if save else 1], scal, L.ravel(), U.ravel(), Qb.ravel(),
                            np.array([o["x_filt_mu"][0] for o in oo]).ravel(), np.full(N, dt), p.ravel(),
                            *[np.asarray(e, dtype=float).ravel() for e in extra]]).astype(np.float64)
-    exe = _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=True, cta=cta, defs=defs)
+    exe = _build_warp(problem, q, G, GS, adaptive, dynamic, save, tsan=True, cta=cta, defs=defs, preamble=preamble)
     if drop_syncwarp:
         exe2 = exe.replace(".exe", "_nosync.exe")
         if not os.path.exists(exe2) or os.path.getmtime(exe2) < os.path.getmtime(exe):
             subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fsanitize=thread", "-g", "-DPN_EMU_MAIN=1", "-DPN_SHIM_DROP_SYNCWARP=1", "-I", CSRC,
-                            f"-DPN_EMU_PROBLEM={STRUCT[problem]}", f"-DPN_EMU_Q={q}", f"-DPN_EMU_G={G}", f"-DPN_EMU_GS={GS}",
+                            f"-DPN_EMU_PROBLEM={STRUCT.get(problem, 'UserProb')}", f"-DPN_EMU_Q={q}", f"-DPN_EMU_G={G}", f"-DPN_EMU_GS={GS}",
                             f"-DPN_EMU_ADAPTIVE={int(adaptive)}", f"-DPN_EMU_DYNAMIC={int(dynamic)}", f"-DPN_EMU_SAVE={save}",
                             os.path.join(HERE, "emulation", "pn_warp_host.cpp"), "-o", exe2, "-lpthread"], check=True)
         exe = exe2
@@ -737,3 +739,28 @@ def test_dense_output_kernel_as_a_warp(oracle, dynamic, calibrate):
                 assert _rel(k["dense_cov"][i, j], uc) < 1e-9
             else:
                 assert np.all(k["dense_cov"][i, j] == 0.0)
+
+
+def test_threadsanitizer_racecheck_generated_preamble_builds(oracle):
+    """The builds of pn_small.cuh with a generated preamble under ThreadSanitizer: pn_observation_noise (fixed steps, saving pass), the mass-matrix
+    build on ROBER as a DAE (adaptive) and forward data updates (adaptive, tstops).  All clean."""
+    Rn = 0.01 * np.eye(2)
+    M = np.diag([1.0, 1.0, 0.0])
+    pdr = problems.lookup("rober_dae")
+    rng = np.random.default_rng(43)
+    pr = np.array(pdr.p)[None, :] * (1.0 + 0.05 * rng.standard_normal((6, 3)))
+    data_t, data_u = np.array([0.5, 1.0]), np.array([[1.9, 0.2], [1.7, 0.6]])
+    runs = [
+        _tsan_run("fitzhugh_nagumo", 3, 4, 8, N=9, t1=0.5, dt=0.05, adaptive=False, dynamic=False, save=2, smooth=0, oracle=oracle,
+                  okw=dict(pn_observation_noise=Rn), preamble="#define PN_OBSN 1\n" + _table("pn_obsn_cov", Rn) + _table("pn_obsn_rt", np.linalg.cholesky(Rn).T)),
+        _tsan_run("rober_dae", 3, 4, 8, N=6, t1=1.0, dt=1e-4, adaptive=True, dynamic=True, save=0, smooth=0, oracle=oracle, okw=dict(mass_matrix=M),
+                  p_override=(np.tile(np.array(pdr.u0, dtype=float), (6, 1)), pr),
+                  preamble="#define PN_MASS 1\n" + _table("pn_mass", M) + _table("pn_mass_inv", np.linalg.inv(M + 1e-20 * np.eye(3)))),
+        _tsan_run("fitzhugh_nagumo", 3, 4, 8, N=9, t1=1.0, dt=1e-2, adaptive=True, dynamic=True, save=0, smooth=0, oracle=oracle,
+                  okw=dict(data=(data_t, data_u), observation_noise_cov=0.25), extra=([4, 2, 2], data_t, data_u),
+                  preamble="#define PN_DATA 1\n#define PN_DATA_O 2\n" + _table("pn_data_H", np.eye(8)[:2]) + _table("pn_data_cov", 0.25 * np.eye(2)) +
+                  _table("pn_data_rt", 0.5 * np.eye(2))),
+    ]
+    for r, nacc in runs:
+        assert "ThreadSanitizer" not in r.stderr, r.stderr[:4000]
+        assert r.returncode == 0 and f"accepted {nacc} " in r.stdout, (r.returncode, r.stdout, r.stderr[:2000])
