@@ -94,6 +94,8 @@ alignas(16) double pn_smc_shared[32768];
 alignas(16) double pn_smr_shared[32768];
 alignas(16) double pn_sm_shared[32768];
 
+/* modelled dimension: Prob is the first-order form of dimension 2 d for a SecondOrderODEProblem (PN_SECOND), sol.u = (du, u) keeps length Prob::d */
+static constexpr int PN_EMU_DM = PN_SECOND ? PN_EMU_PROBLEM::d / 2 : PN_EMU_PROBLEM::d;
 extern "C" int pn_emu_d(void) { return PN_EMU_PROBLEM::d; }
 extern "C" int pn_emu_n_p(void) { return PN_EMU_PROBLEM::n_p; }
 extern "C" int pn_emu_q(void) { return PN_EMU_Q; }
@@ -214,7 +216,7 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
         Dn.rate = g_rate;
         for (int i = 0; i < 16; i++) Dn.glx[i] = g_glx[i], Dn.glw[i] = g_glw[i];
         Dn.out_u = g_dense_u, Dn.out_cov = g_dense_cov;
-        run_warp(lanes, [&]() { pn_dense_predict_entry<PN_EMU_PROBLEM::d, PN_EMU_Q, PN_EMU_GD>(Dn); });
+        run_warp(lanes, [&]() { pn_dense_predict_entry<PN_EMU_DM, PN_EMU_Q, PN_EMU_GD>(Dn); });
     }
 #endif
 #if PN_EMU_SAVE >= 2
@@ -223,7 +225,7 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
         std::memset(&S, 0, sizeof S);
         counter = 0;
         S.n_traj = n_traj;
-        S.d = PN_EMU_PROBLEM::d, S.q = PN_EMU_Q;
+        S.d = PN_EMU_DM, S.q = PN_EMU_Q;
         S.dynamic = (PN_EMU_DYNAMIC != 0);
         S.calibrate = calibrate;
         S.initial_diffusion = P.initial_diffusion;
@@ -245,8 +247,8 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
 #endif
         if (smooth == 3) { /* pn_smooth_kernel: PN_SM_WARPS warps per CTA, one trajectory per warp; work matrices in shared memory when the four
                               warps' share fits the device's 200 KB, else in a global workspace -- the product's rule (pnode_api.cu launch_sweep) */
-            constexpr int D = PN_EMU_PROBLEM::d * n;
-            const size_t per_warp = 7 * D * D + 4 * D + 2 * n * n + 2 * n + (S.gen_prior ? PN_SMOOTH_GEN_EXTRA(D, PN_EMU_PROBLEM::d, n) : 0) +
+            constexpr int D = PN_EMU_DM * n;
+            const size_t per_warp = 7 * D * D + 4 * D + 2 * n * n + 2 * n + (S.gen_prior ? PN_SMOOTH_GEN_EXTRA(D, PN_EMU_DM, n) : 0) +
                                     (S.fenrir_ll ? PN_FENRIR_EXTRA(D, S.n_obs) : 0);
             std::vector<double> ws;
             if (per_warp * 8 > 200 * 1024) {
@@ -259,9 +261,9 @@ extern "C" void pn_emu_warp_solve(long long n_traj, int lanes, const double* sca
         }
 #if PN_EMU_KERNEL == 0
         else if (smooth == 1)
-            run_warp(lanes, [&]() { pn_smooth_col_entry<PN_EMU_PROBLEM::d, PN_EMU_Q, PN_EMU_GS>(S); });
+            run_warp(lanes, [&]() { pn_smooth_col_entry<PN_EMU_DM, PN_EMU_Q, PN_EMU_GS>(S); });
         else
-            run_warp(lanes, [&]() { pn_smooth_reg_entry<PN_EMU_PROBLEM::d, PN_EMU_Q, PN_EMU_GS>(S); });
+            run_warp(lanes, [&]() { pn_smooth_reg_entry<PN_EMU_DM, PN_EMU_Q, PN_EMU_GS>(S); });
 #endif
     }
 #endif
@@ -281,7 +283,7 @@ int main(int argc, char** argv) {
     size_t got;
     while ((got = std::fread(buf, 8, 1024, f)) > 0) in.insert(in.end(), buf, buf + got);
     std::fclose(f);
-    constexpr int n = PN_EMU_Q + 1, d = PN_EMU_PROBLEM::d, D = d * n, np_ = PN_EMU_PROBLEM::n_p;
+    constexpr int n = PN_EMU_Q + 1, d = PN_EMU_PROBLEM::d, D = PN_EMU_DM * n, np_ = PN_EMU_PROBLEM::n_p;
     const double* c = in.data();
     const long long N = (long long)c[0];
     const int lanes = (int)c[1], smooth = (int)c[2], write_x = (int)c[3];

@@ -764,3 +764,31 @@ def test_threadsanitizer_racecheck_generated_preamble_builds(oracle):
     for r, nacc in runs:
         assert "ThreadSanitizer" not in r.stderr, r.stderr[:4000]
         assert r.returncode == 0 and f"accepted {nacc} " in r.stdout, (r.returncode, r.stdout, r.stderr[:2000])
+
+
+def test_second_order_problem_on_the_group_kernel_and_column_sweep(oracle):
+    """SecondOrderODEProblem (test/secondorderode.jl:15-19, the two-body problem; d = 2 positions, D = 8 at order 3, sol.u = (du, u)) on pn_small.cuh and
+    pn_smooth_col.cuh built with PN_SECOND, traced at run time: filtered and smoothed points 1e-10 / 1e-9 against the oracle's second-order route."""
+    pd = problems.lookup("twobody")
+    q, N, dt, t1 = 3, 9, 0.005, 0.1
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, 4, 1), q)
+    rng = np.random.default_rng(47)
+    u0 = np.array(pd.u0)[None, :] * (1.0 + 0.02 * rng.standard_normal((N, 4)))
+    p = np.array(pd.p)[None, :] * (1.0 + 0.05 * rng.standard_normal((N, 1)))
+    kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=False, adaptive=False, dt=dt, t0=0.0, t1=t1, save_everystep=True, second_order=True)
+    of = [oracle.solve(oracle.make_config(2, q, 1, smooth=False, cov_backend=oracle.COV_REF, **kw), rhs, u0[i], p[i]) for i in range(N)]
+    os_ = [oracle.solve(oracle.make_config(2, q, 1, smooth=True, cov_backend=oracle.COV_REF, **kw), rhs, u0[i], p[i]) for i in range(N)]
+    os2 = [oracle.solve(oracle.make_config(2, q, 1, smooth=True, cov_backend=oracle.COV_QR, **kw), rhs, u0[i], p[i]) for i in range(N)]
+    ns = of[0]["n"]
+    off = np.arange(N + 1) * ns
+    mu0 = np.array([o["x_filt_mu"][0] for o in of])
+    assert mu0.shape == (N, 8)
+    kf = _run_warp("twobody", q, 4, 8, mu0, p, off, t1=t1, dt=dt, save=2, smooth=0, defs=("PN_SECOND=1",))
+    ks = _run_warp("twobody", q, 4, 8, mu0, p, off, t1=t1, dt=dt, save=2, smooth=1, defs=("PN_SECOND=1",))
+    for i in range(N):
+        sl = slice(off[i], off[i + 1])
+        assert _rel(kf["s_u"][sl], of[i]["pu_mu"]) < 1e-10
+        assert _rel(kf["s_cov"][sl][1:], of[i]["pu_cov"][1:]) < 1e-9
+        assert kf["scal"][i, 1] == pytest.approx(of[i]["loglik"], rel=1e-9)
+        assert _rel(ks["s_u"][sl], os_[i]["pu_mu"]) < 1e-10
+        assert _rel(ks["s_cov"][sl][1:], os_[i]["pu_cov"][1:]) < max(1e-9, 20 * _rel(os2[i]["pu_cov"][1:], os_[i]["pu_cov"][1:]))
