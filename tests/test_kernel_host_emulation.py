@@ -792,3 +792,25 @@ def test_second_order_problem_on_the_group_kernel_and_column_sweep(oracle):
         assert kf["scal"][i, 1] == pytest.approx(of[i]["loglik"], rel=1e-9)
         assert _rel(ks["s_u"][sl], os_[i]["pu_mu"]) < 1e-10
         assert _rel(ks["s_cov"][sl][1:], os_[i]["pu_cov"][1:]) < max(1e-9, 20 * _rel(os2[i]["pu_cov"][1:], os_[i]["pu_cov"][1:]))
+
+
+@pytest.mark.parametrize("sweep", [1, 2, 3])
+def test_calibrated_fixed_diffusion_through_the_sweeps(oracle, sweep):
+    """FixedDiffusion(calibrate = true) (calibrate_solution!, src/integrator_utils.jl:46-57; global MLE, src/diffusions/calibration.jl:49-66): the step kernel
+    reports sigma_hat^2 and the sweeps scale the smoothed covariances by it -- FitzHugh-Nagumo EK1(3), fixed steps, all three sweeps, against the oracle:
+    global diffusion 1e-10, smoothed means 1e-10, calibrated covariances 1e-9 / floor."""
+    pd = problems.PROBLEMS["fitzhugh_nagumo"]
+    q, N, dt, t1 = 3, 9, 0.05, 1.0
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N, seed=53)
+    kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_FIXED, calibrate=True, adaptive=False, dt=dt, t0=0.0, t1=t1, save_everystep=True, smooth=True)
+    os_ = [oracle.solve(oracle.make_config(2, q, pd.n_p, cov_backend=oracle.COV_REF, **kw), rhs, u0[i], p[i]) for i in range(N)]
+    os2 = [oracle.solve(oracle.make_config(2, q, pd.n_p, cov_backend=oracle.COV_QR, **kw), rhs, u0[i], p[i]) for i in range(N)]
+    ns = os_[0]["n"]
+    off = np.arange(N + 1) * ns
+    ks = _run_warp("fitzhugh_nagumo", q, 4, 8, np.array([o["x_filt_mu"][0] for o in os_]), p, off, t1=t1, dt=dt, calibrate=True, save=2, smooth=sweep)
+    for i in range(N):
+        sl = slice(off[i], off[i + 1])
+        assert ks["scal"][i, 2] == pytest.approx(os_[i]["global_diffusion"], rel=1e-10)
+        assert _rel(ks["s_u"][sl], os_[i]["pu_mu"]) < 1e-10
+        assert _rel(ks["s_cov"][sl][1:], os_[i]["pu_cov"][1:]) < max(1e-9, 20 * _rel(os2[i]["pu_cov"][1:], os_[i]["pu_cov"][1:]))
