@@ -814,3 +814,27 @@ def test_calibrated_fixed_diffusion_through_the_sweeps(oracle, sweep):
         assert ks["scal"][i, 2] == pytest.approx(os_[i]["global_diffusion"], rel=1e-10)
         assert _rel(ks["s_u"][sl], os_[i]["pu_mu"]) < 1e-10
         assert _rel(ks["s_cov"][sl][1:], os_[i]["pu_cov"][1:]) < max(1e-9, 20 * _rel(os2[i]["pu_cov"][1:], os_[i]["pu_cov"][1:]))
+
+
+@pytest.mark.parametrize("problem,q,G,GS,t1,dt", [("fitzhugh_nagumo", 3, 4, 8, 1.0, 0.05), ("vanderpol", 5, 8, 8, 0.01, 2.5e-4)])
+@pytest.mark.parametrize("sweep", [1, 2])
+def test_dynamic_diffusion_through_the_register_sweeps(oracle, problem, q, G, GS, t1, dt, sweep):
+    """DynamicDiffusion (the reference's default; src/diffusions/calibration.jl:123-133): the local estimate of every step is saved and scales that step's
+    process noise in the backward sweep.  cfg1 / cfg3 shapes, fixed steps, both register sweeps against the oracle; tolerances are 20 x the oracle's own
+    Cholesky-vs-QR floor measured here (with a per-step diffusion the covariances of the two routes sit further apart than under FixedDiffusion), at
+    least 1e-10 (means) / 1e-9 (covariances)."""
+    pd = problems.PROBLEMS[problem]
+    N = 6
+    rhs = oracle.compile_rhs(tracer.trace(pd.f, pd.d, pd.n_p), q)
+    u0, p = _ensemble(pd, N, seed=59)
+    kw = dict(alg=oracle.EK1, diffusion=oracle.DIFF_DYNAMIC, adaptive=False, dt=dt, t0=0.0, t1=t1, save_everystep=True, smooth=True)
+    os_ = [oracle.solve(oracle.make_config(pd.d, q, pd.n_p, cov_backend=oracle.COV_REF, **kw), rhs, u0[i], p[i]) for i in range(N)]
+    os2 = [oracle.solve(oracle.make_config(pd.d, q, pd.n_p, cov_backend=oracle.COV_QR, **kw), rhs, u0[i], p[i]) for i in range(N)]
+    ns = os_[0]["n"]
+    off = np.arange(N + 1) * ns
+    ks = _run_warp(problem, q, G, GS, np.array([o["x_filt_mu"][0] for o in os_]), p, off, t1=t1, dt=dt, dynamic=True, save=2, smooth=sweep)
+    for i in range(N):
+        sl = slice(off[i], off[i + 1])
+        assert _rel(ks["s_diff"][sl][:-1], os_[i]["diffusions"][:ns - 1]) < 1e-8
+        assert _rel(ks["s_u"][sl], os_[i]["pu_mu"]) < max(1e-10, 20 * _rel(os2[i]["pu_mu"], os_[i]["pu_mu"]))
+        assert _rel(ks["s_cov"][sl][1:], os_[i]["pu_cov"][1:]) < max(1e-9, 20 * _rel(os2[i]["pu_cov"][1:], os_[i]["pu_cov"][1:]))
